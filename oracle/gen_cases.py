@@ -1,0 +1,64 @@
+"""Seeded case definitions shared by oracle/gen_golden.py and the tests (TEST INFRASTRUCTURE).
+
+Each entry returns (cfg, seed, dims, extra) so that the fixture generator (which
+imports the reference) and the tests (which do not) build identical inputs."""
+import copy
+
+import torch
+
+import msa_tts_b200 as pkg
+
+CRIT = dict(reduction="none", pos_weight=10.0)
+
+
+def _small(**attn):
+    c = pkg.small_params()
+    c["attention_params"].update(attn)
+    return c
+
+
+def _spklin():
+    c = pkg.small_params()
+    c["speaker_emb_type"] = "static+linear"
+    return c
+
+
+CASES = {
+    "small_train": lambda: (_small(), 11, (3, 12, 9), CRIT),
+    "small_train_meanloss": lambda: (_small(), 12, (2, 10, 12), dict(reduction="mean", pos_weight=10.0)),
+    "small_train_fwdattn_sigmoid": lambda: (_small(norm="sigmoid", forward_attn=True, trans_agent=True), 13, (3, 12, 9), CRIT),
+    "small_train_spklin": lambda: (_spklin(), 14, (3, 11, 10), CRIT),
+    "small_train_sigmoid": lambda: (_small(norm="sigmoid"), 15, (4, 13, 10), CRIT),
+    # BASELINE.json configs[0]: default dims, batch 4, 200 mel frames, 80 mels
+    "default_train_b4_t200": lambda: (pkg.default_params(), 0, (4, 200, 64), CRIT),
+}
+
+
+def _infer(early=False, thr=0.5, **attn):
+    c = _small(**attn)
+    c["max_decoder_steps"] = 24
+    c["decoder_no_early_stopping"] = not early
+    c["gate_threshold"] = thr
+    return c
+
+
+INFER_CASES = {
+    "small_infer": lambda: (_infer(), 21, (3, 9), 24),
+    # threshold picked by gen_golden.pick_threshold so that the rows stop at different steps
+    "small_infer_earlystop": lambda: (_infer(early=True, thr=0.62), 22, (3, 9), 24),
+    "small_infer_window_fwdmask": lambda: (_infer(windowing=True, forward_attn=True, forward_attn_mask=True,
+                                                  trans_agent=True), 23, (3, 14), 24),
+}
+
+
+def infer_stats(P, cfg, seed):
+    """Non-trivial BN running statistics, as left by a few adaptation passes."""
+    from oracle import model as OM
+    g = torch.Generator().manual_seed(seed + 7)
+    stats = OM.fresh_bn_stats(P, cfg)
+    for k in stats:
+        if k.endswith("running_mean"):
+            stats[k] = 0.2 * torch.randn(stats[k].shape, generator=g)
+        elif k.endswith("running_var"):
+            stats[k] = 0.5 + torch.rand(stats[k].shape, generator=g)
+    return stats
