@@ -1,0 +1,188 @@
+/*
+ * msa_b200.h -- C ABI of the B200-native meta-training hot path of
+ * HamedHemati/MetaSpeakerAdaptation-TTS (Tacotron2NV adapt-then-evaluate pass).
+ *
+ * The reference is pure Python/PyTorch and has NO FFI of its own;
+ * every entry point below names the reference code it replaces (paths relative
+ * to /root/reference/msa_tts/).  INTEGRATION.md shows the ctypes binding a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C: device pointers + sizes, no torch types, no C++ exceptions.
+ *   - every function returns int: 0 = ok, <0 = argument/shape/unsupported
+ *     error (MSA_E_*), >0 = cudaError_t / (1000 + cublasStatus_t).
+ *     msa_last_error_string() describes the last failure of the calling thread.
+ *   - all device memory is owned by the caller (PyTorch caching allocator);
+ *     the handle owns only its cuBLAS handle and small host-side tables.
+ *   - all work is enqueued on the cudaStream_t passed in (as void*), nothing
+ *     synchronises the host except where stated.
+ *   - one host thread per handle; handles are independent.
+ *   - there is no CPU fallback: without a CUDA device msa_create fails.
+ *
+ * Layouts (fp32 unless stated; "tm" = time-major)
+ *   params / grads / m / v / fisher / means : one flat buffer, tensors in
+ *       model.parameters() order, each starting on a 32-float boundary
+ *       (msa_param_info gives name/offset/numel).
+ *   bn_stats : per BatchNorm layer [running_mean(Cpad), running_var(Cpad)],
+ *       Cpad = C rounded up to 32 (msa_bn_info).
+ *   tokens int64 [B, L]; token_lengths int64 [B] sorted descending;
+ *   mels [B, n_mel, T]; mel_lengths int64 [B]; speaker vectors [B, Ds];
+ *   stop targets [B, T]  -- exactly the reference batch tuple
+ *       (dataloaders/dataloader_meta.py:133-179, metatrainer.py:95-117).
+ *   dropout keep-masks: one uint8 buffer (1 = keep), sections in the order of
+ *       the reference's F.dropout calls, layouts given by msa_mask_info.
+ */
+#ifndef MSA_B200_H
+#define MSA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSA_OK 0
+#define MSA_E_ARG (-1)          /* bad pointer / size / shape */
+#define MSA_E_UNSUPPORTED (-2)  /* configuration outside the implemented path */
+#define MSA_E_WORKSPACE (-3)    /* workspace too small */
+#define MSA_E_NODEVICE (-4)     /* no sm_100 CUDA device */
+#define MSA_E_STATE (-5)        /* call order (e.g. backward without forward) */
+
+/* mirrors params["model"] of Tacotron2NV(params) (models/tacotron2nv.py:11-66) */
+typedef struct msa_config {
+    int32_t n_symbols;            /* n_symbols */
+    int32_t enc_dim;              /* encoder_embedding_dim == symbols_embedding_dim */
+    int32_t enc_kernel;           /* encoder_kernel_size */
+    int32_t enc_n_convs;          /* encoder_n_convolutions */
+    int32_t spk_mode;             /* 0 static, 1 static+linear, 2 learnable_lookup */
+    int32_t spk_in_dim;           /* speaker_embedding_dim */
+    int32_t spk_dim;              /* width appended to the encoder output */
+    int32_t num_speakers;
+    int32_t n_mel;                /* n_mel_channels (n_frames_per_step == 1) */
+    int32_t prenet_dim;
+    int32_t attn_rnn_dim;         /* hidden of decoder.attention_rnn (after the ctor swap) */
+    int32_t dec_rnn_dim;          /* hidden of decoder.decoder_rnn */
+    int32_t attn_dim;
+    int32_t loc_filters;
+    int32_t loc_kernel;
+    int32_t post_dim;
+    int32_t post_kernel;
+    int32_t post_n_convs;
+    int32_t attn_norm;            /* 0 softmax, 1 sigmoid (forward_attn.py:200-207) */
+    int32_t forward_attn;         /* forward_attn.py:154-176 */
+    int32_t trans_agent;
+    int32_t windowing;            /* eval only, forward_attn.py:139-152 */
+    int32_t forward_attn_mask;    /* eval only, forward_attn.py:163-173 */
+    int32_t max_decoder_steps;
+    int32_t early_stopping;       /* not decoder_no_early_stopping */
+    int32_t loss_reduction;       /* 0 "none" (length-normalised masks), 1 "mean" */
+    int32_t gemm_tf32;            /* 0: fp32 GEMMs, 1: TF32 tensor-core GEMMs */
+    float p_attn_dropout;
+    float p_dec_dropout;
+    float gate_threshold;
+    float loss_pos_weight;
+} msa_config;
+
+typedef struct msa_handle msa_handle;
+
+const char* msa_last_error_string(void);
+int msa_version(void);
+
+/* ---- handle ------------------------------------------------------------------------ */
+int msa_create(const msa_config* cfg, int device, msa_handle** out);
+int msa_destroy(msa_handle* h);
+/* number of SMs / cooperative grid size the persistent kernels use */
+int msa_sm_count(const msa_handle* h);
+
+/* ---- flat layout (replaces iterating model.parameters(), maml.py:71-76) -------------- */
+int msa_param_count(const msa_handle* h);
+int64_t msa_param_total(const msa_handle* h);           /* floats in a flat buffer (incl. padding) */
+int msa_param_info(const msa_handle* h, int index, const char** name, int64_t* offset, int64_t* numel);
+int msa_bn_count(const msa_handle* h);
+int64_t msa_bn_total(const msa_handle* h);
+int msa_bn_info(const msa_handle* h, int index, int64_t* offset, int32_t* channels);
+/* dropout mask sections: index in call order; *rows x *cols uint8, layout string for docs */
+int msa_mask_count(const msa_handle* h);
+int64_t msa_mask_total(const msa_handle* h, int B, int T, int L);
+int msa_mask_info(const msa_handle* h, int index, int B, int T, int L, const char** name, int64_t* offset,
+                  int64_t* numel, float* p);
+/* counter-based keep-mask generator (production path; parity tests inject masks instead) */
+int msa_masks_generate(msa_handle* h, uint8_t* masks, int B, int T, int L, uint64_t seed, void* stream);
+
+/* ---- one teacher-forced pass: Tacotron2NV.forward + Tacotron2Loss -------------------
+ * replaces fmodel(**inputs) + criterion(...) (maml.py:50-53, reptile.py:52-55,
+ * models/tacotron2nv.py:81-127, modules_tacotron2nv/tacotron2nv_loss.py:17-52).
+ * Outputs are in the reference layouts: mel / mel_post [B, n_mel, T], gate [B, T],
+ * align [B, T, L]; loss is one device float.  bn_stats (may be NULL) is updated in
+ * place like BatchNorm1d in train mode.  Intermediates stay in `ws` for backward. */
+size_t msa_workspace_bytes(const msa_handle* h, int B, int T, int L);
+int msa_train_forward(msa_handle* h, void* ws, size_t ws_bytes, const float* params, float* bn_stats,
+                      const int64_t* tokens, const int64_t* token_lengths, const float* mels,
+                      const int64_t* mel_lengths, const float* speaker_vecs, const int64_t* speaker_ids,
+                      const float* stop_targets, const uint8_t* masks, int B, int T, int L,
+                      float* mel_out, float* mel_post_out, float* gate_out, float* align_out,
+                      float* loss_out, void* stream);
+/* replaces diffopt.step's autograd.grad / torch.autograd.grad(loss_test, ...) / loss.backward()
+ * (maml.py:54,71-74; continual_ewc.py:355-356).  d_mel/d_mel_post/d_gate are upstream
+ * gradients in the output layouts; pass NULL for all three to use d(loss)/d(outputs) of
+ * the loss computed by the matching msa_train_forward.  grads (flat) is overwritten
+ * (accumulate == 0) or accumulated into (accumulate != 0) with grad_scale * gradient. */
+int msa_train_backward(msa_handle* h, void* ws, size_t ws_bytes, const float* params, const float* d_mel,
+                       const float* d_mel_post, const float* d_gate, float* grads, int accumulate,
+                       float grad_scale, void* stream);
+/* d(loss)/d(mel, mel_post, gate) of the last forward, reference layouts (for autograd glue) */
+int msa_loss_grads(msa_handle* h, void* ws, float* d_mel, float* d_mel_post, float* d_gate, void* stream);
+/* test hook: device pointer + element count of a named intermediate of the last pass */
+int msa_get_buffer(msa_handle* h, void* ws, const char* name, void** ptr, int64_t* numel);
+
+/* ---- free-running inference: Tacotron2NV.infer (models/tacotron2nv.py:130-162,
+ * modules_tacotron2nv/decoder.py:334-411).  bn_stats are the (private) running statistics;
+ * prenet_masks uint8 [max_steps, 2, B, prenet_dim] (dropout stays on).
+ * Outputs: mel_post [B, n_mel, max_steps] (first *n_steps frames valid), mel_lengths
+ * int32 [B], align [B, max_steps, L]; n_steps_out is one device int32. */
+size_t msa_infer_workspace_bytes(const msa_handle* h, int B, int L, int max_steps);
+int msa_infer(msa_handle* h, void* ws, size_t ws_bytes, const float* params, const float* bn_stats,
+              const int64_t* tokens, const int64_t* token_lengths, const float* speaker_vecs,
+              const int64_t* speaker_ids, const uint8_t* prenet_masks, int B, int L, int max_steps,
+              float* mel_post_out, int32_t* mel_lengths_out, float* align_out, int32_t* n_steps_out,
+              void* stream);
+
+/* ---- fused multi-tensor kernels over flat buffers (n floats) -------------------------- */
+/* higher's functional SGD step, p' = p - lr*(g + wd*p) with optional momentum buffer
+ * (diffopt.step, maml.py:54 / reptile.py:56; torch.optim.SGD rule).  p_out may alias p. */
+int msa_flat_sgd_step(const float* p, const float* g, float* p_out, float* momentum_buf, int64_t n, float lr,
+                      float momentum, float dampening, float weight_decay, int nesterov, int first_step,
+                      void* stream);
+/* mix_grad: acc = (init ? 0 : acc) + w * g   (utils/grad_utils.py:23-31, maml.py:94-98) */
+int msa_flat_axpy(float* acc, const float* g, int64_t n, float w, int init, void* stream);
+/* Reptile task "gradient" acc = (init ? 0 : acc) + w * -(p_T - p_0)   (reptile.py:73-77) */
+int msa_flat_reptile_delta(float* acc, const float* p_T, const float* p_0, int64_t n, float w, int init,
+                           void* stream);
+/* apply_grad's norm (utils/grad_utils.py:8-20) / clip_grad_norm_'s total norm: out[0] = sum(g*g).
+ * `partials` is caller scratch of msa_flat_partials() floats. */
+int msa_flat_partials(void);
+int msa_flat_sumsq(const float* g, int64_t n, float* partials, float* out, void* stream);
+/* clip_grad_norm_ + outer_optimizer.step() (maml.py:101-105, reptile.py:85-89) fused:
+ * coef = min(1, max_norm / (sqrt(*sumsq) + 1e-6)) (max_norm <= 0: no clipping);
+ * SGD:  p -= lr * coef * g  (+ momentum/weight decay as torch.optim.SGD)
+ * Adam: torch.optim.Adam (no amsgrad), step = 1-based step index. */
+int msa_flat_clip_sgd(float* p, const float* g, float* momentum_buf, const float* sumsq, int64_t n, float lr,
+                      float max_norm, float momentum, float dampening, float weight_decay, int nesterov,
+                      int first_step, void* stream);
+int msa_flat_clip_adam(float* p, const float* g, float* m, float* v, const float* sumsq, int64_t n, float lr,
+                       float beta1, float beta2, float eps, float weight_decay, int step, float max_norm,
+                       void* stream);
+/* EWC (continual_ewc.py): fisher += g*g / n_batches (59-82);
+ * penalty = sum F (p-mu)^2 -> out[0] (84-89);
+ * fused step p -= lr * (g + 2*lam*F*(p-mu)) and penalty in the same pass (345-357). */
+int msa_ewc_fisher_accum(float* fisher, const float* g, int64_t n, float inv_n_batches, int init, void* stream);
+int msa_ewc_penalty(const float* p, const float* mu, const float* fisher, int64_t n, float* partials,
+                    float* out, void* stream);
+int msa_ewc_sgd_step(float* p, const float* g, const float* mu, const float* fisher, int64_t n, float lr,
+                     float lam, float* partials, float* penalty_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSA_B200_H */

@@ -1,0 +1,133 @@
+// Internal launcher declarations (host side) for the hot-path kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace msa {
+
+// ---------------- persistent LSTM recurrence (lstm_rec.cu) ----------------
+struct LstmRecParams {
+    int T, B, H, ndir;
+    const float* zin;          // [ndir][T][B][4H]  W_ih.x + b_ih + b_hh, gate-major rows (i,f,g,o)
+    const float* whh;          // [4H][H] per direction
+    int64_t whh_dir_stride;    // floats between the two directions' W_hh
+    float* hout;               // [ndir][T][B][H]   (post-dropout) hidden = recurrent state
+    float* cout;               // [ndir][T][B][H]
+    float* gates;              // [ndir][T][B][4H]  post-activation i,f,g,o (stash for backward)
+    const uint8_t* mask;       // [T][B][H] keep-mask or nullptr
+    float drop_scale;          // 1/(1-p)
+    const int64_t* lengths;    // [B] packed-sequence lengths or nullptr
+    unsigned int* barrier;
+};
+struct LstmRecBwdParams {
+    int T, B, H, ndir;
+    const float* whh;
+    int64_t whh_dir_stride;
+    const float* gates;
+    const float* cout;
+    const float* dh_ext;       // [ndir][T][B][H] grad w.r.t. hout from everything but the recurrence
+    float* dz;                 // [ndir][T][B][4H] grad w.r.t. gate pre-activations
+    const uint8_t* mask;
+    float drop_scale;
+    const int64_t* lengths;
+    unsigned int* barrier;
+};
+size_t lstm_rec_fwd_smem(int B, int H);
+size_t lstm_rec_bwd_smem(int B, int H);
+int launch_lstm_rec_fwd(const LstmRecParams& p, int sm_count, size_t smem_limit, cudaStream_t st);
+int launch_lstm_rec_bwd(const LstmRecBwdParams& p, int sm_count, size_t smem_limit, cudaStream_t st);
+
+// ---------------- attention-RNN + location-sensitive attention chain (attn_chain.cu) ----------------
+struct AttnChainParams {
+    int T, B, L, Ha, A, F, Kl, norm;   // norm: 0 softmax, 1 sigmoid
+    const float* xw;       // [T][B][4Ha]  W_ih[:, :prenet].x_t + b_ih + b_hh
+    const float* whh;      // [4Ha][Ha]
+    const float* mw_rm;    // [4Ha][B*L]   (W_ih[:, prenet:] . memory^T), row-major over gate rows
+    const float* wq;       // [A][Ha]
+    const float* pm;       // [B][L][A]    processed memory
+    const float* wloc;     // [F][2][Kl]
+    const float* wld;      // [A][F]
+    const float* v;        // [A]
+    const float* bv;       // [1]
+    const uint8_t* mask;   // [T][B][Ha]
+    float drop_scale;
+    float* ha;             // [T][B][Ha]
+    float* ca;             // [T][B][Ha]
+    float* ga;             // [T][B][4Ha]
+    float* q;              // [T][B][A]
+    float* align;          // [T][B][L]
+    float* cum;            // [T][B][L]   cumulative weights fed to the location conv at step t
+    float* s;              // [T][B][L][A] tanh(q + loc + pm)
+    float* convf;          // [T][B][L][F]
+    float* znorm;          // [T][B]      normaliser (sum of sigmoids) for norm == 1
+    float* ebuf;           // [B][L] scratch
+    unsigned int* barrier;
+};
+struct AttnChainBwdParams {
+    int T, B, L, Ha, A, F, Kl, norm;
+    const float* whh;
+    const float* mw_pm;    // [B*L][4Ha]
+    const float* wq;
+    const float* wloc;
+    const float* wld;
+    const float* v;
+    const uint8_t* mask;
+    float drop_scale;
+    const float* ga;
+    const float* ca;
+    const float* align;
+    const float* s;
+    const float* znorm;
+    const float* dha_ext;  // [T][B][Ha]
+    const float* da_ext;   // [T][B][L]
+    float* dza;            // [T][B][4Ha]
+    float* dq;             // [T][B][A]
+    float* de;             // [T][B][L]
+    float* ds;             // [T][B][L][A]
+    float* dconvf;         // [T][B][L][F]
+    float* dat;            // [B][L] scratch
+    unsigned int* barrier;
+};
+size_t attn_chain_fwd_smem(int B, int L, int Ha, int A, int F, int Kl, int sm_count, bool mw_resident);
+size_t attn_chain_bwd_smem(int B, int L, int Ha, int A, int F, int Kl, int sm_count);
+int launch_attn_chain_fwd(const AttnChainParams& p, int sm_count, size_t smem_limit, cudaStream_t st);
+int launch_attn_chain_bwd(const AttnChainBwdParams& p, int sm_count, size_t smem_limit, cudaStream_t st);
+
+// ---------------- element-wise / layout / reduction kernels (model_kernels.cu) ----------------
+int k_embedding_fwd(const float* w, const int64_t* tok, float* x, int rows, int C, int n_symbols, cudaStream_t st);
+int k_embedding_bwd(const float* dx, const int64_t* tok, float* gw, int rows, int C, int n_symbols, float scale, int accumulate, cudaStream_t st);
+int k_im2col(const float* x, float* col, int B, int T, int C, int K, cudaStream_t st);
+int k_col2im(const float* dcol, float* dx, int B, int T, int C, int K, cudaStream_t st);
+int k_conv_w_pack(const float* w, float* w2, int Co, int Ci, int K, cudaStream_t st);
+int k_conv_w_unpack_grad(const float* dw2, float* gw, int Co, int Ci, int K, float scale, int accumulate, cudaStream_t st);
+int k_fill_rows(float* y, const float* b1, const float* b2, int64_t rows, int N, cudaStream_t st);
+int k_colsum(const float* x, int64_t rows, int N, int ld, float* out, float scale, int accumulate, float* out2, cudaStream_t st);
+int k_bn_stats(const float* y, int64_t rows, int C, float* mean, float* invstd, float* running, int Cpad, cudaStream_t st);
+int k_bn_eval_stats(const float* running, int C, int Cpad, float* mean, float* invstd, cudaStream_t st);
+// act: 0 none, 1 relu, 2 tanh
+int k_bn_act_drop_fwd(const float* y, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                      const uint8_t* mask, float drop_scale, int act, float* out, int64_t rows, int C, cudaStream_t st);
+int k_bn_act_drop_bwd(const float* dout, const float* y, const float* mean, const float* invstd, const float* gamma,
+                      const float* beta, const uint8_t* mask, float drop_scale, int act, float* dy, float* ggamma,
+                      float* gbeta, float* scratch, int64_t rows, int C, float scale, int accumulate, cudaStream_t st);
+int k_relu_drop_fwd(float* x, const uint8_t* mask, float drop_scale, int64_t n, cudaStream_t st);
+int k_relu_drop_bwd(float* dx, const float* out, const uint8_t* mask, float drop_scale, int64_t n, cudaStream_t st);
+int k_transpose01(const float* in, float* out, int D0, int D1, int C, cudaStream_t st);   // [D0][D1][C] -> [D1][D0][C]
+int k_prep_mels(const float* mels, float* frames_tm, float* target_bt, int B, int M, int T, cudaStream_t st);
+int k_build_memory(const float* enc_h, const float* spk, float* memory, int B, int L, int Hh, int Ds, cudaStream_t st);
+int k_split_dmemory(const float* dmem, float* denc_h, float* dspk, int B, int L, int Hh, int Ds, cudaStream_t st);
+int k_bt_to_ref(const float* x_bt, float* out, int B, int T, int M, cudaStream_t st);      // [B][T][M] -> [B][M][T]
+int k_ref_to_bt(const float* x, float* out_bt, int B, int T, int M, cudaStream_t st);      // [B][M][T] -> [B][T][M]
+int k_add(const float* a, const float* b, float* out, int64_t n, cudaStream_t st);
+int k_add3(const float* a, const float* b, const float* c, float* out, int64_t n, cudaStream_t st);
+int k_loss(const float* pre_bt, const float* post_bt, const float* gate_bt, const float* target_bt, const float* stop,
+           const int64_t* mel_len, int B, int T, int M, int reduction, float pos_weight, float* partials, float* loss,
+           float* dpre, float* dpost, float* dgate, cudaStream_t st);
+int k_sum_over_t(const float* x, float* out, int T, int64_t n, cudaStream_t st);           // out[n] = sum_t x[t][n]
+int k_wloc_grad(const float* dconvf, const float* align, const float* cum, float* gw, int T, int B, int L, int F, int Kl,
+                float scale, int accumulate, cudaStream_t st);
+int k_dot_rows(const float* a, const float* b, int64_t n, float* partials, float* out, float scale, int accumulate, cudaStream_t st);
+int k_masks_generate(uint8_t* masks, const int64_t* offsets, const int64_t* numels, const float* ps, int nsec, uint64_t seed, cudaStream_t st);
+int k_scale_copy(const float* in, float* out, int64_t n, float scale, int accumulate, cudaStream_t st);
+
+}  // namespace msa

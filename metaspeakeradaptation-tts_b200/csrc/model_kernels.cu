@@ -1,0 +1,607 @@
+// Element-wise, layout, normalisation, loss and small reduction kernels of the teacher-forced pass.
+// All are HBM/L2-bound: coalesced (128-bit where the shape allows) accesses, deterministic
+// reductions (fixed order, no float atomics), grids sized by the work.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace msa {
+
+constexpr int kTh = 256;
+static inline int grid_for(int64_t n, int per_block = kTh, int cap = 148 * 16) {
+    int64_t g = (n + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    return (int)(g > cap ? cap : g);
+}
+#define GSL(i, n) for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
+
+// ---------------- embedding (tacotron2nv.py:88) ----------------
+__global__ void ker_embedding_fwd(const float* __restrict__ w, const int64_t* __restrict__ tok, float* x, int64_t n, int C, int nsym) {
+    GSL(i, n) {
+        const int64_t row = i / C;
+        const int c = (int)(i % C);
+        int64_t id = tok[row];
+        id = id < 0 ? 0 : (id >= nsym ? nsym - 1 : id);
+        x[i] = w[id * C + c];
+    }
+}
+// deterministic scatter-add: one thread per (symbol, channel) scans the token list in order
+__global__ void ker_embedding_bwd(const float* __restrict__ dx, const int64_t* __restrict__ tok, float* gw, int rows, int C,
+                                  int nsym, float scale, int accumulate) {
+    GSL(i, (int64_t)nsym * C) {
+        const int64_t v = i / C;
+        const int c = (int)(i % C);
+        float s = 0.f;
+        for (int r = 0; r < rows; ++r)
+            if (tok[r] == v) s += dx[(int64_t)r * C + c];
+        gw[i] = accumulate ? gw[i] + scale * s : scale * s;
+    }
+}
+
+// ---------------- conv1d as im2col + GEMM (encoder.py:18-28, decoder.py:23-61) ----------------
+// x [B][T][C] -> col [B*T][K][C], zero padded ("same")
+__global__ void ker_im2col(const float* __restrict__ x, float* col, int B, int T, int C, int K) {
+    const int pad = (K - 1) / 2;
+    const int64_t n = (int64_t)B * T * K * C;
+    GSL(i, n) {
+        const int c = (int)(i % C);
+        const int k = (int)((i / C) % K);
+        const int64_t bt = i / ((int64_t)C * K);
+        const int t = (int)(bt % T), b = (int)(bt / T);
+        const int ts = t + k - pad;
+        col[i] = (ts >= 0 && ts < T) ? x[((int64_t)b * T + ts) * C + c] : 0.f;
+    }
+}
+// dx[b][t][c] = sum_k dcol[b][t-k+pad][k][c]
+__global__ void ker_col2im(const float* __restrict__ dcol, float* dx, int B, int T, int C, int K) {
+    const int pad = (K - 1) / 2;
+    const int64_t n = (int64_t)B * T * C;
+    GSL(i, n) {
+        const int c = (int)(i % C);
+        const int t = (int)((i / C) % T), b = (int)(i / ((int64_t)C * T));
+        float s = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const int to = t - k + pad;
+            if (to >= 0 && to < T) s += dcol[(((int64_t)b * T + to) * K + k) * C + c];
+        }
+        dx[i] = s;
+    }
+}
+// w [Co][Ci][K] -> w2 [Co][K][Ci]
+__global__ void ker_w_pack(const float* __restrict__ w, float* w2, int Co, int Ci, int K) {
+    const int64_t n = (int64_t)Co * Ci * K;
+    GSL(i, n) {
+        const int ci = (int)(i % Ci);
+        const int k = (int)((i / Ci) % K);
+        const int64_t co = i / ((int64_t)Ci * K);
+        w2[i] = w[(co * Ci + ci) * K + k];
+    }
+}
+__global__ void ker_w_unpack_grad(const float* __restrict__ dw2, float* gw, int Co, int Ci, int K, float scale, int accumulate) {
+    const int64_t n = (int64_t)Co * Ci * K;
+    GSL(i, n) {
+        const int k = (int)(i % K);
+        const int ci = (int)((i / K) % Ci);
+        const int64_t co = i / ((int64_t)Ci * K);
+        const float v = scale * dw2[(co * K + k) * Ci + ci];
+        gw[i] = accumulate ? gw[i] + v : v;
+    }
+}
+
+// y[r][n] = b1[n] (+ b2[n])
+__global__ void ker_fill_rows(float* y, const float* __restrict__ b1, const float* __restrict__ b2, int64_t total, int N) {
+    GSL(i, total) {
+        const int n = (int)(i % N);
+        y[i] = b1[n] + (b2 ? b2[n] : 0.f);
+    }
+}
+// out[n] = sum_r x[r*ld + n]; block = 32 columns x 8 row lanes
+__global__ void ker_colsum(const float* __restrict__ x, int64_t rows, int N, int ld, float* out, float scale, int accumulate, float* out2) {
+    __shared__ float sh[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + cx;
+    float s = 0.f;
+    if (n < N)
+        for (int64_t r = ry; r < rows; r += 8) s += x[r * ld + n];
+    sh[ry][cx] = s;
+    __syncthreads();
+    if (ry == 0 && n < N) {
+        float t = 0.f;
+        for (int j = 0; j < 8; ++j) t += sh[j][cx];
+        t *= scale;
+        out[n] = accumulate ? out[n] + t : t;
+        if (out2) out2[n] = accumulate ? out2[n] + t : t;
+    }
+}
+
+// ---------------- BatchNorm1d (train) + activation + dropout ----------------
+// y [rows][C]; two-pass mean / biased variance per channel; running stats updated with unbiased variance.
+__global__ void ker_bn_stats(const float* __restrict__ y, int64_t rows, int C, float* mean, float* invstd, float* running, int Cpad) {
+    __shared__ float sh[8][33];
+    __shared__ float mu[32];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
+    float s = 0.f;
+    if (c < C)
+        for (int64_t r = ry; r < rows; r += 8) s += y[r * C + c];
+    sh[ry][cx] = s;
+    __syncthreads();
+    if (ry == 0) {
+        float t = 0.f;
+        for (int j = 0; j < 8; ++j) t += sh[j][cx];
+        mu[cx] = t / (float)rows;
+    }
+    __syncthreads();
+    const float m = mu[cx];
+    s = 0.f;
+    if (c < C)
+        for (int64_t r = ry; r < rows; r += 8) {
+            const float d = y[r * C + c] - m;
+            s += d * d;
+        }
+    sh[ry][cx] = s;
+    __syncthreads();
+    if (ry == 0 && c < C) {
+        float t = 0.f;
+        for (int j = 0; j < 8; ++j) t += sh[j][cx];
+        const float var = t / (float)rows;
+        mean[c] = m;
+        invstd[c] = 1.f / sqrtf(var + 1e-5f);
+        if (running) {
+            const float unb = rows > 1 ? t / (float)(rows - 1) : var;
+            running[c] = 0.9f * running[c] + 0.1f * m;
+            running[Cpad + c] = 0.9f * running[Cpad + c] + 0.1f * unb;
+        }
+    }
+}
+__global__ void ker_bn_eval_stats(const float* __restrict__ running, int C, int Cpad, float* mean, float* invstd) {
+    GSL(i, C) {
+        mean[i] = running[i];
+        invstd[i] = 1.f / sqrtf(running[Cpad + i] + 1e-5f);
+    }
+}
+__device__ __forceinline__ float act_fwd(float u, int act) { return act == 1 ? fmaxf(u, 0.f) : (act == 2 ? tanhf(u) : u); }
+__global__ void ker_bn_act_drop_fwd(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const uint8_t* __restrict__ mask, float ds, int act, float* out, int64_t total, int C) {
+    GSL(i, total) {
+        const int c = (int)(i % C);
+        const float u = gamma[c] * (y[i] - mean[c]) * invstd[c] + beta[c];
+        float v = act_fwd(u, act);
+        if (mask) v = mask[i] ? v * ds : 0.f;
+        out[i] = v;
+    }
+}
+__device__ __forceinline__ float bn_du(float dout, float u, uint8_t keep, bool has_mask, float ds, int act) {
+    float d = has_mask ? (keep ? dout * ds : 0.f) : dout;
+    if (act == 1) d = u > 0.f ? d : 0.f;
+    else if (act == 2) { const float th = tanhf(u); d = d * (1.f - th * th); }
+    return d;
+}
+// per channel: sum du, sum du*xhat  -> scratch[c], scratch[C + c]
+__global__ void ker_bn_bwd_reduce(const float* __restrict__ dout, const float* __restrict__ y, const float* __restrict__ mean,
+                                  const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  const uint8_t* __restrict__ mask, float ds, int act, float* scratch, int64_t rows, int C) {
+    __shared__ float sh1[8][33], sh2[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
+    float s1 = 0.f, s2 = 0.f;
+    if (c < C) {
+        const float m = mean[c], is = invstd[c], g = gamma[c], be = beta[c];
+        for (int64_t r = ry; r < rows; r += 8) {
+            const int64_t i = r * C + c;
+            const float xh = (y[i] - m) * is;
+            const float du = bn_du(dout[i], g * xh + be, mask ? mask[i] : 1, mask != nullptr, ds, act);
+            s1 += du;
+            s2 += du * xh;
+        }
+    }
+    sh1[ry][cx] = s1;
+    sh2[ry][cx] = s2;
+    __syncthreads();
+    if (ry == 0 && c < C) {
+        float t1 = 0.f, t2 = 0.f;
+        for (int j = 0; j < 8; ++j) { t1 += sh1[j][cx]; t2 += sh2[j][cx]; }
+        scratch[c] = t1;
+        scratch[C + c] = t2;
+    }
+}
+__global__ void ker_bn_bwd_apply(const float* __restrict__ dout, const float* __restrict__ y, const float* __restrict__ mean,
+                                 const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 const uint8_t* __restrict__ mask, float ds, int act, const float* __restrict__ scratch, float* dy,
+                                 int64_t rows, int C) {
+    const int64_t total = rows * C;
+    const float inv_n = 1.f / (float)rows;
+    GSL(i, total) {
+        const int c = (int)(i % C);
+        const float is = invstd[c], g = gamma[c];
+        const float xh = (y[i] - mean[c]) * is;
+        const float du = bn_du(dout[i], g * xh + beta[c], mask ? mask[i] : 1, mask != nullptr, ds, act);
+        dy[i] = g * is * (du - scratch[c] * inv_n - xh * scratch[C + c] * inv_n);
+    }
+}
+__global__ void ker_bn_param_grads(const float* __restrict__ scratch, float* ggamma, float* gbeta, int C, float scale, int accumulate) {
+    GSL(i, C) {
+        const float gb = scale * scratch[i], gg = scale * scratch[C + i];
+        gbeta[i] = accumulate ? gbeta[i] + gb : gb;
+        ggamma[i] = accumulate ? ggamma[i] + gg : gg;
+    }
+}
+
+// ---------------- prenet relu + always-on dropout (decoder.py:17-20) ----------------
+__global__ void ker_relu_drop_fwd(float* x, const uint8_t* __restrict__ mask, float ds, int64_t n) {
+    GSL(i, n) {
+        const float v = fmaxf(x[i], 0.f);
+        x[i] = mask[i] ? v * ds : 0.f;
+    }
+}
+__global__ void ker_relu_drop_bwd(float* dx, const float* __restrict__ out, const uint8_t* __restrict__ mask, float ds, int64_t n) {
+    GSL(i, n) { dx[i] = (mask[i] && out[i] > 0.f) ? dx[i] * ds : 0.f; }
+}
+
+// ---------------- layout helpers ----------------
+// [D0][D1][C] -> [D1][D0][C]
+__global__ void ker_transpose01(const float* __restrict__ in, float* out, int D0, int D1, int C) {
+    const int64_t n = (int64_t)D0 * D1 * C;
+    GSL(i, n) {
+        const int c = (int)(i % C);
+        const int d1 = (int)((i / C) % D1);
+        const int d0 = (int)(i / ((int64_t)C * D1));
+        out[((int64_t)d1 * D0 + d0) * C + c] = in[i];
+    }
+}
+// mels [B][M][T] -> frames_tm [T+1][B][M] (frame 0 = go frame of zeros, decoder.py:290-292) and target_bt [B][T][M]
+__global__ void ker_prep_mels(const float* __restrict__ mels, float* frames, float* target, int B, int M, int T) {
+    const int64_t n = (int64_t)B * T * M;
+    GSL(i, n) {
+        const int m = (int)(i % M);
+        const int t = (int)((i / M) % T);
+        const int b = (int)(i / ((int64_t)M * T));
+        const float v = mels[((int64_t)b * M + m) * T + t];
+        target[i] = v;
+        frames[((int64_t)(t + 1) * B + b) * M + m] = v;
+    }
+    GSL(j, (int64_t)B * M) frames[j] = 0.f;
+}
+// enc_h [2][L][B][Hh] + speaker vector [B][Ds] -> memory [B][L][2Hh+Ds]  (tacotron2nv.py:104-111)
+__global__ void ker_build_memory(const float* __restrict__ enc_h, const float* __restrict__ spk, float* mem, int B, int L, int Hh, int Ds) {
+    const int E = 2 * Hh + Ds;
+    const int64_t n = (int64_t)B * L * E;
+    GSL(i, n) {
+        const int e = (int)(i % E);
+        const int l = (int)((i / E) % L);
+        const int b = (int)(i / ((int64_t)E * L));
+        float v;
+        if (e < 2 * Hh) {
+            const int dir = e / Hh, u = e % Hh;
+            v = enc_h[(((int64_t)dir * L + l) * B + b) * Hh + u];
+        } else {
+            v = spk[(int64_t)b * Ds + (e - 2 * Hh)];
+        }
+        mem[i] = v;
+    }
+}
+__global__ void ker_split_dmemory(const float* __restrict__ dmem, float* denc_h, float* dspk, int B, int L, int Hh, int Ds) {
+    const int E = 2 * Hh + Ds;
+    const int64_t n = (int64_t)2 * L * B * Hh;
+    GSL(i, n) {
+        const int u = (int)(i % Hh);
+        const int b = (int)((i / Hh) % B);
+        const int l = (int)((i / ((int64_t)Hh * B)) % L);
+        const int dir = (int)(i / ((int64_t)Hh * B * L));
+        denc_h[i] = dmem[((int64_t)b * L + l) * E + dir * Hh + u];
+    }
+    if (dspk) {
+        GSL(j, (int64_t)B * Ds) {
+            const int d = (int)(j % Ds), b = (int)(j / Ds);
+            float s = 0.f;
+            for (int l = 0; l < L; ++l) s += dmem[((int64_t)b * L + l) * E + 2 * Hh + d];
+            dspk[j] = s;
+        }
+    }
+}
+__global__ void ker_bt_to_ref(const float* __restrict__ x, float* out, int B, int T, int M) {
+    const int64_t n = (int64_t)B * T * M;
+    GSL(i, n) {   // i indexes the OUTPUT [B][M][T] so that stores coalesce
+        const int t = (int)(i % T);
+        const int m = (int)((i / T) % M);
+        const int b = (int)(i / ((int64_t)T * M));
+        out[i] = x[((int64_t)b * T + t) * M + m];
+    }
+}
+__global__ void ker_ref_to_bt(const float* __restrict__ x, float* out, int B, int T, int M) {
+    const int64_t n = (int64_t)B * T * M;
+    GSL(i, n) {
+        const int m = (int)(i % M);
+        const int t = (int)((i / M) % T);
+        const int b = (int)(i / ((int64_t)M * T));
+        out[i] = x[((int64_t)b * M + m) * T + t];
+    }
+}
+__global__ void ker_add(const float* __restrict__ a, const float* __restrict__ b, float* out, int64_t n) {
+    GSL(i, n) out[i] = a[i] + b[i];
+}
+__global__ void ker_add3(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c, float* out, int64_t n) {
+    GSL(i, n) out[i] = a[i] + b[i] + c[i];
+}
+__global__ void ker_scale_copy(const float* __restrict__ in, float* out, int64_t n, float scale, int accumulate) {
+    GSL(i, n) out[i] = accumulate ? out[i] + scale * in[i] : scale * in[i];
+}
+
+// ---------------- Tacotron2Loss forward + backward (tacotron2nv_loss.py:17-52) ----------------
+// pre/post/target [B][T][M], gate/stop [B][T].  One block per (b,t) row chunk; deterministic 2-stage sum.
+__global__ void ker_loss(const float* __restrict__ pre, const float* __restrict__ post, const float* __restrict__ gate,
+                         const float* __restrict__ target, const float* __restrict__ stop, const int64_t* __restrict__ mel_len,
+                         int B, int T, int M, int reduction, float pw, float* partials, float* dpre, float* dpost, float* dgate) {
+    __shared__ float red[33];
+    const int64_t nrows = (int64_t)B * T;
+    float acc = 0.f;
+    for (int64_t row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int b = (int)(row / T), t = (int)(row % T);
+        float wmel, wgate;
+        if (reduction == 0) {
+            const int len = (int)mel_len[b];
+            const float w = (t < len) ? 1.f / (float)len : 0.f;         // masks / masks.sum (tacotron2nv_loss.py:39-41)
+            wmel = w / (float)(B * M);
+            wgate = w / (float)B;
+        } else {
+            wmel = 1.f / (float)((int64_t)B * T * M);
+            wgate = 1.f / (float)((int64_t)B * T);
+        }
+        for (int m = threadIdx.x; m < M; m += blockDim.x) {
+            const int64_t i = row * M + m;
+            const float y = target[i];
+            const float d1 = post[i] - y, d0 = pre[i] - y;
+            acc += wmel * (fabsf(d1) + fabsf(d0) + d1 * d1 + d0 * d0);
+            const float s1 = d1 > 0.f ? 1.f : (d1 < 0.f ? -1.f : 0.f), s0 = d0 > 0.f ? 1.f : (d0 < 0.f ? -1.f : 0.f);
+            dpost[i] = wmel * (s1 + 2.f * d1);
+            dpre[i] = wmel * (s0 + 2.f * d0);
+        }
+        if (threadIdx.x == 0) {
+            const float x = gate[row], y = stop[row];
+            // BCEWithLogits with pos_weight: (1-y)*x + (1+(pw-1)*y) * softplus(-x)
+            const float sp = log1pf(expf(-fabsf(x))) + fmaxf(-x, 0.f);
+            acc += wgate * ((1.f - y) * x + (1.f + (pw - 1.f) * y) * sp);
+            const float sg = 1.f / (1.f + expf(-x));
+            dgate[row] = wgate * (sg * (1.f - y + pw * y) - pw * y);
+        }
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+__global__ void ker_sum_partials(const float* __restrict__ partials, int n, float* out, float scale, int accumulate) {
+    __shared__ float red[33];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += partials[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[0] = accumulate ? out[0] + scale * s : scale * s;
+}
+
+// out[n] = sum_t x[t][n]
+__global__ void ker_sum_over_t(const float* __restrict__ x, float* out, int T, int64_t n) {
+    GSL(i, n) {
+        float s = 0.f;
+        for (int t = 0; t < T; ++t) s += x[(int64_t)t * n + i];
+        out[i] = s;
+    }
+}
+
+// d W_loc[f][c][k] = sum_{t,b,l} dconvf[t][b][l][f] * in_c[t][b][l+k-pad]; in_0 = align[t-1] (0 at t=0), in_1 = cum[t]
+// one block per (c,k); threads = f (fast) x row lanes
+__global__ void ker_wloc_grad(const float* __restrict__ dconvf, const float* __restrict__ align, const float* __restrict__ cum,
+                              float* gw, int T, int B, int L, int F, int Kl, float scale, int accumulate) {
+    __shared__ float sh[8][33];
+    const int c = blockIdx.x / Kl, k = blockIdx.x % Kl, pad = (Kl - 1) / 2;
+    const int f = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    float s = 0.f;
+    const int64_t rows = (int64_t)T * B * L;
+    if (f < F) {
+        for (int64_t r = ry; r < rows; r += 8) {
+            const int l = (int)(r % L);
+            const int64_t tb = r / L;
+            const int t = (int)(tb / B);
+            const int li = l + k - pad;
+            if (li < 0 || li >= L) continue;
+            float v;
+            if (c == 0) v = t > 0 ? align[(tb - B) * L + li] : 0.f;
+            else v = cum[tb * L + li];
+            s += dconvf[r * F + f] * v;
+        }
+    }
+    sh[ry][f] = s;
+    __syncthreads();
+    if (ry == 0 && f < F) {
+        float tsum = 0.f;
+        for (int j = 0; j < 8; ++j) tsum += sh[j][f];
+        const int64_t o = ((int64_t)f * 2 + c) * Kl + k;
+        gw[o] = accumulate ? gw[o] + scale * tsum : scale * tsum;
+    }
+}
+
+// out[0] (+)= scale * sum_i a[i]*b[i]   (b == nullptr: sum a)
+__global__ void ker_dot_partial(const float* __restrict__ a, const float* __restrict__ b, int64_t n, float* partials) {
+    __shared__ float red[33];
+    float s = 0.f;
+    GSL(i, n) s += b ? a[i] * b[i] : a[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+// ---------------- counter-based keep-mask generator ----------------
+__device__ __forceinline__ uint32_t mix32(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return (uint32_t)(x >> 11);
+}
+__global__ void ker_masks(uint8_t* masks, int64_t off, int64_t n, float p, uint64_t seed) {
+    const uint32_t thr = (uint32_t)(p * 2097152.0f);   // 21 random bits
+    GSL(i, n) {
+        const uint32_t r = mix32(seed ^ ((uint64_t)(off + i) * 0x9E3779B97F4A7C15ULL)) & 0x1FFFFF;
+        masks[off + i] = r >= thr ? 1 : 0;
+    }
+}
+
+// ======================= host wrappers =======================
+#define ST (st)
+int k_embedding_fwd(const float* w, const int64_t* tok, float* x, int rows, int C, int nsym, cudaStream_t st) {
+    const int64_t n = (int64_t)rows * C;
+    ker_embedding_fwd<<<grid_for(n), kTh, 0, ST>>>(w, tok, x, n, C, nsym);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_embedding_bwd(const float* dx, const int64_t* tok, float* gw, int rows, int C, int nsym, float scale, int acc, cudaStream_t st) {
+    ker_embedding_bwd<<<grid_for((int64_t)nsym * C), kTh, 0, ST>>>(dx, tok, gw, rows, C, nsym, scale, acc);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_im2col(const float* x, float* col, int B, int T, int C, int K, cudaStream_t st) {
+    ker_im2col<<<grid_for((int64_t)B * T * C * K), kTh, 0, ST>>>(x, col, B, T, C, K);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_col2im(const float* dcol, float* dx, int B, int T, int C, int K, cudaStream_t st) {
+    ker_col2im<<<grid_for((int64_t)B * T * C), kTh, 0, ST>>>(dcol, dx, B, T, C, K);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_conv_w_pack(const float* w, float* w2, int Co, int Ci, int K, cudaStream_t st) {
+    ker_w_pack<<<grid_for((int64_t)Co * Ci * K), kTh, 0, ST>>>(w, w2, Co, Ci, K);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_conv_w_unpack_grad(const float* dw2, float* gw, int Co, int Ci, int K, float scale, int acc, cudaStream_t st) {
+    ker_w_unpack_grad<<<grid_for((int64_t)Co * Ci * K), kTh, 0, ST>>>(dw2, gw, Co, Ci, K, scale, acc);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_fill_rows(float* y, const float* b1, const float* b2, int64_t rows, int N, cudaStream_t st) {
+    ker_fill_rows<<<grid_for(rows * N), kTh, 0, ST>>>(y, b1, b2, rows * N, N);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_colsum(const float* x, int64_t rows, int N, int ld, float* out, float scale, int acc, float* out2, cudaStream_t st) {
+    ker_colsum<<<cdiv(N, 32), 256, 0, ST>>>(x, rows, N, ld, out, scale, acc, out2);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_bn_stats(const float* y, int64_t rows, int C, float* mean, float* invstd, float* running, int Cpad, cudaStream_t st) {
+    ker_bn_stats<<<cdiv(C, 32), 256, 0, ST>>>(y, rows, C, mean, invstd, running, Cpad);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_bn_eval_stats(const float* running, int C, int Cpad, float* mean, float* invstd, cudaStream_t st) {
+    ker_bn_eval_stats<<<grid_for(C), kTh, 0, ST>>>(running, C, Cpad, mean, invstd);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_bn_act_drop_fwd(const float* y, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                      const uint8_t* mask, float ds, int act, float* out, int64_t rows, int C, cudaStream_t st) {
+    ker_bn_act_drop_fwd<<<grid_for(rows * C), kTh, 0, ST>>>(y, mean, invstd, gamma, beta, mask, ds, act, out, rows * C, C);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_bn_act_drop_bwd(const float* dout, const float* y, const float* mean, const float* invstd, const float* gamma,
+                      const float* beta, const uint8_t* mask, float ds, int act, float* dy, float* ggamma, float* gbeta,
+                      float* scratch, int64_t rows, int C, float scale, int acc, cudaStream_t st) {
+    ker_bn_bwd_reduce<<<cdiv(C, 32), 256, 0, ST>>>(dout, y, mean, invstd, gamma, beta, mask, ds, act, scratch, rows, C);
+    MSA_LAUNCH_CHECK();
+    ker_bn_bwd_apply<<<grid_for(rows * C), kTh, 0, ST>>>(dout, y, mean, invstd, gamma, beta, mask, ds, act, scratch, dy, rows, C);
+    MSA_LAUNCH_CHECK();
+    ker_bn_param_grads<<<grid_for(C), kTh, 0, ST>>>(scratch, ggamma, gbeta, C, scale, acc);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_relu_drop_fwd(float* x, const uint8_t* mask, float ds, int64_t n, cudaStream_t st) {
+    ker_relu_drop_fwd<<<grid_for(n), kTh, 0, ST>>>(x, mask, ds, n);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_relu_drop_bwd(float* dx, const float* out, const uint8_t* mask, float ds, int64_t n, cudaStream_t st) {
+    ker_relu_drop_bwd<<<grid_for(n), kTh, 0, ST>>>(dx, out, mask, ds, n);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_transpose01(const float* in, float* out, int D0, int D1, int C, cudaStream_t st) {
+    ker_transpose01<<<grid_for((int64_t)D0 * D1 * C), kTh, 0, ST>>>(in, out, D0, D1, C);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_prep_mels(const float* mels, float* frames_tm, float* target_bt, int B, int M, int T, cudaStream_t st) {
+    ker_prep_mels<<<grid_for((int64_t)B * M * T), kTh, 0, ST>>>(mels, frames_tm, target_bt, B, M, T);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_build_memory(const float* enc_h, const float* spk, float* memory, int B, int L, int Hh, int Ds, cudaStream_t st) {
+    ker_build_memory<<<grid_for((int64_t)B * L * (2 * Hh + Ds)), kTh, 0, ST>>>(enc_h, spk, memory, B, L, Hh, Ds);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_split_dmemory(const float* dmem, float* denc_h, float* dspk, int B, int L, int Hh, int Ds, cudaStream_t st) {
+    ker_split_dmemory<<<grid_for((int64_t)2 * L * B * Hh), kTh, 0, ST>>>(dmem, denc_h, dspk, B, L, Hh, Ds);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_bt_to_ref(const float* x_bt, float* out, int B, int T, int M, cudaStream_t st) {
+    ker_bt_to_ref<<<grid_for((int64_t)B * T * M), kTh, 0, ST>>>(x_bt, out, B, T, M);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_ref_to_bt(const float* x, float* out_bt, int B, int T, int M, cudaStream_t st) {
+    ker_ref_to_bt<<<grid_for((int64_t)B * T * M), kTh, 0, ST>>>(x, out_bt, B, T, M);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_add(const float* a, const float* b, float* out, int64_t n, cudaStream_t st) {
+    ker_add<<<grid_for(n), kTh, 0, ST>>>(a, b, out, n);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_add3(const float* a, const float* b, const float* c, float* out, int64_t n, cudaStream_t st) {
+    ker_add3<<<grid_for(n), kTh, 0, ST>>>(a, b, c, out, n);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_scale_copy(const float* in, float* out, int64_t n, float scale, int acc, cudaStream_t st) {
+    ker_scale_copy<<<grid_for(n), kTh, 0, ST>>>(in, out, n, scale, acc);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+constexpr int kLossBlocks = 296;
+int k_loss(const float* pre_bt, const float* post_bt, const float* gate_bt, const float* target_bt, const float* stop,
+           const int64_t* mel_len, int B, int T, int M, int reduction, float pos_weight, float* partials, float* loss,
+           float* dpre, float* dpost, float* dgate, cudaStream_t st) {
+    int grid = (int)std::min<int64_t>((int64_t)B * T, kLossBlocks);
+    ker_loss<<<grid, 128, 0, ST>>>(pre_bt, post_bt, gate_bt, target_bt, stop, mel_len, B, T, M, reduction, pos_weight,
+                                   partials, dpre, dpost, dgate);
+    MSA_LAUNCH_CHECK();
+    ker_sum_partials<<<1, 256, 0, ST>>>(partials, grid, loss, 1.f, 0);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_sum_over_t(const float* x, float* out, int T, int64_t n, cudaStream_t st) {
+    ker_sum_over_t<<<grid_for(n), kTh, 0, ST>>>(x, out, T, n);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_wloc_grad(const float* dconvf, const float* align, const float* cum, float* gw, int T, int B, int L, int F, int Kl,
+                float scale, int acc, cudaStream_t st) {
+    ker_wloc_grad<<<2 * Kl, 256, 0, ST>>>(dconvf, align, cum, gw, T, B, L, F, Kl, scale, acc);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_dot_rows(const float* a, const float* b, int64_t n, float* partials, float* out, float scale, int acc, cudaStream_t st) {
+    int grid = grid_for(n, kTh, 296);
+    ker_dot_partial<<<grid, kTh, 0, ST>>>(a, b, n, partials);
+    MSA_LAUNCH_CHECK();
+    ker_sum_partials<<<1, 256, 0, ST>>>(partials, grid, out, scale, acc);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_masks_generate(uint8_t* masks, const int64_t* offsets, const int64_t* numels, const float* ps, int nsec, uint64_t seed,
+                     cudaStream_t st) {
+    for (int i = 0; i < nsec; ++i) {
+        ker_masks<<<grid_for(numels[i]), kTh, 0, ST>>>(masks, offsets[i], numels[i], ps[i], seed);
+        MSA_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+}  // namespace msa

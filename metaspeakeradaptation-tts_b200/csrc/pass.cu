@@ -1,0 +1,779 @@
+// Host-side orchestration of one teacher-forced pass (forward + loss, backward) and the C ABI.
+//
+// Restates Tacotron2NV.forward (models/tacotron2nv.py:81-127) and Tacotron2Loss
+// (modules_tacotron2nv/tacotron2nv_loss.py:17-52) and derives their backward by hand
+//  as: batched GEMMs for everything that does not sit on a sequential
+// dependency (cuBLAS, fp32 or TF32) + three persistent cooperative kernels for the parts that do
+// (encoder BiLSTM, attention chain, decoder-RNN chain; lstm_rec.cu / attn_chain.cu) + small fused
+// element-wise kernels (model_kernels.cu).
+#include <cublas_v2.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace msa {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+#define MSA_BLAS(expr)                                                                        \
+    do {                                                                                      \
+        cublasStatus_t _s = (expr);                                                           \
+        if (_s != CUBLAS_STATUS_SUCCESS) {                                                    \
+            msa::set_error("%s failed: cublas status %d (%s:%d)", #expr, (int)_s, __FILE__, __LINE__); \
+            return 1000 + (int)_s;                                                            \
+        }                                                                                     \
+    } while (0)
+
+struct Dims {
+    int B, T, L;
+    int C, Kc, nEnc, Hh, Ds, Dsin, E, Pd, Ha, Hd, A, F, Kl, M, Cp, Kp, nPost, Cmax;
+    int64_t BL, TB, BT, TBL;
+};
+
+}  // namespace msa
+
+using namespace msa;
+
+struct msa_handle {
+    msa_config cfg;
+    int device = 0, sm_count = 0;
+    size_t smem_limit = 0;
+    cublasHandle_t blas = nullptr;
+    std::vector<std::string> names;
+    std::vector<int64_t> offs, numels;
+    std::map<std::string, int64_t> off_by_name;
+    int64_t total = 0;
+    std::vector<int64_t> bn_offs;
+    std::vector<int> bn_ch;
+    int64_t bn_total = 0;
+    // state of the last forward (for backward / get_buffer)
+    bool fwd_valid = false;
+    Dims d{};
+    const int64_t *tokens = nullptr, *tok_len = nullptr, *mel_len = nullptr, *spk_ids = nullptr;
+    const float* spk_in = nullptr;
+    const uint8_t* masks = nullptr;
+    int64_t off(const std::string& n) const { return off_by_name.at(n); }
+};
+
+namespace msa {
+
+static void add_param(msa_handle* h, const std::string& name, int64_t numel) {
+    h->names.push_back(name);
+    h->offs.push_back(h->total);
+    h->numels.push_back(numel);
+    h->off_by_name[name] = h->total;
+    h->total += align_up(numel);
+}
+
+static void build_layout(msa_handle* h) {
+    const msa_config& c = h->cfg;
+    const int C = c.enc_dim, Hh = C / 2, E = C + c.spk_dim;
+    add_param(h, "embedding.weight", (int64_t)c.n_symbols * C);
+    for (int i = 0; i < c.enc_n_convs; ++i) {
+        const std::string p = "encoder.convolutions." + std::to_string(i);
+        add_param(h, p + ".0.conv.weight", (int64_t)C * C * c.enc_kernel);
+        add_param(h, p + ".0.conv.bias", C);
+        add_param(h, p + ".1.weight", C);
+        add_param(h, p + ".1.bias", C);
+    }
+    for (const char* sfx : {"", "_reverse"}) {
+        add_param(h, std::string("encoder.lstm.weight_ih_l0") + sfx, (int64_t)4 * Hh * C);
+        add_param(h, std::string("encoder.lstm.weight_hh_l0") + sfx, (int64_t)4 * Hh * Hh);
+        add_param(h, std::string("encoder.lstm.bias_ih_l0") + sfx, 4 * Hh);
+        add_param(h, std::string("encoder.lstm.bias_hh_l0") + sfx, 4 * Hh);
+    }
+    if (c.spk_mode == 2) add_param(h, "speaker_embedder.weight", (int64_t)c.num_speakers * c.spk_in_dim);
+    if (c.spk_mode == 1) {
+        add_param(h, "speaker_lin.weight", (int64_t)c.spk_dim * c.spk_in_dim);
+        add_param(h, "speaker_lin.bias", c.spk_dim);
+    }
+    add_param(h, "decoder.prenet.layers.0.linear_layer.weight", (int64_t)c.prenet_dim * c.n_mel);
+    add_param(h, "decoder.prenet.layers.1.linear_layer.weight", (int64_t)c.prenet_dim * c.prenet_dim);
+    add_param(h, "decoder.attention_rnn.weight_ih", (int64_t)4 * c.attn_rnn_dim * (c.prenet_dim + E));
+    add_param(h, "decoder.attention_rnn.weight_hh", (int64_t)4 * c.attn_rnn_dim * c.attn_rnn_dim);
+    add_param(h, "decoder.attention_rnn.bias_ih", 4 * c.attn_rnn_dim);
+    add_param(h, "decoder.attention_rnn.bias_hh", 4 * c.attn_rnn_dim);
+    const std::string a = "decoder.attention_layer.";
+    add_param(h, a + "query_layer.linear_layer.weight", (int64_t)c.attn_dim * c.attn_rnn_dim);
+    add_param(h, a + "inputs_layer.linear_layer.weight", (int64_t)c.attn_dim * E);
+    add_param(h, a + "v.linear_layer.weight", c.attn_dim);
+    add_param(h, a + "v.linear_layer.bias", 1);
+    if (c.trans_agent) {
+        add_param(h, a + "ta.weight", c.attn_rnn_dim + E);
+        add_param(h, a + "ta.bias", 1);
+    }
+    add_param(h, a + "location_layer.location_conv1d.weight", (int64_t)c.loc_filters * 2 * c.loc_kernel);
+    add_param(h, a + "location_layer.location_dense.linear_layer.weight", (int64_t)c.attn_dim * c.loc_filters);
+    add_param(h, "decoder.decoder_rnn.weight_ih", (int64_t)4 * c.dec_rnn_dim * (c.attn_rnn_dim + E));
+    add_param(h, "decoder.decoder_rnn.weight_hh", (int64_t)4 * c.dec_rnn_dim * c.dec_rnn_dim);
+    add_param(h, "decoder.decoder_rnn.bias_ih", 4 * c.dec_rnn_dim);
+    add_param(h, "decoder.decoder_rnn.bias_hh", 4 * c.dec_rnn_dim);
+    add_param(h, "decoder.linear_projection.linear_layer.weight", (int64_t)c.n_mel * (c.dec_rnn_dim + E));
+    add_param(h, "decoder.linear_projection.linear_layer.bias", c.n_mel);
+    add_param(h, "decoder.gate_layer.linear_layer.weight", c.dec_rnn_dim + E);
+    add_param(h, "decoder.gate_layer.linear_layer.bias", 1);
+    for (int i = 0; i < c.post_n_convs; ++i) {
+        const std::string p = "postnet.convolutions." + std::to_string(i);
+        const int ci = i == 0 ? c.n_mel : c.post_dim, co = i == c.post_n_convs - 1 ? c.n_mel : c.post_dim;
+        add_param(h, p + ".0.conv.weight", (int64_t)co * ci * c.post_kernel);
+        add_param(h, p + ".0.conv.bias", co);
+        add_param(h, p + ".1.weight", co);
+        add_param(h, p + ".1.bias", co);
+    }
+    for (int i = 0; i < c.enc_n_convs + c.post_n_convs; ++i) {
+        const int ch = i < c.enc_n_convs ? C : (i == c.enc_n_convs + c.post_n_convs - 1 ? c.n_mel : c.post_dim);
+        h->bn_ch.push_back(ch);
+        h->bn_offs.push_back(h->bn_total);
+        h->bn_total += 2 * align_up(ch);
+    }
+}
+
+static Dims make_dims(const msa_config& c, int B, int T, int L) {
+    Dims d;
+    d.B = B; d.T = T; d.L = L;
+    d.C = c.enc_dim; d.Kc = c.enc_kernel; d.nEnc = c.enc_n_convs; d.Hh = d.C / 2;
+    d.Ds = c.spk_dim; d.Dsin = c.spk_in_dim; d.E = d.C + d.Ds; d.Pd = c.prenet_dim;
+    d.Ha = c.attn_rnn_dim; d.Hd = c.dec_rnn_dim; d.A = c.attn_dim; d.F = c.loc_filters; d.Kl = c.loc_kernel;
+    d.M = c.n_mel; d.Cp = c.post_dim; d.Kp = c.post_kernel; d.nPost = c.post_n_convs;
+    d.Cmax = std::max(d.M, d.Cp);
+    d.BL = (int64_t)B * L; d.TB = (int64_t)T * B; d.BT = d.TB; d.TBL = d.TB * L;
+    return d;
+}
+
+// ---- workspace -------------------------------------------------------------------------------------
+#define WS_LIST(X)                                                                                     \
+    X(spk_vec, d.B * d.Ds)                                                                             \
+    X(enc_x, (d.nEnc + 1) * d.BL * d.C) X(enc_y, d.nEnc * d.BL * d.C) X(enc_bn, d.nEnc * 2 * d.C)      \
+    X(enc_col, d.BL * d.Kc * d.C) X(enc_w2, (int64_t)d.C * d.Kc * d.C) X(x3_tm, d.BL * d.C)            \
+    X(enc_zx, 2 * d.BL * 4 * d.Hh) X(enc_g, 2 * d.BL * 4 * d.Hh) X(enc_c, 2 * d.BL * d.Hh)             \
+    X(enc_h, 2 * d.BL * d.Hh) X(memory, d.BL * d.E)                                                    \
+    X(frames, (d.TB + d.B) * d.M) X(target, d.BT * d.M) X(p1, (d.TB + d.B) * d.Pd)                     \
+    X(xpre, (d.TB + d.B) * d.Pd) X(xw, d.TB * 4 * d.Ha) X(pm, d.BL * d.A)                              \
+    X(mw_rm, d.BL * 4 * d.Ha) X(mw_pm, d.BL * 4 * d.Ha)                                                \
+    X(ha, d.TB * d.Ha) X(ca, d.TB * d.Ha) X(ga, d.TB * 4 * d.Ha) X(q, d.TB * d.A)                      \
+    X(align_tm, d.TBL) X(cum, d.TBL) X(s, d.TBL * d.A) X(convf, d.TBL * d.F) X(znorm, d.TB)            \
+    X(ebuf, d.BL) X(ctx, d.TB * d.E)                                                                   \
+    X(zd, d.TB * 4 * d.Hd) X(hd, d.TB * d.Hd) X(cd, d.TB * d.Hd) X(gd, d.TB * 4 * d.Hd)                \
+    X(mel_tm, d.TB * d.M) X(gate_tm, d.TB)                                                             \
+    X(post_x, (d.nPost + 1) * d.BT * d.Cmax) X(post_y, d.nPost * d.BT * d.Cmax)                        \
+    X(post_bn, d.nPost * 2 * d.Cmax) X(post_col, d.BT * d.Kp * d.Cmax)                                 \
+    X(post_w2, (int64_t)d.Cmax * d.Kp * d.Cmax) X(post_bt, d.BT * d.M) X(gate_bt, d.BT)                \
+    X(loss_part, 1024) X(loss, 32) X(dpre, d.BT * d.M) X(dpost, d.BT * d.M) X(dgate, d.BT)             \
+    X(bdx0, d.BT * d.Cmax) X(bdx1, d.BT * d.Cmax) X(bdy, d.BT * d.Cmax)                                \
+    X(bdcol, d.BT * d.Kp * d.Cmax) X(bdw2, (int64_t)d.Cmax * d.Kp * d.Cmax)                            \
+    X(bn_scr, 2 * std::max(d.Cmax, d.C)) X(dmel_bt, d.BT * d.M) X(dmel_tm, d.TB * d.M)                 \
+    X(dgate_tm, d.TB) X(dhd, d.TB * d.Hd) X(dzd, d.TB * 4 * d.Hd) X(dha, d.TB * d.Ha)                  \
+    X(dctx, d.TB * d.E) X(da_ext, d.TBL) X(dza, d.TB * 4 * d.Ha) X(dq, d.TB * d.A) X(de, d.TBL)        \
+    X(ds, d.TBL * d.A) X(dconvf, d.TBL * d.F) X(dat, d.BL) X(dpm, d.BL * d.A)                          \
+    X(dmw, d.BL * 4 * d.Ha) X(dmem, d.BL * d.E) X(dxp, (d.TB + d.B) * d.Pd)                            \
+    X(dp1, (d.TB + d.B) * d.Pd) X(denc_h, 2 * d.BL * d.Hh) X(dzx, 2 * d.BL * 4 * d.Hh)                 \
+    X(dx3_tm, d.BL * d.C) X(edx0, d.BL * d.C) X(edx1, d.BL * d.C) X(edy, d.BL * d.C)                   \
+    X(edcol, d.BL * d.Kc * d.C) X(edw2, (int64_t)d.C * d.Kc * d.C) X(dspk, d.B * d.Ds)
+
+struct Ws {
+#define X(name, n) float* name; int64_t n_##name;
+    WS_LIST(X)
+#undef X
+    unsigned int* barrier;
+    void* blas_ws;
+    size_t blas_ws_bytes;
+    size_t total_bytes;
+};
+constexpr size_t kBlasWs = 64u << 20;
+
+static Ws ws_layout(const Dims& d, void* base) {
+    Ws w;
+    size_t o = 0;
+    char* b = static_cast<char*>(base);
+#define X(name, n)                                        \
+    w.n_##name = (int64_t)(n);                            \
+    w.name = reinterpret_cast<float*>(b + o);             \
+    o += (size_t)align_up((int64_t)(n), 64) * sizeof(float);
+    WS_LIST(X)
+#undef X
+    w.barrier = reinterpret_cast<unsigned int*>(b + o);
+    o += 256;
+    w.blas_ws = b + o;
+    w.blas_ws_bytes = kBlasWs;
+    o += kBlasWs;
+    w.total_bytes = o;
+    return w;
+}
+
+// ---- mask sections ---------------------------------------------------------------------------------
+struct MaskSec {
+    std::string name;
+    int64_t off, numel;
+    float p;
+};
+static std::vector<MaskSec> mask_sections(const msa_config& c, int B, int T, int L) {
+    std::vector<MaskSec> v;
+    int64_t o = 0;
+    auto add = [&](const std::string& n, int64_t numel, float p) {
+        v.push_back({n, o, numel, p});
+        o += align_up(numel, 16);
+    };
+    for (int i = 0; i < c.enc_n_convs; ++i) add("enc" + std::to_string(i) + " [B][L][C]", (int64_t)B * L * c.enc_dim, 0.5f);
+    add("prenet0 [T+1][B][P]", (int64_t)(T + 1) * B * c.prenet_dim, 0.5f);
+    add("prenet1 [T+1][B][P]", (int64_t)(T + 1) * B * c.prenet_dim, 0.5f);
+    add("attn_h [T][B][Ha]", (int64_t)T * B * c.attn_rnn_dim, c.p_attn_dropout);
+    add("dec_h [T][B][Hd]", (int64_t)T * B * c.dec_rnn_dim, c.p_dec_dropout);
+    for (int i = 0; i < c.post_n_convs; ++i)
+        add("post" + std::to_string(i) + " [B][T][C]", (int64_t)B * T * (i == c.post_n_convs - 1 ? c.n_mel : c.post_dim), 0.5f);
+    v.push_back({"", o, 0, 0.f});  // sentinel: total
+    return v;
+}
+
+// ---- cuBLAS, row-major convention: C[MxN] = alpha * op(A) op(B) + beta * C -------------------------
+static int gemm(msa_handle* h, bool ta, bool tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda,
+                const float* Bm, int64_t ldb, float beta, float* Cm, int64_t ldc) {
+    if (M == 0 || N == 0) return 0;
+    if (K == 0) {
+        MSA_CHECK(beta == 1.f, MSA_E_ARG, "gemm: K == 0 with beta != 1");
+        return 0;
+    }
+    const cublasComputeType_t ct = h->cfg.gemm_tf32 ? CUBLAS_COMPUTE_32F_FAST_TF32 : CUBLAS_COMPUTE_32F;
+    MSA_BLAS(cublasGemmEx(h->blas, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, (int)N, (int)M, (int)K, &alpha,
+                          Bm, CUDA_R_32F, (int)ldb, A, CUDA_R_32F, (int)lda, &beta, Cm, CUDA_R_32F, (int)ldc, ct,
+                          CUBLAS_GEMM_DEFAULT));
+    return 0;
+}
+static int gemm_batched(msa_handle* h, bool ta, bool tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda,
+                        int64_t sa, const float* Bm, int64_t ldb, int64_t sb, float beta, float* Cm, int64_t ldc, int64_t sc,
+                        int batch) {
+    if (M == 0 || N == 0 || batch == 0) return 0;
+    if (K == 0) return 0;
+    const cublasComputeType_t ct = h->cfg.gemm_tf32 ? CUBLAS_COMPUTE_32F_FAST_TF32 : CUBLAS_COMPUTE_32F;
+    MSA_BLAS(cublasGemmStridedBatchedEx(h->blas, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, (int)N, (int)M,
+                                        (int)K, &alpha, Bm, CUDA_R_32F, (int)ldb, sb, A, CUDA_R_32F, (int)lda, sa, &beta, Cm,
+                                        CUDA_R_32F, (int)ldc, sc, batch, ct, CUBLAS_GEMM_DEFAULT));
+    return 0;
+}
+
+// conv1d ("same") + BatchNorm(train) + activation + dropout, channels-last rows = B*Tn
+static int conv_bn_fwd(msa_handle* h, cudaStream_t st, const float* params, const std::string& pfx, const float* x, float* y,
+                       float* xout, float* col, float* w2, float* bn_mean, float* bn_invstd, float* running, int B, int Tn,
+                       int Ci, int Co, int K, int act, const uint8_t* mask) {
+    const int64_t rows = (int64_t)B * Tn;
+    MSA_TRY(k_conv_w_pack(params + h->off(pfx + ".0.conv.weight"), w2, Co, Ci, K, st));
+    MSA_TRY(k_im2col(x, col, B, Tn, Ci, K, st));
+    MSA_TRY(k_fill_rows(y, params + h->off(pfx + ".0.conv.bias"), nullptr, rows, Co, st));
+    MSA_TRY(gemm(h, false, true, rows, Co, (int64_t)K * Ci, 1.f, col, (int64_t)K * Ci, w2, (int64_t)K * Ci, 1.f, y, Co));
+    MSA_TRY(k_bn_stats(y, rows, Co, bn_mean, bn_invstd, running, (int)align_up(Co), st));
+    MSA_TRY(k_bn_act_drop_fwd(y, bn_mean, bn_invstd, params + h->off(pfx + ".1.weight"), params + h->off(pfx + ".1.bias"), mask,
+                              2.0f, act, xout, rows, Co, st));
+    return 0;
+}
+// backward of the above: dout -> dx (through dropout, act, BN, conv); parameter grads into `grads`
+static int conv_bn_bwd(msa_handle* h, cudaStream_t st, const float* params, float* grads, float gs, int acc,
+                       const std::string& pfx, const float* x, const float* y, const float* dout, float* dx, float* dy, float* col,
+                       float* w2, float* dcol, float* dw2, float* scr, const float* bn_mean, const float* bn_invstd, int B, int Tn,
+                       int Ci, int Co, int K, int act, const uint8_t* mask, bool need_dx) {
+    const int64_t rows = (int64_t)B * Tn, KC = (int64_t)K * Ci;
+    MSA_TRY(k_bn_act_drop_bwd(dout, y, bn_mean, bn_invstd, params + h->off(pfx + ".1.weight"), params + h->off(pfx + ".1.bias"),
+                              mask, 2.0f, act, dy, grads + h->off(pfx + ".1.weight"), grads + h->off(pfx + ".1.bias"), scr, rows,
+                              Co, gs, acc, st));
+    MSA_TRY(k_colsum(dy, rows, Co, Co, grads + h->off(pfx + ".0.conv.bias"), gs, acc, nullptr, st));
+    MSA_TRY(k_im2col(x, col, B, Tn, Ci, K, st));
+    MSA_TRY(gemm(h, true, false, Co, KC, rows, 1.f, dy, Co, col, KC, 0.f, dw2, KC));
+    MSA_TRY(k_conv_w_unpack_grad(dw2, grads + h->off(pfx + ".0.conv.weight"), Co, Ci, K, gs, acc, st));
+    if (need_dx) {
+        MSA_TRY(k_conv_w_pack(params + h->off(pfx + ".0.conv.weight"), w2, Co, Ci, K, st));
+        MSA_TRY(gemm(h, false, false, rows, KC, Co, 1.f, dy, Co, w2, KC, 0.f, dcol, KC));
+        MSA_TRY(k_col2im(dcol, dx, B, Tn, Ci, K, st));
+    }
+    return 0;
+}
+
+static int check_cfg(const msa_config& c) {
+    MSA_CHECK(c.enc_dim > 0 && c.enc_dim % 8 == 0, MSA_E_UNSUPPORTED, "encoder_embedding_dim must be a positive multiple of 8");
+    MSA_CHECK(c.enc_kernel % 2 == 1 && c.post_kernel % 2 == 1 && c.loc_kernel % 2 == 1, MSA_E_UNSUPPORTED, "kernel sizes must be odd");
+    MSA_CHECK(c.attn_rnn_dim % 4 == 0 && c.dec_rnn_dim % 4 == 0, MSA_E_UNSUPPORTED, "rnn dims must be multiples of 4");
+    MSA_CHECK(c.spk_mode >= 0 && c.spk_mode <= 2, MSA_E_ARG, "spk_mode");
+    MSA_CHECK(c.loc_filters >= 1 && c.loc_filters <= 32, MSA_E_UNSUPPORTED, "attention_location_n_filters must be in [1,32]");
+    MSA_CHECK(c.attn_norm == 0 || c.attn_norm == 1, MSA_E_ARG, "attn_norm");
+    MSA_CHECK(c.enc_n_convs >= 1 && c.post_n_convs >= 2, MSA_E_UNSUPPORTED, "need >= 1 encoder conv and >= 2 postnet convs");
+    return 0;
+}
+
+static int train_check(const msa_handle* h) {
+    const msa_config& c = h->cfg;
+    MSA_CHECK(!c.forward_attn && !c.trans_agent, MSA_E_UNSUPPORTED,
+              "forward_attn / trans_agent are not implemented in the CUDA training path yet (forward_attn.py:154-176,222-224)");
+    return 0;
+}
+
+}  // namespace msa
+
+// =====================================================================================================
+extern "C" {
+
+const char* msa_last_error_string(void) { return g_err; }
+int msa_version(void) { return 1; }
+
+int msa_create(const msa_config* cfg, int device, msa_handle** out) {
+    MSA_CHECK(cfg && out, MSA_E_ARG, "msa_create: null argument");
+    MSA_TRY(check_cfg(*cfg));
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    MSA_CHECK(e == cudaSuccess && ndev > 0, MSA_E_NODEVICE, "msa_create: no CUDA device (%s); there is no CPU fallback",
+              cudaGetErrorString(e));
+    MSA_CHECK(device >= 0 && device < ndev, MSA_E_ARG, "msa_create: device %d out of range", device);
+    MSA_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MSA_CUDA(cudaGetDeviceProperties(&prop, device));
+    MSA_CHECK(prop.major >= 10, MSA_E_NODEVICE, "msa_create: device %s is sm_%d%d, this library is built for sm_100a only", prop.name,
+              prop.major, prop.minor);
+    int coop = 0;
+    MSA_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    MSA_CHECK(coop, MSA_E_NODEVICE, "msa_create: device does not support cooperative launches");
+    msa_handle* h = new msa_handle();
+    h->cfg = *cfg;
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_limit = prop.sharedMemPerBlockOptin;
+    build_layout(h);
+    cublasStatus_t s = cublasCreate(&h->blas);
+    if (s != CUBLAS_STATUS_SUCCESS) {
+        delete h;
+        set_error("cublasCreate failed: %d", (int)s);
+        return 1000 + (int)s;
+    }
+    cublasSetPointerMode(h->blas, CUBLAS_POINTER_MODE_HOST);
+    *out = h;
+    return 0;
+}
+
+int msa_destroy(msa_handle* h) {
+    if (!h) return 0;
+    if (h->blas) cublasDestroy(h->blas);
+    delete h;
+    return 0;
+}
+
+int msa_sm_count(const msa_handle* h) { return h ? h->sm_count : 0; }
+int msa_param_count(const msa_handle* h) { return h ? (int)h->names.size() : 0; }
+int64_t msa_param_total(const msa_handle* h) { return h ? h->total : 0; }
+int msa_param_info(const msa_handle* h, int i, const char** name, int64_t* offset, int64_t* numel) {
+    MSA_CHECK(h && i >= 0 && i < (int)h->names.size(), MSA_E_ARG, "msa_param_info: index");
+    if (name) *name = h->names[i].c_str();
+    if (offset) *offset = h->offs[i];
+    if (numel) *numel = h->numels[i];
+    return 0;
+}
+int msa_bn_count(const msa_handle* h) { return h ? (int)h->bn_ch.size() : 0; }
+int64_t msa_bn_total(const msa_handle* h) { return h ? h->bn_total : 0; }
+int msa_bn_info(const msa_handle* h, int i, int64_t* offset, int32_t* channels) {
+    MSA_CHECK(h && i >= 0 && i < (int)h->bn_ch.size(), MSA_E_ARG, "msa_bn_info: index");
+    if (offset) *offset = h->bn_offs[i];
+    if (channels) *channels = h->bn_ch[i];
+    return 0;
+}
+int msa_mask_count(const msa_handle* h) { return h ? h->cfg.enc_n_convs + 4 + h->cfg.post_n_convs : 0; }
+int64_t msa_mask_total(const msa_handle* h, int B, int T, int L) {
+    if (!h) return 0;
+    return mask_sections(h->cfg, B, T, L).back().off;
+}
+int msa_mask_info(const msa_handle* h, int i, int B, int T, int L, const char** name, int64_t* offset, int64_t* numel, float* p) {
+    MSA_CHECK(h, MSA_E_ARG, "msa_mask_info: null handle");
+    static thread_local std::vector<MaskSec> secs;
+    secs = mask_sections(h->cfg, B, T, L);
+    MSA_CHECK(i >= 0 && i + 1 < (int)secs.size(), MSA_E_ARG, "msa_mask_info: index");
+    if (name) *name = secs[i].name.c_str();
+    if (offset) *offset = secs[i].off;
+    if (numel) *numel = secs[i].numel;
+    if (p) *p = secs[i].p;
+    return 0;
+}
+int msa_masks_generate(msa_handle* h, uint8_t* masks, int B, int T, int L, uint64_t seed, void* stream) {
+    MSA_CHECK(h && masks, MSA_E_ARG, "msa_masks_generate: null argument");
+    auto secs = mask_sections(h->cfg, B, T, L);
+    std::vector<int64_t> offs, ns;
+    std::vector<float> ps;
+    for (size_t i = 0; i + 1 < secs.size(); ++i) { offs.push_back(secs[i].off); ns.push_back(secs[i].numel); ps.push_back(secs[i].p); }
+    return k_masks_generate(masks, offs.data(), ns.data(), ps.data(), (int)offs.size(), seed, (cudaStream_t)stream);
+}
+
+size_t msa_workspace_bytes(const msa_handle* h, int B, int T, int L) {
+    if (!h || B <= 0 || T <= 0 || L <= 0) return 0;
+    return ws_layout(make_dims(h->cfg, B, T, L), nullptr).total_bytes;
+}
+
+int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, float* bn_stats, const int64_t* tokens,
+                      const int64_t* token_lengths, const float* mels, const int64_t* mel_lengths, const float* speaker_vecs,
+                      const int64_t* speaker_ids, const float* stop_targets, const uint8_t* masks, int B, int T, int L,
+                      float* mel_out, float* mel_post_out, float* gate_out, float* align_out, float* loss_out, void* stream) {
+    MSA_CHECK(h && wsp && params && tokens && token_lengths && mels && mel_lengths && masks, MSA_E_ARG, "msa_train_forward: null argument");
+    MSA_CHECK(B >= 1 && T >= 1 && L >= 1, MSA_E_ARG, "msa_train_forward: bad dims B=%d T=%d L=%d", B, T, L);
+    MSA_CHECK(h->cfg.spk_mode == 2 ? speaker_ids != nullptr : speaker_vecs != nullptr, MSA_E_ARG, "msa_train_forward: speaker input missing");
+    MSA_TRY(train_check(h));
+    const Dims d = make_dims(h->cfg, B, T, L);
+    const Ws w = ws_layout(d, wsp);
+    MSA_CHECK(ws_bytes >= w.total_bytes, MSA_E_WORKSPACE, "msa_train_forward: workspace %zu < %zu bytes", ws_bytes, w.total_bytes);
+    MSA_CHECK(((uintptr_t)wsp & 255) == 0, MSA_E_ARG, "msa_train_forward: workspace must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    MSA_CUDA(cudaSetDevice(h->device));
+    MSA_BLAS(cublasSetStream(h->blas, st));
+    MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
+    h->fwd_valid = false;
+    const msa_config& c = h->cfg;
+    const auto secs = mask_sections(c, B, T, L);
+    auto mk = [&](int i) { return masks + secs[i].off; };
+    const int iPre = d.nEnc, iAttn = d.nEnc + 2, iDec = d.nEnc + 3, iPost = d.nEnc + 4;
+    auto P = [&](const std::string& n) { return params + h->off(n); };
+
+    // ---- speaker vector (tacotron2nv.py:104-109) ----
+    if (c.spk_mode == 0) {
+        MSA_TRY(k_scale_copy(speaker_vecs, w.spk_vec, (int64_t)B * d.Ds, 1.f, 0, st));
+    } else if (c.spk_mode == 1) {
+        MSA_TRY(k_fill_rows(w.spk_vec, P("speaker_lin.bias"), nullptr, B, d.Ds, st));
+        MSA_TRY(gemm(h, false, true, B, d.Ds, d.Dsin, 1.f, speaker_vecs, d.Dsin, P("speaker_lin.weight"), d.Dsin, 1.f, w.spk_vec, d.Ds));
+    } else {
+        MSA_TRY(k_embedding_fwd(P("speaker_embedder.weight"), speaker_ids, w.spk_vec, B, d.Ds, c.num_speakers, st));
+    }
+    // ---- encoder (tacotron2nv.py:88, encoder.py:35-52) ----
+    MSA_TRY(k_embedding_fwd(P("embedding.weight"), tokens, w.enc_x, (int)d.BL, d.C, c.n_symbols, st));
+    const int64_t ex = d.BL * d.C;
+    for (int i = 0; i < d.nEnc; ++i) {
+        float* run = bn_stats ? bn_stats + h->bn_offs[i] : nullptr;
+        MSA_TRY(conv_bn_fwd(h, st, params, "encoder.convolutions." + std::to_string(i), w.enc_x + i * ex, w.enc_y + i * ex,
+                            w.enc_x + (i + 1) * ex, w.enc_col, w.enc_w2, w.enc_bn + i * 2 * d.C, w.enc_bn + i * 2 * d.C + d.C, run, B, L,
+                            d.C, d.C, d.Kc, 1, mk(i)));
+    }
+    MSA_TRY(k_transpose01(w.enc_x + d.nEnc * ex, w.x3_tm, B, L, d.C, st));
+    const int H4e = 4 * d.Hh;
+    for (int dir = 0; dir < 2; ++dir) {
+        const std::string sfx = dir ? "_reverse" : "";
+        float* zx = w.enc_zx + (int64_t)dir * d.BL * H4e;
+        MSA_TRY(k_fill_rows(zx, P("encoder.lstm.bias_ih_l0" + sfx), P("encoder.lstm.bias_hh_l0" + sfx), d.BL, H4e, st));
+        MSA_TRY(gemm(h, false, true, d.BL, H4e, d.C, 1.f, w.x3_tm, d.C, P("encoder.lstm.weight_ih_l0" + sfx), d.C, 1.f, zx, H4e));
+    }
+    {
+        LstmRecParams lp{};
+        lp.T = L; lp.B = B; lp.H = d.Hh; lp.ndir = 2;
+        lp.zin = w.enc_zx; lp.whh = P("encoder.lstm.weight_hh_l0");
+        lp.whh_dir_stride = h->off("encoder.lstm.weight_hh_l0_reverse") - h->off("encoder.lstm.weight_hh_l0");
+        lp.hout = w.enc_h; lp.cout = w.enc_c; lp.gates = w.enc_g; lp.mask = nullptr; lp.drop_scale = 1.f;
+        lp.lengths = token_lengths; lp.barrier = w.barrier;
+        MSA_TRY(launch_lstm_rec_fwd(lp, h->sm_count, h->smem_limit, st));
+    }
+    MSA_TRY(k_build_memory(w.enc_h, w.spk_vec, w.memory, B, L, d.Hh, d.Ds, st));
+    // ---- decoder set-up (decoder.py:290-302, forward_attn.py:103-116) ----
+    const std::string at = "decoder.attention_layer.";
+    const int H4a = 4 * d.Ha, H4d = 4 * d.Hd, ldA = d.Pd + d.E, ldD = d.Ha + d.E, ldP = d.Hd + d.E;
+    MSA_TRY(gemm(h, false, true, d.BL, d.A, d.E, 1.f, w.memory, d.E, P(at + "inputs_layer.linear_layer.weight"), d.E, 0.f, w.pm, d.A));
+    const float* Wia = P("decoder.attention_rnn.weight_ih");
+    MSA_TRY(gemm(h, false, true, H4a, d.BL, d.E, 1.f, Wia + d.Pd, ldA, w.memory, d.E, 0.f, w.mw_rm, d.BL));
+    MSA_TRY(k_prep_mels(mels, w.frames, w.target, B, d.M, T, st));
+    const int64_t nfr = d.TB + B;
+    MSA_TRY(gemm(h, false, true, nfr, d.Pd, d.M, 1.f, w.frames, d.M, P("decoder.prenet.layers.0.linear_layer.weight"), d.M, 0.f, w.p1, d.Pd));
+    MSA_TRY(k_relu_drop_fwd(w.p1, mk(iPre), 2.f, nfr * d.Pd, st));
+    MSA_TRY(gemm(h, false, true, nfr, d.Pd, d.Pd, 1.f, w.p1, d.Pd, P("decoder.prenet.layers.1.linear_layer.weight"), d.Pd, 0.f, w.xpre, d.Pd));
+    MSA_TRY(k_relu_drop_fwd(w.xpre, mk(iPre + 1), 2.f, nfr * d.Pd, st));
+    MSA_TRY(k_fill_rows(w.xw, P("decoder.attention_rnn.bias_ih"), P("decoder.attention_rnn.bias_hh"), d.TB, H4a, st));
+    MSA_TRY(gemm(h, false, true, d.TB, H4a, d.Pd, 1.f, w.xpre, d.Pd, Wia, ldA, 1.f, w.xw, H4a));
+    // ---- attention chain (persistent) ----
+    {
+        AttnChainParams ap{};
+        ap.T = T; ap.B = B; ap.L = L; ap.Ha = d.Ha; ap.A = d.A; ap.F = d.F; ap.Kl = d.Kl; ap.norm = c.attn_norm;
+        ap.xw = w.xw; ap.whh = P("decoder.attention_rnn.weight_hh"); ap.mw_rm = w.mw_rm;
+        ap.wq = P(at + "query_layer.linear_layer.weight"); ap.pm = w.pm;
+        ap.wloc = P(at + "location_layer.location_conv1d.weight");
+        ap.wld = P(at + "location_layer.location_dense.linear_layer.weight");
+        ap.v = P(at + "v.linear_layer.weight"); ap.bv = P(at + "v.linear_layer.bias");
+        ap.mask = c.p_attn_dropout > 0.f ? mk(iAttn) : nullptr;
+        ap.drop_scale = 1.f / (1.f - c.p_attn_dropout);
+        ap.ha = w.ha; ap.ca = w.ca; ap.ga = w.ga; ap.q = w.q; ap.align = w.align_tm; ap.cum = w.cum; ap.s = w.s;
+        ap.convf = w.convf; ap.znorm = w.znorm; ap.ebuf = w.ebuf; ap.barrier = w.barrier;
+        MSA_TRY(launch_attn_chain_fwd(ap, h->sm_count, h->smem_limit, st));
+    }
+    // ctx[t][b] = a[t][b] . memory[b]  (forward_attn.py:217), batched over b
+    MSA_TRY(gemm_batched(h, false, false, T, d.E, L, 1.f, w.align_tm, d.BL, L, w.memory, d.E, (int64_t)L * d.E, 0.f, w.ctx,
+                         (int64_t)B * d.E, d.E, B));
+    // ---- decoder RNN chain (decoder.py:260-265) ----
+    const float* Wid = P("decoder.decoder_rnn.weight_ih");
+    MSA_TRY(k_fill_rows(w.zd, P("decoder.decoder_rnn.bias_ih"), P("decoder.decoder_rnn.bias_hh"), d.TB, H4d, st));
+    MSA_TRY(gemm(h, false, true, d.TB, H4d, d.Ha, 1.f, w.ha, d.Ha, Wid, ldD, 1.f, w.zd, H4d));
+    MSA_TRY(gemm(h, false, true, d.TB, H4d, d.E, 1.f, w.ctx, d.E, Wid + d.Ha, ldD, 1.f, w.zd, H4d));
+    {
+        LstmRecParams lp{};
+        lp.T = T; lp.B = B; lp.H = d.Hd; lp.ndir = 1;
+        lp.zin = w.zd; lp.whh = P("decoder.decoder_rnn.weight_hh"); lp.whh_dir_stride = 0;
+        lp.hout = w.hd; lp.cout = w.cd; lp.gates = w.gd;
+        lp.mask = c.p_dec_dropout > 0.f ? mk(iDec) : nullptr;
+        lp.drop_scale = 1.f / (1.f - c.p_dec_dropout);
+        lp.lengths = nullptr; lp.barrier = w.barrier;
+        MSA_TRY(launch_lstm_rec_fwd(lp, h->sm_count, h->smem_limit, st));
+    }
+    // ---- mel / gate projections (decoder.py:267-270) ----
+    const float* Wp = P("decoder.linear_projection.linear_layer.weight");
+    const float* Wg = P("decoder.gate_layer.linear_layer.weight");
+    MSA_TRY(k_fill_rows(w.mel_tm, P("decoder.linear_projection.linear_layer.bias"), nullptr, d.TB, d.M, st));
+    MSA_TRY(gemm(h, false, true, d.TB, d.M, d.Hd, 1.f, w.hd, d.Hd, Wp, ldP, 1.f, w.mel_tm, d.M));
+    MSA_TRY(gemm(h, false, true, d.TB, d.M, d.E, 1.f, w.ctx, d.E, Wp + d.Hd, ldP, 1.f, w.mel_tm, d.M));
+    MSA_TRY(k_fill_rows(w.gate_tm, P("decoder.gate_layer.linear_layer.bias"), nullptr, d.TB, 1, st));
+    MSA_TRY(gemm(h, false, true, d.TB, 1, d.Hd, 1.f, w.hd, d.Hd, Wg, ldP, 1.f, w.gate_tm, 1));
+    MSA_TRY(gemm(h, false, true, d.TB, 1, d.E, 1.f, w.ctx, d.E, Wg + d.Hd, ldP, 1.f, w.gate_tm, 1));
+    // ---- postnet (decoder.py:63-72, tacotron2nv.py:123-124) ----
+    const int64_t px = d.BT * d.Cmax;
+    MSA_TRY(k_transpose01(w.mel_tm, w.post_x, T, B, d.M, st));       // [T][B][M] -> [B][T][M]
+    MSA_TRY(k_transpose01(w.gate_tm, w.gate_bt, T, B, 1, st));
+    for (int i = 0; i < d.nPost; ++i) {
+        const int ci = i == 0 ? d.M : d.Cp, co = i == d.nPost - 1 ? d.M : d.Cp;
+        float* run = bn_stats ? bn_stats + h->bn_offs[d.nEnc + i] : nullptr;
+        MSA_TRY(conv_bn_fwd(h, st, params, "postnet.convolutions." + std::to_string(i), w.post_x + i * px, w.post_y + i * px,
+                            w.post_x + (i + 1) * px, w.post_col, w.post_w2, w.post_bn + i * 2 * d.Cmax,
+                            w.post_bn + i * 2 * d.Cmax + d.Cmax, run, B, T, ci, co, d.Kp, i < d.nPost - 1 ? 2 : 0, mk(iPost + i)));
+    }
+    MSA_TRY(k_add(w.post_x, w.post_x + d.nPost * px, w.post_bt, d.BT * d.M, st));
+    // ---- outputs in the reference layouts ----
+    if (mel_out) MSA_TRY(k_bt_to_ref(w.post_x, mel_out, B, T, d.M, st));
+    if (mel_post_out) MSA_TRY(k_bt_to_ref(w.post_bt, mel_post_out, B, T, d.M, st));
+    if (gate_out) MSA_TRY(k_scale_copy(w.gate_bt, gate_out, d.BT, 1.f, 0, st));
+    if (align_out) MSA_TRY(k_transpose01(w.align_tm, align_out, T, B, L, st));
+    // ---- loss + d(loss)/d(outputs) ----
+    if (stop_targets) {
+        MSA_TRY(k_loss(w.post_x, w.post_bt, w.gate_bt, w.target, stop_targets, mel_lengths, B, T, d.M, c.loss_reduction,
+                       c.loss_pos_weight, w.loss_part, w.loss, w.dpre, w.dpost, w.dgate, st));
+        if (loss_out) MSA_TRY(k_scale_copy(w.loss, loss_out, 1, 1.f, 0, st));
+    }
+    h->d = d;
+    h->tokens = tokens; h->tok_len = token_lengths; h->mel_len = mel_lengths; h->spk_ids = speaker_ids; h->spk_in = speaker_vecs;
+    h->masks = masks;
+    h->fwd_valid = true;
+    return 0;
+}
+
+int msa_loss_grads(msa_handle* h, void* wsp, float* d_mel, float* d_mel_post, float* d_gate, void* stream) {
+    MSA_CHECK(h && wsp && h->fwd_valid, MSA_E_STATE, "msa_loss_grads: no forward pass in this workspace");
+    const Dims& d = h->d;
+    const Ws w = ws_layout(d, wsp);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_mel) MSA_TRY(k_bt_to_ref(w.dpre, d_mel, d.B, d.T, d.M, st));
+    if (d_mel_post) MSA_TRY(k_bt_to_ref(w.dpost, d_mel_post, d.B, d.T, d.M, st));
+    if (d_gate) MSA_TRY(k_scale_copy(w.dgate, d_gate, d.BT, 1.f, 0, st));
+    return 0;
+}
+
+int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, const float* d_mel, const float* d_mel_post,
+                       const float* d_gate, float* grads, int acc, float gs, void* stream) {
+    MSA_CHECK(h && wsp && params && grads, MSA_E_ARG, "msa_train_backward: null argument");
+    MSA_CHECK(h->fwd_valid, MSA_E_STATE, "msa_train_backward: call msa_train_forward first");
+    const Dims d = h->d;
+    const Ws w = ws_layout(d, wsp);
+    MSA_CHECK(ws_bytes >= w.total_bytes, MSA_E_WORKSPACE, "msa_train_backward: workspace too small");
+    const bool ext = d_mel || d_mel_post || d_gate;
+    MSA_CHECK(!ext || (d_mel && d_mel_post && d_gate), MSA_E_ARG, "msa_train_backward: pass all three upstream gradients or none");
+    cudaStream_t st = (cudaStream_t)stream;
+    MSA_CUDA(cudaSetDevice(h->device));
+    MSA_BLAS(cublasSetStream(h->blas, st));
+    MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
+    const msa_config& c = h->cfg;
+    const int B = d.B, T = d.T, L = d.L;
+    const auto secs = mask_sections(c, B, T, L);
+    auto mk = [&](int i) { return h->masks + secs[i].off; };
+    const int iPre = d.nEnc, iAttn = d.nEnc + 2, iDec = d.nEnc + 3, iPost = d.nEnc + 4;
+    auto P = [&](const std::string& n) { return params + h->off(n); };
+    auto G = [&](const std::string& n) { return grads + h->off(n); };
+    const float beta = acc ? 1.f : 0.f;
+    const int H4a = 4 * d.Ha, H4d = 4 * d.Hd, H4e = 4 * d.Hh, ldA = d.Pd + d.E, ldD = d.Ha + d.E, ldP = d.Hd + d.E;
+    const std::string at = "decoder.attention_layer.";
+
+    if (ext) {
+        MSA_TRY(k_ref_to_bt(d_mel, w.dpre, B, T, d.M, st));
+        MSA_TRY(k_ref_to_bt(d_mel_post, w.dpost, B, T, d.M, st));
+        MSA_TRY(k_scale_copy(d_gate, w.dgate, d.BT, 1.f, 0, st));
+    }
+    // ---- postnet backward ----
+    const int64_t px = d.BT * d.Cmax;
+    const float* dcur = w.dpost;
+    float* pingpong[2] = {w.bdx0, w.bdx1};
+    for (int i = d.nPost - 1; i >= 0; --i) {
+        const int ci = i == 0 ? d.M : d.Cp, co = i == d.nPost - 1 ? d.M : d.Cp;
+        float* dx = pingpong[i & 1];
+        MSA_TRY(conv_bn_bwd(h, st, params, grads, gs, acc, "postnet.convolutions." + std::to_string(i), w.post_x + i * px,
+                            w.post_y + i * px, dcur, dx, w.bdy, w.post_col, w.post_w2, w.bdcol, w.bdw2, w.bn_scr,
+                            w.post_bn + i * 2 * d.Cmax, w.post_bn + i * 2 * d.Cmax + d.Cmax, B, T, ci, co, d.Kp,
+                            i < d.nPost - 1 ? 2 : 0, mk(iPost + i), true));
+        dcur = dx;
+    }
+    // d(pre-postnet mel) = loss term + residual + postnet input (tacotron2nv.py:123-124)
+    MSA_TRY(k_add3(w.dpre, w.dpost, dcur, w.dmel_bt, d.BT * d.M, st));
+    MSA_TRY(k_transpose01(w.dmel_bt, w.dmel_tm, B, T, d.M, st));
+    MSA_TRY(k_transpose01(w.dgate, w.dgate_tm, B, T, 1, st));
+    // ---- projections backward (decoder.py:267-270) ----
+    const float* Wp = P("decoder.linear_projection.linear_layer.weight");
+    const float* Wg = P("decoder.gate_layer.linear_layer.weight");
+    float* gWp = G("decoder.linear_projection.linear_layer.weight");
+    float* gWg = G("decoder.gate_layer.linear_layer.weight");
+    MSA_TRY(gemm(h, false, false, d.TB, d.Hd, d.M, 1.f, w.dmel_tm, d.M, Wp, ldP, 0.f, w.dhd, d.Hd));
+    MSA_TRY(gemm(h, false, false, d.TB, d.Hd, 1, 1.f, w.dgate_tm, 1, Wg, ldP, 1.f, w.dhd, d.Hd));
+    MSA_TRY(gemm(h, false, false, d.TB, d.E, d.M, 1.f, w.dmel_tm, d.M, Wp + d.Hd, ldP, 0.f, w.dctx, d.E));
+    MSA_TRY(gemm(h, false, false, d.TB, d.E, 1, 1.f, w.dgate_tm, 1, Wg + d.Hd, ldP, 1.f, w.dctx, d.E));
+    MSA_TRY(gemm(h, true, false, d.M, d.Hd, d.TB, gs, w.dmel_tm, d.M, w.hd, d.Hd, beta, gWp, ldP));
+    MSA_TRY(gemm(h, true, false, d.M, d.E, d.TB, gs, w.dmel_tm, d.M, w.ctx, d.E, beta, gWp + d.Hd, ldP));
+    MSA_TRY(gemm(h, true, false, 1, d.Hd, d.TB, gs, w.dgate_tm, 1, w.hd, d.Hd, beta, gWg, ldP));
+    MSA_TRY(gemm(h, true, false, 1, d.E, d.TB, gs, w.dgate_tm, 1, w.ctx, d.E, beta, gWg + d.Hd, ldP));
+    MSA_TRY(k_colsum(w.dmel_tm, d.TB, d.M, d.M, G("decoder.linear_projection.linear_layer.bias"), gs, acc, nullptr, st));
+    MSA_TRY(k_colsum(w.dgate_tm, d.TB, 1, 1, G("decoder.gate_layer.linear_layer.bias"), gs, acc, nullptr, st));
+    // ---- decoder RNN chain backward ----
+    {
+        LstmRecBwdParams bp{};
+        bp.T = T; bp.B = B; bp.H = d.Hd; bp.ndir = 1;
+        bp.whh = P("decoder.decoder_rnn.weight_hh"); bp.whh_dir_stride = 0;
+        bp.gates = w.gd; bp.cout = w.cd; bp.dh_ext = w.dhd; bp.dz = w.dzd;
+        bp.mask = c.p_dec_dropout > 0.f ? mk(iDec) : nullptr;
+        bp.drop_scale = 1.f / (1.f - c.p_dec_dropout);
+        bp.lengths = nullptr; bp.barrier = w.barrier;
+        MSA_TRY(launch_lstm_rec_bwd(bp, h->sm_count, h->smem_limit, st));
+    }
+    const float* Wid = P("decoder.decoder_rnn.weight_ih");
+    float* gWid = G("decoder.decoder_rnn.weight_ih");
+    MSA_TRY(gemm(h, false, false, d.TB, d.Ha, H4d, 1.f, w.dzd, H4d, Wid, ldD, 0.f, w.dha, d.Ha));
+    MSA_TRY(gemm(h, false, false, d.TB, d.E, H4d, 1.f, w.dzd, H4d, Wid + d.Ha, ldD, 1.f, w.dctx, d.E));
+    MSA_TRY(gemm(h, true, false, H4d, d.Ha, d.TB, gs, w.dzd, H4d, w.ha, d.Ha, beta, gWid, ldD));
+    MSA_TRY(gemm(h, true, false, H4d, d.E, d.TB, gs, w.dzd, H4d, w.ctx, d.E, beta, gWid + d.Ha, ldD));
+    float* gWhd = G("decoder.decoder_rnn.weight_hh");
+    if (T > 1) {
+        MSA_TRY(gemm(h, true, false, H4d, d.Hd, d.TB - B, gs, w.dzd + (int64_t)B * H4d, H4d, w.hd, d.Hd, beta, gWhd, d.Hd));
+    } else if (!acc) {
+        MSA_CUDA(cudaMemsetAsync(gWhd, 0, sizeof(float) * (size_t)H4d * d.Hd, st));
+    }
+    MSA_TRY(k_colsum(w.dzd, d.TB, H4d, H4d, G("decoder.decoder_rnn.bias_ih"), gs, acc, G("decoder.decoder_rnn.bias_hh"), st));
+    // ---- context backward: ctx = align . memory ----
+    MSA_TRY(gemm_batched(h, false, true, T, L, d.E, 1.f, w.dctx, (int64_t)B * d.E, d.E, w.memory, d.E, (int64_t)L * d.E, 0.f,
+                         w.da_ext, d.BL, L, B));
+    MSA_TRY(gemm_batched(h, true, false, L, d.E, T, 1.f, w.align_tm, d.BL, L, w.dctx, (int64_t)B * d.E, d.E, 0.f, w.dmem, d.E,
+                         (int64_t)L * d.E, B));
+    // ---- attention chain backward (persistent) ----
+    const float* Wia = P("decoder.attention_rnn.weight_ih");
+    float* gWia = G("decoder.attention_rnn.weight_ih");
+    MSA_TRY(gemm(h, false, true, d.BL, H4a, d.E, 1.f, w.memory, d.E, Wia + d.Pd, ldA, 0.f, w.mw_pm, H4a));
+    {
+        AttnChainBwdParams bp{};
+        bp.T = T; bp.B = B; bp.L = L; bp.Ha = d.Ha; bp.A = d.A; bp.F = d.F; bp.Kl = d.Kl; bp.norm = c.attn_norm;
+        bp.whh = P("decoder.attention_rnn.weight_hh"); bp.mw_pm = w.mw_pm;
+        bp.wq = P(at + "query_layer.linear_layer.weight");
+        bp.wloc = P(at + "location_layer.location_conv1d.weight");
+        bp.wld = P(at + "location_layer.location_dense.linear_layer.weight");
+        bp.v = P(at + "v.linear_layer.weight");
+        bp.mask = c.p_attn_dropout > 0.f ? mk(iAttn) : nullptr;
+        bp.drop_scale = 1.f / (1.f - c.p_attn_dropout);
+        bp.ga = w.ga; bp.ca = w.ca; bp.align = w.align_tm; bp.s = w.s; bp.znorm = w.znorm;
+        bp.dha_ext = w.dha; bp.da_ext = w.da_ext;
+        bp.dza = w.dza; bp.dq = w.dq; bp.de = w.de; bp.ds = w.ds; bp.dconvf = w.dconvf; bp.dat = w.dat;
+        bp.barrier = w.barrier;
+        MSA_TRY(launch_attn_chain_bwd(bp, h->sm_count, h->smem_limit, st));
+    }
+    // ---- deferred attention / attention-RNN parameter gradients ----
+    const int64_t nfr = d.TB + B;
+    MSA_TRY(gemm(h, false, false, d.TB, d.Pd, H4a, 1.f, w.dza, H4a, Wia, ldA, 0.f, w.dxp, d.Pd));
+    MSA_CUDA(cudaMemsetAsync(w.dxp + d.TB * d.Pd, 0, sizeof(float) * (size_t)B * d.Pd, st));   // last prenet frame is unused (decoder.py:305)
+    MSA_TRY(gemm(h, true, false, H4a, d.Pd, d.TB, gs, w.dza, H4a, w.xpre, d.Pd, beta, gWia, ldA));
+    float* gWha = G("decoder.attention_rnn.weight_hh");
+    if (T > 1) {
+        MSA_TRY(gemm(h, true, false, H4a, d.Ha, d.TB - B, gs, w.dza + (int64_t)B * H4a, H4a, w.ha, d.Ha, beta, gWha, d.Ha));
+        // dMW[b][l][r] = sum_t a[t][b][l] * dz_a[t+1][b][r]
+        MSA_TRY(gemm_batched(h, true, false, L, H4a, T - 1, 1.f, w.align_tm, d.BL, L, w.dza + (int64_t)B * H4a, (int64_t)B * H4a, H4a,
+                             0.f, w.dmw, H4a, (int64_t)L * H4a, B));
+    } else {
+        if (!acc) MSA_CUDA(cudaMemsetAsync(gWha, 0, sizeof(float) * (size_t)H4a * d.Ha, st));
+        MSA_CUDA(cudaMemsetAsync(w.dmw, 0, sizeof(float) * (size_t)d.BL * H4a, st));
+    }
+    MSA_TRY(k_colsum(w.dza, d.TB, H4a, H4a, G("decoder.attention_rnn.bias_ih"), gs, acc, G("decoder.attention_rnn.bias_hh"), st));
+    MSA_TRY(gemm(h, true, false, H4a, d.E, d.BL, gs, w.dmw, H4a, w.memory, d.E, beta, gWia + d.Pd, ldA));
+    MSA_TRY(gemm(h, false, false, d.BL, d.E, H4a, 1.f, w.dmw, H4a, Wia + d.Pd, ldA, 1.f, w.dmem, d.E));
+    MSA_TRY(gemm(h, true, false, d.A, d.Ha, d.TB, gs, w.dq, d.A, w.ha, d.Ha, beta, G(at + "query_layer.linear_layer.weight"), d.Ha));
+    MSA_TRY(k_sum_over_t(w.ds, w.dpm, T, d.BL * d.A, st));
+    MSA_TRY(gemm(h, true, false, d.A, d.E, d.BL, gs, w.dpm, d.A, w.memory, d.E, beta, G(at + "inputs_layer.linear_layer.weight"), d.E));
+    MSA_TRY(gemm(h, false, false, d.BL, d.E, d.A, 1.f, w.dpm, d.A, P(at + "inputs_layer.linear_layer.weight"), d.E, 1.f, w.dmem, d.E));
+    MSA_TRY(gemm(h, true, false, 1, d.A, d.TBL, gs, w.de, 1, w.s, d.A, beta, G(at + "v.linear_layer.weight"), d.A));
+    MSA_TRY(k_dot_rows(w.de, nullptr, d.TBL, w.loss_part, G(at + "v.linear_layer.bias"), gs, acc, st));
+    MSA_TRY(gemm(h, true, false, d.A, d.F, d.TBL, gs, w.ds, d.A, w.convf, d.F, beta,
+                 G(at + "location_layer.location_dense.linear_layer.weight"), d.F));
+    MSA_TRY(k_wloc_grad(w.dconvf, w.align_tm, w.cum, G(at + "location_layer.location_conv1d.weight"), T, B, L, d.F, d.Kl, gs, acc, st));
+    // ---- prenet backward (decoder.py:9-20) ----
+    MSA_TRY(k_relu_drop_bwd(w.dxp, w.xpre, mk(iPre + 1), 2.f, nfr * d.Pd, st));
+    MSA_TRY(gemm(h, true, false, d.Pd, d.Pd, nfr, gs, w.dxp, d.Pd, w.p1, d.Pd, beta, G("decoder.prenet.layers.1.linear_layer.weight"), d.Pd));
+    MSA_TRY(gemm(h, false, false, nfr, d.Pd, d.Pd, 1.f, w.dxp, d.Pd, P("decoder.prenet.layers.1.linear_layer.weight"), d.Pd, 0.f, w.dp1, d.Pd));
+    MSA_TRY(k_relu_drop_bwd(w.dp1, w.p1, mk(iPre), 2.f, nfr * d.Pd, st));
+    MSA_TRY(gemm(h, true, false, d.Pd, d.M, nfr, gs, w.dp1, d.Pd, w.frames, d.M, beta, G("decoder.prenet.layers.0.linear_layer.weight"), d.M));
+    // ---- memory -> encoder output + speaker path (tacotron2nv.py:104-111) ----
+    MSA_TRY(k_split_dmemory(w.dmem, w.denc_h, c.spk_mode ? w.dspk : nullptr, B, L, d.Hh, d.Ds, st));
+    if (c.spk_mode == 1) {
+        MSA_TRY(gemm(h, true, false, d.Ds, d.Dsin, B, gs, w.dspk, d.Ds, h->spk_in, d.Dsin, beta, G("speaker_lin.weight"), d.Dsin));
+        MSA_TRY(k_colsum(w.dspk, B, d.Ds, d.Ds, G("speaker_lin.bias"), gs, acc, nullptr, st));
+    } else if (c.spk_mode == 2) {
+        MSA_TRY(k_embedding_bwd(w.dspk, h->spk_ids, G("speaker_embedder.weight"), B, d.Ds, c.num_speakers, gs, acc, st));
+    }
+    // ---- encoder BiLSTM backward ----
+    {
+        LstmRecBwdParams bp{};
+        bp.T = L; bp.B = B; bp.H = d.Hh; bp.ndir = 2;
+        bp.whh = P("encoder.lstm.weight_hh_l0");
+        bp.whh_dir_stride = h->off("encoder.lstm.weight_hh_l0_reverse") - h->off("encoder.lstm.weight_hh_l0");
+        bp.gates = w.enc_g; bp.cout = w.enc_c; bp.dh_ext = w.denc_h; bp.dz = w.dzx; bp.mask = nullptr; bp.drop_scale = 1.f;
+        bp.lengths = h->tok_len; bp.barrier = w.barrier;
+        MSA_TRY(launch_lstm_rec_bwd(bp, h->sm_count, h->smem_limit, st));
+    }
+    for (int dir = 0; dir < 2; ++dir) {
+        const std::string sfx = dir ? "_reverse" : "";
+        const float* dzx = w.dzx + (int64_t)dir * d.BL * H4e;
+        const float* eh = w.enc_h + (int64_t)dir * d.BL * d.Hh;
+        MSA_TRY(gemm(h, false, false, d.BL, d.C, H4e, 1.f, dzx, H4e, P("encoder.lstm.weight_ih_l0" + sfx), d.C, dir ? 1.f : 0.f, w.dx3_tm, d.C));
+        MSA_TRY(gemm(h, true, false, H4e, d.C, d.BL, gs, dzx, H4e, w.x3_tm, d.C, beta, G("encoder.lstm.weight_ih_l0" + sfx), d.C));
+        float* gWhh = G("encoder.lstm.weight_hh_l0" + sfx);
+        if (L > 1) {
+            if (dir == 0)   // z(t) uses h(t-1)
+                MSA_TRY(gemm(h, true, false, H4e, d.Hh, d.BL - B, gs, dzx + (int64_t)B * H4e, H4e, eh, d.Hh, beta, gWhh, d.Hh));
+            else            // reverse direction: z(t) uses h(t+1)
+                MSA_TRY(gemm(h, true, false, H4e, d.Hh, d.BL - B, gs, dzx, H4e, eh + (int64_t)B * d.Hh, d.Hh, beta, gWhh, d.Hh));
+        } else if (!acc) {
+            MSA_CUDA(cudaMemsetAsync(gWhh, 0, sizeof(float) * (size_t)H4e * d.Hh, st));
+        }
+        MSA_TRY(k_colsum(dzx, d.BL, H4e, H4e, G("encoder.lstm.bias_ih_l0" + sfx), gs, acc, G("encoder.lstm.bias_hh_l0" + sfx), st));
+    }
+    // ---- encoder convolutions backward ----
+    const int64_t ex = d.BL * d.C;
+    float* epp[2] = {w.edx0, w.edx1};
+    MSA_TRY(k_transpose01(w.dx3_tm, epp[d.nEnc & 1], L, B, d.C, st));   // [L][B][C] -> [B][L][C]
+    dcur = epp[d.nEnc & 1];
+    for (int i = d.nEnc - 1; i >= 0; --i) {
+        float* dx = epp[i & 1];
+        MSA_TRY(conv_bn_bwd(h, st, params, grads, gs, acc, "encoder.convolutions." + std::to_string(i), w.enc_x + i * ex,
+                            w.enc_y + i * ex, dcur, dx, w.edy, w.enc_col, w.enc_w2, w.edcol, w.edw2, w.bn_scr, w.enc_bn + i * 2 * d.C,
+                            w.enc_bn + i * 2 * d.C + d.C, B, L, d.C, d.C, d.Kc, 1, mk(i), true));
+        dcur = dx;
+    }
+    MSA_TRY(k_embedding_bwd(dcur, h->tokens, G("embedding.weight"), (int)d.BL, d.C, c.n_symbols, gs, acc, st));
+    return 0;
+}
+
+int msa_get_buffer(msa_handle* h, void* wsp, const char* name, void** ptr, int64_t* numel) {
+    MSA_CHECK(h && wsp && name && h->fwd_valid, MSA_E_STATE, "msa_get_buffer: no forward pass in this workspace");
+    const Ws w = ws_layout(h->d, wsp);
+#define X(nm, n)                                   \
+    if (!strcmp(name, #nm)) {                      \
+        if (ptr) *ptr = w.nm;                      \
+        if (numel) *numel = w.n_##nm;              \
+        return 0;                                  \
+    }
+    WS_LIST(X)
+#undef X
+    MSA_CHECK(false, MSA_E_ARG, "msa_get_buffer: unknown buffer '%s'", name);
+    return 0;
+}
+
+}  // extern "C"

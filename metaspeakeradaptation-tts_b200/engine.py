@@ -1,0 +1,305 @@
+"""Host driver of the CUDA hot path: flat buffers, workspace, one teacher-forced pass.
+
+This is the thin layer between the reference-shaped Python API (model.py, innerloop.py, maml.py ...)
+and the C ABI (include/msa_b200.h).  PyTorch is used only for device memory, streams and (in
+parallel.py) torch.distributed; every computation is a call into libmsa_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .config import rnn_dims, speaker_dim
+from .layout import FlatLayout
+
+_SPK_MODES = {"static": 0, "static+linear": 1, "learnable_lookup": 2}
+
+
+def make_c_config(cfg: dict, reduction: str = "none", pos_weight: float = 10.0, gemm_tf32: bool = False) -> "_lib.MsaConfig":
+    """params["model"] (+ criterion settings, metatrainer.py:83-86) -> msa_config."""
+    ap = cfg["attention_params"]
+    if ap["attention_type"] != "ForwardAttention":
+        raise NotImplementedError('attention_type "LSA" is broken in the reference itself (SURVEY.md Q1)')
+    if cfg["n_frames_per_step"] != 1:
+        raise NotImplementedError("n_frames_per_step > 1 cannot train in the reference (SURVEY.md Q14)")
+    if cfg.get("mask_padding", False):
+        raise NotImplementedError("mask_padding=True breaks backward in the reference (SURVEY.md Q3)")
+    for k in ("freeze_charemb", "freeze_encoder", "freeze_decoder", "use_residual_encoder"):
+        if cfg.get(k, False):
+            raise NotImplementedError(f"{k}=True is outside the implemented hot path")
+    if cfg["symbols_embedding_dim"] != cfg["encoder_embedding_dim"]:
+        raise ValueError("symbols_embedding_dim must equal encoder_embedding_dim (tacotron2nv.py:88)")
+    ha, hd = rnn_dims(cfg)
+    c = _lib.MsaConfig()
+    c.n_symbols = cfg["n_symbols"]
+    c.enc_dim = cfg["encoder_embedding_dim"]
+    c.enc_kernel = cfg["encoder_kernel_size"]
+    c.enc_n_convs = cfg["encoder_n_convolutions"]
+    c.spk_mode = _SPK_MODES[cfg["speaker_emb_type"]]
+    c.spk_in_dim = cfg["speaker_embedding_dim"]
+    c.spk_dim = speaker_dim(cfg)
+    c.num_speakers = cfg.get("num_speakers", 1)
+    c.n_mel = cfg["n_mel_channels"]
+    c.prenet_dim = cfg["prenet_dim"]
+    c.attn_rnn_dim = ha
+    c.dec_rnn_dim = hd
+    c.attn_dim = ap["attention_dim"]
+    c.loc_filters = ap["attention_location_n_filters"]
+    c.loc_kernel = ap["attention_location_kernel_size"]
+    c.post_dim = cfg["postnet_embedding_dim"]
+    c.post_kernel = cfg["postnet_kernel_size"]
+    c.post_n_convs = cfg["postnet_n_convolutions"]
+    c.attn_norm = {"softmax": 0, "sigmoid": 1}[ap["norm"]]
+    c.forward_attn = int(ap["forward_attn"])
+    c.trans_agent = int(ap["trans_agent"])
+    c.windowing = int(ap["windowing"])
+    c.forward_attn_mask = int(ap["forward_attn_mask"])
+    c.max_decoder_steps = cfg["max_decoder_steps"]
+    c.early_stopping = int(not cfg["decoder_no_early_stopping"])
+    c.loss_reduction = {"none": 0, "mean": 1}[reduction]
+    c.gemm_tf32 = int(gemm_tf32)
+    c.p_attn_dropout = cfg["p_attention_dropout"]
+    c.p_dec_dropout = cfg["p_decoder_dropout"]
+    c.gate_threshold = cfg["gate_threshold"]
+    c.loss_pos_weight = pos_weight
+    return c
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    """One msa_handle + its workspace on one GPU."""
+
+    def __init__(self, cfg: dict, device: Optional[torch.device] = None, reduction: str = "none",
+                 pos_weight: float = 10.0, gemm_tf32: bool = False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("msa_tts_b200 needs a CUDA (sm_100a) device: there is no CPU fallback")
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.layout = FlatLayout(cfg)
+        self._ccfg = make_c_config(cfg, reduction, pos_weight, gemm_tf32)
+        h = C.c_void_p()
+        _lib.check(self.lib.msa_create(C.byref(self._ccfg), self.device.index or 0, C.byref(h)), "msa_create")
+        self.h = h
+        self._check_layout()
+        self._ws: Optional[torch.Tensor] = None
+        self._partials = torch.empty(self.lib.msa_flat_partials(), dtype=torch.float32, device=self.device)
+        self._keep: tuple = ()
+        self.launches = 0   # kernels of this library enqueued by the calls below (bench.py's gpu_launches)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.msa_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ---- layout -----------------------------------------------------------------------------------
+    def _check_layout(self) -> None:
+        n = self.lib.msa_param_count(self.h)
+        names = self.layout.names()
+        if n != len(names) or self.lib.msa_param_total(self.h) != self.layout.total:
+            raise RuntimeError("flat layout mismatch between layout.py and libmsa_b200")
+        for i, name in enumerate(names):
+            cn, off, ne = C.c_char_p(), C.c_int64(), C.c_int64()
+            _lib.check(self.lib.msa_param_info(self.h, i, C.byref(cn), C.byref(off), C.byref(ne)), "msa_param_info")
+            if cn.value.decode() != name or off.value != self.layout.offsets[name] or ne.value != self.layout.numel(name):
+                raise RuntimeError(f"flat layout mismatch at {name}")
+        if self.lib.msa_bn_total(self.h) != self.layout.bn_total:
+            raise RuntimeError("BN layout mismatch")
+
+    def new_flat(self, fill: Optional[float] = 0.0) -> torch.Tensor:
+        t = torch.empty(self.layout.total, dtype=torch.float32, device=self.device)
+        if fill is not None:
+            t.fill_(fill)
+        return t
+
+    def flat_from_dict(self, P: Dict[str, torch.Tensor]) -> torch.Tensor:
+        flat = torch.zeros(self.layout.total, dtype=torch.float32)
+        for name in self.layout.names():
+            o, n = self.layout.offsets[name], self.layout.numel(name)
+            flat[o:o + n] = P[name].detach().reshape(-1).float().cpu()
+        return flat.to(self.device)
+
+    def dict_from_flat(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        return {n: flat[self.layout.offsets[n]:self.layout.offsets[n] + self.layout.numel(n)].view(self.layout.shapes[n])
+                for n in self.layout.names()}
+
+    def new_bn_stats(self) -> torch.Tensor:
+        """Fresh BatchNorm running stats (mean 0, var 1), private per task."""
+        t = torch.zeros(self.layout.bn_total, dtype=torch.float32)
+        for o, c in zip(self.layout.bn_offsets, self.layout.bn_ch):
+            cp = (c + 31) // 32 * 32
+            t[o + cp:o + cp + c] = 1.0
+        return t.to(self.device)
+
+    def bn_dict(self, stats: torch.Tensor) -> Dict[str, torch.Tensor]:
+        out = {}
+        for name, o, c in zip(self.layout.bn_names, self.layout.bn_offsets, self.layout.bn_ch):
+            cp = (c + 31) // 32 * 32
+            out[name + ".running_mean"] = stats[o:o + c]
+            out[name + ".running_var"] = stats[o + cp:o + cp + c]
+        return out
+
+    # ---- masks ------------------------------------------------------------------------------------
+    def mask_bytes(self, B: int, T: int, L: int) -> int:
+        return int(self.lib.msa_mask_total(self.h, B, T, L))
+
+    def mask_sections(self, B: int, T: int, L: int):
+        out = []
+        for i in range(self.lib.msa_mask_count(self.h)):
+            nm, off, ne, p = C.c_char_p(), C.c_int64(), C.c_int64(), C.c_float()
+            _lib.check(self.lib.msa_mask_info(self.h, i, B, T, L, C.byref(nm), C.byref(off), C.byref(ne), C.byref(p)), "msa_mask_info")
+            out.append((nm.value.decode(), off.value, ne.value, p.value))
+        return out
+
+    def pack_masks(self, masks: dict, B: int, T: int, L: int) -> torch.Tensor:
+        """Reference-layout keep-masks (synth.make_masks / oracle) -> the library's uint8 buffer."""
+        secs = self.mask_sections(B, T, L)
+        parts = [m.permute(0, 2, 1) for m in masks["enc"]] + list(masks["prenet"]) + [masks["attn_h"], masks["dec_h"]] + \
+                [m.permute(0, 2, 1) for m in masks["post"]]
+        assert len(parts) == len(secs)
+        buf = torch.zeros(self.mask_bytes(B, T, L), dtype=torch.uint8)
+        for (_, off, ne, _), m in zip(secs, parts):
+            assert m.numel() == ne, (m.shape, ne)
+            buf[off:off + ne] = m.contiguous().reshape(-1).to(torch.uint8)
+        return buf.to(self.device)
+
+    def generate_masks(self, B: int, T: int, L: int, seed: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if out is None:
+            out = torch.empty(self.mask_bytes(B, T, L), dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.msa_masks_generate(self.h, _ptr(out), B, T, L, C.c_uint64(seed & (2 ** 64 - 1)), _stream()),
+                   "msa_masks_generate")
+        self.launches += self.lib.msa_mask_count(self.h)
+        return out
+
+    # ---- one pass -----------------------------------------------------------------------------------
+    def _workspace(self, B: int, T: int, L: int) -> torch.Tensor:
+        need = int(self.lib.msa_workspace_bytes(self.h, B, T, L))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _ws_ptr(self):
+        a = self._ws.data_ptr()
+        return C.c_void_p((a + 255) // 256 * 256)
+
+    def forward(self, params: torch.Tensor, bn_stats: Optional[torch.Tensor], batch_dev: dict, masks: torch.Tensor,
+                outputs: bool = True):
+        """batch_dev: dict of device tensors (inputs, input_lengths, melspecs, melspec_lengths, speaker_vecs, stop)."""
+        inp, mel = batch_dev["inputs"], batch_dev["melspecs"]
+        B, L = inp.shape
+        T = mel.shape[2]
+        self._workspace(B, T, L)
+        dev = self.device
+        out = None
+        if outputs:
+            out = [torch.empty(B, self.cfg["n_mel_channels"], T, device=dev), torch.empty(B, self.cfg["n_mel_channels"], T, device=dev),
+                   torch.empty(B, T, device=dev), torch.empty(B, T, L, device=dev)]
+        loss = torch.empty(1, device=dev)
+        spk = batch_dev["speaker_vecs"]
+        spk_f = spk if spk.dtype.is_floating_point else None
+        spk_i = None if spk.dtype.is_floating_point else spk
+        self._keep = (params, bn_stats, batch_dev, masks)          # the library keeps raw pointers until backward
+        rc = self.lib.msa_train_forward(self.h, self._ws_ptr(), C.c_size_t(self._ws.numel() - 256), _ptr(params), _ptr(bn_stats),
+                                        _ptr(inp), _ptr(batch_dev["input_lengths"]), _ptr(mel), _ptr(batch_dev["melspec_lengths"]),
+                                        _ptr(spk_f), _ptr(spk_i), _ptr(batch_dev.get("stop")), _ptr(masks), B, T, L,
+                                        _ptr(out[0]) if out else None, _ptr(out[1]) if out else None,
+                                        _ptr(out[2]) if out else None, _ptr(out[3]) if out else None, _ptr(loss), _stream())
+        _lib.check(rc, "msa_train_forward")
+        self.launches += 1
+        return out, loss
+
+    def backward(self, params: torch.Tensor, grads: torch.Tensor, accumulate: bool = False, scale: float = 1.0,
+                 d_outputs: Optional[Sequence[torch.Tensor]] = None) -> None:
+        d = [None, None, None] if d_outputs is None else [x.contiguous() for x in d_outputs]
+        rc = self.lib.msa_train_backward(self.h, self._ws_ptr(), C.c_size_t(self._ws.numel() - 256), _ptr(params), _ptr(d[0]),
+                                         _ptr(d[1]), _ptr(d[2]), _ptr(grads), int(accumulate), C.c_float(scale), _stream())
+        _lib.check(rc, "msa_train_backward")
+        self.launches += 1
+
+    def loss_grads(self, B: int, T: int):
+        M = self.cfg["n_mel_channels"]
+        d = [torch.empty(B, M, T, device=self.device), torch.empty(B, M, T, device=self.device), torch.empty(B, T, device=self.device)]
+        _lib.check(self.lib.msa_loss_grads(self.h, self._ws_ptr(), _ptr(d[0]), _ptr(d[1]), _ptr(d[2]), _stream()), "msa_loss_grads")
+        return d
+
+    def get_buffer(self, name: str) -> torch.Tensor:
+        """Copy of a named intermediate of the last pass (tests only)."""
+        p, n = C.c_void_p(), C.c_int64()
+        _lib.check(self.lib.msa_get_buffer(self.h, self._ws_ptr(), name.encode(), C.byref(p), C.byref(n)), "msa_get_buffer")
+        off = (p.value - self._ws.data_ptr())
+        return self._ws[off:off + 4 * n.value].view(torch.float32).clone()
+
+    # ---- flat-buffer kernels ----------------------------------------------------------------------------
+    def sgd_step(self, p, g, p_out=None, lr=1e-3, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False, buf=None,
+                 first_step=True):
+        p_out = p if p_out is None else p_out
+        _lib.check(self.lib.msa_flat_sgd_step(_ptr(p), _ptr(g), _ptr(p_out), _ptr(buf), p.numel(), lr, momentum, dampening,
+                                              weight_decay, int(nesterov), int(first_step), _stream()), "msa_flat_sgd_step")
+        self.launches += 1
+        return p_out
+
+    def axpy(self, acc, g, w: float, init: bool):
+        _lib.check(self.lib.msa_flat_axpy(_ptr(acc), _ptr(g), acc.numel(), w, int(init), _stream()), "msa_flat_axpy")
+        self.launches += 1
+
+    def reptile_delta(self, acc, p_T, p_0, w: float, init: bool):
+        _lib.check(self.lib.msa_flat_reptile_delta(_ptr(acc), _ptr(p_T), _ptr(p_0), acc.numel(), w, int(init), _stream()),
+                   "msa_flat_reptile_delta")
+        self.launches += 1
+
+    def sumsq(self, g, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        out = torch.empty(1, device=self.device) if out is None else out
+        _lib.check(self.lib.msa_flat_sumsq(_ptr(g), g.numel(), _ptr(self._partials), _ptr(out), _stream()), "msa_flat_sumsq")
+        self.launches += 2
+        return out
+
+    def clip_sgd(self, p, g, sumsq, lr, max_norm=0.0, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False, buf=None,
+                 first_step=True):
+        _lib.check(self.lib.msa_flat_clip_sgd(_ptr(p), _ptr(g), _ptr(buf), _ptr(sumsq), p.numel(), lr, max_norm, momentum, dampening,
+                                              weight_decay, int(nesterov), int(first_step), _stream()), "msa_flat_clip_sgd")
+        self.launches += 1
+
+    def clip_adam(self, p, g, m, v, sumsq, lr, step, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_norm=0.0):
+        _lib.check(self.lib.msa_flat_clip_adam(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(sumsq), p.numel(), lr, betas[0], betas[1], eps,
+                                               weight_decay, step, max_norm, _stream()), "msa_flat_clip_adam")
+        self.launches += 1
+
+    def ewc_fisher_accum(self, fisher, g, inv_n: float, init: bool):
+        _lib.check(self.lib.msa_ewc_fisher_accum(_ptr(fisher), _ptr(g), g.numel(), inv_n, int(init), _stream()), "msa_ewc_fisher_accum")
+        self.launches += 1
+
+    def ewc_penalty(self, p, mu, fisher) -> torch.Tensor:
+        out = torch.empty(1, device=self.device)
+        _lib.check(self.lib.msa_ewc_penalty(_ptr(p), _ptr(mu), _ptr(fisher), p.numel(), _ptr(self._partials), _ptr(out), _stream()),
+                   "msa_ewc_penalty")
+        self.launches += 2
+        return out
+
+    def ewc_sgd_step(self, p, g, mu, fisher, lr: float, lam: float) -> torch.Tensor:
+        out = torch.empty(1, device=self.device)
+        _lib.check(self.lib.msa_ewc_sgd_step(_ptr(p), _ptr(g), _ptr(mu), _ptr(fisher), p.numel(), lr, lam, _ptr(self._partials),
+                                             _ptr(out), _stream()), "msa_ewc_sgd_step")
+        self.launches += 2
+        return out
+
+
+def batch_to_device(batch: tuple, device, speaker_emb_type: str = "static", non_blocking: bool = False) -> dict:
+    """MetaTrainer._unpack_batch (metatrainer.py:95-117): batch tuple -> kwargs dict on the device."""
+    _, inp, inp_len, mels, mel_len, spk_ids, spk_embs, stop = batch
+    spk = spk_ids if speaker_emb_type == "learnable_lookup" else spk_embs
+    mv = lambda t: t.to(device, non_blocking=non_blocking).contiguous()
+    return {"inputs": mv(inp), "input_lengths": mv(inp_len), "melspecs": mv(mels), "melspec_lengths": mv(mel_len),
+            "speaker_vecs": mv(spk), "stop": mv(stop)}
