@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (contract: see DESIGN.md "Measurement").
+
+Workload (BASELINE.json configs[1]): one first-order MAML meta-step over 8 synthetic speaker tasks, 1 inner SGD
+step each, every split a batch of B=4 utterances x T=200 mel frames x L=64 tokens at the Tacotron-2 default
+dimensions (30.33 M parameters): 16 teacher-forced forward+backward passes, 8 fused inner SGD steps, the fused
+meta-gradient accumulation, clip + outer Adam step.  With N GPUs the 8 tasks are sharded (task i -> rank i % N) and
+joined by one NCCL allreduce of the flat meta-gradient: total work is fixed => "scaling": "strong".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [...]                          # the reference algorithm on the host CPU
+
+`value`  : meta-steps/s, inputs already resident in HBM when the timed region starts.
+`e2e`    : the same metric through the public API with HOST (pinned) batches: H2D of every batch and a D2H read of
+           the per-task losses inside the timed region.
+`roofline`, `cpu_baseline`, `clocks`, `gpu_launches`: see DESIGN.md.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TASKS, B, T, L = 8, 4, 200, 64
+INNER_LR, N_INNER = 1e-3, 1
+WORKLOAD = f"fomaml_meta_step_{N_TASKS}tasks_{N_INNER}inner_B{B}_T{T}_L{L}_default_dims"
+
+
+def trainer_params(gemm_tf32: int):
+    import msa_tts_b200 as pkg
+    return {
+        "model": pkg.default_params(),
+        "criterion": {"criterion_type": "Tacotron2Loss", "reduction": "none", "pos_weight": 10.0},
+        "optim_inner": {"optimizer_name": "SGD", "optim_params": {"lr": str(INNER_LR)}},
+        "optim_outer": {"optimizer_name": "Adam", "optim_params": {"lr": "1e-4"}},
+        "n_inner_train": N_INNER, "track_higher_grads": False, "clip_grad_norm": True, "grad_clip_thresh": 1.0,
+        "meta_batch_size": N_TASKS, "dataset_random_seed": 1234, "gemm_tf32": gemm_tf32,
+    }
+
+
+def make_tasks(cfg, pinned=True):
+    from msa_tts_b200 import synth
+    items = {}
+    for i in range(N_TASKS):
+        task = synth.make_task(cfg, B, T, L, 1234 + i)
+        if pinned:
+            task = {k: tuple(x.pin_memory() if hasattr(x, "pin_memory") else x for x in v) for k, v in task.items()}
+        items[f"spk{i}"] = task
+    return items
+
+
+def batch_bytes(batch):
+    return sum(x.numel() * x.element_size() for x in batch[1:] if hasattr(x, "numel"))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algo_bytes(cfg, kernel: str) -> float:
+    """Compulsory HBM bytes of one launch (every operand read once, every result written once)."""
+    from msa_tts_b200.config import memory_dim, rnn_dims
+    Ha, Hd = rnn_dims(cfg)
+    E, A = memory_dim(cfg), cfg["attention_params"]["attention_dim"]
+    F_, Hh = cfg["attention_params"]["attention_location_n_filters"], cfg["encoder_embedding_dim"] // 2
+    TB, BL, TBL = T * B, B * L, T * B * L
+    f = 4.0
+    if kernel == "attn_chain_fwd":
+        rd = TB * 4 * Ha + 4 * Ha * Ha + 4 * Ha * BL + A * Ha + BL * A
+        wr = TB * (2 * Ha + 4 * Ha + A + 1) + 2 * TBL + TBL * A + TBL * F_
+        return f * (rd + wr) + TB * Ha
+    if kernel == "attn_chain_bwd":
+        rd = 4 * Ha * Ha + BL * 4 * Ha + TB * (4 * Ha + Ha + Ha + 1) + 2 * TBL + TBL * A
+        wr = TB * (4 * Ha + A) + TBL + TBL * A + TBL * F_
+        return f * (rd + wr) + TB * Ha
+    if kernel == "dec_lstm_fwd":
+        return f * (TB * 4 * Hd + 4 * Hd * Hd + TB * (2 * Hd + 4 * Hd)) + TB * Hd
+    if kernel == "dec_lstm_bwd":
+        return f * (4 * Hd * Hd + TB * (4 * Hd + Hd + Hd) + TB * 4 * Hd) + TB * Hd
+    if kernel == "enc_lstm_fwd":
+        return f * 2 * (BL * 4 * Hh + 4 * Hh * Hh + BL * (2 * Hh + 4 * Hh))
+    if kernel == "enc_lstm_bwd":
+        return f * 2 * (4 * Hh * Hh + BL * (4 * Hh + 2 * Hh) + BL * 4 * Hh)
+    raise KeyError(kernel)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_reference_task(n_threads=None):
+    """One FOMAML task (1 inner SGD step on the train split + fwd/bwd on the test split) with the oracle port of the
+    reference on the host CPU: a 1/8 sample of the meta-step.  Returns (seconds, threads)."""
+    import torch
+    import msa_tts_b200 as pkg
+    from msa_tts_b200 import synth
+    from oracle import meta as OMeta
+    from oracle import model as OM
+    if n_threads:
+        torch.set_num_threads(n_threads)
+    cfg = pkg.default_params()
+    crit = dict(reduction="none", pos_weight=10.0)
+    P = synth.init_params(cfg, 0)
+    task = synth.make_task(cfg, B, T, L, 1234)
+    masks = [synth.make_masks(cfg, B, T, L, 77 + i) for i in range(N_INNER + 1)]
+    names = OM.param_names(cfg)
+
+    def step():
+        t0 = time.perf_counter()
+        OMeta.fomaml_task(P, cfg, task, masks, crit, names, N_INNER, INNER_LR)
+        return time.perf_counter() - t0
+    return step, torch.get_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm for this path on the host cores (the reference is pure Python and
+    `higher` is absent, so this is the oracle restatement pinned to it; kind = "port").  One step = one task of the
+    8-task meta-step (a 1/8 sample), so that K steps finish in minutes."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step, threads = cpu_reference_task()
+    for _ in range(args.warmup):
+        step()
+    ts = [step() for _ in range(args.steps)]
+    t_task = sum(ts) / len(ts)
+    value = 1.0 / (N_TASKS * t_task)
+    line = {"impl": "reference", "metric": "meta_steps_per_s", "value": value, "unit": "meta-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * N_TASKS * t_task, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "tasks": N_TASKS, "inner_steps": N_INNER, "B": B, "T": T, "L": L},
+            "cpu_baseline": {"value": value, "unit": "meta-steps/s", "cores": threads, "kind": "port",
+                             "sample": "1 of the 8 tasks per step (1 inner SGD step + test fwd/bwd), extrapolated x8"},
+            "e2e": {"value": value, "unit": "meta-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "mel_frames_per_s": value * N_TASKS * 2 * B * T}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--gemm", default="tf32x", choices=["fp32", "tf32x", "tf32"], help="GEMM precision policy (DESIGN.md section 5)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    from msa_tts_b200.maml import MAML
+    from msa_tts_b200.engine import batch_to_device
+
+    gemm_mode = {"fp32": 0, "tf32x": 1, "tf32": 2}[args.gemm]
+    params = trainer_params(gemm_mode)
+    tr = MAML(**params)
+    eng = tr.engine
+    cfg = params["model"]
+    host_items = make_tasks(cfg, pinned=True)
+    dev_items = {s: {k: tuple(x.to(tr.device) if hasattr(x, "to") else x for x in v) for k, v in t.items()} for s, t in host_items.items()}
+    mine = tr.shard.my_tasks(N_TASKS)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(items, steps, read_losses):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            log = tr._metatrain_step(items)
+            if read_losses:
+                log["loss_test"].cpu()            # D2H read of the step's result
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=tr.device)
+        tr.shard.allreduce_max(ms)
+        return float(ms)
+
+    for _ in range(args.warmup):
+        tr._metatrain_step(dev_items)
+    # ---- device-resident leg (value) with live per-kernel event timing and clock sampling ----
+    l0 = eng.kernel_launches()
+    eng.profile(True)
+    with ClockSampler(local_rank) as clk:
+        ms_dev = timed(dev_items, args.steps, read_losses=False)
+    prof = eng.profile_read()
+    eng.profile(False)
+    launches = eng.kernel_launches() - l0
+    # ---- end-to-end leg: pinned host batches, H2D inside, D2H of the losses ----
+    for _ in range(2):
+        tr._metatrain_step(host_items)
+    ms_e2e = timed(host_items, args.steps, read_losses=True)
+    h2d = sum(batch_bytes(host_items[f"spk{i}"][k]) for i in mine for k in ("train", "test"))
+    d2h = 4 * len(mine)
+
+    # ---- flat-buffer kernels timed alone (HBM roofline) ----
+    def time_flat(fn, reps=20):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    n = eng.layout.total
+    flat_ms = {
+        "flat_sgd_step": (time_flat(lambda: eng.sgd_step(tr.fast, tr.task_grad, lr=1e-3)), 12.0 * n),
+        "flat_clip_adam": (time_flat(lambda: eng.clip_adam(tr.fast, tr.task_grad, tr.outer_m, tr.outer_v, tr.sumsq, lr=1e-9, step=1, max_norm=1.0)), 28.0 * n),
+        "flat_sumsq": (time_flat(lambda: eng.sumsq(tr.task_grad)), 4.0 * n),
+    }
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        kern = []
+        for name, (ms, cnt) in prof.items():
+            if cnt:
+                ab = algo_bytes(cfg, name)
+                per = ms / cnt
+                kern.append({"kernel": name, "launches_per_step": cnt / args.steps, "ms_per_launch": per,
+                             "share_of_step": ms / ms_dev, "algo_bytes": ab, "achieved_gbs": ab / per / 1e6,
+                             "frac": ab / per / 1e6 / peak})
+        for name, (ms, ab) in flat_ms.items():
+            kern.append({"kernel": name, "ms_per_launch": ms, "algo_bytes": ab, "achieved_gbs": ab / ms / 1e6,
+                         "frac": ab / ms / 1e6 / peak, "timed": "alone, 20 reps"})
+        dom = max((k for k in kern if "share_of_step" in k), key=lambda k: k["share_of_step"])
+        ms_step = ms_dev / args.steps
+        value = 1000.0 / ms_step
+        e2e_value = 1000.0 * args.steps / ms_e2e
+        line = {
+            "metric": "meta_steps_per_s", "value": value, "unit": "meta-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "tasks": N_TASKS, "inner_steps": N_INNER, "B": B, "T": T, "L": L,
+                       "params": eng.layout.n_params, "gemm": args.gemm, "parallelism": f"task-shard x{world} + 1 allreduce",
+                       "l2": "per-step working set (4 flat buffers 485 MB + workspace) > 126 MB L2, no explicit flush"},
+            "mel_frames_per_s": value * N_TASKS * 2 * B * T,
+            "e2e": {"value": e2e_value, "unit": "meta-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                         "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                         "note": "persistent recurrent kernel: weights stay in shared memory, time is set by 3 grid barriers "
+                                 "per decoder step, not by HBM (DESIGN.md section 4)",
+                         "ms_per_launch": dom["ms_per_launch"], "share_of_step": dom["share_of_step"]},
+            "kernels": kern,
+            "clocks": clk.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            step, threads = cpu_reference_task()
+            step()
+            ts = [step() for _ in range(2)]
+            t_task = min(ts)
+            line["cpu_baseline"] = {"value": 1.0 / (N_TASKS * t_task), "unit": "meta-steps/s", "cores": threads, "kind": "port",
+                                    "sample": "1 of the 8 tasks (1 inner SGD step + test fwd/bwd) on the host CPU, best of 2 after "
+                                              "1 warm-up, extrapolated x8"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

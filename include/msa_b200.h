@@ -77,7 +77,7 @@ typedef struct msa_config {
     int32_t max_decoder_steps;
     int32_t early_stopping;       /* not decoder_no_early_stopping */
     int32_t loss_reduction;       /* 0 "none" (length-normalised masks), 1 "mean" */
-    int32_t gemm_tf32;            /* 0: fp32 GEMMs, 1: TF32 tensor-core GEMMs */
+    int32_t gemm_tf32;            /* batched-GEMM precision: 0 fp32 everywhere, 1 fp32 forward + TF32 backward, 2 TF32 everywhere */
     float p_attn_dropout;
     float p_dec_dropout;
     float gate_threshold;
@@ -94,6 +94,15 @@ int msa_create(const msa_config* cfg, int device, msa_handle** out);
 int msa_destroy(msa_handle* h);
 /* number of SMs / cooperative grid size the persistent kernels use */
 int msa_sm_count(const msa_handle* h);
+
+/* number of kernels of THIS library enqueued so far by the process (cuBLAS GEMMs are not counted) */
+long long msa_launch_count(void);
+/* per-kernel device timing of the persistent kernels with CUDA events on the launch stream:
+ * enable, run passes, then read (synchronises) total milliseconds and launch counts per kernel id */
+int msa_profile_enable(msa_handle* h, int enable);
+int msa_profile_kernels(void);
+const char* msa_profile_name(int id);
+int msa_profile_read(msa_handle* h, double* total_ms, int64_t* counts);
 
 /* ---- flat layout (replaces iterating model.parameters(), maml.py:71-76) -------------- */
 int msa_param_count(const msa_handle* h);
@@ -131,6 +140,11 @@ int msa_train_forward(msa_handle* h, void* ws, size_t ws_bytes, const float* par
 int msa_train_backward(msa_handle* h, void* ws, size_t ws_bytes, const float* params, const float* d_mel,
                        const float* d_mel_post, const float* d_gate, float* grads, int accumulate,
                        float grad_scale, void* stream);
+/* Tacotron2Loss.__call__ (modules_tacotron2nv/tacotron2nv_loss.py:17-52) on the outputs of the last
+ * msa_train_forward in `ws`, with the criterion's own reduction (0 "none", 1 "mean") and pos_weight
+ * (metatrainer.py:83-86); also refreshes d(loss)/d(outputs) used by msa_train_backward(NULL,...). */
+int msa_train_loss(msa_handle* h, void* ws, const float* stop_targets, const int64_t* mel_lengths, int reduction,
+                   float pos_weight, float* loss_out, void* stream);
 /* d(loss)/d(mel, mel_post, gate) of the last forward, reference layouts (for autograd glue) */
 int msa_loss_grads(msa_handle* h, void* ws, float* d_mel, float* d_mel_post, float* d_gate, void* stream);
 /* test hook: device pointer + element count of a named intermediate of the last pass */

@@ -29,6 +29,11 @@ SIGNATURES = {
     "msa_create": (I, [C.POINTER(MsaConfig), I, C.POINTER(V)]),
     "msa_destroy": (I, [V]),
     "msa_sm_count": (I, [V]),
+    "msa_launch_count": (C.c_longlong, []),
+    "msa_profile_enable": (I, [V, I]),
+    "msa_profile_kernels": (I, []),
+    "msa_profile_name": (C.c_char_p, [I]),
+    "msa_profile_read": (I, [V, C.POINTER(C.c_double), C.POINTER(I64)]),
     "msa_param_count": (I, [V]),
     "msa_param_total": (I64, [V]),
     "msa_param_info": (I, [V, I, C.POINTER(C.c_char_p), C.POINTER(I64), C.POINTER(I64)]),
@@ -42,6 +47,7 @@ SIGNATURES = {
     "msa_workspace_bytes": (SZ, [V, I, I, I]),
     "msa_train_forward": (I, [V, V, SZ, V, V, V, V, V, V, V, V, V, V, I, I, I, V, V, V, V, V, V]),
     "msa_train_backward": (I, [V, V, SZ, V, V, V, V, V, I, F, V]),
+    "msa_train_loss": (I, [V, V, V, V, I, F, V, V]),
     "msa_loss_grads": (I, [V, V, V, V, V, V]),
     "msa_get_buffer": (I, [V, V, C.c_char_p, C.POINTER(V), C.POINTER(I64)]),
     "msa_infer_workspace_bytes": (SZ, [V, I, I, I]),

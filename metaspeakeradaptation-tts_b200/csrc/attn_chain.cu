@@ -462,6 +462,7 @@ int launch_attn_chain_fwd(const AttnChainParams& p, int sm_count, size_t smem_li
     AttnChainParams pp = p;
     void* args[] = {&pp, &mw_res};
     MSA_CUDA(cudaLaunchCooperativeKernel((void*)k_attn_chain_fwd, dim3(sm_count), dim3(kRecThreads), args, smem, st));
+    count_launch();
     return 0;
 }
 
@@ -474,6 +475,7 @@ int launch_attn_chain_bwd(const AttnChainBwdParams& p, int sm_count, size_t smem
     AttnChainBwdParams pp = p;
     void* args[] = {&pp};
     MSA_CUDA(cudaLaunchCooperativeKernel((void*)k_attn_chain_bwd, dim3(sm_count), dim3(kRecThreads), args, smem, st));
+    count_launch();
     return 0;
 }
 

@@ -32,7 +32,14 @@ void set_error(const char* fmt, ...);
         int _r = (expr);                                                                   \
         if (_r != 0) return _r;                                                            \
     } while (0)
-#define MSA_LAUNCH_CHECK() MSA_CUDA(cudaGetLastError())
+// every kernel of this library is launched through a wrapper that ends in MSA_LAUNCH_CHECK (or count_launch for
+// cooperative launches), so msa_launch_count() is the number of OUR kernels enqueued (cuBLAS calls are not counted)
+void count_launch();
+#define MSA_LAUNCH_CHECK()              \
+    do {                                \
+        msa::count_launch();            \
+        MSA_CUDA(cudaGetLastError());   \
+    } while (0)
 
 constexpr int kAlign = 32;  // floats; every flat-buffer tensor starts on a 128-byte boundary
 inline int64_t align_up(int64_t n, int64_t a = kAlign) { return (n + a - 1) / a * a; }

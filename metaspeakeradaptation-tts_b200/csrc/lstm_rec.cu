@@ -177,6 +177,7 @@ int launch_lstm_rec_fwd(const LstmRecParams& p, int sm_count, size_t smem_limit,
     LstmRecParams pp = p;
     void* args[] = {&pp};
     MSA_CUDA(cudaLaunchCooperativeKernel((void*)k_lstm_rec_fwd, dim3(sm_count), dim3(kRecThreads), args, smem, st));
+    count_launch();
     return 0;
 }
 
@@ -189,6 +190,7 @@ int launch_lstm_rec_bwd(const LstmRecBwdParams& p, int sm_count, size_t smem_lim
     LstmRecBwdParams pp = p;
     void* args[] = {&pp};
     MSA_CUDA(cudaLaunchCooperativeKernel((void*)k_lstm_rec_bwd, dim3(sm_count), dim3(kRecThreads), args, smem, st));
+    count_launch();
     return 0;
 }
 

@@ -9,6 +9,7 @@
 #include <cublas_v2.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <map>
 #include <string>
@@ -20,6 +21,8 @@
 namespace msa {
 
 static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -61,6 +64,12 @@ struct msa_handle {
     // state of the last forward (for backward / get_buffer)
     bool fwd_valid = false;
     Dims d{};
+    // optional per-kernel timing with CUDA events on the launch stream (bench.py's roofline leg)
+    bool in_bwd = false;   // GEMM precision policy 1: fp32 GEMMs in the forward pass, TF32 in the backward pass
+    bool prof = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
+    std::vector<int> prof_id;
+    size_t prof_used = 0;
     const int64_t *tokens = nullptr, *tok_len = nullptr, *mel_len = nullptr, *spk_ids = nullptr;
     const float* spk_in = nullptr;
     const uint8_t* masks = nullptr;
@@ -244,7 +253,8 @@ static int gemm(msa_handle* h, bool ta, bool tb, int64_t M, int64_t N, int64_t K
         MSA_CHECK(beta == 1.f, MSA_E_ARG, "gemm: K == 0 with beta != 1");
         return 0;
     }
-    const cublasComputeType_t ct = h->cfg.gemm_tf32 ? CUBLAS_COMPUTE_32F_FAST_TF32 : CUBLAS_COMPUTE_32F;
+    const bool tf32 = h->cfg.gemm_tf32 >= 2 || (h->cfg.gemm_tf32 == 1 && h->in_bwd);
+    const cublasComputeType_t ct = tf32 ? CUBLAS_COMPUTE_32F_FAST_TF32 : CUBLAS_COMPUTE_32F;
     MSA_BLAS(cublasGemmEx(h->blas, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, (int)N, (int)M, (int)K, &alpha,
                           Bm, CUDA_R_32F, (int)ldb, A, CUDA_R_32F, (int)lda, &beta, Cm, CUDA_R_32F, (int)ldc, ct,
                           CUBLAS_GEMM_DEFAULT));
@@ -255,7 +265,8 @@ static int gemm_batched(msa_handle* h, bool ta, bool tb, int64_t M, int64_t N, i
                         int batch) {
     if (M == 0 || N == 0 || batch == 0) return 0;
     if (K == 0) return 0;
-    const cublasComputeType_t ct = h->cfg.gemm_tf32 ? CUBLAS_COMPUTE_32F_FAST_TF32 : CUBLAS_COMPUTE_32F;
+    const bool tf32 = h->cfg.gemm_tf32 >= 2 || (h->cfg.gemm_tf32 == 1 && h->in_bwd);
+    const cublasComputeType_t ct = tf32 ? CUBLAS_COMPUTE_32F_FAST_TF32 : CUBLAS_COMPUTE_32F;
     MSA_BLAS(cublasGemmStridedBatchedEx(h->blas, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, (int)N, (int)M,
                                         (int)K, &alpha, Bm, CUDA_R_32F, (int)ldb, sb, A, CUDA_R_32F, (int)lda, sa, &beta, Cm,
                                         CUDA_R_32F, (int)ldc, sc, batch, ct, CUBLAS_GEMM_DEFAULT));
@@ -296,6 +307,25 @@ static int conv_bn_bwd(msa_handle* h, cudaStream_t st, const float* params, floa
     }
     return 0;
 }
+
+enum ProfId { PROF_ENC_LSTM_FWD = 0, PROF_ATTN_FWD, PROF_DEC_LSTM_FWD, PROF_DEC_LSTM_BWD, PROF_ATTN_BWD, PROF_ENC_LSTM_BWD, PROF_N };
+static const char* kProfNames[PROF_N] = {"enc_lstm_fwd", "attn_chain_fwd", "dec_lstm_fwd", "dec_lstm_bwd", "attn_chain_bwd", "enc_lstm_bwd"};
+struct ProfScope {
+    msa_handle* h; cudaStream_t st; int slot = -1;
+    ProfScope(msa_handle* h_, int id, cudaStream_t st_) : h(h_), st(st_) {
+        if (!h->prof) return;
+        if (h->prof_used == h->prof_ev.size()) {
+            cudaEvent_t a, b;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+            h->prof_ev.push_back({a, b});
+            h->prof_id.push_back(id);
+        }
+        slot = (int)h->prof_used++;
+        h->prof_id[slot] = id;
+        cudaEventRecord(h->prof_ev[slot].first, st);
+    }
+    ~ProfScope() { if (slot >= 0) cudaEventRecord(h->prof_ev[slot].second, st); }
+};
 
 static int check_cfg(const msa_config& c) {
     MSA_CHECK(c.enc_dim > 0 && c.enc_dim % 8 == 0, MSA_E_UNSUPPORTED, "encoder_embedding_dim must be a positive multiple of 8");
@@ -359,11 +389,34 @@ int msa_create(const msa_config* cfg, int device, msa_handle** out) {
 int msa_destroy(msa_handle* h) {
     if (!h) return 0;
     if (h->blas) cublasDestroy(h->blas);
+    for (auto& e : h->prof_ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     delete h;
     return 0;
 }
 
 int msa_sm_count(const msa_handle* h) { return h ? h->sm_count : 0; }
+long long msa_launch_count(void) { return g_launches.load(); }
+int msa_profile_enable(msa_handle* h, int enable) {
+    MSA_CHECK(h, MSA_E_ARG, "msa_profile_enable: null handle");
+    h->prof = enable != 0;
+    h->prof_used = 0;
+    return 0;
+}
+int msa_profile_kernels(void) { return PROF_N; }
+const char* msa_profile_name(int id) { return id >= 0 && id < PROF_N ? kProfNames[id] : ""; }
+int msa_profile_read(msa_handle* h, double* total_ms, int64_t* counts) {
+    MSA_CHECK(h && total_ms && counts, MSA_E_ARG, "msa_profile_read: null argument");
+    for (int i = 0; i < PROF_N; ++i) { total_ms[i] = 0.0; counts[i] = 0; }
+    for (size_t i = 0; i < h->prof_used; ++i) {
+        MSA_CUDA(cudaEventSynchronize(h->prof_ev[i].second));
+        float ms = 0.f;
+        MSA_CUDA(cudaEventElapsedTime(&ms, h->prof_ev[i].first, h->prof_ev[i].second));
+        total_ms[h->prof_id[i]] += ms;
+        counts[h->prof_id[i]] += 1;
+    }
+    h->prof_used = 0;
+    return 0;
+}
 int msa_param_count(const msa_handle* h) { return h ? (int)h->names.size() : 0; }
 int64_t msa_param_total(const msa_handle* h) { return h ? h->total : 0; }
 int msa_param_info(const msa_handle* h, int i, const char** name, int64_t* offset, int64_t* numel) {
@@ -428,6 +481,7 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
     MSA_BLAS(cublasSetStream(h->blas, st));
     MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
     h->fwd_valid = false;
+    h->in_bwd = false;
     const msa_config& c = h->cfg;
     const auto secs = mask_sections(c, B, T, L);
     auto mk = [&](int i) { return masks + secs[i].off; };
@@ -467,6 +521,7 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
         lp.whh_dir_stride = h->off("encoder.lstm.weight_hh_l0_reverse") - h->off("encoder.lstm.weight_hh_l0");
         lp.hout = w.enc_h; lp.cout = w.enc_c; lp.gates = w.enc_g; lp.mask = nullptr; lp.drop_scale = 1.f;
         lp.lengths = token_lengths; lp.barrier = w.barrier;
+        ProfScope ps(h, PROF_ENC_LSTM_FWD, st);
         MSA_TRY(launch_lstm_rec_fwd(lp, h->sm_count, h->smem_limit, st));
     }
     MSA_TRY(k_build_memory(w.enc_h, w.spk_vec, w.memory, B, L, d.Hh, d.Ds, st));
@@ -497,6 +552,7 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
         ap.drop_scale = 1.f / (1.f - c.p_attn_dropout);
         ap.ha = w.ha; ap.ca = w.ca; ap.ga = w.ga; ap.q = w.q; ap.align = w.align_tm; ap.cum = w.cum; ap.s = w.s;
         ap.convf = w.convf; ap.znorm = w.znorm; ap.ebuf = w.ebuf; ap.barrier = w.barrier;
+        ProfScope ps(h, PROF_ATTN_FWD, st);
         MSA_TRY(launch_attn_chain_fwd(ap, h->sm_count, h->smem_limit, st));
     }
     // ctx[t][b] = a[t][b] . memory[b]  (forward_attn.py:217), batched over b
@@ -515,6 +571,7 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
         lp.mask = c.p_dec_dropout > 0.f ? mk(iDec) : nullptr;
         lp.drop_scale = 1.f / (1.f - c.p_dec_dropout);
         lp.lengths = nullptr; lp.barrier = w.barrier;
+        ProfScope ps(h, PROF_DEC_LSTM_FWD, st);
         MSA_TRY(launch_lstm_rec_fwd(lp, h->sm_count, h->smem_limit, st));
     }
     // ---- mel / gate projections (decoder.py:267-270) ----
@@ -556,6 +613,20 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
     return 0;
 }
 
+int msa_train_loss(msa_handle* h, void* wsp, const float* stop_targets, const int64_t* mel_lengths, int reduction, float pos_weight,
+                   float* loss_out, void* stream) {
+    MSA_CHECK(h && wsp && h->fwd_valid, MSA_E_STATE, "msa_train_loss: no forward pass in this workspace");
+    MSA_CHECK(stop_targets && mel_lengths && loss_out, MSA_E_ARG, "msa_train_loss: null argument");
+    MSA_CHECK(reduction == 0 || reduction == 1, MSA_E_ARG, "msa_train_loss: reduction must be 0 (none) or 1 (mean)");
+    const Dims& d = h->d;
+    const Ws w = ws_layout(d, wsp);
+    cudaStream_t st = (cudaStream_t)stream;
+    MSA_TRY(k_loss(w.post_x, w.post_bt, w.gate_bt, w.target, stop_targets, mel_lengths, d.B, d.T, d.M, reduction, pos_weight,
+                   w.loss_part, w.loss, w.dpre, w.dpost, w.dgate, st));
+    MSA_TRY(k_scale_copy(w.loss, loss_out, 1, 1.f, 0, st));
+    return 0;
+}
+
 int msa_loss_grads(msa_handle* h, void* wsp, float* d_mel, float* d_mel_post, float* d_gate, void* stream) {
     MSA_CHECK(h && wsp && h->fwd_valid, MSA_E_STATE, "msa_loss_grads: no forward pass in this workspace");
     const Dims& d = h->d;
@@ -581,6 +652,7 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
     MSA_BLAS(cublasSetStream(h->blas, st));
     MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
     const msa_config& c = h->cfg;
+    h->in_bwd = true;
     const int B = d.B, T = d.T, L = d.L;
     const auto secs = mask_sections(c, B, T, L);
     auto mk = [&](int i) { return h->masks + secs[i].off; };
@@ -637,6 +709,7 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
         bp.mask = c.p_dec_dropout > 0.f ? mk(iDec) : nullptr;
         bp.drop_scale = 1.f / (1.f - c.p_dec_dropout);
         bp.lengths = nullptr; bp.barrier = w.barrier;
+        ProfScope ps(h, PROF_DEC_LSTM_BWD, st);
         MSA_TRY(launch_lstm_rec_bwd(bp, h->sm_count, h->smem_limit, st));
     }
     const float* Wid = P("decoder.decoder_rnn.weight_ih");
@@ -675,6 +748,7 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
         bp.dha_ext = w.dha; bp.da_ext = w.da_ext;
         bp.dza = w.dza; bp.dq = w.dq; bp.de = w.de; bp.ds = w.ds; bp.dconvf = w.dconvf; bp.dat = w.dat;
         bp.barrier = w.barrier;
+        ProfScope ps(h, PROF_ATTN_BWD, st);
         MSA_TRY(launch_attn_chain_bwd(bp, h->sm_count, h->smem_limit, st));
     }
     // ---- deferred attention / attention-RNN parameter gradients ----
@@ -726,6 +800,7 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
         bp.whh_dir_stride = h->off("encoder.lstm.weight_hh_l0_reverse") - h->off("encoder.lstm.weight_hh_l0");
         bp.gates = w.enc_g; bp.cout = w.enc_c; bp.dh_ext = w.denc_h; bp.dz = w.dzx; bp.mask = nullptr; bp.drop_scale = 1.f;
         bp.lengths = h->tok_len; bp.barrier = w.barrier;
+        ProfScope ps(h, PROF_ENC_LSTM_BWD, st);
         MSA_TRY(launch_lstm_rec_bwd(bp, h->sm_count, h->smem_limit, st));
     }
     for (int dir = 0; dir < 2; ++dir) {

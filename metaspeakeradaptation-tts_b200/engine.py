@@ -18,7 +18,7 @@ from .layout import FlatLayout
 _SPK_MODES = {"static": 0, "static+linear": 1, "learnable_lookup": 2}
 
 
-def make_c_config(cfg: dict, reduction: str = "none", pos_weight: float = 10.0, gemm_tf32: bool = False) -> "_lib.MsaConfig":
+def make_c_config(cfg: dict, reduction: str = "none", pos_weight: float = 10.0, gemm_tf32: int = 0) -> "_lib.MsaConfig":
     """params["model"] (+ criterion settings, metatrainer.py:83-86) -> msa_config."""
     ap = cfg["attention_params"]
     if ap["attention_type"] != "ForwardAttention":
@@ -80,7 +80,7 @@ class Engine:
     """One msa_handle + its workspace on one GPU."""
 
     def __init__(self, cfg: dict, device: Optional[torch.device] = None, reduction: str = "none",
-                 pos_weight: float = 10.0, gemm_tf32: bool = False):
+                 pos_weight: float = 10.0, gemm_tf32: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("msa_tts_b200 needs a CUDA (sm_100a) device: there is no CPU fallback")
         self.lib = _lib.load()
@@ -229,6 +229,14 @@ class Engine:
         _lib.check(rc, "msa_train_backward")
         self.launches += 1
 
+    def loss(self, stop: torch.Tensor, mel_lengths: torch.Tensor, reduction: str = "none", pos_weight: float = 10.0) -> torch.Tensor:
+        """Tacotron2Loss on the outputs of the last forward (tacotron2nv_loss.py:17-52)."""
+        out = torch.empty(1, device=self.device)
+        _lib.check(self.lib.msa_train_loss(self.h, self._ws_ptr(), _ptr(stop), _ptr(mel_lengths), {"none": 0, "mean": 1}[reduction],
+                                           C.c_float(pos_weight), _ptr(out), _stream()), "msa_train_loss")
+        self.launches += 1
+        return out
+
     def loss_grads(self, B: int, T: int):
         M = self.cfg["n_mel_channels"]
         d = [torch.empty(B, M, T, device=self.device), torch.empty(B, M, T, device=self.device), torch.empty(B, T, device=self.device)]
@@ -241,6 +249,20 @@ class Engine:
         _lib.check(self.lib.msa_get_buffer(self.h, self._ws_ptr(), name.encode(), C.byref(p), C.byref(n)), "msa_get_buffer")
         off = (p.value - self._ws.data_ptr())
         return self._ws[off:off + 4 * n.value].view(torch.float32).clone()
+
+    # ---- instrumentation ---------------------------------------------------------------------------------
+    def kernel_launches(self) -> int:
+        """Kernels of libmsa_b200 enqueued so far by this process (cuBLAS GEMMs excluded)."""
+        return int(self.lib.msa_launch_count())
+
+    def profile(self, enable: bool) -> None:
+        _lib.check(self.lib.msa_profile_enable(self.h, int(enable)), "msa_profile_enable")
+
+    def profile_read(self) -> dict:
+        n = self.lib.msa_profile_kernels()
+        ms, cnt = (C.c_double * n)(), (C.c_int64 * n)()
+        _lib.check(self.lib.msa_profile_read(self.h, ms, cnt), "msa_profile_read")
+        return {self.lib.msa_profile_name(i).decode(): (ms[i], cnt[i]) for i in range(n)}
 
     # ---- flat-buffer kernels ----------------------------------------------------------------------------
     def sgd_step(self, p, g, p_out=None, lr=1e-3, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False, buf=None,

@@ -1,0 +1,62 @@
+"""MAML / first-order MAML driver: mirror of msa_tts/maml.py on the CUDA hot path.
+
+``MAML._metatrain_step(items_b)`` is the body of the reference's loop over meta-batches (maml.py:36-105):
+for each speaker adapt ``n_inner_train`` steps on the "train" split, evaluate on the "test" split, take the
+gradient of the test loss w.r.t. the adapted weights (first-order, ``track_higher_grads=False``: maml.py:73-74),
+average over speakers with weights 1/N (94-98), clip (101-103) and take the outer step (105).
+The weighted accumulation is fused into the backward pass of the test split (its GEMM epilogues write
+``meta_grad += w * g``), speakers are sharded over ranks and ONE allreduce joins them (parallel.py).
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch
+
+from .metatrainer import MetaTrainer
+
+
+class MAML(MetaTrainer):
+    def __init__(self, **params):
+        super().__init__(**params)
+        if params.get("track_higher_grads", False):
+            raise NotImplementedError("second-order MAML needs double-backward through the fused kernels "
+                                      "(SURVEY.md 8f item 2); use track_higher_grads=False (FOMAML)")
+
+    def _metatrain_step(self, items_b: Dict[str, Dict[str, tuple]]) -> dict:
+        """One meta-step on one meta-batch {speaker: {"train": batch, "test": batch}} (maml.py:36-105)."""
+        eng = self.engine
+        speakers = list(items_b.keys())
+        N = len(speakers)
+        mine = self.shard.my_tasks(N)
+        n_inner = self.params["n_inner_train"]
+        losses = []
+        if not mine:
+            self.meta_grad.zero_()
+        for j, i in enumerate(mine):
+            task = items_b[speakers[i]]
+            self._adapt(i, task["train"], n_inner)
+            inputs, _ = self._unpack_batch(task["test"])
+            B, L = inputs["inputs"].shape
+            T = inputs["melspecs"].shape[2]
+            _, loss = eng.forward(self.fast, self.task_bn, inputs, self._masks(i, n_inner, B, T, L), outputs=False)
+            # task_grads = autograd.grad(loss_test, fmodel.parameters(time=-1)); mix_grad weight 1/N (maml.py:73-74, 94-98)
+            eng.backward(self.fast, self.meta_grad, accumulate=(j > 0), scale=1.0 / N)
+            losses.append(loss)
+        sumsq = self._outer_update()
+        local = torch.cat(losses) if losses else torch.zeros(0, device=self.device)
+        return {"loss_test": local, "task_index": mine, "grad_sumsq": sumsq}
+
+    def _metatrain(self, epoch: int, dataloader_metatrain) -> List[dict]:
+        """maml.py:33-108 over an iterable of meta-batches (the reference's DataLoader is out of scope)."""
+        logs = []
+        for items_b in dataloader_metatrain:
+            logs.append(self._metatrain_step(items_b))
+        return logs
+
+    def run(self, dataloader_metatrain, n_epochs: int = 1):
+        self.step_global = 0
+        out = []
+        for epoch in range(1, n_epochs + 1):
+            out += self._metatrain(epoch, dataloader_metatrain)
+        return out

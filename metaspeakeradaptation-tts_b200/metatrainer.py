@@ -1,0 +1,143 @@
+"""MetaTrainer: host-side mirror of msa_tts/metatrainer.py for the hot path.
+
+Keeps the reference's call surface for the part that is in scope -- model / criterion /
+inner + outer optimizer set-up from the ``params`` dict (metatrainer.py:33-56, 81-93),
+``_unpack_batch`` (95-117), checkpoint save / load with the reference's ``state_dict`` keys
+(119-122, 138-146) -- and owns what the B200 design adds: the flat parameter / gradient /
+optimizer-state buffers, the per-task fast weights and private BatchNorm statistics
+(SURVEY.md Q18), the dropout-mask stream keyed by (meta-step, task, pass) so that sharded and
+unsharded runs agree, and the task-to-rank sharding with ONE allreduce.
+
+Out of scope here: data loaders, audio, TensorBoard, plotting.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional
+
+import torch
+
+from .engine import Engine, batch_to_device
+from .helpers import optimizer_hparams
+from .parallel import ShardInfo
+
+
+class MetaTrainer:
+    def __init__(self, **params):
+        self.params = params
+        self.model_params = params["model"]
+        crit = params.get("criterion", {"criterion_type": "Tacotron2Loss", "reduction": "none", "pos_weight": 10.0})
+        if crit["criterion_type"] != "Tacotron2Loss":
+            raise RuntimeError(f"Criterion {crit} not defined.")            # metatrainer.py:88-89
+        self.shard = ShardInfo.from_env(params.get("distributed", None))
+        self.device = torch.device(f"cuda:{self.shard.local_rank}")
+        torch.cuda.set_device(self.device)
+        self.speaker_emb_type = self.model_params["speaker_emb_type"]
+        self.engine = Engine(self.model_params, self.device, reduction=crit["reduction"], pos_weight=crit["pos_weight"],
+                             gemm_tf32=params.get("gemm_tf32", 0))
+        self.layout = self.engine.layout
+        # inner / outer optimizers: name + eval'ed string hyper-parameters, like helpers.get_optimizer (helpers.py:20-26)
+        self.inner = optimizer_hparams(params["optim_inner"])
+        self.outer = optimizer_hparams(params["optim_outer"])
+        if self.inner["name"] != "SGD":
+            raise NotImplementedError("inner optimizer: only the SGD rule is implemented (SURVEY.md 8f item 3)")
+        if self.outer["name"] not in ("SGD", "Adam"):
+            raise NotImplementedError("outer optimizer: SGD and Adam are implemented")
+        # flat state
+        from .synth import init_params
+        self.theta = self.engine.flat_from_dict(init_params(self.model_params, params.get("init_seed", 0)))
+        self.base_bn = self.engine.new_bn_stats()      # never updated by MAML/Reptile
+        self.meta_grad = self.engine.new_flat()
+        self.fast = self.engine.new_flat()
+        self.task_grad = self.engine.new_flat()
+        self.task_bn = self.engine.new_bn_stats()
+        self.inner_buf = self.engine.new_flat() if self.inner.get("momentum", 0.0) else None
+        self.outer_m = self.engine.new_flat() if (self.outer["name"] == "Adam" or self.outer.get("momentum", 0.0)) else None
+        self.outer_v = self.engine.new_flat() if self.outer["name"] == "Adam" else None
+        self.sumsq = torch.zeros(1, device=self.device)
+        self.step_global = 0
+        self.mask_seed = int(params.get("dataset_random_seed", 1234))
+        self._mask_bufs: Dict[tuple, torch.Tensor] = {}
+        self.injected_masks = None       # parity tests: {(task_index, pass_index): reference-layout mask dict}
+        if params.get("finetune", False):
+            self._load_checkpoint()
+
+    # ---- data ------------------------------------------------------------------------------------
+    def _unpack_batch(self, batch_items):
+        """metatrainer.py:95-117."""
+        d = batch_to_device(batch_items, self.device, self.speaker_emb_type, non_blocking=True)
+        stop = d["stop"]
+        return d, stop
+
+    def _masks(self, task_index: int, pass_index: int, B: int, T: int, L: int) -> torch.Tensor:
+        """Dropout keep-masks for one pass, keyed by (meta-step, task, pass) -- independent of sharding."""
+        if self.injected_masks is not None:
+            return self.engine.pack_masks(self.injected_masks[(task_index, pass_index)], B, T, L)
+        key = (B, T, L)
+        if key not in self._mask_bufs:
+            self._mask_bufs[key] = torch.empty(self.engine.mask_bytes(B, T, L), dtype=torch.uint8, device=self.device)
+        seed = (self.mask_seed * 1000003 + self.step_global) * 1000003 + task_index * 64 + pass_index
+        return self.engine.generate_masks(B, T, L, seed, self._mask_bufs[key])
+
+    # ---- inner loop (higher.innerloop_ctx + diffopt.step, maml.py:40-54) ------------------------------
+    def _adapt(self, task_index: int, batch, n_inner: int):
+        """fast <- theta; n_inner x (forward, backward, functional SGD step) on the train split."""
+        eng = self.engine
+        self.fast.copy_(self.theta)
+        self.task_bn.copy_(self.base_bn)
+        inputs, _ = self._unpack_batch(batch)
+        B, L = inputs["inputs"].shape
+        T = inputs["melspecs"].shape[2]
+        h = self.inner
+        losses = []
+        for it in range(n_inner):
+            _, loss = eng.forward(self.fast, self.task_bn, inputs, self._masks(task_index, it, B, T, L), outputs=False)
+            eng.backward(self.fast, self.task_grad)
+            eng.sgd_step(self.fast, self.task_grad, lr=h["lr"], momentum=h.get("momentum", 0.0), dampening=h.get("dampening", 0.0),
+                         weight_decay=h.get("weight_decay", 0.0), nesterov=h.get("nesterov", False), buf=self.inner_buf,
+                         first_step=(it == 0))
+            losses.append(loss)
+        return losses
+
+    # ---- outer update (maml.py:94-105 / reptile.py:82-89) ----------------------------------------------
+    def _outer_update(self) -> torch.Tensor:
+        """allreduce(sum) of the locally weighted meta-gradient, grad-norm, clip, optimizer step -- all on flat buffers."""
+        eng = self.engine
+        self.shard.allreduce_sum(self.meta_grad)
+        eng.sumsq(self.meta_grad, self.sumsq)                     # apply_grad's norm / clip_grad_norm_'s total norm
+        thr = float(self.params["grad_clip_thresh"]) if self.params.get("clip_grad_norm", False) else 0.0
+        o = self.outer
+        if o["name"] == "SGD":
+            eng.clip_sgd(self.theta, self.meta_grad, self.sumsq, lr=o["lr"], max_norm=thr, momentum=o.get("momentum", 0.0),
+                         dampening=o.get("dampening", 0.0), weight_decay=o.get("weight_decay", 0.0), nesterov=o.get("nesterov", False),
+                         buf=self.outer_m, first_step=(self.step_global == 0))
+        else:
+            eng.clip_adam(self.theta, self.meta_grad, self.outer_m, self.outer_v, self.sumsq, lr=o["lr"], step=self.step_global + 1,
+                          betas=o.get("betas", (0.9, 0.999)), eps=o.get("eps", 1e-8), weight_decay=o.get("weight_decay", 0.0),
+                          max_norm=thr)
+        self.step_global += 1
+        return self.sumsq
+
+    # ---- checkpoints (metatrainer.py:119-122, 138-146) --------------------------------------------------
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        sd = {k: v.detach().cpu().clone() for k, v in self.engine.dict_from_flat(self.theta).items()}
+        for k, v in self.engine.bn_dict(self.base_bn).items():
+            sd[k] = v.detach().cpu().clone()
+        for name in self.layout.bn_names:
+            sd[name + ".num_batches_tracked"] = torch.zeros((), dtype=torch.int64)
+        return sd
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        P = {n: sd[n] for n in self.layout.names()}
+        self.theta.copy_(self.engine.flat_from_dict(P))
+
+    def _save_checkpoint(self, path: Optional[str] = None) -> str:
+        k = self.step_global // 100
+        path = path or os.path.join(self.params.get("output_path", "."), f"checkpoint_{k}.pt")
+        if self.shard.rank == 0:
+            torch.save(self.state_dict(), path)
+        return path
+
+    def _load_checkpoint(self) -> None:
+        sd = torch.load(self.params["finetune_checkpoint_path"], map_location="cpu")
+        self.load_state_dict(sd)

@@ -1,0 +1,59 @@
+"""Reptile driver: mirror of msa_tts/reptile.py on the CUDA hot path.
+
+Per speaker: adapt ``n_inner_train`` SGD steps from theta_0, task "gradient" = -(theta_T - theta_0)
+(reptile.py:42, 73-77).  Two outer-loop semantics are provided:
+  * ``batched`` (default, BASELINE.json config 3): all speakers of the meta-batch start from the same theta_0,
+    the deltas are averaged with weights 1/N and joined by ONE allreduce -- the only form that shards.
+  * ``sequential=True``: the reference's literal behaviour -- an outer step after EACH speaker, each starting from
+    the already updated weights (reptile.py:37-39, 82-89).  Cannot shard; world size must be 1.
+With one speaker per meta-batch the two coincide.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+from .metatrainer import MetaTrainer
+
+
+class Reptile(MetaTrainer):
+    def __init__(self, **params):
+        super().__init__(**params)
+        self.sequential = bool(params.get("reptile_sequential", False))
+        if self.sequential and self.shard.world > 1:
+            raise ValueError("sequential Reptile (the reference's literal semantics) cannot be sharded")
+
+    def _eval_test(self, i: int, task, n_inner: int) -> torch.Tensor:
+        """reptile.py:58-70: test loss of the adapted weights, no gradient."""
+        inputs, _ = self._unpack_batch(task["test"])
+        B, L = inputs["inputs"].shape
+        T = inputs["melspecs"].shape[2]
+        _, loss = self.engine.forward(self.fast, self.task_bn, inputs, self._masks(i, n_inner, B, T, L), outputs=False)
+        return loss
+
+    def _metatrain_step(self, items_b: Dict[str, Dict[str, tuple]], eval_test: bool = True) -> dict:
+        eng = self.engine
+        speakers = list(items_b.keys())
+        N = len(speakers)
+        n_inner = self.params["n_inner_train"]
+        losses = []
+        if self.sequential:
+            for i, spk in enumerate(speakers):
+                self._adapt(i, items_b[spk]["train"], n_inner)
+                if eval_test:
+                    losses.append(self._eval_test(i, items_b[spk], n_inner))
+                eng.reptile_delta(self.meta_grad, self.fast, self.theta, 1.0, init=True)       # reptile.py:75-77
+                sumsq = self._outer_update()                                                     # reptile.py:82-89
+            return {"loss_test": torch.cat(losses) if losses else None, "task_index": list(range(N)), "grad_sumsq": sumsq}
+        mine = self.shard.my_tasks(N)
+        if not mine:
+            self.meta_grad.zero_()
+        for j, i in enumerate(mine):
+            task = items_b[speakers[i]]
+            self._adapt(i, task["train"], n_inner)
+            if eval_test:
+                losses.append(self._eval_test(i, task, n_inner))
+            eng.reptile_delta(self.meta_grad, self.fast, self.theta, 1.0 / N, init=(j == 0))
+        sumsq = self._outer_update()
+        return {"loss_test": torch.cat(losses) if losses else None, "task_index": mine, "grad_sumsq": sumsq}
