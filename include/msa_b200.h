@@ -147,6 +147,17 @@ int msa_train_loss(msa_handle* h, void* ws, const float* stop_targets, const int
                    float pos_weight, float* loss_out, void* stream);
 /* d(loss)/d(mel, mel_post, gate) of the last forward, reference layouts (for autograd glue) */
 int msa_loss_grads(msa_handle* h, void* ws, float* d_mel, float* d_mel_post, float* d_gate, void* stream);
+/* The persistent kernels hand data between CTAs by polling (no grid barrier); a producer that never arrives makes
+ * the consumers give up after a bounded spin and raise a flag instead of hanging the GPU.  Synchronises `stream`
+ * and returns MSA_E_STATE if any kernel of the passes run in `ws` since the last msa_train_forward gave up. */
+int msa_check_abort(msa_handle* h, void* ws, void* stream);
+/* cycles per phase recorded by thread 0 of every CTA of persistent kernel `id` (msa_profile_name) during the last
+ * pass run with profiling enabled: out[ncta][8] (synchronises the device; profiles only) */
+int msa_profile_phases(msa_handle* h, void* ws, int id, int64_t* out, int ncta);
+/* development tracer: {SM clock, globaltimer ns} of lane 0 of every warp at every phase mark of the steps
+ * [t0, t0+4) of persistent kernel `id`: out[ncta][16 warps][4 steps][12 tags][2] (synchronises the device) */
+int msa_profile_trace_step(msa_handle* h, int t0);
+int msa_profile_trace(msa_handle* h, void* ws, int id, int64_t* out, int ncta);
 /* test hook: device pointer + element count of a named intermediate of the last pass */
 int msa_get_buffer(msa_handle* h, void* ws, const char* name, void** ptr, int64_t* numel);
 

@@ -49,6 +49,10 @@ SIGNATURES = {
     "msa_train_backward": (I, [V, V, SZ, V, V, V, V, V, I, F, V]),
     "msa_train_loss": (I, [V, V, V, V, I, F, V, V]),
     "msa_loss_grads": (I, [V, V, V, V, V, V]),
+    "msa_check_abort": (I, [V, V, V]),
+    "msa_profile_phases": (I, [V, V, I, C.POINTER(I64), I]),
+    "msa_profile_trace_step": (I, [V, I]),
+    "msa_profile_trace": (I, [V, V, I, C.POINTER(I64), I]),
     "msa_get_buffer": (I, [V, V, C.c_char_p, C.POINTER(V), C.POINTER(I64)]),
     "msa_infer_workspace_bytes": (SZ, [V, I, I, I]),
     "msa_infer": (I, [V, V, SZ, V, V, V, V, V, V, V, I, I, I, V, V, V, V, V]),

@@ -12,336 +12,429 @@
 // sequential loop and becomes batched GEMMs (pass.cu).  What stays in the loop is exactly the
 // dependency chain h_a -> q -> e -> a -> h_a.
 //
-// One cooperative launch, one CTA per SM.  CTA roles (every CTA plays all three):
-//   unit owner : hidden units [u0,u1) of the attention LSTM, W_hh rows resident in smem (fp32)
+// One cooperative launch (all CTAs co-resident), one CTA per SM.  CTA roles (every CTA plays all three):
+//   unit owner : hidden units [u0,u1) of the attention LSTM, W_hh rows (+ their MW rows) resident in smem (fp32)
 //   pair owner : (b,l) positions [p0,p1): location conv + dense + energy for those positions
 //   query owner: attention dims [d0,d1): q[b][d] = Wq[d,:].h_a'[b,:]
-// Three grid barriers per step (h_a all-gather, q all-gather, e all-gather).
+// Three hand-offs per step (h_a, q, e), each ONE L2 round trip: the producer stores into the per-step stash array
+// (ha[t], q[t], e[t] -- the arrays the backward pass reads anyway) and the consumers poll the data words themselves
+// against the canary the host pre-filled (common.cuh).  No grid barrier, no atomics, no fences.
 #include "rec_common.cuh"
 #include "kernels.h"
 
 namespace msa {
 
 struct AttnSmemFwd {
-    size_t wsm, mws, hs, as_, cums, part, zs, cs, wqs, wlocT, wldT, vs, pre, cf, total;
+    size_t wsm, mws, hs, as_, ah, es, qs, part, wqs, wloc, wldT, vs, pm, pre, ctr, cf, total;
+    int KP, BP, LP, LH, CKP;
 };
 __host__ __device__ inline AttnSmemFwd attn_fwd_layout(int B, int L, int Ha, int A, int F, int Kl, int ncta, bool mw_res) {
     AttnSmemFwd s;
-    const int BP = (B + 3) & ~3;
+    s.KP = round_up_i(Ha, 128);
+    s.BP = (B + 3) & ~3;
+    s.LP = round_up_i(L, 4);
+    s.LH = round_up_i(L + Kl - 1, 4);
+    s.CKP = 2 * Kl + 1;
     const int np_max = (B * L + ncta - 1) / ncta, nd_max = (A + ncta - 1) / ncta;
     size_t o = 0;
     auto take = [&](size_t n) { size_t r = o; o += (n + 3) & ~(size_t)3; return r; };
-    s.wsm = take((size_t)4 * kUMax * Ha);
-    s.mws = take(mw_res ? (size_t)4 * kUMax * B * L : 0);
-    s.hs = take((size_t)BP * Ha);
-    s.as_ = take((size_t)B * L);
-    s.cums = take((size_t)B * L);
-    s.part = take(kRecWarps * 32);
-    s.zs = take(32 * BP);
-    s.cs = take(kUMax * BP);
-    s.wqs = take((size_t)nd_max * Ha);
-    s.wlocT = take((size_t)2 * Kl * F);
+    s.wsm = take((size_t)4 * kUMax * s.KP);
+    s.mws = take(mw_res ? (size_t)4 * kUMax * B * s.LP : 0);
+    s.hs = take((size_t)s.BP * s.KP);
+    s.as_ = take((size_t)B * s.LP);
+    s.ah = take((size_t)2 * B * s.LH);
+    s.es = take((size_t)B * L);
+    s.qs = take((size_t)B * A);
+    s.part = take((size_t)kBTiles * kRecWarps * 32);
+    s.wqs = take((size_t)nd_max * s.KP);
+    s.wloc = take((size_t)F * s.CKP);
     s.wldT = take((size_t)F * A);
     s.vs = take(A);
+    s.pm = take((size_t)np_max * A);
     s.pre = take((size_t)np_max * A);
-    s.cf = take(kRecWarps * 32);
+    s.ctr = take((size_t)np_max * A);
+    s.cf = take((size_t)np_max * F);
     s.total = o;
     return s;
 }
 
-// normalise energies (row per warp): softmax or sigmoid/sum.  e_src may be global (ld_cg) .
-__device__ __forceinline__ void normalise_rows(const float* e_src, float* a_dst, float* zn_dst, int B, int L, int norm) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int b = w; b < B; b += kRecWarps) {
-        if (norm == 0) {
-            float m = -INFINITY;
-            for (int l = lane; l < L; l += 32) m = fmaxf(m, ld_cg(e_src + b * L + l));
-            m = warp_max(m);
-            float sum = 0.f;
-            for (int l = lane; l < L; l += 32) {
-                const float x = expf(ld_cg(e_src + b * L + l) - m);
-                a_dst[b * L + l] = x;
-                sum += x;
-            }
-            sum = warp_sum(sum);
-            for (int l = lane; l < L; l += 32) a_dst[b * L + l] = a_dst[b * L + l] / sum;
-            if (lane == 0 && zn_dst) zn_dst[b] = sum;
-        } else {
-            float sum = 0.f;
-            for (int l = lane; l < L; l += 32) {
-                const float x = sigmoidf_(ld_cg(e_src + b * L + l));
-                a_dst[b * L + l] = x;
-                sum += x;
-            }
-            sum = warp_sum(sum);
-            for (int l = lane; l < L; l += 32) a_dst[b * L + l] = a_dst[b * L + l] / sum;
-            if (lane == 0 && zn_dst) zn_dst[b] = sum;
-        }
-    }
-}
-
 __global__ void __launch_bounds__(kRecThreads, 1) k_attn_chain_fwd(AttnChainParams p, int mw_res) {
     extern __shared__ __align__(16) float smem[];
-    __shared__ float zn_s[16];
+    __shared__ float zn_s[kBMax];
     const int T = p.T, B = p.B, L = p.L, Ha = p.Ha, A = p.A, F = p.F, Kl = p.Kl, H4 = 4 * Ha;
-    const int BP = (B + 3) & ~3, BL = B * L, pl = (Kl - 1) / 2;
+    const int BL = B * L, pl = (Kl - 1) / 2;
     const int ncta = gridDim.x, cta = blockIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const AttnSmemFwd lay = attn_fwd_layout(B, L, Ha, A, F, Kl, ncta, mw_res != 0);
-    float* Wsm = smem + lay.wsm;
-    float* MWs = smem + lay.mws;
-    float* hs = smem + lay.hs;
-    float* as_ = smem + lay.as_;
-    float* cums = smem + lay.cums;
+    const int KP = lay.KP, KP4 = KP >> 2, LP = lay.LP, LH = lay.LH, CKP = lay.CKP;
+    float* Wsm = smem + lay.wsm;       // [RG*8][KP]     W_hh rows of the owned units (local row = ul*4 + gate), zero-padded
+    float* MWs = smem + lay.mws;       // [RG*8][B][LP]  (W_ih[:, prenet:] . memory^T) rows of the owned units
+    float* hs = smem + lay.hs;         // [BP][KP]       h_a'(t-1), zero-padded
+    float* as_ = smem + lay.as_;       // [B][LP]        a(t-1)
+    float* ah = smem + lay.ah;         // [2][B][LH]     a(t-1) and cum(t-1) with a zero halo of pl on both sides (conv input)
+    float* es = smem + lay.es;
+    float* q_s = smem + lay.qs;
     float* part = smem + lay.part;
-    float* zs = smem + lay.zs;
-    float* cs = smem + lay.cs;
     float* wqs = smem + lay.wqs;
-    float* wlocT = smem + lay.wlocT;
-    float* wldT = smem + lay.wldT;
+    float* wloc_s = smem + lay.wloc;   // [F][CKP]
+    float* wldT = smem + lay.wldT;     // [F][A]
     float* vs = smem + lay.vs;
-    float* pre_s = smem + lay.pre;
-    float* cf_s = smem + lay.cf;
+    float* pm_s = smem + lay.pm;       // [np][A] processed memory of the owned positions (constant over t)
+    float* pre_s = smem + lay.pre;     // [np][A] loc + pm of the current step
+    float* ctr_s = smem + lay.ctr;     // [np][A] v[d]*tanh(.) terms of the current step
+    float* cf_s = smem + lay.cf;       // [np][F]
 
     const int u0 = part_lo(cta, Ha, ncta), u1 = part_lo(cta + 1, Ha, ncta), U = u1 - u0, R = 4 * U;
+    const int RG = R > 0 ? (R + 7) >> 3 : 1;
     const int p0 = part_lo(cta, BL, ncta), p1 = part_lo(cta + 1, BL, ncta), np = p1 - p0;
     const int d0 = part_lo(cta, A, ncta), d1 = part_lo(cta + 1, A, ncta), nd = d1 - d0;
 
     // ---- one-time staging of the resident operands ----
-    for (int idx = threadIdx.x; idx < R * (Ha >> 2); idx += kRecThreads) {
-        const int rl = idx / (Ha >> 2), k4 = idx % (Ha >> 2), g = rl & 3, ul = rl >> 2;
-        reinterpret_cast<float4*>(Wsm)[(size_t)rl * (Ha >> 2) + k4] =
-            __ldg(reinterpret_cast<const float4*>(p.whh + (size_t)(g * Ha + u0 + ul) * Ha) + k4);
+    for (int idx = threadIdx.x; idx < RG * 8 * KP4; idx += kRecThreads) {
+        const int rl = idx / KP4, k4 = idx % KP4, g = rl & 3, ul = rl >> 2;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rl < R && k4 < (Ha >> 2)) v = __ldg(reinterpret_cast<const float4*>(p.whh + (size_t)(g * Ha + u0 + ul) * Ha) + k4);
+        reinterpret_cast<float4*>(Wsm)[idx] = v;
     }
     if (mw_res) {
-        for (int idx = threadIdx.x; idx < R * BL; idx += kRecThreads) {
-            const int rl = idx / BL, j = idx % BL, g = rl & 3, ul = rl >> 2;
-            MWs[idx] = __ldg(p.mw_rm + (size_t)(g * Ha + u0 + ul) * BL + j);
+        for (int idx = threadIdx.x; idx < RG * 8 * B * LP; idx += kRecThreads) {
+            const int rl = idx / (B * LP), j = idx % (B * LP), b = j / LP, l = j % LP, g = rl & 3, ul = rl >> 2;
+            MWs[idx] = (rl < R && l < L) ? __ldg(p.mw_rm + (size_t)(g * Ha + u0 + ul) * BL + b * L + l) : 0.f;
         }
     }
-    for (int idx = threadIdx.x; idx < nd * Ha; idx += kRecThreads) wqs[idx] = __ldg(p.wq + (size_t)d0 * Ha + idx);
+    for (int idx = threadIdx.x; idx < nd * KP; idx += kRecThreads) {
+        const int di = idx / KP, k = idx % KP;
+        wqs[idx] = k < Ha ? __ldg(p.wq + (size_t)(d0 + di) * Ha + k) : 0.f;
+    }
     for (int idx = threadIdx.x; idx < F * 2 * Kl; idx += kRecThreads) {
-        const int f = idx / (2 * Kl), ck = idx % (2 * Kl);          // wloc[f][c][k] -> wlocT[c*Kl+k][f]
-        wlocT[ck * F + f] = __ldg(p.wloc + idx);
+        const int f = idx / (2 * Kl), ck = idx % (2 * Kl);          // wloc[f][c][k] -> wloc_s[f][c*Kl+k]
+        wloc_s[f * CKP + ck] = __ldg(p.wloc + idx);
     }
     for (int idx = threadIdx.x; idx < A * F; idx += kRecThreads) {
         const int d = idx / F, f = idx % F;                          // wld[d][f] -> wldT[f][d]
         wldT[f * A + d] = __ldg(p.wld + idx);
     }
     for (int idx = threadIdx.x; idx < A; idx += kRecThreads) vs[idx] = __ldg(p.v + idx);
-    for (int idx = threadIdx.x; idx < kUMax * BP; idx += kRecThreads) cs[idx] = 0.f;
-    for (int idx = threadIdx.x; idx < BL; idx += kRecThreads) { as_[idx] = 0.f; cums[idx] = 0.f; }
+    for (int idx = threadIdx.x; idx < np * A; idx += kRecThreads) pm_s[idx] = __ldg(p.pm + (size_t)p0 * A + idx);
+    for (int idx = threadIdx.x; idx < B * LP; idx += kRecThreads) as_[idx] = 0.f;
+    for (int idx = threadIdx.x; idx < 2 * B * LH; idx += kRecThreads) ah[idx] = 0.f;
+    for (int idx = threadIdx.x; idx < lay.BP * KP; idx += kRecThreads) hs[idx] = 0.f;
+    for (int i = threadIdx.x; i < np; i += kRecThreads) p.cum[p0 + i] = 0.f;       // cum fed to the conv at t = 0
     const float bv = __ldg(p.bv);
-    GridBarrier gb;
-    gb.init(p.barrier);
+
+    // point-wise role of the LSTM: 4 lanes per cell (ul, b), lane g evaluates gate g; streaming inputs fetched one step ahead
+    const bool pw = (int)threadIdx.x < 4 * U * B;
+    const int g = threadIdx.x & 3, cell = threadIdx.x >> 2;
+    const int ul = pw ? cell / B : 0, pb = pw ? cell % B : 0, u = u0 + ul;
+    float xz = 0.f, cstate = 0.f;
+    unsigned char mk = 1;
+    auto fetch = [&](int t) {
+        xz = __ldg(p.xw + ((size_t)t * B + pb) * H4 + (size_t)g * Ha + u);
+        if (p.mask && g == 0) mk = p.mask[((size_t)t * B + pb) * Ha + u];
+    };
+    if (pw) fetch(0);
+    SpinGuard sg(p.abort_word);
+    ChainProf prof;
+    prof.start(p.prof, p.trace, p.trace_t0);
     __syncthreads();
 
-    for (int t = 0; t <= T; ++t) {
-        // ---- phase 0: a(t-1) = normalise(e(t-1)); cum(t-1) += a(t-1) (forward_attn.py:200-210) ----
-        if (t > 0) {
-            normalise_rows(p.ebuf, as_, zn_s, B, L, p.norm);
-            __syncthreads();
-            for (int idx = threadIdx.x; idx < BL; idx += kRecThreads) {
-                const float a = as_[idx];
-                cums[idx] += a;
-                if (cta == 0) p.align[(size_t)(t - 1) * BL + idx] = a;
-            }
-            if (cta == 0 && (int)threadIdx.x < B) p.znorm[(size_t)(t - 1) * B + threadIdx.x] = zn_s[threadIdx.x];
-        }
-        if (t == T) break;
-        if (cta == 0)
-            for (int idx = threadIdx.x; idx < BL; idx += kRecThreads) p.cum[(size_t)t * BL + idx] = cums[idx];
-        __syncthreads();
-
-        // ---- phase 1a: location features for the owned (b,l) positions (forward_attn.py:121-127) ----
-        for (int pi = w; pi < np; pi += kRecWarps) {
-            const int pp = p0 + pi, b = pp / L, l = pp % L;
-            float cf = 0.f;
-            if (lane < F) {
-                for (int k = 0; k < Kl; ++k) {
-                    const int ll = l + k - pl;
-                    if (ll >= 0 && ll < L)
-                        cf += wlocT[(0 * Kl + k) * F + lane] * as_[b * L + ll] + wlocT[(1 * Kl + k) * F + lane] * cums[b * L + ll];
-                }
-                p.convf[((size_t)t * BL + pp) * F + lane] = cf;
-            }
-            cf_s[w * 32 + lane] = cf;
-            __syncwarp();
-            for (int d = lane; d < A; d += 32) {
-                float loc = 0.f;
-                for (int f = 0; f < F; ++f) loc += wldT[f * A + d] * cf_s[w * 32 + f];
-                pre_s[pi * A + d] = loc + __ldg(p.pm + (size_t)pp * A + d);
-            }
-            __syncwarp();
-        }
-
-        // ---- phase 1b: attention LSTMCell for the owned units (decoder.py:253-256) ----
+    for (int t = 0; t < T; ++t) {
+        // ---- phase 1: attention LSTMCell for the owned units (decoder.py:253-256); publishes h_a'(t) ----
         if (U > 0) {
-            for (int idx = threadIdx.x; idx < B * (Ha >> 2); idx += kRecThreads) {
-                float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (t > 0) v4 = ld_cg4(p.ha + (size_t)(t - 1) * B * Ha + (size_t)idx * 4);
-                reinterpret_cast<float4*>(hs)[idx] = v4;
+            if (mw_res) cta_matvec_fwd<true>(Wsm, RG, KP, hs, MWs, LP, as_, B, part);
+            else cta_matvec_fwd<false>(Wsm, RG, KP, hs, nullptr, 0, nullptr, B, part);
+        }
+        prof.mark(0, t);
+        __syncthreads();
+        if (pw) {
+            const size_t zb = ((size_t)t * B + pb) * H4;
+            float z = lstm_gate_sum(part, RG, ul * 4 + g, pb) + xz;
+            if (!mw_res) {   // context term from global memory (text too long for the resident slice)
+                const float* mrow = p.mw_rm + (size_t)(g * Ha + u) * BL + pb * L;
+                float zc = 0.f;
+                for (int l = 0; l < L; ++l) zc += __ldg(mrow + l) * as_[pb * LP + l];
+                z += zc;
             }
+            const float act = g == 2 ? fast_tanh(z) : fast_sigmoid(z);
+            const unsigned int gm = 0xFu << (threadIdx.x & 28);
+            const float ai = __shfl_sync(gm, act, 0, 4), af = __shfl_sync(gm, act, 1, 4);
+            const float ag = __shfl_sync(gm, act, 2, 4), ao = __shfl_sync(gm, act, 3, 4);
+            if (g == 0) {
+                const float cn = af * cstate + ai * ag;
+                cstate = cn;
+                float hv = ao * fast_tanh(cn);
+                if (p.mask) hv = mk ? hv * p.drop_scale : 0.f;
+                st_pub(p.ha + ((size_t)t * B + pb) * Ha + u, hv);
+                p.ca[((size_t)t * B + pb) * Ha + u] = cn;
+            }
+            p.ga[zb + (size_t)g * Ha + u] = act;
+            if (t + 1 < T) fetch(t + 1);
+        }
+        prof.mark(1, t);
+        // ---- phase 1a: location features of the owned (b,l) positions (forward_attn.py:121-127); overlaps the h hand-off ----
+        // conv: item (pi, f, ks) sums taps ck = ks, ks+8, ... ; 8 consecutive lanes share (pi, f)
+        for (int base = 0; base < np * F * 8; base += kRecThreads) {     // warp-uniform trip count (full-mask shuffles inside)
+            const int it = base + threadIdx.x;
+            const bool valid = it < np * F * 8;
+            const int ks = it & 7, f = valid ? (it >> 3) % F : 0, pi = valid ? (it >> 3) / F : 0;
+            const int pp = p0 + pi, b = pp / L, l = pp - b * L;
+            float cf = 0.f;
+            if (valid)
+                for (int ck = ks; ck < 2 * Kl; ck += 8) {
+                    const int c = ck >= Kl ? 1 : 0, k = ck - c * Kl;
+                    cf += wloc_s[f * CKP + ck] * ah[(c * B + b) * LH + l + k];
+                }
+            cf += __shfl_xor_sync(0xffffffffu, cf, 1);
+            cf += __shfl_xor_sync(0xffffffffu, cf, 2);
+            cf += __shfl_xor_sync(0xffffffffu, cf, 4);
+            if (valid && ks == 0) {
+                cf_s[pi * F + f] = cf;
+                p.convf[((size_t)t * BL + pp) * F + f] = cf;
+            }
+        }
+        prof.mark(2, t);
+        __syncthreads();
+        for (int it = threadIdx.x; it < np * A; it += kRecThreads) {
+            const int pi = it / A, d = it - pi * A;
+            float l0 = 0.f, l1 = 0.f;
+            int f = 0;
+            for (; f + 1 < F; f += 2) {
+                l0 += wldT[f * A + d] * cf_s[pi * F + f];
+                l1 += wldT[(f + 1) * A + d] * cf_s[pi * F + f + 1];
+            }
+            if (f < F) l0 += wldT[f * A + d] * cf_s[pi * F + f];
+            pre_s[it] = l0 + l1 + pm_s[it];
+        }
+        prof.mark(3, t);
+        // ---- hand-off 1: all of h_a'(t) -> shared (operand of q now and of the mat-vec at t+1) ----
+        if (p.flags & kFlagGate) {
+            const float* hrow = p.ha + ((size_t)t * B + (B - 1)) * Ha;
+            gate_wait(ncta, [&](int c) { const int e = part_lo(c + 1, Ha, ncta); return e > 0 ? hrow + e - 1 : nullptr; }, sg);
             __syncthreads();
-            if (mw_res)
-                cta_matvec_fwd<true>(Wsm, R, Ha, hs, MWs, BL, 0, 0, L, as_, B, part, zs, BP);
-            else
-                cta_matvec_fwd<true>(Wsm, R, Ha, hs, p.mw_rm, BL, Ha, u0, L, as_, B, part, zs, BP);
-            if ((int)threadIdx.x < U * B) {
-                const int ul = threadIdx.x / B, b = threadIdx.x % B, u = u0 + ul;
-                const size_t zb = ((size_t)t * B + b) * H4;
-                LstmPoint r = lstm_point_fwd(zs[(ul * 4 + 0) * BP + b] + __ldg(p.xw + zb + 0 * Ha + u),
-                                             zs[(ul * 4 + 1) * BP + b] + __ldg(p.xw + zb + 1 * Ha + u),
-                                             zs[(ul * 4 + 2) * BP + b] + __ldg(p.xw + zb + 2 * Ha + u),
-                                             zs[(ul * 4 + 3) * BP + b] + __ldg(p.xw + zb + 3 * Ha + u), cs[ul * BP + b]);
-                cs[ul * BP + b] = r.c;
-                float hv = r.h;
-                if (p.mask) hv = p.mask[((size_t)t * B + b) * Ha + u] ? hv * p.drop_scale : 0.f;
-                p.ga[zb + 0 * Ha + u] = r.i;
-                p.ga[zb + 1 * Ha + u] = r.f;
-                p.ga[zb + 2 * Ha + u] = r.g;
-                p.ga[zb + 3 * Ha + u] = r.o;
-                p.ca[((size_t)t * B + b) * Ha + u] = r.c;
-                p.ha[((size_t)t * B + b) * Ha + u] = hv;
-            }
         }
-        gb.sync();
-
-        // ---- phase 2: query projection for the owned attention dims (forward_attn.py:125) ----
-        for (int di = w; di < nd; di += kRecWarps) {
-            for (int bt = 0; bt < B; bt += 4) {
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                for (int k = lane * 4; k < Ha; k += 128) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(wqs + (size_t)di * Ha + k);
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        if (bt + b < B) {
-                            const float4 h4 = ld_cg4(p.ha + ((size_t)t * B + bt + b) * Ha + k);
-                            acc[b] += w4.x * h4.x + w4.y * h4.y + w4.z * h4.z + w4.w * h4.w;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const float sacc = warp_sum(acc[b]);
-                    if (lane == 0 && bt + b < B) p.q[((size_t)t * B + bt + b) * A + d0 + di] = sacc;
-                }
+        poll_copy_rows(hs, KP4, p.ha + (size_t)t * B * Ha, B, Ha >> 2, sg);
+        prof.mark(4, t);
+        __syncthreads();
+        // ---- phase 2: query projection for the owned attention dims (forward_attn.py:125); publishes q(t) ----
+        for (int it = kRecWarps - 1 - w; it < nd * B; it += kRecWarps) {     // top warps: warp 0 is the gatherer
+            const int di = it / B, b = it - di * B;
+            const float4* w4p = reinterpret_cast<const float4*>(wqs) + (size_t)di * KP4;
+            const float4* h4p = reinterpret_cast<const float4*>(hs) + (size_t)b * KP4;
+            float a0 = 0.f, a1 = 0.f;
+            int k4 = lane;
+            for (; k4 + 32 < KP4; k4 += 64) {
+                a0 += dot4(w4p[k4], h4p[k4]);
+                a1 += dot4(w4p[k4 + 32], h4p[k4 + 32]);
             }
+            if (k4 < KP4) a0 += dot4(w4p[k4], h4p[k4]);
+            const float sacc = warp_sum(a0 + a1);
+            if (lane == 0) st_pub(p.q + ((size_t)t * B + b) * A + d0 + di, sacc);
         }
-        gb.sync();
-
-        // ---- phase 3: energies for the owned positions (forward_attn.py:128-131) ----
+        prof.mark(5, t);
+        // ---- phase 3 (after hand-off 2: q): energies for the owned positions (forward_attn.py:128-131); publishes e(t) ----
+        gather_words(q_s, p.q + (size_t)t * B * A, B * A, (p.flags & kFlagWarp0) != 0, sg);
+        prof.mark(6, t);
+        __syncthreads();
+        for (int it = threadIdx.x; it < np * A; it += kRecThreads) {
+            const int pi = it / A, d = it - pi * A, pp = p0 + pi, b = pp / L;
+            const float sv = fast_tanh(q_s[b * A + d] + pre_s[it]);
+            p.s[((size_t)t * BL + pp) * A + d] = sv;
+            ctr_s[it] = vs[d] * sv;
+        }
+        prof.mark(7, t);
+        __syncthreads();
         for (int pi = w; pi < np; pi += kRecWarps) {
-            const int pp = p0 + pi, b = pp / L;
             float e = 0.f;
-            for (int d = lane; d < A; d += 32) {
-                const float sv = tanhf(ld_cg(p.q + ((size_t)t * B + b) * A + d) + pre_s[pi * A + d]);
-                p.s[((size_t)t * BL + pp) * A + d] = sv;
-                e += vs[d] * sv;
-            }
+            for (int d = lane; d < A; d += 32) e += ctr_s[pi * A + d];
             e = warp_sum(e);
-            if (lane == 0) p.ebuf[pp] = e + bv;
+            if (lane == 0) st_pub(p.e + (size_t)t * BL + p0 + pi, e + bv);
         }
-        gb.sync();
+        prof.mark(8, t);
+        // ---- hand-off 3: all energies of step t; a(t) = normalise(e(t)); cum += a(t) (forward_attn.py:200-210) ----
+        gather_words(es, p.e + (size_t)t * BL, BL, (p.flags & kFlagWarp0) != 0, sg);
+        prof.mark(9, t);
+        __syncthreads();
+        for (int b = w; b < B; b += kRecWarps) {     // one row per warp: softmax or sigmoid/sum
+            float m = 0.f;
+            if (p.norm == 0) {
+                m = -INFINITY;
+                for (int l = lane; l < L; l += 32) m = fmaxf(m, es[b * L + l]);
+                m = warp_max(m);
+            }
+            float sum = 0.f;
+            for (int l = lane; l < L; l += 32) {
+                const float x = p.norm == 0 ? __expf(es[b * L + l] - m) : fast_sigmoid(es[b * L + l]);
+                es[b * L + l] = x;
+                sum += x;
+            }
+            sum = warp_sum(sum);
+            const float inv = 1.f / sum;
+            for (int l = lane; l < L; l += 32) {
+                const float a = es[b * L + l] * inv;
+                as_[b * LP + l] = a;
+                ah[(0 * B + b) * LH + pl + l] = a;
+                ah[(1 * B + b) * LH + pl + l] += a;
+            }
+            if (lane == 0) zn_s[b] = sum;
+        }
+        prof.mark(10, t);
+        __syncthreads();
+        for (int i = threadIdx.x; i < np; i += kRecThreads) {
+            const int pp = p0 + i, b = pp / L, l = pp - b * L;
+            p.align[(size_t)t * BL + pp] = as_[b * LP + l];
+            if (t + 1 < T) p.cum[(size_t)(t + 1) * BL + pp] = ah[(1 * B + b) * LH + pl + l];
+        }
+        if (cta == 0 && (int)threadIdx.x < B) p.znorm[(size_t)t * B + threadIdx.x] = zn_s[threadIdx.x];
+        prof.mark(11, t);
     }
 }
 
 // =====================================================================================
 // backward
 struct AttnSmemBwd {
-    size_t wt, part, dhs, dcs, wqT, das, als, des, wld, wlocT, vs, dss, gcum, dprev, pout, dqs, total;
+    size_t wt, mwp, part, dhs, wqT, das, als, des, tq, wldT, wloc, vs, dss, gcum, dprev, pout, dqs, qd, cpart, total;
+    int BP, AP;
 };
-__host__ __device__ inline AttnSmemBwd attn_bwd_layout(int B, int L, int Ha, int A, int F, int Kl, int ncta) {
+__host__ __device__ inline AttnSmemBwd attn_bwd_layout(int B, int L, int Ha, int A, int F, int Kl, int ncta, bool mwp_res) {
     AttnSmemBwd s;
-    const int BP = (B + 3) & ~3;
+    s.BP = (B + 3) & ~3;
+    s.AP = A + 1;
     const int np_max = (B * L + ncta - 1) / ncta;
     size_t o = 0;
     auto take = [&](size_t n) { size_t r = o; o += (n + 3) & ~(size_t)3; return r; };
     s.wt = take((size_t)kUMax * 4 * Ha);
+    s.mwp = take(mwp_res ? (size_t)np_max * 4 * Ha : 0);
     s.part = take(kRecWarps * 32);
-    s.dhs = take(kUMax * BP);
-    s.dcs = take(kUMax * BP);
+    s.dhs = take(kUMax * s.BP);
     s.wqT = take((size_t)kUMax * A);
     s.das = take((size_t)B * L);
     s.als = take((size_t)B * L);
     s.des = take((size_t)B * L);
-    s.wld = take((size_t)A * F);
-    s.wlocT = take((size_t)2 * Kl * F);
+    s.tq = take((size_t)B * L);
+    s.wldT = take((size_t)F * s.AP);
+    s.wloc = take((size_t)F * (2 * Kl + 1));
     s.vs = take(A);
-    s.dss = take((size_t)kRecWarps * A);
+    s.dss = take((size_t)np_max * A);
     s.gcum = take(np_max);
     s.dprev = take(np_max);
     s.pout = take(np_max);
     s.dqs = take((size_t)B * A);
+    s.qd = take((size_t)kUMax * kBMax);
+    s.cpart = take((size_t)np_max * Kl * 2);
     s.total = o;
     return s;
 }
 
-__global__ void __launch_bounds__(kRecThreads, 1) k_attn_chain_bwd(AttnChainBwdParams p) {
+__global__ void __launch_bounds__(kRecThreads, 1) k_attn_chain_bwd(AttnChainBwdParams p, int mwp_res) {
     extern __shared__ __align__(16) float smem[];
-    __shared__ float red[33];
-    __shared__ float zn_s[16];
+    __shared__ float red[kRecWarps * kPairMax];
+    __shared__ float zn_s[kBMax];
     const int T = p.T, B = p.B, L = p.L, Ha = p.Ha, A = p.A, F = p.F, Kl = p.Kl, H4 = 4 * Ha;
-    const int BP = (B + 3) & ~3, BL = B * L, pl = (Kl - 1) / 2;
+    const int BL = B * L, pl = (Kl - 1) / 2, CKP = 2 * Kl + 1;
     const int ncta = gridDim.x, cta = blockIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const AttnSmemBwd lay = attn_bwd_layout(B, L, Ha, A, F, Kl, ncta);
-    float* WT = smem + lay.wt;
+    const AttnSmemBwd lay = attn_bwd_layout(B, L, Ha, A, F, Kl, ncta, mwp_res != 0);
+    const int BP = lay.BP, AP = lay.AP;
+    float* WT = smem + lay.wt;         // [kUMax][4Ha]  WT[ul][r] = W_hh[r][u0+ul], zero rows beyond the owned units
+    float* MWp = smem + lay.mwp;       // [np][4Ha]     rows of (memory . Wc^T) of the owned positions
     float* part = smem + lay.part;
     float* dhs = smem + lay.dhs;
-    float* dcs = smem + lay.dcs;
-    float* wqT = smem + lay.wqT;
+    float* wqT = smem + lay.wqT;       // [kUMax][A]    Wq columns of the owned units
     float* das = smem + lay.das;
     float* als = smem + lay.als;
     float* des = smem + lay.des;
-    float* wld_s = smem + lay.wld;
-    float* wlocT = smem + lay.wlocT;
+    float* tq_s = smem + lay.tq;
+    float* wldT = smem + lay.wldT;     // [F][A+1]
+    float* wloc_s = smem + lay.wloc;   // [F][2Kl+1]
     float* vs = smem + lay.vs;
-    float* ds_s = smem + lay.dss;
+    float* ds_s = smem + lay.dss;      // [np][A]
     float* gcum_s = smem + lay.gcum;
     float* dprev_s = smem + lay.dprev;
     float* pout = smem + lay.pout;
     float* dq_s = smem + lay.dqs;
+    float* qd_s = smem + lay.qd;       // [U*B]
+    float* cpart = smem + lay.cpart;   // [np*Kl][2]
 
     const int u0 = part_lo(cta, Ha, ncta), u1 = part_lo(cta + 1, Ha, ncta), U = u1 - u0;
     const int p0 = part_lo(cta, BL, ncta), p1 = part_lo(cta + 1, BL, ncta), np = p1 - p0;
     const int d0 = part_lo(cta, A, ncta), d1 = part_lo(cta + 1, A, ncta), nd = d1 - d0;
 
-    for (int idx = threadIdx.x; idx < U * H4; idx += kRecThreads) {
+    for (int idx = threadIdx.x; idx < kUMax * H4; idx += kRecThreads) {
         const int ul = idx / H4, r = idx % H4;
-        WT[idx] = __ldg(p.whh + (size_t)r * Ha + u0 + ul);
+        WT[idx] = ul < U ? __ldg(p.whh + (size_t)r * Ha + u0 + ul) : 0.f;
     }
+    if (mwp_res)
+        for (int idx = threadIdx.x; idx < np * (H4 >> 2); idx += kRecThreads)
+            reinterpret_cast<float4*>(MWp)[idx] = __ldg(reinterpret_cast<const float4*>(p.mw_pm + (size_t)p0 * H4) + idx);
+    const float* mwp_src = mwp_res ? MWp : p.mw_pm + (size_t)p0 * H4;
     for (int idx = threadIdx.x; idx < U * A; idx += kRecThreads) {
         const int ul = idx / A, d = idx % A;
         wqT[idx] = __ldg(p.wq + (size_t)d * Ha + u0 + ul);
     }
-    for (int idx = threadIdx.x; idx < A * F; idx += kRecThreads) wld_s[idx] = __ldg(p.wld + idx);
+    for (int idx = threadIdx.x; idx < A * F; idx += kRecThreads) {
+        const int d = idx / F, f = idx % F;
+        wldT[f * AP + d] = __ldg(p.wld + idx);
+    }
     for (int idx = threadIdx.x; idx < F * 2 * Kl; idx += kRecThreads) {
         const int f = idx / (2 * Kl), ck = idx % (2 * Kl);
-        wlocT[ck * F + f] = __ldg(p.wloc + idx);
+        wloc_s[f * CKP + ck] = __ldg(p.wloc + idx);
     }
     for (int idx = threadIdx.x; idx < A; idx += kRecThreads) vs[idx] = __ldg(p.v + idx);
-    for (int idx = threadIdx.x; idx < kUMax * BP; idx += kRecThreads) { dcs[idx] = 0.f; dhs[idx] = 0.f; }
+    for (int idx = threadIdx.x; idx < kUMax * BP; idx += kRecThreads) dhs[idx] = 0.f;
     for (int idx = threadIdx.x; idx < np; idx += kRecThreads) { gcum_s[idx] = 0.f; dprev_s[idx] = 0.f; pout[idx] = 0.f; }
-    GridBarrier gb;
-    gb.init(p.barrier);
+
+    // point-wise role of the LSTM backward: thread (ul, b); forward stash + external gradient fetched one step ahead
+    const bool pw = (int)threadIdx.x < U * B;
+    const int ul = pw ? threadIdx.x / B : 0, pb = pw ? threadIdx.x % B : 0, u = u0 + ul;
+    float gi[4] = {0.f, 0.f, 0.f, 0.f}, cc = 0.f, cp = 0.f, dhe = 0.f, dcarry = 0.f;
+    unsigned char mk = 1;
+    // streaming forward stash of the attention part, fetched one step ahead as well:
+    //   sv_own : s[t][owned position][d] for item = threadIdx.x (< np*A), da_own: da_ext[t][owned position]
+    //   sv_q   : s[t][(b,l) = threadIdx.x][d0] for the first owned attention dim
+    float sv_own = 0.f, sv_q = 0.f, da_own = 0.f;
+    auto fetch = [&](int t) {
+        if (pw) {
+            const size_t zb = ((size_t)t * B + pb) * H4, hb = ((size_t)t * B + pb) * Ha + u;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) gi[g] = __ldg(p.ga + zb + (size_t)g * Ha + u);
+            cc = __ldg(p.ca + hb);
+            cp = t > 0 ? __ldg(p.ca + hb - (size_t)B * Ha) : 0.f;
+            dhe = __ldg(p.dha_ext + hb);
+            if (p.mask) mk = p.mask[hb];
+        }
+        if ((int)threadIdx.x < np * A) sv_own = __ldg(p.s + ((size_t)t * BL + p0) * A + threadIdx.x);
+        if (nd > 0 && (int)threadIdx.x < BL) sv_q = __ldg(p.s + ((size_t)t * BL + threadIdx.x) * A + d0);
+        if ((int)threadIdx.x < np) da_own = __ldg(p.da_ext + (size_t)t * BL + p0 + threadIdx.x);
+    };
+    fetch(T - 1);
+    SpinGuard sg(p.abort_word);
+    ChainProf prof;
+    prof.start(p.prof, p.trace, p.trace_t0);
     __syncthreads();
 
     for (int t = T - 1; t >= 0; --t) {
-        // ---- P1: recurrent terms from dz_a(t+1): W_hh^T.dz (units) and (Wc.memory[l]).dz (positions) ----
-        if (t < T - 1)
-            cta_matvec_bwd(WT, U, H4, p.dza + (size_t)(t + 1) * B * H4, B, part, dhs, BP, p.mw_pm, p0, np, L, pout, red);
-        for (int i = threadIdx.x; i < np; i += kRecThreads)
-            p.dat[p0 + i] = __ldg(p.da_ext + (size_t)t * BL + p0 + i) + pout[i] + gcum_s[i] + dprev_s[i];
-        gb.sync();
-
-        // ---- P2: normalisation backward, dS, d(conv features), dq ----
-        for (int idx = threadIdx.x; idx < BL; idx += kRecThreads) {
-            das[idx] = ld_cg(p.dat + idx);
-            als[idx] = __ldg(p.align + (size_t)t * BL + idx);
+        // ---- P1: recurrent terms from dz_a(t+1): W_hh^T.dz (units) and (Wc.memory[l]).dz (positions); publishes dat(t) ----
+        if (t < T - 1 && (p.flags & kFlagGate)) {
+            const float* zrow = p.dza + ((size_t)(t + 1) * B + (B - 1)) * H4 + (size_t)3 * Ha;
+            gate_wait(ncta, [&](int c) { const int e = part_lo(c + 1, Ha, ncta); return e > 0 ? zrow + e - 1 : nullptr; }, sg);
+            __syncthreads();
         }
+        if (t < T - 1)
+            cta_matvec_bwd(WT, H4, p.dza + (size_t)(t + 1) * B * H4, B, part, dhs, BP, mwp_src, (size_t)H4, p0, np, L, pout, red, sg);
+        prof.mark(0, T - 1 - t);
+        for (int i = threadIdx.x; i < np; i += kRecThreads) {
+            const float dae = i == (int)threadIdx.x ? da_own : __ldg(p.da_ext + (size_t)t * BL + p0 + i);
+            st_pub(p.dat + (size_t)t * BL + p0 + i, dae + pout[i] + gcum_s[i] + dprev_s[i]);
+        }
+        // forward stash of this step that the next phase needs (plain data of an earlier kernel)
+        for (int idx = threadIdx.x; idx < BL; idx += kRecThreads) als[idx] = __ldg(p.align + (size_t)t * BL + idx);
         if ((int)threadIdx.x < B) zn_s[threadIdx.x] = __ldg(p.znorm + (size_t)t * B + threadIdx.x);
+        prof.mark(1, T - 1 - t);
+        // ---- hand-off 1: d a(t) of every position ----
+        gather_words(das, p.dat + (size_t)t * BL, BL, (p.flags & kFlagWarp0) != 0, sg);
         __syncthreads();
+        prof.mark(2, T - 1 - t);
+        // ---- P2: normalisation backward, dS, d(conv features), dq; publishes dconvf(t), dq(t) ----
         for (int b = w; b < B; b += kRecWarps) {
             float sd = 0.f;
             for (int l = lane; l < L; l += 32) sd += als[b * L + l] * das[b * L + l];
@@ -351,97 +444,128 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_attn_chain_bwd(AttnChainBwdP
                 float de = a * (das[b * L + l] - sd);                       // softmax backward
                 if (p.norm == 1) de = de * (1.f - a * zn_s[b]);             // sigmoid/sum backward: s = a*Z
                 des[b * L + l] = de;
-                if (cta == 0) p.de[(size_t)t * BL + b * L + l] = de;
             }
         }
         __syncthreads();
-        for (int pi = w; pi < np; pi += kRecWarps) {
-            const int pp = p0 + pi;
-            const float de = des[pp];
-            for (int d = lane; d < A; d += 32) {
-                const float sv = __ldg(p.s + ((size_t)t * BL + pp) * A + d);
-                const float dS = de * vs[d] * (1.f - sv * sv);
-                p.ds[((size_t)t * BL + pp) * A + d] = dS;
-                ds_s[w * A + d] = dS;
-            }
-            __syncwarp();
-            if (lane < F) {
-                float acc = 0.f;
-                for (int d = 0; d < A; ++d) acc += ds_s[w * A + d] * wld_s[d * F + lane];
-                p.dconvf[((size_t)t * BL + pp) * F + lane] = acc;
-            }
-            __syncwarp();
+        for (int i = threadIdx.x; i < np; i += kRecThreads) p.de[(size_t)t * BL + p0 + i] = des[p0 + i];
+        for (int it = threadIdx.x; it < np * A; it += kRecThreads) {
+            const int pi = it / A, d = it - pi * A;
+            const float sv = it == (int)threadIdx.x ? sv_own : __ldg(p.s + ((size_t)t * BL + p0) * A + it);
+            const float dS = des[p0 + pi] * vs[d] * (1.f - sv * sv);
+            p.ds[((size_t)t * BL + p0) * A + it] = dS;
+            ds_s[it] = dS;
         }
-        for (int di = w; di < nd; di += kRecWarps) {
-            const int d = d0 + di;
-            for (int b = 0; b < B; ++b) {
-                float acc = 0.f;
+        if (nd > 0)       // terms of dq for the first owned attention dim (prefetched column of s)
+            for (int idx = threadIdx.x; idx < BL; idx += kRecThreads) {
+                const float sv = idx == (int)threadIdx.x ? sv_q : __ldg(p.s + ((size_t)t * BL + idx) * A + d0);
+                tq_s[idx] = des[idx] * (1.f - sv * sv);
+            }
+        __syncthreads();
+        // d(conv features) of the owned positions: item (pi, f, js) sums d = js, js+8, ...; 8 consecutive lanes share (pi, f)
+        for (int base = 0; base < np * F * 8; base += kRecThreads) {     // warp-uniform trip count (full-mask shuffles inside)
+            const int it = base + threadIdx.x;
+            const bool valid = it < np * F * 8;
+            const int js = it & 7, f = valid ? (it >> 3) % F : 0, pi = valid ? (it >> 3) / F : 0;
+            float acc = 0.f;
+            if (valid)
+                for (int d = js; d < A; d += 8) acc += ds_s[pi * A + d] * wldT[f * AP + d];
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            if (valid && js == 0) st_pub(p.dconvf + ((size_t)t * BL + p0 + pi) * F + f, acc);
+        }
+        for (int it = kRecWarps - 1 - w; it < nd * B; it += kRecWarps) {
+            const int di = it / B, b = it - di * B, d = d0 + di;
+            float acc = 0.f;
+            if (di == 0) {
+                for (int l = lane; l < L; l += 32) acc += tq_s[b * L + l];
+            } else {
                 for (int l = lane; l < L; l += 32) {
                     const float sv = __ldg(p.s + ((size_t)t * BL + b * L + l) * A + d);
                     acc += des[b * L + l] * (1.f - sv * sv);
                 }
-                acc = warp_sum(acc);
-                if (lane == 0) p.dq[((size_t)t * B + b) * A + d] = vs[d] * acc;
             }
+            acc = warp_sum(acc);
+            if (lane == 0) st_pub(p.dq + ((size_t)t * B + b) * A + d, vs[d] * acc);
         }
-        gb.sync();
-
-        // ---- P3: LSTM point-wise backward (units) and location-conv backward (positions) ----
-        for (int idx = threadIdx.x; idx < B * A; idx += kRecThreads) dq_s[idx] = ld_cg(p.dq + (size_t)t * B * A + idx);
+        prof.mark(3, T - 1 - t);
+        // ---- hand-off 2: dq(t) ----
+        gather_words(dq_s, p.dq + (size_t)t * B * A, B * A, (p.flags & kFlagWarp0) != 0, sg);
         __syncthreads();
-        if ((int)threadIdx.x < U * B) {
-            const int ul = threadIdx.x / B, b = threadIdx.x % B, u = u0 + ul;
-            const size_t zb = ((size_t)t * B + b) * H4;
-            float dh = __ldg(p.dha_ext + ((size_t)t * B + b) * Ha + u) + (t < T - 1 ? dhs[ul * BP + b] : 0.f);
-            float qd = 0.f;
-            for (int d = 0; d < A; ++d) qd += wqT[ul * A + d] * dq_s[b * A + d];
-            dh += qd;
-            if (p.mask) dh = p.mask[((size_t)t * B + b) * Ha + u] ? dh * p.drop_scale : 0.f;
-            const float cprev = t > 0 ? __ldg(p.ca + ((size_t)(t - 1) * B + b) * Ha + u) : 0.f;
-            LstmGrad g = lstm_point_bwd(__ldg(p.ga + zb + 0 * Ha + u), __ldg(p.ga + zb + 1 * Ha + u),
-                                        __ldg(p.ga + zb + 2 * Ha + u), __ldg(p.ga + zb + 3 * Ha + u),
-                                        __ldg(p.ca + ((size_t)t * B + b) * Ha + u), cprev, dh, dcs[ul * BP + b]);
-            dcs[ul * BP + b] = g.dc_prev;
-            p.dza[zb + 0 * Ha + u] = g.di;
-            p.dza[zb + 1 * Ha + u] = g.df;
-            p.dza[zb + 2 * Ha + u] = g.dg;
-            p.dza[zb + 3 * Ha + u] = g.do_;
+        prof.mark(4, T - 1 - t);
+        // ---- P3: LSTM point-wise backward (units); publishes dz_a(t) ----
+        // q-path term of dh: qd[cell] = sum_d Wq[d][u] dq[b][d], 16 lanes per cell
+        for (int base = 0; base < U * B * 16; base += kRecThreads) {     // warp-uniform trip count (full-mask shuffles inside)
+            const int it = base + threadIdx.x;
+            const bool valid = it < U * B * 16;
+            const int js = it & 15, cell = valid ? it >> 4 : 0, cu = cell / B, cb = cell - cu * B;
+            float acc = 0.f;
+            if (valid)
+                for (int d = js; d < A; d += 16) acc += wqT[cu * A + d] * dq_s[cb * A + d];
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+            if (valid && js == 0) qd_s[cell] = acc;
         }
-        for (int pi = w; pi < np; pi += kRecWarps) {
-            const int pp = p0 + pi, b = pp / L, l = pp % L;
+        __syncthreads();
+        if (pw) {
+            const size_t zb = ((size_t)t * B + pb) * H4;
+            float dh = dhe + (t < T - 1 ? dhs[ul * BP + pb] : 0.f) + qd_s[threadIdx.x];
+            if (p.mask) dh = mk ? dh * p.drop_scale : 0.f;
+            const LstmGrad gr = lstm_point_bwd(gi[0], gi[1], gi[2], gi[3], cc, cp, dh, dcarry);
+            dcarry = gr.dc_prev;
+            st_pub(p.dza + zb + 0 * Ha + u, gr.di);
+            st_pub(p.dza + zb + 1 * Ha + u, gr.df);
+            st_pub(p.dza + zb + 2 * Ha + u, gr.dg);
+            st_pub(p.dza + zb + 3 * Ha + u, gr.do_);
+        }
+        if (t > 0) fetch(t - 1);
+        prof.mark(5, T - 1 - t);
+        // ---- hand-off 3 (dconvf of the +-pad neighbours) + location-conv backward for the owned positions ----
+        // item (pi, k): one warp, lane = filter; output position lo = l - k + pad is fed by input l through tap k
+        for (int it = w; it < np * Kl; it += kRecWarps) {
+            const int pi = it / Kl, k = it - pi * Kl;
+            const int pp = p0 + pi, b = pp / L, l = pp - b * L, lo = l - k + pl;
             float a0 = 0.f, a1 = 0.f;
-            if (lane < F) {
-                for (int k = 0; k < Kl; ++k) {
-                    const int lo = l - k + pl;                               // output position fed by input l through tap k
-                    if (lo >= 0 && lo < L) {
-                        const float dv = ld_cg(p.dconvf + ((size_t)t * BL + b * L + lo) * F + lane);
-                        a0 += wlocT[(0 * Kl + k) * F + lane] * dv;
-                        a1 += wlocT[(1 * Kl + k) * F + lane] * dv;
-                    }
-                }
+            if (lo >= 0 && lo < L && lane < F) {
+                const float dv = poll1(p.dconvf + ((size_t)t * BL + b * L + lo) * F + lane, sg);
+                a0 = wloc_s[lane * CKP + k] * dv;
+                a1 = wloc_s[lane * CKP + Kl + k] * dv;
             }
             a0 = warp_sum(a0);
             a1 = warp_sum(a1);
             if (lane == 0) {
-                dprev_s[pi] = a0;          // d/d a(t-1) through the "previous alignment" channel
-                gcum_s[pi] += a1;          // running d/d cum(t-1)
+                cpart[it * 2 + 0] = a0;
+                cpart[it * 2 + 1] = a1;
             }
         }
-        if (t > 0) gb.sync();
+        __syncthreads();
+        for (int i = threadIdx.x; i < np; i += kRecThreads) {
+            float a0 = 0.f, a1 = 0.f;
+            for (int k = 0; k < Kl; ++k) {
+                a0 += cpart[(i * Kl + k) * 2 + 0];
+                a1 += cpart[(i * Kl + k) * 2 + 1];
+            }
+            dprev_s[i] = a0;          // d/d a(t-1) through the "previous alignment" channel
+            gcum_s[i] += a1;          // running d/d cum(t-1)
+        }
+        __syncthreads();
+        prof.mark(6, T - 1 - t);
     }
 }
 
 size_t attn_chain_fwd_smem(int B, int L, int Ha, int A, int F, int Kl, int sm_count, bool mw_resident) {
     return attn_fwd_layout(B, L, Ha, A, F, Kl, sm_count, mw_resident).total * sizeof(float);
 }
-size_t attn_chain_bwd_smem(int B, int L, int Ha, int A, int F, int Kl, int sm_count) {
-    return attn_bwd_layout(B, L, Ha, A, F, Kl, sm_count).total * sizeof(float);
+size_t attn_chain_bwd_smem(int B, int L, int Ha, int A, int F, int Kl, int sm_count, bool mwp_resident) {
+    return attn_bwd_layout(B, L, Ha, A, F, Kl, sm_count, mwp_resident).total * sizeof(float);
 }
 
 static int attn_check(int B, int Ha, int A, int F, int sm_count) {
     MSA_CHECK(Ha % 4 == 0, MSA_E_UNSUPPORTED, "attn_chain: attention_rnn_dim %d must be a multiple of 4", Ha);
     MSA_CHECK(F <= 32, MSA_E_UNSUPPORTED, "attn_chain: attention_location_n_filters %d > 32", F);
-    MSA_CHECK(B >= 1 && B <= 16, MSA_E_UNSUPPORTED, "attn_chain: batch %d outside [1,16]", B);
+    MSA_CHECK(B >= 1 && B <= kBMax, MSA_E_UNSUPPORTED, "attn_chain: batch %d outside [1,%d]", B, kBMax);
     MSA_CHECK((Ha + sm_count - 1) / sm_count <= kUMax, MSA_E_UNSUPPORTED,
               "attn_chain: attention_rnn_dim %d needs more than %d units per CTA on %d CTAs", Ha, kUMax, sm_count);
     (void)A;
@@ -458,7 +582,11 @@ int launch_attn_chain_fwd(const AttnChainParams& p, int sm_count, size_t smem_li
     }
     MSA_CHECK(smem <= smem_limit, MSA_E_UNSUPPORTED, "attn_chain_fwd: needs %zu bytes of shared memory (> %zu)", smem, smem_limit);
     MSA_CUDA(cudaFuncSetAttribute(k_attn_chain_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MSA_CUDA(cudaMemsetAsync(p.barrier, 0, sizeof(unsigned int), st));
+    // canaries of the three hand-off arrays (common.cuh)
+    const size_t TB = (size_t)p.T * p.B;
+    MSA_CUDA(cudaMemsetAsync(p.ha, 0xFF, sizeof(float) * TB * p.Ha, st));
+    MSA_CUDA(cudaMemsetAsync(p.q, 0xFF, sizeof(float) * TB * p.A, st));
+    MSA_CUDA(cudaMemsetAsync(p.e, 0xFF, sizeof(float) * TB * p.L, st));
     AttnChainParams pp = p;
     void* args[] = {&pp, &mw_res};
     MSA_CUDA(cudaLaunchCooperativeKernel((void*)k_attn_chain_fwd, dim3(sm_count), dim3(kRecThreads), args, smem, st));
@@ -468,12 +596,21 @@ int launch_attn_chain_fwd(const AttnChainParams& p, int sm_count, size_t smem_li
 
 int launch_attn_chain_bwd(const AttnChainBwdParams& p, int sm_count, size_t smem_limit, cudaStream_t st) {
     MSA_TRY(attn_check(p.B, p.Ha, p.A, p.F, sm_count));
-    const size_t smem = attn_chain_bwd_smem(p.B, p.L, p.Ha, p.A, p.F, p.Kl, sm_count);
+    int mwp_res = 1;
+    size_t smem = attn_chain_bwd_smem(p.B, p.L, p.Ha, p.A, p.F, p.Kl, sm_count, true);
+    if (smem > smem_limit) {
+        mwp_res = 0;
+        smem = attn_chain_bwd_smem(p.B, p.L, p.Ha, p.A, p.F, p.Kl, sm_count, false);
+    }
     MSA_CHECK(smem <= smem_limit, MSA_E_UNSUPPORTED, "attn_chain_bwd: needs %zu bytes of shared memory (> %zu)", smem, smem_limit);
     MSA_CUDA(cudaFuncSetAttribute(k_attn_chain_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MSA_CUDA(cudaMemsetAsync(p.barrier, 0, sizeof(unsigned int), st));
+    const size_t TB = (size_t)p.T * p.B;
+    MSA_CUDA(cudaMemsetAsync(p.dza, 0xFF, sizeof(float) * TB * 4 * p.Ha, st));
+    MSA_CUDA(cudaMemsetAsync(p.dq, 0xFF, sizeof(float) * TB * p.A, st));
+    MSA_CUDA(cudaMemsetAsync(p.dat, 0xFF, sizeof(float) * TB * p.L, st));
+    MSA_CUDA(cudaMemsetAsync(p.dconvf, 0xFF, sizeof(float) * TB * p.L * p.F, st));
     AttnChainBwdParams pp = p;
-    void* args[] = {&pp};
+    void* args[] = {&pp, &mwp_res};
     MSA_CUDA(cudaLaunchCooperativeKernel((void*)k_attn_chain_bwd, dim3(sm_count), dim3(kRecThreads), args, smem, st));
     count_launch();
     return 0;

@@ -95,26 +95,72 @@ __device__ __forceinline__ float warp_transpose_reduce32(float (&a)[32]) {
 __device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
-// Grid-wide barrier for cooperative (co-resident) launches: monotonically increasing arrival counter.
-struct GridBarrier {
-    unsigned int* counter;  // zeroed before launch
-    unsigned int target;    // per-thread copy of the next release value
-    __device__ __forceinline__ void init(unsigned int* c) { counter = c; target = 0; }
-    __device__ __forceinline__ void sync() {
-        target += gridDim.x;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();  // release: publish this block's writes (cumulative over the bar.sync)
-            atomicAdd(counter, 1u);
-            unsigned int v;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-            } while ((int)(v - target) < 0);
-            __threadfence();  // acquire side + L1 invalidation for the block's later plain loads
+// ---- cross-CTA hand-off inside the persistent kernels: "canary polling" -------------------------------------------
+// Every per-step array that one CTA produces and other CTAs consume in the same launch (h, q, energies, dz, ...)
+// is ALSO the stash the backward pass / the batched GEMMs read later, so each word is written exactly once per launch.
+// The host fills those arrays with 0xFF bytes before the launch; a consumer spins on the data words themselves until
+// none of them is the canary.  Aligned 32-bit words are single-copy atomic, so no flag, no fence and no atomic is
+// needed: one L2 round trip from the producer's store to the consumer's load.  0xFFFFFFFF is a NaN pattern no
+// arithmetic instruction produces (hardware NaNs are 0x7FFFFFFF), so finite data can never be mistaken for it.
+constexpr unsigned int kCanary = 0xFFFFFFFFu;
+__device__ __forceinline__ bool is_canary(float x) { return __float_as_uint(x) == kCanary; }
+__device__ __forceinline__ bool ready4(const float4& v) { return !(is_canary(v.x) | is_canary(v.y) | is_canary(v.z) | is_canary(v.w)); }
+__device__ __forceinline__ float ld_poll(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_poll4(const float* p) {
+    float4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_pub(float* p, float v) {
+    asm volatile("st.relaxed.gpu.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_pub4(float* p, const float4& v) {
+    asm volatile("st.relaxed.gpu.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// Bounded spinning: a producer that never arrives (a bug, or NaN data) must not hang the GPU.  After ~4M empty polls a
+// thread raises the launch-wide abort word; every spinner checks it every 1024 polls and gives up.  The host checks the
+// word after the pass (msa_train_forward/backward return MSA_E_STATE on the next call if it is set).
+struct SpinGuard {
+    unsigned int* abort_word;
+    unsigned int n;
+    bool dead;      // sticky: once this thread has seen the abort it never waits again (the launch drains in microseconds)
+    __device__ __forceinline__ explicit SpinGuard(unsigned int* a) : abort_word(a), n(0), dead(false) {}
+    __device__ __forceinline__ bool bail() {
+        if (dead) return true;
+        if ((++n & 1023u) == 0u) {
+            if (*reinterpret_cast<volatile unsigned int*>(abort_word) != 0u) dead = true;
+            else if (n > (1u << 21)) {
+                *reinterpret_cast<volatile unsigned int*>(abort_word) = 1u;
+                dead = true;
+            }
         }
-        __syncthreads();
+        return dead;
     }
+    __device__ __forceinline__ void reset() { n = 0; }
 };
+__device__ __forceinline__ float poll1(const float* p, SpinGuard& sg) {
+    float v = ld_poll(p);
+    sg.reset();
+    while (is_canary(v)) {
+        if (sg.bail()) break;
+        v = ld_poll(p);
+    }
+    return v;
+}
+__device__ __forceinline__ float4 poll4(const float* p, SpinGuard& sg) {
+    float4 v = ld_poll4(p);
+    sg.reset();
+    while (!ready4(v)) {
+        if (sg.bail()) break;
+        v = ld_poll4(p);
+    }
+    return v;
+}
 #endif  // __CUDACC__
 
 }  // namespace msa

@@ -17,7 +17,11 @@ struct LstmRecParams {
     const uint8_t* mask;       // [T][B][H] keep-mask or nullptr
     float drop_scale;          // 1/(1-p)
     const int64_t* lengths;    // [B] packed-sequence lengths or nullptr
-    unsigned int* barrier;
+    unsigned int* abort_word;  // zeroed once per workspace; set by a kernel whose polling timed out
+    long long* prof;           // optional [grid][8] per-phase cycle counters (nullptr = off)
+    long long* trace;          // optional per-warp time stamps (rec_common.cuh)
+    int trace_t0;
+    int flags;                 // hand-off variant (kFlagGate | kFlagWarp0, rec_common.cuh)
 };
 struct LstmRecBwdParams {
     int T, B, H, ndir;
@@ -30,7 +34,11 @@ struct LstmRecBwdParams {
     const uint8_t* mask;
     float drop_scale;
     const int64_t* lengths;
-    unsigned int* barrier;
+    unsigned int* abort_word;
+    long long* prof;
+    long long* trace;
+    int trace_t0;
+    int flags;
 };
 size_t lstm_rec_fwd_smem(int B, int H);
 size_t lstm_rec_bwd_smem(int B, int H);
@@ -60,8 +68,12 @@ struct AttnChainParams {
     float* s;              // [T][B][L][A] tanh(q + loc + pm)
     float* convf;          // [T][B][L][F]
     float* znorm;          // [T][B]      normaliser (sum of sigmoids) for norm == 1
-    float* ebuf;           // [B][L] scratch
-    unsigned int* barrier;
+    float* e;              // [T][B][L]   energies (pre-normalisation)
+    unsigned int* abort_word;
+    long long* prof;       // optional [grid][8] per-phase cycle counters
+    long long* trace;
+    int trace_t0;
+    int flags;
 };
 struct AttnChainBwdParams {
     int T, B, L, Ha, A, F, Kl, norm;
@@ -85,11 +97,15 @@ struct AttnChainBwdParams {
     float* de;             // [T][B][L]
     float* ds;             // [T][B][L][A]
     float* dconvf;         // [T][B][L][F]
-    float* dat;            // [B][L] scratch
-    unsigned int* barrier;
+    float* dat;            // [T][B][L]   total d a(t)
+    unsigned int* abort_word;
+    long long* prof;
+    long long* trace;
+    int trace_t0;
+    int flags;
 };
 size_t attn_chain_fwd_smem(int B, int L, int Ha, int A, int F, int Kl, int sm_count, bool mw_resident);
-size_t attn_chain_bwd_smem(int B, int L, int Ha, int A, int F, int Kl, int sm_count);
+size_t attn_chain_bwd_smem(int B, int L, int Ha, int A, int F, int Kl, int sm_count, bool mwp_resident);
 int launch_attn_chain_fwd(const AttnChainParams& p, int sm_count, size_t smem_limit, cudaStream_t st);
 int launch_attn_chain_bwd(const AttnChainBwdParams& p, int sm_count, size_t smem_limit, cudaStream_t st);
 
@@ -124,8 +140,9 @@ int k_loss(const float* pre_bt, const float* post_bt, const float* gate_bt, cons
            const int64_t* mel_len, int B, int T, int M, int reduction, float pos_weight, float* partials, float* loss,
            float* dpre, float* dpost, float* dgate, cudaStream_t st);
 int k_sum_over_t(const float* x, float* out, int T, int64_t n, cudaStream_t st);           // out[n] = sum_t x[t][n]
-int k_wloc_grad(const float* dconvf, const float* align, const float* cum, float* gw, int T, int B, int L, int F, int Kl,
-                float scale, int accumulate, cudaStream_t st);
+int wloc_grad_partials(int T, int B);   // number of partial tables of F*2*Kl floats k_wloc_grad needs as scratch
+int k_wloc_grad(const float* dconvf, const float* align, const float* cum, float* gw, float* partials, int T, int B, int L, int F,
+                int Kl, float scale, int accumulate, cudaStream_t st);
 int k_dot_rows(const float* a, const float* b, int64_t n, float* partials, float* out, float scale, int accumulate, cudaStream_t st);
 int k_masks_generate(uint8_t* masks, const int64_t* offsets, const int64_t* numels, const float* ps, int nsec, uint64_t seed, cudaStream_t st);
 int k_scale_copy(const float* in, float* out, int64_t n, float scale, int accumulate, cudaStream_t st);

@@ -11,82 +11,123 @@
 
 namespace msa {
 
+// Per-step hand-off: h(t) (forward) / dz(t) (backward) are published with plain stores into the stash arrays the later
+// GEMMs read anyway, and consumed by canary polling (common.cuh) -- no grid barrier, no atomics.  The streaming
+// per-step inputs of the point-wise update (zin, gates, c, dh_ext, mask) are fetched one step ahead so that their
+// DRAM/L2 latency overlaps the wait for the other CTAs.
+struct LstmFwdSmem {
+    size_t wsm, hs, part, total;
+    int KP, BP;
+};
+__host__ __device__ inline LstmFwdSmem lstm_fwd_layout(int B, int H) {
+    LstmFwdSmem s;
+    s.KP = round_up_i(H, 128);
+    s.BP = (B + 3) & ~3;
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o += (n + 3) & ~(size_t)3; return r; };
+    s.wsm = take((size_t)4 * kUMax * s.KP);
+    s.hs = take((size_t)s.BP * s.KP);
+    s.part = take((size_t)kBTiles * kRecWarps * 32);
+    s.total = o;
+    return s;
+}
+
 __global__ void __launch_bounds__(kRecThreads, 1) k_lstm_rec_fwd(LstmRecParams p) {
     extern __shared__ __align__(16) float smem[];
     const int H = p.H, B = p.B, T = p.T, H4 = 4 * H;
-    const int BP = (B + 3) & ~3;
     const int ncta_dir = gridDim.x / p.ndir;
     const int dir = blockIdx.x / ncta_dir;
     const bool idle = dir >= p.ndir;
     const int ci = blockIdx.x % ncta_dir;
     const int u0 = idle ? 0 : part_lo(ci, H, ncta_dir), u1 = idle ? 0 : part_lo(ci + 1, H, ncta_dir);
-    const int U = u1 - u0, R = 4 * U;
+    const int U = u1 - u0, R = 4 * U, RG = (R + 7) >> 3;
+    if (U == 0) return;   // nothing to own: this CTA neither produces nor consumes
 
-    float* Wsm = smem;                               // [4*kUMax][H]
-    float* hs = Wsm + (size_t)4 * kUMax * H;         // [BP][H]
-    float* part = hs + (size_t)BP * H;               // [warps*32]
-    float* zs = part + kRecWarps * 32;               // [32][BP]
-    float* cs = zs + 32 * BP;                        // [kUMax][BP]
+    const LstmFwdSmem lay = lstm_fwd_layout(B, H);
+    const int KP = lay.KP, KP4 = KP >> 2;
+    float* Wsm = smem + lay.wsm;                     // [RG*8][KP]  local row rl = ul*4 + gate, zero-padded
+    float* hs = smem + lay.hs;                       // [BP][KP]    zero-padded
+    float* part = smem + lay.part;
 
-    const int dd = idle ? 0 : dir;
-    const float* whh = p.whh + (size_t)dd * p.whh_dir_stride;
-    const float* zin = p.zin + (size_t)dd * T * B * H4;
-    float* hout = p.hout + (size_t)dd * T * B * H;
-    float* cout = p.cout + (size_t)dd * T * B * H;
-    float* gates = p.gates + (size_t)dd * T * B * H4;
+    const float* whh = p.whh + (size_t)dir * p.whh_dir_stride;
+    const float* zin = p.zin + (size_t)dir * T * B * H4;
+    float* hout = p.hout + (size_t)dir * T * B * H;
+    float* cout = p.cout + (size_t)dir * T * B * H;
+    float* gates = p.gates + (size_t)dir * T * B * H4;
 
-    for (int idx = threadIdx.x; idx < R * (H >> 2); idx += kRecThreads) {
-        const int rl = idx / (H >> 2), k4 = idx % (H >> 2);
+    for (int idx = threadIdx.x; idx < RG * 8 * KP4; idx += kRecThreads) {
+        const int rl = idx / KP4, k4 = idx % KP4;
         const int g = rl & 3, ul = rl >> 2;
-        reinterpret_cast<float4*>(Wsm)[(size_t)rl * (H >> 2) + k4] =
-            __ldg(reinterpret_cast<const float4*>(whh + (size_t)(g * H + u0 + ul) * H) + k4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rl < R && k4 < (H >> 2)) v = __ldg(reinterpret_cast<const float4*>(whh + (size_t)(g * H + u0 + ul) * H) + k4);
+        reinterpret_cast<float4*>(Wsm)[idx] = v;
     }
-    for (int idx = threadIdx.x; idx < kUMax * BP; idx += kRecThreads) cs[idx] = 0.f;
-    GridBarrier gb;
-    gb.init(p.barrier);
+    for (int idx = threadIdx.x; idx < lay.BP * KP; idx += kRecThreads) hs[idx] = 0.f;
+
+    // point-wise role: 4 lanes per cell (ul, b), lane g evaluates gate g; the cell state lives in lane 0's register
+    const bool pw = (int)threadIdx.x < 4 * U * B;
+    const int g = threadIdx.x & 3, cell = threadIdx.x >> 2;
+    const int ul = pw ? cell / B : 0, b = pw ? cell % B : 0, u = u0 + ul;
+    const int len = (pw && p.lengths) ? (int)p.lengths[b] : T;
+    float zi = 0.f, cstate = 0.f;
+    unsigned char mk = 1;
+    auto fetch = [&](int t) {
+        zi = __ldg(zin + ((size_t)t * B + b) * H4 + (size_t)g * H + u);
+        if (p.mask && g == 0) mk = p.mask[((size_t)t * B + b) * H + u];
+    };
+    if (pw) fetch(dir == 0 ? 0 : T - 1);
+    SpinGuard sg(p.abort_word);
+    ChainProf prof;
+    prof.start(p.prof, p.trace, p.trace_t0);
     __syncthreads();
 
     for (int s = 0; s < T; ++s) {
         const int t = (dir == 0) ? s : T - 1 - s;
         const int tp = (dir == 0) ? t - 1 : t + 1;
-        if (U > 0) {
-            for (int idx = threadIdx.x; idx < B * (H >> 2); idx += kRecThreads) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (s > 0) v = ld_cg4(hout + (size_t)tp * B * H + (size_t)idx * 4);
-                reinterpret_cast<float4*>(hs)[idx] = v;
-            }
+        if (s > 0 && (p.flags & kFlagGate)) {
+            // sentinel of producer CTA c: h of its last cell (unit u1(c)-1, row B-1), the last word it publishes
+            const float* hrow = hout + ((size_t)tp * B + (B - 1)) * H;
+            gate_wait(ncta_dir, [&](int c) { const int e = part_lo(c + 1, H, ncta_dir); return e > 0 ? hrow + e - 1 : nullptr; }, sg);
             __syncthreads();
-            cta_matvec_fwd<false>(Wsm, R, H, hs, nullptr, 0, 0, 0, 0, nullptr, B, part, zs, BP);
-            if ((int)threadIdx.x < U * B) {
-                const int ul = threadIdx.x / B, b = threadIdx.x % B, u = u0 + ul;
-                const size_t zb = ((size_t)t * B + b) * H4;
-                const bool active = p.lengths ? (t < (int)p.lengths[b]) : true;
-                float hv = 0.f;
-                LstmPoint r = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (active) {
-                    r = lstm_point_fwd(zs[(ul * 4 + 0) * BP + b] + __ldg(zin + zb + 0 * H + u),
-                                       zs[(ul * 4 + 1) * BP + b] + __ldg(zin + zb + 1 * H + u),
-                                       zs[(ul * 4 + 2) * BP + b] + __ldg(zin + zb + 2 * H + u),
-                                       zs[(ul * 4 + 3) * BP + b] + __ldg(zin + zb + 3 * H + u), cs[ul * BP + b]);
-                    cs[ul * BP + b] = r.c;
-                    hv = r.h;
-                    if (p.mask) hv = p.mask[((size_t)t * B + b) * H + u] ? hv * p.drop_scale : 0.f;
-                }
-                gates[zb + 0 * H + u] = r.i;
-                gates[zb + 1 * H + u] = r.f;
-                gates[zb + 2 * H + u] = r.g;
-                gates[zb + 3 * H + u] = r.o;
-                cout[((size_t)t * B + b) * H + u] = r.c;
-                hout[((size_t)t * B + b) * H + u] = hv;
-            }
         }
-        if (s + 1 < T) gb.sync();
+        if (s > 0) {
+            poll_copy_rows(hs, KP4, hout + (size_t)tp * B * H, B, H >> 2, sg);
+            __syncthreads();
+        }
+        prof.mark(0, s);
+        cta_matvec_fwd<false>(Wsm, RG, KP, hs, nullptr, 0, nullptr, B, part);
+        __syncthreads();
+        prof.mark(1, s);
+        if (pw) {
+            const size_t zb = ((size_t)t * B + b) * H4;
+            const bool active = t < len;
+            const float z = lstm_gate_sum(part, RG, ul * 4 + g, b) + zi;
+            float act = g == 2 ? fast_tanh(z) : fast_sigmoid(z);
+            if (!active) act = 0.f;
+            const unsigned int gm = 0xFu << (threadIdx.x & 28);                 // the 4 lanes of this cell
+            const float ai = __shfl_sync(gm, act, 0, 4), af = __shfl_sync(gm, act, 1, 4);
+            const float ag = __shfl_sync(gm, act, 2, 4), ao = __shfl_sync(gm, act, 3, 4);
+            gates[zb + (size_t)g * H + u] = act;
+            if (g == 0) {
+                float hv = 0.f, cn = 0.f;
+                if (active) {
+                    cn = af * cstate + ai * ag;
+                    cstate = cn;
+                    hv = ao * fast_tanh(cn);
+                    if (p.mask) hv = mk ? hv * p.drop_scale : 0.f;
+                }
+                st_pub(hout + ((size_t)t * B + b) * H + u, hv);      // consumed by every CTA at the next step
+                cout[((size_t)t * B + b) * H + u] = cn;
+            }
+            if (s + 1 < T) fetch(dir == 0 ? t + 1 : t - 1);
+        }
+        prof.mark(2, s);
     }
 }
 
 __global__ void __launch_bounds__(kRecThreads, 1) k_lstm_rec_bwd(LstmRecBwdParams p) {
     extern __shared__ __align__(16) float smem[];
-    __shared__ float red[33];
+    __shared__ float red[kRecWarps * kPairMax];
     const int H = p.H, B = p.B, T = p.T, H4 = 4 * H;
     const int BP = (B + 3) & ~3;
     const int ncta_dir = gridDim.x / p.ndir;
@@ -95,77 +136,89 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_lstm_rec_bwd(LstmRecBwdParam
     const int ci = blockIdx.x % ncta_dir;
     const int u0 = idle ? 0 : part_lo(ci, H, ncta_dir), u1 = idle ? 0 : part_lo(ci + 1, H, ncta_dir);
     const int U = u1 - u0;
+    if (U == 0) return;
 
-    float* WT = smem;                                // [kUMax][4H]   WT[ul][r] = W_hh[r][u0+ul]
+    float* WT = smem;                                // [kUMax][4H]   WT[ul][r] = W_hh[r][u0+ul], zero rows for ul >= U
     float* part = WT + (size_t)kUMax * H4;           // [warps*32]
     float* dhs = part + kRecWarps * 32;              // [kUMax][BP]
-    float* dcs = dhs + kUMax * BP;                   // [kUMax][BP]
 
-    const int dd = idle ? 0 : dir;
-    const float* whh = p.whh + (size_t)dd * p.whh_dir_stride;
-    const float* gates = p.gates + (size_t)dd * T * B * H4;
-    const float* cst = p.cout + (size_t)dd * T * B * H;
-    const float* dh_ext = p.dh_ext + (size_t)dd * T * B * H;
-    float* dz = p.dz + (size_t)dd * T * B * H4;
+    const float* whh = p.whh + (size_t)dir * p.whh_dir_stride;
+    const float* gates = p.gates + (size_t)dir * T * B * H4;
+    const float* cst = p.cout + (size_t)dir * T * B * H;
+    const float* dh_ext = p.dh_ext + (size_t)dir * T * B * H;
+    float* dz = p.dz + (size_t)dir * T * B * H4;
 
-    for (int idx = threadIdx.x; idx < U * H4; idx += kRecThreads) {
+    for (int idx = threadIdx.x; idx < kUMax * H4; idx += kRecThreads) {
         const int ul = idx / H4, r = idx % H4;
-        WT[idx] = __ldg(whh + (size_t)r * H + u0 + ul);
+        WT[idx] = ul < U ? __ldg(whh + (size_t)r * H + u0 + ul) : 0.f;
     }
-    for (int idx = threadIdx.x; idx < kUMax * BP; idx += kRecThreads) { dcs[idx] = 0.f; dhs[idx] = 0.f; }
-    GridBarrier gb;
-    gb.init(p.barrier);
+    for (int idx = threadIdx.x; idx < kUMax * BP; idx += kRecThreads) dhs[idx] = 0.f;
+
+    const bool pw = (int)threadIdx.x < U * B;
+    const int ul = pw ? threadIdx.x / B : 0, b = pw ? threadIdx.x % B : 0, u = u0 + ul;
+    const int len = (pw && p.lengths) ? (int)p.lengths[b] : T;
+    float gi[4] = {0.f, 0.f, 0.f, 0.f}, cc = 0.f, cp = 0.f, dhe = 0.f, dcarry = 0.f;
+    unsigned char mk = 1;
+    auto fetch = [&](int t) {   // stash of forward step t + the external gradient of h(t)
+        const int tp = (dir == 0) ? t - 1 : t + 1;
+        const size_t zb = ((size_t)t * B + b) * H4, hb = ((size_t)t * B + b) * H + u;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) gi[g] = __ldg(gates + zb + (size_t)g * H + u);
+        cc = __ldg(cst + hb);
+        cp = (tp >= 0 && tp < T) ? __ldg(cst + ((size_t)tp * B + b) * H + u) : 0.f;
+        dhe = __ldg(dh_ext + hb);
+        if (p.mask) mk = p.mask[hb];
+    };
+    if (pw) fetch(dir == 0 ? T - 1 : 0);
+    SpinGuard sg(p.abort_word);
+    ChainProf prof;
+    prof.start(p.prof, p.trace, p.trace_t0);
     __syncthreads();
 
     for (int s = 0; s < T; ++s) {
         const int t = (dir == 0) ? T - 1 - s : s;     // reverse of the forward processing order
         const int tn = (dir == 0) ? t + 1 : t - 1;    // step processed just before (forward-order successor)
-        const int tp = (dir == 0) ? t - 1 : t + 1;    // forward-order predecessor (source of c_prev)
-        if (U > 0) {
-            if (s > 0) {
-                cta_matvec_bwd(WT, U, H4, dz + (size_t)tn * B * H4, B, part, dhs, BP, nullptr, 0, 0, 1, nullptr, red);
-            }
-            if ((int)threadIdx.x < U * B) {
-                const int ul = threadIdx.x / B, b = threadIdx.x % B, u = u0 + ul;
-                const size_t zb = ((size_t)t * B + b) * H4;
-                const bool active = p.lengths ? (t < (int)p.lengths[b]) : true;
-                LstmGrad g = {0.f, 0.f, 0.f, 0.f, 0.f};
-                if (active) {
-                    float dh = __ldg(dh_ext + ((size_t)t * B + b) * H + u) + (s > 0 ? dhs[ul * BP + b] : 0.f);
-                    if (p.mask) dh = p.mask[((size_t)t * B + b) * H + u] ? dh * p.drop_scale : 0.f;
-                    const bool has_prev = (tp >= 0 && tp < T);
-                    const float cprev = has_prev ? cst[((size_t)tp * B + b) * H + u] : 0.f;
-                    g = lstm_point_bwd(__ldg(gates + zb + 0 * H + u), __ldg(gates + zb + 1 * H + u),
-                                       __ldg(gates + zb + 2 * H + u), __ldg(gates + zb + 3 * H + u),
-                                       cst[((size_t)t * B + b) * H + u], cprev, dh, dcs[ul * BP + b]);
-                    dcs[ul * BP + b] = g.dc_prev;
-                }
-                dz[zb + 0 * H + u] = g.di;
-                dz[zb + 1 * H + u] = g.df;
-                dz[zb + 2 * H + u] = g.dg;
-                dz[zb + 3 * H + u] = g.do_;
-            }
+        if (s > 0 && (p.flags & kFlagGate)) {
+            // sentinel of producer CTA c: the output-gate gradient of its last cell, the last word it publishes
+            const float* zrow = dz + ((size_t)tn * B + (B - 1)) * H4 + (size_t)3 * H;
+            gate_wait(ncta_dir, [&](int c) { const int e = part_lo(c + 1, H, ncta_dir); return e > 0 ? zrow + e - 1 : nullptr; }, sg);
+            __syncthreads();
         }
-        if (s + 1 < T) gb.sync();
+        if (s > 0) cta_matvec_bwd(WT, H4, dz + (size_t)tn * B * H4, B, part, dhs, BP, nullptr, 0, 0, 0, 1, nullptr, red, sg);
+        prof.mark(0, s);
+        if (pw) {
+            const size_t zb = ((size_t)t * B + b) * H4;
+            const bool active = t < len;
+            LstmGrad g = {0.f, 0.f, 0.f, 0.f, 0.f};
+            if (active) {
+                float dh = dhe + (s > 0 ? dhs[ul * BP + b] : 0.f);
+                if (p.mask) dh = mk ? dh * p.drop_scale : 0.f;
+                g = lstm_point_bwd(gi[0], gi[1], gi[2], gi[3], cc, cp, dh, dcarry);
+                dcarry = g.dc_prev;
+            }
+            st_pub(dz + zb + 0 * H + u, g.di);
+            st_pub(dz + zb + 1 * H + u, g.df);
+            st_pub(dz + zb + 2 * H + u, g.dg);
+            st_pub(dz + zb + 3 * H + u, g.do_);
+            if (s + 1 < T) fetch(dir == 0 ? t - 1 : t + 1);
+        }
+        prof.mark(1, s);
     }
 }
 
 static int rec_check(int B, int H, int ndir, int sm_count) {
     MSA_CHECK(H % 4 == 0, MSA_E_UNSUPPORTED, "lstm_rec: hidden size %d must be a multiple of 4", H);
-    MSA_CHECK(B >= 1 && B <= 16, MSA_E_UNSUPPORTED, "lstm_rec: batch %d outside [1,16]", B);
+    MSA_CHECK(B >= 1 && B <= kBMax, MSA_E_UNSUPPORTED, "lstm_rec: batch %d outside [1,%d]", B, kBMax);
     const int ncta_dir = sm_count / ndir;
     MSA_CHECK(ncta_dir >= 1 && (H + ncta_dir - 1) / ncta_dir <= kUMax, MSA_E_UNSUPPORTED,
               "lstm_rec: hidden size %d needs more than %d units per CTA on %d CTAs", H, kUMax, ncta_dir);
     return 0;
 }
 
-size_t lstm_rec_fwd_smem(int B, int H) {
-    const int BP = (B + 3) & ~3;
-    return sizeof(float) * ((size_t)4 * kUMax * H + (size_t)BP * H + kRecWarps * 32 + 32 * BP + kUMax * BP);
-}
+size_t lstm_rec_fwd_smem(int B, int H) { return sizeof(float) * lstm_fwd_layout(B, H).total; }
 size_t lstm_rec_bwd_smem(int B, int H) {
     const int BP = (B + 3) & ~3;
-    return sizeof(float) * ((size_t)kUMax * 4 * H + kRecWarps * 32 + 2 * kUMax * BP);
+    return sizeof(float) * ((size_t)kUMax * 4 * H + kRecWarps * 32 + kUMax * BP);
 }
 
 int launch_lstm_rec_fwd(const LstmRecParams& p, int sm_count, size_t smem_limit, cudaStream_t st) {
@@ -173,7 +226,7 @@ int launch_lstm_rec_fwd(const LstmRecParams& p, int sm_count, size_t smem_limit,
     const size_t smem = lstm_rec_fwd_smem(p.B, p.H);
     MSA_CHECK(smem <= smem_limit, MSA_E_UNSUPPORTED, "lstm_rec_fwd: needs %zu bytes of shared memory (> %zu)", smem, smem_limit);
     MSA_CUDA(cudaFuncSetAttribute(k_lstm_rec_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MSA_CUDA(cudaMemsetAsync(p.barrier, 0, sizeof(unsigned int), st));
+    MSA_CUDA(cudaMemsetAsync(p.hout, 0xFF, sizeof(float) * (size_t)p.ndir * p.T * p.B * p.H, st));   // canaries (common.cuh)
     LstmRecParams pp = p;
     void* args[] = {&pp};
     MSA_CUDA(cudaLaunchCooperativeKernel((void*)k_lstm_rec_fwd, dim3(sm_count), dim3(kRecThreads), args, smem, st));
@@ -186,7 +239,7 @@ int launch_lstm_rec_bwd(const LstmRecBwdParams& p, int sm_count, size_t smem_lim
     const size_t smem = lstm_rec_bwd_smem(p.B, p.H);
     MSA_CHECK(smem <= smem_limit, MSA_E_UNSUPPORTED, "lstm_rec_bwd: needs %zu bytes of shared memory (> %zu)", smem, smem_limit);
     MSA_CUDA(cudaFuncSetAttribute(k_lstm_rec_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MSA_CUDA(cudaMemsetAsync(p.barrier, 0, sizeof(unsigned int), st));
+    MSA_CUDA(cudaMemsetAsync(p.dz, 0xFF, sizeof(float) * (size_t)p.ndir * p.T * p.B * 4 * p.H, st));  // canaries (common.cuh)
     LstmRecBwdParams pp = p;
     void* args[] = {&pp};
     MSA_CUDA(cudaLaunchCooperativeKernel((void*)k_lstm_rec_bwd, dim3(sm_count), dim3(kRecThreads), args, smem, st));

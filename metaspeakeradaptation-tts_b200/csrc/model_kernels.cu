@@ -1,6 +1,8 @@
 // Element-wise, layout, normalisation, loss and small reduction kernels of the teacher-forced pass.
 // All are HBM/L2-bound: coalesced (128-bit where the shape allows) accesses, deterministic
 // reductions (fixed order, no float atomics), grids sized by the work.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -386,34 +388,62 @@ __global__ void ker_sum_over_t(const float* __restrict__ x, float* out, int T, i
 }
 
 // d W_loc[f][c][k] = sum_{t,b,l} dconvf[t][b][l][f] * in_c[t][b][l+k-pad]; in_0 = align[t-1] (0 at t=0), in_1 = cum[t]
-// one block per (c,k); threads = f (fast) x row lanes
-__global__ void ker_wloc_grad(const float* __restrict__ dconvf, const float* __restrict__ align, const float* __restrict__ cum,
-                              float* gw, int T, int B, int L, int F, int Kl, float scale, int accumulate) {
-    __shared__ float sh[8][33];
-    const int c = blockIdx.x / Kl, k = blockIdx.x % Kl, pad = (Kl - 1) / 2;
-    const int f = threadIdx.x & 31, ry = threadIdx.x >> 5;
-    float s = 0.f;
-    const int64_t rows = (int64_t)T * B * L;
-    if (f < F) {
-        for (int64_t r = ry; r < rows; r += 8) {
-            const int l = (int)(r % L);
-            const int64_t tb = r / L;
-            const int t = (int)(tb / B);
-            const int li = l + k - pad;
-            if (li < 0 || li >= L) continue;
-            float v;
-            if (c == 0) v = t > 0 ? align[(tb - B) * L + li] : 0.f;
-            else v = cum[tb * L + li];
-            s += dconvf[r * F + f] * v;
+// (backward of forward_attn.py:121-123's location conv w.r.t. its weight).  Two deterministic stages:
+//   stage 1: block g walks the (t,b) rows g, g+G, ...; per row it stages the two padded input channels and the
+//            [L][F] slab of dconvf in shared memory; thread (f = lane, ck = warp + 8j) keeps 8 running sums.
+//   stage 2: fixed-order sum of the G partial tables.
+constexpr int kWlocCk = 8;   // (c,k) outputs per thread
+__global__ void __launch_bounds__(256) ker_wloc_grad_partial(const float* __restrict__ dconvf, const float* __restrict__ align,
+                                                             const float* __restrict__ cum, float* partials, int T, int B, int L,
+                                                             int F, int Kl) {
+    extern __shared__ float sm[];
+    const int pad = (Kl - 1) / 2, Lp = L + 2 * pad, CK = 2 * Kl;
+    float* in_s = sm;                 // [2][Lp]
+    float* dc_s = sm + 2 * Lp;        // [L][F]
+    const int f = threadIdx.x & 31, g = threadIdx.x >> 5;
+    float acc[kWlocCk];
+#pragma unroll
+    for (int j = 0; j < kWlocCk; ++j) acc[j] = 0.f;
+    int off[kWlocCk];
+#pragma unroll
+    for (int j = 0; j < kWlocCk; ++j) {
+        const int ck = g + 8 * j;
+        off[j] = ck < CK ? (ck / Kl) * Lp + (ck % Kl) : -1;
+    }
+    const int TB = T * B;
+    for (int tb = blockIdx.x; tb < TB; tb += gridDim.x) {
+        const int t = tb / B;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * Lp; i += blockDim.x) {
+            const int c = i / Lp, l = i % Lp - pad;
+            float v = 0.f;
+            if (l >= 0 && l < L) v = c == 0 ? (t > 0 ? align[(size_t)(tb - B) * L + l] : 0.f) : cum[(size_t)tb * L + l];
+            in_s[i] = v;
+        }
+        for (int i = threadIdx.x; i < L * F; i += blockDim.x) dc_s[i] = dconvf[(size_t)tb * L * F + i];
+        __syncthreads();
+        if (f < F) {
+            for (int l = 0; l < L; ++l) {
+                const float d = dc_s[l * F + f];
+#pragma unroll
+                for (int j = 0; j < kWlocCk; ++j)
+                    if (off[j] >= 0) acc[j] += d * in_s[off[j] + l];
+            }
         }
     }
-    sh[ry][f] = s;
-    __syncthreads();
-    if (ry == 0 && f < F) {
-        float tsum = 0.f;
-        for (int j = 0; j < 8; ++j) tsum += sh[j][f];
-        const int64_t o = ((int64_t)f * 2 + c) * Kl + k;
-        gw[o] = accumulate ? gw[o] + scale * tsum : scale * tsum;
+    if (f < F) {
+#pragma unroll
+        for (int j = 0; j < kWlocCk; ++j) {
+            const int ck = g + 8 * j;
+            if (ck < CK) partials[(size_t)blockIdx.x * F * CK + (size_t)f * CK + ck] = acc[j];
+        }
+    }
+}
+__global__ void ker_wloc_grad_final(const float* __restrict__ partials, int G, int n, float* gw, float scale, int accumulate) {
+    GSL(i, n) {
+        float s = 0.f;
+        for (int g = 0; g < G; ++g) s += partials[(size_t)g * n + i];
+        gw[i] = accumulate ? gw[i] + scale * s : scale * s;
     }
 }
 
@@ -581,9 +611,16 @@ int k_sum_over_t(const float* x, float* out, int T, int64_t n, cudaStream_t st) 
     MSA_LAUNCH_CHECK();
     return 0;
 }
-int k_wloc_grad(const float* dconvf, const float* align, const float* cum, float* gw, int T, int B, int L, int F, int Kl,
-                float scale, int acc, cudaStream_t st) {
-    ker_wloc_grad<<<2 * Kl, 256, 0, ST>>>(dconvf, align, cum, gw, T, B, L, F, Kl, scale, acc);
+int wloc_grad_partials(int T, int B) { return std::min(T * B, 296); }
+int k_wloc_grad(const float* dconvf, const float* align, const float* cum, float* gw, float* partials, int T, int B, int L, int F,
+                int Kl, float scale, int acc, cudaStream_t st) {
+    MSA_CHECK(F <= 32 && 2 * Kl <= 8 * kWlocCk, MSA_E_UNSUPPORTED, "wloc_grad: needs F <= 32 and location kernel <= 32 taps");
+    const int G = wloc_grad_partials(T, B);
+    const size_t smem = sizeof(float) * ((size_t)2 * (L + Kl - 1) + (size_t)L * F);
+    MSA_CHECK(smem <= 48 * 1024, MSA_E_UNSUPPORTED, "wloc_grad: text length %d too long for the shared-memory slab", L);
+    ker_wloc_grad_partial<<<G, 256, smem, ST>>>(dconvf, align, cum, partials, T, B, L, F, Kl);
+    MSA_LAUNCH_CHECK();
+    ker_wloc_grad_final<<<grid_for((int64_t)F * 2 * Kl), kTh, 0, ST>>>(partials, G, F * 2 * Kl, gw, scale, acc);
     MSA_LAUNCH_CHECK();
     return 0;
 }

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -67,6 +68,8 @@ struct msa_handle {
     // optional per-kernel timing with CUDA events on the launch stream (bench.py's roofline leg)
     bool in_bwd = false;   // GEMM precision policy 1: fp32 GEMMs in the forward pass, TF32 in the backward pass
     bool prof = false;
+    int trace_t0 = 0;
+    int rec_flags = 0;     // hand-off variant of the persistent kernels (env MSA_REC_FLAGS, development only)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
     std::vector<int> prof_id;
     size_t prof_used = 0;
@@ -173,7 +176,7 @@ static Dims make_dims(const msa_config& c, int B, int T, int L) {
     X(mw_rm, d.BL * 4 * d.Ha) X(mw_pm, d.BL * 4 * d.Ha)                                                \
     X(ha, d.TB * d.Ha) X(ca, d.TB * d.Ha) X(ga, d.TB * 4 * d.Ha) X(q, d.TB * d.A)                      \
     X(align_tm, d.TBL) X(cum, d.TBL) X(s, d.TBL * d.A) X(convf, d.TBL * d.F) X(znorm, d.TB)            \
-    X(ebuf, d.BL) X(ctx, d.TB * d.E)                                                                   \
+    X(ebuf, d.TBL) X(ctx, d.TB * d.E)                                                                   \
     X(zd, d.TB * 4 * d.Hd) X(hd, d.TB * d.Hd) X(cd, d.TB * d.Hd) X(gd, d.TB * 4 * d.Hd)                \
     X(mel_tm, d.TB * d.M) X(gate_tm, d.TB)                                                             \
     X(post_x, (d.nPost + 1) * d.BT * d.Cmax) X(post_y, d.nPost * d.BT * d.Cmax)                        \
@@ -185,22 +188,27 @@ static Dims make_dims(const msa_config& c, int B, int T, int L) {
     X(bn_scr, 2 * std::max(d.Cmax, d.C)) X(dmel_bt, d.BT * d.M) X(dmel_tm, d.TB * d.M)                 \
     X(dgate_tm, d.TB) X(dhd, d.TB * d.Hd) X(dzd, d.TB * 4 * d.Hd) X(dha, d.TB * d.Ha)                  \
     X(dctx, d.TB * d.E) X(da_ext, d.TBL) X(dza, d.TB * 4 * d.Ha) X(dq, d.TB * d.A) X(de, d.TBL)        \
-    X(ds, d.TBL * d.A) X(dconvf, d.TBL * d.F) X(dat, d.BL) X(dpm, d.BL * d.A)                          \
+    X(ds, d.TBL * d.A) X(dconvf, d.TBL * d.F) X(dat, d.TBL) X(dpm, d.BL * d.A)                          \
     X(dmw, d.BL * 4 * d.Ha) X(dmem, d.BL * d.E) X(dxp, (d.TB + d.B) * d.Pd)                            \
     X(dp1, (d.TB + d.B) * d.Pd) X(denc_h, 2 * d.BL * d.Hh) X(dzx, 2 * d.BL * 4 * d.Hh)                 \
     X(dx3_tm, d.BL * d.C) X(edx0, d.BL * d.C) X(edx1, d.BL * d.C) X(edy, d.BL * d.C)                   \
-    X(edcol, d.BL * d.Kc * d.C) X(edw2, (int64_t)d.C * d.Kc * d.C) X(dspk, d.B * d.Ds)
+    X(edcol, d.BL * d.Kc * d.C) X(edw2, (int64_t)d.C * d.Kc * d.C) X(dspk, d.B * d.Ds)                             \
+    X(wloc_part, (int64_t)wloc_grad_partials(d.T, d.B) * d.F * 2 * d.Kl) X(prof, kProfFloats) X(trace, kTraceFloats)
 
+constexpr int64_t kProfFloats = 2 * 6 * 256 * 8;
+constexpr int64_t kTraceWordsPerKernel = (int64_t)256 * 16 * 4 * 12 * 2;   // int64 words: [ctas][warps][steps][tags][2]
+constexpr int64_t kTraceFloats = 2 * 6 * kTraceWordsPerKernel;
 struct Ws {
 #define X(name, n) float* name; int64_t n_##name;
     WS_LIST(X)
 #undef X
-    unsigned int* barrier;
+    unsigned int* abort_word;
     void* blas_ws;
     size_t blas_ws_bytes;
     size_t total_bytes;
 };
 constexpr size_t kBlasWs = 64u << 20;
+constexpr int kProfCtas = 256, kProfSlots = 8;   // phase-cycle counters: [PROF_N kernels][kProfCtas][kProfSlots] int64
 
 static Ws ws_layout(const Dims& d, void* base) {
     Ws w;
@@ -212,7 +220,7 @@ static Ws ws_layout(const Dims& d, void* base) {
     o += (size_t)align_up((int64_t)(n), 64) * sizeof(float);
     WS_LIST(X)
 #undef X
-    w.barrier = reinterpret_cast<unsigned int*>(b + o);
+    w.abort_word = reinterpret_cast<unsigned int*>(b + o);
     o += 256;
     w.blas_ws = b + o;
     w.blas_ws_bytes = kBlasWs;
@@ -327,6 +335,15 @@ struct ProfScope {
     ~ProfScope() { if (slot >= 0) cudaEventRecord(h->prof_ev[slot].second, st); }
 };
 
+// per-phase cycle counters of the persistent kernels live in the workspace ("prof"); written only while profiling is on
+static long long* prof_ptr(const msa_handle* h, const Ws& w, int id) {
+    return h->prof ? reinterpret_cast<long long*>(w.prof) + (size_t)id * kProfCtas * kProfSlots : nullptr;
+}
+
+static long long* trace_ptr(const msa_handle* h, const Ws& w, int id) {
+    return h->prof ? reinterpret_cast<long long*>(w.trace) + (size_t)id * kTraceWordsPerKernel : nullptr;
+}
+
 static int check_cfg(const msa_config& c) {
     MSA_CHECK(c.enc_dim > 0 && c.enc_dim % 8 == 0, MSA_E_UNSUPPORTED, "encoder_embedding_dim must be a positive multiple of 8");
     MSA_CHECK(c.enc_kernel % 2 == 1 && c.post_kernel % 2 == 1 && c.loc_kernel % 2 == 1, MSA_E_UNSUPPORTED, "kernel sizes must be odd");
@@ -374,6 +391,7 @@ int msa_create(const msa_config* cfg, int device, msa_handle** out) {
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
     h->smem_limit = prop.sharedMemPerBlockOptin;
+    if (const char* e = getenv("MSA_REC_FLAGS")) h->rec_flags = atoi(e);
     build_layout(h);
     cublasStatus_t s = cublasCreate(&h->blas);
     if (s != CUBLAS_STATUS_SUCCESS) {
@@ -485,6 +503,7 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
     const msa_config& c = h->cfg;
     const auto secs = mask_sections(c, B, T, L);
     auto mk = [&](int i) { return masks + secs[i].off; };
+    MSA_CUDA(cudaMemsetAsync(w.abort_word, 0, 256, st));
     const int iPre = d.nEnc, iAttn = d.nEnc + 2, iDec = d.nEnc + 3, iPost = d.nEnc + 4;
     auto P = [&](const std::string& n) { return params + h->off(n); };
 
@@ -520,7 +539,7 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
         lp.zin = w.enc_zx; lp.whh = P("encoder.lstm.weight_hh_l0");
         lp.whh_dir_stride = h->off("encoder.lstm.weight_hh_l0_reverse") - h->off("encoder.lstm.weight_hh_l0");
         lp.hout = w.enc_h; lp.cout = w.enc_c; lp.gates = w.enc_g; lp.mask = nullptr; lp.drop_scale = 1.f;
-        lp.lengths = token_lengths; lp.barrier = w.barrier;
+        lp.lengths = token_lengths; lp.abort_word = w.abort_word; lp.prof = prof_ptr(h, w, PROF_ENC_LSTM_FWD); lp.trace = trace_ptr(h, w, PROF_ENC_LSTM_FWD); lp.trace_t0 = h->trace_t0; lp.flags = h->rec_flags;
         ProfScope ps(h, PROF_ENC_LSTM_FWD, st);
         MSA_TRY(launch_lstm_rec_fwd(lp, h->sm_count, h->smem_limit, st));
     }
@@ -551,7 +570,7 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
         ap.mask = c.p_attn_dropout > 0.f ? mk(iAttn) : nullptr;
         ap.drop_scale = 1.f / (1.f - c.p_attn_dropout);
         ap.ha = w.ha; ap.ca = w.ca; ap.ga = w.ga; ap.q = w.q; ap.align = w.align_tm; ap.cum = w.cum; ap.s = w.s;
-        ap.convf = w.convf; ap.znorm = w.znorm; ap.ebuf = w.ebuf; ap.barrier = w.barrier;
+        ap.convf = w.convf; ap.znorm = w.znorm; ap.e = w.ebuf; ap.abort_word = w.abort_word; ap.prof = prof_ptr(h, w, PROF_ATTN_FWD); ap.trace = trace_ptr(h, w, PROF_ATTN_FWD); ap.trace_t0 = h->trace_t0; ap.flags = h->rec_flags;
         ProfScope ps(h, PROF_ATTN_FWD, st);
         MSA_TRY(launch_attn_chain_fwd(ap, h->sm_count, h->smem_limit, st));
     }
@@ -570,7 +589,7 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
         lp.hout = w.hd; lp.cout = w.cd; lp.gates = w.gd;
         lp.mask = c.p_dec_dropout > 0.f ? mk(iDec) : nullptr;
         lp.drop_scale = 1.f / (1.f - c.p_dec_dropout);
-        lp.lengths = nullptr; lp.barrier = w.barrier;
+        lp.lengths = nullptr; lp.abort_word = w.abort_word; lp.prof = prof_ptr(h, w, PROF_DEC_LSTM_FWD); lp.trace = trace_ptr(h, w, PROF_DEC_LSTM_FWD); lp.trace_t0 = h->trace_t0; lp.flags = h->rec_flags;
         ProfScope ps(h, PROF_DEC_LSTM_FWD, st);
         MSA_TRY(launch_lstm_rec_fwd(lp, h->sm_count, h->smem_limit, st));
     }
@@ -708,7 +727,7 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
         bp.gates = w.gd; bp.cout = w.cd; bp.dh_ext = w.dhd; bp.dz = w.dzd;
         bp.mask = c.p_dec_dropout > 0.f ? mk(iDec) : nullptr;
         bp.drop_scale = 1.f / (1.f - c.p_dec_dropout);
-        bp.lengths = nullptr; bp.barrier = w.barrier;
+        bp.lengths = nullptr; bp.abort_word = w.abort_word; bp.prof = prof_ptr(h, w, PROF_DEC_LSTM_BWD); bp.trace = trace_ptr(h, w, PROF_DEC_LSTM_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags;
         ProfScope ps(h, PROF_DEC_LSTM_BWD, st);
         MSA_TRY(launch_lstm_rec_bwd(bp, h->sm_count, h->smem_limit, st));
     }
@@ -747,7 +766,7 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
         bp.ga = w.ga; bp.ca = w.ca; bp.align = w.align_tm; bp.s = w.s; bp.znorm = w.znorm;
         bp.dha_ext = w.dha; bp.da_ext = w.da_ext;
         bp.dza = w.dza; bp.dq = w.dq; bp.de = w.de; bp.ds = w.ds; bp.dconvf = w.dconvf; bp.dat = w.dat;
-        bp.barrier = w.barrier;
+        bp.abort_word = w.abort_word; bp.prof = prof_ptr(h, w, PROF_ATTN_BWD); bp.trace = trace_ptr(h, w, PROF_ATTN_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags;
         ProfScope ps(h, PROF_ATTN_BWD, st);
         MSA_TRY(launch_attn_chain_bwd(bp, h->sm_count, h->smem_limit, st));
     }
@@ -777,7 +796,8 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
     MSA_TRY(k_dot_rows(w.de, nullptr, d.TBL, w.loss_part, G(at + "v.linear_layer.bias"), gs, acc, st));
     MSA_TRY(gemm(h, true, false, d.A, d.F, d.TBL, gs, w.ds, d.A, w.convf, d.F, beta,
                  G(at + "location_layer.location_dense.linear_layer.weight"), d.F));
-    MSA_TRY(k_wloc_grad(w.dconvf, w.align_tm, w.cum, G(at + "location_layer.location_conv1d.weight"), T, B, L, d.F, d.Kl, gs, acc, st));
+    MSA_TRY(k_wloc_grad(w.dconvf, w.align_tm, w.cum, G(at + "location_layer.location_conv1d.weight"), w.wloc_part, T, B, L, d.F, d.Kl, gs,
+                        acc, st));
     // ---- prenet backward (decoder.py:9-20) ----
     MSA_TRY(k_relu_drop_bwd(w.dxp, w.xpre, mk(iPre + 1), 2.f, nfr * d.Pd, st));
     MSA_TRY(gemm(h, true, false, d.Pd, d.Pd, nfr, gs, w.dxp, d.Pd, w.p1, d.Pd, beta, G("decoder.prenet.layers.1.linear_layer.weight"), d.Pd));
@@ -799,7 +819,7 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
         bp.whh = P("encoder.lstm.weight_hh_l0");
         bp.whh_dir_stride = h->off("encoder.lstm.weight_hh_l0_reverse") - h->off("encoder.lstm.weight_hh_l0");
         bp.gates = w.enc_g; bp.cout = w.enc_c; bp.dh_ext = w.denc_h; bp.dz = w.dzx; bp.mask = nullptr; bp.drop_scale = 1.f;
-        bp.lengths = h->tok_len; bp.barrier = w.barrier;
+        bp.lengths = h->tok_len; bp.abort_word = w.abort_word; bp.prof = prof_ptr(h, w, PROF_ENC_LSTM_BWD); bp.trace = trace_ptr(h, w, PROF_ENC_LSTM_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags;
         ProfScope ps(h, PROF_ENC_LSTM_BWD, st);
         MSA_TRY(launch_lstm_rec_bwd(bp, h->sm_count, h->smem_limit, st));
     }
@@ -833,6 +853,41 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
         dcur = dx;
     }
     MSA_TRY(k_embedding_bwd(dcur, h->tokens, G("embedding.weight"), (int)d.BL, d.C, c.n_symbols, gs, acc, st));
+    return 0;
+}
+
+int msa_check_abort(msa_handle* h, void* wsp, void* stream) {
+    MSA_CHECK(h && wsp && h->fwd_valid, MSA_E_STATE, "msa_check_abort: no forward pass in this workspace");
+    const Ws w = ws_layout(h->d, wsp);
+    unsigned int flag = 0;
+    MSA_CUDA(cudaMemcpyAsync(&flag, w.abort_word, sizeof(flag), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    MSA_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    MSA_CHECK(flag == 0, MSA_E_STATE, "a persistent kernel gave up waiting for data of another CTA (polling time-out): results are invalid");
+    return 0;
+}
+
+int msa_profile_trace(msa_handle* h, void* wsp, int id, int64_t* out, int ncta) {
+    MSA_CHECK(h && wsp && out && h->fwd_valid, MSA_E_STATE, "msa_profile_trace: no forward pass in this workspace");
+    MSA_CHECK(id >= 0 && id < PROF_N && ncta >= 1 && ncta <= 256, MSA_E_ARG, "msa_profile_trace: bad kernel id / cta count");
+    const Ws w = ws_layout(h->d, wsp);
+    MSA_CUDA(cudaDeviceSynchronize());
+    MSA_CUDA(cudaMemcpy(out, reinterpret_cast<const long long*>(w.trace) + (size_t)id * kTraceWordsPerKernel,
+                        sizeof(int64_t) * (size_t)ncta * 16 * 4 * 12 * 2, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int msa_profile_trace_step(msa_handle* h, int t0) {
+    MSA_CHECK(h, MSA_E_ARG, "msa_profile_trace_step: null handle");
+    h->trace_t0 = t0;
+    return 0;
+}
+
+int msa_profile_phases(msa_handle* h, void* wsp, int id, int64_t* out, int ncta) {
+    MSA_CHECK(h && wsp && out && h->fwd_valid, MSA_E_STATE, "msa_profile_phases: no forward pass in this workspace");
+    MSA_CHECK(id >= 0 && id < PROF_N && ncta >= 1 && ncta <= kProfCtas, MSA_E_ARG, "msa_profile_phases: bad kernel id / cta count");
+    const Ws w = ws_layout(h->d, wsp);
+    MSA_CUDA(cudaDeviceSynchronize());
+    MSA_CUDA(cudaMemcpy(out, reinterpret_cast<const long long*>(w.prof) + (size_t)id * kProfCtas * kProfSlots,
+                        sizeof(int64_t) * (size_t)ncta * kProfSlots, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -3,10 +3,14 @@
 // Work decomposition (forward): the 4H gate rows of an LSTMCell are split by HIDDEN UNIT across the
 // co-resident CTAs of a cooperative launch; CTA c owns units [u0,u1) and keeps the 4*(u1-u0) rows
 // of W_hh resident in shared memory (fp32) for all T steps.  Each step is a skinny mat-vec
-// (rows x K) . (K x B) from shared memory, the LSTM point-wise update for the owned units, a
-// store of the owned slice of h, and one grid barrier (the all-gather of h).
+// (rows x K) . (K x B) from shared memory, the LSTM point-wise update for the owned units and a
+// store of the owned slice of h into the per-step stash array, which the other CTAs poll (common.cuh).
 // Backward: CTA c owns the same units and keeps the matching COLUMNS of W_hh (i.e. rows of W_hh^T)
 // resident; dh_rec[u] = sum_r W_hh[r][u] * dz[r] is computed with each thread owning a slice of r.
+//
+// Everything in the step loop is written for LATENCY, not throughput: operands are zero-padded in shared
+// memory so that the inner loops have no bounds checks or divergent branches, all loads of a tile are issued
+// before the first FMA, reductions are warp-shuffle trees, and every phase spreads over all 512 threads.
 #pragma once
 #include "common.cuh"
 
@@ -14,30 +18,62 @@ namespace msa {
 
 constexpr int kRecThreads = 512;
 constexpr int kRecWarps = kRecThreads / 32;
-constexpr int kUMax = 8;  // max hidden units per CTA (=> 32 gate rows, one transpose-reduce)
+constexpr int kUMax = 8;        // max hidden units per CTA (=> 32 gate rows, one transpose-reduce)
+constexpr int kBMax = 16;       // max batch rows of one pass through the recurrent kernels
+constexpr int kBTiles = kBMax / 4;
 
-struct LstmPoint {
-    float i, f, g, o, c, h;
+__host__ __device__ inline int round_up_i(int n, int m) { return (n + m - 1) / m * m; }
+
+// Development instrumentation (profiles/): off unless a buffer is passed.
+//   prof : [grid][8]  cycles per phase summed over the steps, thread 0 of each CTA (accumulated in global memory so that it costs
+//          no registers in the production path)
+//   trace: [grid][kRecWarps][kTraceSteps][kTraceTags][2]  {clock64, globaltimer} of lane 0 of every warp at every mark of the
+//          steps [trace_t0, trace_t0 + kTraceSteps)
+constexpr int kProfSlots = 8, kTraceSteps = 4, kTraceTags = 12;
+struct ChainProf {
+    long long* out;
+    long long* trace;
+    long long last;
+    int t0;
+    __device__ __forceinline__ void start(long long* prof_buf, long long* trace_buf, int trace_t0) {
+        out = threadIdx.x == 0 ? prof_buf : nullptr;
+        trace = (threadIdx.x & 31) == 0 ? trace_buf : nullptr;
+        t0 = trace_t0;
+        if (out) {
+            for (int i = 0; i < kProfSlots; ++i) out[(size_t)blockIdx.x * kProfSlots + i] = 0;
+            last = clock64();
+        }
+    }
+    __device__ __forceinline__ void mark(int i, int step) {
+        if (out) {
+            const long long c = clock64();
+            out[(size_t)blockIdx.x * kProfSlots + i] += c - last;
+            last = c;
+        }
+        if (trace && step >= t0 && step < t0 + kTraceSteps) {
+            unsigned long long gt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            long long* e = trace + ((((size_t)blockIdx.x * kRecWarps + (threadIdx.x >> 5)) * kTraceSteps + (step - t0)) * kTraceTags + i) * 2;
+            e[0] = clock64();
+            e[1] = (long long)gt;
+        }
+    }
 };
-__device__ __forceinline__ LstmPoint lstm_point_fwd(float zi, float zf, float zg, float zo, float cprev) {
-    LstmPoint r;
-    r.i = sigmoidf_(zi);
-    r.f = sigmoidf_(zf);
-    r.g = tanhf(zg);
-    r.o = sigmoidf_(zo);
-    r.c = r.f * cprev + r.i * r.g;
-    r.h = r.o * tanhf(r.c);
-    return r;
-}
-// dh: grad w.r.t. the (pre-dropout) hidden output; dc_in: grad carried from the later step.
-// Returns gate pre-activation grads and the carry for the earlier step.
+
+// exp2-based activations (ex2.approx + fast division): absolute error ~1e-7, far inside the fp32 parity tolerance,
+// and a fraction of the dependent-instruction latency of expf/tanhf on the per-step critical path
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+
 struct LstmGrad {
     float di, df, dg, do_, dc_prev;
 };
+// dh: grad w.r.t. the (pre-dropout) hidden output; dc_in: grad carried from the later step.
+// Returns gate pre-activation grads and the carry for the earlier step.
 __device__ __forceinline__ LstmGrad lstm_point_bwd(float i, float f, float g, float o, float c, float cprev, float dh,
                                                    float dc_in) {
     LstmGrad r;
-    const float tc = tanhf(c);
+    const float tc = fast_tanh(c);
     r.do_ = dh * tc * o * (1.f - o);
     const float dc = dc_in + dh * o * (1.f - tc * tc);
     r.di = dc * g * i * (1.f - i);
@@ -50,133 +86,269 @@ __device__ __forceinline__ LstmGrad lstm_point_bwd(float i, float f, float g, fl
 // Balanced partition of n items over parts: [lo, hi) of part i.
 __device__ __host__ __forceinline__ int part_lo(int i, int n, int parts) { return (int)(((long long)i * n) / parts); }
 
-// zs[rl*BP + b] = sum_k Wsm[rl*K + k] * hs[b*K + k]  (+ sum_l MW[row(rl)*mw_stride + b*L + l] * as[b*L + l] if HAS_MW)
-// for rl < R (R <= 32... any R <= 8*warps), b < B.  All threads of the CTA must call (contains __syncthreads).
-// K % 4 == 0, Wsm/hs 16-byte aligned rows.  `part` scratch: kRecWarps*32 floats.
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+
+// ---- forward mat-vec ------------------------------------------------------------------------------------------------
+// part[((tile*KS + ks)*RG + rg)*32 + rr*4 + bl] = partial over the K-range of warp (rg, ks) of
+//     sum_k Wsm[(rg*8+rr)*KP + k] * hs[(tile*4+bl)*KP + k]  (+ sum_l MWs[((rg*8+rr)*B + b)*LP + l] * as[b*LP + l] if HAS_MW)
+// Wsm [RG*8][KP] and hs [BP][KP] are zero-padded (KP % 128 == 0, BP % 4 == 0); MWs rows are zero for padded gate rows and
+// as/MWs are zero-padded to LP % 4 == 0.  RG = ceil(rows/8), KS = kRecWarps / RG.  No __syncthreads inside: the caller
+// synchronises once and then sums the KS partials of each output (lstm_gate_sum).
 template <bool HAS_MW>
-__device__ __forceinline__ void cta_matvec_fwd(const float* __restrict__ Wsm, int R, int K, const float* __restrict__ hs,
-                                               const float* __restrict__ MW, int mw_stride, int mw_gs, int mw_u0, int L,
-                                               const float* __restrict__ as, int B, float* part, float* zs, int BP) {
+__device__ __forceinline__ void cta_matvec_fwd(const float* __restrict__ Wsm, int RG, int KP, const float* __restrict__ hs,
+                                               const float* __restrict__ MWs, int LP, const float* __restrict__ as_, int B,
+                                               float* __restrict__ part) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int RG = (R + 7) >> 3;
-    const int KS = RG > 0 ? kRecWarps / RG : 0;
-    const int rg = RG > 0 ? w % RG : 0, ks = RG > 0 ? w / RG : 0;
-    const int KCh = (K + 127) >> 7;
-    const int KCl = HAS_MW ? ((L + 31) >> 5) : 0;
-    for (int bt = 0; bt < B; bt += 4) {
+    const int KS = kRecWarps / RG;
+    const int rg = w % RG, ks = w / RG;
+    if (ks >= KS) return;
+    const int KP4 = KP >> 2, LP4 = LP >> 2;
+    const int nK = KP >> 7;
+    const int nLc = HAS_MW ? (LP + 127) >> 7 : 0;
+    const float4* W4 = reinterpret_cast<const float4*>(Wsm) + (size_t)(rg * 8) * KP4;
+    const float4* h4p = reinterpret_cast<const float4*>(hs);
+    const int ntile = (B + 3) >> 2;
+    for (int tile = 0; tile < ntile; ++tile) {
         float acc[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-        if (ks < KS) {
-            for (int j = ks; j < KCh + KCl; j += KS) {
-                if (j < KCh) {
-                    const int k = (j << 7) + (lane << 2);
-                    if (k < K) {
-                        float4 h4[4];
+        for (int j = ks; j < nK + 4 * nLc; j += KS) {
+            if (j < nK) {
+                const int c4 = j * 32 + lane;
+                float4 h4[4], w4[8];
 #pragma unroll
-                        for (int b = 0; b < 4; ++b)
-                            h4[b] = (bt + b < B) ? *reinterpret_cast<const float4*>(hs + (size_t)(bt + b) * K + k)
-                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int b = 0; b < 4; ++b) h4[b] = h4p[(size_t)(tile * 4 + b) * KP4 + c4];
 #pragma unroll
-                        for (int rr = 0; rr < 8; ++rr) {
-                            const int rl = rg * 8 + rr;
-                            if (rl < R) {
-                                const float4 w4 = *reinterpret_cast<const float4*>(Wsm + (size_t)rl * K + k);
+                for (int rr = 0; rr < 8; ++rr) w4[rr] = W4[(size_t)rr * KP4 + c4];
 #pragma unroll
-                                for (int b = 0; b < 4; ++b)
-                                    acc[rr * 4 + b] += w4.x * h4[b].x + w4.y * h4[b].y + w4.z * h4[b].z + w4.w * h4[b].w;
-                            }
-                        }
-                    }
-                } else if (HAS_MW) {
-                    const int l = ((j - KCh) << 5) + lane;
-                    if (l < L) {
-                        float a4[4];
+                for (int rr = 0; rr < 8; ++rr)
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) a4[b] = (bt + b < B) ? as[(bt + b) * L + l] : 0.f;
+                    for (int b = 0; b < 4; ++b) acc[rr * 4 + b] += dot4(w4[rr], h4[b]);
+            } else if (HAS_MW) {
+                const int m = j - nK, bl = m & 3, lc = m >> 2, b = tile * 4 + bl;
+                const int l4 = lc * 32 + lane;
+                float tmp[8];
 #pragma unroll
-                        for (int rr = 0; rr < 8; ++rr) {
-                            const int rl = rg * 8 + rr;
-                            if (rl < R) {
-                                // resident slice: local row order; global fallback: gate-major rows of the full matrix
-                                const int mrow = mw_gs ? ((rl & 3) * mw_gs + mw_u0 + (rl >> 2)) : rl;
+                for (int rr = 0; rr < 8; ++rr) tmp[rr] = 0.f;
+                if (b < B && l4 < LP4) {
+                    const float4 a4 = reinterpret_cast<const float4*>(as_)[(size_t)b * LP4 + l4];
+                    float4 m4[8];
 #pragma unroll
-                                for (int b = 0; b < 4; ++b)
-                                    if (bt + b < B) acc[rr * 4 + b] += MW[(size_t)mrow * mw_stride + (bt + b) * L + l] * a4[b];
-                            }
-                        }
-                    }
+                    for (int rr = 0; rr < 8; ++rr)
+                        m4[rr] = reinterpret_cast<const float4*>(MWs)[((size_t)(rg * 8 + rr) * B + b) * LP4 + l4];
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) tmp[rr] = dot4(m4[rr], a4);
                 }
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb)
+                    if (bl == bb) {
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr) acc[rr * 4 + bb] += tmp[rr];
+                    }
             }
         }
         const float tot = warp_transpose_reduce32(acc);
-        if (ks < KS) part[(ks * RG + rg) * 32 + lane] = tot;
-        __syncthreads();
-        if ((int)threadIdx.x < R * 4) {
-            const int rl = threadIdx.x >> 2, b = threadIdx.x & 3;
-            const int rg2 = rl >> 3, idx = (rl & 7) * 4 + b;
-            float s = 0.f;
-            for (int q = 0; q < KS; ++q) s += part[(q * RG + rg2) * 32 + idx];
-            if (bt + b < B) zs[rl * BP + bt + b] = s;
+        part[((size_t)(tile * KS + ks) * RG + rg) * 32 + lane] = tot;
+    }
+}
+// pre-activation of gate row rl (local row index) for batch row b: sum of the KS partials
+__device__ __forceinline__ float lstm_gate_sum(const float* part, int RG, int rl, int b) {
+    const int KS = kRecWarps / RG;
+    const float* p = part + ((size_t)((b >> 2) * KS) * RG + (rl >> 3)) * 32 + (rl & 7) * 4 + (b & 3);
+    float s = 0.f;
+    for (int q = 0; q < KS; ++q) s += p[(size_t)q * RG * 32];
+    return s;
+}
+
+// Copy rows x n4 float4 words that OTHER CTAs publish during this launch (canary-polled, common.cuh) from global
+// (row stride n4 float4) to shared (row stride dst_stride4 float4).  All loads of a thread are issued before the first
+// one is checked (memory-level parallelism while spinning).
+__device__ __forceinline__ void poll_copy_rows(float* dst_smem, int dst_stride4, const float* src, int rows, int n4, SpinGuard& sg) {
+    constexpr int kBatch = 4;
+    const int total = rows * n4;
+    for (int base = threadIdx.x; base < total; base += kBatch * kRecThreads) {
+        float4 v[kBatch];
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+            const int idx = base + j * kRecThreads;
+            if (idx < total) v[j] = ld_poll4(src + (size_t)idx * 4);
         }
-        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+            const int idx = base + j * kRecThreads;
+            if (idx < total) {
+                sg.reset();
+                while (!ready4(v[j])) {
+                    if (sg.bail()) break;
+                    v[j] = ld_poll4(src + (size_t)idx * 4);
+                }
+                const int r = idx / n4, c = idx - r * n4;
+                reinterpret_cast<float4*>(dst_smem)[(size_t)r * dst_stride4 + c] = v[j];
+            }
+        }
     }
 }
 
-// Backward recurrent term for the owned units:
-//   out[ul*BP + b] = sum_r WT[ul*R4 + r] * dz[b*R4 + r],  ul < U (<= 8), b < B, r < R4 (= 4H, multiple of 4)
-// dz lives in global memory, written by other CTAs in the previous step (read through L2).
-// If npairs > 0 also computes pair_out[i] = sum_r MWp[(pair0+i)*R4 + r] * dz[b_i*R4 + r] with b_i = (pair0+i)/L.
-// All threads must call.  `part` scratch: kRecWarps*32 floats, `red` scratch 33 floats.
-__device__ __forceinline__ void cta_matvec_bwd(const float* __restrict__ WT, int U, int R4, const float* dz, int B,
-                                               float* part, float* out, int BP, const float* __restrict__ MWp,
-                                               int pair0, int npairs, int L, float* pair_out, float* red) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int nchunk = R4 >> 2;
-    for (int bt = 0; bt < B; bt += 4) {
-        float acc[32];
+// ---- gated hand-offs ------------------------------------------------------------------------------------------------
+// Spinning on not-yet-written data with all 512 threads of all 148 CTAs saturates the L2 request bandwidth and delays the
+// very stores everybody is waiting for.  So only WARP 0 of a CTA spins; the other warps park at the following
+// __syncthreads (no memory traffic).  Small gathers (energies, queries, d a, dq) are fetched whole by warp 0; for the large
+// ones (h, dz) warp 0 waits for one sentinel word per producer CTA -- the last word that producer stores -- and then all
+// threads fetch the bulk once (still canary-checked word by word: the sentinel is a hint, never the correctness argument).
+template <class AddrFn>
+__device__ __forceinline__ void gate_wait(int n, AddrFn addr, SpinGuard& sg) {
+    if (threadIdx.x >= 32) return;
+    constexpr int kBatch = 8;
+    for (int base = 0; base < n; base += 32 * kBatch) {
+        float v[kBatch];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-        for (int ch = threadIdx.x; ch < nchunk; ch += kRecThreads) {
-            const int r = ch << 2;
-            float4 d4[4];
+        for (int j = 0; j < kBatch; ++j) {
+            const int i = base + j * 32 + threadIdx.x;
+            v[j] = 0.f;
+            if (i < n) {
+                const float* a = addr(i);
+                if (a) v[j] = ld_poll(a);
+            }
+        }
 #pragma unroll
-            for (int b = 0; b < 4; ++b)
-                d4[b] = (bt + b < B) ? ld_cg4(dz + (size_t)(bt + b) * R4 + r) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int ul = 0; ul < kUMax; ++ul) {
-                if (ul < U) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(WT + (size_t)ul * R4 + r);
-#pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        acc[ul * 4 + b] += w4.x * d4[b].x + w4.y * d4[b].y + w4.z * d4[b].z + w4.w * d4[b].w;
+        for (int j = 0; j < kBatch; ++j) {
+            const int i = base + j * 32 + threadIdx.x;
+            if (i < n) {
+                const float* a = addr(i);
+                sg.reset();
+                while (a && is_canary(v[j])) {
+                    if (sg.bail()) break;
+                    v[j] = ld_poll(a);
                 }
             }
         }
-        const float tot = warp_transpose_reduce32(acc);
-        part[w * 32 + lane] = tot;
-        __syncthreads();
-        if ((int)threadIdx.x < U * 4) {
-            const int ul = threadIdx.x >> 2, b = threadIdx.x & 3;
-            float s = 0.f;
-            for (int q = 0; q < kRecWarps; ++q) s += part[q * 32 + ul * 4 + b];
-            if (bt + b < B) out[ul * BP + bt + b] = s;
-        }
-        __syncthreads();
     }
-    for (int i = 0; i < npairs; ++i) {
-        const int p = pair0 + i, b = p / L;
-        float s = 0.f;
-        for (int ch = threadIdx.x; ch < nchunk; ch += kRecThreads) {
-            const int r = ch << 2;
-            const float4 d = ld_cg4(dz + (size_t)b * R4 + r);
-            const float4 m = __ldg(reinterpret_cast<const float4*>(MWp + (size_t)p * R4 + r));
-            s += m.x * d.x + m.y * d.y + m.z * d.z + m.w * d.w;
+}
+// warp 0 copies n words that other CTAs publish during this launch from global to shared, polling each word
+__device__ __forceinline__ void gather_small(float* dst_smem, const float* src, int n, SpinGuard& sg) {
+    if (threadIdx.x >= 32) return;
+    constexpr int kBatch = 8;
+    for (int base = 0; base < n; base += 32 * kBatch) {
+        float v[kBatch];
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+            const int i = base + j * 32 + threadIdx.x;
+            if (i < n) v[j] = ld_poll(src + i);
         }
-        s = block_sum(s, red);
-        if (threadIdx.x == 0) pair_out[i] = s;
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+            const int i = base + j * 32 + threadIdx.x;
+            if (i < n) {
+                sg.reset();
+                while (is_canary(v[j])) {
+                    if (sg.bail()) break;
+                    v[j] = ld_poll(src + i);
+                }
+                dst_smem[i] = v[j];
+            }
+        }
     }
-    __syncthreads();
+}
+
+// n words published by other CTAs -> shared: by warp 0 alone (the others park at the caller's barrier) or by all threads
+__device__ __forceinline__ void gather_words(float* dst_smem, const float* src, int n, bool warp0_only, SpinGuard& sg) {
+    if (warp0_only) {
+        gather_small(dst_smem, src, n, sg);
+    } else {
+        for (int i = threadIdx.x; i < n; i += kRecThreads) dst_smem[i] = poll1(src + i, sg);
+    }
+}
+constexpr int kFlagGate = 1;    // large gathers: warp 0 waits for one sentinel per producer before the bulk fetch
+constexpr int kFlagWarp0 = 2;   // small gathers: by warp 0 only
+
+constexpr int kPairMax = 4;   // (b,l) positions per CTA whose context-path dot product rides along the backward mat-vec
+
+// ---- backward mat-vec -----------------------------------------------------------------------------------------------
+//   out[ul*BP + b] = sum_r WT[ul*R4 + r] * dz[b*R4 + r],  ul < 8 (rows of WT beyond the owned units are zero), b < B
+// dz lives in global memory and is being published by the other CTAs (canary-polled).
+// If npairs > 0 also computes pair_out[i] = sum_r MWp[i*mwp_stride + r] * dz[b_i*R4 + r] with b_i = (pair0+i)/L
+// (MWp = rows pair0.. of the [B*L][R4] matrix, resident in shared memory or in global memory).
+// All threads must call.  `part` scratch: kRecWarps*32 floats, `red` scratch: kRecWarps*kPairMax floats.
+__device__ __forceinline__ void cta_matvec_bwd(const float* __restrict__ WT, int R4, const float* dz, int B, float* part,
+                                               float* out, int BP, const float* __restrict__ MWp, size_t mwp_stride, int pair0,
+                                               int npairs, int L, float* pair_out, float* red, SpinGuard& sg) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nchunk = R4 >> 2;
+    for (int pbase = 0; pbase == 0 || pbase < npairs; pbase += kPairMax) {
+        float accp[kPairMax];
+#pragma unroll
+        for (int i = 0; i < kPairMax; ++i) accp[i] = 0.f;
+        int pb[kPairMax];
+#pragma unroll
+        for (int i = 0; i < kPairMax; ++i) pb[i] = pbase + i < npairs ? (pair0 + pbase + i) / L : -1;
+        for (int bt = 0; bt < B; bt += 4) {
+            float acc[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+            for (int ch = threadIdx.x; ch < nchunk; ch += kRecThreads) {
+                const int r = ch << 2;
+                float4 d4[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    d4[b] = (bt + b < B) ? ld_poll4(dz + (size_t)(bt + b) * R4 + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    if (bt + b < B) {
+                        sg.reset();
+                        while (!ready4(d4[b])) {
+                            if (sg.bail()) break;
+                            d4[b] = ld_poll4(dz + (size_t)(bt + b) * R4 + r);
+                        }
+                    }
+                }
+                if (pbase == 0) {
+                    float4 w4[kUMax];
+#pragma unroll
+                    for (int ul = 0; ul < kUMax; ++ul) w4[ul] = *reinterpret_cast<const float4*>(WT + (size_t)ul * R4 + r);
+#pragma unroll
+                    for (int ul = 0; ul < kUMax; ++ul)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) acc[ul * 4 + b] += dot4(w4[ul], d4[b]);
+                }
+#pragma unroll
+                for (int i = 0; i < kPairMax; ++i) {
+                    const int bi = pb[i] - bt;
+                    if (pb[i] >= 0 && bi >= 0 && bi < 4) {
+                        const float4 m = *reinterpret_cast<const float4*>(MWp + (size_t)(pbase + i) * mwp_stride + r);
+                        const float4 d = bi == 0 ? d4[0] : (bi == 1 ? d4[1] : (bi == 2 ? d4[2] : d4[3]));
+                        accp[i] += dot4(m, d);
+                    }
+                }
+            }
+            if (pbase == 0) {
+                const float tot = warp_transpose_reduce32(acc);
+                part[w * 32 + lane] = tot;
+                __syncthreads();
+                if ((int)threadIdx.x < 32) {
+                    const int ul = threadIdx.x >> 2, b = threadIdx.x & 3;
+                    float s = 0.f;
+#pragma unroll
+                    for (int q = 0; q < kRecWarps; ++q) s += part[q * 32 + threadIdx.x];
+                    if (bt + b < B) out[ul * BP + bt + b] = s;
+                }
+                __syncthreads();
+            }
+        }
+        if (npairs > 0) {
+#pragma unroll
+            for (int i = 0; i < kPairMax; ++i) {
+                const float s = warp_sum(accp[i]);
+                if (lane == 0) red[w * kPairMax + i] = s;
+            }
+            __syncthreads();
+            if ((int)threadIdx.x < kPairMax && pbase + (int)threadIdx.x < npairs) {
+                float s = 0.f;
+                for (int q = 0; q < kRecWarps; ++q) s += red[q * kPairMax + threadIdx.x];
+                pair_out[pbase + threadIdx.x] = s;
+            }
+            __syncthreads();
+        }
+    }
 }
 
 }  // namespace msa

@@ -258,6 +258,29 @@ class Engine:
     def profile(self, enable: bool) -> None:
         _lib.check(self.lib.msa_profile_enable(self.h, int(enable)), "msa_profile_enable")
 
+    def check_abort(self) -> None:
+        """Raise if a persistent kernel of the last passes timed out while polling (synchronises)."""
+        _lib.check(self.lib.msa_check_abort(self.h, self._ws_ptr(), _stream()), "msa_check_abort")
+
+    def profile_phases(self, name: str):
+        """[ncta][8] cycles per phase of persistent kernel `name` in the last profiled pass (profiles only)."""
+        n = self.lib.msa_profile_kernels()
+        ids = {self.lib.msa_profile_name(i).decode(): i for i in range(n)}
+        ncta = self.lib.msa_sm_count(self.h)
+        out = (C.c_int64 * (ncta * 8))()
+        _lib.check(self.lib.msa_profile_phases(self.h, self._ws_ptr(), ids[name], out, ncta), "msa_profile_phases")
+        return [[out[i * 8 + j] for j in range(8)] for i in range(ncta)]
+
+    def profile_trace(self, name: str):
+        """numpy [ncta][16][4][12][2] int64 {SM clock, globaltimer ns} of the traced steps (profiles only)."""
+        import numpy as np
+        n = self.lib.msa_profile_kernels()
+        ids = {self.lib.msa_profile_name(i).decode(): i for i in range(n)}
+        ncta = self.lib.msa_sm_count(self.h)
+        out = (C.c_int64 * (ncta * 16 * 4 * 12 * 2))()
+        _lib.check(self.lib.msa_profile_trace(self.h, self._ws_ptr(), ids[name], out, ncta), "msa_profile_trace")
+        return np.ctypeslib.as_array(out).reshape(ncta, 16, 4, 12, 2).copy()
+
     def profile_read(self) -> dict:
         n = self.lib.msa_profile_kernels()
         ms, cnt = (C.c_double * n)(), (C.c_int64 * n)()

@@ -54,6 +54,7 @@ def cuda_pass(eng, cfg, P, batch, masks, backward=True):
         eng.backward(flat, gflat, accumulate=False, scale=1.0)
         grads = {k: v.clone() for k, v in eng.dict_from_flat(gflat).items()}
     torch.cuda.synchronize()
+    eng.check_abort()      # a persistent kernel that timed out while polling invalidates everything
     return out, loss, grads, eng.bn_dict(bn)
 
 
