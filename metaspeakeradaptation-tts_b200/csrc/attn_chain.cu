@@ -24,8 +24,12 @@
 
 namespace msa {
 
+// 256 threads per CTA: with 512 the 128-register cap makes the compiler spill the per-thread LSTM state, and every spill
+// reload sits on the critical path of a step; everything here is latency-bound, not issue-bound
+constexpr int kAttnThreads = 256;
+
 struct AttnSmemFwd {
-    size_t wsm, mws, hs, as_, ah, es, qs, part, wqs, wloc, wldT, vs, pm, pre, ctr, cf, total;
+    size_t wsm, mws, hs, as_, ah, es, qs, part, part2, zm, wqs, wloc, wldT, vs, pm, pre, ctr, cf, total;
     int KP, BP, LP, LH, CKP;
 };
 __host__ __device__ inline AttnSmemFwd attn_fwd_layout(int B, int L, int Ha, int A, int F, int Kl, int ncta, bool mw_res) {
@@ -45,7 +49,10 @@ __host__ __device__ inline AttnSmemFwd attn_fwd_layout(int B, int L, int Ha, int
     s.ah = take((size_t)2 * B * s.LH);
     s.es = take((size_t)B * L);
     s.qs = take((size_t)B * A);
-    s.part = take((size_t)kBTiles * kRecWarps * 32);
+    const int ntile = (B + 3) >> 2;
+    s.part = take((size_t)ntile * kRecWarps * 32);
+    s.part2 = take((size_t)ntile * kRecWarps * 32);
+    s.zm = take((size_t)4 * kUMax * s.BP);
     s.wqs = take((size_t)nd_max * s.KP);
     s.wloc = take((size_t)F * s.CKP);
     s.wldT = take((size_t)F * A);
@@ -58,7 +65,9 @@ __host__ __device__ inline AttnSmemFwd attn_fwd_layout(int B, int L, int Ha, int
     return s;
 }
 
-__global__ void __launch_bounds__(kRecThreads, 1) k_attn_chain_fwd(AttnChainParams p, int mw_res) {
+template <bool kProf, int NT>
+__global__ void __launch_bounds__(NT, 1) k_attn_chain_fwd(AttnChainParams p, int mw_res) {
+    constexpr int NW = NT / 32;
     extern __shared__ __align__(16) float smem[];
     __shared__ float zn_s[kBMax];
     const int T = p.T, B = p.B, L = p.L, Ha = p.Ha, A = p.A, F = p.F, Kl = p.Kl, H4 = 4 * Ha;
@@ -74,7 +83,9 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_attn_chain_fwd(AttnChainPara
     float* ah = smem + lay.ah;         // [2][B][LH]     a(t-1) and cum(t-1) with a zero halo of pl on both sides (conv input)
     float* es = smem + lay.es;
     float* q_s = smem + lay.qs;
-    float* part = smem + lay.part;
+    float* part = smem + lay.part;     // W_hh . h_a'(t-1), first / second half of the K range (computed in the shadow
+    float* part2 = smem + lay.part2;   //   of the q and e hand-offs of step t-1)
+    float* zm = smem + lay.zm;         // [RG*8][BP] context term MW . a(t-1)
     float* wqs = smem + lay.wqs;
     float* wloc_s = smem + lay.wloc;   // [F][CKP]
     float* wldT = smem + lay.wldT;     // [F][A]
@@ -90,36 +101,36 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_attn_chain_fwd(AttnChainPara
     const int d0 = part_lo(cta, A, ncta), d1 = part_lo(cta + 1, A, ncta), nd = d1 - d0;
 
     // ---- one-time staging of the resident operands ----
-    for (int idx = threadIdx.x; idx < RG * 8 * KP4; idx += kRecThreads) {
+    for (int idx = threadIdx.x; idx < RG * 8 * KP4; idx += NT) {
         const int rl = idx / KP4, k4 = idx % KP4, g = rl & 3, ul = rl >> 2;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (rl < R && k4 < (Ha >> 2)) v = __ldg(reinterpret_cast<const float4*>(p.whh + (size_t)(g * Ha + u0 + ul) * Ha) + k4);
         reinterpret_cast<float4*>(Wsm)[idx] = v;
     }
     if (mw_res) {
-        for (int idx = threadIdx.x; idx < RG * 8 * B * LP; idx += kRecThreads) {
+        for (int idx = threadIdx.x; idx < RG * 8 * B * LP; idx += NT) {
             const int rl = idx / (B * LP), j = idx % (B * LP), b = j / LP, l = j % LP, g = rl & 3, ul = rl >> 2;
             MWs[idx] = (rl < R && l < L) ? __ldg(p.mw_rm + (size_t)(g * Ha + u0 + ul) * BL + b * L + l) : 0.f;
         }
     }
-    for (int idx = threadIdx.x; idx < nd * KP; idx += kRecThreads) {
+    for (int idx = threadIdx.x; idx < nd * KP; idx += NT) {
         const int di = idx / KP, k = idx % KP;
         wqs[idx] = k < Ha ? __ldg(p.wq + (size_t)(d0 + di) * Ha + k) : 0.f;
     }
-    for (int idx = threadIdx.x; idx < F * 2 * Kl; idx += kRecThreads) {
+    for (int idx = threadIdx.x; idx < F * 2 * Kl; idx += NT) {
         const int f = idx / (2 * Kl), ck = idx % (2 * Kl);          // wloc[f][c][k] -> wloc_s[f][c*Kl+k]
         wloc_s[f * CKP + ck] = __ldg(p.wloc + idx);
     }
-    for (int idx = threadIdx.x; idx < A * F; idx += kRecThreads) {
+    for (int idx = threadIdx.x; idx < A * F; idx += NT) {
         const int d = idx / F, f = idx % F;                          // wld[d][f] -> wldT[f][d]
         wldT[f * A + d] = __ldg(p.wld + idx);
     }
-    for (int idx = threadIdx.x; idx < A; idx += kRecThreads) vs[idx] = __ldg(p.v + idx);
-    for (int idx = threadIdx.x; idx < np * A; idx += kRecThreads) pm_s[idx] = __ldg(p.pm + (size_t)p0 * A + idx);
-    for (int idx = threadIdx.x; idx < B * LP; idx += kRecThreads) as_[idx] = 0.f;
-    for (int idx = threadIdx.x; idx < 2 * B * LH; idx += kRecThreads) ah[idx] = 0.f;
-    for (int idx = threadIdx.x; idx < lay.BP * KP; idx += kRecThreads) hs[idx] = 0.f;
-    for (int i = threadIdx.x; i < np; i += kRecThreads) p.cum[p0 + i] = 0.f;       // cum fed to the conv at t = 0
+    for (int idx = threadIdx.x; idx < A; idx += NT) vs[idx] = __ldg(p.v + idx);
+    for (int idx = threadIdx.x; idx < np * A; idx += NT) pm_s[idx] = __ldg(p.pm + (size_t)p0 * A + idx);
+    for (int idx = threadIdx.x; idx < B * LP; idx += NT) as_[idx] = 0.f;
+    for (int idx = threadIdx.x; idx < 2 * B * LH; idx += NT) ah[idx] = 0.f;
+    for (int idx = threadIdx.x; idx < lay.BP * KP; idx += NT) hs[idx] = 0.f;
+    for (int i = threadIdx.x; i < np; i += NT) p.cum[p0 + i] = 0.f;       // cum fed to the conv at t = 0
     const float bv = __ldg(p.bv);
 
     // point-wise role of the LSTM: 4 lanes per cell (ul, b), lane g evaluates gate g; streaming inputs fetched one step ahead
@@ -134,27 +145,29 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_attn_chain_fwd(AttnChainPara
     };
     if (pw) fetch(0);
     SpinGuard sg(p.abort_word);
-    ChainProf prof;
+    ChainProf<kProf> prof;
     prof.start(p.prof, p.trace, p.trace_t0);
     __syncthreads();
 
+    // Step schedule (critical path in CAPITALS, everything else runs in the shadow of a hand-off):
+    //   CONTEXT TERM MW.a(t-1) -> POINT-WISE -> publish h(t) | location features of step t | GATHER h(t) -> Q -> publish q(t)
+    //   | first half of W_hh.h(t) | GATHER q(t) -> ENERGIES -> publish e(t) | second half of W_hh.h(t) | GATHER e(t) -> SOFTMAX
+    const int nK = KP >> 7, nKh = (nK + 1) >> 1, BPz = lay.BP;
+    for (int idx = threadIdx.x; idx < ((B + 3) >> 2) * kRecWarps * 32; idx += NT) { part[idx] = 0.f; part2[idx] = 0.f; }
+    __syncthreads();
     for (int t = 0; t < T; ++t) {
         // ---- phase 1: attention LSTMCell for the owned units (decoder.py:253-256); publishes h_a'(t) ----
         if (U > 0) {
-            if (mw_res) cta_matvec_fwd<true>(Wsm, RG, KP, hs, MWs, LP, as_, B, part);
-            else cta_matvec_fwd<false>(Wsm, RG, KP, hs, nullptr, 0, nullptr, B, part);
+            if (mw_res) cta_context_term<NT>(MWs, as_, R, B, BPz, LP, zm);
+            else cta_context_term_global<NT>(p.mw_rm, [&](int rl) { return (rl & 3) * Ha + u0 + (rl >> 2); }, as_, R, B, BPz, L, LP, zm);
         }
         prof.mark(0, t);
         __syncthreads();
         if (pw) {
             const size_t zb = ((size_t)t * B + pb) * H4;
-            float z = lstm_gate_sum(part, RG, ul * 4 + g, pb) + xz;
-            if (!mw_res) {   // context term from global memory (text too long for the resident slice)
-                const float* mrow = p.mw_rm + (size_t)(g * Ha + u) * BL + pb * L;
-                float zc = 0.f;
-                for (int l = 0; l < L; ++l) zc += __ldg(mrow + l) * as_[pb * LP + l];
-                z += zc;
-            }
+            const int rl = ul * 4 + g;
+            float z = lstm_gate_sum<NT>(part, RG, rl, pb) + lstm_gate_sum<NT>(part2, RG, rl, pb) + xz;
+            z += zm[rl * BPz + pb];
             const float act = g == 2 ? fast_tanh(z) : fast_sigmoid(z);
             const unsigned int gm = 0xFu << (threadIdx.x & 28);
             const float ai = __shfl_sync(gm, act, 0, 4), af = __shfl_sync(gm, act, 1, 4);
@@ -173,7 +186,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_attn_chain_fwd(AttnChainPara
         prof.mark(1, t);
         // ---- phase 1a: location features of the owned (b,l) positions (forward_attn.py:121-127); overlaps the h hand-off ----
         // conv: item (pi, f, ks) sums taps ck = ks, ks+8, ... ; 8 consecutive lanes share (pi, f)
-        for (int base = 0; base < np * F * 8; base += kRecThreads) {     // warp-uniform trip count (full-mask shuffles inside)
+        for (int base = 0; base < np * F * 8; base += NT) {     // warp-uniform trip count (full-mask shuffles inside)
             const int it = base + threadIdx.x;
             const bool valid = it < np * F * 8;
             const int ks = it & 7, f = valid ? (it >> 3) % F : 0, pi = valid ? (it >> 3) / F : 0;
@@ -194,7 +207,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_attn_chain_fwd(AttnChainPara
         }
         prof.mark(2, t);
         __syncthreads();
-        for (int it = threadIdx.x; it < np * A; it += kRecThreads) {
+        for (int it = threadIdx.x; it < np * A; it += NT) {
             const int pi = it / A, d = it - pi * A;
             float l0 = 0.f, l1 = 0.f;
             int f = 0;
@@ -206,17 +219,17 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_attn_chain_fwd(AttnChainPara
             pre_s[it] = l0 + l1 + pm_s[it];
         }
         prof.mark(3, t);
-        // ---- hand-off 1: all of h_a'(t) -> shared (operand of q now and of the mat-vec at t+1) ----
+        // ---- hand-off 1: all of h_a'(t) -> shared (operand of q now and of the mat-vec for step t+1) ----
         if (p.flags & kFlagGate) {
             const float* hrow = p.ha + ((size_t)t * B + (B - 1)) * Ha;
             gate_wait(ncta, [&](int c) { const int e = part_lo(c + 1, Ha, ncta); return e > 0 ? hrow + e - 1 : nullptr; }, sg);
             __syncthreads();
         }
-        poll_copy_rows(hs, KP4, p.ha + (size_t)t * B * Ha, B, Ha >> 2, sg);
+        poll_copy_rows<NT>(hs, KP4, p.ha + (size_t)t * B * Ha, B, Ha >> 2, sg);
         prof.mark(4, t);
         __syncthreads();
         // ---- phase 2: query projection for the owned attention dims (forward_attn.py:125); publishes q(t) ----
-        for (int it = kRecWarps - 1 - w; it < nd * B; it += kRecWarps) {     // top warps: warp 0 is the gatherer
+        for (int it = NW - 1 - w; it < nd * B; it += NW) {     // top warps: warp 0 is the gatherer
             const int di = it / B, b = it - di * B;
             const float4* w4p = reinterpret_cast<const float4*>(wqs) + (size_t)di * KP4;
             const float4* h4p = reinterpret_cast<const float4*>(hs) + (size_t)b * KP4;
@@ -231,11 +244,13 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_attn_chain_fwd(AttnChainPara
             if (lane == 0) st_pub(p.q + ((size_t)t * B + b) * A + d0 + di, sacc);
         }
         prof.mark(5, t);
+        // in the shadow of the q hand-off: first half of W_hh . h_a'(t) for step t+1
+        if (U > 0) cta_matvec_fwd<NT>(Wsm, RG, KP, hs, B, part, 0, nKh);
         // ---- phase 3 (after hand-off 2: q): energies for the owned positions (forward_attn.py:128-131); publishes e(t) ----
-        gather_words(q_s, p.q + (size_t)t * B * A, B * A, (p.flags & kFlagWarp0) != 0, sg);
+        gather_words<NT>(q_s, p.q + (size_t)t * B * A, B * A, (p.flags & kFlagWarp0) != 0, sg);
         prof.mark(6, t);
         __syncthreads();
-        for (int it = threadIdx.x; it < np * A; it += kRecThreads) {
+        for (int it = threadIdx.x; it < np * A; it += NT) {
             const int pi = it / A, d = it - pi * A, pp = p0 + pi, b = pp / L;
             const float sv = fast_tanh(q_s[b * A + d] + pre_s[it]);
             p.s[((size_t)t * BL + pp) * A + d] = sv;
@@ -243,18 +258,20 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_attn_chain_fwd(AttnChainPara
         }
         prof.mark(7, t);
         __syncthreads();
-        for (int pi = w; pi < np; pi += kRecWarps) {
+        for (int pi = w; pi < np; pi += NW) {
             float e = 0.f;
             for (int d = lane; d < A; d += 32) e += ctr_s[pi * A + d];
             e = warp_sum(e);
             if (lane == 0) st_pub(p.e + (size_t)t * BL + p0 + pi, e + bv);
         }
         prof.mark(8, t);
+        // in the shadow of the e hand-off: second half of W_hh . h_a'(t)
+        if (U > 0) cta_matvec_fwd<NT>(Wsm, RG, KP, hs, B, part2, nKh, nK);
         // ---- hand-off 3: all energies of step t; a(t) = normalise(e(t)); cum += a(t) (forward_attn.py:200-210) ----
-        gather_words(es, p.e + (size_t)t * BL, BL, (p.flags & kFlagWarp0) != 0, sg);
+        gather_words<NT>(es, p.e + (size_t)t * BL, BL, (p.flags & kFlagWarp0) != 0, sg);
         prof.mark(9, t);
         __syncthreads();
-        for (int b = w; b < B; b += kRecWarps) {     // one row per warp: softmax or sigmoid/sum
+        for (int b = w; b < B; b += NW) {     // one row per warp: softmax or sigmoid/sum
             float m = 0.f;
             if (p.norm == 0) {
                 m = -INFINITY;
@@ -279,7 +296,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_attn_chain_fwd(AttnChainPara
         }
         prof.mark(10, t);
         __syncthreads();
-        for (int i = threadIdx.x; i < np; i += kRecThreads) {
+        for (int i = threadIdx.x; i < np; i += NT) {
             const int pp = p0 + i, b = pp / L, l = pp - b * L;
             p.align[(size_t)t * BL + pp] = as_[b * LP + l];
             if (t + 1 < T) p.cum[(size_t)(t + 1) * BL + pp] = ah[(1 * B + b) * LH + pl + l];
@@ -325,9 +342,11 @@ __host__ __device__ inline AttnSmemBwd attn_bwd_layout(int B, int L, int Ha, int
     return s;
 }
 
-__global__ void __launch_bounds__(kRecThreads, 1) k_attn_chain_bwd(AttnChainBwdParams p, int mwp_res) {
+template <bool kProf, int NT>
+__global__ void __launch_bounds__(NT, 1) k_attn_chain_bwd(AttnChainBwdParams p, int mwp_res) {
+    constexpr int NW = NT / 32;
     extern __shared__ __align__(16) float smem[];
-    __shared__ float red[kRecWarps * kPairMax];
+    __shared__ float red[NW * kPairMax];
     __shared__ float zn_s[kBMax];
     const int T = p.T, B = p.B, L = p.L, Ha = p.Ha, A = p.A, F = p.F, Kl = p.Kl, H4 = 4 * Ha;
     const int BL = B * L, pl = (Kl - 1) / 2, CKP = 2 * Kl + 1;
@@ -359,29 +378,29 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_attn_chain_bwd(AttnChainBwdP
     const int p0 = part_lo(cta, BL, ncta), p1 = part_lo(cta + 1, BL, ncta), np = p1 - p0;
     const int d0 = part_lo(cta, A, ncta), d1 = part_lo(cta + 1, A, ncta), nd = d1 - d0;
 
-    for (int idx = threadIdx.x; idx < kUMax * H4; idx += kRecThreads) {
+    for (int idx = threadIdx.x; idx < kUMax * H4; idx += NT) {
         const int ul = idx / H4, r = idx % H4;
         WT[idx] = ul < U ? __ldg(p.whh + (size_t)r * Ha + u0 + ul) : 0.f;
     }
     if (mwp_res)
-        for (int idx = threadIdx.x; idx < np * (H4 >> 2); idx += kRecThreads)
+        for (int idx = threadIdx.x; idx < np * (H4 >> 2); idx += NT)
             reinterpret_cast<float4*>(MWp)[idx] = __ldg(reinterpret_cast<const float4*>(p.mw_pm + (size_t)p0 * H4) + idx);
     const float* mwp_src = mwp_res ? MWp : p.mw_pm + (size_t)p0 * H4;
-    for (int idx = threadIdx.x; idx < U * A; idx += kRecThreads) {
+    for (int idx = threadIdx.x; idx < U * A; idx += NT) {
         const int ul = idx / A, d = idx % A;
         wqT[idx] = __ldg(p.wq + (size_t)d * Ha + u0 + ul);
     }
-    for (int idx = threadIdx.x; idx < A * F; idx += kRecThreads) {
+    for (int idx = threadIdx.x; idx < A * F; idx += NT) {
         const int d = idx / F, f = idx % F;
         wldT[f * AP + d] = __ldg(p.wld + idx);
     }
-    for (int idx = threadIdx.x; idx < F * 2 * Kl; idx += kRecThreads) {
+    for (int idx = threadIdx.x; idx < F * 2 * Kl; idx += NT) {
         const int f = idx / (2 * Kl), ck = idx % (2 * Kl);
         wloc_s[f * CKP + ck] = __ldg(p.wloc + idx);
     }
-    for (int idx = threadIdx.x; idx < A; idx += kRecThreads) vs[idx] = __ldg(p.v + idx);
-    for (int idx = threadIdx.x; idx < kUMax * BP; idx += kRecThreads) dhs[idx] = 0.f;
-    for (int idx = threadIdx.x; idx < np; idx += kRecThreads) { gcum_s[idx] = 0.f; dprev_s[idx] = 0.f; pout[idx] = 0.f; }
+    for (int idx = threadIdx.x; idx < A; idx += NT) vs[idx] = __ldg(p.v + idx);
+    for (int idx = threadIdx.x; idx < kUMax * BP; idx += NT) dhs[idx] = 0.f;
+    for (int idx = threadIdx.x; idx < np; idx += NT) { gcum_s[idx] = 0.f; dprev_s[idx] = 0.f; pout[idx] = 0.f; }
 
     // point-wise role of the LSTM backward: thread (ul, b); forward stash + external gradient fetched one step ahead
     const bool pw = (int)threadIdx.x < U * B;
@@ -408,34 +427,35 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_attn_chain_bwd(AttnChainBwdP
     };
     fetch(T - 1);
     SpinGuard sg(p.abort_word);
-    ChainProf prof;
+    ChainProf<kProf> prof;
     prof.start(p.prof, p.trace, p.trace_t0);
     __syncthreads();
 
     for (int t = T - 1; t >= 0; --t) {
-        // ---- P1: recurrent terms from dz_a(t+1): W_hh^T.dz (units) and (Wc.memory[l]).dz (positions); publishes dat(t) ----
+        // ---- P1: context-path recurrent term of the owned positions from dz_a(t+1); publishes dat(t) ----
         if (t < T - 1 && (p.flags & kFlagGate)) {
             const float* zrow = p.dza + ((size_t)(t + 1) * B + (B - 1)) * H4 + (size_t)3 * Ha;
             gate_wait(ncta, [&](int c) { const int e = part_lo(c + 1, Ha, ncta); return e > 0 ? zrow + e - 1 : nullptr; }, sg);
             __syncthreads();
         }
-        if (t < T - 1)
-            cta_matvec_bwd(WT, H4, p.dza + (size_t)(t + 1) * B * H4, B, part, dhs, BP, mwp_src, (size_t)H4, p0, np, L, pout, red, sg);
+        if (t < T - 1) cta_pair_dots<NT>(mwp_src, (size_t)H4, p.dza + (size_t)(t + 1) * B * H4, H4, p0, np, L, pout, red, sg);
         prof.mark(0, T - 1 - t);
-        for (int i = threadIdx.x; i < np; i += kRecThreads) {
+        for (int i = threadIdx.x; i < np; i += NT) {
             const float dae = i == (int)threadIdx.x ? da_own : __ldg(p.da_ext + (size_t)t * BL + p0 + i);
             st_pub(p.dat + (size_t)t * BL + p0 + i, dae + pout[i] + gcum_s[i] + dprev_s[i]);
         }
         // forward stash of this step that the next phase needs (plain data of an earlier kernel)
-        for (int idx = threadIdx.x; idx < BL; idx += kRecThreads) als[idx] = __ldg(p.align + (size_t)t * BL + idx);
+        for (int idx = threadIdx.x; idx < BL; idx += NT) als[idx] = __ldg(p.align + (size_t)t * BL + idx);
         if ((int)threadIdx.x < B) zn_s[threadIdx.x] = __ldg(p.znorm + (size_t)t * B + threadIdx.x);
+        // in the shadow of the dat hand-off: W_hh^T . dz_a(t+1) for the owned units (needed by the point-wise phase)
+        if (t < T - 1) cta_matvec_bwd<NT>(WT, H4, p.dza + (size_t)(t + 1) * B * H4, B, part, dhs, BP, sg);
         prof.mark(1, T - 1 - t);
         // ---- hand-off 1: d a(t) of every position ----
-        gather_words(das, p.dat + (size_t)t * BL, BL, (p.flags & kFlagWarp0) != 0, sg);
+        gather_words<NT>(das, p.dat + (size_t)t * BL, BL, (p.flags & kFlagWarp0) != 0, sg);
         __syncthreads();
         prof.mark(2, T - 1 - t);
         // ---- P2: normalisation backward, dS, d(conv features), dq; publishes dconvf(t), dq(t) ----
-        for (int b = w; b < B; b += kRecWarps) {
+        for (int b = w; b < B; b += NW) {
             float sd = 0.f;
             for (int l = lane; l < L; l += 32) sd += als[b * L + l] * das[b * L + l];
             sd = warp_sum(sd);
@@ -447,8 +467,8 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_attn_chain_bwd(AttnChainBwdP
             }
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < np; i += kRecThreads) p.de[(size_t)t * BL + p0 + i] = des[p0 + i];
-        for (int it = threadIdx.x; it < np * A; it += kRecThreads) {
+        for (int i = threadIdx.x; i < np; i += NT) p.de[(size_t)t * BL + p0 + i] = des[p0 + i];
+        for (int it = threadIdx.x; it < np * A; it += NT) {
             const int pi = it / A, d = it - pi * A;
             const float sv = it == (int)threadIdx.x ? sv_own : __ldg(p.s + ((size_t)t * BL + p0) * A + it);
             const float dS = des[p0 + pi] * vs[d] * (1.f - sv * sv);
@@ -456,13 +476,13 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_attn_chain_bwd(AttnChainBwdP
             ds_s[it] = dS;
         }
         if (nd > 0)       // terms of dq for the first owned attention dim (prefetched column of s)
-            for (int idx = threadIdx.x; idx < BL; idx += kRecThreads) {
+            for (int idx = threadIdx.x; idx < BL; idx += NT) {
                 const float sv = idx == (int)threadIdx.x ? sv_q : __ldg(p.s + ((size_t)t * BL + idx) * A + d0);
                 tq_s[idx] = des[idx] * (1.f - sv * sv);
             }
         __syncthreads();
         // d(conv features) of the owned positions: item (pi, f, js) sums d = js, js+8, ...; 8 consecutive lanes share (pi, f)
-        for (int base = 0; base < np * F * 8; base += kRecThreads) {     // warp-uniform trip count (full-mask shuffles inside)
+        for (int base = 0; base < np * F * 8; base += NT) {     // warp-uniform trip count (full-mask shuffles inside)
             const int it = base + threadIdx.x;
             const bool valid = it < np * F * 8;
             const int js = it & 7, f = valid ? (it >> 3) % F : 0, pi = valid ? (it >> 3) / F : 0;
@@ -474,7 +494,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_attn_chain_bwd(AttnChainBwdP
             acc += __shfl_xor_sync(0xffffffffu, acc, 4);
             if (valid && js == 0) st_pub(p.dconvf + ((size_t)t * BL + p0 + pi) * F + f, acc);
         }
-        for (int it = kRecWarps - 1 - w; it < nd * B; it += kRecWarps) {
+        for (int it = NW - 1 - w; it < nd * B; it += NW) {
             const int di = it / B, b = it - di * B, d = d0 + di;
             float acc = 0.f;
             if (di == 0) {
@@ -490,12 +510,12 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_attn_chain_bwd(AttnChainBwdP
         }
         prof.mark(3, T - 1 - t);
         // ---- hand-off 2: dq(t) ----
-        gather_words(dq_s, p.dq + (size_t)t * B * A, B * A, (p.flags & kFlagWarp0) != 0, sg);
+        gather_words<NT>(dq_s, p.dq + (size_t)t * B * A, B * A, (p.flags & kFlagWarp0) != 0, sg);
         __syncthreads();
         prof.mark(4, T - 1 - t);
         // ---- P3: LSTM point-wise backward (units); publishes dz_a(t) ----
         // q-path term of dh: qd[cell] = sum_d Wq[d][u] dq[b][d], 16 lanes per cell
-        for (int base = 0; base < U * B * 16; base += kRecThreads) {     // warp-uniform trip count (full-mask shuffles inside)
+        for (int base = 0; base < U * B * 16; base += NT) {     // warp-uniform trip count (full-mask shuffles inside)
             const int it = base + threadIdx.x;
             const bool valid = it < U * B * 16;
             const int js = it & 15, cell = valid ? it >> 4 : 0, cu = cell / B, cb = cell - cu * B;
@@ -524,24 +544,40 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_attn_chain_bwd(AttnChainBwdP
         prof.mark(5, T - 1 - t);
         // ---- hand-off 3 (dconvf of the +-pad neighbours) + location-conv backward for the owned positions ----
         // item (pi, k): one warp, lane = filter; output position lo = l - k + pad is fed by input l through tap k
-        for (int it = w; it < np * Kl; it += kRecWarps) {
-            const int pi = it / Kl, k = it - pi * Kl;
-            const int pp = p0 + pi, b = pp / L, l = pp - b * L, lo = l - k + pl;
-            float a0 = 0.f, a1 = 0.f;
-            if (lo >= 0 && lo < L && lane < F) {
-                const float dv = poll1(p.dconvf + ((size_t)t * BL + b * L + lo) * F + lane, sg);
-                a0 = wloc_s[lane * CKP + k] * dv;
-                a1 = wloc_s[lane * CKP + Kl + k] * dv;
+        for (int base = w; base < np * Kl; base += 4 * NW) {      // 4 items per warp in flight: the polls overlap
+            float dv[4];
+            bool ok[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int it = base + j * NW, pi = it / Kl, k = it - pi * Kl;
+                const int pp = p0 + pi, b = pp / L, l = pp - b * L, lo = l - k + pl;
+                ok[j] = it < np * Kl && lo >= 0 && lo < L && lane < F;
+                dv[j] = ok[j] ? ld_poll(p.dconvf + ((size_t)t * BL + b * L + lo) * F + lane) : 0.f;
             }
-            a0 = warp_sum(a0);
-            a1 = warp_sum(a1);
-            if (lane == 0) {
-                cpart[it * 2 + 0] = a0;
-                cpart[it * 2 + 1] = a1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int it = base + j * NW, pi = it / Kl, k = it - pi * Kl;
+                const int pp = p0 + pi, b = pp / L, l = pp - b * L, lo = l - k + pl;
+                float a0 = 0.f, a1 = 0.f;
+                if (ok[j]) {
+                    sg.reset();
+                    while (is_canary(dv[j])) {
+                        if (sg.bail()) break;
+                        dv[j] = ld_poll(p.dconvf + ((size_t)t * BL + b * L + lo) * F + lane);
+                    }
+                    a0 = wloc_s[lane * CKP + k] * dv[j];
+                    a1 = wloc_s[lane * CKP + Kl + k] * dv[j];
+                }
+                a0 = warp_sum(a0);
+                a1 = warp_sum(a1);
+                if (lane == 0 && it < np * Kl) {
+                    cpart[it * 2 + 0] = a0;
+                    cpart[it * 2 + 1] = a1;
+                }
             }
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < np; i += kRecThreads) {
+        for (int i = threadIdx.x; i < np; i += NT) {
             float a0 = 0.f, a1 = 0.f;
             for (int k = 0; k < Kl; ++k) {
                 a0 += cpart[(i * Kl + k) * 2 + 0];
@@ -581,15 +617,15 @@ int launch_attn_chain_fwd(const AttnChainParams& p, int sm_count, size_t smem_li
         smem = attn_chain_fwd_smem(p.B, p.L, p.Ha, p.A, p.F, p.Kl, sm_count, false);
     }
     MSA_CHECK(smem <= smem_limit, MSA_E_UNSUPPORTED, "attn_chain_fwd: needs %zu bytes of shared memory (> %zu)", smem, smem_limit);
-    MSA_CUDA(cudaFuncSetAttribute(k_attn_chain_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MSA_CUDA(cudaFuncSetAttribute(p.prof ? k_attn_chain_fwd<true, kAttnThreads> : k_attn_chain_fwd<false, kAttnThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // canaries of the three hand-off arrays (common.cuh)
     const size_t TB = (size_t)p.T * p.B;
-    MSA_CUDA(cudaMemsetAsync(p.ha, 0xFF, sizeof(float) * TB * p.Ha, st));
-    MSA_CUDA(cudaMemsetAsync(p.q, 0xFF, sizeof(float) * TB * p.A, st));
-    MSA_CUDA(cudaMemsetAsync(p.e, 0xFF, sizeof(float) * TB * p.L, st));
+    MSA_TRY(k_fill_canary(p.ha, (int64_t)(TB * p.Ha), st));
+    MSA_TRY(k_fill_canary(p.q, (int64_t)(TB * p.A), st));
+    MSA_TRY(k_fill_canary(p.e, (int64_t)(TB * p.L), st));
     AttnChainParams pp = p;
     void* args[] = {&pp, &mw_res};
-    MSA_CUDA(cudaLaunchCooperativeKernel((void*)k_attn_chain_fwd, dim3(sm_count), dim3(kRecThreads), args, smem, st));
+    MSA_CUDA(cudaLaunchCooperativeKernel(pp.prof ? (void*)k_attn_chain_fwd<true, kAttnThreads> : (void*)k_attn_chain_fwd<false, kAttnThreads>, dim3(sm_count), dim3(kAttnThreads), args, smem, st));
     count_launch();
     return 0;
 }
@@ -603,15 +639,15 @@ int launch_attn_chain_bwd(const AttnChainBwdParams& p, int sm_count, size_t smem
         smem = attn_chain_bwd_smem(p.B, p.L, p.Ha, p.A, p.F, p.Kl, sm_count, false);
     }
     MSA_CHECK(smem <= smem_limit, MSA_E_UNSUPPORTED, "attn_chain_bwd: needs %zu bytes of shared memory (> %zu)", smem, smem_limit);
-    MSA_CUDA(cudaFuncSetAttribute(k_attn_chain_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MSA_CUDA(cudaFuncSetAttribute(p.prof ? k_attn_chain_bwd<true, kRecThreads> : k_attn_chain_bwd<false, kRecThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t TB = (size_t)p.T * p.B;
-    MSA_CUDA(cudaMemsetAsync(p.dza, 0xFF, sizeof(float) * TB * 4 * p.Ha, st));
-    MSA_CUDA(cudaMemsetAsync(p.dq, 0xFF, sizeof(float) * TB * p.A, st));
-    MSA_CUDA(cudaMemsetAsync(p.dat, 0xFF, sizeof(float) * TB * p.L, st));
-    MSA_CUDA(cudaMemsetAsync(p.dconvf, 0xFF, sizeof(float) * TB * p.L * p.F, st));
+    MSA_TRY(k_fill_canary(p.dza, (int64_t)(TB * 4 * p.Ha), st));
+    MSA_TRY(k_fill_canary(p.dq, (int64_t)(TB * p.A), st));
+    MSA_TRY(k_fill_canary(p.dat, (int64_t)(TB * p.L), st));
+    MSA_TRY(k_fill_canary(p.dconvf, (int64_t)(TB * p.L * p.F), st));
     AttnChainBwdParams pp = p;
     void* args[] = {&pp, &mwp_res};
-    MSA_CUDA(cudaLaunchCooperativeKernel((void*)k_attn_chain_bwd, dim3(sm_count), dim3(kRecThreads), args, smem, st));
+    MSA_CUDA(cudaLaunchCooperativeKernel(pp.prof ? (void*)k_attn_chain_bwd<true, kRecThreads> : (void*)k_attn_chain_bwd<false, kRecThreads>, dim3(sm_count), dim3(kRecThreads), args, smem, st));
     count_launch();
     return 0;
 }

@@ -145,6 +145,7 @@ int k_wloc_grad(const float* dconvf, const float* align, const float* cum, float
                 int Kl, float scale, int accumulate, cudaStream_t st);
 int k_dot_rows(const float* a, const float* b, int64_t n, float* partials, float* out, float scale, int accumulate, cudaStream_t st);
 int k_masks_generate(uint8_t* masks, const int64_t* offsets, const int64_t* numels, const float* ps, int nsec, uint64_t seed, cudaStream_t st);
+int k_fill_canary(float* p, int64_t n, cudaStream_t st);   // n floats (multiple of 4, 16-byte aligned) <- 0xFFFFFFFF
 int k_scale_copy(const float* in, float* out, int64_t n, float scale, int accumulate, cudaStream_t st);
 
 }  // namespace msa

@@ -32,7 +32,9 @@ __host__ __device__ inline LstmFwdSmem lstm_fwd_layout(int B, int H) {
     return s;
 }
 
-__global__ void __launch_bounds__(kRecThreads, 1) k_lstm_rec_fwd(LstmRecParams p) {
+template <bool kProf, int NT>
+__global__ void __launch_bounds__(NT, 1) k_lstm_rec_fwd(LstmRecParams p) {
+    constexpr int NW = NT / 32;
     extern __shared__ __align__(16) float smem[];
     const int H = p.H, B = p.B, T = p.T, H4 = 4 * H;
     const int ncta_dir = gridDim.x / p.ndir;
@@ -55,14 +57,14 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_lstm_rec_fwd(LstmRecParams p
     float* cout = p.cout + (size_t)dir * T * B * H;
     float* gates = p.gates + (size_t)dir * T * B * H4;
 
-    for (int idx = threadIdx.x; idx < RG * 8 * KP4; idx += kRecThreads) {
+    for (int idx = threadIdx.x; idx < RG * 8 * KP4; idx += NT) {
         const int rl = idx / KP4, k4 = idx % KP4;
         const int g = rl & 3, ul = rl >> 2;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (rl < R && k4 < (H >> 2)) v = __ldg(reinterpret_cast<const float4*>(whh + (size_t)(g * H + u0 + ul) * H) + k4);
         reinterpret_cast<float4*>(Wsm)[idx] = v;
     }
-    for (int idx = threadIdx.x; idx < lay.BP * KP; idx += kRecThreads) hs[idx] = 0.f;
+    for (int idx = threadIdx.x; idx < lay.BP * KP; idx += NT) hs[idx] = 0.f;
 
     // point-wise role: 4 lanes per cell (ul, b), lane g evaluates gate g; the cell state lives in lane 0's register
     const bool pw = (int)threadIdx.x < 4 * U * B;
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_lstm_rec_fwd(LstmRecParams p
     };
     if (pw) fetch(dir == 0 ? 0 : T - 1);
     SpinGuard sg(p.abort_word);
-    ChainProf prof;
+    ChainProf<kProf> prof;
     prof.start(p.prof, p.trace, p.trace_t0);
     __syncthreads();
 
@@ -91,17 +93,17 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_lstm_rec_fwd(LstmRecParams p
             __syncthreads();
         }
         if (s > 0) {
-            poll_copy_rows(hs, KP4, hout + (size_t)tp * B * H, B, H >> 2, sg);
+            poll_copy_rows<NT>(hs, KP4, hout + (size_t)tp * B * H, B, H >> 2, sg);
             __syncthreads();
         }
         prof.mark(0, s);
-        cta_matvec_fwd<false>(Wsm, RG, KP, hs, nullptr, 0, nullptr, B, part);
+        cta_matvec_fwd<NT>(Wsm, RG, KP, hs, B, part, 0, KP >> 7);
         __syncthreads();
         prof.mark(1, s);
         if (pw) {
             const size_t zb = ((size_t)t * B + b) * H4;
             const bool active = t < len;
-            const float z = lstm_gate_sum(part, RG, ul * 4 + g, b) + zi;
+            const float z = lstm_gate_sum<NT>(part, RG, ul * 4 + g, b) + zi;
             float act = g == 2 ? fast_tanh(z) : fast_sigmoid(z);
             if (!active) act = 0.f;
             const unsigned int gm = 0xFu << (threadIdx.x & 28);                 // the 4 lanes of this cell
@@ -125,9 +127,10 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_lstm_rec_fwd(LstmRecParams p
     }
 }
 
-__global__ void __launch_bounds__(kRecThreads, 1) k_lstm_rec_bwd(LstmRecBwdParams p) {
+template <bool kProf, int NT>
+__global__ void __launch_bounds__(NT, 1) k_lstm_rec_bwd(LstmRecBwdParams p) {
+    constexpr int NW = NT / 32;
     extern __shared__ __align__(16) float smem[];
-    __shared__ float red[kRecWarps * kPairMax];
     const int H = p.H, B = p.B, T = p.T, H4 = 4 * H;
     const int BP = (B + 3) & ~3;
     const int ncta_dir = gridDim.x / p.ndir;
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_lstm_rec_bwd(LstmRecBwdParam
 
     float* WT = smem;                                // [kUMax][4H]   WT[ul][r] = W_hh[r][u0+ul], zero rows for ul >= U
     float* part = WT + (size_t)kUMax * H4;           // [warps*32]
-    float* dhs = part + kRecWarps * 32;              // [kUMax][BP]
+    float* dhs = part + NW * 32;              // [kUMax][BP]
 
     const float* whh = p.whh + (size_t)dir * p.whh_dir_stride;
     const float* gates = p.gates + (size_t)dir * T * B * H4;
@@ -148,11 +151,11 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_lstm_rec_bwd(LstmRecBwdParam
     const float* dh_ext = p.dh_ext + (size_t)dir * T * B * H;
     float* dz = p.dz + (size_t)dir * T * B * H4;
 
-    for (int idx = threadIdx.x; idx < kUMax * H4; idx += kRecThreads) {
+    for (int idx = threadIdx.x; idx < kUMax * H4; idx += NT) {
         const int ul = idx / H4, r = idx % H4;
         WT[idx] = ul < U ? __ldg(whh + (size_t)r * H + u0 + ul) : 0.f;
     }
-    for (int idx = threadIdx.x; idx < kUMax * BP; idx += kRecThreads) dhs[idx] = 0.f;
+    for (int idx = threadIdx.x; idx < kUMax * BP; idx += NT) dhs[idx] = 0.f;
 
     const bool pw = (int)threadIdx.x < U * B;
     const int ul = pw ? threadIdx.x / B : 0, b = pw ? threadIdx.x % B : 0, u = u0 + ul;
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_lstm_rec_bwd(LstmRecBwdParam
     };
     if (pw) fetch(dir == 0 ? T - 1 : 0);
     SpinGuard sg(p.abort_word);
-    ChainProf prof;
+    ChainProf<kProf> prof;
     prof.start(p.prof, p.trace, p.trace_t0);
     __syncthreads();
 
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) k_lstm_rec_bwd(LstmRecBwdParam
             gate_wait(ncta_dir, [&](int c) { const int e = part_lo(c + 1, H, ncta_dir); return e > 0 ? zrow + e - 1 : nullptr; }, sg);
             __syncthreads();
         }
-        if (s > 0) cta_matvec_bwd(WT, H4, dz + (size_t)tn * B * H4, B, part, dhs, BP, nullptr, 0, 0, 0, 1, nullptr, red, sg);
+        if (s > 0) cta_matvec_bwd<NT>(WT, H4, dz + (size_t)tn * B * H4, B, part, dhs, BP, sg);
         prof.mark(0, s);
         if (pw) {
             const size_t zb = ((size_t)t * B + b) * H4;
@@ -225,11 +228,11 @@ int launch_lstm_rec_fwd(const LstmRecParams& p, int sm_count, size_t smem_limit,
     MSA_TRY(rec_check(p.B, p.H, p.ndir, sm_count));
     const size_t smem = lstm_rec_fwd_smem(p.B, p.H);
     MSA_CHECK(smem <= smem_limit, MSA_E_UNSUPPORTED, "lstm_rec_fwd: needs %zu bytes of shared memory (> %zu)", smem, smem_limit);
-    MSA_CUDA(cudaFuncSetAttribute(k_lstm_rec_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MSA_CUDA(cudaMemsetAsync(p.hout, 0xFF, sizeof(float) * (size_t)p.ndir * p.T * p.B * p.H, st));   // canaries (common.cuh)
+    MSA_CUDA(cudaFuncSetAttribute(p.prof ? k_lstm_rec_fwd<true, kRecThreads> : k_lstm_rec_fwd<false, kRecThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MSA_TRY(k_fill_canary(p.hout, (int64_t)((size_t)p.ndir * p.T * p.B * p.H), st));   // canaries (common.cuh)
     LstmRecParams pp = p;
     void* args[] = {&pp};
-    MSA_CUDA(cudaLaunchCooperativeKernel((void*)k_lstm_rec_fwd, dim3(sm_count), dim3(kRecThreads), args, smem, st));
+    MSA_CUDA(cudaLaunchCooperativeKernel(pp.prof ? (void*)k_lstm_rec_fwd<true, kRecThreads> : (void*)k_lstm_rec_fwd<false, kRecThreads>, dim3(sm_count), dim3(kRecThreads), args, smem, st));
     count_launch();
     return 0;
 }
@@ -238,11 +241,11 @@ int launch_lstm_rec_bwd(const LstmRecBwdParams& p, int sm_count, size_t smem_lim
     MSA_TRY(rec_check(p.B, p.H, p.ndir, sm_count));
     const size_t smem = lstm_rec_bwd_smem(p.B, p.H);
     MSA_CHECK(smem <= smem_limit, MSA_E_UNSUPPORTED, "lstm_rec_bwd: needs %zu bytes of shared memory (> %zu)", smem, smem_limit);
-    MSA_CUDA(cudaFuncSetAttribute(k_lstm_rec_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MSA_CUDA(cudaMemsetAsync(p.dz, 0xFF, sizeof(float) * (size_t)p.ndir * p.T * p.B * 4 * p.H, st));  // canaries (common.cuh)
+    MSA_CUDA(cudaFuncSetAttribute(p.prof ? k_lstm_rec_bwd<true, kRecThreads> : k_lstm_rec_bwd<false, kRecThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MSA_TRY(k_fill_canary(p.dz, (int64_t)((size_t)p.ndir * p.T * p.B * 4 * p.H), st));  // canaries (common.cuh)
     LstmRecBwdParams pp = p;
     void* args[] = {&pp};
-    MSA_CUDA(cudaLaunchCooperativeKernel((void*)k_lstm_rec_bwd, dim3(sm_count), dim3(kRecThreads), args, smem, st));
+    MSA_CUDA(cudaLaunchCooperativeKernel(pp.prof ? (void*)k_lstm_rec_bwd<true, kRecThreads> : (void*)k_lstm_rec_bwd<false, kRecThreads>, dim3(sm_count), dim3(kRecThreads), args, smem, st));
     count_launch();
     return 0;
 }

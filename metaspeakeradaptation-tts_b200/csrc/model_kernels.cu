@@ -589,6 +589,19 @@ int k_add3(const float* a, const float* b, const float* c, float* out, int64_t n
     MSA_LAUNCH_CHECK();
     return 0;
 }
+// canary fill of the hand-off arrays of the persistent kernels (common.cuh): plain 128-bit stores from a kernel, NOT
+// cudaMemset -- the lines must be ordinary resident L2 lines when the 4-byte publishes and the polls hit them
+__global__ void ker_fill_canary(uint4* p, int64_t n4) {
+    GSL(i, n4) p[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+}
+int k_fill_canary(float* p, int64_t n, cudaStream_t st) {
+    // n is rounded up to a multiple of 4 floats: every workspace buffer is padded to a multiple of 64 floats (pass.cu)
+    MSA_CHECK((reinterpret_cast<uintptr_t>(p) & 15) == 0, MSA_E_ARG, "k_fill_canary: buffer must be 16-byte aligned");
+    const int64_t n4 = (n + 3) >> 2;
+    ker_fill_canary<<<grid_for(n4, kTh, 148 * 8), kTh, 0, ST>>>(reinterpret_cast<uint4*>(p), n4);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
 int k_scale_copy(const float* in, float* out, int64_t n, float scale, int acc, cudaStream_t st) {
     ker_scale_copy<<<grid_for(n), kTh, 0, ST>>>(in, out, n, scale, acc);
     MSA_LAUNCH_CHECK();

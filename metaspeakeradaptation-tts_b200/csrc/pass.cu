@@ -69,7 +69,7 @@ struct msa_handle {
     bool in_bwd = false;   // GEMM precision policy 1: fp32 GEMMs in the forward pass, TF32 in the backward pass
     bool prof = false;
     int trace_t0 = 0;
-    int rec_flags = 0;     // hand-off variant of the persistent kernels (env MSA_REC_FLAGS, development only)
+    int rec_flags = -1;    // hand-off variant of the persistent kernels; -1 = per-kernel default (env MSA_REC_FLAGS overrides, development only)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
     std::vector<int> prof_id;
     size_t prof_used = 0;
@@ -539,7 +539,7 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
         lp.zin = w.enc_zx; lp.whh = P("encoder.lstm.weight_hh_l0");
         lp.whh_dir_stride = h->off("encoder.lstm.weight_hh_l0_reverse") - h->off("encoder.lstm.weight_hh_l0");
         lp.hout = w.enc_h; lp.cout = w.enc_c; lp.gates = w.enc_g; lp.mask = nullptr; lp.drop_scale = 1.f;
-        lp.lengths = token_lengths; lp.abort_word = w.abort_word; lp.prof = prof_ptr(h, w, PROF_ENC_LSTM_FWD); lp.trace = trace_ptr(h, w, PROF_ENC_LSTM_FWD); lp.trace_t0 = h->trace_t0; lp.flags = h->rec_flags;
+        lp.lengths = token_lengths; lp.abort_word = w.abort_word; lp.prof = prof_ptr(h, w, PROF_ENC_LSTM_FWD); lp.trace = trace_ptr(h, w, PROF_ENC_LSTM_FWD); lp.trace_t0 = h->trace_t0; lp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
         ProfScope ps(h, PROF_ENC_LSTM_FWD, st);
         MSA_TRY(launch_lstm_rec_fwd(lp, h->sm_count, h->smem_limit, st));
     }
@@ -570,7 +570,7 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
         ap.mask = c.p_attn_dropout > 0.f ? mk(iAttn) : nullptr;
         ap.drop_scale = 1.f / (1.f - c.p_attn_dropout);
         ap.ha = w.ha; ap.ca = w.ca; ap.ga = w.ga; ap.q = w.q; ap.align = w.align_tm; ap.cum = w.cum; ap.s = w.s;
-        ap.convf = w.convf; ap.znorm = w.znorm; ap.e = w.ebuf; ap.abort_word = w.abort_word; ap.prof = prof_ptr(h, w, PROF_ATTN_FWD); ap.trace = trace_ptr(h, w, PROF_ATTN_FWD); ap.trace_t0 = h->trace_t0; ap.flags = h->rec_flags;
+        ap.convf = w.convf; ap.znorm = w.znorm; ap.e = w.ebuf; ap.abort_word = w.abort_word; ap.prof = prof_ptr(h, w, PROF_ATTN_FWD); ap.trace = trace_ptr(h, w, PROF_ATTN_FWD); ap.trace_t0 = h->trace_t0; ap.flags = h->rec_flags >= 0 ? h->rec_flags : 0;
         ProfScope ps(h, PROF_ATTN_FWD, st);
         MSA_TRY(launch_attn_chain_fwd(ap, h->sm_count, h->smem_limit, st));
     }
@@ -589,7 +589,7 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
         lp.hout = w.hd; lp.cout = w.cd; lp.gates = w.gd;
         lp.mask = c.p_dec_dropout > 0.f ? mk(iDec) : nullptr;
         lp.drop_scale = 1.f / (1.f - c.p_dec_dropout);
-        lp.lengths = nullptr; lp.abort_word = w.abort_word; lp.prof = prof_ptr(h, w, PROF_DEC_LSTM_FWD); lp.trace = trace_ptr(h, w, PROF_DEC_LSTM_FWD); lp.trace_t0 = h->trace_t0; lp.flags = h->rec_flags;
+        lp.lengths = nullptr; lp.abort_word = w.abort_word; lp.prof = prof_ptr(h, w, PROF_DEC_LSTM_FWD); lp.trace = trace_ptr(h, w, PROF_DEC_LSTM_FWD); lp.trace_t0 = h->trace_t0; lp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
         ProfScope ps(h, PROF_DEC_LSTM_FWD, st);
         MSA_TRY(launch_lstm_rec_fwd(lp, h->sm_count, h->smem_limit, st));
     }
@@ -727,7 +727,7 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
         bp.gates = w.gd; bp.cout = w.cd; bp.dh_ext = w.dhd; bp.dz = w.dzd;
         bp.mask = c.p_dec_dropout > 0.f ? mk(iDec) : nullptr;
         bp.drop_scale = 1.f / (1.f - c.p_dec_dropout);
-        bp.lengths = nullptr; bp.abort_word = w.abort_word; bp.prof = prof_ptr(h, w, PROF_DEC_LSTM_BWD); bp.trace = trace_ptr(h, w, PROF_DEC_LSTM_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags;
+        bp.lengths = nullptr; bp.abort_word = w.abort_word; bp.prof = prof_ptr(h, w, PROF_DEC_LSTM_BWD); bp.trace = trace_ptr(h, w, PROF_DEC_LSTM_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
         ProfScope ps(h, PROF_DEC_LSTM_BWD, st);
         MSA_TRY(launch_lstm_rec_bwd(bp, h->sm_count, h->smem_limit, st));
     }
@@ -766,7 +766,7 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
         bp.ga = w.ga; bp.ca = w.ca; bp.align = w.align_tm; bp.s = w.s; bp.znorm = w.znorm;
         bp.dha_ext = w.dha; bp.da_ext = w.da_ext;
         bp.dza = w.dza; bp.dq = w.dq; bp.de = w.de; bp.ds = w.ds; bp.dconvf = w.dconvf; bp.dat = w.dat;
-        bp.abort_word = w.abort_word; bp.prof = prof_ptr(h, w, PROF_ATTN_BWD); bp.trace = trace_ptr(h, w, PROF_ATTN_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags;
+        bp.abort_word = w.abort_word; bp.prof = prof_ptr(h, w, PROF_ATTN_BWD); bp.trace = trace_ptr(h, w, PROF_ATTN_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 0;
         ProfScope ps(h, PROF_ATTN_BWD, st);
         MSA_TRY(launch_attn_chain_bwd(bp, h->sm_count, h->smem_limit, st));
     }
@@ -819,7 +819,7 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
         bp.whh = P("encoder.lstm.weight_hh_l0");
         bp.whh_dir_stride = h->off("encoder.lstm.weight_hh_l0_reverse") - h->off("encoder.lstm.weight_hh_l0");
         bp.gates = w.enc_g; bp.cout = w.enc_c; bp.dh_ext = w.denc_h; bp.dz = w.dzx; bp.mask = nullptr; bp.drop_scale = 1.f;
-        bp.lengths = h->tok_len; bp.abort_word = w.abort_word; bp.prof = prof_ptr(h, w, PROF_ENC_LSTM_BWD); bp.trace = trace_ptr(h, w, PROF_ENC_LSTM_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags;
+        bp.lengths = h->tok_len; bp.abort_word = w.abort_word; bp.prof = prof_ptr(h, w, PROF_ENC_LSTM_BWD); bp.trace = trace_ptr(h, w, PROF_ENC_LSTM_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
         ProfScope ps(h, PROF_ENC_LSTM_BWD, st);
         MSA_TRY(launch_lstm_rec_bwd(bp, h->sm_count, h->smem_limit, st));
     }

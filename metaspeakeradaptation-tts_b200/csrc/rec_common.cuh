@@ -30,12 +30,14 @@ __host__ __device__ inline int round_up_i(int n, int m) { return (n + m - 1) / m
 //   trace: [grid][kRecWarps][kTraceSteps][kTraceTags][2]  {clock64, globaltimer} of lane 0 of every warp at every mark of the
 //          steps [trace_t0, trace_t0 + kTraceSteps)
 constexpr int kProfSlots = 8, kTraceSteps = 4, kTraceTags = 12;
+template <bool kOn>
 struct ChainProf {
     long long* out;
     long long* trace;
     long long last;
     int t0;
     __device__ __forceinline__ void start(long long* prof_buf, long long* trace_buf, int trace_t0) {
+        if (!kOn) return;
         out = threadIdx.x == 0 ? prof_buf : nullptr;
         trace = (threadIdx.x & 31) == 0 ? trace_buf : nullptr;
         t0 = trace_t0;
@@ -45,9 +47,10 @@ struct ChainProf {
         }
     }
     __device__ __forceinline__ void mark(int i, int step) {
+        if (!kOn) return;
         if (out) {
             const long long c = clock64();
-            out[(size_t)blockIdx.x * kProfSlots + i] += c - last;
+            out[(size_t)blockIdx.x * kProfSlots + (i < kProfSlots ? i : kProfSlots - 1)] += c - last;
             last = c;
         }
         if (trace && step >= t0 && step < t0 + kTraceSteps) {
@@ -89,22 +92,18 @@ __device__ __host__ __forceinline__ int part_lo(int i, int n, int parts) { retur
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 
 // ---- forward mat-vec ------------------------------------------------------------------------------------------------
-// part[((tile*KS + ks)*RG + rg)*32 + rr*4 + bl] = partial over the K-range of warp (rg, ks) of
-//     sum_k Wsm[(rg*8+rr)*KP + k] * hs[(tile*4+bl)*KP + k]  (+ sum_l MWs[((rg*8+rr)*B + b)*LP + l] * as[b*LP + l] if HAS_MW)
-// Wsm [RG*8][KP] and hs [BP][KP] are zero-padded (KP % 128 == 0, BP % 4 == 0); MWs rows are zero for padded gate rows and
-// as/MWs are zero-padded to LP % 4 == 0.  RG = ceil(rows/8), KS = kRecWarps / RG.  No __syncthreads inside: the caller
-// synchronises once and then sums the KS partials of each output (lstm_gate_sum).
-template <bool HAS_MW>
-__device__ __forceinline__ void cta_matvec_fwd(const float* __restrict__ Wsm, int RG, int KP, const float* __restrict__ hs,
-                                               const float* __restrict__ MWs, int LP, const float* __restrict__ as_, int B,
-                                               float* __restrict__ part) {
+// part[((tile*KS + ks)*RG + rg)*32 + rr*4 + bl] = partial over the K-chunks (of 128 columns) j0 <= j < j1 that warp (rg, ks)
+// handles (j = j0 + ks, j0 + ks + KS, ...) of   sum_k Wsm[(rg*8+rr)*KP + k] * hs[(tile*4+bl)*KP + k].
+// Wsm [RG*8][KP] and hs [BP][KP] are zero-padded (KP % 128 == 0, BP % 4 == 0).  RG = ceil(rows/8), KS = (NT / 32) / RG.
+// No __syncthreads inside: the caller synchronises and then sums the KS partials of each output (lstm_gate_sum).
+template <int NT>
+__device__ __forceinline__ void cta_matvec_fwd(const float* __restrict__ Wsm, int RG, int KP, const float* __restrict__ hs, int B,
+                                               float* __restrict__ part, int j0, int j1) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int KS = kRecWarps / RG;
+    const int KS = (NT / 32) / RG;
     const int rg = w % RG, ks = w / RG;
     if (ks >= KS) return;
-    const int KP4 = KP >> 2, LP4 = LP >> 2;
-    const int nK = KP >> 7;
-    const int nLc = HAS_MW ? (LP + 127) >> 7 : 0;
+    const int KP4 = KP >> 2;
     const float4* W4 = reinterpret_cast<const float4*>(Wsm) + (size_t)(rg * 8) * KP4;
     const float4* h4p = reinterpret_cast<const float4*>(hs);
     const int ntile = (B + 3) >> 2;
@@ -112,39 +111,20 @@ __device__ __forceinline__ void cta_matvec_fwd(const float* __restrict__ Wsm, in
         float acc[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-        for (int j = ks; j < nK + 4 * nLc; j += KS) {
-            if (j < nK) {
-                const int c4 = j * 32 + lane;
-                float4 h4[4], w4[8];
+        for (int j = j0 + ks; j < j1; j += KS) {
+            const int c4 = j * 32 + lane;
+            float4 h4[4];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) h4[b] = h4p[(size_t)(tile * 4 + b) * KP4 + c4];
+            for (int b = 0; b < 4; ++b) h4[b] = h4p[(size_t)(tile * 4 + b) * KP4 + c4];
 #pragma unroll
-                for (int rr = 0; rr < 8; ++rr) w4[rr] = W4[(size_t)rr * KP4 + c4];
+            for (int half = 0; half < 2; ++half) {       // 4 rows at a time: 16 + 16 + 32 live registers
+                float4 w4[4];
 #pragma unroll
-                for (int rr = 0; rr < 8; ++rr)
+                for (int rr = 0; rr < 4; ++rr) w4[rr] = W4[(size_t)(half * 4 + rr) * KP4 + c4];
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) acc[rr * 4 + b] += dot4(w4[rr], h4[b]);
-            } else if (HAS_MW) {
-                const int m = j - nK, bl = m & 3, lc = m >> 2, b = tile * 4 + bl;
-                const int l4 = lc * 32 + lane;
-                float tmp[8];
+                for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
-                for (int rr = 0; rr < 8; ++rr) tmp[rr] = 0.f;
-                if (b < B && l4 < LP4) {
-                    const float4 a4 = reinterpret_cast<const float4*>(as_)[(size_t)b * LP4 + l4];
-                    float4 m4[8];
-#pragma unroll
-                    for (int rr = 0; rr < 8; ++rr)
-                        m4[rr] = reinterpret_cast<const float4*>(MWs)[((size_t)(rg * 8 + rr) * B + b) * LP4 + l4];
-#pragma unroll
-                    for (int rr = 0; rr < 8; ++rr) tmp[rr] = dot4(m4[rr], a4);
-                }
-#pragma unroll
-                for (int bb = 0; bb < 4; ++bb)
-                    if (bl == bb) {
-#pragma unroll
-                        for (int rr = 0; rr < 8; ++rr) acc[rr * 4 + bb] += tmp[rr];
-                    }
+                    for (int b = 0; b < 4; ++b) acc[(half * 4 + rr) * 4 + b] += dot4(w4[rr], h4[b]);
             }
         }
         const float tot = warp_transpose_reduce32(acc);
@@ -152,30 +132,55 @@ __device__ __forceinline__ void cta_matvec_fwd(const float* __restrict__ Wsm, in
     }
 }
 // pre-activation of gate row rl (local row index) for batch row b: sum of the KS partials
+template <int NT>
 __device__ __forceinline__ float lstm_gate_sum(const float* part, int RG, int rl, int b) {
-    const int KS = kRecWarps / RG;
+    const int KS = (NT / 32) / RG;
     const float* p = part + ((size_t)((b >> 2) * KS) * RG + (rl >> 3)) * 32 + (rl & 7) * 4 + (b & 3);
     float s = 0.f;
     for (int q = 0; q < KS; ++q) s += p[(size_t)q * RG * 32];
     return s;
 }
+// Context term of the attention LSTM: zm[rl*BP + b] = sum_l MWs[(rl*B + b)*LP + l] * as[b*LP + l] for the nrows (multiple
+// of 8) local gate rows.  Warp w takes rows w, w+16, ...; lane = (b-in-tile, l-eighth); 3-shuffle reduction.  No sync inside.
+template <int NT>
+__device__ __forceinline__ void cta_context_term(const float* __restrict__ MWs, const float* __restrict__ as_, int nrows, int B,
+                                                 int BP, int LP, float* __restrict__ zm) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int bl = lane >> 3, lq = lane & 7, LP4 = LP >> 2;
+    for (int tile = 0; tile < ((B + 3) >> 2); ++tile) {
+        const int b = tile * 4 + bl;
+        for (int rl = w; rl < nrows; rl += (NT / 32)) {
+            float acc = 0.f;
+            if (b < B) {
+                const float4* m4 = reinterpret_cast<const float4*>(MWs) + ((size_t)rl * B + b) * LP4;
+                const float4* a4 = reinterpret_cast<const float4*>(as_) + (size_t)b * LP4;
+                for (int l4 = lq; l4 < LP4; l4 += 8) acc += dot4(m4[l4], a4[l4]);
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            if (lq == 0 && b < BP) zm[rl * BP + b] = acc;
+        }
+    }
+}
 
 // Copy rows x n4 float4 words that OTHER CTAs publish during this launch (canary-polled, common.cuh) from global
 // (row stride n4 float4) to shared (row stride dst_stride4 float4).  All loads of a thread are issued before the first
 // one is checked (memory-level parallelism while spinning).
+template <int NT>
 __device__ __forceinline__ void poll_copy_rows(float* dst_smem, int dst_stride4, const float* src, int rows, int n4, SpinGuard& sg) {
     constexpr int kBatch = 4;
     const int total = rows * n4;
-    for (int base = threadIdx.x; base < total; base += kBatch * kRecThreads) {
+    for (int base = threadIdx.x; base < total; base += kBatch * NT) {
         float4 v[kBatch];
 #pragma unroll
         for (int j = 0; j < kBatch; ++j) {
-            const int idx = base + j * kRecThreads;
+            const int idx = base + j * NT;
             if (idx < total) v[j] = ld_poll4(src + (size_t)idx * 4);
         }
 #pragma unroll
         for (int j = 0; j < kBatch; ++j) {
-            const int idx = base + j * kRecThreads;
+            const int idx = base + j * NT;
             if (idx < total) {
                 sg.reset();
                 while (!ready4(v[j])) {
@@ -185,6 +190,29 @@ __device__ __forceinline__ void poll_copy_rows(float* dst_smem, int dst_stride4,
                 const int r = idx / n4, c = idx - r * n4;
                 reinterpret_cast<float4*>(dst_smem)[(size_t)r * dst_stride4 + c] = v[j];
             }
+        }
+    }
+}
+
+// Same term when the MW slice does not fit in shared memory: rows are read from the global [4Ha][B*L] matrix (gate-major rows,
+// L2-resident after the first step).  grow(rl) = global row of local row rl.
+template <int NT, class RowFn>
+__device__ __forceinline__ void cta_context_term_global(const float* __restrict__ MW, RowFn grow, const float* __restrict__ as_,
+                                                        int nrows, int B, int BP, int L, int LP, float* __restrict__ zm) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int bl = lane >> 3, lq = lane & 7;
+    for (int tile = 0; tile < ((B + 3) >> 2); ++tile) {
+        const int b = tile * 4 + bl;
+        for (int rl = w; rl < nrows; rl += (NT / 32)) {
+            float acc = 0.f;
+            if (b < B) {
+                const float* m = MW + (size_t)grow(rl) * B * L + (size_t)b * L;
+                for (int l = lq; l < L; l += 8) acc += __ldg(m + l) * as_[b * LP + l];
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            if (lq == 0 && b < BP) zm[rl * BP + b] = acc;
         }
     }
 }
@@ -251,11 +279,15 @@ __device__ __forceinline__ void gather_small(float* dst_smem, const float* src, 
 }
 
 // n words published by other CTAs -> shared: by warp 0 alone (the others park at the caller's barrier) or by all threads
+// (128-bit polls when the block is 16-byte aligned: a quarter of the L2 requests on the few hot lines)
+template <int NT>
 __device__ __forceinline__ void gather_words(float* dst_smem, const float* src, int n, bool warp0_only, SpinGuard& sg) {
     if (warp0_only) {
         gather_small(dst_smem, src, n, sg);
+    } else if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst_smem)) & 15) == 0) {
+        for (int i = threadIdx.x; i < (n >> 2); i += NT) reinterpret_cast<float4*>(dst_smem)[i] = poll4(src + (size_t)i * 4, sg);
     } else {
-        for (int i = threadIdx.x; i < n; i += kRecThreads) dst_smem[i] = poll1(src + i, sg);
+        for (int i = threadIdx.x; i < n; i += NT) dst_smem[i] = poll1(src + i, sg);
     }
 }
 constexpr int kFlagGate = 1;    // large gathers: warp 0 waits for one sentinel per producer before the bulk fetch
@@ -266,88 +298,95 @@ constexpr int kPairMax = 4;   // (b,l) positions per CTA whose context-path dot 
 // ---- backward mat-vec -----------------------------------------------------------------------------------------------
 //   out[ul*BP + b] = sum_r WT[ul*R4 + r] * dz[b*R4 + r],  ul < 8 (rows of WT beyond the owned units are zero), b < B
 // dz lives in global memory and is being published by the other CTAs (canary-polled).
-// If npairs > 0 also computes pair_out[i] = sum_r MWp[i*mwp_stride + r] * dz[b_i*R4 + r] with b_i = (pair0+i)/L
-// (MWp = rows pair0.. of the [B*L][R4] matrix, resident in shared memory or in global memory).
-// All threads must call.  `part` scratch: kRecWarps*32 floats, `red` scratch: kRecWarps*kPairMax floats.
+// All threads must call.  `part` scratch: (NT / 32)*32 floats.
+template <int NT>
 __device__ __forceinline__ void cta_matvec_bwd(const float* __restrict__ WT, int R4, const float* dz, int B, float* part,
-                                               float* out, int BP, const float* __restrict__ MWp, size_t mwp_stride, int pair0,
-                                               int npairs, int L, float* pair_out, float* red, SpinGuard& sg) {
+                                               float* out, int BP, SpinGuard& sg) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int nchunk = R4 >> 2;
-    for (int pbase = 0; pbase == 0 || pbase < npairs; pbase += kPairMax) {
+    for (int bt = 0; bt < B; bt += 4) {
+        float acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+        for (int ch = threadIdx.x; ch < nchunk; ch += NT) {
+            const int r = ch << 2;
+            float4 d4[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                d4[b] = (bt + b < B) ? ld_poll4(dz + (size_t)(bt + b) * R4 + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                if (bt + b < B) {
+                    sg.reset();
+                    while (!ready4(d4[b])) {
+                        if (sg.bail()) break;
+                        d4[b] = ld_poll4(dz + (size_t)(bt + b) * R4 + r);
+                    }
+                }
+            }
+            float4 w4[kUMax];
+#pragma unroll
+            for (int ul = 0; ul < kUMax; ++ul) w4[ul] = *reinterpret_cast<const float4*>(WT + (size_t)ul * R4 + r);
+#pragma unroll
+            for (int ul = 0; ul < kUMax; ++ul)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[ul * 4 + b] += dot4(w4[ul], d4[b]);
+        }
+        const float tot = warp_transpose_reduce32(acc);
+        part[w * 32 + lane] = tot;
+        __syncthreads();
+        if ((int)threadIdx.x < 32) {
+            const int ul = threadIdx.x >> 2, b = threadIdx.x & 3;
+            float s = 0.f;
+#pragma unroll
+            for (int q = 0; q < (NT / 32); ++q) s += part[q * 32 + threadIdx.x];
+            if (bt + b < B) out[ul * BP + bt + b] = s;
+        }
+        __syncthreads();
+    }
+}
+// Context-path recurrent term of the owned positions: pair_out[i] = sum_r MWp[i*mwp_stride + r] * dz[b_i*R4 + r] with
+// b_i = (pair0+i)/L (MWp = rows pair0.. of the [B*L][R4] matrix, resident in shared memory or in global memory).
+// All threads must call.  `red` scratch: (NT / 32)*kPairMax floats.
+template <int NT>
+__device__ __forceinline__ void cta_pair_dots(const float* __restrict__ MWp, size_t mwp_stride, const float* dz, int R4, int pair0,
+                                              int npairs, int L, float* pair_out, float* red, SpinGuard& sg) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nchunk = R4 >> 2;
+    for (int pbase = 0; pbase < npairs; pbase += kPairMax) {
         float accp[kPairMax];
 #pragma unroll
         for (int i = 0; i < kPairMax; ++i) accp[i] = 0.f;
-        int pb[kPairMax];
+        for (int ch = threadIdx.x; ch < nchunk; ch += NT) {
+            const int r = ch << 2;
+            float4 d4[kPairMax];
 #pragma unroll
-        for (int i = 0; i < kPairMax; ++i) pb[i] = pbase + i < npairs ? (pair0 + pbase + i) / L : -1;
-        for (int bt = 0; bt < B; bt += 4) {
-            float acc[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-            for (int ch = threadIdx.x; ch < nchunk; ch += kRecThreads) {
-                const int r = ch << 2;
-                float4 d4[4];
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    d4[b] = (bt + b < B) ? ld_poll4(dz + (size_t)(bt + b) * R4 + r) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    if (bt + b < B) {
-                        sg.reset();
-                        while (!ready4(d4[b])) {
-                            if (sg.bail()) break;
-                            d4[b] = ld_poll4(dz + (size_t)(bt + b) * R4 + r);
-                        }
-                    }
-                }
-                if (pbase == 0) {
-                    float4 w4[kUMax];
-#pragma unroll
-                    for (int ul = 0; ul < kUMax; ++ul) w4[ul] = *reinterpret_cast<const float4*>(WT + (size_t)ul * R4 + r);
-#pragma unroll
-                    for (int ul = 0; ul < kUMax; ++ul)
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) acc[ul * 4 + b] += dot4(w4[ul], d4[b]);
-                }
-#pragma unroll
-                for (int i = 0; i < kPairMax; ++i) {
-                    const int bi = pb[i] - bt;
-                    if (pb[i] >= 0 && bi >= 0 && bi < 4) {
-                        const float4 m = *reinterpret_cast<const float4*>(MWp + (size_t)(pbase + i) * mwp_stride + r);
-                        const float4 d = bi == 0 ? d4[0] : (bi == 1 ? d4[1] : (bi == 2 ? d4[2] : d4[3]));
-                        accp[i] += dot4(m, d);
-                    }
-                }
-            }
-            if (pbase == 0) {
-                const float tot = warp_transpose_reduce32(acc);
-                part[w * 32 + lane] = tot;
-                __syncthreads();
-                if ((int)threadIdx.x < 32) {
-                    const int ul = threadIdx.x >> 2, b = threadIdx.x & 3;
-                    float s = 0.f;
-#pragma unroll
-                    for (int q = 0; q < kRecWarps; ++q) s += part[q * 32 + threadIdx.x];
-                    if (bt + b < B) out[ul * BP + bt + b] = s;
-                }
-                __syncthreads();
-            }
-        }
-        if (npairs > 0) {
+            for (int i = 0; i < kPairMax; ++i)
+                if (pbase + i < npairs) d4[i] = ld_poll4(dz + (size_t)((pair0 + pbase + i) / L) * R4 + r);
 #pragma unroll
             for (int i = 0; i < kPairMax; ++i) {
-                const float s = warp_sum(accp[i]);
-                if (lane == 0) red[w * kPairMax + i] = s;
+                if (pbase + i < npairs) {
+                    sg.reset();
+                    while (!ready4(d4[i])) {
+                        if (sg.bail()) break;
+                        d4[i] = ld_poll4(dz + (size_t)((pair0 + pbase + i) / L) * R4 + r);
+                    }
+                    accp[i] += dot4(*reinterpret_cast<const float4*>(MWp + (size_t)(pbase + i) * mwp_stride + r), d4[i]);
+                }
             }
-            __syncthreads();
-            if ((int)threadIdx.x < kPairMax && pbase + (int)threadIdx.x < npairs) {
-                float s = 0.f;
-                for (int q = 0; q < kRecWarps; ++q) s += red[q * kPairMax + threadIdx.x];
-                pair_out[pbase + threadIdx.x] = s;
-            }
-            __syncthreads();
         }
+#pragma unroll
+        for (int i = 0; i < kPairMax; ++i) {
+            const float s = warp_sum(accp[i]);
+            if (lane == 0) red[w * kPairMax + i] = s;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < kPairMax && pbase + (int)threadIdx.x < npairs) {
+            float s = 0.f;
+            for (int q = 0; q < (NT / 32); ++q) s += red[q * kPairMax + threadIdx.x];
+            pair_out[pbase + threadIdx.x] = s;
+        }
+        __syncthreads();
     }
 }
 
