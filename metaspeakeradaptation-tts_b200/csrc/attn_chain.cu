@@ -604,6 +604,8 @@ static int attn_check(int B, int Ha, int A, int F, int sm_count) {
     MSA_CHECK(B >= 1 && B <= kBMax, MSA_E_UNSUPPORTED, "attn_chain: batch %d outside [1,%d]", B, kBMax);
     MSA_CHECK((Ha + sm_count - 1) / sm_count <= kUMax, MSA_E_UNSUPPORTED,
               "attn_chain: attention_rnn_dim %d needs more than %d units per CTA on %d CTAs", Ha, kUMax, sm_count);
+    MSA_CHECK(4 * ((Ha + sm_count - 1) / sm_count) * B <= kAttnThreads, MSA_E_UNSUPPORTED,
+              "attn_chain: %d units x %d batch rows per CTA exceed the point-wise thread budget", (Ha + sm_count - 1) / sm_count, B);
     (void)A;
     return 0;
 }

@@ -145,6 +145,33 @@ int k_wloc_grad(const float* dconvf, const float* align, const float* cum, float
                 int Kl, float scale, int accumulate, cudaStream_t st);
 int k_dot_rows(const float* a, const float* b, int64_t n, float* partials, float* out, float scale, int accumulate, cudaStream_t st);
 int k_masks_generate(uint8_t* masks, const int64_t* offsets, const int64_t* numels, const float* ps, int nsec, uint64_t seed, cudaStream_t st);
+// ---------------- free-running inference, per-step kernels (infer_kernels.cu) ----------------
+struct InferAttnParams {
+    int B, L, Ha, A, F, Kl, E, norm, max_steps;
+    const float* ha; int ld_ha;
+    const float* wq;
+    const float* wloc;
+    const float* wld;
+    const float* v; const float* bv;
+    const float* pm;
+    const float* memory;
+    float* prev; float* cum;
+    float* ctx1; int ld1; float* ctx2; int ld2; float* ctx3; int ld3;
+    float* align_out;
+    const int* state;
+};
+int k_fill_ones_i32(int* p, int n, cudaStream_t st);
+int k_infer_relu_drop(float* x, int ld, const uint8_t* masks, int layer, int B, int N, const int* state, cudaStream_t st);
+int k_infer_lstm_point(const float* z, const float* b_ih, const float* b_hh, float* c, float* h1, int ld1, float* h2, int ld2,
+                       int B, int H, const int* state, cudaStream_t st);
+size_t infer_attention_smem(int L, int A, int F, int Kl);
+int k_infer_attention(const InferAttnParams& p, cudaStream_t st);
+int k_infer_finish(const float* mel_raw, const float* bp, const float* gate_raw, const float* bg, float* mel_tm, float* frame,
+                   int* not_finished, int* mel_lengths, int B, int M, float threshold, int early, int max_steps, int* state,
+                   cudaStream_t st);
+int k_tm_to_ref_ld(const float* x_tm, float* out, int T, int B, int M, int ld, cudaStream_t st);
+int k_bt_to_ref_ld(const float* x_bt, float* out, int B, int T, int M, int ld, cudaStream_t st);
+
 int k_fill_canary(float* p, int64_t n, cudaStream_t st);   // n floats (multiple of 4, 16-byte aligned) <- 0xFFFFFFFF
 int k_scale_copy(const float* in, float* out, int64_t n, float scale, int accumulate, cudaStream_t st);
 

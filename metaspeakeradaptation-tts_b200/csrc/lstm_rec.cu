@@ -213,8 +213,9 @@ static int rec_check(int B, int H, int ndir, int sm_count) {
     MSA_CHECK(H % 4 == 0, MSA_E_UNSUPPORTED, "lstm_rec: hidden size %d must be a multiple of 4", H);
     MSA_CHECK(B >= 1 && B <= kBMax, MSA_E_UNSUPPORTED, "lstm_rec: batch %d outside [1,%d]", B, kBMax);
     const int ncta_dir = sm_count / ndir;
-    MSA_CHECK(ncta_dir >= 1 && (H + ncta_dir - 1) / ncta_dir <= kUMax, MSA_E_UNSUPPORTED,
-              "lstm_rec: hidden size %d needs more than %d units per CTA on %d CTAs", H, kUMax, ncta_dir);
+    const int umax = ncta_dir >= 1 ? (H + ncta_dir - 1) / ncta_dir : kUMax + 1;
+    MSA_CHECK(umax <= kUMax, MSA_E_UNSUPPORTED, "lstm_rec: hidden size %d needs more than %d units per CTA on %d CTAs", H, kUMax, ncta_dir);
+    MSA_CHECK(4 * umax * B <= kRecThreads, MSA_E_UNSUPPORTED, "lstm_rec: %d units x %d batch rows per CTA exceed the point-wise thread budget", umax, B);
     return 0;
 }
 

@@ -907,3 +907,257 @@ int msa_get_buffer(msa_handle* h, void* wsp, const char* name, void** ptr, int64
 }
 
 }  // extern "C"
+
+// =====================================================================================================
+// free-running inference (Tacotron2NV.infer, models/tacotron2nv.py:130-162; Decoder.infer, decoder.py:334-411)
+namespace msa {
+
+#define IWS_LIST(X)                                                                                       \
+    X(spk_vec, d.B * d.Ds) X(enc_x, 2 * d.BL * d.C) X(enc_y, d.BL * d.C) X(enc_bn, 2 * std::max(d.C, d.Cmax)) \
+    X(enc_col, d.BL * d.Kc * d.C) X(enc_w2, (int64_t)d.C * d.Kc * d.C) X(x3_tm, d.BL * d.C)              \
+    X(enc_zx, 2 * d.BL * 4 * d.Hh) X(enc_g, 2 * d.BL * 4 * d.Hh) X(enc_c, 2 * d.BL * d.Hh)               \
+    X(enc_h, 2 * d.BL * d.Hh) X(memory, d.BL * d.E) X(pm, d.BL * d.A)                                    \
+    X(xin_a, d.B * (d.Pd + d.E)) X(p1, d.B * d.Pd) X(ha, d.B * d.Ha) X(ca, d.B * d.Ha)                   \
+    X(xin_d, d.B * (d.Ha + d.E)) X(hd, d.B * d.Hd) X(cd, d.B * d.Hd) X(xin_p, d.B * (d.Hd + d.E))        \
+    X(za, d.B * 4 * d.Ha) X(zd, d.B * 4 * d.Hd) X(mel_raw, d.B * d.M) X(gate_raw, d.B) X(frame, d.B * d.M) \
+    X(prev, d.BL) X(cum, d.BL) X(mel_tm, (int64_t)d.T * d.B * d.M) X(ints, 64 + d.B)                      \
+    X(post_x, 2 * d.BT * d.Cmax) X(post_y, d.BT * d.Cmax) X(post_col, d.BT * d.Kp * d.Cmax)              \
+    X(post_w2, (int64_t)d.Cmax * d.Kp * d.Cmax) X(post_bt, d.BT * d.M)
+
+struct IWs {
+#define X(name, n) float* name; int64_t n_##name;
+    IWS_LIST(X)
+#undef X
+    unsigned int* abort_word;
+    void* blas_ws;
+    size_t blas_ws_bytes;
+    size_t total_bytes;
+};
+static IWs iws_layout(const Dims& d, void* base) {
+    IWs w;
+    size_t o = 0;
+    char* b = static_cast<char*>(base);
+#define X(name, n)                                        \
+    w.n_##name = (int64_t)(n);                            \
+    w.name = reinterpret_cast<float*>(b + o);             \
+    o += (size_t)align_up((int64_t)(n), 64) * sizeof(float);
+    IWS_LIST(X)
+#undef X
+    w.abort_word = reinterpret_cast<unsigned int*>(b + o);
+    o += 256;
+    w.blas_ws = b + o;
+    w.blas_ws_bytes = kBlasWs;
+    o += kBlasWs;
+    w.total_bytes = o;
+    return w;
+}
+
+// conv1d ("same") + BatchNorm(eval: running statistics) + activation, channels-last rows = B*Tn (no dropout in eval)
+static int conv_bn_eval(msa_handle* h, cudaStream_t st, const float* params, const std::string& pfx, const float* x, float* y,
+                        float* xout, float* col, float* w2, float* bn_mean, float* bn_invstd, const float* running, int B, int Tn,
+                        int Ci, int Co, int K, int act) {
+    const int64_t rows = (int64_t)B * Tn;
+    MSA_TRY(k_conv_w_pack(params + h->off(pfx + ".0.conv.weight"), w2, Co, Ci, K, st));
+    MSA_TRY(k_im2col(x, col, B, Tn, Ci, K, st));
+    MSA_TRY(k_fill_rows(y, params + h->off(pfx + ".0.conv.bias"), nullptr, rows, Co, st));
+    MSA_TRY(gemm(h, false, true, rows, Co, (int64_t)K * Ci, 1.f, col, (int64_t)K * Ci, w2, (int64_t)K * Ci, 1.f, y, Co));
+    MSA_TRY(k_bn_eval_stats(running, Co, (int)align_up(Co), bn_mean, bn_invstd, st));
+    MSA_TRY(k_bn_act_drop_fwd(y, bn_mean, bn_invstd, params + h->off(pfx + ".1.weight"), params + h->off(pfx + ".1.bias"), nullptr,
+                              1.0f, act, xout, rows, Co, st));
+    return 0;
+}
+
+static int infer_check(const msa_handle* h) {
+    const msa_config& c = h->cfg;
+    MSA_CHECK(!c.forward_attn && !c.trans_agent && !c.windowing && !c.forward_attn_mask, MSA_E_UNSUPPORTED,
+              "msa_infer: forward_attn / trans_agent / windowing / forward_attn_mask are not implemented in the CUDA inference path yet "
+              "(forward_attn.py:139-176,222-224)");
+    return 0;
+}
+
+}  // namespace msa
+
+extern "C" {
+
+size_t msa_infer_workspace_bytes(const msa_handle* h, int B, int L, int max_steps) {
+    if (!h || B <= 0 || L <= 0 || max_steps <= 0) return 0;
+    return iws_layout(make_dims(h->cfg, B, max_steps, L), nullptr).total_bytes;
+}
+
+int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, const float* bn_stats, const int64_t* tokens,
+              const int64_t* token_lengths, const float* speaker_vecs, const int64_t* speaker_ids, const uint8_t* prenet_masks,
+              int B, int L, int max_steps, float* mel_post_out, int32_t* mel_lengths_out, float* align_out, int32_t* n_steps_out,
+              void* stream) {
+    MSA_CHECK(h && wsp && params && bn_stats && tokens && token_lengths && prenet_masks && mel_post_out && mel_lengths_out &&
+              align_out && n_steps_out, MSA_E_ARG, "msa_infer: null argument");
+    MSA_CHECK(B >= 1 && L >= 1 && max_steps >= 1, MSA_E_ARG, "msa_infer: bad dims B=%d L=%d max_steps=%d", B, L, max_steps);
+    MSA_CHECK(h->cfg.spk_mode == 2 ? speaker_ids != nullptr : speaker_vecs != nullptr, MSA_E_ARG, "msa_infer: speaker input missing");
+    MSA_TRY(infer_check(h));
+    const Dims d = make_dims(h->cfg, B, max_steps, L);
+    const IWs w = iws_layout(d, wsp);
+    MSA_CHECK(ws_bytes >= w.total_bytes, MSA_E_WORKSPACE, "msa_infer: workspace %zu < %zu bytes", ws_bytes, w.total_bytes);
+    MSA_CHECK(((uintptr_t)wsp & 255) == 0, MSA_E_ARG, "msa_infer: workspace must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    MSA_CUDA(cudaSetDevice(h->device));
+    MSA_BLAS(cublasSetStream(h->blas, st));
+    MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
+    h->in_bwd = false;
+    h->fwd_valid = false;
+    const msa_config& c = h->cfg;
+    auto P = [&](const std::string& n) { return params + h->off(n); };
+    MSA_CUDA(cudaMemsetAsync(w.abort_word, 0, 256, st));
+
+    // ---- speaker vector + encoder in eval mode (tacotron2nv.py:137-148, encoder.py:55-71) ----
+    if (c.spk_mode == 0) {
+        MSA_TRY(k_scale_copy(speaker_vecs, w.spk_vec, (int64_t)B * d.Ds, 1.f, 0, st));
+    } else if (c.spk_mode == 1) {
+        MSA_TRY(k_fill_rows(w.spk_vec, P("speaker_lin.bias"), nullptr, B, d.Ds, st));
+        MSA_TRY(gemm(h, false, true, B, d.Ds, d.Dsin, 1.f, speaker_vecs, d.Dsin, P("speaker_lin.weight"), d.Dsin, 1.f, w.spk_vec, d.Ds));
+    } else {
+        MSA_TRY(k_embedding_fwd(P("speaker_embedder.weight"), speaker_ids, w.spk_vec, B, d.Ds, c.num_speakers, st));
+    }
+    const int64_t ex = d.BL * d.C;
+    MSA_TRY(k_embedding_fwd(P("embedding.weight"), tokens, w.enc_x, (int)d.BL, d.C, c.n_symbols, st));
+    for (int i = 0; i < d.nEnc; ++i)
+        MSA_TRY(conv_bn_eval(h, st, params, "encoder.convolutions." + std::to_string(i), w.enc_x + (i & 1) * ex, w.enc_y,
+                             w.enc_x + ((i + 1) & 1) * ex, w.enc_col, w.enc_w2, w.enc_bn, w.enc_bn + std::max(d.C, d.Cmax),
+                             bn_stats + h->bn_offs[i], B, L, d.C, d.C, d.Kc, 1));
+    MSA_TRY(k_transpose01(w.enc_x + (d.nEnc & 1) * ex, w.x3_tm, B, L, d.C, st));
+    const int H4e = 4 * d.Hh;
+    for (int dir = 0; dir < 2; ++dir) {
+        const std::string sfx = dir ? "_reverse" : "";
+        float* zx = w.enc_zx + (int64_t)dir * d.BL * H4e;
+        MSA_TRY(k_fill_rows(zx, P("encoder.lstm.bias_ih_l0" + sfx), P("encoder.lstm.bias_hh_l0" + sfx), d.BL, H4e, st));
+        MSA_TRY(gemm(h, false, true, d.BL, H4e, d.C, 1.f, w.x3_tm, d.C, P("encoder.lstm.weight_ih_l0" + sfx), d.C, 1.f, zx, H4e));
+    }
+    {
+        LstmRecParams lp{};
+        lp.T = L; lp.B = B; lp.H = d.Hh; lp.ndir = 2;
+        lp.zin = w.enc_zx; lp.whh = P("encoder.lstm.weight_hh_l0");
+        lp.whh_dir_stride = h->off("encoder.lstm.weight_hh_l0_reverse") - h->off("encoder.lstm.weight_hh_l0");
+        lp.hout = w.enc_h; lp.cout = w.enc_c; lp.gates = w.enc_g; lp.mask = nullptr; lp.drop_scale = 1.f;
+        lp.lengths = token_lengths; lp.abort_word = w.abort_word; lp.prof = nullptr; lp.trace = nullptr; lp.trace_t0 = 0;
+        lp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
+        MSA_TRY(launch_lstm_rec_fwd(lp, h->sm_count, h->smem_limit, st));
+    }
+    MSA_TRY(k_build_memory(w.enc_h, w.spk_vec, w.memory, B, L, d.Hh, d.Ds, st));
+    const std::string at = "decoder.attention_layer.";
+    MSA_TRY(gemm(h, false, true, d.BL, d.A, d.E, 1.f, w.memory, d.E, P(at + "inputs_layer.linear_layer.weight"), d.E, 0.f, w.pm, d.A));
+
+    // ---- decoder state (decoder.py:337-360, forward_attn.py:103-116) ----
+    const int KA = d.Pd + d.E, KD = d.Ha + d.E, KP = d.Hd + d.E;
+    int* ints = reinterpret_cast<int*>(w.ints);
+    int* state = ints;                 // [0] step, [1] done, [2] steps produced
+    int* not_finished = ints + 64;     // [B]
+    MSA_CUDA(cudaMemsetAsync(w.xin_a, 0, sizeof(float) * (size_t)B * KA, st));
+    MSA_CUDA(cudaMemsetAsync(w.ha, 0, sizeof(float) * (size_t)B * d.Ha, st));
+    MSA_CUDA(cudaMemsetAsync(w.ca, 0, sizeof(float) * (size_t)B * d.Ha, st));
+    MSA_CUDA(cudaMemsetAsync(w.xin_d, 0, sizeof(float) * (size_t)B * KD, st));
+    MSA_CUDA(cudaMemsetAsync(w.hd, 0, sizeof(float) * (size_t)B * d.Hd, st));
+    MSA_CUDA(cudaMemsetAsync(w.cd, 0, sizeof(float) * (size_t)B * d.Hd, st));
+    MSA_CUDA(cudaMemsetAsync(w.xin_p, 0, sizeof(float) * (size_t)B * KP, st));
+    MSA_CUDA(cudaMemsetAsync(w.frame, 0, sizeof(float) * (size_t)B * d.M, st));
+    MSA_CUDA(cudaMemsetAsync(w.prev, 0, sizeof(float) * (size_t)d.BL, st));
+    MSA_CUDA(cudaMemsetAsync(w.cum, 0, sizeof(float) * (size_t)d.BL, st));
+    MSA_CUDA(cudaMemsetAsync(ints, 0, sizeof(int) * 64, st));
+    MSA_CUDA(cudaMemsetAsync(mel_lengths_out, 0, sizeof(int32_t) * (size_t)B, st));
+    MSA_TRY(k_fill_ones_i32(not_finished, B, st));
+    MSA_CUDA(cudaMemsetAsync(align_out, 0, sizeof(float) * (size_t)B * max_steps * L, st));
+    MSA_CUDA(cudaMemsetAsync(mel_post_out, 0, sizeof(float) * (size_t)B * d.M * max_steps, st));
+
+    // ---- one decoder step (decoder.py:362-399 -> decode 234-274); the step index lives on the device ----
+    const float* Wia = P("decoder.attention_rnn.weight_ih");
+    const float* Wid = P("decoder.decoder_rnn.weight_ih");
+    auto step = [&]() -> int {
+        // prenet, dropout always on (decoder.py:9-20,366)
+        MSA_TRY(gemm(h, false, true, B, d.Pd, d.M, 1.f, w.frame, d.M, P("decoder.prenet.layers.0.linear_layer.weight"), d.M, 0.f, w.p1, d.Pd));
+        MSA_TRY(k_infer_relu_drop(w.p1, d.Pd, prenet_masks, 0, B, d.Pd, state, st));
+        MSA_TRY(gemm(h, false, true, B, d.Pd, d.Pd, 1.f, w.p1, d.Pd, P("decoder.prenet.layers.1.linear_layer.weight"), d.Pd, 0.f, w.xin_a, KA));
+        MSA_TRY(k_infer_relu_drop(w.xin_a, KA, prenet_masks, 1, B, d.Pd, state, st));
+        // attention LSTMCell on [prenet; ctx(t-1)] (decoder.py:253-255)
+        MSA_TRY(gemm(h, false, true, B, 4 * d.Ha, KA, 1.f, w.xin_a, KA, Wia, KA, 0.f, w.za, 4 * d.Ha));
+        MSA_TRY(gemm(h, false, true, B, 4 * d.Ha, d.Ha, 1.f, w.ha, d.Ha, P("decoder.attention_rnn.weight_hh"), d.Ha, 1.f, w.za, 4 * d.Ha));
+        MSA_TRY(k_infer_lstm_point(w.za, P("decoder.attention_rnn.bias_ih"), P("decoder.attention_rnn.bias_hh"), w.ca, w.ha, d.Ha,
+                                   w.xin_d, KD, B, d.Ha, state, st));
+        // attention (forward_attn.py:178-219)
+        InferAttnParams ap{};
+        ap.B = B; ap.L = L; ap.Ha = d.Ha; ap.A = d.A; ap.F = d.F; ap.Kl = d.Kl; ap.E = d.E; ap.norm = c.attn_norm; ap.max_steps = max_steps;
+        ap.ha = w.ha; ap.ld_ha = d.Ha;
+        ap.wq = P(at + "query_layer.linear_layer.weight"); ap.wloc = P(at + "location_layer.location_conv1d.weight");
+        ap.wld = P(at + "location_layer.location_dense.linear_layer.weight");
+        ap.v = P(at + "v.linear_layer.weight"); ap.bv = P(at + "v.linear_layer.bias");
+        ap.pm = w.pm; ap.memory = w.memory; ap.prev = w.prev; ap.cum = w.cum;
+        ap.ctx1 = w.xin_a + d.Pd; ap.ld1 = KA; ap.ctx2 = w.xin_d + d.Ha; ap.ld2 = KD; ap.ctx3 = w.xin_p + d.Hd; ap.ld3 = KP;
+        ap.align_out = align_out; ap.state = state;
+        MSA_TRY(k_infer_attention(ap, st));
+        // decoder LSTMCell on [h_a; ctx] (decoder.py:260-264)
+        MSA_TRY(gemm(h, false, true, B, 4 * d.Hd, KD, 1.f, w.xin_d, KD, Wid, KD, 0.f, w.zd, 4 * d.Hd));
+        MSA_TRY(gemm(h, false, true, B, 4 * d.Hd, d.Hd, 1.f, w.hd, d.Hd, P("decoder.decoder_rnn.weight_hh"), d.Hd, 1.f, w.zd, 4 * d.Hd));
+        MSA_TRY(k_infer_lstm_point(w.zd, P("decoder.decoder_rnn.bias_ih"), P("decoder.decoder_rnn.bias_hh"), w.cd, w.hd, d.Hd,
+                                   w.xin_p, KP, B, d.Hd, state, st));
+        // projections + stop logic (decoder.py:267-270, 381-395)
+        MSA_TRY(gemm(h, false, true, B, d.M, KP, 1.f, w.xin_p, KP, P("decoder.linear_projection.linear_layer.weight"), KP, 0.f, w.mel_raw, d.M));
+        MSA_TRY(gemm(h, false, true, B, 1, KP, 1.f, w.xin_p, KP, P("decoder.gate_layer.linear_layer.weight"), KP, 0.f, w.gate_raw, 1));
+        MSA_TRY(k_infer_finish(w.mel_raw, P("decoder.linear_projection.linear_layer.bias"), w.gate_raw,
+                               P("decoder.gate_layer.linear_layer.bias"), w.mel_tm, w.frame, not_finished, mel_lengths_out, B, d.M,
+                               c.gate_threshold, c.early_stopping, max_steps, state, st));
+        return 0;
+    };
+    // capture one step as a CUDA graph and replay it; fall back to direct launches if capture is refused
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    int enqueued = 0;
+    if (getenv("MSA_INFER_NO_GRAPH") == nullptr && max_steps > 1) {
+        MSA_TRY(step());      // step 0 directly: lets cuBLAS pick its kernels / workspace outside the capture
+        enqueued = 1;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const int rc = step();
+            const cudaError_t e = cudaStreamEndCapture(st, &graph);
+            if (rc != 0 || e != cudaSuccess || !graph || cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) {
+                if (graph) cudaGraphDestroy(graph);
+                graph = nullptr;
+                gexec = nullptr;
+                cudaGetLastError();
+                MSA_CHECK(rc == 0, MSA_E_STATE, "msa_infer: a decoder step failed during graph capture");
+            }
+        } else {
+            cudaGetLastError();
+        }
+    }
+    int host_state[4] = {0, 0, 0, 0};
+    const int check_every = 128;
+    for (int s = enqueued; s < max_steps; ++s) {
+        if (gexec) MSA_CUDA(cudaGraphLaunch(gexec, st));
+        else MSA_TRY(step());
+        if (c.early_stopping && (s % check_every) == check_every - 1) {      // all rows finished: stop enqueueing no-op steps
+            MSA_CUDA(cudaMemcpyAsync(host_state, state, sizeof(int) * 3, cudaMemcpyDeviceToHost, st));
+            MSA_CUDA(cudaStreamSynchronize(st));
+            if (host_state[1]) break;
+        }
+    }
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
+    MSA_CUDA(cudaMemcpyAsync(host_state, state, sizeof(int) * 3, cudaMemcpyDeviceToHost, st));
+    MSA_CUDA(cudaStreamSynchronize(st));      // the postnet needs T' on the host (its "same" padding ends at T')
+    const int Tn = host_state[2];
+    MSA_CHECK(Tn >= 1 && Tn <= max_steps, MSA_E_STATE, "msa_infer: decoder produced %d steps", Tn);
+    MSA_CUDA(cudaMemcpyAsync(n_steps_out, state + 2, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+
+    // ---- postnet in eval mode on [B, T', M] + residual (decoder.py:63-72, tacotron2nv.py:155-157) ----
+    const int64_t px = (int64_t)B * Tn * d.Cmax;
+    MSA_TRY(k_transpose01(w.mel_tm, w.post_bt, Tn, B, d.M, st));      // [T'][B][M] -> mel [B][T'][M]
+    const float* src = w.post_bt;
+    for (int i = 0; i < d.nPost; ++i) {
+        const int ci = i == 0 ? d.M : d.Cp, co = i == d.nPost - 1 ? d.M : d.Cp;
+        float* dst = w.post_x + (i & 1) * px;
+        MSA_TRY(conv_bn_eval(h, st, params, "postnet.convolutions." + std::to_string(i), src, w.post_y, dst, w.post_col, w.post_w2,
+                             w.enc_bn, w.enc_bn + std::max(d.C, d.Cmax), bn_stats + h->bn_offs[d.nEnc + i], B, Tn, ci, co, d.Kp,
+                             i < d.nPost - 1 ? 2 : 0));
+        src = dst;
+    }
+    MSA_TRY(k_add(w.post_bt, src, w.post_y, (int64_t)B * Tn * d.M, st));
+    MSA_TRY(k_bt_to_ref_ld(w.post_y, mel_post_out, B, Tn, d.M, max_steps, st));
+    return 0;
+}
+
+}  // extern "C"

@@ -19,7 +19,7 @@ namespace msa {
 constexpr int kRecThreads = 512;
 constexpr int kRecWarps = kRecThreads / 32;
 constexpr int kUMax = 8;        // max hidden units per CTA (=> 32 gate rows, one transpose-reduce)
-constexpr int kBMax = 16;       // max batch rows of one pass through the recurrent kernels
+constexpr int kBMax = 32;       // max batch rows of one pass through the recurrent kernels (also: 4*units*B <= threads)
 constexpr int kBTiles = kBMax / 4;
 
 __host__ __device__ inline int round_up_i(int n, int m) { return (n + m - 1) / m * m; }

@@ -144,6 +144,15 @@ class Engine:
             t[o + cp:o + cp + c] = 1.0
         return t.to(self.device)
 
+    def bn_from_dict(self, stats: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """{"<bn layer>.running_mean" / ".running_var": tensor} (reference state_dict keys) -> flat BN buffer."""
+        t = torch.zeros(self.layout.bn_total, dtype=torch.float32)
+        for name, o, c in zip(self.layout.bn_names, self.layout.bn_offsets, self.layout.bn_ch):
+            cp = (c + 31) // 32 * 32
+            t[o:o + c] = stats[name + ".running_mean"].detach().float().cpu()
+            t[o + cp:o + cp + c] = stats[name + ".running_var"].detach().float().cpu()
+        return t.to(self.device)
+
     def bn_dict(self, stats: torch.Tensor) -> Dict[str, torch.Tensor]:
         out = {}
         for name, o, c in zip(self.layout.bn_names, self.layout.bn_offsets, self.layout.bn_ch):
@@ -242,6 +251,38 @@ class Engine:
         d = [torch.empty(B, M, T, device=self.device), torch.empty(B, M, T, device=self.device), torch.empty(B, T, device=self.device)]
         _lib.check(self.lib.msa_loss_grads(self.h, self._ws_ptr(), _ptr(d[0]), _ptr(d[1]), _ptr(d[2]), _stream()), "msa_loss_grads")
         return d
+
+    def infer(self, params: torch.Tensor, bn_stats: torch.Tensor, inputs: torch.Tensor, input_lengths: torch.Tensor,
+              speaker_vecs: torch.Tensor, prenet_masks: torch.Tensor, max_steps: Optional[int] = None):
+        """Tacotron2NV.infer (tacotron2nv.py:130-162): -> (mel_post [B, n_mel, T'], mel_lengths int32 [B], align [B, T', L]).
+
+        prenet_masks: uint8 keep-masks [max_steps, 2, B, prenet_dim] (the prenet dropout stays on in eval)."""
+        B, L = inputs.shape
+        max_steps = int(max_steps or self.cfg["max_decoder_steps"])
+        M = self.cfg["n_mel_channels"]
+        need = int(self.lib.msa_infer_workspace_bytes(self.h, B, L, max_steps))
+        if self._ws is None or self._ws.numel() < need + 256:
+            self._ws = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+        dev = self.device
+        mel_post = torch.empty(B, M, max_steps, device=dev)
+        mel_len = torch.empty(B, dtype=torch.int32, device=dev)
+        align = torch.empty(B, max_steps, L, device=dev)
+        n_steps = torch.zeros(1, dtype=torch.int32, device=dev)
+        pm = prenet_masks.to(device=dev, dtype=torch.uint8).contiguous()
+        if pm.numel() < max_steps * 2 * B * self.cfg["prenet_dim"]:
+            raise ValueError("prenet_masks must cover max_steps decoder steps")
+        spk = speaker_vecs.to(dev).contiguous()
+        spk_f = spk if spk.dtype.is_floating_point else None
+        spk_i = None if spk.dtype.is_floating_point else spk
+        inp = inputs.to(dev).contiguous()
+        inl = input_lengths.to(dev).contiguous()
+        rc = self.lib.msa_infer(self.h, self._ws_ptr(), C.c_size_t(self._ws.numel() - 256), _ptr(params), _ptr(bn_stats), _ptr(inp),
+                                _ptr(inl), _ptr(spk_f), _ptr(spk_i), _ptr(pm), B, L, max_steps, _ptr(mel_post), _ptr(mel_len),
+                                _ptr(align), _ptr(n_steps), _stream())
+        _lib.check(rc, "msa_infer")
+        self.launches += 1
+        T = int(n_steps.item())
+        return mel_post[:, :, :T], mel_len, align[:, :T, :]
 
     def get_buffer(self, name: str) -> torch.Tensor:
         """Copy of a named intermediate of the last pass (tests only)."""
