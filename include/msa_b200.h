@@ -145,6 +145,14 @@ int msa_train_backward(msa_handle* h, void* ws, size_t ws_bytes, const float* pa
  * (metatrainer.py:83-86); also refreshes d(loss)/d(outputs) used by msa_train_backward(NULL,...). */
 int msa_train_loss(msa_handle* h, void* ws, const float* stop_targets, const int64_t* mel_lengths, int reduction,
                    float pos_weight, float* loss_out, void* stream);
+/* Tacotron2Loss.__call__ as a stand-alone operator on reference-layout tensors (tacotron2nv_loss.py:17-52):
+ * mel / mel_post / mel_target [B, n_mel, T], gate / stop_targets [B, T], mel_lengths int64 [B]; writes the scalar loss and,
+ * where the pointers are not NULL, d(loss)/d(mel, mel_post, gate).  scratch: msa_loss_scratch_floats(B, T, n_mel) floats. */
+size_t msa_loss_scratch_floats(int B, int T, int n_mel);
+int msa_tacotron2_loss(const float* mel, const float* mel_post, const float* gate, const float* mel_target,
+                       const float* stop_targets, const int64_t* mel_lengths, int B, int T, int n_mel, int reduction,
+                       float pos_weight, float* scratch, float* loss_out, float* d_mel, float* d_mel_post, float* d_gate,
+                       void* stream);
 /* d(loss)/d(mel, mel_post, gate) of the last forward, reference layouts (for autograd glue) */
 int msa_loss_grads(msa_handle* h, void* ws, float* d_mel, float* d_mel_post, float* d_gate, void* stream);
 /* The persistent kernels hand data between CTAs by polling (no grid barrier); a producer that never arrives makes

@@ -12,4 +12,20 @@ PyTorch fallback.
 from .config import default_params, small_params  # noqa: F401
 from .layout import FlatLayout  # noqa: F401
 
-__all__ = ["default_params", "small_params", "FlatLayout"]
+__all__ = ["default_params", "small_params", "FlatLayout", "Tacotron2NV", "Tacotron2Loss", "innerloop_ctx", "EWC"]
+
+
+def __getattr__(name):      # GPU-facing classes import lazily: the pure-Python pieces above work on a CPU-only box
+    if name == "Tacotron2NV":
+        from .model import Tacotron2NV
+        return Tacotron2NV
+    if name == "Tacotron2Loss":
+        from .loss import Tacotron2Loss
+        return Tacotron2Loss
+    if name == "innerloop_ctx":
+        from .innerloop import innerloop_ctx
+        return innerloop_ctx
+    if name == "EWC":
+        from .ewc import EWC
+        return EWC
+    raise AttributeError(name)

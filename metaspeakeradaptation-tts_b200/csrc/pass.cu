@@ -646,6 +646,32 @@ int msa_train_loss(msa_handle* h, void* wsp, const float* stop_targets, const in
     return 0;
 }
 
+size_t msa_loss_scratch_floats(int B, int T, int n_mel) {
+    return (size_t)7 * align_up((int64_t)B * T * n_mel, 64) + (size_t)2 * align_up((int64_t)B * T, 64) + 2048;
+}
+int msa_tacotron2_loss(const float* mel, const float* mel_post, const float* gate, const float* mel_target, const float* stop_targets,
+                       const int64_t* mel_lengths, int B, int T, int n_mel, int reduction, float pos_weight, float* scratch,
+                       float* loss_out, float* d_mel, float* d_mel_post, float* d_gate, void* stream) {
+    MSA_CHECK(mel && mel_post && gate && mel_target && stop_targets && mel_lengths && scratch && loss_out, MSA_E_ARG,
+              "msa_tacotron2_loss: null argument");
+    MSA_CHECK(B >= 1 && T >= 1 && n_mel >= 1 && (reduction == 0 || reduction == 1), MSA_E_ARG, "msa_tacotron2_loss: bad dims / reduction");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = align_up((int64_t)B * T * n_mel, 64), ng = align_up((int64_t)B * T, 64);
+    float *pre_bt = scratch, *post_bt = pre_bt + n, *tgt_bt = post_bt + n, *dpre = tgt_bt + n, *dpost = dpre + n, *dgate = dpost + n;
+    float* part = dgate + ng;      // 1024 partials + the scalar
+    float* lossb = part + 1024;
+    MSA_TRY(k_ref_to_bt(mel, pre_bt, B, T, n_mel, st));
+    MSA_TRY(k_ref_to_bt(mel_post, post_bt, B, T, n_mel, st));
+    MSA_TRY(k_ref_to_bt(mel_target, tgt_bt, B, T, n_mel, st));
+    MSA_TRY(k_loss(pre_bt, post_bt, gate, tgt_bt, stop_targets, mel_lengths, B, T, n_mel, reduction, pos_weight, part, lossb, dpre, dpost,
+                   dgate, st));
+    MSA_TRY(k_scale_copy(lossb, loss_out, 1, 1.f, 0, st));
+    if (d_mel) MSA_TRY(k_bt_to_ref(dpre, d_mel, B, T, n_mel, st));
+    if (d_mel_post) MSA_TRY(k_bt_to_ref(dpost, d_mel_post, B, T, n_mel, st));
+    if (d_gate) MSA_TRY(k_scale_copy(dgate, d_gate, (int64_t)B * T, 1.f, 0, st));
+    return 0;
+}
+
 int msa_loss_grads(msa_handle* h, void* wsp, float* d_mel, float* d_mel_post, float* d_gate, void* stream) {
     MSA_CHECK(h && wsp && h->fwd_valid, MSA_E_STATE, "msa_loss_grads: no forward pass in this workspace");
     const Dims& d = h->d;

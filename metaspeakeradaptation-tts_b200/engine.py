@@ -96,6 +96,7 @@ class Engine:
         self._partials = torch.empty(self.lib.msa_flat_partials(), dtype=torch.float32, device=self.device)
         self._keep: tuple = ()
         self.launches = 0   # kernels of this library enqueued by the calls below (bench.py's gpu_launches)
+        self._last_out = None
 
     def __del__(self):
         try:

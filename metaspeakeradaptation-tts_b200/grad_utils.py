@@ -1,8 +1,9 @@
 """Drop-in for msa_tts/utils/grad_utils.py on flat buffers.
 
-``mix_grad`` / ``apply_grad`` keep the reference signatures (lists of per-parameter tensors) for callers that
-want them; tensors that are views of flat buffers are combined with ONE fused launch per task instead of
-61 x N tiny ones (utils/grad_utils.py:23-31 stacks and sums tensor by tensor)."""
+``mix_grad`` / ``apply_grad`` keep the reference signatures (lists of per-parameter tensors).  Gradient lists produced by
+this package are views of ONE flat buffer (``Tacotron2NV.layout_views``), so the weighted sum over tasks is one fused launch
+per task instead of 61 x N tiny ones (utils/grad_utils.py:23-31 stacks and sums tensor by tensor), and ``apply_grad`` is one
+copy / accumulate plus the fused norm."""
 from __future__ import annotations
 
 from typing import List, Sequence
@@ -11,21 +12,21 @@ import torch
 
 
 def _flat_of(tensors: Sequence[torch.Tensor]):
-    """The flat buffer a list of per-parameter views came from (set by Engine.param_views), else None."""
-    base = getattr(tensors[0], "_msa_flat", None)
-    return base
+    """The flat buffer a list of per-parameter views came from (set by Tacotron2NV.layout_views), else None."""
+    return getattr(tensors[0], "_msa_flat", None)
 
 
-def mix_grad(grad_list, weight_list, engine=None) -> List[torch.Tensor]:
-    """Weighted sum of per-task gradient lists (grad_utils.py:23-31)."""
+def mix_grad(grad_list, weight_list, model) -> List[torch.Tensor]:
+    """Weighted sum of per-task gradient lists (grad_utils.py:23-31): sum_i w_i * g_i."""
     flats = [_flat_of(g) for g in grad_list]
-    if engine is None or any(f is None for f in flats):
-        raise RuntimeError("mix_grad: pass gradient lists produced by this package (views of flat buffers) and the Engine; "
+    if any(f is None for f in flats):
+        raise RuntimeError("mix_grad: pass gradient lists produced by this package (views of flat buffers); "
                            "there is no per-tensor PyTorch fallback")
-    acc = engine.new_flat(None)
+    eng = model.engine
+    acc = eng.new_flat(None)
     for i, f in enumerate(flats):
-        engine.axpy(acc, f, float(weight_list[i]), init=(i == 0))
-    return engine.param_views(acc)
+        eng.axpy(acc, f, float(weight_list[i]), init=(i == 0))
+    return model.layout_views(acc)
 
 
 def apply_grad(model, grad) -> float:

@@ -1,0 +1,109 @@
+"""Drop-in for the part of ``higher`` the reference trainers use (maml.py:40-54,71-74; reptile.py:40-56; infer.py:266-293):
+
+    with innerloop_ctx(model, inner_optimizer, track_higher_grads=False) as (fmodel, diffopt):
+        outputs = fmodel(**inputs); loss = criterion(...); diffopt.step(loss)
+        grads = torch.autograd.grad(loss_test, fmodel.parameters(time=-1))
+
+``fmodel`` is a functional copy: it clones the parameters AND the BatchNorm buffers of ``model`` (higher's semantics,
+SURVEY.md Appendix C), so the base model is never touched.  The fast weights live in ONE flat buffer; ``diffopt.step`` is
+autograd.grad of the loss w.r.t. that flat leaf followed by the fused functional SGD kernel (msa_flat_sgd_step).  Only the
+first-order mode exists (``track_higher_grads=False``): second-order MAML needs a double backward through the fused kernels.
+"""
+from __future__ import annotations
+
+from contextlib import contextmanager
+from typing import List
+
+import torch
+
+from .model import Tacotron2NV, _PassFn
+
+
+class FunctionalTacotron2NV:
+    def __init__(self, model: Tacotron2NV):
+        self.model = model
+        self.engine = model.engine
+        self.training = model.training
+        self._fast: List[torch.Tensor] = []      # flat fast weights, time 0 .. -1
+        self._views: List[List[torch.Tensor]] = []  # per-parameter LEAF views of each (what autograd.grad is asked about)
+        self._push(model.flat.detach().clone())
+        self.bn_flat = model.bn_flat.clone()
+        self.injected_masks = None
+        self._calls = 0
+
+    def _push(self, flat: torch.Tensor) -> None:
+        views = [v.requires_grad_(True) for v in self.model.layout_views(flat.detach())]
+        for v in views:
+            v._msa_flat = flat
+        self._fast.append(flat)
+        self._views.append(views)
+
+    def __call__(self, inputs, input_lengths, melspecs, melspec_lengths, speaker_vecs):
+        m = self.model
+        dev = self.engine.device
+        bd = {"inputs": inputs.to(dev).contiguous(), "input_lengths": input_lengths.to(dev).contiguous(),
+              "melspecs": melspecs.to(dev).contiguous(), "melspec_lengths": melspec_lengths.to(dev).contiguous(),
+              "speaker_vecs": speaker_vecs.to(dev).contiguous()}
+        B, L = bd["inputs"].shape
+        T = bd["melspecs"].shape[2]
+        if self.injected_masks is not None:
+            masks = self.engine.pack_masks(self.injected_masks[self._calls], B, T, L)
+        else:
+            masks = m._masks(B, T, L)
+        self._calls += 1
+        out = _PassFn.apply(m, self._fast[-1], self.bn_flat, bd, masks, *self._views[-1])
+        self.engine._last_out = out
+        return list(out)
+
+    def parameters(self, time: int = -1):
+        """Leaf views of the fast weights at ``time`` in ``model.parameters()`` order (maml.py:71-74)."""
+        return self._views[time]
+
+    def fast_flat(self, time: int = -1) -> torch.Tensor:
+        return self._fast[time]
+
+    def state_dict(self):
+        sd = {k: v.detach() for k, v in self.engine.dict_from_flat(self._fast[-1]).items()}
+        sd.update(self.engine.bn_dict(self.bn_flat))
+        return sd
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode: bool = True):
+        self.training = mode
+        return self
+
+
+class DifferentiableSGD:
+    """``diffopt.step(loss)`` with torch.optim.SGD hyper-parameters read from the passed optimizer (maml.py:54)."""
+
+    def __init__(self, fmodel: FunctionalTacotron2NV, opt: torch.optim.Optimizer):
+        if not isinstance(opt, torch.optim.SGD):
+            raise NotImplementedError("inner optimizer: only torch.optim.SGD is implemented on the fused path (SURVEY.md 8f item 3)")
+        g = opt.param_groups[0]
+        self.h = dict(lr=g["lr"], momentum=g.get("momentum", 0.0), dampening=g.get("dampening", 0.0),
+                      weight_decay=g.get("weight_decay", 0.0), nesterov=g.get("nesterov", False))
+        self.fmodel = fmodel
+        self.buf = fmodel.engine.new_flat() if self.h["momentum"] else None
+        self.steps = 0
+
+    def step(self, loss: torch.Tensor):
+        fm = self.fmodel
+        grads = torch.autograd.grad(loss, fm._views[-1])             # first-order: the graph is not kept
+        g = grads[0]._msa_flat                                       # the 61 gradients are views of ONE flat buffer
+        new = fm.engine.new_flat(None)
+        fm.engine.sgd_step(fm._fast[-1], g, p_out=new, buf=self.buf, first_step=(self.steps == 0), **self.h)
+        self.steps += 1
+        fm._push(new)                                                # re-leafed like higher with track_higher_grads=False
+        return fm.parameters(-1)
+
+
+@contextmanager
+def innerloop_ctx(model: Tacotron2NV, opt: torch.optim.Optimizer, copy_initial_weights: bool = True,
+                  track_higher_grads: bool = False):
+    if track_higher_grads:
+        raise NotImplementedError("second-order MAML (track_higher_grads=True) needs a double backward through the fused kernels")
+    fmodel = FunctionalTacotron2NV(model)
+    yield fmodel, DifferentiableSGD(fmodel, opt)

@@ -1,0 +1,137 @@
+"""The reference-shaped Python surface (Tacotron2NV / Tacotron2Loss / innerloop_ctx / mix_grad / apply_grad / EWC) on the CUDA
+path, written the way the reference trainers call it (maml.py:40-76,94-105; continual_ewc.py:28-89,345-357) and checked
+against the oracle.  Tolerance: fp32, 2e-4 (outputs per tensor, gradients relative to the global gradient norm)."""
+import pytest
+import torch
+
+import msa_tts_b200 as pkg
+from msa_tts_b200 import synth
+from oracle import meta as OMeta
+from oracle import model as OM
+from helpers import oracle_pass, rel
+
+pytestmark = pytest.mark.gpu
+CRIT = dict(reduction="none", pos_weight=10.0)
+TOL = 2e-4
+
+
+def _inputs(batch):
+    _, inp, inp_len, mels, mel_len, _, spk, stop = batch
+    return dict(inputs=inp, input_lengths=inp_len, melspecs=mels, melspec_lengths=mel_len, speaker_vecs=spk), (mels, stop), mel_len
+
+
+def _model(cfg, P):
+    model = pkg.Tacotron2NV(cfg)
+    sd = model.state_dict()
+    assert [k for k in sd if "running" not in k and "num_batches" not in k] == list(P.keys()), "state_dict keys / order = reference"
+    missing, unexpected = model.load_state_dict({k: v for k, v in P.items()}, strict=False)
+    assert not unexpected and all("running" in k or "num_batches" in k for k in missing)
+    return model
+
+
+def _gerr(grads, o_g, names):
+    gn = float(torch.sqrt(sum((v.double() ** 2).sum() for v in o_g.values())))
+    return max(float((g.double().cpu() - o_g[n].double()).norm()) / gn for n, g in zip(names, grads))
+
+
+def test_module_forward_loss_backward_like_baseline_py():
+    cfg = pkg.small_params()
+    B, T, L = 3, 11, 9
+    P = synth.init_params(cfg, 3)
+    batch = synth.make_batch(cfg, B, T, L, 103)
+    masks = synth.make_masks(cfg, B, T, L, 203)
+    o_out, o_loss, o_g, _, _ = oracle_pass(cfg, P, batch, masks, CRIT)
+    model = _model(cfg, P)
+    model.train()
+    model.injected_masks = masks
+    criterion = pkg.Tacotron2Loss(1, CRIT["reduction"], CRIT["pos_weight"])
+    kw, targets, mel_len = _inputs(batch)
+    out = model(**kw)
+    loss = criterion(out, targets, mel_len)
+    loss.backward()
+    for a, b in zip(out, o_out):
+        assert rel(a.detach(), b) < TOL
+    assert abs(float(loss) - float(o_loss)) < TOL * abs(float(o_loss))
+    names = list(P.keys())
+    assert _gerr([p.grad for p in model.parameters()], o_g, names) < TOL
+    # stock torch calls of the trainers keep working on the views (maml.py:101-105)
+    torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    before = model.flat.clone()
+    opt.step()
+    assert not torch.equal(before, model.flat), "optimizer.step() on the per-tensor views updates the flat buffer"
+    with pytest.raises(NotImplementedError):
+        model.eval()(**kw)
+
+
+def test_innerloop_fomaml_task_like_maml_py():
+    cfg = pkg.small_params()
+    B, T, L, lr = 3, 10, 8, 0.05
+    P = synth.init_params(cfg, 5)
+    task = synth.make_task(cfg, B, T, L, 3)
+    masks = [synth.make_masks(cfg, B, T, L, 900 + i) for i in range(2)]
+    names = OM.param_names(cfg)
+    o_loss, o_g, _, _, _ = OMeta.fomaml_task(P, cfg, task, masks, CRIT, names, 1, lr)
+    model = _model(cfg, P)
+    criterion = pkg.Tacotron2Loss(1, "none", 10.0)
+    inner_opt = torch.optim.SGD(model.parameters(), lr=lr)
+    theta0 = model.flat.clone()
+    with pkg.innerloop_ctx(model, inner_opt, track_higher_grads=False) as (fmodel, diffopt):      # maml.py:40-41
+        fmodel.injected_masks = masks
+        kw, targets, mel_len = _inputs(task["train"])
+        diffopt.step(criterion(fmodel(**kw), targets, mel_len))                                   # maml.py:50-54
+        kw, targets, mel_len = _inputs(task["test"])
+        loss_test = criterion(fmodel(**kw), targets, mel_len)
+        task_grads = torch.autograd.grad(loss_test, fmodel.parameters(time=-1))                  # maml.py:73-74
+    assert torch.equal(theta0, model.flat), "the base model is never touched inside the inner loop"
+    assert abs(float(loss_test) - float(o_loss)) < TOL * abs(float(o_loss))
+    assert _gerr(task_grads, o_g, names) < TOL
+    # mix_grad / apply_grad (maml.py:94-99, utils/grad_utils.py:8-31)
+    from msa_tts_b200.grad_utils import apply_grad, mix_grad
+    mixed = mix_grad([task_grads, task_grads], [0.25, 0.75], model)
+    assert _gerr(mixed, o_g, names) < TOL
+    norm = apply_grad(model, mixed)
+    gn = float(torch.sqrt(sum((v.double() ** 2).sum() for v in o_g.values())))
+    assert abs(norm - gn) < TOL * gn
+    assert _gerr([p.grad for p in model.parameters()], o_g, names) < TOL
+    with pytest.raises(NotImplementedError):
+        with pkg.innerloop_ctx(model, inner_opt, track_higher_grads=True):
+            pass
+
+
+def test_ewc_fisher_penalty_and_fused_step_like_continual_ewc_py():
+    cfg = pkg.small_params()
+    B, T, L = 3, 9, 8
+    P = synth.init_params(cfg, 7)
+    names = OM.param_names(cfg)
+    buf = [synth.make_batch(cfg, B, T, L, 400 + i) for i in range(3)]
+    bmasks = [synth.make_masks(cfg, B, T, L, 500 + i) for i in range(3)]
+    F_ = OMeta.ewc_fisher(P, cfg, buf, bmasks, CRIT, names)
+    model = _model(cfg, P)
+    ewc = pkg.EWC(model, buf, masks=bmasks)
+    fd = model.engine.dict_from_flat(ewc.fisher)
+    fn = float(torch.sqrt(sum((v.double() ** 2).sum() for v in F_.values())))
+    assert max(float((fd[n].double().cpu() - F_[n].double()).norm()) / fn for n in names) < 5e-4
+    # move the weights, then penalty and the fused EWC step against the oracle (continual_ewc.py:84-89,345-357)
+    g = torch.Generator().manual_seed(1)
+    P2 = {n: v + 0.01 * torch.randn(v.shape, generator=g) for n, v in P.items()}
+    model.load_state_dict(P2, strict=False)
+    pen = ewc.penalty(model)
+    o_pen = OMeta.ewc_penalty(P2, F_, P, names)
+    assert abs(float(pen) - float(o_pen)) < 1e-3 * abs(float(o_pen))
+    batch = synth.make_batch(cfg, B, T, L, 600)
+    masks = synth.make_masks(cfg, B, T, L, 700)
+    lam, lr = 50.0, 0.01
+    stats = OM.fresh_bn_stats(P2, cfg)
+    o_total, _, o_new = OMeta.ewc_step(P2, cfg, batch, masks, stats, CRIT, names, F_, P, lam, lr)
+    from msa_tts_b200.engine import batch_to_device
+    eng = model.engine
+    bd = batch_to_device(batch, eng.device)
+    _, loss = eng.forward(model.flat, model.bn_flat, bd, eng.pack_masks(masks, B, T, L), outputs=False)
+    gflat = eng.new_flat()
+    eng.backward(model.flat, gflat)
+    pen2 = ewc.sgd_step(gflat, lr, lam)
+    assert abs(float(loss) + lam * float(pen2) - float(o_total)) < 1e-3 * abs(float(o_total))
+    new = eng.dict_from_flat(model.flat)
+    pn = float(torch.sqrt(sum((v.double() ** 2).sum() for v in o_new.values())))
+    assert max(float((new[n].double().cpu() - o_new[n].double()).norm()) / pn for n in names) < 1e-5
