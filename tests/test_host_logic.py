@@ -1,0 +1,95 @@
+"""Host-side logic that needs no GPU: flat layout, optimizer spec parsing, task sharding, and the sharded meta-gradient
+reduction over a 2-process gloo group (the N>1 path of parallel.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import msa_tts_b200 as pkg
+from msa_tts_b200.helpers import optimizer_hparams
+from msa_tts_b200.layout import FlatLayout
+from msa_tts_b200.parallel import ShardInfo
+from oracle import model as OM
+
+
+def test_flat_layout_matches_reference_parameter_order():
+    for cfg in (pkg.small_params(), pkg.default_params()):
+        lay = FlatLayout(cfg)
+        assert lay.names() == OM.param_names(cfg)
+        offs = [lay.offsets[n] for n in lay.names()]
+        assert offs == sorted(offs) and all(o % 32 == 0 for o in offs), "tensors start on 128-byte boundaries, in order"
+        assert lay.total >= lay.n_params
+    assert FlatLayout(pkg.default_params()).n_params == 30331010
+
+
+def test_optimizer_spec_strings_are_evaluated_like_helpers_get_optimizer():
+    h = optimizer_hparams({"optimizer_name": "Adam", "optim_params": {"lr": "1e-3", "betas": "(0.9, 0.98)", "weight_decay": "0"}})
+    assert h == {"name": "Adam", "lr": 1e-3, "betas": (0.9, 0.98), "weight_decay": 0}
+    with pytest.raises(ValueError):
+        optimizer_hparams({"optimizer_name": "SGD", "optim_params": {}})
+
+
+def test_task_sharding_is_a_partition():
+    for world in (1, 2, 3, 8):
+        for n in (1, 8, 16, 5):
+            seen = sorted(i for r in range(world) for i in ShardInfo(r, world).my_tasks(n))
+            assert seen == list(range(n))
+            assert max(len(ShardInfo(r, world).my_tasks(n)) for r in range(world)) - \
+                   min(len(ShardInfo(r, world).my_tasks(n)) for r in range(world)) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_tasks, n, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        shard = ShardInfo.from_env()
+        assert (shard.rank, shard.world) == (rank, world)
+        acc = torch.zeros(n)
+        losses = []
+        for i in shard.my_tasks(n_tasks):                       # each rank adapts its own subset (maml.py:38-41)
+            g = torch.Generator().manual_seed(100 + i)
+            acc += torch.randn(n, generator=g) / n_tasks        # sum_local w_i g_i, w_i = 1/N (maml.py:94-98)
+            losses.append(float(i))
+        shard.allreduce_sum(acc)                                # the ONE collective of a meta-step
+        full = shard.gather_scalars(torch.tensor(losses), n_tasks)
+        mx = torch.tensor([float(rank)])
+        shard.allreduce_max(mx)
+        shard.barrier()
+        if rank == 0:
+            out.put((acc.numpy(), full.numpy(), float(mx)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_tasks", [8, 5])
+def test_sharded_meta_gradient_equals_unsharded_gloo_world2(n_tasks):
+    n, world = 4096, 2
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_tasks, n, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    acc, losses, mx = out.get()
+    ref = torch.zeros(n)
+    for i in range(n_tasks):
+        g = torch.Generator().manual_seed(100 + i)
+        ref += torch.randn(n, generator=g) / n_tasks
+    assert np.allclose(acc, ref.numpy(), rtol=0, atol=1e-6), "sharded sum = unsharded mix_grad up to fp32 summation order"
+    assert losses.tolist() == [float(i) for i in range(n_tasks)]
+    assert mx == 1.0
