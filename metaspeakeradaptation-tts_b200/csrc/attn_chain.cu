@@ -24,9 +24,9 @@
 
 namespace msa {
 
-// 256 threads per CTA: with 512 the 128-register cap makes the compiler spill the per-thread LSTM state, and every spill
-// reload sits on the critical path of a step; everything here is latency-bound, not issue-bound
-constexpr int kAttnThreads = 256;
+// thread count of the attention-chain kernels (the forward kernel carries a few register spills at 512 threads; 256 threads
+// measured slower because the mat-vecs in the hand-off shadows take twice as long)
+constexpr int kAttnThreads = 512;
 
 struct AttnSmemFwd {
     size_t wsm, mws, hs, as_, ah, es, qs, part, part2, zm, wqs, wloc, wldT, vs, pm, pre, ctr, cf, total;

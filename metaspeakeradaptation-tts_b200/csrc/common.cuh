@@ -91,6 +91,22 @@ __device__ __forceinline__ float warp_transpose_reduce32(float (&a)[32]) {
     return a[0];
 }
 
+// 16 per-lane accumulators -> lanes i and i+16 hold the warp-wide total of accumulator i (16 shuffles).
+__device__ __forceinline__ float warp_transpose_reduce16(float (&a)[16]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int half = 8; half >= 1; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            float keep = upper ? a[i + half] : a[i];
+            float send = upper ? a[i] : a[i + half];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return a[0] + __shfl_xor_sync(0xffffffffu, a[0], 16);
+}
+
 // Loads of data written by OTHER thread blocks of the same (persistent) kernel: bypass L1.
 __device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }

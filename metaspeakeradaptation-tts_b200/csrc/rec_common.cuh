@@ -108,26 +108,28 @@ __device__ __forceinline__ void cta_matvec_fwd(const float* __restrict__ Wsm, in
     const float4* h4p = reinterpret_cast<const float4*>(hs);
     const int ntile = (B + 3) >> 2;
     for (int tile = 0; tile < ntile; ++tile) {
-        float acc[32];
+        // two passes of 4 gate rows x 4 batch rows: 16 accumulators + 16 + 16 operand registers live at a time
+        float tot = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-        for (int j = j0 + ks; j < j1; j += KS) {
-            const int c4 = j * 32 + lane;
-            float4 h4[4];
+        for (int half = 0; half < 2; ++half) {
+            float acc[16];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) h4[b] = h4p[(size_t)(tile * 4 + b) * KP4 + c4];
+            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+            for (int j = j0 + ks; j < j1; j += KS) {
+                const int c4 = j * 32 + lane;
+                float4 h4[4], w4[4];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {       // 4 rows at a time: 16 + 16 + 32 live registers
-                float4 w4[4];
+                for (int b = 0; b < 4; ++b) h4[b] = h4p[(size_t)(tile * 4 + b) * KP4 + c4];
 #pragma unroll
                 for (int rr = 0; rr < 4; ++rr) w4[rr] = W4[(size_t)(half * 4 + rr) * KP4 + c4];
 #pragma unroll
                 for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) acc[(half * 4 + rr) * 4 + b] += dot4(w4[rr], h4[b]);
+                    for (int b = 0; b < 4; ++b) acc[rr * 4 + b] += dot4(w4[rr], h4[b]);
             }
+            const float th = warp_transpose_reduce16(acc);      // lanes i, i+16: total of accumulator i
+            if ((lane >> 4) == half) tot = th;                   // lane = (half*4 + rr)*4 + b, as with 32 accumulators
         }
-        const float tot = warp_transpose_reduce32(acc);
         part[((size_t)(tile * KS + ks) * RG + rg) * 32 + lane] = tot;
     }
 }
