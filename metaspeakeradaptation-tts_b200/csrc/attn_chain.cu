@@ -447,8 +447,8 @@ __global__ void __launch_bounds__(NT, 1) k_attn_chain_bwd(AttnChainBwdParams p, 
         // forward stash of this step that the next phase needs (plain data of an earlier kernel)
         for (int idx = threadIdx.x; idx < BL; idx += NT) als[idx] = __ldg(p.align + (size_t)t * BL + idx);
         if ((int)threadIdx.x < B) zn_s[threadIdx.x] = __ldg(p.znorm + (size_t)t * B + threadIdx.x);
-        // in the shadow of the dat hand-off: W_hh^T . dz_a(t+1) for the owned units (needed by the point-wise phase)
-        if (t < T - 1) cta_matvec_bwd<NT>(WT, H4, p.dza + (size_t)(t + 1) * B * H4, B, part, dhs, BP, sg);
+        // in the shadow of the dat hand-off: first half of W_hh^T . dz_a(t+1) for the owned units (needed by the point-wise phase)
+        if (t < T - 1) cta_matvec_bwd<NT>(WT, H4, p.dza + (size_t)(t + 1) * B * H4, B, part, dhs, BP, sg, 0, 2);
         prof.mark(1, T - 1 - t);
         // ---- hand-off 1: d a(t) of every position ----
         gather_words<NT>(das, p.dat + (size_t)t * BL, BL, (p.flags & kFlagWarp0) != 0, sg);
@@ -509,6 +509,8 @@ __global__ void __launch_bounds__(NT, 1) k_attn_chain_bwd(AttnChainBwdParams p, 
             if (lane == 0) st_pub(p.dq + ((size_t)t * B + b) * A + d, vs[d] * acc);
         }
         prof.mark(3, T - 1 - t);
+        // in the shadow of the dq hand-off: second half of W_hh^T . dz_a(t+1)
+        if (t < T - 1) cta_matvec_bwd<NT>(WT, H4, p.dza + (size_t)(t + 1) * B * H4, B, part, dhs, BP, sg, 1, 2);
         // ---- hand-off 2: dq(t) ----
         gather_words<NT>(dq_s, p.dq + (size_t)t * B * A, B * A, (p.flags & kFlagWarp0) != 0, sg);
         __syncthreads();
@@ -577,14 +579,18 @@ __global__ void __launch_bounds__(NT, 1) k_attn_chain_bwd(AttnChainBwdParams p, 
             }
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < np; i += NT) {
+        for (int i = w; i < np; i += NW) {            // one warp per owned position, lanes over the taps (fixed order)
             float a0 = 0.f, a1 = 0.f;
-            for (int k = 0; k < Kl; ++k) {
+            for (int k = lane; k < Kl; k += 32) {
                 a0 += cpart[(i * Kl + k) * 2 + 0];
                 a1 += cpart[(i * Kl + k) * 2 + 1];
             }
-            dprev_s[i] = a0;          // d/d a(t-1) through the "previous alignment" channel
-            gcum_s[i] += a1;          // running d/d cum(t-1)
+            a0 = warp_sum(a0);
+            a1 = warp_sum(a1);
+            if (lane == 0) {
+                dprev_s[i] = a0;          // d/d a(t-1) through the "previous alignment" channel
+                gcum_s[i] += a1;          // running d/d cum(t-1)
+            }
         }
         __syncthreads();
         prof.mark(6, T - 1 - t);

@@ -303,14 +303,16 @@ constexpr int kPairMax = 4;   // (b,l) positions per CTA whose context-path dot 
 // All threads must call.  `part` scratch: (NT / 32)*32 floats.
 template <int NT>
 __device__ __forceinline__ void cta_matvec_bwd(const float* __restrict__ WT, int R4, const float* dz, int B, float* part,
-                                               float* out, int BP, SpinGuard& sg) {
+                                               float* out, int BP, SpinGuard& sg, int pass = 0, int npass = 1) {
+    // pass / npass: the r range is split into npass interleaved slices (chunk index % npass == pass) so that the mat-vec can be
+    // spread over the shadows of several hand-offs; pass 0 overwrites `out`, later passes accumulate into it
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int nchunk = R4 >> 2;
     for (int bt = 0; bt < B; bt += 4) {
         float acc[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-        for (int ch = threadIdx.x; ch < nchunk; ch += NT) {
+        for (int ch = threadIdx.x * npass + pass; ch < nchunk; ch += NT * npass) {
             const int r = ch << 2;
             float4 d4[4];
 #pragma unroll
@@ -342,7 +344,7 @@ __device__ __forceinline__ void cta_matvec_bwd(const float* __restrict__ WT, int
             float s = 0.f;
 #pragma unroll
             for (int q = 0; q < (NT / 32); ++q) s += part[q * 32 + threadIdx.x];
-            if (bt + b < B) out[ul * BP + bt + b] = s;
+            if (bt + b < B) out[ul * BP + bt + b] = pass == 0 ? s : out[ul * BP + bt + b] + s;
         }
         __syncthreads();
     }
