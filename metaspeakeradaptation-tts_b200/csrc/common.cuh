@@ -148,6 +148,9 @@ struct SpinGuard {
     __device__ __forceinline__ explicit SpinGuard(unsigned int* a) : abort_word(a), n(0), dead(false) {}
     __device__ __forceinline__ bool bail() {
         if (dead) return true;
+#ifdef MSA_POLL_BACKOFF
+        __nanosleep(MSA_POLL_BACKOFF);      // experiment: thin out the polling traffic
+#endif
         if ((++n & 1023u) == 0u) {
             if (*reinterpret_cast<volatile unsigned int*>(abort_word) != 0u) dead = true;
             else if (n > (1u << 21)) {

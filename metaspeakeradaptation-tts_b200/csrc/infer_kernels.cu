@@ -43,39 +43,50 @@ __global__ void ker_infer_lstm_point(const float* __restrict__ z, const float* _
 }
 
 // Location-sensitive attention for one batch row per CTA (forward_attn.py:121-131,178-219, eval, no windowing / forward
-// attention): q = Wq.h_a; loc = dense(conv([prev; cum])); e = v.tanh(q + loc + pm) + bv; a = softmax | sigmoid-norm;
-// cum += a; prev = a; ctx = a.memory.  ctx is written to the three packed GEMM inputs that consume it.
-__global__ void __launch_bounds__(256) ker_infer_attention(InferAttnParams p) {
+// attention): loc = dense(conv([prev; cum])); e = v.tanh(q + loc + pm) + bv; a = softmax | sigmoid-norm; cum += a; prev = a;
+// ctx = a.memory.  q = Wq.h_a comes from a GEMM before this kernel; the location weights are staged in shared memory
+// (coalesced) so that every inner loop reads shared memory only.  ctx is written to the three packed GEMM inputs.
+constexpr int kInferAttnThreads = 512;
+__global__ void __launch_bounds__(kInferAttnThreads) ker_infer_attention(InferAttnParams p) {
     if (p.state[1]) return;
     extern __shared__ float sm[];
     const int t = p.state[0], b = blockIdx.x;
-    const int L = p.L, A = p.A, F = p.F, Kl = p.Kl, pl = (Kl - 1) / 2, LH = L + Kl - 1;
-    float* in_s = sm;                       // [2][LH] prev / cum with zero halo
-    float* q_s = in_s + 2 * LH;             // [A]
-    float* cf_s = q_s + A;                  // [L][F]
-    float* e_s = cf_s + (size_t)L * F;      // [L]
-    float* red = e_s + L;                   // [32]
+    const int L = p.L, A = p.A, F = p.F, Kl = p.Kl, pl = (Kl - 1) / 2, LH = L + Kl - 1, FP = F + 1;
+    float* in_s = sm;                         // [2][LH] prev / cum with zero halo
+    float* q_s = in_s + 2 * LH;               // [A]
+    float* v_s = q_s + A;                     // [A]
+    float* wloc_s = v_s + A;                  // [2*Kl][F]   wloc[f][c][k] -> [c*Kl+k][f]
+    float* wldT_s = wloc_s + 2 * Kl * F;      // [F][A]      wld[d][f] -> [f][d]
+    float* cf_s = wldT_s + (size_t)F * A;     // [L][F+1]
+    float* e_s = cf_s + (size_t)L * FP;       // [L]
+    float* red = e_s + L;                     // [40]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int i = threadIdx.x; i < 2 * LH; i += blockDim.x) {
         const int c = i / LH, l = i % LH - pl;
         in_s[i] = (l >= 0 && l < L) ? (c == 0 ? p.prev[(size_t)b * L + l] : p.cum[(size_t)b * L + l]) : 0.f;
     }
-    // query projection: one warp per attention dim
-    const float* h = p.ha + (size_t)b * p.ld_ha;
-    for (int d = w; d < A; d += nw) {
-        float acc = 0.f;
-        for (int k = lane; k < p.Ha; k += 32) acc += __ldg(p.wq + (size_t)d * p.Ha + k) * h[k];
-        acc = warp_sum(acc);
-        if (lane == 0) q_s[d] = acc;
+    for (int i = threadIdx.x; i < A; i += blockDim.x) {
+        q_s[i] = p.q[(size_t)b * A + i];
+        v_s[i] = __ldg(p.v + i);
+    }
+    for (int i = threadIdx.x; i < F * 2 * Kl; i += blockDim.x) {
+        const int f = i / (2 * Kl), ck = i % (2 * Kl);
+        wloc_s[ck * F + f] = __ldg(p.wloc + i);
+    }
+    for (int i = threadIdx.x; i < A * F; i += blockDim.x) {
+        const int d = i / F, f = i % F;
+        wldT_s[f * A + d] = __ldg(p.wld + i);
     }
     __syncthreads();
-    // location conv: (l, f) items
+    // location conv: (l, f) items, lanes over f
     for (int i = threadIdx.x; i < L * F; i += blockDim.x) {
         const int l = i / F, f = i - l * F;
-        float acc = 0.f;
-        for (int c = 0; c < 2; ++c)
-            for (int k = 0; k < Kl; ++k) acc += __ldg(p.wloc + ((size_t)f * 2 + c) * Kl + k) * in_s[c * LH + l + k];
-        cf_s[i] = acc;
+        float a0 = 0.f, a1 = 0.f;
+        for (int k = 0; k < Kl; ++k) {
+            a0 += wloc_s[k * F + f] * in_s[l + k];
+            a1 += wloc_s[(Kl + k) * F + f] * in_s[LH + l + k];
+        }
+        cf_s[l * FP + f] = a0 + a1;
     }
     __syncthreads();
     // energies: one warp per position, lanes over attention dims
@@ -83,9 +94,14 @@ __global__ void __launch_bounds__(256) ker_infer_attention(InferAttnParams p) {
     for (int l = w; l < L; l += nw) {
         float e = 0.f;
         for (int d = lane; d < A; d += 32) {
-            float loc = 0.f;
-            for (int f = 0; f < F; ++f) loc += __ldg(p.wld + (size_t)d * F + f) * cf_s[l * F + f];
-            e += __ldg(p.v + d) * tanhf(q_s[d] + loc + __ldg(p.pm + ((size_t)b * L + l) * A + d));
+            float l0 = 0.f, l1 = 0.f;
+            int f = 0;
+            for (; f + 1 < F; f += 2) {
+                l0 += wldT_s[f * A + d] * cf_s[l * FP + f];
+                l1 += wldT_s[(f + 1) * A + d] * cf_s[l * FP + f + 1];
+            }
+            if (f < F) l0 += wldT_s[f * A + d] * cf_s[l * FP + f];
+            e += v_s[d] * tanhf(q_s[d] + l0 + l1 + __ldg(p.pm + ((size_t)b * L + l) * A + d));
         }
         e = warp_sum(e);
         if (lane == 0) e_s[l] = e + bv;
@@ -117,10 +133,20 @@ __global__ void __launch_bounds__(256) ker_infer_attention(InferAttnParams p) {
         p.align_out[((size_t)b * p.max_steps + t) * L + l] = a;
     }
     __syncthreads();
-    // context
+    // context: threads over memory channels (coalesced rows), 4 positions in flight
     for (int e = threadIdx.x; e < p.E; e += blockDim.x) {
-        float acc = 0.f;
-        for (int l = 0; l < L; ++l) acc += e_s[l] * __ldg(p.memory + ((size_t)b * L + l) * p.E + e);
+        const float* mrow = p.memory + (size_t)b * L * p.E + e;
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+        int l = 0;
+        for (; l + 3 < L; l += 4) {
+            c0 += e_s[l] * __ldg(mrow + (size_t)l * p.E);
+            c1 += e_s[l + 1] * __ldg(mrow + (size_t)(l + 1) * p.E);
+            c2 += e_s[l + 2] * __ldg(mrow + (size_t)(l + 2) * p.E);
+            c3 += e_s[l + 3] * __ldg(mrow + (size_t)(l + 3) * p.E);
+        }
+        for (; l < L; ++l) c0 += e_s[l] * __ldg(mrow + (size_t)l * p.E);
+        // fixed summation tree; matches the sequential reference to fp32 rounding
+        const float acc = (c0 + c1) + (c2 + c3);
         p.ctx1[(size_t)b * p.ld1 + e] = acc;
         p.ctx2[(size_t)b * p.ld2 + e] = acc;
         p.ctx3[(size_t)b * p.ld3 + e] = acc;
@@ -195,13 +221,13 @@ int k_infer_lstm_point(const float* z, const float* b_ih, const float* b_hh, flo
     return 0;
 }
 size_t infer_attention_smem(int L, int A, int F, int Kl) {
-    return sizeof(float) * ((size_t)2 * (L + Kl - 1) + A + (size_t)L * F + L + 40);
+    return sizeof(float) * ((size_t)2 * (L + Kl - 1) + 2 * A + (size_t)2 * Kl * F + (size_t)F * A + (size_t)L * (F + 1) + L + 48);
 }
 int k_infer_attention(const InferAttnParams& p, cudaStream_t st) {
     const size_t smem = infer_attention_smem(p.L, p.A, p.F, p.Kl);
     MSA_CHECK(smem <= 200 * 1024, MSA_E_UNSUPPORTED, "infer attention: text length %d too long for the shared-memory tile", p.L);
     if (smem > 48 * 1024) MSA_CUDA(cudaFuncSetAttribute(ker_infer_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ker_infer_attention<<<p.B, 256, smem, st>>>(p);
+    ker_infer_attention<<<p.B, kInferAttnThreads, smem, st>>>(p);
     MSA_LAUNCH_CHECK();
     return 0;
 }

@@ -148,8 +148,7 @@ int k_masks_generate(uint8_t* masks, const int64_t* offsets, const int64_t* nume
 // ---------------- free-running inference, per-step kernels (infer_kernels.cu) ----------------
 struct InferAttnParams {
     int B, L, Ha, A, F, Kl, E, norm, max_steps;
-    const float* ha; int ld_ha;
-    const float* wq;
+    const float* q;                   // [B][A]  Wq.h_a of this step (GEMM before the kernel)
     const float* wloc;
     const float* wld;
     const float* v; const float* bv;

@@ -945,7 +945,7 @@ namespace msa {
     X(enc_h, 2 * d.BL * d.Hh) X(memory, d.BL * d.E) X(pm, d.BL * d.A)                                    \
     X(xin_a, d.B * (d.Pd + d.E)) X(p1, d.B * d.Pd) X(ha, d.B * d.Ha) X(ca, d.B * d.Ha)                   \
     X(xin_d, d.B * (d.Ha + d.E)) X(hd, d.B * d.Hd) X(cd, d.B * d.Hd) X(xin_p, d.B * (d.Hd + d.E))        \
-    X(za, d.B * 4 * d.Ha) X(zd, d.B * 4 * d.Hd) X(mel_raw, d.B * d.M) X(gate_raw, d.B) X(frame, d.B * d.M) \
+    X(za, d.B * 4 * d.Ha) X(zd, d.B * 4 * d.Hd) X(qbuf, d.B * d.A) X(mel_raw, d.B * d.M) X(gate_raw, d.B) X(frame, d.B * d.M) \
     X(prev, d.BL) X(cum, d.BL) X(mel_tm, (int64_t)d.T * d.B * d.M) X(ints, 64 + d.B)                      \
     X(post_x, 2 * d.BT * d.Cmax) X(post_y, d.BT * d.Cmax) X(post_col, d.BT * d.Kp * d.Cmax)              \
     X(post_w2, (int64_t)d.Cmax * d.Kp * d.Cmax) X(post_bt, d.BT * d.M)
@@ -1108,8 +1108,8 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
         // attention (forward_attn.py:178-219)
         InferAttnParams ap{};
         ap.B = B; ap.L = L; ap.Ha = d.Ha; ap.A = d.A; ap.F = d.F; ap.Kl = d.Kl; ap.E = d.E; ap.norm = c.attn_norm; ap.max_steps = max_steps;
-        ap.ha = w.ha; ap.ld_ha = d.Ha;
-        ap.wq = P(at + "query_layer.linear_layer.weight"); ap.wloc = P(at + "location_layer.location_conv1d.weight");
+        MSA_TRY(gemm(h, false, true, B, d.A, d.Ha, 1.f, w.ha, d.Ha, P(at + "query_layer.linear_layer.weight"), d.Ha, 0.f, w.qbuf, d.A));
+        ap.q = w.qbuf; ap.wloc = P(at + "location_layer.location_conv1d.weight");
         ap.wld = P(at + "location_layer.location_dense.linear_layer.weight");
         ap.v = P(at + "v.linear_layer.weight"); ap.bv = P(at + "v.linear_layer.bias");
         ap.pm = w.pm; ap.memory = w.memory; ap.prev = w.prev; ap.cum = w.cum;
@@ -1133,7 +1133,8 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
     int enqueued = 0;
-    if (getenv("MSA_INFER_NO_GRAPH") == nullptr && max_steps > 1) {
+    if (getenv("MSA_INFER_GRAPH") != nullptr && max_steps > 1) {     // measured on B200: replaying the captured step is slower than
+                                                                      // plain stream-ordered launches (the queue stays ahead of the GPU)
         MSA_TRY(step());      // step 0 directly: lets cuBLAS pick its kernels / workspace outside the capture
         enqueued = 1;
         if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {

@@ -60,9 +60,9 @@ def test_infer_unsupported_variants_fail_loudly():
 def test_infer_graph_and_direct_launch_agree():
     """The CUDA-graph replay of the decoder step and plain per-step launches are the same computation."""
     (post, lens, align), _, _ = _run("small_infer")
-    os.environ["MSA_INFER_NO_GRAPH"] = "1"
+    os.environ["MSA_INFER_GRAPH"] = "1"
     try:
         (post2, lens2, align2), _, _ = _run("small_infer")
     finally:
-        del os.environ["MSA_INFER_NO_GRAPH"]
+        del os.environ["MSA_INFER_GRAPH"]
     assert torch.equal(post, post2) and torch.equal(lens, lens2) and torch.equal(align, align2)
