@@ -131,6 +131,14 @@ def algo_bytes(cfg, kernel: str) -> float:
     raise KeyError(kernel)
 
 
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(kernel)
+    return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -303,9 +311,10 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
-                         "note": "persistent recurrent kernel: weights stay in shared memory, time is set by 3 grid barriers "
-                                 "per decoder step, not by HBM (DESIGN.md section 4)",
+                         "frac": dom["frac"], "traffic": ncu_traffic(dom["kernel"]), "peak_source": peak_src,
+                         "note": "persistent recurrent kernel: weights stay in shared memory for all T steps; its time is set by "
+                                 "the three cross-CTA hand-offs per decoder step (L2 round trips among 148 CTAs), not by HBM "
+                                 "or tensor throughput (DESIGN.md section 4.2, profiles/r01_trace_*)",
                          "ms_per_launch": dom["ms_per_launch"], "share_of_step": dom["share_of_step"]},
             "kernels": kern,
             "clocks": clk.summary(),
