@@ -215,6 +215,15 @@ int msa_ewc_penalty(const float* p, const float* mu, const float* fisher, int64_
 int msa_ewc_sgd_step(float* p, const float* g, const float* mu, const float* fisher, int64_t n, float lr,
                      float lam, float* partials, float* penalty_out, void* stream);
 
+/* ---- tensor-core GEMM building block (exported for tests / profiles) ------------------------------------------
+ * C[M,N] = alpha * A[M,K] . B[N,K]^T + beta * C, row-major, both operands K-contiguous (torch.nn.functional.linear's
+ * contraction, the shape of every forward projection of the model).  tcgen05 TF32 MMAs fed by TMA; mode 0 = 3xTF32
+ * split (fp32-accurate, needs scratch of msa_gemm_nt_scratch_floats floats), mode 1 = single TF32 product.
+ * Requires lda, ldb multiples of 4 floats and 16-byte aligned A, B. */
+size_t msa_gemm_nt_scratch_floats(int64_t M, int64_t N, int64_t K);
+int msa_gemm_nt(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb,
+                float beta, float* C, int64_t ldc, int mode, float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

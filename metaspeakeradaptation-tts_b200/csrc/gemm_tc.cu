@@ -1,0 +1,284 @@
+// Hand-written sm_100a tensor-core GEMM for the batched (non-recurrent) contractions of the pass:
+//     C[M x N] = alpha * A[M x K] . B[N x K]^T + beta * C          (row-major, both operands K-contiguous: "x . W^T")
+// i.e. every forward projection of Tacotron2NV (prenet, LSTM input projections with M = T*B rows, memory / query layers,
+// mel / gate projections, im2col convolutions).  tcgen05.mma kind::tf32 with fp32 accumulators in TMEM, operands brought
+// in by TMA (128-byte swizzle), a 3-stage mbarrier pipeline, one TMA warp + one MMA warp + four epilogue warps.
+//
+// Precision: a single TF32 product loses 13 mantissa bits of each operand, which the forward pass cannot afford
+// (mel_post 2.5e-3 vs the 1e-3 tolerance).  Mode 0 therefore evaluates the "3xTF32" split
+//     A.B ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo,   x_hi = the 19 bits the tensor core reads, x_lo = x - x_hi (exact in fp32)
+// (three MMAs per k-step on tiles of the four operand arrays; the lo arrays are produced by a streaming split kernel), which
+// is fp32-accurate to ~2^-21.  Mode 1 is the plain single TF32 product (backward-pass policy).
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace msa {
+
+constexpr int kTcBM = 128, kTcBN = 128, kTcBK = 32;        // CTA tile; BK floats = one 128-byte swizzle row
+constexpr int kTcStages = 3;
+constexpr int kTcTileBytes = kTcBM * kTcBK * 4;             // 16 KB per operand tile
+constexpr int kTcThreads = 192;                             // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-5 epilogue
+constexpr int kTcTmemCols = 128;
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+// shared-memory matrix descriptor: K-major operand tile [rows][32 floats] with the 128-byte swizzle TMA wrote
+// (canonical layout ((8,n),2):((8,SBO),1) in 16-byte units: LBO = 1, SBO = 8 rows * 128 B = 64, version 1, layout SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)64 << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = 128
+constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(kTcIdesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct TcSmem {
+    uint64_t full[kTcStages], empty[kTcStages], tmem_full;
+    uint32_t tmem_base;
+};
+
+template <bool kSplit>
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
+               const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo, float* __restrict__ C, int ldc,
+               int M, int N, int K, float alpha, float beta) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte aligned operand tiles (swizzle atom = 8 rows x 128 B), then the barriers
+    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int kOps = kSplit ? 4 : 2;
+    TcSmem* sb = reinterpret_cast<TcSmem*>(tiles + (size_t)kTcStages * kOps * kTcTileBytes);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kTcBM, n0 = blockIdx.y * kTcBN;
+    const int num_kb = (K + kTcBK - 1) / kTcBK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTcStages; ++s) { mbar_init(&sb->full[s], 1); mbar_init(&sb->empty[s], 1); }
+        mbar_init(&sb->tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM allocation (whole warp), 128 fp32 accumulator columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sb->tmem_base)), "r"(kTcTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_acc = sb->tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kTcStages, it = kb / kTcStages;
+                mbar_wait(&sb->empty[s], (it & 1) ^ 1);                       // slot free (first pass: passes immediately)
+                mbar_expect_tx(&sb->full[s], kOps * kTcTileBytes);
+                uint8_t* st = tiles + (size_t)s * kOps * kTcTileBytes;
+                tma_load_2d(st, &mapA, kb * kTcBK, m0, &sb->full[s]);
+                tma_load_2d(st + kTcTileBytes, &mapB, kb * kTcBK, n0, &sb->full[s]);
+                if (kSplit) {
+                    tma_load_2d(st + 2 * kTcTileBytes, &mapAlo, kb * kTcBK, m0, &sb->full[s]);
+                    tma_load_2d(st + 3 * kTcTileBytes, &mapBlo, kb * kTcBK, n0, &sb->full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kTcStages, it = kb / kTcStages;
+                mbar_wait(&sb->full[s], it & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = smem_u32(tiles + (size_t)s * kOps * kTcTileBytes);
+                const uint64_t dA = umma_desc_k128(st), dB = umma_desc_k128(st + kTcTileBytes);
+                const uint64_t dAl = umma_desc_k128(st + 2 * kTcTileBytes), dBl = umma_desc_k128(st + 3 * kTcTileBytes);
+#pragma unroll
+                for (int k = 0; k < kTcBK / 8; ++k) {                          // UMMA_K = 8 tf32 = 32 bytes = 2 descriptor units
+                    const uint64_t adv = (uint64_t)(k * 2);
+                    umma_tf32(tmem_acc, dA + adv, dB + adv, (kb | k) != 0);
+                    if (kSplit) {
+                        umma_tf32(tmem_acc, dAl + adv, dB + adv, 1u);
+                        umma_tf32(tmem_acc, dA + adv, dBl + adv, 1u);
+                    }
+                }
+                umma_commit(&sb->empty[s]);                                    // frees the stage when these MMAs retire
+            }
+            umma_commit(&sb->tmem_full);                                       // accumulator complete
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> global (alpha / beta), warp q handles TMEM lanes [32q, 32q+32) =====
+        const int q = warp & 3;
+        mbar_wait(&sb->tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+        for (int cc = 0; cc < kTcBN / 32; ++cc) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                  "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                  "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < M) {
+                float* crow = C + (size_t)row * ldc + n0 + cc * 32;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int col = n0 + cc * 32 + c;
+                    if (col < N) {
+                        const float acc = alpha * __uint_as_float(v[c]);
+                        crow[c] = beta != 0.f ? acc + beta * crow[c] : acc;
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(kTcTmemCols) : "memory");
+    }
+}
+
+// x_lo = x - (x with the 13 low mantissa bits cleared)  on a [rows][K] block (row stride ld) -> compact [rows][ldo]
+__global__ void ker_split_lo(const float* __restrict__ x, int ld, float* __restrict__ lo, int ldo, int rows, int K) {
+    const int64_t n = (int64_t)rows * ldo;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / ldo), k = (int)(i - (int64_t)r * ldo);
+        float v = 0.f;
+        if (k < K) {
+            const float xv = x[(size_t)r * ld + k];
+            v = xv - __uint_as_float(__float_as_uint(xv) & 0xFFFFE000u);
+        }
+        lo[i] = v;
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+static int make_map(CUtensorMap* map, const float* base, int rows, int K, int ld) {
+    EncodeTiledFn enc = get_encode();
+    MSA_CHECK(enc != nullptr, MSA_E_NODEVICE, "gemm_tc: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)kTcBM};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MSA_CHECK(r == CUDA_SUCCESS, MSA_E_ARG, "gemm_tc: cuTensorMapEncodeTiled failed (%d) for a [%d x %d] operand, ld %d", (int)r, rows, K, ld);
+    return 0;
+}
+
+bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb, const float* C, int64_t ldc) {
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    (void)C; (void)ldc;
+    return M >= 1 && N >= 1 && K >= 1 && (lda % 4) == 0 && (ldb % 4) == 0 && al16(A) && al16(B) && M < (1 << 30) && N < (1 << 30) &&
+           K < (1 << 30);
+}
+size_t gemm_tc_scratch_floats(int64_t M, int64_t N, int64_t K) {
+    const int64_t ldo = (K + 3) / 4 * 4;
+    return (size_t)((M + N) * ldo + 64);
+}
+
+// mode 0: 3xTF32 (fp32-accurate), needs `scratch` of gemm_tc_scratch_floats(M, N, K); mode 1: single TF32 product
+int gemm_tc_nt(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
+               float* C, int64_t ldc, int mode, float* scratch, cudaStream_t st) {
+    MSA_CHECK(gemm_tc_supported(M, N, K, A, lda, B, ldb, C, ldc), MSA_E_UNSUPPORTED, "gemm_tc_nt: operand alignment / leading dimensions");
+    CUtensorMap mA, mB, mAl, mBl;
+    MSA_TRY(make_map(&mA, A, (int)M, (int)K, (int)lda));
+    MSA_TRY(make_map(&mB, B, (int)N, (int)K, (int)ldb));
+    const dim3 grid((unsigned)((M + kTcBM - 1) / kTcBM), (unsigned)((N + kTcBN - 1) / kTcBN));
+    if (mode == 0) {
+        MSA_CHECK(scratch != nullptr && (reinterpret_cast<uintptr_t>(scratch) & 15) == 0, MSA_E_ARG, "gemm_tc_nt: 3xTF32 needs 16-byte aligned scratch");
+        const int ldo = (int)((K + 3) / 4 * 4);
+        float* alo = scratch;
+        float* blo = scratch + (size_t)M * ldo;
+        blo = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(blo) + 15) & ~(uintptr_t)15);
+        ker_split_lo<<<(unsigned)std::min<int64_t>((M * ldo + 255) / 256, 148 * 8), 256, 0, st>>>(A, (int)lda, alo, ldo, (int)M, (int)K);
+        MSA_LAUNCH_CHECK();
+        ker_split_lo<<<(unsigned)std::min<int64_t>((N * ldo + 255) / 256, 148 * 8), 256, 0, st>>>(B, (int)ldb, blo, ldo, (int)N, (int)K);
+        MSA_LAUNCH_CHECK();
+        MSA_TRY(make_map(&mAl, alo, (int)M, (int)K, ldo));
+        MSA_TRY(make_map(&mBl, blo, (int)N, (int)K, ldo));
+        const size_t smem = (size_t)kTcStages * 4 * kTcTileBytes + sizeof(TcSmem) + 1024;
+        MSA_CUDA(cudaFuncSetAttribute(k_gemm_tf32_nt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_gemm_tf32_nt<true><<<grid, kTcThreads, smem, st>>>(mA, mAl, mB, mBl, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta);
+    } else {
+        const size_t smem = (size_t)kTcStages * 2 * kTcTileBytes + sizeof(TcSmem) + 1024;
+        MSA_CUDA(cudaFuncSetAttribute(k_gemm_tf32_nt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_gemm_tf32_nt<false><<<grid, kTcThreads, smem, st>>>(mA, mA, mB, mB, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta);
+    }
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace msa
+
+extern "C" {
+size_t msa_gemm_nt_scratch_floats(int64_t M, int64_t N, int64_t K) { return msa::gemm_tc_scratch_floats(M, N, K); }
+int msa_gemm_nt(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
+                float* C, int64_t ldc, int mode, float* scratch, void* stream) {
+    return msa::gemm_tc_nt(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, mode, scratch, (cudaStream_t)stream);
+}
+}

@@ -69,6 +69,11 @@ struct msa_handle {
     bool in_bwd = false;   // GEMM precision policy 1: fp32 GEMMs in the forward pass, TF32 in the backward pass
     bool prof = false;
     int trace_t0 = 0;
+    float* gemm_scratch = nullptr;   // 3xTF32 split scratch of the tcgen05 GEMM (in the pass workspace)
+    size_t gemm_scratch_floats = 0;
+    cudaStream_t cur_stream = nullptr;
+    bool tc_enabled = false;         // env MSA_GEMM_TC=1 routes the x.W^T contractions to the hand-written tcgen05 kernel (gemm_tc.cu);
+                                     // off by default: measured 1.5-2x slower than cuBLAS at these shapes so far
     int rec_flags = -1;    // hand-off variant of the persistent kernels; -1 = per-kernel default (env MSA_REC_FLAGS overrides, development only)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
     std::vector<int> prof_id;
@@ -193,11 +198,18 @@ static Dims make_dims(const msa_config& c, int B, int T, int L) {
     X(dp1, (d.TB + d.B) * d.Pd) X(denc_h, 2 * d.BL * d.Hh) X(dzx, 2 * d.BL * 4 * d.Hh)                 \
     X(dx3_tm, d.BL * d.C) X(edx0, d.BL * d.C) X(edx1, d.BL * d.C) X(edy, d.BL * d.C)                   \
     X(edcol, d.BL * d.Kc * d.C) X(edw2, (int64_t)d.C * d.Kc * d.C) X(dspk, d.B * d.Ds)                             \
-    X(wloc_part, (int64_t)wloc_grad_partials(d.T, d.B) * d.F * 2 * d.Kl) X(prof, kProfFloats) X(trace, kTraceFloats)
+    X(wloc_part, (int64_t)wloc_grad_partials(d.T, d.B) * d.F * 2 * d.Kl) X(gemm_lo, tc_scratch_floats(d)) X(prof, kProfFloats) X(trace, kTraceFloats)
 
 constexpr int64_t kProfFloats = 2 * 6 * 256 * 8;
 constexpr int64_t kTraceWordsPerKernel = (int64_t)256 * 16 * 4 * 12 * 2;   // int64 words: [ctas][warps][steps][tags][2]
 constexpr int64_t kTraceFloats = 2 * 6 * kTraceWordsPerKernel;
+// scratch of the 3xTF32 operand split: (rows of A + rows of B) x padded K of the largest x.W^T contraction of the pass
+static int64_t tc_scratch_floats(const Dims& d) {
+    const int64_t rows_a = std::max<int64_t>(std::max<int64_t>(d.TB + d.B, d.BL), d.BT);
+    const int64_t rows_b = std::max<int64_t>(std::max<int64_t>(4 * d.Ha, 4 * d.Hd), std::max<int64_t>(std::max<int64_t>(4 * d.Hh, d.C), d.Cmax));
+    const int64_t k = std::max<int64_t>(std::max<int64_t>((int64_t)d.Kc * d.C, (int64_t)d.Kp * d.Cmax), std::max<int64_t>(d.Ha, d.Hd) + d.E + d.Pd);
+    return (std::max(rows_a, rows_b) + rows_b) * ((k + 3) / 4 * 4) + 128;
+}
 struct Ws {
 #define X(name, n) float* name; int64_t n_##name;
     WS_LIST(X)
@@ -262,6 +274,11 @@ static int gemm(msa_handle* h, bool ta, bool tb, int64_t M, int64_t N, int64_t K
         return 0;
     }
     const bool tf32 = h->cfg.gemm_tf32 >= 2 || (h->cfg.gemm_tf32 == 1 && h->in_bwd);
+    // x . W^T contractions (both operands K-contiguous) go to the hand-written tcgen05 / TMA kernel (gemm_tc.cu) under the
+    // tensor-core policies: 3xTF32 split where fp32 accuracy is required (forward of policy 1), single TF32 otherwise
+    if (!ta && tb && h->tc_enabled && h->cfg.gemm_tf32 >= 1 && N >= 8 && M * N >= 4096 && gemm_tc_supported(M, N, K, A, lda, Bm, ldb, Cm, ldc) &&
+        (tf32 || (h->gemm_scratch && gemm_tc_scratch_floats(M, N, K) <= h->gemm_scratch_floats)))
+        return gemm_tc_nt(M, N, K, alpha, A, lda, Bm, ldb, beta, Cm, ldc, tf32 ? 1 : 0, h->gemm_scratch, h->cur_stream);
     const cublasComputeType_t ct = tf32 ? CUBLAS_COMPUTE_32F_FAST_TF32 : CUBLAS_COMPUTE_32F;
     MSA_BLAS(cublasGemmEx(h->blas, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, (int)N, (int)M, (int)K, &alpha,
                           Bm, CUDA_R_32F, (int)ldb, A, CUDA_R_32F, (int)lda, &beta, Cm, CUDA_R_32F, (int)ldc, ct,
@@ -392,6 +409,7 @@ int msa_create(const msa_config* cfg, int device, msa_handle** out) {
     h->sm_count = prop.multiProcessorCount;
     h->smem_limit = prop.sharedMemPerBlockOptin;
     if (const char* e = getenv("MSA_REC_FLAGS")) h->rec_flags = atoi(e);
+    if (const char* e = getenv("MSA_GEMM_TC")) h->tc_enabled = atoi(e) != 0;
     build_layout(h);
     cublasStatus_t s = cublasCreate(&h->blas);
     if (s != CUBLAS_STATUS_SUCCESS) {
@@ -500,6 +518,7 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
     MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
     h->fwd_valid = false;
     h->in_bwd = false;
+    h->gemm_scratch = w.gemm_lo; h->gemm_scratch_floats = (size_t)w.n_gemm_lo; h->cur_stream = st;
     const msa_config& c = h->cfg;
     const auto secs = mask_sections(c, B, T, L);
     auto mk = [&](int i) { return masks + secs[i].off; };
@@ -698,6 +717,7 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
     MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
     const msa_config& c = h->cfg;
     h->in_bwd = true;
+    h->gemm_scratch = w.gemm_lo; h->gemm_scratch_floats = (size_t)w.n_gemm_lo; h->cur_stream = st;
     const int B = d.B, T = d.T, L = d.L;
     const auto secs = mask_sections(c, B, T, L);
     auto mk = [&](int i) { return h->masks + secs[i].off; };
@@ -1029,6 +1049,7 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
     MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
     h->in_bwd = false;
     h->fwd_valid = false;
+    h->gemm_scratch = nullptr; h->gemm_scratch_floats = 0; h->cur_stream = st;      // inference GEMMs (M = B rows) stay on cuBLAS
     const msa_config& c = h->cfg;
     auto P = [&](const std::string& n) { return params + h->off(n); };
     MSA_CUDA(cudaMemsetAsync(w.abort_word, 0, 256, st));
