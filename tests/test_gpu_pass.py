@@ -162,3 +162,36 @@ def test_backward_accumulate_and_scale():
     eng.forward(flat, None, bd, mflat)
     eng.backward(flat, g3)
     assert torch.equal(g3, g1), "the pass must be deterministic (idempotence)"
+
+
+@pytest.mark.parametrize("dims", [(2, 24, 150), (8, 16, 64), (1, 30, 64)])
+def test_default_dims_other_shapes_fp32(dims):
+    """Default model dimensions away from the bench shape: a long text (the MW slices no longer fit in shared memory: the
+    global-memory fallbacks of the attention chain run), bigger batches (several batch tiles), a single row."""
+    cfg = pkg.default_params()
+    crit = dict(reduction="none", pos_weight=10.0)
+    B, T, L = dims
+    eng = _engine(cfg, crit)
+    P = synth.init_params(cfg, 3)
+    batch = synth.make_batch(cfg, B, T, L, 77)
+    masks = synth.make_masks(cfg, B, T, L, 78)
+    o_out, o_loss, o_grads, _, _ = oracle_pass(cfg, P, batch, masks, crit)
+    c_out, c_loss, c_grads, _ = cuda_pass(eng, cfg, P, batch, masks)
+    for key, a, b in zip(("mel", "mel_post", "gate", "align"), c_out, o_out):
+        assert rel(a, b) < 3e-4, (key, rel(a, b))
+    assert abs(float(c_loss) - float(o_loss)) < 3e-4 * abs(float(o_loss))
+    gn = float(torch.sqrt(sum((g.double() ** 2).sum() for g in o_grads.values())))
+    worst = max((float((c_grads[n].double().cpu() - o_grads[n].double()).norm()) / gn, n) for n in o_grads)
+    assert worst[0] < 3e-4, worst
+
+
+def test_batch_beyond_the_shared_memory_budget_is_a_loud_error():
+    """At the default dimensions the attention chain keeps h for all batch rows in shared memory next to its weight slice:
+    B <= 8 fits, B = 16 does not -- the library says so instead of computing something else."""
+    cfg = pkg.default_params()
+    crit = dict(reduction="none", pos_weight=10.0)
+    eng = _engine(cfg, crit)
+    B, T, L = 16, 6, 40
+    P = synth.init_params(cfg, 3)
+    with pytest.raises(RuntimeError, match="shared memory"):
+        cuda_pass(eng, cfg, P, synth.make_batch(cfg, B, T, L, 77), synth.make_masks(cfg, B, T, L, 78), backward=False)
