@@ -1,0 +1,50 @@
+"""Continual-learning steps of the reference on the CUDA hot path (BASELINE.json configs[3]).
+
+* ER-KD soft targets (continual_erkd.py:73-83,105-115): a teacher-forced forward pass under ``no_grad`` -- in TRAIN mode, the
+  reference never calls ``eval()`` there -- whose FIRST output (the pre-postnet mel, SURVEY.md Q9: the variable is named
+  ``out_post`` but ``Tacotron2NV.forward`` returns ``[mel, mel_post, gate, align]``) trimmed to each item's length becomes the
+  stored target of the replay item.
+* The training step itself (continual_erkd.py:318-336, continual_ewc.py:338-357) is forward, loss, backward and one optimizer
+  step; with EWC the penalty gradient and the SGD update are one fused kernel (``EWC.sgd_step``).
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional
+
+import torch
+
+from .engine import batch_to_device
+
+
+def make_soft_targets(model, batches: Iterable[tuple], masks: Optional[list] = None) -> Dict[str, torch.Tensor]:
+    """{item_id: soft mel [n_mel, len]} for every item of the replay batches (continual_erkd.py:73-83)."""
+    eng = model.engine
+    out: Dict[str, torch.Tensor] = {}
+    for i, batch in enumerate(batches):
+        item_ids = batch[0]
+        bd = batch_to_device(batch, eng.device, model.params["speaker_emb_type"])
+        B, L = bd["inputs"].shape
+        T = bd["melspecs"].shape[2]
+        mk = eng.pack_masks(masks[i], B, T, L) if masks is not None else model._masks(B, T, L)
+        outs, _ = eng.forward(model.flat, model.bn_flat, bd, mk, outputs=True)     # train mode: BN batch stats, running stats move
+        mel = outs[0]
+        lens = bd["melspec_lengths"].tolist()
+        for j, item in enumerate(item_ids):
+            out[item] = mel[j, :, :lens[j]].detach().cpu()
+    return out
+
+
+def sgd_train_step(model, batch: tuple, lr: float, ewc=None, importance: float = 0.0, masks: Optional[dict] = None) -> dict:
+    """One continual training step with plain SGD: loss (+ importance * EWC penalty), backward, update."""
+    eng = model.engine
+    bd = batch_to_device(batch, eng.device, model.params["speaker_emb_type"])
+    B, L = bd["inputs"].shape
+    T = bd["melspecs"].shape[2]
+    mk = eng.pack_masks(masks, B, T, L) if masks is not None else model._masks(B, T, L)
+    _, loss = eng.forward(model.flat, model.bn_flat, bd, mk, outputs=False)
+    eng.backward(model.flat, model.grad_flat)
+    if ewc is not None:
+        penalty = ewc.sgd_step(model.grad_flat, lr, importance)                     # fused penalty gradient + update
+        return {"loss": loss, "penalty": penalty}
+    eng.sgd_step(model.flat, model.grad_flat, lr=lr)
+    return {"loss": loss}

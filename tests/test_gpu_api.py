@@ -135,3 +135,30 @@ def test_ewc_fisher_penalty_and_fused_step_like_continual_ewc_py():
     new = eng.dict_from_flat(model.flat)
     pn = float(torch.sqrt(sum((v.double() ** 2).sum() for v in o_new.values())))
     assert max(float((new[n].double().cpu() - o_new[n].double()).norm()) / pn for n in names) < 1e-5
+
+
+def test_erkd_soft_targets_like_continual_erkd_py():
+    """continual_erkd.py:73-83: the stored soft target is the FIRST model output (pre-postnet mel, Q9) trimmed to length."""
+    from msa_tts_b200.continual import make_soft_targets, sgd_train_step
+    cfg = pkg.small_params()
+    B, T, L = 3, 10, 8
+    P = synth.init_params(cfg, 8)
+    batch = synth.make_batch(cfg, B, T, L, 808)
+    masks = synth.make_masks(cfg, B, T, L, 809)
+    o_out, o_loss, o_g, _, _ = oracle_pass(cfg, P, batch, masks, CRIT)
+    model = _model(cfg, P)
+    soft = make_soft_targets(model, [batch], masks=[masks])
+    lens = batch[4].tolist()
+    assert list(soft.keys()) == list(batch[0])
+    for j, item in enumerate(batch[0]):
+        assert soft[item].shape == (cfg["n_mel_channels"], lens[j])
+        assert rel(soft[item], o_out[0][j, :, :lens[j]]) < TOL
+    # and the plain replay training step (continual_erkd.py:318-336 with SGD)
+    before = {k: v.clone() for k, v in model.engine.dict_from_flat(model.flat).items()}
+    log = sgd_train_step(model, batch, 0.01, masks=masks)
+    assert abs(float(log["loss"]) - float(o_loss)) < TOL * abs(float(o_loss))
+    after = model.engine.dict_from_flat(model.flat)
+    names = list(P.keys())
+    num = sum(float(((after[n] - (before[n] - 0.01 * o_g[n].to(after[n].device))).double() ** 2).sum()) for n in names)
+    den = sum(float(((0.01 * o_g[n]).double() ** 2).sum()) for n in names)
+    assert (num / den) ** 0.5 < TOL
