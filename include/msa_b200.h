@@ -98,7 +98,9 @@ int msa_sm_count(const msa_handle* h);
 /* number of kernels of THIS library enqueued so far by the process (cuBLAS GEMMs are not counted) */
 long long msa_launch_count(void);
 /* per-kernel device timing of the persistent kernels with CUDA events on the launch stream:
- * enable, run passes, then read (synchronises) total milliseconds and launch counts per kernel id */
+ * enable (1), run passes, then read (synchronises) total milliseconds and launch counts per kernel id.
+ * enable = 2 additionally switches the kernels to their instrumented variants (per-phase cycle counters and per-warp
+ * traces, msa_profile_phases / msa_profile_trace): for the profiles/ scripts only, the kernels run slower. */
 int msa_profile_enable(msa_handle* h, int enable);
 int msa_profile_kernels(void);
 const char* msa_profile_name(int id);

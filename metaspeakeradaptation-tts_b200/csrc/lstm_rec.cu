@@ -92,12 +92,10 @@ __global__ void __launch_bounds__(NT, 1) k_lstm_rec_fwd(LstmRecParams p) {
             gate_wait(ncta_dir, [&](int c) { const int e = part_lo(c + 1, H, ncta_dir); return e > 0 ? hrow + e - 1 : nullptr; }, sg);
             __syncthreads();
         }
-        if (s > 0) {
-            poll_copy_rows<NT>(hs, KP4, hout + (size_t)tp * B * H, B, H >> 2, sg);
-            __syncthreads();
-        }
         prof.mark(0, s);
-        cta_matvec_fwd<NT>(Wsm, RG, KP, hs, B, part, 0, KP >> 7);
+        // h(t-1) goes from global memory (L2) straight into the mat-vec registers, canary-checked; at s == 0 it is zero
+        if (s > 0) cta_matvec_fwd<NT, true>(Wsm, RG, KP, hout + (size_t)tp * B * H, B, part, 0, KP >> 7, H, &sg);
+        else for (int i = threadIdx.x; i < kBTiles * kRecWarps * 32; i += NT) part[i] = 0.f;
         __syncthreads();
         prof.mark(1, s);
         if (pw) {
@@ -109,18 +107,20 @@ __global__ void __launch_bounds__(NT, 1) k_lstm_rec_fwd(LstmRecParams p) {
             const unsigned int gm = 0xFu << (threadIdx.x & 28);                 // the 4 lanes of this cell
             const float ai = __shfl_sync(gm, act, 0, 4), af = __shfl_sync(gm, act, 1, 4);
             const float ag = __shfl_sync(gm, act, 2, 4), ao = __shfl_sync(gm, act, 3, 4);
-            gates[zb + (size_t)g * H + u] = act;
+            float cn = 0.f;
             if (g == 0) {
-                float hv = 0.f, cn = 0.f;
+                float hv = 0.f;
                 if (active) {
                     cn = af * cstate + ai * ag;
                     cstate = cn;
                     hv = ao * fast_tanh(cn);
                     if (p.mask) hv = mk ? hv * p.drop_scale : 0.f;
                 }
-                st_pub(hout + ((size_t)t * B + b) * H + u, hv);      // consumed by every CTA at the next step
-                cout[((size_t)t * B + b) * H + u] = cn;
+                st_pub(hout + ((size_t)t * B + b) * H + u, hv);      // consumed by every CTA at the next step: first memory op
+                if (p.flags & 8) __threadfence();
             }
+            gates[zb + (size_t)g * H + u] = act;                      // stash for the backward pass: off the critical path
+            if (g == 0) cout[((size_t)t * B + b) * H + u] = cn;
             if (s + 1 < T) fetch(dir == 0 ? t + 1 : t - 1);
         }
         prof.mark(2, s);

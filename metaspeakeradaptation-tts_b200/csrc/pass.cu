@@ -67,7 +67,8 @@ struct msa_handle {
     Dims d{};
     // optional per-kernel timing with CUDA events on the launch stream (bench.py's roofline leg)
     bool in_bwd = false;   // GEMM precision policy 1: fp32 GEMMs in the forward pass, TF32 in the backward pass
-    bool prof = false;
+    bool prof = false;       // CUDA-event timing of the persistent kernels (bench.py)
+    bool prof_inkernel = false;   // + per-phase cycle counters / per-warp traces inside them (profiles/ scripts only: slower kernels)
     int trace_t0 = 0;
     float* gemm_scratch = nullptr;   // 3xTF32 split scratch of the tcgen05 GEMM (in the pass workspace)
     size_t gemm_scratch_floats = 0;
@@ -354,11 +355,11 @@ struct ProfScope {
 
 // per-phase cycle counters of the persistent kernels live in the workspace ("prof"); written only while profiling is on
 static long long* prof_ptr(const msa_handle* h, const Ws& w, int id) {
-    return h->prof ? reinterpret_cast<long long*>(w.prof) + (size_t)id * kProfCtas * kProfSlots : nullptr;
+    return h->prof_inkernel ? reinterpret_cast<long long*>(w.prof) + (size_t)id * kProfCtas * kProfSlots : nullptr;
 }
 
 static long long* trace_ptr(const msa_handle* h, const Ws& w, int id) {
-    return h->prof ? reinterpret_cast<long long*>(w.trace) + (size_t)id * kTraceWordsPerKernel : nullptr;
+    return h->prof_inkernel ? reinterpret_cast<long long*>(w.trace) + (size_t)id * kTraceWordsPerKernel : nullptr;
 }
 
 static int check_cfg(const msa_config& c) {
@@ -435,6 +436,7 @@ long long msa_launch_count(void) { return g_launches.load(); }
 int msa_profile_enable(msa_handle* h, int enable) {
     MSA_CHECK(h, MSA_E_ARG, "msa_profile_enable: null handle");
     h->prof = enable != 0;
+    h->prof_inkernel = enable >= 2;
     h->prof_used = 0;
     return 0;
 }

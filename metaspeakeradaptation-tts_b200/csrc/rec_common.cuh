@@ -96,9 +96,11 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) { return
 // handles (j = j0 + ks, j0 + ks + KS, ...) of   sum_k Wsm[(rg*8+rr)*KP + k] * hs[(tile*4+bl)*KP + k].
 // Wsm [RG*8][KP] and hs [BP][KP] are zero-padded (KP % 128 == 0, BP % 4 == 0).  RG = ceil(rows/8), KS = (NT / 32) / RG.
 // No __syncthreads inside: the caller synchronises and then sums the KS partials of each output (lstm_gate_sum).
-template <int NT>
+template <int NT, bool kGlobalH = false>
 __device__ __forceinline__ void cta_matvec_fwd(const float* __restrict__ Wsm, int RG, int KP, const float* __restrict__ hs, int B,
-                                               float* __restrict__ part, int j0, int j1) {
+                                               float* __restrict__ part, int j0, int j1, int Hg = 0, SpinGuard* sg = nullptr) {
+    // kGlobalH: hs is the [B][Hg] row block other CTAs are publishing in global memory (canary-polled straight into
+    // registers, no staging pass through shared memory); otherwise the zero-padded [BP][KP] copy in shared memory
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int KS = (NT / 32) / RG;
     const int rg = w % RG, ks = w / RG;
@@ -108,6 +110,43 @@ __device__ __forceinline__ void cta_matvec_fwd(const float* __restrict__ Wsm, in
     const float4* h4p = reinterpret_cast<const float4*>(hs);
     const int ntile = (B + 3) >> 2;
     for (int tile = 0; tile < ntile; ++tile) {
+        if (kGlobalH) {
+            // one pass, 32 accumulators: every h word is fetched from L2 exactly once per warp
+            float acc[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+            for (int j = j0 + ks; j < j1; j += KS) {
+                const int c4 = j * 32 + lane;
+                const bool in = c4 < (Hg >> 2);
+                float4 h4[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    h4[b] = (in && tile * 4 + b < B) ? ld_poll4(hs + (size_t)(tile * 4 + b) * Hg + (size_t)c4 * 4)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    if (in && tile * 4 + b < B) {
+                        sg->reset();
+                        while (!ready4(h4[b])) {
+                            if (sg->bail()) break;
+                            h4[b] = ld_poll4(hs + (size_t)(tile * 4 + b) * Hg + (size_t)c4 * 4);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float4 w4[4];
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) w4[rr] = W4[(size_t)(half * 4 + rr) * KP4 + c4];
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) acc[(half * 4 + rr) * 4 + b] += dot4(w4[rr], h4[b]);
+                }
+            }
+            part[((size_t)(tile * KS + ks) * RG + rg) * 32 + lane] = warp_transpose_reduce32(acc);
+            continue;
+        }
         // two passes of 4 gate rows x 4 batch rows: 16 accumulators + 16 + 16 operand registers live at a time
         float tot = 0.f;
 #pragma unroll
@@ -221,37 +260,16 @@ __device__ __forceinline__ void cta_context_term_global(const float* __restrict_
 
 // ---- gated hand-offs ------------------------------------------------------------------------------------------------
 // Spinning on not-yet-written data with all 512 threads of all 148 CTAs saturates the L2 request bandwidth and delays the
-// very stores everybody is waiting for.  So only WARP 0 of a CTA spins; the other warps park at the following
-// __syncthreads (no memory traffic).  Small gathers (energies, queries, d a, dq) are fetched whole by warp 0; for the large
-// ones (h, dz) warp 0 waits for one sentinel word per producer CTA -- the last word that producer stores -- and then all
-// threads fetch the bulk once (still canary-checked word by word: the sentinel is a hint, never the correctness argument).
+// very stores everybody is waiting for.  For the large gathers (h, dz) the first ncta threads therefore wait for ONE sentinel
+// word per producer CTA -- the last word that producer stores -- while the other warps park at the following __syncthreads
+// (no memory traffic), and then all threads fetch the bulk once (still canary-checked word by word: the sentinel is a hint,
+// never the correctness argument).  Small gathers (energies, queries, d a, dq) can be fetched whole by warp 0 (kFlagWarp0).
 template <class AddrFn>
 __device__ __forceinline__ void gate_wait(int n, AddrFn addr, SpinGuard& sg) {
-    if (threadIdx.x >= 32) return;
-    constexpr int kBatch = 8;
-    for (int base = 0; base < n; base += 32 * kBatch) {
-        float v[kBatch];
-#pragma unroll
-        for (int j = 0; j < kBatch; ++j) {
-            const int i = base + j * 32 + threadIdx.x;
-            v[j] = 0.f;
-            if (i < n) {
-                const float* a = addr(i);
-                if (a) v[j] = ld_poll(a);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < kBatch; ++j) {
-            const int i = base + j * 32 + threadIdx.x;
-            if (i < n) {
-                const float* a = addr(i);
-                sg.reset();
-                while (a && is_canary(v[j])) {
-                    if (sg.bail()) break;
-                    v[j] = ld_poll(a);
-                }
-            }
-        }
+    // one sentinel per thread (the first n threads): every sentinel is polled independently, one L2 round trip each
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float* a = addr(i);
+        if (a) (void)poll1(a, sg);
     }
 }
 // warp 0 copies n words that other CTAs publish during this launch from global to shared, polling each word

@@ -297,8 +297,9 @@ class Engine:
         """Kernels of libmsa_b200 enqueued so far by this process (cuBLAS GEMMs excluded)."""
         return int(self.lib.msa_launch_count())
 
-    def profile(self, enable: bool) -> None:
-        _lib.check(self.lib.msa_profile_enable(self.h, int(enable)), "msa_profile_enable")
+    def profile(self, enable, inkernel: bool = False) -> None:
+        """CUDA-event timing of the persistent kernels; inkernel=True also selects their instrumented variants."""
+        _lib.check(self.lib.msa_profile_enable(self.h, (2 if inkernel else 1) if enable else 0), "msa_profile_enable")
 
     def check_abort(self) -> None:
         """Raise if a persistent kernel of the last passes timed out while polling (synchronises)."""

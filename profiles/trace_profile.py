@@ -20,7 +20,7 @@ items = {s: {k: tuple(x.to(tr.device) if hasattr(x, "to") else x for x in v) for
 for _ in range(2):
     tr._metatrain_step(items)
 eng = tr.engine
-eng.profile(True)
+eng.profile(True, inkernel=True)
 _lib.check(eng.lib.msa_profile_trace_step(eng.h, t0))
 tr._metatrain_step(items)
 torch.cuda.synchronize()
