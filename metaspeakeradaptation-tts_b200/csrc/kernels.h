@@ -145,10 +145,30 @@ int k_wloc_grad(const float* dconvf, const float* align, const float* cum, float
                 int Kl, float scale, int accumulate, cudaStream_t st);
 int k_dot_rows(const float* a, const float* b, int64_t n, float* partials, float* out, float scale, int accumulate, cudaStream_t st);
 int k_masks_generate(uint8_t* masks, const int64_t* offsets, const int64_t* numels, const float* ps, int nsec, uint64_t seed, cudaStream_t st);
-// ---------------- free-running inference, per-step kernels (infer_kernels.cu) ----------------
+// ---------------- free-running inference, fused per-step kernels (infer_decode.cu, infer_kernels.cu) ----------------
+enum { IR_EPI_BIAS = 0, IR_EPI_RELU_DROP = 1, IR_EPI_LSTM = 2 };
+// out[b][n] = sum over the K segments of W_s[n][:] . x_s[b][:]  (+ epilogue), B rows in tiles of 32
+struct InferRowsParams {
+    int B, N, nseg, rotate;
+    const float* x[2]; int ldx[2]; int K[2];      // inputs [B][ldx], K columns each (multiples of 4, 16-byte aligned rows)
+    const float* W[2]; int ldw[2];                // weights [N][ldw]
+    const float* Wb; int nsplit;                  // rows >= nsplit (if > 0) come from a second matrix Wb (segment 0 only)
+    int epi;
+    const float* bias1; const float* bias2;       // BIAS: bias of rows < nsplit / >= nsplit; LSTM: b_ih, b_hh
+    float* out; int ldo; float* out2; int ldo2;   // BIAS / RELU_DROP outputs (out2: rows >= nsplit)
+    const uint8_t* mask; int mask_layer;          // RELU_DROP: prenet masks [steps][2][B][N]
+    float* c; float* h1; int ldh1; float* h2; int ldh2; int H;     // LSTM: cell state (in place), two copies of the new h
+    const int* state;                             // [0] step, [1] done, [2] steps produced
+    // end-of-step logic run by the last CTA (finish != 0): out = mel frame [B][M], out2 = gate [B]
+    int finish, M, early, max_steps;
+    float threshold;
+    float* mel_tm; float* frame; int* not_finished; int* mel_lengths; int* state_rw; unsigned int* counter;
+};
+int k_infer_rows(const InferRowsParams& p, int sm_count, cudaStream_t st);
 struct InferAttnParams {
     int B, L, Ha, A, F, Kl, E, norm, max_steps;
-    const float* q;                   // [B][A]  Wq.h_a of this step (GEMM before the kernel)
+    const float* h; int ldh;          // [B][ldh] h_a'(t)
+    const float* wq;                  // [A][Ha]
     const float* wloc;
     const float* wld;
     const float* v; const float* bv;
@@ -160,14 +180,8 @@ struct InferAttnParams {
     const int* state;
 };
 int k_fill_ones_i32(int* p, int n, cudaStream_t st);
-int k_infer_relu_drop(float* x, int ld, const uint8_t* masks, int layer, int B, int N, const int* state, cudaStream_t st);
-int k_infer_lstm_point(const float* z, const float* b_ih, const float* b_hh, float* c, float* h1, int ld1, float* h2, int ld2,
-                       int B, int H, const int* state, cudaStream_t st);
-size_t infer_attention_smem(int L, int A, int F, int Kl);
+size_t infer_attention_smem(int L, int Ha, int A, int F, int Kl, int E);
 int k_infer_attention(const InferAttnParams& p, cudaStream_t st);
-int k_infer_finish(const float* mel_raw, const float* bp, const float* gate_raw, const float* bg, float* mel_tm, float* frame,
-                   int* not_finished, int* mel_lengths, int B, int M, float threshold, int early, int max_steps, int* state,
-                   cudaStream_t st);
 int k_tm_to_ref_ld(const float* x_tm, float* out, int T, int B, int M, int ld, cudaStream_t st);
 int k_bt_to_ref_ld(const float* x_bt, float* out, int B, int T, int M, int ld, cudaStream_t st);
 

@@ -965,9 +965,9 @@ namespace msa {
     X(enc_col, d.BL * d.Kc * d.C) X(enc_w2, (int64_t)d.C * d.Kc * d.C) X(x3_tm, d.BL * d.C)              \
     X(enc_zx, 2 * d.BL * 4 * d.Hh) X(enc_g, 2 * d.BL * 4 * d.Hh) X(enc_c, 2 * d.BL * d.Hh)               \
     X(enc_h, 2 * d.BL * d.Hh) X(memory, d.BL * d.E) X(pm, d.BL * d.A)                                    \
-    X(xin_a, d.B * (d.Pd + d.E)) X(p1, d.B * d.Pd) X(ha, d.B * d.Ha) X(ca, d.B * d.Ha)                   \
-    X(xin_d, d.B * (d.Ha + d.E)) X(hd, d.B * d.Hd) X(cd, d.B * d.Hd) X(xin_p, d.B * (d.Hd + d.E))        \
-    X(za, d.B * 4 * d.Ha) X(zd, d.B * 4 * d.Hd) X(qbuf, d.B * d.A) X(mel_raw, d.B * d.M) X(gate_raw, d.B) X(frame, d.B * d.M) \
+    X(xin_a, d.B * (d.Pd + d.E)) X(p1, d.B * d.Pd) X(ha, 2 * d.B * d.Ha) X(ca, d.B * d.Ha)               \
+    X(xin_d, d.B * (d.Ha + d.E)) X(hd, 2 * d.B * d.Hd) X(cd, d.B * d.Hd) X(xin_p, d.B * (d.Hd + d.E))    \
+    X(mel_raw, d.B * d.M) X(gate_raw, d.B) X(frame, d.B * d.M)                                           \
     X(prev, d.BL) X(cum, d.BL) X(mel_tm, (int64_t)d.T * d.B * d.M) X(ints, 64 + d.B)                      \
     X(post_x, 2 * d.BT * d.Cmax) X(post_y, d.BT * d.Cmax) X(post_col, d.BT * d.Kp * d.Cmax)              \
     X(post_w2, (int64_t)d.Cmax * d.Kp * d.Cmax) X(post_bt, d.BT * d.M)
@@ -1051,7 +1051,7 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
     MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
     h->in_bwd = false;
     h->fwd_valid = false;
-    h->gemm_scratch = nullptr; h->gemm_scratch_floats = 0; h->cur_stream = st;      // inference GEMMs (M = B rows) stay on cuBLAS
+    h->gemm_scratch = nullptr; h->gemm_scratch_floats = 0; h->cur_stream = st;      // encoder / postnet GEMMs of inference stay on cuBLAS
     const msa_config& c = h->cfg;
     auto P = [&](const std::string& n) { return params + h->off(n); };
     MSA_CUDA(cudaMemsetAsync(w.abort_word, 0, 256, st));
@@ -1099,10 +1099,10 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
     int* state = ints;                 // [0] step, [1] done, [2] steps produced
     int* not_finished = ints + 64;     // [B]
     MSA_CUDA(cudaMemsetAsync(w.xin_a, 0, sizeof(float) * (size_t)B * KA, st));
-    MSA_CUDA(cudaMemsetAsync(w.ha, 0, sizeof(float) * (size_t)B * d.Ha, st));
+    MSA_CUDA(cudaMemsetAsync(w.ha, 0, sizeof(float) * (size_t)2 * B * d.Ha, st));
     MSA_CUDA(cudaMemsetAsync(w.ca, 0, sizeof(float) * (size_t)B * d.Ha, st));
     MSA_CUDA(cudaMemsetAsync(w.xin_d, 0, sizeof(float) * (size_t)B * KD, st));
-    MSA_CUDA(cudaMemsetAsync(w.hd, 0, sizeof(float) * (size_t)B * d.Hd, st));
+    MSA_CUDA(cudaMemsetAsync(w.hd, 0, sizeof(float) * (size_t)2 * B * d.Hd, st));
     MSA_CUDA(cudaMemsetAsync(w.cd, 0, sizeof(float) * (size_t)B * d.Hd, st));
     MSA_CUDA(cudaMemsetAsync(w.xin_p, 0, sizeof(float) * (size_t)B * KP, st));
     MSA_CUDA(cudaMemsetAsync(w.frame, 0, sizeof(float) * (size_t)B * d.M, st));
@@ -1114,25 +1114,37 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
     MSA_CUDA(cudaMemsetAsync(align_out, 0, sizeof(float) * (size_t)B * max_steps * L, st));
     MSA_CUDA(cudaMemsetAsync(mel_post_out, 0, sizeof(float) * (size_t)B * d.M * max_steps, st));
 
-    // ---- one decoder step (decoder.py:362-399 -> decode 234-274); the step index lives on the device ----
+    // ---- one decoder step (decoder.py:362-399 -> decode 234-274) = six fused launches (infer_decode.cu); the step index
+    // lives on the device.  The recurrent h of both LSTMCells ping-pongs between two buffers by step parity (a CTA may not
+    // overwrite h(t-1) while another CTA still reads it); a second copy goes into the packed input of the next product. ----
     const float* Wia = P("decoder.attention_rnn.weight_ih");
     const float* Wid = P("decoder.decoder_rnn.weight_ih");
-    auto step = [&]() -> int {
+    unsigned int* counter = reinterpret_cast<unsigned int*>(ints + 8);
+    auto step = [&](int s) -> int {
+        const int cur = s & 1, nxt = cur ^ 1;
+        InferRowsParams rp{};
+        rp.B = B; rp.state = state;
         // prenet, dropout always on (decoder.py:9-20,366)
-        MSA_TRY(gemm(h, false, true, B, d.Pd, d.M, 1.f, w.frame, d.M, P("decoder.prenet.layers.0.linear_layer.weight"), d.M, 0.f, w.p1, d.Pd));
-        MSA_TRY(k_infer_relu_drop(w.p1, d.Pd, prenet_masks, 0, B, d.Pd, state, st));
-        MSA_TRY(gemm(h, false, true, B, d.Pd, d.Pd, 1.f, w.p1, d.Pd, P("decoder.prenet.layers.1.linear_layer.weight"), d.Pd, 0.f, w.xin_a, KA));
-        MSA_TRY(k_infer_relu_drop(w.xin_a, KA, prenet_masks, 1, B, d.Pd, state, st));
+        rp.N = d.Pd; rp.nseg = 1; rp.epi = IR_EPI_RELU_DROP; rp.mask = prenet_masks;
+        rp.x[0] = w.frame; rp.ldx[0] = d.M; rp.K[0] = d.M; rp.W[0] = P("decoder.prenet.layers.0.linear_layer.weight"); rp.ldw[0] = d.M;
+        rp.out = w.p1; rp.ldo = d.Pd; rp.mask_layer = 0;
+        MSA_TRY(k_infer_rows(rp, h->sm_count, st));
+        rp.x[0] = w.p1; rp.ldx[0] = d.Pd; rp.K[0] = d.Pd; rp.W[0] = P("decoder.prenet.layers.1.linear_layer.weight"); rp.ldw[0] = d.Pd;
+        rp.out = w.xin_a; rp.ldo = KA; rp.mask_layer = 1;
+        MSA_TRY(k_infer_rows(rp, h->sm_count, st));
         // attention LSTMCell on [prenet; ctx(t-1)] (decoder.py:253-255)
-        MSA_TRY(gemm(h, false, true, B, 4 * d.Ha, KA, 1.f, w.xin_a, KA, Wia, KA, 0.f, w.za, 4 * d.Ha));
-        MSA_TRY(gemm(h, false, true, B, 4 * d.Ha, d.Ha, 1.f, w.ha, d.Ha, P("decoder.attention_rnn.weight_hh"), d.Ha, 1.f, w.za, 4 * d.Ha));
-        MSA_TRY(k_infer_lstm_point(w.za, P("decoder.attention_rnn.bias_ih"), P("decoder.attention_rnn.bias_hh"), w.ca, w.ha, d.Ha,
-                                   w.xin_d, KD, B, d.Ha, state, st));
-        // attention (forward_attn.py:178-219)
+        InferRowsParams la{};
+        la.B = B; la.state = state; la.N = 4 * d.Ha; la.H = d.Ha; la.nseg = 2; la.epi = IR_EPI_LSTM;
+        la.x[0] = w.xin_a; la.ldx[0] = KA; la.K[0] = KA; la.W[0] = Wia; la.ldw[0] = KA;
+        la.x[1] = w.ha + (size_t)cur * B * d.Ha; la.ldx[1] = d.Ha; la.K[1] = d.Ha; la.W[1] = P("decoder.attention_rnn.weight_hh"); la.ldw[1] = d.Ha;
+        la.bias1 = P("decoder.attention_rnn.bias_ih"); la.bias2 = P("decoder.attention_rnn.bias_hh");
+        la.c = w.ca; la.h1 = w.ha + (size_t)nxt * B * d.Ha; la.ldh1 = d.Ha; la.h2 = w.xin_d; la.ldh2 = KD;
+        MSA_TRY(k_infer_rows(la, h->sm_count, st));
+        // attention (forward_attn.py:178-219), one CTA per row; writes ctx(t) into the three packed inputs
         InferAttnParams ap{};
         ap.B = B; ap.L = L; ap.Ha = d.Ha; ap.A = d.A; ap.F = d.F; ap.Kl = d.Kl; ap.E = d.E; ap.norm = c.attn_norm; ap.max_steps = max_steps;
-        MSA_TRY(gemm(h, false, true, B, d.A, d.Ha, 1.f, w.ha, d.Ha, P(at + "query_layer.linear_layer.weight"), d.Ha, 0.f, w.qbuf, d.A));
-        ap.q = w.qbuf; ap.wloc = P(at + "location_layer.location_conv1d.weight");
+        ap.h = w.xin_d; ap.ldh = KD; ap.wq = P(at + "query_layer.linear_layer.weight");
+        ap.wloc = P(at + "location_layer.location_conv1d.weight");
         ap.wld = P(at + "location_layer.location_dense.linear_layer.weight");
         ap.v = P(at + "v.linear_layer.weight"); ap.bv = P(at + "v.linear_layer.bias");
         ap.pm = w.pm; ap.memory = w.memory; ap.prev = w.prev; ap.cum = w.cum;
@@ -1140,28 +1152,39 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
         ap.align_out = align_out; ap.state = state;
         MSA_TRY(k_infer_attention(ap, st));
         // decoder LSTMCell on [h_a; ctx] (decoder.py:260-264)
-        MSA_TRY(gemm(h, false, true, B, 4 * d.Hd, KD, 1.f, w.xin_d, KD, Wid, KD, 0.f, w.zd, 4 * d.Hd));
-        MSA_TRY(gemm(h, false, true, B, 4 * d.Hd, d.Hd, 1.f, w.hd, d.Hd, P("decoder.decoder_rnn.weight_hh"), d.Hd, 1.f, w.zd, 4 * d.Hd));
-        MSA_TRY(k_infer_lstm_point(w.zd, P("decoder.decoder_rnn.bias_ih"), P("decoder.decoder_rnn.bias_hh"), w.cd, w.hd, d.Hd,
-                                   w.xin_p, KP, B, d.Hd, state, st));
+        InferRowsParams ld{};
+        ld.B = B; ld.state = state; ld.N = 4 * d.Hd; ld.H = d.Hd; ld.nseg = 2; ld.epi = IR_EPI_LSTM;
+        ld.x[0] = w.xin_d; ld.ldx[0] = KD; ld.K[0] = KD; ld.W[0] = Wid; ld.ldw[0] = KD;
+        ld.x[1] = w.hd + (size_t)cur * B * d.Hd; ld.ldx[1] = d.Hd; ld.K[1] = d.Hd; ld.W[1] = P("decoder.decoder_rnn.weight_hh"); ld.ldw[1] = d.Hd;
+        ld.bias1 = P("decoder.decoder_rnn.bias_ih"); ld.bias2 = P("decoder.decoder_rnn.bias_hh");
+        ld.c = w.cd; ld.h1 = w.hd + (size_t)nxt * B * d.Hd; ld.ldh1 = d.Hd; ld.h2 = w.xin_p; ld.ldh2 = KP;
+        MSA_TRY(k_infer_rows(ld, h->sm_count, st));
         // projections + stop logic (decoder.py:267-270, 381-395)
-        MSA_TRY(gemm(h, false, true, B, d.M, KP, 1.f, w.xin_p, KP, P("decoder.linear_projection.linear_layer.weight"), KP, 0.f, w.mel_raw, d.M));
-        MSA_TRY(gemm(h, false, true, B, 1, KP, 1.f, w.xin_p, KP, P("decoder.gate_layer.linear_layer.weight"), KP, 0.f, w.gate_raw, 1));
-        MSA_TRY(k_infer_finish(w.mel_raw, P("decoder.linear_projection.linear_layer.bias"), w.gate_raw,
-                               P("decoder.gate_layer.linear_layer.bias"), w.mel_tm, w.frame, not_finished, mel_lengths_out, B, d.M,
-                               c.gate_threshold, c.early_stopping, max_steps, state, st));
+        InferRowsParams pp{};
+        pp.B = B; pp.state = state; pp.N = d.M + 1; pp.nseg = 1; pp.epi = IR_EPI_BIAS;
+        pp.x[0] = w.xin_p; pp.ldx[0] = KP; pp.K[0] = KP; pp.W[0] = P("decoder.linear_projection.linear_layer.weight"); pp.ldw[0] = KP;
+        pp.Wb = P("decoder.gate_layer.linear_layer.weight"); pp.nsplit = d.M;
+        pp.bias1 = P("decoder.linear_projection.linear_layer.bias"); pp.bias2 = P("decoder.gate_layer.linear_layer.bias");
+        pp.out = w.mel_raw; pp.ldo = d.M; pp.out2 = w.gate_raw; pp.ldo2 = 1;
+        pp.finish = 1; pp.M = d.M; pp.early = c.early_stopping; pp.max_steps = max_steps; pp.threshold = c.gate_threshold;
+        pp.mel_tm = w.mel_tm; pp.frame = w.frame; pp.not_finished = not_finished; pp.mel_lengths = mel_lengths_out; pp.state_rw = state;
+        pp.counter = counter;
+        MSA_TRY(k_infer_rows(pp, h->sm_count, st));
         return 0;
     };
-    // capture one step as a CUDA graph and replay it; fall back to direct launches if capture is refused
+    // optional: capture a PAIR of steps (both ping-pong parities) as a CUDA graph and replay it; steps enqueued beyond the end
+    // are no-ops (every kernel returns at once when the done flag is set)
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
     int enqueued = 0;
-    if (getenv("MSA_INFER_GRAPH") != nullptr && max_steps > 1) {     // measured on B200: replaying the captured step is slower than
-                                                                      // plain stream-ordered launches (the queue stays ahead of the GPU)
-        MSA_TRY(step());      // step 0 directly: lets cuBLAS pick its kernels / workspace outside the capture
-        enqueued = 1;
+    if (getenv("MSA_INFER_GRAPH") != nullptr && max_steps > 2) {     // measured on B200: replaying the captured step is not faster
+                                                                      // than plain stream-ordered launches (the queue stays ahead)
+        MSA_TRY(step(0));
+        MSA_TRY(step(1));
+        enqueued = 2;
         if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-            const int rc = step();
+            int rc = step(0);
+            if (rc == 0) rc = step(1);
             const cudaError_t e = cudaStreamEndCapture(st, &graph);
             if (rc != 0 || e != cudaSuccess || !graph || cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) {
                 if (graph) cudaGraphDestroy(graph);
@@ -1176,10 +1199,10 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
     }
     int host_state[4] = {0, 0, 0, 0};
     const int check_every = 128;
-    for (int s = enqueued; s < max_steps; ++s) {
+    for (int s = enqueued; s < max_steps; s += gexec ? 2 : 1) {
         if (gexec) MSA_CUDA(cudaGraphLaunch(gexec, st));
-        else MSA_TRY(step());
-        if (c.early_stopping && (s % check_every) == check_every - 1) {      // all rows finished: stop enqueueing no-op steps
+        else MSA_TRY(step(s));
+        if (c.early_stopping && (s % check_every) >= check_every - 2 && (gexec || (s % check_every) == check_every - 1)) {      // all rows finished: stop enqueueing no-op steps
             MSA_CUDA(cudaMemcpyAsync(host_state, state, sizeof(int) * 3, cudaMemcpyDeviceToHost, st));
             MSA_CUDA(cudaStreamSynchronize(st));
             if (host_state[1]) break;
