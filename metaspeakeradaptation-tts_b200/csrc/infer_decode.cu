@@ -365,7 +365,7 @@ constexpr int kIaDJ = 4;          // attention dims per lane in the energy phase
 
 struct IaSmem {
     int LHp, FS, FP4, Lc, LcP;
-    size_t in_s, h_s, q_s, v_s, wloc_s, wld4_s, cf_s, e_s, part_s, total;
+    size_t in_s, h_s, q_s, v_s, wloc_s, wld4_s, cf_s, e_s, part_s, alpha_s, anew_s, ta_s, total;
 };
 __host__ __device__ inline IaSmem ia_layout(int L, int Ha, int A, int F, int Kl, int E) {
     IaSmem s;
@@ -385,6 +385,9 @@ __host__ __device__ inline IaSmem ia_layout(int L, int Ha, int A, int F, int Kl,
     s.cf_s = take((size_t)s.LcP * s.FS);
     s.e_s = take((size_t)s.Lc * kIaCl);
     s.part_s = take((size_t)8 * (((E + kIaCl - 1) / kIaCl + 3) & ~3));
+    s.alpha_s = take((size_t)s.Lc * kIaCl + 4);      // forward attention: alpha(t-1) with a zero in front (the shifted copy)
+    s.anew_s = take((size_t)s.Lc * kIaCl);
+    s.ta_s = take(64);
     s.total = o;
     return s;
 }
@@ -424,6 +427,9 @@ __global__ void __launch_bounds__(kIaThreads, 1) ker_infer_attn(InferAttnParams 
     float* cf_s = sm + lay.cf_s;        // [LcP][FS]     location features of the owned positions, zero beyond lend / F
     float* e_s = sm + lay.e_s;          // [kIaCl*Lc]    energies, all-gathered; then the alignment
     float* part_s = sm + lay.part_s;    // [8][Ec]       partial context sums
+    float* alpha_s = sm + lay.alpha_s + 1;   // [-1..L)    alpha(t-1), alpha_s[-1] = 0
+    float* anew_s = sm + lay.anew_s;
+    float* ta_s = sm + lay.ta_s;        // [kIaCl] partial transition-agent dots (rank 0), [32..] block-reduction scratch
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     constexpr int NW = kIaThreads / 32;
 
@@ -443,6 +449,8 @@ __global__ void __launch_bounds__(kIaThreads, 1) ker_infer_attn(InferAttnParams 
         wld4_s[i] = f < F ? __ldg(p.wld + (size_t)d * F + f) : 0.f;
     }
     for (int i = threadIdx.x; i < lay.LcP * FS; i += kIaThreads) cf_s[i] = 0.f;
+    if (p.forward_attn)
+        for (int i = threadIdx.x; i <= L; i += kIaThreads) alpha_s[i - 1] = i == 0 ? 0.f : p.alpha[(size_t)b * L + i - 1];
     cluster_sync_();         // staging done; every CTA of the cluster is running (required before remote shared-memory stores)
 
     // ---- query projection (forward_attn.py:125) for the dims d = r (mod kIaCl): two dims per warp pass, 8 loads in flight ----
@@ -546,31 +554,117 @@ __global__ void __launch_bounds__(kIaThreads, 1) ker_infer_attn(InferAttnParams 
         }
     }
     cluster_sync_();         // all energies of the row in every CTA; no remote store after this point
-    // ---- normalise (forward_attn.py:200-207): recomputed by every CTA; cum += a, prev = a (208-210, 219) by the owner ----
+    // ---- windowing, normalisation, forward attention (forward_attn.py:139-176,200-219): recomputed by warp 0 of every CTA of
+    // the cluster; the owner of a position writes the state (cum += a, prev = a', alpha = a') ----
     if (w == 0) {
-        float m = 0.f;
-        if (p.norm == 0) {
-            m = -INFINITY;
-            for (int l = lane; l < L; l += 32) m = fmaxf(m, e_s[l]);
+        if (p.windowing) {
+            // eval only: the window follows the argmax of BATCH ROW 0 of the previous step for every row
+            const int win = p.win[t & 1], back = win - 2, front = win + 6;
+            float m = -INFINITY;
+            for (int l = lane; l < L; l += 32) {
+                float e = e_s[l];
+                if ((back > 0 && l < back) || (front < L && l >= front)) e = -INFINITY;
+                e_s[l] = e;
+                m = fmaxf(m, e);
+            }
             m = warp_max(m);
-        }
-        float s = 0.f;
-        for (int l = lane; l < L; l += 32) {
-            const float x = p.norm == 0 ? expf(e_s[l] - m) : sigmoidf_(e_s[l]);
-            e_s[l] = x;
-            s += x;
-        }
-        s = warp_sum(s);
-        for (int l = lane; l < L; l += 32) {
-            const float a = e_s[l] / s;
-            e_s[l] = a;
-            if (l >= lbeg && l < lend) {
-                p.prev[(size_t)b * L + l] = a;
-                p.cum[(size_t)b * L + l] += a;
-                p.align_out[((size_t)b * p.max_steps + t) * L + l] = a;
+            if (p.phase == 1) {
+                // first step (win = -1): attention[:, 0] = attention.max() is a maximum over the WHOLE batch: this launch only
+                // contributes the row maximum, the step is then run again with phase 2
+                if (r == 0 && lane == 0) {
+                    if (m >= 0.f) atomicMax(reinterpret_cast<int*>(p.gmax), __float_as_int(m));
+                    else atomicMin(reinterpret_cast<unsigned int*>(p.gmax), __float_as_uint(m));
+                }
+            } else {
+                __syncwarp();
+                if (win == -1 && lane == 0) e_s[0] = *reinterpret_cast<volatile float*>(p.gmax);
+                __syncwarp();
+                if (b == 0 && r == 0) {
+                    // argmax(attention, 1)[0]: first index of the maximum
+                    float bm = -INFINITY;
+                    int bi = 0x7fffffff;
+                    for (int l = lane; l < L; l += 32)
+                        if (e_s[l] > bm) { bm = e_s[l]; bi = l; }
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float om = __shfl_xor_sync(0xffffffffu, bm, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                        if (om > bm || (om == bm && oi < bi)) { bm = om; bi = oi; }
+                    }
+                    if (lane == 0) p.win[(t + 1) & 1] = bi == 0x7fffffff ? 0 : bi;
+                }
             }
         }
+        if (p.phase != 1) {
+            float m = 0.f;
+            if (p.norm == 0) {
+                m = -INFINITY;
+                for (int l = lane; l < L; l += 32) m = fmaxf(m, e_s[l]);
+                m = warp_max(m);
+            }
+            float s = 0.f;
+            for (int l = lane; l < L; l += 32) {
+                const float x = p.norm == 0 ? expf(e_s[l] - m) : sigmoidf_(e_s[l]);
+                e_s[l] = x;
+                s += x;
+            }
+            s = warp_sum(s);
+            for (int l = lane; l < L; l += 32) {
+                const float a = e_s[l] / s;
+                e_s[l] = a;
+                if (l >= lbeg && l < lend) p.cum[(size_t)b * L + l] += a;      // the location features see the plain alignment
+            }
+            if (p.forward_attn) {
+                // alpha' = ((1-u) alpha + u shift(alpha) + 1e-8) * a, renormalised (forward_attn.py:154-176)
+                const float u = p.u[b];
+                float vmax = -INFINITY, smax = -INFINITY;
+                int sidx = 0x7fffffff;
+                __syncwarp();
+                for (int l = lane; l < L; l += 32) {
+                    const float sh = alpha_s[l - 1];
+                    const float an = (((1.f - u) * alpha_s[l] + u * sh) + 1e-8f) * e_s[l];
+                    anew_s[l] = an;
+                    vmax = fmaxf(vmax, an);
+                    if (sh > smax) { smax = sh; sidx = l; }
+                }
+                if (p.forward_attn_mask) {
+                    // eval only: keep the states around n = argmax(shifted alpha), with the reference's Python slice /
+                    // negative-index semantics: alpha[n+3:] = 0; alpha[:n-1] = 0; alpha[n-2] = 0.01 max(alpha')
+                    vmax = warp_max(vmax);
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float om = __shfl_xor_sync(0xffffffffu, smax, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, sidx, o);
+                        if (om > smax || (om == smax && oi < sidx)) { smax = om; sidx = oi; }
+                    }
+                    const int n = sidx == 0x7fffffff ? 0 : sidx;
+                    const int stop = n - 1 >= 0 ? n - 1 : max(L + n - 1, 0);
+                    int idx = n - 2;
+                    if (idx < 0) idx += L;
+                    __syncwarp();
+                    for (int l = lane; l < L; l += 32) {
+                        float an = anew_s[l];
+                        if (l >= n + 3 || l < stop) an = 0.f;
+                        if (l == idx) an = 0.01f * vmax;
+                        anew_s[l] = an;
+                    }
+                }
+                __syncwarp();
+                float sa = 0.f;
+                for (int l = lane; l < L; l += 32) sa += anew_s[l];
+                sa = warp_sum(sa);
+                for (int l = lane; l < L; l += 32) {
+                    const float a = anew_s[l] / sa;
+                    e_s[l] = a;
+                    if (l >= lbeg && l < lend) p.alpha[(size_t)b * L + l] = a;
+                }
+            }
+            for (int l = lane; l < L; l += 32)
+                if (l >= lbeg && l < lend) {
+                    p.prev[(size_t)b * L + l] = e_s[l];
+                    p.align_out[((size_t)b * p.max_steps + t) * L + l] = e_s[l];
+                }
+        }
     }
+    if (p.phase == 1) return;      // launch-uniform
     __syncthreads();
     // ---- context (forward_attn.py:217) for the owned memory channels: thread = (channel, one of 8 interleaved position sets) ----
     const int Ec = (E + kIaCl - 1) / kIaCl, EcP = (Ec + 3) & ~3, e0 = r * Ec, ne = min(Ec, E - e0);
@@ -600,6 +694,43 @@ __global__ void __launch_bounds__(kIaThreads, 1) ker_infer_attn(InferAttnParams 
         p.ctx2[(size_t)b * p.ld2 + e] = acc;
         p.ctx3[(size_t)b * p.ld3 + e] = acc;
     }
+    if (p.trans_agent) {
+        // u = sigmoid(W_ta . [ctx; h_a'] + b_ta) (forward_attn.py:222-224): every CTA dots its context channels and its quarter of
+        // the query, rank 0 adds the four partials
+        float acc = 0.f;
+        for (int ec = threadIdx.x; ec < ne; ec += kIaThreads) {
+            float c = 0.f;
+#pragma unroll
+            for (int ls = 0; ls < 8; ++ls) c += part_s[ls * EcP + ec];
+            acc += __ldg(p.wta + e0 + ec) * c;
+        }
+        const int Hq = (Ha + kIaCl - 1) / kIaCl, k0 = r * Hq, k1 = min(Ha, k0 + Hq);
+        for (int k = k0 + threadIdx.x; k < k1; k += kIaThreads) acc += __ldg(p.wta + E + k) * h_s[k];
+        acc = block_sum(acc, ta_s + 16);
+        if (threadIdx.x == 0) st_cluster(ta_s + r, 0, acc);
+        cluster_sync_();
+        if (r == 0 && threadIdx.x == 0) {
+            float z = __ldg(p.bta);
+            for (int i = 0; i < kIaCl; ++i) z += ta_s[i];
+            p.u[b] = sigmoidf_(z);
+        }
+    }
+}
+
+__global__ void ker_init_fwd_attn(float* alpha, float* u, int* win, float* gmax, int B, int L) {
+    // init_forward_attn / init_win_idx (forward_attn.py:85-96): alpha = [1, 1e-7, ...], u = 0.5, win_idx = -1
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * L; i += gridDim.x * blockDim.x) alpha[i] = (i % L) == 0 ? 1.f : 1e-7f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) u[i] = 0.5f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        win[0] = -1;
+        win[1] = -1;
+        *gmax = -INFINITY;
+    }
+}
+int k_init_fwd_attn(float* alpha, float* u, int* win, float* gmax, int B, int L, cudaStream_t st) {
+    ker_init_fwd_attn<<<cdiv((int64_t)B * L, 256), 256, 0, st>>>(alpha, u, win, gmax, B, L);
+    MSA_LAUNCH_CHECK();
+    return 0;
 }
 
 size_t infer_attention_smem(int L, int Ha, int A, int F, int Kl, int E) { return sizeof(float) * ia_layout(L, Ha, A, F, Kl, E).total; }

@@ -178,7 +178,15 @@ struct InferAttnParams {
     float* ctx1; int ld1; float* ctx2; int ld2; float* ctx3; int ld3;
     float* align_out;
     const int* state;
+    // eval-time variants (forward_attn.py:139-176,222-224)
+    int windowing, forward_attn, forward_attn_mask, trans_agent;
+    int phase;                        // 0 whole step; windowing, first step: 1 = contribute the batch-wide energy maximum, 2 = the step
+    int* win;                         // [2] window index by step parity
+    float* gmax;                      // batch-wide maximum of the first step's windowed energies
+    float* alpha; float* u;           // [B][L], [B] forward-attention state
+    const float* wta; const float* bta;
 };
+int k_init_fwd_attn(float* alpha, float* u, int* win, float* gmax, int B, int L, cudaStream_t st);
 int k_fill_ones_i32(int* p, int n, cudaStream_t st);
 size_t infer_attention_smem(int L, int Ha, int A, int F, int Kl, int E);
 int k_infer_attention(const InferAttnParams& p, cudaStream_t st);

@@ -968,7 +968,7 @@ namespace msa {
     X(xin_a, d.B * (d.Pd + d.E)) X(p1, d.B * d.Pd) X(ha, 2 * d.B * d.Ha) X(ca, d.B * d.Ha)               \
     X(xin_d, d.B * (d.Ha + d.E)) X(hd, 2 * d.B * d.Hd) X(cd, d.B * d.Hd) X(xin_p, d.B * (d.Hd + d.E))    \
     X(mel_raw, d.B * d.M) X(gate_raw, d.B) X(frame, d.B * d.M)                                           \
-    X(prev, d.BL) X(cum, d.BL) X(mel_tm, (int64_t)d.T * d.B * d.M) X(ints, 64 + d.B)                      \
+    X(prev, d.BL) X(cum, d.BL) X(fa_alpha, d.BL) X(fa_u, d.B + 4) X(mel_tm, (int64_t)d.T * d.B * d.M) X(ints, 64 + d.B)                      \
     X(post_x, 2 * d.BT * d.Cmax) X(post_y, d.BT * d.Cmax) X(post_col, d.BT * d.Kp * d.Cmax)              \
     X(post_w2, (int64_t)d.Cmax * d.Kp * d.Cmax) X(post_bt, d.BT * d.M)
 
@@ -1017,9 +1017,7 @@ static int conv_bn_eval(msa_handle* h, cudaStream_t st, const float* params, con
 
 static int infer_check(const msa_handle* h) {
     const msa_config& c = h->cfg;
-    MSA_CHECK(!c.forward_attn && !c.trans_agent && !c.windowing && !c.forward_attn_mask, MSA_E_UNSUPPORTED,
-              "msa_infer: forward_attn / trans_agent / windowing / forward_attn_mask are not implemented in the CUDA inference path yet "
-              "(forward_attn.py:139-176,222-224)");
+    MSA_CHECK(!c.trans_agent || c.forward_attn, MSA_E_ARG, "msa_infer: trans_agent needs forward_attn (forward_attn.py:222)");
     return 0;
 }
 
@@ -1111,6 +1109,9 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
     MSA_CUDA(cudaMemsetAsync(ints, 0, sizeof(int) * 64, st));
     MSA_CUDA(cudaMemsetAsync(mel_lengths_out, 0, sizeof(int32_t) * (size_t)B, st));
     MSA_TRY(k_fill_ones_i32(not_finished, B, st));
+    int* win = ints + 16;                                   // [2] window index by step parity
+    float* gmax = reinterpret_cast<float*>(ints + 18);
+    MSA_TRY(k_init_fwd_attn(w.fa_alpha, w.fa_u, win, gmax, B, L, st));
     MSA_CUDA(cudaMemsetAsync(align_out, 0, sizeof(float) * (size_t)B * max_steps * L, st));
     MSA_CUDA(cudaMemsetAsync(mel_post_out, 0, sizeof(float) * (size_t)B * d.M * max_steps, st));
 
@@ -1120,7 +1121,7 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
     const float* Wia = P("decoder.attention_rnn.weight_ih");
     const float* Wid = P("decoder.decoder_rnn.weight_ih");
     unsigned int* counter = reinterpret_cast<unsigned int*>(ints + 8);
-    auto step = [&](int s) -> int {
+    auto step = [&](int s, bool first) -> int {
         const int cur = s & 1, nxt = cur ^ 1;
         InferRowsParams rp{};
         rp.B = B; rp.state = state;
@@ -1150,6 +1151,17 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
         ap.pm = w.pm; ap.memory = w.memory; ap.prev = w.prev; ap.cum = w.cum;
         ap.ctx1 = w.xin_a + d.Pd; ap.ld1 = KA; ap.ctx2 = w.xin_d + d.Ha; ap.ld2 = KD; ap.ctx3 = w.xin_p + d.Hd; ap.ld3 = KP;
         ap.align_out = align_out; ap.state = state;
+        ap.windowing = c.windowing; ap.forward_attn = c.forward_attn; ap.forward_attn_mask = c.forward_attn && c.forward_attn_mask;
+        ap.trans_agent = c.forward_attn && c.trans_agent;
+        ap.win = win; ap.gmax = gmax; ap.alpha = w.fa_alpha; ap.u = w.fa_u;
+        if (ap.trans_agent) { ap.wta = P(at + "ta.weight"); ap.bta = P(at + "ta.bias"); }
+        if (c.windowing && first) {
+            // first step: attention[:, 0] = attention.max() spans the batch (forward_attn.py:148-149): one launch collects the
+            // maximum, the second one is the step
+            ap.phase = 1;
+            MSA_TRY(k_infer_attention(ap, st));
+            ap.phase = 2;
+        }
         MSA_TRY(k_infer_attention(ap, st));
         // decoder LSTMCell on [h_a; ctx] (decoder.py:260-264)
         InferRowsParams ld{};
@@ -1179,12 +1191,12 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
     int enqueued = 0;
     if (getenv("MSA_INFER_GRAPH") != nullptr && max_steps > 2) {     // measured on B200: replaying the captured step is not faster
                                                                       // than plain stream-ordered launches (the queue stays ahead)
-        MSA_TRY(step(0));
-        MSA_TRY(step(1));
+        MSA_TRY(step(0, true));
+        MSA_TRY(step(1, false));
         enqueued = 2;
         if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-            int rc = step(0);
-            if (rc == 0) rc = step(1);
+            int rc = step(0, false);
+            if (rc == 0) rc = step(1, false);
             const cudaError_t e = cudaStreamEndCapture(st, &graph);
             if (rc != 0 || e != cudaSuccess || !graph || cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) {
                 if (graph) cudaGraphDestroy(graph);
@@ -1201,7 +1213,7 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
     const int check_every = 128;
     for (int s = enqueued; s < max_steps; s += gexec ? 2 : 1) {
         if (gexec) MSA_CUDA(cudaGraphLaunch(gexec, st));
-        else MSA_TRY(step(s));
+        else MSA_TRY(step(s, s == 0));
         if (c.early_stopping && (s % check_every) >= check_every - 2 && (gexec || (s % check_every) == check_every - 1)) {      // all rows finished: stop enqueueing no-op steps
             MSA_CUDA(cudaMemcpyAsync(host_state, state, sizeof(int) * 3, cudaMemcpyDeviceToHost, st));
             MSA_CUDA(cudaStreamSynchronize(st));

@@ -46,15 +46,51 @@ def test_infer_small(name):
     assert rel(post, z["mel_post"][:, :, :T]) < TOL and rel(align, z["align"][:, :T]) < TOL
 
 
-def test_infer_unsupported_variants_fail_loudly():
+def test_infer_window_fwdmask_transagent_golden():
+    """Eval-only attention features on the device: windowing driven by batch row 0, forward attention with the transition agent
+    and the forward-attention mask with the reference's Python slice / negative-index semantics (forward_attn.py:139-176,222-224,
+    SURVEY Q16) -- against the golden output of the unmodified reference."""
+    (post, lens, align), (o_post, o_lens, o_align), z = _run("small_infer_window_fwdmask")
+    T = int(z["steps"])
+    assert post.shape[2] == T == o_post.shape[2]
+    assert torch.equal(lens.cpu(), o_lens) and np.array_equal(lens.cpu().numpy(), z["mel_lengths"])
+    assert rel(post, o_post) < TOL and rel(align, o_align) < TOL
+    assert rel(post, z["mel_post"][:, :, :T]) < TOL and rel(align, z["align"][:, :T]) < TOL
+    # alignment-index handling is exact: the masked-out positions are exactly zero on both sides
+    assert torch.equal(align.cpu() == 0, o_align == 0)
+
+
+VARIANTS = {
+    "fwd": dict(forward_attn=True),
+    "fwd_ta": dict(forward_attn=True, trans_agent=True),
+    "fwd_mask": dict(forward_attn=True, forward_attn_mask=True),
+    "fwd_ta_mask_sigmoid": dict(forward_attn=True, trans_agent=True, forward_attn_mask=True, norm="sigmoid"),
+    "window": dict(windowing=True),
+    "window_sigmoid": dict(windowing=True, norm="sigmoid"),
+    "window_fwd": dict(windowing=True, forward_attn=True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(VARIANTS))
+@pytest.mark.parametrize("B,L", [(3, 14), (5, 37)])
+def test_infer_attention_variants_vs_oracle(name, B, L):
+    """Every combination of the eval-time attention switches against the oracle restatement (no golden: same arithmetic, pinned
+    through small_infer_window_fwdmask), incl. a text length that spans more than one warp pass and uneven cluster shares."""
     from msa_tts_b200.engine import Engine
-    cfg, seed, (B, L), steps = INFER_CASES["small_infer_window_fwdmask"]()
+    from oracle.gen_cases import _infer
+    cfg, seed, steps = _infer(**VARIANTS[name]), 40 + len(name), 16
+    cfg["max_decoder_steps"] = steps
     eng = Engine(cfg)
     P = synth.init_params(cfg, seed)
     _, inp, inp_len, _, _, _, spk, _ = synth.make_batch(cfg, B, 8, L, seed + 100)
+    stats = infer_stats(P, cfg, seed)
     pm = synth.make_infer_masks(cfg, B, steps, seed + 300)
-    with pytest.raises(RuntimeError, match="not implemented"):
-        eng.infer(eng.flat_from_dict(P), eng.new_bn_stats(), inp, inp_len, spk, pm, max_steps=steps)
+    post, lens, align = eng.infer(eng.flat_from_dict(P), eng.bn_from_dict(stats), inp, inp_len, spk, pm, max_steps=steps)
+    torch.cuda.synchronize()
+    o_post, o_lens, o_align = OM.infer(P, cfg, inp, inp_len, spk, pm, stats)
+    assert post.shape == o_post.shape and torch.equal(lens.cpu(), o_lens)
+    assert rel(post, o_post) < TOL and rel(align, o_align) < TOL
+    assert torch.equal(align.cpu() == 0, o_align == 0)
 
 
 def test_infer_graph_and_direct_launch_agree():
