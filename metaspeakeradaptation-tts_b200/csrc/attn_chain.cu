@@ -29,10 +29,10 @@ namespace msa {
 constexpr int kAttnThreads = 512;
 
 struct AttnSmemFwd {
-    size_t wsm, mws, hs, as_, ah, es, qs, part, part2, zm, wqs, wloc, wldT, vs, pm, pre, ctr, cf, total;
+    size_t wsm, mws, hs, as_, ah, es, qs, part, part2, zm, wqs, wloc, wldT, vs, pm, pre, ctr, cf, apl, mta, wta, total;
     int KP, BP, LP, LH, CKP;
 };
-__host__ __device__ inline AttnSmemFwd attn_fwd_layout(int B, int L, int Ha, int A, int F, int Kl, int ncta, bool mw_res) {
+__host__ __device__ inline AttnSmemFwd attn_fwd_layout(int B, int L, int Ha, int A, int F, int Kl, int ncta, bool mw_res, bool fa = false) {
     AttnSmemFwd s;
     s.KP = round_up_i(Ha, 128);
     s.BP = (B + 3) & ~3;
@@ -61,20 +61,24 @@ __host__ __device__ inline AttnSmemFwd attn_fwd_layout(int B, int L, int Ha, int
     s.pre = take((size_t)np_max * A);
     s.ctr = take((size_t)np_max * A);
     s.cf = take((size_t)np_max * F);
+    s.apl = take(fa ? (size_t)B * L : 0);
+    s.mta = take(fa ? (size_t)B * L : 0);
+    s.wta = take(fa ? (size_t)s.KP : 0);
     s.total = o;
     return s;
 }
 
-template <bool kProf, int NT>
+template <bool kProf, int NT, bool kFa>
 __global__ void __launch_bounds__(NT, 1) k_attn_chain_fwd(AttnChainParams p, int mw_res) {
     constexpr int NW = NT / 32;
     extern __shared__ __align__(16) float smem[];
     __shared__ float zn_s[kBMax];
+    __shared__ float u_s[kBMax], uold_s[kBMax], fs_s[kBMax];     // forward attention: u(t-1) -> u(t), u used at t, sum alpha'
     const int T = p.T, B = p.B, L = p.L, Ha = p.Ha, A = p.A, F = p.F, Kl = p.Kl, H4 = 4 * Ha;
     const int BL = B * L, pl = (Kl - 1) / 2;
     const int ncta = gridDim.x, cta = blockIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const AttnSmemFwd lay = attn_fwd_layout(B, L, Ha, A, F, Kl, ncta, mw_res != 0);
+    const AttnSmemFwd lay = attn_fwd_layout(B, L, Ha, A, F, Kl, ncta, mw_res != 0, kFa != 0);
     const int KP = lay.KP, KP4 = KP >> 2, LP = lay.LP, LH = lay.LH, CKP = lay.CKP;
     float* Wsm = smem + lay.wsm;       // [RG*8][KP]     W_hh rows of the owned units (local row = ul*4 + gate), zero-padded
     float* MWs = smem + lay.mws;       // [RG*8][B][LP]  (W_ih[:, prenet:] . memory^T) rows of the owned units
@@ -94,6 +98,9 @@ __global__ void __launch_bounds__(NT, 1) k_attn_chain_fwd(AttnChainParams p, int
     float* pre_s = smem + lay.pre;     // [np][A] loc + pm of the current step
     float* ctr_s = smem + lay.ctr;     // [np][A] v[d]*tanh(.) terms of the current step
     float* cf_s = smem + lay.cf;       // [np][F]
+    float* apl_s = smem + lay.apl;     // [B][L]  forward attention: normalise(e(t)) of the current step
+    float* mta_s = smem + lay.mta;     // [B][L]  memory . W_ta[:E]
+    float* wta_s = smem + lay.wta;     // [KP]    W_ta[E:], zero-padded
 
     const int u0 = part_lo(cta, Ha, ncta), u1 = part_lo(cta + 1, Ha, ncta), U = u1 - u0, R = 4 * U;
     const int RG = R > 0 ? (R + 7) >> 3 : 1;
@@ -129,6 +136,13 @@ __global__ void __launch_bounds__(NT, 1) k_attn_chain_fwd(AttnChainParams p, int
     for (int idx = threadIdx.x; idx < np * A; idx += NT) pm_s[idx] = __ldg(p.pm + (size_t)p0 * A + idx);
     for (int idx = threadIdx.x; idx < B * LP; idx += NT) as_[idx] = 0.f;
     for (int idx = threadIdx.x; idx < 2 * B * LH; idx += NT) ah[idx] = 0.f;
+    if (kFa) {
+        for (int idx = threadIdx.x; idx < BL; idx += NT) mta_s[idx] = p.ta ? __ldg(p.mta + idx) : 0.f;
+        for (int idx = threadIdx.x; idx < KP; idx += NT) wta_s[idx] = (p.ta && idx < Ha) ? __ldg(p.wta_h + idx) : 0.f;
+        for (int idx = threadIdx.x; idx < kBMax; idx += NT) u_s[idx] = 0.5f;      // init_forward_attn (forward_attn.py:90-96)
+    }
+    __shared__ float bta_s;
+    if (threadIdx.x == 0) bta_s = (kFa && p.ta) ? __ldg(p.bta) : 0.f;
     for (int idx = threadIdx.x; idx < lay.BP * KP; idx += NT) hs[idx] = 0.f;
     for (int i = threadIdx.x; i < np; i += NT) p.cum[p0 + i] = 0.f;       // cum fed to the conv at t = 0
     const float bv = __ldg(p.bv);
@@ -286,11 +300,44 @@ __global__ void __launch_bounds__(NT, 1) k_attn_chain_fwd(AttnChainParams p, int
             }
             sum = warp_sum(sum);
             const float inv = 1.f / sum;
-            for (int l = lane; l < L; l += 32) {
-                const float a = es[b * L + l] * inv;
-                as_[b * LP + l] = a;
-                ah[(0 * B + b) * LH + pl + l] = a;
-                ah[(1 * B + b) * LH + pl + l] += a;
+            if (!kFa) {
+                for (int l = lane; l < L; l += 32) {
+                    const float a = es[b * L + l] * inv;
+                    as_[b * LP + l] = a;
+                    ah[(0 * B + b) * LH + pl + l] = a;
+                    ah[(1 * B + b) * LH + pl + l] += a;
+                }
+            } else {
+                // forward attention (forward_attn.py:154-176, training: no mask): alpha' = ((1-u) alpha + u shift(alpha) + 1e-8) * a,
+                // alpha(t) = alpha' / sum(alpha'); the location conv sees prev = alpha(t) and cum = sum of the PLAIN a (208-210)
+                const float u = u_s[b];
+                float S = 0.f;
+                for (int l = lane; l < L; l += 32) {
+                    const float a = es[b * L + l] * inv;
+                    apl_s[b * L + l] = a;
+                    ah[(1 * B + b) * LH + pl + l] += a;
+                    // alpha(-1) = [1, 1e-7, ...] (as_ is zero before the first step)
+                    const float al = t > 0 ? as_[b * LP + l] : (l == 0 ? 1.f : 1e-7f);
+                    const float sh = l > 0 ? (t > 0 ? as_[b * LP + l - 1] : (l == 1 ? 1.f : 1e-7f)) : 0.f;
+                    const float ap = (((1.f - u) * al + u * sh) + 1e-8f) * a;
+                    es[b * L + l] = ap;
+                    S += ap;
+                }
+                S = warp_sum(S);          // (also orders the reads of alpha(t-1) above before the writes below)
+                float zu = 0.f;
+                for (int l = lane; l < L; l += 32) {
+                    const float al = es[b * L + l] / S;
+                    as_[b * LP + l] = al;
+                    ah[(0 * B + b) * LH + pl + l] = al;
+                    zu += al * mta_s[b * L + l];
+                }
+                if (lane == 0) { uold_s[b] = u; fs_s[b] = S; }
+                if (p.ta) {
+                    // transition agent u(t) = sigmoid(W_ta . [ctx(t); h_a'(t)] + b) with ctx(t) = alpha(t) . memory (222-224)
+                    for (int k = lane; k < KP; k += 32) zu += wta_s[k] * hs[(size_t)b * KP + k];
+                    zu = warp_sum(zu);
+                    if (lane == 0) u_s[b] = fast_sigmoid(zu + bta_s);
+                }
             }
             if (lane == 0) zn_s[b] = sum;
         }
@@ -299,9 +346,16 @@ __global__ void __launch_bounds__(NT, 1) k_attn_chain_fwd(AttnChainParams p, int
         for (int i = threadIdx.x; i < np; i += NT) {
             const int pp = p0 + i, b = pp / L, l = pp - b * L;
             p.align[(size_t)t * BL + pp] = as_[b * LP + l];
+            if (kFa) p.aplain[(size_t)t * BL + pp] = apl_s[pp];
             if (t + 1 < T) p.cum[(size_t)(t + 1) * BL + pp] = ah[(1 * B + b) * LH + pl + l];
         }
-        if (cta == 0 && (int)threadIdx.x < B) p.znorm[(size_t)t * B + threadIdx.x] = zn_s[threadIdx.x];
+        if (cta == 0 && (int)threadIdx.x < B) {
+            p.znorm[(size_t)t * B + threadIdx.x] = zn_s[threadIdx.x];
+            if (kFa) {
+                p.fsum[(size_t)t * B + threadIdx.x] = fs_s[threadIdx.x];
+                p.ustash[(size_t)t * B + threadIdx.x] = uold_s[threadIdx.x];
+            }
+        }
         prof.mark(11, t);
     }
 }
@@ -309,10 +363,10 @@ __global__ void __launch_bounds__(NT, 1) k_attn_chain_fwd(AttnChainParams p, int
 // =====================================================================================
 // backward
 struct AttnSmemBwd {
-    size_t wt, mwp, part, dhs, wqT, das, als, des, tq, wldT, wloc, vs, dss, gcum, dprev, pout, dqs, qd, cpart, total;
+    size_t wt, mwp, part, dhs, wqT, das, als, des, tq, wldT, wloc, vs, dss, gcum, dprev, pout, dqs, qd, cpart, apl, apr, drec, dws, mta, total;
     int BP, AP;
 };
-__host__ __device__ inline AttnSmemBwd attn_bwd_layout(int B, int L, int Ha, int A, int F, int Kl, int ncta, bool mwp_res) {
+__host__ __device__ inline AttnSmemBwd attn_bwd_layout(int B, int L, int Ha, int A, int F, int Kl, int ncta, bool mwp_res, bool fa = false) {
     AttnSmemBwd s;
     s.BP = (B + 3) & ~3;
     s.AP = A + 1;
@@ -324,7 +378,7 @@ __host__ __device__ inline AttnSmemBwd attn_bwd_layout(int B, int L, int Ha, int
     s.part = take(kRecWarps * 32);
     s.dhs = take(kUMax * s.BP);
     s.wqT = take((size_t)kUMax * A);
-    s.das = take((size_t)B * L);
+    s.das = take((size_t)B * L * (fa ? 2 : 1));
     s.als = take((size_t)B * L);
     s.des = take((size_t)B * L);
     s.tq = take((size_t)B * L);
@@ -338,21 +392,29 @@ __host__ __device__ inline AttnSmemBwd attn_bwd_layout(int B, int L, int Ha, int
     s.dqs = take((size_t)B * A);
     s.qd = take((size_t)kUMax * kBMax);
     s.cpart = take((size_t)np_max * Kl * 2);
+    const size_t nfa = fa ? (size_t)B * L : 0;
+    s.apl = take(nfa);
+    s.apr = take(nfa);
+    s.drec = take(nfa);
+    s.dws = take(nfa);
+    s.mta = take(nfa);
     s.total = o;
     return s;
 }
 
-template <bool kProf, int NT>
+template <bool kProf, int NT, bool kFa>
 __global__ void __launch_bounds__(NT, 1) k_attn_chain_bwd(AttnChainBwdParams p, int mwp_res) {
     constexpr int NW = NT / 32;
     extern __shared__ __align__(16) float smem[];
     __shared__ float red[NW * kPairMax];
     __shared__ float zn_s[kBMax];
+    __shared__ float us_s[kBMax], fs_s[kBMax], dzu_s[2][kBMax];      // forward attention: u used at t, sum alpha'(t), d zu by step parity
     const int T = p.T, B = p.B, L = p.L, Ha = p.Ha, A = p.A, F = p.F, Kl = p.Kl, H4 = 4 * Ha;
     const int BL = B * L, pl = (Kl - 1) / 2, CKP = 2 * Kl + 1;
+    const int DS = kFa ? 2 * BL : BL;      // words of the d a hand-off per step
     const int ncta = gridDim.x, cta = blockIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const AttnSmemBwd lay = attn_bwd_layout(B, L, Ha, A, F, Kl, ncta, mwp_res != 0);
+    const AttnSmemBwd lay = attn_bwd_layout(B, L, Ha, A, F, Kl, ncta, mwp_res != 0, kFa != 0);
     const int BP = lay.BP, AP = lay.AP;
     float* WT = smem + lay.wt;         // [kUMax][4Ha]  WT[ul][r] = W_hh[r][u0+ul], zero rows beyond the owned units
     float* MWp = smem + lay.mwp;       // [np][4Ha]     rows of (memory . Wc^T) of the owned positions
@@ -373,6 +435,11 @@ __global__ void __launch_bounds__(NT, 1) k_attn_chain_bwd(AttnChainBwdParams p, 
     float* dq_s = smem + lay.dqs;
     float* qd_s = smem + lay.qd;       // [U*B]
     float* cpart = smem + lay.cpart;   // [np*Kl][2]
+    float* apl_s = smem + lay.apl;     // forward attention: [B][L] plain a(t), alpha(t-1), d alpha(t) from step t+1, d w scratch, mta
+    float* apr_s = smem + lay.apr;
+    float* drec_s = smem + lay.drec;
+    float* dws_s = smem + lay.dws;
+    float* mta_s = smem + lay.mta;
 
     const int u0 = part_lo(cta, Ha, ncta), u1 = part_lo(cta + 1, Ha, ncta), U = u1 - u0;
     const int p0 = part_lo(cta, BL, ncta), p1 = part_lo(cta + 1, BL, ncta), np = p1 - p0;
@@ -401,10 +468,19 @@ __global__ void __launch_bounds__(NT, 1) k_attn_chain_bwd(AttnChainBwdParams p, 
     for (int idx = threadIdx.x; idx < A; idx += NT) vs[idx] = __ldg(p.v + idx);
     for (int idx = threadIdx.x; idx < kUMax * BP; idx += NT) dhs[idx] = 0.f;
     for (int idx = threadIdx.x; idx < np; idx += NT) { gcum_s[idx] = 0.f; dprev_s[idx] = 0.f; pout[idx] = 0.f; }
+    if (kFa) {
+        for (int idx = threadIdx.x; idx < BL; idx += NT) {
+            mta_s[idx] = p.ta ? __ldg(p.mta + idx) : 0.f;
+            drec_s[idx] = 0.f;
+        }
+        for (int idx = threadIdx.x; idx < 2 * kBMax; idx += NT) (&dzu_s[0][0])[idx] = 0.f;
+        if (cta == 0 && (int)threadIdx.x < B) p.dzu[(size_t)(T - 1) * B + threadIdx.x] = 0.f;      // u(T-1) is never used
+    }
 
     // point-wise role of the LSTM backward: thread (ul, b); forward stash + external gradient fetched one step ahead
     const bool pw = (int)threadIdx.x < U * B;
     const int ul = pw ? threadIdx.x / B : 0, pb = pw ? threadIdx.x % B : 0, u = u0 + ul;
+    const float wta_u = (kFa && p.ta && pw) ? __ldg(p.wta_h + u) : 0.f;      // query half of the transition agent, owned unit
     float gi[4] = {0.f, 0.f, 0.f, 0.f}, cc = 0.f, cp = 0.f, dhe = 0.f, dcarry = 0.f;
     unsigned char mk = 1;
     // streaming forward stash of the attention part, fetched one step ahead as well:
@@ -442,25 +518,70 @@ __global__ void __launch_bounds__(NT, 1) k_attn_chain_bwd(AttnChainBwdParams p, 
         prof.mark(0, T - 1 - t);
         for (int i = threadIdx.x; i < np; i += NT) {
             const float dae = i == (int)threadIdx.x ? da_own : __ldg(p.da_ext + (size_t)t * BL + p0 + i);
-            st_pub(p.dat + (size_t)t * BL + p0 + i, dae + pout[i] + gcum_s[i] + dprev_s[i]);
+            if (!kFa) {
+                st_pub(p.dat + (size_t)t * DS + p0 + i, dae + pout[i] + gcum_s[i] + dprev_s[i]);
+            } else {      // d alpha(t) (context, MW and "previous alignment" paths) and d a(t) (cumulative path) separately
+                st_pub(p.dat + (size_t)t * DS + p0 + i, dae + pout[i] + dprev_s[i]);
+                st_pub(p.dat + (size_t)t * DS + BL + p0 + i, gcum_s[i]);
+            }
         }
         // forward stash of this step that the next phase needs (plain data of an earlier kernel)
         for (int idx = threadIdx.x; idx < BL; idx += NT) als[idx] = __ldg(p.align + (size_t)t * BL + idx);
         if ((int)threadIdx.x < B) zn_s[threadIdx.x] = __ldg(p.znorm + (size_t)t * B + threadIdx.x);
+        if (kFa) {
+            for (int idx = threadIdx.x; idx < BL; idx += NT) {
+                apl_s[idx] = __ldg(p.aplain + (size_t)t * BL + idx);
+                const int l = idx % L;
+                apr_s[idx] = t > 0 ? __ldg(p.align + (size_t)(t - 1) * BL + idx) : (l == 0 ? 1.f : 1e-7f);
+            }
+            if ((int)threadIdx.x < B) {
+                us_s[threadIdx.x] = __ldg(p.ustash + (size_t)t * B + threadIdx.x);
+                fs_s[threadIdx.x] = __ldg(p.fsum + (size_t)t * B + threadIdx.x);
+            }
+        }
         // in the shadow of the dat hand-off: first half of W_hh^T . dz_a(t+1) for the owned units (needed by the point-wise phase)
         if (t < T - 1) cta_matvec_bwd<NT>(WT, H4, p.dza + (size_t)(t + 1) * B * H4, B, part, dhs, BP, sg, 0, 2);
         prof.mark(1, T - 1 - t);
         // ---- hand-off 1: d a(t) of every position ----
-        gather_words<NT>(das, p.dat + (size_t)t * BL, BL, (p.flags & kFlagWarp0) != 0, sg);
+        gather_words<NT>(das, p.dat + (size_t)t * DS, DS, (p.flags & kFlagWarp0) != 0, sg);
         __syncthreads();
         prof.mark(2, T - 1 - t);
         // ---- P2: normalisation backward, dS, d(conv features), dq; publishes dconvf(t), dq(t) ----
         for (int b = w; b < B; b += NW) {
+            const float* arow = kFa ? apl_s + b * L : als + b * L;      // normalise(e(t))
+            if (kFa) {
+                // forward-attention backward (forward_attn.py:154-176): alpha = alpha'/S, alpha' = w * a,
+                // w = (1-u) alpha(t-1) + u shift(alpha(t-1)) + 1e-8, u = u(t-1) = sigmoid(zu(t-1))
+                const float uu = us_s[b], S = fs_s[b];
+                float sd = 0.f;
+                for (int l = lane; l < L; l += 32) sd += (das[b * L + l] + drec_s[b * L + l]) * als[b * L + l];
+                sd = warp_sum(sd);
+                float du = 0.f;
+                for (int l = lane; l < L; l += 32) {
+                    const float dap = ((das[b * L + l] + drec_s[b * L + l]) - sd) / S;
+                    const float al = apr_s[b * L + l], sh = l > 0 ? apr_s[b * L + l - 1] : 0.f;
+                    const float wl = ((1.f - uu) * al + uu * sh) + 1e-8f;
+                    das[b * L + l] = dap * wl + das[BL + b * L + l];          // d a(t): recursion path + cumulative path
+                    const float dw = dap * arow[l];
+                    dws_s[b * L + l] = dw;
+                    du += dw * (sh - al);
+                }
+                du = warp_sum(du);
+                __syncwarp();
+                const float dzu = (p.ta && t > 0) ? du * uu * (1.f - uu) : 0.f;   // u(-1) = 0.5 is a constant
+                for (int l = lane; l < L; l += 32)      // d alpha(t-1): recursion + context half of the transition agent u(t-1)
+                    drec_s[b * L + l] = (1.f - uu) * dws_s[b * L + l] + uu * (l + 1 < L ? dws_s[b * L + l + 1] : 0.f) + dzu * mta_s[b * L + l];
+                if (lane == 0 && t > 0) {
+                    dzu_s[(t - 1) & 1][b] = dzu;
+                    if (cta == 0) p.dzu[(size_t)(t - 1) * B + b] = dzu;
+                }
+                __syncwarp();
+            }
             float sd = 0.f;
-            for (int l = lane; l < L; l += 32) sd += als[b * L + l] * das[b * L + l];
+            for (int l = lane; l < L; l += 32) sd += arow[l] * das[b * L + l];
             sd = warp_sum(sd);
             for (int l = lane; l < L; l += 32) {
-                const float a = als[b * L + l];
+                const float a = arow[l];
                 float de = a * (das[b * L + l] - sd);                       // softmax backward
                 if (p.norm == 1) de = de * (1.f - a * zn_s[b]);             // sigmoid/sum backward: s = a*Z
                 des[b * L + l] = de;
@@ -534,6 +655,7 @@ __global__ void __launch_bounds__(NT, 1) k_attn_chain_bwd(AttnChainBwdParams p, 
         if (pw) {
             const size_t zb = ((size_t)t * B + pb) * H4;
             float dh = dhe + (t < T - 1 ? dhs[ul * BP + pb] : 0.f) + qd_s[threadIdx.x];
+            if (kFa) dh += dzu_s[t & 1][pb] * wta_u;      // query half of the transition agent u(t)
             if (p.mask) dh = mk ? dh * p.drop_scale : 0.f;
             const LstmGrad gr = lstm_point_bwd(gi[0], gi[1], gi[2], gi[3], cc, cp, dh, dcarry);
             dcarry = gr.dc_prev;
@@ -597,11 +719,11 @@ __global__ void __launch_bounds__(NT, 1) k_attn_chain_bwd(AttnChainBwdParams p, 
     }
 }
 
-size_t attn_chain_fwd_smem(int B, int L, int Ha, int A, int F, int Kl, int sm_count, bool mw_resident) {
-    return attn_fwd_layout(B, L, Ha, A, F, Kl, sm_count, mw_resident).total * sizeof(float);
+size_t attn_chain_fwd_smem(int B, int L, int Ha, int A, int F, int Kl, int sm_count, bool mw_resident, bool fa) {
+    return attn_fwd_layout(B, L, Ha, A, F, Kl, sm_count, mw_resident, fa).total * sizeof(float);
 }
-size_t attn_chain_bwd_smem(int B, int L, int Ha, int A, int F, int Kl, int sm_count, bool mwp_resident) {
-    return attn_bwd_layout(B, L, Ha, A, F, Kl, sm_count, mwp_resident).total * sizeof(float);
+size_t attn_chain_bwd_smem(int B, int L, int Ha, int A, int F, int Kl, int sm_count, bool mwp_resident, bool fa) {
+    return attn_bwd_layout(B, L, Ha, A, F, Kl, sm_count, mwp_resident, fa).total * sizeof(float);
 }
 
 static int attn_check(int B, int Ha, int A, int F, int sm_count) {
@@ -619,13 +741,15 @@ static int attn_check(int B, int Ha, int A, int F, int sm_count) {
 int launch_attn_chain_fwd(const AttnChainParams& p, int sm_count, size_t smem_limit, cudaStream_t st) {
     MSA_TRY(attn_check(p.B, p.Ha, p.A, p.F, sm_count));
     int mw_res = 1;
-    size_t smem = attn_chain_fwd_smem(p.B, p.L, p.Ha, p.A, p.F, p.Kl, sm_count, true);
+    size_t smem = attn_chain_fwd_smem(p.B, p.L, p.Ha, p.A, p.F, p.Kl, sm_count, true, p.fa != 0);
     if (smem > smem_limit) {
         mw_res = 0;
-        smem = attn_chain_fwd_smem(p.B, p.L, p.Ha, p.A, p.F, p.Kl, sm_count, false);
+        smem = attn_chain_fwd_smem(p.B, p.L, p.Ha, p.A, p.F, p.Kl, sm_count, false, p.fa != 0);
     }
     MSA_CHECK(smem <= smem_limit, MSA_E_UNSUPPORTED, "attn_chain_fwd: needs %zu bytes of shared memory (> %zu)", smem, smem_limit);
-    MSA_CUDA(cudaFuncSetAttribute(p.prof ? k_attn_chain_fwd<true, kAttnThreads> : k_attn_chain_fwd<false, kAttnThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void* fn = p.fa ? (p.prof ? (void*)k_attn_chain_fwd<true, kAttnThreads, true> : (void*)k_attn_chain_fwd<false, kAttnThreads, true>)
+                    : (p.prof ? (void*)k_attn_chain_fwd<true, kAttnThreads, false> : (void*)k_attn_chain_fwd<false, kAttnThreads, false>);
+    MSA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // canaries of the three hand-off arrays (common.cuh)
     const size_t TB = (size_t)p.T * p.B;
     MSA_TRY(k_fill_canary(p.ha, (int64_t)(TB * p.Ha), st));
@@ -633,7 +757,7 @@ int launch_attn_chain_fwd(const AttnChainParams& p, int sm_count, size_t smem_li
     MSA_TRY(k_fill_canary(p.e, (int64_t)(TB * p.L), st));
     AttnChainParams pp = p;
     void* args[] = {&pp, &mw_res};
-    MSA_CUDA(cudaLaunchCooperativeKernel(pp.prof ? (void*)k_attn_chain_fwd<true, kAttnThreads> : (void*)k_attn_chain_fwd<false, kAttnThreads>, dim3(sm_count), dim3(kAttnThreads), args, smem, st));
+    MSA_CUDA(cudaLaunchCooperativeKernel(fn, dim3(sm_count), dim3(kAttnThreads), args, smem, st));
     count_launch();
     return 0;
 }
@@ -641,21 +765,23 @@ int launch_attn_chain_fwd(const AttnChainParams& p, int sm_count, size_t smem_li
 int launch_attn_chain_bwd(const AttnChainBwdParams& p, int sm_count, size_t smem_limit, cudaStream_t st) {
     MSA_TRY(attn_check(p.B, p.Ha, p.A, p.F, sm_count));
     int mwp_res = 1;
-    size_t smem = attn_chain_bwd_smem(p.B, p.L, p.Ha, p.A, p.F, p.Kl, sm_count, true);
+    size_t smem = attn_chain_bwd_smem(p.B, p.L, p.Ha, p.A, p.F, p.Kl, sm_count, true, p.fa != 0);
     if (smem > smem_limit) {
         mwp_res = 0;
-        smem = attn_chain_bwd_smem(p.B, p.L, p.Ha, p.A, p.F, p.Kl, sm_count, false);
+        smem = attn_chain_bwd_smem(p.B, p.L, p.Ha, p.A, p.F, p.Kl, sm_count, false, p.fa != 0);
     }
     MSA_CHECK(smem <= smem_limit, MSA_E_UNSUPPORTED, "attn_chain_bwd: needs %zu bytes of shared memory (> %zu)", smem, smem_limit);
-    MSA_CUDA(cudaFuncSetAttribute(p.prof ? k_attn_chain_bwd<true, kRecThreads> : k_attn_chain_bwd<false, kRecThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void* fn = p.fa ? (p.prof ? (void*)k_attn_chain_bwd<true, kRecThreads, true> : (void*)k_attn_chain_bwd<false, kRecThreads, true>)
+                    : (p.prof ? (void*)k_attn_chain_bwd<true, kRecThreads, false> : (void*)k_attn_chain_bwd<false, kRecThreads, false>);
+    MSA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t TB = (size_t)p.T * p.B;
     MSA_TRY(k_fill_canary(p.dza, (int64_t)(TB * 4 * p.Ha), st));
     MSA_TRY(k_fill_canary(p.dq, (int64_t)(TB * p.A), st));
-    MSA_TRY(k_fill_canary(p.dat, (int64_t)(TB * p.L), st));
+    MSA_TRY(k_fill_canary(p.dat, (int64_t)(TB * p.L * (p.fa ? 2 : 1)), st));
     MSA_TRY(k_fill_canary(p.dconvf, (int64_t)(TB * p.L * p.F), st));
     AttnChainBwdParams pp = p;
     void* args[] = {&pp, &mwp_res};
-    MSA_CUDA(cudaLaunchCooperativeKernel(pp.prof ? (void*)k_attn_chain_bwd<true, kRecThreads> : (void*)k_attn_chain_bwd<false, kRecThreads>, dim3(sm_count), dim3(kRecThreads), args, smem, st));
+    MSA_CUDA(cudaLaunchCooperativeKernel(fn, dim3(sm_count), dim3(kRecThreads), args, smem, st));
     count_launch();
     return 0;
 }

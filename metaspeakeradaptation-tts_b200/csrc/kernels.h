@@ -69,6 +69,14 @@ struct AttnChainParams {
     float* convf;          // [T][B][L][F]
     float* znorm;          // [T][B]      normaliser (sum of sigmoids) for norm == 1
     float* e;              // [T][B][L]   energies (pre-normalisation)
+    // forward attention (forward_attn.py:154-176,222-224); align then holds the forward-attended alignment alpha(t)
+    int fa, ta;            // forward_attn, trans_agent
+    const float* mta;      // [B][L]      memory . W_ta[:E]  (context half of the transition agent, ctx = alpha . memory)
+    const float* wta_h;    // [Ha]        W_ta[E:]           (query half)
+    const float* bta;      // [1]
+    float* aplain;         // [T][B][L]   normalise(e(t)) before the forward-attention recursion
+    float* fsum;           // [T][B]      sum_l alpha'(t)[l] (renormaliser)
+    float* ustash;         // [T][B]      transition probability used at step t (= u(t-1); 0.5 without the agent)
     unsigned int* abort_word;
     long long* prof;       // optional [grid][8] per-phase cycle counters
     long long* trace;
@@ -97,15 +105,19 @@ struct AttnChainBwdParams {
     float* de;             // [T][B][L]
     float* ds;             // [T][B][L][A]
     float* dconvf;         // [T][B][L][F]
-    float* dat;            // [T][B][L]   total d a(t)
+    float* dat;            // [T][B][L]   total d a(t);  forward attention: [T][2][B][L] = {d alpha(t), d a(t) through cum}
+    int fa, ta;
+    const float* mta; const float* wta_h;
+    const float* aplain; const float* fsum; const float* ustash;
+    float* dzu;            // [T][B]      gradient of the transition agent's pre-activation
     unsigned int* abort_word;
     long long* prof;
     long long* trace;
     int trace_t0;
     int flags;
 };
-size_t attn_chain_fwd_smem(int B, int L, int Ha, int A, int F, int Kl, int sm_count, bool mw_resident);
-size_t attn_chain_bwd_smem(int B, int L, int Ha, int A, int F, int Kl, int sm_count, bool mwp_resident);
+size_t attn_chain_fwd_smem(int B, int L, int Ha, int A, int F, int Kl, int sm_count, bool mw_resident, bool fa = false);
+size_t attn_chain_bwd_smem(int B, int L, int Ha, int A, int F, int Kl, int sm_count, bool mwp_resident, bool fa = false);
 int launch_attn_chain_fwd(const AttnChainParams& p, int sm_count, size_t smem_limit, cudaStream_t st);
 int launch_attn_chain_bwd(const AttnChainBwdParams& p, int sm_count, size_t smem_limit, cudaStream_t st);
 

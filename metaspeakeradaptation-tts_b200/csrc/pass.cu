@@ -194,7 +194,8 @@ static Dims make_dims(const msa_config& c, int B, int T, int L) {
     X(bn_scr, 2 * std::max(d.Cmax, d.C)) X(dmel_bt, d.BT * d.M) X(dmel_tm, d.TB * d.M)                 \
     X(dgate_tm, d.TB) X(dhd, d.TB * d.Hd) X(dzd, d.TB * 4 * d.Hd) X(dha, d.TB * d.Ha)                  \
     X(dctx, d.TB * d.E) X(da_ext, d.TBL) X(dza, d.TB * 4 * d.Ha) X(dq, d.TB * d.A) X(de, d.TBL)        \
-    X(ds, d.TBL * d.A) X(dconvf, d.TBL * d.F) X(dat, d.TBL) X(dpm, d.BL * d.A)                          \
+    X(ds, d.TBL * d.A) X(dconvf, d.TBL * d.F) X(dat, 2 * d.TBL) X(dpm, d.BL * d.A)                      \
+    X(aplain, d.TBL) X(fsum, d.TB) X(ustash, d.TB) X(dzu, d.TB) X(mta, d.BL)                            \
     X(dmw, d.BL * 4 * d.Ha) X(dmem, d.BL * d.E) X(dxp, (d.TB + d.B) * d.Pd)                            \
     X(dp1, (d.TB + d.B) * d.Pd) X(denc_h, 2 * d.BL * d.Hh) X(dzx, 2 * d.BL * 4 * d.Hh)                 \
     X(dx3_tm, d.BL * d.C) X(edx0, d.BL * d.C) X(edx1, d.BL * d.C) X(edy, d.BL * d.C)                   \
@@ -375,8 +376,7 @@ static int check_cfg(const msa_config& c) {
 
 static int train_check(const msa_handle* h) {
     const msa_config& c = h->cfg;
-    MSA_CHECK(!c.forward_attn && !c.trans_agent, MSA_E_UNSUPPORTED,
-              "forward_attn / trans_agent are not implemented in the CUDA training path yet (forward_attn.py:154-176,222-224)");
+    MSA_CHECK(!c.trans_agent || c.forward_attn, MSA_E_ARG, "trans_agent needs forward_attn (forward_attn.py:222)");
     return 0;
 }
 
@@ -579,6 +579,9 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
     MSA_TRY(k_relu_drop_fwd(w.xpre, mk(iPre + 1), 2.f, nfr * d.Pd, st));
     MSA_TRY(k_fill_rows(w.xw, P("decoder.attention_rnn.bias_ih"), P("decoder.attention_rnn.bias_hh"), d.TB, H4a, st));
     MSA_TRY(gemm(h, false, true, d.TB, H4a, d.Pd, 1.f, w.xpre, d.Pd, Wia, ldA, 1.f, w.xw, H4a));
+    const bool fa = c.forward_attn != 0, ta = fa && c.trans_agent != 0;
+    if (ta)     // context half of the transition agent: ctx(t) = alpha(t) . memory  =>  W_ta[:E] . ctx(t) = alpha(t) . (memory . W_ta[:E])
+        MSA_TRY(gemm(h, false, true, d.BL, 1, d.E, 1.f, w.memory, d.E, P(at + "ta.weight"), d.E + d.Ha, 0.f, w.mta, 1));
     // ---- attention chain (persistent) ----
     {
         AttnChainParams ap{};
@@ -591,6 +594,8 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
         ap.mask = c.p_attn_dropout > 0.f ? mk(iAttn) : nullptr;
         ap.drop_scale = 1.f / (1.f - c.p_attn_dropout);
         ap.ha = w.ha; ap.ca = w.ca; ap.ga = w.ga; ap.q = w.q; ap.align = w.align_tm; ap.cum = w.cum; ap.s = w.s;
+        ap.fa = fa; ap.ta = ta; ap.aplain = w.aplain; ap.fsum = w.fsum; ap.ustash = w.ustash;
+        if (ta) { ap.mta = w.mta; ap.wta_h = P(at + "ta.weight") + d.E; ap.bta = P(at + "ta.bias"); }
         ap.convf = w.convf; ap.znorm = w.znorm; ap.e = w.ebuf; ap.abort_word = w.abort_word; ap.prof = prof_ptr(h, w, PROF_ATTN_FWD); ap.trace = trace_ptr(h, w, PROF_ATTN_FWD); ap.trace_t0 = h->trace_t0; ap.flags = h->rec_flags >= 0 ? h->rec_flags : 0;
         ProfScope ps(h, PROF_ATTN_FWD, st);
         MSA_TRY(launch_attn_chain_fwd(ap, h->sm_count, h->smem_limit, st));
@@ -798,6 +803,7 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
     MSA_TRY(gemm_batched(h, true, false, L, d.E, T, 1.f, w.align_tm, d.BL, L, w.dctx, (int64_t)B * d.E, d.E, 0.f, w.dmem, d.E,
                          (int64_t)L * d.E, B));
     // ---- attention chain backward (persistent) ----
+    const bool fa = c.forward_attn != 0, ta = fa && c.trans_agent != 0;
     const float* Wia = P("decoder.attention_rnn.weight_ih");
     float* gWia = G("decoder.attention_rnn.weight_ih");
     MSA_TRY(gemm(h, false, true, d.BL, H4a, d.E, 1.f, w.memory, d.E, Wia + d.Pd, ldA, 0.f, w.mw_pm, H4a));
@@ -814,11 +820,24 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
         bp.ga = w.ga; bp.ca = w.ca; bp.align = w.align_tm; bp.s = w.s; bp.znorm = w.znorm;
         bp.dha_ext = w.dha; bp.da_ext = w.da_ext;
         bp.dza = w.dza; bp.dq = w.dq; bp.de = w.de; bp.ds = w.ds; bp.dconvf = w.dconvf; bp.dat = w.dat;
+        bp.fa = fa; bp.ta = ta; bp.aplain = w.aplain; bp.fsum = w.fsum; bp.ustash = w.ustash; bp.dzu = w.dzu;
+        if (ta) { bp.mta = w.mta; bp.wta_h = P(at + "ta.weight") + d.E; }
         bp.abort_word = w.abort_word; bp.prof = prof_ptr(h, w, PROF_ATTN_BWD); bp.trace = trace_ptr(h, w, PROF_ATTN_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 0;
         ProfScope ps(h, PROF_ATTN_BWD, st);
         MSA_TRY(launch_attn_chain_bwd(bp, h->sm_count, h->smem_limit, st));
     }
     // ---- deferred attention / attention-RNN parameter gradients ----
+    if (ta) {
+        // transition agent u(t) = sigmoid(W_ta . [ctx(t); h_a'(t)] + b) (forward_attn.py:222-224), dzu [T][B] from the chain
+        float* gWta = G(at + "ta.weight");
+        MSA_TRY(gemm(h, true, false, 1, d.E, d.TB, gs, w.dzu, 1, w.ctx, d.E, beta, gWta, d.E + d.Ha));
+        MSA_TRY(gemm(h, true, false, 1, d.Ha, d.TB, gs, w.dzu, 1, w.ha, d.Ha, beta, gWta + d.E, d.E + d.Ha));
+        MSA_TRY(k_colsum(w.dzu, d.TB, 1, 1, G(at + "ta.bias"), gs, acc, nullptr, st));
+        // d memory += sum_t alpha(t)^T . (dzu(t) (x) W_ta[:E])   (w.dctx is free after the context backward above)
+        MSA_TRY(gemm(h, false, false, d.TB, d.E, 1, 1.f, w.dzu, 1, P(at + "ta.weight"), d.E + d.Ha, 0.f, w.dctx, d.E));
+        MSA_TRY(gemm_batched(h, true, false, L, d.E, T, 1.f, w.align_tm, d.BL, L, w.dctx, (int64_t)B * d.E, d.E, 1.f, w.dmem, d.E,
+                             (int64_t)L * d.E, B));
+    }
     const int64_t nfr = d.TB + B;
     MSA_TRY(gemm(h, false, false, d.TB, d.Pd, H4a, 1.f, w.dza, H4a, Wia, ldA, 0.f, w.dxp, d.Pd));
     MSA_CUDA(cudaMemsetAsync(w.dxp + d.TB * d.Pd, 0, sizeof(float) * (size_t)B * d.Pd, st));   // last prenet frame is unused (decoder.py:305)

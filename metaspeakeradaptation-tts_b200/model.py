@@ -10,8 +10,10 @@ What is different underneath: every parameter is a VIEW into one flat fp32 buffe
 view into ``model.grad_flat``; the forward / backward are single calls into libmsa_b200.so through a
 ``torch.autograd.Function``.  There is no PyTorch implementation of the model here and no CPU fallback.
 
-Restrictions (loud errors, never silent fallbacks): training-mode forward only (the teacher-forced pass in ``eval()`` mode
-is not implemented; ``infer`` is), ``ForwardAttention`` with ``forward_attn=False`` for training, one backward per forward.
+Restrictions (loud errors, never silent fallbacks): training-mode forward only (the reference never runs the teacher-forced
+pass in ``eval()`` mode on this path; ``infer`` is implemented), one backward per forward.  ``ForwardAttention`` is supported
+with every switch the reference has: ``norm``, ``forward_attn`` and ``trans_agent`` in training and inference, ``windowing`` and
+``forward_attn_mask`` (eval-only features) in ``infer``.
 """
 from __future__ import annotations
 

@@ -15,7 +15,7 @@ from helpers import cuda_pass, intermediates_report, oracle_pass, rel
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-CUDA_TRAIN_CASES = ["small_train", "small_train_meanloss", "small_train_spklin", "small_train_sigmoid"]
+CUDA_TRAIN_CASES = ["small_train", "small_train_meanloss", "small_train_spklin", "small_train_sigmoid", "small_train_fwdattn_sigmoid"]
 
 
 def _engine(cfg, crit, tf32=0):
@@ -68,6 +68,17 @@ def test_small_cases_fp32(name):
     gn = np.sqrt(sum(float((gold["grad/" + n].astype(np.float64) ** 2).sum()) for n in c_grads))
     for n, g in c_grads.items():
         assert float((g.double().cpu() - torch.as_tensor(gold["grad/" + n]).double()).norm()) / gn < 2e-4, ("golden grad", n)
+
+
+@pytest.mark.parametrize("attn", [dict(forward_attn=True), dict(forward_attn=True, trans_agent=True),
+                                  dict(forward_attn=True, trans_agent=True, norm="sigmoid")])
+def test_forward_attention_variants_fp32(attn):
+    """Forward attention in the training chain kernels (recursion alpha' = ((1-u) alpha + u shift(alpha) + 1e-8) a, transition
+    agent u = sigmoid(W_ta [ctx; h] + b), forward_attn.py:154-176,222-224) incl. their backward, ragged sizes, vs the oracle."""
+    cfg = pkg.small_params()
+    cfg["attention_params"].update(attn)
+    crit = dict(reduction="none", pos_weight=10.0)
+    _check(_engine(cfg, crit), cfg, 33 + len(attn), (5, 17, 13), crit, 2e-4, 2e-4, report=f"parity_fwdattn_{len(attn)}.txt")
 
 
 def test_ragged_odd_sizes_fp32():
