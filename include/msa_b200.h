@@ -208,6 +208,12 @@ int msa_flat_clip_sgd(float* p, const float* g, float* momentum_buf, const float
 int msa_flat_clip_adam(float* p, const float* g, float* m, float* v, const float* sumsq, int64_t n, float lr,
                        float beta1, float beta2, float eps, float weight_decay, int step, float max_norm,
                        void* stream);
+/* Functional Adam step of the inner loop (higher's differentiable optimizer for a torch.optim.Adam inner optimizer -- the
+ * reference builds the inner optimizer from YAML with any torch.optim class, utils/helpers.py:20-26; call sites maml.py:54,
+ * reptile.py:56): torch.optim.Adam's rule (no amsgrad), p_out = p - lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps); p is not modified
+ * (p_out may alias it); m, v are the per-context moment buffers, step is 1-based. */
+int msa_flat_adam_step(const float* p, const float* g, float* p_out, float* m, float* v, int64_t n, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int step, void* stream);
 /* EWC (continual_ewc.py): fisher += g*g / n_batches (59-82);
  * penalty = sum F (p-mu)^2 -> out[0] (84-89);
  * fused step p -= lr * (g + 2*lam*F*(p-mu)) and penalty in the same pass (345-357). */

@@ -67,6 +67,7 @@ SIGNATURES = {
     "msa_flat_sumsq": (I, [V, I64, V, V, V]),
     "msa_flat_clip_sgd": (I, [V, V, V, V, I64, F, F, F, F, F, I, I, V]),
     "msa_flat_clip_adam": (I, [V, V, V, V, V, I64, F, F, F, F, F, I, F, V]),
+    "msa_flat_adam_step": (I, [V, V, V, V, V, I64, F, F, F, F, F, I, V]),
     "msa_ewc_fisher_accum": (I, [V, V, I64, F, I, V]),
     "msa_ewc_penalty": (I, [V, V, V, I64, V, V, V]),
     "msa_ewc_sgd_step": (I, [V, V, V, V, I64, F, F, V, V, V]),

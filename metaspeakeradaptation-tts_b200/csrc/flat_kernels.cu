@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(kFlatThreads) k_clip_sgd(float* p, const float
     }
 }
 
-__global__ void __launch_bounds__(kFlatThreads) k_clip_adam(float* p, const float* __restrict__ g, float* m, float* v,
+// p_out may alias p (in-place outer step) or be a fresh buffer (functional inner-loop step: p stays intact)
+__global__ void __launch_bounds__(kFlatThreads) k_clip_adam(const float* p, float* p_out, const float* __restrict__ g, float* m, float* v,
                                                           const float* __restrict__ sumsq, int64_t n4, float lr, float b1,
                                                           float b2, float eps, float wd, float bc1, float bc2_sqrt,
                                                           float max_norm) {
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(kFlatThreads) k_clip_adam(float* p, const floa
              float denom = sqrtf(v2) / bc2_sqrt + eps; C4(pv) = C4(pv) - step_size * (mm / denom);)
         st4(m, i, mv);
         st4(v, i, vv);
-        st4(p, i, pv);
+        st4(p_out, i, pv);
     }
 }
 
@@ -215,8 +216,19 @@ int msa_flat_clip_adam(float* p, const float* g, float* m, float* v, const float
     MSA_CHECK(step >= 1, MSA_E_ARG, "msa_flat_clip_adam: step is 1-based");
     MSA_CHECK(max_norm <= 0.f || sumsq != nullptr, MSA_E_ARG, "msa_flat_clip_adam: clipping needs sumsq");
     double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
-    k_clip_adam<<<flat_grid(n / 4), kFlatThreads, 0, (cudaStream_t)stream>>>(p, g, m, v, sumsq, n / 4, lr, beta1, beta2, eps,
+    k_clip_adam<<<flat_grid(n / 4), kFlatThreads, 0, (cudaStream_t)stream>>>(p, p, g, m, v, sumsq, n / 4, lr, beta1, beta2, eps,
                                                                              weight_decay, (float)bc1, (float)sqrt(bc2), max_norm);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+
+int msa_flat_adam_step(const float* p, const float* g, float* p_out, float* m, float* v, int64_t n, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int step, void* stream) {
+    MSA_TRY(check_flat(p, n)); MSA_TRY(check_flat(g, n)); MSA_TRY(check_flat(p_out, n)); MSA_TRY(check_flat(m, n)); MSA_TRY(check_flat(v, n));
+    MSA_CHECK(step >= 1, MSA_E_ARG, "msa_flat_adam_step: step is 1-based");
+    double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+    k_clip_adam<<<flat_grid(n / 4), kFlatThreads, 0, (cudaStream_t)stream>>>(p, p_out, g, m, v, nullptr, n / 4, lr, beta1, beta2, eps,
+                                                                             weight_decay, (float)bc1, (float)sqrt(bc2), 0.f);
     MSA_LAUNCH_CHECK();
     return 0;
 }

@@ -365,6 +365,12 @@ class Engine:
                                                weight_decay, step, max_norm, _stream()), "msa_flat_clip_adam")
         self.launches += 1
 
+    def adam_step(self, p, g, p_out, m, v, lr, step, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        """Functional (out-of-place) Adam step of the inner loop; m, v are updated in place."""
+        _lib.check(self.lib.msa_flat_adam_step(_ptr(p), _ptr(g), _ptr(p_out), _ptr(m), _ptr(v), p.numel(), lr, betas[0], betas[1], eps,
+                                               weight_decay, step, _stream()), "msa_flat_adam_step")
+        self.launches += 1
+
     def ewc_fisher_accum(self, fisher, g, inv_n: float, init: bool):
         _lib.check(self.lib.msa_ewc_fisher_accum(_ptr(fisher), _ptr(g), g.numel(), inv_n, int(init), _stream()), "msa_ewc_fisher_accum")
         self.launches += 1

@@ -6,7 +6,8 @@
 
 ``fmodel`` is a functional copy: it clones the parameters AND the BatchNorm buffers of ``model`` (higher's semantics,
 SURVEY.md Appendix C), so the base model is never touched.  The fast weights live in ONE flat buffer; ``diffopt.step`` is
-autograd.grad of the loss w.r.t. that flat leaf followed by the fused functional SGD kernel (msa_flat_sgd_step).  Only the
+autograd.grad of the loss w.r.t. that flat leaf followed by the fused functional SGD or Adam kernel (msa_flat_sgd_step,
+msa_flat_adam_step; the reference builds the inner optimizer from YAML, utils/helpers.py:20-26).  Only the
 first-order mode exists (``track_higher_grads=False``): second-order MAML needs a double backward through the fused kernels.
 """
 from __future__ import annotations
@@ -80,8 +81,6 @@ class DifferentiableSGD:
     """``diffopt.step(loss)`` with torch.optim.SGD hyper-parameters read from the passed optimizer (maml.py:54)."""
 
     def __init__(self, fmodel: FunctionalTacotron2NV, opt: torch.optim.Optimizer):
-        if not isinstance(opt, torch.optim.SGD):
-            raise NotImplementedError("inner optimizer: only torch.optim.SGD is implemented on the fused path (SURVEY.md 8f item 3)")
         g = opt.param_groups[0]
         self.h = dict(lr=g["lr"], momentum=g.get("momentum", 0.0), dampening=g.get("dampening", 0.0),
                       weight_decay=g.get("weight_decay", 0.0), nesterov=g.get("nesterov", False))
@@ -100,10 +99,41 @@ class DifferentiableSGD:
         return fm.parameters(-1)
 
 
+class DifferentiableAdam:
+    """``diffopt.step(loss)`` for a torch.optim.Adam inner optimizer: fresh moment buffers per context (higher creates the
+    optimizer state inside ``innerloop_ctx``), torch.optim.Adam's update rule, first-order (re-leafed) fast weights."""
+
+    def __init__(self, fmodel: FunctionalTacotron2NV, opt: torch.optim.Optimizer):
+        g = opt.param_groups[0]
+        if g.get("amsgrad", False) or g.get("maximize", False):
+            raise NotImplementedError("inner Adam: amsgrad / maximize are not implemented")
+        self.h = dict(lr=float(g["lr"]), betas=tuple(g["betas"]), eps=float(g["eps"]), weight_decay=float(g.get("weight_decay", 0.0)))
+        self.fmodel = fmodel
+        self.m = torch.zeros_like(fmodel.fast_flat(0))
+        self.v = torch.zeros_like(fmodel.fast_flat(0))
+        self.steps = 0
+
+    def step(self, loss: torch.Tensor):
+        fm = self.fmodel
+        grads = torch.autograd.grad(loss, fm._views[-1])
+        g = grads[0]._msa_flat
+        new = fm.engine.new_flat(None)
+        self.steps += 1
+        fm.engine.adam_step(fm._fast[-1], g, new, self.m, self.v, step=self.steps, **self.h)
+        fm._push(new)
+        return fm.parameters(-1)
+
+
 @contextmanager
 def innerloop_ctx(model: Tacotron2NV, opt: torch.optim.Optimizer, copy_initial_weights: bool = True,
                   track_higher_grads: bool = False):
     if track_higher_grads:
         raise NotImplementedError("second-order MAML (track_higher_grads=True) needs a double backward through the fused kernels")
     fmodel = FunctionalTacotron2NV(model)
-    yield fmodel, DifferentiableSGD(fmodel, opt)
+    if isinstance(opt, torch.optim.SGD):
+        diffopt = DifferentiableSGD(fmodel, opt)
+    elif type(opt) is torch.optim.Adam:
+        diffopt = DifferentiableAdam(fmodel, opt)
+    else:
+        raise NotImplementedError(f"inner optimizer {type(opt).__name__}: SGD and Adam are implemented on the fused path")
+    yield fmodel, diffopt

@@ -99,6 +99,54 @@ def test_innerloop_fomaml_task_like_maml_py():
             pass
 
 
+def test_innerloop_with_adam_inner_optimizer():
+    """The reference builds the inner optimizer from YAML with any torch.optim class (utils/helpers.py:20-26): Adam inner
+    steps on the fused path against oracle gradients + torch.optim.Adam on the CPU (two inner steps, then the test loss)."""
+    from helpers import oracle_pass
+    cfg = pkg.small_params()
+    B, T, L = 3, 10, 8
+    P = synth.init_params(cfg, 6)
+    task = synth.make_task(cfg, B, T, L, 4)
+    masks = [synth.make_masks(cfg, B, T, L, 950 + i) for i in range(3)]
+    names = OM.param_names(cfg)
+    hyper = dict(lr=3e-3, betas=(0.9, 0.98), eps=1e-8)
+    # CPU side: oracle gradients, torch.optim.Adam on per-tensor leaves (fresh state, as inside innerloop_ctx)
+    Pc = {n: torch.nn.Parameter(P[n].clone()) for n in names}
+    copt = torch.optim.Adam([Pc[n] for n in names], **hyper)
+    for i in range(2):
+        cur = dict(P)
+        cur.update({n: Pc[n].detach().clone() for n in names})
+        _, _, g, _, _ = oracle_pass(cfg, cur, task["train"], masks[i], CRIT)
+        for n in names:
+            Pc[n].grad = g[n].clone()
+        copt.step()
+    cur = dict(P)
+    cur.update({n: Pc[n].detach().clone() for n in names})
+    _, o_loss, o_g, _, _ = oracle_pass(cfg, cur, task["test"], masks[2], CRIT)
+    # CUDA side, written like maml.py:40-74
+    model = _model(cfg, P)
+    criterion = pkg.Tacotron2Loss(1, "none", 10.0)
+    inner_opt = torch.optim.Adam(model.parameters(), **hyper)
+    with pkg.innerloop_ctx(model, inner_opt, track_higher_grads=False) as (fmodel, diffopt):
+        fmodel.injected_masks = masks
+        for _ in range(2):
+            kw, targets, mel_len = _inputs(task["train"])
+            diffopt.step(criterion(fmodel(**kw), targets, mel_len))
+        kw, targets, mel_len = _inputs(task["test"])
+        loss_test = criterion(fmodel(**kw), targets, mel_len)
+        task_grads = torch.autograd.grad(loss_test, fmodel.parameters(time=-1))
+        fast = fmodel.state_dict()
+    # Adam normalises the step: where the gradient is rounding noise (|g| ~ 1e-9, e.g. rows of unused symbols) the two sides move
+    # by +-lr in different directions, so the fast weights are compared against the size of the whole update (sanity bound) and
+    # the quantities that matter -- test loss and meta-gradient -- at tolerances relative to their own size
+    upd = float(torch.sqrt(sum(((Pc[n].detach() - P[n]).double() ** 2).sum() for n in names)))
+    dif = float(torch.sqrt(sum(((fast[n].cpu() - Pc[n].detach()).double() ** 2).sum() for n in names)))
+    lerr, gerr = abs(float(loss_test) - float(o_loss)) / abs(float(o_loss)), _gerr(task_grads, o_g, names)
+    print(f"inner Adam: fast-weight diff / update {dif / upd:.3e}, loss rel {lerr:.3e}, meta-grad err/|G| {gerr:.3e}")
+    assert dif < 0.15 * upd, (dif, upd)
+    assert lerr < TOL and gerr < TOL, (lerr, gerr)
+
+
 def test_ewc_fisher_penalty_and_fused_step_like_continual_ewc_py():
     cfg = pkg.small_params()
     B, T, L = 3, 9, 8

@@ -90,6 +90,23 @@ def test_clip_adam(eng):
     assert close(q, pt.data, 2e-6)
 
 
+def test_functional_adam_step(eng):
+    """Inner-loop Adam (msa_flat_adam_step): torch.optim.Adam's rule with weight decay, out of place (p stays intact)."""
+    p = _r(N, 70)
+    pt = torch.nn.Parameter(p.clone())
+    opt = torch.optim.Adam([pt], lr=2e-3, betas=(0.8, 0.95), eps=1e-7, weight_decay=0.01)
+    cur, m, v = p.clone(), torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        g = _r(N, 70 + step)
+        pt.grad = g.clone()
+        opt.step()
+        keep, new = cur.clone(), torch.empty_like(cur)
+        eng.adam_step(cur, g, new, m, v, lr=2e-3, step=step, betas=(0.8, 0.95), eps=1e-7, weight_decay=0.01)
+        assert torch.equal(cur, keep), "functional step: the input fast weights are not modified"
+        cur = new
+    assert close(cur, pt.data, 2e-6)
+
+
 def test_ewc(eng):
     p, mu, g = _r(N, 60), _r(N, 61), _r(N, 62)
     f = torch.empty(N, device="cuda")
