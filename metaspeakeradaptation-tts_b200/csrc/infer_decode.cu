@@ -101,9 +101,12 @@ __global__ void __launch_bounds__(kIrThreads, 1) ker_infer_rows(InferRowsParams 
         for (int s = 0; s < 2; ++s) rowp[s][r] = nullptr;
     __syncthreads();
 
-    const int nch0 = (p.K[0] + kIrKC - 1) / kIrKC, nch1 = p.nseg > 1 ? (p.K[1] + kIrKC - 1) / kIrKC : 0, nch = nch0 + nch1;
+    const int nch0 = (p.K[0] + kIrKC - 1) / kIrKC, nch1 = p.nseg > 1 ? (p.K[1] + kIrKC - 1) / kIrKC : 0, nch_all = nch0 + nch1;
+    // K split over blockIdx.z (few output rows, long K: the projection): this CTA takes the chunks [coff, coff + nch)
+    const int coff = (int)(((long long)blockIdx.z * nch_all) / gridDim.z);
+    const int nch = (int)(((long long)(blockIdx.z + 1) * nch_all) / gridDim.z) - coff;
     // every CTA walks the chunks in a different rotation (all CTAs read the same x rows: spreads those requests over the L2 slices)
-    const int rot = p.rotate ? (int)((blockIdx.x * 7u) % (unsigned)nch) : 0;
+    const int rot = (p.rotate && nch > 0) ? (int)((blockIdx.x * 7u) % (unsigned)nch) : 0;
     // copy slots of this thread: rows r0, r0 + RSTEP, ... at the 16-byte column c4
     constexpr int C4 = kIrKC / 4, RSTEP = kIrThreads / C4, NSLOT = (ROWS + RSTEP - 1) / RSTEP;
     const int c4 = threadIdx.x % C4, r0 = threadIdx.x / C4;
@@ -117,6 +120,7 @@ __global__ void __launch_bounds__(kIrThreads, 1) ker_infer_rows(InferRowsParams 
     auto issue = [&](int cc, int stage) {
         int c = cc + rot;
         if (c >= nch) c -= nch;
+        c += coff;
         const int s = c < nch0 ? 0 : 1, k0 = (s ? c - nch0 : c) * kIrKC;
         const bool kin = k0 + c4 * 4 < p.K[s];
         float* dst = sm + ((size_t)stage * ROWS + r0) * kIrLd + c4 * 4;
@@ -169,6 +173,7 @@ __global__ void __launch_bounds__(kIrThreads, 1) ker_infer_rows(InferRowsParams 
         {
             int cr = c + rot;
             if (cr >= nch) cr -= nch;
+            cr += coff;
             const int s = cr < nch0 ? 0 : 1;
             kvalid = min(kIrKC, p.K[s] - (s ? cr - nch0 : cr) * kIrKC);
         }
@@ -264,6 +269,8 @@ __global__ void __launch_bounds__(kIrThreads, 1) ker_infer_rows(InferRowsParams 
             v = fmaxf(v, 0.f);
             const uint8_t mk = p.mask[(((size_t)t * 2 + p.mask_layer) * p.B + b0 + b) * p.N + gr];
             p.out[(size_t)(b0 + b) * p.ldo + gr] = mk ? v * 2.f : 0.f;
+        } else if (gridDim.z > 1) {
+            p.part[((size_t)blockIdx.z * p.B + b0 + b) * p.N + gr] = v;      // K-split partial; summed in fixed order by the last CTA
         } else if (p.nsplit > 0 && gr >= p.nsplit) {
             p.out2[(size_t)(b0 + b) * p.ldo2 + gr - p.nsplit] = v + (p.bias2 ? p.bias2[gr - p.nsplit] : 0.f);
         } else {
@@ -275,7 +282,7 @@ __global__ void __launch_bounds__(kIrThreads, 1) ker_infer_rows(InferRowsParams 
     // (decoder.py:381-395): dec = sigmoid(gate) <= threshold; not_finished *= dec; mel_lengths += not_finished
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) last_s = atomicAdd(p.counter, 1u) == gridDim.x * gridDim.y - 1 ? 1 : 0;
+    if (threadIdx.x == 0) last_s = atomicAdd(p.counter, 1u) == gridDim.x * gridDim.y * gridDim.z - 1 ? 1 : 0;
     __syncthreads();
     if (!last_s) return;
     __threadfence();
@@ -283,6 +290,17 @@ __global__ void __launch_bounds__(kIrThreads, 1) ker_infer_rows(InferRowsParams 
     if (threadIdx.x == 0) any = 0;
     __syncthreads();
     const int BM = p.B * p.M;
+    if (gridDim.z > 1) {
+        // sum the K-split partials (fixed order: deterministic) + bias -> mel frame [B][M] and gate [B]
+        for (int i = threadIdx.x; i < p.B * p.N; i += kIrThreads) {
+            const int b = i / p.N, gr = i - b * p.N;
+            float v = 0.f;
+            for (int z = 0; z < (int)gridDim.z; ++z) v += __ldcg(p.part + ((size_t)z * p.B + b) * p.N + gr);
+            if (p.nsplit > 0 && gr >= p.nsplit) p.out2[(size_t)b * p.ldo2 + gr - p.nsplit] = v + (p.bias2 ? p.bias2[gr - p.nsplit] : 0.f);
+            else p.out[(size_t)b * p.ldo + gr] = v + (p.bias1 ? p.bias1[gr] : 0.f);
+        }
+        __syncthreads();
+    }
     for (int i = threadIdx.x; i < BM; i += kIrThreads) {
         const float v = __ldcg(p.out + i);
         p.mel_tm[(size_t)t * BM + i] = v;
@@ -316,7 +334,7 @@ static int launch_rows(const InferRowsParams& p, int gx, cudaStream_t st) {
         MSA_CUDA(cudaFuncSetAttribute(ker_infer_rows<RPG, KC, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    ker_infer_rows<RPG, KC, NS><<<dim3(gx, (p.B + kIrBT - 1) / kIrBT), kIrThreads, smem, st>>>(p);
+    ker_infer_rows<RPG, KC, NS><<<dim3(gx, (p.B + kIrBT - 1) / kIrBT, p.ksplit > 1 ? p.ksplit : 1), kIrThreads, smem, st>>>(p);
     MSA_LAUNCH_CHECK();
     return 0;
 }
@@ -340,6 +358,7 @@ int k_infer_rows(const InferRowsParams& p_in, int sm_count, cudaStream_t st) {
                   MSA_E_UNSUPPORTED, "infer_rows: segment %d (K=%d, ldx=%d, ldw=%d) is not 16-byte aligned", s, p.K[s], p.ldx[s], p.ldw[s]);
     }
     MSA_CHECK(p.nsplit == 0 || ((uintptr_t)p.Wb & 15) == 0, MSA_E_UNSUPPORTED, "infer_rows: second weight block is not 16-byte aligned");
+    MSA_CHECK(p.ksplit <= 1 || (p.finish && p.part && p.epi == IR_EPI_BIAS), MSA_E_ARG, "infer_rows: K split needs the finishing CTA and a partial buffer");
     if (p.epi == IR_EPI_LSTM) {
         // units split over min(#SMs, H) CTAs when that leaves <= 7 units per CTA, else one CTA per 7 units
         int gx = p.H < sm_count ? p.H : sm_count;

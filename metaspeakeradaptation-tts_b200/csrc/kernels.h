@@ -175,6 +175,7 @@ struct InferRowsParams {
     int finish, M, early, max_steps;
     float threshold;
     float* mel_tm; float* frame; int* not_finished; int* mel_lengths; int* state_rw; unsigned int* counter;
+    int ksplit; float* part;                      // finish only: K split over blockIdx.z, partials [ksplit][B][N]
 };
 int k_infer_rows(const InferRowsParams& p, int sm_count, cudaStream_t st);
 struct InferAttnParams {

@@ -986,7 +986,7 @@ namespace msa {
     X(enc_h, 2 * d.BL * d.Hh) X(memory, d.BL * d.E) X(pm, d.BL * d.A)                                    \
     X(xin_a, d.B * (d.Pd + d.E)) X(p1, d.B * d.Pd) X(ha, 2 * d.B * d.Ha) X(ca, d.B * d.Ha)               \
     X(xin_d, d.B * (d.Ha + d.E)) X(hd, 2 * d.B * d.Hd) X(cd, d.B * d.Hd) X(xin_p, d.B * (d.Hd + d.E))    \
-    X(mel_raw, d.B * d.M) X(gate_raw, d.B) X(frame, d.B * d.M)                                           \
+    X(mel_raw, d.B * d.M) X(gate_raw, d.B) X(frame, d.B * d.M) X(proj_part, 16 * d.B * (d.M + 1))        \
     X(prev, d.BL) X(cum, d.BL) X(fa_alpha, d.BL) X(fa_u, d.B + 4) X(mel_tm, (int64_t)d.T * d.B * d.M) X(ints, 64 + d.B)                      \
     X(post_x, 2 * d.BT * d.Cmax) X(post_y, d.BT * d.Cmax) X(post_col, d.BT * d.Kp * d.Cmax)              \
     X(post_w2, (int64_t)d.Cmax * d.Kp * d.Cmax) X(post_bt, d.BT * d.M)
@@ -1200,6 +1200,12 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
         pp.finish = 1; pp.M = d.M; pp.early = c.early_stopping; pp.max_steps = max_steps; pp.threshold = c.gate_threshold;
         pp.mel_tm = w.mel_tm; pp.frame = w.frame; pp.not_finished = not_finished; pp.mel_lengths = mel_lengths_out; pp.state_rw = state;
         pp.counter = counter;
+        // optional K split of the projection over blockIdx.z (MSA_PROJ_KSPLIT=n, <= 16): measured on B200 the kernel's 20 us are
+        // launch ramp + the serial stop-logic tail of the last CTA, not the K loop (SM-active 4.4 us with 7 slices), and the extra
+        // partial-sum pass made the step 5 us slower end to end, so the default is 1 (profiles/r01_infer_notes.txt)
+        static const int ks_env = getenv("MSA_PROJ_KSPLIT") ? atoi(getenv("MSA_PROJ_KSPLIT")) : 1;
+        pp.ksplit = std::max(1, std::min(std::min(16, (KP + 127) / 128), ks_env));
+        pp.part = w.proj_part;
         MSA_TRY(k_infer_rows(pp, h->sm_count, st));
         return 0;
     };
