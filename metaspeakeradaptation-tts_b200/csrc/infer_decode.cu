@@ -55,6 +55,13 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], 
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// Programmatic dependent launch: every kernel of the decoder step is launched with programmatic stream serialization, lets its
+// successor start launching at once (launch_dependents) and waits for its predecessor's memory before the first global read
+// (wait): the launch latency / ramp of kernel n+1 overlaps the tail of kernel n.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 __device__ __forceinline__ float dot4f(const float4& a, const float4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 __device__ __host__ __forceinline__ int ir_part_lo(int i, int n, int parts) { return (int)(((long long)i * n) / parts); }
 
@@ -63,6 +70,7 @@ __device__ __host__ __forceinline__ int ir_part_lo(int i, int n, int parts) { re
 // Fragments come from the padded row-major shared tiles by ldmatrix.x4 (conflict-free: consecutive rows start 4 banks apart).
 template <int RPG, int kIrKC, int NS>
 __global__ void __launch_bounds__(kIrThreads, 1) ker_infer_rows(InferRowsParams p) {
+    pdl_prologue();
     if (p.state[1]) return;
     constexpr int R = 4 * RPG, MT = (R + 15) / 16, ROWS = kIrBT + 16 * MT, kIrLd = kIrKC + 4, KSTEPS = kIrKC / 8;
     static_assert(KSTEPS % (kIrThreads / 32) == 0, "every warp takes the same number of k8 steps per chunk");
@@ -332,9 +340,21 @@ static int launch_rows(const InferRowsParams& p, int gx, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         MSA_CUDA(cudaFuncSetAttribute(ker_infer_rows<RPG, KC, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // the same (maximal) shared-memory carve-out for every kernel of the step: no L1 / shared reconfiguration between launches
+        MSA_CUDA(cudaFuncSetAttribute(ker_infer_rows<RPG, KC, NS>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
-    ker_infer_rows<RPG, KC, NS><<<dim3(gx, (p.B + kIrBT - 1) / kIrBT, p.ksplit > 1 ? p.ksplit : 1), kIrThreads, smem, st>>>(p);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(gx, (p.B + kIrBT - 1) / kIrBT, p.ksplit > 1 ? p.ksplit : 1);
+    cfg.blockDim = dim3(kIrThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    MSA_CUDA(cudaLaunchKernelEx(&cfg, ker_infer_rows<RPG, KC, NS>, p));
     MSA_LAUNCH_CHECK();
     return 0;
 }
@@ -429,6 +449,7 @@ __device__ __forceinline__ void st_cluster(float* local_ptr, unsigned int rank, 
 
 __global__ void __launch_bounds__(kIaThreads, 1) ker_infer_attn(InferAttnParams p) {
     // no early return before the cluster barriers: every CTA of a cluster takes the same path (the flag is launch-uniform)
+    pdl_prologue();
     if (p.state[1]) return;
     extern __shared__ __align__(16) float sm[];
     const int t = p.state[0], b = blockIdx.x / kIaCl;
@@ -761,18 +782,25 @@ int k_infer_attention(const InferAttnParams& p, cudaStream_t st) {
     const size_t smem = infer_attention_smem(p.L, p.Ha, p.A, p.F, p.Kl, p.E);
     MSA_CHECK(smem <= 200 * 1024, MSA_E_UNSUPPORTED, "infer attention: text length %d too long for the shared-memory tile", p.L);
     if (smem > 48 * 1024) MSA_CUDA(cudaFuncSetAttribute(ker_infer_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool carve_set = false;
+    if (!carve_set) {
+        MSA_CUDA(cudaFuncSetAttribute(ker_infer_attn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        carve_set = true;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(p.B * kIaCl);
     cfg.blockDim = dim3(kIaThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = kIaCl;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     MSA_CUDA(cudaLaunchKernelEx(&cfg, ker_infer_attn, p));
     MSA_LAUNCH_CHECK();
     return 0;
