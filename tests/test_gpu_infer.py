@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 import torch
 
+import msa_tts_b200 as pkg
 from msa_tts_b200 import synth
 from oracle import model as OM
 from oracle.gen_cases import INFER_CASES, infer_stats
@@ -91,6 +92,29 @@ def test_infer_attention_variants_vs_oracle(name, B, L):
     assert post.shape == o_post.shape and torch.equal(lens.cpu(), o_lens)
     assert rel(post, o_post) < TOL and rel(align, o_align) < TOL
     assert torch.equal(align.cpu() == 0, o_align == 0)
+
+
+@pytest.mark.parametrize("B,L,attn", [(32, 64, {}), (5, 61, dict(forward_attn=True, trans_agent=True, norm="sigmoid"))])
+def test_infer_default_dims_vs_oracle(B, L, attn):
+    """Default (Tacotron-2) dimensions: the multi-chunk K ring, 7 hidden units per CTA on all SMs, the two-segment LSTM products,
+    the 81-row projection with its second weight matrix and the 4-CTA attention clusters -- none of which the small model
+    exercises -- against the oracle for a few free-running steps (BASELINE configs[4] batch shape and a ragged one)."""
+    from msa_tts_b200.engine import Engine
+    steps = 6
+    cfg = pkg.default_params()
+    cfg["attention_params"].update(attn)
+    cfg["max_decoder_steps"] = steps
+    cfg["decoder_no_early_stopping"] = True
+    eng = Engine(cfg)
+    P = synth.init_params(cfg, 3)
+    _, inp, inp_len, _, _, _, spk, _ = synth.make_batch(cfg, B, 8, L, 77)
+    stats = infer_stats(P, cfg, 3)
+    pm = synth.make_infer_masks(cfg, B, steps, 78)
+    post, lens, align = eng.infer(eng.flat_from_dict(P), eng.bn_from_dict(stats), inp, inp_len, spk, pm, max_steps=steps)
+    torch.cuda.synchronize()
+    o_post, o_lens, o_align = OM.infer(P, cfg, inp, inp_len, spk, pm, stats)
+    assert post.shape == o_post.shape and torch.equal(lens.cpu(), o_lens)
+    assert rel(post, o_post) < TOL and rel(align, o_align) < TOL, (rel(post, o_post), rel(align, o_align))
 
 
 def test_infer_graph_and_direct_launch_agree():
