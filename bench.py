@@ -194,6 +194,38 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bench_infer(torch, tr, world, sync, B=32, L_=64, steps=1000):
+    import msa_tts_b200 as pkg
+    from msa_tts_b200 import synth
+    from msa_tts_b200.engine import Engine
+    cfg = pkg.default_params()
+    cfg["max_decoder_steps"] = steps
+    cfg["decoder_no_early_stopping"] = True
+    eng = Engine(cfg, tr.device)
+    lens = torch.arange(L_, L_ - B, -1)
+    g = torch.Generator().manual_seed(4321)
+    inp = torch.randint(1, 123, (B, L_), generator=g)
+    for b in range(B):
+        inp[b, lens[b]:] = 0
+    spk = torch.randn(B, cfg["speaker_embedding_dim"], generator=g)
+    pm = synth.make_infer_masks(cfg, B, steps, 5)
+    flat, bn = tr.theta, eng.new_bn_stats()
+    eng.infer(flat, bn, inp, lens, spk, pm, max_steps=steps)          # warm-up (workspace, L2)
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = eng.infer(flat, bn, inp, lens, spk, pm, max_steps=steps)     # host tokens in, encoder + 1000 steps + postnet
+    out[1].cpu()                                                       # D2H of mel_lengths
+    e1.record()
+    sync()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=tr.device)
+    tr.shard.allreduce_max(ms)
+    n_steps = int(out[0].shape[2])
+    return {"metric": "decoder_mel_frames_per_s", "value": world * B * n_steps / float(ms) * 1e3, "unit": "mel-frames/s",
+            "us_per_step": float(ms) * 1e3 / n_steps, "scaling": "weak",
+            "workload": f"free-running inference, B={B} per GPU, L={L_}, {n_steps} decoder steps, default dims, encoder and postnet included"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -282,6 +314,14 @@ def main():
         "flat_sumsq": (time_flat(lambda: eng.sumsq(tr.task_grad)), 4.0 * n),
     }
 
+    # ---- decoder mel-frames/s of free-running inference (BASELINE configs[4]: B=32 per GPU, L=64, 1000 steps, no early stop);
+    # every rank decodes its own batch (inference shards by batch rows, no collective), time = max over ranks ----
+    infer_line = None
+    try:
+        infer_line = bench_infer(torch, tr, world, sync)
+    except Exception as e:      # the meta-step line must not depend on this leg
+        infer_line = {"error": str(e)[:200]}
+
     if rank == 0:
         peak, peak_src = measured_peak()
         kern = []
@@ -318,6 +358,7 @@ def main():
                          "ms_per_launch": dom["ms_per_launch"], "share_of_step": dom["share_of_step"]},
             "kernels": kern,
             "clocks": clk.summary(),
+            "infer": infer_line,
         }
         if world == 1 and not args.no_cpu_baseline:
             step, threads = cpu_reference_task()
