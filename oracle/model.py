@@ -95,7 +95,7 @@ def encoder(P, cfg, inputs, input_lengths, masks, stats, train, inter=None):
         order = range(L - 1, -1, -1) if rev else range(L)
         for t in order:
             # packed-sequence semantics: rows with t >= len are not stepped and output 0
-            act = (t < input_lengths).to(x.dtype).unsqueeze(1)
+            act = (t < input_lengths.to(x.device)).to(x.dtype).unsqueeze(1)
             h2, c2 = lstm_cell(x[:, t], h, c, w_ih, w_hh, b_ih, b_hh)
             h = act * h2 + (1 - act) * h
             c = act * c2 + (1 - act) * c
@@ -304,8 +304,8 @@ def infer(P, cfg, inputs, input_lengths, speaker_vecs, prenet_masks, stats, max_
         st = AttnState(P, cfg, memory)
         state = _zero_state(cfg, memory)
         frame = memory.new_zeros(B, cfg["n_mel_channels"])
-        mel_lengths = torch.zeros(B, dtype=torch.int32)
-        not_finished = torch.ones(B, dtype=torch.int32)
+        mel_lengths = torch.zeros(B, dtype=torch.int32, device=memory.device)
+        not_finished = torch.ones(B, dtype=torch.int32, device=memory.device)
         max_steps = max_steps or cfg["max_decoder_steps"]
         early = not cfg["decoder_no_early_stopping"]
         mels, aligns, gates = [], [], []
@@ -335,7 +335,7 @@ def loss_fn(outputs, targets, mel_len, reduction="none", pos_weight=10.0, n_fram
     pre, post, gate, _ = outputs
     mel, stop = targets
     B, n_mel, T = mel.shape
-    pw = torch.tensor(pos_weight, dtype=gate.dtype)
+    pw = torch.tensor(pos_weight, dtype=gate.dtype, device=gate.device)
     l1 = (post - mel).abs() + (pre - mel).abs()
     mse = (post - mel) ** 2 + (pre - mel) ** 2
     bce = F.binary_cross_entropy_with_logits(gate, stop.to(gate.dtype), pos_weight=pw, reduction="none")
@@ -345,7 +345,7 @@ def loss_fn(outputs, targets, mel_len, reduction="none", pos_weight=10.0, n_fram
         rem = max_len % r
         pad_len = max_len + (r - rem) if rem > 0 else max_len
         assert pad_len == T, "Tacotron2Loss(reduction='none') needs T == padded max(mel_len)"
-        m = (torch.arange(T)[None, :] < mel_len[:, None]).to(mel.dtype)        # [B, T]
+        m = (torch.arange(T, device=mel.device)[None, :] < mel_len.to(mel.device)[:, None]).to(mel.dtype)        # [B, T]
         w = m / m.sum(dim=1, keepdim=True)
         ow = (w / (B * n_mel)).unsqueeze(1)                                    # [B, 1, T]
         lw = w / B
