@@ -282,7 +282,12 @@ __global__ void __launch_bounds__(kIrThreads, 1) ker_infer_rows(InferRowsParams 
         } else if (p.nsplit > 0 && gr >= p.nsplit) {
             p.out2[(size_t)(b0 + b) * p.ldo2 + gr - p.nsplit] = v + (p.bias2 ? p.bias2[gr - p.nsplit] : 0.f);
         } else {
-            p.out[(size_t)(b0 + b) * p.ldo + gr] = v + (p.bias1 ? p.bias1[gr] : 0.f);
+            v += p.bias1 ? p.bias1[gr] : 0.f;
+            p.out[(size_t)(b0 + b) * p.ldo + gr] = v;
+            if (p.finish) {      // the mel frame goes straight to the output and to the next prenet input (off the serial tail)
+                p.mel_tm[((size_t)t * p.B + b0 + b) * p.M + gr] = v;
+                p.frame[(size_t)(b0 + b) * p.M + gr] = v;
+            }
         }
     }
     if (!p.finish) return;
@@ -309,11 +314,12 @@ __global__ void __launch_bounds__(kIrThreads, 1) ker_infer_rows(InferRowsParams 
         }
         __syncthreads();
     }
-    for (int i = threadIdx.x; i < BM; i += kIrThreads) {
-        const float v = __ldcg(p.out + i);
-        p.mel_tm[(size_t)t * BM + i] = v;
-        p.frame[i] = v;
-    }
+    if (gridDim.z > 1)
+        for (int i = threadIdx.x; i < BM; i += kIrThreads) {
+            const float v = __ldcg(p.out + i);
+            p.mel_tm[(size_t)t * BM + i] = v;
+            p.frame[i] = v;
+        }
     for (int b = threadIdx.x; b < p.B; b += kIrThreads) {
         const float g = __ldcg(p.out2 + b);
         const int dec = (1.f / (1.f + expf(-g))) <= p.threshold ? 1 : 0;
