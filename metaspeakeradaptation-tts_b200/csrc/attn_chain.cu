@@ -539,7 +539,10 @@ __global__ void __launch_bounds__(NT, 1) k_attn_chain_bwd(AttnChainBwdParams p, 
                 fs_s[threadIdx.x] = __ldg(p.fsum + (size_t)t * B + threadIdx.x);
             }
         }
-        // in the shadow of the dat hand-off: first half of W_hh^T . dz_a(t+1) for the owned units (needed by the point-wise phase)
+        // in the shadow of the d a(t) hand-off: first half of W_hh^T . dz_a(t+1) for the owned units (needed by the point-wise phase).
+        // A hand-off that is waited on directly costs ~2.5 us from the last publish to the release (measured,
+        // profiles/r01_trace_attn_chain_bwd_v7.txt; independent of polling back-off), one that is given >= 2 us of independent
+        // work costs nothing, so the mat-vec is split over the two hand-offs that have nothing else to hide behind.
         if (t < T - 1) cta_matvec_bwd<NT>(WT, H4, p.dza + (size_t)(t + 1) * B * H4, B, part, dhs, BP, sg, 0, 2);
         prof.mark(1, T - 1 - t);
         // ---- hand-off 1: d a(t) of every position ----
@@ -588,33 +591,14 @@ __global__ void __launch_bounds__(NT, 1) k_attn_chain_bwd(AttnChainBwdParams p, 
             }
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < np; i += NT) p.de[(size_t)t * BL + p0 + i] = des[p0 + i];
-        for (int it = threadIdx.x; it < np * A; it += NT) {
-            const int pi = it / A, d = it - pi * A;
-            const float sv = it == (int)threadIdx.x ? sv_own : __ldg(p.s + ((size_t)t * BL + p0) * A + it);
-            const float dS = des[p0 + pi] * vs[d] * (1.f - sv * sv);
-            p.ds[((size_t)t * BL + p0) * A + it] = dS;
-            ds_s[it] = dS;
-        }
+        // dq first: it is the next hand-off, everything else of this phase is local work
         if (nd > 0)       // terms of dq for the first owned attention dim (prefetched column of s)
             for (int idx = threadIdx.x; idx < BL; idx += NT) {
                 const float sv = idx == (int)threadIdx.x ? sv_q : __ldg(p.s + ((size_t)t * BL + idx) * A + d0);
                 tq_s[idx] = des[idx] * (1.f - sv * sv);
             }
+        for (int i = threadIdx.x; i < np; i += NT) p.de[(size_t)t * BL + p0 + i] = des[p0 + i];
         __syncthreads();
-        // d(conv features) of the owned positions: item (pi, f, js) sums d = js, js+8, ...; 8 consecutive lanes share (pi, f)
-        for (int base = 0; base < np * F * 8; base += NT) {     // warp-uniform trip count (full-mask shuffles inside)
-            const int it = base + threadIdx.x;
-            const bool valid = it < np * F * 8;
-            const int js = it & 7, f = valid ? (it >> 3) % F : 0, pi = valid ? (it >> 3) / F : 0;
-            float acc = 0.f;
-            if (valid)
-                for (int d = js; d < A; d += 8) acc += ds_s[pi * A + d] * wldT[f * AP + d];
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-            if (valid && js == 0) st_pub(p.dconvf + ((size_t)t * BL + p0 + pi) * F + f, acc);
-        }
         for (int it = NW - 1 - w; it < nd * B; it += NW) {
             const int di = it / B, b = it - di * B, d = d0 + di;
             float acc = 0.f;
@@ -629,9 +613,31 @@ __global__ void __launch_bounds__(NT, 1) k_attn_chain_bwd(AttnChainBwdParams p, 
             acc = warp_sum(acc);
             if (lane == 0) st_pub(p.dq + ((size_t)t * B + b) * A + d, vs[d] * acc);
         }
+        for (int it = threadIdx.x; it < np * A; it += NT) {
+            const int pi = it / A, d = it - pi * A;
+            const float sv = it == (int)threadIdx.x ? sv_own : __ldg(p.s + ((size_t)t * BL + p0) * A + it);
+            const float dS = des[p0 + pi] * vs[d] * (1.f - sv * sv);
+            p.ds[((size_t)t * BL + p0) * A + it] = dS;
+            ds_s[it] = dS;
+        }
+        __syncthreads();
+        // d(conv features) of the owned positions: item (pi, f, js) sums d = js, js+8, ...; 8 consecutive lanes share (pi, f)
+        for (int base = 0; base < np * F * 8; base += NT) {     // warp-uniform trip count (full-mask shuffles inside)
+            const int it = base + threadIdx.x;
+            const bool valid = it < np * F * 8;
+            const int js = it & 7, f = valid ? (it >> 3) % F : 0, pi = valid ? (it >> 3) / F : 0;
+            float acc = 0.f;
+            if (valid)
+                for (int d = js; d < A; d += 8) acc += ds_s[pi * A + d] * wldT[f * AP + d];
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            if (valid && js == 0) st_pub(p.dconvf + ((size_t)t * BL + p0 + pi) * F + f, acc);
+        }
         prof.mark(3, T - 1 - t);
         // in the shadow of the dq hand-off: second half of W_hh^T . dz_a(t+1)
         if (t < T - 1) cta_matvec_bwd<NT>(WT, H4, p.dza + (size_t)(t + 1) * B * H4, B, part, dhs, BP, sg, 1, 2);
+        prof.mark(7, T - 1 - t);
         // ---- hand-off 2: dq(t) ----
         gather_words<NT>(dq_s, p.dq + (size_t)t * B * A, B * A, (p.flags & kFlagWarp0) != 0, sg);
         __syncthreads();
@@ -652,6 +658,7 @@ __global__ void __launch_bounds__(NT, 1) k_attn_chain_bwd(AttnChainBwdParams p, 
             if (valid && js == 0) qd_s[cell] = acc;
         }
         __syncthreads();
+        prof.mark(8, T - 1 - t);
         if (pw) {
             const size_t zb = ((size_t)t * B + pb) * H4;
             float dh = dhe + (t < T - 1 ? dhs[ul * BP + pb] : 0.f) + qd_s[threadIdx.x];
@@ -701,6 +708,7 @@ __global__ void __launch_bounds__(NT, 1) k_attn_chain_bwd(AttnChainBwdParams p, 
             }
         }
         __syncthreads();
+        prof.mark(9, T - 1 - t);
         for (int i = w; i < np; i += NW) {            // one warp per owned position, lanes over the taps (fixed order)
             float a0 = 0.f, a1 = 0.f;
             for (int k = lane; k < Kl; k += 32) {
