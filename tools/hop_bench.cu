@@ -147,7 +147,7 @@ int main() {
     int dev = 0; CK(cudaSetDevice(dev));
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, dev));
     const int nsm = prop.multiProcessorCount, steps = 400;
-    for (int ncta : {nsm, nsm / 2, nsm / 4}) {
+    for (int ncta : {nsm, nsm / 2, nsm / 4, 18, 8, 2}) {
     printf("---- %d CTAs ----\n", ncta);
     float *buf, *dram, *sink; unsigned int* counter; long long* out;
     const size_t nbuf = (size_t)steps * ncta * WMAX;
@@ -157,7 +157,7 @@ int main() {
     const char* names[] = {"gate(warp0 sentinels)+bulk", "gate only", "mass polling", "gate+bulk with DRAM prefetch loads in flight", "grid barrier (fence+atomic)+bulk", "gate+bulk, publish via atomicExch", "gate+bulk, __threadfence after publish", "ping-pong CTA0<->CTA1 (round trip)", "batched gate only", "batched gate + bulk", "distributed gate (1 sentinel/thread) + bulk", "polling by 128 threads, 4 loads in flight", "mass polling, 2 replicas", "mass polling, 4 replicas", "mass polling, 8 replicas", "mass polling, 16 replicas", "4 words/CTA interleaved [b][cta] (false sharing)", "4 words/CTA in a private 32B sector"};
     for (int Wv = 8; Wv <= 32; Wv *= 4)
     for (int mode = 0; mode < 18; ++mode) {
-        if (mode != 2 && mode != 16) continue;
+        if (mode != 0 && mode != 2 && mode != 7) continue;
         for (int rep = 0; rep < 2; ++rep) {
             CK(cudaMemset(buf, 0, nbuf * 4)); CK(cudaMemset(repbuf, 0, nbuf * 16 * 4)); CK(cudaMemset(counter, 0, 4));
             int st = steps; int md = mode;
