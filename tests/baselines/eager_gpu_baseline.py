@@ -1,14 +1,15 @@
 """"PyTorch-eager-on-B200 running the same modules" -- the library-kernel bar on the same box.  The reference tree
 cannot travel to the GPU box, so the oracle restatement (plain torch ops, oracle/model.py, pinned to the reference by the golden
 fixtures) is run with CUDA tensors: cuBLAS / cuDNN / ATen kernels launched op by op from Python, exactly how the reference
-trainers would run on a GPU.  A reported baseline (profiles/ only), never part of the product path.
-    python profiles/eager_gpu_baseline.py"""
+trainers would run on a GPU.  A reported baseline, never part of the product path: it lives under tests/ because only tests/,
+smoke() and bench.py's CPU legs may execute the oracle.
+    python tests/baselines/eager_gpu_baseline.py"""
 import json
 import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 
 import msa_tts_b200 as pkg
