@@ -199,6 +199,20 @@ struct InferAttnParams {
     float* alpha; float* u;           // [B][L], [B] forward-attention state
     const float* wta; const float* bta;
 };
+// LSTMCell of the inference step with TMA tensor-map boxes feeding the tensor cores (infer_lstm_tma.cu); maps are 128-byte
+// CUtensorMap objects (opaque here), built once per msa_infer call
+struct InferLstmTmaLaunch {
+    int B, H, K0, K1;
+    const void* map_x0; const void* map_w0;       // [input | ...] segment: x0 [B][K0], W_ih [4H][K0]
+    const void* map_x1; const void* map_w1;       // recurrent segment: h [B][H], W_hh [4H][H]
+    const float* bias_ih; const float* bias_hh;
+    float* c; float* h1; int ldh1; float* h2; int ldh2;
+    const int* state;
+};
+bool infer_lstm_tma_supported(int H, int K0, int ld0, int K1, int ld1, int sm_count);
+int infer_lstm_tma_map_x(void* map_out, const float* x, int B, int K, int ld);
+int infer_lstm_tma_map_w(void* map_out, const float* W, int H, int K, int ld);
+int k_infer_lstm_tma(const InferLstmTmaLaunch& a, int sm_count, cudaStream_t st);
 int k_init_fwd_attn(float* alpha, float* u, int* win, float* gmax, int B, int L, cudaStream_t st);
 int k_fill_ones_i32(int* p, int n, cudaStream_t st);
 size_t infer_attention_smem(int L, int Ha, int A, int F, int Kl, int E);

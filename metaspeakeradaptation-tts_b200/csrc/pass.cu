@@ -1140,6 +1140,23 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
     const float* Wia = P("decoder.attention_rnn.weight_ih");
     const float* Wid = P("decoder.decoder_rnn.weight_ih");
     unsigned int* counter = reinterpret_cast<unsigned int*>(ints + 8);
+    // TMA path of the two LSTMCells: tensor maps of the (fixed) weight matrices and of the packed / ping-pong input buffers
+    static const bool tma_env = !(getenv("MSA_INFER_TMA") && atoi(getenv("MSA_INFER_TMA")) == 0);
+    const bool use_tma = tma_env && infer_lstm_tma_supported(d.Ha, KA, KA, d.Ha, d.Ha, h->sm_count) &&
+                         infer_lstm_tma_supported(d.Hd, KD, KD, d.Hd, d.Hd, h->sm_count);
+    alignas(64) unsigned char tmaps[10][128];
+    if (use_tma) {
+        MSA_TRY(infer_lstm_tma_map_x(tmaps[0], w.xin_a, B, KA, KA));
+        MSA_TRY(infer_lstm_tma_map_x(tmaps[1], w.ha, B, d.Ha, d.Ha));
+        MSA_TRY(infer_lstm_tma_map_x(tmaps[2], w.ha + (size_t)B * d.Ha, B, d.Ha, d.Ha));
+        MSA_TRY(infer_lstm_tma_map_w(tmaps[3], Wia, d.Ha, KA, KA));
+        MSA_TRY(infer_lstm_tma_map_w(tmaps[4], P("decoder.attention_rnn.weight_hh"), d.Ha, d.Ha, d.Ha));
+        MSA_TRY(infer_lstm_tma_map_x(tmaps[5], w.xin_d, B, KD, KD));
+        MSA_TRY(infer_lstm_tma_map_x(tmaps[6], w.hd, B, d.Hd, d.Hd));
+        MSA_TRY(infer_lstm_tma_map_x(tmaps[7], w.hd + (size_t)B * d.Hd, B, d.Hd, d.Hd));
+        MSA_TRY(infer_lstm_tma_map_w(tmaps[8], Wid, d.Hd, KD, KD));
+        MSA_TRY(infer_lstm_tma_map_w(tmaps[9], P("decoder.decoder_rnn.weight_hh"), d.Hd, d.Hd, d.Hd));
+    }
     auto step = [&](int s, bool first) -> int {
         const int cur = s & 1, nxt = cur ^ 1;
         InferRowsParams rp{};
@@ -1159,7 +1176,15 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
         la.x[1] = w.ha + (size_t)cur * B * d.Ha; la.ldx[1] = d.Ha; la.K[1] = d.Ha; la.W[1] = P("decoder.attention_rnn.weight_hh"); la.ldw[1] = d.Ha;
         la.bias1 = P("decoder.attention_rnn.bias_ih"); la.bias2 = P("decoder.attention_rnn.bias_hh");
         la.c = w.ca; la.h1 = w.ha + (size_t)nxt * B * d.Ha; la.ldh1 = d.Ha; la.h2 = w.xin_d; la.ldh2 = KD;
-        MSA_TRY(k_infer_rows(la, h->sm_count, st));
+        if (use_tma) {
+            InferLstmTmaLaunch ta{};
+            ta.B = B; ta.H = d.Ha; ta.K0 = KA; ta.K1 = d.Ha; ta.map_x0 = tmaps[0]; ta.map_w0 = tmaps[3]; ta.map_x1 = tmaps[1 + cur];
+            ta.map_w1 = tmaps[4]; ta.bias_ih = la.bias1; ta.bias_hh = la.bias2; ta.c = la.c; ta.h1 = la.h1; ta.ldh1 = la.ldh1;
+            ta.h2 = la.h2; ta.ldh2 = la.ldh2; ta.state = state;
+            MSA_TRY(k_infer_lstm_tma(ta, h->sm_count, st));
+        } else {
+            MSA_TRY(k_infer_rows(la, h->sm_count, st));
+        }
         // attention (forward_attn.py:178-219), one CTA per row; writes ctx(t) into the three packed inputs
         InferAttnParams ap{};
         ap.B = B; ap.L = L; ap.Ha = d.Ha; ap.A = d.A; ap.F = d.F; ap.Kl = d.Kl; ap.E = d.E; ap.norm = c.attn_norm; ap.max_steps = max_steps;
@@ -1189,7 +1214,15 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
         ld.x[1] = w.hd + (size_t)cur * B * d.Hd; ld.ldx[1] = d.Hd; ld.K[1] = d.Hd; ld.W[1] = P("decoder.decoder_rnn.weight_hh"); ld.ldw[1] = d.Hd;
         ld.bias1 = P("decoder.decoder_rnn.bias_ih"); ld.bias2 = P("decoder.decoder_rnn.bias_hh");
         ld.c = w.cd; ld.h1 = w.hd + (size_t)nxt * B * d.Hd; ld.ldh1 = d.Hd; ld.h2 = w.xin_p; ld.ldh2 = KP;
-        MSA_TRY(k_infer_rows(ld, h->sm_count, st));
+        if (use_tma) {
+            InferLstmTmaLaunch ta{};
+            ta.B = B; ta.H = d.Hd; ta.K0 = KD; ta.K1 = d.Hd; ta.map_x0 = tmaps[5]; ta.map_w0 = tmaps[8]; ta.map_x1 = tmaps[6 + cur];
+            ta.map_w1 = tmaps[9]; ta.bias_ih = ld.bias1; ta.bias_hh = ld.bias2; ta.c = ld.c; ta.h1 = ld.h1; ta.ldh1 = ld.ldh1;
+            ta.h2 = ld.h2; ta.ldh2 = ld.ldh2; ta.state = state;
+            MSA_TRY(k_infer_lstm_tma(ta, h->sm_count, st));
+        } else {
+            MSA_TRY(k_infer_rows(ld, h->sm_count, st));
+        }
         // projections + stop logic (decoder.py:267-270, 381-395)
         InferRowsParams pp{};
         pp.B = B; pp.state = state; pp.N = d.M + 1; pp.nseg = 1; pp.epi = IR_EPI_BIAS;
