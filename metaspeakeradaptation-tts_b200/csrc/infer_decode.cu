@@ -410,9 +410,11 @@ constexpr int kIaDJ = 4;          // attention dims per lane in the energy phase
 
 struct IaSmem {
     int LHp, FS, FP4, Lc, LcP;
-    size_t in_s, h_s, q_s, v_s, wloc_s, wld4_s, cf_s, e_s, part_s, alpha_s, anew_s, ta_s, total;
+    size_t in_s, h_s, q_s, v_s, wloc_s, wld4_s, cf_s, e_s, part_s, alpha_s, anew_s, ta_s, mem_s, total;
 };
-__host__ __device__ inline IaSmem ia_layout(int L, int Ha, int A, int F, int Kl, int E) {
+// mem_res: the CTA's [L][E/4] tile of the encoder memory is prefetched into shared memory at kernel start
+__host__ __device__ inline bool ia_mem_tile_ok(int E) { return E % 4 == 0 && ((E + kIaCl - 1) / kIaCl) % 4 == 0; }
+__host__ __device__ inline IaSmem ia_layout(int L, int Ha, int A, int F, int Kl, int E, bool mem_res = false) {
     IaSmem s;
     s.Lc = (((L + kIaCl - 1) / kIaCl) + 3) & ~3;          // owned positions per CTA, multiple of 4
     s.LcP = s.Lc + 4;
@@ -433,6 +435,7 @@ __host__ __device__ inline IaSmem ia_layout(int L, int Ha, int A, int F, int Kl,
     s.alpha_s = take((size_t)s.Lc * kIaCl + 4);      // forward attention: alpha(t-1) with a zero in front (the shifted copy)
     s.anew_s = take((size_t)s.Lc * kIaCl);
     s.ta_s = take(64);
+    s.mem_s = take(mem_res ? (size_t)L * ((E + kIaCl - 1) / kIaCl) : 0);
     s.total = o;
     return s;
 }
@@ -461,7 +464,7 @@ __global__ void __launch_bounds__(kIaThreads, 1) ker_infer_attn(InferAttnParams 
     const int t = p.state[0], b = blockIdx.x / kIaCl;
     const int r = (int)cluster_ctarank_();
     const int L = p.L, A = p.A, F = p.F, Kl = p.Kl, Ha = p.Ha, E = p.E, pl = (Kl - 1) / 2;
-    const IaSmem lay = ia_layout(L, Ha, A, F, Kl, E);
+    const IaSmem lay = ia_layout(L, Ha, A, F, Kl, E, p.mem_res != 0);
     const int LHp = lay.LHp, FS = lay.FS, FP4 = lay.FP4, Lc = lay.Lc;
     const int lbeg = r * Lc, lend = min(L, lbeg + Lc);      // owned positions
     float* in_s = sm + lay.in_s;        // [2][LHp]      prev / cum of the whole row with a zero halo of pl in front
@@ -476,27 +479,39 @@ __global__ void __launch_bounds__(kIaThreads, 1) ker_infer_attn(InferAttnParams 
     float* alpha_s = sm + lay.alpha_s + 1;   // [-1..L)    alpha(t-1), alpha_s[-1] = 0
     float* anew_s = sm + lay.anew_s;
     float* ta_s = sm + lay.ta_s;        // [kIaCl] partial transition-agent dots (rank 0), [32..] block-reduction scratch
+    float* mem_s = sm + lay.mem_s;      // [L][Ec]       memory[b][:, owned channels] (prefetched)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     constexpr int NW = kIaThreads / 32;
 
+    // Everything this CTA reads that does not depend on its own progress is requested up front as four cp.async groups, in the
+    // order of first use: h_a' (query projection), location conv weights, location dense weights, the memory tile of the context
+    // phase.  The phases wait for their group only; the loads overlap the phases before them.
+    const int Ec = (E + kIaCl - 1) / kIaCl, e0 = r * Ec, ne = max(0, min(Ec, E - e0));
+    for (int i = threadIdx.x; i < (Ha >> 2); i += kIaThreads) cp_async16(h_s + i * 4, p.h + (size_t)b * p.ldh + i * 4, true);
+    cp_async_commit();
+    for (int i = threadIdx.x; i < (F * 2 * Kl) >> 2; i += kIaThreads) cp_async16(wloc_s + i * 4, p.wloc_t + i * 4, true);
+    cp_async_commit();
+    for (int i = threadIdx.x; i < FP4 * A; i += kIaThreads) cp_async16(wld4_s + i * 4, p.wld4 + i * 4, true);
+    cp_async_commit();
+    if (p.mem_res) {
+        const int E4 = Ec >> 2;
+        for (int i = threadIdx.x; i < L * E4; i += kIaThreads) {
+            const int l = i / E4, c4 = i - l * E4;
+            const bool ok = c4 * 4 < ne;
+            cp_async16(mem_s + (size_t)l * Ec + c4 * 4, ok ? p.memory + ((size_t)b * L + l) * E + e0 + c4 * 4 : p.memory, ok);
+        }
+    }
+    cp_async_commit();
     for (int i = threadIdx.x; i < 2 * LHp; i += kIaThreads) {
         const int c = i / LHp, l = i - c * LHp - pl;
         in_s[i] = (l >= 0 && l < L) ? (c == 0 ? p.prev[(size_t)b * L + l] : p.cum[(size_t)b * L + l]) : 0.f;
     }
-    for (int i = threadIdx.x; i < (Ha >> 2); i += kIaThreads)
-        reinterpret_cast<float4*>(h_s)[i] = *reinterpret_cast<const float4*>(p.h + (size_t)b * p.ldh + i * 4);
     for (int i = threadIdx.x; i < A; i += kIaThreads) v_s[i] = __ldg(p.v + i);
-    for (int i = threadIdx.x; i < F * 2 * Kl; i += kIaThreads) {
-        const int f = i / (2 * Kl), ck = i - f * (2 * Kl);
-        wloc_s[ck * F + f] = __ldg(p.wloc + i);
-    }
-    for (int i = threadIdx.x; i < FP4 * A * 4; i += kIaThreads) {
-        const int fq = i & 3, d = (i >> 2) % A, fc = (i >> 2) / A, f = fc * 4 + fq;
-        wld4_s[i] = f < F ? __ldg(p.wld + (size_t)d * F + f) : 0.f;
-    }
+    for (int i = ((F * 2 * Kl) & ~3) + threadIdx.x; i < F * 2 * Kl; i += kIaThreads) wloc_s[i] = __ldg(p.wloc_t + i);
     for (int i = threadIdx.x; i < lay.LcP * FS; i += kIaThreads) cf_s[i] = 0.f;
     if (p.forward_attn)
         for (int i = threadIdx.x; i <= L; i += kIaThreads) alpha_s[i - 1] = i == 0 ? 0.f : p.alpha[(size_t)b * L + i - 1];
+    cp_async_wait<2>();      // h_a' and the location conv weights have landed (this thread's copies; the barrier covers the rest)
     cluster_sync_();         // staging done; every CTA of the cluster is running (required before remote shared-memory stores)
 
     // ---- query projection (forward_attn.py:125) for the dims d = r (mod kIaCl): two dims per warp pass, 8 loads in flight ----
@@ -507,16 +522,16 @@ __global__ void __launch_bounds__(kIaThreads, 1) ker_infer_attn(InferAttnParams 
         const float4* w0 = reinterpret_cast<const float4*>(p.wq + (size_t)d0 * Ha);
         const float4* w1 = reinterpret_cast<const float4*>(p.wq + (size_t)(two ? d1 : d0) * Ha);
         float a0 = 0.f, a1 = 0.f;
-        for (int k4 = lane; k4 < Ha4; k4 += 128) {
-            float4 r0[4], r1[4];
+        for (int k4 = lane; k4 < Ha4; k4 += 256) {      // 16 independent 128-bit loads in flight per lane
+            float4 r0[8], r1[8];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
+            for (int m = 0; m < 8; ++m) {
                 const int idx = k4 + 32 * m;
                 r0[m] = idx < Ha4 ? __ldg(w0 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
                 r1[m] = (two && idx < Ha4) ? __ldg(w1 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
+            for (int m = 0; m < 8; ++m) {
                 const int idx = k4 + 32 * m;
                 if (idx < Ha4) {
                     const float4 hv = reinterpret_cast<const float4*>(h_s)[idx];
@@ -555,6 +570,7 @@ __global__ void __launch_bounds__(kIaThreads, 1) ker_infer_attn(InferAttnParams 
         for (int j = 0; j < 4; ++j)
             if (l0 + j < L) cf_s[(lo + j) * FS + f] = acc[j];
     }
+    cp_async_wait<1>();      // location dense weights
     cluster_sync_();         // q complete in every CTA (also a CTA barrier: cf_s complete)
     // ---- energies (forward_attn.py:126-131) for the owned positions: warp = 2 positions, lane = attention dims lane + 32 j ----
     const float bv = __ldg(p.bv);
@@ -710,23 +726,38 @@ __global__ void __launch_bounds__(kIaThreads, 1) ker_infer_attn(InferAttnParams 
                 }
         }
     }
+    cp_async_wait<0>();      // memory tile (also before the early return: no copy may land after the CTA has exited)
     if (p.phase == 1) return;      // launch-uniform
     __syncthreads();
     // ---- context (forward_attn.py:217) for the owned memory channels: thread = (channel, one of 8 interleaved position sets) ----
-    const int Ec = (E + kIaCl - 1) / kIaCl, EcP = (Ec + 3) & ~3, e0 = r * Ec, ne = min(Ec, E - e0);
+    const int EcP = (Ec + 3) & ~3;
     for (int it = threadIdx.x; it < 8 * EcP; it += kIaThreads) {
         const int ls = it / EcP, ec = it - ls * EcP;
         float acc = 0.f;
-        if (ec < ne) {
-            const float* mrow = p.memory + (size_t)b * L * E + e0 + ec;
+        if (ec < ne && p.mem_res) {
             float c0 = 0.f, c1 = 0.f;
             int l = ls;
             for (; l + 8 < L; l += 16) {
-                c0 += e_s[l] * __ldg(mrow + (size_t)l * E);
-                c1 += e_s[l + 8] * __ldg(mrow + (size_t)(l + 8) * E);
+                c0 += e_s[l] * mem_s[(size_t)l * Ec + ec];
+                c1 += e_s[l + 8] * mem_s[(size_t)(l + 8) * Ec + ec];
             }
-            if (l < L) c0 += e_s[l] * __ldg(mrow + (size_t)l * E);
+            if (l < L) c0 += e_s[l] * mem_s[(size_t)l * Ec + ec];
             acc = c0 + c1;
+        } else if (ec < ne) {
+            const float* mrow = p.memory + (size_t)b * L * E + e0 + ec;
+            // positions ls, ls + 8, ls + 16, ...: eight independent loads in flight per pass
+            float cacc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cacc[j] = 0.f;
+            for (int l0 = ls; l0 < L; l0 += 64) {
+                float mv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) mv[j] = l0 + 8 * j < L ? __ldg(mrow + (size_t)(l0 + 8 * j) * E) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (l0 + 8 * j < L) cacc[j] += e_s[l0 + 8 * j] * mv[j];
+            }
+            acc = ((cacc[0] + cacc[1]) + (cacc[2] + cacc[3])) + ((cacc[4] + cacc[5]) + (cacc[6] + cacc[7]));
         }
         part_s[it] = acc;
     }
@@ -763,6 +794,26 @@ __global__ void __launch_bounds__(kIaThreads, 1) ker_infer_attn(InferAttnParams 
     }
 }
 
+// wloc [F][2][Kl] -> wloc_t [2*Kl][F];  wld [A][F] -> wld4 [ceil(F/4)][A][4] (zero beyond F): the layouts ker_infer_attn keeps in
+// shared memory, written once per msa_infer call
+__global__ void ker_infer_attn_prep(const float* __restrict__ wloc, const float* __restrict__ wld, float* wloc_t, float* wld4, int F,
+                                    int Kl, int A) {
+    const int FP4 = (F + 3) >> 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < F * 2 * Kl; i += gridDim.x * blockDim.x) {
+        const int f = i / (2 * Kl), ck = i - f * (2 * Kl);
+        wloc_t[ck * F + f] = wloc[i];
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < FP4 * A * 4; i += gridDim.x * blockDim.x) {
+        const int fq = i & 3, d = (i >> 2) % A, fc = (i >> 2) / A, f = fc * 4 + fq;
+        wld4[i] = f < F ? wld[(size_t)d * F + f] : 0.f;
+    }
+}
+int k_infer_attn_prep(const float* wloc, const float* wld, float* wloc_t, float* wld4, int F, int Kl, int A, cudaStream_t st) {
+    ker_infer_attn_prep<<<8, 256, 0, st>>>(wloc, wld, wloc_t, wld4, F, Kl, A);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+
 __global__ void ker_init_fwd_attn(float* alpha, float* u, int* win, float* gmax, int B, int L) {
     // init_forward_attn / init_win_idx (forward_attn.py:85-96): alpha = [1, 1e-7, ...], u = 0.5, win_idx = -1
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * L; i += gridDim.x * blockDim.x) alpha[i] = (i % L) == 0 ? 1.f : 1e-7f;
@@ -779,14 +830,20 @@ int k_init_fwd_attn(float* alpha, float* u, int* win, float* gmax, int B, int L,
     return 0;
 }
 
-size_t infer_attention_smem(int L, int Ha, int A, int F, int Kl, int E) { return sizeof(float) * ia_layout(L, Ha, A, F, Kl, E).total; }
+size_t infer_attention_smem(int L, int Ha, int A, int F, int Kl, int E, bool mem_res) {
+    return sizeof(float) * ia_layout(L, Ha, A, F, Kl, E, mem_res).total;
+}
 
 int k_infer_attention(const InferAttnParams& p, cudaStream_t st) {
     MSA_CHECK(p.A <= 32 * kIaDJ, MSA_E_UNSUPPORTED, "infer attention: attention_dim %d > %d", p.A, 32 * kIaDJ);
     MSA_CHECK(p.Ha % 4 == 0 && p.ldh % 4 == 0 && ((uintptr_t)p.h & 15) == 0 && ((uintptr_t)p.wq & 15) == 0, MSA_E_UNSUPPORTED,
               "infer attention: attention_rnn_dim %d / row stride %d must be multiples of 4", p.Ha, p.ldh);
-    const size_t smem = infer_attention_smem(p.L, p.Ha, p.A, p.F, p.Kl, p.E);
+    InferAttnParams pm = p;
+    pm.mem_res = ia_mem_tile_ok(p.E) && infer_attention_smem(p.L, p.Ha, p.A, p.F, p.Kl, p.E, true) <= 200 * 1024;
+    const size_t smem = infer_attention_smem(p.L, p.Ha, p.A, p.F, p.Kl, p.E, pm.mem_res != 0);
     MSA_CHECK(smem <= 200 * 1024, MSA_E_UNSUPPORTED, "infer attention: text length %d too long for the shared-memory tile", p.L);
+    MSA_CHECK(((uintptr_t)p.wloc_t & 15) == 0 && ((uintptr_t)p.wld4 & 15) == 0 && ((uintptr_t)p.memory & 15) == 0, MSA_E_ARG,
+              "infer attention: prepared weights / memory must be 16-byte aligned");
     if (smem > 48 * 1024) MSA_CUDA(cudaFuncSetAttribute(ker_infer_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     static bool carve_set = false;
     if (!carve_set) {
@@ -807,7 +864,7 @@ int k_infer_attention(const InferAttnParams& p, cudaStream_t st) {
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = 2;
-    MSA_CUDA(cudaLaunchKernelEx(&cfg, ker_infer_attn, p));
+    MSA_CUDA(cudaLaunchKernelEx(&cfg, ker_infer_attn, pm));
     MSA_LAUNCH_CHECK();
     return 0;
 }

@@ -182,8 +182,8 @@ struct InferAttnParams {
     int B, L, Ha, A, F, Kl, E, norm, max_steps;
     const float* h; int ldh;          // [B][ldh] h_a'(t)
     const float* wq;                  // [A][Ha]
-    const float* wloc;
-    const float* wld;
+    const float* wloc_t;              // [2*Kl][F]            location conv weights, transposed (k_infer_attn_prep)
+    const float* wld4;                // [ceil(F/4)][A][4]    location dense weights, blocked (k_infer_attn_prep)
     const float* v; const float* bv;
     const float* pm;
     const float* memory;
@@ -198,6 +198,7 @@ struct InferAttnParams {
     float* gmax;                      // batch-wide maximum of the first step's windowed energies
     float* alpha; float* u;           // [B][L], [B] forward-attention state
     const float* wta; const float* bta;
+    int mem_res;                      // set by k_infer_attention: the memory tile is prefetched into shared memory
 };
 // LSTMCell of the inference step with TMA tensor-map boxes feeding the tensor cores (infer_lstm_tma.cu); maps are 128-byte
 // CUtensorMap objects (opaque here), built once per msa_infer call
@@ -215,8 +216,9 @@ int infer_lstm_tma_map_w(void* map_out, const float* W, int H, int K, int ld);
 int k_infer_lstm_tma(const InferLstmTmaLaunch& a, int sm_count, cudaStream_t st);
 int k_init_fwd_attn(float* alpha, float* u, int* win, float* gmax, int B, int L, cudaStream_t st);
 int k_fill_ones_i32(int* p, int n, cudaStream_t st);
-size_t infer_attention_smem(int L, int Ha, int A, int F, int Kl, int E);
+size_t infer_attention_smem(int L, int Ha, int A, int F, int Kl, int E, bool mem_res);
 int k_infer_attention(const InferAttnParams& p, cudaStream_t st);
+int k_infer_attn_prep(const float* wloc, const float* wld, float* wloc_t, float* wld4, int F, int Kl, int A, cudaStream_t st);
 int k_tm_to_ref_ld(const float* x_tm, float* out, int T, int B, int M, int ld, cudaStream_t st);
 int k_bt_to_ref_ld(const float* x_bt, float* out, int B, int T, int M, int ld, cudaStream_t st);
 

@@ -987,7 +987,8 @@ namespace msa {
     X(xin_a, d.B * (d.Pd + d.E)) X(p1, d.B * d.Pd) X(ha, 2 * d.B * d.Ha) X(ca, d.B * d.Ha)               \
     X(xin_d, d.B * (d.Ha + d.E)) X(hd, 2 * d.B * d.Hd) X(cd, d.B * d.Hd) X(xin_p, d.B * (d.Hd + d.E))    \
     X(mel_raw, d.B * d.M) X(gate_raw, d.B) X(frame, d.B * d.M) X(proj_part, 16 * d.B * (d.M + 1))        \
-    X(prev, d.BL) X(cum, d.BL) X(fa_alpha, d.BL) X(fa_u, d.B + 4) X(mel_tm, (int64_t)d.T * d.B * d.M) X(ints, 64 + d.B)                      \
+    X(prev, d.BL) X(cum, d.BL) X(fa_alpha, d.BL) X(fa_u, d.B + 4) X(attn_wloc_t, 2 * d.Kl * d.F + 4)      \
+    X(attn_wld4, ((d.F + 3) / 4) * d.A * 4) X(mel_tm, (int64_t)d.T * d.B * d.M) X(ints, 64 + d.B)                      \
     X(post_x, 2 * d.BT * d.Cmax) X(post_y, d.BT * d.Cmax) X(post_col, d.BT * d.Kp * d.Cmax)              \
     X(post_w2, (int64_t)d.Cmax * d.Kp * d.Cmax) X(post_bt, d.BT * d.M)
 
@@ -1131,6 +1132,8 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
     int* win = ints + 16;                                   // [2] window index by step parity
     float* gmax = reinterpret_cast<float*>(ints + 18);
     MSA_TRY(k_init_fwd_attn(w.fa_alpha, w.fa_u, win, gmax, B, L, st));
+    MSA_TRY(k_infer_attn_prep(P(at + "location_layer.location_conv1d.weight"), P(at + "location_layer.location_dense.linear_layer.weight"),
+                              w.attn_wloc_t, w.attn_wld4, d.F, d.Kl, d.A, st));
     MSA_CUDA(cudaMemsetAsync(align_out, 0, sizeof(float) * (size_t)B * max_steps * L, st));
     MSA_CUDA(cudaMemsetAsync(mel_post_out, 0, sizeof(float) * (size_t)B * d.M * max_steps, st));
 
@@ -1189,8 +1192,7 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
         InferAttnParams ap{};
         ap.B = B; ap.L = L; ap.Ha = d.Ha; ap.A = d.A; ap.F = d.F; ap.Kl = d.Kl; ap.E = d.E; ap.norm = c.attn_norm; ap.max_steps = max_steps;
         ap.h = w.xin_d; ap.ldh = KD; ap.wq = P(at + "query_layer.linear_layer.weight");
-        ap.wloc = P(at + "location_layer.location_conv1d.weight");
-        ap.wld = P(at + "location_layer.location_dense.linear_layer.weight");
+        ap.wloc_t = w.attn_wloc_t; ap.wld4 = w.attn_wld4;
         ap.v = P(at + "v.linear_layer.weight"); ap.bv = P(at + "v.linear_layer.bias");
         ap.pm = w.pm; ap.memory = w.memory; ap.prev = w.prev; ap.cum = w.cum;
         ap.ctx1 = w.xin_a + d.Pd; ap.ld1 = KA; ap.ctx2 = w.xin_d + d.Ha; ap.ld2 = KD; ap.ctx3 = w.xin_p + d.Hd; ap.ld3 = KP;
