@@ -814,6 +814,150 @@ int k_infer_attn_prep(const float* wloc, const float* wld, float* wloc_t, float*
     return 0;
 }
 
+// =====================================================================================================================
+// Both prenet layers (decoder.py:9-20,366) in ONE launch: a cluster of 8 CTAs per batch tile, CTA r owns the output columns
+// [r*Pc, (r+1)*Pc) of both layers.  Layer 1 = relu(W1 . frame) * mask on the tensor cores (3xTF32), its [32][Pc] slice is written
+// into the layer-2 input tile of ALL eight CTAs through distributed shared memory, one cluster barrier, layer 2 the same way from
+// shared memory, result into the packed attention-LSTM input.  The weights (42 KB per CTA) are requested before the
+// programmatic-dependency wait.  Two separate launches of the generic rows kernel cost ~9 us each for < 1 us of work.
+constexpr int kPnThreads = 256;
+constexpr int kPnCl = 8;
+struct PnSmem {
+    int S1, S2, Pc;
+    size_t x1, w1, p1, w2, total;
+};
+__host__ __device__ inline PnSmem pn_layout(int M, int Pd) {
+    PnSmem s;
+    s.S1 = ((M + 15) & ~15) + 4;
+    s.S2 = ((Pd + 15) & ~15) + 4;
+    s.Pc = (Pd + kPnCl - 1) / kPnCl;
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o += (n + 3) & ~(size_t)3; return r; };
+    s.x1 = take((size_t)32 * s.S1);
+    s.w1 = take((size_t)32 * s.S1);
+    s.p1 = take((size_t)32 * s.S2);
+    s.w2 = take((size_t)32 * s.S2);
+    s.total = o;
+    return s;
+}
+// one warp = one 16 x 8 tile of D[weight row][batch row] = sum_k W[row][k] x[b][k], two k8 steps per iteration
+__device__ __forceinline__ void pn_tile(float (&acc)[4], const float* Ws, const float* Xs, int S, int K16, int mt, int nt, int lane) {
+    const int mi = lane >> 3, mr = lane & 7;
+    const float* ap = Ws + (size_t)(mt * 16 + (mi & 1) * 8 + mr) * S + (mi >> 1) * 4;      // {rows 0-7, 8-15} x {k 0-3, 4-7}
+    const float* bp = Xs + (size_t)(nt * 8 + mr) * S + mi * 4;                            // k 0-3, 4-7, 8-11, 12-15
+    for (int k = 0; k < K16; k += 16) {
+        unsigned b4[4], a4[4], ah[4], al[4], bh[4], bl[4];
+        ldsm_x4(b4, bp + k);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_tf32(b4[i], bh[i], bl[i]);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            ldsm_x4(a4, ap + k + half * 8);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_tf32(a4[i], ah[i], al[i]);
+            mma_tf32(acc, al, bh[2 * half], bh[2 * half + 1]);
+            mma_tf32(acc, ah, bl[2 * half], bl[2 * half + 1]);
+            mma_tf32(acc, ah, bh[2 * half], bh[2 * half + 1]);
+        }
+    }
+}
+__global__ void __launch_bounds__(kPnThreads, 1) ker_infer_prenet(InferPrenetParams p) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    extern __shared__ __align__(16) float sm[];
+    const int M = p.M, Pd = p.Pd;
+    const PnSmem lay = pn_layout(M, Pd);
+    const int S1 = lay.S1, S2 = lay.S2, Pc = lay.Pc;
+    float* X1 = sm + lay.x1;      // [32][S1] frame rows (zero beyond B / M)
+    float* W1 = sm + lay.w1;      // [32][S1] rows of W1 owned by this CTA (zero beyond Pc / M)
+    float* P1 = sm + lay.p1;      // [32][S2] layer-1 output of the whole cluster (zero beyond Pd)
+    float* W2 = sm + lay.w2;      // [32][S2] rows of W2 owned by this CTA
+    const int r = (int)cluster_ctarank_(), lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int b0 = blockIdx.y * 32, nb = min(32, p.B - b0);
+    const int c0 = r * Pc, nc = max(0, min(Pc, Pd - c0));
+    const int M4 = (S1 - 4) >> 2, P4 = (S2 - 4) >> 2;
+    // weights first (independent of the previous kernel), zero-filled beyond the owned rows / K
+    for (int i = threadIdx.x; i < 32 * M4; i += kPnThreads) {
+        const int row = i / M4, c4 = i - row * M4;
+        const bool ok = row < nc && c4 * 4 < M;
+        cp_async16(W1 + (size_t)row * S1 + c4 * 4, ok ? p.w1 + (size_t)(c0 + row) * M + c4 * 4 : p.w1, ok);
+    }
+    for (int i = threadIdx.x; i < 32 * P4; i += kPnThreads) {
+        const int row = i / P4, c4 = i - row * P4;
+        const bool ok = row < nc && c4 * 4 < Pd;
+        cp_async16(W2 + (size_t)row * S2 + c4 * 4, ok ? p.w2 + (size_t)(c0 + row) * Pd + c4 * 4 : p.w2, ok);
+    }
+    cp_async_commit();
+    for (int i = threadIdx.x; i < 32 * S2; i += kPnThreads) P1[i] = 0.f;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const bool done = p.state[1] != 0;      // launch-uniform; no early return before the cluster barriers / pending copies
+    const int t = p.state[0];
+    for (int i = threadIdx.x; i < 32 * M4; i += kPnThreads) {
+        const int row = i / M4, c4 = i - row * M4;
+        const bool ok = !done && row < nb && c4 * 4 < M;
+        cp_async16(X1 + (size_t)row * S1 + c4 * 4, ok ? p.frame + (size_t)(b0 + row) * M + c4 * 4 : p.frame, ok);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    cluster_sync_();          // tiles complete; every CTA of the cluster is running (remote stores below)
+    if (done) return;
+    const int mt = w & 1, nt = w >> 1, g = lane >> 2, tq = lane & 3;      // 8 warps = 2 x 4 output tiles
+    // ---- layer 1 ----
+    {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        pn_tile(acc, W1, X1, S1, S1 - 4, mt, nt, lane);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int col = mt * 16 + g + (i >> 1) * 8, b = nt * 8 + 2 * tq + (i & 1);      // local column, batch row
+            if (col < nc && b < nb) {
+                const uint8_t mk = p.mask[(((size_t)t * 2 + 0) * p.B + b0 + b) * Pd + c0 + col];
+                const float v = mk ? fmaxf(acc[i], 0.f) * 2.f : 0.f;
+#pragma unroll
+                for (int dst = 0; dst < kPnCl; ++dst) st_cluster(P1 + (size_t)b * S2 + c0 + col, dst, v);
+            }
+        }
+    }
+    cluster_sync_();          // the whole layer-1 output is in every CTA
+    // ---- layer 2 ----
+    {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        pn_tile(acc, W2, P1, S2, S2 - 4, mt, nt, lane);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int col = mt * 16 + g + (i >> 1) * 8, b = nt * 8 + 2 * tq + (i & 1);
+            if (col < nc && b < nb) {
+                const uint8_t mk = p.mask[(((size_t)t * 2 + 1) * p.B + b0 + b) * Pd + c0 + col];
+                p.out[(size_t)(b0 + b) * p.ldo + c0 + col] = mk ? fmaxf(acc[i], 0.f) * 2.f : 0.f;
+            }
+        }
+    }
+}
+bool infer_prenet_supported(int M, int Pd) { return M % 4 == 0 && Pd % 4 == 0 && (Pd + kPnCl - 1) / kPnCl <= 32; }
+int k_infer_prenet(const InferPrenetParams& p, cudaStream_t st) {
+    MSA_CHECK(infer_prenet_supported(p.M, p.Pd), MSA_E_UNSUPPORTED, "infer prenet: n_mel %d / prenet_dim %d", p.M, p.Pd);
+    MSA_CHECK(((uintptr_t)p.w1 & 15) == 0 && ((uintptr_t)p.w2 & 15) == 0 && ((uintptr_t)p.frame & 15) == 0, MSA_E_ARG,
+              "infer prenet: operands must be 16-byte aligned");
+    const size_t smem = sizeof(float) * pn_layout(p.M, p.Pd).total;
+    MSA_CHECK(smem <= 200 * 1024, MSA_E_UNSUPPORTED, "infer prenet: prenet_dim %d too large for the shared-memory tiles", p.Pd);
+    if (smem > 48 * 1024) MSA_CUDA(cudaFuncSetAttribute(ker_infer_prenet, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(kPnCl, (p.B + 31) / 32);
+    cfg.blockDim = dim3(kPnThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = kPnCl;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 2;
+    MSA_CUDA(cudaLaunchKernelEx(&cfg, ker_infer_prenet, p));
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+
 __global__ void ker_init_fwd_attn(float* alpha, float* u, int* win, float* gmax, int B, int L) {
     // init_forward_attn / init_win_idx (forward_attn.py:85-96): alpha = [1, 1e-7, ...], u = 0.5, win_idx = -1
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * L; i += gridDim.x * blockDim.x) alpha[i] = (i % L) == 0 ? 1.f : 1e-7f;

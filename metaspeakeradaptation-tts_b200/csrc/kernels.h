@@ -214,6 +214,17 @@ bool infer_lstm_tma_supported(int H, int K0, int ld0, int K1, int ld1, int sm_co
 int infer_lstm_tma_map_x(void* map_out, const float* x, int B, int K, int ld);
 int infer_lstm_tma_map_w(void* map_out, const float* W, int H, int K, int ld);
 int k_infer_lstm_tma(const InferLstmTmaLaunch& a, int sm_count, cudaStream_t st);
+// both prenet layers in one cluster launch (infer_decode.cu)
+struct InferPrenetParams {
+    int B, M, Pd;
+    const float* frame;               // [B][M] previous mel frame
+    const float* w1; const float* w2; // [Pd][M], [Pd][Pd]
+    const uint8_t* mask;              // [steps][2][B][Pd]
+    float* out; int ldo;              // packed attention-LSTM input [B][ldo], first Pd columns
+    const int* state;
+};
+bool infer_prenet_supported(int M, int Pd);
+int k_infer_prenet(const InferPrenetParams& p, cudaStream_t st);
 int k_init_fwd_attn(float* alpha, float* u, int* win, float* gmax, int B, int L, cudaStream_t st);
 int k_fill_ones_i32(int* p, int n, cudaStream_t st);
 size_t infer_attention_smem(int L, int Ha, int A, int F, int Kl, int E, bool mem_res);

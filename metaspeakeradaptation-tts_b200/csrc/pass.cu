@@ -1162,16 +1162,25 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
     }
     auto step = [&](int s, bool first) -> int {
         const int cur = s & 1, nxt = cur ^ 1;
-        InferRowsParams rp{};
-        rp.B = B; rp.state = state;
-        // prenet, dropout always on (decoder.py:9-20,366)
-        rp.N = d.Pd; rp.nseg = 1; rp.epi = IR_EPI_RELU_DROP; rp.mask = prenet_masks;
-        rp.x[0] = w.frame; rp.ldx[0] = d.M; rp.K[0] = d.M; rp.W[0] = P("decoder.prenet.layers.0.linear_layer.weight"); rp.ldw[0] = d.M;
-        rp.out = w.p1; rp.ldo = d.Pd; rp.mask_layer = 0;
-        MSA_TRY(k_infer_rows(rp, h->sm_count, st));
-        rp.x[0] = w.p1; rp.ldx[0] = d.Pd; rp.K[0] = d.Pd; rp.W[0] = P("decoder.prenet.layers.1.linear_layer.weight"); rp.ldw[0] = d.Pd;
-        rp.out = w.xin_a; rp.ldo = KA; rp.mask_layer = 1;
-        MSA_TRY(k_infer_rows(rp, h->sm_count, st));
+        // prenet, dropout always on (decoder.py:9-20,366): both layers in one cluster launch
+        static const bool pn_env = !(getenv("MSA_INFER_PRENET") && atoi(getenv("MSA_INFER_PRENET")) == 0);
+        if (pn_env && infer_prenet_supported(d.M, d.Pd)) {
+            InferPrenetParams pn{};
+            pn.B = B; pn.M = d.M; pn.Pd = d.Pd; pn.frame = w.frame; pn.w1 = P("decoder.prenet.layers.0.linear_layer.weight");
+            pn.w2 = P("decoder.prenet.layers.1.linear_layer.weight"); pn.mask = prenet_masks; pn.out = w.xin_a; pn.ldo = KA;
+            pn.state = state;
+            MSA_TRY(k_infer_prenet(pn, st));
+        } else {
+            InferRowsParams rp{};
+            rp.B = B; rp.state = state;
+            rp.N = d.Pd; rp.nseg = 1; rp.epi = IR_EPI_RELU_DROP; rp.mask = prenet_masks;
+            rp.x[0] = w.frame; rp.ldx[0] = d.M; rp.K[0] = d.M; rp.W[0] = P("decoder.prenet.layers.0.linear_layer.weight"); rp.ldw[0] = d.M;
+            rp.out = w.p1; rp.ldo = d.Pd; rp.mask_layer = 0;
+            MSA_TRY(k_infer_rows(rp, h->sm_count, st));
+            rp.x[0] = w.p1; rp.ldx[0] = d.Pd; rp.K[0] = d.Pd; rp.W[0] = P("decoder.prenet.layers.1.linear_layer.weight"); rp.ldw[0] = d.Pd;
+            rp.out = w.xin_a; rp.ldo = KA; rp.mask_layer = 1;
+            MSA_TRY(k_infer_rows(rp, h->sm_count, st));
+        }
         // attention LSTMCell on [prenet; ctx(t-1)] (decoder.py:253-255)
         InferRowsParams la{};
         la.B = B; la.state = state; la.N = 4 * d.Ha; la.H = d.Ha; la.nseg = 2; la.epi = IR_EPI_LSTM;
