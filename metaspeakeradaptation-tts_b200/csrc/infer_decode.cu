@@ -958,6 +958,137 @@ int k_infer_prenet(const InferPrenetParams& p, cudaStream_t st) {
     return 0;
 }
 
+// =====================================================================================================================
+// Mel / gate projection + stop logic (decoder.py:267-270, 381-395) in one 8-CTA cluster: CTA r multiplies the K slice
+// [r*Ks, (r+1)*Ks) of [h_d; ctx] with the same slice of all N = n_mel + 1 weight rows (3xTF32 mma.sync), pushes the partial
+// rows [j*Rc, (j+1)*Rc) to CTA j over distributed shared memory (reduce-scatter), and after one cluster barrier CTA j sums its
+// rows in a fixed order, adds the bias and writes the mel frame (output + next prenet input); the CTA that owns the gate row
+// runs the stop logic.  The generic rows kernel streams ALL of x through each of its 21 CTAs (17.8 us for 0.3 MFLOP per row).
+constexpr int kPjThreads = 256;
+constexpr int kPjCl = 8;
+constexpr int kPjMT = 6;          // 16-row tiles of weight rows: N <= 96
+struct PjSmem {
+    int S, Ks, Rc;
+    size_t x, w, part, total;
+};
+__host__ __device__ inline PjSmem pj_layout(int N, int K) {
+    PjSmem s;
+    s.Ks = (((K + kPjCl - 1) / kPjCl) + 15) & ~15;
+    s.S = s.Ks + 4;
+    s.Rc = (N + kPjCl - 1) / kPjCl;
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o += (n + 3) & ~(size_t)3; return r; };
+    s.x = take((size_t)32 * s.S);
+    s.w = take((size_t)16 * kPjMT * s.S);
+    s.part = take((size_t)kPjCl * s.Rc * 32);
+    s.total = o;
+    return s;
+}
+__global__ void __launch_bounds__(kPjThreads, 1) ker_infer_proj(InferProjParams p) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    extern __shared__ __align__(16) float sm[];
+    __shared__ int any_s;
+    const int N = p.M + 1, K = p.K;
+    const PjSmem lay = pj_layout(N, K);
+    const int S = lay.S, Ks = lay.Ks, Rc = lay.Rc;
+    float* Xs = sm + lay.x;          // [32][S]      K slice of [h_d; ctx] (zero beyond B / K)
+    float* Ws = sm + lay.w;          // [96][S]      K slice of the N weight rows (zero beyond N / K)
+    float* part = sm + lay.part;     // [8][Rc][32]  partial sums of the owned rows from every CTA of the cluster
+    const int r = (int)cluster_ctarank_(), lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int k0 = r * Ks, kn = max(0, min(Ks, K - k0)), K4 = Ks >> 2;
+    for (int i = threadIdx.x; i < 16 * kPjMT * K4; i += kPjThreads) {
+        const int row = i / K4, c4 = i - row * K4;
+        const bool ok = row < N && c4 * 4 < kn;
+        const float* src = row < p.M ? p.wp + (size_t)row * K : p.wg;      // rows 0..M-1: mel projection, row M: gate layer
+        cp_async16(Ws + (size_t)row * S + c4 * 4, ok ? src + k0 + c4 * 4 : p.wp, ok);
+    }
+    cp_async_commit();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const bool done = p.state[1] != 0;      // launch-uniform
+    const int t = p.state[0];
+    for (int i = threadIdx.x; i < 32 * K4; i += kPjThreads) {
+        const int row = i / K4, c4 = i - row * K4;
+        const bool ok = !done && row < p.B && c4 * 4 < kn;
+        cp_async16(Xs + (size_t)row * S + c4 * 4, ok ? p.x + (size_t)row * p.ldx + k0 + c4 * 4 : p.x, ok);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    cluster_sync_();
+    if (done) return;
+    // 8 warps: n-tile = w & 3, m-tiles (w >> 2), (w >> 2) + 2, (w >> 2) + 4
+    const int nt = w & 3, g = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int mt = (w >> 2) + 2 * j;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        pn_tile(acc, Ws, Xs, S, Ks, mt, nt, lane);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = mt * 16 + g + (i >> 1) * 8, b = nt * 8 + 2 * tq + (i & 1);
+            if (row < N) st_cluster(part + ((size_t)r * Rc + row % Rc) * 32 + b, row / Rc, acc[i]);
+        }
+    }
+    cluster_sync_();          // every partial of the owned rows has arrived
+    if (threadIdx.x == 0) any_s = 0;
+    __syncthreads();
+    const int row0 = r * Rc;
+    bool gate_owner = false;
+    for (int i = threadIdx.x; i < Rc * 32; i += kPjThreads) {
+        const int rl = i >> 5, b = i & 31, row = row0 + rl;
+        if (row >= N || b >= p.B) continue;
+        float v = 0.f;
+#pragma unroll
+        for (int q = 0; q < kPjCl; ++q) v += part[((size_t)q * Rc + rl) * 32 + b];
+        if (row < p.M) {
+            v += p.bp[row];
+            p.mel_tm[((size_t)t * p.B + b) * p.M + row] = v;
+            p.frame[(size_t)b * p.M + row] = v;
+        } else {
+            // stop gate (decoder.py:381-395): dec = sigmoid(gate) <= threshold; not_finished *= dec; mel_lengths += not_finished
+            v += p.bg[0];
+            const int dec = (1.f / (1.f + expf(-v))) <= p.threshold ? 1 : 0;
+            const int nf = p.not_finished[b] * dec;
+            p.not_finished[b] = nf;
+            p.mel_lengths[b] += nf;
+            if (nf) atomicOr(&any_s, 1);
+        }
+    }
+    if (row0 <= p.M && p.M < row0 + Rc) gate_owner = true;
+    __syncthreads();
+    if (gate_owner && threadIdx.x == 0) {
+        p.state_rw[2] = t + 1;
+        if ((p.early && !any_s) || t + 1 >= p.max_steps) p.state_rw[1] = 1;
+        p.state_rw[0] = t + 1;
+    }
+}
+bool infer_proj_supported(int B, int M, int K, int ldx) {
+    return B <= 32 && M + 1 <= 16 * kPjMT && K % 4 == 0 && ldx % 4 == 0 && sizeof(float) * pj_layout(M + 1, K).total <= 200 * 1024;
+}
+int k_infer_proj(const InferProjParams& p, cudaStream_t st) {
+    MSA_CHECK(infer_proj_supported(p.B, p.M, p.K, p.ldx), MSA_E_UNSUPPORTED, "infer proj: B %d, n_mel %d, K %d", p.B, p.M, p.K);
+    MSA_CHECK(((uintptr_t)p.wp & 15) == 0 && ((uintptr_t)p.wg & 15) == 0 && ((uintptr_t)p.x & 15) == 0, MSA_E_ARG,
+              "infer proj: operands must be 16-byte aligned");
+    const size_t smem = sizeof(float) * pj_layout(p.M + 1, p.K).total;
+    if (smem > 48 * 1024) MSA_CUDA(cudaFuncSetAttribute(ker_infer_proj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(kPjCl);
+    cfg.blockDim = dim3(kPjThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = kPjCl;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 2;
+    MSA_CUDA(cudaLaunchKernelEx(&cfg, ker_infer_proj, p));
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+
 __global__ void ker_init_fwd_attn(float* alpha, float* u, int* win, float* gmax, int B, int L) {
     // init_forward_attn / init_win_idx (forward_attn.py:85-96): alpha = [1, 1e-7, ...], u = 0.5, win_idx = -1
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * L; i += gridDim.x * blockDim.x) alpha[i] = (i % L) == 0 ? 1.f : 1e-7f;

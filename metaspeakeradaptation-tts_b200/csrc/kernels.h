@@ -225,6 +225,18 @@ struct InferPrenetParams {
 };
 bool infer_prenet_supported(int M, int Pd);
 int k_infer_prenet(const InferPrenetParams& p, cudaStream_t st);
+// mel / gate projection + stop logic in one cluster launch (infer_decode.cu), B <= 32
+struct InferProjParams {
+    int B, M, K;                      // batch rows, n_mel, columns of [h_d; ctx]
+    const float* x; int ldx;          // [B][ldx]
+    const float* wp; const float* bp; // linear_projection [M][K], [M]
+    const float* wg; const float* bg; // gate_layer [1][K], [1]
+    float* mel_tm; float* frame; int* not_finished; int* mel_lengths;
+    const int* state; int* state_rw;
+    int early, max_steps; float threshold;
+};
+bool infer_proj_supported(int B, int M, int K, int ldx);
+int k_infer_proj(const InferProjParams& p, cudaStream_t st);
 int k_init_fwd_attn(float* alpha, float* u, int* win, float* gmax, int B, int L, cudaStream_t st);
 int k_fill_ones_i32(int* p, int n, cudaStream_t st);
 size_t infer_attention_smem(int L, int Ha, int A, int F, int Kl, int E, bool mem_res);

@@ -1235,6 +1235,17 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
             MSA_TRY(k_infer_rows(ld, h->sm_count, st));
         }
         // projections + stop logic (decoder.py:267-270, 381-395)
+        static const bool pj_env = !(getenv("MSA_INFER_PROJ") && atoi(getenv("MSA_INFER_PROJ")) == 0);
+        if (pj_env && infer_proj_supported(B, d.M, KP, KP)) {
+            InferProjParams pj{};
+            pj.B = B; pj.M = d.M; pj.K = KP; pj.x = w.xin_p; pj.ldx = KP;
+            pj.wp = P("decoder.linear_projection.linear_layer.weight"); pj.bp = P("decoder.linear_projection.linear_layer.bias");
+            pj.wg = P("decoder.gate_layer.linear_layer.weight"); pj.bg = P("decoder.gate_layer.linear_layer.bias");
+            pj.mel_tm = w.mel_tm; pj.frame = w.frame; pj.not_finished = not_finished; pj.mel_lengths = mel_lengths_out;
+            pj.state = state; pj.state_rw = state; pj.early = c.early_stopping; pj.max_steps = max_steps; pj.threshold = c.gate_threshold;
+            MSA_TRY(k_infer_proj(pj, st));
+            return 0;
+        }
         InferRowsParams pp{};
         pp.B = B; pp.state = state; pp.N = d.M + 1; pp.nseg = 1; pp.epi = IR_EPI_BIAS;
         pp.x[0] = w.xin_p; pp.ldx[0] = KP; pp.K[0] = KP; pp.W[0] = P("decoder.linear_projection.linear_layer.weight"); pp.ldw[0] = KP;
