@@ -204,6 +204,7 @@ struct InferAttnParams {
 // CUtensorMap objects (opaque here), built once per msa_infer call
 struct InferLstmTmaLaunch {
     int B, H, K0, K1;
+    int tf32;                                      // 1: plain TF32 products (GEMM policy 2), 0: 3xTF32 (fp32-accurate)
     const void* map_x0; const void* map_w0;       // [input | ...] segment: x0 [B][K0], W_ih [4H][K0]
     const void* map_x1; const void* map_w1;       // recurrent segment: h [B][H], W_hh [4H][H]
     const float* bias_ih; const float* bias_hh;

@@ -1190,7 +1190,7 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
         la.c = w.ca; la.h1 = w.ha + (size_t)nxt * B * d.Ha; la.ldh1 = d.Ha; la.h2 = w.xin_d; la.ldh2 = KD;
         if (use_tma) {
             InferLstmTmaLaunch ta{};
-            ta.B = B; ta.H = d.Ha; ta.K0 = KA; ta.K1 = d.Ha; ta.map_x0 = tmaps[0]; ta.map_w0 = tmaps[3]; ta.map_x1 = tmaps[1 + cur];
+            ta.B = B; ta.H = d.Ha; ta.tf32 = c.gemm_tf32 >= 2; ta.K0 = KA; ta.K1 = d.Ha; ta.map_x0 = tmaps[0]; ta.map_w0 = tmaps[3]; ta.map_x1 = tmaps[1 + cur];
             ta.map_w1 = tmaps[4]; ta.bias_ih = la.bias1; ta.bias_hh = la.bias2; ta.c = la.c; ta.h1 = la.h1; ta.ldh1 = la.ldh1;
             ta.h2 = la.h2; ta.ldh2 = la.ldh2; ta.state = state;
             MSA_TRY(k_infer_lstm_tma(ta, h->sm_count, st));
@@ -1227,7 +1227,7 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
         ld.c = w.cd; ld.h1 = w.hd + (size_t)nxt * B * d.Hd; ld.ldh1 = d.Hd; ld.h2 = w.xin_p; ld.ldh2 = KP;
         if (use_tma) {
             InferLstmTmaLaunch ta{};
-            ta.B = B; ta.H = d.Hd; ta.K0 = KD; ta.K1 = d.Hd; ta.map_x0 = tmaps[5]; ta.map_w0 = tmaps[8]; ta.map_x1 = tmaps[6 + cur];
+            ta.B = B; ta.H = d.Hd; ta.tf32 = c.gemm_tf32 >= 2; ta.K0 = KD; ta.K1 = d.Hd; ta.map_x0 = tmaps[5]; ta.map_w0 = tmaps[8]; ta.map_x1 = tmaps[6 + cur];
             ta.map_w1 = tmaps[9]; ta.bias_ih = ld.bias1; ta.bias_hh = ld.bias2; ta.c = ld.c; ta.h1 = ld.h1; ta.ldh1 = ld.ldh1;
             ta.h2 = ld.h2; ta.ldh2 = ld.ldh2; ta.state = state;
             MSA_TRY(k_infer_lstm_tma(ta, h->sm_count, st));

@@ -117,6 +117,51 @@ def test_infer_default_dims_vs_oracle(B, L, attn):
     assert rel(post, o_post) < TOL and rel(align, o_align) < TOL, (rel(post, o_post), rel(align, o_align))
 
 
+def test_infer_long_horizon_default_dims():
+    """150 free-running steps at the default dimensions: the tensor-core products of the decoder step are 3xTF32 (fp32-accurate),
+    so the error against the fp32 oracle must not grow with the horizon (a single-TF32 step would drift beyond the tolerance)."""
+    from msa_tts_b200.engine import Engine
+    B, L, steps = 2, 40, 150
+    cfg = pkg.default_params()
+    cfg["max_decoder_steps"] = steps
+    cfg["decoder_no_early_stopping"] = True
+    eng = Engine(cfg)
+    P = synth.init_params(cfg, 8)
+    _, inp, inp_len, _, _, _, spk, _ = synth.make_batch(cfg, B, 8, L, 91)
+    stats = infer_stats(P, cfg, 8)
+    pm = synth.make_infer_masks(cfg, B, steps, 92)
+    post, lens, align = eng.infer(eng.flat_from_dict(P), eng.bn_from_dict(stats), inp, inp_len, spk, pm, max_steps=steps)
+    torch.cuda.synchronize()
+    o_post, o_lens, o_align = OM.infer(P, cfg, inp, inp_len, spk, pm, stats)
+    assert post.shape == o_post.shape and torch.equal(lens.cpu(), o_lens)
+    first, last = slice(0, 30), slice(steps - 30, steps)
+    e_first, e_last = rel(post[:, :, first], o_post[:, :, first]), rel(post[:, :, last], o_post[:, :, last])
+    print(f"long horizon: rel err first 30 steps {e_first:.2e}, last 30 steps {e_last:.2e}, alignments {rel(align, o_align):.2e}")
+    assert rel(post, o_post) < TOL and rel(align, o_align) < TOL and e_last < TOL
+
+
+def test_infer_tf32_policy_within_stated_tolerance():
+    """GEMM policy 2 ("TF32 everywhere"): the decoder LSTMCells use plain TF32 products.  north_star tolerance for a TF32 path:
+    rel 1e-3 on the mel outputs; mel_lengths / number of steps stay bit-exact."""
+    from msa_tts_b200.engine import Engine
+    B, L, steps = 4, 48, 60
+    cfg = pkg.default_params()
+    cfg["max_decoder_steps"] = steps
+    cfg["decoder_no_early_stopping"] = True
+    eng = Engine(cfg, gemm_tf32=2)
+    P = synth.init_params(cfg, 9)
+    _, inp, inp_len, _, _, _, spk, _ = synth.make_batch(cfg, B, 8, L, 93)
+    stats = infer_stats(P, cfg, 9)
+    pm = synth.make_infer_masks(cfg, B, steps, 94)
+    post, lens, align = eng.infer(eng.flat_from_dict(P), eng.bn_from_dict(stats), inp, inp_len, spk, pm, max_steps=steps)
+    torch.cuda.synchronize()
+    o_post, o_lens, o_align = OM.infer(P, cfg, inp, inp_len, spk, pm, stats)
+    assert post.shape == o_post.shape and torch.equal(lens.cpu(), o_lens)
+    e = rel(post, o_post)
+    print(f"tf32 policy: rel err mel_post {e:.2e}, alignments {rel(align, o_align):.2e}")
+    assert 1e-6 < e < 1e-3 and rel(align, o_align) < 1e-3      # (> 1e-6: the TF32 path really ran)
+
+
 def test_infer_graph_and_direct_launch_agree():
     """The CUDA-graph replay of the decoder step and plain per-step launches are the same computation."""
     (post, lens, align), _, _ = _run("small_infer")
