@@ -117,6 +117,39 @@ def test_infer_default_dims_vs_oracle(B, L, attn):
     assert rel(post, o_post) < TOL and rel(align, o_align) < TOL, (rel(post, o_post), rel(align, o_align))
 
 
+def test_infer_more_than_32_rows_fails_loudly():
+    """One msa_infer call takes at most 32 rows (the persistent encoder BiLSTM keeps one batch tile resident; BASELINE configs[4]
+    is B = 32): larger batches are split by the caller, and the library says so instead of computing something else."""
+    from msa_tts_b200.engine import Engine
+    from oracle.gen_cases import _infer
+    cfg = _infer()
+    eng = Engine(cfg)
+    P = synth.init_params(cfg, 5)
+    _, inp, inp_len, _, _, _, spk, _ = synth.make_batch(cfg, 40, 8, 9, 105)
+    pm = synth.make_infer_masks(cfg, 40, 8, 305)
+    with pytest.raises(RuntimeError, match="batch 40"):
+        eng.infer(eng.flat_from_dict(P), eng.new_bn_stats(), inp, inp_len, spk, pm, max_steps=8)
+
+
+@pytest.mark.parametrize("B,L,early", [(32, 11, False), (17, 23, True), (1, 7, False)])
+def test_infer_batch_shapes_small_model(B, L, early):
+    """A full batch tile, a ragged one with early stopping, and a single row -- small model, vs the oracle."""
+    from msa_tts_b200.engine import Engine
+    from oracle.gen_cases import _infer
+    cfg, seed, steps = _infer(early=early, thr=0.62), 61, 20
+    cfg["max_decoder_steps"] = steps
+    eng = Engine(cfg)
+    P = synth.init_params(cfg, seed)
+    _, inp, inp_len, _, _, _, spk, _ = synth.make_batch(cfg, B, 8, L, seed + 100)
+    stats = infer_stats(P, cfg, seed)
+    pm = synth.make_infer_masks(cfg, B, steps, seed + 300)
+    post, lens, align = eng.infer(eng.flat_from_dict(P), eng.bn_from_dict(stats), inp, inp_len, spk, pm, max_steps=steps)
+    torch.cuda.synchronize()
+    o_post, o_lens, o_align = OM.infer(P, cfg, inp, inp_len, spk, pm, stats)
+    assert post.shape == o_post.shape and torch.equal(lens.cpu(), o_lens)
+    assert rel(post, o_post) < TOL and rel(align, o_align) < TOL
+
+
 def test_infer_long_horizon_default_dims():
     """150 free-running steps at the default dimensions: the tensor-core products of the decoder step are 3xTF32 (fp32-accurate),
     so the error against the fp32 oracle must not grow with the horizon (a single-TF32 step would drift beyond the tolerance)."""
