@@ -129,15 +129,19 @@ int k_col2im(const float* dcol, float* dx, int B, int T, int C, int K, cudaStrea
 int k_conv_w_pack(const float* w, float* w2, int Co, int Ci, int K, cudaStream_t st);
 int k_conv_w_unpack_grad(const float* dw2, float* gw, int Co, int Ci, int K, float scale, int accumulate, cudaStream_t st);
 int k_fill_rows(float* y, const float* b1, const float* b2, int64_t rows, int N, cudaStream_t st);
-int k_colsum(const float* x, int64_t rows, int N, int ld, float* out, float scale, int accumulate, float* out2, cudaStream_t st);
-int k_bn_stats(const float* y, int64_t rows, int C, float* mean, float* invstd, float* running, int Cpad, cudaStream_t st);
+// Reduction scratch (`red_scr`, may be null = single-chunk reductions): kRedTickets zero-initialised uint tickets followed by
+// kRedChunks x kRedCols floats of partials; shared by the column reductions of one stream (they run back to back).
+constexpr int kRedTickets = 256, kRedChunks = 16, kRedCols = 8192;
+constexpr int64_t kRedScrFloats = kRedTickets + (int64_t)kRedChunks * kRedCols;
+int k_colsum(const float* x, int64_t rows, int N, int ld, float* out, float scale, int accumulate, float* out2, float* red_scr, cudaStream_t st);
+int k_bn_stats(const float* y, int64_t rows, int C, float* mean, float* invstd, float* running, int Cpad, float* red_scr, cudaStream_t st);
 int k_bn_eval_stats(const float* running, int C, int Cpad, float* mean, float* invstd, cudaStream_t st);
 // act: 0 none, 1 relu, 2 tanh
 int k_bn_act_drop_fwd(const float* y, const float* mean, const float* invstd, const float* gamma, const float* beta,
                       const uint8_t* mask, float drop_scale, int act, float* out, int64_t rows, int C, cudaStream_t st);
 int k_bn_act_drop_bwd(const float* dout, const float* y, const float* mean, const float* invstd, const float* gamma,
                       const float* beta, const uint8_t* mask, float drop_scale, int act, float* dy, float* ggamma,
-                      float* gbeta, float* scratch, int64_t rows, int C, float scale, int accumulate, cudaStream_t st);
+                      float* gbeta, float* scratch, int64_t rows, int C, float scale, int accumulate, float* red_scr, cudaStream_t st);
 int k_relu_drop_fwd(float* x, const uint8_t* mask, float drop_scale, int64_t n, cudaStream_t st);
 int k_relu_drop_bwd(float* dx, const float* out, const uint8_t* mask, float drop_scale, int64_t n, cudaStream_t st);
 int k_transpose01(const float* in, float* out, int D0, int D1, int C, cudaStream_t st);   // [D0][D1][C] -> [D1][D0][C]

@@ -96,19 +96,54 @@ __global__ void ker_fill_rows(float* y, const float* __restrict__ b1, const floa
         y[i] = b1[n] + (b2 ? b2[n] : 0.f);
     }
 }
-// out[n] = sum_r x[r*ld + n]; block = 32 columns x 8 row lanes
-__global__ void ker_colsum(const float* __restrict__ x, int64_t rows, int N, int ld, float* out, float scale, int accumulate, float* out2) {
+// ---- column reductions over the rows of a [rows][N] matrix --------------------------------------------------------------
+// Block = 32 columns x 8 row lanes; the rows are split into gridDim.y chunks so that the grid covers the SMs (32-column groups
+// alone are 16 CTAs for 512 channels: ~30 us per reduction, measured), every block writes its partial to `part[chunk][N]`, and
+// the LAST block of a column group to arrive (atomic ticket, reset for the next launch) combines the partials in chunk order:
+// deterministic, one launch.  `ticket`: gridDim.x zero-initialised counters.
+__device__ __forceinline__ bool red_is_last_block(unsigned int* ticket) {
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int v = atomicAdd(ticket + blockIdx.x, 1u);
+        last = v == gridDim.y - 1;
+        if (last) ticket[blockIdx.x] = 0u;
+    }
+    __syncthreads();
+    if (last) __threadfence();
+    return last;
+}
+__device__ __forceinline__ void red_chunk(int64_t rows, int64_t& r0, int64_t& r1) {
+    const int64_t rc = (rows + gridDim.y - 1) / gridDim.y;
+    r0 = (int64_t)blockIdx.y * rc;
+    r1 = r0 + rc < rows ? r0 + rc : rows;
+}
+// out[n] = sum_r x[r*ld + n]
+__global__ void ker_colsum(const float* __restrict__ x, int64_t rows, int N, int ld, float* out, float scale, int accumulate, float* out2,
+                           float* part, unsigned int* ticket) {
     __shared__ float sh[8][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int n = blockIdx.x * 32 + cx;
+    int64_t r0, r1;
+    red_chunk(rows, r0, r1);
     float s = 0.f;
     if (n < N)
-        for (int64_t r = ry; r < rows; r += 8) s += x[r * ld + n];
+        for (int64_t r = r0 + ry; r < r1; r += 8) s += x[r * ld + n];
     sh[ry][cx] = s;
     __syncthreads();
+    float t = 0.f;
     if (ry == 0 && n < N) {
-        float t = 0.f;
         for (int j = 0; j < 8; ++j) t += sh[j][cx];
+        if (gridDim.y > 1) part[(size_t)blockIdx.y * N + n] = t;
+    }
+    if (gridDim.y > 1) {
+        if (!red_is_last_block(ticket)) return;
+        t = 0.f;
+        if (ry == 0 && n < N)
+            for (int pch = 0; pch < (int)gridDim.y; ++pch) t += __ldcg(part + (size_t)pch * N + n);
+    }
+    if (ry == 0 && n < N) {
         t *= scale;
         out[n] = accumulate ? out[n] + t : t;
         if (out2) out2[n] = accumulate ? out2[n] + t : t;
@@ -116,40 +151,71 @@ __global__ void ker_colsum(const float* __restrict__ x, int64_t rows, int N, int
 }
 
 // ---------------- BatchNorm1d (train) + activation + dropout ----------------
-// y [rows][C]; two-pass mean / biased variance per channel; running stats updated with unbiased variance.
-__global__ void ker_bn_stats(const float* __restrict__ y, int64_t rows, int C, float* mean, float* invstd, float* running, int Cpad) {
+// y [rows][C]; mean / biased variance per channel; running stats updated with unbiased variance.  Every row chunk computes its
+// own two-pass (mean, M2); the last block merges the chunks with Chan's parallel-variance update in chunk order.
+__global__ void ker_bn_stats(const float* __restrict__ y, int64_t rows, int C, float* mean, float* invstd, float* running, int Cpad,
+                             float* part, unsigned int* ticket) {
     __shared__ float sh[8][33];
     __shared__ float mu[32];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cx;
+    int64_t r0, r1;
+    red_chunk(rows, r0, r1);
+    const float nc = (float)(r1 > r0 ? r1 - r0 : 0);
     float s = 0.f;
     if (c < C)
-        for (int64_t r = ry; r < rows; r += 8) s += y[r * C + c];
+        for (int64_t r = r0 + ry; r < r1; r += 8) s += y[r * C + c];
     sh[ry][cx] = s;
     __syncthreads();
     if (ry == 0) {
         float t = 0.f;
         for (int j = 0; j < 8; ++j) t += sh[j][cx];
-        mu[cx] = t / (float)rows;
+        mu[cx] = nc > 0.f ? t / nc : 0.f;
     }
     __syncthreads();
-    const float m = mu[cx];
+    float m = mu[cx];
     s = 0.f;
     if (c < C)
-        for (int64_t r = ry; r < rows; r += 8) {
+        for (int64_t r = r0 + ry; r < r1; r += 8) {
             const float d = y[r * C + c] - m;
             s += d * d;
         }
+    __syncthreads();
     sh[ry][cx] = s;
     __syncthreads();
+    float M2 = 0.f;
     if (ry == 0 && c < C) {
-        float t = 0.f;
-        for (int j = 0; j < 8; ++j) t += sh[j][cx];
-        const float var = t / (float)rows;
+        for (int j = 0; j < 8; ++j) M2 += sh[j][cx];
+        if (gridDim.y > 1) {
+            part[((size_t)blockIdx.y * 2 + 0) * C + c] = m;
+            part[((size_t)blockIdx.y * 2 + 1) * C + c] = M2;
+        }
+    }
+    if (gridDim.y > 1) {
+        if (!red_is_last_block(ticket)) return;
+        if (ry == 0 && c < C) {
+            const int64_t rc = (rows + gridDim.y - 1) / gridDim.y;
+            float n = 0.f;
+            m = 0.f;
+            M2 = 0.f;
+            for (int pch = 0; pch < (int)gridDim.y; ++pch) {
+                const int64_t a = (int64_t)pch * rc, b = a + rc < rows ? a + rc : rows;
+                const float np = (float)(b > a ? b - a : 0);
+                if (np <= 0.f) continue;
+                const float mp = __ldcg(part + ((size_t)pch * 2 + 0) * C + c), qp = __ldcg(part + ((size_t)pch * 2 + 1) * C + c);
+                const float delta = mp - m, nn = n + np;
+                m += delta * np / nn;
+                M2 += qp + delta * delta * n * np / nn;
+                n = nn;
+            }
+        }
+    }
+    if (ry == 0 && c < C) {
+        const float var = M2 / (float)rows;
         mean[c] = m;
         invstd[c] = 1.f / sqrtf(var + 1e-5f);
         if (running) {
-            const float unb = rows > 1 ? t / (float)(rows - 1) : var;
+            const float unb = rows > 1 ? M2 / (float)(rows - 1) : var;
             running[c] = 0.9f * running[c] + 0.1f * m;
             running[Cpad + c] = 0.9f * running[Cpad + c] + 0.1f * unb;
         }
@@ -182,14 +248,17 @@ __device__ __forceinline__ float bn_du(float dout, float u, uint8_t keep, bool h
 // per channel: sum du, sum du*xhat  -> scratch[c], scratch[C + c]
 __global__ void ker_bn_bwd_reduce(const float* __restrict__ dout, const float* __restrict__ y, const float* __restrict__ mean,
                                   const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                  const uint8_t* __restrict__ mask, float ds, int act, float* scratch, int64_t rows, int C) {
+                                  const uint8_t* __restrict__ mask, float ds, int act, float* scratch, int64_t rows, int C, float* part,
+                                  unsigned int* ticket) {
     __shared__ float sh1[8][33], sh2[8][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cx;
+    int64_t r0, r1;
+    red_chunk(rows, r0, r1);
     float s1 = 0.f, s2 = 0.f;
     if (c < C) {
         const float m = mean[c], is = invstd[c], g = gamma[c], be = beta[c];
-        for (int64_t r = ry; r < rows; r += 8) {
+        for (int64_t r = r0 + ry; r < r1; r += 8) {
             const int64_t i = r * C + c;
             const float xh = (y[i] - m) * is;
             const float du = bn_du(dout[i], g * xh + be, mask ? mask[i] : 1, mask != nullptr, ds, act);
@@ -200,9 +269,25 @@ __global__ void ker_bn_bwd_reduce(const float* __restrict__ dout, const float* _
     sh1[ry][cx] = s1;
     sh2[ry][cx] = s2;
     __syncthreads();
+    float t1 = 0.f, t2 = 0.f;
     if (ry == 0 && c < C) {
-        float t1 = 0.f, t2 = 0.f;
         for (int j = 0; j < 8; ++j) { t1 += sh1[j][cx]; t2 += sh2[j][cx]; }
+        if (gridDim.y > 1) {
+            part[((size_t)blockIdx.y * 2 + 0) * C + c] = t1;
+            part[((size_t)blockIdx.y * 2 + 1) * C + c] = t2;
+        }
+    }
+    if (gridDim.y > 1) {
+        if (!red_is_last_block(ticket)) return;
+        t1 = 0.f;
+        t2 = 0.f;
+        if (ry == 0 && c < C)
+            for (int pch = 0; pch < (int)gridDim.y; ++pch) {
+                t1 += __ldcg(part + ((size_t)pch * 2 + 0) * C + c);
+                t2 += __ldcg(part + ((size_t)pch * 2 + 1) * C + c);
+            }
+    }
+    if (ry == 0 && c < C) {
         scratch[c] = t1;
         scratch[C + c] = t2;
     }
@@ -482,8 +567,26 @@ int k_embedding_bwd(const float* dx, const int64_t* tok, float* gw, int rows, in
     MSA_LAUNCH_CHECK();
     return 0;
 }
+// 128-bit version (C % 4 == 0): one float4 of one (row, tap) per thread, rows of C/4 consecutive threads
+__global__ void ker_im2col4(const float4* __restrict__ x, float4* col, int B, int T, int C4, int K) {
+    const int pad = (K - 1) / 2;
+    const int64_t n = (int64_t)B * T * K * C4;
+    GSL(i, n) {
+        const int c = (int)(i % C4);
+        const int64_t bk = i / C4;
+        const int k = (int)(bk % K);
+        const int64_t bt = bk / K;
+        const int t = (int)(bt % T);
+        const int ts = t + k - pad;
+        col[i] = (ts >= 0 && ts < T) ? x[(bt + (k - pad)) * C4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
 int k_im2col(const float* x, float* col, int B, int T, int C, int K, cudaStream_t st) {
-    ker_im2col<<<grid_for((int64_t)B * T * C * K), kTh, 0, ST>>>(x, col, B, T, C, K);
+    if ((C & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(col)) & 15) == 0)
+        ker_im2col4<<<grid_for((int64_t)B * T * (C >> 2) * K), kTh, 0, ST>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(col),
+                                                                             B, T, C >> 2, K);
+    else
+        ker_im2col<<<grid_for((int64_t)B * T * C * K), kTh, 0, ST>>>(x, col, B, T, C, K);
     MSA_LAUNCH_CHECK();
     return 0;
 }
@@ -507,13 +610,28 @@ int k_fill_rows(float* y, const float* b1, const float* b2, int64_t rows, int N,
     MSA_LAUNCH_CHECK();
     return 0;
 }
-int k_colsum(const float* x, int64_t rows, int N, int ld, float* out, float scale, int acc, float* out2, cudaStream_t st) {
-    ker_colsum<<<cdiv(N, 32), 256, 0, ST>>>(x, rows, N, ld, out, scale, acc, out2);
+// row chunks of a column reduction: enough blocks to cover the SMs, >= 32 rows per chunk, partial scratch for <= kRedChunks
+static int red_chunks(int64_t rows, int ncolgroups, const float* red_scr) {
+    if (!red_scr) return 1;
+    int64_t p = rows / 32;
+    const int64_t want = (2 * 148 + ncolgroups - 1) / ncolgroups;
+    if (p > want) p = want;
+    if (p > kRedChunks) p = kRedChunks;
+    return p < 1 ? 1 : (int)p;
+}
+int k_colsum(const float* x, int64_t rows, int N, int ld, float* out, float scale, int acc, float* out2, float* red_scr, cudaStream_t st) {
+    MSA_CHECK(!red_scr || (cdiv(N, 32) <= kRedTickets && (int64_t)N <= kRedCols), MSA_E_ARG, "colsum: %d columns exceed the reduction scratch", N);
+    const int P = red_chunks(rows, cdiv(N, 32), red_scr);
+    ker_colsum<<<dim3(cdiv(N, 32), P), 256, 0, ST>>>(x, rows, N, ld, out, scale, acc, out2, red_scr ? red_scr + kRedTickets : nullptr,
+                                                     reinterpret_cast<unsigned int*>(red_scr));
     MSA_LAUNCH_CHECK();
     return 0;
 }
-int k_bn_stats(const float* y, int64_t rows, int C, float* mean, float* invstd, float* running, int Cpad, cudaStream_t st) {
-    ker_bn_stats<<<cdiv(C, 32), 256, 0, ST>>>(y, rows, C, mean, invstd, running, Cpad);
+int k_bn_stats(const float* y, int64_t rows, int C, float* mean, float* invstd, float* running, int Cpad, float* red_scr, cudaStream_t st) {
+    MSA_CHECK(!red_scr || (cdiv(C, 32) <= kRedTickets && 2 * (int64_t)C <= kRedCols), MSA_E_ARG, "bn_stats: %d channels exceed the reduction scratch", C);
+    const int P = red_chunks(rows, cdiv(C, 32), red_scr);
+    ker_bn_stats<<<dim3(cdiv(C, 32), P), 256, 0, ST>>>(y, rows, C, mean, invstd, running, Cpad, red_scr ? red_scr + kRedTickets : nullptr,
+                                                       reinterpret_cast<unsigned int*>(red_scr));
     MSA_LAUNCH_CHECK();
     return 0;
 }
@@ -530,8 +648,11 @@ int k_bn_act_drop_fwd(const float* y, const float* mean, const float* invstd, co
 }
 int k_bn_act_drop_bwd(const float* dout, const float* y, const float* mean, const float* invstd, const float* gamma,
                       const float* beta, const uint8_t* mask, float ds, int act, float* dy, float* ggamma, float* gbeta,
-                      float* scratch, int64_t rows, int C, float scale, int acc, cudaStream_t st) {
-    ker_bn_bwd_reduce<<<cdiv(C, 32), 256, 0, ST>>>(dout, y, mean, invstd, gamma, beta, mask, ds, act, scratch, rows, C);
+                      float* scratch, int64_t rows, int C, float scale, int acc, float* red_scr, cudaStream_t st) {
+    MSA_CHECK(!red_scr || (cdiv(C, 32) <= kRedTickets && 2 * (int64_t)C <= kRedCols), MSA_E_ARG, "bn bwd: %d channels exceed the reduction scratch", C);
+    const int P = red_chunks(rows, cdiv(C, 32), red_scr);
+    ker_bn_bwd_reduce<<<dim3(cdiv(C, 32), P), 256, 0, ST>>>(dout, y, mean, invstd, gamma, beta, mask, ds, act, scratch, rows, C,
+                                                            red_scr ? red_scr + kRedTickets : nullptr, reinterpret_cast<unsigned int*>(red_scr));
     MSA_LAUNCH_CHECK();
     ker_bn_bwd_apply<<<grid_for(rows * C), kTh, 0, ST>>>(dout, y, mean, invstd, gamma, beta, mask, ds, act, scratch, dy, rows, C);
     MSA_LAUNCH_CHECK();

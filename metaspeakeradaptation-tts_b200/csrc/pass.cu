@@ -174,7 +174,7 @@ static Dims make_dims(const msa_config& c, int B, int T, int L) {
 #define WS_LIST(X)                                                                                     \
     X(spk_vec, d.B * d.Ds)                                                                             \
     X(enc_x, (d.nEnc + 1) * d.BL * d.C) X(enc_y, d.nEnc * d.BL * d.C) X(enc_bn, d.nEnc * 2 * d.C)      \
-    X(enc_col, d.BL * d.Kc * d.C) X(enc_w2, (int64_t)d.C * d.Kc * d.C) X(x3_tm, d.BL * d.C)            \
+    X(enc_col, d.nEnc * d.BL * d.Kc * d.C) X(enc_w2, d.nEnc * (int64_t)d.C * d.Kc * d.C) X(x3_tm, d.BL * d.C)            \
     X(enc_zx, 2 * d.BL * 4 * d.Hh) X(enc_g, 2 * d.BL * 4 * d.Hh) X(enc_c, 2 * d.BL * d.Hh)             \
     X(enc_h, 2 * d.BL * d.Hh) X(memory, d.BL * d.E)                                                    \
     X(frames, (d.TB + d.B) * d.M) X(target, d.BT * d.M) X(p1, (d.TB + d.B) * d.Pd)                     \
@@ -186,8 +186,8 @@ static Dims make_dims(const msa_config& c, int B, int T, int L) {
     X(zd, d.TB * 4 * d.Hd) X(hd, d.TB * d.Hd) X(cd, d.TB * d.Hd) X(gd, d.TB * 4 * d.Hd)                \
     X(mel_tm, d.TB * d.M) X(gate_tm, d.TB)                                                             \
     X(post_x, (d.nPost + 1) * d.BT * d.Cmax) X(post_y, d.nPost * d.BT * d.Cmax)                        \
-    X(post_bn, d.nPost * 2 * d.Cmax) X(post_col, d.BT * d.Kp * d.Cmax)                                 \
-    X(post_w2, (int64_t)d.Cmax * d.Kp * d.Cmax) X(post_bt, d.BT * d.M) X(gate_bt, d.BT)                \
+    X(post_bn, d.nPost * 2 * d.Cmax) X(post_col, d.nPost * d.BT * d.Kp * d.Cmax)                       \
+    X(post_w2, d.nPost * (int64_t)d.Cmax * d.Kp * d.Cmax) X(post_bt, d.BT * d.M) X(gate_bt, d.BT) X(red_scr, kRedScrFloats) \
     X(loss_part, 1024) X(loss, 32) X(dpre, d.BT * d.M) X(dpost, d.BT * d.M) X(dgate, d.BT)             \
     X(bdx0, d.BT * d.Cmax) X(bdx1, d.BT * d.Cmax) X(bdy, d.BT * d.Cmax)                                \
     X(bdcol, d.BT * d.Kp * d.Cmax) X(bdw2, (int64_t)d.Cmax * d.Kp * d.Cmax)                            \
@@ -303,13 +303,14 @@ static int gemm_batched(msa_handle* h, bool ta, bool tb, int64_t M, int64_t N, i
 // conv1d ("same") + BatchNorm(train) + activation + dropout, channels-last rows = B*Tn
 static int conv_bn_fwd(msa_handle* h, cudaStream_t st, const float* params, const std::string& pfx, const float* x, float* y,
                        float* xout, float* col, float* w2, float* bn_mean, float* bn_invstd, float* running, int B, int Tn,
-                       int Ci, int Co, int K, int act, const uint8_t* mask) {
+                       int Ci, int Co, int K, int act, const uint8_t* mask, float* red_scr) {
+    // col (im2col of the layer input) and w2 (packed weights) are per-layer buffers: the backward pass reuses both
     const int64_t rows = (int64_t)B * Tn;
     MSA_TRY(k_conv_w_pack(params + h->off(pfx + ".0.conv.weight"), w2, Co, Ci, K, st));
     MSA_TRY(k_im2col(x, col, B, Tn, Ci, K, st));
     MSA_TRY(k_fill_rows(y, params + h->off(pfx + ".0.conv.bias"), nullptr, rows, Co, st));
     MSA_TRY(gemm(h, false, true, rows, Co, (int64_t)K * Ci, 1.f, col, (int64_t)K * Ci, w2, (int64_t)K * Ci, 1.f, y, Co));
-    MSA_TRY(k_bn_stats(y, rows, Co, bn_mean, bn_invstd, running, (int)align_up(Co), st));
+    MSA_TRY(k_bn_stats(y, rows, Co, bn_mean, bn_invstd, running, (int)align_up(Co), red_scr, st));
     MSA_TRY(k_bn_act_drop_fwd(y, bn_mean, bn_invstd, params + h->off(pfx + ".1.weight"), params + h->off(pfx + ".1.bias"), mask,
                               2.0f, act, xout, rows, Co, st));
     return 0;
@@ -318,17 +319,16 @@ static int conv_bn_fwd(msa_handle* h, cudaStream_t st, const float* params, cons
 static int conv_bn_bwd(msa_handle* h, cudaStream_t st, const float* params, float* grads, float gs, int acc,
                        const std::string& pfx, const float* x, const float* y, const float* dout, float* dx, float* dy, float* col,
                        float* w2, float* dcol, float* dw2, float* scr, const float* bn_mean, const float* bn_invstd, int B, int Tn,
-                       int Ci, int Co, int K, int act, const uint8_t* mask, bool need_dx) {
+                       int Ci, int Co, int K, int act, const uint8_t* mask, bool need_dx, float* red_scr) {
+    (void)x;      // its im2col is still in `col`, the packed weights in `w2` (written by conv_bn_fwd of the same pass)
     const int64_t rows = (int64_t)B * Tn, KC = (int64_t)K * Ci;
     MSA_TRY(k_bn_act_drop_bwd(dout, y, bn_mean, bn_invstd, params + h->off(pfx + ".1.weight"), params + h->off(pfx + ".1.bias"),
                               mask, 2.0f, act, dy, grads + h->off(pfx + ".1.weight"), grads + h->off(pfx + ".1.bias"), scr, rows,
-                              Co, gs, acc, st));
-    MSA_TRY(k_colsum(dy, rows, Co, Co, grads + h->off(pfx + ".0.conv.bias"), gs, acc, nullptr, st));
-    MSA_TRY(k_im2col(x, col, B, Tn, Ci, K, st));
+                              Co, gs, acc, red_scr, st));
+    MSA_TRY(k_colsum(dy, rows, Co, Co, grads + h->off(pfx + ".0.conv.bias"), gs, acc, nullptr, red_scr, st));
     MSA_TRY(gemm(h, true, false, Co, KC, rows, 1.f, dy, Co, col, KC, 0.f, dw2, KC));
     MSA_TRY(k_conv_w_unpack_grad(dw2, grads + h->off(pfx + ".0.conv.weight"), Co, Ci, K, gs, acc, st));
     if (need_dx) {
-        MSA_TRY(k_conv_w_pack(params + h->off(pfx + ".0.conv.weight"), w2, Co, Ci, K, st));
         MSA_TRY(gemm(h, false, false, rows, KC, Co, 1.f, dy, Co, w2, KC, 0.f, dcol, KC));
         MSA_TRY(k_col2im(dcol, dx, B, Tn, Ci, K, st));
     }
@@ -525,6 +525,7 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
     const auto secs = mask_sections(c, B, T, L);
     auto mk = [&](int i) { return masks + secs[i].off; };
     MSA_CUDA(cudaMemsetAsync(w.abort_word, 0, 256, st));
+    MSA_CUDA(cudaMemsetAsync(w.red_scr, 0, sizeof(unsigned int) * kRedTickets, st));      // tickets of the chunked column reductions
     const int iPre = d.nEnc, iAttn = d.nEnc + 2, iDec = d.nEnc + 3, iPost = d.nEnc + 4;
     auto P = [&](const std::string& n) { return params + h->off(n); };
 
@@ -543,8 +544,8 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
     for (int i = 0; i < d.nEnc; ++i) {
         float* run = bn_stats ? bn_stats + h->bn_offs[i] : nullptr;
         MSA_TRY(conv_bn_fwd(h, st, params, "encoder.convolutions." + std::to_string(i), w.enc_x + i * ex, w.enc_y + i * ex,
-                            w.enc_x + (i + 1) * ex, w.enc_col, w.enc_w2, w.enc_bn + i * 2 * d.C, w.enc_bn + i * 2 * d.C + d.C, run, B, L,
-                            d.C, d.C, d.Kc, 1, mk(i)));
+                            w.enc_x + (i + 1) * ex, w.enc_col + i * d.BL * d.Kc * d.C, w.enc_w2 + i * (int64_t)d.C * d.Kc * d.C,
+                            w.enc_bn + i * 2 * d.C, w.enc_bn + i * 2 * d.C + d.C, run, B, L, d.C, d.C, d.Kc, 1, mk(i), w.red_scr));
     }
     MSA_TRY(k_transpose01(w.enc_x + d.nEnc * ex, w.x3_tm, B, L, d.C, st));
     const int H4e = 4 * d.Hh;
@@ -636,8 +637,9 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
         const int ci = i == 0 ? d.M : d.Cp, co = i == d.nPost - 1 ? d.M : d.Cp;
         float* run = bn_stats ? bn_stats + h->bn_offs[d.nEnc + i] : nullptr;
         MSA_TRY(conv_bn_fwd(h, st, params, "postnet.convolutions." + std::to_string(i), w.post_x + i * px, w.post_y + i * px,
-                            w.post_x + (i + 1) * px, w.post_col, w.post_w2, w.post_bn + i * 2 * d.Cmax,
-                            w.post_bn + i * 2 * d.Cmax + d.Cmax, run, B, T, ci, co, d.Kp, i < d.nPost - 1 ? 2 : 0, mk(iPost + i)));
+                            w.post_x + (i + 1) * px, w.post_col + i * d.BT * d.Kp * d.Cmax, w.post_w2 + i * (int64_t)d.Cmax * d.Kp * d.Cmax,
+                            w.post_bn + i * 2 * d.Cmax, w.post_bn + i * 2 * d.Cmax + d.Cmax, run, B, T, ci, co, d.Kp,
+                            i < d.nPost - 1 ? 2 : 0, mk(iPost + i), w.red_scr));
     }
     MSA_TRY(k_add(w.post_x, w.post_x + d.nPost * px, w.post_bt, d.BT * d.M, st));
     // ---- outputs in the reference layouts ----
@@ -748,9 +750,10 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
         const int ci = i == 0 ? d.M : d.Cp, co = i == d.nPost - 1 ? d.M : d.Cp;
         float* dx = pingpong[i & 1];
         MSA_TRY(conv_bn_bwd(h, st, params, grads, gs, acc, "postnet.convolutions." + std::to_string(i), w.post_x + i * px,
-                            w.post_y + i * px, dcur, dx, w.bdy, w.post_col, w.post_w2, w.bdcol, w.bdw2, w.bn_scr,
+                            w.post_y + i * px, dcur, dx, w.bdy, w.post_col + i * d.BT * d.Kp * d.Cmax,
+                            w.post_w2 + i * (int64_t)d.Cmax * d.Kp * d.Cmax, w.bdcol, w.bdw2, w.bn_scr,
                             w.post_bn + i * 2 * d.Cmax, w.post_bn + i * 2 * d.Cmax + d.Cmax, B, T, ci, co, d.Kp,
-                            i < d.nPost - 1 ? 2 : 0, mk(iPost + i), true));
+                            i < d.nPost - 1 ? 2 : 0, mk(iPost + i), true, w.red_scr));
         dcur = dx;
     }
     // d(pre-postnet mel) = loss term + residual + postnet input (tacotron2nv.py:123-124)
@@ -770,8 +773,8 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
     MSA_TRY(gemm(h, true, false, d.M, d.E, d.TB, gs, w.dmel_tm, d.M, w.ctx, d.E, beta, gWp + d.Hd, ldP));
     MSA_TRY(gemm(h, true, false, 1, d.Hd, d.TB, gs, w.dgate_tm, 1, w.hd, d.Hd, beta, gWg, ldP));
     MSA_TRY(gemm(h, true, false, 1, d.E, d.TB, gs, w.dgate_tm, 1, w.ctx, d.E, beta, gWg + d.Hd, ldP));
-    MSA_TRY(k_colsum(w.dmel_tm, d.TB, d.M, d.M, G("decoder.linear_projection.linear_layer.bias"), gs, acc, nullptr, st));
-    MSA_TRY(k_colsum(w.dgate_tm, d.TB, 1, 1, G("decoder.gate_layer.linear_layer.bias"), gs, acc, nullptr, st));
+    MSA_TRY(k_colsum(w.dmel_tm, d.TB, d.M, d.M, G("decoder.linear_projection.linear_layer.bias"), gs, acc, nullptr, w.red_scr, st));
+    MSA_TRY(k_colsum(w.dgate_tm, d.TB, 1, 1, G("decoder.gate_layer.linear_layer.bias"), gs, acc, nullptr, w.red_scr, st));
     // ---- decoder RNN chain backward ----
     {
         LstmRecBwdParams bp{};
@@ -796,7 +799,7 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
     } else if (!acc) {
         MSA_CUDA(cudaMemsetAsync(gWhd, 0, sizeof(float) * (size_t)H4d * d.Hd, st));
     }
-    MSA_TRY(k_colsum(w.dzd, d.TB, H4d, H4d, G("decoder.decoder_rnn.bias_ih"), gs, acc, G("decoder.decoder_rnn.bias_hh"), st));
+    MSA_TRY(k_colsum(w.dzd, d.TB, H4d, H4d, G("decoder.decoder_rnn.bias_ih"), gs, acc, G("decoder.decoder_rnn.bias_hh"), w.red_scr, st));
     // ---- context backward: ctx = align . memory ----
     MSA_TRY(gemm_batched(h, false, true, T, L, d.E, 1.f, w.dctx, (int64_t)B * d.E, d.E, w.memory, d.E, (int64_t)L * d.E, 0.f,
                          w.da_ext, d.BL, L, B));
@@ -832,7 +835,7 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
         float* gWta = G(at + "ta.weight");
         MSA_TRY(gemm(h, true, false, 1, d.E, d.TB, gs, w.dzu, 1, w.ctx, d.E, beta, gWta, d.E + d.Ha));
         MSA_TRY(gemm(h, true, false, 1, d.Ha, d.TB, gs, w.dzu, 1, w.ha, d.Ha, beta, gWta + d.E, d.E + d.Ha));
-        MSA_TRY(k_colsum(w.dzu, d.TB, 1, 1, G(at + "ta.bias"), gs, acc, nullptr, st));
+        MSA_TRY(k_colsum(w.dzu, d.TB, 1, 1, G(at + "ta.bias"), gs, acc, nullptr, w.red_scr, st));
         // d memory += sum_t alpha(t)^T . (dzu(t) (x) W_ta[:E])   (w.dctx is free after the context backward above)
         MSA_TRY(gemm(h, false, false, d.TB, d.E, 1, 1.f, w.dzu, 1, P(at + "ta.weight"), d.E + d.Ha, 0.f, w.dctx, d.E));
         MSA_TRY(gemm_batched(h, true, false, L, d.E, T, 1.f, w.align_tm, d.BL, L, w.dctx, (int64_t)B * d.E, d.E, 1.f, w.dmem, d.E,
@@ -852,7 +855,7 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
         if (!acc) MSA_CUDA(cudaMemsetAsync(gWha, 0, sizeof(float) * (size_t)H4a * d.Ha, st));
         MSA_CUDA(cudaMemsetAsync(w.dmw, 0, sizeof(float) * (size_t)d.BL * H4a, st));
     }
-    MSA_TRY(k_colsum(w.dza, d.TB, H4a, H4a, G("decoder.attention_rnn.bias_ih"), gs, acc, G("decoder.attention_rnn.bias_hh"), st));
+    MSA_TRY(k_colsum(w.dza, d.TB, H4a, H4a, G("decoder.attention_rnn.bias_ih"), gs, acc, G("decoder.attention_rnn.bias_hh"), w.red_scr, st));
     MSA_TRY(gemm(h, true, false, H4a, d.E, d.BL, gs, w.dmw, H4a, w.memory, d.E, beta, gWia + d.Pd, ldA));
     MSA_TRY(gemm(h, false, false, d.BL, d.E, H4a, 1.f, w.dmw, H4a, Wia + d.Pd, ldA, 1.f, w.dmem, d.E));
     MSA_TRY(gemm(h, true, false, d.A, d.Ha, d.TB, gs, w.dq, d.A, w.ha, d.Ha, beta, G(at + "query_layer.linear_layer.weight"), d.Ha));
@@ -875,7 +878,7 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
     MSA_TRY(k_split_dmemory(w.dmem, w.denc_h, c.spk_mode ? w.dspk : nullptr, B, L, d.Hh, d.Ds, st));
     if (c.spk_mode == 1) {
         MSA_TRY(gemm(h, true, false, d.Ds, d.Dsin, B, gs, w.dspk, d.Ds, h->spk_in, d.Dsin, beta, G("speaker_lin.weight"), d.Dsin));
-        MSA_TRY(k_colsum(w.dspk, B, d.Ds, d.Ds, G("speaker_lin.bias"), gs, acc, nullptr, st));
+        MSA_TRY(k_colsum(w.dspk, B, d.Ds, d.Ds, G("speaker_lin.bias"), gs, acc, nullptr, w.red_scr, st));
     } else if (c.spk_mode == 2) {
         MSA_TRY(k_embedding_bwd(w.dspk, h->spk_ids, G("speaker_embedder.weight"), B, d.Ds, c.num_speakers, gs, acc, st));
     }
@@ -905,7 +908,7 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
         } else if (!acc) {
             MSA_CUDA(cudaMemsetAsync(gWhh, 0, sizeof(float) * (size_t)H4e * d.Hh, st));
         }
-        MSA_TRY(k_colsum(dzx, d.BL, H4e, H4e, G("encoder.lstm.bias_ih_l0" + sfx), gs, acc, G("encoder.lstm.bias_hh_l0" + sfx), st));
+        MSA_TRY(k_colsum(dzx, d.BL, H4e, H4e, G("encoder.lstm.bias_ih_l0" + sfx), gs, acc, G("encoder.lstm.bias_hh_l0" + sfx), w.red_scr, st));
     }
     // ---- encoder convolutions backward ----
     const int64_t ex = d.BL * d.C;
@@ -915,8 +918,9 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
     for (int i = d.nEnc - 1; i >= 0; --i) {
         float* dx = epp[i & 1];
         MSA_TRY(conv_bn_bwd(h, st, params, grads, gs, acc, "encoder.convolutions." + std::to_string(i), w.enc_x + i * ex,
-                            w.enc_y + i * ex, dcur, dx, w.edy, w.enc_col, w.enc_w2, w.edcol, w.edw2, w.bn_scr, w.enc_bn + i * 2 * d.C,
-                            w.enc_bn + i * 2 * d.C + d.C, B, L, d.C, d.C, d.Kc, 1, mk(i), true));
+                            w.enc_y + i * ex, dcur, dx, w.edy, w.enc_col + i * d.BL * d.Kc * d.C, w.enc_w2 + i * (int64_t)d.C * d.Kc * d.C,
+                            w.edcol, w.edw2, w.bn_scr, w.enc_bn + i * 2 * d.C, w.enc_bn + i * 2 * d.C + d.C, B, L, d.C, d.C, d.Kc, 1, mk(i),
+                            true, w.red_scr));
         dcur = dx;
     }
     MSA_TRY(k_embedding_bwd(dcur, h->tokens, G("embedding.weight"), (int)d.BL, d.C, c.n_symbols, gs, acc, st));
