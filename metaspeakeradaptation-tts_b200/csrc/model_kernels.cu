@@ -546,11 +546,23 @@ __device__ __forceinline__ uint32_t mix32(uint64_t x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
     return (uint32_t)(x >> 11);
 }
-__global__ void ker_masks(uint8_t* masks, int64_t off, int64_t n, float p, uint64_t seed) {
-    const uint32_t thr = (uint32_t)(p * 2097152.0f);   // 21 random bits
-    GSL(i, n) {
-        const uint32_t r = mix32(seed ^ ((uint64_t)(off + i) * 0x9E3779B97F4A7C15ULL)) & 0x1FFFFF;
-        masks[off + i] = r >= thr ? 1 : 0;
+// all sections of the mask buffer in ONE launch (a pass has 12 of them); the keep decision depends only on (seed, absolute byte
+// index, p of the section), so the values do not depend on how the work is split
+constexpr int kMaskSecMax = 24;
+struct MaskSecTable {
+    int n;
+    long long off[kMaskSecMax], end[kMaskSecMax];
+    unsigned int thr[kMaskSecMax];      // 21 random bits: keep if r >= p * 2^21
+};
+__global__ void ker_masks(uint8_t* masks, MaskSecTable tb, long long lo, long long hi, uint64_t seed) {
+    GSL(j, hi - lo) {
+        const long long i = lo + j;      // absolute byte index
+        int sct = -1;
+        for (int k = 0; k < tb.n; ++k)
+            if (i >= tb.off[k] && i < tb.end[k]) sct = k;
+        if (sct < 0) continue;      // alignment gap between sections
+        const uint32_t r = mix32(seed ^ ((uint64_t)i * 0x9E3779B97F4A7C15ULL)) & 0x1FFFFF;
+        masks[i] = r >= tb.thr[sct] ? 1 : 0;
     }
 }
 
@@ -768,8 +780,19 @@ int k_dot_rows(const float* a, const float* b, int64_t n, float* partials, float
 }
 int k_masks_generate(uint8_t* masks, const int64_t* offsets, const int64_t* numels, const float* ps, int nsec, uint64_t seed,
                      cudaStream_t st) {
-    for (int i = 0; i < nsec; ++i) {
-        ker_masks<<<grid_for(numels[i]), kTh, 0, ST>>>(masks, offsets[i], numels[i], ps[i], seed);
+    for (int base = 0; base < nsec; base += kMaskSecMax) {
+        MaskSecTable tb{};
+        long long lo = -1, hi = 0;
+        tb.n = nsec - base < kMaskSecMax ? nsec - base : kMaskSecMax;
+        for (int k = 0; k < tb.n; ++k) {
+            tb.off[k] = offsets[base + k];
+            tb.end[k] = offsets[base + k] + numels[base + k];
+            tb.thr[k] = (unsigned int)(ps[base + k] * 2097152.0f);
+            if (lo < 0 || tb.off[k] < lo) lo = tb.off[k];
+            if (tb.end[k] > hi) hi = tb.end[k];
+        }
+        if (hi <= lo) continue;
+        ker_masks<<<grid_for(hi - lo), kTh, 0, ST>>>(masks, tb, lo, hi, seed);
         MSA_LAUNCH_CHECK();
     }
     return 0;

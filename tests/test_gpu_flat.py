@@ -107,6 +107,27 @@ def test_functional_adam_step(eng):
     assert close(cur, pt.data, 2e-6)
 
 
+def test_device_dropout_masks(eng):
+    """msa_masks_generate: one launch for all sections; keep rate 1 - p per section, values a function of (seed, byte index) only,
+    bytes between sections untouched."""
+    B, T, L = 3, 20, 9
+    secs = eng.mask_sections(B, T, L)
+    a = torch.full((eng.mask_bytes(B, T, L),), 7, dtype=torch.uint8, device="cuda")
+    eng.generate_masks(B, T, L, 1234, out=a)
+    b = eng.generate_masks(B, T, L, 1234)
+    c = eng.generate_masks(B, T, L, 1235)
+    covered = torch.zeros_like(a, dtype=torch.bool)
+    for name, off, ne, p in secs:
+        m = a[off:off + ne]
+        assert int(m.max()) <= 1
+        keep = float(m.float().mean())
+        sigma = (p * (1 - p) / ne) ** 0.5
+        assert abs(keep - (1 - p)) < 5 * sigma + 1e-9, (name, keep, p)
+        assert torch.equal(m, b[off:off + ne]) and not torch.equal(m, c[off:off + ne])
+        covered[off:off + ne] = True
+    assert bool((a[~covered] == 7).all()), "alignment gaps are not written"
+
+
 def test_ewc(eng):
     p, mu, g = _r(N, 60), _r(N, 61), _r(N, 62)
     f = torch.empty(N, device="cuda")
