@@ -73,8 +73,13 @@ struct msa_handle {
     float* gemm_scratch = nullptr;   // 3xTF32 split scratch of the tcgen05 GEMM (in the pass workspace)
     size_t gemm_scratch_floats = 0;
     cudaStream_t cur_stream = nullptr;
-    bool tc_enabled = false;         // env MSA_GEMM_TC=1 routes the x.W^T contractions to the hand-written tcgen05 kernel (gemm_tc.cu);
-                                     // off by default: measured 1.5-2x slower than cuBLAS at these shapes so far
+    // Hand-written tcgen05 / TMA GEMM (gemm_tc.cu) for the x.W^T contractions.  tc_mode 2 (default): the fp32-accurate 3xTF32
+    // products of at least tc_min MACs -- at the default dimensions the decoder-RNN gate GEMMs [T*B x 4Hd] x K = 1024 / 768, where
+    // it is measured faster than cuBLAS's SIMT sgemm; 1: every eligible contraction incl. the single-TF32 ones (slower than
+    // cuBLAS's tensor-op kernels: DESIGN.md 4.5); 0: cuBLAS only.  Env MSA_GEMM_TC / MSA_GEMM_TC_MIN.
+    int tc_mode = 2;
+    long long tc_min = 2000000000LL;
+    bool tc_enabled = true;
     int rec_flags = -1;    // hand-off variant of the persistent kernels; -1 = per-kernel default (env MSA_REC_FLAGS overrides, development only)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
     std::vector<int> prof_id;
@@ -278,7 +283,8 @@ static int gemm(msa_handle* h, bool ta, bool tb, int64_t M, int64_t N, int64_t K
     const bool tf32 = h->cfg.gemm_tf32 >= 2 || (h->cfg.gemm_tf32 == 1 && h->in_bwd);
     // x . W^T contractions (both operands K-contiguous) go to the hand-written tcgen05 / TMA kernel (gemm_tc.cu) under the
     // tensor-core policies: 3xTF32 split where fp32 accuracy is required (forward of policy 1), single TF32 otherwise
-    if (!ta && tb && h->tc_enabled && h->cfg.gemm_tf32 >= 1 && N >= 8 && M * N >= 4096 && gemm_tc_supported(M, N, K, A, lda, Bm, ldb, Cm, ldc) &&
+    if (!ta && tb && h->tc_enabled && (h->tc_mode != 2 || !tf32) && (long long)M * N * K >= h->tc_min && h->cfg.gemm_tf32 >= 1 && N >= 8 &&
+        M * N >= 4096 && gemm_tc_supported(M, N, K, A, lda, Bm, ldb, Cm, ldc) &&
         (tf32 || (h->gemm_scratch && gemm_tc_scratch_floats(M, N, K) <= h->gemm_scratch_floats)))
         return gemm_tc_nt(M, N, K, alpha, A, lda, Bm, ldb, beta, Cm, ldc, tf32 ? 1 : 0, h->gemm_scratch, h->cur_stream);
     const cublasComputeType_t ct = tf32 ? CUBLAS_COMPUTE_32F_FAST_TF32 : CUBLAS_COMPUTE_32F;
@@ -410,7 +416,12 @@ int msa_create(const msa_config* cfg, int device, msa_handle** out) {
     h->sm_count = prop.multiProcessorCount;
     h->smem_limit = prop.sharedMemPerBlockOptin;
     if (const char* e = getenv("MSA_REC_FLAGS")) h->rec_flags = atoi(e);
-    if (const char* e = getenv("MSA_GEMM_TC")) h->tc_enabled = atoi(e) != 0;
+    if (const char* e = getenv("MSA_GEMM_TC")) {
+        h->tc_mode = atoi(e);
+        h->tc_enabled = h->tc_mode != 0;
+        if (h->tc_mode == 1) h->tc_min = 0;
+    }
+    if (const char* e = getenv("MSA_GEMM_TC_MIN")) h->tc_min = atoll(e);
     build_layout(h);
     cublasStatus_t s = cublasCreate(&h->blas);
     if (s != CUBLAS_STATUS_SUCCESS) {

@@ -92,6 +92,7 @@ class Engine:
         _lib.check(self.lib.msa_create(C.byref(self._ccfg), self.device.index or 0, C.byref(h)), "msa_create")
         self.h = h
         self._check_layout()
+        self._gap_idx = self._make_gap_index()
         self._ws: Optional[torch.Tensor] = None
         self._partials = torch.empty(self.lib.msa_flat_partials(), dtype=torch.float32, device=self.device)
         self._keep: tuple = ()
@@ -121,10 +122,24 @@ class Engine:
             raise RuntimeError("BN layout mismatch")
 
     def new_flat(self, fill: Optional[float] = 0.0) -> torch.Tensor:
+        """A flat buffer in the parameter layout.  ``fill=None``: the tensor regions are left uninitialised (the caller overwrites
+        them), but the alignment gaps between tensors are always zeroed: the fused kernels stream over the WHOLE buffer, so garbage
+        in a gap would end up in norms, Fisher sums and penalties."""
         t = torch.empty(self.layout.total, dtype=torch.float32, device=self.device)
         if fill is not None:
             t.fill_(fill)
+        elif self._gap_idx.numel():
+            t.index_fill_(0, self._gap_idx, 0.0)
         return t
+
+    def _make_gap_index(self) -> torch.Tensor:
+        idx, pos = [], 0
+        for name in self.layout.names():
+            off = self.layout.offsets[name]
+            idx.extend(range(pos, off))
+            pos = off + self.layout.numel(name)
+        idx.extend(range(pos, self.layout.total))
+        return torch.tensor(idx, dtype=torch.int64, device=self.device)
 
     def flat_from_dict(self, P: Dict[str, torch.Tensor]) -> torch.Tensor:
         flat = torch.zeros(self.layout.total, dtype=torch.float32)

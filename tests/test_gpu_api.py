@@ -99,6 +99,21 @@ def test_innerloop_fomaml_task_like_maml_py():
             pass
 
 
+def test_flat_buffer_gaps_are_zero_even_when_uninitialised():
+    """The fused kernels stream over whole flat buffers: the alignment gaps between tensors must never hold garbage (it would
+    reach gradient norms, Fisher sums and EWC penalties)."""
+    from msa_tts_b200.engine import Engine
+    eng = Engine(pkg.small_params())
+    junk = torch.full((eng.layout.total + 1024,), float("inf"), device="cuda")      # poison the allocator's free list
+    del junk
+    t = eng.new_flat(None)
+    assert eng._gap_idx.numel() > 0
+    assert bool((t[eng._gap_idx] == 0).all())
+    for n, v in eng.dict_from_flat(t).items():
+        v.zero_()
+    assert float(eng.sumsq(t)) == 0.0
+
+
 def test_innerloop_with_adam_inner_optimizer():
     """The reference builds the inner optimizer from YAML with any torch.optim class (utils/helpers.py:20-26): Adam inner
     steps on the fused path against oracle gradients + torch.optim.Adam on the CPU (two inner steps, then the test loss)."""
