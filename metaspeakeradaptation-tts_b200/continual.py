@@ -34,8 +34,19 @@ def make_soft_targets(model, batches: Iterable[tuple], masks: Optional[list] = N
     return out
 
 
-def sgd_train_step(model, batch: tuple, lr: float, ewc=None, importance: float = 0.0, masks: Optional[dict] = None) -> dict:
-    """One continual training step with plain SGD: loss (+ importance * EWC penalty), backward, update."""
+def adaptive_weight_decay(weightdecay_value: float, spk_similarity: float) -> float:
+    """continual_er_reg.py:213-216 (``regularizaton_method == "adaptive_weightdecay"``): the optimizer's weight decay for the next
+    speaker is ``weightdecay_value * (1 - similarity)``; a similarity of exactly 1.0 keeps the configured value (the reference only
+    overrides it ``if spk_similarity != 1.0``) -- pass ``None`` as ``weight_decay`` to ``sgd_train_step`` in that case.
+    The sibling method "adaptive_weightclipping" (continual_er_reg.py:356-360) clips the STALE gradients of the previous step right
+    before ``zero_grad()`` and therefore changes nothing; there is deliberately no kernel for it."""
+    return float(weightdecay_value) * (1.0 - float(spk_similarity))
+
+
+def sgd_train_step(model, batch: tuple, lr: float, ewc=None, importance: float = 0.0, masks: Optional[dict] = None,
+                   weight_decay: float = 0.0) -> dict:
+    """One continual training step with plain SGD: loss (+ importance * EWC penalty), backward, update.
+    ``weight_decay`` is torch.optim.SGD's (g += wd * p), folded into the same streaming update kernel."""
     eng = model.engine
     bd = batch_to_device(batch, eng.device, model.params["speaker_emb_type"])
     B, L = bd["inputs"].shape
@@ -44,7 +55,9 @@ def sgd_train_step(model, batch: tuple, lr: float, ewc=None, importance: float =
     _, loss = eng.forward(model.flat, model.bn_flat, bd, mk, outputs=False)
     eng.backward(model.flat, model.grad_flat)
     if ewc is not None:
+        if weight_decay:
+            raise NotImplementedError("EWC step with weight decay: the reference never combines them (continual_ewc.py:338-357)")
         penalty = ewc.sgd_step(model.grad_flat, lr, importance)                     # fused penalty gradient + update
         return {"loss": loss, "penalty": penalty}
-    eng.sgd_step(model.flat, model.grad_flat, lr=lr)
+    eng.sgd_step(model.flat, model.grad_flat, lr=lr, weight_decay=weight_decay)
     return {"loss": loss}

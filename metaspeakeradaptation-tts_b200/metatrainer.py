@@ -39,8 +39,10 @@ class MetaTrainer:
         # inner / outer optimizers: name + eval'ed string hyper-parameters, like helpers.get_optimizer (helpers.py:20-26)
         self.inner = optimizer_hparams(params["optim_inner"])
         self.outer = optimizer_hparams(params["optim_outer"])
-        if self.inner["name"] != "SGD":
-            raise NotImplementedError("inner optimizer: only the SGD rule is implemented (SURVEY.md 8f item 3)")
+        if self.inner["name"] not in ("SGD", "Adam"):
+            raise NotImplementedError("inner optimizer: the SGD and Adam rules are implemented (SURVEY.md 8f item 3)")
+        if self.inner["name"] == "Adam" and (self.inner.get("amsgrad", False) or self.inner.get("maximize", False)):
+            raise NotImplementedError("inner Adam: amsgrad / maximize are not implemented")
         if self.outer["name"] not in ("SGD", "Adam"):
             raise NotImplementedError("outer optimizer: SGD and Adam are implemented")
         # flat state
@@ -51,7 +53,10 @@ class MetaTrainer:
         self.fast = self.engine.new_flat()
         self.task_grad = self.engine.new_flat()
         self.task_bn = self.engine.new_bn_stats()
-        self.inner_buf = self.engine.new_flat() if self.inner.get("momentum", 0.0) else None
+        self.inner_buf = self.engine.new_flat() if (self.inner["name"] == "SGD" and self.inner.get("momentum", 0.0)) else None
+        # inner Adam: moment buffers, reset for every task (higher builds the optimizer state inside innerloop_ctx)
+        self.inner_m = self.engine.new_flat() if self.inner["name"] == "Adam" else None
+        self.inner_v = self.engine.new_flat() if self.inner["name"] == "Adam" else None
         self.outer_m = self.engine.new_flat() if (self.outer["name"] == "Adam" or self.outer.get("momentum", 0.0)) else None
         self.outer_v = self.engine.new_flat() if self.outer["name"] == "Adam" else None
         self.sumsq = torch.zeros(1, device=self.device)
@@ -90,12 +95,19 @@ class MetaTrainer:
         T = inputs["melspecs"].shape[2]
         h = self.inner
         losses = []
+        if h["name"] == "Adam":
+            self.inner_m.zero_()
+            self.inner_v.zero_()
         for it in range(n_inner):
             _, loss = eng.forward(self.fast, self.task_bn, inputs, self._masks(task_index, it, B, T, L), outputs=False)
             eng.backward(self.fast, self.task_grad)
-            eng.sgd_step(self.fast, self.task_grad, lr=h["lr"], momentum=h.get("momentum", 0.0), dampening=h.get("dampening", 0.0),
-                         weight_decay=h.get("weight_decay", 0.0), nesterov=h.get("nesterov", False), buf=self.inner_buf,
-                         first_step=(it == 0))
+            if h["name"] == "Adam":
+                eng.adam_step(self.fast, self.task_grad, self.fast, self.inner_m, self.inner_v, lr=h["lr"], step=it + 1,
+                              betas=h.get("betas", (0.9, 0.999)), eps=h.get("eps", 1e-8), weight_decay=h.get("weight_decay", 0.0))
+            else:
+                eng.sgd_step(self.fast, self.task_grad, lr=h["lr"], momentum=h.get("momentum", 0.0), dampening=h.get("dampening", 0.0),
+                             weight_decay=h.get("weight_decay", 0.0), nesterov=h.get("nesterov", False), buf=self.inner_buf,
+                             first_step=(it == 0))
             losses.append(loss)
         return losses
 

@@ -225,3 +225,26 @@ def test_erkd_soft_targets_like_continual_erkd_py():
     num = sum(float(((after[n] - (before[n] - 0.01 * o_g[n].to(after[n].device))).double() ** 2).sum()) for n in names)
     den = sum(float(((0.01 * o_g[n]).double() ** 2).sum()) for n in names)
     assert (num / den) ** 0.5 < TOL
+
+
+def test_er_reg_adaptive_weight_decay_step_like_continual_er_reg_py():
+    """continual_er_reg.py:213-216: weight_decay = weightdecay_value * (1 - similarity), then torch.optim.SGD's rule
+    g <- g + wd * p; p <- p - lr * g (one fused streaming kernel here)."""
+    from msa_tts_b200.continual import adaptive_weight_decay, sgd_train_step
+    cfg = pkg.small_params()
+    B, T, L = 3, 10, 8
+    P = synth.init_params(cfg, 9)
+    batch = synth.make_batch(cfg, B, T, L, 818)
+    masks = synth.make_masks(cfg, B, T, L, 819)
+    _, o_loss, o_g, _, _ = oracle_pass(cfg, P, batch, masks, CRIT)
+    wd = adaptive_weight_decay(0.2, 0.75)
+    assert abs(wd - 0.05) < 1e-12
+    model = _model(cfg, P)
+    log = sgd_train_step(model, batch, 0.01, masks=masks, weight_decay=wd)
+    assert abs(float(log["loss"]) - float(o_loss)) < TOL * abs(float(o_loss))
+    after = model.engine.dict_from_flat(model.flat)
+    names = list(P.keys())
+    want = {n: P[n] - 0.01 * (o_g[n] + wd * P[n]) for n in names}
+    num = sum(float(((after[n].cpu() - want[n]).double() ** 2).sum()) for n in names)
+    den = sum(float(((want[n] - P[n]).double() ** 2).sum()) for n in names)
+    assert (num / den) ** 0.5 < TOL
