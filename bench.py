@@ -131,6 +131,21 @@ def algo_bytes(cfg, kernel: str) -> float:
     raise KeyError(kernel)
 
 
+# Cross-CTA hand-offs (all-gathers through L2 among the 148 co-resident CTAs) on the serial path of ONE recurrence step, and the
+# bare cost of one such hand-off measured on B200 with nothing else in flight (tools/hop_bench.cu, mass polling of the data
+# words, 2268 cycles at 1.965 GHz; profiles/r01_trace_attn_chain_bwd_v7.txt).  T x hand-offs x that latency is the floor of a
+# persistent recurrent kernel whose weights are already on chip ("2 x grid-barrier latency" per step).
+HAND_OFFS = {"attn_chain_fwd": 3, "attn_chain_bwd": 4, "dec_lstm_fwd": 1, "dec_lstm_bwd": 1, "enc_lstm_fwd": 1, "enc_lstm_bwd": 1}
+HAND_OFF_US = 2268 / 1965.0
+
+
+def latency_bound(kernel: str, ms_per_launch: float):
+    steps = L if kernel.startswith("enc_") else T
+    bound_ms = steps * HAND_OFFS[kernel] * HAND_OFF_US * 1e-3
+    return {"steps": steps, "hand_offs_per_step": HAND_OFFS[kernel], "hand_off_us": HAND_OFF_US, "bound_ms": bound_ms,
+            "frac": bound_ms / ms_per_launch, "source": "tools/hop_bench.cu on B200: bare 148-CTA all-gather through L2"}
+
+
 def ncu_traffic(kernel: str):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json), or None."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -331,7 +346,7 @@ def main():
                 per = ms / cnt
                 kern.append({"kernel": name, "launches_per_step": cnt / args.steps, "ms_per_launch": per,
                              "share_of_step": ms / ms_dev, "algo_bytes": ab, "achieved_gbs": ab / per / 1e6,
-                             "frac": ab / per / 1e6 / peak})
+                             "frac": ab / per / 1e6 / peak, "latency_bound": latency_bound(name, per)})
         for name, (ms, ab) in flat_ms.items():
             kern.append({"kernel": name, "ms_per_launch": ms, "algo_bytes": ab, "achieved_gbs": ab / ms / 1e6,
                          "frac": ab / ms / 1e6 / peak, "timed": "alone, 20 reps"})
@@ -355,7 +370,8 @@ def main():
                          "note": "persistent recurrent kernel: weights stay in shared memory for all T steps; its time is set by "
                                  "the three cross-CTA hand-offs per decoder step (L2 round trips among 148 CTAs), not by HBM "
                                  "or tensor throughput (DESIGN.md section 4.2, profiles/r01_trace_*)",
-                         "ms_per_launch": dom["ms_per_launch"], "share_of_step": dom["share_of_step"]},
+                         "ms_per_launch": dom["ms_per_launch"], "share_of_step": dom["share_of_step"],
+                         "latency_bound": dom["latency_bound"]},
             "kernels": kern,
             "clocks": clk.summary(),
             "infer": infer_line,
