@@ -1,0 +1,117 @@
+"""Size-independent properties of the CUDA path at BASELINE.json's FULL sizes (default dimensions, B=4, T=200, L=64, 8 tasks),
+where the CPU oracle is too slow to be the checker for every case: bitwise repeatability, linearity of the backward pass in the
+upstream gradients, and "fused accumulation == mean of separately computed task gradients" for the whole FOMAML meta-step.
+(The same shapes against the reference's golden outputs: tests/test_gpu_pass.py::test_default_dims_config1_fp32_and_tf32.)
+"""
+import pytest
+import torch
+
+import msa_tts_b200 as pkg
+from msa_tts_b200 import synth
+from helpers import rel
+
+pytestmark = pytest.mark.gpu
+B, T, L = 4, 200, 64
+
+
+def _engine(tf32):
+    from msa_tts_b200.engine import Engine
+    return Engine(pkg.default_params(), reduction="none", pos_weight=10.0, gemm_tf32=tf32)
+
+
+def _inputs(eng, seed=11):
+    from msa_tts_b200.engine import batch_to_device
+    cfg = eng.cfg
+    flat = eng.flat_from_dict(synth.init_params(cfg, 0))
+    bd = batch_to_device(synth.make_batch(cfg, B, T, L, seed), eng.device)
+    masks = eng.generate_masks(B, T, L, 77)
+    return flat, bd, masks
+
+
+@pytest.mark.parametrize("tf32", [0, 1])
+def test_full_size_pass_is_bitwise_repeatable(tf32):
+    """Same inputs, same masks -> the same bits, run to run and engine to engine: the persistent kernels hand data over in a fixed
+    order, the column reductions combine partials in a fixed order, nothing uses floating-point atomics."""
+    runs = []
+    for _ in range(2):
+        eng = _engine(tf32)
+        flat, bd, masks = _inputs(eng)
+        for _ in range(2):
+            out, loss = eng.forward(flat, eng.new_bn_stats(), bd, masks)
+            g = eng.new_flat(0.0)
+            eng.backward(flat, g)
+            torch.cuda.synchronize()
+            eng.check_abort()
+            runs.append(([o.clone() for o in out], loss.clone(), g))
+        del eng
+    ref = runs[0]
+    assert bool(torch.isfinite(ref[2]).all()) and float(ref[2].abs().sum()) > 0
+    for out, loss, g in runs[1:]:
+        for a, b in zip(out, ref[0]):
+            assert torch.equal(a, b)
+        assert torch.equal(loss, ref[1]) and torch.equal(g, ref[2])
+
+
+def test_full_size_backward_is_linear_in_the_upstream_gradients():
+    """backward(a*d1 + b*d2) == a*backward(d1) + b*backward(d2) (fp32 GEMMs; 1e-5 of the gradient norm): every kernel of the
+    backward pass -- both recurrent chains included -- is a linear map of the upstream gradients for a fixed forward pass."""
+    eng = _engine(0)
+    flat, bd, masks = _inputs(eng, seed=12)
+    eng.forward(flat, eng.new_bn_stats(), bd, masks, outputs=False)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    M = eng.cfg["n_mel_channels"]
+
+    def rand_d():
+        return [torch.randn(B, M, T, device="cuda", generator=gen) * 1e-2, torch.randn(B, M, T, device="cuda", generator=gen) * 1e-2,
+                torch.randn(B, T, device="cuda", generator=gen) * 1e-2]
+    d1, d2 = rand_d(), rand_d()
+    a, b = 0.75, -1.5
+
+    def bwd(d):
+        g = eng.new_flat(0.0)
+        eng.backward(flat, g, d_outputs=d)
+        return g
+    g1, g2 = bwd(d1), bwd(d2)
+    g12 = bwd([a * x + b * y for x, y in zip(d1, d2)])
+    torch.cuda.synchronize()
+    eng.check_abort()
+    want = a * g1.double() + b * g2.double()
+    assert float(want.norm()) > 0
+    assert float((g12.double() - want).norm()) < 1e-5 * float(want.norm()), rel(g12, want)
+    # and the scale argument is the same linear map applied to the gradient
+    gs = eng.new_flat(0.0)
+    eng.backward(flat, gs, scale=0.125, d_outputs=d1)
+    assert rel(gs, 0.125 * g1) < 1e-6
+
+
+def test_full_size_fomaml_meta_gradient_is_the_mean_of_the_task_gradients():
+    """BASELINE configs[1] (8 tasks, 1 inner SGD step, bench GEMM policy): the meta-gradient that the test-split backward passes
+    accumulate in their epilogues (meta_grad += g/8) equals the mean of the 8 task gradients computed one by one into separate
+    buffers (utils/grad_utils.py:23-31), and the task losses agree bit for bit."""
+    import bench
+    from msa_tts_b200.maml import MAML
+    params = bench.trainer_params(1)
+    params["optim_outer"] = {"optimizer_name": "SGD", "optim_params": {"lr": "0.0"}}       # keep theta: the tasks are re-run below
+    tr = MAML(**params)
+    items = bench.make_tasks(tr.model_params, pinned=False)
+    log = tr._metatrain_step(items)
+    torch.cuda.synchronize()
+    tr.engine.check_abort()
+    meta = tr.meta_grad.clone()
+    losses = log["loss_test"].clone()
+    tr.step_global = 0                                                                       # same dropout-mask keys as above
+    eng, n = tr.engine, len(items)
+    acc = torch.zeros_like(meta, dtype=torch.float64)
+    g = eng.new_flat(0.0)
+    for i, spk in enumerate(items):
+        tr._adapt(i, items[spk]["train"], 1)
+        inputs, _ = tr._unpack_batch(items[spk]["test"])
+        _, loss = eng.forward(tr.fast, tr.task_bn, inputs, tr._masks(i, 1, B, T, L), outputs=False)
+        eng.backward(tr.fast, g)
+        torch.cuda.synchronize()
+        assert torch.equal(loss, losses[i:i + 1])
+        acc += g.double()
+    eng.check_abort()
+    want = acc / n
+    assert float((meta.double() - want).norm()) < 2e-6 * float(want.norm())
+    assert abs(float(log["grad_sumsq"]) ** 0.5 - float(want.norm())) < 1e-5 * float(want.norm())
