@@ -21,7 +21,8 @@ namespace msa {
 constexpr int kTcBM = 128, kTcBN = 128, kTcBK = 32;        // CTA tile; BK floats = one 128-byte swizzle row
 constexpr int kTcStages = 3;
 constexpr int kTcTileBytes = kTcBM * kTcBK * 4;             // 16 KB per operand tile
-constexpr int kTcThreads = 192;                             // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-5 epilogue
+constexpr int kTcThreads = 320;                             // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-9 lo-tile converters, 2-5 epilogue
+constexpr int kTcConv = kTcThreads - 64;                    // converter threads
 constexpr int kTcTmemCols = 128;
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------------------
@@ -74,15 +75,23 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 struct TcSmem {
-    uint64_t full[kTcStages], empty[kTcStages], tmem_full;
+    uint64_t full[kTcStages], conv[kTcStages], empty[kTcStages], tmem_full;
     uint32_t tmem_base;
 };
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// x_lo = x - (the 19 bits the tensor core reads), exact in fp32
+__device__ __forceinline__ float tc_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
+// grid = (M tiles, N tiles, K splits).  Split z handles the K blocks [z * kb_per_split, ...) and, when `partial` is given, stores
+// its raw accumulator tile to partial[z][M][N] (ker_splitk_reduce applies alpha / beta in a fixed order); otherwise it writes C.
+// kSplit (3xTF32): only the fp32 tiles A and B come in by TMA; the four converter / epilogue warps derive the lo tiles in shared
+// memory (same swizzled position, 32 KB further up) while the next stage is in flight, which halves the bytes every SM ingests.
 template <bool kSplit>
 __global__ void __launch_bounds__(kTcThreads, 1)
-k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
-               const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo, float* __restrict__ C, int ldc,
-               int M, int N, int K, float alpha, float beta) {
+k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float* __restrict__ C, int ldc,
+               int M, int N, int K, float alpha, float beta, float* __restrict__ partial, int kb_per_split) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte aligned operand tiles (swizzle atom = 8 rows x 128 B), then the barriers
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -91,9 +100,11 @@ k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * kTcBM, n0 = blockIdx.y * kTcBN;
     const int num_kb = (K + kTcBK - 1) / kTcBK;
+    const int kb0 = blockIdx.z * kb_per_split;
+    const int nkb = min(num_kb, kb0 + kb_per_split) - kb0;          // >= 1 (host)
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kTcStages; ++s) { mbar_init(&sb->full[s], 1); mbar_init(&sb->empty[s], 1); }
+        for (int s = 0; s < kTcStages; ++s) { mbar_init(&sb->full[s], 1); mbar_init(&sb->conv[s], kTcConv); mbar_init(&sb->empty[s], 1); }
         mbar_init(&sb->tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -109,25 +120,21 @@ k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kTcStages, it = kb / kTcStages;
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % kTcStages, it = i / kTcStages;
                 mbar_wait(&sb->empty[s], (it & 1) ^ 1);                       // slot free (first pass: passes immediately)
-                mbar_expect_tx(&sb->full[s], kOps * kTcTileBytes);
+                mbar_expect_tx(&sb->full[s], 2 * kTcTileBytes);
                 uint8_t* st = tiles + (size_t)s * kOps * kTcTileBytes;
-                tma_load_2d(st, &mapA, kb * kTcBK, m0, &sb->full[s]);
-                tma_load_2d(st + kTcTileBytes, &mapB, kb * kTcBK, n0, &sb->full[s]);
-                if (kSplit) {
-                    tma_load_2d(st + 2 * kTcTileBytes, &mapAlo, kb * kTcBK, m0, &sb->full[s]);
-                    tma_load_2d(st + 3 * kTcTileBytes, &mapBlo, kb * kTcBK, n0, &sb->full[s]);
-                }
+                tma_load_2d(st, &mapA, (kb0 + i) * kTcBK, m0, &sb->full[s]);
+                tma_load_2d(st + kTcTileBytes, &mapB, (kb0 + i) * kTcBK, n0, &sb->full[s]);
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kTcStages, it = kb / kTcStages;
-                mbar_wait(&sb->full[s], it & 1);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % kTcStages, it = i / kTcStages;
+                mbar_wait(kSplit ? &sb->conv[s] : &sb->full[s], it & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = smem_u32(tiles + (size_t)s * kOps * kTcTileBytes);
                 const uint64_t dA = umma_desc_k128(st), dB = umma_desc_k128(st + kTcTileBytes);
@@ -135,7 +142,7 @@ k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                 for (int k = 0; k < kTcBK / 8; ++k) {                          // UMMA_K = 8 tf32 = 32 bytes = 2 descriptor units
                     const uint64_t adv = (uint64_t)(k * 2);
-                    umma_tf32(tmem_acc, dA + adv, dB + adv, (kb | k) != 0);
+                    umma_tf32(tmem_acc, dA + adv, dB + adv, (i | k) != 0);
                     if (kSplit) {
                         umma_tf32(tmem_acc, dAl + adv, dB + adv, 1u);
                         umma_tf32(tmem_acc, dA + adv, dBl + adv, 1u);
@@ -146,11 +153,34 @@ k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             umma_commit(&sb->tmem_full);                                       // accumulator complete
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> global (alpha / beta), warp q handles TMEM lanes [32q, 32q+32) =====
         const int q = warp & 3;
+        if (kSplit) {
+            // ===== lo tiles: [A | B] (32 KB, as TMA swizzled them) -> [A_lo | B_lo] at the same positions 32 KB further up =====
+            const int ct = threadIdx.x - 64;                                   // 0 .. kTcConv-1
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % kTcStages, it = i / kTcStages;
+                mbar_wait(&sb->full[s], it & 1);
+                const float4* src = reinterpret_cast<const float4*>(tiles + (size_t)s * kOps * kTcTileBytes);
+                float4* dst = reinterpret_cast<float4*>(tiles + (size_t)s * kOps * kTcTileBytes + 2 * kTcTileBytes);
+                constexpr int kPer = 2 * kTcTileBytes / 16 / kTcConv;          // float4 words per thread (8)
+                float4 v[kPer];
+#pragma unroll
+                for (int j = 0; j < kPer; ++j) v[j] = src[ct + j * kTcConv];
+#pragma unroll
+                for (int j = 0; j < kPer; ++j) dst[ct + j * kTcConv] = make_float4(tc_lo(v[j].x), tc_lo(v[j].y), tc_lo(v[j].z), tc_lo(v[j].w));
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+                mbar_arrive(&sb->conv[s]);
+            }
+        }
+        if (warp >= 6) goto done;                                              // converter-only warps
+        // ===== epilogue: TMEM -> registers -> shared (transpose) -> global; warp q handles TMEM lanes [32q, 32q+32) =====
+        // (a thread owns an accumulator ROW; going through a 32 x 33 tile in the now idle operand ring turns the stores into
+        // 128-byte row segments instead of 32 scattered words per instruction)
         mbar_wait(&sb->tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = m0 + q * 32 + lane;
+        float* xp = reinterpret_cast<float*>(tiles) + q * (32 * 33);
+        float* obase = partial != nullptr ? partial + (size_t)blockIdx.z * M * N : C;
+        const int ldo = partial != nullptr ? N : ldc;
 #pragma unroll 1
         for (int cc = 0; cc < kTcBN / 32; ++cc) {
             uint32_t v[32];
@@ -166,19 +196,23 @@ k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 : "r"(taddr)
                 : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < M) {
-                float* crow = C + (size_t)row * ldc + n0 + cc * 32;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const int col = n0 + cc * 32 + c;
-                    if (col < N) {
-                        const float acc = alpha * __uint_as_float(v[c]);
-                        crow[c] = beta != 0.f ? acc + beta * crow[c] : acc;
-                    }
+            for (int c = 0; c < 32; ++c) xp[lane * 33 + c] = __uint_as_float(v[c]);
+            __syncwarp();
+            const int col = n0 + cc * 32 + lane;
+            if (col < N) {
+                const int rows = min(32, M - (m0 + q * 32));
+                for (int r = 0; r < rows; ++r) {
+                    float* out = obase + (size_t)(m0 + q * 32 + r) * ldo + col;
+                    const float acc = xp[r * 33 + lane];
+                    if (partial != nullptr) *out = acc;
+                    else *out = beta != 0.f ? alpha * acc + beta * *out : alpha * acc;
                 }
             }
+            __syncwarp();
         }
     }
+done:
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
@@ -186,17 +220,16 @@ k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
 }
 
-// x_lo = x - (x with the 13 low mantissa bits cleared)  on a [rows][K] block (row stride ld) -> compact [rows][ldo]
-__global__ void ker_split_lo(const float* __restrict__ x, int ld, float* __restrict__ lo, int ldo, int rows, int K) {
-    const int64_t n = (int64_t)rows * ldo;
+// C = alpha * (partial[0] + partial[1] + ...) + beta * C, splits summed in index order (deterministic)
+__global__ void ker_splitk_reduce(const float* __restrict__ partial, int splits, int M, int N, float* __restrict__ C, int ldc,
+                                  float alpha, float beta) {
+    const int64_t n = (int64_t)M * N;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int r = (int)(i / ldo), k = (int)(i - (int64_t)r * ldo);
-        float v = 0.f;
-        if (k < K) {
-            const float xv = x[(size_t)r * ld + k];
-            v = xv - __uint_as_float(__float_as_uint(xv) & 0xFFFFE000u);
-        }
-        lo[i] = v;
+        float s = partial[i];
+        for (int z = 1; z < splits; ++z) s += partial[(size_t)z * n + i];
+        const int r = (int)(i / N), c = (int)(i - (int64_t)r * N);
+        float* out = C + (size_t)r * ldc + c;
+        *out = beta != 0.f ? alpha * s + beta * *out : alpha * s;
     }
 }
 
@@ -236,40 +269,51 @@ bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, const float* A, int64_t 
     return M >= 1 && N >= 1 && K >= 1 && (lda % 4) == 0 && (ldb % 4) == 0 && al16(A) && al16(B) && M < (1 << 30) && N < (1 << 30) &&
            K < (1 << 30);
 }
+// K split: under-filled grids (few output tiles, long K) are spread over ~one wave of the 148 SMs, at least 4 K blocks per split
+static int tc_plan_splits(int64_t M, int64_t N, int64_t K) {
+    const int64_t tiles = ((M + kTcBM - 1) / kTcBM) * ((N + kTcBN - 1) / kTcBN);
+    const int64_t num_kb = (K + kTcBK - 1) / kTcBK;
+    int64_t splits = std::min<int64_t>(148 / std::max<int64_t>(tiles, 1), num_kb / 4);
+    if (splits < 2) return 1;
+    const int64_t per = (num_kb + splits - 1) / splits;
+    return (int)((num_kb + per - 1) / per);
+}
 size_t gemm_tc_scratch_floats(int64_t M, int64_t N, int64_t K) {
-    const int64_t ldo = (K + 3) / 4 * 4;
-    return (size_t)((M + N) * ldo + 64);
+    const int splits = tc_plan_splits(M, N, K);
+    return splits > 1 ? (size_t)splits * M * N + 64 : 64;
 }
 
-// mode 0: 3xTF32 (fp32-accurate), needs `scratch` of gemm_tc_scratch_floats(M, N, K); mode 1: single TF32 product
+// mode 0: 3xTF32 (fp32-accurate); mode 1: single TF32 product.  `scratch` (gemm_tc_scratch_floats(M, N, K) floats, 16-byte
+// aligned) holds the partial tiles of a K split; with scratch == nullptr the K range is not split.
 int gemm_tc_nt(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
                float* C, int64_t ldc, int mode, float* scratch, cudaStream_t st) {
     MSA_CHECK(gemm_tc_supported(M, N, K, A, lda, B, ldb, C, ldc), MSA_E_UNSUPPORTED, "gemm_tc_nt: operand alignment / leading dimensions");
-    CUtensorMap mA, mB, mAl, mBl;
+    CUtensorMap mA, mB;
     MSA_TRY(make_map(&mA, A, (int)M, (int)K, (int)lda));
     MSA_TRY(make_map(&mB, B, (int)N, (int)K, (int)ldb));
-    const dim3 grid((unsigned)((M + kTcBM - 1) / kTcBM), (unsigned)((N + kTcBN - 1) / kTcBN));
+    const int num_kb = (int)((K + kTcBK - 1) / kTcBK);
+    const int splits = scratch != nullptr ? tc_plan_splits(M, N, K) : 1;
+    const int per = (num_kb + splits - 1) / splits;
+    float* partial = splits > 1 ? scratch : nullptr;
+    const dim3 grid((unsigned)((M + kTcBM - 1) / kTcBM), (unsigned)((N + kTcBN - 1) / kTcBN), (unsigned)splits);
     if (mode == 0) {
-        MSA_CHECK(scratch != nullptr && (reinterpret_cast<uintptr_t>(scratch) & 15) == 0, MSA_E_ARG, "gemm_tc_nt: 3xTF32 needs 16-byte aligned scratch");
-        const int ldo = (int)((K + 3) / 4 * 4);
-        float* alo = scratch;
-        float* blo = scratch + (size_t)M * ldo;
-        blo = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(blo) + 15) & ~(uintptr_t)15);
-        ker_split_lo<<<(unsigned)std::min<int64_t>((M * ldo + 255) / 256, 148 * 8), 256, 0, st>>>(A, (int)lda, alo, ldo, (int)M, (int)K);
-        MSA_LAUNCH_CHECK();
-        ker_split_lo<<<(unsigned)std::min<int64_t>((N * ldo + 255) / 256, 148 * 8), 256, 0, st>>>(B, (int)ldb, blo, ldo, (int)N, (int)K);
-        MSA_LAUNCH_CHECK();
-        MSA_TRY(make_map(&mAl, alo, (int)M, (int)K, ldo));
-        MSA_TRY(make_map(&mBl, blo, (int)N, (int)K, ldo));
         const size_t smem = (size_t)kTcStages * 4 * kTcTileBytes + sizeof(TcSmem) + 1024;
-        MSA_CUDA(cudaFuncSetAttribute(k_gemm_tf32_nt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_gemm_tf32_nt<true><<<grid, kTcThreads, smem, st>>>(mA, mAl, mB, mBl, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta);
+        static bool attr0 = false;
+        if (!attr0) { MSA_CUDA(cudaFuncSetAttribute(k_gemm_tf32_nt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr0 = true; }
+        k_gemm_tf32_nt<true><<<grid, kTcThreads, smem, st>>>(mA, mB, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta, partial, per);
     } else {
         const size_t smem = (size_t)kTcStages * 2 * kTcTileBytes + sizeof(TcSmem) + 1024;
-        MSA_CUDA(cudaFuncSetAttribute(k_gemm_tf32_nt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_gemm_tf32_nt<false><<<grid, kTcThreads, smem, st>>>(mA, mA, mB, mB, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta);
+        static bool attr1 = false;
+        if (!attr1) { MSA_CUDA(cudaFuncSetAttribute(k_gemm_tf32_nt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr1 = true; }
+        k_gemm_tf32_nt<false><<<grid, kTcThreads, smem, st>>>(mA, mB, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta, partial, per);
     }
     MSA_LAUNCH_CHECK();
+    if (splits > 1) {
+        const int64_t n = M * N;
+        ker_splitk_reduce<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(partial, splits, (int)M, (int)N, C, (int)ldc,
+                                                                                                 alpha, beta);
+        MSA_LAUNCH_CHECK();
+    }
     return 0;
 }
 

@@ -70,15 +70,16 @@ struct msa_handle {
     bool prof = false;       // CUDA-event timing of the persistent kernels (bench.py)
     bool prof_inkernel = false;   // + per-phase cycle counters / per-warp traces inside them (profiles/ scripts only: slower kernels)
     int trace_t0 = 0;
-    float* gemm_scratch = nullptr;   // 3xTF32 split scratch of the tcgen05 GEMM (in the pass workspace)
+    float* gemm_scratch = nullptr;   // K-split partial tiles of the tcgen05 GEMM (in the pass workspace)
     size_t gemm_scratch_floats = 0;
     cudaStream_t cur_stream = nullptr;
     // Hand-written tcgen05 / TMA GEMM (gemm_tc.cu) for the x.W^T contractions.  tc_mode 2 (default): the fp32-accurate 3xTF32
-    // products of at least tc_min MACs -- at the default dimensions the decoder-RNN gate GEMMs [T*B x 4Hd] x K = 1024 / 768, where
-    // it is measured faster than cuBLAS's SIMT sgemm; 1: every eligible contraction incl. the single-TF32 ones (slower than
-    // cuBLAS's tensor-op kernels: DESIGN.md 4.5); 0: cuBLAS only.  Env MSA_GEMM_TC / MSA_GEMM_TC_MIN.
+    // products of at least tc_min MACs (3 x tc_min when K < 1024) -- at the default dimensions the LSTM input projections, the
+    // k=5 convolutions of encoder and postnet, MW and the mel / gate projection, 1.4-4x faster there than cuBLAS's SIMT sgemm;
+    // 1: every eligible contraction incl. the single-TF32 ones (cuBLAS's tensor-op kernels are a little faster: DESIGN.md 4.5);
+    // 0: cuBLAS only.  Env MSA_GEMM_TC / MSA_GEMM_TC_MIN.
     int tc_mode = 2;
-    long long tc_min = 2000000000LL;
+    long long tc_min = 100000000LL;
     bool tc_enabled = true;
     int rec_flags = -1;    // hand-off variant of the persistent kernels; -1 = per-kernel default (env MSA_REC_FLAGS overrides, development only)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
@@ -283,7 +284,10 @@ static int gemm(msa_handle* h, bool ta, bool tb, int64_t M, int64_t N, int64_t K
     const bool tf32 = h->cfg.gemm_tf32 >= 2 || (h->cfg.gemm_tf32 == 1 && h->in_bwd);
     // x . W^T contractions (both operands K-contiguous) go to the hand-written tcgen05 / TMA kernel (gemm_tc.cu) under the
     // tensor-core policies: 3xTF32 split where fp32 accuracy is required (forward of policy 1), single TF32 otherwise
-    if (!ta && tb && h->tc_enabled && (h->tc_mode != 2 || !tf32) && (long long)M * N * K >= h->tc_min && h->cfg.gemm_tf32 >= 1 && N >= 8 &&
+    // (measured on B200, profiles/r01_gemm_tc_v14.txt: the kernel has ~10 us of fixed cost, so short-K / small products stay on cuBLAS)
+    const long long macs = (long long)M * N * K;
+    const bool tc_size = macs >= h->tc_min && (macs >= 3 * h->tc_min || K >= 1024);
+    if (!ta && tb && h->tc_enabled && (h->tc_mode != 2 || !tf32) && tc_size && h->cfg.gemm_tf32 >= 1 && N >= 8 &&
         M * N >= 4096 && gemm_tc_supported(M, N, K, A, lda, Bm, ldb, Cm, ldc) &&
         (tf32 || (h->gemm_scratch && gemm_tc_scratch_floats(M, N, K) <= h->gemm_scratch_floats)))
         return gemm_tc_nt(M, N, K, alpha, A, lda, Bm, ldb, beta, Cm, ldc, tf32 ? 1 : 0, h->gemm_scratch, h->cur_stream);
