@@ -15,7 +15,7 @@ steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 cfg = pkg.default_params()
 cfg["max_decoder_steps"] = steps
 cfg["decoder_no_early_stopping"] = True
-eng = Engine(cfg, torch.device("cuda:0"))
+eng = Engine(cfg, torch.device("cuda:0"), gemm_tf32=int(os.environ.get("MSA_POLICY", "0")))     # 0 fp32-accurate, 2 TF32
 B = 32
 lens = torch.arange(64, 64 - B, -1)
 inp = torch.randint(1, 123, (B, 64))
