@@ -202,11 +202,20 @@ k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int col = n0 + cc * 32 + lane;
             if (col < N) {
                 const int rows = min(32, M - (m0 + q * 32));
-                for (int r = 0; r < rows; ++r) {
-                    float* out = obase + (size_t)(m0 + q * 32 + r) * ldo + col;
-                    const float acc = xp[r * 33 + lane];
-                    if (partial != nullptr) *out = acc;
-                    else *out = beta != 0.f ? alpha * acc + beta * *out : alpha * acc;
+                float* out = obase + (size_t)(m0 + q * 32) * ldo + col;
+                if (partial == nullptr && beta != 0.f) {
+                    // C is read for all 32 rows before the first store: one memory round trip per tile column block instead of 32
+                    // dependent ones (most products of the pass accumulate onto a bias-filled C with beta = 1)
+                    float old[32];
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) old[r] = r < rows ? __ldcs(out + (size_t)r * ldo) : 0.f;
+#pragma unroll
+                    for (int r = 0; r < 32; ++r)
+                        if (r < rows) out[(size_t)r * ldo] = alpha * xp[r * 33 + lane] + beta * old[r];
+                } else {
+                    const float sc = partial != nullptr ? 1.f : alpha;
+#pragma unroll 8
+                    for (int r = 0; r < rows; ++r) out[(size_t)r * ldo] = sc * xp[r * 33 + lane];
                 }
             }
             __syncwarp();

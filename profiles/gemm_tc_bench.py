@@ -37,6 +37,34 @@ def timed(fn, reps=20):
 
 
 P = lambda t: C.c_void_p(t.data_ptr())
+# ---- the same products with the leading dimensions they have inside the pass, L2-hot and with the L2 flushed before every call ----
+flush_buf = torch.empty(64 * 1024 * 1024, device="cuda")           # 256 MB > 126 MB of L2
+PASS_LD = [("dec gates h_a part, ldb 1792", 800, 4096, 1024, 1024, 1792, 0.0), ("dec gates ctx part, beta 1", 800, 4096, 768, 768, 1792, 1.0),
+           ("attn-LSTM prenet part, ldb 1024", 804, 4096, 256, 256, 1024, 0.0)]
+print(f"{'contraction (pass leading dims)':36s} | tc 3xTF32 hot / cold | cuBLAS fp32 hot / cold   (us, cold = after an L2 flush, flush time subtracted)")
+for name, M, N, K, lda, ldb, beta in PASS_LD:
+    A, B = torch.randn(M, lda, device="cuda"), torch.randn(N, ldb, device="cuda")
+    Cm = torch.zeros(M, N, device="cuda")
+    scratch = torch.empty(int(lib.msa_gemm_nt_scratch_floats(M, N, K)) + 4, device="cuda")
+
+    def tc0():
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(lib.msa_gemm_nt(M, N, K, C.c_float(1.0), P(A), lda, P(B), ldb, C.c_float(beta), P(Cm), N, 0, P(scratch), st), "msa_gemm_nt")
+
+    def cb():
+        if beta:
+            torch.addmm(Cm, A[:, :K], B[:, :K].t(), out=Cm)
+        else:
+            torch.mm(A[:, :K], B[:, :K].t(), out=Cm)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    tf = timed(lambda: flush_buf.zero_())
+    res = []
+    for fn in (tc0, cb):
+        hot = timed(fn)
+        cold = timed(lambda: (flush_buf.zero_(), fn())) - tf
+        res += [hot, cold]
+    print(f"{name:36s} | {res[0]:9.1f} / {res[1]:6.1f}  | {res[2]:9.1f} / {res[3]:6.1f}")
+print()
 print(f"{'contraction':28s} {'M':>5s} {'N':>5s} {'K':>5s} | tc 3xTF32  tc TF32 | cuBLAS fp32  cuBLAS TF32   (us)   err(3x)")
 for name, M, N, K in SHAPES:
     A, B = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda")
