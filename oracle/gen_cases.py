@@ -62,3 +62,18 @@ def infer_stats(P, cfg, seed):
         elif k.endswith("running_var"):
             stats[k] = 0.5 + torch.rand(stats[k].shape, generator=g)
     return stats
+
+
+def collate_items(seed: int, n: int, n_mels: int = 8, n_symbols: int = 40, spk_dim: int = 6):
+    """n raw dataset items in the reference's format (dataloader_meta.py:82-110): (item_id, transcript LongTensor [len],
+    speaker_id int, "waveform" slot, spk_emb FloatTensor [Ds]) -- with a ready mel-spectrogram [1, n_mels, len] in the waveform
+    slot (the audio front end is out of scope).  Ragged lengths, unsorted, with ties in the transcript length."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    items = []
+    for i in range(n):
+        tl = int(torch.randint(3, 9, (1,), generator=g))
+        ml = int(torch.randint(5, 14, (1,), generator=g))
+        items.append((f"item_{seed}_{i}.wav", torch.randint(1, n_symbols, (tl,), generator=g, dtype=torch.int64), (seed + i) % 3,
+                      torch.randn(1, n_mels, ml, generator=g), torch.randn(spk_dim, generator=g)))
+    return items

@@ -216,3 +216,43 @@ def test_checkpoint_round_trip_keeps_the_reference_state_dict_keys(tmp_path):
     assert extra and all(k.endswith(("running_mean", "running_var", "num_batches_tracked")) for k in extra)
     tr2 = MAML(**_params(cfg, _sgd(0.05), _sgd(0.02), n_inner, None, finetune=True, finetune_checkpoint_path=path, init_seed=99))
     assert torch.equal(tr2.theta, tr.theta)                                  # bit-exact through the file
+
+
+def test_meta_step_on_collated_ragged_batches_from_pinned_memory():
+    """The data contract end to end: raw items -> MetaCollator (pinned host memory, the reference's tuple layout,
+    dataloader_meta.py:133-179) -> MAML._metatrain_step, with different B / T / L for the train and the test split of each speaker,
+    against the oracle on the same collated tuples."""
+    import msa_tts_b200 as pkg
+    from msa_tts_b200 import synth
+    from msa_tts_b200.data import MetaCollator
+    from msa_tts_b200.maml import MAML
+    from oracle import meta as OMeta
+    from oracle import model as OM
+    from oracle.gen_cases import collate_items
+    cfg = pkg.small_params()
+    kw = dict(n_mels=cfg["n_mel_channels"], n_symbols=cfg["n_symbols"], spk_dim=cfg["speaker_embedding_dim"])
+    raw = [("spkA", {"train": collate_items(70, 4, **kw), "test": collate_items(71, 3, **kw)}),
+           ("spkB", {"train": collate_items(72, 2, **kw), "test": collate_items(73, 4, **kw)})]
+    items = MetaCollator(cfg["n_frames_per_step"], pin_memory=True)(raw)
+    assert all(t.is_pinned() for spk in items.values() for b in spk.values() for t in b[1:])
+    masks = {}
+    for i, spk in enumerate(items):
+        for p, mode in enumerate(("train", "test")):
+            b = items[spk][mode]
+            masks[(i, p)] = synth.make_masks(cfg, b[1].shape[0], b[3].shape[2], b[1].shape[1], 9000 + 8 * i + p)
+    tr = MAML(**_params(cfg, _sgd(0.05), _sgd(0.02), 1, None))
+    tr.injected_masks = masks
+    log = tr._metatrain_step(items)
+    torch.cuda.synchronize()
+    tr.engine.check_abort()
+    names = OM.param_names(cfg)
+    P0 = synth.init_params(cfg, 5)
+    grads, losses = [], []
+    for i, spk in enumerate(items):
+        loss, g, _, _, _ = OMeta.fomaml_task(P0, cfg, items[spk], [masks[(i, 0)], masks[(i, 1)]], CRIT, names, 1, 0.05)
+        grads.append(g)
+        losses.append(float(loss))
+    mixed = OMeta.mix_grad(grads, [0.5, 0.5], names)
+    for a, b in zip(log["loss_test"].tolist(), losses):
+        assert abs(a - b) < TOL * abs(b)
+    _check_tensors(tr.engine.dict_from_flat(tr.meta_grad), mixed, names, OMeta.grad_norm(mixed, names), "meta-gradient")

@@ -93,3 +93,32 @@ def test_sharded_meta_gradient_equals_unsharded_gloo_world2(n_tasks):
     assert np.allclose(acc, ref.numpy(), rtol=0, atol=1e-6), "sharded sum = unsharded mix_grad up to fp32 summation order"
     assert losses.tolist() == [float(i) for i in range(n_tasks)]
     assert mx == 1.0
+
+
+@pytest.mark.parametrize("r", [1, 2, 3])
+def test_collators_match_the_reference_collators_bit_for_bit(r):
+    """msa_tts_b200.data.Collator / MetaCollator against tests/golden/collate.npz, which holds the outputs of the reference's own
+    collators on the same raw items (oracle/gen_golden_collate.py): order of the sorted items, padding values, padding to a
+    multiple of the reduction factor, stop targets, dtypes -- all exact."""
+    from msa_tts_b200.data import Collator, MetaCollator
+    from oracle.gen_cases import collate_items
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "collate.npz"))
+    keys = ("transcripts", "trans_lengths", "melspecs", "melspec_lengths", "speaker_ids", "spk_embs", "stop_targets")
+
+    def check(batch, prefix):
+        assert list(batch[0]) == list(z[prefix + "/item_ids"])
+        for k, t in zip(keys, batch[1:]):
+            ref = z[f"{prefix}/{k}"]
+            assert tuple(t.shape) == ref.shape and np.array_equal(t.numpy(), ref), (prefix, k)
+            if f"{prefix}/{k}/dtype" in z:
+                assert str(t.dtype) == str(z[f"{prefix}/{k}/dtype"])
+        assert batch[3].shape[2] % r == 0 and batch[7].shape[1] == batch[3].shape[2]
+
+    check(Collator(r)(collate_items(10 + r, 5)), f"default_r{r}")
+    meta = [("spkA", {"train": collate_items(20 + r, 4), "test": collate_items(30 + r, 3)}),
+            ("spkB", {"train": collate_items(40 + r, 2), "test": collate_items(50 + r, 4)})]
+    d = MetaCollator(r)(meta)
+    assert list(d.keys()) == ["spkA", "spkB"]
+    for spk in d:
+        for mode in ("train", "test"):
+            check(d[spk][mode], f"meta_r{r}/{spk}/{mode}")
