@@ -56,6 +56,18 @@ class FunctionalTacotron2NV:
         self.engine._last_out = out
         return list(out)
 
+    def infer(self, inputs, input_lengths, speaker_vecs, prenet_masks=None):
+        """``fmodel.eval(); fmodel.infer(...)`` of the few-shot adaptation script (infer.py:266-293, tacotron2nv.py:130-162): free-running
+        decoding with the ADAPTED weights and with the functional copy's BatchNorm running statistics -- the ones the adaptation
+        passes (train mode) have been moving, not the base model's (higher clones the buffers)."""
+        cfg = self.model.params
+        steps = cfg["max_decoder_steps"]
+        if prenet_masks is None:
+            g = torch.Generator().manual_seed(self.model._mask_seed + 7919 * (self._calls + 1))
+            prenet_masks = (torch.rand(steps, 2, inputs.shape[0], cfg["prenet_dim"], generator=g) >= 0.5)
+        with torch.no_grad():
+            return self.engine.infer(self._fast[-1], self.bn_flat, inputs, input_lengths, speaker_vecs, prenet_masks, steps)
+
     def parameters(self, time: int = -1):
         """Leaf views of the fast weights at ``time`` in ``model.parameters()`` order (maml.py:71-74)."""
         return self._views[time]
@@ -66,6 +78,10 @@ class FunctionalTacotron2NV:
     def state_dict(self):
         sd = {k: v.detach() for k, v in self.engine.dict_from_flat(self._fast[-1]).items()}
         sd.update(self.engine.bn_dict(self.bn_flat))
+        base = self.model.state_dict()
+        for name in self.model.layout.bn_names:        # every train-mode forward of the copy counts one batch per BatchNorm layer
+            k = name + ".num_batches_tracked"
+            sd[k] = base[k].detach().cpu() + self._calls
         return sd
 
     def eval(self):

@@ -248,3 +248,49 @@ def test_er_reg_adaptive_weight_decay_step_like_continual_er_reg_py():
     num = sum(float(((after[n].cpu() - want[n]).double() ** 2).sum()) for n in names)
     den = sum(float(((want[n] - P[n]).double() ** 2).sum()) for n in names)
     assert (num / den) ** 0.5 < TOL
+
+
+def test_few_shot_adaptation_then_infer_like_infer_py():
+    """infer.py:258-293 (BASELINE configs[4]): adapt on the speaker's train split inside innerloop_ctx, ``fmodel.eval()``, then
+    free-running ``fmodel.infer`` -- with the adapted weights AND the functional copy's BatchNorm running statistics, which the
+    train-mode adaptation passes have moved (the base model's stay untouched).  mel_lengths / step count exact, mels 2e-4."""
+    cfg = dict(pkg.small_params())
+    cfg["max_decoder_steps"], cfg["decoder_no_early_stopping"] = 14, True
+    B, T, L, n_inner, lr = 3, 10, 8, 2, 0.05
+    P = synth.init_params(cfg, 12)
+    task = synth.make_task(cfg, B, T, L, 21)
+    masks = [synth.make_masks(cfg, B, T, L, 970 + i) for i in range(n_inner)]
+    names = OM.param_names(cfg)
+    from oracle import meta as OMeta
+    P_T, stats, _ = OMeta.adapt_task(P, cfg, task, masks, CRIT, names, n_inner, lr)
+    _, q_inp, q_len, _, _, _, q_spk, _ = synth.make_batch(cfg, 2, 6, 7, 333)
+    pm = synth.make_infer_masks(cfg, 2, cfg["max_decoder_steps"], 77)
+    o_post, o_lens, o_align = OM.infer(P_T, cfg, q_inp, q_len, q_spk, pm, stats)
+
+    model = _model(cfg, P)
+    base_bn = model.bn_flat.clone()
+    criterion = pkg.Tacotron2Loss(1, "none", 10.0)
+    inner_opt = torch.optim.SGD(model.parameters(), lr=lr)
+    with pkg.innerloop_ctx(model, inner_opt, track_higher_grads=False) as (fmodel, diffopt):
+        fmodel.injected_masks = masks
+        for _ in range(n_inner):
+            kw, targets, mel_len = _inputs(task["train"])
+            diffopt.step(criterion(fmodel(**kw), targets, mel_len))
+        fmodel.eval()
+        post, lens, align = fmodel.infer(q_inp, q_len, q_spk, prenet_masks=pm)
+        adapted = fmodel.state_dict()
+    torch.cuda.synchronize()
+    assert post.shape == o_post.shape and torch.equal(lens.cpu(), o_lens)
+    assert rel(post, o_post) < TOL and rel(align, o_align) < TOL
+    assert torch.equal(model.bn_flat, base_bn), "the base model's running statistics must not move (higher clones the buffers)"
+    for k, v in stats.items():                                   # the functional copy's did, exactly like the oracle's
+        if k.endswith("num_batches_tracked"):
+            assert int(adapted[k]) == int(v) == n_inner, k
+        else:
+            assert rel(adapted[k], v) < TOL, k
+    # infer.py:287-288: model_spk.load_state_dict(fmodel.state_dict()) -- the adapted copy is a loadable checkpoint
+    spk_model = pkg.Tacotron2NV(cfg)
+    missing, unexpected = spk_model.load_state_dict(adapted, strict=False)
+    assert not unexpected and not missing
+    post2, lens2, _ = spk_model.infer(q_inp, q_len, q_spk, prenet_masks=pm)
+    assert torch.equal(post2, post) and torch.equal(lens2, lens)
