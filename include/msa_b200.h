@@ -147,6 +147,13 @@ int msa_train_backward(msa_handle* h, void* ws, size_t ws_bytes, const float* pa
  * (metatrainer.py:83-86); also refreshes d(loss)/d(outputs) used by msa_train_backward(NULL,...). */
 int msa_train_loss(msa_handle* h, void* ws, const float* stop_targets, const int64_t* mel_lengths, int reduction,
                    float pos_weight, float* loss_out, void* stream);
+/* replaces utils/metrics.py:15-22 mcd_batch as called by the trainers' per-task logs (maml.py:78-82,
+ * baseline.py, continual_*.py): K * mean_b mean_{t < len_b} ||mel_target - out||_2 with
+ * K = 10 / ln(10) * sqrt(2), on the device, from the outputs of the last msa_train_forward in `ws`
+ * (no device->host copy of the mel outputs, no host sync).  which = 0: the model's FIRST output
+ * (pre-postnet mel -- the tensor the reference's logs call "out_post"), 1: mel_post.
+ * mcd_out: 1 float on the device. */
+int msa_train_mcd(msa_handle* h, void* ws, const int64_t* mel_lengths, int which, float* mcd_out, void* stream);
 /* Tacotron2Loss.__call__ as a stand-alone operator on reference-layout tensors (tacotron2nv_loss.py:17-52):
  * mel / mel_post / mel_target [B, n_mel, T], gate / stop_targets [B, T], mel_lengths int64 [B]; writes the scalar loss and,
  * where the pointers are not NULL, d(loss)/d(mel, mel_post, gate).  scratch: msa_loss_scratch_floats(B, T, n_mel) floats. */

@@ -48,6 +48,7 @@ SIGNATURES = {
     "msa_train_forward": (I, [V, V, SZ, V, V, V, V, V, V, V, V, V, V, I, I, I, V, V, V, V, V, V]),
     "msa_train_backward": (I, [V, V, SZ, V, V, V, V, V, I, F, V]),
     "msa_train_loss": (I, [V, V, V, V, I, F, V, V]),
+    "msa_train_mcd": (I, [V, V, V, I, V, V]),
     "msa_loss_scratch_floats": (SZ, [I, I, I]),
     "msa_tacotron2_loss": (I, [V, V, V, V, V, V, I, I, I, I, F, V, V, V, V, V, V]),
     "msa_loss_grads": (I, [V, V, V, V, V, V]),

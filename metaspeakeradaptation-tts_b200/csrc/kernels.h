@@ -152,6 +152,8 @@ int k_bt_to_ref(const float* x_bt, float* out, int B, int T, int M, cudaStream_t
 int k_ref_to_bt(const float* x, float* out_bt, int B, int T, int M, cudaStream_t st);      // [B][M][T] -> [B][T][M]
 int k_add(const float* a, const float* b, float* out, int64_t n, cudaStream_t st);
 int k_add3(const float* a, const float* b, const float* c, float* out, int64_t n, cudaStream_t st);
+int k_mcd(const float* out_bt, const float* target_bt, const int64_t* mel_len, int B, int T, int M, float* partials, float* result,
+          cudaStream_t st);
 int k_loss(const float* pre_bt, const float* post_bt, const float* gate_bt, const float* target_bt, const float* stop,
            const int64_t* mel_len, int B, int T, int M, int reduction, float pos_weight, float* partials, float* loss,
            float* dpre, float* dpost, float* dgate, cudaStream_t st);

@@ -455,6 +455,28 @@ __global__ void ker_loss(const float* __restrict__ pre, const float* __restrict_
     acc = block_sum(acc, red);
     if (threadIdx.x == 0) partials[blockIdx.x] = acc;
 }
+// mel-cepstral-distortion style metric of the trainers' logs (utils/metrics.py:15-22): K * mean_b mean_{t < len_b} ||target - out||_2,
+// out / target [B][T][M]; one block per (b, t) row chunk, deterministic 2-stage sum (partials scaled by 1 / (len_b * B))
+__global__ void ker_mcd(const float* __restrict__ out, const float* __restrict__ target, const int64_t* __restrict__ mel_len, int B, int T,
+                        int M, float* partials) {
+    __shared__ float red[33];
+    const int64_t nrows = (int64_t)B * T;
+    float acc = 0.f;
+    for (int64_t row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int b = (int)(row / T), t = (int)(row % T);
+        const int len = (int)mel_len[b];
+        float ss = 0.f;
+        if (t < len)
+            for (int m = threadIdx.x; m < M; m += blockDim.x) {
+                const float d = target[row * M + m] - out[row * M + m];
+                ss += d * d;
+            }
+        ss = block_sum(ss, red);          // every thread of the block takes part (uniform trip count)
+        if (threadIdx.x == 0 && t < len) acc += sqrtf(ss) / ((float)len * (float)B);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
 __global__ void ker_sum_partials(const float* __restrict__ partials, int n, float* out, float scale, int accumulate) {
     __shared__ float red[33];
     float s = 0.f;
@@ -749,6 +771,15 @@ int k_loss(const float* pre_bt, const float* post_bt, const float* gate_bt, cons
                                    partials, dpre, dpost, dgate);
     MSA_LAUNCH_CHECK();
     ker_sum_partials<<<1, 256, 0, ST>>>(partials, grid, loss, 1.f, 0);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_mcd(const float* out_bt, const float* target_bt, const int64_t* mel_len, int B, int T, int M, float* partials, float* result,
+          cudaStream_t st) {
+    int grid = (int)std::min<int64_t>((int64_t)B * T, kLossBlocks);
+    ker_mcd<<<grid, 128, 0, ST>>>(out_bt, target_bt, mel_len, B, T, M, partials);
+    MSA_LAUNCH_CHECK();
+    ker_sum_partials<<<1, 256, 0, ST>>>(partials, grid, result, 6.1418514f, 0);      // K = 10 / ln(10) * sqrt(2)
     MSA_LAUNCH_CHECK();
     return 0;
 }

@@ -689,6 +689,17 @@ int msa_train_loss(msa_handle* h, void* wsp, const float* stop_targets, const in
     return 0;
 }
 
+int msa_train_mcd(msa_handle* h, void* wsp, const int64_t* mel_lengths, int which, float* mcd_out, void* stream) {
+    MSA_CHECK(h && wsp && h->fwd_valid, MSA_E_STATE, "msa_train_mcd: no forward pass in this workspace");
+    MSA_CHECK(mel_lengths && mcd_out && (which == 0 || which == 1), MSA_E_ARG, "msa_train_mcd: bad argument");
+    const Dims& d = h->d;
+    const Ws w = ws_layout(d, wsp);
+    cudaStream_t st = (cudaStream_t)stream;
+    MSA_TRY(k_mcd(which == 0 ? w.post_x : w.post_bt, w.target, mel_lengths, d.B, d.T, d.M, w.loss_part, w.loss + 8, st));
+    MSA_TRY(k_scale_copy(w.loss + 8, mcd_out, 1, 1.f, 0, st));
+    return 0;
+}
+
 size_t msa_loss_scratch_floats(int B, int T, int n_mel) {
     return (size_t)7 * align_up((int64_t)B * T * n_mel, 64) + (size_t)2 * align_up((int64_t)B * T, 64) + 2048;
 }

@@ -262,6 +262,14 @@ class Engine:
         self.launches += 1
         return out
 
+    def mcd(self, mel_lengths: torch.Tensor, which: int = 0) -> torch.Tensor:
+        """utils/metrics.py:15-22 ``mcd_batch`` of the last forward on the device (1-element tensor, no sync); which = 0: the first
+        model output, the one the reference's logs use (maml.py:78-82), 1: mel_post."""
+        out = torch.empty(1, device=self.device)
+        _lib.check(self.lib.msa_train_mcd(self.h, self._ws_ptr(), _ptr(mel_lengths), int(which), _ptr(out), _stream()), "msa_train_mcd")
+        self.launches += 3
+        return out
+
     def loss_grads(self, B: int, T: int):
         M = self.cfg["n_mel_channels"]
         d = [torch.empty(B, M, T, device=self.device), torch.empty(B, M, T, device=self.device), torch.empty(B, T, device=self.device)]

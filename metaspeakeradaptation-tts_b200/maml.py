@@ -30,7 +30,7 @@ class MAML(MetaTrainer):
         N = len(speakers)
         mine = self.shard.my_tasks(N)
         n_inner = self.params["n_inner_train"]
-        losses = []
+        losses, mcds = [], []
         if not mine:
             self.meta_grad.zero_()
         for j, i in enumerate(mine):
@@ -40,12 +40,14 @@ class MAML(MetaTrainer):
             B, L = inputs["inputs"].shape
             T = inputs["melspecs"].shape[2]
             _, loss = eng.forward(self.fast, self.task_bn, inputs, self._masks(i, n_inner, B, T, L), outputs=False)
+            mcds.append(eng.mcd(inputs["melspec_lengths"]))      # maml.py:78-82, on the device: no copy of the mels, no host sync
             # task_grads = autograd.grad(loss_test, fmodel.parameters(time=-1)); mix_grad weight 1/N (maml.py:73-74, 94-98)
             eng.backward(self.fast, self.meta_grad, accumulate=(j > 0), scale=1.0 / N)
             losses.append(loss)
         sumsq = self._outer_update()
         local = torch.cat(losses) if losses else torch.zeros(0, device=self.device)
-        return {"loss_test": local, "task_index": mine, "grad_sumsq": sumsq}
+        mcd = torch.cat(mcds) if mcds else torch.zeros(0, device=self.device)
+        return {"loss_test": local, "mcd": mcd, "task_index": mine, "grad_sumsq": sumsq}
 
     def _metatrain(self, epoch: int, dataloader_metatrain) -> List[dict]:
         """maml.py:33-108 over an iterable of meta-batches (the reference's DataLoader is out of scope)."""

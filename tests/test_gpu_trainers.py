@@ -71,15 +71,19 @@ def test_fomaml_meta_step_matches_oracle(outer):
     torch.cuda.synchronize()
     tr.engine.check_abort()
 
-    o_losses, o_grads = [], []
+    o_losses, o_grads, o_mcd = [], [], []
     for i, spk in enumerate(tasks):
-        loss, g, _, _, _ = OMeta.fomaml_task(P0, cfg, tasks[spk], [masks[(i, p)] for p in range(n_inner + 1)], CRIT, names, n_inner, lr_in)
+        loss, g, out, _, _ = OMeta.fomaml_task(P0, cfg, tasks[spk], [masks[(i, p)] for p in range(n_inner + 1)], CRIT, names, n_inner, lr_in)
         o_losses.append(float(loss))
         o_grads.append(g)
+        test = tasks[spk]["test"]          # maml.py:78-82: mcd_batch of the FIRST model output against the test mels
+        o_mcd.append(OMeta.mcd_batch(out[0].transpose(1, 2), test[3].transpose(1, 2), test[4].tolist()))
     mixed = OMeta.mix_grad(o_grads, [1.0 / n_tasks] * n_tasks, names)
     gn = OMeta.grad_norm(mixed, names)
     assert log["task_index"] == list(range(n_tasks))
     for a, b in zip(log["loss_test"].tolist(), o_losses):
+        assert abs(a - b) < TOL * abs(b)
+    for a, b in zip(log["mcd"].tolist(), o_mcd):                                # device-side metric of the per-task log
         assert abs(a - b) < TOL * abs(b)
     _check_tensors(tr.engine.dict_from_flat(tr.meta_grad), mixed, names, gn, "meta-gradient")
     assert abs(float(log["grad_sumsq"]) ** 0.5 - gn) < TOL * gn                 # apply_grad's norm (grad_utils.py:8-20)
