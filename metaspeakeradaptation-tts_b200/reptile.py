@@ -30,6 +30,7 @@ class Reptile(MetaTrainer):
         B, L = inputs["inputs"].shape
         T = inputs["melspecs"].shape[2]
         _, loss = self.engine.forward(self.fast, self.task_bn, inputs, self._masks(i, n_inner, B, T, L), outputs=False)
+        self._mcds.append(self.engine.mcd(inputs["melspec_lengths"]))       # reptile.py:62-66, on the device
         return loss
 
     def _metatrain_step(self, items_b: Dict[str, Dict[str, tuple]], eval_test: bool = True) -> dict:
@@ -38,6 +39,7 @@ class Reptile(MetaTrainer):
         N = len(speakers)
         n_inner = self.params["n_inner_train"]
         losses = []
+        self._mcds = []
         if self.sequential:
             for i, spk in enumerate(speakers):
                 self._adapt(i, items_b[spk]["train"], n_inner)
@@ -45,7 +47,8 @@ class Reptile(MetaTrainer):
                     losses.append(self._eval_test(i, items_b[spk], n_inner))
                 eng.reptile_delta(self.meta_grad, self.fast, self.theta, 1.0, init=True)       # reptile.py:75-77
                 sumsq = self._outer_update()                                                     # reptile.py:82-89
-            return {"loss_test": torch.cat(losses) if losses else None, "task_index": list(range(N)), "grad_sumsq": sumsq}
+            return {"loss_test": torch.cat(losses) if losses else None, "mcd": torch.cat(self._mcds) if self._mcds else None,
+                    "task_index": list(range(N)), "grad_sumsq": sumsq}
         mine = self.shard.my_tasks(N)
         if not mine:
             self.meta_grad.zero_()
@@ -56,4 +59,5 @@ class Reptile(MetaTrainer):
                 losses.append(self._eval_test(i, task, n_inner))
             eng.reptile_delta(self.meta_grad, self.fast, self.theta, 1.0 / N, init=(j == 0))
         sumsq = self._outer_update()
-        return {"loss_test": torch.cat(losses) if losses else None, "task_index": mine, "grad_sumsq": sumsq}
+        return {"loss_test": torch.cat(losses) if losses else None, "mcd": torch.cat(self._mcds) if self._mcds else None,
+                "task_index": mine, "grad_sumsq": sumsq}
