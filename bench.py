@@ -249,6 +249,50 @@ def bench_infer(torch, tr, world, sync, B=32, L_=64, steps=1000):
             "workload": f"free-running inference, B={B} per GPU, L={L_}, {n_steps} decoder steps, default dims, encoder and postnet included"}
 
 
+def bench_gemm_tc(torch, eng, reps=20):
+    import ctypes as C
+    from msa_tts_b200.config import rnn_dims
+    Ha, Hd = rnn_dims(eng.cfg)
+    M, N, K = T * B, 4 * Hd, Ha
+    lib = eng.lib
+    dev = eng.device
+    A_, B_, C_ = torch.randn(M, K, device=dev), torch.randn(N, K, device=dev), torch.empty(M, N, device=dev)
+    scratch = torch.empty(int(lib.msa_gemm_nt_scratch_floats(M, N, K)) + 4, device=dev)
+    P = lambda t: C.c_void_p(t.data_ptr())
+
+    def call():
+        rc = lib.msa_gemm_nt(M, N, K, C.c_float(1.0), P(A_), K, P(B_), K, C.c_float(0.0), P(C_), N, 0, P(scratch),
+                             C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"msa_gemm_nt: {rc}")
+    for _ in range(3):
+        call()
+    torch.cuda.synchronize()
+    side, g = torch.cuda.Stream(), torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(reps):
+                call()
+    g.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    peak_bf16 = 1636.7
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        peak_bf16 = float(json.load(open(p)).get("bf16_tflops", peak_bf16))
+    flops = 2.0 * M * N * K
+    return {"kernel": "gemm_tc_3xtf32", "shape": [M, N, K], "ms_per_launch": ms, "timed": "alone, CUDA graph of 20 launches",
+            "fp32_equivalent_tflops": flops / ms / 1e9, "tensor_tflops": 3.0 * flops / ms / 1e9, "bound": "tensor",
+            "peak_tflops": peak_bf16 / 2.0, "peak_source": "TF32 dense = half of the measured bf16 cuBLAS throughput (MEASURED_PEAKS.json)",
+            "frac": 3.0 * flops / ms / 1e9 / (peak_bf16 / 2.0),
+            "note": "3 TF32 MMAs per fp32-accurate product; bound by shared-memory operand bandwidth (DESIGN.md 4.5)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -337,6 +381,14 @@ def main():
         "flat_sumsq": (time_flat(lambda: eng.sumsq(tr.task_grad)), 4.0 * n),
     }
 
+    # ---- the tensor-core shaped kernel of the pass: the hand-written tcgen05 / TMA GEMM on the decoder-RNN gate product
+    # [T*B x 4Hd] x K = Ha in its fp32-accurate 3xTF32 mode, timed alone (CUDA graph of 20 calls: GPU time, no host gaps) ----
+    gemm_line = None
+    try:
+        gemm_line = bench_gemm_tc(torch, eng)
+    except Exception as e:
+        gemm_line = {"error": str(e)[:200]}
+
     # ---- decoder mel-frames/s of free-running inference (BASELINE configs[4]: B=32 per GPU, L=64, 1000 steps, no early stop);
     # every rank decodes its own batch (inference shards by batch rows, no collective), time = max over ranks ----
     infer_line = None
@@ -358,6 +410,8 @@ def main():
         for name, (ms, ab) in flat_ms.items():
             kern.append({"kernel": name, "ms_per_launch": ms, "algo_bytes": ab, "achieved_gbs": ab / ms / 1e6,
                          "frac": ab / ms / 1e6 / peak, "timed": "alone, 20 reps"})
+        if gemm_line is not None:
+            kern.append(gemm_line)
         dom = max((k for k in kern if "share_of_step" in k), key=lambda k: k["share_of_step"])
         ms_step = ms_dev / args.steps
         value = 1000.0 / ms_step
