@@ -91,7 +91,8 @@ __device__ __forceinline__ float tc_lo(float x) { return x - __uint_as_float(__f
 template <bool kSplit>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float* __restrict__ C, int ldc,
-               int M, int N, int K, float alpha, float beta, float* __restrict__ partial, int kb_per_split) {
+               int M, int N, int K, float alpha, float beta, float* __restrict__ partial, int kb_per_split,
+               const float* __restrict__ bias1, const float* __restrict__ bias2) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte aligned operand tiles (swizzle atom = 8 rows x 128 B), then the barriers
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -213,9 +214,12 @@ k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     for (int r = 0; r < 32; ++r)
                         if (r < rows) out[(size_t)r * ldo] = alpha * xp[r * 33 + lane] + beta * old[r];
                 } else {
+                    // bias1 / bias2: column bias instead of a bias-filled C (C is then write-only: no fill launch, no read of C)
                     const float sc = partial != nullptr ? 1.f : alpha;
+                    float bs = 0.f;
+                    if (partial == nullptr && bias1 != nullptr) bs = bias1[col] + (bias2 != nullptr ? bias2[col] : 0.f);
 #pragma unroll 8
-                    for (int r = 0; r < rows; ++r) out[(size_t)r * ldo] = sc * xp[r * 33 + lane];
+                    for (int r = 0; r < rows; ++r) out[(size_t)r * ldo] = sc * xp[r * 33 + lane] + bs;
                 }
             }
             __syncwarp();
@@ -231,14 +235,15 @@ done:
 
 // C = alpha * (partial[0] + partial[1] + ...) + beta * C, splits summed in index order (deterministic)
 __global__ void ker_splitk_reduce(const float* __restrict__ partial, int splits, int M, int N, float* __restrict__ C, int ldc,
-                                  float alpha, float beta) {
+                                  float alpha, float beta, const float* __restrict__ bias1, const float* __restrict__ bias2) {
     const int64_t n = (int64_t)M * N;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float s = partial[i];
         for (int z = 1; z < splits; ++z) s += partial[(size_t)z * n + i];
         const int r = (int)(i / N), c = (int)(i - (int64_t)r * N);
         float* out = C + (size_t)r * ldc + c;
-        *out = beta != 0.f ? alpha * s + beta * *out : alpha * s;
+        const float bs = bias1 != nullptr ? bias1[c] + (bias2 != nullptr ? bias2[c] : 0.f) : 0.f;
+        *out = beta != 0.f ? alpha * s + beta * *out + bs : alpha * s + bs;
     }
 }
 
@@ -295,7 +300,9 @@ size_t gemm_tc_scratch_floats(int64_t M, int64_t N, int64_t K) {
 // mode 0: 3xTF32 (fp32-accurate); mode 1: single TF32 product.  `scratch` (gemm_tc_scratch_floats(M, N, K) floats, 16-byte
 // aligned) holds the partial tiles of a K split; with scratch == nullptr the K range is not split.
 int gemm_tc_nt(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
-               float* C, int64_t ldc, int mode, float* scratch, cudaStream_t st) {
+               float* C, int64_t ldc, int mode, float* scratch, cudaStream_t st, const float* bias1, const float* bias2) {
+    MSA_CHECK(bias1 != nullptr || bias2 == nullptr, MSA_E_ARG, "gemm_tc_nt: bias2 without bias1");
+    MSA_CHECK(bias1 == nullptr || beta == 0.f, MSA_E_ARG, "gemm_tc_nt: a column bias replaces the accumulation onto C (beta must be 0)");
     MSA_CHECK(gemm_tc_supported(M, N, K, A, lda, B, ldb, C, ldc), MSA_E_UNSUPPORTED, "gemm_tc_nt: operand alignment / leading dimensions");
     CUtensorMap mA, mB;
     MSA_TRY(make_map(&mA, A, (int)M, (int)K, (int)lda));
@@ -309,18 +316,18 @@ int gemm_tc_nt(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int
         const size_t smem = (size_t)kTcStages * 4 * kTcTileBytes + sizeof(TcSmem) + 1024;
         static bool attr0 = false;
         if (!attr0) { MSA_CUDA(cudaFuncSetAttribute(k_gemm_tf32_nt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr0 = true; }
-        k_gemm_tf32_nt<true><<<grid, kTcThreads, smem, st>>>(mA, mB, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta, partial, per);
+        k_gemm_tf32_nt<true><<<grid, kTcThreads, smem, st>>>(mA, mB, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta, partial, per, bias1, bias2);
     } else {
         const size_t smem = (size_t)kTcStages * 2 * kTcTileBytes + sizeof(TcSmem) + 1024;
         static bool attr1 = false;
         if (!attr1) { MSA_CUDA(cudaFuncSetAttribute(k_gemm_tf32_nt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr1 = true; }
-        k_gemm_tf32_nt<false><<<grid, kTcThreads, smem, st>>>(mA, mB, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta, partial, per);
+        k_gemm_tf32_nt<false><<<grid, kTcThreads, smem, st>>>(mA, mB, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta, partial, per, bias1, bias2);
     }
     MSA_LAUNCH_CHECK();
     if (splits > 1) {
         const int64_t n = M * N;
         ker_splitk_reduce<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(partial, splits, (int)M, (int)N, C, (int)ldc,
-                                                                                                 alpha, beta);
+                                                                                                 alpha, beta, bias1, bias2);
         MSA_LAUNCH_CHECK();
     }
     return 0;
@@ -332,6 +339,6 @@ extern "C" {
 size_t msa_gemm_nt_scratch_floats(int64_t M, int64_t N, int64_t K) { return msa::gemm_tc_scratch_floats(M, N, K); }
 int msa_gemm_nt(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
                 float* C, int64_t ldc, int mode, float* scratch, void* stream) {
-    return msa::gemm_tc_nt(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, mode, scratch, (cudaStream_t)stream);
+    return msa::gemm_tc_nt(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, mode, scratch, (cudaStream_t)stream, nullptr, nullptr);
 }
 }

@@ -256,7 +256,8 @@ int k_bt_to_ref_ld(const float* x_bt, float* out, int B, int T, int M, int ld, c
 bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb, const float* C, int64_t ldc);
 size_t gemm_tc_scratch_floats(int64_t M, int64_t N, int64_t K);
 int gemm_tc_nt(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
-               float* C, int64_t ldc, int mode, float* scratch, cudaStream_t st);   // mode 0: 3xTF32 (fp32-accurate), 1: TF32
+               float* C, int64_t ldc, int mode, float* scratch, cudaStream_t st, const float* bias1 = nullptr,
+               const float* bias2 = nullptr);   // mode 0: 3xTF32 (fp32-accurate), 1: TF32
 
 int k_fill_canary(float* p, int64_t n, cudaStream_t st);   // n floats (multiple of 4, 16-byte aligned) <- 0xFFFFFFFF
 int k_scale_copy(const float* in, float* out, int64_t n, float scale, int accumulate, cudaStream_t st);

@@ -274,8 +274,11 @@ static std::vector<MaskSec> mask_sections(const msa_config& c, int B, int T, int
 }
 
 // ---- cuBLAS, row-major convention: C[MxN] = alpha * op(A) op(B) + beta * C -------------------------
+// bias1 / bias2 (x . W^T only): C = op(A) op(B) + column bias.  On the tcgen05 route the bias is part of the epilogue (C is
+// write-only); on the cuBLAS route C is filled with the bias rows first and accumulated onto (beta = 1).
 static int gemm(msa_handle* h, bool ta, bool tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda,
-                const float* Bm, int64_t ldb, float beta, float* Cm, int64_t ldc) {
+                const float* Bm, int64_t ldb, float beta, float* Cm, int64_t ldc, const float* bias1 = nullptr,
+                const float* bias2 = nullptr) {
     if (M == 0 || N == 0) return 0;
     if (K == 0) {
         MSA_CHECK(beta == 1.f, MSA_E_ARG, "gemm: K == 0 with beta != 1");
@@ -290,7 +293,12 @@ static int gemm(msa_handle* h, bool ta, bool tb, int64_t M, int64_t N, int64_t K
     if (!ta && tb && h->tc_enabled && (h->tc_mode != 2 || !tf32) && tc_size && h->cfg.gemm_tf32 >= 1 && N >= 8 &&
         M * N >= 4096 && gemm_tc_supported(M, N, K, A, lda, Bm, ldb, Cm, ldc) &&
         (tf32 || (h->gemm_scratch && gemm_tc_scratch_floats(M, N, K) <= h->gemm_scratch_floats)))
-        return gemm_tc_nt(M, N, K, alpha, A, lda, Bm, ldb, beta, Cm, ldc, tf32 ? 1 : 0, h->gemm_scratch, h->cur_stream);
+        return gemm_tc_nt(M, N, K, alpha, A, lda, Bm, ldb, beta, Cm, ldc, tf32 ? 1 : 0, h->gemm_scratch, h->cur_stream, bias1, bias2);
+    if (bias1 != nullptr) {
+        MSA_CHECK(beta == 0.f && ldc == N, MSA_E_ARG, "gemm: a column bias needs beta == 0 and a dense C");
+        MSA_TRY(k_fill_rows(Cm, bias1, bias2, M, (int)N, h->cur_stream));
+        beta = 1.f;
+    }
     const cublasComputeType_t ct = tf32 ? CUBLAS_COMPUTE_32F_FAST_TF32 : CUBLAS_COMPUTE_32F;
     MSA_BLAS(cublasGemmEx(h->blas, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, (int)N, (int)M, (int)K, &alpha,
                           Bm, CUDA_R_32F, (int)ldb, A, CUDA_R_32F, (int)lda, &beta, Cm, CUDA_R_32F, (int)ldc, ct,
@@ -318,8 +326,8 @@ static int conv_bn_fwd(msa_handle* h, cudaStream_t st, const float* params, cons
     const int64_t rows = (int64_t)B * Tn;
     MSA_TRY(k_conv_w_pack(params + h->off(pfx + ".0.conv.weight"), w2, Co, Ci, K, st));
     MSA_TRY(k_im2col(x, col, B, Tn, Ci, K, st));
-    MSA_TRY(k_fill_rows(y, params + h->off(pfx + ".0.conv.bias"), nullptr, rows, Co, st));
-    MSA_TRY(gemm(h, false, true, rows, Co, (int64_t)K * Ci, 1.f, col, (int64_t)K * Ci, w2, (int64_t)K * Ci, 1.f, y, Co));
+    MSA_TRY(gemm(h, false, true, rows, Co, (int64_t)K * Ci, 1.f, col, (int64_t)K * Ci, w2, (int64_t)K * Ci, 0.f, y, Co,
+                 params + h->off(pfx + ".0.conv.bias")));
     MSA_TRY(k_bn_stats(y, rows, Co, bn_mean, bn_invstd, running, (int)align_up(Co), red_scr, st));
     MSA_TRY(k_bn_act_drop_fwd(y, bn_mean, bn_invstd, params + h->off(pfx + ".1.weight"), params + h->off(pfx + ".1.bias"), mask,
                               2.0f, act, xout, rows, Co, st));
@@ -593,8 +601,8 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
     MSA_TRY(k_relu_drop_fwd(w.p1, mk(iPre), 2.f, nfr * d.Pd, st));
     MSA_TRY(gemm(h, false, true, nfr, d.Pd, d.Pd, 1.f, w.p1, d.Pd, P("decoder.prenet.layers.1.linear_layer.weight"), d.Pd, 0.f, w.xpre, d.Pd));
     MSA_TRY(k_relu_drop_fwd(w.xpre, mk(iPre + 1), 2.f, nfr * d.Pd, st));
-    MSA_TRY(k_fill_rows(w.xw, P("decoder.attention_rnn.bias_ih"), P("decoder.attention_rnn.bias_hh"), d.TB, H4a, st));
-    MSA_TRY(gemm(h, false, true, d.TB, H4a, d.Pd, 1.f, w.xpre, d.Pd, Wia, ldA, 1.f, w.xw, H4a));
+    MSA_TRY(gemm(h, false, true, d.TB, H4a, d.Pd, 1.f, w.xpre, d.Pd, Wia, ldA, 0.f, w.xw, H4a, P("decoder.attention_rnn.bias_ih"),
+                 P("decoder.attention_rnn.bias_hh")));
     const bool fa = c.forward_attn != 0, ta = fa && c.trans_agent != 0;
     if (ta)     // context half of the transition agent: ctx(t) = alpha(t) . memory  =>  W_ta[:E] . ctx(t) = alpha(t) . (memory . W_ta[:E])
         MSA_TRY(gemm(h, false, true, d.BL, 1, d.E, 1.f, w.memory, d.E, P(at + "ta.weight"), d.E + d.Ha, 0.f, w.mta, 1));
@@ -621,8 +629,8 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
                          (int64_t)B * d.E, d.E, B));
     // ---- decoder RNN chain (decoder.py:260-265) ----
     const float* Wid = P("decoder.decoder_rnn.weight_ih");
-    MSA_TRY(k_fill_rows(w.zd, P("decoder.decoder_rnn.bias_ih"), P("decoder.decoder_rnn.bias_hh"), d.TB, H4d, st));
-    MSA_TRY(gemm(h, false, true, d.TB, H4d, d.Ha, 1.f, w.ha, d.Ha, Wid, ldD, 1.f, w.zd, H4d));
+    MSA_TRY(gemm(h, false, true, d.TB, H4d, d.Ha, 1.f, w.ha, d.Ha, Wid, ldD, 0.f, w.zd, H4d, P("decoder.decoder_rnn.bias_ih"),
+                 P("decoder.decoder_rnn.bias_hh")));
     MSA_TRY(gemm(h, false, true, d.TB, H4d, d.E, 1.f, w.ctx, d.E, Wid + d.Ha, ldD, 1.f, w.zd, H4d));
     {
         LstmRecParams lp{};
@@ -638,8 +646,8 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
     // ---- mel / gate projections (decoder.py:267-270) ----
     const float* Wp = P("decoder.linear_projection.linear_layer.weight");
     const float* Wg = P("decoder.gate_layer.linear_layer.weight");
-    MSA_TRY(k_fill_rows(w.mel_tm, P("decoder.linear_projection.linear_layer.bias"), nullptr, d.TB, d.M, st));
-    MSA_TRY(gemm(h, false, true, d.TB, d.M, d.Hd, 1.f, w.hd, d.Hd, Wp, ldP, 1.f, w.mel_tm, d.M));
+    MSA_TRY(gemm(h, false, true, d.TB, d.M, d.Hd, 1.f, w.hd, d.Hd, Wp, ldP, 0.f, w.mel_tm, d.M,
+                 P("decoder.linear_projection.linear_layer.bias")));
     MSA_TRY(gemm(h, false, true, d.TB, d.M, d.E, 1.f, w.ctx, d.E, Wp + d.Hd, ldP, 1.f, w.mel_tm, d.M));
     MSA_TRY(k_fill_rows(w.gate_tm, P("decoder.gate_layer.linear_layer.bias"), nullptr, d.TB, 1, st));
     MSA_TRY(gemm(h, false, true, d.TB, 1, d.Hd, 1.f, w.hd, d.Hd, Wg, ldP, 1.f, w.gate_tm, 1));
