@@ -126,8 +126,6 @@ int k_embedding_fwd(const float* w, const int64_t* tok, float* x, int rows, int 
 int k_embedding_bwd(const float* dx, const int64_t* tok, float* gw, int rows, int C, int n_symbols, float scale, int accumulate, cudaStream_t st);
 int k_im2col(const float* x, float* col, int B, int T, int C, int K, cudaStream_t st);
 int k_col2im(const float* dcol, float* dx, int B, int T, int C, int K, cudaStream_t st);
-int k_conv_w_pack(const float* w, float* w2, int Co, int Ci, int K, cudaStream_t st);
-int k_conv_w_unpack_grad(const float* dw2, float* gw, int Co, int Ci, int K, float scale, int accumulate, cudaStream_t st);
 int k_fill_rows(float* y, const float* b1, const float* b2, int64_t rows, int N, cudaStream_t st);
 // Reduction scratch (`red_scr`, may be null = single-chunk reductions): kRedTickets zero-initialised uint tickets followed by
 // kRedChunks x kRedCols floats of partials; shared by the column reductions of one stream (they run back to back).

@@ -41,19 +41,20 @@ __global__ void ker_embedding_bwd(const float* __restrict__ dx, const int64_t* _
 
 // ---------------- conv1d as im2col + GEMM (encoder.py:18-28, decoder.py:23-61) ----------------
 // x [B][T][C] -> col [B*T][K][C], zero padded ("same")
+// Column order of the im2col matrix is (ci, k) -- the order of the native conv weight [Co][Ci][K] -- so the weight tensor itself
+// is the GEMM operand and the weight gradient comes out of its GEMM in the parameter layout: no pack / unpack passes.
 __global__ void ker_im2col(const float* __restrict__ x, float* col, int B, int T, int C, int K) {
     const int pad = (K - 1) / 2;
     const int64_t n = (int64_t)B * T * K * C;
     GSL(i, n) {
-        const int c = (int)(i % C);
-        const int k = (int)((i / C) % K);
+        const int k = (int)(i % K);
+        const int c = (int)((i / K) % C);
         const int64_t bt = i / ((int64_t)C * K);
         const int t = (int)(bt % T), b = (int)(bt / T);
         const int ts = t + k - pad;
         col[i] = (ts >= 0 && ts < T) ? x[((int64_t)b * T + ts) * C + c] : 0.f;
     }
 }
-// dx[b][t][c] = sum_k dcol[b][t-k+pad][k][c]
 __global__ void ker_col2im(const float* __restrict__ dcol, float* dx, int B, int T, int C, int K) {
     const int pad = (K - 1) / 2;
     const int64_t n = (int64_t)B * T * C;
@@ -63,31 +64,12 @@ __global__ void ker_col2im(const float* __restrict__ dcol, float* dx, int B, int
         float s = 0.f;
         for (int k = 0; k < K; ++k) {
             const int to = t - k + pad;
-            if (to >= 0 && to < T) s += dcol[(((int64_t)b * T + to) * K + k) * C + c];
+            if (to >= 0 && to < T) s += dcol[(((int64_t)b * T + to) * C + c) * K + k];
         }
         dx[i] = s;
     }
 }
 // w [Co][Ci][K] -> w2 [Co][K][Ci]
-__global__ void ker_w_pack(const float* __restrict__ w, float* w2, int Co, int Ci, int K) {
-    const int64_t n = (int64_t)Co * Ci * K;
-    GSL(i, n) {
-        const int ci = (int)(i % Ci);
-        const int k = (int)((i / Ci) % K);
-        const int64_t co = i / ((int64_t)Ci * K);
-        w2[i] = w[(co * Ci + ci) * K + k];
-    }
-}
-__global__ void ker_w_unpack_grad(const float* __restrict__ dw2, float* gw, int Co, int Ci, int K, float scale, int accumulate) {
-    const int64_t n = (int64_t)Co * Ci * K;
-    GSL(i, n) {
-        const int k = (int)(i % K);
-        const int ci = (int)((i / K) % Ci);
-        const int64_t co = i / ((int64_t)Ci * K);
-        const float v = scale * dw2[(co * K + k) * Ci + ci];
-        gw[i] = accumulate ? gw[i] + v : v;
-    }
-}
 
 // y[r][n] = b1[n] (+ b2[n])
 __global__ void ker_fill_rows(float* y, const float* __restrict__ b1, const float* __restrict__ b2, int64_t total, int N) {
@@ -602,40 +584,13 @@ int k_embedding_bwd(const float* dx, const int64_t* tok, float* gw, int rows, in
     return 0;
 }
 // 128-bit version (C % 4 == 0): one float4 of one (row, tap) per thread, rows of C/4 consecutive threads
-__global__ void ker_im2col4(const float4* __restrict__ x, float4* col, int B, int T, int C4, int K) {
-    const int pad = (K - 1) / 2;
-    const int64_t n = (int64_t)B * T * K * C4;
-    GSL(i, n) {
-        const int c = (int)(i % C4);
-        const int64_t bk = i / C4;
-        const int k = (int)(bk % K);
-        const int64_t bt = bk / K;
-        const int t = (int)(bt % T);
-        const int ts = t + k - pad;
-        col[i] = (ts >= 0 && ts < T) ? x[(bt + (k - pad)) * C4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-}
 int k_im2col(const float* x, float* col, int B, int T, int C, int K, cudaStream_t st) {
-    if ((C & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(col)) & 15) == 0)
-        ker_im2col4<<<grid_for((int64_t)B * T * (C >> 2) * K), kTh, 0, ST>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(col),
-                                                                             B, T, C >> 2, K);
-    else
-        ker_im2col<<<grid_for((int64_t)B * T * C * K), kTh, 0, ST>>>(x, col, B, T, C, K);
+    ker_im2col<<<grid_for((int64_t)B * T * C * K), kTh, 0, ST>>>(x, col, B, T, C, K);
     MSA_LAUNCH_CHECK();
     return 0;
 }
 int k_col2im(const float* dcol, float* dx, int B, int T, int C, int K, cudaStream_t st) {
     ker_col2im<<<grid_for((int64_t)B * T * C), kTh, 0, ST>>>(dcol, dx, B, T, C, K);
-    MSA_LAUNCH_CHECK();
-    return 0;
-}
-int k_conv_w_pack(const float* w, float* w2, int Co, int Ci, int K, cudaStream_t st) {
-    ker_w_pack<<<grid_for((int64_t)Co * Ci * K), kTh, 0, ST>>>(w, w2, Co, Ci, K);
-    MSA_LAUNCH_CHECK();
-    return 0;
-}
-int k_conv_w_unpack_grad(const float* dw2, float* gw, int Co, int Ci, int K, float scale, int acc, cudaStream_t st) {
-    ker_w_unpack_grad<<<grid_for((int64_t)Co * Ci * K), kTh, 0, ST>>>(dw2, gw, Co, Ci, K, scale, acc);
     MSA_LAUNCH_CHECK();
     return 0;
 }

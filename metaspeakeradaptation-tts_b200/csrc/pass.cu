@@ -324,10 +324,10 @@ static int conv_bn_fwd(msa_handle* h, cudaStream_t st, const float* params, cons
                        int Ci, int Co, int K, int act, const uint8_t* mask, float* red_scr) {
     // col (im2col of the layer input) and w2 (packed weights) are per-layer buffers: the backward pass reuses both
     const int64_t rows = (int64_t)B * Tn;
-    MSA_TRY(k_conv_w_pack(params + h->off(pfx + ".0.conv.weight"), w2, Co, Ci, K, st));
+    (void)w2;     // im2col columns are in (ci, k) order: the native weight [Co][Ci*K] is the GEMM operand
     MSA_TRY(k_im2col(x, col, B, Tn, Ci, K, st));
-    MSA_TRY(gemm(h, false, true, rows, Co, (int64_t)K * Ci, 1.f, col, (int64_t)K * Ci, w2, (int64_t)K * Ci, 0.f, y, Co,
-                 params + h->off(pfx + ".0.conv.bias")));
+    MSA_TRY(gemm(h, false, true, rows, Co, (int64_t)K * Ci, 1.f, col, (int64_t)K * Ci, params + h->off(pfx + ".0.conv.weight"),
+                 (int64_t)K * Ci, 0.f, y, Co, params + h->off(pfx + ".0.conv.bias")));
     MSA_TRY(k_bn_stats(y, rows, Co, bn_mean, bn_invstd, running, (int)align_up(Co), red_scr, st));
     MSA_TRY(k_bn_act_drop_fwd(y, bn_mean, bn_invstd, params + h->off(pfx + ".1.weight"), params + h->off(pfx + ".1.bias"), mask,
                               2.0f, act, xout, rows, Co, st));
@@ -338,16 +338,17 @@ static int conv_bn_bwd(msa_handle* h, cudaStream_t st, const float* params, floa
                        const std::string& pfx, const float* x, const float* y, const float* dout, float* dx, float* dy, float* col,
                        float* w2, float* dcol, float* dw2, float* scr, const float* bn_mean, const float* bn_invstd, int B, int Tn,
                        int Ci, int Co, int K, int act, const uint8_t* mask, bool need_dx, float* red_scr) {
-    (void)x;      // its im2col is still in `col`, the packed weights in `w2` (written by conv_bn_fwd of the same pass)
+    (void)x; (void)w2; (void)dw2;      // the im2col of x is still in `col` (written by conv_bn_fwd of the same pass)
+    const float* wt = params + h->off(pfx + ".0.conv.weight");
     const int64_t rows = (int64_t)B * Tn, KC = (int64_t)K * Ci;
     MSA_TRY(k_bn_act_drop_bwd(dout, y, bn_mean, bn_invstd, params + h->off(pfx + ".1.weight"), params + h->off(pfx + ".1.bias"),
                               mask, 2.0f, act, dy, grads + h->off(pfx + ".1.weight"), grads + h->off(pfx + ".1.bias"), scr, rows,
                               Co, gs, acc, red_scr, st));
     MSA_TRY(k_colsum(dy, rows, Co, Co, grads + h->off(pfx + ".0.conv.bias"), gs, acc, nullptr, red_scr, st));
-    MSA_TRY(gemm(h, true, false, Co, KC, rows, 1.f, dy, Co, col, KC, 0.f, dw2, KC));
-    MSA_TRY(k_conv_w_unpack_grad(dw2, grads + h->off(pfx + ".0.conv.weight"), Co, Ci, K, gs, acc, st));
+    // dW = dy^T . col lands in the parameter layout [Co][Ci][K] directly (scaled / accumulated by the GEMM itself)
+    MSA_TRY(gemm(h, true, false, Co, KC, rows, gs, dy, Co, col, KC, acc ? 1.f : 0.f, grads + h->off(pfx + ".0.conv.weight"), KC));
     if (need_dx) {
-        MSA_TRY(gemm(h, false, false, rows, KC, Co, 1.f, dy, Co, w2, KC, 0.f, dcol, KC));
+        MSA_TRY(gemm(h, false, false, rows, KC, Co, 1.f, dy, Co, wt, KC, 0.f, dcol, KC));
         MSA_TRY(k_col2im(dcol, dx, B, Tn, Ci, K, st));
     }
     return 0;
@@ -1063,10 +1064,11 @@ static int conv_bn_eval(msa_handle* h, cudaStream_t st, const float* params, con
                         float* xout, float* col, float* w2, float* bn_mean, float* bn_invstd, const float* running, int B, int Tn,
                         int Ci, int Co, int K, int act) {
     const int64_t rows = (int64_t)B * Tn;
-    MSA_TRY(k_conv_w_pack(params + h->off(pfx + ".0.conv.weight"), w2, Co, Ci, K, st));
+    (void)w2;
     MSA_TRY(k_im2col(x, col, B, Tn, Ci, K, st));
     MSA_TRY(k_fill_rows(y, params + h->off(pfx + ".0.conv.bias"), nullptr, rows, Co, st));
-    MSA_TRY(gemm(h, false, true, rows, Co, (int64_t)K * Ci, 1.f, col, (int64_t)K * Ci, w2, (int64_t)K * Ci, 1.f, y, Co));
+    MSA_TRY(gemm(h, false, true, rows, Co, (int64_t)K * Ci, 1.f, col, (int64_t)K * Ci, params + h->off(pfx + ".0.conv.weight"),
+                 (int64_t)K * Ci, 1.f, y, Co));
     MSA_TRY(k_bn_eval_stats(running, Co, (int)align_up(Co), bn_mean, bn_invstd, st));
     MSA_TRY(k_bn_act_drop_fwd(y, bn_mean, bn_invstd, params + h->off(pfx + ".1.weight"), params + h->off(pfx + ".1.bias"), nullptr,
                               1.0f, act, xout, rows, Co, st));
