@@ -180,7 +180,7 @@ static Dims make_dims(const msa_config& c, int B, int T, int L) {
 #define WS_LIST(X)                                                                                     \
     X(spk_vec, d.B * d.Ds)                                                                             \
     X(enc_x, (d.nEnc + 1) * d.BL * d.C) X(enc_y, d.nEnc * d.BL * d.C) X(enc_bn, d.nEnc * 2 * d.C)      \
-    X(enc_col, d.nEnc * d.BL * d.Kc * d.C) X(enc_w2, d.nEnc * (int64_t)d.C * d.Kc * d.C) X(x3_tm, d.BL * d.C)            \
+    X(enc_col, d.nEnc * d.BL * d.Kc * d.C) X(x3_tm, d.BL * d.C)            \
     X(enc_zx, 2 * d.BL * 4 * d.Hh) X(enc_g, 2 * d.BL * 4 * d.Hh) X(enc_c, 2 * d.BL * d.Hh)             \
     X(enc_h, 2 * d.BL * d.Hh) X(memory, d.BL * d.E)                                                    \
     X(frames, (d.TB + d.B) * d.M) X(target, d.BT * d.M) X(p1, (d.TB + d.B) * d.Pd)                     \
@@ -193,10 +193,10 @@ static Dims make_dims(const msa_config& c, int B, int T, int L) {
     X(mel_tm, d.TB * d.M) X(gate_tm, d.TB)                                                             \
     X(post_x, (d.nPost + 1) * d.BT * d.Cmax) X(post_y, d.nPost * d.BT * d.Cmax)                        \
     X(post_bn, d.nPost * 2 * d.Cmax) X(post_col, d.nPost * d.BT * d.Kp * d.Cmax)                       \
-    X(post_w2, d.nPost * (int64_t)d.Cmax * d.Kp * d.Cmax) X(post_bt, d.BT * d.M) X(gate_bt, d.BT) X(red_scr, kRedScrFloats) \
+    X(post_bt, d.BT * d.M) X(gate_bt, d.BT) X(red_scr, kRedScrFloats) \
     X(loss_part, 1024) X(loss, 32) X(dpre, d.BT * d.M) X(dpost, d.BT * d.M) X(dgate, d.BT)             \
     X(bdx0, d.BT * d.Cmax) X(bdx1, d.BT * d.Cmax) X(bdy, d.BT * d.Cmax)                                \
-    X(bdcol, d.BT * d.Kp * d.Cmax) X(bdw2, (int64_t)d.Cmax * d.Kp * d.Cmax)                            \
+    X(bdcol, d.BT * d.Kp * d.Cmax)                            \
     X(bn_scr, 2 * std::max(d.Cmax, d.C)) X(dmel_bt, d.BT * d.M) X(dmel_tm, d.TB * d.M)                 \
     X(dgate_tm, d.TB) X(dhd, d.TB * d.Hd) X(dzd, d.TB * 4 * d.Hd) X(dha, d.TB * d.Ha)                  \
     X(dctx, d.TB * d.E) X(da_ext, d.TBL) X(dza, d.TB * 4 * d.Ha) X(dq, d.TB * d.A) X(de, d.TBL)        \
@@ -205,7 +205,7 @@ static Dims make_dims(const msa_config& c, int B, int T, int L) {
     X(dmw, d.BL * 4 * d.Ha) X(dmem, d.BL * d.E) X(dxp, (d.TB + d.B) * d.Pd)                            \
     X(dp1, (d.TB + d.B) * d.Pd) X(denc_h, 2 * d.BL * d.Hh) X(dzx, 2 * d.BL * 4 * d.Hh)                 \
     X(dx3_tm, d.BL * d.C) X(edx0, d.BL * d.C) X(edx1, d.BL * d.C) X(edy, d.BL * d.C)                   \
-    X(edcol, d.BL * d.Kc * d.C) X(edw2, (int64_t)d.C * d.Kc * d.C) X(dspk, d.B * d.Ds)                             \
+    X(edcol, d.BL * d.Kc * d.C) X(dspk, d.B * d.Ds)                             \
     X(wloc_part, (int64_t)wloc_grad_partials(d.T, d.B) * d.F * 2 * d.Kl) X(gemm_lo, tc_scratch_floats(d)) X(prof, kProfFloats) X(trace, kTraceFloats)
 
 constexpr int64_t kProfFloats = 2 * 6 * 256 * 8;
@@ -320,11 +320,11 @@ static int gemm_batched(msa_handle* h, bool ta, bool tb, int64_t M, int64_t N, i
 
 // conv1d ("same") + BatchNorm(train) + activation + dropout, channels-last rows = B*Tn
 static int conv_bn_fwd(msa_handle* h, cudaStream_t st, const float* params, const std::string& pfx, const float* x, float* y,
-                       float* xout, float* col, float* w2, float* bn_mean, float* bn_invstd, float* running, int B, int Tn,
+                       float* xout, float* col, float* bn_mean, float* bn_invstd, float* running, int B, int Tn,
                        int Ci, int Co, int K, int act, const uint8_t* mask, float* red_scr) {
-    // col (im2col of the layer input) and w2 (packed weights) are per-layer buffers: the backward pass reuses both
+    // col (im2col of the layer input) is a per-layer buffer: the backward pass reuses it
     const int64_t rows = (int64_t)B * Tn;
-    (void)w2;     // im2col columns are in (ci, k) order: the native weight [Co][Ci*K] is the GEMM operand
+    // im2col columns are in (ci, k) order: the native weight [Co][Ci*K] is the GEMM operand
     MSA_TRY(k_im2col(x, col, B, Tn, Ci, K, st));
     MSA_TRY(gemm(h, false, true, rows, Co, (int64_t)K * Ci, 1.f, col, (int64_t)K * Ci, params + h->off(pfx + ".0.conv.weight"),
                  (int64_t)K * Ci, 0.f, y, Co, params + h->off(pfx + ".0.conv.bias")));
@@ -336,9 +336,9 @@ static int conv_bn_fwd(msa_handle* h, cudaStream_t st, const float* params, cons
 // backward of the above: dout -> dx (through dropout, act, BN, conv); parameter grads into `grads`
 static int conv_bn_bwd(msa_handle* h, cudaStream_t st, const float* params, float* grads, float gs, int acc,
                        const std::string& pfx, const float* x, const float* y, const float* dout, float* dx, float* dy, float* col,
-                       float* w2, float* dcol, float* dw2, float* scr, const float* bn_mean, const float* bn_invstd, int B, int Tn,
+                       float* dcol, float* scr, const float* bn_mean, const float* bn_invstd, int B, int Tn,
                        int Ci, int Co, int K, int act, const uint8_t* mask, bool need_dx, float* red_scr) {
-    (void)x; (void)w2; (void)dw2;      // the im2col of x is still in `col` (written by conv_bn_fwd of the same pass)
+    (void)x;      // the im2col of x is still in `col` (written by conv_bn_fwd of the same pass)
     const float* wt = params + h->off(pfx + ".0.conv.weight");
     const int64_t rows = (int64_t)B * Tn, KC = (int64_t)K * Ci;
     MSA_TRY(k_bn_act_drop_bwd(dout, y, bn_mean, bn_invstd, params + h->off(pfx + ".1.weight"), params + h->off(pfx + ".1.bias"),
@@ -568,7 +568,7 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
     for (int i = 0; i < d.nEnc; ++i) {
         float* run = bn_stats ? bn_stats + h->bn_offs[i] : nullptr;
         MSA_TRY(conv_bn_fwd(h, st, params, "encoder.convolutions." + std::to_string(i), w.enc_x + i * ex, w.enc_y + i * ex,
-                            w.enc_x + (i + 1) * ex, w.enc_col + i * d.BL * d.Kc * d.C, w.enc_w2 + i * (int64_t)d.C * d.Kc * d.C,
+                            w.enc_x + (i + 1) * ex, w.enc_col + i * d.BL * d.Kc * d.C,
                             w.enc_bn + i * 2 * d.C, w.enc_bn + i * 2 * d.C + d.C, run, B, L, d.C, d.C, d.Kc, 1, mk(i), w.red_scr));
     }
     MSA_TRY(k_transpose01(w.enc_x + d.nEnc * ex, w.x3_tm, B, L, d.C, st));
@@ -661,7 +661,7 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
         const int ci = i == 0 ? d.M : d.Cp, co = i == d.nPost - 1 ? d.M : d.Cp;
         float* run = bn_stats ? bn_stats + h->bn_offs[d.nEnc + i] : nullptr;
         MSA_TRY(conv_bn_fwd(h, st, params, "postnet.convolutions." + std::to_string(i), w.post_x + i * px, w.post_y + i * px,
-                            w.post_x + (i + 1) * px, w.post_col + i * d.BT * d.Kp * d.Cmax, w.post_w2 + i * (int64_t)d.Cmax * d.Kp * d.Cmax,
+                            w.post_x + (i + 1) * px, w.post_col + i * d.BT * d.Kp * d.Cmax,
                             w.post_bn + i * 2 * d.Cmax, w.post_bn + i * 2 * d.Cmax + d.Cmax, run, B, T, ci, co, d.Kp,
                             i < d.nPost - 1 ? 2 : 0, mk(iPost + i), w.red_scr));
     }
@@ -786,7 +786,7 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
         float* dx = pingpong[i & 1];
         MSA_TRY(conv_bn_bwd(h, st, params, grads, gs, acc, "postnet.convolutions." + std::to_string(i), w.post_x + i * px,
                             w.post_y + i * px, dcur, dx, w.bdy, w.post_col + i * d.BT * d.Kp * d.Cmax,
-                            w.post_w2 + i * (int64_t)d.Cmax * d.Kp * d.Cmax, w.bdcol, w.bdw2, w.bn_scr,
+                            w.bdcol, w.bn_scr,
                             w.post_bn + i * 2 * d.Cmax, w.post_bn + i * 2 * d.Cmax + d.Cmax, B, T, ci, co, d.Kp,
                             i < d.nPost - 1 ? 2 : 0, mk(iPost + i), true, w.red_scr));
         dcur = dx;
@@ -953,8 +953,8 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
     for (int i = d.nEnc - 1; i >= 0; --i) {
         float* dx = epp[i & 1];
         MSA_TRY(conv_bn_bwd(h, st, params, grads, gs, acc, "encoder.convolutions." + std::to_string(i), w.enc_x + i * ex,
-                            w.enc_y + i * ex, dcur, dx, w.edy, w.enc_col + i * d.BL * d.Kc * d.C, w.enc_w2 + i * (int64_t)d.C * d.Kc * d.C,
-                            w.edcol, w.edw2, w.bn_scr, w.enc_bn + i * 2 * d.C, w.enc_bn + i * 2 * d.C + d.C, B, L, d.C, d.C, d.Kc, 1, mk(i),
+                            w.enc_y + i * ex, dcur, dx, w.edy, w.enc_col + i * d.BL * d.Kc * d.C,
+                            w.edcol, w.bn_scr, w.enc_bn + i * 2 * d.C, w.enc_bn + i * 2 * d.C + d.C, B, L, d.C, d.C, d.Kc, 1, mk(i),
                             true, w.red_scr));
         dcur = dx;
     }
@@ -1020,7 +1020,7 @@ namespace msa {
 
 #define IWS_LIST(X)                                                                                       \
     X(spk_vec, d.B * d.Ds) X(enc_x, 2 * d.BL * d.C) X(enc_y, d.BL * d.C) X(enc_bn, 2 * std::max(d.C, d.Cmax)) \
-    X(enc_col, d.BL * d.Kc * d.C) X(enc_w2, (int64_t)d.C * d.Kc * d.C) X(x3_tm, d.BL * d.C)              \
+    X(enc_col, d.BL * d.Kc * d.C) X(x3_tm, d.BL * d.C)              \
     X(enc_zx, 2 * d.BL * 4 * d.Hh) X(enc_g, 2 * d.BL * 4 * d.Hh) X(enc_c, 2 * d.BL * d.Hh)               \
     X(enc_h, 2 * d.BL * d.Hh) X(memory, d.BL * d.E) X(pm, d.BL * d.A)                                    \
     X(xin_a, d.B * (d.Pd + d.E)) X(p1, d.B * d.Pd) X(ha, 2 * d.B * d.Ha) X(ca, d.B * d.Ha)               \
@@ -1029,7 +1029,7 @@ namespace msa {
     X(prev, d.BL) X(cum, d.BL) X(fa_alpha, d.BL) X(fa_u, d.B + 4) X(attn_wloc_t, 2 * d.Kl * d.F + 4)      \
     X(attn_wld4, ((d.F + 3) / 4) * d.A * 4) X(mel_tm, (int64_t)d.T * d.B * d.M) X(ints, 64 + d.B)                      \
     X(post_x, 2 * d.BT * d.Cmax) X(post_y, d.BT * d.Cmax) X(post_col, d.BT * d.Kp * d.Cmax)              \
-    X(post_w2, (int64_t)d.Cmax * d.Kp * d.Cmax) X(post_bt, d.BT * d.M)
+    X(post_bt, d.BT * d.M)
 
 struct IWs {
 #define X(name, n) float* name; int64_t n_##name;
@@ -1061,10 +1061,9 @@ static IWs iws_layout(const Dims& d, void* base) {
 
 // conv1d ("same") + BatchNorm(eval: running statistics) + activation, channels-last rows = B*Tn (no dropout in eval)
 static int conv_bn_eval(msa_handle* h, cudaStream_t st, const float* params, const std::string& pfx, const float* x, float* y,
-                        float* xout, float* col, float* w2, float* bn_mean, float* bn_invstd, const float* running, int B, int Tn,
+                        float* xout, float* col, float* bn_mean, float* bn_invstd, const float* running, int B, int Tn,
                         int Ci, int Co, int K, int act) {
     const int64_t rows = (int64_t)B * Tn;
-    (void)w2;
     MSA_TRY(k_im2col(x, col, B, Tn, Ci, K, st));
     MSA_TRY(k_fill_rows(y, params + h->off(pfx + ".0.conv.bias"), nullptr, rows, Co, st));
     MSA_TRY(gemm(h, false, true, rows, Co, (int64_t)K * Ci, 1.f, col, (int64_t)K * Ci, params + h->off(pfx + ".0.conv.weight"),
@@ -1127,7 +1126,7 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
     MSA_TRY(k_embedding_fwd(P("embedding.weight"), tokens, w.enc_x, (int)d.BL, d.C, c.n_symbols, st));
     for (int i = 0; i < d.nEnc; ++i)
         MSA_TRY(conv_bn_eval(h, st, params, "encoder.convolutions." + std::to_string(i), w.enc_x + (i & 1) * ex, w.enc_y,
-                             w.enc_x + ((i + 1) & 1) * ex, w.enc_col, w.enc_w2, w.enc_bn, w.enc_bn + std::max(d.C, d.Cmax),
+                             w.enc_x + ((i + 1) & 1) * ex, w.enc_col, w.enc_bn, w.enc_bn + std::max(d.C, d.Cmax),
                              bn_stats + h->bn_offs[i], B, L, d.C, d.C, d.Kc, 1));
     MSA_TRY(k_transpose01(w.enc_x + (d.nEnc & 1) * ex, w.x3_tm, B, L, d.C, st));
     const int H4e = 4 * d.Hh;
@@ -1355,7 +1354,7 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
     for (int i = 0; i < d.nPost; ++i) {
         const int ci = i == 0 ? d.M : d.Cp, co = i == d.nPost - 1 ? d.M : d.Cp;
         float* dst = w.post_x + (i & 1) * px;
-        MSA_TRY(conv_bn_eval(h, st, params, "postnet.convolutions." + std::to_string(i), src, w.post_y, dst, w.post_col, w.post_w2,
+        MSA_TRY(conv_bn_eval(h, st, params, "postnet.convolutions." + std::to_string(i), src, w.post_y, dst, w.post_col,
                              w.enc_bn, w.enc_bn + std::max(d.C, d.Cmax), bn_stats + h->bn_offs[d.nEnc + i], B, Tn, ci, co, d.Kp,
                              i < d.nPost - 1 ? 2 : 0));
         src = dst;
