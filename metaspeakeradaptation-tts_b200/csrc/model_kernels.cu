@@ -558,15 +558,31 @@ struct MaskSecTable {
     long long off[kMaskSecMax], end[kMaskSecMax];
     unsigned int thr[kMaskSecMax];      // 21 random bits: keep if r >= p * 2^21
 };
+// four bytes per thread (lo is a multiple of 4): one section look-up and one 32-bit store when the four bytes lie in one section,
+// byte by byte across section boundaries and alignment gaps; the value of a byte depends only on (seed, absolute byte index)
 __global__ void ker_masks(uint8_t* masks, MaskSecTable tb, long long lo, long long hi, uint64_t seed) {
-    GSL(j, hi - lo) {
-        const long long i = lo + j;      // absolute byte index
+    auto section = [&](long long i) {
         int sct = -1;
         for (int k = 0; k < tb.n; ++k)
             if (i >= tb.off[k] && i < tb.end[k]) sct = k;
-        if (sct < 0) continue;      // alignment gap between sections
+        return sct;
+    };
+    auto keep = [&](long long i, unsigned int thr) -> uint32_t {
         const uint32_t r = mix32(seed ^ ((uint64_t)i * 0x9E3779B97F4A7C15ULL)) & 0x1FFFFF;
-        masks[i] = r >= tb.thr[sct] ? 1 : 0;
+        return r >= thr ? 1u : 0u;
+    };
+    GSL(j, (hi - lo + 3) >> 2) {
+        const long long i = lo + 4 * j;      // absolute byte index of the first of four bytes
+        const int s0 = section(i);
+        if (s0 >= 0 && i + 3 < tb.end[s0]) {
+            const unsigned int thr = tb.thr[s0];
+            *reinterpret_cast<uint32_t*>(masks + i) = keep(i, thr) | (keep(i + 1, thr) << 8) | (keep(i + 2, thr) << 16) | (keep(i + 3, thr) << 24);
+        } else {
+            for (long long b = i; b < i + 4 && b < hi; ++b) {
+                const int sct = section(b);
+                if (sct >= 0) masks[b] = (uint8_t)keep(b, tb.thr[sct]);
+            }
+        }
     }
 }
 
@@ -583,7 +599,6 @@ int k_embedding_bwd(const float* dx, const int64_t* tok, float* gw, int rows, in
     MSA_LAUNCH_CHECK();
     return 0;
 }
-// 128-bit version (C % 4 == 0): one float4 of one (row, tap) per thread, rows of C/4 consecutive threads
 int k_im2col(const float* x, float* col, int B, int T, int C, int K, cudaStream_t st) {
     ker_im2col<<<grid_for((int64_t)B * T * C * K), kTh, 0, ST>>>(x, col, B, T, C, K);
     MSA_LAUNCH_CHECK();
@@ -778,7 +793,8 @@ int k_masks_generate(uint8_t* masks, const int64_t* offsets, const int64_t* nume
             if (tb.end[k] > hi) hi = tb.end[k];
         }
         if (hi <= lo) continue;
-        ker_masks<<<grid_for(hi - lo), kTh, 0, ST>>>(masks, tb, lo, hi, seed);
+        lo &= ~3LL;     // (the mask buffer itself is at least 16-byte aligned)
+        ker_masks<<<grid_for((hi - lo + 3) >> 2), kTh, 0, ST>>>(masks, tb, lo, hi, seed);
         MSA_LAUNCH_CHECK();
     }
     return 0;

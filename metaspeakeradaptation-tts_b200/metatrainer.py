@@ -86,9 +86,10 @@ class MetaTrainer:
 
     # ---- inner loop (higher.innerloop_ctx + diffopt.step, maml.py:40-54) ------------------------------
     def _adapt(self, task_index: int, batch, n_inner: int):
-        """fast <- theta; n_inner x (forward, backward, functional SGD step) on the train split."""
+        """n_inner x (forward, backward, functional SGD / Adam step) on the train split, starting from theta.  The first step reads
+        theta itself and writes the updated weights to ``fast`` (the functional update is out of place), so the 121 MB
+        ``fast <- theta`` copy of a literal ``innerloop_ctx`` never happens."""
         eng = self.engine
-        self.fast.copy_(self.theta)
         self.task_bn.copy_(self.base_bn)
         inputs, _ = self._unpack_batch(batch)
         B, L = inputs["inputs"].shape
@@ -98,16 +99,19 @@ class MetaTrainer:
         if h["name"] == "Adam":
             self.inner_m.zero_()
             self.inner_v.zero_()
+        if n_inner == 0:
+            self.fast.copy_(self.theta)
         for it in range(n_inner):
-            _, loss = eng.forward(self.fast, self.task_bn, inputs, self._masks(task_index, it, B, T, L), outputs=False)
-            eng.backward(self.fast, self.task_grad)
+            src = self.theta if it == 0 else self.fast
+            _, loss = eng.forward(src, self.task_bn, inputs, self._masks(task_index, it, B, T, L), outputs=False)
+            eng.backward(src, self.task_grad)
             if h["name"] == "Adam":
-                eng.adam_step(self.fast, self.task_grad, self.fast, self.inner_m, self.inner_v, lr=h["lr"], step=it + 1,
+                eng.adam_step(src, self.task_grad, self.fast, self.inner_m, self.inner_v, lr=h["lr"], step=it + 1,
                               betas=h.get("betas", (0.9, 0.999)), eps=h.get("eps", 1e-8), weight_decay=h.get("weight_decay", 0.0))
             else:
-                eng.sgd_step(self.fast, self.task_grad, lr=h["lr"], momentum=h.get("momentum", 0.0), dampening=h.get("dampening", 0.0),
-                             weight_decay=h.get("weight_decay", 0.0), nesterov=h.get("nesterov", False), buf=self.inner_buf,
-                             first_step=(it == 0))
+                eng.sgd_step(src, self.task_grad, p_out=self.fast, lr=h["lr"], momentum=h.get("momentum", 0.0),
+                             dampening=h.get("dampening", 0.0), weight_decay=h.get("weight_decay", 0.0),
+                             nesterov=h.get("nesterov", False), buf=self.inner_buf, first_step=(it == 0))
             losses.append(loss)
         return losses
 
