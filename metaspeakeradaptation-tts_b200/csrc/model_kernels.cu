@@ -55,6 +55,27 @@ __global__ void ker_im2col(const float* __restrict__ x, float* col, int B, int T
         col[i] = (ts >= 0 && ts < T) ? x[((int64_t)b * T + ts) * C + c] : 0.f;
     }
 }
+// four consecutive columns per thread ((C * K) % 4 == 0: a group never crosses a row), one 128-bit store
+__global__ void ker_im2col_v4(const float* __restrict__ x, float4* col, int B, int T, int C, int K) {
+    const int pad = (K - 1) / 2;
+    const int CK = C * K;
+    const int64_t n4 = (int64_t)B * T * CK / 4;
+    GSL(i4, n4) {
+        const int64_t bt = (i4 * 4) / CK;
+        const int j = (int)(i4 * 4 - bt * CK);
+        int c = j / K, k = j - c * K;
+        const int t = (int)(bt % T);
+        const float* xr = x + (bt - t) * C;          // row 0 of this batch element
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int ts = t + k - pad;
+            v[e] = (ts >= 0 && ts < T) ? xr[(int64_t)ts * C + c] : 0.f;
+            if (++k == K) { k = 0; ++c; }
+        }
+        col[i4] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
 __global__ void ker_col2im(const float* __restrict__ dcol, float* dx, int B, int T, int C, int K) {
     const int pad = (K - 1) / 2;
     const int64_t n = (int64_t)B * T * C;
@@ -600,7 +621,10 @@ int k_embedding_bwd(const float* dx, const int64_t* tok, float* gw, int rows, in
     return 0;
 }
 int k_im2col(const float* x, float* col, int B, int T, int C, int K, cudaStream_t st) {
-    ker_im2col<<<grid_for((int64_t)B * T * C * K), kTh, 0, ST>>>(x, col, B, T, C, K);
+    if (((C * K) & 3) == 0 && (reinterpret_cast<uintptr_t>(col) & 15) == 0)
+        ker_im2col_v4<<<grid_for((int64_t)B * T * C * K / 4), kTh, 0, ST>>>(x, reinterpret_cast<float4*>(col), B, T, C, K);
+    else
+        ker_im2col<<<grid_for((int64_t)B * T * C * K), kTh, 0, ST>>>(x, col, B, T, C, K);
     MSA_LAUNCH_CHECK();
     return 0;
 }
