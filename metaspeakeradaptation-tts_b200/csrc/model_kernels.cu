@@ -489,11 +489,17 @@ __global__ void ker_sum_partials(const float* __restrict__ partials, int n, floa
 }
 
 // out[n] = sum_t x[t][n]
+// (eight independent running sums per thread, combined in a fixed order: the T loads of a thread are latency-bound otherwise)
 __global__ void ker_sum_over_t(const float* __restrict__ x, float* out, int T, int64_t n) {
     GSL(i, n) {
-        float s = 0.f;
-        for (int t = 0; t < T; ++t) s += x[(int64_t)t * n + i];
-        out[i] = s;
+        float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int t = 0;
+        for (; t + 8 <= T; t += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] += x[(int64_t)(t + j) * n + i];
+        }
+        for (int j = 0; t < T; ++t, ++j) s[j] += x[(int64_t)t * n + i];
+        out[i] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
     }
 }
 
@@ -549,10 +555,19 @@ __global__ void __launch_bounds__(256) ker_wloc_grad_partial(const float* __rest
         }
     }
 }
-__global__ void ker_wloc_grad_final(const float* __restrict__ partials, int G, int n, float* gw, float scale, int accumulate) {
-    GSL(i, n) {
-        float s = 0.f;
-        for (int g = 0; g < G; ++g) s += partials[(size_t)g * n + i];
+// block = 32 outputs x 8 slices of the G partial tables (slice q sums g = q, q + 8, ...), slices combined in a fixed order
+__global__ void __launch_bounds__(256) ker_wloc_grad_final(const float* __restrict__ partials, int G, int n, float* gw, float scale,
+                                                           int accumulate) {
+    __shared__ float sh[8][33];
+    const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    float s = 0.f;
+    if (i < n)
+        for (int g = q; g < G; g += 8) s += partials[(size_t)g * n + i];
+    sh[q][lane] = s;
+    __syncthreads();
+    if (q == 0 && i < n) {
+        s = ((sh[0][lane] + sh[1][lane]) + (sh[2][lane] + sh[3][lane])) + ((sh[4][lane] + sh[5][lane]) + (sh[6][lane] + sh[7][lane]));
         gw[i] = accumulate ? gw[i] + scale * s : scale * s;
     }
 }
@@ -791,7 +806,7 @@ int k_wloc_grad(const float* dconvf, const float* align, const float* cum, float
     MSA_CHECK(smem <= 48 * 1024, MSA_E_UNSUPPORTED, "wloc_grad: text length %d too long for the shared-memory slab", L);
     ker_wloc_grad_partial<<<G, 256, smem, ST>>>(dconvf, align, cum, partials, T, B, L, F, Kl);
     MSA_LAUNCH_CHECK();
-    ker_wloc_grad_final<<<grid_for((int64_t)F * 2 * Kl), kTh, 0, ST>>>(partials, G, F * 2 * Kl, gw, scale, acc);
+    ker_wloc_grad_final<<<cdiv(F * 2 * Kl, 32), 256, 0, ST>>>(partials, G, F * 2 * Kl, gw, scale, acc);
     MSA_LAUNCH_CHECK();
     return 0;
 }
