@@ -19,6 +19,7 @@ def test_header_declares_the_documented_groups():
     names = _declared()
     for must in ("msa_create", "msa_destroy", "msa_train_forward", "msa_train_backward", "msa_infer", "msa_flat_sgd_step",
                  "msa_flat_axpy", "msa_flat_reptile_delta", "msa_flat_clip_adam", "msa_flat_adam_step", "msa_ewc_sgd_step", "msa_tacotron2_loss",
+                 "msa_train_mcd", "msa_gemm_nt", "msa_masks_generate",
                  "msa_last_error_string"):
         assert must in names
 
