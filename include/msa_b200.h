@@ -233,7 +233,9 @@ int msa_ewc_sgd_step(float* p, const float* g, const float* mu, const float* fis
 /* ---- tensor-core GEMM building block (exported for tests / profiles) ------------------------------------------
  * C[M,N] = alpha * A[M,K] . B[N,K]^T + beta * C, row-major, both operands K-contiguous (torch.nn.functional.linear's
  * contraction, the shape of every forward projection of the model).  tcgen05 TF32 MMAs fed by TMA; mode 0 = 3xTF32
- * split (fp32-accurate, needs scratch of msa_gemm_nt_scratch_floats floats), mode 1 = single TF32 product.
+ * split (fp32-accurate; the lo tiles are derived in shared memory), mode 1 = single TF32 product.  Output grids that
+ * do not fill the GPU are split over K: `scratch` (msa_gemm_nt_scratch_floats(M, N, K) floats, 16-byte aligned)
+ * holds the partial tiles, summed in a fixed order; scratch == NULL disables the K split.
  * Requires lda, ldb multiples of 4 floats and 16-byte aligned A, B. */
 size_t msa_gemm_nt_scratch_floats(int64_t M, int64_t N, int64_t K);
 int msa_gemm_nt(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb,
