@@ -165,9 +165,23 @@ int msa_tacotron2_loss(const float* mel, const float* mel_post, const float* gat
 /* d(loss)/d(mel, mel_post, gate) of the last forward, reference layouts (for autograd glue) */
 int msa_loss_grads(msa_handle* h, void* ws, float* d_mel, float* d_mel_post, float* d_gate, void* stream);
 /* The persistent kernels hand data between CTAs by polling (no grid barrier); a producer that never arrives makes
- * the consumers give up after a bounded spin and raise a flag instead of hanging the GPU.  Synchronises `stream`
- * and returns MSA_E_STATE if any kernel of the passes run in `ws` since the last msa_train_forward gave up. */
+ * the consumers give up after a bounded spin and raise the handle's abort word instead of hanging the GPU.  The word
+ * is STICKY: no pass clears it, so one check per meta-step covers every pass of that step (nothing comparable exists
+ * in the reference -- its autograd graph cannot time out; call sites that consume the guarded results: maml.py:94-105,
+ * reptile.py:82-89).
+ *   msa_check_abort      synchronises `stream`, returns MSA_E_STATE if a kernel of this handle gave up (`ws` is unused)
+ *   msa_abort_guard      device side, no sync: if the word is set, *sumsq <- NaN.  msa_flat_clip_sgd / msa_flat_clip_adam
+ *                        skip their update when *sumsq is not finite, so garbage gradients never reach the weights or
+ *                        the optimizer state
+ *   msa_abort_read_async enqueues a 4-byte device->host copy of the word into (pinned) host memory; the trainers look
+ *                        at it after the step's own synchronisation point and raise
+ *   msa_abort_clear      resets the word (after the error has been reported)
+ *   msa_debug_raise_abort test hook: raises the word exactly as a polling thread that timed out would */
 int msa_check_abort(msa_handle* h, void* ws, void* stream);
+int msa_abort_guard(msa_handle* h, float* sumsq, void* stream);
+int msa_abort_read_async(msa_handle* h, uint32_t* host_flag, void* stream);
+int msa_abort_clear(msa_handle* h, void* stream);
+int msa_debug_raise_abort(msa_handle* h, void* stream);
 /* cycles per phase recorded by thread 0 of every CTA of persistent kernel `id` (msa_profile_name) during the last
  * pass run with profiling enabled: out[ncta][8] (synchronises the device; profiles only) */
 int msa_profile_phases(msa_handle* h, void* ws, int id, int64_t* out, int ncta);
@@ -208,7 +222,9 @@ int msa_flat_sumsq(const float* g, int64_t n, float* partials, float* out, void*
 /* clip_grad_norm_ + outer_optimizer.step() (maml.py:101-105, reptile.py:85-89) fused:
  * coef = min(1, max_norm / (sqrt(*sumsq) + 1e-6)) (max_norm <= 0: no clipping);
  * SGD:  p -= lr * coef * g  (+ momentum/weight decay as torch.optim.SGD)
- * Adam: torch.optim.Adam (no amsgrad), step = 1-based step index. */
+ * Adam: torch.optim.Adam (no amsgrad), step = 1-based step index.
+ * If *sumsq is not finite (NaN from msa_abort_guard, or a diverged gradient) the whole update is skipped: p and the
+ * optimizer state stay as they are. */
 int msa_flat_clip_sgd(float* p, const float* g, float* momentum_buf, const float* sumsq, int64_t n, float lr,
                       float max_norm, float momentum, float dampening, float weight_decay, int nesterov,
                       int first_step, void* stream);

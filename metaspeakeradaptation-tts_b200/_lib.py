@@ -53,6 +53,10 @@ SIGNATURES = {
     "msa_tacotron2_loss": (I, [V, V, V, V, V, V, I, I, I, I, F, V, V, V, V, V, V]),
     "msa_loss_grads": (I, [V, V, V, V, V, V]),
     "msa_check_abort": (I, [V, V, V]),
+    "msa_abort_guard": (I, [V, V, V]),
+    "msa_abort_read_async": (I, [V, V, V]),
+    "msa_abort_clear": (I, [V, V]),
+    "msa_debug_raise_abort": (I, [V, V]),
     "msa_profile_phases": (I, [V, V, I, C.POINTER(I64), I]),
     "msa_profile_trace_step": (I, [V, I]),
     "msa_profile_trace": (I, [V, V, I, C.POINTER(I64), I]),

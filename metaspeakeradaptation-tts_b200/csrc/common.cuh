@@ -139,8 +139,10 @@ __device__ __forceinline__ void st_pub4(float* p, const float4& v) {
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // Bounded spinning: a producer that never arrives (a bug, or NaN data) must not hang the GPU.  After ~4M empty polls a
-// thread raises the launch-wide abort word; every spinner checks it every 1024 polls and gives up.  The host checks the
-// word after the pass (msa_train_forward/backward return MSA_E_STATE on the next call if it is set).
+// thread raises the abort word of the handle; every spinner checks it every 1024 polls and gives up.  The word is sticky
+// (no pass clears it): the trainers fold it into the gradient-norm scalar on the device (msa_abort_guard: the clip + optimizer
+// kernels then skip the update) and read it back with the step's own device->host traffic (msa_abort_read_async); tests
+// call msa_check_abort, which synchronises.
 struct SpinGuard {
     unsigned int* abort_word;
     unsigned int n;

@@ -28,7 +28,8 @@ __device__ __forceinline__ void st4(float* p, int64_t i, float4 v) { reinterpret
 #define FOR4(body) { const int c = 0; body } { const int c = 1; body } { const int c = 2; body } { const int c = 3; body }
 #define C4(v) (reinterpret_cast<float*>(&(v))[c])
 
-__global__ void __launch_bounds__(kFlatThreads) k_sgd_step(const float* __restrict__ p, const float* __restrict__ g,
+// p_out may alias p (in-place step on the fast weights): p carries no __restrict__
+__global__ void __launch_bounds__(kFlatThreads) k_sgd_step(const float* p, const float* __restrict__ g,
                                                          float* p_out, float* buf, int64_t n4, float lr, float mom,
                                                          float damp, float wd, int nesterov, int first) {
     FLAT_LOOP(n4) {
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(kFlatThreads) k_clip_sgd(float* p, const float
                                                          const float* __restrict__ sumsq, int64_t n4, float lr,
                                                          float max_norm, float mom, float damp, float wd, int nesterov,
                                                          int first) {
+    if (sumsq != nullptr && !isfinite(sumsq[0])) return;      // msa_abort_guard / diverged gradient: leave p and the state alone
     const float coef = clip_coef(sumsq, max_norm);
     FLAT_LOOP(n4) {
         float4 pv = ld4(p, i), gv = ld4(g, i);
@@ -111,6 +113,7 @@ __global__ void __launch_bounds__(kFlatThreads) k_clip_adam(const float* p, floa
                                                           const float* __restrict__ sumsq, int64_t n4, float lr, float b1,
                                                           float b2, float eps, float wd, float bc1, float bc2_sqrt,
                                                           float max_norm) {
+    if (sumsq != nullptr && !isfinite(sumsq[0])) return;      // msa_abort_guard / diverged gradient: leave p and the state alone
     const float coef = clip_coef(sumsq, max_norm);
     const float step_size = lr / bc1;
     FLAT_LOOP(n4) {

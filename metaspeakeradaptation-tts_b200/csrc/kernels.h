@@ -257,6 +257,7 @@ int gemm_tc_nt(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int
                float* C, int64_t ldc, int mode, float* scratch, cudaStream_t st, const float* bias1 = nullptr,
                const float* bias2 = nullptr);   // mode 0: 3xTF32 (fp32-accurate), 1: TF32
 
+int k_abort_guard(unsigned int* abort_word, float* sumsq, int raise, cudaStream_t st);   // raise: set the word; else NaN -> *sumsq if set
 int k_fill_canary(float* p, int64_t n, cudaStream_t st);   // n floats (multiple of 4, 16-byte aligned) <- 0xFFFFFFFF
 int k_scale_copy(const float* in, float* out, int64_t n, float scale, int accumulate, cudaStream_t st);
 

@@ -758,6 +758,15 @@ int k_add3(const float* a, const float* b, const float* c, float* out, int64_t n
 __global__ void ker_fill_canary(uint4* p, int64_t n4) {
     GSL(i, n4) p[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
 }
+__global__ void ker_abort_guard(unsigned int* abort_word, float* sumsq, int raise) {
+    if (raise) *abort_word = 1u;
+    else if (*abort_word != 0u) sumsq[0] = __int_as_float(0x7fc00000);
+}
+int k_abort_guard(unsigned int* abort_word, float* sumsq, int raise, cudaStream_t st) {
+    ker_abort_guard<<<1, 1, 0, st>>>(abort_word, sumsq, raise);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
 int k_fill_canary(float* p, int64_t n, cudaStream_t st) {
     // n is rounded up to a multiple of 4 floats: every workspace buffer is padded to a multiple of 64 floats (pass.cu)
     MSA_CHECK((reinterpret_cast<uintptr_t>(p) & 15) == 0, MSA_E_ARG, "k_fill_canary: buffer must be 16-byte aligned");

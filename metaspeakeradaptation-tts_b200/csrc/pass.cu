@@ -73,6 +73,10 @@ struct msa_handle {
     float* gemm_scratch = nullptr;   // K-split partial tiles of the tcgen05 GEMM (in the pass workspace)
     size_t gemm_scratch_floats = 0;
     cudaStream_t cur_stream = nullptr;
+    // Launch-wide abort word of the persistent kernels (common.cuh, SpinGuard): device memory owned by the handle, zeroed at
+    // msa_create and STICKY -- no pass clears it, so a polling time-out anywhere in a meta-step is still visible when the host (or
+    // msa_abort_guard on the device) looks at it; msa_abort_clear resets it.
+    unsigned int* abort_dev = nullptr;
     // Hand-written tcgen05 / TMA GEMM (gemm_tc.cu) for the x.W^T contractions.  tc_mode 2 (default): the fp32-accurate 3xTF32
     // products of at least tc_min MACs (3 x tc_min when K < 1024) -- at the default dimensions the LSTM input projections, the
     // k=5 convolutions of encoder and postnet, MW and the mel / gate projection, 1.4-4x faster there than cuBLAS's SIMT sgemm;
@@ -443,6 +447,12 @@ int msa_create(const msa_config* cfg, int device, msa_handle** out) {
         return 1000 + (int)s;
     }
     cublasSetPointerMode(h->blas, CUBLAS_POINTER_MODE_HOST);
+    if (cudaMalloc(&h->abort_dev, 256) != cudaSuccess || cudaMemset(h->abort_dev, 0, 256) != cudaSuccess) {
+        cublasDestroy(h->blas);
+        delete h;
+        set_error("msa_create: cannot allocate the abort word");
+        return MSA_E_NODEVICE;
+    }
     *out = h;
     return 0;
 }
@@ -450,6 +460,7 @@ int msa_create(const msa_config* cfg, int device, msa_handle** out) {
 int msa_destroy(msa_handle* h) {
     if (!h) return 0;
     if (h->blas) cublasDestroy(h->blas);
+    if (h->abort_dev) cudaFree(h->abort_dev);
     for (auto& e : h->prof_ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     delete h;
     return 0;
@@ -548,7 +559,6 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
     const msa_config& c = h->cfg;
     const auto secs = mask_sections(c, B, T, L);
     auto mk = [&](int i) { return masks + secs[i].off; };
-    MSA_CUDA(cudaMemsetAsync(w.abort_word, 0, 256, st));
     MSA_CUDA(cudaMemsetAsync(w.red_scr, 0, sizeof(unsigned int) * kRedTickets, st));      // tickets of the chunked column reductions
     const int iPre = d.nEnc, iAttn = d.nEnc + 2, iDec = d.nEnc + 3, iPost = d.nEnc + 4;
     auto P = [&](const std::string& n) { return params + h->off(n); };
@@ -585,7 +595,7 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
         lp.zin = w.enc_zx; lp.whh = P("encoder.lstm.weight_hh_l0");
         lp.whh_dir_stride = h->off("encoder.lstm.weight_hh_l0_reverse") - h->off("encoder.lstm.weight_hh_l0");
         lp.hout = w.enc_h; lp.cout = w.enc_c; lp.gates = w.enc_g; lp.mask = nullptr; lp.drop_scale = 1.f;
-        lp.lengths = token_lengths; lp.abort_word = w.abort_word; lp.prof = prof_ptr(h, w, PROF_ENC_LSTM_FWD); lp.trace = trace_ptr(h, w, PROF_ENC_LSTM_FWD); lp.trace_t0 = h->trace_t0; lp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
+        lp.lengths = token_lengths; lp.abort_word = h->abort_dev; lp.prof = prof_ptr(h, w, PROF_ENC_LSTM_FWD); lp.trace = trace_ptr(h, w, PROF_ENC_LSTM_FWD); lp.trace_t0 = h->trace_t0; lp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
         ProfScope ps(h, PROF_ENC_LSTM_FWD, st);
         MSA_TRY(launch_lstm_rec_fwd(lp, h->sm_count, h->smem_limit, st));
     }
@@ -621,7 +631,7 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
         ap.ha = w.ha; ap.ca = w.ca; ap.ga = w.ga; ap.q = w.q; ap.align = w.align_tm; ap.cum = w.cum; ap.s = w.s;
         ap.fa = fa; ap.ta = ta; ap.aplain = w.aplain; ap.fsum = w.fsum; ap.ustash = w.ustash;
         if (ta) { ap.mta = w.mta; ap.wta_h = P(at + "ta.weight") + d.E; ap.bta = P(at + "ta.bias"); }
-        ap.convf = w.convf; ap.znorm = w.znorm; ap.e = w.ebuf; ap.abort_word = w.abort_word; ap.prof = prof_ptr(h, w, PROF_ATTN_FWD); ap.trace = trace_ptr(h, w, PROF_ATTN_FWD); ap.trace_t0 = h->trace_t0; ap.flags = h->rec_flags >= 0 ? h->rec_flags : 0;
+        ap.convf = w.convf; ap.znorm = w.znorm; ap.e = w.ebuf; ap.abort_word = h->abort_dev; ap.prof = prof_ptr(h, w, PROF_ATTN_FWD); ap.trace = trace_ptr(h, w, PROF_ATTN_FWD); ap.trace_t0 = h->trace_t0; ap.flags = h->rec_flags >= 0 ? h->rec_flags : 0;
         ProfScope ps(h, PROF_ATTN_FWD, st);
         MSA_TRY(launch_attn_chain_fwd(ap, h->sm_count, h->smem_limit, st));
     }
@@ -640,7 +650,7 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
         lp.hout = w.hd; lp.cout = w.cd; lp.gates = w.gd;
         lp.mask = c.p_dec_dropout > 0.f ? mk(iDec) : nullptr;
         lp.drop_scale = 1.f / (1.f - c.p_dec_dropout);
-        lp.lengths = nullptr; lp.abort_word = w.abort_word; lp.prof = prof_ptr(h, w, PROF_DEC_LSTM_FWD); lp.trace = trace_ptr(h, w, PROF_DEC_LSTM_FWD); lp.trace_t0 = h->trace_t0; lp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
+        lp.lengths = nullptr; lp.abort_word = h->abort_dev; lp.prof = prof_ptr(h, w, PROF_DEC_LSTM_FWD); lp.trace = trace_ptr(h, w, PROF_DEC_LSTM_FWD); lp.trace_t0 = h->trace_t0; lp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
         ProfScope ps(h, PROF_DEC_LSTM_FWD, st);
         MSA_TRY(launch_lstm_rec_fwd(lp, h->sm_count, h->smem_limit, st));
     }
@@ -818,7 +828,7 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
         bp.gates = w.gd; bp.cout = w.cd; bp.dh_ext = w.dhd; bp.dz = w.dzd;
         bp.mask = c.p_dec_dropout > 0.f ? mk(iDec) : nullptr;
         bp.drop_scale = 1.f / (1.f - c.p_dec_dropout);
-        bp.lengths = nullptr; bp.abort_word = w.abort_word; bp.prof = prof_ptr(h, w, PROF_DEC_LSTM_BWD); bp.trace = trace_ptr(h, w, PROF_DEC_LSTM_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
+        bp.lengths = nullptr; bp.abort_word = h->abort_dev; bp.prof = prof_ptr(h, w, PROF_DEC_LSTM_BWD); bp.trace = trace_ptr(h, w, PROF_DEC_LSTM_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
         ProfScope ps(h, PROF_DEC_LSTM_BWD, st);
         MSA_TRY(launch_lstm_rec_bwd(bp, h->sm_count, h->smem_limit, st));
     }
@@ -860,7 +870,7 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
         bp.dza = w.dza; bp.dq = w.dq; bp.de = w.de; bp.ds = w.ds; bp.dconvf = w.dconvf; bp.dat = w.dat;
         bp.fa = fa; bp.ta = ta; bp.aplain = w.aplain; bp.fsum = w.fsum; bp.ustash = w.ustash; bp.dzu = w.dzu;
         if (ta) { bp.mta = w.mta; bp.wta_h = P(at + "ta.weight") + d.E; }
-        bp.abort_word = w.abort_word; bp.prof = prof_ptr(h, w, PROF_ATTN_BWD); bp.trace = trace_ptr(h, w, PROF_ATTN_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 0;
+        bp.abort_word = h->abort_dev; bp.prof = prof_ptr(h, w, PROF_ATTN_BWD); bp.trace = trace_ptr(h, w, PROF_ATTN_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 0;
         ProfScope ps(h, PROF_ATTN_BWD, st);
         MSA_TRY(launch_attn_chain_bwd(bp, h->sm_count, h->smem_limit, st));
     }
@@ -924,7 +934,7 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
         bp.whh = P("encoder.lstm.weight_hh_l0");
         bp.whh_dir_stride = h->off("encoder.lstm.weight_hh_l0_reverse") - h->off("encoder.lstm.weight_hh_l0");
         bp.gates = w.enc_g; bp.cout = w.enc_c; bp.dh_ext = w.denc_h; bp.dz = w.dzx; bp.mask = nullptr; bp.drop_scale = 1.f;
-        bp.lengths = h->tok_len; bp.abort_word = w.abort_word; bp.prof = prof_ptr(h, w, PROF_ENC_LSTM_BWD); bp.trace = trace_ptr(h, w, PROF_ENC_LSTM_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
+        bp.lengths = h->tok_len; bp.abort_word = h->abort_dev; bp.prof = prof_ptr(h, w, PROF_ENC_LSTM_BWD); bp.trace = trace_ptr(h, w, PROF_ENC_LSTM_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
         ProfScope ps(h, PROF_ENC_LSTM_BWD, st);
         MSA_TRY(launch_lstm_rec_bwd(bp, h->sm_count, h->smem_limit, st));
     }
@@ -963,13 +973,31 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
 }
 
 int msa_check_abort(msa_handle* h, void* wsp, void* stream) {
-    MSA_CHECK(h && wsp && h->fwd_valid, MSA_E_STATE, "msa_check_abort: no forward pass in this workspace");
-    const Ws w = ws_layout(h->d, wsp);
+    (void)wsp;      // the word lives in the handle since round 2; the argument is kept for ABI stability
+    MSA_CHECK(h, MSA_E_ARG, "msa_check_abort: null handle");
     unsigned int flag = 0;
-    MSA_CUDA(cudaMemcpyAsync(&flag, w.abort_word, sizeof(flag), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    MSA_CUDA(cudaMemcpyAsync(&flag, h->abort_dev, sizeof(flag), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     MSA_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     MSA_CHECK(flag == 0, MSA_E_STATE, "a persistent kernel gave up waiting for data of another CTA (polling time-out): results are invalid");
     return 0;
+}
+int msa_abort_clear(msa_handle* h, void* stream) {
+    MSA_CHECK(h, MSA_E_ARG, "msa_abort_clear: null handle");
+    MSA_CUDA(cudaMemsetAsync(h->abort_dev, 0, 256, (cudaStream_t)stream));
+    return 0;
+}
+int msa_abort_guard(msa_handle* h, float* sumsq, void* stream) {
+    MSA_CHECK(h && sumsq, MSA_E_ARG, "msa_abort_guard: null argument");
+    return k_abort_guard(h->abort_dev, sumsq, 0, (cudaStream_t)stream);
+}
+int msa_abort_read_async(msa_handle* h, uint32_t* host_flag, void* stream) {
+    MSA_CHECK(h && host_flag, MSA_E_ARG, "msa_abort_read_async: null argument");
+    MSA_CUDA(cudaMemcpyAsync(host_flag, h->abort_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return 0;
+}
+int msa_debug_raise_abort(msa_handle* h, void* stream) {
+    MSA_CHECK(h, MSA_E_ARG, "msa_debug_raise_abort: null handle");
+    return k_abort_guard(h->abort_dev, nullptr, 1, (cudaStream_t)stream);
 }
 
 int msa_profile_trace(msa_handle* h, void* wsp, int id, int64_t* out, int ncta) {
@@ -1111,7 +1139,6 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
     h->gemm_scratch = nullptr; h->gemm_scratch_floats = 0; h->cur_stream = st;      // encoder / postnet GEMMs of inference stay on cuBLAS
     const msa_config& c = h->cfg;
     auto P = [&](const std::string& n) { return params + h->off(n); };
-    MSA_CUDA(cudaMemsetAsync(w.abort_word, 0, 256, st));
 
     // ---- speaker vector + encoder in eval mode (tacotron2nv.py:137-148, encoder.py:55-71) ----
     if (c.spk_mode == 0) {
@@ -1142,7 +1169,7 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
         lp.zin = w.enc_zx; lp.whh = P("encoder.lstm.weight_hh_l0");
         lp.whh_dir_stride = h->off("encoder.lstm.weight_hh_l0_reverse") - h->off("encoder.lstm.weight_hh_l0");
         lp.hout = w.enc_h; lp.cout = w.enc_c; lp.gates = w.enc_g; lp.mask = nullptr; lp.drop_scale = 1.f;
-        lp.lengths = token_lengths; lp.abort_word = w.abort_word; lp.prof = nullptr; lp.trace = nullptr; lp.trace_t0 = 0;
+        lp.lengths = token_lengths; lp.abort_word = h->abort_dev; lp.prof = nullptr; lp.trace = nullptr; lp.trace_t0 = 0;
         lp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
         MSA_TRY(launch_lstm_rec_fwd(lp, h->sm_count, h->smem_limit, st));
     }

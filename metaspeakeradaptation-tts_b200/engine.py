@@ -98,6 +98,9 @@ class Engine:
         self._keep: tuple = ()
         self.launches = 0   # kernels of this library enqueued by the calls below (bench.py's gpu_launches)
         self._last_out = None
+        self._abort_host: Optional[torch.Tensor] = None
+        self._abort_evt = [None, None]
+        self._abort_k = 0
 
     def __del__(self):
         try:
@@ -325,8 +328,57 @@ class Engine:
         _lib.check(self.lib.msa_profile_enable(self.h, (2 if inkernel else 1) if enable else 0), "msa_profile_enable")
 
     def check_abort(self) -> None:
-        """Raise if a persistent kernel of the last passes timed out while polling (synchronises)."""
-        _lib.check(self.lib.msa_check_abort(self.h, self._ws_ptr(), _stream()), "msa_check_abort")
+        """Raise if a persistent kernel of this engine timed out while polling since the last ``abort_clear`` (synchronises)."""
+        _lib.check(self.lib.msa_check_abort(self.h, None, _stream()), "msa_check_abort")
+
+    def abort_guard(self, sumsq: torch.Tensor) -> None:
+        """Device side, no sync: NaN into the gradient-norm scalar if a persistent kernel gave up; the clip + optimizer kernels skip
+        their update on a non-finite norm, so garbage gradients never reach the weights or the optimizer state."""
+        _lib.check(self.lib.msa_abort_guard(self.h, _ptr(sumsq), _stream()), "msa_abort_guard")
+        self.launches += 1
+
+    def abort_poll(self) -> None:
+        """Deferred host-side check without a stall: enqueue a 4-byte device->host copy of the abort word into pinned memory and
+        raise if the PREVIOUS copy (complete by now in any loop that reads a loss per step) saw it set."""
+        if self._abort_host is None:
+            self._abort_host = torch.zeros(2, dtype=torch.int32).pin_memory()
+            self._abort_evt = [None, None]
+        k = self._abort_k
+        prev = 1 - k
+        if self._abort_evt[prev] is not None:
+            self._abort_evt[prev].synchronize()
+            if int(self._abort_host[prev]) != 0:
+                self._abort_raise()
+        _lib.check(self.lib.msa_abort_read_async(self.h, C.c_void_p(self._abort_host.data_ptr() + 4 * k), _stream()), "msa_abort_read_async")
+        ev = torch.cuda.Event()
+        ev.record()
+        self._abort_evt[k] = ev
+        self._abort_k = prev
+
+    def abort_flush(self) -> None:
+        """Wait for the outstanding ``abort_poll`` copies and raise if one saw the word (end of an epoch / of a bench loop)."""
+        if self._abort_host is None:
+            return
+        for k in (0, 1):
+            if self._abort_evt[k] is not None:
+                self._abort_evt[k].synchronize()
+                self._abort_evt[k] = None
+                if int(self._abort_host[k]) != 0:
+                    self._abort_raise()
+
+    def _abort_raise(self):
+        self._abort_host.zero_()
+        self._abort_evt = [None, None]
+        _lib.check(self.lib.msa_abort_clear(self.h, _stream()), "msa_abort_clear")
+        raise RuntimeError("libmsa_b200: a persistent kernel gave up waiting for data of another CTA (polling time-out); the "
+                           "gradients of this meta-step were discarded on the device (the outer update was skipped)")
+
+    def abort_clear(self) -> None:
+        _lib.check(self.lib.msa_abort_clear(self.h, _stream()), "msa_abort_clear")
+
+    def debug_raise_abort(self) -> None:
+        """Test hook: raise the abort word exactly as a polling thread that timed out would."""
+        _lib.check(self.lib.msa_debug_raise_abort(self.h, _stream()), "msa_debug_raise_abort")
 
     def profile_phases(self, name: str):
         """[ncta][8] cycles per phase of persistent kernel `name` in the last profiled pass (profiles only)."""

@@ -26,8 +26,10 @@ class EWC:
             B, L = bd["inputs"].shape
             T = bd["melspecs"].shape[2]
             mk = eng.pack_masks(masks[i], B, T, L) if masks is not None else model._masks(B, T, L)
-            bn = model.bn_flat.clone()                                   # the Fisher passes must not move the running stats
-            eng.forward(model.flat, bn, bd, mk, outputs=False)
+            # the reference runs the model itself in train mode here (continual_ewc.py:66-72): its BatchNorm running statistics
+            # and num_batches_tracked DO move with every buffer batch, and the checkpoint / inference after EWC see them
+            eng.forward(model.flat, model.bn_flat, bd, mk, outputs=False)
+            model.count_bn_batches()
             eng.backward(model.flat, g)
             eng.ewc_fisher_accum(self.fisher, g, 1.0 / len(batches), init=(i == 0))
 

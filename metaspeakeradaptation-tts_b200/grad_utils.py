@@ -16,12 +16,16 @@ def _flat_of(tensors: Sequence[torch.Tensor]):
     return getattr(tensors[0], "_msa_flat", None)
 
 
-def mix_grad(grad_list, weight_list, model) -> List[torch.Tensor]:
-    """Weighted sum of per-task gradient lists (grad_utils.py:23-31): sum_i w_i * g_i."""
+def mix_grad(grad_list, weight_list, model=None) -> List[torch.Tensor]:
+    """Weighted sum of per-task gradient lists (grad_utils.py:23-31): sum_i w_i * g_i.  Same signature as the reference
+    (``mix_grad(grad_list, weight_list)``, maml.py:96): the owning model travels with the gradient views."""
     flats = [_flat_of(g) for g in grad_list]
     if any(f is None for f in flats):
         raise RuntimeError("mix_grad: pass gradient lists produced by this package (views of flat buffers); "
                            "there is no per-tensor PyTorch fallback")
+    model = model if model is not None else getattr(grad_list[0][0], "_msa_owner", None)
+    if model is None:
+        raise RuntimeError("mix_grad: the gradient views carry no owner (were they produced by Tacotron2NV.layout_views?)")
     eng = model.engine
     acc = eng.new_flat(None)
     for i, f in enumerate(flats):

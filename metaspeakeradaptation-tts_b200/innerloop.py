@@ -36,11 +36,14 @@ class FunctionalTacotron2NV:
         views = [v.requires_grad_(True) for v in self.model.layout_views(flat.detach())]
         for v in views:
             v._msa_flat = flat
+            v._msa_owner = self.model
         self._fast.append(flat)
         self._views.append(views)
 
     def __call__(self, inputs, input_lengths, melspecs, melspec_lengths, speaker_vecs):
         m = self.model
+        if not self.training:      # same loud error as the base model: there is no eval-mode teacher-forced pass on the CUDA path
+            raise NotImplementedError("teacher-forced forward in eval() mode is not implemented on the CUDA path; use infer()")
         dev = self.engine.device
         bd = {"inputs": inputs.to(dev).contiguous(), "input_lengths": input_lengths.to(dev).contiguous(),
               "melspecs": melspecs.to(dev).contiguous(), "melspec_lengths": melspec_lengths.to(dev).contiguous(),

@@ -121,6 +121,9 @@ class MetaTrainer:
         eng = self.engine
         self.shard.allreduce_sum(self.meta_grad)
         eng.sumsq(self.meta_grad, self.sumsq)                     # apply_grad's norm / clip_grad_norm_'s total norm
+        # a persistent kernel that gave up polling leaves garbage gradients: poison the norm on the device (the update kernels below
+        # skip on a non-finite norm, theta and the optimizer state stay intact) and let the host find out without a stall
+        eng.abort_guard(self.sumsq)
         thr = float(self.params["grad_clip_thresh"]) if self.params.get("clip_grad_norm", False) else 0.0
         o = self.outer
         if o["name"] == "SGD":
@@ -132,6 +135,7 @@ class MetaTrainer:
                           betas=o.get("betas", (0.9, 0.999)), eps=o.get("eps", 1e-8), weight_decay=o.get("weight_decay", 0.0),
                           max_norm=thr)
         self.step_global += 1
+        eng.abort_poll()
         return self.sumsq
 
     # ---- checkpoints (metatrainer.py:119-122, 138-146) --------------------------------------------------

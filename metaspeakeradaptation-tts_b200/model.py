@@ -97,6 +97,7 @@ class Tacotron2NV(nn.Module):
         views = list(self.engine.dict_from_flat(flat).values())
         for v in views:
             v._msa_flat = flat
+            v._msa_owner = self
         return views
 
     def bind_grads(self) -> None:
@@ -107,6 +108,11 @@ class Tacotron2NV(nn.Module):
     def zero_grad(self, set_to_none: bool = True) -> None:  # noqa: D102
         super().zero_grad(set_to_none=set_to_none)
         self.grad_flat_set = False
+
+    def count_bn_batches(self, n: int = 1) -> None:
+        """nn.BatchNorm1d bumps ``num_batches_tracked`` on every train-mode forward (checkpoint parity with the reference)."""
+        for name in self.layout.bn_names:
+            _descend(self, name.split(".")).num_batches_tracked += n
 
     def _masks(self, B: int, T: int, L: int) -> torch.Tensor:
         if self.injected_masks is not None:
@@ -125,6 +131,7 @@ class Tacotron2NV(nn.Module):
         B, L = bd["inputs"].shape
         T = bd["melspecs"].shape[2]
         out = _PassFn.apply(self, self.flat, self.bn_flat, bd, self._masks(B, T, L), *self.parameters())
+        self.count_bn_batches()
         self.engine._last_out = out
         return list(out)
 

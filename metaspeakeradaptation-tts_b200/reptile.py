@@ -2,10 +2,12 @@
 
 Per speaker: adapt ``n_inner_train`` SGD steps from theta_0, task "gradient" = -(theta_T - theta_0)
 (reptile.py:42, 73-77).  Two outer-loop semantics are provided:
-  * ``batched`` (default, BASELINE.json config 3): all speakers of the meta-batch start from the same theta_0,
-    the deltas are averaged with weights 1/N and joined by ONE allreduce -- the only form that shards.
-  * ``sequential=True``: the reference's literal behaviour -- an outer step after EACH speaker, each starting from
-    the already updated weights (reptile.py:37-39, 82-89).  Cannot shard; world size must be 1.
+  * ``reptile_sequential=True`` -- the DEFAULT on one GPU: the reference's literal behaviour -- an outer step after EACH
+    speaker, each starting from the already updated weights, ``step_global`` advancing once per speaker
+    (reptile.py:37-39, 82-89).  Cannot shard; world size must be 1.
+  * ``reptile_sequential=False`` (opt-in; BASELINE.json config 3; the default when the run is sharded over several GPUs,
+    with a warning): all speakers of the meta-batch start from the same theta_0, the deltas are averaged with weights 1/N
+    and joined by ONE allreduce -- the only form that shards.
 With one speaker per meta-batch the two coincide.
 """
 from __future__ import annotations
@@ -20,7 +22,15 @@ from .metatrainer import MetaTrainer
 class Reptile(MetaTrainer):
     def __init__(self, **params):
         super().__init__(**params)
-        self.sequential = bool(params.get("reptile_sequential", False))
+        seq = params.get("reptile_sequential", None)
+        if seq is None:
+            seq = self.shard.world == 1
+            if not seq and self.shard.rank == 0:
+                import warnings
+                warnings.warn("Reptile on several GPUs runs the BATCHED variant (all speakers of a meta-batch start from the same "
+                              "weights, one averaged outer step); the reference's per-speaker sequential outer steps cannot be "
+                              "sharded.  Set reptile_sequential explicitly to silence this.")
+        self.sequential = bool(seq)
         if self.sequential and self.shard.world > 1:
             raise ValueError("sequential Reptile (the reference's literal semantics) cannot be sharded")
 

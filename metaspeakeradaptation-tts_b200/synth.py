@@ -42,7 +42,12 @@ def make_batch(cfg: dict, B: int, T: int, L: int, seed: int, spk_vec: Optional[t
     if spk_vec is None:
         spk_vec = torch.randn(cfg["speaker_embedding_dim"], generator=g)
     spk_embs = spk_vec[None, :].expand(B, -1).contiguous()                     # dataloader_meta.py:108
-    speaker_ids = torch.full((B,), seed % max(cfg["num_speakers"], 1), dtype=torch.int64)
+    ns = max(cfg.get("num_speakers", 1), 1)
+    if cfg["speaker_emb_type"] == "learnable_lookup":
+        # rows of different speakers (with a repeat), so that the embedding gather / scatter-add is exercised
+        speaker_ids = (seed + torch.arange(B, dtype=torch.int64) // 2 * 3) % ns
+    else:
+        speaker_ids = torch.full((B,), seed % ns, dtype=torch.int64)
     item_ids = [f"synth_{seed}_{i}" for i in range(B)]
     return (item_ids, transcripts, trans_lengths, mels, mel_lengths, speaker_ids, spk_embs, stop)
 

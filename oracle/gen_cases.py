@@ -23,11 +23,25 @@ def _spklin():
     return c
 
 
+def _lookup():
+    c = pkg.small_params()
+    c["speaker_emb_type"] = "learnable_lookup"
+    c["num_speakers"] = 5
+    return c
+
+
+def speaker_input(cfg, batch):
+    """What the trainers pass as ``speaker_vecs`` (metatrainer.py:95-117): ids for "learnable_lookup", vectors otherwise."""
+    return batch[5] if cfg["speaker_emb_type"] == "learnable_lookup" else batch[6]
+
+
 CASES = {
     "small_train": lambda: (_small(), 11, (3, 12, 9), CRIT),
     "small_train_meanloss": lambda: (_small(), 12, (2, 10, 12), dict(reduction="mean", pos_weight=10.0)),
     "small_train_fwdattn_sigmoid": lambda: (_small(norm="sigmoid", forward_attn=True, trans_agent=True), 13, (3, 12, 9), CRIT),
     "small_train_spklin": lambda: (_spklin(), 14, (3, 11, 10), CRIT),
+    # speaker_emb_type="learnable_lookup" (tacotron2nv.py:31-34,104-105): nn.Embedding over speaker ids, rows of several speakers
+    "small_train_lookup": lambda: (_lookup(), 16, (4, 11, 10), CRIT),
     "small_train_sigmoid": lambda: (_small(norm="sigmoid"), 15, (4, 13, 10), CRIT),
     # BASELINE.json configs[0]: default dims, batch 4, 200 mel frames, 80 mels
     "default_train_b4_t200": lambda: (pkg.default_params(), 0, (4, 200, 64), CRIT),

@@ -25,7 +25,7 @@ sys.path.insert(0, "/root/reference")
 import msa_tts_b200 as pkg                                    # noqa: E402
 from msa_tts_b200 import synth                                # noqa: E402
 from oracle import model as OM                                # noqa: E402
-from oracle.gen_cases import CASES, INFER_CASES, infer_stats  # noqa: E402
+from oracle.gen_cases import CASES, INFER_CASES, infer_stats, speaker_input  # noqa: E402
 
 from msa_tts.models.tacotron2nv import Tacotron2NV            # noqa: E402  (reference)
 from msa_tts.models.modules_tacotron2nv.tacotron2nv_loss import Tacotron2Loss  # noqa: E402
@@ -75,7 +75,8 @@ def build_ref(cfg, P, stats=None):
 
 
 def run_ref_train(cfg, P, batch, masks, crit):
-    _, inp, inp_len, mels, mel_len, _, spk, stop = batch
+    _, inp, inp_len, mels, mel_len, _, _, stop = batch
+    spk = speaker_input(cfg, batch)
     m = build_ref(cfg, P)
     m.train()
     orig = torch.nn.functional.dropout
@@ -94,11 +95,13 @@ def run_ref_train(cfg, P, batch, masks, crit):
 
 
 def run_oracle_train(cfg, P, batch, masks, crit, dtype=torch.float32):
-    _, inp, inp_len, mels, mel_len, _, spk, stop = batch
+    _, inp, inp_len, mels, mel_len, _, _, stop = batch
+    spk = speaker_input(cfg, batch)
+    spk = spk.to(dtype) if spk.dtype.is_floating_point else spk
     Pl = {k: v.to(dtype).clone().requires_grad_(True) for k, v in P.items()}
     stats = OM.fresh_bn_stats(Pl, cfg)
     masks_d = {k: ([x.to(dtype) for x in v] if isinstance(v, list) else v.to(dtype)) for k, v in masks.items()}
-    out = OM.forward(Pl, cfg, inp, inp_len, mels.to(dtype), mel_len, spk.to(dtype), masks_d, stats, True)
+    out = OM.forward(Pl, cfg, inp, inp_len, mels.to(dtype), mel_len, spk, masks_d, stats, True)
     loss = OM.loss_fn(out, (mels.to(dtype), stop.to(dtype)), mel_len, **crit)
     names = list(P.keys())
     g = torch.autograd.grad(loss, [Pl[n] for n in names], allow_unused=True)

@@ -98,6 +98,7 @@ del eng5
 bench.N_TASKS = 16
 params = bench.trainer_params(1)
 params["n_inner_train"] = 5
+params["reptile_sequential"] = False
 tr = Reptile(**params)
 items = bench.make_tasks(cfg, pinned=False)
 items = {s: {k: tuple(x.to(dev) if hasattr(x, "to") else x for x in v) for k, v in t.items()} for s, t in items.items()}

@@ -19,7 +19,9 @@ def rel(a, b):
 
 def oracle_pass(cfg, P, batch, masks, crit, dtype=torch.float32):
     """Oracle forward + loss + autograd grads; returns (outputs, loss, grads dict, bn stats, intermediates)."""
-    _, inp, inp_len, mels, mel_len, _, spk, stop = batch
+    _, inp, inp_len, mels, mel_len, spk_ids, spk, stop = batch
+    if cfg["speaker_emb_type"] == "learnable_lookup":
+        spk = spk_ids
     Pl = {k: v.to(dtype).clone().requires_grad_(True) for k, v in P.items()}
     stats = OM.fresh_bn_stats(Pl, cfg)
     md = {k: ([x.to(dtype) for x in v] if isinstance(v, list) else v.to(dtype)) for k, v in masks.items()}

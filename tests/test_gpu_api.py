@@ -88,7 +88,7 @@ def test_innerloop_fomaml_task_like_maml_py():
     assert _gerr(task_grads, o_g, names) < TOL
     # mix_grad / apply_grad (maml.py:94-99, utils/grad_utils.py:8-31)
     from msa_tts_b200.grad_utils import apply_grad, mix_grad
-    mixed = mix_grad([task_grads, task_grads], [0.25, 0.75], model)
+    mixed = mix_grad([task_grads, task_grads], [0.25, 0.75])      # the reference's own signature (maml.py:96)
     assert _gerr(mixed, o_g, names) < TOL
     norm = apply_grad(model, mixed)
     gn = float(torch.sqrt(sum((v.double() ** 2).sum() for v in o_g.values())))

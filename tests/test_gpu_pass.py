@@ -15,7 +15,8 @@ from helpers import cuda_pass, intermediates_report, oracle_pass, rel
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-CUDA_TRAIN_CASES = ["small_train", "small_train_meanloss", "small_train_spklin", "small_train_sigmoid", "small_train_fwdattn_sigmoid"]
+CUDA_TRAIN_CASES = ["small_train", "small_train_meanloss", "small_train_spklin", "small_train_lookup", "small_train_sigmoid",
+                    "small_train_fwdattn_sigmoid"]
 
 
 def _engine(cfg, crit, tf32=0):
@@ -122,7 +123,9 @@ def test_default_dims_config1_fp32_and_tf32():
     names = list(P.keys())
     # GEMM policy 0: fp32 everywhere; 1: fp32 forward + TF32 backward (bench default); 2: TF32 everywhere (reported, out of
     # the 1e-3 output tolerance because the postnet amplifies decoder-output error ~5x)
-    for tf32, tol_o, tol_g in ((0, 3e-4, 3e-4), (1, 3e-4, 2e-3), (2, 5e-3, 2e-3)):
+    # tol_g bounds BOTH the per-tensor norm error and the sampled-element error (direction / layout), each relative to the global
+    # gradient norm scale; policy 1 is the bench policy and is held to north_star's 1e-3, policy 2 is reported only
+    for tf32, tol_o, tol_g, tol_s in ((0, 3e-4, 3e-4, 3e-4), (1, 3e-4, 1e-3, 1e-3), (2, 5e-3, 2e-3, 3e-2)):
         eng = _engine(cfg, crit, tf32)
         c_out, c_loss, c_grads, c_bn = cuda_pass(eng, cfg, P, batch, masks)
         lines = []
@@ -130,7 +133,7 @@ def test_default_dims_config1_fp32_and_tf32():
             lines.append(f"tf32={tf32} out/{key} {rel(a, z[key]):.3e}")
         lines.append(f"tf32={tf32} out/align {rel(c_out[3][:, ::8], z['align_sample']):.3e}")
         lines.append(f"tf32={tf32} loss {abs(float(c_loss) - float(z['loss'])) / abs(float(z['loss'])):.3e}")
-        worst = 0.0
+        worst, worst_s = 0.0, 0.0
         for i, n in enumerate(names):
             g = c_grads[n]
             flat = g.flatten()
@@ -138,15 +141,19 @@ def test_default_dims_config1_fp32_and_tf32():
             e_norm = abs(float(g.double().norm()) - z["grad_norms"][i]) / gn
             e_samp = float((samp.double() - torch.as_tensor(z["gsample/" + n]).double()).norm()) / (float(np.linalg.norm(z["gsample/" + n])) + 1e-3 * gn)
             worst = max(worst, e_norm)
+            worst_s = max(worst_s, e_samp)
             lines.append(f"tf32={tf32} grad/{n:70s} norm-err {e_norm:.3e} sample-rel {e_samp:.3e}")
         txt = "\n".join(lines)
         print(txt)
-        with open(os.path.join(os.path.dirname(GOLD), "..", "gpurun_out", f"parity_default_tf32_{int(tf32)}.txt"), "w") as f:
+        odir = os.path.join(os.path.dirname(GOLD), "..", "gpurun_out")
+        os.makedirs(odir, exist_ok=True)
+        with open(os.path.join(odir, f"parity_default_tf32_{int(tf32)}.txt"), "w") as f:
             f.write(txt + "\n")
         for key, a in zip(("mel", "mel_post", "gate"), c_out):
             assert rel(a, z[key]) < tol_o, (tf32, key)
         assert abs(float(c_loss) - float(z["loss"])) < tol_o * abs(float(z["loss"]))
         assert worst < tol_g, (tf32, worst)
+        assert worst_s < tol_s, (tf32, worst_s)
         del eng
         torch.cuda.empty_cache()
 

@@ -163,7 +163,7 @@ def test_reptile_batched_meta_step_matches_oracle():
     from oracle import meta as OMeta
     n_tasks, n_inner, lr_in, lr_out = 3, 3, 0.05, 0.5
     cfg, tasks, masks, P0, names = _setup(n_tasks, n_inner)
-    tr = Reptile(**_params(cfg, _sgd(lr_in), _sgd(lr_out), n_inner, 0.05))
+    tr = Reptile(**_params(cfg, _sgd(lr_in), _sgd(lr_out), n_inner, 0.05, reptile_sequential=False))
     tr.injected_masks = masks
     log = tr._metatrain_step(tasks)
     torch.cuda.synchronize()
@@ -189,7 +189,9 @@ def test_reptile_sequential_is_the_reference_literal_loop():
     from oracle import meta as OMeta
     n_tasks, n_inner, lr_in, lr_out = 2, 2, 0.05, 0.5
     cfg, tasks, masks, P0, names = _setup(n_tasks, n_inner)
-    tr = Reptile(**_params(cfg, _sgd(lr_in), _sgd(lr_out), n_inner, None, reptile_sequential=True))
+    # no flag: on one GPU the reference's per-speaker outer steps are the default (the batched variant is opt-in)
+    tr = Reptile(**_params(cfg, _sgd(lr_in), _sgd(lr_out), n_inner, None))
+    assert tr.sequential
     tr.injected_masks = masks
     tr._metatrain_step(tasks)
     torch.cuda.synchronize()

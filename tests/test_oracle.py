@@ -15,7 +15,7 @@ import torch
 import msa_tts_b200 as pkg
 from msa_tts_b200 import synth
 from oracle import model as OM
-from oracle.gen_cases import CASES, INFER_CASES, infer_stats
+from oracle.gen_cases import CASES, INFER_CASES, infer_stats, speaker_input
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 TOL = 2e-5
@@ -33,7 +33,8 @@ def test_train_small(name):
     P = synth.init_params(cfg, seed)
     batch = synth.make_batch(cfg, B, T, L, seed + 100)
     masks = synth.make_masks(cfg, B, T, L, seed + 200)
-    _, inp, inp_len, mels, mel_len, _, spk, stop = batch
+    _, inp, inp_len, mels, mel_len, _, _, stop = batch
+    spk = speaker_input(cfg, batch)
     Pl = {k: v.clone().requires_grad_(True) for k, v in P.items()}
     stats = OM.fresh_bn_stats(Pl, cfg)
     out = OM.forward(Pl, cfg, inp, inp_len, mels, mel_len, spk, masks, stats, True)
