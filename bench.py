@@ -161,52 +161,81 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_reference_task(n_threads=None):
-    """One FOMAML task (1 inner SGD step on the train split + fwd/bwd on the test split) with the oracle port of the
-    reference on the host CPU: a 1/8 sample of the meta-step.  Returns (seconds, threads)."""
-    import torch
+OUTER_LR, CLIP = 1e-4, 1.0
+
+
+def cpu_meta_step_fns(n_threads=None):
+    """The FOMAML meta-step of the workload on the host CPU: the UNMODIFIED reference model / loss / mix_grad / apply_grad when
+    baseline/_ref (oracle/install_reference.py) or /root/reference is importable ("reference"), else the oracle port ("port");
+    the inner loop is the restatement of `higher` either way (oracle/ref_meta.py).  -> (task_fn, outer_fn, kind, threads)"""
     import msa_tts_b200 as pkg
     from msa_tts_b200 import synth
-    from oracle import meta as OMeta
-    from oracle import model as OM
-    if n_threads:
-        torch.set_num_threads(n_threads)
+    from oracle import ref_meta
+    threads = n_threads or ref_meta.host_threads()
     cfg = pkg.default_params()
-    crit = dict(reduction="none", pos_weight=10.0)
-    P = synth.init_params(cfg, 0)
-    task = synth.make_task(cfg, B, T, L, 1234)
-    masks = [synth.make_masks(cfg, B, T, L, 77 + i) for i in range(N_INNER + 1)]
-    names = OM.param_names(cfg)
-
-    def step():
-        t0 = time.perf_counter()
-        OMeta.fomaml_task(P, cfg, task, masks, crit, names, N_INNER, INNER_LR)
-        return time.perf_counter() - t0
-    return step, torch.get_num_threads()
+    tasks = [synth.make_task(cfg, B, T, L, 1234 + i) for i in range(N_TASKS)]
+    task_fn, outer_fn, kind = ref_meta.make_meta_step(cfg, tasks, INNER_LR, N_INNER, OUTER_LR, CLIP, threads)
+    return task_fn, outer_fn, kind, threads
 
 
 def run_reference(args):
-    """--impl reference: the reference's algorithm for this path on the host cores (the reference is pure Python and
-    `higher` is absent, so this is the oracle restatement pinned to it; kind = "port").  One step = one task of the
-    8-task meta-step (a 1/8 sample), so that K steps finish in minutes."""
+    """--impl reference: WHOLE meta-steps (8 tasks x (inner SGD step + test forward/backward) + mix_grad / apply_grad / clip /
+    Adam) of the reference on the host cores, rank 0 only, thread count set explicitly (torchrun exports OMP_NUM_THREADS=1).
+    A meta-step takes ~15-20 s on the box's CPU, so the number of timed steps is bounded by a wall budget (MSA_REF_BUDGET_S,
+    default 170 s) and the line prints the steps and warm-up steps that were REALLY run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    step, threads = cpu_reference_task()
-    for _ in range(args.warmup):
-        step()
-    ts = [step() for _ in range(args.steps)]
-    t_task = sum(ts) / len(ts)
-    value = 1.0 / (N_TASKS * t_task)
+    budget = float(os.environ.get("MSA_REF_BUDGET_S", "170"))
+    t_start = time.perf_counter()
+    task_fn, outer_fn, kind, threads = cpu_meta_step_fns()
+
+    def meta_step():
+        t0 = time.perf_counter()
+        for i in range(N_TASKS):
+            task_fn(i)
+        outer_fn()
+        return time.perf_counter() - t0
+    warm = 1 if args.warmup >= 1 else 0
+    t_warm = meta_step() if warm else 0.0
+    ts = [meta_step()]
+    while len(ts) < args.steps and (time.perf_counter() - t_start) + 1.1 * max(ts) < budget:
+        ts.append(meta_step())
+    t_step = sum(ts) / len(ts)
+    value = 1.0 / t_step
     line = {"impl": "reference", "metric": "meta_steps_per_s", "value": value, "unit": "meta-steps/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * N_TASKS * t_task, "higher_is_better": True,
+            "steps": len(ts), "warmup": warm, "steps_requested": args.steps, "warmup_requested": args.warmup,
+            "ms_per_step": 1000.0 * t_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "tasks": N_TASKS, "inner_steps": N_INNER, "B": B, "T": T, "L": L},
-            "cpu_baseline": {"value": value, "unit": "meta-steps/s", "cores": threads, "kind": "port",
-                             "sample": "1 of the 8 tasks per step (1 inner SGD step + test fwd/bwd), extrapolated x8"},
+            "cpu_baseline": {"value": value, "unit": "meta-steps/s", "cores": threads, "kind": kind,
+                             "sample": f"whole meta-steps (8 tasks x (1 inner SGD step + test fwd/bwd) + mix_grad / apply_grad / clip / "
+                                       f"Adam): {len(ts)} timed of {args.steps} requested after {warm} warm-up (wall budget {budget:.0f} s; "
+                                       f"warm-up step took {t_warm:.1f} s)"},
             "e2e": {"value": value, "unit": "meta-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "mel_frames_per_s": value * N_TASKS * 2 * B * T}
     print(json.dumps(line))
+
+
+def cpu_baseline_sample():
+    """Bounded sample (~10-30 s of CPU work) of the same meta-step for the `cpu_baseline` object of this repo's own line:
+    1 warm-up task, 4 timed tasks and the outer update on their gradients; meta-step time = 8 x mean task + outer update.  Also the
+    same sample under the reference's own 4-thread cap (utils/limit_threads.py:3-7)."""
+    import torch
+    task_fn, outer_fn, kind, threads = cpu_meta_step_fns()
+    task_fn(0)
+    ts = [task_fn(i) for i in range(1, 5)]
+    t_outer = outer_fn()
+    t_task = sum(ts) / len(ts)
+    out = {"value": 1.0 / (N_TASKS * t_task + t_outer), "unit": "meta-steps/s", "cores": threads, "kind": kind,
+           "sample": "4 of the 8 tasks (1 inner SGD step + test fwd/bwd each) timed after 1 warm-up task, plus mix_grad / apply_grad / "
+                     "clip / Adam on their gradients; meta-step = 8 x mean task + outer update"}
+    torch.set_num_threads(4)
+    t4 = [task_fn(i) for i in range(5, 7)]
+    t4_outer = outer_fn()
+    torch.set_num_threads(threads)
+    out["value_at_reference_thread_cap"] = {"value": 1.0 / (N_TASKS * (sum(t4) / len(t4)) + t4_outer), "cores": 4}
+    return out
 
 
 def bench_infer(torch, tr, world, sync, B=32, L_=64, steps=1000):
@@ -440,19 +469,7 @@ def main():
             "infer": infer_line,
         }
         if world == 1 and not args.no_cpu_baseline:
-            step, threads = cpu_reference_task()
-            step()
-            ts = [step() for _ in range(2)]
-            t_task = min(ts)
-            line["cpu_baseline"] = {"value": 1.0 / (N_TASKS * t_task), "unit": "meta-steps/s", "cores": threads, "kind": "port",
-                                    "sample": "1 of the 8 tasks (1 inner SGD step + test fwd/bwd) on the host CPU, best of 2 after "
-                                              "1 warm-up, extrapolated x8"}
-            # the reference caps itself at 4 threads (utils/limit_threads.py:3-7): the same sample under that cap
-            import torch as _t
-            _t.set_num_threads(4)
-            t4 = min(step() for _ in range(2))
-            _t.set_num_threads(threads)
-            line["cpu_baseline"]["value_at_reference_thread_cap"] = {"value": 1.0 / (N_TASKS * t4), "cores": 4}
+            line["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
