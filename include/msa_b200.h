@@ -147,6 +147,24 @@ int msa_train_backward(msa_handle* h, void* ws, size_t ws_bytes, const float* pa
  * (metatrainer.py:83-86); also refreshes d(loss)/d(outputs) used by msa_train_backward(NULL,...). */
 int msa_train_loss(msa_handle* h, void* ws, const float* stop_targets, const int64_t* mel_lengths, int reduction,
                    float pos_weight, float* loss_out, void* stream);
+/* ---- task groups: the train-split passes that all tasks of a meta-batch take from the SAME weights theta_0
+ * (maml.py:38-54, reptile.py:38-56: every `higher.innerloop_ctx` starts from `self.model`) as ONE pass over G tasks.
+ * Everything that is not a recurrence runs task by task; the three persistent recurrences (encoder BiLSTM, attention chain,
+ * decoder-RNN chain) run once for all G*B rows, so their per-step cross-CTA hand-offs are shared by the group.  Results per task
+ * are those of G separate msa_train_forward / msa_train_backward calls (BatchNorm statistics, loss normalisation and parameter
+ * gradients are per task).  All tasks must have the same B, T, L; G <= 8 and G*B <= 32 for the shared launches (otherwise, or
+ * for configurations the grouped kernels do not implement, the recurrences silently run task by task -- same results).
+ * ws: msa_group_workspace_bytes(h, G, B, T, L) bytes, 256-byte aligned; task g's slice (for msa_train_mcd / msa_get_buffer /
+ * msa_train_loss) starts at ws + g * msa_group_workspace_bytes(h, 1, B, T, L).  Per-task arguments are HOST arrays of G device
+ * pointers; loss_out: G floats on the device; grads[g]: flat gradient buffer of task g. */
+size_t msa_group_workspace_bytes(const msa_handle* h, int G, int B, int T, int L);
+int msa_train_forward_group(msa_handle* h, int G, void* ws, size_t ws_bytes, const float* params, float* const* bn_stats,
+                            const int64_t* const* tokens, const int64_t* const* token_lengths, const float* const* mels,
+                            const int64_t* const* mel_lengths, const float* const* speaker_vecs,
+                            const int64_t* const* speaker_ids, const float* const* stop_targets,
+                            const uint8_t* const* masks, int B, int T, int L, float* loss_out, void* stream);
+int msa_train_backward_group(msa_handle* h, void* ws, size_t ws_bytes, const float* params, float* const* grads,
+                             int accumulate, float grad_scale, void* stream);
 /* replaces utils/metrics.py:15-22 mcd_batch as called by the trainers' per-task logs (maml.py:78-82,
  * baseline.py, continual_*.py): K * mean_b mean_{t < len_b} ||mel_target - out||_2 with
  * K = 10 / ln(10) * sqrt(2), on the device, from the outputs of the last msa_train_forward in `ws`

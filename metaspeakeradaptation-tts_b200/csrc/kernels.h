@@ -3,7 +3,14 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+struct msa_config;
+
 namespace msa {
+
+// Task groups: the theta_0 train-split passes of up to kGroupMax speaker tasks share one launch of each recurrence.  Every float
+// array of task g lives at (pointer of task 0) + g * tstride floats (the tasks' workspaces are identical slices of one allocation);
+// masks and lengths are caller-owned and come as per-task pointers.  Row r of a grouped launch = (task r / B, batch row r % B).
+constexpr int kGroupMax = 8;
 
 // ---------------- persistent LSTM recurrence (lstm_rec.cu) ----------------
 struct LstmRecParams {
@@ -22,6 +29,11 @@ struct LstmRecParams {
     long long* trace;          // optional per-warp time stamps (rec_common.cuh)
     int trace_t0;
     int flags;                 // hand-off variant (kFlagGate | kFlagWarp0, rec_common.cuh)
+    // task group (chain_mma.cu only; the single-task kernels ignore these): G tasks of B rows each
+    int G;                     // 0 / 1 = a single task
+    int64_t tstride;           // floats between the copies of every float array of consecutive tasks
+    const uint8_t* mask_g[kGroupMax];
+    const int64_t* lengths_g[kGroupMax];
 };
 struct LstmRecBwdParams {
     int T, B, H, ndir;
@@ -39,6 +51,11 @@ struct LstmRecBwdParams {
     long long* trace;
     int trace_t0;
     int flags;
+    // task group (chain_mma.cu only; the single-task kernels ignore these): G tasks of B rows each
+    int G;                     // 0 / 1 = a single task
+    int64_t tstride;           // floats between the copies of every float array of consecutive tasks
+    const uint8_t* mask_g[kGroupMax];
+    const int64_t* lengths_g[kGroupMax];
 };
 size_t lstm_rec_fwd_smem(int B, int H);
 size_t lstm_rec_bwd_smem(int B, int H);
@@ -82,6 +99,11 @@ struct AttnChainParams {
     long long* trace;
     int trace_t0;
     int flags;
+    // task group (chain_mma.cu only; the single-task kernels ignore these): G tasks of B rows each
+    int G;                     // 0 / 1 = a single task
+    int64_t tstride;           // floats between the copies of every float array of consecutive tasks
+    const uint8_t* mask_g[kGroupMax];
+    const int64_t* lengths_g[kGroupMax];
 };
 struct AttnChainBwdParams {
     int T, B, L, Ha, A, F, Kl, norm;
@@ -115,11 +137,25 @@ struct AttnChainBwdParams {
     long long* trace;
     int trace_t0;
     int flags;
+    // task group (chain_mma.cu only; the single-task kernels ignore these): G tasks of B rows each
+    int G;                     // 0 / 1 = a single task
+    int64_t tstride;           // floats between the copies of every float array of consecutive tasks
+    const uint8_t* mask_g[kGroupMax];
+    const int64_t* lengths_g[kGroupMax];
 };
 size_t attn_chain_fwd_smem(int B, int L, int Ha, int A, int F, int Kl, int sm_count, bool mw_resident, bool fa = false);
 size_t attn_chain_bwd_smem(int B, int L, int Ha, int A, int F, int Kl, int sm_count, bool mwp_resident, bool fa = false);
 int launch_attn_chain_fwd(const AttnChainParams& p, int sm_count, size_t smem_limit, cudaStream_t st);
 int launch_attn_chain_bwd(const AttnChainBwdParams& p, int sm_count, size_t smem_limit, cudaStream_t st);
+
+// ---------------- grouped recurrences with tensor-core gate products (chain_mma.cu) ----------------
+// Same arithmetic as the kernels above for G tasks at once (R = G*B <= 32 rows per hand-off); the per-step gate products run on the
+// tensor cores as bf16x3 split products (hi.hi + hi.lo + lo.hi, fp32 accumulation: ~1e-5 relative, inside the TF32-path tolerance).
+bool chain_mma_supported(const msa_config& cfg, int G, int B, int T, int L, int sm_count, size_t smem_limit);
+int launch_lstm_rec_fwd_mma(const LstmRecParams& p, int sm_count, size_t smem_limit, cudaStream_t st);
+int launch_lstm_rec_bwd_mma(const LstmRecBwdParams& p, int sm_count, size_t smem_limit, cudaStream_t st);
+int launch_attn_chain_fwd_mma(const AttnChainParams& p, int sm_count, size_t smem_limit, cudaStream_t st);
+int launch_attn_chain_bwd_mma(const AttnChainBwdParams& p, int sm_count, size_t smem_limit, cudaStream_t st);
 
 // ---------------- element-wise / layout / reduction kernels (model_kernels.cu) ----------------
 int k_embedding_fwd(const float* w, const int64_t* tok, float* x, int rows, int C, int n_symbols, cudaStream_t st);

@@ -89,9 +89,15 @@ struct msa_handle {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
     std::vector<int> prof_id;
     size_t prof_used = 0;
-    const int64_t *tokens = nullptr, *tok_len = nullptr, *mel_len = nullptr, *spk_ids = nullptr;
-    const float* spk_in = nullptr;
-    const uint8_t* masks = nullptr;
+    // per-task inputs of the last forward (a grouped forward has G of them; a plain one G = 1)
+    int G = 1;
+    size_t ws_stride = 0;          // bytes between the workspaces of consecutive tasks of a group
+    const int64_t *tokens[kGroupMax] = {}, *tok_len[kGroupMax] = {}, *mel_len[kGroupMax] = {}, *spk_ids[kGroupMax] = {};
+    const float* spk_in[kGroupMax] = {};
+    const uint8_t* masks[kGroupMax] = {};
+    // Grouped chain kernels (chain_mma.cu): bf16x3 tensor-core gate products, G*B rows per hand-off.  mma_mode 0: never,
+    // 1 (default): for grouped launches under the tensor-core GEMM policies, 2: also for single passes.  Env MSA_CHAIN_MMA.
+    int mma_mode = 1;
     int64_t off(const std::string& n) const { return off_by_name.at(n); }
 };
 
@@ -433,6 +439,7 @@ int msa_create(const msa_config* cfg, int device, msa_handle** out) {
     h->sm_count = prop.multiProcessorCount;
     h->smem_limit = prop.sharedMemPerBlockOptin;
     if (const char* e = getenv("MSA_REC_FLAGS")) h->rec_flags = atoi(e);
+    if (const char* e = getenv("MSA_CHAIN_MMA")) h->mma_mode = atoi(e);
     if (const char* e = getenv("MSA_GEMM_TC")) {
         h->tc_mode = atoi(e);
         h->tc_enabled = h->tc_mode != 0;
@@ -537,6 +544,251 @@ size_t msa_workspace_bytes(const msa_handle* h, int B, int T, int L) {
     return ws_layout(make_dims(h->cfg, B, T, L), nullptr).total_bytes;
 }
 
+}  // extern "C"
+
+namespace msa {
+
+// per-task inputs / outputs of a (grouped) forward
+struct TaskIO {
+    float* bn_stats;
+    const int64_t *tokens, *tok_len, *mel_len, *spk_ids;
+    const float *mels, *spk_vecs, *stop;
+    const uint8_t* masks;
+    float *mel_out, *mel_post_out, *gate_out, *align_out, *loss_out;
+};
+
+// Grouped chain launches (chain_mma.cu) are used when the configuration is inside what those kernels implement; otherwise the
+// tasks of a group run the single-task persistent kernels one after the other (same results, no sharing of the hand-offs).
+static bool use_mma_chains(const msa_handle* h, int G, int B, int T, int L) {
+    if (h->mma_mode == 0 || h->cfg.gemm_tf32 < 1) return false;          // strict-fp32 policy: no tensor-core arithmetic at all
+    if (h->mma_mode == 1 && G == 1) return false;
+    return chain_mma_supported(h->cfg, G, B, T, L, h->sm_count, h->smem_limit);
+}
+
+// One teacher-forced forward pass for G tasks that share `params` (the theta_0 train-split passes of a meta-batch, maml.py:38-54):
+// everything that is not a recurrence runs task by task in that task's own workspace slice, the three recurrences run ONCE for
+// all G*B rows when the grouped kernels apply.
+static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride, const float* params, const TaskIO* ios, int B, int T,
+                              int L, cudaStream_t st) {
+    MSA_TRY(train_check(h));
+    const Dims d = make_dims(h->cfg, B, T, L);
+    std::vector<Ws> W;
+    for (int g = 0; g < G; ++g) W.push_back(ws_layout(d, wsp + (size_t)g * ws_stride));
+    MSA_CUDA(cudaSetDevice(h->device));
+    MSA_BLAS(cublasSetStream(h->blas, st));
+    MSA_BLAS(cublasSetWorkspace(h->blas, W[0].blas_ws, W[0].blas_ws_bytes));
+    h->fwd_valid = false;
+    h->in_bwd = false;
+    h->cur_stream = st;
+    const msa_config& c = h->cfg;
+    const auto secs = mask_sections(c, B, T, L);
+    const int iPre = d.nEnc, iAttn = d.nEnc + 2, iDec = d.nEnc + 3, iPost = d.nEnc + 4;
+    auto P = [&](const std::string& n) { return params + h->off(n); };
+    const bool mma = use_mma_chains(h, G, B, T, L);
+    const int64_t tstride = (int64_t)(ws_stride / sizeof(float));
+    const int H4e = 4 * d.Hh;
+    const std::string at = "decoder.attention_layer.";
+    const int H4a = 4 * d.Ha, H4d = 4 * d.Hd, ldA = d.Pd + d.E, ldD = d.Ha + d.E, ldP = d.Hd + d.E;
+    const bool fa = c.forward_attn != 0, ta = fa && c.trans_agent != 0;
+
+    // ---- stage 1: speaker vector, encoder convolutions, BiLSTM input projection ----
+    for (int g = 0; g < G; ++g) {
+        const Ws& w = W[g];
+        const TaskIO& io = ios[g];
+        auto mk = [&](int i) { return io.masks + secs[i].off; };
+        h->gemm_scratch = w.gemm_lo; h->gemm_scratch_floats = (size_t)w.n_gemm_lo;
+        MSA_CUDA(cudaMemsetAsync(w.red_scr, 0, sizeof(unsigned int) * kRedTickets, st));      // tickets of the chunked column reductions
+        // speaker vector (tacotron2nv.py:104-109)
+        if (c.spk_mode == 0) {
+            MSA_TRY(k_scale_copy(io.spk_vecs, w.spk_vec, (int64_t)B * d.Ds, 1.f, 0, st));
+        } else if (c.spk_mode == 1) {
+            MSA_TRY(k_fill_rows(w.spk_vec, P("speaker_lin.bias"), nullptr, B, d.Ds, st));
+            MSA_TRY(gemm(h, false, true, B, d.Ds, d.Dsin, 1.f, io.spk_vecs, d.Dsin, P("speaker_lin.weight"), d.Dsin, 1.f, w.spk_vec, d.Ds));
+        } else {
+            MSA_TRY(k_embedding_fwd(P("speaker_embedder.weight"), io.spk_ids, w.spk_vec, B, d.Ds, c.num_speakers, st));
+        }
+        // encoder (tacotron2nv.py:88, encoder.py:35-52)
+        MSA_TRY(k_embedding_fwd(P("embedding.weight"), io.tokens, w.enc_x, (int)d.BL, d.C, c.n_symbols, st));
+        const int64_t ex = d.BL * d.C;
+        for (int i = 0; i < d.nEnc; ++i) {
+            float* run = io.bn_stats ? io.bn_stats + h->bn_offs[i] : nullptr;
+            MSA_TRY(conv_bn_fwd(h, st, params, "encoder.convolutions." + std::to_string(i), w.enc_x + i * ex, w.enc_y + i * ex,
+                                w.enc_x + (i + 1) * ex, w.enc_col + i * d.BL * d.Kc * d.C,
+                                w.enc_bn + i * 2 * d.C, w.enc_bn + i * 2 * d.C + d.C, run, B, L, d.C, d.C, d.Kc, 1, mk(i), w.red_scr));
+        }
+        MSA_TRY(k_transpose01(w.enc_x + d.nEnc * ex, w.x3_tm, B, L, d.C, st));
+        for (int dir = 0; dir < 2; ++dir) {
+            const std::string sfx = dir ? "_reverse" : "";
+            float* zx = w.enc_zx + (int64_t)dir * d.BL * H4e;
+            MSA_TRY(k_fill_rows(zx, P("encoder.lstm.bias_ih_l0" + sfx), P("encoder.lstm.bias_hh_l0" + sfx), d.BL, H4e, st));
+            MSA_TRY(gemm(h, false, true, d.BL, H4e, d.C, 1.f, w.x3_tm, d.C, P("encoder.lstm.weight_ih_l0" + sfx), d.C, 1.f, zx, H4e));
+        }
+    }
+    // ---- encoder BiLSTM (persistent) ----
+    {
+        auto make = [&](int g) {
+            const Ws& w = W[g];
+            LstmRecParams lp{};
+            lp.T = L; lp.B = B; lp.H = d.Hh; lp.ndir = 2;
+            lp.zin = w.enc_zx; lp.whh = P("encoder.lstm.weight_hh_l0");
+            lp.whh_dir_stride = h->off("encoder.lstm.weight_hh_l0_reverse") - h->off("encoder.lstm.weight_hh_l0");
+            lp.hout = w.enc_h; lp.cout = w.enc_c; lp.gates = w.enc_g; lp.mask = nullptr; lp.drop_scale = 1.f;
+            lp.lengths = ios[g].tok_len; lp.abort_word = h->abort_dev; lp.prof = prof_ptr(h, w, PROF_ENC_LSTM_FWD);
+            lp.trace = trace_ptr(h, w, PROF_ENC_LSTM_FWD); lp.trace_t0 = h->trace_t0; lp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
+            return lp;
+        };
+        ProfScope ps(h, PROF_ENC_LSTM_FWD, st);
+        if (mma) {
+            LstmRecParams lp = make(0);
+            lp.G = G; lp.tstride = tstride;
+            for (int g = 0; g < G; ++g) lp.lengths_g[g] = ios[g].tok_len;
+            MSA_TRY(launch_lstm_rec_fwd_mma(lp, h->sm_count, h->smem_limit, st));
+        } else {
+            for (int g = 0; g < G; ++g) MSA_TRY(launch_lstm_rec_fwd(make(g), h->sm_count, h->smem_limit, st));
+        }
+    }
+    // ---- stage 2: memory, decoder set-up (decoder.py:290-302, forward_attn.py:103-116) ----
+    for (int g = 0; g < G; ++g) {
+        const Ws& w = W[g];
+        const TaskIO& io = ios[g];
+        auto mk = [&](int i) { return io.masks + secs[i].off; };
+        h->gemm_scratch = w.gemm_lo; h->gemm_scratch_floats = (size_t)w.n_gemm_lo;
+        MSA_TRY(k_build_memory(w.enc_h, w.spk_vec, w.memory, B, L, d.Hh, d.Ds, st));
+        MSA_TRY(gemm(h, false, true, d.BL, d.A, d.E, 1.f, w.memory, d.E, P(at + "inputs_layer.linear_layer.weight"), d.E, 0.f, w.pm, d.A));
+        const float* Wia = P("decoder.attention_rnn.weight_ih");
+        MSA_TRY(gemm(h, false, true, H4a, d.BL, d.E, 1.f, Wia + d.Pd, ldA, w.memory, d.E, 0.f, w.mw_rm, d.BL));
+        MSA_TRY(k_prep_mels(io.mels, w.frames, w.target, B, d.M, T, st));
+        const int64_t nfr = d.TB + B;
+        MSA_TRY(gemm(h, false, true, nfr, d.Pd, d.M, 1.f, w.frames, d.M, P("decoder.prenet.layers.0.linear_layer.weight"), d.M, 0.f, w.p1, d.Pd));
+        MSA_TRY(k_relu_drop_fwd(w.p1, mk(iPre), 2.f, nfr * d.Pd, st));
+        MSA_TRY(gemm(h, false, true, nfr, d.Pd, d.Pd, 1.f, w.p1, d.Pd, P("decoder.prenet.layers.1.linear_layer.weight"), d.Pd, 0.f, w.xpre, d.Pd));
+        MSA_TRY(k_relu_drop_fwd(w.xpre, mk(iPre + 1), 2.f, nfr * d.Pd, st));
+        MSA_TRY(gemm(h, false, true, d.TB, H4a, d.Pd, 1.f, w.xpre, d.Pd, Wia, ldA, 0.f, w.xw, H4a, P("decoder.attention_rnn.bias_ih"),
+                     P("decoder.attention_rnn.bias_hh")));
+        if (ta)     // context half of the transition agent: ctx(t) = alpha(t) . memory  =>  W_ta[:E] . ctx(t) = alpha(t) . (memory . W_ta[:E])
+            MSA_TRY(gemm(h, false, true, d.BL, 1, d.E, 1.f, w.memory, d.E, P(at + "ta.weight"), d.E + d.Ha, 0.f, w.mta, 1));
+    }
+    // ---- attention chain (persistent) ----
+    {
+        auto make = [&](int g) {
+            const Ws& w = W[g];
+            AttnChainParams ap{};
+            ap.T = T; ap.B = B; ap.L = L; ap.Ha = d.Ha; ap.A = d.A; ap.F = d.F; ap.Kl = d.Kl; ap.norm = c.attn_norm;
+            ap.xw = w.xw; ap.whh = P("decoder.attention_rnn.weight_hh"); ap.mw_rm = w.mw_rm;
+            ap.wq = P(at + "query_layer.linear_layer.weight"); ap.pm = w.pm;
+            ap.wloc = P(at + "location_layer.location_conv1d.weight");
+            ap.wld = P(at + "location_layer.location_dense.linear_layer.weight");
+            ap.v = P(at + "v.linear_layer.weight"); ap.bv = P(at + "v.linear_layer.bias");
+            ap.mask = c.p_attn_dropout > 0.f ? ios[g].masks + secs[iAttn].off : nullptr;
+            ap.drop_scale = 1.f / (1.f - c.p_attn_dropout);
+            ap.ha = w.ha; ap.ca = w.ca; ap.ga = w.ga; ap.q = w.q; ap.align = w.align_tm; ap.cum = w.cum; ap.s = w.s;
+            ap.fa = fa; ap.ta = ta; ap.aplain = w.aplain; ap.fsum = w.fsum; ap.ustash = w.ustash;
+            if (ta) { ap.mta = w.mta; ap.wta_h = P(at + "ta.weight") + d.E; ap.bta = P(at + "ta.bias"); }
+            ap.convf = w.convf; ap.znorm = w.znorm; ap.e = w.ebuf; ap.abort_word = h->abort_dev; ap.prof = prof_ptr(h, w, PROF_ATTN_FWD);
+            ap.trace = trace_ptr(h, w, PROF_ATTN_FWD); ap.trace_t0 = h->trace_t0; ap.flags = h->rec_flags >= 0 ? h->rec_flags : 0;
+            return ap;
+        };
+        ProfScope ps(h, PROF_ATTN_FWD, st);
+        if (mma) {
+            AttnChainParams ap = make(0);
+            ap.G = G; ap.tstride = tstride;
+            for (int g = 0; g < G; ++g) ap.mask_g[g] = c.p_attn_dropout > 0.f ? ios[g].masks + secs[iAttn].off : nullptr;
+            MSA_TRY(launch_attn_chain_fwd_mma(ap, h->sm_count, h->smem_limit, st));
+        } else {
+            for (int g = 0; g < G; ++g) MSA_TRY(launch_attn_chain_fwd(make(g), h->sm_count, h->smem_limit, st));
+        }
+    }
+    // ---- stage 3: context vectors, decoder-RNN input projection ----
+    for (int g = 0; g < G; ++g) {
+        const Ws& w = W[g];
+        h->gemm_scratch = w.gemm_lo; h->gemm_scratch_floats = (size_t)w.n_gemm_lo;
+        // ctx[t][b] = a[t][b] . memory[b]  (forward_attn.py:217), batched over b
+        MSA_TRY(gemm_batched(h, false, false, T, d.E, L, 1.f, w.align_tm, d.BL, L, w.memory, d.E, (int64_t)L * d.E, 0.f, w.ctx,
+                             (int64_t)B * d.E, d.E, B));
+        const float* Wid = P("decoder.decoder_rnn.weight_ih");
+        MSA_TRY(gemm(h, false, true, d.TB, H4d, d.Ha, 1.f, w.ha, d.Ha, Wid, ldD, 0.f, w.zd, H4d, P("decoder.decoder_rnn.bias_ih"),
+                     P("decoder.decoder_rnn.bias_hh")));
+        MSA_TRY(gemm(h, false, true, d.TB, H4d, d.E, 1.f, w.ctx, d.E, Wid + d.Ha, ldD, 1.f, w.zd, H4d));
+    }
+    // ---- decoder RNN chain (decoder.py:260-265, persistent) ----
+    {
+        auto make = [&](int g) {
+            const Ws& w = W[g];
+            LstmRecParams lp{};
+            lp.T = T; lp.B = B; lp.H = d.Hd; lp.ndir = 1;
+            lp.zin = w.zd; lp.whh = P("decoder.decoder_rnn.weight_hh"); lp.whh_dir_stride = 0;
+            lp.hout = w.hd; lp.cout = w.cd; lp.gates = w.gd;
+            lp.mask = c.p_dec_dropout > 0.f ? ios[g].masks + secs[iDec].off : nullptr;
+            lp.drop_scale = 1.f / (1.f - c.p_dec_dropout);
+            lp.lengths = nullptr; lp.abort_word = h->abort_dev; lp.prof = prof_ptr(h, w, PROF_DEC_LSTM_FWD);
+            lp.trace = trace_ptr(h, w, PROF_DEC_LSTM_FWD); lp.trace_t0 = h->trace_t0; lp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
+            return lp;
+        };
+        ProfScope ps(h, PROF_DEC_LSTM_FWD, st);
+        if (mma) {
+            LstmRecParams lp = make(0);
+            lp.G = G; lp.tstride = tstride;
+            for (int g = 0; g < G; ++g) lp.mask_g[g] = c.p_dec_dropout > 0.f ? ios[g].masks + secs[iDec].off : nullptr;
+            MSA_TRY(launch_lstm_rec_fwd_mma(lp, h->sm_count, h->smem_limit, st));
+        } else {
+            for (int g = 0; g < G; ++g) MSA_TRY(launch_lstm_rec_fwd(make(g), h->sm_count, h->smem_limit, st));
+        }
+    }
+    // ---- stage 4: projections, postnet, outputs, loss ----
+    for (int g = 0; g < G; ++g) {
+        const Ws& w = W[g];
+        const TaskIO& io = ios[g];
+        auto mk = [&](int i) { return io.masks + secs[i].off; };
+        h->gemm_scratch = w.gemm_lo; h->gemm_scratch_floats = (size_t)w.n_gemm_lo;
+        // mel / gate projections (decoder.py:267-270)
+        const float* Wp = P("decoder.linear_projection.linear_layer.weight");
+        const float* Wg = P("decoder.gate_layer.linear_layer.weight");
+        MSA_TRY(gemm(h, false, true, d.TB, d.M, d.Hd, 1.f, w.hd, d.Hd, Wp, ldP, 0.f, w.mel_tm, d.M,
+                     P("decoder.linear_projection.linear_layer.bias")));
+        MSA_TRY(gemm(h, false, true, d.TB, d.M, d.E, 1.f, w.ctx, d.E, Wp + d.Hd, ldP, 1.f, w.mel_tm, d.M));
+        MSA_TRY(k_fill_rows(w.gate_tm, P("decoder.gate_layer.linear_layer.bias"), nullptr, d.TB, 1, st));
+        MSA_TRY(gemm(h, false, true, d.TB, 1, d.Hd, 1.f, w.hd, d.Hd, Wg, ldP, 1.f, w.gate_tm, 1));
+        MSA_TRY(gemm(h, false, true, d.TB, 1, d.E, 1.f, w.ctx, d.E, Wg + d.Hd, ldP, 1.f, w.gate_tm, 1));
+        // postnet (decoder.py:63-72, tacotron2nv.py:123-124)
+        const int64_t px = d.BT * d.Cmax;
+        MSA_TRY(k_transpose01(w.mel_tm, w.post_x, T, B, d.M, st));       // [T][B][M] -> [B][T][M]
+        MSA_TRY(k_transpose01(w.gate_tm, w.gate_bt, T, B, 1, st));
+        for (int i = 0; i < d.nPost; ++i) {
+            const int ci = i == 0 ? d.M : d.Cp, co = i == d.nPost - 1 ? d.M : d.Cp;
+            float* run = io.bn_stats ? io.bn_stats + h->bn_offs[d.nEnc + i] : nullptr;
+            MSA_TRY(conv_bn_fwd(h, st, params, "postnet.convolutions." + std::to_string(i), w.post_x + i * px, w.post_y + i * px,
+                                w.post_x + (i + 1) * px, w.post_col + i * d.BT * d.Kp * d.Cmax,
+                                w.post_bn + i * 2 * d.Cmax, w.post_bn + i * 2 * d.Cmax + d.Cmax, run, B, T, ci, co, d.Kp,
+                                i < d.nPost - 1 ? 2 : 0, mk(iPost + i), w.red_scr));
+        }
+        MSA_TRY(k_add(w.post_x, w.post_x + d.nPost * px, w.post_bt, d.BT * d.M, st));
+        // outputs in the reference layouts
+        if (io.mel_out) MSA_TRY(k_bt_to_ref(w.post_x, io.mel_out, B, T, d.M, st));
+        if (io.mel_post_out) MSA_TRY(k_bt_to_ref(w.post_bt, io.mel_post_out, B, T, d.M, st));
+        if (io.gate_out) MSA_TRY(k_scale_copy(w.gate_bt, io.gate_out, d.BT, 1.f, 0, st));
+        if (io.align_out) MSA_TRY(k_transpose01(w.align_tm, io.align_out, T, B, L, st));
+        // loss + d(loss)/d(outputs)
+        if (io.stop) {
+            MSA_TRY(k_loss(w.post_x, w.post_bt, w.gate_bt, w.target, io.stop, io.mel_len, B, T, d.M, c.loss_reduction,
+                           c.loss_pos_weight, w.loss_part, w.loss, w.dpre, w.dpost, w.dgate, st));
+            if (io.loss_out) MSA_TRY(k_scale_copy(w.loss, io.loss_out, 1, 1.f, 0, st));
+        }
+    }
+    h->d = d;
+    h->G = G;
+    h->ws_stride = ws_stride;
+    for (int g = 0; g < G; ++g) {
+        h->tokens[g] = ios[g].tokens; h->tok_len[g] = ios[g].tok_len; h->mel_len[g] = ios[g].mel_len; h->spk_ids[g] = ios[g].spk_ids;
+        h->spk_in[g] = ios[g].spk_vecs; h->masks[g] = ios[g].masks;
+    }
+    h->fwd_valid = true;
+    return 0;
+}
+
+}  // namespace msa
+
+extern "C" {
+
 int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, float* bn_stats, const int64_t* tokens,
                       const int64_t* token_lengths, const float* mels, const int64_t* mel_lengths, const float* speaker_vecs,
                       const int64_t* speaker_ids, const float* stop_targets, const uint8_t* masks, int B, int T, int L,
@@ -544,154 +796,42 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
     MSA_CHECK(h && wsp && params && tokens && token_lengths && mels && mel_lengths && masks, MSA_E_ARG, "msa_train_forward: null argument");
     MSA_CHECK(B >= 1 && T >= 1 && L >= 1, MSA_E_ARG, "msa_train_forward: bad dims B=%d T=%d L=%d", B, T, L);
     MSA_CHECK(h->cfg.spk_mode == 2 ? speaker_ids != nullptr : speaker_vecs != nullptr, MSA_E_ARG, "msa_train_forward: speaker input missing");
-    MSA_TRY(train_check(h));
-    const Dims d = make_dims(h->cfg, B, T, L);
-    const Ws w = ws_layout(d, wsp);
-    MSA_CHECK(ws_bytes >= w.total_bytes, MSA_E_WORKSPACE, "msa_train_forward: workspace %zu < %zu bytes", ws_bytes, w.total_bytes);
+    const size_t need = ws_layout(make_dims(h->cfg, B, T, L), nullptr).total_bytes;
+    MSA_CHECK(ws_bytes >= need, MSA_E_WORKSPACE, "msa_train_forward: workspace %zu < %zu bytes", ws_bytes, need);
     MSA_CHECK(((uintptr_t)wsp & 255) == 0, MSA_E_ARG, "msa_train_forward: workspace must be 256-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
-    MSA_CUDA(cudaSetDevice(h->device));
-    MSA_BLAS(cublasSetStream(h->blas, st));
-    MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
-    h->fwd_valid = false;
-    h->in_bwd = false;
-    h->gemm_scratch = w.gemm_lo; h->gemm_scratch_floats = (size_t)w.n_gemm_lo; h->cur_stream = st;
-    const msa_config& c = h->cfg;
-    const auto secs = mask_sections(c, B, T, L);
-    auto mk = [&](int i) { return masks + secs[i].off; };
-    MSA_CUDA(cudaMemsetAsync(w.red_scr, 0, sizeof(unsigned int) * kRedTickets, st));      // tickets of the chunked column reductions
-    const int iPre = d.nEnc, iAttn = d.nEnc + 2, iDec = d.nEnc + 3, iPost = d.nEnc + 4;
-    auto P = [&](const std::string& n) { return params + h->off(n); };
+    TaskIO io{bn_stats, tokens, token_lengths, mel_lengths, speaker_ids, mels, speaker_vecs, stop_targets, masks,
+              mel_out, mel_post_out, gate_out, align_out, loss_out};
+    return train_forward_impl(h, 1, static_cast<char*>(wsp), 0, params, &io, B, T, L, (cudaStream_t)stream);
+}
 
-    // ---- speaker vector (tacotron2nv.py:104-109) ----
-    if (c.spk_mode == 0) {
-        MSA_TRY(k_scale_copy(speaker_vecs, w.spk_vec, (int64_t)B * d.Ds, 1.f, 0, st));
-    } else if (c.spk_mode == 1) {
-        MSA_TRY(k_fill_rows(w.spk_vec, P("speaker_lin.bias"), nullptr, B, d.Ds, st));
-        MSA_TRY(gemm(h, false, true, B, d.Ds, d.Dsin, 1.f, speaker_vecs, d.Dsin, P("speaker_lin.weight"), d.Dsin, 1.f, w.spk_vec, d.Ds));
-    } else {
-        MSA_TRY(k_embedding_fwd(P("speaker_embedder.weight"), speaker_ids, w.spk_vec, B, d.Ds, c.num_speakers, st));
+size_t msa_group_workspace_bytes(const msa_handle* h, int G, int B, int T, int L) {
+    if (!h || G < 1 || G > kGroupMax || B <= 0 || T <= 0 || L <= 0) return 0;
+    return (size_t)G * ((ws_layout(make_dims(h->cfg, B, T, L), nullptr).total_bytes + 255) / 256 * 256);
+}
+
+int msa_train_forward_group(msa_handle* h, int G, void* wsp, size_t ws_bytes, const float* params, float* const* bn_stats,
+                            const int64_t* const* tokens, const int64_t* const* token_lengths, const float* const* mels,
+                            const int64_t* const* mel_lengths, const float* const* speaker_vecs, const int64_t* const* speaker_ids,
+                            const float* const* stop_targets, const uint8_t* const* masks, int B, int T, int L, float* loss_out,
+                            void* stream) {
+    MSA_CHECK(h && wsp && params && tokens && token_lengths && mels && mel_lengths && masks && stop_targets, MSA_E_ARG,
+              "msa_train_forward_group: null argument");
+    MSA_CHECK(G >= 1 && G <= kGroupMax, MSA_E_ARG, "msa_train_forward_group: G=%d outside [1,%d]", G, kGroupMax);
+    MSA_CHECK(B >= 1 && T >= 1 && L >= 1, MSA_E_ARG, "msa_train_forward_group: bad dims B=%d T=%d L=%d", B, T, L);
+    const size_t stride = msa_group_workspace_bytes(h, 1, B, T, L);
+    MSA_CHECK(ws_bytes >= (size_t)G * stride, MSA_E_WORKSPACE, "msa_train_forward_group: workspace %zu < %zu bytes", ws_bytes, (size_t)G * stride);
+    MSA_CHECK(((uintptr_t)wsp & 255) == 0, MSA_E_ARG, "msa_train_forward_group: workspace must be 256-byte aligned");
+    TaskIO ios[kGroupMax];
+    for (int g = 0; g < G; ++g) {
+        MSA_CHECK(tokens[g] && token_lengths[g] && mels[g] && mel_lengths[g] && masks[g] && stop_targets[g], MSA_E_ARG,
+                  "msa_train_forward_group: null input of task %d", g);
+        const float* sv = speaker_vecs ? speaker_vecs[g] : nullptr;
+        const int64_t* si = speaker_ids ? speaker_ids[g] : nullptr;
+        MSA_CHECK(h->cfg.spk_mode == 2 ? si != nullptr : sv != nullptr, MSA_E_ARG, "msa_train_forward_group: speaker input of task %d missing", g);
+        ios[g] = TaskIO{bn_stats ? bn_stats[g] : nullptr, tokens[g], token_lengths[g], mel_lengths[g], si, mels[g], sv, stop_targets[g],
+                        masks[g], nullptr, nullptr, nullptr, nullptr, loss_out ? loss_out + g : nullptr};
     }
-    // ---- encoder (tacotron2nv.py:88, encoder.py:35-52) ----
-    MSA_TRY(k_embedding_fwd(P("embedding.weight"), tokens, w.enc_x, (int)d.BL, d.C, c.n_symbols, st));
-    const int64_t ex = d.BL * d.C;
-    for (int i = 0; i < d.nEnc; ++i) {
-        float* run = bn_stats ? bn_stats + h->bn_offs[i] : nullptr;
-        MSA_TRY(conv_bn_fwd(h, st, params, "encoder.convolutions." + std::to_string(i), w.enc_x + i * ex, w.enc_y + i * ex,
-                            w.enc_x + (i + 1) * ex, w.enc_col + i * d.BL * d.Kc * d.C,
-                            w.enc_bn + i * 2 * d.C, w.enc_bn + i * 2 * d.C + d.C, run, B, L, d.C, d.C, d.Kc, 1, mk(i), w.red_scr));
-    }
-    MSA_TRY(k_transpose01(w.enc_x + d.nEnc * ex, w.x3_tm, B, L, d.C, st));
-    const int H4e = 4 * d.Hh;
-    for (int dir = 0; dir < 2; ++dir) {
-        const std::string sfx = dir ? "_reverse" : "";
-        float* zx = w.enc_zx + (int64_t)dir * d.BL * H4e;
-        MSA_TRY(k_fill_rows(zx, P("encoder.lstm.bias_ih_l0" + sfx), P("encoder.lstm.bias_hh_l0" + sfx), d.BL, H4e, st));
-        MSA_TRY(gemm(h, false, true, d.BL, H4e, d.C, 1.f, w.x3_tm, d.C, P("encoder.lstm.weight_ih_l0" + sfx), d.C, 1.f, zx, H4e));
-    }
-    {
-        LstmRecParams lp{};
-        lp.T = L; lp.B = B; lp.H = d.Hh; lp.ndir = 2;
-        lp.zin = w.enc_zx; lp.whh = P("encoder.lstm.weight_hh_l0");
-        lp.whh_dir_stride = h->off("encoder.lstm.weight_hh_l0_reverse") - h->off("encoder.lstm.weight_hh_l0");
-        lp.hout = w.enc_h; lp.cout = w.enc_c; lp.gates = w.enc_g; lp.mask = nullptr; lp.drop_scale = 1.f;
-        lp.lengths = token_lengths; lp.abort_word = h->abort_dev; lp.prof = prof_ptr(h, w, PROF_ENC_LSTM_FWD); lp.trace = trace_ptr(h, w, PROF_ENC_LSTM_FWD); lp.trace_t0 = h->trace_t0; lp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
-        ProfScope ps(h, PROF_ENC_LSTM_FWD, st);
-        MSA_TRY(launch_lstm_rec_fwd(lp, h->sm_count, h->smem_limit, st));
-    }
-    MSA_TRY(k_build_memory(w.enc_h, w.spk_vec, w.memory, B, L, d.Hh, d.Ds, st));
-    // ---- decoder set-up (decoder.py:290-302, forward_attn.py:103-116) ----
-    const std::string at = "decoder.attention_layer.";
-    const int H4a = 4 * d.Ha, H4d = 4 * d.Hd, ldA = d.Pd + d.E, ldD = d.Ha + d.E, ldP = d.Hd + d.E;
-    MSA_TRY(gemm(h, false, true, d.BL, d.A, d.E, 1.f, w.memory, d.E, P(at + "inputs_layer.linear_layer.weight"), d.E, 0.f, w.pm, d.A));
-    const float* Wia = P("decoder.attention_rnn.weight_ih");
-    MSA_TRY(gemm(h, false, true, H4a, d.BL, d.E, 1.f, Wia + d.Pd, ldA, w.memory, d.E, 0.f, w.mw_rm, d.BL));
-    MSA_TRY(k_prep_mels(mels, w.frames, w.target, B, d.M, T, st));
-    const int64_t nfr = d.TB + B;
-    MSA_TRY(gemm(h, false, true, nfr, d.Pd, d.M, 1.f, w.frames, d.M, P("decoder.prenet.layers.0.linear_layer.weight"), d.M, 0.f, w.p1, d.Pd));
-    MSA_TRY(k_relu_drop_fwd(w.p1, mk(iPre), 2.f, nfr * d.Pd, st));
-    MSA_TRY(gemm(h, false, true, nfr, d.Pd, d.Pd, 1.f, w.p1, d.Pd, P("decoder.prenet.layers.1.linear_layer.weight"), d.Pd, 0.f, w.xpre, d.Pd));
-    MSA_TRY(k_relu_drop_fwd(w.xpre, mk(iPre + 1), 2.f, nfr * d.Pd, st));
-    MSA_TRY(gemm(h, false, true, d.TB, H4a, d.Pd, 1.f, w.xpre, d.Pd, Wia, ldA, 0.f, w.xw, H4a, P("decoder.attention_rnn.bias_ih"),
-                 P("decoder.attention_rnn.bias_hh")));
-    const bool fa = c.forward_attn != 0, ta = fa && c.trans_agent != 0;
-    if (ta)     // context half of the transition agent: ctx(t) = alpha(t) . memory  =>  W_ta[:E] . ctx(t) = alpha(t) . (memory . W_ta[:E])
-        MSA_TRY(gemm(h, false, true, d.BL, 1, d.E, 1.f, w.memory, d.E, P(at + "ta.weight"), d.E + d.Ha, 0.f, w.mta, 1));
-    // ---- attention chain (persistent) ----
-    {
-        AttnChainParams ap{};
-        ap.T = T; ap.B = B; ap.L = L; ap.Ha = d.Ha; ap.A = d.A; ap.F = d.F; ap.Kl = d.Kl; ap.norm = c.attn_norm;
-        ap.xw = w.xw; ap.whh = P("decoder.attention_rnn.weight_hh"); ap.mw_rm = w.mw_rm;
-        ap.wq = P(at + "query_layer.linear_layer.weight"); ap.pm = w.pm;
-        ap.wloc = P(at + "location_layer.location_conv1d.weight");
-        ap.wld = P(at + "location_layer.location_dense.linear_layer.weight");
-        ap.v = P(at + "v.linear_layer.weight"); ap.bv = P(at + "v.linear_layer.bias");
-        ap.mask = c.p_attn_dropout > 0.f ? mk(iAttn) : nullptr;
-        ap.drop_scale = 1.f / (1.f - c.p_attn_dropout);
-        ap.ha = w.ha; ap.ca = w.ca; ap.ga = w.ga; ap.q = w.q; ap.align = w.align_tm; ap.cum = w.cum; ap.s = w.s;
-        ap.fa = fa; ap.ta = ta; ap.aplain = w.aplain; ap.fsum = w.fsum; ap.ustash = w.ustash;
-        if (ta) { ap.mta = w.mta; ap.wta_h = P(at + "ta.weight") + d.E; ap.bta = P(at + "ta.bias"); }
-        ap.convf = w.convf; ap.znorm = w.znorm; ap.e = w.ebuf; ap.abort_word = h->abort_dev; ap.prof = prof_ptr(h, w, PROF_ATTN_FWD); ap.trace = trace_ptr(h, w, PROF_ATTN_FWD); ap.trace_t0 = h->trace_t0; ap.flags = h->rec_flags >= 0 ? h->rec_flags : 0;
-        ProfScope ps(h, PROF_ATTN_FWD, st);
-        MSA_TRY(launch_attn_chain_fwd(ap, h->sm_count, h->smem_limit, st));
-    }
-    // ctx[t][b] = a[t][b] . memory[b]  (forward_attn.py:217), batched over b
-    MSA_TRY(gemm_batched(h, false, false, T, d.E, L, 1.f, w.align_tm, d.BL, L, w.memory, d.E, (int64_t)L * d.E, 0.f, w.ctx,
-                         (int64_t)B * d.E, d.E, B));
-    // ---- decoder RNN chain (decoder.py:260-265) ----
-    const float* Wid = P("decoder.decoder_rnn.weight_ih");
-    MSA_TRY(gemm(h, false, true, d.TB, H4d, d.Ha, 1.f, w.ha, d.Ha, Wid, ldD, 0.f, w.zd, H4d, P("decoder.decoder_rnn.bias_ih"),
-                 P("decoder.decoder_rnn.bias_hh")));
-    MSA_TRY(gemm(h, false, true, d.TB, H4d, d.E, 1.f, w.ctx, d.E, Wid + d.Ha, ldD, 1.f, w.zd, H4d));
-    {
-        LstmRecParams lp{};
-        lp.T = T; lp.B = B; lp.H = d.Hd; lp.ndir = 1;
-        lp.zin = w.zd; lp.whh = P("decoder.decoder_rnn.weight_hh"); lp.whh_dir_stride = 0;
-        lp.hout = w.hd; lp.cout = w.cd; lp.gates = w.gd;
-        lp.mask = c.p_dec_dropout > 0.f ? mk(iDec) : nullptr;
-        lp.drop_scale = 1.f / (1.f - c.p_dec_dropout);
-        lp.lengths = nullptr; lp.abort_word = h->abort_dev; lp.prof = prof_ptr(h, w, PROF_DEC_LSTM_FWD); lp.trace = trace_ptr(h, w, PROF_DEC_LSTM_FWD); lp.trace_t0 = h->trace_t0; lp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
-        ProfScope ps(h, PROF_DEC_LSTM_FWD, st);
-        MSA_TRY(launch_lstm_rec_fwd(lp, h->sm_count, h->smem_limit, st));
-    }
-    // ---- mel / gate projections (decoder.py:267-270) ----
-    const float* Wp = P("decoder.linear_projection.linear_layer.weight");
-    const float* Wg = P("decoder.gate_layer.linear_layer.weight");
-    MSA_TRY(gemm(h, false, true, d.TB, d.M, d.Hd, 1.f, w.hd, d.Hd, Wp, ldP, 0.f, w.mel_tm, d.M,
-                 P("decoder.linear_projection.linear_layer.bias")));
-    MSA_TRY(gemm(h, false, true, d.TB, d.M, d.E, 1.f, w.ctx, d.E, Wp + d.Hd, ldP, 1.f, w.mel_tm, d.M));
-    MSA_TRY(k_fill_rows(w.gate_tm, P("decoder.gate_layer.linear_layer.bias"), nullptr, d.TB, 1, st));
-    MSA_TRY(gemm(h, false, true, d.TB, 1, d.Hd, 1.f, w.hd, d.Hd, Wg, ldP, 1.f, w.gate_tm, 1));
-    MSA_TRY(gemm(h, false, true, d.TB, 1, d.E, 1.f, w.ctx, d.E, Wg + d.Hd, ldP, 1.f, w.gate_tm, 1));
-    // ---- postnet (decoder.py:63-72, tacotron2nv.py:123-124) ----
-    const int64_t px = d.BT * d.Cmax;
-    MSA_TRY(k_transpose01(w.mel_tm, w.post_x, T, B, d.M, st));       // [T][B][M] -> [B][T][M]
-    MSA_TRY(k_transpose01(w.gate_tm, w.gate_bt, T, B, 1, st));
-    for (int i = 0; i < d.nPost; ++i) {
-        const int ci = i == 0 ? d.M : d.Cp, co = i == d.nPost - 1 ? d.M : d.Cp;
-        float* run = bn_stats ? bn_stats + h->bn_offs[d.nEnc + i] : nullptr;
-        MSA_TRY(conv_bn_fwd(h, st, params, "postnet.convolutions." + std::to_string(i), w.post_x + i * px, w.post_y + i * px,
-                            w.post_x + (i + 1) * px, w.post_col + i * d.BT * d.Kp * d.Cmax,
-                            w.post_bn + i * 2 * d.Cmax, w.post_bn + i * 2 * d.Cmax + d.Cmax, run, B, T, ci, co, d.Kp,
-                            i < d.nPost - 1 ? 2 : 0, mk(iPost + i), w.red_scr));
-    }
-    MSA_TRY(k_add(w.post_x, w.post_x + d.nPost * px, w.post_bt, d.BT * d.M, st));
-    // ---- outputs in the reference layouts ----
-    if (mel_out) MSA_TRY(k_bt_to_ref(w.post_x, mel_out, B, T, d.M, st));
-    if (mel_post_out) MSA_TRY(k_bt_to_ref(w.post_bt, mel_post_out, B, T, d.M, st));
-    if (gate_out) MSA_TRY(k_scale_copy(w.gate_bt, gate_out, d.BT, 1.f, 0, st));
-    if (align_out) MSA_TRY(k_transpose01(w.align_tm, align_out, T, B, L, st));
-    // ---- loss + d(loss)/d(outputs) ----
-    if (stop_targets) {
-        MSA_TRY(k_loss(w.post_x, w.post_bt, w.gate_bt, w.target, stop_targets, mel_lengths, B, T, d.M, c.loss_reduction,
-                       c.loss_pos_weight, w.loss_part, w.loss, w.dpre, w.dpost, w.dgate, st));
-        if (loss_out) MSA_TRY(k_scale_copy(w.loss, loss_out, 1, 1.f, 0, st));
-    }
-    h->d = d;
-    h->tokens = tokens; h->tok_len = token_lengths; h->mel_len = mel_lengths; h->spk_ids = speaker_ids; h->spk_in = speaker_vecs;
-    h->masks = masks;
-    h->fwd_valid = true;
-    return 0;
+    return train_forward_impl(h, G, static_cast<char*>(wsp), stride, params, ios, B, T, L, (cudaStream_t)stream);
 }
 
 int msa_train_loss(msa_handle* h, void* wsp, const float* stop_targets, const int64_t* mel_lengths, int reduction, float pos_weight,
@@ -756,220 +896,322 @@ int msa_loss_grads(msa_handle* h, void* wsp, float* d_mel, float* d_mel_post, fl
     return 0;
 }
 
+}  // extern "C"
+
+namespace msa {
+
+// Backward of train_forward_impl: the gradient of task g's loss w.r.t. the shared parameters goes to grads_g[g]
+// (= autograd.grad(loss_g, fast_weights), maml.py:54 / 71-74); the three reverse-time recurrences run once for the whole group.
+static int train_backward_impl(msa_handle* h, char* wsp, const float* params, const float* const* d_mel, const float* const* d_mel_post,
+                               const float* const* d_gate, float* const* grads_g, int acc, float gs, cudaStream_t st) {
+    const Dims d = h->d;
+    const int NG = h->G;
+    const size_t ws_stride = h->ws_stride;
+    std::vector<Ws> W;
+    for (int g = 0; g < NG; ++g) W.push_back(ws_layout(d, wsp + (size_t)g * ws_stride));
+    const bool ext = d_mel != nullptr;
+    MSA_CUDA(cudaSetDevice(h->device));
+    MSA_BLAS(cublasSetStream(h->blas, st));
+    MSA_BLAS(cublasSetWorkspace(h->blas, W[0].blas_ws, W[0].blas_ws_bytes));
+    const msa_config& c = h->cfg;
+    h->in_bwd = true;
+    h->cur_stream = st;
+    const int B = d.B, T = d.T, L = d.L;
+    const auto secs = mask_sections(c, B, T, L);
+    const int iPre = d.nEnc, iAttn = d.nEnc + 2, iDec = d.nEnc + 3, iPost = d.nEnc + 4;
+    auto P = [&](const std::string& n) { return params + h->off(n); };
+    const float beta = acc ? 1.f : 0.f;
+    const int H4a = 4 * d.Ha, H4d = 4 * d.Hd, H4e = 4 * d.Hh, ldA = d.Pd + d.E, ldD = d.Ha + d.E, ldP = d.Hd + d.E;
+    const std::string at = "decoder.attention_layer.";
+    const bool fa = c.forward_attn != 0, ta = fa && c.trans_agent != 0;
+    const float* Wia = P("decoder.attention_rnn.weight_ih");
+    const bool mma = use_mma_chains(h, NG, B, T, L);
+    const int64_t tstride = (int64_t)(ws_stride / sizeof(float));
+
+    // ---- stage 1: postnet and projections ----
+    for (int g = 0; g < NG; ++g) {
+        const Ws& w = W[g];
+        float* grads = grads_g[g];
+        auto mk = [&](int i) { return h->masks[g] + secs[i].off; };
+        auto G = [&](const std::string& n) { return grads + h->off(n); };
+        h->gemm_scratch = w.gemm_lo; h->gemm_scratch_floats = (size_t)w.n_gemm_lo;
+        (void)mk; (void)G;
+        if (ext) {
+            MSA_TRY(k_ref_to_bt(d_mel[g], w.dpre, B, T, d.M, st));
+            MSA_TRY(k_ref_to_bt(d_mel_post[g], w.dpost, B, T, d.M, st));
+            MSA_TRY(k_scale_copy(d_gate[g], w.dgate, d.BT, 1.f, 0, st));
+        }
+        // ---- postnet backward ----
+        const int64_t px = d.BT * d.Cmax;
+        const float* dcur = w.dpost;
+        float* pingpong[2] = {w.bdx0, w.bdx1};
+        for (int i = d.nPost - 1; i >= 0; --i) {
+            const int ci = i == 0 ? d.M : d.Cp, co = i == d.nPost - 1 ? d.M : d.Cp;
+            float* dx = pingpong[i & 1];
+            MSA_TRY(conv_bn_bwd(h, st, params, grads, gs, acc, "postnet.convolutions." + std::to_string(i), w.post_x + i * px,
+                                w.post_y + i * px, dcur, dx, w.bdy, w.post_col + i * d.BT * d.Kp * d.Cmax,
+                                w.bdcol, w.bn_scr,
+                                w.post_bn + i * 2 * d.Cmax, w.post_bn + i * 2 * d.Cmax + d.Cmax, B, T, ci, co, d.Kp,
+                                i < d.nPost - 1 ? 2 : 0, mk(iPost + i), true, w.red_scr));
+            dcur = dx;
+        }
+        // d(pre-postnet mel) = loss term + residual + postnet input (tacotron2nv.py:123-124)
+        MSA_TRY(k_add3(w.dpre, w.dpost, dcur, w.dmel_bt, d.BT * d.M, st));
+        MSA_TRY(k_transpose01(w.dmel_bt, w.dmel_tm, B, T, d.M, st));
+        MSA_TRY(k_transpose01(w.dgate, w.dgate_tm, B, T, 1, st));
+        // ---- projections backward (decoder.py:267-270) ----
+        const float* Wp = P("decoder.linear_projection.linear_layer.weight");
+        const float* Wg = P("decoder.gate_layer.linear_layer.weight");
+        float* gWp = G("decoder.linear_projection.linear_layer.weight");
+        float* gWg = G("decoder.gate_layer.linear_layer.weight");
+        MSA_TRY(gemm(h, false, false, d.TB, d.Hd, d.M, 1.f, w.dmel_tm, d.M, Wp, ldP, 0.f, w.dhd, d.Hd));
+        MSA_TRY(gemm(h, false, false, d.TB, d.Hd, 1, 1.f, w.dgate_tm, 1, Wg, ldP, 1.f, w.dhd, d.Hd));
+        MSA_TRY(gemm(h, false, false, d.TB, d.E, d.M, 1.f, w.dmel_tm, d.M, Wp + d.Hd, ldP, 0.f, w.dctx, d.E));
+        MSA_TRY(gemm(h, false, false, d.TB, d.E, 1, 1.f, w.dgate_tm, 1, Wg + d.Hd, ldP, 1.f, w.dctx, d.E));
+        MSA_TRY(gemm(h, true, false, d.M, d.Hd, d.TB, gs, w.dmel_tm, d.M, w.hd, d.Hd, beta, gWp, ldP));
+        MSA_TRY(gemm(h, true, false, d.M, d.E, d.TB, gs, w.dmel_tm, d.M, w.ctx, d.E, beta, gWp + d.Hd, ldP));
+        MSA_TRY(gemm(h, true, false, 1, d.Hd, d.TB, gs, w.dgate_tm, 1, w.hd, d.Hd, beta, gWg, ldP));
+        MSA_TRY(gemm(h, true, false, 1, d.E, d.TB, gs, w.dgate_tm, 1, w.ctx, d.E, beta, gWg + d.Hd, ldP));
+        MSA_TRY(k_colsum(w.dmel_tm, d.TB, d.M, d.M, G("decoder.linear_projection.linear_layer.bias"), gs, acc, nullptr, w.red_scr, st));
+        MSA_TRY(k_colsum(w.dgate_tm, d.TB, 1, 1, G("decoder.gate_layer.linear_layer.bias"), gs, acc, nullptr, w.red_scr, st));
+    }
+    // ---- decoder RNN chain backward (persistent) ----
+    {
+        auto make = [&](int g) {
+            const Ws& w = W[g];
+            LstmRecBwdParams bp{};
+            bp.T = T; bp.B = B; bp.H = d.Hd; bp.ndir = 1;
+            bp.whh = P("decoder.decoder_rnn.weight_hh"); bp.whh_dir_stride = 0;
+            bp.gates = w.gd; bp.cout = w.cd; bp.dh_ext = w.dhd; bp.dz = w.dzd;
+            bp.mask = c.p_dec_dropout > 0.f ? h->masks[g] + secs[iDec].off : nullptr;
+            bp.drop_scale = 1.f / (1.f - c.p_dec_dropout);
+            bp.lengths = nullptr; bp.abort_word = h->abort_dev; bp.prof = prof_ptr(h, w, PROF_DEC_LSTM_BWD);
+            bp.trace = trace_ptr(h, w, PROF_DEC_LSTM_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
+            return bp;
+        };
+        ProfScope ps(h, PROF_DEC_LSTM_BWD, st);
+        if (mma) {
+            LstmRecBwdParams bp = make(0);
+            bp.G = NG; bp.tstride = tstride;
+            for (int g = 0; g < NG; ++g) bp.mask_g[g] = c.p_dec_dropout > 0.f ? h->masks[g] + secs[iDec].off : nullptr;
+            MSA_TRY(launch_lstm_rec_bwd_mma(bp, h->sm_count, h->smem_limit, st));
+        } else {
+            for (int g = 0; g < NG; ++g) MSA_TRY(launch_lstm_rec_bwd(make(g), h->sm_count, h->smem_limit, st));
+        }
+    }
+    // ---- stage 2: decoder-RNN input gradients, context backward ----
+    for (int g = 0; g < NG; ++g) {
+        const Ws& w = W[g];
+        float* grads = grads_g[g];
+        auto mk = [&](int i) { return h->masks[g] + secs[i].off; };
+        auto G = [&](const std::string& n) { return grads + h->off(n); };
+        h->gemm_scratch = w.gemm_lo; h->gemm_scratch_floats = (size_t)w.n_gemm_lo;
+        (void)mk; (void)G;
+        const float* Wid = P("decoder.decoder_rnn.weight_ih");
+        float* gWid = G("decoder.decoder_rnn.weight_ih");
+        MSA_TRY(gemm(h, false, false, d.TB, d.Ha, H4d, 1.f, w.dzd, H4d, Wid, ldD, 0.f, w.dha, d.Ha));
+        MSA_TRY(gemm(h, false, false, d.TB, d.E, H4d, 1.f, w.dzd, H4d, Wid + d.Ha, ldD, 1.f, w.dctx, d.E));
+        MSA_TRY(gemm(h, true, false, H4d, d.Ha, d.TB, gs, w.dzd, H4d, w.ha, d.Ha, beta, gWid, ldD));
+        MSA_TRY(gemm(h, true, false, H4d, d.E, d.TB, gs, w.dzd, H4d, w.ctx, d.E, beta, gWid + d.Ha, ldD));
+        float* gWhd = G("decoder.decoder_rnn.weight_hh");
+        if (T > 1) {
+            MSA_TRY(gemm(h, true, false, H4d, d.Hd, d.TB - B, gs, w.dzd + (int64_t)B * H4d, H4d, w.hd, d.Hd, beta, gWhd, d.Hd));
+        } else if (!acc) {
+            MSA_CUDA(cudaMemsetAsync(gWhd, 0, sizeof(float) * (size_t)H4d * d.Hd, st));
+        }
+        MSA_TRY(k_colsum(w.dzd, d.TB, H4d, H4d, G("decoder.decoder_rnn.bias_ih"), gs, acc, G("decoder.decoder_rnn.bias_hh"), w.red_scr, st));
+        // ---- context backward: ctx = align . memory ----
+        MSA_TRY(gemm_batched(h, false, true, T, L, d.E, 1.f, w.dctx, (int64_t)B * d.E, d.E, w.memory, d.E, (int64_t)L * d.E, 0.f,
+                             w.da_ext, d.BL, L, B));
+        MSA_TRY(gemm_batched(h, true, false, L, d.E, T, 1.f, w.align_tm, d.BL, L, w.dctx, (int64_t)B * d.E, d.E, 0.f, w.dmem, d.E,
+                             (int64_t)L * d.E, B));
+        // (W_ih[:, prenet:] . memory^T)^T for the attention chain's context-path backward
+        MSA_TRY(gemm(h, false, true, d.BL, H4a, d.E, 1.f, w.memory, d.E, Wia + d.Pd, ldA, 0.f, w.mw_pm, H4a));
+    }
+    // ---- attention chain backward (persistent) ----
+    {
+        auto make = [&](int g) {
+            const Ws& w = W[g];
+            AttnChainBwdParams bp{};
+            bp.T = T; bp.B = B; bp.L = L; bp.Ha = d.Ha; bp.A = d.A; bp.F = d.F; bp.Kl = d.Kl; bp.norm = c.attn_norm;
+            bp.whh = P("decoder.attention_rnn.weight_hh"); bp.mw_pm = w.mw_pm;
+            bp.wq = P(at + "query_layer.linear_layer.weight");
+            bp.wloc = P(at + "location_layer.location_conv1d.weight");
+            bp.wld = P(at + "location_layer.location_dense.linear_layer.weight");
+            bp.v = P(at + "v.linear_layer.weight");
+            bp.mask = c.p_attn_dropout > 0.f ? h->masks[g] + secs[iAttn].off : nullptr;
+            bp.drop_scale = 1.f / (1.f - c.p_attn_dropout);
+            bp.ga = w.ga; bp.ca = w.ca; bp.align = w.align_tm; bp.s = w.s; bp.znorm = w.znorm;
+            bp.dha_ext = w.dha; bp.da_ext = w.da_ext;
+            bp.dza = w.dza; bp.dq = w.dq; bp.de = w.de; bp.ds = w.ds; bp.dconvf = w.dconvf; bp.dat = w.dat;
+            bp.fa = fa; bp.ta = ta; bp.aplain = w.aplain; bp.fsum = w.fsum; bp.ustash = w.ustash; bp.dzu = w.dzu;
+            if (ta) { bp.mta = w.mta; bp.wta_h = P(at + "ta.weight") + d.E; }
+            bp.abort_word = h->abort_dev; bp.prof = prof_ptr(h, w, PROF_ATTN_BWD); bp.trace = trace_ptr(h, w, PROF_ATTN_BWD);
+            bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 0;
+            return bp;
+        };
+        ProfScope ps(h, PROF_ATTN_BWD, st);
+        if (mma) {
+            AttnChainBwdParams bp = make(0);
+            bp.G = NG; bp.tstride = tstride;
+            for (int g = 0; g < NG; ++g) bp.mask_g[g] = c.p_attn_dropout > 0.f ? h->masks[g] + secs[iAttn].off : nullptr;
+            MSA_TRY(launch_attn_chain_bwd_mma(bp, h->sm_count, h->smem_limit, st));
+        } else {
+            for (int g = 0; g < NG; ++g) MSA_TRY(launch_attn_chain_bwd(make(g), h->sm_count, h->smem_limit, st));
+        }
+    }
+    // ---- stage 3: deferred attention / prenet / speaker gradients ----
+    for (int g = 0; g < NG; ++g) {
+        const Ws& w = W[g];
+        float* grads = grads_g[g];
+        auto mk = [&](int i) { return h->masks[g] + secs[i].off; };
+        auto G = [&](const std::string& n) { return grads + h->off(n); };
+        h->gemm_scratch = w.gemm_lo; h->gemm_scratch_floats = (size_t)w.n_gemm_lo;
+        (void)mk; (void)G;
+        // ---- deferred attention / attention-RNN parameter gradients ----
+        float* gWia = G("decoder.attention_rnn.weight_ih");
+        if (ta) {
+            // transition agent u(t) = sigmoid(W_ta . [ctx(t); h_a'(t)] + b) (forward_attn.py:222-224), dzu [T][B] from the chain
+            float* gWta = G(at + "ta.weight");
+            MSA_TRY(gemm(h, true, false, 1, d.E, d.TB, gs, w.dzu, 1, w.ctx, d.E, beta, gWta, d.E + d.Ha));
+            MSA_TRY(gemm(h, true, false, 1, d.Ha, d.TB, gs, w.dzu, 1, w.ha, d.Ha, beta, gWta + d.E, d.E + d.Ha));
+            MSA_TRY(k_colsum(w.dzu, d.TB, 1, 1, G(at + "ta.bias"), gs, acc, nullptr, w.red_scr, st));
+            // d memory += sum_t alpha(t)^T . (dzu(t) (x) W_ta[:E])   (w.dctx is free after the context backward above)
+            MSA_TRY(gemm(h, false, false, d.TB, d.E, 1, 1.f, w.dzu, 1, P(at + "ta.weight"), d.E + d.Ha, 0.f, w.dctx, d.E));
+            MSA_TRY(gemm_batched(h, true, false, L, d.E, T, 1.f, w.align_tm, d.BL, L, w.dctx, (int64_t)B * d.E, d.E, 1.f, w.dmem, d.E,
+                                 (int64_t)L * d.E, B));
+        }
+        const int64_t nfr = d.TB + B;
+        MSA_TRY(gemm(h, false, false, d.TB, d.Pd, H4a, 1.f, w.dza, H4a, Wia, ldA, 0.f, w.dxp, d.Pd));
+        MSA_CUDA(cudaMemsetAsync(w.dxp + d.TB * d.Pd, 0, sizeof(float) * (size_t)B * d.Pd, st));   // last prenet frame is unused (decoder.py:305)
+        MSA_TRY(gemm(h, true, false, H4a, d.Pd, d.TB, gs, w.dza, H4a, w.xpre, d.Pd, beta, gWia, ldA));
+        float* gWha = G("decoder.attention_rnn.weight_hh");
+        if (T > 1) {
+            MSA_TRY(gemm(h, true, false, H4a, d.Ha, d.TB - B, gs, w.dza + (int64_t)B * H4a, H4a, w.ha, d.Ha, beta, gWha, d.Ha));
+            // dMW[b][l][r] = sum_t a[t][b][l] * dz_a[t+1][b][r]
+            MSA_TRY(gemm_batched(h, true, false, L, H4a, T - 1, 1.f, w.align_tm, d.BL, L, w.dza + (int64_t)B * H4a, (int64_t)B * H4a, H4a,
+                                 0.f, w.dmw, H4a, (int64_t)L * H4a, B));
+        } else {
+            if (!acc) MSA_CUDA(cudaMemsetAsync(gWha, 0, sizeof(float) * (size_t)H4a * d.Ha, st));
+            MSA_CUDA(cudaMemsetAsync(w.dmw, 0, sizeof(float) * (size_t)d.BL * H4a, st));
+        }
+        MSA_TRY(k_colsum(w.dza, d.TB, H4a, H4a, G("decoder.attention_rnn.bias_ih"), gs, acc, G("decoder.attention_rnn.bias_hh"), w.red_scr, st));
+        MSA_TRY(gemm(h, true, false, H4a, d.E, d.BL, gs, w.dmw, H4a, w.memory, d.E, beta, gWia + d.Pd, ldA));
+        MSA_TRY(gemm(h, false, false, d.BL, d.E, H4a, 1.f, w.dmw, H4a, Wia + d.Pd, ldA, 1.f, w.dmem, d.E));
+        MSA_TRY(gemm(h, true, false, d.A, d.Ha, d.TB, gs, w.dq, d.A, w.ha, d.Ha, beta, G(at + "query_layer.linear_layer.weight"), d.Ha));
+        MSA_TRY(k_sum_over_t(w.ds, w.dpm, T, d.BL * d.A, st));
+        MSA_TRY(gemm(h, true, false, d.A, d.E, d.BL, gs, w.dpm, d.A, w.memory, d.E, beta, G(at + "inputs_layer.linear_layer.weight"), d.E));
+        MSA_TRY(gemm(h, false, false, d.BL, d.E, d.A, 1.f, w.dpm, d.A, P(at + "inputs_layer.linear_layer.weight"), d.E, 1.f, w.dmem, d.E));
+        MSA_TRY(gemm(h, true, false, 1, d.A, d.TBL, gs, w.de, 1, w.s, d.A, beta, G(at + "v.linear_layer.weight"), d.A));
+        MSA_TRY(k_dot_rows(w.de, nullptr, d.TBL, w.loss_part, G(at + "v.linear_layer.bias"), gs, acc, st));
+        MSA_TRY(gemm(h, true, false, d.A, d.F, d.TBL, gs, w.ds, d.A, w.convf, d.F, beta,
+                     G(at + "location_layer.location_dense.linear_layer.weight"), d.F));
+        MSA_TRY(k_wloc_grad(w.dconvf, w.align_tm, w.cum, G(at + "location_layer.location_conv1d.weight"), w.wloc_part, T, B, L, d.F, d.Kl, gs,
+                            acc, st));
+        // ---- prenet backward (decoder.py:9-20) ----
+        MSA_TRY(k_relu_drop_bwd(w.dxp, w.xpre, mk(iPre + 1), 2.f, nfr * d.Pd, st));
+        MSA_TRY(gemm(h, true, false, d.Pd, d.Pd, nfr, gs, w.dxp, d.Pd, w.p1, d.Pd, beta, G("decoder.prenet.layers.1.linear_layer.weight"), d.Pd));
+        MSA_TRY(gemm(h, false, false, nfr, d.Pd, d.Pd, 1.f, w.dxp, d.Pd, P("decoder.prenet.layers.1.linear_layer.weight"), d.Pd, 0.f, w.dp1, d.Pd));
+        MSA_TRY(k_relu_drop_bwd(w.dp1, w.p1, mk(iPre), 2.f, nfr * d.Pd, st));
+        MSA_TRY(gemm(h, true, false, d.Pd, d.M, nfr, gs, w.dp1, d.Pd, w.frames, d.M, beta, G("decoder.prenet.layers.0.linear_layer.weight"), d.M));
+        // ---- memory -> encoder output + speaker path (tacotron2nv.py:104-111) ----
+        MSA_TRY(k_split_dmemory(w.dmem, w.denc_h, c.spk_mode ? w.dspk : nullptr, B, L, d.Hh, d.Ds, st));
+        if (c.spk_mode == 1) {
+            MSA_TRY(gemm(h, true, false, d.Ds, d.Dsin, B, gs, w.dspk, d.Ds, h->spk_in[g], d.Dsin, beta, G("speaker_lin.weight"), d.Dsin));
+            MSA_TRY(k_colsum(w.dspk, B, d.Ds, d.Ds, G("speaker_lin.bias"), gs, acc, nullptr, w.red_scr, st));
+        } else if (c.spk_mode == 2) {
+            MSA_TRY(k_embedding_bwd(w.dspk, h->spk_ids[g], G("speaker_embedder.weight"), B, d.Ds, c.num_speakers, gs, acc, st));
+        }
+    }
+    // ---- encoder BiLSTM backward (persistent) ----
+    {
+        auto make = [&](int g) {
+            const Ws& w = W[g];
+            LstmRecBwdParams bp{};
+            bp.T = L; bp.B = B; bp.H = d.Hh; bp.ndir = 2;
+            bp.whh = P("encoder.lstm.weight_hh_l0");
+            bp.whh_dir_stride = h->off("encoder.lstm.weight_hh_l0_reverse") - h->off("encoder.lstm.weight_hh_l0");
+            bp.gates = w.enc_g; bp.cout = w.enc_c; bp.dh_ext = w.denc_h; bp.dz = w.dzx; bp.mask = nullptr; bp.drop_scale = 1.f;
+            bp.lengths = h->tok_len[g]; bp.abort_word = h->abort_dev; bp.prof = prof_ptr(h, w, PROF_ENC_LSTM_BWD);
+            bp.trace = trace_ptr(h, w, PROF_ENC_LSTM_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
+            return bp;
+        };
+        ProfScope ps(h, PROF_ENC_LSTM_BWD, st);
+        if (mma) {
+            LstmRecBwdParams bp = make(0);
+            bp.G = NG; bp.tstride = tstride;
+            for (int g = 0; g < NG; ++g) bp.lengths_g[g] = h->tok_len[g];
+            MSA_TRY(launch_lstm_rec_bwd_mma(bp, h->sm_count, h->smem_limit, st));
+        } else {
+            for (int g = 0; g < NG; ++g) MSA_TRY(launch_lstm_rec_bwd(make(g), h->sm_count, h->smem_limit, st));
+        }
+    }
+    // ---- stage 4: encoder BiLSTM weight gradients, encoder convolutions, embedding ----
+    for (int g = 0; g < NG; ++g) {
+        const Ws& w = W[g];
+        float* grads = grads_g[g];
+        auto mk = [&](int i) { return h->masks[g] + secs[i].off; };
+        auto G = [&](const std::string& n) { return grads + h->off(n); };
+        h->gemm_scratch = w.gemm_lo; h->gemm_scratch_floats = (size_t)w.n_gemm_lo;
+        (void)mk; (void)G;
+        for (int dir = 0; dir < 2; ++dir) {
+            const std::string sfx = dir ? "_reverse" : "";
+            const float* dzx = w.dzx + (int64_t)dir * d.BL * H4e;
+            const float* eh = w.enc_h + (int64_t)dir * d.BL * d.Hh;
+            MSA_TRY(gemm(h, false, false, d.BL, d.C, H4e, 1.f, dzx, H4e, P("encoder.lstm.weight_ih_l0" + sfx), d.C, dir ? 1.f : 0.f, w.dx3_tm, d.C));
+            MSA_TRY(gemm(h, true, false, H4e, d.C, d.BL, gs, dzx, H4e, w.x3_tm, d.C, beta, G("encoder.lstm.weight_ih_l0" + sfx), d.C));
+            float* gWhh = G("encoder.lstm.weight_hh_l0" + sfx);
+            if (L > 1) {
+                if (dir == 0)   // z(t) uses h(t-1)
+                    MSA_TRY(gemm(h, true, false, H4e, d.Hh, d.BL - B, gs, dzx + (int64_t)B * H4e, H4e, eh, d.Hh, beta, gWhh, d.Hh));
+                else            // reverse direction: z(t) uses h(t+1)
+                    MSA_TRY(gemm(h, true, false, H4e, d.Hh, d.BL - B, gs, dzx, H4e, eh + (int64_t)B * d.Hh, d.Hh, beta, gWhh, d.Hh));
+            } else if (!acc) {
+                MSA_CUDA(cudaMemsetAsync(gWhh, 0, sizeof(float) * (size_t)H4e * d.Hh, st));
+            }
+            MSA_TRY(k_colsum(dzx, d.BL, H4e, H4e, G("encoder.lstm.bias_ih_l0" + sfx), gs, acc, G("encoder.lstm.bias_hh_l0" + sfx), w.red_scr, st));
+        }
+        // ---- encoder convolutions backward ----
+        const int64_t ex = d.BL * d.C;
+        float* epp[2] = {w.edx0, w.edx1};
+        MSA_TRY(k_transpose01(w.dx3_tm, epp[d.nEnc & 1], L, B, d.C, st));   // [L][B][C] -> [B][L][C]
+        const float* dcur = epp[d.nEnc & 1];
+        for (int i = d.nEnc - 1; i >= 0; --i) {
+            float* dx = epp[i & 1];
+            MSA_TRY(conv_bn_bwd(h, st, params, grads, gs, acc, "encoder.convolutions." + std::to_string(i), w.enc_x + i * ex,
+                                w.enc_y + i * ex, dcur, dx, w.edy, w.enc_col + i * d.BL * d.Kc * d.C,
+                                w.edcol, w.bn_scr, w.enc_bn + i * 2 * d.C, w.enc_bn + i * 2 * d.C + d.C, B, L, d.C, d.C, d.Kc, 1, mk(i),
+                                true, w.red_scr));
+            dcur = dx;
+        }
+        MSA_TRY(k_embedding_bwd(dcur, h->tokens[g], G("embedding.weight"), (int)d.BL, d.C, c.n_symbols, gs, acc, st));
+    }
+    return 0;
+}
+
+}  // namespace msa
+
+extern "C" {
+
 int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, const float* d_mel, const float* d_mel_post,
                        const float* d_gate, float* grads, int acc, float gs, void* stream) {
     MSA_CHECK(h && wsp && params && grads, MSA_E_ARG, "msa_train_backward: null argument");
     MSA_CHECK(h->fwd_valid, MSA_E_STATE, "msa_train_backward: call msa_train_forward first");
-    const Dims d = h->d;
-    const Ws w = ws_layout(d, wsp);
-    MSA_CHECK(ws_bytes >= w.total_bytes, MSA_E_WORKSPACE, "msa_train_backward: workspace too small");
+    MSA_CHECK(h->G == 1, MSA_E_STATE, "msa_train_backward: the last forward was a grouped one (use msa_train_backward_group)");
+    MSA_CHECK(ws_bytes >= ws_layout(h->d, nullptr).total_bytes, MSA_E_WORKSPACE, "msa_train_backward: workspace too small");
     const bool ext = d_mel || d_mel_post || d_gate;
     MSA_CHECK(!ext || (d_mel && d_mel_post && d_gate), MSA_E_ARG, "msa_train_backward: pass all three upstream gradients or none");
-    cudaStream_t st = (cudaStream_t)stream;
-    MSA_CUDA(cudaSetDevice(h->device));
-    MSA_BLAS(cublasSetStream(h->blas, st));
-    MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
-    const msa_config& c = h->cfg;
-    h->in_bwd = true;
-    h->gemm_scratch = w.gemm_lo; h->gemm_scratch_floats = (size_t)w.n_gemm_lo; h->cur_stream = st;
-    const int B = d.B, T = d.T, L = d.L;
-    const auto secs = mask_sections(c, B, T, L);
-    auto mk = [&](int i) { return h->masks + secs[i].off; };
-    const int iPre = d.nEnc, iAttn = d.nEnc + 2, iDec = d.nEnc + 3, iPost = d.nEnc + 4;
-    auto P = [&](const std::string& n) { return params + h->off(n); };
-    auto G = [&](const std::string& n) { return grads + h->off(n); };
-    const float beta = acc ? 1.f : 0.f;
-    const int H4a = 4 * d.Ha, H4d = 4 * d.Hd, H4e = 4 * d.Hh, ldA = d.Pd + d.E, ldD = d.Ha + d.E, ldP = d.Hd + d.E;
-    const std::string at = "decoder.attention_layer.";
+    return train_backward_impl(h, static_cast<char*>(wsp), params, ext ? &d_mel : nullptr, ext ? &d_mel_post : nullptr,
+                               ext ? &d_gate : nullptr, &grads, acc, gs, (cudaStream_t)stream);
+}
 
-    if (ext) {
-        MSA_TRY(k_ref_to_bt(d_mel, w.dpre, B, T, d.M, st));
-        MSA_TRY(k_ref_to_bt(d_mel_post, w.dpost, B, T, d.M, st));
-        MSA_TRY(k_scale_copy(d_gate, w.dgate, d.BT, 1.f, 0, st));
-    }
-    // ---- postnet backward ----
-    const int64_t px = d.BT * d.Cmax;
-    const float* dcur = w.dpost;
-    float* pingpong[2] = {w.bdx0, w.bdx1};
-    for (int i = d.nPost - 1; i >= 0; --i) {
-        const int ci = i == 0 ? d.M : d.Cp, co = i == d.nPost - 1 ? d.M : d.Cp;
-        float* dx = pingpong[i & 1];
-        MSA_TRY(conv_bn_bwd(h, st, params, grads, gs, acc, "postnet.convolutions." + std::to_string(i), w.post_x + i * px,
-                            w.post_y + i * px, dcur, dx, w.bdy, w.post_col + i * d.BT * d.Kp * d.Cmax,
-                            w.bdcol, w.bn_scr,
-                            w.post_bn + i * 2 * d.Cmax, w.post_bn + i * 2 * d.Cmax + d.Cmax, B, T, ci, co, d.Kp,
-                            i < d.nPost - 1 ? 2 : 0, mk(iPost + i), true, w.red_scr));
-        dcur = dx;
-    }
-    // d(pre-postnet mel) = loss term + residual + postnet input (tacotron2nv.py:123-124)
-    MSA_TRY(k_add3(w.dpre, w.dpost, dcur, w.dmel_bt, d.BT * d.M, st));
-    MSA_TRY(k_transpose01(w.dmel_bt, w.dmel_tm, B, T, d.M, st));
-    MSA_TRY(k_transpose01(w.dgate, w.dgate_tm, B, T, 1, st));
-    // ---- projections backward (decoder.py:267-270) ----
-    const float* Wp = P("decoder.linear_projection.linear_layer.weight");
-    const float* Wg = P("decoder.gate_layer.linear_layer.weight");
-    float* gWp = G("decoder.linear_projection.linear_layer.weight");
-    float* gWg = G("decoder.gate_layer.linear_layer.weight");
-    MSA_TRY(gemm(h, false, false, d.TB, d.Hd, d.M, 1.f, w.dmel_tm, d.M, Wp, ldP, 0.f, w.dhd, d.Hd));
-    MSA_TRY(gemm(h, false, false, d.TB, d.Hd, 1, 1.f, w.dgate_tm, 1, Wg, ldP, 1.f, w.dhd, d.Hd));
-    MSA_TRY(gemm(h, false, false, d.TB, d.E, d.M, 1.f, w.dmel_tm, d.M, Wp + d.Hd, ldP, 0.f, w.dctx, d.E));
-    MSA_TRY(gemm(h, false, false, d.TB, d.E, 1, 1.f, w.dgate_tm, 1, Wg + d.Hd, ldP, 1.f, w.dctx, d.E));
-    MSA_TRY(gemm(h, true, false, d.M, d.Hd, d.TB, gs, w.dmel_tm, d.M, w.hd, d.Hd, beta, gWp, ldP));
-    MSA_TRY(gemm(h, true, false, d.M, d.E, d.TB, gs, w.dmel_tm, d.M, w.ctx, d.E, beta, gWp + d.Hd, ldP));
-    MSA_TRY(gemm(h, true, false, 1, d.Hd, d.TB, gs, w.dgate_tm, 1, w.hd, d.Hd, beta, gWg, ldP));
-    MSA_TRY(gemm(h, true, false, 1, d.E, d.TB, gs, w.dgate_tm, 1, w.ctx, d.E, beta, gWg + d.Hd, ldP));
-    MSA_TRY(k_colsum(w.dmel_tm, d.TB, d.M, d.M, G("decoder.linear_projection.linear_layer.bias"), gs, acc, nullptr, w.red_scr, st));
-    MSA_TRY(k_colsum(w.dgate_tm, d.TB, 1, 1, G("decoder.gate_layer.linear_layer.bias"), gs, acc, nullptr, w.red_scr, st));
-    // ---- decoder RNN chain backward ----
-    {
-        LstmRecBwdParams bp{};
-        bp.T = T; bp.B = B; bp.H = d.Hd; bp.ndir = 1;
-        bp.whh = P("decoder.decoder_rnn.weight_hh"); bp.whh_dir_stride = 0;
-        bp.gates = w.gd; bp.cout = w.cd; bp.dh_ext = w.dhd; bp.dz = w.dzd;
-        bp.mask = c.p_dec_dropout > 0.f ? mk(iDec) : nullptr;
-        bp.drop_scale = 1.f / (1.f - c.p_dec_dropout);
-        bp.lengths = nullptr; bp.abort_word = h->abort_dev; bp.prof = prof_ptr(h, w, PROF_DEC_LSTM_BWD); bp.trace = trace_ptr(h, w, PROF_DEC_LSTM_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
-        ProfScope ps(h, PROF_DEC_LSTM_BWD, st);
-        MSA_TRY(launch_lstm_rec_bwd(bp, h->sm_count, h->smem_limit, st));
-    }
-    const float* Wid = P("decoder.decoder_rnn.weight_ih");
-    float* gWid = G("decoder.decoder_rnn.weight_ih");
-    MSA_TRY(gemm(h, false, false, d.TB, d.Ha, H4d, 1.f, w.dzd, H4d, Wid, ldD, 0.f, w.dha, d.Ha));
-    MSA_TRY(gemm(h, false, false, d.TB, d.E, H4d, 1.f, w.dzd, H4d, Wid + d.Ha, ldD, 1.f, w.dctx, d.E));
-    MSA_TRY(gemm(h, true, false, H4d, d.Ha, d.TB, gs, w.dzd, H4d, w.ha, d.Ha, beta, gWid, ldD));
-    MSA_TRY(gemm(h, true, false, H4d, d.E, d.TB, gs, w.dzd, H4d, w.ctx, d.E, beta, gWid + d.Ha, ldD));
-    float* gWhd = G("decoder.decoder_rnn.weight_hh");
-    if (T > 1) {
-        MSA_TRY(gemm(h, true, false, H4d, d.Hd, d.TB - B, gs, w.dzd + (int64_t)B * H4d, H4d, w.hd, d.Hd, beta, gWhd, d.Hd));
-    } else if (!acc) {
-        MSA_CUDA(cudaMemsetAsync(gWhd, 0, sizeof(float) * (size_t)H4d * d.Hd, st));
-    }
-    MSA_TRY(k_colsum(w.dzd, d.TB, H4d, H4d, G("decoder.decoder_rnn.bias_ih"), gs, acc, G("decoder.decoder_rnn.bias_hh"), w.red_scr, st));
-    // ---- context backward: ctx = align . memory ----
-    MSA_TRY(gemm_batched(h, false, true, T, L, d.E, 1.f, w.dctx, (int64_t)B * d.E, d.E, w.memory, d.E, (int64_t)L * d.E, 0.f,
-                         w.da_ext, d.BL, L, B));
-    MSA_TRY(gemm_batched(h, true, false, L, d.E, T, 1.f, w.align_tm, d.BL, L, w.dctx, (int64_t)B * d.E, d.E, 0.f, w.dmem, d.E,
-                         (int64_t)L * d.E, B));
-    // ---- attention chain backward (persistent) ----
-    const bool fa = c.forward_attn != 0, ta = fa && c.trans_agent != 0;
-    const float* Wia = P("decoder.attention_rnn.weight_ih");
-    float* gWia = G("decoder.attention_rnn.weight_ih");
-    MSA_TRY(gemm(h, false, true, d.BL, H4a, d.E, 1.f, w.memory, d.E, Wia + d.Pd, ldA, 0.f, w.mw_pm, H4a));
-    {
-        AttnChainBwdParams bp{};
-        bp.T = T; bp.B = B; bp.L = L; bp.Ha = d.Ha; bp.A = d.A; bp.F = d.F; bp.Kl = d.Kl; bp.norm = c.attn_norm;
-        bp.whh = P("decoder.attention_rnn.weight_hh"); bp.mw_pm = w.mw_pm;
-        bp.wq = P(at + "query_layer.linear_layer.weight");
-        bp.wloc = P(at + "location_layer.location_conv1d.weight");
-        bp.wld = P(at + "location_layer.location_dense.linear_layer.weight");
-        bp.v = P(at + "v.linear_layer.weight");
-        bp.mask = c.p_attn_dropout > 0.f ? mk(iAttn) : nullptr;
-        bp.drop_scale = 1.f / (1.f - c.p_attn_dropout);
-        bp.ga = w.ga; bp.ca = w.ca; bp.align = w.align_tm; bp.s = w.s; bp.znorm = w.znorm;
-        bp.dha_ext = w.dha; bp.da_ext = w.da_ext;
-        bp.dza = w.dza; bp.dq = w.dq; bp.de = w.de; bp.ds = w.ds; bp.dconvf = w.dconvf; bp.dat = w.dat;
-        bp.fa = fa; bp.ta = ta; bp.aplain = w.aplain; bp.fsum = w.fsum; bp.ustash = w.ustash; bp.dzu = w.dzu;
-        if (ta) { bp.mta = w.mta; bp.wta_h = P(at + "ta.weight") + d.E; }
-        bp.abort_word = h->abort_dev; bp.prof = prof_ptr(h, w, PROF_ATTN_BWD); bp.trace = trace_ptr(h, w, PROF_ATTN_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 0;
-        ProfScope ps(h, PROF_ATTN_BWD, st);
-        MSA_TRY(launch_attn_chain_bwd(bp, h->sm_count, h->smem_limit, st));
-    }
-    // ---- deferred attention / attention-RNN parameter gradients ----
-    if (ta) {
-        // transition agent u(t) = sigmoid(W_ta . [ctx(t); h_a'(t)] + b) (forward_attn.py:222-224), dzu [T][B] from the chain
-        float* gWta = G(at + "ta.weight");
-        MSA_TRY(gemm(h, true, false, 1, d.E, d.TB, gs, w.dzu, 1, w.ctx, d.E, beta, gWta, d.E + d.Ha));
-        MSA_TRY(gemm(h, true, false, 1, d.Ha, d.TB, gs, w.dzu, 1, w.ha, d.Ha, beta, gWta + d.E, d.E + d.Ha));
-        MSA_TRY(k_colsum(w.dzu, d.TB, 1, 1, G(at + "ta.bias"), gs, acc, nullptr, w.red_scr, st));
-        // d memory += sum_t alpha(t)^T . (dzu(t) (x) W_ta[:E])   (w.dctx is free after the context backward above)
-        MSA_TRY(gemm(h, false, false, d.TB, d.E, 1, 1.f, w.dzu, 1, P(at + "ta.weight"), d.E + d.Ha, 0.f, w.dctx, d.E));
-        MSA_TRY(gemm_batched(h, true, false, L, d.E, T, 1.f, w.align_tm, d.BL, L, w.dctx, (int64_t)B * d.E, d.E, 1.f, w.dmem, d.E,
-                             (int64_t)L * d.E, B));
-    }
-    const int64_t nfr = d.TB + B;
-    MSA_TRY(gemm(h, false, false, d.TB, d.Pd, H4a, 1.f, w.dza, H4a, Wia, ldA, 0.f, w.dxp, d.Pd));
-    MSA_CUDA(cudaMemsetAsync(w.dxp + d.TB * d.Pd, 0, sizeof(float) * (size_t)B * d.Pd, st));   // last prenet frame is unused (decoder.py:305)
-    MSA_TRY(gemm(h, true, false, H4a, d.Pd, d.TB, gs, w.dza, H4a, w.xpre, d.Pd, beta, gWia, ldA));
-    float* gWha = G("decoder.attention_rnn.weight_hh");
-    if (T > 1) {
-        MSA_TRY(gemm(h, true, false, H4a, d.Ha, d.TB - B, gs, w.dza + (int64_t)B * H4a, H4a, w.ha, d.Ha, beta, gWha, d.Ha));
-        // dMW[b][l][r] = sum_t a[t][b][l] * dz_a[t+1][b][r]
-        MSA_TRY(gemm_batched(h, true, false, L, H4a, T - 1, 1.f, w.align_tm, d.BL, L, w.dza + (int64_t)B * H4a, (int64_t)B * H4a, H4a,
-                             0.f, w.dmw, H4a, (int64_t)L * H4a, B));
-    } else {
-        if (!acc) MSA_CUDA(cudaMemsetAsync(gWha, 0, sizeof(float) * (size_t)H4a * d.Ha, st));
-        MSA_CUDA(cudaMemsetAsync(w.dmw, 0, sizeof(float) * (size_t)d.BL * H4a, st));
-    }
-    MSA_TRY(k_colsum(w.dza, d.TB, H4a, H4a, G("decoder.attention_rnn.bias_ih"), gs, acc, G("decoder.attention_rnn.bias_hh"), w.red_scr, st));
-    MSA_TRY(gemm(h, true, false, H4a, d.E, d.BL, gs, w.dmw, H4a, w.memory, d.E, beta, gWia + d.Pd, ldA));
-    MSA_TRY(gemm(h, false, false, d.BL, d.E, H4a, 1.f, w.dmw, H4a, Wia + d.Pd, ldA, 1.f, w.dmem, d.E));
-    MSA_TRY(gemm(h, true, false, d.A, d.Ha, d.TB, gs, w.dq, d.A, w.ha, d.Ha, beta, G(at + "query_layer.linear_layer.weight"), d.Ha));
-    MSA_TRY(k_sum_over_t(w.ds, w.dpm, T, d.BL * d.A, st));
-    MSA_TRY(gemm(h, true, false, d.A, d.E, d.BL, gs, w.dpm, d.A, w.memory, d.E, beta, G(at + "inputs_layer.linear_layer.weight"), d.E));
-    MSA_TRY(gemm(h, false, false, d.BL, d.E, d.A, 1.f, w.dpm, d.A, P(at + "inputs_layer.linear_layer.weight"), d.E, 1.f, w.dmem, d.E));
-    MSA_TRY(gemm(h, true, false, 1, d.A, d.TBL, gs, w.de, 1, w.s, d.A, beta, G(at + "v.linear_layer.weight"), d.A));
-    MSA_TRY(k_dot_rows(w.de, nullptr, d.TBL, w.loss_part, G(at + "v.linear_layer.bias"), gs, acc, st));
-    MSA_TRY(gemm(h, true, false, d.A, d.F, d.TBL, gs, w.ds, d.A, w.convf, d.F, beta,
-                 G(at + "location_layer.location_dense.linear_layer.weight"), d.F));
-    MSA_TRY(k_wloc_grad(w.dconvf, w.align_tm, w.cum, G(at + "location_layer.location_conv1d.weight"), w.wloc_part, T, B, L, d.F, d.Kl, gs,
-                        acc, st));
-    // ---- prenet backward (decoder.py:9-20) ----
-    MSA_TRY(k_relu_drop_bwd(w.dxp, w.xpre, mk(iPre + 1), 2.f, nfr * d.Pd, st));
-    MSA_TRY(gemm(h, true, false, d.Pd, d.Pd, nfr, gs, w.dxp, d.Pd, w.p1, d.Pd, beta, G("decoder.prenet.layers.1.linear_layer.weight"), d.Pd));
-    MSA_TRY(gemm(h, false, false, nfr, d.Pd, d.Pd, 1.f, w.dxp, d.Pd, P("decoder.prenet.layers.1.linear_layer.weight"), d.Pd, 0.f, w.dp1, d.Pd));
-    MSA_TRY(k_relu_drop_bwd(w.dp1, w.p1, mk(iPre), 2.f, nfr * d.Pd, st));
-    MSA_TRY(gemm(h, true, false, d.Pd, d.M, nfr, gs, w.dp1, d.Pd, w.frames, d.M, beta, G("decoder.prenet.layers.0.linear_layer.weight"), d.M));
-    // ---- memory -> encoder output + speaker path (tacotron2nv.py:104-111) ----
-    MSA_TRY(k_split_dmemory(w.dmem, w.denc_h, c.spk_mode ? w.dspk : nullptr, B, L, d.Hh, d.Ds, st));
-    if (c.spk_mode == 1) {
-        MSA_TRY(gemm(h, true, false, d.Ds, d.Dsin, B, gs, w.dspk, d.Ds, h->spk_in, d.Dsin, beta, G("speaker_lin.weight"), d.Dsin));
-        MSA_TRY(k_colsum(w.dspk, B, d.Ds, d.Ds, G("speaker_lin.bias"), gs, acc, nullptr, w.red_scr, st));
-    } else if (c.spk_mode == 2) {
-        MSA_TRY(k_embedding_bwd(w.dspk, h->spk_ids, G("speaker_embedder.weight"), B, d.Ds, c.num_speakers, gs, acc, st));
-    }
-    // ---- encoder BiLSTM backward ----
-    {
-        LstmRecBwdParams bp{};
-        bp.T = L; bp.B = B; bp.H = d.Hh; bp.ndir = 2;
-        bp.whh = P("encoder.lstm.weight_hh_l0");
-        bp.whh_dir_stride = h->off("encoder.lstm.weight_hh_l0_reverse") - h->off("encoder.lstm.weight_hh_l0");
-        bp.gates = w.enc_g; bp.cout = w.enc_c; bp.dh_ext = w.denc_h; bp.dz = w.dzx; bp.mask = nullptr; bp.drop_scale = 1.f;
-        bp.lengths = h->tok_len; bp.abort_word = h->abort_dev; bp.prof = prof_ptr(h, w, PROF_ENC_LSTM_BWD); bp.trace = trace_ptr(h, w, PROF_ENC_LSTM_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
-        ProfScope ps(h, PROF_ENC_LSTM_BWD, st);
-        MSA_TRY(launch_lstm_rec_bwd(bp, h->sm_count, h->smem_limit, st));
-    }
-    for (int dir = 0; dir < 2; ++dir) {
-        const std::string sfx = dir ? "_reverse" : "";
-        const float* dzx = w.dzx + (int64_t)dir * d.BL * H4e;
-        const float* eh = w.enc_h + (int64_t)dir * d.BL * d.Hh;
-        MSA_TRY(gemm(h, false, false, d.BL, d.C, H4e, 1.f, dzx, H4e, P("encoder.lstm.weight_ih_l0" + sfx), d.C, dir ? 1.f : 0.f, w.dx3_tm, d.C));
-        MSA_TRY(gemm(h, true, false, H4e, d.C, d.BL, gs, dzx, H4e, w.x3_tm, d.C, beta, G("encoder.lstm.weight_ih_l0" + sfx), d.C));
-        float* gWhh = G("encoder.lstm.weight_hh_l0" + sfx);
-        if (L > 1) {
-            if (dir == 0)   // z(t) uses h(t-1)
-                MSA_TRY(gemm(h, true, false, H4e, d.Hh, d.BL - B, gs, dzx + (int64_t)B * H4e, H4e, eh, d.Hh, beta, gWhh, d.Hh));
-            else            // reverse direction: z(t) uses h(t+1)
-                MSA_TRY(gemm(h, true, false, H4e, d.Hh, d.BL - B, gs, dzx, H4e, eh + (int64_t)B * d.Hh, d.Hh, beta, gWhh, d.Hh));
-        } else if (!acc) {
-            MSA_CUDA(cudaMemsetAsync(gWhh, 0, sizeof(float) * (size_t)H4e * d.Hh, st));
-        }
-        MSA_TRY(k_colsum(dzx, d.BL, H4e, H4e, G("encoder.lstm.bias_ih_l0" + sfx), gs, acc, G("encoder.lstm.bias_hh_l0" + sfx), w.red_scr, st));
-    }
-    // ---- encoder convolutions backward ----
-    const int64_t ex = d.BL * d.C;
-    float* epp[2] = {w.edx0, w.edx1};
-    MSA_TRY(k_transpose01(w.dx3_tm, epp[d.nEnc & 1], L, B, d.C, st));   // [L][B][C] -> [B][L][C]
-    dcur = epp[d.nEnc & 1];
-    for (int i = d.nEnc - 1; i >= 0; --i) {
-        float* dx = epp[i & 1];
-        MSA_TRY(conv_bn_bwd(h, st, params, grads, gs, acc, "encoder.convolutions." + std::to_string(i), w.enc_x + i * ex,
-                            w.enc_y + i * ex, dcur, dx, w.edy, w.enc_col + i * d.BL * d.Kc * d.C,
-                            w.edcol, w.bn_scr, w.enc_bn + i * 2 * d.C, w.enc_bn + i * 2 * d.C + d.C, B, L, d.C, d.C, d.Kc, 1, mk(i),
-                            true, w.red_scr));
-        dcur = dx;
-    }
-    MSA_TRY(k_embedding_bwd(dcur, h->tokens, G("embedding.weight"), (int)d.BL, d.C, c.n_symbols, gs, acc, st));
-    return 0;
+int msa_train_backward_group(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, float* const* grads, int acc, float gs,
+                             void* stream) {
+    MSA_CHECK(h && wsp && params && grads, MSA_E_ARG, "msa_train_backward_group: null argument");
+    MSA_CHECK(h->fwd_valid, MSA_E_STATE, "msa_train_backward_group: call msa_train_forward_group first");
+    MSA_CHECK(ws_bytes >= (size_t)h->G * std::max<size_t>(h->ws_stride, 1), MSA_E_WORKSPACE, "msa_train_backward_group: workspace too small");
+    for (int g = 0; g < h->G; ++g) MSA_CHECK(grads[g] != nullptr, MSA_E_ARG, "msa_train_backward_group: null gradient buffer of task %d", g);
+    return train_backward_impl(h, static_cast<char*>(wsp), params, nullptr, nullptr, nullptr, grads, acc, gs, (cudaStream_t)stream);
 }
 
 int msa_check_abort(msa_handle* h, void* wsp, void* stream) {

@@ -257,6 +257,62 @@ class Engine:
         _lib.check(rc, "msa_train_backward")
         self.launches += 1
 
+    # ---- task groups: the theta_0 train-split passes of several tasks as one pass ------------------------------
+    GROUP_MAX = 8
+
+    def group_size(self, n_tasks: int, B: int) -> int:
+        """Largest number of tasks one grouped pass may carry: at most 8 tasks and 32 rows per shared recurrence launch."""
+        return max(1, min(n_tasks, self.GROUP_MAX, 32 // max(B, 1)))
+
+    def _ptr_array(self, tensors):
+        return (C.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+
+    def forward_group(self, params: torch.Tensor, bn_stats: Sequence[Optional[torch.Tensor]], batches_dev: Sequence[dict],
+                      masks: Sequence[torch.Tensor]) -> torch.Tensor:
+        """One grouped forward of ``len(batches_dev)`` tasks from the SAME weights (include/msa_b200.h "task groups").  Returns the
+        per-task losses [G] (device).  All tasks must share B, T, L."""
+        G = len(batches_dev)
+        B, L = batches_dev[0]["inputs"].shape
+        T = batches_dev[0]["melspecs"].shape[2]
+        for bd in batches_dev:
+            if tuple(bd["inputs"].shape) != (B, L) or bd["melspecs"].shape[2] != T:
+                raise ValueError("forward_group: all tasks of a group must have the same B, T, L")
+        need = int(self.lib.msa_group_workspace_bytes(self.h, G, B, T, L))
+        if self._ws is None or self._ws.numel() < need + 256:
+            self._ws = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+        self._group = (G, B, T, L, int(self.lib.msa_group_workspace_bytes(self.h, 1, B, T, L)))
+        loss = torch.empty(G, device=self.device)
+        spk = [bd["speaker_vecs"] for bd in batches_dev]
+        fl = spk[0].dtype.is_floating_point
+        self._keep = (params, list(bn_stats), list(batches_dev), list(masks))
+        A = self._ptr_array
+        rc = self.lib.msa_train_forward_group(
+            self.h, G, self._ws_ptr(), C.c_size_t(self._ws.numel() - 256), _ptr(params), A(list(bn_stats)),
+            A([bd["inputs"] for bd in batches_dev]), A([bd["input_lengths"] for bd in batches_dev]),
+            A([bd["melspecs"] for bd in batches_dev]), A([bd["melspec_lengths"] for bd in batches_dev]),
+            A(spk) if fl else None, None if fl else A(spk), A([bd["stop"] for bd in batches_dev]), A(list(masks)), B, T, L,
+            _ptr(loss), _stream())
+        _lib.check(rc, "msa_train_forward_group")
+        self.launches += 1
+        return loss
+
+    def backward_group(self, params: torch.Tensor, grads: Sequence[torch.Tensor], accumulate: bool = False, scale: float = 1.0) -> None:
+        """grads[g] <- (or +=) scale * d loss_g / d params for every task of the last ``forward_group``."""
+        rc = self.lib.msa_train_backward_group(self.h, self._ws_ptr(), C.c_size_t(self._ws.numel() - 256), _ptr(params),
+                                               self._ptr_array(list(grads)), int(accumulate), C.c_float(scale), _stream())
+        _lib.check(rc, "msa_train_backward_group")
+        self.launches += 1
+
+    def group_ws_ptr(self, g: int):
+        a = (self._ws.data_ptr() + 255) // 256 * 256
+        return C.c_void_p(a + g * self._group[4])
+
+    def mcd_group(self, g: int, mel_lengths: torch.Tensor, which: int = 0) -> torch.Tensor:
+        out = torch.empty(1, device=self.device)
+        _lib.check(self.lib.msa_train_mcd(self.h, self.group_ws_ptr(g), _ptr(mel_lengths), int(which), _ptr(out), _stream()), "msa_train_mcd")
+        self.launches += 3
+        return out
+
     def loss(self, stop: torch.Tensor, mel_lengths: torch.Tensor, reduction: str = "none", pos_weight: float = 10.0) -> torch.Tensor:
         """Tacotron2Loss on the outputs of the last forward (tacotron2nv_loss.py:17-52)."""
         out = torch.empty(1, device=self.device)

@@ -115,3 +115,42 @@ def test_full_size_fomaml_meta_gradient_is_the_mean_of_the_task_gradients():
     want = acc / n
     assert float((meta.double() - want).norm()) < 2e-6 * float(want.norm())
     assert abs(float(log["grad_sumsq"]) ** 0.5 - float(want.norm())) < 1e-5 * float(want.norm())
+
+
+def _group_case(cfg, G, B, T, L, tf32):
+    from msa_tts_b200.engine import Engine, batch_to_device
+    eng = Engine(cfg, gemm_tf32=tf32)
+    flat = eng.flat_from_dict(synth.init_params(cfg, 3))
+    bds = [batch_to_device(synth.make_batch(cfg, B, T, L, 500 + g), eng.device) for g in range(G)]
+    masks = [eng.generate_masks(B, T, L, 900 + g) for g in range(G)]
+    return eng, flat, bds, masks
+
+
+@pytest.mark.parametrize("shape", [("small", 3, 3, 11, 9, 0), ("small", 8, 4, 9, 8, 1), ("default", 2, 4, 12, 20, 1), ("default", 8, 4, 10, 16, 1)])
+def test_grouped_pass_equals_the_passes_one_by_one(shape):
+    """msa_train_forward_group / msa_train_backward_group (the theta_0 train passes of a meta-batch as ONE pass, maml.py:38-54):
+    per-task losses, BatchNorm running statistics and parameter gradients equal those of G separate passes.  Under the strict
+    fp32 policy the recurrences run task by task inside the group (bitwise equal); under the tensor-core policy the grouped
+    kernels run them with bf16x3 products (tolerance 2e-4 of the gradient norm, north_star allows 1e-3)."""
+    which, G, B, T, L, tf32 = shape
+    cfg = pkg.small_params() if which == "small" else pkg.default_params()
+    eng, flat, bds, masks = _group_case(cfg, G, B, T, L, tf32)
+    bn_g = [eng.new_bn_stats() for _ in range(G)]
+    grads_g = [eng.new_flat() for _ in range(G)]
+    loss_g = eng.forward_group(flat, bn_g, bds, masks)
+    eng.backward_group(flat, grads_g)
+    torch.cuda.synchronize()
+    eng.check_abort()
+    for g in range(G):
+        bn, gr = eng.new_bn_stats(), eng.new_flat()
+        _, loss = eng.forward(flat, bn, bds[g], masks[g], outputs=False)
+        eng.backward(flat, gr)
+        torch.cuda.synchronize()
+        gn = float(gr.double().norm())
+        e_loss = abs(float(loss_g[g]) - float(loss)) / abs(float(loss))
+        e_bn = float((bn_g[g] - bn).double().norm() / bn.double().norm())
+        e_g = float((grads_g[g] - gr).double().norm()) / gn
+        print(f"task {g}: loss {e_loss:.2e} bn {e_bn:.2e} grad {e_g:.2e}")
+        tol = 1e-6 if tf32 == 0 else 2e-4
+        assert e_loss < tol and e_bn < tol and e_g < tol, (g, e_loss, e_bn, e_g)
+    eng.check_abort()
