@@ -559,10 +559,13 @@ struct TaskIO {
 
 // Grouped chain launches (chain_mma.cu) are used when the configuration is inside what those kernels implement; otherwise the
 // tasks of a group run the single-task persistent kernels one after the other (same results, no sharing of the hand-offs).
-static bool use_mma_chains(const msa_handle* h, int G, int B, int T, int L) {
-    if (h->mma_mode == 0 || h->cfg.gemm_tf32 < 1) return false;          // strict-fp32 policy: no tensor-core arithmetic at all
+static bool use_mma_chains(const msa_handle* h, int G, int B, int T, int L, bool attn) {
+    if (h->mma_mode == 0 || (h->cfg.gemm_tf32 < 1 && h->mma_mode != 4)) return false;   // strict-fp32 policy: no tensor-core arithmetic
+                                                                                         // (mode 4, tests: force the grouped kernels)
     if (h->mma_mode == 1 && G == 1) return false;
-    return chain_mma_supported(h->cfg, G, B, T, L, h->sm_count, h->smem_limit);
+    if (h->mma_mode == 3 && attn) return false;                           // development: LSTM recurrences only
+    return attn ? attn_chain_mma_supported(h->cfg, G, B, T, L, h->sm_count, h->smem_limit)
+                : chain_mma_supported(h->cfg, G, B, T, L, h->sm_count, h->smem_limit);
 }
 
 // One teacher-forced forward pass for G tasks that share `params` (the theta_0 train-split passes of a meta-batch, maml.py:38-54):
@@ -584,7 +587,7 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
     const auto secs = mask_sections(c, B, T, L);
     const int iPre = d.nEnc, iAttn = d.nEnc + 2, iDec = d.nEnc + 3, iPost = d.nEnc + 4;
     auto P = [&](const std::string& n) { return params + h->off(n); };
-    const bool mma = use_mma_chains(h, G, B, T, L);
+    const bool mma = use_mma_chains(h, G, B, T, L, false), mma_attn = use_mma_chains(h, G, B, T, L, true);
     const int64_t tstride = (int64_t)(ws_stride / sizeof(float));
     const int H4e = 4 * d.Hh;
     const std::string at = "decoder.attention_layer.";
@@ -689,7 +692,7 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
             return ap;
         };
         ProfScope ps(h, PROF_ATTN_FWD, st);
-        if (mma) {
+        if (mma_attn) {
             AttnChainParams ap = make(0);
             ap.G = G; ap.tstride = tstride;
             for (int g = 0; g < G; ++g) ap.mask_g[g] = c.p_attn_dropout > 0.f ? ios[g].masks + secs[iAttn].off : nullptr;
@@ -925,7 +928,7 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
     const std::string at = "decoder.attention_layer.";
     const bool fa = c.forward_attn != 0, ta = fa && c.trans_agent != 0;
     const float* Wia = P("decoder.attention_rnn.weight_ih");
-    const bool mma = use_mma_chains(h, NG, B, T, L);
+    const bool mma = use_mma_chains(h, NG, B, T, L, false), mma_attn = use_mma_chains(h, NG, B, T, L, true);
     const int64_t tstride = (int64_t)(ws_stride / sizeof(float));
 
     // ---- stage 1: postnet and projections ----
@@ -1051,7 +1054,7 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
             return bp;
         };
         ProfScope ps(h, PROF_ATTN_BWD, st);
-        if (mma) {
+        if (mma_attn) {
             AttnChainBwdParams bp = make(0);
             bp.G = NG; bp.tstride = tstride;
             for (int g = 0; g < NG; ++g) bp.mask_g[g] = c.p_attn_dropout > 0.f ? h->masks[g] + secs[iAttn].off : nullptr;

@@ -126,13 +126,19 @@ def _group_case(cfg, G, B, T, L, tf32):
     return eng, flat, bds, masks
 
 
-@pytest.mark.parametrize("shape", [("small", 3, 3, 11, 9, 0), ("small", 8, 4, 9, 8, 1), ("default", 2, 4, 12, 20, 1), ("default", 8, 4, 10, 16, 1)])
-def test_grouped_pass_equals_the_passes_one_by_one(shape):
+@pytest.mark.parametrize("shape", [("small", 3, 3, 11, 9, 0, 1), ("small", 8, 4, 9, 8, 0, 4), ("small", 5, 3, 9, 8, 0, 4), ("small", 1, 5, 9, 8, 0, 4),
+                                   ("default", 2, 4, 12, 20, 0, 4), ("default", 8, 4, 10, 16, 0, 4), ("default", 3, 6, 10, 16, 0, 4),
+                                   ("default", 8, 4, 10, 16, 1, 1)])
+def test_grouped_pass_equals_the_passes_one_by_one(shape, monkeypatch):
     """msa_train_forward_group / msa_train_backward_group (the theta_0 train passes of a meta-batch as ONE pass, maml.py:38-54):
-    per-task losses, BatchNorm running statistics and parameter gradients equal those of G separate passes.  Under the strict
-    fp32 policy the recurrences run task by task inside the group (bitwise equal); under the tensor-core policy the grouped
-    kernels run them with bf16x3 products (tolerance 2e-4 of the gradient norm, north_star allows 1e-3)."""
-    which, G, B, T, L, tf32 = shape
+    per-task losses, BatchNorm running statistics and parameter gradients equal those of G separate passes.
+    * strict fp32 policy, default kernel choice: the recurrences run task by task inside the group -- equal to rounding;
+    * fp32 GEMMs with the grouped tensor-core kernels FORCED (MSA_CHAIN_MMA=4, a test mode): their bf16x3 gate products against
+      the fp32 FMA recurrences of the single-task kernels -- 5e-5 of the gradient norm;
+    * the bench policy (TF32 backward GEMMs, grouped kernels by default): 1e-3, the north star's TF32-path tolerance (TF32
+      operand rounding turns the 1e-5 differences of the recurrences into ~1e-4 differences of the weight gradients)."""
+    which, G, B, T, L, tf32, mode = shape
+    monkeypatch.setenv("MSA_CHAIN_MMA", str(mode))
     cfg = pkg.small_params() if which == "small" else pkg.default_params()
     eng, flat, bds, masks = _group_case(cfg, G, B, T, L, tf32)
     bn_g = [eng.new_bn_stats() for _ in range(G)]
@@ -141,16 +147,19 @@ def test_grouped_pass_equals_the_passes_one_by_one(shape):
     eng.backward_group(flat, grads_g)
     torch.cuda.synchronize()
     eng.check_abort()
+    monkeypatch.setenv("MSA_CHAIN_MMA", "0")
+    from msa_tts_b200.engine import Engine
+    ref = Engine(cfg, gemm_tf32=tf32)             # single-task fp32-FMA recurrences
     for g in range(G):
-        bn, gr = eng.new_bn_stats(), eng.new_flat()
-        _, loss = eng.forward(flat, bn, bds[g], masks[g], outputs=False)
-        eng.backward(flat, gr)
+        bn, gr = ref.new_bn_stats(), ref.new_flat()
+        _, loss = ref.forward(flat, bn, bds[g], masks[g], outputs=False)
+        ref.backward(flat, gr)
         torch.cuda.synchronize()
         gn = float(gr.double().norm())
         e_loss = abs(float(loss_g[g]) - float(loss)) / abs(float(loss))
         e_bn = float((bn_g[g] - bn).double().norm() / bn.double().norm())
         e_g = float((grads_g[g] - gr).double().norm()) / gn
         print(f"task {g}: loss {e_loss:.2e} bn {e_bn:.2e} grad {e_g:.2e}")
-        tol = 1e-6 if tf32 == 0 else 2e-4
+        tol = 1e-3 if tf32 else (5e-5 if mode == 4 else 1e-6)
         assert e_loss < tol and e_bn < tol and e_g < tol, (g, e_loss, e_bn, e_g)
-    eng.check_abort()
+    ref.check_abort()
