@@ -456,6 +456,473 @@ int coop_launch(Kern kern, const Params& p, int sm_count, size_t smem, cudaStrea
     return 0;
 }
 
+// =====================================================================================================================
+// Attention chain, forward (same recurrence as attn_chain.cu::k_attn_chain_fwd without the forward-attention options):
+//     z_a(t) = XW[t] + MW . a(t-1) + W_hh . h_a'(t-1);  h_a'(t) = dropout(LSTMCell);  q(t) = W_q . h_a'(t)
+//     e(t) = v . tanh(q + loc(a(t-1), cum(t-1)) + PM) + b_v;  a(t) = normalise(e(t))            (decoder.py:253-258, forward_attn.py:121-131)
+// for R = G*B rows.  CTA roles as there (unit owner / position owner / query owner); three hand-offs per step (h, q, e).
+// The W_hh product and the query projection are ONE tensor-core tile: the CTA's gate rows sit in local rows gate*8 + ul
+// (ul < U <= 7) and the W_q row of the owned attention dim in the free slot ul = 7 of gate 0, so q(t)[r] falls out of the same
+// mma as "gate i of pseudo-unit 7".  The context term MW . a(t-1) streams the CTA's MW rows from L2 (they are 1 MB per batch row
+// and cannot be resident for a whole group).
+// =====================================================================================================================
+struct AttnFwdMmaLay {
+    size_t afrag, part, as_, ah, wldT, wloc, vs, pm, pre, cf, zm, qs, epos, total;     // byte offsets
+    int KS, LP, LH, CKP, NPmax, NRown, RP;
+};
+__host__ __device__ inline AttnFwdMmaLay attn_fwd_mma_layout(int R, int L, int Ha, int A, int F, int Kl, int ncta, int NT) {
+    AttnFwdMmaLay s;
+    s.KS = (Ha + 255) / 256;
+    s.LP = round_up_i(L, 4);
+    s.LH = round_up_i(L + Kl - 1, 4);
+    s.CKP = 2 * Kl + 1;
+    s.NPmax = (R * L + ncta - 1) / ncta;
+    s.NRown = (s.NPmax + L - 2) / L + 1;          // batch rows a run of NPmax consecutive positions can touch
+    s.RP = round_up_i(R, 4);
+    const int NTP = NT < 2 ? NT : 2;              // partial tiles are reduced two n tiles at a time
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return r; };
+    s.afrag = take((size_t)kMW * s.KS * 2 * 2 * 32 * sizeof(uint4));
+    // partial tiles; the gathered energies [R*L] and the gathered queries [NRown][A] reuse the region later in the step
+    size_t pbytes = (size_t)kMW * NTP * 2 * 4 * 32 * sizeof(float);
+    const size_t gbytes = ((size_t)R * L + (size_t)s.NRown * A) * sizeof(float) + 32;
+    if (gbytes > pbytes) pbytes = gbytes;
+    s.part = take(pbytes);
+    s.as_ = take((size_t)R * s.LP * sizeof(float));
+    s.ah = take((size_t)2 * s.NRown * s.LH * sizeof(float));
+    s.wldT = take((size_t)F * A * sizeof(float));
+    s.wloc = take((size_t)F * s.CKP * sizeof(float));
+    s.vs = take((size_t)A * sizeof(float));
+    s.pm = take((size_t)s.NPmax * A * sizeof(float));
+    s.pre = take((size_t)s.NPmax * A * sizeof(float));
+    s.cf = take((size_t)s.NPmax * F * sizeof(float));
+    s.zm = take((size_t)32 * s.RP * sizeof(float));
+    s.total = o;
+    return s;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float zn_s[kBMax];
+    const int T = p.T, L = p.L, Ha = p.Ha, A = p.A, F = p.F, Kl = p.Kl, H4 = 4 * Ha;
+    const Grp gr{p.G, p.B, p.G * p.B, p.tstride};
+    const int R = gr.R, Bt = gr.Bt, BtL = Bt * L, RL = R * L, pl = (Kl - 1) / 2;
+    const int ncta = gridDim.x, cta = blockIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lg = lane >> 2, lj = lane & 3;
+    const AttnFwdMmaLay lay = attn_fwd_mma_layout(R, L, Ha, A, F, Kl, ncta, NT);
+    const int KS = lay.KS, LP = lay.LP, LH = lay.LH, CKP = lay.CKP, RP = lay.RP;
+    constexpr int NTP = NT < 2 ? NT : 2;
+    uint4* Afrag = reinterpret_cast<uint4*>(smem_raw + lay.afrag);
+    float* part = reinterpret_cast<float*>(smem_raw + lay.part);
+    float* es = part;                                  // [R*L]        gathered energies (after the tile reduction)
+    float* q_s = part + ((RL + 3) & ~3);               // [NRown][A]   gathered queries of the owned rows
+    float* as_ = reinterpret_cast<float*>(smem_raw + lay.as_);     // [R][LP]   a(t-1)
+    float* ah = reinterpret_cast<float*>(smem_raw + lay.ah);       // [2][NRown][LH] a(t-1), cum(t-1) of the owned rows, zero halo
+    float* wldT = reinterpret_cast<float*>(smem_raw + lay.wldT);   // [F][A]
+    float* wloc_s = reinterpret_cast<float*>(smem_raw + lay.wloc); // [F][CKP]
+    float* vs = reinterpret_cast<float*>(smem_raw + lay.vs);
+    float* pm_s = reinterpret_cast<float*>(smem_raw + lay.pm);     // [np][A]
+    float* pre_s = reinterpret_cast<float*>(smem_raw + lay.pre);   // [np][A]  loc + pm, then v * tanh(.)
+    float* cf_s = reinterpret_cast<float*>(smem_raw + lay.cf);     // [np][F]
+    float* zm = reinterpret_cast<float*>(smem_raw + lay.zm);       // [32][RP] context term of the local gate rows
+
+    const int u0 = part_lo(cta, Ha, ncta), u1 = part_lo(cta + 1, Ha, ncta), U = u1 - u0;
+    const int p0 = part_lo(cta, RL, ncta), p1 = part_lo(cta + 1, RL, ncta), np = p1 - p0;
+    const int d0 = part_lo(cta, A, ncta), d1 = part_lo(cta + 1, A, ncta);
+    const bool has_q = d1 > d0;                        // at most one attention dim per CTA (launcher checks A <= ncta, U <= 7)
+    const int r_lo = np > 0 ? p0 / L : 0, r_hi = np > 0 ? (p1 - 1) / L : -1, nrown = r_hi - r_lo + 1;
+    // position pp = r*L + l of the group -> offset inside a [.. per task ..][Bt*L] array of task g = r / Bt
+    auto pos_task = [&](int pp) { return (pp / L) / Bt; };
+
+    // ---- one-time staging ----
+    for (int idx = threadIdx.x; idx < kMW * KS * 2 * 32; idx += kMT) {
+        const int ln = idx & 31, mt = (idx >> 5) & 1, s = (idx >> 6) % KS, ww = (idx >> 6) / KS;
+        const int g = ln >> 2, j = ln & 3;
+        const int col = (ww * KS + s) * 16 + 4 * j;
+        float v[2][4];
+#pragma unroll
+        for (int hr = 0; hr < 2; ++hr) {
+            const int rl = mt * 16 + hr * 8 + g;
+            const int gate = rl >> 3, ul = rl & 7;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float x = 0.f;
+                if (col + c < Ha) {
+                    if (ul < U) x = __ldg(p.whh + (size_t)(gate * Ha + u0 + ul) * Ha + col + c);
+                    else if (has_q && ul == 7 && gate == 0) x = __ldg(p.wq + (size_t)d0 * Ha + col + c);
+                }
+                v[hr][c] = x;
+            }
+        }
+        uint4 hi, lo;
+        split2(v[0][0], v[0][1], hi.x, lo.x);
+        split2(v[1][0], v[1][1], hi.y, lo.y);
+        split2(v[0][2], v[0][3], hi.z, lo.z);
+        split2(v[1][2], v[1][3], hi.w, lo.w);
+        const size_t o = (((size_t)ww * KS + s) * 2 + mt) * 2 * 32;
+        Afrag[o + ln] = hi;
+        Afrag[o + 32 + ln] = lo;
+    }
+    for (int idx = threadIdx.x; idx < F * 2 * Kl; idx += kMT) {
+        const int f = idx / (2 * Kl), ck = idx % (2 * Kl);
+        wloc_s[f * CKP + ck] = __ldg(p.wloc + idx);
+    }
+    for (int idx = threadIdx.x; idx < A * F; idx += kMT) {
+        const int d = idx / F, f = idx % F;
+        wldT[f * A + d] = __ldg(p.wld + idx);
+    }
+    for (int idx = threadIdx.x; idx < A; idx += kMT) vs[idx] = __ldg(p.v + idx);
+    for (int idx = threadIdx.x; idx < np * A; idx += kMT) {
+        const int pi = idx / A, d = idx - pi * A, pp = p0 + pi, g = pos_task(pp);
+        pm_s[idx] = __ldg(p.pm + g * gr.tstride + (size_t)(pp - g * BtL) * A + d);
+    }
+    for (int idx = threadIdx.x; idx < R * LP; idx += kMT) as_[idx] = 0.f;
+    for (int idx = threadIdx.x; idx < 2 * lay.NRown * LH; idx += kMT) ah[idx] = 0.f;
+    for (int idx = threadIdx.x; idx < 32 * RP; idx += kMT) zm[idx] = 0.f;
+    for (int i = threadIdx.x; i < np; i += kMT) {       // cum fed to the conv at t = 0
+        const int pp = p0 + i, g = pos_task(pp);
+        p.cum[g * gr.tstride + (pp - g * BtL)] = 0.f;
+    }
+    const float bv = __ldg(p.bv);
+
+    // point-wise role: thread c < NT*64 owns cell (slot ul, row r); slot 7 of a query-owning CTA is the query "cell"
+    const int c_nt = threadIdx.x >> 6, c_par = (threadIdx.x >> 5) & 1, c_ln = threadIdx.x & 31;
+    const int c_ul = c_ln >> 2, c_r = c_nt * 8 + (c_ln & 3) * 2 + c_par;
+    const bool c_in = (int)threadIdx.x < NT * 64 && c_r < R;
+    const bool pw = c_in && c_ul < U, qcell = c_in && has_q && c_ul == 7;
+    const int c_g = c_in ? gr.task(c_r) : 0, c_b = c_in ? gr.brow(c_r) : 0, c_u = u0 + c_ul;
+    const float* xw_c = p.xw + c_g * gr.tstride;
+    float* ha_c = p.ha + c_g * gr.tstride;
+    float* ca_c = p.ca + c_g * gr.tstride;
+    float* ga_c = p.ga + c_g * gr.tstride;
+    float* q_c = p.q + c_g * gr.tstride;
+    const uint8_t* mask_c = pw ? (p.G > 1 ? p.mask_g[c_g] : p.mask) : nullptr;
+    float xz[4] = {0.f, 0.f, 0.f, 0.f}, zacc[4] = {0.f, 0.f, 0.f, 0.f}, cstate = 0.f;
+    unsigned char mk = 1;
+    auto fetch = [&](int t) {
+        const size_t zb = ((size_t)t * Bt + c_b) * H4;
+#pragma unroll
+        for (int gate = 0; gate < 4; ++gate) xz[gate] = __ldg(xw_c + zb + (size_t)gate * Ha + c_u);
+        if (mask_c) mk = mask_c[((size_t)t * Bt + c_b) * Ha + c_u];
+    };
+    if (pw) fetch(0);
+
+    // streaming role of the tile product: lane (lg, lj) of warp w loads h[row nt*8 + lg][4 columns] per k16 step
+    const float* hrow[NT];
+    bool rowok[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const int r = nt * 8 + lg;
+        rowok[nt] = r < R;
+        const int rr = rowok[nt] ? r : 0;
+        hrow[nt] = p.ha + gr.task(rr) * gr.tstride + (size_t)gr.brow(rr) * Ha;
+    }
+    const bool vecL = (L & 3) == 0;
+    SpinGuard sg(p.abort_word);
+    ChainProf<true> prof;      // per-phase cycles of thread 0 when a buffer is passed (profiles/), one predictable branch otherwise
+    prof.start(p.prof, nullptr, 0);
+    __syncthreads();
+
+    for (int t = 0; t < T; ++t) {
+        // ---- P1: context term zm[rl][r] = sum_l MW[row rl][r][l] * a(t-1)[r][l] (zero at t = 0: zm starts zeroed) ----
+        if (t > 0 && U > 0) {
+            // one dot product per half-warp: pair index = (gate*U + ul) * R + r; the MW loads of eight pairs are issued before the
+            // first one is used (the slice streams from L2: it is 4*U*R*L floats per step)
+            const int npair = 4 * U * R, hw = lane >> 4, hl = lane & 15;
+            constexpr int PB = 8;
+            for (int base = w * 2 + hw; base < npair; base += kMW * 2 * PB) {
+                const float* mrow[PB];
+                int prl[PB], pr[PB];
+                bool ok[PB];
+#pragma unroll
+                for (int k = 0; k < PB; ++k) {
+                    const int pi = base + k * kMW * 2;
+                    ok[k] = pi < npair;
+                    const int pq = ok[k] ? pi : 0;
+                    const int gu = pq / R, r = pq - gu * R, gate = gu / U, ul = gu - gate * U;
+                    prl[k] = gate * 8 + ul;
+                    pr[k] = r;
+                    mrow[k] = p.mw_rm + gr.task(r) * gr.tstride + (size_t)(gate * Ha + u0 + ul) * BtL + (size_t)gr.brow(r) * L;
+                }
+                float acc[PB];
+                if (vecL && L <= 64) {
+                    float4 mv[PB];
+#pragma unroll
+                    for (int k = 0; k < PB; ++k)
+                        mv[k] = (ok[k] && hl * 4 < L) ? __ldcg(reinterpret_cast<const float4*>(mrow[k]) + hl) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < PB; ++k)
+                        acc[k] = hl * 4 < L ? dot4(mv[k], *reinterpret_cast<const float4*>(as_ + pr[k] * LP + hl * 4)) : 0.f;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < PB; ++k) {
+                        acc[k] = 0.f;
+                        if (ok[k])
+                            for (int l = hl; l < L; l += 16) acc[k] += __ldcg(mrow[k] + l) * as_[pr[k] * LP + l];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < PB; ++k) {
+                    float a = acc[k];
+                    a += __shfl_xor_sync(0xffffffffu, a, 1);
+                    a += __shfl_xor_sync(0xffffffffu, a, 2);
+                    a += __shfl_xor_sync(0xffffffffu, a, 4);
+                    a += __shfl_xor_sync(0xffffffffu, a, 8);
+                    if (hl == 0 && ok[k]) zm[prl[k] * RP + pr[k]] = a;
+                }
+            }
+        }
+        prof.mark(0, t);
+        __syncthreads();
+        // ---- P2: attention LSTMCell of the owned cells; publishes h_a'(t) ----
+        if (pw) {
+            float z[4];
+#pragma unroll
+            for (int gate = 0; gate < 4; ++gate) z[gate] = zacc[gate] + xz[gate] + zm[(gate * 8 + c_ul) * RP + c_r];
+            const float ai = fast_sigmoid(z[0]), af = fast_sigmoid(z[1]), ag = fast_tanh(z[2]), ao = fast_sigmoid(z[3]);
+            const float cn = af * cstate + ai * ag;
+            cstate = cn;
+            float hv = ao * fast_tanh(cn);
+            if (mask_c) hv = mk ? hv * p.drop_scale : 0.f;
+            const size_t hb = ((size_t)t * Bt + c_b) * Ha + c_u, zb = ((size_t)t * Bt + c_b) * H4;
+            st_pub(ha_c + hb, hv);
+            ca_c[hb] = cn;
+            ga_c[zb + 0 * (size_t)Ha + c_u] = ai;
+            ga_c[zb + 1 * (size_t)Ha + c_u] = af;
+            ga_c[zb + 2 * (size_t)Ha + c_u] = ag;
+            ga_c[zb + 3 * (size_t)Ha + c_u] = ao;
+            if (t + 1 < T) fetch(t + 1);
+        }
+        prof.mark(1, t);
+        // ---- P3 (shadow of the h hand-off): location features of the owned positions (forward_attn.py:121-127) ----
+        for (int base = 0; base < np * F * 8; base += kMT) {
+            const int it = base + threadIdx.x;
+            const bool valid = it < np * F * 8;
+            const int ks = it & 7, f = valid ? (it >> 3) % F : 0, pi = valid ? (it >> 3) / F : 0;
+            const int pp = p0 + pi, r = pp / L, l = pp - r * L, ro = r - r_lo;
+            float cf = 0.f;
+            if (valid)
+                for (int ck = ks; ck < 2 * Kl; ck += 8) {
+                    const int c = ck >= Kl ? 1 : 0, k = ck - c * Kl;
+                    cf += wloc_s[f * CKP + ck] * ah[(c * lay.NRown + ro) * LH + l + k];
+                }
+            cf += __shfl_xor_sync(0xffffffffu, cf, 1);
+            cf += __shfl_xor_sync(0xffffffffu, cf, 2);
+            cf += __shfl_xor_sync(0xffffffffu, cf, 4);
+            if (valid && ks == 0) {
+                cf_s[pi * F + f] = cf;
+                const int g = r / Bt;
+                p.convf[g * gr.tstride + ((size_t)t * BtL + (pp - g * BtL)) * F + f] = cf;
+            }
+        }
+        __syncthreads();
+        if ((A & 3) == 0) {       // four attention dims per thread: one 128-bit weight load per filter
+            for (int it = threadIdx.x; it < np * (A >> 2); it += kMT) {
+                const int pi = it / (A >> 2), d = (it - pi * (A >> 2)) * 4;
+                float4 acc = *reinterpret_cast<const float4*>(pm_s + pi * A + d);
+                for (int f = 0; f < F; ++f) {
+                    const float4 wv = *reinterpret_cast<const float4*>(wldT + f * A + d);
+                    const float c = cf_s[pi * F + f];
+                    acc.x += wv.x * c; acc.y += wv.y * c; acc.z += wv.z * c; acc.w += wv.w * c;
+                }
+                *reinterpret_cast<float4*>(pre_s + pi * A + d) = acc;
+            }
+        } else {
+            for (int it = threadIdx.x; it < np * A; it += kMT) {
+                const int pi = it / A, d = it - pi * A;
+                float l0 = pm_s[it];
+                for (int f = 0; f < F; ++f) l0 += wldT[f * A + d] * cf_s[pi * F + f];
+                pre_s[it] = l0;
+            }
+        }
+        prof.mark(2, t);
+        // ---- hand-off 1: h_a'(t) of every row; tile product [gate rows + query row] x h_a'(t) ----
+        {
+            const int rl_ = R - 1;
+            const float* hlast = p.ha + gr.task(rl_) * gr.tstride + ((size_t)t * Bt + gr.brow(rl_)) * Ha;
+            gate_wait(ncta, [&](int c) { const int e = part_lo(c + 1, Ha, ncta); return e > part_lo(c, Ha, ncta) ? hlast + e - 1 : nullptr; }, sg);
+            __syncthreads();
+        }
+        prof.mark(3, t);
+        {
+            float acc[NT][2][4];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[nt][mt][i] = 0.f;
+            const size_t toff = (size_t)t * Bt * Ha;
+            constexpr int PF = MSA_PF_FWD;
+            float4 hv[PF][NT];
+            auto issue = [&](int s, float4 (&dst)[NT]) {
+                const int col = (w * KS + s) * 16 + 4 * lj;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+                    dst[nt] = (rowok[nt] && col < Ha) ? ld_poll4(hrow[nt] + toff + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            auto process = [&](int s, float4 (&cur)[NT]) {
+                const int col = (w * KS + s) * 16 + 4 * lj;
+                uint32_t bhi[NT][2], blo[NT][2];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    if (rowok[nt] && col < Ha) {
+                        sg.reset();
+                        while (!ready4(cur[nt])) {
+                            if (sg.bail()) break;
+                            cur[nt] = ld_poll4(hrow[nt] + toff + col);
+                        }
+                    }
+                    split2(cur[nt].x, cur[nt].y, bhi[nt][0], blo[nt][0]);
+                    split2(cur[nt].z, cur[nt].w, bhi[nt][1], blo[nt][1]);
+                }
+                const uint4* af = Afrag + ((size_t)w * KS + s) * 2 * 2 * 32;
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const uint4 ahi = af[(mt * 2 + 0) * 32 + lane], alo = af[(mt * 2 + 1) * 32 + lane];
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) mma3(acc[nt][mt], ahi, alo, bhi[nt], blo[nt]);
+                }
+            };
+#pragma unroll
+            for (int i = 0; i < PF; ++i)
+                if (i < KS) issue(i, hv[i]);
+            for (int s0 = 0; s0 < KS; s0 += PF) {
+#pragma unroll
+                for (int i = 0; i < PF; ++i) {
+                    const int s = s0 + i;
+                    if (s < KS) {
+                        process(s, hv[i]);
+                        if (s + PF < KS) issue(s + PF, hv[i]);
+                    }
+                }
+            }
+            // cross-warp reduction of the K slices, two n tiles per round; the cell threads keep the sums in registers
+#pragma unroll
+            for (int rd = 0; rd < (NT + 1) / 2; ++rd) {
+                if (rd > 0) __syncthreads();
+#pragma unroll
+                for (int k = 0; k < NTP; ++k) {
+                    const int nt = rd * 2 + k;
+                    if (nt < NT) {
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) part[((((size_t)w * NTP + k) * 2 + mt) * 4 + i) * 32 + lane] = acc[nt][mt][i];
+                    }
+                }
+                __syncthreads();
+                if (c_in && (c_nt >> 1) == rd && (pw || qcell)) {
+                    const int k = c_nt & 1;
+#pragma unroll
+                    for (int gate = 0; gate < 4; ++gate) {
+                        float sum = 0.f;
+                        const float* pp = part + ((((size_t)k) * 2 + (gate >> 1)) * 4 + (gate & 1) * 2 + c_par) * 32 + c_ln;
+#pragma unroll
+                        for (int ww = 0; ww < kMW; ++ww) sum += pp[(size_t)ww * NTP * 2 * 4 * 32];
+                        zacc[gate] = sum;
+                    }
+                    if (qcell) st_pub(q_c + ((size_t)t * Bt + c_b) * A + d0, zacc[0]);      // q(t)[r][d0]
+                }
+            }
+        }
+        prof.mark(4, t);
+        __syncthreads();      // the partial-tile region becomes the gather buffer
+        // ---- hand-off 2: queries of the owned rows ----
+        if ((A & 3) == 0) {
+            for (int i = threadIdx.x; i < nrown * (A >> 2); i += kMT) {
+                const int ro = i / (A >> 2), d4 = i - ro * (A >> 2), r = r_lo + ro;
+                reinterpret_cast<float4*>(q_s)[i] = poll4(p.q + gr.task(r) * gr.tstride + ((size_t)t * Bt + gr.brow(r)) * A + d4 * 4, sg);
+            }
+        } else {
+            for (int i = threadIdx.x; i < nrown * A; i += kMT) {
+                const int ro = i / A, d = i - ro * A, r = r_lo + ro;
+                q_s[i] = poll1(p.q + gr.task(r) * gr.tstride + ((size_t)t * Bt + gr.brow(r)) * A + d, sg);
+            }
+        }
+        __syncthreads();
+        prof.mark(5, t);
+        // ---- P5: energies of the owned positions (forward_attn.py:128-131); publishes e(t) ----
+        for (int it = threadIdx.x; it < np * A; it += kMT) {
+            const int pi = it / A, d = it - pi * A, pp = p0 + pi, r = pp / L, g = r / Bt;
+            const float sv = fast_tanh(q_s[(r - r_lo) * A + d] + pre_s[it]);
+            p.s[g * gr.tstride + ((size_t)t * BtL + (pp - g * BtL)) * A + d] = sv;
+            pre_s[it] = vs[d] * sv;
+        }
+        __syncthreads();
+        for (int pi = w; pi < np; pi += kMW) {
+            float e = 0.f;
+            for (int d = lane; d < A; d += 32) e += pre_s[pi * A + d];
+            e = warp_sum(e);
+            if (lane == 0) {
+                const int pp = p0 + pi, g = pos_task(pp);
+                st_pub(p.e + g * gr.tstride + (size_t)t * BtL + (pp - g * BtL), e + bv);
+            }
+        }
+        prof.mark(6, t);
+        // ---- hand-off 3: all energies of step t; a(t) = normalise(e(t)); cum += a(t) (forward_attn.py:200-210) ----
+        if ((BtL & 3) == 0) {      // 128-bit polls: one L2 round trip for the whole gather
+            for (int i4 = threadIdx.x; i4 < (RL >> 2); i4 += kMT) {
+                const int i = i4 * 4, g = i / BtL;
+                reinterpret_cast<float4*>(es)[i4] = poll4(p.e + g * gr.tstride + (size_t)t * BtL + (i - g * BtL), sg);
+            }
+        } else {
+            for (int i = threadIdx.x; i < RL; i += kMT) {
+                const int g = pos_task(i);
+                es[i] = poll1(p.e + g * gr.tstride + (size_t)t * BtL + (i - g * BtL), sg);
+            }
+        }
+        __syncthreads();
+        for (int r = w; r < R; r += kMW) {
+            float m = 0.f;
+            if (p.norm == 0) {
+                m = -INFINITY;
+                for (int l = lane; l < L; l += 32) m = fmaxf(m, es[r * L + l]);
+                m = warp_max(m);
+            }
+            float sum = 0.f;
+            for (int l = lane; l < L; l += 32) {
+                const float x = p.norm == 0 ? __expf(es[r * L + l] - m) : fast_sigmoid(es[r * L + l]);
+                es[r * L + l] = x;
+                sum += x;
+            }
+            sum = warp_sum(sum);
+            const float inv = 1.f / sum;
+            const bool own = r >= r_lo && r <= r_hi;
+            for (int l = lane; l < L; l += 32) {
+                const float a = es[r * L + l] * inv;
+                as_[r * LP + l] = a;
+                if (own) {
+                    ah[(0 * lay.NRown + (r - r_lo)) * LH + pl + l] = a;
+                    ah[(1 * lay.NRown + (r - r_lo)) * LH + pl + l] += a;
+                }
+            }
+            if (lane == 0) zn_s[r] = sum;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < np; i += kMT) {
+            const int pp = p0 + i, r = pp / L, l = pp - r * L, g = r / Bt;
+            const size_t o = g * gr.tstride + (size_t)(pp - g * BtL);
+            p.align[o + (size_t)t * BtL] = as_[r * LP + l];
+            if (t + 1 < T) p.cum[o + (size_t)(t + 1) * BtL] = ah[(1 * lay.NRown + (r - r_lo)) * LH + pl + l];
+        }
+        if (cta == 0 && (int)threadIdx.x < R) {
+            const int r = threadIdx.x;
+            p.znorm[gr.task(r) * gr.tstride + (size_t)t * Bt + gr.brow(r)] = zn_s[r];
+        }
+        prof.mark(7, t);
+    }
+}
+
+static bool attn_fwd_mma_ok(const msa_config& cfg, int R, int L, int sm_count, size_t smem_limit) {
+    const int Ha = cfg.attn_rnn_dim, A = cfg.attn_dim;
+    if (cfg.forward_attn || R < 1 || R > 32 || Ha % 4 != 0 || cfg.loc_filters > 32) return false;
+    if (A > sm_count) return false;                                  // one query dim per CTA
+    if ((Ha + sm_count - 1) / sm_count > 7) return false;          // slot 7 of the tile is the query row
+    return attn_fwd_mma_layout(R, L, Ha, A, cfg.loc_filters, cfg.loc_kernel, sm_count, (R + 7) / 8).total + 256 <= smem_limit;
+}
+
 }  // namespace
 
 int launch_lstm_rec_fwd_mma(const LstmRecParams& p0, int sm_count, size_t smem_limit, cudaStream_t st) {
@@ -495,10 +962,34 @@ bool chain_mma_supported(const msa_config& cfg, int G, int B, int T, int L, int 
     return lstm_mma_ok(R, cfg.dec_rnn_dim, 1, sm_count, smem_limit) && lstm_mma_ok(R, cfg.enc_dim / 2, 2, sm_count, smem_limit);
 }
 bool attn_chain_mma_supported(const msa_config& cfg, int G, int B, int T, int L, int sm_count, size_t smem_limit) {
+    (void)T;
+    return attn_fwd_mma_ok(cfg, G * B, L, sm_count, smem_limit);
+}
+int launch_attn_chain_fwd_mma(const AttnChainParams& p0, int sm_count, size_t smem_limit, cudaStream_t st) {
+    AttnChainParams p = p0;
+    if (p.G < 1) p.G = 1;
+    const int R = p.G * p.B, NT = (R + 7) / 8;
+    MSA_CHECK(!p.fa && R <= 32 && p.A <= sm_count && (p.Ha + sm_count - 1) / sm_count <= 7, MSA_E_UNSUPPORTED,
+              "attn_chain_fwd_mma: configuration outside the grouped kernel (rows %d, attention dim %d)", R, p.A);
+    const size_t smem = attn_fwd_mma_layout(R, p.L, p.Ha, p.A, p.F, p.Kl, sm_count, NT).total;
+    MSA_CHECK(smem <= smem_limit, MSA_E_UNSUPPORTED, "attn_chain_fwd_mma: needs %zu bytes of shared memory (> %zu)", smem, smem_limit);
+    const size_t TB = (size_t)p.T * p.B;
+    for (int g = 0; g < p.G; ++g) {       // canaries of the three hand-off arrays of every task (common.cuh)
+        MSA_TRY(k_fill_canary(p.ha + g * p.tstride, (int64_t)(TB * p.Ha), st));
+        MSA_TRY(k_fill_canary(p.q + g * p.tstride, (int64_t)(TB * p.A), st));
+        MSA_TRY(k_fill_canary(p.e + g * p.tstride, (int64_t)(TB * p.L), st));
+    }
+    switch (NT) {
+        case 1: return coop_launch(k_attn_fwd_mma<1>, p, sm_count, smem, st);
+        case 2: return coop_launch(k_attn_fwd_mma<2>, p, sm_count, smem, st);
+        case 3: return coop_launch(k_attn_fwd_mma<3>, p, sm_count, smem, st);
+        default: return coop_launch(k_attn_fwd_mma<4>, p, sm_count, smem, st);
+    }
+}
+bool attn_chain_bwd_mma_supported(const msa_config& cfg, int G, int B, int T, int L, int sm_count, size_t smem_limit) {
     (void)cfg; (void)G; (void)B; (void)T; (void)L; (void)sm_count; (void)smem_limit;
     return false;
 }
-int launch_attn_chain_fwd_mma(const AttnChainParams&, int, size_t, cudaStream_t) { set_error("attn_chain_fwd_mma: not built"); return MSA_E_UNSUPPORTED; }
 int launch_attn_chain_bwd_mma(const AttnChainBwdParams&, int, size_t, cudaStream_t) { set_error("attn_chain_bwd_mma: not built"); return MSA_E_UNSUPPORTED; }
 
 }  // namespace msa

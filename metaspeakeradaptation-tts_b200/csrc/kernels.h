@@ -152,7 +152,8 @@ int launch_attn_chain_bwd(const AttnChainBwdParams& p, int sm_count, size_t smem
 // Same arithmetic as the kernels above for G tasks at once (R = G*B <= 32 rows per hand-off); the per-step gate products run on the
 // tensor cores as bf16x3 split products (hi.hi + hi.lo + lo.hi, fp32 accumulation: ~1e-5 relative, inside the TF32-path tolerance).
 bool chain_mma_supported(const msa_config& cfg, int G, int B, int T, int L, int sm_count, size_t smem_limit);        // LSTM recurrences
-bool attn_chain_mma_supported(const msa_config& cfg, int G, int B, int T, int L, int sm_count, size_t smem_limit);   // attention chain
+bool attn_chain_mma_supported(const msa_config& cfg, int G, int B, int T, int L, int sm_count, size_t smem_limit);   // attention chain, forward
+bool attn_chain_bwd_mma_supported(const msa_config& cfg, int G, int B, int T, int L, int sm_count, size_t smem_limit);   // ... backward
 int launch_lstm_rec_fwd_mma(const LstmRecParams& p, int sm_count, size_t smem_limit, cudaStream_t st);
 int launch_lstm_rec_bwd_mma(const LstmRecBwdParams& p, int sm_count, size_t smem_limit, cudaStream_t st);
 int launch_attn_chain_fwd_mma(const AttnChainParams& p, int sm_count, size_t smem_limit, cudaStream_t st);

@@ -928,7 +928,8 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
     const std::string at = "decoder.attention_layer.";
     const bool fa = c.forward_attn != 0, ta = fa && c.trans_agent != 0;
     const float* Wia = P("decoder.attention_rnn.weight_ih");
-    const bool mma = use_mma_chains(h, NG, B, T, L, false), mma_attn = use_mma_chains(h, NG, B, T, L, true);
+    const bool mma = use_mma_chains(h, NG, B, T, L, false);
+    const bool mma_attn = use_mma_chains(h, NG, B, T, L, true) && attn_chain_bwd_mma_supported(h->cfg, NG, B, T, L, h->sm_count, h->smem_limit);
     const int64_t tstride = (int64_t)(ws_stride / sizeof(float));
 
     // ---- stage 1: postnet and projections ----
