@@ -33,17 +33,26 @@ class MAML(MetaTrainer):
         losses, mcds = [], []
         if not mine:
             self.meta_grad.zero_()
-        for j, i in enumerate(mine):
-            task = items_b[speakers[i]]
-            self._adapt(i, task["train"], n_inner)
-            inputs, _ = self._unpack_batch(task["test"])
-            B, L = inputs["inputs"].shape
-            T = inputs["melspecs"].shape[2]
-            _, loss = eng.forward(self.fast, self.task_bn, inputs, self._masks(i, n_inner, B, T, L), outputs=False)
-            mcds.append(eng.mcd(inputs["melspec_lengths"]))      # maml.py:78-82, on the device: no copy of the mels, no host sync
-            # task_grads = autograd.grad(loss_test, fmodel.parameters(time=-1)); mix_grad weight 1/N (maml.py:73-74, 94-98)
-            eng.backward(self.fast, self.meta_grad, accumulate=(j > 0), scale=1.0 / N)
-            losses.append(loss)
+        train = {i: items_b[speakers[i]]["train"] for i in mine}
+        j = 0
+        for group in self._group_plan(mine, train):
+            if len(group) == 1:
+                self._adapt(group[0], train[group[0]], n_inner)
+                slots = [(self.fast, self.task_grad, self.task_bn)]
+            else:       # first inner step of the whole group as one pass (the recurrences share their per-step hand-offs)
+                self._adapt_group(group, train, n_inner)
+                slots = [self._slot(k) for k in range(len(group))]
+            for k, i in enumerate(group):
+                fast, _, bn = slots[k]
+                inputs, _ = self._unpack_batch(items_b[speakers[i]]["test"])
+                B, L = inputs["inputs"].shape
+                T = inputs["melspecs"].shape[2]
+                _, loss = eng.forward(fast, bn, inputs, self._masks(i, n_inner, B, T, L), outputs=False)
+                mcds.append(eng.mcd(inputs["melspec_lengths"]))      # maml.py:78-82, on the device: no copy of the mels, no host sync
+                # task_grads = autograd.grad(loss_test, fmodel.parameters(time=-1)); mix_grad weight 1/N (maml.py:73-74, 94-98)
+                eng.backward(fast, self.meta_grad, accumulate=(j > 0), scale=1.0 / N)
+                losses.append(loss)
+                j += 1
         sumsq = self._outer_update()
         local = torch.cat(losses) if losses else torch.zeros(0, device=self.device)
         mcd = torch.cat(mcds) if mcds else torch.zeros(0, device=self.device)

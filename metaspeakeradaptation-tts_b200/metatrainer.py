@@ -63,6 +63,7 @@ class MetaTrainer:
         self.step_global = 0
         self.mask_seed = int(params.get("dataset_random_seed", 1234))
         self._mask_bufs: Dict[tuple, torch.Tensor] = {}
+        self._slots: list = []
         self.injected_masks = None       # parity tests: {(task_index, pass_index): reference-layout mask dict}
         if params.get("finetune", False):
             self._load_checkpoint()
@@ -74,11 +75,12 @@ class MetaTrainer:
         stop = d["stop"]
         return d, stop
 
-    def _masks(self, task_index: int, pass_index: int, B: int, T: int, L: int) -> torch.Tensor:
-        """Dropout keep-masks for one pass, keyed by (meta-step, task, pass) -- independent of sharding."""
+    def _masks(self, task_index: int, pass_index: int, B: int, T: int, L: int, slot: int = 0) -> torch.Tensor:
+        """Dropout keep-masks for one pass, keyed by (meta-step, task, pass) -- independent of sharding and of task grouping
+        (``slot`` only selects the buffer: the passes of a group need their masks alive at the same time)."""
         if self.injected_masks is not None:
             return self.engine.pack_masks(self.injected_masks[(task_index, pass_index)], B, T, L)
-        key = (B, T, L)
+        key = (B, T, L, slot)
         if key not in self._mask_bufs:
             self._mask_bufs[key] = torch.empty(self.engine.mask_bytes(B, T, L), dtype=torch.uint8, device=self.device)
         seed = (self.mask_seed * 1000003 + self.step_global) * 1000003 + task_index * 64 + pass_index
@@ -114,6 +116,77 @@ class MetaTrainer:
                              nesterov=h.get("nesterov", False), buf=self.inner_buf, first_step=(it == 0))
             losses.append(loss)
         return losses
+
+    # ---- grouped first inner step ------------------------------------------------------------------------------
+    def _group_plan(self, mine: List[int], batches: Dict[int, tuple]) -> List[List[int]]:
+        """Tasks whose FIRST inner step can share one grouped pass (include/msa_b200.h "task groups"): every task of a meta-batch
+        starts from the same theta (maml.py:38-41), so the train-split passes of tasks with equal (B, T, L) run as one pass whose
+        recurrences hand their data over once per step for all rows.  Later inner steps have per-task weights and run one by one.
+        Returns lists of task indices; singletons take the plain path."""
+        n_inner = self.params["n_inner_train"]
+        h = self.inner
+        stateful = (h["name"] == "Adam") or bool(h.get("momentum", 0.0))
+        if n_inner < 1 or not self.params.get("group_tasks", True) or (stateful and n_inner > 1):
+            return [[i] for i in mine]
+        by_shape: Dict[tuple, List[int]] = {}
+        for i in mine:
+            b = batches[i]
+            by_shape.setdefault((tuple(b[1].shape), b[3].shape[2]), []).append(i)
+        plan = []
+        for (shape, _), idx in by_shape.items():
+            gmax = self.engine.group_size(len(idx), shape[0])
+            for k in range(0, len(idx), gmax):
+                plan.append(idx[k:k + gmax])
+        plan.sort(key=lambda g: g[0])
+        return plan
+
+    def _slot(self, k: int):
+        """Per-slot fast weights / gradient / BatchNorm buffers of a group (slot 0 = the buffers of the plain path)."""
+        while len(self._slots) <= k:
+            if not self._slots:
+                self._slots.append((self.fast, self.task_grad, self.task_bn))
+            else:
+                self._slots.append((self.engine.new_flat(), self.engine.new_flat(), self.engine.new_bn_stats()))
+        return self._slots[k]
+
+    def _inner_step(self, src, grad, dst, it: int) -> None:
+        eng, h = self.engine, self.inner
+        if h["name"] == "Adam":
+            eng.adam_step(src, grad, dst, self.inner_m, self.inner_v, lr=h["lr"], step=it + 1,
+                          betas=h.get("betas", (0.9, 0.999)), eps=h.get("eps", 1e-8), weight_decay=h.get("weight_decay", 0.0))
+        else:
+            eng.sgd_step(src, grad, p_out=dst, lr=h["lr"], momentum=h.get("momentum", 0.0),
+                         dampening=h.get("dampening", 0.0), weight_decay=h.get("weight_decay", 0.0),
+                         nesterov=h.get("nesterov", False), buf=self.inner_buf, first_step=(it == 0))
+
+    def _adapt_group(self, group: List[int], batches: Dict[int, tuple], n_inner: int):
+        """First inner step of all tasks of ``group`` as ONE grouped pass from theta, then the remaining inner steps task by task.
+        Afterwards slot k holds the adapted weights and the private BatchNorm statistics of task group[k]."""
+        eng = self.engine
+        slots = [self._slot(k) for k in range(len(group))]
+        bds = []
+        for k, i in enumerate(group):
+            slots[k][2].copy_(self.base_bn)
+            bds.append(self._unpack_batch(batches[i])[0])
+        B, L = bds[0]["inputs"].shape
+        T = bds[0]["melspecs"].shape[2]
+        masks = [self._masks(i, 0, B, T, L, slot=k) for k, i in enumerate(group)]
+        losses = eng.forward_group(self.theta, [s[2] for s in slots], bds, masks)
+        eng.backward_group(self.theta, [s[1] for s in slots])
+        for k in range(len(group)):
+            if self.inner["name"] == "Adam":
+                self.inner_m.zero_()
+                self.inner_v.zero_()
+            self._inner_step(self.theta, slots[k][1], slots[k][0], 0)
+        out = [[losses[k:k + 1]] for k in range(len(group))]
+        for k, i in enumerate(group):
+            for it in range(1, n_inner):
+                fast, grad, bn = slots[k]
+                _, loss = eng.forward(fast, bn, bds[k], self._masks(i, it, B, T, L), outputs=False)
+                eng.backward(fast, grad)
+                self._inner_step(fast, grad, fast, it)
+                out[k].append(loss)
+        return out
 
     # ---- outer update (maml.py:94-105 / reptile.py:82-89) ----------------------------------------------
     def _outer_update(self) -> torch.Tensor:

@@ -84,13 +84,18 @@ def test_full_size_backward_is_linear_in_the_upstream_gradients():
     assert rel(gs, 0.125 * g1) < 1e-6
 
 
-def test_full_size_fomaml_meta_gradient_is_the_mean_of_the_task_gradients():
+@pytest.mark.parametrize("grouped", [False, True])
+def test_full_size_fomaml_meta_gradient_is_the_mean_of_the_task_gradients(grouped):
     """BASELINE configs[1] (8 tasks, 1 inner SGD step, bench GEMM policy): the meta-gradient that the test-split backward passes
     accumulate in their epilogues (meta_grad += g/8) equals the mean of the 8 task gradients computed one by one into separate
-    buffers (utils/grad_utils.py:23-31), and the task losses agree bit for bit."""
+    buffers (utils/grad_utils.py:23-31).  Without task grouping the task losses agree bit for bit and the gradients to 2e-6;
+    with the first inner steps of the 8 tasks grouped into one pass (the bench's default: bf16x3 tensor-core recurrences for
+    the train split) the adapted weights differ by ~1e-5 of the inner update, the test losses by < 1e-6 and the meta-gradient
+    stays inside the TF32-path tolerance of the north star (1e-3; measured ~1e-4: TF32 operand rounding of the backward GEMMs)."""
     import bench
     from msa_tts_b200.maml import MAML
     params = bench.trainer_params(1)
+    params["group_tasks"] = grouped
     params["optim_outer"] = {"optimizer_name": "SGD", "optim_params": {"lr": "0.0"}}       # keep theta: the tasks are re-run below
     tr = MAML(**params)
     items = bench.make_tasks(tr.model_params, pinned=False)
@@ -109,12 +114,17 @@ def test_full_size_fomaml_meta_gradient_is_the_mean_of_the_task_gradients():
         _, loss = eng.forward(tr.fast, tr.task_bn, inputs, tr._masks(i, 1, B, T, L), outputs=False)
         eng.backward(tr.fast, g)
         torch.cuda.synchronize()
-        assert torch.equal(loss, losses[i:i + 1])
+        if grouped:
+            assert abs(float(loss) - float(losses[i])) < 1e-5 * abs(float(loss))
+        else:
+            assert torch.equal(loss, losses[i:i + 1])
         acc += g.double()
     eng.check_abort()
     want = acc / n
-    assert float((meta.double() - want).norm()) < 2e-6 * float(want.norm())
-    assert abs(float(log["grad_sumsq"]) ** 0.5 - float(want.norm())) < 1e-5 * float(want.norm())
+    err = float((meta.double() - want).norm()) / float(want.norm())
+    print(f"grouped={grouped}: meta-gradient vs mean of one-by-one task gradients {err:.2e}")
+    assert err < (1e-3 if grouped else 2e-6)
+    assert abs(float(log["grad_sumsq"]) ** 0.5 - float(want.norm())) < (1e-3 if grouped else 1e-5) * float(want.norm())
 
 
 def _group_case(cfg, G, B, T, L, tf32):
