@@ -923,6 +923,483 @@ static bool attn_fwd_mma_ok(const msa_config& cfg, int R, int L, int sm_count, s
     return attn_fwd_mma_layout(R, L, Ha, A, cfg.loc_filters, cfg.loc_kernel, sm_count, (R + 7) / 8).total + 256 <= smem_limit;
 }
 
+// =====================================================================================================================
+// Attention chain, backward (reverse-time counterpart of k_attn_fwd_mma; same arithmetic as attn_chain.cu::k_attn_chain_bwd
+// without the forward-attention options) for R = G*B rows.  Per step t, descending:
+//   A  dz_a(t+1) arrives: context-path term of the owned positions pout = MWp . dz_a(t+1) (one warp per position, MWp rows
+//      streamed from L2); publishes d a(t) of the owned positions
+//   C  recurrent term dz_a(t+1) . W_hh for the owned units: bf16x3 tensor-core tile, accumulators stay in registers
+//   D  d a(t) of every position arrives; normalisation backward -> d e(t); dq of the owned attention dim; dS, d(conv features)
+//      of the owned positions; publishes dq(t), dconvf(t)
+//   F  dq(t) arrives: dq(t) . W_q for the owned units goes into the SAME accumulators (eight more k16 steps), one cross-warp
+//      reduction, LSTM point-wise backward; publishes dz_a(t)
+//   H  dconvf(t) of the +-pad neighbours arrives: location-conv backward -> d a(t-1) ("previous alignment" channel) and the
+//      running d cum
+// =====================================================================================================================
+struct AttnBwdMmaLay {
+    size_t bfrag, bq, part, das, als, wld, wloc, vs, dss, dcw, small, total;      // byte offsets
+    int KS, KQ, NPmax, NRown, CKP, WIN, FP;
+};
+__host__ __device__ inline AttnBwdMmaLay attn_bwd_mma_layout(int R, int L, int Ha, int A, int F, int Kl, int ncta, int MTL) {
+    AttnBwdMmaLay s;
+    s.KS = (4 * Ha + 255) / 256;
+    s.KQ = (A + 15) / 16;
+    s.CKP = 2 * Kl + 1;
+    s.FP = F + 1;
+    s.NPmax = (R * L + ncta - 1) / ncta;
+    s.NRown = (s.NPmax + L - 2) / L + 1;
+    s.WIN = s.NPmax + Kl - 1 < L ? s.NPmax + Kl - 1 : L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return r; };
+    s.bfrag = take((size_t)kMW * s.KS * 2 * 32 * sizeof(uint2));
+    s.bq = take((size_t)s.KQ * 2 * 32 * sizeof(uint2));
+    // partial tiles [kMW][MTL][4][32]; earlier in the step the region holds tq [R*L] and the dconvf partials [4][NPmax][F]
+    size_t pb = (size_t)kMW * MTL * 4 * 32 * sizeof(float);
+    const size_t alt = ((size_t)((R * L + 3) & ~3) + (size_t)4 * s.NPmax * F) * sizeof(float);
+    if (alt > pb) pb = alt;
+    s.part = take(pb);
+    s.das = take((size_t)R * L * sizeof(float));
+    s.als = take((size_t)R * L * sizeof(float));
+    s.wld = take((size_t)A * F * sizeof(float));
+    s.wloc = take((size_t)F * s.CKP * sizeof(float));
+    s.vs = take((size_t)A * sizeof(float));
+    s.dss = take((size_t)s.NPmax * A * sizeof(float));
+    s.dcw = take((size_t)s.NRown * s.WIN * s.FP * sizeof(float));
+    s.small = take((size_t)(3 * s.NPmax + 64) * sizeof(float));
+    s.total = o;
+    return s;
+}
+
+template <int MTL>
+__global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float zn_s[kBMax];
+    const int T = p.T, L = p.L, Ha = p.Ha, A = p.A, F = p.F, Kl = p.Kl, H4 = 4 * Ha;
+    const Grp gr{p.G, p.B, p.G * p.B, p.tstride};
+    const int R = gr.R, Bt = gr.Bt, BtL = Bt * L, RL = R * L, pl = (Kl - 1) / 2;
+    const int ncta = gridDim.x, cta = blockIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lg = lane >> 2, lj = lane & 3;
+    const AttnBwdMmaLay lay = attn_bwd_mma_layout(R, L, Ha, A, F, Kl, ncta, MTL);
+    const int KS = lay.KS, KQ = lay.KQ, CKP = lay.CKP, WIN = lay.WIN, FP = lay.FP;
+    uint2* Bfrag = reinterpret_cast<uint2*>(smem_raw + lay.bfrag);    // [kMW][KS][hi|lo][32]  W_hh^T slice
+    uint2* Bq = reinterpret_cast<uint2*>(smem_raw + lay.bq);          // [KQ][hi|lo][32]       W_q^T slice
+    float* part = reinterpret_cast<float*>(smem_raw + lay.part);
+    float* tq_s = part;                                                // [R*L]      d e * (1 - s^2) for the owned attention dim
+    float* dcp_s = part + ((RL + 3) & ~3);                             // [4][np][F] partial d(conv features)
+    float* das = reinterpret_cast<float*>(smem_raw + lay.das);        // [R*L]      d a(t), then d e(t)
+    float* als = reinterpret_cast<float*>(smem_raw + lay.als);        // [R*L]      a(t)
+    float* wld_s = reinterpret_cast<float*>(smem_raw + lay.wld);      // [A][F]
+    float* wloc_s = reinterpret_cast<float*>(smem_raw + lay.wloc);    // [F][CKP]
+    float* vs = reinterpret_cast<float*>(smem_raw + lay.vs);
+    float* ds_s = reinterpret_cast<float*>(smem_raw + lay.dss);       // [np][A]
+    float* dcw = reinterpret_cast<float*>(smem_raw + lay.dcw);        // [NRown][WIN][FP] gathered d(conv features) window
+    float* gcum_s = reinterpret_cast<float*>(smem_raw + lay.small);   // [np] running d cum
+    float* dprev_s = gcum_s + lay.NPmax;                               // [np] d a(t-1) through the "previous alignment" channel
+    float* pout_s = dprev_s + lay.NPmax;                               // [np]
+
+    const int u0 = part_lo(cta, Ha, ncta), u1 = part_lo(cta + 1, Ha, ncta), U = u1 - u0;
+    const int p0 = part_lo(cta, RL, ncta), p1 = part_lo(cta + 1, RL, ncta), np = p1 - p0;
+    const int d0 = part_lo(cta, A, ncta), d1 = part_lo(cta + 1, A, ncta);
+    const bool has_q = d1 > d0;
+    const int r_lo = np > 0 ? p0 / L : 0, r_hi = np > 0 ? (p1 - 1) / L : -1, nrown = r_hi - r_lo + 1;
+    auto pos_task = [&](int pp) { return (pp / L) / Bt; };
+    // window of output positions whose conv features feed the owned positions of own row ro: [wlo(ro), whi(ro)]
+    auto own_lmin = [&](int ro) { return ro == 0 ? p0 - r_lo * L : 0; };
+    auto own_lmax = [&](int ro) { return ro == nrown - 1 ? (p1 - 1) - r_hi * L : L - 1; };
+    auto wlo = [&](int ro) { const int a = own_lmin(ro) - pl; return a > 0 ? a : 0; };
+    auto whi = [&](int ro) { const int a = own_lmax(ro) + pl; return a < L - 1 ? a : L - 1; };
+
+    // ---- one-time staging ----
+    for (int idx = threadIdx.x; idx < kMW * KS * 32; idx += kMT) {
+        const int ln = idx & 31, s = (idx >> 5) % KS, ww = (idx >> 5) / KS;
+        const int g = ln >> 2, j = ln & 3;
+        const int kb = (ww * KS + s) * 16 + 4 * j;
+        float v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = (g < U && kb + c < H4) ? __ldg(p.whh + (size_t)(kb + c) * Ha + u0 + g) : 0.f;
+        uint2 hi, lo;
+        split2(v[0], v[1], hi.x, lo.x);
+        split2(v[2], v[3], hi.y, lo.y);
+        const size_t o = ((size_t)ww * KS + s) * 2 * 32;
+        Bfrag[o + ln] = hi;
+        Bfrag[o + 32 + ln] = lo;
+    }
+    for (int idx = threadIdx.x; idx < KQ * 32; idx += kMT) {
+        const int ln = idx & 31, s = idx >> 5;
+        const int g = ln >> 2, j = ln & 3;
+        const int kb = s * 16 + 4 * j;
+        float v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = (g < U && kb + c < A) ? __ldg(p.wq + (size_t)(kb + c) * Ha + u0 + g) : 0.f;
+        uint2 hi, lo;
+        split2(v[0], v[1], hi.x, lo.x);
+        split2(v[2], v[3], hi.y, lo.y);
+        Bq[(size_t)s * 2 * 32 + ln] = hi;
+        Bq[(size_t)s * 2 * 32 + 32 + ln] = lo;
+    }
+    for (int idx = threadIdx.x; idx < A * F; idx += kMT) wld_s[idx] = __ldg(p.wld + idx);
+    for (int idx = threadIdx.x; idx < F * 2 * Kl; idx += kMT) {
+        const int f = idx / (2 * Kl), ck = idx % (2 * Kl);
+        wloc_s[f * CKP + ck] = __ldg(p.wloc + idx);
+    }
+    for (int idx = threadIdx.x; idx < A; idx += kMT) vs[idx] = __ldg(p.v + idx);
+    for (int idx = threadIdx.x; idx < np; idx += kMT) { gcum_s[idx] = 0.f; dprev_s[idx] = 0.f; pout_s[idx] = 0.f; }
+
+    // point-wise role: thread c < MTL*128 owns cell (row r, unit ul)
+    const int c_mt = threadIdx.x >> 7, c_reg = (threadIdx.x >> 5) & 3, c_ln = threadIdx.x & 31;
+    const int c_r = c_mt * 16 + (c_reg >> 1) * 8 + (c_ln >> 2), c_ul = (c_ln & 3) * 2 + (c_reg & 1);
+    const bool pw = (int)threadIdx.x < MTL * 128 && c_ul < U && c_r < R;
+    const int c_g = pw ? gr.task(c_r) : 0, c_b = pw ? gr.brow(c_r) : 0, c_u = u0 + c_ul;
+    const float* ga_c = p.ga + c_g * gr.tstride;
+    const float* ca_c = p.ca + c_g * gr.tstride;
+    const float* dhe_c = p.dha_ext + c_g * gr.tstride;
+    float* dza_c = p.dza + c_g * gr.tstride;
+    const uint8_t* mask_c = pw ? (p.G > 1 ? p.mask_g[c_g] : p.mask) : nullptr;
+    float gi[4] = {0.f, 0.f, 0.f, 0.f}, cc = 0.f, cp = 0.f, dhe = 0.f, dcarry = 0.f;
+    unsigned char mk = 1;
+    // forward stash of the attention part, fetched one step ahead: s of the owned positions (item = tid + k*kMT < np*A),
+    // the d0 column of s for every position (tid + k*kMT < R*L), d a_ext of the owned positions handled by this warp
+    constexpr int KV = 4;
+    float sv_own[KV], sv_q[KV];
+    auto s_addr = [&](int t, int pp, int d) {
+        const int g = pos_task(pp);
+        return p.s + g * gr.tstride + ((size_t)t * BtL + (pp - g * BtL)) * A + d;
+    };
+    auto fetch = [&](int t) {
+        if (pw) {
+            const size_t zb = ((size_t)t * Bt + c_b) * H4, hb = ((size_t)t * Bt + c_b) * Ha + c_u;
+#pragma unroll
+            for (int gate = 0; gate < 4; ++gate) gi[gate] = __ldg(ga_c + zb + (size_t)gate * Ha + c_u);
+            cc = __ldg(ca_c + hb);
+            cp = t > 0 ? __ldg(ca_c + hb - (size_t)Bt * Ha) : 0.f;
+            dhe = __ldg(dhe_c + hb);
+            if (mask_c) mk = mask_c[hb];
+        }
+#pragma unroll
+        for (int k = 0; k < KV; ++k) {
+            const int it = threadIdx.x + k * kMT;
+            if (it < np * A) sv_own[k] = __ldg(s_addr(t, p0 + it / A, it % A));
+            if (has_q && it < RL) sv_q[k] = __ldg(s_addr(t, it, d0));
+        }
+    };
+    fetch(T - 1);
+
+    // streaming role of the recurrent tile: lane (lg, lj) loads dz[rows mt*16 + lg, +8][4 gate rows] per k16 step
+    const float* zrow[MTL][2];
+    bool rowok[MTL][2];
+#pragma unroll
+    for (int mt = 0; mt < MTL; ++mt)
+#pragma unroll
+        for (int hr = 0; hr < 2; ++hr) {
+            const int r = mt * 16 + hr * 8 + lg;
+            rowok[mt][hr] = r < R;
+            const int rr = rowok[mt][hr] ? r : 0;
+            zrow[mt][hr] = p.dza + gr.task(rr) * gr.tstride + (size_t)gr.brow(rr) * H4;
+        }
+    SpinGuard sg(p.abort_word);
+    ChainProf<true> prof;
+    prof.start(p.prof, nullptr, 0);
+    __syncthreads();
+
+    for (int t = T - 1; t >= 0; --t) {
+        float acc[MTL][4];
+#pragma unroll
+        for (int mt = 0; mt < MTL; ++mt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][i] = 0.f;
+        // ---- A: dz_a(t+1) of every row ----
+        if (t < T - 1) {
+            const int rl_ = R - 1;
+            const float* zlast = p.dza + gr.task(rl_) * gr.tstride + ((size_t)(t + 1) * Bt + gr.brow(rl_)) * H4 + (size_t)3 * Ha;
+            gate_wait(ncta, [&](int c) { const int e = part_lo(c + 1, Ha, ncta); return e > part_lo(c, Ha, ncta) ? zlast + e - 1 : nullptr; }, sg);
+            __syncthreads();
+        }
+        prof.mark(0, T - 1 - t);
+        // context-path recurrent term of the owned positions (one warp per position) and their d a(t)
+        for (int i = w; i < np; i += kMW) {
+            const int pp = p0 + i, r = pp / L, g = r / Bt;
+            float a = 0.f;
+            if (t < T - 1) {
+                const float4* m4 = reinterpret_cast<const float4*>(p.mw_pm + g * gr.tstride + (size_t)(pp - g * BtL) * H4);
+                const float* zr = p.dza + g * gr.tstride + ((size_t)(t + 1) * Bt + (r - g * Bt)) * H4;
+                constexpr int NB = 4;
+                for (int c0 = lane; c0 < (H4 >> 2); c0 += 32 * NB) {
+                    float4 mv[NB], zv[NB];
+#pragma unroll
+                    for (int k = 0; k < NB; ++k) {
+                        const int c = c0 + k * 32;
+                        if (c < (H4 >> 2)) { mv[k] = __ldcg(m4 + c); zv[k] = ld_poll4(zr + (size_t)c * 4); }
+                    }
+#pragma unroll
+                    for (int k = 0; k < NB; ++k) {
+                        const int c = c0 + k * 32;
+                        if (c < (H4 >> 2)) {
+                            sg.reset();
+                            while (!ready4(zv[k])) {
+                                if (sg.bail()) break;
+                                zv[k] = ld_poll4(zr + (size_t)c * 4);
+                            }
+                            a += dot4(mv[k], zv[k]);
+                        }
+                    }
+                }
+                a = warp_sum(a);
+            }
+            if (lane == 0) {
+                const size_t o = g * gr.tstride + (size_t)t * BtL + (pp - g * BtL);
+                pout_s[i] = a;
+                st_pub(p.dat + o, __ldg(p.da_ext + o) + a + gcum_s[i] + dprev_s[i]);
+            }
+        }
+        prof.mark(1, T - 1 - t);
+        // ---- C (shadow of the d a hand-off): recurrent tile dz_a(t+1) . W_hh for the owned units ----
+        if (t < T - 1) {
+            const size_t toff = (size_t)(t + 1) * Bt * H4;
+            constexpr int PF = MSA_PF_BWD;
+            float4 zv[PF][MTL][2];
+            auto issue = [&](int s, float4 (&dst)[MTL][2]) {
+                const int col = (w * KS + s) * 16 + 4 * lj;
+#pragma unroll
+                for (int mt = 0; mt < MTL; ++mt)
+#pragma unroll
+                    for (int hr = 0; hr < 2; ++hr)
+                        dst[mt][hr] = (rowok[mt][hr] && col < H4) ? ld_poll4(zrow[mt][hr] + toff + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            auto process = [&](int s, float4 (&cur)[MTL][2]) {
+                const int col = (w * KS + s) * 16 + 4 * lj;
+                const uint2* bf = Bfrag + ((size_t)w * KS + s) * 2 * 32;
+                const uint2 bh = bf[lane], bl = bf[32 + lane];
+                const uint32_t bhi[2] = {bh.x, bh.y}, blo[2] = {bl.x, bl.y};
+#pragma unroll
+                for (int mt = 0; mt < MTL; ++mt) {
+#pragma unroll
+                    for (int hr = 0; hr < 2; ++hr) {
+                        if (rowok[mt][hr] && col < H4) {
+                            sg.reset();
+                            while (!ready4(cur[mt][hr])) {
+                                if (sg.bail()) break;
+                                cur[mt][hr] = ld_poll4(zrow[mt][hr] + toff + col);
+                            }
+                        }
+                    }
+                    uint4 ahi, alo;
+                    split2(cur[mt][0].x, cur[mt][0].y, ahi.x, alo.x);
+                    split2(cur[mt][1].x, cur[mt][1].y, ahi.y, alo.y);
+                    split2(cur[mt][0].z, cur[mt][0].w, ahi.z, alo.z);
+                    split2(cur[mt][1].z, cur[mt][1].w, ahi.w, alo.w);
+                    mma3(acc[mt], ahi, alo, bhi, blo);
+                }
+            };
+#pragma unroll
+            for (int i = 0; i < PF; ++i)
+                if (i < KS) issue(i, zv[i]);
+            for (int s0 = 0; s0 < KS; s0 += PF) {
+#pragma unroll
+                for (int i = 0; i < PF; ++i) {
+                    const int s = s0 + i;
+                    if (s < KS) {
+                        process(s, zv[i]);
+                        if (s + PF < KS) issue(s + PF, zv[i]);
+                    }
+                }
+            }
+        }
+        prof.mark(2, T - 1 - t);
+        // ---- D: d a(t) of every position, a(t), normaliser ----
+        if ((BtL & 3) == 0) {
+            for (int i4 = threadIdx.x; i4 < (RL >> 2); i4 += kMT) {
+                const int i = i4 * 4, g = i / BtL;
+                const size_t o = g * gr.tstride + (size_t)t * BtL + (i - g * BtL);
+                reinterpret_cast<float4*>(als)[i4] = __ldg(reinterpret_cast<const float4*>(p.align + o));
+                reinterpret_cast<float4*>(das)[i4] = poll4(p.dat + o, sg);
+            }
+        } else {
+            for (int i = threadIdx.x; i < RL; i += kMT) {
+                const int g = pos_task(i);
+                const size_t o = g * gr.tstride + (size_t)t * BtL + (i - g * BtL);
+                als[i] = __ldg(p.align + o);
+                das[i] = poll1(p.dat + o, sg);
+            }
+        }
+        if ((int)threadIdx.x < R) zn_s[threadIdx.x] = __ldg(p.znorm + gr.task(threadIdx.x) * gr.tstride + (size_t)t * Bt + gr.brow(threadIdx.x));
+        __syncthreads();
+        prof.mark(3, T - 1 - t);
+        // normalisation backward (softmax, or sigmoid / sum): d e(t) in place of d a(t)
+        for (int r = w; r < R; r += kMW) {
+            float sd = 0.f;
+            for (int l = lane; l < L; l += 32) sd += als[r * L + l] * das[r * L + l];
+            sd = warp_sum(sd);
+            for (int l = lane; l < L; l += 32) {
+                const float a = als[r * L + l];
+                float de = a * (das[r * L + l] - sd);
+                if (p.norm == 1) de = de * (1.f - a * zn_s[r]);
+                das[r * L + l] = de;
+            }
+        }
+        __syncthreads();
+        // terms of dq for the owned attention dim; d e and dS of the owned positions
+        if (has_q) {
+#pragma unroll
+            for (int k = 0; k < KV; ++k) {
+                const int it = threadIdx.x + k * kMT;
+                if (it < RL) tq_s[it] = das[it] * (1.f - sv_q[k] * sv_q[k]);
+            }
+            for (int it = threadIdx.x + KV * kMT; it < RL; it += kMT) {
+                const float sv = __ldg(s_addr(t, it, d0));
+                tq_s[it] = das[it] * (1.f - sv * sv);
+            }
+        }
+        for (int i = threadIdx.x; i < np; i += kMT) {
+            const int pp = p0 + i, g = pos_task(pp);
+            p.de[g * gr.tstride + (size_t)t * BtL + (pp - g * BtL)] = das[pp];
+        }
+        {
+            auto do_item = [&](int it, float sv) {
+                const int pi = it / A, d = it - pi * A, pp = p0 + pi, g = pos_task(pp);
+                const float dS = das[pp] * vs[d] * (1.f - sv * sv);
+                p.ds[g * gr.tstride + ((size_t)t * BtL + (pp - g * BtL)) * A + d] = dS;
+                ds_s[it] = dS;
+            };
+#pragma unroll
+            for (int k = 0; k < KV; ++k) {
+                const int it = threadIdx.x + k * kMT;
+                if (it < np * A) do_item(it, sv_own[k]);
+            }
+            for (int it = threadIdx.x + KV * kMT; it < np * A; it += kMT) do_item(it, __ldg(s_addr(t, p0 + it / A, it % A)));
+        }
+        __syncthreads();
+        prof.mark(4, T - 1 - t);
+        // dq(t)[r][d0] = v[d0] * sum_l tq[r][l]  (one warp per row); publishes dq
+        if (has_q)
+            for (int r = w; r < R; r += kMW) {
+                float a = 0.f;
+                for (int l = lane; l < L; l += 32) a += tq_s[r * L + l];
+                a = warp_sum(a);
+                if (lane == 0) st_pub(p.dq + gr.task(r) * gr.tstride + ((size_t)t * Bt + gr.brow(r)) * A + d0, vs[d0] * a);
+            }
+        // d(conv features)[pi][f] = sum_d dS[pi][d] wld[d][f]: warp (block of 4 positions, quarter of the d range), lane = filter
+        {
+            const int nblk = (np + 3) >> 2;
+            for (int job = w; job < nblk * 4; job += kMW) {
+                const int blk = job >> 2, dq4 = job & 3;
+                const int dlo = part_lo(dq4, A, 4), dhi = part_lo(dq4 + 1, A, 4);
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                const float* ds0 = ds_s + (size_t)(blk * 4) * A;
+                const bool v1 = blk * 4 + 1 < np, v2 = blk * 4 + 2 < np, v3 = blk * 4 + 3 < np;
+                if (lane < F)
+                    for (int d = dlo; d < dhi; ++d) {
+                        const float wv = wld_s[d * F + lane];
+                        a0 += ds0[d] * wv;
+                        if (v1) a1 += ds0[A + d] * wv;
+                        if (v2) a2 += ds0[2 * A + d] * wv;
+                        if (v3) a3 += ds0[3 * A + d] * wv;
+                    }
+                if (lane < F) {
+                    float* o = dcp_s + ((size_t)dq4 * lay.NPmax + blk * 4) * F + lane;
+                    o[0] = a0;
+                    if (v1) o[F] = a1;
+                    if (v2) o[2 * F] = a2;
+                    if (v3) o[3 * F] = a3;
+                }
+            }
+        }
+        __syncthreads();
+        for (int it = threadIdx.x; it < np * F; it += kMT) {
+            const int pi = it / F, f = it - pi * F, pp = p0 + pi, g = pos_task(pp);
+            const float a = (dcp_s[(size_t)(0 * lay.NPmax + pi) * F + f] + dcp_s[(size_t)(1 * lay.NPmax + pi) * F + f]) +
+                            (dcp_s[(size_t)(2 * lay.NPmax + pi) * F + f] + dcp_s[(size_t)(3 * lay.NPmax + pi) * F + f]);
+            st_pub(p.dconvf + g * gr.tstride + ((size_t)t * BtL + (pp - g * BtL)) * F + f, a);
+        }
+        prof.mark(5, T - 1 - t);
+        __syncthreads();      // tq / dconvf partials are done: the region becomes the partial-tile buffer
+        // ---- F: dq(t) arrives: dq(t) . W_q for the owned units into the same accumulators, then one reduction ----
+        for (int s = w; s < KQ; s += kMW) {
+            const int col = s * 16 + 4 * lj;
+            const uint2 bh = Bq[(size_t)s * 2 * 32 + lane], bl = Bq[(size_t)s * 2 * 32 + 32 + lane];
+            const uint32_t bhi[2] = {bh.x, bh.y}, blo[2] = {bl.x, bl.y};
+            const size_t toff = (size_t)t * Bt * A;
+#pragma unroll
+            for (int mt = 0; mt < MTL; ++mt) {
+                float4 cur[2];
+#pragma unroll
+                for (int hr = 0; hr < 2; ++hr) {
+                    const int r = mt * 16 + hr * 8 + lg, rr = r < R ? r : 0;
+                    const float* qrow = p.dq + gr.task(rr) * gr.tstride + (size_t)gr.brow(rr) * A;
+                    cur[hr] = (r < R && col < A) ? poll4(qrow + toff + col, sg) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                uint4 ahi, alo;
+                split2(cur[0].x, cur[0].y, ahi.x, alo.x);
+                split2(cur[1].x, cur[1].y, ahi.y, alo.y);
+                split2(cur[0].z, cur[0].w, ahi.z, alo.z);
+                split2(cur[1].z, cur[1].w, ahi.w, alo.w);
+                mma3(acc[mt], ahi, alo, bhi, blo);
+            }
+        }
+#pragma unroll
+        for (int mt = 0; mt < MTL; ++mt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) part[(((size_t)w * MTL + mt) * 4 + i) * 32 + lane] = acc[mt][i];
+        __syncthreads();
+        prof.mark(6, T - 1 - t);
+        if (pw) {
+            float drec = 0.f;
+            const float* pp_ = part + ((size_t)c_mt * 4 + c_reg) * 32 + c_ln;
+#pragma unroll
+            for (int ww = 0; ww < kMW; ++ww) drec += pp_[(size_t)ww * MTL * 4 * 32];
+            const size_t zb = ((size_t)t * Bt + c_b) * H4;
+            float dh = dhe + drec;
+            if (mask_c) dh = mk ? dh * p.drop_scale : 0.f;
+            const LstmGrad g = lstm_point_bwd(gi[0], gi[1], gi[2], gi[3], cc, cp, dh, dcarry);
+            dcarry = g.dc_prev;
+            st_pub(dza_c + zb + 0 * (size_t)Ha + c_u, g.di);
+            st_pub(dza_c + zb + 1 * (size_t)Ha + c_u, g.df);
+            st_pub(dza_c + zb + 2 * (size_t)Ha + c_u, g.dg);
+            st_pub(dza_c + zb + 3 * (size_t)Ha + c_u, g.do_);
+        }
+        if (t > 0) fetch(t - 1);
+        // ---- H: d(conv features) of the +-pad neighbours; location-conv backward for the owned positions ----
+        for (int ro = 0; ro < nrown; ++ro) {
+            const int r = r_lo + ro, g = r / Bt, lo0 = wlo(ro), nwin = whi(ro) - lo0 + 1;
+            const float* src = p.dconvf + g * gr.tstride + ((size_t)t * BtL + (size_t)(r - g * Bt) * L + lo0) * F;
+            for (int it = threadIdx.x; it < nwin * F; it += kMT) {
+                const int wl = it / F, f = it - wl * F;
+                dcw[((size_t)ro * WIN + wl) * FP + f] = poll1(src + it, sg);
+            }
+        }
+        __syncthreads();
+        prof.mark(7, T - 1 - t);
+        // one warp per owned position (input position of the conv), lanes over the taps: output position lo = l - k + pad
+        for (int i = w; i < np; i += kMW) {
+            const int pp = p0 + i, r = pp / L, l = pp - r * L, ro = r - r_lo, lo0 = wlo(ro);
+            float a0 = 0.f, a1 = 0.f;
+            for (int k = lane; k < Kl; k += 32) {
+                const int lo = l - k + pl;
+                if (lo >= 0 && lo < L) {
+                    const float* dv = dcw + ((size_t)ro * WIN + (lo - lo0)) * FP;
+                    for (int f = 0; f < F; ++f) {
+                        a0 += wloc_s[f * CKP + k] * dv[f];
+                        a1 += wloc_s[f * CKP + Kl + k] * dv[f];
+                    }
+                }
+            }
+            a0 = warp_sum(a0);
+            a1 = warp_sum(a1);
+            if (lane == 0) {
+                dprev_s[i] = a0;
+                gcum_s[i] += a1;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static bool attn_bwd_mma_ok(const msa_config& cfg, int R, int L, int sm_count, size_t smem_limit) {
+    const int Ha = cfg.attn_rnn_dim, A = cfg.attn_dim;
+    if (cfg.forward_attn || R < 1 || R > 32 || Ha % 4 != 0 || A % 4 != 0 || cfg.loc_filters > 32) return false;
+    if (A > sm_count || (Ha + sm_count - 1) / sm_count > 8) return false;
+    return attn_bwd_mma_layout(R, L, Ha, A, cfg.loc_filters, cfg.loc_kernel, sm_count, (R + 15) / 16).total + 256 <= smem_limit;
+}
+
 }  // namespace
 
 int launch_lstm_rec_fwd_mma(const LstmRecParams& p0, int sm_count, size_t smem_limit, cudaStream_t st) {
@@ -987,9 +1464,26 @@ int launch_attn_chain_fwd_mma(const AttnChainParams& p0, int sm_count, size_t sm
     }
 }
 bool attn_chain_bwd_mma_supported(const msa_config& cfg, int G, int B, int T, int L, int sm_count, size_t smem_limit) {
-    (void)cfg; (void)G; (void)B; (void)T; (void)L; (void)sm_count; (void)smem_limit;
-    return false;
+    (void)T;
+    return attn_bwd_mma_ok(cfg, G * B, L, sm_count, smem_limit);
 }
-int launch_attn_chain_bwd_mma(const AttnChainBwdParams&, int, size_t, cudaStream_t) { set_error("attn_chain_bwd_mma: not built"); return MSA_E_UNSUPPORTED; }
+int launch_attn_chain_bwd_mma(const AttnChainBwdParams& p0, int sm_count, size_t smem_limit, cudaStream_t st) {
+    AttnChainBwdParams p = p0;
+    if (p.G < 1) p.G = 1;
+    const int R = p.G * p.B, MTL = (R + 15) / 16;
+    MSA_CHECK(!p.fa && R <= 32 && p.A <= sm_count && p.A % 4 == 0 && (p.Ha + sm_count - 1) / sm_count <= 8, MSA_E_UNSUPPORTED,
+              "attn_chain_bwd_mma: configuration outside the grouped kernel (rows %d, attention dim %d)", R, p.A);
+    const size_t smem = attn_bwd_mma_layout(R, p.L, p.Ha, p.A, p.F, p.Kl, sm_count, MTL).total;
+    MSA_CHECK(smem <= smem_limit, MSA_E_UNSUPPORTED, "attn_chain_bwd_mma: needs %zu bytes of shared memory (> %zu)", smem, smem_limit);
+    const size_t TB = (size_t)p.T * p.B;
+    for (int g = 0; g < p.G; ++g) {       // canaries of the four hand-off arrays of every task (common.cuh)
+        MSA_TRY(k_fill_canary(p.dza + g * p.tstride, (int64_t)(TB * 4 * p.Ha), st));
+        MSA_TRY(k_fill_canary(p.dq + g * p.tstride, (int64_t)(TB * p.A), st));
+        MSA_TRY(k_fill_canary(p.dat + g * p.tstride, (int64_t)(TB * p.L), st));
+        MSA_TRY(k_fill_canary(p.dconvf + g * p.tstride, (int64_t)(TB * p.L * p.F), st));
+    }
+    if (MTL == 1) return coop_launch(k_attn_bwd_mma<1>, p, sm_count, smem, st);
+    return coop_launch(k_attn_bwd_mma<2>, p, sm_count, smem, st);
+}
 
 }  // namespace msa
