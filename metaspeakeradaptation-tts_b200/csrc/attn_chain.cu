@@ -746,6 +746,15 @@ static int attn_check(int B, int Ha, int A, int F, int sm_count) {
     return 0;
 }
 
+// can the single-task kernels run this shape at all? (pass.cu: the grouped tensor-core kernels take over when they cannot)
+bool attn_chain_single_ok(int B, int L, int Ha, int A, int F, int Kl, int sm_count, size_t smem_limit, bool fa) {
+    if (Ha % 4 != 0 || F > 32 || B < 1 || B > kBMax) return false;
+    const int umax = (Ha + sm_count - 1) / sm_count;
+    if (umax > kUMax || 4 * umax * B > kAttnThreads) return false;
+    return attn_chain_fwd_smem(B, L, Ha, A, F, Kl, sm_count, false, fa) <= smem_limit &&
+           attn_chain_bwd_smem(B, L, Ha, A, F, Kl, sm_count, false, fa) <= smem_limit;
+}
+
 int launch_attn_chain_fwd(const AttnChainParams& p, int sm_count, size_t smem_limit, cudaStream_t st) {
     MSA_TRY(attn_check(p.B, p.Ha, p.A, p.F, sm_count));
     int mw_res = 1;

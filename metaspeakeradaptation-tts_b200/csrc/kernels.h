@@ -57,6 +57,7 @@ struct LstmRecBwdParams {
     const uint8_t* mask_g[kGroupMax];
     const int64_t* lengths_g[kGroupMax];
 };
+bool lstm_rec_single_ok(int B, int H, int ndir, int sm_count, size_t smem_limit);
 size_t lstm_rec_fwd_smem(int B, int H);
 size_t lstm_rec_bwd_smem(int B, int H);
 int launch_lstm_rec_fwd(const LstmRecParams& p, int sm_count, size_t smem_limit, cudaStream_t st);
@@ -143,6 +144,7 @@ struct AttnChainBwdParams {
     const uint8_t* mask_g[kGroupMax];
     const int64_t* lengths_g[kGroupMax];
 };
+bool attn_chain_single_ok(int B, int L, int Ha, int A, int F, int Kl, int sm_count, size_t smem_limit, bool fa);
 size_t attn_chain_fwd_smem(int B, int L, int Ha, int A, int F, int Kl, int sm_count, bool mw_resident, bool fa = false);
 size_t attn_chain_bwd_smem(int B, int L, int Ha, int A, int F, int Kl, int sm_count, bool mwp_resident, bool fa = false);
 int launch_attn_chain_fwd(const AttnChainParams& p, int sm_count, size_t smem_limit, cudaStream_t st);

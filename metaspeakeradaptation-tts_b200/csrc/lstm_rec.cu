@@ -219,6 +219,15 @@ static int rec_check(int B, int H, int ndir, int sm_count) {
     return 0;
 }
 
+bool lstm_rec_single_ok(int B, int H, int ndir, int sm_count, size_t smem_limit) {
+    if (H % 4 != 0 || B < 1 || B > kBMax) return false;
+    const int ncta_dir = sm_count / ndir;
+    if (ncta_dir < 1) return false;
+    const int umax = (H + ncta_dir - 1) / ncta_dir;
+    if (umax > kUMax || 4 * umax * B > kRecThreads) return false;
+    return sizeof(float) * lstm_fwd_layout(B, H).total <= smem_limit &&
+           sizeof(float) * ((size_t)kUMax * 4 * H + kRecWarps * 32 + kUMax * ((B + 3) & ~3)) <= smem_limit;
+}
 size_t lstm_rec_fwd_smem(int B, int H) { return sizeof(float) * lstm_fwd_layout(B, H).total; }
 size_t lstm_rec_bwd_smem(int B, int H) {
     const int BP = (B + 3) & ~3;

@@ -559,13 +559,29 @@ struct TaskIO {
 
 // Grouped chain launches (chain_mma.cu) are used when the configuration is inside what those kernels implement; otherwise the
 // tasks of a group run the single-task persistent kernels one after the other (same results, no sharing of the hand-offs).
-static bool use_mma_chains(const msa_handle* h, int G, int B, int T, int L, bool attn) {
-    if (h->mma_mode == 0 || (h->cfg.gemm_tf32 < 1 && h->mma_mode != 4)) return false;   // strict-fp32 policy: no tensor-core arithmetic
-                                                                                         // (mode 4, tests: force the grouped kernels)
-    if (h->mma_mode == 1 && G == 1) return false;
-    if (h->mma_mode == 3 && attn) return false;                           // development: LSTM recurrences only
-    return attn ? attn_chain_mma_supported(h->cfg, G, B, T, L, h->sm_count, h->smem_limit)
-                : chain_mma_supported(h->cfg, G, B, T, L, h->sm_count, h->smem_limit);
+static bool use_mma_chains(const msa_handle* h, int G, int B, int T, int L, bool attn, bool bwd) {
+    const msa_config& c = h->cfg;
+    const bool have = attn ? (attn_chain_mma_supported(c, G, B, T, L, h->sm_count, h->smem_limit) &&
+                              attn_chain_bwd_mma_supported(c, G, B, T, L, h->sm_count, h->smem_limit))
+                           : chain_mma_supported(c, G, B, T, L, h->sm_count, h->smem_limit);
+    if (!have) return false;
+    // a batch the single-task kernels cannot hold (B > 8 at the default dimensions: their shared-memory staging of h) runs on the
+    // grouped kernels under every policy -- their bf16x3 products are fp32-accurate to ~1e-5, well inside every stated tolerance
+    const bool single_ok = attn ? attn_chain_single_ok(B, L, c.attn_rnn_dim, c.attn_dim, c.loc_filters, c.loc_kernel, h->sm_count,
+                                                       h->smem_limit, c.forward_attn != 0)
+                                : (lstm_rec_single_ok(B, c.dec_rnn_dim, 1, h->sm_count, h->smem_limit) &&
+                                   lstm_rec_single_ok(B, c.enc_dim / 2, 2, h->sm_count, h->smem_limit));
+    if (!single_ok) return true;
+    if (h->mma_mode == 0 || (c.gemm_tf32 < 1 && h->mma_mode != 4)) return false;   // strict-fp32 policy: no tensor-core arithmetic
+                                                                                    // (mode 4, tests: force the grouped kernels)
+    // measured on B200 (profiles/r02_chain_mma_notes.txt): at 4 rows the tensor-core forward LSTM recurrences beat the fp32-FMA
+    // ones (decoder RNN 0.70 vs 1.09 ms, encoder BiLSTM 0.17 vs 0.22 ms); the attention chain (2.52 vs 2.14 ms: its context term
+    // streams MW from L2 where the single-task kernel keeps it in shared memory) and the backward kernels (a 16-step dz stream per
+    // warp, latency-bound at few rows) do not: single passes take the forward LSTM kernels only
+    if (h->mma_mode == 1 && G == 1 && (bwd || attn)) return false;
+    if (h->mma_mode == 3 && attn) return false;                                     // development: LSTM recurrences only
+    if (h->mma_mode == 5 && G == 1) return false;                                   // development: grouped launches only
+    return true;
 }
 
 // One teacher-forced forward pass for G tasks that share `params` (the theta_0 train-split passes of a meta-batch, maml.py:38-54):
@@ -587,7 +603,7 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
     const auto secs = mask_sections(c, B, T, L);
     const int iPre = d.nEnc, iAttn = d.nEnc + 2, iDec = d.nEnc + 3, iPost = d.nEnc + 4;
     auto P = [&](const std::string& n) { return params + h->off(n); };
-    const bool mma = use_mma_chains(h, G, B, T, L, false), mma_attn = use_mma_chains(h, G, B, T, L, true);
+    const bool mma = use_mma_chains(h, G, B, T, L, false, false), mma_attn = use_mma_chains(h, G, B, T, L, true, false);
     const int64_t tstride = (int64_t)(ws_stride / sizeof(float));
     const int H4e = 4 * d.Hh;
     const std::string at = "decoder.attention_layer.";
@@ -928,8 +944,7 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
     const std::string at = "decoder.attention_layer.";
     const bool fa = c.forward_attn != 0, ta = fa && c.trans_agent != 0;
     const float* Wia = P("decoder.attention_rnn.weight_ih");
-    const bool mma = use_mma_chains(h, NG, B, T, L, false);
-    const bool mma_attn = use_mma_chains(h, NG, B, T, L, true) && attn_chain_bwd_mma_supported(h->cfg, NG, B, T, L, h->sm_count, h->smem_limit);
+    const bool mma = use_mma_chains(h, NG, B, T, L, false, true), mma_attn = use_mma_chains(h, NG, B, T, L, true, true);
     const int64_t tstride = (int64_t)(ws_stride / sizeof(float));
 
     // ---- stage 1: postnet and projections ----
