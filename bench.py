@@ -104,13 +104,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def algo_bytes(cfg, kernel: str) -> float:
-    """Compulsory HBM bytes of one launch (every operand read once, every result written once)."""
+def algo_bytes(cfg, kernel: str, rows: int = B) -> float:
+    """Compulsory HBM bytes of one launch (every operand read once, every result written once).
+    ``rows``: batch rows the launch carries (B for a single pass, G*B for a grouped launch, kernel names ending in "_grp")."""
     from msa_tts_b200.config import memory_dim, rnn_dims
+    kernel = kernel[:-4] if kernel.endswith("_grp") else kernel
     Ha, Hd = rnn_dims(cfg)
     E, A = memory_dim(cfg), cfg["attention_params"]["attention_dim"]
     F_, Hh = cfg["attention_params"]["attention_location_n_filters"], cfg["encoder_embedding_dim"] // 2
-    TB, BL, TBL = T * B, B * L, T * B * L
+    TB, BL, TBL = T * rows, rows * L, T * rows * L
     f = 4.0
     if kernel == "attn_chain_fwd":
         rd = TB * 4 * Ha + 4 * Ha * Ha + 4 * Ha * BL + A * Ha + BL * A
@@ -140,6 +142,7 @@ HAND_OFF_US = 2268 / 1965.0
 
 
 def latency_bound(kernel: str, ms_per_launch: float):
+    kernel = kernel[:-4] if kernel.endswith("_grp") else kernel
     steps = L if kernel.startswith("enc_") else T
     bound_ms = steps * HAND_OFFS[kernel] * HAND_OFF_US * 1e-3
     return {"steps": steps, "hand_offs_per_step": HAND_OFFS[kernel], "hand_off_us": HAND_OFF_US, "bound_ms": bound_ms,
@@ -278,6 +281,77 @@ def bench_infer(torch, tr, world, sync, B=32, L_=64, steps=1000):
             "workload": f"free-running inference, B={B} per GPU, L={L_}, {n_steps} decoder steps, default dims, encoder and postnet included"}
 
 
+def bench_other_configs(torch, tr, world, sync, gemm_mode):
+    """BASELINE.json configs[0] (one forward+backward pass, B=4, T=200, 80 mels), configs[2] (Reptile meta-step, 16 tasks x 5 inner
+    steps, batched variant, parameter-delta allreduce) and configs[3] (continual EWC step with the fused penalty + update kernel, ER-KD
+    soft-target pass) on this repo's CUDA path; device-resident inputs, CUDA events, max over ranks."""
+    import msa_tts_b200 as pkg
+    from msa_tts_b200 import synth
+    from msa_tts_b200.engine import batch_to_device
+    from msa_tts_b200.reptile import Reptile
+    eng, dev, cfg = tr.engine, tr.device, tr.model_params
+
+    def timed(fn, reps, warm=2):
+        for _ in range(warm):
+            fn()
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+        tr.shard.allreduce_max(ms)
+        return float(ms)
+    out = {}
+    bd = batch_to_device(synth.make_batch(cfg, B, T, L, 100), dev)
+    masks = eng.generate_masks(B, T, L, 7)
+    bn, g = eng.new_bn_stats(), tr.task_grad
+
+    def one_pass():
+        eng.forward(tr.fast, bn, bd, masks, outputs=False)
+        eng.backward(tr.fast, g)
+    ms = timed(one_pass, 10)
+    out["config0_fwd_bwd_pass"] = {"ms_per_pass": ms, "mel_frames_per_s": world * B * T / ms * 1e3, "scaling": "replicas",
+                                   "workload": f"one forward+backward pass per GPU, B={B}, T={T}, L={L}, default dims"}
+    mu, fisher = tr.meta_grad, tr.outer_m          # any two flat buffers: the kernels are bandwidth-bound, the values do not matter
+    fisher.abs_()
+
+    def ewc_step():
+        one_pass()
+        eng.ewc_sgd_step(tr.fast, g, mu, fisher, 1e-9, 100.0)
+    ms = timed(ewc_step, 10)
+    ms_u = timed(lambda: eng.ewc_sgd_step(tr.fast, g, mu, fisher, 1e-9, 100.0), 20)
+    n = eng.layout.total
+    ms_kd = timed(lambda: eng.forward(tr.fast, bn, bd, masks, outputs=True), 10)
+    out["config3_continual"] = {"ewc_step_ms": ms, "ewc_fused_penalty_update_ms": ms_u,
+                                "ewc_fused_penalty_update_frac_of_hbm_peak": 20.0 * n / ms_u / 1e6 / measured_peak()[0],
+                                "erkd_soft_target_pass_ms": ms_kd, "scaling": "replicas",
+                                "workload": "EWC: forward+backward + fused penalty-gradient/SGD update; ER-KD: teacher-forced soft-target pass"}
+    eng.check_abort()
+    # Reptile: 16 tasks x 5 inner steps, all tasks from the same theta_0 (batched variant, the one that shards), one delta allreduce
+    global N_TASKS
+    keep = N_TASKS
+    N_TASKS = 16
+    try:
+        params = trainer_params(gemm_mode)
+        params["n_inner_train"] = 5
+        params["reptile_sequential"] = False
+        rp = Reptile(**params)
+        items = make_tasks(cfg, pinned=False)
+        items = {s_: {k: tuple(x.to(dev) if hasattr(x, "to") else x for x in v) for k, v in t_.items()} for s_, t_ in items.items()}
+        ms = timed(lambda: rp._metatrain_step(items), 2, warm=1)
+        rp.engine.abort_flush()
+        rp.engine.check_abort()
+        out["config2_reptile"] = {"ms_per_meta_step": ms, "meta_steps_per_s": 1e3 / ms, "scaling": "strong",
+                                  "workload": "batched Reptile meta-step, 16 tasks x 5 inner SGD steps + test forward, parameter-delta allreduce"}
+        del rp
+    finally:
+        N_TASKS = keep
+    return out
+
+
 def bench_gemm_tc(torch, eng, reps=20):
     import ctypes as C
     from msa_tts_b200.config import rnn_dims
@@ -390,6 +464,8 @@ def main():
     ms_e2e = timed(host_items, args.steps, read_losses=True)
     h2d = sum(batch_bytes(host_items[f"spk{i}"][k]) for i in mine for k in ("train", "test"))
     d2h = 4 * len(mine)
+    eng.abort_flush()          # a persistent kernel that gave up polling invalidates the numbers: raise here
+    eng.check_abort()
 
     # ---- flat-buffer kernels timed alone (HBM roofline) ----
     def time_flat(fn, reps=20):
@@ -427,14 +503,23 @@ def main():
     except Exception as e:      # the meta-step line must not depend on this leg
         infer_line = {"error": str(e)[:200]}
 
+    # ---- the other BASELINE configs as extra legs (configs[0], [2], [3]; the headline stays configs[1]) ----
+    other = None
+    try:
+        other = bench_other_configs(torch, tr, world, sync, gemm_mode)
+    except Exception as e:
+        other = {"error": str(e)[:200]}
+
     if rank == 0:
         peak, peak_src = measured_peak()
         kern = []
         for name, (ms, cnt) in prof.items():
             if cnt:
-                ab = algo_bytes(cfg, name)
+                rows = B * (eng.group_size(len(mine), B) if name.endswith("_grp") else 1)
+                ab = algo_bytes(cfg, name, rows)
                 per = ms / cnt
-                kern.append({"kernel": name, "launches_per_step": cnt / args.steps, "ms_per_launch": per,
+                kern.append({"kernel": name, "rows_per_launch": rows, "us_per_step_per_row": per * 1e3 / (L if name.startswith("enc_") else T) / rows,
+                             "launches_per_step": cnt / args.steps, "ms_per_launch": per,
                              "share_of_step": ms / ms_dev, "algo_bytes": ab, "achieved_gbs": ab / per / 1e6,
                              "frac": ab / per / 1e6 / peak, "latency_bound": latency_bound(name, per)})
         for name, (ms, ab) in flat_ms.items():
@@ -459,14 +544,16 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
                          "frac": dom["frac"], "traffic": ncu_traffic(dom["kernel"]), "peak_source": peak_src,
-                         "note": "persistent recurrent kernel: weights stay in shared memory for all T steps; its time is set by "
-                                 "the three cross-CTA hand-offs per decoder step (L2 round trips among 148 CTAs), not by HBM "
-                                 "or tensor throughput (DESIGN.md section 4.2, profiles/r01_trace_*)",
+                         "note": "persistent recurrent kernel: the weight slices stay in shared memory for all T steps; its time is "
+                                 "set by the cross-CTA hand-offs of every decoder step (L2 round trips among 148 CTAs) and, for "
+                                 "the grouped launches, by the L2 -> SM streams of h / dz / MW -- not by HBM or tensor throughput "
+                                 "(DESIGN.md section 4.2, profiles/r02_*)",
                          "ms_per_launch": dom["ms_per_launch"], "share_of_step": dom["share_of_step"],
                          "latency_bound": dom["latency_bound"]},
             "kernels": kern,
             "clocks": clk.summary(),
             "infer": infer_line,
+            "other_configs": other,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()

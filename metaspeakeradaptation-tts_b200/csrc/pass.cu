@@ -364,8 +364,11 @@ static int conv_bn_bwd(msa_handle* h, cudaStream_t st, const float* params, floa
     return 0;
 }
 
-enum ProfId { PROF_ENC_LSTM_FWD = 0, PROF_ATTN_FWD, PROF_DEC_LSTM_FWD, PROF_DEC_LSTM_BWD, PROF_ATTN_BWD, PROF_ENC_LSTM_BWD, PROF_N };
-static const char* kProfNames[PROF_N] = {"enc_lstm_fwd", "attn_chain_fwd", "dec_lstm_fwd", "dec_lstm_bwd", "attn_chain_bwd", "enc_lstm_bwd"};
+// event-timing slots: the six single-task recurrences, then the same six as grouped launches (chain_mma.cu with G > 1); the
+// in-kernel phase counters / traces exist once per recurrence (PROF_BASE slots)
+enum ProfId { PROF_ENC_LSTM_FWD = 0, PROF_ATTN_FWD, PROF_DEC_LSTM_FWD, PROF_DEC_LSTM_BWD, PROF_ATTN_BWD, PROF_ENC_LSTM_BWD, PROF_BASE, PROF_N = 2 * PROF_BASE };
+static const char* kProfNames[PROF_N] = {"enc_lstm_fwd", "attn_chain_fwd", "dec_lstm_fwd", "dec_lstm_bwd", "attn_chain_bwd", "enc_lstm_bwd",
+                                         "enc_lstm_fwd_grp", "attn_chain_fwd_grp", "dec_lstm_fwd_grp", "dec_lstm_bwd_grp", "attn_chain_bwd_grp", "enc_lstm_bwd_grp"};
 struct ProfScope {
     msa_handle* h; cudaStream_t st; int slot = -1;
     ProfScope(msa_handle* h_, int id, cudaStream_t st_) : h(h_), st(st_) {
@@ -656,7 +659,7 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
             lp.trace = trace_ptr(h, w, PROF_ENC_LSTM_FWD); lp.trace_t0 = h->trace_t0; lp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
             return lp;
         };
-        ProfScope ps(h, PROF_ENC_LSTM_FWD, st);
+        ProfScope ps(h, PROF_ENC_LSTM_FWD + (mma && G > 1 ? PROF_BASE : 0), st);
         if (mma) {
             LstmRecParams lp = make(0);
             lp.G = G; lp.tstride = tstride;
@@ -707,7 +710,7 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
             ap.trace = trace_ptr(h, w, PROF_ATTN_FWD); ap.trace_t0 = h->trace_t0; ap.flags = h->rec_flags >= 0 ? h->rec_flags : 0;
             return ap;
         };
-        ProfScope ps(h, PROF_ATTN_FWD, st);
+        ProfScope ps(h, PROF_ATTN_FWD + (mma_attn && G > 1 ? PROF_BASE : 0), st);
         if (mma_attn) {
             AttnChainParams ap = make(0);
             ap.G = G; ap.tstride = tstride;
@@ -743,7 +746,7 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
             lp.trace = trace_ptr(h, w, PROF_DEC_LSTM_FWD); lp.trace_t0 = h->trace_t0; lp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
             return lp;
         };
-        ProfScope ps(h, PROF_DEC_LSTM_FWD, st);
+        ProfScope ps(h, PROF_DEC_LSTM_FWD + (mma && G > 1 ? PROF_BASE : 0), st);
         if (mma) {
             LstmRecParams lp = make(0);
             lp.G = G; lp.tstride = tstride;
@@ -1008,7 +1011,7 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
             bp.trace = trace_ptr(h, w, PROF_DEC_LSTM_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
             return bp;
         };
-        ProfScope ps(h, PROF_DEC_LSTM_BWD, st);
+        ProfScope ps(h, PROF_DEC_LSTM_BWD + (mma && NG > 1 ? PROF_BASE : 0), st);
         if (mma) {
             LstmRecBwdParams bp = make(0);
             bp.G = NG; bp.tstride = tstride;
@@ -1069,7 +1072,7 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
             bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 0;
             return bp;
         };
-        ProfScope ps(h, PROF_ATTN_BWD, st);
+        ProfScope ps(h, PROF_ATTN_BWD + (mma_attn && NG > 1 ? PROF_BASE : 0), st);
         if (mma_attn) {
             AttnChainBwdParams bp = make(0);
             bp.G = NG; bp.tstride = tstride;
@@ -1155,7 +1158,7 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
             bp.trace = trace_ptr(h, w, PROF_ENC_LSTM_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
             return bp;
         };
-        ProfScope ps(h, PROF_ENC_LSTM_BWD, st);
+        ProfScope ps(h, PROF_ENC_LSTM_BWD + (mma && NG > 1 ? PROF_BASE : 0), st);
         if (mma) {
             LstmRecBwdParams bp = make(0);
             bp.G = NG; bp.tstride = tstride;
@@ -1264,6 +1267,7 @@ int msa_debug_raise_abort(msa_handle* h, void* stream) {
 int msa_profile_trace(msa_handle* h, void* wsp, int id, int64_t* out, int ncta) {
     MSA_CHECK(h && wsp && out && h->fwd_valid, MSA_E_STATE, "msa_profile_trace: no forward pass in this workspace");
     MSA_CHECK(id >= 0 && id < PROF_N && ncta >= 1 && ncta <= 256, MSA_E_ARG, "msa_profile_trace: bad kernel id / cta count");
+    id %= PROF_BASE;
     const Ws w = ws_layout(h->d, wsp);
     MSA_CUDA(cudaDeviceSynchronize());
     MSA_CUDA(cudaMemcpy(out, reinterpret_cast<const long long*>(w.trace) + (size_t)id * kTraceWordsPerKernel,
@@ -1279,6 +1283,7 @@ int msa_profile_trace_step(msa_handle* h, int t0) {
 int msa_profile_phases(msa_handle* h, void* wsp, int id, int64_t* out, int ncta) {
     MSA_CHECK(h && wsp && out && h->fwd_valid, MSA_E_STATE, "msa_profile_phases: no forward pass in this workspace");
     MSA_CHECK(id >= 0 && id < PROF_N && ncta >= 1 && ncta <= kProfCtas, MSA_E_ARG, "msa_profile_phases: bad kernel id / cta count");
+    id %= PROF_BASE;
     const Ws w = ws_layout(h->d, wsp);
     MSA_CUDA(cudaDeviceSynchronize());
     MSA_CUDA(cudaMemcpy(out, reinterpret_cast<const long long*>(w.prof) + (size_t)id * kProfCtas * kProfSlots,

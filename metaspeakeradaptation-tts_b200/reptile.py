@@ -34,12 +34,14 @@ class Reptile(MetaTrainer):
         if self.sequential and self.shard.world > 1:
             raise ValueError("sequential Reptile (the reference's literal semantics) cannot be sharded")
 
-    def _eval_test(self, i: int, task, n_inner: int) -> torch.Tensor:
+    def _eval_test(self, i: int, task, n_inner: int, fast=None, bn=None) -> torch.Tensor:
         """reptile.py:58-70: test loss of the adapted weights, no gradient."""
+        fast = self.fast if fast is None else fast
+        bn = self.task_bn if bn is None else bn
         inputs, _ = self._unpack_batch(task["test"])
         B, L = inputs["inputs"].shape
         T = inputs["melspecs"].shape[2]
-        _, loss = self.engine.forward(self.fast, self.task_bn, inputs, self._masks(i, n_inner, B, T, L), outputs=False)
+        _, loss = self.engine.forward(fast, bn, inputs, self._masks(i, n_inner, B, T, L), outputs=False)
         self._mcds.append(self.engine.mcd(inputs["melspec_lengths"]))       # reptile.py:62-66, on the device
         return loss
 
@@ -62,12 +64,21 @@ class Reptile(MetaTrainer):
         mine = self.shard.my_tasks(N)
         if not mine:
             self.meta_grad.zero_()
-        for j, i in enumerate(mine):
-            task = items_b[speakers[i]]
-            self._adapt(i, task["train"], n_inner)
-            if eval_test:
-                losses.append(self._eval_test(i, task, n_inner))
-            eng.reptile_delta(self.meta_grad, self.fast, self.theta, 1.0 / N, init=(j == 0))
+        train = {i: items_b[speakers[i]]["train"] for i in mine}
+        j = 0
+        for group in self._group_plan(mine, train):
+            if len(group) == 1:
+                self._adapt(group[0], train[group[0]], n_inner)
+                slots = [(self.fast, self.task_grad, self.task_bn)]
+            else:       # the first inner step of the group as one pass from theta_0, the other steps task by task
+                self._adapt_group(group, train, n_inner)
+                slots = [self._slot(k) for k in range(len(group))]
+            for k, i in enumerate(group):
+                fast, _, bn = slots[k]
+                if eval_test:
+                    losses.append(self._eval_test(i, items_b[speakers[i]], n_inner, fast, bn))
+                eng.reptile_delta(self.meta_grad, fast, self.theta, 1.0 / N, init=(j == 0))
+                j += 1
         sumsq = self._outer_update()
         return {"loss_test": torch.cat(losses) if losses else None, "mcd": torch.cat(self._mcds) if self._mcds else None,
                 "task_index": mine, "grad_sumsq": sumsq}
