@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmsa_b200.so")
+# MSA_LIB_PATH: development only (A/B runs of differently compiled builds of the same library)
+LIB_PATH = os.environ.get("MSA_LIB_PATH") or os.path.join(HERE, "libmsa_b200.so")
 
 c_f32p = C.c_void_p
 c_i64p = C.c_void_p

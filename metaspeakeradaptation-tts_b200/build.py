@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmsa_b200.so")
 SOURCES = ["flat_kernels.cu", "model_kernels.cu", "lstm_rec.cu", "attn_chain.cu", "chain_mma.cu", "pass.cu", "infer_kernels.cu", "infer_decode.cu", "infer_lstm_tma.cu", "gemm_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = (["-DMSA_POLL_BACKOFF=" + os.environ["MSA_POLL_BACKOFF"]] if os.environ.get("MSA_POLL_BACKOFF") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+FLAGS = os.environ.get("MSA_NVCC_DEFS", "").split() + (["-DMSA_POLL_BACKOFF=" + os.environ["MSA_POLL_BACKOFF"]] if os.environ.get("MSA_POLL_BACKOFF") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=default"]
 
 

@@ -23,12 +23,22 @@ namespace msa {
 
 namespace {
 
+#ifndef MSA_SENT_LAST
+#define MSA_SENT_LAST 0
+#endif
+#ifndef MSA_SLICE_ROT
+#define MSA_SLICE_ROT 1
+#endif
 #ifndef MSA_PF_FWD
 #define MSA_PF_FWD 2
 #endif
-#ifndef MSA_PF_BWD
-#define MSA_PF_BWD 2
+#ifndef MSA_PF_BWD1
+#define MSA_PF_BWD1 2
 #endif
+#ifndef MSA_PF_BWD2
+#define MSA_PF_BWD2 2
+#endif
+#define MSA_PF_BWD (MTL == 1 ? MSA_PF_BWD1 : MSA_PF_BWD2)
 constexpr int kMT = 512;              // threads per CTA
 constexpr int kMW = kMT / 32;         // warps = K slices of the gate product
 
@@ -51,6 +61,54 @@ __device__ __forceinline__ void mma3(float (&d)[4], const uint4& ahi, const uint
     mma_bf16(d, alo.x, alo.y, alo.z, alo.w, bhi[0], bhi[1]);
     mma_bf16(d, ahi.x, ahi.y, ahi.z, ahi.w, blo[0], blo[1]);
     mma_bf16(d, ahi.x, ahi.y, ahi.z, ahi.w, bhi[0], bhi[1]);
+}
+
+// Polling slow paths, deliberately NOT inlined: the fast path of every hand-off load is one canary test; only a load that came back
+// too early calls in here.  (Inlined spin loops with their time-out bookkeeping at every poll site had grown the attention kernels to
+// 130-170 KB of SASS -- far beyond the instruction caches, every step re-fetched its code from L2.)
+__device__ __noinline__ float4 poll4_slow(const float* p, unsigned int* abort_word) {
+    float4 v = ld_poll4(p);
+    if (*reinterpret_cast<volatile unsigned int*>(abort_word) != 0u) return v;
+    unsigned int n = 0;
+    while (!ready4(v)) {
+        if ((++n & 1023u) == 0u) {
+            if (*reinterpret_cast<volatile unsigned int*>(abort_word) != 0u) break;
+            if (n > (1u << 21)) { *reinterpret_cast<volatile unsigned int*>(abort_word) = 1u; break; }
+        }
+        v = ld_poll4(p);
+    }
+    return v;
+}
+__device__ __noinline__ float poll1_slow(const float* p, unsigned int* abort_word) {
+    float v = ld_poll(p);
+    if (*reinterpret_cast<volatile unsigned int*>(abort_word) != 0u) return v;
+    unsigned int n = 0;
+    while (is_canary(v)) {
+        if ((++n & 1023u) == 0u) {
+            if (*reinterpret_cast<volatile unsigned int*>(abort_word) != 0u) break;
+            if (n > (1u << 21)) { *reinterpret_cast<volatile unsigned int*>(abort_word) = 1u; break; }
+        }
+        v = ld_poll(p);
+    }
+    return v;
+}
+__device__ __forceinline__ float4 pollq4(const float* p, unsigned int* abort_word) {
+    float4 v = ld_poll4(p);
+    if (!ready4(v)) v = poll4_slow(p, abort_word);
+    return v;
+}
+__device__ __forceinline__ float pollq1(const float* p, unsigned int* abort_word) {
+    float v = ld_poll(p);
+    if (is_canary(v)) v = poll1_slow(p, abort_word);
+    return v;
+}
+// first n threads wait for one sentinel word each (rec_common.cuh::gate_wait with the out-of-line poller)
+template <class AddrFn>
+__device__ __forceinline__ void gate_waitq(int n, AddrFn addr, unsigned int* abort_word) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float* a = addr(i);
+        if (a) (void)pollq1(a, abort_word);
+    }
 }
 
 // Fragment column permutation: within a k16 block, lane j (= lane & 3) owns the four PHYSICAL columns 4j .. 4j+3 and feeds them
@@ -82,6 +140,9 @@ __global__ void __launch_bounds__(kMT, 1) k_lstm_fwd_mma(LstmRecParams p) {
     const int u0 = part_lo(ci, H, ncta_dir), u1 = part_lo(ci + 1, H, ncta_dir), U = u1 - u0;
     if (U == 0) return;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lg = lane >> 2, lj = lane & 3;
+    // K slice of this warp, rotated by the CTA index: the 148 CTAs stream the SAME h / dz rows, without the rotation they would all
+    // ask the same L2 slices for the same lines at the same moment
+    const int wsl = MSA_SLICE_ROT ? (w + blockIdx.x) % kMW : w;
     const int KS = (H + 255) / 256;                       // k16 steps per warp; warp w owns columns [w*KS*16, (w+1)*KS*16)
     uint4* Afrag = reinterpret_cast<uint4*>(smem_raw);   // [kMW][KS][2][2][32]
     float* part = reinterpret_cast<float*>(Afrag + (size_t)kMW * KS * 2 * 2 * 32);      // [kMW][NT][2][4][32]
@@ -117,6 +178,7 @@ __global__ void __launch_bounds__(kMT, 1) k_lstm_fwd_mma(LstmRecParams p) {
     const int c_nt = threadIdx.x >> 6, c_par = (threadIdx.x >> 5) & 1, c_ln = threadIdx.x & 31;
     const int c_ul = c_ln >> 2, c_r = c_nt * 8 + (c_ln & 3) * 2 + c_par;
     const bool pw = (int)threadIdx.x < NT * 64 && c_ul < U && c_r < R;
+    const bool is_sent = MSA_SENT_LAST && pw && c_ul == U - 1 && c_r == R - 1;
     const int c_g = pw ? gr.task(c_r) : 0, c_b = pw ? gr.brow(c_r) : 0, c_u = u0 + c_ul;
     const float* zin = p.zin + c_g * gr.tstride + dir_off_z;
     float* hout_c = p.hout + c_g * gr.tstride + dir_off_h;
@@ -145,7 +207,6 @@ __global__ void __launch_bounds__(kMT, 1) k_lstm_fwd_mma(LstmRecParams p) {
         const int rr = rowok[nt] ? r : 0;
         hrow[nt] = p.hout + gr.task(rr) * gr.tstride + dir_off_h + (size_t)gr.brow(rr) * H;
     }
-    SpinGuard sg(p.abort_word);
     __syncthreads();
 
     for (int s_ = 0; s_ < T; ++s_) {
@@ -163,7 +224,7 @@ __global__ void __launch_bounds__(kMT, 1) k_lstm_fwd_mma(LstmRecParams p) {
             {
                 const int rl_ = R - 1;
                 const float* hlast = p.hout + gr.task(rl_) * gr.tstride + dir_off_h + ((size_t)tp * gr.Bt + gr.brow(rl_)) * H;
-                gate_wait(ncta_dir, [&](int c) { const int e = part_lo(c + 1, H, ncta_dir); return e > part_lo(c, H, ncta_dir) ? hlast + e - 1 : nullptr; }, sg);
+                gate_waitq(ncta_dir, [&](int c) { const int e = part_lo(c + 1, H, ncta_dir); return e > part_lo(c, H, ncta_dir) ? hlast + e - 1 : nullptr; }, p.abort_word);
                 __syncthreads();
             }
             const size_t toff = (size_t)tp * gr.Bt * H;
@@ -172,27 +233,23 @@ __global__ void __launch_bounds__(kMT, 1) k_lstm_fwd_mma(LstmRecParams p) {
             constexpr int PF = MSA_PF_FWD;      // measured on B200: 2 in flight beats 4 (803 vs 736 us at R = 8): later loads find their data published
             float4 hv[PF][NT];
             auto issue = [&](int s, float4 (&dst)[NT]) {
-                const int col = (w * KS + s) * 16 + 4 * lj;
+                const int col = (wsl * KS + s) * 16 + 4 * lj;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt)
                     dst[nt] = (rowok[nt] && col < H) ? ld_poll4(hrow[nt] + toff + col) : make_float4(0.f, 0.f, 0.f, 0.f);
             };
             auto process = [&](int s, float4 (&cur)[NT]) {
-                const int col = (w * KS + s) * 16 + 4 * lj;
+                const int col = (wsl * KS + s) * 16 + 4 * lj;
                 uint32_t bhi[NT][2], blo[NT][2];
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     if (rowok[nt] && col < H) {
-                        sg.reset();
-                        while (!ready4(cur[nt])) {
-                            if (sg.bail()) break;
-                            cur[nt] = ld_poll4(hrow[nt] + toff + col);
-                        }
+                        if (!ready4(cur[nt])) cur[nt] = poll4_slow(hrow[nt] + toff + col, p.abort_word);
                     }
                     split2(cur[nt].x, cur[nt].y, bhi[nt][0], blo[nt][0]);
                     split2(cur[nt].z, cur[nt].w, bhi[nt][1], blo[nt][1]);
                 }
-                const uint4* af = Afrag + ((size_t)w * KS + s) * 2 * 2 * 32;
+                const uint4* af = Afrag + ((size_t)wsl * KS + s) * 2 * 2 * 32;
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
                     const uint4 ahi = af[(mt * 2 + 0) * 32 + lane], alo = af[(mt * 2 + 1) * 32 + lane];
@@ -222,7 +279,10 @@ __global__ void __launch_bounds__(kMT, 1) k_lstm_fwd_mma(LstmRecParams p) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) part[((((size_t)w * NT + nt) * 2 + mt) * 4 + i) * 32 + lane] = acc[nt][mt][i];
         __syncthreads();
-        if (pw) {
+        if ((int)threadIdx.x < NT * 64) {
+          float hvv = 0.f;
+          size_t hb = 0;
+          if (pw) {
             // gate (i, f, g, o) of cell (c_ul, c_r): m tile = gate >> 1, reg = (gate & 1) * 2 + parity, lane c_ln
             float z[4];
 #pragma unroll
@@ -235,7 +295,7 @@ __global__ void __launch_bounds__(kMT, 1) k_lstm_fwd_mma(LstmRecParams p) {
             }
             const bool active = t < len;
             float ai = fast_sigmoid(z[0]), af = fast_sigmoid(z[1]), ag = fast_tanh(z[2]), ao = fast_sigmoid(z[3]);
-            float cn = 0.f, hvv = 0.f;
+            float cn = 0.f;
             if (active) {
                 cn = af * cstate + ai * ag;
                 cstate = cn;
@@ -244,14 +304,19 @@ __global__ void __launch_bounds__(kMT, 1) k_lstm_fwd_mma(LstmRecParams p) {
             } else {
                 ai = af = ag = ao = 0.f;
             }
-            const size_t hb = ((size_t)t * gr.Bt + c_b) * H + c_u, zb = ((size_t)t * gr.Bt + c_b) * H4;
-            st_pub(hout_c + hb, hvv);              // consumed by every CTA at the next step: first memory operation
+            hb = ((size_t)t * gr.Bt + c_b) * H + c_u;
+            const size_t zb = ((size_t)t * gr.Bt + c_b) * H4;
+            if (!is_sent) st_pub(hout_c + hb, hvv);              // consumed by every CTA at the next step: first memory operation
             gates_c[zb + 0 * (size_t)H + c_u] = ai;
             gates_c[zb + 1 * (size_t)H + c_u] = af;
             gates_c[zb + 2 * (size_t)H + c_u] = ag;
             gates_c[zb + 3 * (size_t)H + c_u] = ao;
             cout_c[hb] = cn;
             if (s_ + 1 < T) fetch(dir == 0 ? t + 1 : t - 1);
+          }
+          // the sentinel word (the one the consumers' gate waits for) leaves after every other cell of this CTA has been published
+          if (MSA_SENT_LAST) asm volatile("bar.sync 1, %0;" ::"n"(NT * 64));
+          if (is_sent) st_pub(hout_c + hb, hvv);
         }
         // (no barrier here: `part` is rewritten only after the barrier that follows the next step's gate_wait)
     }
@@ -274,6 +339,9 @@ __global__ void __launch_bounds__(kMT, 1) k_lstm_bwd_mma(LstmRecBwdParams p) {
     const int u0 = part_lo(ci, H, ncta_dir), u1 = part_lo(ci + 1, H, ncta_dir), U = u1 - u0;
     if (U == 0) return;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lg = lane >> 2, lj = lane & 3;
+    // K slice of this warp, rotated by the CTA index: the 148 CTAs stream the SAME h / dz rows, without the rotation they would all
+    // ask the same L2 slices for the same lines at the same moment
+    const int wsl = MSA_SLICE_ROT ? (w + blockIdx.x) % kMW : w;
     const int KS = (H4 + 255) / 256;                      // k16 steps per warp over the 4H gate rows
     uint2* Bfrag = reinterpret_cast<uint2*>(smem_raw);   // [kMW][KS][hi|lo][32]
     float* part = reinterpret_cast<float*>(Bfrag + (size_t)kMW * KS * 2 * 32);           // [kMW][MTL][4][32]
@@ -300,6 +368,7 @@ __global__ void __launch_bounds__(kMT, 1) k_lstm_bwd_mma(LstmRecBwdParams p) {
     const int c_mt = threadIdx.x >> 7, c_reg = (threadIdx.x >> 5) & 3, c_ln = threadIdx.x & 31;
     const int c_r = c_mt * 16 + (c_reg >> 1) * 8 + (c_ln >> 2), c_ul = (c_ln & 3) * 2 + (c_reg & 1);
     const bool pw = (int)threadIdx.x < MTL * 128 && c_ul < U && c_r < R;
+    const bool is_sent = MSA_SENT_LAST && pw && c_ul == U - 1 && c_r == R - 1;
     const int c_g = pw ? gr.task(c_r) : 0, c_b = pw ? gr.brow(c_r) : 0, c_u = u0 + c_ul;
     const float* gates_c = p.gates + c_g * gr.tstride + dir_off_z;
     const float* cst_c = p.cout + c_g * gr.tstride + dir_off_h;
@@ -334,7 +403,6 @@ __global__ void __launch_bounds__(kMT, 1) k_lstm_bwd_mma(LstmRecBwdParams p) {
             const int rr = rowok[mt][hr] ? r : 0;
             zrow[mt][hr] = p.dz + gr.task(rr) * gr.tstride + dir_off_z + (size_t)gr.brow(rr) * H4;
         }
-    SpinGuard sg(p.abort_word);
     __syncthreads();
 
     for (int s_ = 0; s_ < T; ++s_) {
@@ -349,14 +417,14 @@ __global__ void __launch_bounds__(kMT, 1) k_lstm_bwd_mma(LstmRecBwdParams p) {
             {
                 const int rl_ = R - 1;
                 const float* zlast = p.dz + gr.task(rl_) * gr.tstride + dir_off_z + ((size_t)tn * gr.Bt + gr.brow(rl_)) * H4 + (size_t)3 * H;
-                gate_wait(ncta_dir, [&](int c) { const int e = part_lo(c + 1, H, ncta_dir); return e > part_lo(c, H, ncta_dir) ? zlast + e - 1 : nullptr; }, sg);
+                gate_waitq(ncta_dir, [&](int c) { const int e = part_lo(c + 1, H, ncta_dir); return e > part_lo(c, H, ncta_dir) ? zlast + e - 1 : nullptr; }, p.abort_word);
                 __syncthreads();
             }
             const size_t toff = (size_t)tn * gr.Bt * H4;
             constexpr int PF = MSA_PF_BWD;      // measured on B200: 2 in flight beats 4 / 8 (2639 vs 3395 us at R = 32)
             float4 zv[PF][MTL][2];
             auto issue = [&](int s, float4 (&dst)[MTL][2]) {
-                const int col = (w * KS + s) * 16 + 4 * lj;
+                const int col = (wsl * KS + s) * 16 + 4 * lj;
 #pragma unroll
                 for (int mt = 0; mt < MTL; ++mt)
 #pragma unroll
@@ -364,8 +432,8 @@ __global__ void __launch_bounds__(kMT, 1) k_lstm_bwd_mma(LstmRecBwdParams p) {
                         dst[mt][hr] = (rowok[mt][hr] && col < H4) ? ld_poll4(zrow[mt][hr] + toff + col) : make_float4(0.f, 0.f, 0.f, 0.f);
             };
             auto process = [&](int s, float4 (&cur)[MTL][2]) {
-                const int col = (w * KS + s) * 16 + 4 * lj;
-                const uint2* bf = Bfrag + ((size_t)w * KS + s) * 2 * 32;
+                const int col = (wsl * KS + s) * 16 + 4 * lj;
+                const uint2* bf = Bfrag + ((size_t)wsl * KS + s) * 2 * 32;
                 const uint2 bh = bf[lane], bl = bf[32 + lane];
                 const uint32_t bhi[2] = {bh.x, bh.y}, blo[2] = {bl.x, bl.y};
 #pragma unroll
@@ -373,11 +441,7 @@ __global__ void __launch_bounds__(kMT, 1) k_lstm_bwd_mma(LstmRecBwdParams p) {
 #pragma unroll
                     for (int hr = 0; hr < 2; ++hr) {
                         if (rowok[mt][hr] && col < H4) {
-                            sg.reset();
-                            while (!ready4(cur[mt][hr])) {
-                                if (sg.bail()) break;
-                                cur[mt][hr] = ld_poll4(zrow[mt][hr] + toff + col);
-                            }
+                            if (!ready4(cur[mt][hr])) cur[mt][hr] = poll4_slow(zrow[mt][hr] + toff + col, p.abort_word);
                         }
                     }
                     uint4 ahi, alo;
@@ -407,7 +471,10 @@ __global__ void __launch_bounds__(kMT, 1) k_lstm_bwd_mma(LstmRecBwdParams p) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) part[(((size_t)w * MTL + mt) * 4 + i) * 32 + lane] = acc[mt][i];
         __syncthreads();
-        if (pw) {
+        if ((int)threadIdx.x < MTL * 128) {
+          float dzo = 0.f;
+          size_t zo = 0;
+          if (pw) {
             float drec = 0.f;
             const float* pp = part + ((size_t)c_mt * 4 + c_reg) * 32 + c_ln;
 #pragma unroll
@@ -424,8 +491,13 @@ __global__ void __launch_bounds__(kMT, 1) k_lstm_bwd_mma(LstmRecBwdParams p) {
             st_pub(dz_c + zb + 0 * (size_t)H + c_u, g.di);
             st_pub(dz_c + zb + 1 * (size_t)H + c_u, g.df);
             st_pub(dz_c + zb + 2 * (size_t)H + c_u, g.dg);
-            st_pub(dz_c + zb + 3 * (size_t)H + c_u, g.do_);
+            dzo = g.do_;
+            zo = zb + 3 * (size_t)H + c_u;
+            if (!is_sent) st_pub(dz_c + zo, dzo);
             if (s_ + 1 < T) fetch(dir == 0 ? t - 1 : t + 1);
+          }
+          if (MSA_SENT_LAST) asm volatile("bar.sync 1, %0;" ::"n"(MTL * 128));      // the sentinel word leaves last (see the forward kernel)
+          if (is_sent) st_pub(dz_c + zo, dzo);
         }
     }
 }
@@ -510,6 +582,9 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
     const int R = gr.R, Bt = gr.Bt, BtL = Bt * L, RL = R * L, pl = (Kl - 1) / 2;
     const int ncta = gridDim.x, cta = blockIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lg = lane >> 2, lj = lane & 3;
+    // K slice of this warp, rotated by the CTA index: the 148 CTAs stream the SAME h / dz rows, without the rotation they would all
+    // ask the same L2 slices for the same lines at the same moment
+    const int wsl = MSA_SLICE_ROT ? (w + blockIdx.x) % kMW : w;
     const AttnFwdMmaLay lay = attn_fwd_mma_layout(R, L, Ha, A, F, Kl, ncta, NT);
     const int KS = lay.KS, LP = lay.LP, LH = lay.LH, CKP = lay.CKP, RP = lay.RP;
     constexpr int NTP = NT < 2 ? NT : 2;
@@ -619,7 +694,6 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
         hrow[nt] = p.ha + gr.task(rr) * gr.tstride + (size_t)gr.brow(rr) * Ha;
     }
     const bool vecL = (L & 3) == 0;
-    SpinGuard sg(p.abort_word);
     ChainProf<true> prof;      // per-phase cycles of thread 0 when a buffer is passed (profiles/), one predictable branch otherwise
     prof.start(p.prof, nullptr, 0);
     __syncthreads();
@@ -741,7 +815,7 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
         {
             const int rl_ = R - 1;
             const float* hlast = p.ha + gr.task(rl_) * gr.tstride + ((size_t)t * Bt + gr.brow(rl_)) * Ha;
-            gate_wait(ncta, [&](int c) { const int e = part_lo(c + 1, Ha, ncta); return e > part_lo(c, Ha, ncta) ? hlast + e - 1 : nullptr; }, sg);
+            gate_waitq(ncta, [&](int c) { const int e = part_lo(c + 1, Ha, ncta); return e > part_lo(c, Ha, ncta) ? hlast + e - 1 : nullptr; }, p.abort_word);
             __syncthreads();
         }
         prof.mark(3, t);
@@ -757,27 +831,23 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
             constexpr int PF = MSA_PF_FWD;
             float4 hv[PF][NT];
             auto issue = [&](int s, float4 (&dst)[NT]) {
-                const int col = (w * KS + s) * 16 + 4 * lj;
+                const int col = (wsl * KS + s) * 16 + 4 * lj;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt)
                     dst[nt] = (rowok[nt] && col < Ha) ? ld_poll4(hrow[nt] + toff + col) : make_float4(0.f, 0.f, 0.f, 0.f);
             };
             auto process = [&](int s, float4 (&cur)[NT]) {
-                const int col = (w * KS + s) * 16 + 4 * lj;
+                const int col = (wsl * KS + s) * 16 + 4 * lj;
                 uint32_t bhi[NT][2], blo[NT][2];
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     if (rowok[nt] && col < Ha) {
-                        sg.reset();
-                        while (!ready4(cur[nt])) {
-                            if (sg.bail()) break;
-                            cur[nt] = ld_poll4(hrow[nt] + toff + col);
-                        }
+                        if (!ready4(cur[nt])) cur[nt] = poll4_slow(hrow[nt] + toff + col, p.abort_word);
                     }
                     split2(cur[nt].x, cur[nt].y, bhi[nt][0], blo[nt][0]);
                     split2(cur[nt].z, cur[nt].w, bhi[nt][1], blo[nt][1]);
                 }
-                const uint4* af = Afrag + ((size_t)w * KS + s) * 2 * 2 * 32;
+                const uint4* af = Afrag + ((size_t)wsl * KS + s) * 2 * 2 * 32;
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
                     const uint4 ahi = af[(mt * 2 + 0) * 32 + lane], alo = af[(mt * 2 + 1) * 32 + lane];
@@ -833,12 +903,12 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
         if ((A & 3) == 0) {
             for (int i = threadIdx.x; i < nrown * (A >> 2); i += kMT) {
                 const int ro = i / (A >> 2), d4 = i - ro * (A >> 2), r = r_lo + ro;
-                reinterpret_cast<float4*>(q_s)[i] = poll4(p.q + gr.task(r) * gr.tstride + ((size_t)t * Bt + gr.brow(r)) * A + d4 * 4, sg);
+                reinterpret_cast<float4*>(q_s)[i] = pollq4(p.q + gr.task(r) * gr.tstride + ((size_t)t * Bt + gr.brow(r)) * A + d4 * 4, p.abort_word);
             }
         } else {
             for (int i = threadIdx.x; i < nrown * A; i += kMT) {
                 const int ro = i / A, d = i - ro * A, r = r_lo + ro;
-                q_s[i] = poll1(p.q + gr.task(r) * gr.tstride + ((size_t)t * Bt + gr.brow(r)) * A + d, sg);
+                q_s[i] = pollq1(p.q + gr.task(r) * gr.tstride + ((size_t)t * Bt + gr.brow(r)) * A + d, p.abort_word);
             }
         }
         __syncthreads();
@@ -865,12 +935,12 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
         if ((BtL & 3) == 0) {      // 128-bit polls: one L2 round trip for the whole gather
             for (int i4 = threadIdx.x; i4 < (RL >> 2); i4 += kMT) {
                 const int i = i4 * 4, g = i / BtL;
-                reinterpret_cast<float4*>(es)[i4] = poll4(p.e + g * gr.tstride + (size_t)t * BtL + (i - g * BtL), sg);
+                reinterpret_cast<float4*>(es)[i4] = pollq4(p.e + g * gr.tstride + (size_t)t * BtL + (i - g * BtL), p.abort_word);
             }
         } else {
             for (int i = threadIdx.x; i < RL; i += kMT) {
                 const int g = pos_task(i);
-                es[i] = poll1(p.e + g * gr.tstride + (size_t)t * BtL + (i - g * BtL), sg);
+                es[i] = pollq1(p.e + g * gr.tstride + (size_t)t * BtL + (i - g * BtL), p.abort_word);
             }
         }
         __syncthreads();
@@ -979,6 +1049,9 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
     const int R = gr.R, Bt = gr.Bt, BtL = Bt * L, RL = R * L, pl = (Kl - 1) / 2;
     const int ncta = gridDim.x, cta = blockIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lg = lane >> 2, lj = lane & 3;
+    // K slice of this warp, rotated by the CTA index: the 148 CTAs stream the SAME h / dz rows, without the rotation they would all
+    // ask the same L2 slices for the same lines at the same moment
+    const int wsl = MSA_SLICE_ROT ? (w + blockIdx.x) % kMW : w;
     const AttnBwdMmaLay lay = attn_bwd_mma_layout(R, L, Ha, A, F, Kl, ncta, MTL);
     const int KS = lay.KS, KQ = lay.KQ, CKP = lay.CKP, WIN = lay.WIN, FP = lay.FP;
     uint2* Bfrag = reinterpret_cast<uint2*>(smem_raw + lay.bfrag);    // [kMW][KS][hi|lo][32]  W_hh^T slice
@@ -1096,7 +1169,6 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
             const int rr = rowok[mt][hr] ? r : 0;
             zrow[mt][hr] = p.dza + gr.task(rr) * gr.tstride + (size_t)gr.brow(rr) * H4;
         }
-    SpinGuard sg(p.abort_word);
     ChainProf<true> prof;
     prof.start(p.prof, nullptr, 0);
     __syncthreads();
@@ -1111,7 +1183,7 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
         if (t < T - 1) {
             const int rl_ = R - 1;
             const float* zlast = p.dza + gr.task(rl_) * gr.tstride + ((size_t)(t + 1) * Bt + gr.brow(rl_)) * H4 + (size_t)3 * Ha;
-            gate_wait(ncta, [&](int c) { const int e = part_lo(c + 1, Ha, ncta); return e > part_lo(c, Ha, ncta) ? zlast + e - 1 : nullptr; }, sg);
+            gate_waitq(ncta, [&](int c) { const int e = part_lo(c + 1, Ha, ncta); return e > part_lo(c, Ha, ncta) ? zlast + e - 1 : nullptr; }, p.abort_word);
             __syncthreads();
         }
         prof.mark(0, T - 1 - t);
@@ -1134,11 +1206,7 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
                     for (int k = 0; k < NB; ++k) {
                         const int c = c0 + k * 32;
                         if (c < (H4 >> 2)) {
-                            sg.reset();
-                            while (!ready4(zv[k])) {
-                                if (sg.bail()) break;
-                                zv[k] = ld_poll4(zr + (size_t)c * 4);
-                            }
+                            if (!ready4(zv[k])) zv[k] = poll4_slow(zr + (size_t)c * 4, p.abort_word);
                             a += dot4(mv[k], zv[k]);
                         }
                     }
@@ -1158,7 +1226,7 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
             constexpr int PF = MSA_PF_BWD;
             float4 zv[PF][MTL][2];
             auto issue = [&](int s, float4 (&dst)[MTL][2]) {
-                const int col = (w * KS + s) * 16 + 4 * lj;
+                const int col = (wsl * KS + s) * 16 + 4 * lj;
 #pragma unroll
                 for (int mt = 0; mt < MTL; ++mt)
 #pragma unroll
@@ -1166,8 +1234,8 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
                         dst[mt][hr] = (rowok[mt][hr] && col < H4) ? ld_poll4(zrow[mt][hr] + toff + col) : make_float4(0.f, 0.f, 0.f, 0.f);
             };
             auto process = [&](int s, float4 (&cur)[MTL][2]) {
-                const int col = (w * KS + s) * 16 + 4 * lj;
-                const uint2* bf = Bfrag + ((size_t)w * KS + s) * 2 * 32;
+                const int col = (wsl * KS + s) * 16 + 4 * lj;
+                const uint2* bf = Bfrag + ((size_t)wsl * KS + s) * 2 * 32;
                 const uint2 bh = bf[lane], bl = bf[32 + lane];
                 const uint32_t bhi[2] = {bh.x, bh.y}, blo[2] = {bl.x, bl.y};
 #pragma unroll
@@ -1175,11 +1243,7 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
 #pragma unroll
                     for (int hr = 0; hr < 2; ++hr) {
                         if (rowok[mt][hr] && col < H4) {
-                            sg.reset();
-                            while (!ready4(cur[mt][hr])) {
-                                if (sg.bail()) break;
-                                cur[mt][hr] = ld_poll4(zrow[mt][hr] + toff + col);
-                            }
+                            if (!ready4(cur[mt][hr])) cur[mt][hr] = poll4_slow(zrow[mt][hr] + toff + col, p.abort_word);
                         }
                     }
                     uint4 ahi, alo;
@@ -1211,14 +1275,14 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
                 const int i = i4 * 4, g = i / BtL;
                 const size_t o = g * gr.tstride + (size_t)t * BtL + (i - g * BtL);
                 reinterpret_cast<float4*>(als)[i4] = __ldg(reinterpret_cast<const float4*>(p.align + o));
-                reinterpret_cast<float4*>(das)[i4] = poll4(p.dat + o, sg);
+                reinterpret_cast<float4*>(das)[i4] = pollq4(p.dat + o, p.abort_word);
             }
         } else {
             for (int i = threadIdx.x; i < RL; i += kMT) {
                 const int g = pos_task(i);
                 const size_t o = g * gr.tstride + (size_t)t * BtL + (i - g * BtL);
                 als[i] = __ldg(p.align + o);
-                das[i] = poll1(p.dat + o, sg);
+                das[i] = pollq1(p.dat + o, p.abort_word);
             }
         }
         if ((int)threadIdx.x < R) zn_s[threadIdx.x] = __ldg(p.znorm + gr.task(threadIdx.x) * gr.tstride + (size_t)t * Bt + gr.brow(threadIdx.x));
@@ -1325,7 +1389,7 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
                 for (int hr = 0; hr < 2; ++hr) {
                     const int r = mt * 16 + hr * 8 + lg, rr = r < R ? r : 0;
                     const float* qrow = p.dq + gr.task(rr) * gr.tstride + (size_t)gr.brow(rr) * A;
-                    cur[hr] = (r < R && col < A) ? poll4(qrow + toff + col, sg) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    cur[hr] = (r < R && col < A) ? pollq4(qrow + toff + col, p.abort_word) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 uint4 ahi, alo;
                 split2(cur[0].x, cur[0].y, ahi.x, alo.x);
@@ -1363,7 +1427,7 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
             const float* src = p.dconvf + g * gr.tstride + ((size_t)t * BtL + (size_t)(r - g * Bt) * L + lo0) * F;
             for (int it = threadIdx.x; it < nwin * F; it += kMT) {
                 const int wl = it / F, f = it - wl * F;
-                dcw[((size_t)ro * WIN + wl) * FP + f] = poll1(src + it, sg);
+                dcw[((size_t)ro * WIN + wl) * FP + f] = pollq1(src + it, p.abort_word);
             }
         }
         __syncthreads();

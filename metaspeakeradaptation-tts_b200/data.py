@@ -12,7 +12,8 @@ item carries a ready mel-spectrogram where the reference carries a waveform: ``(
 melspec FloatTensor [1, n_mels, len] or [n_mels, len], spk_emb FloatTensor [Ds])``.
 
 B200 side of the contract: with ``pin_memory=True`` every tensor of a batch is written straight into page-locked host memory, so
-``batch_to_device(..., non_blocking=True)`` turns into asynchronous copies that the copy engine overlaps with the previous task.
+``MetaTrainer._stage`` can enqueue the host -> device copies of all batches of a meta-batch on a side stream: the copy engine moves
+the later tasks' batches while the compute stream runs the earlier tasks' passes (each pass waits for its own batch's event).
 """
 from __future__ import annotations
 

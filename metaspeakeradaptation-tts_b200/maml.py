@@ -33,7 +33,10 @@ class MAML(MetaTrainer):
         losses, mcds = [], []
         if not mine:
             self.meta_grad.zero_()
-        train = {i: items_b[speakers[i]]["train"] for i in mine}
+        # every batch of this rank's tasks goes to the copy stream up front: H2D of the later tasks overlaps the earlier tasks' passes
+        staged = self._stage([items_b[speakers[i]][k] for i in mine for k in ("train", "test")])
+        train = {i: staged[2 * n] for n, i in enumerate(mine)}
+        test = {i: staged[2 * n + 1] for n, i in enumerate(mine)}
         j = 0
         for group in self._group_plan(mine, train):
             if len(group) == 1:
@@ -44,7 +47,7 @@ class MAML(MetaTrainer):
                 slots = [self._slot(k) for k in range(len(group))]
             for k, i in enumerate(group):
                 fast, _, bn = slots[k]
-                inputs, _ = self._unpack_batch(items_b[speakers[i]]["test"])
+                inputs, _ = self._unpack_batch(test[i])
                 B, L = inputs["inputs"].shape
                 T = inputs["melspecs"].shape[2]
                 _, loss = eng.forward(fast, bn, inputs, self._masks(i, n_inner, B, T, L), outputs=False)

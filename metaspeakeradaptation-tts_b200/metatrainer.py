@@ -22,6 +22,16 @@ from .helpers import optimizer_hparams
 from .parallel import ShardInfo
 
 
+class _Staged:
+    """A batch tuple whose device copy is in flight on the copy stream; indexable like the tuple (shapes for the group plan)."""
+
+    def __init__(self, host, dev, event):
+        self.host, self.dev, self.event = host, dev, event
+
+    def __getitem__(self, i):
+        return self.host[i]
+
+
 class MetaTrainer:
     def __init__(self, **params):
         self.params = params
@@ -64,16 +74,41 @@ class MetaTrainer:
         self.mask_seed = int(params.get("dataset_random_seed", 1234))
         self._mask_bufs: Dict[tuple, torch.Tensor] = {}
         self._slots: list = []
+        self._copy_stream = None
         self.injected_masks = None       # parity tests: {(task_index, pass_index): reference-layout mask dict}
         if params.get("finetune", False):
             self._load_checkpoint()
 
     # ---- data ------------------------------------------------------------------------------------
     def _unpack_batch(self, batch_items):
-        """metatrainer.py:95-117."""
+        """metatrainer.py:95-117.  A batch that ``_stage`` has already put on the copy stream is only waited for."""
+        if isinstance(batch_items, _Staged):
+            torch.cuda.current_stream().wait_event(batch_items.event)
+            return batch_items.dev, batch_items.dev["stop"]
         d = batch_to_device(batch_items, self.device, self.speaker_emb_type, non_blocking=True)
         stop = d["stop"]
         return d, stop
+
+    def _stage(self, batches: List[tuple]) -> List["_Staged"]:
+        """Host -> device copies of the coming batches on a SIDE stream: with pinned host tensors
+        (``MetaCollator(pin_memory=True)``) the copy engine moves the batches of the later tasks while the compute stream works on the
+        earlier ones; every consumer waits for its batch's own event.  Batches that already live on the device pass through."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream()
+        out = []
+        with torch.cuda.stream(self._copy_stream):
+            for b in batches:
+                if isinstance(b, _Staged):
+                    out.append(b)
+                    continue
+                d = batch_to_device(b, self.device, self.speaker_emb_type, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+                for t in d.values():
+                    t.record_stream(cur)
+                out.append(_Staged(b, d, ev))
+        return out
 
     def _masks(self, task_index: int, pass_index: int, B: int, T: int, L: int, slot: int = 0) -> torch.Tensor:
         """Dropout keep-masks for one pass, keyed by (meta-step, task, pass) -- independent of sharding and of task grouping

@@ -204,3 +204,21 @@ def test_infer_graph_and_direct_launch_agree():
     finally:
         del os.environ["MSA_INFER_GRAPH"]
     assert torch.equal(post, post2) and torch.equal(lens, lens2) and torch.equal(align, align2)
+
+
+def test_vocoder_hand_off_like_infer_py():
+    """infer.py:311-328 hands each utterance's mel to the vocoder as a [1, n_mel, len] tensor on the vocoder's device: here the
+    inference output stays on the GPU and is sliced per utterance (views), or packed as one padded batch."""
+    from msa_tts_b200.vocoder import vocoder_batch, vocoder_inputs
+    (post, lens, _), _, z = _run("small_infer_earlystop")
+    items = vocoder_inputs(post, lens)
+    assert len(items) == post.shape[0]
+    for b, x in enumerate(items):
+        n = min(int(z["mel_lengths"][b]), post.shape[2])
+        assert x.is_cuda and tuple(x.shape) == (1, post.shape[1], n)
+        assert x.data_ptr() == post[b:b + 1].data_ptr(), "a view of the inference output, no copy"
+        assert rel(x[0], z["mel_post"][b, :, :n]) < TOL
+    batch = vocoder_batch(post, lens, pad_value=-7.0)
+    for b in range(post.shape[0]):
+        n = min(int(z["mel_lengths"][b]), batch.shape[2])
+        assert torch.equal(batch[b, :, :n], post[b, :, :n]) and bool((batch[b, :, n:] == -7.0).all())
