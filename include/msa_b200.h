@@ -274,6 +274,13 @@ int msa_ewc_sgd_step(float* p, const float* g, const float* mu, const float* fis
 size_t msa_gemm_nt_scratch_floats(int64_t M, int64_t N, int64_t K);
 int msa_gemm_nt(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb,
                 float beta, float* C, int64_t ldc, int mode, float* scratch, void* stream);
+/* The general row-major form C = alpha * op(A) . op(B) + beta * C on the same kernel: trans_a: A is given as [K][M] (else [M][K]),
+ * trans_b: B is given as [N][K] (else [K][N]).  (0, 1) is msa_gemm_nt; (0, 0) is the input-gradient contraction dX = dY . W and
+ * (1, 0) the weight-gradient contraction dW = dY^T . X of autograd's Linear / conv backward (maml.py:71-74 runs them through
+ * torch.autograd.grad): operands whose contraction index is the ROW index are fed to tcgen05.mma as MN-major shared-memory tiles,
+ * nothing is transposed in memory.  Leading dimensions multiples of 4 floats, 16-byte aligned operands. */
+int msa_gemm(int trans_a, int trans_b, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda,
+             const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int mode, float* scratch, void* stream);
 
 #ifdef __cplusplus
 }

@@ -69,6 +69,7 @@ SIGNATURES = {
     "msa_infer": (I, [V, V, SZ, V, V, V, V, V, V, V, I, I, I, V, V, V, V, V]),
     "msa_gemm_nt_scratch_floats": (SZ, [I64, I64, I64]),
     "msa_gemm_nt": (I, [I64, I64, I64, F, V, I64, V, I64, F, V, I64, I, V, V]),
+    "msa_gemm": (I, [I, I, I64, I64, I64, F, V, I64, V, I64, F, V, I64, I, V, V]),
     "msa_flat_sgd_step": (I, [V, V, V, V, I64, F, F, F, F, I, I, V]),
     "msa_flat_axpy": (I, [V, V, I64, F, I, V]),
     "msa_flat_reptile_delta": (I, [V, V, V, I64, F, I, V]),

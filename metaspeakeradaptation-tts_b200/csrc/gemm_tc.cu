@@ -1,8 +1,12 @@
 // Hand-written sm_100a tensor-core GEMM for the batched (non-recurrent) contractions of the pass:
-//     C[M x N] = alpha * A[M x K] . B[N x K]^T + beta * C          (row-major, both operands K-contiguous: "x . W^T")
-// i.e. every forward projection of Tacotron2NV (prenet, LSTM input projections with M = T*B rows, memory / query layers,
-// mel / gate projections, im2col convolutions).  tcgen05.mma kind::tf32 with fp32 accumulators in TMEM, operands brought
-// in by TMA (128-byte swizzle), a 3-stage mbarrier pipeline, one TMA warp + one MMA warp + four epilogue warps.
+//     C[M x N] = alpha * op(A) . op(B) + beta * C          (row-major)
+// Forward projections of Tacotron2NV are "x . W^T" (both operands K-contiguous = K-major tiles); the backward pass needs the
+// input gradients dX = dY . W (B is [K][N], N-contiguous) and the weight gradients dW = dY^T . X (both operands are [K][.] with
+// the contraction index as the ROW index) -- those operands are MN-major tiles.  tcgen05.mma kind::tf32 reads both kinds straight
+// from shared memory (instruction-descriptor bits 15 / 16), so no operand is ever transposed in memory: a K-major tile is one
+// TMA box {32 K-floats, 128 rows} with the 128-byte swizzle, an MN-major tile four boxes {32 MN-floats, 32 K-rows} with the
+// 128-byte swizzle of 32-byte atoms (the only MN-major layout the tensor core accepts for 32-bit operands).
+// fp32 accumulators in TMEM, a 3-stage mbarrier pipeline, one TMA warp + one MMA warp + four epilogue warps.
 //
 // Precision: a single TF32 product loses 13 mantissa bits of each operand, which the forward pass cannot afford
 // (mel_post 2.5e-3 vs the 1e-3 tolerance).  Mode 0 therefore evaluates the "3xTF32" split
@@ -61,13 +65,27 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = 128
+// shared-memory matrix descriptor: MN-major operand tile = four blocks [32 K-rows][32 MN-floats = 128 B].  For 32-bit operands the
+// tensor core transposes 32-byte units, so MN-major TF32 tiles must use the "128-byte swizzle with 32-byte atoms" (layout type 1,
+// SWIZZLE_128B_BASE32B; TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): canonical layout
+// ((T,8,m),(4,k)):((1,T,LBO),(.,SBO)), T = 4 floats per 16 bytes -- LBO = distance between the 32-float MN blocks (4 KB),
+// SBO = distance between groups of 4 K-rows (512 B); one UMMA (K = 8) reads the K-rows [8j, 8j+8).
+__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(4096 >> 4) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;
+    return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, M = 128, N = 128; bit 15 / 16: A / B is MN-major
 constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate, uint32_t idesc = kTcIdesc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(kTcIdesc), "r"(accumulate)
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -92,7 +110,7 @@ template <bool kSplit>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float* __restrict__ C, int ldc,
                int M, int N, int K, float alpha, float beta, float* __restrict__ partial, int kb_per_split,
-               const float* __restrict__ bias1, const float* __restrict__ bias2) {
+               const float* __restrict__ bias1, const float* __restrict__ bias2, int amn, int bmn) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte aligned operand tiles (swizzle atom = 8 rows x 128 B), then the barriers
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -126,8 +144,12 @@ k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 mbar_wait(&sb->empty[s], (it & 1) ^ 1);                       // slot free (first pass: passes immediately)
                 mbar_expect_tx(&sb->full[s], 2 * kTcTileBytes);
                 uint8_t* st = tiles + (size_t)s * kOps * kTcTileBytes;
-                tma_load_2d(st, &mapA, (kb0 + i) * kTcBK, m0, &sb->full[s]);
-                tma_load_2d(st + kTcTileBytes, &mapB, (kb0 + i) * kTcBK, n0, &sb->full[s]);
+                if (!amn) tma_load_2d(st, &mapA, (kb0 + i) * kTcBK, m0, &sb->full[s]);
+                else
+                    for (int b = 0; b < 4; ++b) tma_load_2d(st + b * 4096, &mapA, m0 + 32 * b, (kb0 + i) * kTcBK, &sb->full[s]);
+                if (!bmn) tma_load_2d(st + kTcTileBytes, &mapB, (kb0 + i) * kTcBK, n0, &sb->full[s]);
+                else
+                    for (int b = 0; b < 4; ++b) tma_load_2d(st + kTcTileBytes + b * 4096, &mapB, n0 + 32 * b, (kb0 + i) * kTcBK, &sb->full[s]);
             }
         }
     } else if (warp == 1) {
@@ -138,15 +160,20 @@ k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 mbar_wait(kSplit ? &sb->conv[s] : &sb->full[s], it & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = smem_u32(tiles + (size_t)s * kOps * kTcTileBytes);
-                const uint64_t dA = umma_desc_k128(st), dB = umma_desc_k128(st + kTcTileBytes);
-                const uint64_t dAl = umma_desc_k128(st + 2 * kTcTileBytes), dBl = umma_desc_k128(st + 3 * kTcTileBytes);
+                const uint32_t idesc = kTcIdesc | (amn ? 1u << 15 : 0u) | (bmn ? 1u << 16 : 0u);
+                const uint64_t dA = amn ? umma_desc_mn128(st) : umma_desc_k128(st);
+                const uint64_t dB = bmn ? umma_desc_mn128(st + kTcTileBytes) : umma_desc_k128(st + kTcTileBytes);
+                const uint64_t dAl = amn ? umma_desc_mn128(st + 2 * kTcTileBytes) : umma_desc_k128(st + 2 * kTcTileBytes);
+                const uint64_t dBl = bmn ? umma_desc_mn128(st + 3 * kTcTileBytes) : umma_desc_k128(st + 3 * kTcTileBytes);
+                // one UMMA = 8 K-floats: 32 bytes further in a K-major tile (2 descriptor units), 8 K-rows = 1 KB further (64 units)
+                const uint64_t sa = amn ? 64 : 2, sbk = bmn ? 64 : 2;
 #pragma unroll
-                for (int k = 0; k < kTcBK / 8; ++k) {                          // UMMA_K = 8 tf32 = 32 bytes = 2 descriptor units
-                    const uint64_t adv = (uint64_t)(k * 2);
-                    umma_tf32(tmem_acc, dA + adv, dB + adv, (i | k) != 0);
+                for (int k = 0; k < kTcBK / 8; ++k) {
+                    const uint64_t ada = (uint64_t)k * sa, adb = (uint64_t)k * sbk;
+                    umma_tf32(tmem_acc, dA + ada, dB + adb, (i | k) != 0, idesc);
                     if (kSplit) {
-                        umma_tf32(tmem_acc, dAl + adv, dB + adv, 1u);
-                        umma_tf32(tmem_acc, dA + adv, dBl + adv, 1u);
+                        umma_tf32(tmem_acc, dAl + ada, dB + adb, 1u, idesc);
+                        umma_tf32(tmem_acc, dA + ada, dBl + adb, 1u, idesc);
                     }
                 }
                 umma_commit(&sb->empty[s]);                                    // frees the stage when these MMAs retire
@@ -263,15 +290,18 @@ static EncodeTiledFn get_encode() {
     }
     return fn;
 }
-static int make_map(CUtensorMap* map, const float* base, int rows, int K, int ld) {
+// K-major operand: memory [rows = M or N][K] (K contiguous), box {32 K, 128 rows}; MN-major operand (mn): memory [K][rows = M or N]
+// (the M / N index contiguous), box {32 MN, 32 K-rows}
+static int make_map(CUtensorMap* map, const float* base, int rows, int K, int ld, bool mn = false) {
     EncodeTiledFn enc = get_encode();
     MSA_CHECK(enc != nullptr, MSA_E_NODEVICE, "gemm_tc: cuTensorMapEncodeTiled is not available from this driver");
-    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t dims[2] = {(cuuint64_t)(mn ? rows : K), (cuuint64_t)(mn ? K : rows)};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)kTcBM};
+    const cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)(mn ? kTcBK : kTcBM)};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MSA_CHECK(r == CUDA_SUCCESS, MSA_E_ARG, "gemm_tc: cuTensorMapEncodeTiled failed (%d) for a [%d x %d] operand, ld %d", (int)r, rows, K, ld);
     return 0;
@@ -301,12 +331,19 @@ size_t gemm_tc_scratch_floats(int64_t M, int64_t N, int64_t K) {
 // aligned) holds the partial tiles of a K split; with scratch == nullptr the K range is not split.
 int gemm_tc_nt(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
                float* C, int64_t ldc, int mode, float* scratch, cudaStream_t st, const float* bias1, const float* bias2) {
-    MSA_CHECK(bias1 != nullptr || bias2 == nullptr, MSA_E_ARG, "gemm_tc_nt: bias2 without bias1");
-    MSA_CHECK(bias1 == nullptr || beta == 0.f, MSA_E_ARG, "gemm_tc_nt: a column bias replaces the accumulation onto C (beta must be 0)");
-    MSA_CHECK(gemm_tc_supported(M, N, K, A, lda, B, ldb, C, ldc), MSA_E_UNSUPPORTED, "gemm_tc_nt: operand alignment / leading dimensions");
+    return gemm_tc(false, true, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, mode, scratch, st, bias1, bias2);
+}
+
+// General form, row-major: ta: A is given as [K][M] (else [M][K]); tb: B is given as [N][K] (else [K][N]).
+int gemm_tc(bool ta, bool tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb,
+            float beta, float* C, int64_t ldc, int mode, float* scratch, cudaStream_t st, const float* bias1, const float* bias2) {
+    MSA_CHECK(bias1 != nullptr || bias2 == nullptr, MSA_E_ARG, "gemm_tc: bias2 without bias1");
+    MSA_CHECK(bias1 == nullptr || beta == 0.f, MSA_E_ARG, "gemm_tc: a column bias replaces the accumulation onto C (beta must be 0)");
+    MSA_CHECK(gemm_tc_supported(M, N, K, A, lda, B, ldb, C, ldc), MSA_E_UNSUPPORTED, "gemm_tc: operand alignment / leading dimensions");
+    const int amn = ta ? 1 : 0, bmn = tb ? 0 : 1;
     CUtensorMap mA, mB;
-    MSA_TRY(make_map(&mA, A, (int)M, (int)K, (int)lda));
-    MSA_TRY(make_map(&mB, B, (int)N, (int)K, (int)ldb));
+    MSA_TRY(make_map(&mA, A, (int)M, (int)K, (int)lda, amn != 0));
+    MSA_TRY(make_map(&mB, B, (int)N, (int)K, (int)ldb, bmn != 0));
     const int num_kb = (int)((K + kTcBK - 1) / kTcBK);
     const int splits = scratch != nullptr ? tc_plan_splits(M, N, K) : 1;
     const int per = (num_kb + splits - 1) / splits;
@@ -316,12 +353,12 @@ int gemm_tc_nt(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int
         const size_t smem = (size_t)kTcStages * 4 * kTcTileBytes + sizeof(TcSmem) + 1024;
         static bool attr0 = false;
         if (!attr0) { MSA_CUDA(cudaFuncSetAttribute(k_gemm_tf32_nt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr0 = true; }
-        k_gemm_tf32_nt<true><<<grid, kTcThreads, smem, st>>>(mA, mB, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta, partial, per, bias1, bias2);
+        k_gemm_tf32_nt<true><<<grid, kTcThreads, smem, st>>>(mA, mB, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta, partial, per, bias1, bias2, amn, bmn);
     } else {
         const size_t smem = (size_t)kTcStages * 2 * kTcTileBytes + sizeof(TcSmem) + 1024;
         static bool attr1 = false;
         if (!attr1) { MSA_CUDA(cudaFuncSetAttribute(k_gemm_tf32_nt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr1 = true; }
-        k_gemm_tf32_nt<false><<<grid, kTcThreads, smem, st>>>(mA, mB, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta, partial, per, bias1, bias2);
+        k_gemm_tf32_nt<false><<<grid, kTcThreads, smem, st>>>(mA, mB, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta, partial, per, bias1, bias2, amn, bmn);
     }
     MSA_LAUNCH_CHECK();
     if (splits > 1) {
@@ -340,5 +377,10 @@ size_t msa_gemm_nt_scratch_floats(int64_t M, int64_t N, int64_t K) { return msa:
 int msa_gemm_nt(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
                 float* C, int64_t ldc, int mode, float* scratch, void* stream) {
     return msa::gemm_tc_nt(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, mode, scratch, (cudaStream_t)stream, nullptr, nullptr);
+}
+int msa_gemm(int trans_a, int trans_b, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B,
+             int64_t ldb, float beta, float* C, int64_t ldc, int mode, float* scratch, void* stream) {
+    return msa::gemm_tc(trans_a != 0, trans_b != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, mode, scratch, (cudaStream_t)stream,
+                        nullptr, nullptr);
 }
 }

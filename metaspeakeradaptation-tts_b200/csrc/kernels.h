@@ -296,6 +296,10 @@ size_t gemm_tc_scratch_floats(int64_t M, int64_t N, int64_t K);
 int gemm_tc_nt(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
                float* C, int64_t ldc, int mode, float* scratch, cudaStream_t st, const float* bias1 = nullptr,
                const float* bias2 = nullptr);   // mode 0: 3xTF32 (fp32-accurate), 1: TF32
+// general row-major form: ta: A is given as [K][M] (else [M][K]); tb: B is given as [N][K] (else [K][N])
+int gemm_tc(bool ta, bool tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb,
+            float beta, float* C, int64_t ldc, int mode, float* scratch, cudaStream_t st, const float* bias1 = nullptr,
+            const float* bias2 = nullptr);
 
 int k_abort_guard(unsigned int* abort_word, float* sumsq, int raise, cudaStream_t st);   // raise: set the word; else NaN -> *sumsq if set
 int k_fill_canary(float* p, int64_t n, cudaStream_t st);   // n floats (multiple of 4, 16-byte aligned) <- 0xFFFFFFFF

@@ -84,6 +84,7 @@ struct msa_handle {
     // 0: cuBLAS only.  Env MSA_GEMM_TC / MSA_GEMM_TC_MIN.
     int tc_mode = 2;
     long long tc_min = 100000000LL;
+    long long tc_min_bwd = 30000000LL;     // mode 3: smallest backward contraction (MACs) routed to the tcgen05 kernel
     bool tc_enabled = true;
     int rec_flags = -1;    // hand-off variant of the persistent kernels; -1 = per-kernel default (env MSA_REC_FLAGS overrides, development only)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
@@ -300,10 +301,17 @@ static int gemm(msa_handle* h, bool ta, bool tb, int64_t M, int64_t N, int64_t K
     // (measured on B200, profiles/r01_gemm_tc_v14.txt: the kernel has ~10 us of fixed cost, so short-K / small products stay on cuBLAS)
     const long long macs = (long long)M * N * K;
     const bool tc_size = macs >= h->tc_min && (macs >= 3 * h->tc_min || K >= 1024);
-    if (!ta && tb && h->tc_enabled && (h->tc_mode != 2 || !tf32) && tc_size && h->cfg.gemm_tf32 >= 1 && N >= 8 &&
-        M * N >= 4096 && gemm_tc_supported(M, N, K, A, lda, Bm, ldb, Cm, ldc) &&
-        (tf32 || (h->gemm_scratch && gemm_tc_scratch_floats(M, N, K) <= h->gemm_scratch_floats)))
-        return gemm_tc_nt(M, N, K, alpha, A, lda, Bm, ldb, beta, Cm, ldc, tf32 ? 1 : 0, h->gemm_scratch, h->cur_stream, bias1, bias2);
+    const bool nt = !ta && tb;
+    const bool own_ok = h->tc_enabled && h->cfg.gemm_tf32 >= 1 && N >= 8 && M * N >= 4096 && gemm_tc_supported(M, N, K, A, lda, Bm, ldb, Cm, ldc) &&
+                        (tf32 || (h->gemm_scratch && gemm_tc_scratch_floats(M, N, K) <= h->gemm_scratch_floats));
+    // tc_mode 2: the fp32-accurate x . W^T products; 1: every eligible x . W^T product; 3: every eligible product incl. the backward
+    // contractions with MN-major operands (dX = dY . W, dW = dY^T . X)
+    const bool route = own_ok && ((h->tc_mode == 2 && !tf32 && nt && tc_size) || (h->tc_mode == 1 && nt && tc_size) ||
+                                  (h->tc_mode == 3 && (nt ? (tc_size || tf32) : macs >= h->tc_min_bwd)));
+    if (route)
+        return gemm_tc(ta, tb, M, N, K, alpha, A, lda, Bm, ldb, beta, Cm, ldc, tf32 ? 1 : 0,
+                       (h->gemm_scratch && gemm_tc_scratch_floats(M, N, K) <= h->gemm_scratch_floats) ? h->gemm_scratch : nullptr,
+                       h->cur_stream, bias1, bias2);
     if (bias1 != nullptr) {
         MSA_CHECK(beta == 0.f && ldc == N, MSA_E_ARG, "gemm: a column bias needs beta == 0 and a dense C");
         MSA_TRY(k_fill_rows(Cm, bias1, bias2, M, (int)N, h->cur_stream));
@@ -449,6 +457,7 @@ int msa_create(const msa_config* cfg, int device, msa_handle** out) {
         if (h->tc_mode == 1) h->tc_min = 0;
     }
     if (const char* e = getenv("MSA_GEMM_TC_MIN")) h->tc_min = atoll(e);
+    if (const char* e = getenv("MSA_GEMM_TC_MIN_BWD")) h->tc_min_bwd = atoll(e);
     build_layout(h);
     cublasStatus_t s = cublasCreate(&h->blas);
     if (s != CUBLAS_STATUS_SUCCESS) {

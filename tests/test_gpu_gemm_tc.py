@@ -70,3 +70,37 @@ def test_pass_parity_with_tcgen05_forward_gemms(monkeypatch):
         assert rel(a, b) < 3e-4
     gn = float(torch.sqrt(sum((g.double() ** 2).sum() for g in o_g.values())))
     assert max(float((c_g[n].double().cpu() - o_g[n].double()).norm()) / gn for n in o_g) < 2e-3
+
+
+def _run_general(ta, tb, M, N, K, mode, alpha=1.0, beta=0.0, pad=0, seed=0):
+    """C = alpha op(A) op(B) + beta C through msa_gemm; operands stored [K][M] / [K][N] when their contraction index is the row."""
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    a_shape = (K, M + pad) if ta else (M, K + pad)
+    b_shape = (N, K + pad) if tb else (K, N + pad)
+    A = torch.randn(*a_shape, device="cuda", generator=g)
+    B = torch.randn(*b_shape, device="cuda", generator=g)
+    Cm = torch.randn(M, N + pad, device="cuda", generator=g)
+    C0 = Cm.clone()
+    scratch = torch.empty(int(lib.msa_gemm_nt_scratch_floats(M, N, K)) + 4, device="cuda")
+    P = lambda t: C.c_void_p(t.data_ptr())
+    rc = lib.msa_gemm(int(ta), int(tb), M, N, K, C.c_float(alpha), P(A), a_shape[1], P(B), b_shape[1], C.c_float(beta), P(Cm), N + pad,
+                      mode, P(scratch), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "msa_gemm")
+    torch.cuda.synchronize()
+    Ad = (A[:, :M].double().t() if ta else A[:, :K].double())
+    Bd = (B[:, :K].double().t() if tb else B[:, :N].double())
+    ref = alpha * (Ad @ Bd) + beta * C0[:, :N].double()
+    return float((Cm[:, :N].double() - ref).norm() / ref.norm())
+
+
+@pytest.mark.parametrize("tt", [(0, 0), (1, 0), (1, 1), (0, 1)])
+@pytest.mark.parametrize("shape", [(128, 128, 32), (256, 384, 160), (4096, 1024, 800), (800, 1792, 4096), (100, 36, 52), (512, 2560, 800)])
+def test_gemm_transposed_operands_as_mn_major_tiles(tt, shape):
+    """The backward contractions dX = dY . W (0, 0) and dW = dY^T . X (1, 0) (and (1, 1) for completeness) on the tcgen05 kernel:
+    operands whose contraction index is the row index are MN-major shared-memory tiles, nothing is transposed in memory."""
+    M, N, K = shape
+    if (tt[0] and M % 4) or (not tt[1] and N % 4):
+        pytest.skip("leading dimension of an MN-major operand must be a multiple of 4 floats")
+    assert _run_general(tt[0], tt[1], M, N, K, mode=0) < 4e-6 + 1e-8 * K
+    assert _run_general(tt[0], tt[1], M, N, K, mode=1, alpha=0.5, beta=1.0, pad=4) < 2e-3
