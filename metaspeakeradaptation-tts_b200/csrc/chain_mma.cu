@@ -23,6 +23,9 @@ namespace msa {
 
 namespace {
 
+#ifndef MSA_LSTM_GATE
+#define MSA_LSTM_GATE 1
+#endif
 #ifndef MSA_SENT_LAST
 #define MSA_SENT_LAST 0
 #endif
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(kMT, 1) k_lstm_fwd_mma(LstmRecParams p) {
                 for (int i = 0; i < 4; ++i) acc[nt][mt][i] = 0.f;
         if (s_ > 0) {
             // sentinel of producer CTA c: h of its last unit for the last row (a hint only: every word is canary-checked below)
-            {
+            if (MSA_LSTM_GATE) {
                 const int rl_ = R - 1;
                 const float* hlast = p.hout + gr.task(rl_) * gr.tstride + dir_off_h + ((size_t)tp * gr.Bt + gr.brow(rl_)) * H;
                 gate_waitq(ncta_dir, [&](int c) { const int e = part_lo(c + 1, H, ncta_dir); return e > part_lo(c, H, ncta_dir) ? hlast + e - 1 : nullptr; }, p.abort_word);

@@ -99,6 +99,12 @@ struct msa_handle {
     // Grouped chain kernels (chain_mma.cu): bf16x3 tensor-core gate products, G*B rows per hand-off.  mma_mode 0: never,
     // 1 (default): for grouped launches under the tensor-core GEMM policies, 2: also for single passes.  Env MSA_CHAIN_MMA.
     int mma_mode = 1;
+    // side streams of a grouped pass: between two recurrences the tasks' GEMMs / element-wise kernels are independent (each task
+    // has its own workspace slice, cuBLAS workspace and reduction scratch), so task g's stage runs on stream g and fills the SMs the
+    // small per-task kernels of one task leave idle; fork / join with events around every stage.  Env MSA_GROUP_STREAMS=0: off.
+    cudaStream_t aux[kGroupMax] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kGroupMax] = {};
+    bool group_streams = true;
     int64_t off(const std::string& n) const { return off_by_name.at(n); }
 };
 
@@ -451,6 +457,7 @@ int msa_create(const msa_config* cfg, int device, msa_handle** out) {
     h->smem_limit = prop.sharedMemPerBlockOptin;
     if (const char* e = getenv("MSA_REC_FLAGS")) h->rec_flags = atoi(e);
     if (const char* e = getenv("MSA_CHAIN_MMA")) h->mma_mode = atoi(e);
+    if (const char* e = getenv("MSA_GROUP_STREAMS")) h->group_streams = atoi(e) != 0;
     if (const char* e = getenv("MSA_GEMM_TC")) {
         h->tc_mode = atoi(e);
         h->tc_enabled = h->tc_mode != 0;
@@ -480,6 +487,11 @@ int msa_destroy(msa_handle* h) {
     if (!h) return 0;
     if (h->blas) cublasDestroy(h->blas);
     if (h->abort_dev) cudaFree(h->abort_dev);
+    for (int g = 0; g < kGroupMax; ++g) {
+        if (h->aux[g]) cudaStreamDestroy(h->aux[g]);
+        if (h->ev_join[g]) cudaEventDestroy(h->ev_join[g]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     for (auto& e : h->prof_ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     delete h;
     return 0;
@@ -596,6 +608,46 @@ static bool use_mma_chains(const msa_handle* h, int G, int B, int T, int L, bool
     return true;
 }
 
+// Fork / join of the per-task stages of a grouped pass over the handle's side streams (created on first use).
+struct StageFork {
+    msa_handle* h; cudaStream_t main; int G; bool on;
+    StageFork(msa_handle* h_, cudaStream_t main_, int G_) : h(h_), main(main_), G(G_), on(false) {
+        if (G <= 1 || !h->group_streams) return;
+        for (int g = 1; g < G; ++g)
+            if (!h->aux[g] && cudaStreamCreateWithFlags(&h->aux[g], cudaStreamNonBlocking) != cudaSuccess) return;
+        if (!h->ev_fork && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) return;
+        for (int g = 1; g < G; ++g)
+            if (!h->ev_join[g] && cudaEventCreateWithFlags(&h->ev_join[g], cudaEventDisableTiming) != cudaSuccess) return;
+        on = true;
+    }
+    // stream of task g's stage (task 0 stays on the caller's stream); begin() before the first task, end() after the last one
+    int begin() {
+        if (!on) return 0;
+        MSA_CUDA(cudaEventRecord(h->ev_fork, main));
+        for (int g = 1; g < G; ++g) MSA_CUDA(cudaStreamWaitEvent(h->aux[g], h->ev_fork, 0));
+        return 0;
+    }
+    cudaStream_t stream(int g) const { return on && g > 0 ? h->aux[g] : main; }
+    int enter(int g) {
+        cudaStream_t s = stream(g);
+        h->cur_stream = s;
+        MSA_BLAS(cublasSetStream(h->blas, s));
+        return 0;
+    }
+    int end(const std::vector<Ws>& W) {
+        if (on) {
+            for (int g = 1; g < G; ++g) {
+                MSA_CUDA(cudaEventRecord(h->ev_join[g], h->aux[g]));
+                MSA_CUDA(cudaStreamWaitEvent(main, h->ev_join[g], 0));
+            }
+        }
+        h->cur_stream = main;
+        MSA_BLAS(cublasSetStream(h->blas, main));
+        MSA_BLAS(cublasSetWorkspace(h->blas, W[0].blas_ws, W[0].blas_ws_bytes));
+        return 0;
+    }
+};
+
 // One teacher-forced forward pass for G tasks that share `params` (the theta_0 train-split passes of a meta-batch, maml.py:38-54):
 // everything that is not a recurrence runs task by task in that task's own workspace slice, the three recurrences run ONCE for
 // all G*B rows when the grouped kernels apply.
@@ -617,14 +669,19 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
     auto P = [&](const std::string& n) { return params + h->off(n); };
     const bool mma = use_mma_chains(h, G, B, T, L, false, false), mma_attn = use_mma_chains(h, G, B, T, L, true, false);
     const int64_t tstride = (int64_t)(ws_stride / sizeof(float));
+    StageFork fk(h, st, G);
     const int H4e = 4 * d.Hh;
     const std::string at = "decoder.attention_layer.";
     const int H4a = 4 * d.Ha, H4d = 4 * d.Hd, ldA = d.Pd + d.E, ldD = d.Ha + d.E, ldP = d.Hd + d.E;
     const bool fa = c.forward_attn != 0, ta = fa && c.trans_agent != 0;
 
     // ---- stage 1: speaker vector, encoder convolutions, BiLSTM input projection ----
+    MSA_TRY(fk.begin());
     for (int g = 0; g < G; ++g) {
         const Ws& w = W[g];
+        MSA_TRY(fk.enter(g));
+        cudaStream_t st = fk.stream(g);      // this task's stage stream (shadows the pass stream)
+        MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
         const TaskIO& io = ios[g];
         auto mk = [&](int i) { return io.masks + secs[i].off; };
         h->gemm_scratch = w.gemm_lo; h->gemm_scratch_floats = (size_t)w.n_gemm_lo;
@@ -655,6 +712,7 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
             MSA_TRY(gemm(h, false, true, d.BL, H4e, d.C, 1.f, w.x3_tm, d.C, P("encoder.lstm.weight_ih_l0" + sfx), d.C, 1.f, zx, H4e));
         }
     }
+    MSA_TRY(fk.end(W));
     // ---- encoder BiLSTM (persistent) ----
     {
         auto make = [&](int g) {
@@ -679,8 +737,12 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
         }
     }
     // ---- stage 2: memory, decoder set-up (decoder.py:290-302, forward_attn.py:103-116) ----
+    MSA_TRY(fk.begin());
     for (int g = 0; g < G; ++g) {
         const Ws& w = W[g];
+        MSA_TRY(fk.enter(g));
+        cudaStream_t st = fk.stream(g);      // this task's stage stream (shadows the pass stream)
+        MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
         const TaskIO& io = ios[g];
         auto mk = [&](int i) { return io.masks + secs[i].off; };
         h->gemm_scratch = w.gemm_lo; h->gemm_scratch_floats = (size_t)w.n_gemm_lo;
@@ -699,6 +761,7 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
         if (ta)     // context half of the transition agent: ctx(t) = alpha(t) . memory  =>  W_ta[:E] . ctx(t) = alpha(t) . (memory . W_ta[:E])
             MSA_TRY(gemm(h, false, true, d.BL, 1, d.E, 1.f, w.memory, d.E, P(at + "ta.weight"), d.E + d.Ha, 0.f, w.mta, 1));
     }
+    MSA_TRY(fk.end(W));
     // ---- attention chain (persistent) ----
     {
         auto make = [&](int g) {
@@ -730,8 +793,12 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
         }
     }
     // ---- stage 3: context vectors, decoder-RNN input projection ----
+    MSA_TRY(fk.begin());
     for (int g = 0; g < G; ++g) {
         const Ws& w = W[g];
+        MSA_TRY(fk.enter(g));
+        cudaStream_t st = fk.stream(g);      // this task's stage stream (shadows the pass stream)
+        MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
         h->gemm_scratch = w.gemm_lo; h->gemm_scratch_floats = (size_t)w.n_gemm_lo;
         // ctx[t][b] = a[t][b] . memory[b]  (forward_attn.py:217), batched over b
         MSA_TRY(gemm_batched(h, false, false, T, d.E, L, 1.f, w.align_tm, d.BL, L, w.memory, d.E, (int64_t)L * d.E, 0.f, w.ctx,
@@ -741,6 +808,7 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
                      P("decoder.decoder_rnn.bias_hh")));
         MSA_TRY(gemm(h, false, true, d.TB, H4d, d.E, 1.f, w.ctx, d.E, Wid + d.Ha, ldD, 1.f, w.zd, H4d));
     }
+    MSA_TRY(fk.end(W));
     // ---- decoder RNN chain (decoder.py:260-265, persistent) ----
     {
         auto make = [&](int g) {
@@ -766,8 +834,12 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
         }
     }
     // ---- stage 4: projections, postnet, outputs, loss ----
+    MSA_TRY(fk.begin());
     for (int g = 0; g < G; ++g) {
         const Ws& w = W[g];
+        MSA_TRY(fk.enter(g));
+        cudaStream_t st = fk.stream(g);      // this task's stage stream (shadows the pass stream)
+        MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
         const TaskIO& io = ios[g];
         auto mk = [&](int i) { return io.masks + secs[i].off; };
         h->gemm_scratch = w.gemm_lo; h->gemm_scratch_floats = (size_t)w.n_gemm_lo;
@@ -805,6 +877,7 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
             if (io.loss_out) MSA_TRY(k_scale_copy(w.loss, io.loss_out, 1, 1.f, 0, st));
         }
     }
+    MSA_TRY(fk.end(W));
     h->d = d;
     h->G = G;
     h->ws_stride = ws_stride;
@@ -958,10 +1031,15 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
     const float* Wia = P("decoder.attention_rnn.weight_ih");
     const bool mma = use_mma_chains(h, NG, B, T, L, false, true), mma_attn = use_mma_chains(h, NG, B, T, L, true, true);
     const int64_t tstride = (int64_t)(ws_stride / sizeof(float));
+    StageFork fk(h, st, NG);
 
     // ---- stage 1: postnet and projections ----
+    MSA_TRY(fk.begin());
     for (int g = 0; g < NG; ++g) {
         const Ws& w = W[g];
+        MSA_TRY(fk.enter(g));
+        cudaStream_t st = fk.stream(g);      // this task's stage stream (shadows the pass stream)
+        MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
         float* grads = grads_g[g];
         auto mk = [&](int i) { return h->masks[g] + secs[i].off; };
         auto G = [&](const std::string& n) { return grads + h->off(n); };
@@ -1006,6 +1084,7 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
         MSA_TRY(k_colsum(w.dmel_tm, d.TB, d.M, d.M, G("decoder.linear_projection.linear_layer.bias"), gs, acc, nullptr, w.red_scr, st));
         MSA_TRY(k_colsum(w.dgate_tm, d.TB, 1, 1, G("decoder.gate_layer.linear_layer.bias"), gs, acc, nullptr, w.red_scr, st));
     }
+    MSA_TRY(fk.end(W));
     // ---- decoder RNN chain backward (persistent) ----
     {
         auto make = [&](int g) {
@@ -1031,8 +1110,12 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
         }
     }
     // ---- stage 2: decoder-RNN input gradients, context backward ----
+    MSA_TRY(fk.begin());
     for (int g = 0; g < NG; ++g) {
         const Ws& w = W[g];
+        MSA_TRY(fk.enter(g));
+        cudaStream_t st = fk.stream(g);      // this task's stage stream (shadows the pass stream)
+        MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
         float* grads = grads_g[g];
         auto mk = [&](int i) { return h->masks[g] + secs[i].off; };
         auto G = [&](const std::string& n) { return grads + h->off(n); };
@@ -1059,6 +1142,7 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
         // (W_ih[:, prenet:] . memory^T)^T for the attention chain's context-path backward
         MSA_TRY(gemm(h, false, true, d.BL, H4a, d.E, 1.f, w.memory, d.E, Wia + d.Pd, ldA, 0.f, w.mw_pm, H4a));
     }
+    MSA_TRY(fk.end(W));
     // ---- attention chain backward (persistent) ----
     {
         auto make = [&](int g) {
@@ -1092,8 +1176,12 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
         }
     }
     // ---- stage 3: deferred attention / prenet / speaker gradients ----
+    MSA_TRY(fk.begin());
     for (int g = 0; g < NG; ++g) {
         const Ws& w = W[g];
+        MSA_TRY(fk.enter(g));
+        cudaStream_t st = fk.stream(g);      // this task's stage stream (shadows the pass stream)
+        MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
         float* grads = grads_g[g];
         auto mk = [&](int i) { return h->masks[g] + secs[i].off; };
         auto G = [&](const std::string& n) { return grads + h->off(n); };
@@ -1154,6 +1242,7 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
             MSA_TRY(k_embedding_bwd(w.dspk, h->spk_ids[g], G("speaker_embedder.weight"), B, d.Ds, c.num_speakers, gs, acc, st));
         }
     }
+    MSA_TRY(fk.end(W));
     // ---- encoder BiLSTM backward (persistent) ----
     {
         auto make = [&](int g) {
@@ -1178,8 +1267,12 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
         }
     }
     // ---- stage 4: encoder BiLSTM weight gradients, encoder convolutions, embedding ----
+    MSA_TRY(fk.begin());
     for (int g = 0; g < NG; ++g) {
         const Ws& w = W[g];
+        MSA_TRY(fk.enter(g));
+        cudaStream_t st = fk.stream(g);      // this task's stage stream (shadows the pass stream)
+        MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
         float* grads = grads_g[g];
         auto mk = [&](int i) { return h->masks[g] + secs[i].off; };
         auto G = [&](const std::string& n) { return grads + h->off(n); };
@@ -1217,6 +1310,7 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
         }
         MSA_TRY(k_embedding_bwd(dcur, h->tokens[g], G("embedding.weight"), (int)d.BL, d.C, c.n_symbols, gs, acc, st));
     }
+    MSA_TRY(fk.end(W));
     return 0;
 }
 
