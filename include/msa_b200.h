@@ -156,14 +156,17 @@ int msa_train_loss(msa_handle* h, void* ws, const float* stop_targets, const int
  * for configurations the grouped kernels do not implement, the recurrences silently run task by task -- same results).
  * ws: msa_group_workspace_bytes(h, G, B, T, L) bytes, 256-byte aligned; task g's slice (for msa_train_mcd / msa_get_buffer /
  * msa_train_loss) starts at ws + g * msa_group_workspace_bytes(h, 1, B, T, L).  Per-task arguments are HOST arrays of G device
- * pointers; loss_out: G floats on the device; grads[g]: flat gradient buffer of task g. */
+ * pointers; loss_out: G floats on the device; grads[g]: flat gradient buffer of task g.
+ * params[g]: the weights of task g.  All equal (the theta_0 train passes): the recurrences share one launch.  Different per task
+ * (the test-split passes with the adapted weights, maml.py:56-76): every recurrence runs task by task, but the stages between
+ * them still overlap across the tasks on the library's side streams (each task has its own workspace slice). */
 size_t msa_group_workspace_bytes(const msa_handle* h, int G, int B, int T, int L);
-int msa_train_forward_group(msa_handle* h, int G, void* ws, size_t ws_bytes, const float* params, float* const* bn_stats,
+int msa_train_forward_group(msa_handle* h, int G, void* ws, size_t ws_bytes, const float* const* params, float* const* bn_stats,
                             const int64_t* const* tokens, const int64_t* const* token_lengths, const float* const* mels,
                             const int64_t* const* mel_lengths, const float* const* speaker_vecs,
                             const int64_t* const* speaker_ids, const float* const* stop_targets,
                             const uint8_t* const* masks, int B, int T, int L, float* loss_out, void* stream);
-int msa_train_backward_group(msa_handle* h, void* ws, size_t ws_bytes, const float* params, float* const* grads,
+int msa_train_backward_group(msa_handle* h, void* ws, size_t ws_bytes, const float* const* params, float* const* grads,
                              int accumulate, float grad_scale, void* stream);
 /* replaces utils/metrics.py:15-22 mcd_batch as called by the trainers' per-task logs (maml.py:78-82,
  * baseline.py, continual_*.py): K * mean_b mean_{t < len_b} ||mel_target - out||_2 with

@@ -651,7 +651,7 @@ struct StageFork {
 // One teacher-forced forward pass for G tasks that share `params` (the theta_0 train-split passes of a meta-batch, maml.py:38-54):
 // everything that is not a recurrence runs task by task in that task's own workspace slice, the three recurrences run ONCE for
 // all G*B rows when the grouped kernels apply.
-static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride, const float* params, const TaskIO* ios, int B, int T,
+static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride, const float* const* params_g, const TaskIO* ios, int B, int T,
                               int L, cudaStream_t st) {
     MSA_TRY(train_check(h));
     const Dims d = make_dims(h->cfg, B, T, L);
@@ -666,8 +666,11 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
     const msa_config& c = h->cfg;
     const auto secs = mask_sections(c, B, T, L);
     const int iPre = d.nEnc, iAttn = d.nEnc + 2, iDec = d.nEnc + 3, iPost = d.nEnc + 4;
-    auto P = [&](const std::string& n) { return params + h->off(n); };
-    const bool mma = use_mma_chains(h, G, B, T, L, false, false), mma_attn = use_mma_chains(h, G, B, T, L, true, false);
+    auto PG = [&](int g, const std::string& n) { return params_g[g] + h->off(n); };
+    bool shared = true;      // one weight buffer for the whole group (the theta_0 train passes) or per-task weights (the test passes)
+    for (int g = 1; g < G; ++g) shared = shared && params_g[g] == params_g[0];
+    const int Gk = shared ? G : 1;      // tasks one recurrence launch can carry
+    const bool mma = use_mma_chains(h, Gk, B, T, L, false, false), mma_attn = use_mma_chains(h, Gk, B, T, L, true, false);
     const int64_t tstride = (int64_t)(ws_stride / sizeof(float));
     StageFork fk(h, st, G);
     const int H4e = 4 * d.Hh;
@@ -681,6 +684,8 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
         const Ws& w = W[g];
         MSA_TRY(fk.enter(g));
         cudaStream_t st = fk.stream(g);      // this task's stage stream (shadows the pass stream)
+        const float* params = params_g[g];
+        auto P = [&](const std::string& n) { return params + h->off(n); };
         MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
         const TaskIO& io = ios[g];
         auto mk = [&](int i) { return io.masks + secs[i].off; };
@@ -719,19 +724,25 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
             const Ws& w = W[g];
             LstmRecParams lp{};
             lp.T = L; lp.B = B; lp.H = d.Hh; lp.ndir = 2;
-            lp.zin = w.enc_zx; lp.whh = P("encoder.lstm.weight_hh_l0");
+            lp.zin = w.enc_zx; lp.whh = PG(g, "encoder.lstm.weight_hh_l0");
             lp.whh_dir_stride = h->off("encoder.lstm.weight_hh_l0_reverse") - h->off("encoder.lstm.weight_hh_l0");
             lp.hout = w.enc_h; lp.cout = w.enc_c; lp.gates = w.enc_g; lp.mask = nullptr; lp.drop_scale = 1.f;
             lp.lengths = ios[g].tok_len; lp.abort_word = h->abort_dev; lp.prof = prof_ptr(h, w, PROF_ENC_LSTM_FWD);
             lp.trace = trace_ptr(h, w, PROF_ENC_LSTM_FWD); lp.trace_t0 = h->trace_t0; lp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
             return lp;
         };
-        ProfScope ps(h, PROF_ENC_LSTM_FWD + (mma && G > 1 ? PROF_BASE : 0), st);
-        if (mma) {
+        ProfScope ps(h, PROF_ENC_LSTM_FWD + (mma && shared && G > 1 ? PROF_BASE : 0), st);
+        if (mma && shared) {
             LstmRecParams lp = make(0);
             lp.G = G; lp.tstride = tstride;
             for (int g = 0; g < G; ++g) lp.lengths_g[g] = ios[g].tok_len;
             MSA_TRY(launch_lstm_rec_fwd_mma(lp, h->sm_count, h->smem_limit, st));
+        } else if (mma) {       // per-task weights: one launch per task (G = 1, that task's pointers)
+            for (int g = 0; g < G; ++g) {
+                LstmRecParams lp = make(g);
+                lp.G = 1; lp.tstride = 0;
+                MSA_TRY(launch_lstm_rec_fwd_mma(lp, h->sm_count, h->smem_limit, st));
+            }
         } else {
             for (int g = 0; g < G; ++g) MSA_TRY(launch_lstm_rec_fwd(make(g), h->sm_count, h->smem_limit, st));
         }
@@ -742,6 +753,8 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
         const Ws& w = W[g];
         MSA_TRY(fk.enter(g));
         cudaStream_t st = fk.stream(g);      // this task's stage stream (shadows the pass stream)
+        const float* params = params_g[g];
+        auto P = [&](const std::string& n) { return params + h->off(n); };
         MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
         const TaskIO& io = ios[g];
         auto mk = [&](int i) { return io.masks + secs[i].off; };
@@ -768,26 +781,32 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
             const Ws& w = W[g];
             AttnChainParams ap{};
             ap.T = T; ap.B = B; ap.L = L; ap.Ha = d.Ha; ap.A = d.A; ap.F = d.F; ap.Kl = d.Kl; ap.norm = c.attn_norm;
-            ap.xw = w.xw; ap.whh = P("decoder.attention_rnn.weight_hh"); ap.mw_rm = w.mw_rm;
-            ap.wq = P(at + "query_layer.linear_layer.weight"); ap.pm = w.pm;
-            ap.wloc = P(at + "location_layer.location_conv1d.weight");
-            ap.wld = P(at + "location_layer.location_dense.linear_layer.weight");
-            ap.v = P(at + "v.linear_layer.weight"); ap.bv = P(at + "v.linear_layer.bias");
+            ap.xw = w.xw; ap.whh = PG(g, "decoder.attention_rnn.weight_hh"); ap.mw_rm = w.mw_rm;
+            ap.wq = PG(g, at + "query_layer.linear_layer.weight"); ap.pm = w.pm;
+            ap.wloc = PG(g, at + "location_layer.location_conv1d.weight");
+            ap.wld = PG(g, at + "location_layer.location_dense.linear_layer.weight");
+            ap.v = PG(g, at + "v.linear_layer.weight"); ap.bv = PG(g, at + "v.linear_layer.bias");
             ap.mask = c.p_attn_dropout > 0.f ? ios[g].masks + secs[iAttn].off : nullptr;
             ap.drop_scale = 1.f / (1.f - c.p_attn_dropout);
             ap.ha = w.ha; ap.ca = w.ca; ap.ga = w.ga; ap.q = w.q; ap.align = w.align_tm; ap.cum = w.cum; ap.s = w.s;
             ap.fa = fa; ap.ta = ta; ap.aplain = w.aplain; ap.fsum = w.fsum; ap.ustash = w.ustash;
-            if (ta) { ap.mta = w.mta; ap.wta_h = P(at + "ta.weight") + d.E; ap.bta = P(at + "ta.bias"); }
+            if (ta) { ap.mta = w.mta; ap.wta_h = PG(g, at + "ta.weight") + d.E; ap.bta = PG(g, at + "ta.bias"); }
             ap.convf = w.convf; ap.znorm = w.znorm; ap.e = w.ebuf; ap.abort_word = h->abort_dev; ap.prof = prof_ptr(h, w, PROF_ATTN_FWD);
             ap.trace = trace_ptr(h, w, PROF_ATTN_FWD); ap.trace_t0 = h->trace_t0; ap.flags = h->rec_flags >= 0 ? h->rec_flags : 0;
             return ap;
         };
-        ProfScope ps(h, PROF_ATTN_FWD + (mma_attn && G > 1 ? PROF_BASE : 0), st);
-        if (mma_attn) {
+        ProfScope ps(h, PROF_ATTN_FWD + (mma_attn && shared && G > 1 ? PROF_BASE : 0), st);
+        if (mma_attn && shared) {
             AttnChainParams ap = make(0);
             ap.G = G; ap.tstride = tstride;
             for (int g = 0; g < G; ++g) ap.mask_g[g] = c.p_attn_dropout > 0.f ? ios[g].masks + secs[iAttn].off : nullptr;
             MSA_TRY(launch_attn_chain_fwd_mma(ap, h->sm_count, h->smem_limit, st));
+        } else if (mma_attn) {       // per-task weights: one launch per task (G = 1, that task's pointers)
+            for (int g = 0; g < G; ++g) {
+                AttnChainParams ap = make(g);
+                ap.G = 1; ap.tstride = 0;
+                MSA_TRY(launch_attn_chain_fwd_mma(ap, h->sm_count, h->smem_limit, st));
+            }
         } else {
             for (int g = 0; g < G; ++g) MSA_TRY(launch_attn_chain_fwd(make(g), h->sm_count, h->smem_limit, st));
         }
@@ -798,6 +817,8 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
         const Ws& w = W[g];
         MSA_TRY(fk.enter(g));
         cudaStream_t st = fk.stream(g);      // this task's stage stream (shadows the pass stream)
+        const float* params = params_g[g];
+        auto P = [&](const std::string& n) { return params + h->off(n); };
         MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
         h->gemm_scratch = w.gemm_lo; h->gemm_scratch_floats = (size_t)w.n_gemm_lo;
         // ctx[t][b] = a[t][b] . memory[b]  (forward_attn.py:217), batched over b
@@ -815,7 +836,7 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
             const Ws& w = W[g];
             LstmRecParams lp{};
             lp.T = T; lp.B = B; lp.H = d.Hd; lp.ndir = 1;
-            lp.zin = w.zd; lp.whh = P("decoder.decoder_rnn.weight_hh"); lp.whh_dir_stride = 0;
+            lp.zin = w.zd; lp.whh = PG(g, "decoder.decoder_rnn.weight_hh"); lp.whh_dir_stride = 0;
             lp.hout = w.hd; lp.cout = w.cd; lp.gates = w.gd;
             lp.mask = c.p_dec_dropout > 0.f ? ios[g].masks + secs[iDec].off : nullptr;
             lp.drop_scale = 1.f / (1.f - c.p_dec_dropout);
@@ -823,12 +844,18 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
             lp.trace = trace_ptr(h, w, PROF_DEC_LSTM_FWD); lp.trace_t0 = h->trace_t0; lp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
             return lp;
         };
-        ProfScope ps(h, PROF_DEC_LSTM_FWD + (mma && G > 1 ? PROF_BASE : 0), st);
-        if (mma) {
+        ProfScope ps(h, PROF_DEC_LSTM_FWD + (mma && shared && G > 1 ? PROF_BASE : 0), st);
+        if (mma && shared) {
             LstmRecParams lp = make(0);
             lp.G = G; lp.tstride = tstride;
             for (int g = 0; g < G; ++g) lp.mask_g[g] = c.p_dec_dropout > 0.f ? ios[g].masks + secs[iDec].off : nullptr;
             MSA_TRY(launch_lstm_rec_fwd_mma(lp, h->sm_count, h->smem_limit, st));
+        } else if (mma) {       // per-task weights: one launch per task (G = 1, that task's pointers)
+            for (int g = 0; g < G; ++g) {
+                LstmRecParams lp = make(g);
+                lp.G = 1; lp.tstride = 0;
+                MSA_TRY(launch_lstm_rec_fwd_mma(lp, h->sm_count, h->smem_limit, st));
+            }
         } else {
             for (int g = 0; g < G; ++g) MSA_TRY(launch_lstm_rec_fwd(make(g), h->sm_count, h->smem_limit, st));
         }
@@ -839,6 +866,8 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
         const Ws& w = W[g];
         MSA_TRY(fk.enter(g));
         cudaStream_t st = fk.stream(g);      // this task's stage stream (shadows the pass stream)
+        const float* params = params_g[g];
+        auto P = [&](const std::string& n) { return params + h->off(n); };
         MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
         const TaskIO& io = ios[g];
         auto mk = [&](int i) { return io.masks + secs[i].off; };
@@ -905,7 +934,7 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
     MSA_CHECK(((uintptr_t)wsp & 255) == 0, MSA_E_ARG, "msa_train_forward: workspace must be 256-byte aligned");
     TaskIO io{bn_stats, tokens, token_lengths, mel_lengths, speaker_ids, mels, speaker_vecs, stop_targets, masks,
               mel_out, mel_post_out, gate_out, align_out, loss_out};
-    return train_forward_impl(h, 1, static_cast<char*>(wsp), 0, params, &io, B, T, L, (cudaStream_t)stream);
+    return train_forward_impl(h, 1, static_cast<char*>(wsp), 0, &params, &io, B, T, L, (cudaStream_t)stream);
 }
 
 size_t msa_group_workspace_bytes(const msa_handle* h, int G, int B, int T, int L) {
@@ -913,7 +942,7 @@ size_t msa_group_workspace_bytes(const msa_handle* h, int G, int B, int T, int L
     return (size_t)G * ((ws_layout(make_dims(h->cfg, B, T, L), nullptr).total_bytes + 255) / 256 * 256);
 }
 
-int msa_train_forward_group(msa_handle* h, int G, void* wsp, size_t ws_bytes, const float* params, float* const* bn_stats,
+int msa_train_forward_group(msa_handle* h, int G, void* wsp, size_t ws_bytes, const float* const* params, float* const* bn_stats,
                             const int64_t* const* tokens, const int64_t* const* token_lengths, const float* const* mels,
                             const int64_t* const* mel_lengths, const float* const* speaker_vecs, const int64_t* const* speaker_ids,
                             const float* const* stop_targets, const uint8_t* const* masks, int B, int T, int L, float* loss_out,
@@ -935,6 +964,7 @@ int msa_train_forward_group(msa_handle* h, int G, void* wsp, size_t ws_bytes, co
         ios[g] = TaskIO{bn_stats ? bn_stats[g] : nullptr, tokens[g], token_lengths[g], mel_lengths[g], si, mels[g], sv, stop_targets[g],
                         masks[g], nullptr, nullptr, nullptr, nullptr, loss_out ? loss_out + g : nullptr};
     }
+    for (int g = 0; g < G; ++g) MSA_CHECK(params[g] != nullptr, MSA_E_ARG, "msa_train_forward_group: null weights of task %d", g);
     return train_forward_impl(h, G, static_cast<char*>(wsp), stride, params, ios, B, T, L, (cudaStream_t)stream);
 }
 
@@ -1006,7 +1036,7 @@ namespace msa {
 
 // Backward of train_forward_impl: the gradient of task g's loss w.r.t. the shared parameters goes to grads_g[g]
 // (= autograd.grad(loss_g, fast_weights), maml.py:54 / 71-74); the three reverse-time recurrences run once for the whole group.
-static int train_backward_impl(msa_handle* h, char* wsp, const float* params, const float* const* d_mel, const float* const* d_mel_post,
+static int train_backward_impl(msa_handle* h, char* wsp, const float* const* params_g, const float* const* d_mel, const float* const* d_mel_post,
                                const float* const* d_gate, float* const* grads_g, int acc, float gs, cudaStream_t st) {
     const Dims d = h->d;
     const int NG = h->G;
@@ -1023,13 +1053,15 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
     const int B = d.B, T = d.T, L = d.L;
     const auto secs = mask_sections(c, B, T, L);
     const int iPre = d.nEnc, iAttn = d.nEnc + 2, iDec = d.nEnc + 3, iPost = d.nEnc + 4;
-    auto P = [&](const std::string& n) { return params + h->off(n); };
+    auto PG = [&](int g, const std::string& n) { return params_g[g] + h->off(n); };
+    bool shared = true;      // one weight buffer for the whole group (the theta_0 train passes) or per-task weights (the test passes)
+    for (int g = 1; g < NG; ++g) shared = shared && params_g[g] == params_g[0];
+    const int Gk = shared ? NG : 1;      // tasks one recurrence launch can carry
     const float beta = acc ? 1.f : 0.f;
     const int H4a = 4 * d.Ha, H4d = 4 * d.Hd, H4e = 4 * d.Hh, ldA = d.Pd + d.E, ldD = d.Ha + d.E, ldP = d.Hd + d.E;
     const std::string at = "decoder.attention_layer.";
     const bool fa = c.forward_attn != 0, ta = fa && c.trans_agent != 0;
-    const float* Wia = P("decoder.attention_rnn.weight_ih");
-    const bool mma = use_mma_chains(h, NG, B, T, L, false, true), mma_attn = use_mma_chains(h, NG, B, T, L, true, true);
+    const bool mma = use_mma_chains(h, Gk, B, T, L, false, true), mma_attn = use_mma_chains(h, Gk, B, T, L, true, true);
     const int64_t tstride = (int64_t)(ws_stride / sizeof(float));
     StageFork fk(h, st, NG);
 
@@ -1039,6 +1071,10 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
         const Ws& w = W[g];
         MSA_TRY(fk.enter(g));
         cudaStream_t st = fk.stream(g);      // this task's stage stream (shadows the pass stream)
+        const float* params = params_g[g];
+        auto P = [&](const std::string& n) { return params + h->off(n); };
+        const float* Wia = P("decoder.attention_rnn.weight_ih");
+        (void)Wia;
         MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
         float* grads = grads_g[g];
         auto mk = [&](int i) { return h->masks[g] + secs[i].off; };
@@ -1091,7 +1127,7 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
             const Ws& w = W[g];
             LstmRecBwdParams bp{};
             bp.T = T; bp.B = B; bp.H = d.Hd; bp.ndir = 1;
-            bp.whh = P("decoder.decoder_rnn.weight_hh"); bp.whh_dir_stride = 0;
+            bp.whh = PG(g, "decoder.decoder_rnn.weight_hh"); bp.whh_dir_stride = 0;
             bp.gates = w.gd; bp.cout = w.cd; bp.dh_ext = w.dhd; bp.dz = w.dzd;
             bp.mask = c.p_dec_dropout > 0.f ? h->masks[g] + secs[iDec].off : nullptr;
             bp.drop_scale = 1.f / (1.f - c.p_dec_dropout);
@@ -1099,12 +1135,18 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
             bp.trace = trace_ptr(h, w, PROF_DEC_LSTM_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
             return bp;
         };
-        ProfScope ps(h, PROF_DEC_LSTM_BWD + (mma && NG > 1 ? PROF_BASE : 0), st);
-        if (mma) {
+        ProfScope ps(h, PROF_DEC_LSTM_BWD + (mma && shared && NG > 1 ? PROF_BASE : 0), st);
+        if (mma && shared) {
             LstmRecBwdParams bp = make(0);
             bp.G = NG; bp.tstride = tstride;
             for (int g = 0; g < NG; ++g) bp.mask_g[g] = c.p_dec_dropout > 0.f ? h->masks[g] + secs[iDec].off : nullptr;
             MSA_TRY(launch_lstm_rec_bwd_mma(bp, h->sm_count, h->smem_limit, st));
+        } else if (mma) {       // per-task weights: one launch per task (G = 1, that task's pointers)
+            for (int g = 0; g < NG; ++g) {
+                LstmRecBwdParams bp = make(g);
+                bp.G = 1; bp.tstride = 0;
+                MSA_TRY(launch_lstm_rec_bwd_mma(bp, h->sm_count, h->smem_limit, st));
+            }
         } else {
             for (int g = 0; g < NG; ++g) MSA_TRY(launch_lstm_rec_bwd(make(g), h->sm_count, h->smem_limit, st));
         }
@@ -1115,6 +1157,10 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
         const Ws& w = W[g];
         MSA_TRY(fk.enter(g));
         cudaStream_t st = fk.stream(g);      // this task's stage stream (shadows the pass stream)
+        const float* params = params_g[g];
+        auto P = [&](const std::string& n) { return params + h->off(n); };
+        const float* Wia = P("decoder.attention_rnn.weight_ih");
+        (void)Wia;
         MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
         float* grads = grads_g[g];
         auto mk = [&](int i) { return h->masks[g] + secs[i].off; };
@@ -1149,28 +1195,34 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
             const Ws& w = W[g];
             AttnChainBwdParams bp{};
             bp.T = T; bp.B = B; bp.L = L; bp.Ha = d.Ha; bp.A = d.A; bp.F = d.F; bp.Kl = d.Kl; bp.norm = c.attn_norm;
-            bp.whh = P("decoder.attention_rnn.weight_hh"); bp.mw_pm = w.mw_pm;
-            bp.wq = P(at + "query_layer.linear_layer.weight");
-            bp.wloc = P(at + "location_layer.location_conv1d.weight");
-            bp.wld = P(at + "location_layer.location_dense.linear_layer.weight");
-            bp.v = P(at + "v.linear_layer.weight");
+            bp.whh = PG(g, "decoder.attention_rnn.weight_hh"); bp.mw_pm = w.mw_pm;
+            bp.wq = PG(g, at + "query_layer.linear_layer.weight");
+            bp.wloc = PG(g, at + "location_layer.location_conv1d.weight");
+            bp.wld = PG(g, at + "location_layer.location_dense.linear_layer.weight");
+            bp.v = PG(g, at + "v.linear_layer.weight");
             bp.mask = c.p_attn_dropout > 0.f ? h->masks[g] + secs[iAttn].off : nullptr;
             bp.drop_scale = 1.f / (1.f - c.p_attn_dropout);
             bp.ga = w.ga; bp.ca = w.ca; bp.align = w.align_tm; bp.s = w.s; bp.znorm = w.znorm;
             bp.dha_ext = w.dha; bp.da_ext = w.da_ext;
             bp.dza = w.dza; bp.dq = w.dq; bp.de = w.de; bp.ds = w.ds; bp.dconvf = w.dconvf; bp.dat = w.dat;
             bp.fa = fa; bp.ta = ta; bp.aplain = w.aplain; bp.fsum = w.fsum; bp.ustash = w.ustash; bp.dzu = w.dzu;
-            if (ta) { bp.mta = w.mta; bp.wta_h = P(at + "ta.weight") + d.E; }
+            if (ta) { bp.mta = w.mta; bp.wta_h = PG(g, at + "ta.weight") + d.E; }
             bp.abort_word = h->abort_dev; bp.prof = prof_ptr(h, w, PROF_ATTN_BWD); bp.trace = trace_ptr(h, w, PROF_ATTN_BWD);
             bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 0;
             return bp;
         };
-        ProfScope ps(h, PROF_ATTN_BWD + (mma_attn && NG > 1 ? PROF_BASE : 0), st);
-        if (mma_attn) {
+        ProfScope ps(h, PROF_ATTN_BWD + (mma_attn && shared && NG > 1 ? PROF_BASE : 0), st);
+        if (mma_attn && shared) {
             AttnChainBwdParams bp = make(0);
             bp.G = NG; bp.tstride = tstride;
             for (int g = 0; g < NG; ++g) bp.mask_g[g] = c.p_attn_dropout > 0.f ? h->masks[g] + secs[iAttn].off : nullptr;
             MSA_TRY(launch_attn_chain_bwd_mma(bp, h->sm_count, h->smem_limit, st));
+        } else if (mma_attn) {       // per-task weights: one launch per task (G = 1, that task's pointers)
+            for (int g = 0; g < NG; ++g) {
+                AttnChainBwdParams bp = make(g);
+                bp.G = 1; bp.tstride = 0;
+                MSA_TRY(launch_attn_chain_bwd_mma(bp, h->sm_count, h->smem_limit, st));
+            }
         } else {
             for (int g = 0; g < NG; ++g) MSA_TRY(launch_attn_chain_bwd(make(g), h->sm_count, h->smem_limit, st));
         }
@@ -1181,6 +1233,10 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
         const Ws& w = W[g];
         MSA_TRY(fk.enter(g));
         cudaStream_t st = fk.stream(g);      // this task's stage stream (shadows the pass stream)
+        const float* params = params_g[g];
+        auto P = [&](const std::string& n) { return params + h->off(n); };
+        const float* Wia = P("decoder.attention_rnn.weight_ih");
+        (void)Wia;
         MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
         float* grads = grads_g[g];
         auto mk = [&](int i) { return h->masks[g] + secs[i].off; };
@@ -1249,19 +1305,25 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
             const Ws& w = W[g];
             LstmRecBwdParams bp{};
             bp.T = L; bp.B = B; bp.H = d.Hh; bp.ndir = 2;
-            bp.whh = P("encoder.lstm.weight_hh_l0");
+            bp.whh = PG(g, "encoder.lstm.weight_hh_l0");
             bp.whh_dir_stride = h->off("encoder.lstm.weight_hh_l0_reverse") - h->off("encoder.lstm.weight_hh_l0");
             bp.gates = w.enc_g; bp.cout = w.enc_c; bp.dh_ext = w.denc_h; bp.dz = w.dzx; bp.mask = nullptr; bp.drop_scale = 1.f;
             bp.lengths = h->tok_len[g]; bp.abort_word = h->abort_dev; bp.prof = prof_ptr(h, w, PROF_ENC_LSTM_BWD);
             bp.trace = trace_ptr(h, w, PROF_ENC_LSTM_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
             return bp;
         };
-        ProfScope ps(h, PROF_ENC_LSTM_BWD + (mma && NG > 1 ? PROF_BASE : 0), st);
-        if (mma) {
+        ProfScope ps(h, PROF_ENC_LSTM_BWD + (mma && shared && NG > 1 ? PROF_BASE : 0), st);
+        if (mma && shared) {
             LstmRecBwdParams bp = make(0);
             bp.G = NG; bp.tstride = tstride;
             for (int g = 0; g < NG; ++g) bp.lengths_g[g] = h->tok_len[g];
             MSA_TRY(launch_lstm_rec_bwd_mma(bp, h->sm_count, h->smem_limit, st));
+        } else if (mma) {       // per-task weights: one launch per task (G = 1, that task's pointers)
+            for (int g = 0; g < NG; ++g) {
+                LstmRecBwdParams bp = make(g);
+                bp.G = 1; bp.tstride = 0;
+                MSA_TRY(launch_lstm_rec_bwd_mma(bp, h->sm_count, h->smem_limit, st));
+            }
         } else {
             for (int g = 0; g < NG; ++g) MSA_TRY(launch_lstm_rec_bwd(make(g), h->sm_count, h->smem_limit, st));
         }
@@ -1272,6 +1334,10 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* params, co
         const Ws& w = W[g];
         MSA_TRY(fk.enter(g));
         cudaStream_t st = fk.stream(g);      // this task's stage stream (shadows the pass stream)
+        const float* params = params_g[g];
+        auto P = [&](const std::string& n) { return params + h->off(n); };
+        const float* Wia = P("decoder.attention_rnn.weight_ih");
+        (void)Wia;
         MSA_BLAS(cublasSetWorkspace(h->blas, w.blas_ws, w.blas_ws_bytes));
         float* grads = grads_g[g];
         auto mk = [&](int i) { return h->masks[g] + secs[i].off; };
@@ -1326,16 +1392,16 @@ int msa_train_backward(msa_handle* h, void* wsp, size_t ws_bytes, const float* p
     MSA_CHECK(ws_bytes >= ws_layout(h->d, nullptr).total_bytes, MSA_E_WORKSPACE, "msa_train_backward: workspace too small");
     const bool ext = d_mel || d_mel_post || d_gate;
     MSA_CHECK(!ext || (d_mel && d_mel_post && d_gate), MSA_E_ARG, "msa_train_backward: pass all three upstream gradients or none");
-    return train_backward_impl(h, static_cast<char*>(wsp), params, ext ? &d_mel : nullptr, ext ? &d_mel_post : nullptr,
+    return train_backward_impl(h, static_cast<char*>(wsp), &params, ext ? &d_mel : nullptr, ext ? &d_mel_post : nullptr,
                                ext ? &d_gate : nullptr, &grads, acc, gs, (cudaStream_t)stream);
 }
 
-int msa_train_backward_group(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, float* const* grads, int acc, float gs,
+int msa_train_backward_group(msa_handle* h, void* wsp, size_t ws_bytes, const float* const* params, float* const* grads, int acc, float gs,
                              void* stream) {
     MSA_CHECK(h && wsp && params && grads, MSA_E_ARG, "msa_train_backward_group: null argument");
     MSA_CHECK(h->fwd_valid, MSA_E_STATE, "msa_train_backward_group: call msa_train_forward_group first");
     MSA_CHECK(ws_bytes >= (size_t)h->G * std::max<size_t>(h->ws_stride, 1), MSA_E_WORKSPACE, "msa_train_backward_group: workspace too small");
-    for (int g = 0; g < h->G; ++g) MSA_CHECK(grads[g] != nullptr, MSA_E_ARG, "msa_train_backward_group: null gradient buffer of task %d", g);
+    for (int g = 0; g < h->G; ++g) MSA_CHECK(grads[g] != nullptr && params[g] != nullptr, MSA_E_ARG, "msa_train_backward_group: null buffer of task %d", g);
     return train_backward_impl(h, static_cast<char*>(wsp), params, nullptr, nullptr, nullptr, grads, acc, gs, (cudaStream_t)stream);
 }
 

@@ -267,11 +267,16 @@ class Engine:
     def _ptr_array(self, tensors):
         return (C.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
 
-    def forward_group(self, params: torch.Tensor, bn_stats: Sequence[Optional[torch.Tensor]], batches_dev: Sequence[dict],
+    def forward_group(self, params, bn_stats: Sequence[Optional[torch.Tensor]], batches_dev: Sequence[dict],
                       masks: Sequence[torch.Tensor]) -> torch.Tensor:
-        """One grouped forward of ``len(batches_dev)`` tasks from the SAME weights (include/msa_b200.h "task groups").  Returns the
-        per-task losses [G] (device).  All tasks must share B, T, L."""
+        """One grouped forward of ``len(batches_dev)`` tasks (include/msa_b200.h "task groups").  ``params``: ONE flat weight buffer
+        shared by all tasks (the theta_0 train passes: the recurrences share one launch) or a list with one buffer per task (the
+        test passes with the adapted weights: recurrences task by task, the stages between them overlapped across tasks).
+        Returns the per-task losses [G] (device).  All tasks must share B, T, L."""
         G = len(batches_dev)
+        plist = list(params) if isinstance(params, (list, tuple)) else [params] * G
+        if len(plist) != G:
+            raise ValueError("forward_group: one weight buffer per task (or a single shared one)")
         B, L = batches_dev[0]["inputs"].shape
         T = batches_dev[0]["melspecs"].shape[2]
         for bd in batches_dev:
@@ -284,10 +289,10 @@ class Engine:
         loss = torch.empty(G, device=self.device)
         spk = [bd["speaker_vecs"] for bd in batches_dev]
         fl = spk[0].dtype.is_floating_point
-        self._keep = (params, list(bn_stats), list(batches_dev), list(masks))
+        self._keep = (plist, list(bn_stats), list(batches_dev), list(masks))
         A = self._ptr_array
         rc = self.lib.msa_train_forward_group(
-            self.h, G, self._ws_ptr(), C.c_size_t(self._ws.numel() - 256), _ptr(params), A(list(bn_stats)),
+            self.h, G, self._ws_ptr(), C.c_size_t(self._ws.numel() - 256), A(plist), A(list(bn_stats)),
             A([bd["inputs"] for bd in batches_dev]), A([bd["input_lengths"] for bd in batches_dev]),
             A([bd["melspecs"] for bd in batches_dev]), A([bd["melspec_lengths"] for bd in batches_dev]),
             A(spk) if fl else None, None if fl else A(spk), A([bd["stop"] for bd in batches_dev]), A(list(masks)), B, T, L,
@@ -296,9 +301,10 @@ class Engine:
         self.launches += 1
         return loss
 
-    def backward_group(self, params: torch.Tensor, grads: Sequence[torch.Tensor], accumulate: bool = False, scale: float = 1.0) -> None:
-        """grads[g] <- (or +=) scale * d loss_g / d params for every task of the last ``forward_group``."""
-        rc = self.lib.msa_train_backward_group(self.h, self._ws_ptr(), C.c_size_t(self._ws.numel() - 256), _ptr(params),
+    def backward_group(self, params, grads: Sequence[torch.Tensor], accumulate: bool = False, scale: float = 1.0) -> None:
+        """grads[g] <- (or +=) scale * d loss_g / d params[g] for every task of the last ``forward_group`` (same ``params``)."""
+        plist = list(params) if isinstance(params, (list, tuple)) else [params] * len(grads)
+        rc = self.lib.msa_train_backward_group(self.h, self._ws_ptr(), C.c_size_t(self._ws.numel() - 256), self._ptr_array(plist),
                                                self._ptr_array(list(grads)), int(accumulate), C.c_float(scale), _stream())
         _lib.check(rc, "msa_train_backward_group")
         self.launches += 1

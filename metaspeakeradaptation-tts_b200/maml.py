@@ -45,6 +45,24 @@ class MAML(MetaTrainer):
             else:       # first inner step of the whole group as one pass (the recurrences share their per-step hand-offs)
                 self._adapt_group(group, train, n_inner)
                 slots = [self._slot(k) for k in range(len(group))]
+            tshape = {(tuple(test[i][1].shape), test[i][3].shape[2]) for i in group}
+            if len(group) > 1 and len(tshape) == 1 and self.params.get("group_tasks", True):
+                # the test-split passes of the group as ONE grouped pass with per-task weights: the recurrences run task by task (every
+                # task has its own adapted weights), everything between them overlaps across the tasks; the task gradients land in the
+                # slots' gradient buffers and are mixed with weights 1/N afterwards (maml.py:73-74, 94-98)
+                bds = [self._unpack_batch(test[i])[0] for i in group]
+                B, L = bds[0]["inputs"].shape
+                T = bds[0]["melspecs"].shape[2]
+                masks = [self._masks(i, n_inner, B, T, L, slot=k) for k, i in enumerate(group)]
+                lg = eng.forward_group([s_[0] for s_ in slots], [s_[2] for s_ in slots], bds, masks)
+                for k in range(len(group)):
+                    mcds.append(eng.mcd_group(k, bds[k]["melspec_lengths"]))
+                    losses.append(lg[k:k + 1])
+                eng.backward_group([s_[0] for s_ in slots], [s_[1] for s_ in slots])
+                for k in range(len(group)):
+                    eng.axpy(self.meta_grad, slots[k][1], 1.0 / N, init=(j == 0))
+                    j += 1
+                continue
             for k, i in enumerate(group):
                 fast, _, bn = slots[k]
                 inputs, _ = self._unpack_batch(test[i])
