@@ -214,13 +214,16 @@ class MetaTrainer:
                 self.inner_v.zero_()
             self._inner_step(self.theta, slots[k][1], slots[k][0], 0)
         out = [[losses[k:k + 1]] for k in range(len(group))]
-        for k, i in enumerate(group):
-            for it in range(1, n_inner):
-                fast, grad, bn = slots[k]
-                _, loss = eng.forward(fast, bn, bds[k], self._masks(i, it, B, T, L), outputs=False)
-                eng.backward(fast, grad)
+        # the later inner steps have per-task weights: still ONE grouped pass per step (recurrences task by task, everything between
+        # them overlapped across the tasks), then the per-task functional update
+        for it in range(1, n_inner):
+            masks = [self._masks(i, it, B, T, L, slot=k) for k, i in enumerate(group)]
+            lg = eng.forward_group([s_[0] for s_ in slots], [s_[2] for s_ in slots], bds, masks)
+            eng.backward_group([s_[0] for s_ in slots], [s_[1] for s_ in slots])
+            for k in range(len(group)):
+                fast, grad, _ = slots[k]
                 self._inner_step(fast, grad, fast, it)
-                out[k].append(loss)
+                out[k].append(lg[k:k + 1])
         return out
 
     # ---- outer update (maml.py:94-105 / reptile.py:82-89) ----------------------------------------------

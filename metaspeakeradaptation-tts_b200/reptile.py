@@ -73,9 +73,24 @@ class Reptile(MetaTrainer):
             else:       # the first inner step of the group as one pass from theta_0, the other steps task by task
                 self._adapt_group(group, train, n_inner)
                 slots = [self._slot(k) for k in range(len(group))]
+            tests = [items_b[speakers[i]]["test"] for i in group]
+            if eval_test and len(group) > 1 and len({(tuple(b[1].shape), b[3].shape[2]) for b in tests}) == 1:
+                # reptile.py:58-70 for the whole group: one grouped forward with per-task weights (recurrences task by task, the rest
+                # overlapped across the tasks)
+                bds = [self._unpack_batch(b)[0] for b in tests]
+                B, L = bds[0]["inputs"].shape
+                T = bds[0]["melspecs"].shape[2]
+                masks = [self._masks(i, n_inner, B, T, L, slot=k) for k, i in enumerate(group)]
+                lg = eng.forward_group([s_[0] for s_ in slots], [s_[2] for s_ in slots], bds, masks)
+                for k in range(len(group)):
+                    losses.append(lg[k:k + 1])
+                    self._mcds.append(eng.mcd_group(k, bds[k]["melspec_lengths"]))
+                done_test = True
+            else:
+                done_test = False
             for k, i in enumerate(group):
                 fast, _, bn = slots[k]
-                if eval_test:
+                if eval_test and not done_test:
                     losses.append(self._eval_test(i, items_b[speakers[i]], n_inner, fast, bn))
                 eng.reptile_delta(self.meta_grad, fast, self.theta, 1.0 / N, init=(j == 0))
                 j += 1
