@@ -220,6 +220,88 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def cpu_infer_sample(B_=32, L_=64, steps=16):
+    """BASELINE configs[4] on the host CPU: ``Tacotron2NV.infer`` of the unmodified reference model (B=32, L=64) for a bounded number
+    of free-running decoder steps; mel-frames/s = rows x steps / time (encoder and postnet included, like the GPU leg)."""
+    import copy
+    import io
+    from contextlib import redirect_stdout
+    import torch
+    import msa_tts_b200 as pkg
+    from msa_tts_b200 import synth
+    from oracle import ref_meta
+    ref = ref_meta.load_reference()
+    if ref is None:
+        return None
+    threads = ref_meta.host_threads()
+    torch.set_num_threads(threads)
+    cfg = pkg.default_params()
+    cfg["max_decoder_steps"] = steps
+    cfg["decoder_no_early_stopping"] = True
+    with redirect_stdout(io.StringIO()):
+        model = ref[0](copy.deepcopy(cfg))
+        sd = model.state_dict()
+        for k, v in synth.init_params(cfg, 0).items():
+            sd[k] = v.clone()
+        model.load_state_dict(sd)
+        model.eval()
+    g = torch.Generator().manual_seed(4321)
+    lens = torch.arange(L_, L_ - B_, -1)
+    inp = torch.randint(1, 123, (B_, L_), generator=g)
+    for b in range(B_):
+        inp[b, lens[b]:] = 0
+    spk = torch.randn(B_, cfg["speaker_embedding_dim"], generator=g)
+    best = None
+    with torch.no_grad(), redirect_stdout(io.StringIO()):
+        for _ in range(2):
+            t0 = time.perf_counter()
+            out = model.infer(inp, lens, spk)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    n = int(out[0].shape[2])
+    return {"value": B_ * n / best, "unit": "mel-frames/s", "us_per_step": best / n * 1e6, "cores": threads, "kind": "reference",
+            "sample": f"Tacotron2NV.infer of the unmodified reference, B={B_}, L={L_}, {n} decoder steps (of the GPU leg's 1000), best of 2"}
+
+
+def eager_gpu_reference_pass(torch, dev):
+    """The 'library kernels on the same box' bar of SURVEY.md 8d: the unmodified reference model run by PyTorch eager ON THE SAME GPU,
+    one forward + loss + backward pass at BASELINE configs[0] (B=4, T=200, L=64).  None if the reference is not importable."""
+    import copy
+    import io
+    from contextlib import redirect_stdout
+    import msa_tts_b200 as pkg
+    from msa_tts_b200 import synth
+    from oracle import ref_meta
+    ref = ref_meta.load_reference()
+    if ref is None:
+        return None
+    cfg = pkg.default_params()
+    with redirect_stdout(io.StringIO()):
+        model = ref[0](copy.deepcopy(cfg))
+        sd = model.state_dict()
+        for k, v in synth.init_params(cfg, 0).items():
+            sd[k] = v.clone()
+        model.load_state_dict(sd)
+    model.to(dev).train()
+    crit = ref[1](cfg["n_frames_per_step"], "none", 10.0, dev)
+    _, inp, inp_len, mels, mel_len, _, spk, stop = [x.to(dev) if hasattr(x, "to") else x for x in synth.make_batch(cfg, B, T, L, 100)]
+
+    def one():
+        model.zero_grad(set_to_none=True)
+        out = model(inputs=inp, input_lengths=inp_len, melspecs=mels, melspec_lengths=mel_len, speaker_vecs=spk)
+        crit(out, (mels, stop), mel_len).backward()
+    for _ in range(2):
+        one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    return {"ms_per_pass": e0.elapsed_time(e1) / 3, "kind": "reference model, PyTorch eager (library kernels) on the same GPU"}
+
+
 def cpu_baseline_sample():
     """Bounded sample (~10-30 s of CPU work) of the same meta-step for the `cpu_baseline` object of this repo's own line:
     1 warm-up task, 4 timed tasks and the outer update on their gradients; meta-step time = 8 x mean task + outer update.  Also the
@@ -275,9 +357,20 @@ def bench_infer(torch, tr, world, sync, B=32, L_=64, steps=1000):
         n_steps = int(out[0].shape[2])
         res[policy] = {"value": world * B * n_steps / float(ms) * 1e3, "us_per_step": float(ms) * 1e3 / n_steps}
         del eng
+    # stream bound of a decoder step: the 79.7 MB of fp32 LSTMCell / projection weights are read once per step
+    # (L2-resident after the first step; the measured HBM copy peak stands in as the stream bound)
+    from msa_tts_b200.config import memory_dim, rnn_dims
+    Ha, Hd = rnn_dims(cfg)
+    E = memory_dim(cfg)
+    wbytes = 4.0 * (4 * Ha * (cfg["prenet_dim"] + E + Ha) + 4 * Hd * (Ha + E + Hd) + (cfg["n_mel_channels"] + 1) * (Hd + E) +
+                    cfg["prenet_dim"] * (cfg["n_mel_channels"] + cfg["prenet_dim"]) + cfg["attention_params"]["attention_dim"] * Ha)
+    peak, peak_src = measured_peak()
+    roof = {"bound": "hbm", "achieved": wbytes / res["tf32"]["us_per_step"] / 1e3, "peak": peak, "unit": "GB/s",
+            "frac": wbytes / res["tf32"]["us_per_step"] / 1e3 / peak, "traffic": None, "peak_source": peak_src,
+            "algo_bytes_per_step": wbytes, "note": "decoder-step weights streamed once per step (L2-resident, five launches per step)"}
     return {"metric": "decoder_mel_frames_per_s", "value": res["tf32"]["value"], "unit": "mel-frames/s",
             "us_per_step": res["tf32"]["us_per_step"], "scaling": "weak", "gemm": "tf32 (rel 1e-3 path, tested)",
-            "fp32_accurate": res["fp32"],
+            "fp32_accurate": res["fp32"], "roofline": roof,
             "workload": f"free-running inference, B={B} per GPU, L={L_}, {n_steps} decoder steps, default dims, encoder and postnet included"}
 
 
@@ -557,6 +650,13 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()
+            try:
+                if isinstance(infer_line, dict) and "error" not in infer_line:
+                    infer_line["cpu_baseline"] = cpu_infer_sample()
+                if isinstance(other, dict) and "config0_fwd_bwd_pass" in other:
+                    other["config0_fwd_bwd_pass"]["eager_gpu_baseline"] = eager_gpu_reference_pass(torch, tr.device)
+            except Exception as e:
+                line["baseline_legs_error"] = str(e)[:200]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

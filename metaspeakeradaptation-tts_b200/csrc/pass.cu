@@ -731,20 +731,24 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
             lp.trace = trace_ptr(h, w, PROF_ENC_LSTM_FWD); lp.trace_t0 = h->trace_t0; lp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
             return lp;
         };
-        ProfScope ps(h, PROF_ENC_LSTM_FWD + (mma && shared && G > 1 ? PROF_BASE : 0), st);
         if (mma && shared) {
+            ProfScope ps(h, PROF_ENC_LSTM_FWD + (G > 1 ? PROF_BASE : 0), st);
             LstmRecParams lp = make(0);
             lp.G = G; lp.tstride = tstride;
             for (int g = 0; g < G; ++g) lp.lengths_g[g] = ios[g].tok_len;
             MSA_TRY(launch_lstm_rec_fwd_mma(lp, h->sm_count, h->smem_limit, st));
         } else if (mma) {       // per-task weights: one launch per task (G = 1, that task's pointers)
             for (int g = 0; g < G; ++g) {
+                ProfScope ps(h, PROF_ENC_LSTM_FWD, st);
                 LstmRecParams lp = make(g);
                 lp.G = 1; lp.tstride = 0;
                 MSA_TRY(launch_lstm_rec_fwd_mma(lp, h->sm_count, h->smem_limit, st));
             }
         } else {
-            for (int g = 0; g < G; ++g) MSA_TRY(launch_lstm_rec_fwd(make(g), h->sm_count, h->smem_limit, st));
+            for (int g = 0; g < G; ++g) {
+                ProfScope ps(h, PROF_ENC_LSTM_FWD, st);
+                MSA_TRY(launch_lstm_rec_fwd(make(g), h->sm_count, h->smem_limit, st));
+            }
         }
     }
     // ---- stage 2: memory, decoder set-up (decoder.py:290-302, forward_attn.py:103-116) ----
@@ -795,20 +799,24 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
             ap.trace = trace_ptr(h, w, PROF_ATTN_FWD); ap.trace_t0 = h->trace_t0; ap.flags = h->rec_flags >= 0 ? h->rec_flags : 0;
             return ap;
         };
-        ProfScope ps(h, PROF_ATTN_FWD + (mma_attn && shared && G > 1 ? PROF_BASE : 0), st);
         if (mma_attn && shared) {
+            ProfScope ps(h, PROF_ATTN_FWD + (G > 1 ? PROF_BASE : 0), st);
             AttnChainParams ap = make(0);
             ap.G = G; ap.tstride = tstride;
             for (int g = 0; g < G; ++g) ap.mask_g[g] = c.p_attn_dropout > 0.f ? ios[g].masks + secs[iAttn].off : nullptr;
             MSA_TRY(launch_attn_chain_fwd_mma(ap, h->sm_count, h->smem_limit, st));
         } else if (mma_attn) {       // per-task weights: one launch per task (G = 1, that task's pointers)
             for (int g = 0; g < G; ++g) {
+                ProfScope ps(h, PROF_ATTN_FWD, st);
                 AttnChainParams ap = make(g);
                 ap.G = 1; ap.tstride = 0;
                 MSA_TRY(launch_attn_chain_fwd_mma(ap, h->sm_count, h->smem_limit, st));
             }
         } else {
-            for (int g = 0; g < G; ++g) MSA_TRY(launch_attn_chain_fwd(make(g), h->sm_count, h->smem_limit, st));
+            for (int g = 0; g < G; ++g) {
+                ProfScope ps(h, PROF_ATTN_FWD, st);
+                MSA_TRY(launch_attn_chain_fwd(make(g), h->sm_count, h->smem_limit, st));
+            }
         }
     }
     // ---- stage 3: context vectors, decoder-RNN input projection ----
@@ -844,20 +852,24 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
             lp.trace = trace_ptr(h, w, PROF_DEC_LSTM_FWD); lp.trace_t0 = h->trace_t0; lp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
             return lp;
         };
-        ProfScope ps(h, PROF_DEC_LSTM_FWD + (mma && shared && G > 1 ? PROF_BASE : 0), st);
         if (mma && shared) {
+            ProfScope ps(h, PROF_DEC_LSTM_FWD + (G > 1 ? PROF_BASE : 0), st);
             LstmRecParams lp = make(0);
             lp.G = G; lp.tstride = tstride;
             for (int g = 0; g < G; ++g) lp.mask_g[g] = c.p_dec_dropout > 0.f ? ios[g].masks + secs[iDec].off : nullptr;
             MSA_TRY(launch_lstm_rec_fwd_mma(lp, h->sm_count, h->smem_limit, st));
         } else if (mma) {       // per-task weights: one launch per task (G = 1, that task's pointers)
             for (int g = 0; g < G; ++g) {
+                ProfScope ps(h, PROF_DEC_LSTM_FWD, st);
                 LstmRecParams lp = make(g);
                 lp.G = 1; lp.tstride = 0;
                 MSA_TRY(launch_lstm_rec_fwd_mma(lp, h->sm_count, h->smem_limit, st));
             }
         } else {
-            for (int g = 0; g < G; ++g) MSA_TRY(launch_lstm_rec_fwd(make(g), h->sm_count, h->smem_limit, st));
+            for (int g = 0; g < G; ++g) {
+                ProfScope ps(h, PROF_DEC_LSTM_FWD, st);
+                MSA_TRY(launch_lstm_rec_fwd(make(g), h->sm_count, h->smem_limit, st));
+            }
         }
     }
     // ---- stage 4: projections, postnet, outputs, loss ----
@@ -1135,20 +1147,24 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* const* par
             bp.trace = trace_ptr(h, w, PROF_DEC_LSTM_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
             return bp;
         };
-        ProfScope ps(h, PROF_DEC_LSTM_BWD + (mma && shared && NG > 1 ? PROF_BASE : 0), st);
         if (mma && shared) {
+            ProfScope ps(h, PROF_DEC_LSTM_BWD + (NG > 1 ? PROF_BASE : 0), st);
             LstmRecBwdParams bp = make(0);
             bp.G = NG; bp.tstride = tstride;
             for (int g = 0; g < NG; ++g) bp.mask_g[g] = c.p_dec_dropout > 0.f ? h->masks[g] + secs[iDec].off : nullptr;
             MSA_TRY(launch_lstm_rec_bwd_mma(bp, h->sm_count, h->smem_limit, st));
         } else if (mma) {       // per-task weights: one launch per task (G = 1, that task's pointers)
             for (int g = 0; g < NG; ++g) {
+                ProfScope ps(h, PROF_DEC_LSTM_BWD, st);
                 LstmRecBwdParams bp = make(g);
                 bp.G = 1; bp.tstride = 0;
                 MSA_TRY(launch_lstm_rec_bwd_mma(bp, h->sm_count, h->smem_limit, st));
             }
         } else {
-            for (int g = 0; g < NG; ++g) MSA_TRY(launch_lstm_rec_bwd(make(g), h->sm_count, h->smem_limit, st));
+            for (int g = 0; g < NG; ++g) {
+                ProfScope ps(h, PROF_DEC_LSTM_BWD, st);
+                MSA_TRY(launch_lstm_rec_bwd(make(g), h->sm_count, h->smem_limit, st));
+            }
         }
     }
     // ---- stage 2: decoder-RNN input gradients, context backward ----
@@ -1211,20 +1227,24 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* const* par
             bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 0;
             return bp;
         };
-        ProfScope ps(h, PROF_ATTN_BWD + (mma_attn && shared && NG > 1 ? PROF_BASE : 0), st);
         if (mma_attn && shared) {
+            ProfScope ps(h, PROF_ATTN_BWD + (NG > 1 ? PROF_BASE : 0), st);
             AttnChainBwdParams bp = make(0);
             bp.G = NG; bp.tstride = tstride;
             for (int g = 0; g < NG; ++g) bp.mask_g[g] = c.p_attn_dropout > 0.f ? h->masks[g] + secs[iAttn].off : nullptr;
             MSA_TRY(launch_attn_chain_bwd_mma(bp, h->sm_count, h->smem_limit, st));
         } else if (mma_attn) {       // per-task weights: one launch per task (G = 1, that task's pointers)
             for (int g = 0; g < NG; ++g) {
+                ProfScope ps(h, PROF_ATTN_BWD, st);
                 AttnChainBwdParams bp = make(g);
                 bp.G = 1; bp.tstride = 0;
                 MSA_TRY(launch_attn_chain_bwd_mma(bp, h->sm_count, h->smem_limit, st));
             }
         } else {
-            for (int g = 0; g < NG; ++g) MSA_TRY(launch_attn_chain_bwd(make(g), h->sm_count, h->smem_limit, st));
+            for (int g = 0; g < NG; ++g) {
+                ProfScope ps(h, PROF_ATTN_BWD, st);
+                MSA_TRY(launch_attn_chain_bwd(make(g), h->sm_count, h->smem_limit, st));
+            }
         }
     }
     // ---- stage 3: deferred attention / prenet / speaker gradients ----
@@ -1312,20 +1332,24 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* const* par
             bp.trace = trace_ptr(h, w, PROF_ENC_LSTM_BWD); bp.trace_t0 = h->trace_t0; bp.flags = h->rec_flags >= 0 ? h->rec_flags : 1;
             return bp;
         };
-        ProfScope ps(h, PROF_ENC_LSTM_BWD + (mma && shared && NG > 1 ? PROF_BASE : 0), st);
         if (mma && shared) {
+            ProfScope ps(h, PROF_ENC_LSTM_BWD + (NG > 1 ? PROF_BASE : 0), st);
             LstmRecBwdParams bp = make(0);
             bp.G = NG; bp.tstride = tstride;
             for (int g = 0; g < NG; ++g) bp.lengths_g[g] = h->tok_len[g];
             MSA_TRY(launch_lstm_rec_bwd_mma(bp, h->sm_count, h->smem_limit, st));
         } else if (mma) {       // per-task weights: one launch per task (G = 1, that task's pointers)
             for (int g = 0; g < NG; ++g) {
+                ProfScope ps(h, PROF_ENC_LSTM_BWD, st);
                 LstmRecBwdParams bp = make(g);
                 bp.G = 1; bp.tstride = 0;
                 MSA_TRY(launch_lstm_rec_bwd_mma(bp, h->sm_count, h->smem_limit, st));
             }
         } else {
-            for (int g = 0; g < NG; ++g) MSA_TRY(launch_lstm_rec_bwd(make(g), h->sm_count, h->smem_limit, st));
+            for (int g = 0; g < NG; ++g) {
+                ProfScope ps(h, PROF_ENC_LSTM_BWD, st);
+                MSA_TRY(launch_lstm_rec_bwd(make(g), h->sm_count, h->smem_limit, st));
+            }
         }
     }
     // ---- stage 4: encoder BiLSTM weight gradients, encoder convolutions, embedding ----

@@ -341,6 +341,30 @@ class Engine:
         _lib.check(self.lib.msa_loss_grads(self.h, self._ws_ptr(), _ptr(d[0]), _ptr(d[1]), _ptr(d[2]), _stream()), "msa_loss_grads")
         return d
 
+    INFER_ROWS = 32      # rows of one msa_infer call (one batch tile of the fused decoder-step kernels)
+
+    def _infer_chunked(self, params, bn_stats, inputs, input_lengths, speaker_vecs, prenet_masks, max_steps):
+        """Batches beyond one 32-row tile: inference has no cross-row coupling in eval mode (BatchNorm uses running statistics), so the
+        rows are decoded tile by tile.  ``mel_lengths`` and every frame below a row's length are those of one big call; the output
+        is as long as the longest tile ran, and a tile that stopped earlier is zero-padded there (the reference keeps decoding
+        finished rows until the whole batch has stopped -- frames nobody reads, infer.py uses ``mel_lengths``)."""
+        B = inputs.shape[0]
+        outs = []
+        pm = prenet_masks.to(device=self.device, dtype=torch.uint8)
+        for b0 in range(0, B, self.INFER_ROWS):
+            sl = slice(b0, min(B, b0 + self.INFER_ROWS))
+            outs.append(self.infer(params, bn_stats, inputs[sl], input_lengths[sl], speaker_vecs[sl], pm[:, :, sl].contiguous(), max_steps))
+        T = max(o[0].shape[2] for o in outs)
+        post = torch.zeros(B, outs[0][0].shape[1], T, device=self.device)
+        align = torch.zeros(B, T, inputs.shape[1], device=self.device)
+        b0 = 0
+        for mp, _, al in outs:
+            n, t = mp.shape[0], mp.shape[2]
+            post[b0:b0 + n, :, :t] = mp
+            align[b0:b0 + n, :t] = al
+            b0 += n
+        return post, torch.cat([o[1] for o in outs]), align
+
     def infer(self, params: torch.Tensor, bn_stats: torch.Tensor, inputs: torch.Tensor, input_lengths: torch.Tensor,
               speaker_vecs: torch.Tensor, prenet_masks: torch.Tensor, max_steps: Optional[int] = None):
         """Tacotron2NV.infer (tacotron2nv.py:130-162): -> (mel_post [B, n_mel, T'], mel_lengths int32 [B], align [B, T', L]).
@@ -349,6 +373,8 @@ class Engine:
         B, L = inputs.shape
         max_steps = int(max_steps or self.cfg["max_decoder_steps"])
         M = self.cfg["n_mel_channels"]
+        if B > self.INFER_ROWS:
+            return self._infer_chunked(params, bn_stats, inputs, input_lengths, speaker_vecs, prenet_masks, max_steps)
         need = int(self.lib.msa_infer_workspace_bytes(self.h, B, L, max_steps))
         if self._ws is None or self._ws.numel() < need + 256:
             self._ws = torch.empty(need + 256, dtype=torch.uint8, device=self.device)

@@ -22,6 +22,27 @@ from .helpers import optimizer_hparams
 from .parallel import ShardInfo
 
 
+def plan_task_groups(mine, shapes, n_inner: int, stateful_inner: bool, enabled: bool, group_size) -> List[List[int]]:
+    """Which tasks of a meta-batch share grouped passes (include/msa_b200.h "task groups").  Every task of a meta-batch starts from
+    the same theta (maml.py:38-41), so the train-split passes of tasks with equal (B, T, L) run as one pass whose recurrences hand
+    their data over once per step for all rows; later inner steps and the test passes of the same group run as grouped passes with
+    per-task weights.  ``mine``: task indices of this rank; ``shapes[i]``: ((B, L), T) of task i's train batch; ``group_size(n, B)``:
+    most tasks one grouped pass may carry.  A stateful inner optimizer (momentum / Adam) with more than one inner step keeps its
+    state per task and takes the plain path.  Returns lists of task indices in task order; singletons take the plain path."""
+    if n_inner < 1 or not enabled or (stateful_inner and n_inner > 1):
+        return [[i] for i in mine]
+    by_shape: Dict[tuple, List[int]] = {}
+    for i in mine:
+        by_shape.setdefault(shapes[i], []).append(i)
+    plan = []
+    for shape, idx in by_shape.items():
+        gmax = max(1, int(group_size(len(idx), shape[0][0])))
+        for k in range(0, len(idx), gmax):
+            plan.append(idx[k:k + gmax])
+    plan.sort(key=lambda g: g[0])
+    return plan
+
+
 class _Staged:
     """A batch tuple whose device copy is in flight on the copy stream; indexable like the tuple (shapes for the group plan)."""
 
@@ -154,26 +175,12 @@ class MetaTrainer:
 
     # ---- grouped first inner step ------------------------------------------------------------------------------
     def _group_plan(self, mine: List[int], batches: Dict[int, tuple]) -> List[List[int]]:
-        """Tasks whose FIRST inner step can share one grouped pass (include/msa_b200.h "task groups"): every task of a meta-batch
-        starts from the same theta (maml.py:38-41), so the train-split passes of tasks with equal (B, T, L) run as one pass whose
-        recurrences hand their data over once per step for all rows.  Later inner steps have per-task weights and run one by one.
-        Returns lists of task indices; singletons take the plain path."""
-        n_inner = self.params["n_inner_train"]
+        """Tasks whose inner steps can share grouped passes (``plan_task_groups``)."""
         h = self.inner
         stateful = (h["name"] == "Adam") or bool(h.get("momentum", 0.0))
-        if n_inner < 1 or not self.params.get("group_tasks", True) or (stateful and n_inner > 1):
-            return [[i] for i in mine]
-        by_shape: Dict[tuple, List[int]] = {}
-        for i in mine:
-            b = batches[i]
-            by_shape.setdefault((tuple(b[1].shape), b[3].shape[2]), []).append(i)
-        plan = []
-        for (shape, _), idx in by_shape.items():
-            gmax = self.engine.group_size(len(idx), shape[0])
-            for k in range(0, len(idx), gmax):
-                plan.append(idx[k:k + gmax])
-        plan.sort(key=lambda g: g[0])
-        return plan
+        shapes = {i: (tuple(batches[i][1].shape), batches[i][3].shape[2]) for i in mine}
+        return plan_task_groups(mine, shapes, self.params["n_inner_train"], stateful, self.params.get("group_tasks", True),
+                                self.engine.group_size)
 
     def _slot(self, k: int):
         """Per-slot fast weights / gradient / BatchNorm buffers of a group (slot 0 = the buffers of the plain path)."""

@@ -117,18 +117,34 @@ def test_infer_default_dims_vs_oracle(B, L, attn):
     assert rel(post, o_post) < TOL and rel(align, o_align) < TOL, (rel(post, o_post), rel(align, o_align))
 
 
-def test_infer_more_than_32_rows_fails_loudly():
-    """One msa_infer call takes at most 32 rows (the persistent encoder BiLSTM keeps one batch tile resident; BASELINE configs[4]
-    is B = 32): larger batches are split by the caller, and the library says so instead of computing something else."""
+def test_infer_more_than_32_rows_is_decoded_tile_by_tile():
+    """One msa_infer call takes one 32-row tile (BASELINE configs[4] is B = 32); the host layer decodes larger batches tile by tile
+    (eval mode has no cross-row coupling): mel_lengths bit-exact and every frame below a row's length equal to the oracle's run of
+    the whole batch."""
     from msa_tts_b200.engine import Engine
     from oracle.gen_cases import _infer
-    cfg = _infer()
+    cfg, steps, B = _infer(early=True, thr=0.62), 12, 40
+    cfg["max_decoder_steps"] = steps
     eng = Engine(cfg)
     P = synth.init_params(cfg, 5)
-    _, inp, inp_len, _, _, _, spk, _ = synth.make_batch(cfg, 40, 8, 9, 105)
-    pm = synth.make_infer_masks(cfg, 40, 8, 305)
+    _, inp, inp_len, _, _, _, spk, _ = synth.make_batch(cfg, B, 8, 9, 105)
+    stats = infer_stats(P, cfg, 5)
+    pm = synth.make_infer_masks(cfg, B, steps, 305)
+    post, lens, align = eng.infer(eng.flat_from_dict(P), eng.bn_from_dict(stats), inp, inp_len, spk, pm, max_steps=steps)
+    torch.cuda.synchronize()
+    o_post, o_lens, o_align = OM.infer(P, cfg, inp, inp_len, spk, pm, stats)
+    assert torch.equal(lens.cpu(), o_lens)
+    assert post.shape[0] == B and post.shape[2] <= o_post.shape[2]
+    for b in range(B):
+        n = min(int(o_lens[b]), post.shape[2])
+        assert rel(post[b, :, :n], o_post[b, :, :n]) < TOL and rel(align[b, :n], o_align[b, :n]) < TOL, b
+    # the raw C entry point still refuses more than one tile loudly
     with pytest.raises(RuntimeError, match="batch 40"):
-        eng.infer(eng.flat_from_dict(P), eng.new_bn_stats(), inp, inp_len, spk, pm, max_steps=8)
+        Engine.INFER_ROWS, keep = 64, Engine.INFER_ROWS
+        try:
+            eng.infer(eng.flat_from_dict(P), eng.new_bn_stats(), inp, inp_len, spk, pm, max_steps=steps)
+        finally:
+            Engine.INFER_ROWS = keep
 
 
 @pytest.mark.parametrize("B,L,early", [(32, 11, False), (17, 23, True), (1, 7, False)])

@@ -122,3 +122,23 @@ def test_collators_match_the_reference_collators_bit_for_bit(r):
     for spk in d:
         for mode in ("train", "test"):
             check(d[spk][mode], f"meta_r{r}/{spk}/{mode}")
+
+
+def test_task_group_plan():
+    """Host logic of the grouped passes: tasks of a rank are grouped by the shape of their train batch, at most 8 tasks and 32 rows
+    per group; stateful inner optimizers with several inner steps, n_inner = 0 and group_tasks=False take the plain path."""
+    from msa_tts_b200.metatrainer import plan_task_groups
+    gs = lambda n, B: max(1, min(n, 8, 32 // max(B, 1)))
+    same = {i: ((4, 64), 200) for i in range(8)}
+    assert plan_task_groups(list(range(8)), same, 1, False, True, gs) == [list(range(8))]
+    assert plan_task_groups([0, 2, 4, 6], same, 1, False, True, gs) == [[0, 2, 4, 6]]          # rank 0 of 2
+    assert plan_task_groups(list(range(8)), same, 1, False, False, gs) == [[i] for i in range(8)]
+    assert plan_task_groups(list(range(8)), same, 0, False, True, gs) == [[i] for i in range(8)]
+    assert plan_task_groups(list(range(8)), same, 5, True, True, gs) == [[i] for i in range(8)]   # momentum / Adam, 5 inner steps
+    assert plan_task_groups(list(range(8)), same, 1, True, True, gs) == [list(range(8))]          # ... one step: state starts at zero
+    b16 = {i: ((16, 64), 200) for i in range(5)}
+    assert plan_task_groups(list(range(5)), b16, 2, False, True, gs) == [[0, 1], [2, 3], [4]]      # 32 rows per launch
+    mixed = {0: ((4, 64), 200), 1: ((4, 60), 200), 2: ((4, 64), 200), 3: ((4, 64), 180), 4: ((4, 60), 200)}
+    assert plan_task_groups(list(range(5)), mixed, 1, False, True, gs) == [[0, 2], [1, 4], [3]]    # ragged speakers: by shape
+    many = {i: ((4, 64), 200) for i in range(16)}
+    assert plan_task_groups(list(range(16)), many, 5, False, True, gs) == [list(range(8)), list(range(8, 16))]
