@@ -22,7 +22,9 @@ def _params(cfg, n_inner, outer):
     return {"model": cfg, "criterion": {"criterion_type": "Tacotron2Loss", "reduction": "none", "pos_weight": 10.0},
             "optim_inner": {"optimizer_name": "SGD", "optim_params": {"lr": "0.05"}},
             "optim_outer": {"optimizer_name": outer, "optim_params": {"lr": "0.01"}},
-            "n_inner_train": n_inner, "track_higher_grads": False, "clip_grad_norm": True, "grad_clip_thresh": 0.5, "init_seed": 5}
+            "n_inner_train": n_inner, "track_higher_grads": False, "clip_grad_norm": True, "grad_clip_thresh": 0.5, "init_seed": 5,
+            # the batched Reptile variant is the one that shards (on one GPU the reference's per-speaker sequential loop is the default)
+            "reptile_sequential": False}
 
 
 def _run(kind, n_tasks, n_inner, steps=2):
