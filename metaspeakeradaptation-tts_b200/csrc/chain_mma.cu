@@ -542,7 +542,7 @@ int coop_launch(Kern kern, const Params& p, int sm_count, size_t smem, cudaStrea
 // and cannot be resident for a whole group).
 // =====================================================================================================================
 struct AttnFwdMmaLay {
-    size_t afrag, part, as_, ah, wldT, wloc, vs, pm, pre, cf, zm, qs, epos, total;     // byte offsets
+    size_t afrag, part, as_, ah, wldT, wloc, vs, pm, pre, cf, zm, rowoff, posoff, posrl, total;     // byte offsets
     int KS, LP, LH, CKP, NPmax, NRown, RP;
 };
 __host__ __device__ inline AttnFwdMmaLay attn_fwd_mma_layout(int R, int L, int Ha, int A, int F, int Kl, int ncta, int NT) {
@@ -550,7 +550,8 @@ __host__ __device__ inline AttnFwdMmaLay attn_fwd_mma_layout(int R, int L, int H
     s.KS = (Ha + 255) / 256;
     s.LP = round_up_i(L, 4);
     s.LH = round_up_i(L + Kl - 1, 4);
-    s.CKP = 2 * Kl + 1;
+    s.CKP = ((2 * Kl + 7) & ~7) + 8;              // filter stride = 8 banks (mod 32): the 4 filters x 8 taps of a warp hit 32 banks
+    if ((s.CKP & 31) != 8) s.CKP = ((s.CKP + 31) & ~31) + 8;
     s.NPmax = (R * L + ncta - 1) / ncta;
     s.NRown = (s.NPmax + L - 2) / L + 1;          // batch rows a run of NPmax consecutive positions can touch
     s.RP = round_up_i(R, 4);
@@ -572,6 +573,9 @@ __host__ __device__ inline AttnFwdMmaLay attn_fwd_mma_layout(int R, int L, int H
     s.pre = take((size_t)s.NPmax * A * sizeof(float));
     s.cf = take((size_t)s.NPmax * F * sizeof(float));
     s.zm = take((size_t)32 * s.RP * sizeof(float));
+    s.rowoff = take((size_t)64 * sizeof(long long));            // row r -> task(r) * tstride; [32 + r] -> ... + brow(r) * L (floats)
+    s.posoff = take((size_t)s.NPmax * sizeof(long long));      // owned position -> task * tstride (floats)
+    s.posrl = take((size_t)s.NPmax * 3 * sizeof(int));         // owned position -> (row r, l, index inside the task's [B*L] arrays)
     s.total = o;
     return s;
 }
@@ -604,6 +608,9 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
     float* pre_s = reinterpret_cast<float*>(smem_raw + lay.pre);   // [np][A]  loc + pm, then v * tanh(.)
     float* cf_s = reinterpret_cast<float*>(smem_raw + lay.cf);     // [np][F]
     float* zm = reinterpret_cast<float*>(smem_raw + lay.zm);       // [32][RP] context term of the local gate rows
+    long long* rowoff = reinterpret_cast<long long*>(smem_raw + lay.rowoff);
+    long long* posoff = reinterpret_cast<long long*>(smem_raw + lay.posoff);
+    int* posrl = reinterpret_cast<int*>(smem_raw + lay.posrl);
 
     const int u0 = part_lo(cta, Ha, ncta), u1 = part_lo(cta + 1, Ha, ncta), U = u1 - u0;
     const int p0 = part_lo(cta, RL, ncta), p1 = part_lo(cta + 1, RL, ncta), np = p1 - p0;
@@ -662,6 +669,17 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
         const int pp = p0 + i, g = pos_task(pp);
         p.cum[g * gr.tstride + (pp - g * BtL)] = 0.f;
     }
+    for (int r = threadIdx.x; r < R; r += kMT) {
+        rowoff[r] = (long long)gr.task(r) * gr.tstride;
+        rowoff[32 + r] = rowoff[r] + (long long)gr.brow(r) * L;
+    }
+    for (int i = threadIdx.x; i < np; i += kMT) {
+        const int pp = p0 + i, r = pp / L, g = r / Bt;
+        posoff[i] = (long long)g * gr.tstride;
+        posrl[3 * i] = r;
+        posrl[3 * i + 1] = pp - r * L;
+        posrl[3 * i + 2] = pp - g * BtL;
+    }
     const float bv = __ldg(p.bv);
 
     // point-wise role: thread c < NT*64 owns cell (slot ul, row r); slot 7 of a query-owning CTA is the query "cell"
@@ -704,49 +722,50 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
     for (int t = 0; t < T; ++t) {
         // ---- P1: context term zm[rl][r] = sum_l MW[row rl][r][l] * a(t-1)[r][l] (zero at t = 0: zm starts zeroed) ----
         if (t > 0 && U > 0) {
-            // one dot product per half-warp: pair index = (gate*U + ul) * R + r; the MW loads of eight pairs are issued before the
-            // first one is used (the slice streams from L2: it is 4*U*R*L floats per step)
-            const int npair = 4 * U * R, hw = lane >> 4, hl = lane & 15;
+            // one dot product per half-warp; warp w owns the local rows w, w + 16, ... (gate-major list of the 4*U real rows), its two
+            // half-warps alternate over the batch rows; the MW loads of eight dots are issued before the first one is used (the slice
+            // streams from L2: 4*U*R*L floats per step)
+            const int hw = lane >> 4, hl = lane & 15;
             constexpr int PB = 8;
-            for (int base = w * 2 + hw; base < npair; base += kMW * 2 * PB) {
-                const float* mrow[PB];
-                int prl[PB], pr[PB];
-                bool ok[PB];
+            for (int j = w; j < 4 * U; j += kMW) {
+                const int gate = j / U, ul = j - gate * U, rl = gate * 8 + ul;
+                const float* mbase = p.mw_rm + (size_t)(gate * Ha + u0 + ul) * BtL;
+                for (int r0 = hw; r0 < R; r0 += 2 * PB) {
+                    float acc[PB];
+                    if (vecL && L <= 64) {
+                        float4 mv[PB];
 #pragma unroll
-                for (int k = 0; k < PB; ++k) {
-                    const int pi = base + k * kMW * 2;
-                    ok[k] = pi < npair;
-                    const int pq = ok[k] ? pi : 0;
-                    const int gu = pq / R, r = pq - gu * R, gate = gu / U, ul = gu - gate * U;
-                    prl[k] = gate * 8 + ul;
-                    pr[k] = r;
-                    mrow[k] = p.mw_rm + gr.task(r) * gr.tstride + (size_t)(gate * Ha + u0 + ul) * BtL + (size_t)gr.brow(r) * L;
-                }
-                float acc[PB];
-                if (vecL && L <= 64) {
-                    float4 mv[PB];
+                        for (int k = 0; k < PB; ++k) {
+                            const int r = r0 + 2 * k;
+                            mv[k] = (r < R && hl * 4 < L) ? __ldcg(reinterpret_cast<const float4*>(mbase + rowoff[32 + r]) + hl)
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
 #pragma unroll
-                    for (int k = 0; k < PB; ++k)
-                        mv[k] = (ok[k] && hl * 4 < L) ? __ldcg(reinterpret_cast<const float4*>(mrow[k]) + hl) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int k = 0; k < PB; ++k) {
+                            const int r = r0 + 2 * k;
+                            acc[k] = (r < R && hl * 4 < L) ? dot4(mv[k], *reinterpret_cast<const float4*>(as_ + r * LP + hl * 4)) : 0.f;
+                        }
+                    } else {
 #pragma unroll
-                    for (int k = 0; k < PB; ++k)
-                        acc[k] = hl * 4 < L ? dot4(mv[k], *reinterpret_cast<const float4*>(as_ + pr[k] * LP + hl * 4)) : 0.f;
-                } else {
+                        for (int k = 0; k < PB; ++k) {
+                            const int r = r0 + 2 * k;
+                            acc[k] = 0.f;
+                            if (r < R) {
+                                const float* mrow = mbase + rowoff[32 + r];
+                                for (int l = hl; l < L; l += 16) acc[k] += __ldcg(mrow + l) * as_[r * LP + l];
+                            }
+                        }
+                    }
 #pragma unroll
                     for (int k = 0; k < PB; ++k) {
-                        acc[k] = 0.f;
-                        if (ok[k])
-                            for (int l = hl; l < L; l += 16) acc[k] += __ldcg(mrow[k] + l) * as_[pr[k] * LP + l];
+                        const int r = r0 + 2 * k;
+                        float a = acc[k];
+                        a += __shfl_xor_sync(0xffffffffu, a, 1);
+                        a += __shfl_xor_sync(0xffffffffu, a, 2);
+                        a += __shfl_xor_sync(0xffffffffu, a, 4);
+                        a += __shfl_xor_sync(0xffffffffu, a, 8);
+                        if (hl == 0 && r < R) zm[rl * RP + r] = a;
                     }
-                }
-#pragma unroll
-                for (int k = 0; k < PB; ++k) {
-                    float a = acc[k];
-                    a += __shfl_xor_sync(0xffffffffu, a, 1);
-                    a += __shfl_xor_sync(0xffffffffu, a, 2);
-                    a += __shfl_xor_sync(0xffffffffu, a, 4);
-                    a += __shfl_xor_sync(0xffffffffu, a, 8);
-                    if (hl == 0 && ok[k]) zm[prl[k] * RP + pr[k]] = a;
                 }
             }
         }
@@ -773,24 +792,29 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
         }
         prof.mark(1, t);
         // ---- P3 (shadow of the h hand-off): location features of the owned positions (forward_attn.py:121-127) ----
-        for (int base = 0; base < np * F * 8; base += kMT) {
-            const int it = base + threadIdx.x;
-            const bool valid = it < np * F * 8;
-            const int ks = it & 7, f = valid ? (it >> 3) % F : 0, pi = valid ? (it >> 3) / F : 0;
-            const int pp = p0 + pi, r = pp / L, l = pp - r * L, ro = r - r_lo;
-            float cf = 0.f;
-            if (valid)
-                for (int ck = ks; ck < 2 * Kl; ck += 8) {
-                    const int c = ck >= Kl ? 1 : 0, k = ck - c * Kl;
-                    cf += wloc_s[f * CKP + ck] * ah[(c * lay.NRown + ro) * LH + l + k];
+        // item (position, filter, tap residue): 8 consecutive lanes share (position, filter); kMT / (8 F) positions per sweep
+        {
+            const int ipp = F * 8, ppi = kMT / ipp;                 // items per position, positions per sweep (threads beyond ppi * ipp idle)
+            const int sub = threadIdx.x / ipp, rem = threadIdx.x - sub * ipp, f = rem >> 3, ks = rem & 7;
+            for (int pb = 0; pb < np; pb += ppi) {
+                const int pi = pb + sub;
+                const bool valid = sub < ppi && pi < np;
+                float cf = 0.f;
+                if (valid) {
+                    const int ro = posrl[3 * pi] - r_lo, l = posrl[3 * pi + 1];
+                    const float* a0 = ah + (size_t)ro * LH + l;
+                    const float* a1 = ah + (size_t)(lay.NRown + ro) * LH + l;
+                    const float* wl = wloc_s + f * CKP;
+                    for (int k = ks; k < Kl; k += 8) cf += wl[k] * a0[k];
+                    for (int k = ks; k < Kl; k += 8) cf += wl[Kl + k] * a1[k];
                 }
-            cf += __shfl_xor_sync(0xffffffffu, cf, 1);
-            cf += __shfl_xor_sync(0xffffffffu, cf, 2);
-            cf += __shfl_xor_sync(0xffffffffu, cf, 4);
-            if (valid && ks == 0) {
-                cf_s[pi * F + f] = cf;
-                const int g = r / Bt;
-                p.convf[g * gr.tstride + ((size_t)t * BtL + (pp - g * BtL)) * F + f] = cf;
+                cf += __shfl_xor_sync(0xffffffffu, cf, 1);
+                cf += __shfl_xor_sync(0xffffffffu, cf, 2);
+                cf += __shfl_xor_sync(0xffffffffu, cf, 4);
+                if (valid && ks == 0) {
+                    cf_s[pi * F + f] = cf;
+                    p.convf[posoff[pi] + ((size_t)t * BtL + posrl[3 * pi + 2]) * F + f] = cf;
+                }
             }
         }
         __syncthreads();
@@ -918,9 +942,9 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
         prof.mark(5, t);
         // ---- P5: energies of the owned positions (forward_attn.py:128-131); publishes e(t) ----
         for (int it = threadIdx.x; it < np * A; it += kMT) {
-            const int pi = it / A, d = it - pi * A, pp = p0 + pi, r = pp / L, g = r / Bt;
-            const float sv = fast_tanh(q_s[(r - r_lo) * A + d] + pre_s[it]);
-            p.s[g * gr.tstride + ((size_t)t * BtL + (pp - g * BtL)) * A + d] = sv;
+            const int pi = it / A, d = it - pi * A;
+            const float sv = fast_tanh(q_s[(posrl[3 * pi] - r_lo) * A + d] + pre_s[it]);
+            p.s[posoff[pi] + ((size_t)t * BtL + posrl[3 * pi + 2]) * A + d] = sv;
             pre_s[it] = vs[d] * sv;
         }
         __syncthreads();
@@ -928,10 +952,7 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
             float e = 0.f;
             for (int d = lane; d < A; d += 32) e += pre_s[pi * A + d];
             e = warp_sum(e);
-            if (lane == 0) {
-                const int pp = p0 + pi, g = pos_task(pp);
-                st_pub(p.e + g * gr.tstride + (size_t)t * BtL + (pp - g * BtL), e + bv);
-            }
+            if (lane == 0) st_pub(p.e + posoff[pi] + (size_t)t * BtL + posrl[3 * pi + 2], e + bv);
         }
         prof.mark(6, t);
         // ---- hand-off 3: all energies of step t; a(t) = normalise(e(t)); cum += a(t) (forward_attn.py:200-210) ----
@@ -975,8 +996,8 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
         }
         __syncthreads();
         for (int i = threadIdx.x; i < np; i += kMT) {
-            const int pp = p0 + i, r = pp / L, l = pp - r * L, g = r / Bt;
-            const size_t o = g * gr.tstride + (size_t)(pp - g * BtL);
+            const int r = posrl[3 * i], l = posrl[3 * i + 1];
+            const size_t o = posoff[i] + (size_t)posrl[3 * i + 2];
             p.align[o + (size_t)t * BtL] = as_[r * LP + l];
             if (t + 1 < T) p.cum[o + (size_t)(t + 1) * BtL] = ah[(1 * lay.NRown + (r - r_lo)) * LH + pl + l];
         }
