@@ -114,6 +114,21 @@ __device__ __forceinline__ void gate_waitq(int n, AddrFn addr, unsigned int* abo
     }
 }
 
+// Streaming of ready-made weight fragments (per-task-weight variants): 16-byte asynchronous copies into a per-warp ring; every lane
+// copies and later reads only its own 16-byte slots, so the copies need no cross-lane synchronisation.
+#ifndef MSA_RING_FWD
+#define MSA_RING_FWD 4
+#endif
+constexpr int kRingF = MSA_RING_FWD;  // forward: ring stages of 2 KB per warp (4 stages: 128 KB per SM in flight between product phases)
+constexpr int kRing = 3;              // backward: ring stages of G x 512 bytes per warp
+__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // Fragment column permutation: within a k16 block, lane j (= lane & 3) owns the four PHYSICAL columns 4j .. 4j+3 and feeds them
 // as the logical k indices {2j, 2j+1, 2j+8, 2j+9} -- one 128-bit load per row and k16 block on the streaming side; the resident
 // side is packed with the same mapping once.
@@ -541,11 +556,61 @@ int coop_launch(Kern kern, const Params& p, int sm_count, size_t smem, cudaStrea
 // mma as "gate i of pseudo-unit 7".  The context term MW . a(t-1) streams the CTA's MW rows from L2 (they are 1 MB per batch row
 // and cannot be resident for a whole group).
 // =====================================================================================================================
+// A fragment idx = ((K slice ww * KS + k16 step s) * 2 + m tile mt) * 32 + lane of the CTA that owns units [u0, u0 + U) and (has_q)
+// attention dim d0: local row rl = mt * 16 + hr * 8 + g is gate rl >> 3 of unit slot rl & 7; slot 7 of gate 0 is the W_q row
+__device__ __forceinline__ void attn_fwd_frag(const float* __restrict__ whh, const float* __restrict__ wq, int Ha, int KS, int u0, int U,
+                                              bool has_q, int d0, int idx, uint4& hi, uint4& lo) {
+    const int ln = idx & 31, mt = (idx >> 5) & 1, s = (idx >> 6) % KS, ww = (idx >> 6) / KS;
+    const int g = ln >> 2, j = ln & 3;
+    const int col = (ww * KS + s) * 16 + 4 * j;
+    float v[2][4];
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+        const int rl = mt * 16 + hr * 8 + g;
+        const int gate = rl >> 3, ul = rl & 7;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float x = 0.f;
+            if (col + c < Ha) {
+                if (ul < U) x = __ldg(whh + (size_t)(gate * Ha + u0 + ul) * Ha + col + c);
+                else if (has_q && ul == 7 && gate == 0) x = __ldg(wq + (size_t)d0 * Ha + col + c);
+            }
+            v[hr][c] = x;
+        }
+    }
+    split2(v[0][0], v[0][1], hi.x, lo.x);
+    split2(v[1][0], v[1][1], hi.y, lo.y);
+    split2(v[0][2], v[0][3], hi.z, lo.z);
+    split2(v[1][2], v[1][3], hi.w, lo.w);
+}
+// the same fragments of G tasks written to global memory in the order the PT kernel streams them: [task][cta][ww][s][mt][hi|lo][lane]
+struct FragSrc {
+    const float* whh[kPtGroupMax];
+    const float* wq[kPtGroupMax];
+};
+__global__ void __launch_bounds__(kMT) k_attn_frag_fwd(FragSrc src, int Ha, int A, int64_t stride, uint4* out) {
+    const int task = blockIdx.y, cta = blockIdx.x, ncta = gridDim.x;
+    const float* whh = src.whh[task];
+    const float* wq = src.wq[task];
+    const int KS = (Ha + 255) / 256;
+    const int u0 = part_lo(cta, Ha, ncta), U = part_lo(cta + 1, Ha, ncta) - u0;
+    const int d0 = part_lo(cta, A, ncta);
+    const bool has_q = part_lo(cta + 1, A, ncta) > d0;
+    uint4* o = out + (size_t)task * stride + (size_t)cta * kMW * KS * 128;
+    for (int idx = threadIdx.x; idx < kMW * KS * 2 * 32; idx += kMT) {
+        uint4 hi, lo;
+        attn_fwd_frag(whh, wq, Ha, KS, u0, U, has_q, d0, idx, hi, lo);
+        const size_t b = (size_t)(idx >> 5) * 2 * 32;
+        o[b + (idx & 31)] = hi;
+        o[b + 32 + (idx & 31)] = lo;
+    }
+}
+
 struct AttnFwdMmaLay {
     size_t afrag, part, as_, ah, wldT, wloc, vs, pm, pre, cf, zm, rowoff, posoff, posrl, total;     // byte offsets
     int KS, LP, LH, CKP, NPmax, NRown, RP;
 };
-__host__ __device__ inline AttnFwdMmaLay attn_fwd_mma_layout(int R, int L, int Ha, int A, int F, int Kl, int ncta, int NT) {
+__host__ __device__ inline AttnFwdMmaLay attn_fwd_mma_layout(int R, int L, int Ha, int A, int F, int Kl, int ncta, int NT, int pt = 0) {
     AttnFwdMmaLay s;
     s.KS = (Ha + 255) / 256;
     s.LP = round_up_i(L, 4);
@@ -558,7 +623,9 @@ __host__ __device__ inline AttnFwdMmaLay attn_fwd_mma_layout(int R, int L, int H
     const int NTP = NT < 2 ? NT : 2;              // partial tiles are reduced two n tiles at a time
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return r; };
-    s.afrag = take((size_t)kMW * s.KS * 2 * 2 * 32 * sizeof(uint4));
+    // resident A fragments, or (per-task weights) the ring of streamed fragments: kRingF stages of one (k16 step, task) chunk per warp
+    s.afrag = take(pt ? (size_t)kMW * kRingF * 2 * 2 * 32 * sizeof(uint4) : (size_t)kMW * s.KS * 2 * 2 * 32 * sizeof(uint4));
+    const int NW = pt ? 2 : 1;                    // weight sets of the small attention weights: the tasks of the owned positions
     // partial tiles; the gathered energies [R*L] and the gathered queries [NRown][A] reuse the region later in the step
     size_t pbytes = (size_t)kMW * NTP * 2 * 4 * 32 * sizeof(float);
     const size_t gbytes = ((size_t)R * L + (size_t)s.NRown * A) * sizeof(float) + 32;
@@ -566,21 +633,23 @@ __host__ __device__ inline AttnFwdMmaLay attn_fwd_mma_layout(int R, int L, int H
     s.part = take(pbytes);
     s.as_ = take((size_t)R * s.LP * sizeof(float));
     s.ah = take((size_t)2 * s.NRown * s.LH * sizeof(float));
-    s.wldT = take((size_t)F * A * sizeof(float));
-    s.wloc = take((size_t)F * s.CKP * sizeof(float));
-    s.vs = take((size_t)A * sizeof(float));
+    s.wldT = take((size_t)NW * F * A * sizeof(float));
+    s.wloc = take((size_t)NW * F * s.CKP * sizeof(float));
+    s.vs = take((size_t)NW * (A + 4) * sizeof(float));           // v, then b_v at [A]
     s.pm = take((size_t)s.NPmax * A * sizeof(float));
     s.pre = take((size_t)s.NPmax * A * sizeof(float));
     s.cf = take((size_t)s.NPmax * F * sizeof(float));
     s.zm = take((size_t)32 * s.RP * sizeof(float));
     s.rowoff = take((size_t)64 * sizeof(long long));            // row r -> task(r) * tstride; [32 + r] -> ... + brow(r) * L (floats)
     s.posoff = take((size_t)s.NPmax * sizeof(long long));      // owned position -> task * tstride (floats)
-    s.posrl = take((size_t)s.NPmax * 3 * sizeof(int));         // owned position -> (row r, l, index inside the task's [B*L] arrays)
+    s.posrl = take((size_t)s.NPmax * 4 * sizeof(int));         // owned position -> (row r, l, index inside the task's [B*L] arrays, weight set)
     s.total = o;
     return s;
 }
 
-template <int NT>
+// PT (per-task weights): n tile nt holds the Bt <= 8 rows of task nt (NT = G <= 4), the A fragments of every (k16 step, task) are
+// streamed through the per-warp ring, the small attention weights are staged for the (at most two) tasks of the owned positions.
+template <int NT, bool PT>
 __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ float zn_s[kBMax];
@@ -592,10 +661,11 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
     // K slice of this warp, rotated by the CTA index: the 148 CTAs stream the SAME h / dz rows, without the rotation they would all
     // ask the same L2 slices for the same lines at the same moment
     const int wsl = MSA_SLICE_ROT ? (w + blockIdx.x) % kMW : w;
-    const AttnFwdMmaLay lay = attn_fwd_mma_layout(R, L, Ha, A, F, Kl, ncta, NT);
+    const AttnFwdMmaLay lay = attn_fwd_mma_layout(R, L, Ha, A, F, Kl, ncta, NT, PT ? 1 : 0);
     const int KS = lay.KS, LP = lay.LP, LH = lay.LH, CKP = lay.CKP, RP = lay.RP;
     constexpr int NTP = NT < 2 ? NT : 2;
     uint4* Afrag = reinterpret_cast<uint4*>(smem_raw + lay.afrag);
+    uint4* ring = Afrag + (size_t)w * kRingF * 128;      // PT: this warp's kRingF stages of [m tile][hi|lo][32] uint4
     float* part = reinterpret_cast<float*>(smem_raw + lay.part);
     float* es = part;                                  // [R*L]        gathered energies (after the tile reduction)
     float* q_s = part + ((RL + 3) & ~3);               // [NRown][A]   gathered queries of the owned rows
@@ -603,7 +673,7 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
     float* ah = reinterpret_cast<float*>(smem_raw + lay.ah);       // [2][NRown][LH] a(t-1), cum(t-1) of the owned rows, zero halo
     float* wldT = reinterpret_cast<float*>(smem_raw + lay.wldT);   // [F][A]
     float* wloc_s = reinterpret_cast<float*>(smem_raw + lay.wloc); // [F][CKP]
-    float* vs = reinterpret_cast<float*>(smem_raw + lay.vs);
+    float* vs = reinterpret_cast<float*>(smem_raw + lay.vs);       // [weight set][A + 4]: v, b_v
     float* pm_s = reinterpret_cast<float*>(smem_raw + lay.pm);     // [np][A]
     float* pre_s = reinterpret_cast<float*>(smem_raw + lay.pre);   // [np][A]  loc + pm, then v * tanh(.)
     float* cf_s = reinterpret_cast<float*>(smem_raw + lay.cf);     // [np][F]
@@ -621,43 +691,34 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
     auto pos_task = [&](int pp) { return (pp / L) / Bt; };
 
     // ---- one-time staging ----
-    for (int idx = threadIdx.x; idx < kMW * KS * 2 * 32; idx += kMT) {
-        const int ln = idx & 31, mt = (idx >> 5) & 1, s = (idx >> 6) % KS, ww = (idx >> 6) / KS;
-        const int g = ln >> 2, j = ln & 3;
-        const int col = (ww * KS + s) * 16 + 4 * j;
-        float v[2][4];
-#pragma unroll
-        for (int hr = 0; hr < 2; ++hr) {
-            const int rl = mt * 16 + hr * 8 + g;
-            const int gate = rl >> 3, ul = rl & 7;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float x = 0.f;
-                if (col + c < Ha) {
-                    if (ul < U) x = __ldg(p.whh + (size_t)(gate * Ha + u0 + ul) * Ha + col + c);
-                    else if (has_q && ul == 7 && gate == 0) x = __ldg(p.wq + (size_t)d0 * Ha + col + c);
-                }
-                v[hr][c] = x;
-            }
+    if (!PT) {
+        for (int idx = threadIdx.x; idx < kMW * KS * 2 * 32; idx += kMT) {
+            uint4 hi, lo;
+            attn_fwd_frag(p.whh, p.wq, Ha, KS, u0, U, has_q, d0, idx, hi, lo);
+            const size_t o = (size_t)(idx >> 5) * 2 * 32;
+            Afrag[o + (idx & 31)] = hi;
+            Afrag[o + 32 + (idx & 31)] = lo;
         }
-        uint4 hi, lo;
-        split2(v[0][0], v[0][1], hi.x, lo.x);
-        split2(v[1][0], v[1][1], hi.y, lo.y);
-        split2(v[0][2], v[0][3], hi.z, lo.z);
-        split2(v[1][2], v[1][3], hi.w, lo.w);
-        const size_t o = (((size_t)ww * KS + s) * 2 + mt) * 2 * 32;
-        Afrag[o + ln] = hi;
-        Afrag[o + 32 + ln] = lo;
     }
-    for (int idx = threadIdx.x; idx < F * 2 * Kl; idx += kMT) {
-        const int f = idx / (2 * Kl), ck = idx % (2 * Kl);
-        wloc_s[f * CKP + ck] = __ldg(p.wloc + idx);
+    // small attention weights: one set, or (PT) one per task of the owned positions (at most two: the launcher checks NPmax <= L)
+    const int g_lo = r_lo / Bt, nset = PT ? (np > 0 ? r_hi / Bt - g_lo + 1 : 0) : 1;
+    const int WLS = F * CKP, WDS = F * A, VSS = A + 4;      // strides of a weight set
+    for (int ws = 0; ws < nset; ++ws) {
+        const float* wloc_g = PT ? p.wloc_g[g_lo + ws] : p.wloc;
+        const float* wld_g = PT ? p.wld_g[g_lo + ws] : p.wld;
+        const float* v_g = PT ? p.v_g[g_lo + ws] : p.v;
+        const float* bv_g = PT ? p.bv_g[g_lo + ws] : p.bv;
+        for (int idx = threadIdx.x; idx < F * 2 * Kl; idx += kMT) {
+            const int f = idx / (2 * Kl), ck = idx % (2 * Kl);
+            wloc_s[ws * WLS + f * CKP + ck] = __ldg(wloc_g + idx);
+        }
+        for (int idx = threadIdx.x; idx < A * F; idx += kMT) {
+            const int d = idx / F, f = idx % F;
+            wldT[ws * WDS + f * A + d] = __ldg(wld_g + idx);
+        }
+        for (int idx = threadIdx.x; idx < A; idx += kMT) vs[ws * VSS + idx] = __ldg(v_g + idx);
+        if (threadIdx.x == 0) vs[ws * VSS + A] = __ldg(bv_g);
     }
-    for (int idx = threadIdx.x; idx < A * F; idx += kMT) {
-        const int d = idx / F, f = idx % F;
-        wldT[f * A + d] = __ldg(p.wld + idx);
-    }
-    for (int idx = threadIdx.x; idx < A; idx += kMT) vs[idx] = __ldg(p.v + idx);
     for (int idx = threadIdx.x; idx < np * A; idx += kMT) {
         const int pi = idx / A, d = idx - pi * A, pp = p0 + pi, g = pos_task(pp);
         pm_s[idx] = __ldg(p.pm + g * gr.tstride + (size_t)(pp - g * BtL) * A + d);
@@ -676,16 +737,17 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
     for (int i = threadIdx.x; i < np; i += kMT) {
         const int pp = p0 + i, r = pp / L, g = r / Bt;
         posoff[i] = (long long)g * gr.tstride;
-        posrl[3 * i] = r;
-        posrl[3 * i + 1] = pp - r * L;
-        posrl[3 * i + 2] = pp - g * BtL;
+        posrl[4 * i] = r;
+        posrl[4 * i + 1] = pp - r * L;
+        posrl[4 * i + 2] = pp - g * BtL;
+        posrl[4 * i + 3] = PT ? g - g_lo : 0;
     }
-    const float bv = __ldg(p.bv);
 
     // point-wise role: thread c < NT*64 owns cell (slot ul, row r); slot 7 of a query-owning CTA is the query "cell"
     const int c_nt = threadIdx.x >> 6, c_par = (threadIdx.x >> 5) & 1, c_ln = threadIdx.x & 31;
-    const int c_ul = c_ln >> 2, c_r = c_nt * 8 + (c_ln & 3) * 2 + c_par;
-    const bool c_in = (int)threadIdx.x < NT * 64 && c_r < R;
+    const int c_ul = c_ln >> 2, c_col = (c_ln & 3) * 2 + c_par;      // column of the n tile
+    const int c_r = PT ? c_nt * Bt + c_col : c_nt * 8 + c_col;
+    const bool c_in = (int)threadIdx.x < NT * 64 && (PT ? (c_col < Bt && c_nt < p.G) : c_r < R);
     const bool pw = c_in && c_ul < U, qcell = c_in && has_q && c_ul == 7;
     const int c_g = c_in ? gr.task(c_r) : 0, c_b = c_in ? gr.brow(c_r) : 0, c_u = u0 + c_ul;
     const float* xw_c = p.xw + c_g * gr.tstride;
@@ -709,10 +771,26 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
     bool rowok[NT];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-        const int r = nt * 8 + lg;
-        rowok[nt] = r < R;
+        const int r = PT ? nt * Bt + lg : nt * 8 + lg;
+        rowok[nt] = PT ? (lg < Bt && nt < p.G) : r < R;
         const int rr = rowok[nt] ? r : 0;
         hrow[nt] = p.ha + gr.task(rr) * gr.tstride + (size_t)gr.brow(rr) * Ha;
+    }
+    // PT: the ring of streamed A fragments; chunk (k16 step s, task nt) in the order the product consumes them, period KS * NT
+    const uint4* fsrc = PT ? p.wfrag + ((size_t)cta * kMW + wsl) * KS * 128 + lane : nullptr;
+    int rs = 0, rnt = 0, rslot = 0;      // next chunk to issue and the ring slot it goes to
+    auto ring_issue = [&]() {
+        const uint4* src = fsrc + (size_t)rnt * p.wfrag_stride + (size_t)rs * 128;
+        uint4* dst = ring + rslot * 128 + lane;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) cp_async16(dst + qd * 32, src + qd * 32);
+        cp_async_commit();
+        if (++rnt == NT) { rnt = 0; if (++rs == KS) rs = 0; }
+        if (++rslot == kRingF) rslot = 0;
+    };
+    if (PT) {
+#pragma unroll
+        for (int i = 0; i < kRingF; ++i) ring_issue();
     }
     const bool vecL = (L & 3) == 0;
     ChainProf<true> prof;      // per-phase cycles of thread 0 when a buffer is passed (profiles/), one predictable branch otherwise
@@ -801,10 +879,10 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
                 const bool valid = sub < ppi && pi < np;
                 float cf = 0.f;
                 if (valid) {
-                    const int ro = posrl[3 * pi] - r_lo, l = posrl[3 * pi + 1];
+                    const int ro = posrl[4 * pi] - r_lo, l = posrl[4 * pi + 1];
                     const float* a0 = ah + (size_t)ro * LH + l;
                     const float* a1 = ah + (size_t)(lay.NRown + ro) * LH + l;
-                    const float* wl = wloc_s + f * CKP;
+                    const float* wl = wloc_s + posrl[4 * pi + 3] * WLS + f * CKP;
                     for (int k = ks; k < Kl; k += 8) cf += wl[k] * a0[k];
                     for (int k = ks; k < Kl; k += 8) cf += wl[Kl + k] * a1[k];
                 }
@@ -813,7 +891,7 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
                 cf += __shfl_xor_sync(0xffffffffu, cf, 4);
                 if (valid && ks == 0) {
                     cf_s[pi * F + f] = cf;
-                    p.convf[posoff[pi] + ((size_t)t * BtL + posrl[3 * pi + 2]) * F + f] = cf;
+                    p.convf[posoff[pi] + ((size_t)t * BtL + posrl[4 * pi + 2]) * F + f] = cf;
                 }
             }
         }
@@ -822,8 +900,9 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
             for (int it = threadIdx.x; it < np * (A >> 2); it += kMT) {
                 const int pi = it / (A >> 2), d = (it - pi * (A >> 2)) * 4;
                 float4 acc = *reinterpret_cast<const float4*>(pm_s + pi * A + d);
+                const float* wd = wldT + posrl[4 * pi + 3] * WDS;
                 for (int f = 0; f < F; ++f) {
-                    const float4 wv = *reinterpret_cast<const float4*>(wldT + f * A + d);
+                    const float4 wv = *reinterpret_cast<const float4*>(wd + f * A + d);
                     const float c = cf_s[pi * F + f];
                     acc.x += wv.x * c; acc.y += wv.y * c; acc.z += wv.z * c; acc.w += wv.w * c;
                 }
@@ -833,7 +912,8 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
             for (int it = threadIdx.x; it < np * A; it += kMT) {
                 const int pi = it / A, d = it - pi * A;
                 float l0 = pm_s[it];
-                for (int f = 0; f < F; ++f) l0 += wldT[f * A + d] * cf_s[pi * F + f];
+                const float* wd = wldT + posrl[4 * pi + 3] * WDS;
+                for (int f = 0; f < F; ++f) l0 += wd[f * A + d] * cf_s[pi * F + f];
                 pre_s[it] = l0;
             }
         }
@@ -874,12 +954,24 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
                     split2(cur[nt].x, cur[nt].y, bhi[nt][0], blo[nt][0]);
                     split2(cur[nt].z, cur[nt].w, bhi[nt][1], blo[nt][1]);
                 }
-                const uint4* af = Afrag + ((size_t)wsl * KS + s) * 2 * 2 * 32;
+                if (PT) {      // the fragments of (s, task nt) arrive through the ring, in this order
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    const uint4 ahi = af[(mt * 2 + 0) * 32 + lane], alo = af[(mt * 2 + 1) * 32 + lane];
+                    for (int nt = 0; nt < NT; ++nt) {
+                        cp_async_wait<kRingF - 1>();
+                        const uint4* af = ring + rslot * 128 + lane;
+                        const uint4 ahi0 = af[0], alo0 = af[32], ahi1 = af[64], alo1 = af[96];
+                        mma3(acc[nt][0], ahi0, alo0, bhi[nt], blo[nt]);
+                        mma3(acc[nt][1], ahi1, alo1, bhi[nt], blo[nt]);
+                        ring_issue();      // refills the slot just read with the chunk kRingF ahead
+                    }
+                } else {
+                    const uint4* af = Afrag + ((size_t)wsl * KS + s) * 2 * 2 * 32;
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) mma3(acc[nt][mt], ahi, alo, bhi[nt], blo[nt]);
+                    for (int mt = 0; mt < 2; ++mt) {
+                        const uint4 ahi = af[(mt * 2 + 0) * 32 + lane], alo = af[(mt * 2 + 1) * 32 + lane];
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) mma3(acc[nt][mt], ahi, alo, bhi[nt], blo[nt]);
+                    }
                 }
             };
 #pragma unroll
@@ -943,16 +1035,16 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
         // ---- P5: energies of the owned positions (forward_attn.py:128-131); publishes e(t) ----
         for (int it = threadIdx.x; it < np * A; it += kMT) {
             const int pi = it / A, d = it - pi * A;
-            const float sv = fast_tanh(q_s[(posrl[3 * pi] - r_lo) * A + d] + pre_s[it]);
-            p.s[posoff[pi] + ((size_t)t * BtL + posrl[3 * pi + 2]) * A + d] = sv;
-            pre_s[it] = vs[d] * sv;
+            const float sv = fast_tanh(q_s[(posrl[4 * pi] - r_lo) * A + d] + pre_s[it]);
+            p.s[posoff[pi] + ((size_t)t * BtL + posrl[4 * pi + 2]) * A + d] = sv;
+            pre_s[it] = vs[posrl[4 * pi + 3] * VSS + d] * sv;
         }
         __syncthreads();
         for (int pi = w; pi < np; pi += kMW) {
             float e = 0.f;
             for (int d = lane; d < A; d += 32) e += pre_s[pi * A + d];
             e = warp_sum(e);
-            if (lane == 0) st_pub(p.e + posoff[pi] + (size_t)t * BtL + posrl[3 * pi + 2], e + bv);
+            if (lane == 0) st_pub(p.e + posoff[pi] + (size_t)t * BtL + posrl[4 * pi + 2], e + vs[posrl[4 * pi + 3] * VSS + A]);
         }
         prof.mark(6, t);
         // ---- hand-off 3: all energies of step t; a(t) = normalise(e(t)); cum += a(t) (forward_attn.py:200-210) ----
@@ -996,8 +1088,8 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
         }
         __syncthreads();
         for (int i = threadIdx.x; i < np; i += kMT) {
-            const int r = posrl[3 * i], l = posrl[3 * i + 1];
-            const size_t o = posoff[i] + (size_t)posrl[3 * i + 2];
+            const int r = posrl[4 * i], l = posrl[4 * i + 1];
+            const size_t o = posoff[i] + (size_t)posrl[4 * i + 2];
             p.align[o + (size_t)t * BtL] = as_[r * LP + l];
             if (t + 1 < T) p.cum[o + (size_t)(t + 1) * BtL] = ah[(1 * lay.NRown + (r - r_lo)) * LH + pl + l];
         }
@@ -1007,6 +1099,7 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
         }
         prof.mark(7, t);
     }
+    if (PT) cp_async_wait<0>();      // the ring runs kRingF chunks ahead of the last step
 }
 
 static bool attn_fwd_mma_ok(const msa_config& cfg, int R, int L, int sm_count, size_t smem_limit) {
@@ -1034,7 +1127,7 @@ struct AttnBwdMmaLay {
     size_t bfrag, bq, part, das, als, wld, wloc, vs, dss, dcw, small, total;      // byte offsets
     int KS, KQ, NPmax, NRown, CKP, WIN, FP;
 };
-__host__ __device__ inline AttnBwdMmaLay attn_bwd_mma_layout(int R, int L, int Ha, int A, int F, int Kl, int ncta, int MTL) {
+__host__ __device__ inline AttnBwdMmaLay attn_bwd_mma_layout(int R, int L, int Ha, int A, int F, int Kl, int ncta, int MTL, int pt = 0) {
     AttnBwdMmaLay s;
     s.KS = (4 * Ha + 255) / 256;
     s.KQ = (A + 15) / 16;
@@ -1045,8 +1138,10 @@ __host__ __device__ inline AttnBwdMmaLay attn_bwd_mma_layout(int R, int L, int H
     s.WIN = s.NPmax + Kl - 1 < L ? s.NPmax + Kl - 1 : L;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return r; };
-    s.bfrag = take((size_t)kMW * s.KS * 2 * 32 * sizeof(uint2));
-    s.bq = take((size_t)s.KQ * 2 * 32 * sizeof(uint2));
+    // resident B fragments, or (per-task weights) the ring: kRing stages of one k16 step x MTL tasks per warp; W_q^T per task
+    s.bfrag = take(pt ? (size_t)kMW * kRing * MTL * 32 * sizeof(uint4) : (size_t)kMW * s.KS * 2 * 32 * sizeof(uint2));
+    s.bq = take((size_t)(pt ? MTL : 1) * s.KQ * 2 * 32 * sizeof(uint2));
+    const int NW = pt ? 2 : 1;
     // partial tiles [kMW][MTL][4][32]; earlier in the step the region holds tq [R*L] and the dconvf partials [4][NPmax][F]
     size_t pb = (size_t)kMW * MTL * 4 * 32 * sizeof(float);
     const size_t alt = ((size_t)((R * L + 3) & ~3) + (size_t)4 * s.NPmax * F) * sizeof(float);
@@ -1054,9 +1149,9 @@ __host__ __device__ inline AttnBwdMmaLay attn_bwd_mma_layout(int R, int L, int H
     s.part = take(pb);
     s.das = take((size_t)R * L * sizeof(float));
     s.als = take((size_t)R * L * sizeof(float));
-    s.wld = take((size_t)A * F * sizeof(float));
-    s.wloc = take((size_t)F * s.CKP * sizeof(float));
-    s.vs = take((size_t)A * sizeof(float));
+    s.wld = take((size_t)NW * A * F * sizeof(float));
+    s.wloc = take((size_t)NW * F * s.CKP * sizeof(float));
+    s.vs = take((size_t)(NW * A + 8) * sizeof(float));           // v per weight set, then v[d0] of every task
     s.dss = take((size_t)s.NPmax * A * sizeof(float));
     s.dcw = take((size_t)s.NRown * s.WIN * s.FP * sizeof(float));
     s.small = take((size_t)(3 * s.NPmax + 64) * sizeof(float));
@@ -1064,7 +1159,34 @@ __host__ __device__ inline AttnBwdMmaLay attn_bwd_mma_layout(int R, int L, int H
     return s;
 }
 
-template <int MTL>
+// W_hh^T fragment idx = (K slice ww * KS + k16 step s) * 32 + lane for the CTA that owns units [u0, u0 + U): n = unit lane >> 2,
+// k rows kb + 4j .. 4j + 3 (gate rows of W_hh)
+__device__ __forceinline__ void attn_bwd_frag(const float* __restrict__ whh, int Ha, int KS, int u0, int U, int idx, uint2& hi, uint2& lo) {
+    const int ln = idx & 31, s = (idx >> 5) % KS, ww = (idx >> 5) / KS;
+    const int g = ln >> 2, j = ln & 3;
+    const int kb = (ww * KS + s) * 16 + 4 * j;
+    float v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = (g < U && kb + c < 4 * Ha) ? __ldg(whh + (size_t)(kb + c) * Ha + u0 + g) : 0.f;
+    split2(v[0], v[1], hi.x, lo.x);
+    split2(v[2], v[3], hi.y, lo.y);
+}
+// the fragments of G tasks in the order the PT kernel streams them: [task][cta][ww][s][lane] {hi.x, hi.y, lo.x, lo.y}
+__global__ void __launch_bounds__(kMT) k_attn_frag_bwd(FragSrc src, int Ha, int64_t stride, uint4* out) {
+    const int task = blockIdx.y, cta = blockIdx.x, ncta = gridDim.x;
+    const int KS = (4 * Ha + 255) / 256;
+    const int u0 = part_lo(cta, Ha, ncta), U = part_lo(cta + 1, Ha, ncta) - u0;
+    uint4* o = out + (size_t)task * stride + (size_t)cta * kMW * KS * 32;
+    for (int idx = threadIdx.x; idx < kMW * KS * 32; idx += kMT) {
+        uint2 hi, lo;
+        attn_bwd_frag(src.whh[task], Ha, KS, u0, U, idx, hi, lo);
+        o[idx] = make_uint4(hi.x, hi.y, lo.x, lo.y);
+    }
+}
+
+// PT (per-task weights): m tile mt holds the Bt <= 8 rows of task mt (MTL = G <= 4; fragment rows 8..15 are zero), the B fragments of
+// every (k16 step, task) are streamed through the per-warp ring, W_q^T and the small attention weights are staged per task.
+template <int MTL, bool PT>
 __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ float zn_s[kBMax];
@@ -1076,9 +1198,11 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
     // K slice of this warp, rotated by the CTA index: the 148 CTAs stream the SAME h / dz rows, without the rotation they would all
     // ask the same L2 slices for the same lines at the same moment
     const int wsl = MSA_SLICE_ROT ? (w + blockIdx.x) % kMW : w;
-    const AttnBwdMmaLay lay = attn_bwd_mma_layout(R, L, Ha, A, F, Kl, ncta, MTL);
+    const AttnBwdMmaLay lay = attn_bwd_mma_layout(R, L, Ha, A, F, Kl, ncta, MTL, PT ? 1 : 0);
     const int KS = lay.KS, KQ = lay.KQ, CKP = lay.CKP, WIN = lay.WIN, FP = lay.FP;
+    constexpr int HR = PT ? 1 : 2;                                     // row halves of an m tile that can hold real rows
     uint2* Bfrag = reinterpret_cast<uint2*>(smem_raw + lay.bfrag);    // [kMW][KS][hi|lo][32]  W_hh^T slice
+    uint4* ring = reinterpret_cast<uint4*>(smem_raw + lay.bfrag) + (size_t)w * kRing * MTL * 32;      // PT: [kRing][MTL][32]
     uint2* Bq = reinterpret_cast<uint2*>(smem_raw + lay.bq);          // [KQ][hi|lo][32]       W_q^T slice
     float* part = reinterpret_cast<float*>(smem_raw + lay.part);
     float* tq_s = part;                                                // [R*L]      d e * (1 - s^2) for the owned attention dim
@@ -1107,45 +1231,55 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
     auto whi = [&](int ro) { const int a = own_lmax(ro) + pl; return a < L - 1 ? a : L - 1; };
 
     // ---- one-time staging ----
-    for (int idx = threadIdx.x; idx < kMW * KS * 32; idx += kMT) {
-        const int ln = idx & 31, s = (idx >> 5) % KS, ww = (idx >> 5) / KS;
-        const int g = ln >> 2, j = ln & 3;
-        const int kb = (ww * KS + s) * 16 + 4 * j;
-        float v[4];
+    if (!PT) {
+        for (int idx = threadIdx.x; idx < kMW * KS * 32; idx += kMT) {
+            uint2 hi, lo;
+            attn_bwd_frag(p.whh, Ha, KS, u0, U, idx, hi, lo);
+            const size_t o = (size_t)(idx >> 5) * 2 * 32;
+            Bfrag[o + (idx & 31)] = hi;
+            Bfrag[o + 32 + (idx & 31)] = lo;
+        }
+    }
+    for (int tk = 0; tk < (PT ? p.G : 1); ++tk) {      // W_q^T slice(s): [task][KQ][hi|lo][32]
+        const float* wq = PT ? p.wq_g[tk] : p.wq;
+        for (int idx = threadIdx.x; idx < KQ * 32; idx += kMT) {
+            const int ln = idx & 31, s = idx >> 5;
+            const int g = ln >> 2, j = ln & 3;
+            const int kb = s * 16 + 4 * j;
+            float v[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) v[c] = (g < U && kb + c < H4) ? __ldg(p.whh + (size_t)(kb + c) * Ha + u0 + g) : 0.f;
-        uint2 hi, lo;
-        split2(v[0], v[1], hi.x, lo.x);
-        split2(v[2], v[3], hi.y, lo.y);
-        const size_t o = ((size_t)ww * KS + s) * 2 * 32;
-        Bfrag[o + ln] = hi;
-        Bfrag[o + 32 + ln] = lo;
+            for (int c = 0; c < 4; ++c) v[c] = (g < U && kb + c < A) ? __ldg(wq + (size_t)(kb + c) * Ha + u0 + g) : 0.f;
+            uint2 hi, lo;
+            split2(v[0], v[1], hi.x, lo.x);
+            split2(v[2], v[3], hi.y, lo.y);
+            Bq[((size_t)tk * KQ + s) * 2 * 32 + ln] = hi;
+            Bq[((size_t)tk * KQ + s) * 2 * 32 + 32 + ln] = lo;
+        }
     }
-    for (int idx = threadIdx.x; idx < KQ * 32; idx += kMT) {
-        const int ln = idx & 31, s = idx >> 5;
-        const int g = ln >> 2, j = ln & 3;
-        const int kb = s * 16 + 4 * j;
-        float v[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) v[c] = (g < U && kb + c < A) ? __ldg(p.wq + (size_t)(kb + c) * Ha + u0 + g) : 0.f;
-        uint2 hi, lo;
-        split2(v[0], v[1], hi.x, lo.x);
-        split2(v[2], v[3], hi.y, lo.y);
-        Bq[(size_t)s * 2 * 32 + ln] = hi;
-        Bq[(size_t)s * 2 * 32 + 32 + ln] = lo;
+    // small attention weights: one set, or (PT) one per task of the owned positions (at most two: the launcher checks NPmax <= L)
+    const int g_lo = r_lo / Bt, nset = PT ? (np > 0 ? r_hi / Bt - g_lo + 1 : 0) : 1;
+    const int WLS = F * CKP, WDS = A * F;
+    float* vq_s = vs + (PT ? 2 : 1) * A;               // v[d0] of every task (the dq term of the query-owning CTA)
+    for (int ws = 0; ws < nset; ++ws) {
+        const float* wloc_g = PT ? p.wloc_g[g_lo + ws] : p.wloc;
+        const float* wld_g = PT ? p.wld_g[g_lo + ws] : p.wld;
+        const float* v_g = PT ? p.v_g[g_lo + ws] : p.v;
+        for (int idx = threadIdx.x; idx < A * F; idx += kMT) wld_s[ws * WDS + idx] = __ldg(wld_g + idx);
+        for (int idx = threadIdx.x; idx < F * 2 * Kl; idx += kMT) {
+            const int f = idx / (2 * Kl), ck = idx % (2 * Kl);
+            wloc_s[ws * WLS + f * CKP + ck] = __ldg(wloc_g + idx);
+        }
+        for (int idx = threadIdx.x; idx < A; idx += kMT) vs[ws * A + idx] = __ldg(v_g + idx);
     }
-    for (int idx = threadIdx.x; idx < A * F; idx += kMT) wld_s[idx] = __ldg(p.wld + idx);
-    for (int idx = threadIdx.x; idx < F * 2 * Kl; idx += kMT) {
-        const int f = idx / (2 * Kl), ck = idx % (2 * Kl);
-        wloc_s[f * CKP + ck] = __ldg(p.wloc + idx);
-    }
-    for (int idx = threadIdx.x; idx < A; idx += kMT) vs[idx] = __ldg(p.v + idx);
+    if (has_q && (int)threadIdx.x < p.G) vq_s[threadIdx.x] = __ldg((PT ? p.v_g[threadIdx.x] : p.v) + d0);
+    auto pos_set = [&](int pp) { return PT ? (pp / L) / Bt - g_lo : 0; };      // weight set of an owned position
     for (int idx = threadIdx.x; idx < np; idx += kMT) { gcum_s[idx] = 0.f; dprev_s[idx] = 0.f; pout_s[idx] = 0.f; }
 
     // point-wise role: thread c < MTL*128 owns cell (row r, unit ul)
     const int c_mt = threadIdx.x >> 7, c_reg = (threadIdx.x >> 5) & 3, c_ln = threadIdx.x & 31;
-    const int c_r = c_mt * 16 + (c_reg >> 1) * 8 + (c_ln >> 2), c_ul = (c_ln & 3) * 2 + (c_reg & 1);
-    const bool pw = (int)threadIdx.x < MTL * 128 && c_ul < U && c_r < R;
+    const int c_row = (c_reg >> 1) * 8 + (c_ln >> 2);                  // row of the m tile
+    const int c_r = PT ? c_mt * Bt + c_row : c_mt * 16 + c_row, c_ul = (c_ln & 3) * 2 + (c_reg & 1);
+    const bool pw = (int)threadIdx.x < MTL * 128 && c_ul < U && (PT ? (c_row < Bt && c_mt < p.G) : c_r < R);
     const int c_g = pw ? gr.task(c_r) : 0, c_b = pw ? gr.brow(c_r) : 0, c_u = u0 + c_ul;
     const float* ga_c = p.ga + c_g * gr.tstride;
     const float* ca_c = p.ca + c_g * gr.tstride;
@@ -1182,17 +1316,32 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
     fetch(T - 1);
 
     // streaming role of the recurrent tile: lane (lg, lj) loads dz[rows mt*16 + lg, +8][4 gate rows] per k16 step
-    const float* zrow[MTL][2];
-    bool rowok[MTL][2];
+    const float* zrow[MTL][HR];
+    bool rowok[MTL][HR];
 #pragma unroll
     for (int mt = 0; mt < MTL; ++mt)
 #pragma unroll
-        for (int hr = 0; hr < 2; ++hr) {
-            const int r = mt * 16 + hr * 8 + lg;
-            rowok[mt][hr] = r < R;
+        for (int hr = 0; hr < HR; ++hr) {
+            const int r = PT ? mt * Bt + lg : mt * 16 + hr * 8 + lg;
+            rowok[mt][hr] = PT ? (lg < Bt && mt < p.G) : r < R;
             const int rr = rowok[mt][hr] ? r : 0;
             zrow[mt][hr] = p.dza + gr.task(rr) * gr.tstride + (size_t)gr.brow(rr) * H4;
         }
+    // PT: the ring of streamed B fragments; stage = k16 step s of all MTL tasks, period KS
+    const uint4* fsrc = PT ? p.wfrag + ((size_t)cta * kMW + wsl) * KS * 32 + lane : nullptr;
+    int rs = 0, rslot = 0;
+    auto ring_issue = [&]() {
+        uint4* dst = ring + (size_t)rslot * MTL * 32 + lane;
+#pragma unroll
+        for (int mt = 0; mt < MTL; ++mt) cp_async16(dst + mt * 32, fsrc + (size_t)mt * p.wfrag_stride + (size_t)rs * 32);
+        cp_async_commit();
+        if (++rs == KS) rs = 0;
+        if (++rslot == kRing) rslot = 0;
+    };
+    if (PT) {
+#pragma unroll
+        for (int i = 0; i < kRing; ++i) ring_issue();
+    }
     ChainProf<true> prof;
     prof.start(p.prof, nullptr, 0);
     __syncthreads();
@@ -1248,35 +1397,49 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
         if (t < T - 1) {
             const size_t toff = (size_t)(t + 1) * Bt * H4;
             constexpr int PF = MSA_PF_BWD;
-            float4 zv[PF][MTL][2];
-            auto issue = [&](int s, float4 (&dst)[MTL][2]) {
+            float4 zv[PF][MTL][HR];
+            auto issue = [&](int s, float4 (&dst)[MTL][HR]) {
                 const int col = (wsl * KS + s) * 16 + 4 * lj;
 #pragma unroll
                 for (int mt = 0; mt < MTL; ++mt)
 #pragma unroll
-                    for (int hr = 0; hr < 2; ++hr)
+                    for (int hr = 0; hr < HR; ++hr)
                         dst[mt][hr] = (rowok[mt][hr] && col < H4) ? ld_poll4(zrow[mt][hr] + toff + col) : make_float4(0.f, 0.f, 0.f, 0.f);
             };
-            auto process = [&](int s, float4 (&cur)[MTL][2]) {
+            auto process = [&](int s, float4 (&cur)[MTL][HR]) {
                 const int col = (wsl * KS + s) * 16 + 4 * lj;
-                const uint2* bf = Bfrag + ((size_t)wsl * KS + s) * 2 * 32;
-                const uint2 bh = bf[lane], bl = bf[32 + lane];
-                const uint32_t bhi[2] = {bh.x, bh.y}, blo[2] = {bl.x, bl.y};
+                uint2 bh = make_uint2(0u, 0u), bl = make_uint2(0u, 0u);
+                const uint4* rf = nullptr;
+                if (PT) {
+                    cp_async_wait<kRing - 1>();
+                    rf = ring + (size_t)rslot * MTL * 32 + lane;
+                } else {
+                    const uint2* bf = Bfrag + ((size_t)wsl * KS + s) * 2 * 32;
+                    bh = bf[lane]; bl = bf[32 + lane];
+                }
 #pragma unroll
                 for (int mt = 0; mt < MTL; ++mt) {
 #pragma unroll
-                    for (int hr = 0; hr < 2; ++hr) {
+                    for (int hr = 0; hr < HR; ++hr) {
                         if (rowok[mt][hr] && col < H4) {
                             if (!ready4(cur[mt][hr])) cur[mt][hr] = poll4_slow(zrow[mt][hr] + toff + col, p.abort_word);
                         }
                     }
-                    uint4 ahi, alo;
+                    if (PT) {
+                        const uint4 b = rf[mt * 32];
+                        bh = make_uint2(b.x, b.y); bl = make_uint2(b.z, b.w);
+                    }
+                    const uint32_t bhi[2] = {bh.x, bh.y}, blo[2] = {bl.x, bl.y};
+                    uint4 ahi = make_uint4(0u, 0u, 0u, 0u), alo = make_uint4(0u, 0u, 0u, 0u);
                     split2(cur[mt][0].x, cur[mt][0].y, ahi.x, alo.x);
-                    split2(cur[mt][1].x, cur[mt][1].y, ahi.y, alo.y);
                     split2(cur[mt][0].z, cur[mt][0].w, ahi.z, alo.z);
-                    split2(cur[mt][1].z, cur[mt][1].w, ahi.w, alo.w);
+                    if (!PT) {
+                        split2(cur[mt][HR - 1].x, cur[mt][HR - 1].y, ahi.y, alo.y);
+                        split2(cur[mt][HR - 1].z, cur[mt][HR - 1].w, ahi.w, alo.w);
+                    }
                     mma3(acc[mt], ahi, alo, bhi, blo);
                 }
+                if (PT) ring_issue();      // refills the stage just read with the one kRing ahead
             };
 #pragma unroll
             for (int i = 0; i < PF; ++i)
@@ -1344,7 +1507,7 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
         {
             auto do_item = [&](int it, float sv) {
                 const int pi = it / A, d = it - pi * A, pp = p0 + pi, g = pos_task(pp);
-                const float dS = das[pp] * vs[d] * (1.f - sv * sv);
+                const float dS = das[pp] * vs[pos_set(pp) * A + d] * (1.f - sv * sv);
                 p.ds[g * gr.tstride + ((size_t)t * BtL + (pp - g * BtL)) * A + d] = dS;
                 ds_s[it] = dS;
             };
@@ -1363,7 +1526,7 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
                 float a = 0.f;
                 for (int l = lane; l < L; l += 32) a += tq_s[r * L + l];
                 a = warp_sum(a);
-                if (lane == 0) st_pub(p.dq + gr.task(r) * gr.tstride + ((size_t)t * Bt + gr.brow(r)) * A + d0, vs[d0] * a);
+                if (lane == 0) st_pub(p.dq + gr.task(r) * gr.tstride + ((size_t)t * Bt + gr.brow(r)) * A + d0, vq_s[PT ? gr.task(r) : 0] * a);
             }
         // d(conv features)[pi][f] = sum_d dS[pi][d] wld[d][f]: warp (block of 4 positions, quarter of the d range), lane = filter
         {
@@ -1374,14 +1537,29 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
                 const float* ds0 = ds_s + (size_t)(blk * 4) * A;
                 const bool v1 = blk * 4 + 1 < np, v2 = blk * 4 + 2 < np, v3 = blk * 4 + 3 < np;
-                if (lane < F)
+                // weight set of the block's first and last position (a block can straddle two tasks)
+                const int st0 = pos_set(p0 + blk * 4), st3 = pos_set(p0 + (blk * 4 + 3 < np ? blk * 4 + 3 : np - 1));
+                if (lane < F && st0 == st3) {
+                    const float* wd = wld_s + st0 * WDS;
                     for (int d = dlo; d < dhi; ++d) {
-                        const float wv = wld_s[d * F + lane];
+                        const float wv = wd[d * F + lane];
                         a0 += ds0[d] * wv;
                         if (v1) a1 += ds0[A + d] * wv;
                         if (v2) a2 += ds0[2 * A + d] * wv;
                         if (v3) a3 += ds0[3 * A + d] * wv;
                     }
+                } else if (lane < F) {
+                    const float* w0 = wld_s + st0 * WDS;
+                    const float* w1 = wld_s + (v1 ? pos_set(p0 + blk * 4 + 1) : 0) * WDS;
+                    const float* w2 = wld_s + (v2 ? pos_set(p0 + blk * 4 + 2) : 0) * WDS;
+                    const float* w3 = wld_s + (v3 ? pos_set(p0 + blk * 4 + 3) : 0) * WDS;
+                    for (int d = dlo; d < dhi; ++d) {
+                        a0 += ds0[d] * w0[d * F + lane];
+                        if (v1) a1 += ds0[A + d] * w1[d * F + lane];
+                        if (v2) a2 += ds0[2 * A + d] * w2[d * F + lane];
+                        if (v3) a3 += ds0[3 * A + d] * w3[d * F + lane];
+                    }
+                }
                 if (lane < F) {
                     float* o = dcp_s + ((size_t)dq4 * lay.NPmax + blk * 4) * F + lane;
                     o[0] = a0;
@@ -1403,23 +1581,28 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
         // ---- F: dq(t) arrives: dq(t) . W_q for the owned units into the same accumulators, then one reduction ----
         for (int s = w; s < KQ; s += kMW) {
             const int col = s * 16 + 4 * lj;
-            const uint2 bh = Bq[(size_t)s * 2 * 32 + lane], bl = Bq[(size_t)s * 2 * 32 + 32 + lane];
-            const uint32_t bhi[2] = {bh.x, bh.y}, blo[2] = {bl.x, bl.y};
             const size_t toff = (size_t)t * Bt * A;
 #pragma unroll
             for (int mt = 0; mt < MTL; ++mt) {
-                float4 cur[2];
+                const uint2* bqf = Bq + ((size_t)(PT ? mt : 0) * KQ + s) * 2 * 32;
+                const uint2 bh = bqf[lane], bl = bqf[32 + lane];
+                const uint32_t bhi[2] = {bh.x, bh.y}, blo[2] = {bl.x, bl.y};
+                float4 cur[HR];
 #pragma unroll
-                for (int hr = 0; hr < 2; ++hr) {
-                    const int r = mt * 16 + hr * 8 + lg, rr = r < R ? r : 0;
+                for (int hr = 0; hr < HR; ++hr) {
+                    const int r = PT ? mt * Bt + lg : mt * 16 + hr * 8 + lg;
+                    const bool ok = PT ? (lg < Bt && mt < p.G) : r < R;
+                    const int rr = ok ? r : 0;
                     const float* qrow = p.dq + gr.task(rr) * gr.tstride + (size_t)gr.brow(rr) * A;
-                    cur[hr] = (r < R && col < A) ? pollq4(qrow + toff + col, p.abort_word) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    cur[hr] = (ok && col < A) ? pollq4(qrow + toff + col, p.abort_word) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                uint4 ahi, alo;
+                uint4 ahi = make_uint4(0u, 0u, 0u, 0u), alo = make_uint4(0u, 0u, 0u, 0u);
                 split2(cur[0].x, cur[0].y, ahi.x, alo.x);
-                split2(cur[1].x, cur[1].y, ahi.y, alo.y);
                 split2(cur[0].z, cur[0].w, ahi.z, alo.z);
-                split2(cur[1].z, cur[1].w, ahi.w, alo.w);
+                if (!PT) {
+                    split2(cur[HR - 1].x, cur[HR - 1].y, ahi.y, alo.y);
+                    split2(cur[HR - 1].z, cur[HR - 1].w, ahi.w, alo.w);
+                }
                 mma3(acc[mt], ahi, alo, bhi, blo);
             }
         }
@@ -1459,14 +1642,15 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
         // one warp per owned position (input position of the conv), lanes over the taps: output position lo = l - k + pad
         for (int i = w; i < np; i += kMW) {
             const int pp = p0 + i, r = pp / L, l = pp - r * L, ro = r - r_lo, lo0 = wlo(ro);
+            const float* wl_ = wloc_s + pos_set(pp) * WLS;
             float a0 = 0.f, a1 = 0.f;
             for (int k = lane; k < Kl; k += 32) {
                 const int lo = l - k + pl;
                 if (lo >= 0 && lo < L) {
                     const float* dv = dcw + ((size_t)ro * WIN + (lo - lo0)) * FP;
                     for (int f = 0; f < F; ++f) {
-                        a0 += wloc_s[f * CKP + k] * dv[f];
-                        a1 += wloc_s[f * CKP + Kl + k] * dv[f];
+                        a0 += wl_[f * CKP + k] * dv[f];
+                        a1 += wl_[f * CKP + Kl + k] * dv[f];
                     }
                 }
             }
@@ -1479,6 +1663,7 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
         }
         __syncthreads();
     }
+    if (PT) cp_async_wait<0>();      // the ring runs kRing stages ahead of the last step
 }
 
 static bool attn_bwd_mma_ok(const msa_config& cfg, int R, int L, int sm_count, size_t smem_limit) {
@@ -1530,25 +1715,62 @@ bool attn_chain_mma_supported(const msa_config& cfg, int G, int B, int T, int L,
     (void)T;
     return attn_fwd_mma_ok(cfg, G * B, L, sm_count, smem_limit);
 }
+// per-task weights: what one launch can carry
+static bool attn_pt_ok(const msa_config& cfg, int G, int B, int L, int sm_count, size_t smem_limit) {
+    const int Ha = cfg.attn_rnn_dim, A = cfg.attn_dim, R = G * B;
+    if (G < 2 || G > kPtGroupMax || B < 1 || B > 8) return false;
+    if (!attn_fwd_mma_ok(cfg, R, L, sm_count, smem_limit) || !attn_bwd_mma_ok(cfg, R, L, sm_count, smem_limit)) return false;
+    if ((R * L + sm_count - 1) / sm_count > L) return false;      // the owned positions of a CTA touch at most two tasks
+    return attn_fwd_mma_layout(R, L, Ha, A, cfg.loc_filters, cfg.loc_kernel, sm_count, G, 1).total + 256 <= smem_limit &&
+           attn_bwd_mma_layout(R, L, Ha, A, cfg.loc_filters, cfg.loc_kernel, sm_count, G, 1).total + 256 <= smem_limit;
+}
+bool attn_chain_pt_supported(const msa_config& cfg, int G, int B, int T, int L, int sm_count, size_t smem_limit) {
+    (void)T;
+    return attn_pt_ok(cfg, G, B, L, sm_count, smem_limit);
+}
+size_t attn_chain_pt_frag_bytes(const msa_config& cfg, int sm_count) {
+    const int Ha = cfg.attn_rnn_dim;
+    const size_t fwd = (size_t)sm_count * kMW * ((Ha + 255) / 256) * 128 * sizeof(uint4);
+    const size_t bwd = (size_t)sm_count * kMW * ((4 * Ha + 255) / 256) * 32 * sizeof(uint4);
+    return fwd > bwd ? fwd : bwd;
+}
+
 int launch_attn_chain_fwd_mma(const AttnChainParams& p0, int sm_count, size_t smem_limit, cudaStream_t st) {
     AttnChainParams p = p0;
     if (p.G < 1) p.G = 1;
-    const int R = p.G * p.B, NT = (R + 7) / 8;
+    const int R = p.G * p.B, NT = p.pt ? p.G : (R + 7) / 8;
     MSA_CHECK(!p.fa && R <= 32 && p.A <= sm_count && (p.Ha + sm_count - 1) / sm_count <= 7, MSA_E_UNSUPPORTED,
               "attn_chain_fwd_mma: configuration outside the grouped kernel (rows %d, attention dim %d)", R, p.A);
-    const size_t smem = attn_fwd_mma_layout(R, p.L, p.Ha, p.A, p.F, p.Kl, sm_count, NT).total;
+    const AttnFwdMmaLay lay = attn_fwd_mma_layout(R, p.L, p.Ha, p.A, p.F, p.Kl, sm_count, NT, p.pt);
+    const size_t smem = lay.total;
     MSA_CHECK(smem <= smem_limit, MSA_E_UNSUPPORTED, "attn_chain_fwd_mma: needs %zu bytes of shared memory (> %zu)", smem, smem_limit);
+    if (p.pt) {
+        MSA_CHECK(p.G >= 2 && p.G <= kPtGroupMax && p.B <= 8 && lay.NPmax <= p.L && p.wfrag, MSA_E_UNSUPPORTED,
+                  "attn_chain_fwd_mma: per-task weights need 2..%d tasks of <= 8 rows (G=%d, B=%d)", kPtGroupMax, p.G, p.B);
+        FragSrc src{};
+        for (int g = 0; g < p.G; ++g) { src.whh[g] = p.whh_g[g]; src.wq[g] = p.wq_g[g]; }
+        k_attn_frag_fwd<<<dim3(sm_count, p.G), kMT, 0, st>>>(src, p.Ha, p.A, p.wfrag_stride, const_cast<uint4*>(p.wfrag));
+        MSA_CUDA(cudaGetLastError());
+        count_launch();
+    }
     const size_t TB = (size_t)p.T * p.B;
     for (int g = 0; g < p.G; ++g) {       // canaries of the three hand-off arrays of every task (common.cuh)
         MSA_TRY(k_fill_canary(p.ha + g * p.tstride, (int64_t)(TB * p.Ha), st));
         MSA_TRY(k_fill_canary(p.q + g * p.tstride, (int64_t)(TB * p.A), st));
         MSA_TRY(k_fill_canary(p.e + g * p.tstride, (int64_t)(TB * p.L), st));
     }
+    if (p.pt) {
+        switch (NT) {
+            case 2: return coop_launch(k_attn_fwd_mma<2, true>, p, sm_count, smem, st);
+            case 3: return coop_launch(k_attn_fwd_mma<3, true>, p, sm_count, smem, st);
+            default: return coop_launch(k_attn_fwd_mma<4, true>, p, sm_count, smem, st);
+        }
+    }
     switch (NT) {
-        case 1: return coop_launch(k_attn_fwd_mma<1>, p, sm_count, smem, st);
-        case 2: return coop_launch(k_attn_fwd_mma<2>, p, sm_count, smem, st);
-        case 3: return coop_launch(k_attn_fwd_mma<3>, p, sm_count, smem, st);
-        default: return coop_launch(k_attn_fwd_mma<4>, p, sm_count, smem, st);
+        case 1: return coop_launch(k_attn_fwd_mma<1, false>, p, sm_count, smem, st);
+        case 2: return coop_launch(k_attn_fwd_mma<2, false>, p, sm_count, smem, st);
+        case 3: return coop_launch(k_attn_fwd_mma<3, false>, p, sm_count, smem, st);
+        default: return coop_launch(k_attn_fwd_mma<4, false>, p, sm_count, smem, st);
     }
 }
 bool attn_chain_bwd_mma_supported(const msa_config& cfg, int G, int B, int T, int L, int sm_count, size_t smem_limit) {
@@ -1558,11 +1780,21 @@ bool attn_chain_bwd_mma_supported(const msa_config& cfg, int G, int B, int T, in
 int launch_attn_chain_bwd_mma(const AttnChainBwdParams& p0, int sm_count, size_t smem_limit, cudaStream_t st) {
     AttnChainBwdParams p = p0;
     if (p.G < 1) p.G = 1;
-    const int R = p.G * p.B, MTL = (R + 15) / 16;
+    const int R = p.G * p.B, MTL = p.pt ? p.G : (R + 15) / 16;
     MSA_CHECK(!p.fa && R <= 32 && p.A <= sm_count && p.A % 4 == 0 && (p.Ha + sm_count - 1) / sm_count <= 8, MSA_E_UNSUPPORTED,
               "attn_chain_bwd_mma: configuration outside the grouped kernel (rows %d, attention dim %d)", R, p.A);
-    const size_t smem = attn_bwd_mma_layout(R, p.L, p.Ha, p.A, p.F, p.Kl, sm_count, MTL).total;
+    const AttnBwdMmaLay lay = attn_bwd_mma_layout(R, p.L, p.Ha, p.A, p.F, p.Kl, sm_count, MTL, p.pt);
+    const size_t smem = lay.total;
     MSA_CHECK(smem <= smem_limit, MSA_E_UNSUPPORTED, "attn_chain_bwd_mma: needs %zu bytes of shared memory (> %zu)", smem, smem_limit);
+    if (p.pt) {
+        MSA_CHECK(p.G >= 2 && p.G <= kPtGroupMax && p.B <= 8 && lay.NPmax <= p.L && p.wfrag, MSA_E_UNSUPPORTED,
+                  "attn_chain_bwd_mma: per-task weights need 2..%d tasks of <= 8 rows (G=%d, B=%d)", kPtGroupMax, p.G, p.B);
+        FragSrc src{};
+        for (int g = 0; g < p.G; ++g) src.whh[g] = p.whh_g[g];
+        k_attn_frag_bwd<<<dim3(sm_count, p.G), kMT, 0, st>>>(src, p.Ha, p.wfrag_stride, const_cast<uint4*>(p.wfrag));
+        MSA_CUDA(cudaGetLastError());
+        count_launch();
+    }
     const size_t TB = (size_t)p.T * p.B;
     for (int g = 0; g < p.G; ++g) {       // canaries of the four hand-off arrays of every task (common.cuh)
         MSA_TRY(k_fill_canary(p.dza + g * p.tstride, (int64_t)(TB * 4 * p.Ha), st));
@@ -1570,8 +1802,15 @@ int launch_attn_chain_bwd_mma(const AttnChainBwdParams& p0, int sm_count, size_t
         MSA_TRY(k_fill_canary(p.dat + g * p.tstride, (int64_t)(TB * p.L), st));
         MSA_TRY(k_fill_canary(p.dconvf + g * p.tstride, (int64_t)(TB * p.L * p.F), st));
     }
-    if (MTL == 1) return coop_launch(k_attn_bwd_mma<1>, p, sm_count, smem, st);
-    return coop_launch(k_attn_bwd_mma<2>, p, sm_count, smem, st);
+    if (p.pt) {
+        switch (MTL) {
+            case 2: return coop_launch(k_attn_bwd_mma<2, true>, p, sm_count, smem, st);
+            case 3: return coop_launch(k_attn_bwd_mma<3, true>, p, sm_count, smem, st);
+            default: return coop_launch(k_attn_bwd_mma<4, true>, p, sm_count, smem, st);
+        }
+    }
+    if (MTL == 1) return coop_launch(k_attn_bwd_mma<1, false>, p, sm_count, smem, st);
+    return coop_launch(k_attn_bwd_mma<2, false>, p, sm_count, smem, st);
 }
 
 }  // namespace msa

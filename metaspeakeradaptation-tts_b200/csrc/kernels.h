@@ -11,6 +11,7 @@ namespace msa {
 // array of task g lives at (pointer of task 0) + g * tstride floats (the tasks' workspaces are identical slices of one allocation);
 // masks and lengths are caller-owned and come as per-task pointers.  Row r of a grouped launch = (task r / B, batch row r % B).
 constexpr int kGroupMax = 8;
+constexpr int kPtGroupMax = 4;      // tasks per launch of the per-task-weight variants (their weight stream must stay L2-resident)
 
 // ---------------- persistent LSTM recurrence (lstm_rec.cu) ----------------
 struct LstmRecParams {
@@ -105,6 +106,18 @@ struct AttnChainParams {
     int64_t tstride;           // floats between the copies of every float array of consecutive tasks
     const uint8_t* mask_g[kGroupMax];
     const int64_t* lengths_g[kGroupMax];
+    // per-task weights (the test-split passes of a meta-batch: every task has its own adapted weights, maml.py:56-76): pt = 1,
+    // G <= kPtGroupMax tasks; the recurrent weight slices are streamed every step from ready-made fragment arrays (L2-resident,
+    // written by launch_attn_frag_fwd) instead of being resident in shared memory; the small attention weights per task
+    int pt;
+    const uint4* wfrag;        // [G][ncta][16 warps][KS][m tile][hi|lo][32] A fragments of (W_hh rows, W_q row)
+    int64_t wfrag_stride;      // uint4 words between consecutive tasks
+    const float* whh_g[kPtGroupMax];
+    const float* wq_g[kPtGroupMax];
+    const float* wloc_g[kPtGroupMax];
+    const float* wld_g[kPtGroupMax];
+    const float* v_g[kPtGroupMax];
+    const float* bv_g[kPtGroupMax];
 };
 struct AttnChainBwdParams {
     int T, B, L, Ha, A, F, Kl, norm;
@@ -143,6 +156,15 @@ struct AttnChainBwdParams {
     int64_t tstride;           // floats between the copies of every float array of consecutive tasks
     const uint8_t* mask_g[kGroupMax];
     const int64_t* lengths_g[kGroupMax];
+    // per-task weights (see AttnChainParams): B fragments of W_hh^T streamed from wfrag, W_q^T and the small weights per task
+    int pt;
+    const uint4* wfrag;        // [G][ncta][16 warps][KS][32] {hi.x, hi.y, lo.x, lo.y}
+    int64_t wfrag_stride;
+    const float* whh_g[kPtGroupMax];
+    const float* wq_g[kPtGroupMax];
+    const float* wloc_g[kPtGroupMax];
+    const float* wld_g[kPtGroupMax];
+    const float* v_g[kPtGroupMax];
 };
 bool attn_chain_single_ok(int B, int L, int Ha, int A, int F, int Kl, int sm_count, size_t smem_limit, bool fa);
 size_t attn_chain_fwd_smem(int B, int L, int Ha, int A, int F, int Kl, int sm_count, bool mw_resident, bool fa = false);
@@ -160,6 +182,11 @@ int launch_lstm_rec_fwd_mma(const LstmRecParams& p, int sm_count, size_t smem_li
 int launch_lstm_rec_bwd_mma(const LstmRecBwdParams& p, int sm_count, size_t smem_limit, cudaStream_t st);
 int launch_attn_chain_fwd_mma(const AttnChainParams& p, int sm_count, size_t smem_limit, cudaStream_t st);
 int launch_attn_chain_bwd_mma(const AttnChainBwdParams& p, int sm_count, size_t smem_limit, cudaStream_t st);
+// Per-task weights (params.pt = 1): G <= kPtGroupMax tasks of B <= 8 rows per launch, every task with its own weights (whh_g, wq_g,
+// ...); the launchers first write the tasks' recurrent weight slices as ready-made fragments into params.wfrag (at least
+// G * attn_chain_pt_frag_bytes; the kernels stream them from L2 every step) and then launch the chain.
+bool attn_chain_pt_supported(const msa_config& cfg, int G, int B, int T, int L, int sm_count, size_t smem_limit);
+size_t attn_chain_pt_frag_bytes(const msa_config& cfg, int sm_count);      // per task; forward and backward fragments have this size
 
 // ---------------- element-wise / layout / reduction kernels (model_kernels.cu) ----------------
 int k_embedding_fwd(const float* w, const int64_t* tok, float* x, int rows, int C, int n_symbols, cudaStream_t st);

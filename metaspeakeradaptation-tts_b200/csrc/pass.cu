@@ -105,6 +105,17 @@ struct msa_handle {
     cudaStream_t aux[kGroupMax] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[kGroupMax] = {};
     bool group_streams = true;
+    // Per-task-weight groups (the test-split passes and later inner steps of a meta-batch: every task has its own adapted weights):
+    // up to pt_group tasks per attention-chain launch, their recurrent weight slices streamed from L2 as ready-made fragments
+    // (chain_mma.cu, PT variants).  pt_frag: the fragment buffer (pt_group x attn_chain_pt_frag_bytes, allocated on first use).
+    // Env MSA_PT_GROUP (0 / 1: one launch per task).  Measured on B200 (default dims, B = 4, T = 200; ms per task): forward 2.13 single,
+    // 1.69 / 1.48 / 1.70 in groups of 2 / 3 / 4 (four tasks' fragments, 78 MB, no longer stay in L2 next to MW); backward 2.52 single,
+    // 2.95 / 2.67 / 2.76 grouped (its dz gather and the fragment stream are both bound by the loads a warp keeps in flight) -- so
+    // the forward chains are grouped by three and the backward chains stay single-task launches unless MSA_PT_BWD=1.
+    int pt_group = 3;
+    bool pt_bwd = false;
+    void* pt_frag = nullptr;
+    size_t pt_frag_task_bytes = 0;
     int64_t off(const std::string& n) const { return off_by_name.at(n); }
 };
 
@@ -458,6 +469,8 @@ int msa_create(const msa_config* cfg, int device, msa_handle** out) {
     if (const char* e = getenv("MSA_REC_FLAGS")) h->rec_flags = atoi(e);
     if (const char* e = getenv("MSA_CHAIN_MMA")) h->mma_mode = atoi(e);
     if (const char* e = getenv("MSA_GROUP_STREAMS")) h->group_streams = atoi(e) != 0;
+    if (const char* e = getenv("MSA_PT_GROUP")) h->pt_group = std::min(atoi(e), (int)kPtGroupMax);
+    if (const char* e = getenv("MSA_PT_BWD")) h->pt_bwd = atoi(e) != 0;
     if (const char* e = getenv("MSA_GEMM_TC")) {
         h->tc_mode = atoi(e);
         h->tc_enabled = h->tc_mode != 0;
@@ -487,6 +500,7 @@ int msa_destroy(msa_handle* h) {
     if (!h) return 0;
     if (h->blas) cublasDestroy(h->blas);
     if (h->abort_dev) cudaFree(h->abort_dev);
+    if (h->pt_frag) cudaFree(h->pt_frag);
     for (int g = 0; g < kGroupMax; ++g) {
         if (h->aux[g]) cudaStreamDestroy(h->aux[g]);
         if (h->ev_join[g]) cudaEventDestroy(h->ev_join[g]);
@@ -606,6 +620,34 @@ static bool use_mma_chains(const msa_handle* h, int G, int B, int T, int L, bool
     if (h->mma_mode == 3 && attn) return false;                                     // development: LSTM recurrences only
     if (h->mma_mode == 5 && G == 1) return false;                                   // development: grouped launches only
     return true;
+}
+
+// Per-task-weight groups: the G tasks are cut into chunks of at most pt_group tasks, as even as possible (8 -> 4 + 4, 5 -> 3 + 2); a
+// chunk of two or more tasks is one launch of the per-task-weight attention chain, a chunk of one task a single-task launch.
+static std::vector<std::pair<int, int>> pt_chunks(const msa_handle* h, int G, int B, int T, int L, bool bwd) {
+    std::vector<std::pair<int, int>> out;      // (first task, tasks)
+    const int cap = h->pt_group;
+    bool ok = G >= 2 && cap >= 2 && (!bwd || h->pt_bwd) && use_mma_chains(h, 2, B, T, L, true, bwd);
+    const int n = ok ? (G + cap - 1) / cap : G;
+    int g0 = 0;
+    for (int i = 0; i < n; ++i) {
+        const int sz = G / n + (i < G % n ? 1 : 0);
+        out.push_back({g0, sz});
+        g0 += sz;
+    }
+    for (auto& ch : out)
+        if (ch.second >= 2 && !attn_chain_pt_supported(h->cfg, ch.second, B, T, L, h->sm_count, h->smem_limit)) ok = false;
+    if (!ok) {
+        out.clear();
+        for (int g = 0; g < G; ++g) out.push_back({g, 1});
+    }
+    return out;
+}
+static int pt_frag_ensure(msa_handle* h) {
+    if (h->pt_frag) return 0;
+    h->pt_frag_task_bytes = attn_chain_pt_frag_bytes(h->cfg, h->sm_count);
+    MSA_CUDA(cudaMalloc(&h->pt_frag, h->pt_frag_task_bytes * (size_t)kPtGroupMax));
+    return 0;
 }
 
 // Fork / join of the per-task stages of a grouped pass over the handle's side streams (created on first use).
@@ -805,17 +847,35 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
             ap.G = G; ap.tstride = tstride;
             for (int g = 0; g < G; ++g) ap.mask_g[g] = c.p_attn_dropout > 0.f ? ios[g].masks + secs[iAttn].off : nullptr;
             MSA_TRY(launch_attn_chain_fwd_mma(ap, h->sm_count, h->smem_limit, st));
-        } else if (mma_attn) {       // per-task weights: one launch per task (G = 1, that task's pointers)
-            for (int g = 0; g < G; ++g) {
-                ProfScope ps(h, PROF_ATTN_FWD, st);
-                AttnChainParams ap = make(g);
-                ap.G = 1; ap.tstride = 0;
-                MSA_TRY(launch_attn_chain_fwd_mma(ap, h->sm_count, h->smem_limit, st));
-            }
-        } else {
-            for (int g = 0; g < G; ++g) {
-                ProfScope ps(h, PROF_ATTN_FWD, st);
-                MSA_TRY(launch_attn_chain_fwd(make(g), h->sm_count, h->smem_limit, st));
+        } else {       // per-task weights: chunks of tasks on the streamed-weight kernel, single tasks on the single-task kernels
+            for (const auto& ch : pt_chunks(h, G, B, T, L, false)) {
+                const int g0 = ch.first, Gc = ch.second;
+                if (Gc >= 2) {
+                    ProfScope ps(h, PROF_ATTN_FWD + PROF_BASE, st);
+                    MSA_TRY(pt_frag_ensure(h));
+                    AttnChainParams ap = make(g0);
+                    ap.G = Gc; ap.tstride = tstride; ap.pt = 1;
+                    ap.wfrag = static_cast<const uint4*>(h->pt_frag); ap.wfrag_stride = (int64_t)(h->pt_frag_task_bytes / sizeof(uint4));
+                    for (int i = 0; i < Gc; ++i) {
+                        const int g = g0 + i;
+                        ap.mask_g[i] = c.p_attn_dropout > 0.f ? ios[g].masks + secs[iAttn].off : nullptr;
+                        ap.whh_g[i] = PG(g, "decoder.attention_rnn.weight_hh");
+                        ap.wq_g[i] = PG(g, at + "query_layer.linear_layer.weight");
+                        ap.wloc_g[i] = PG(g, at + "location_layer.location_conv1d.weight");
+                        ap.wld_g[i] = PG(g, at + "location_layer.location_dense.linear_layer.weight");
+                        ap.v_g[i] = PG(g, at + "v.linear_layer.weight");
+                        ap.bv_g[i] = PG(g, at + "v.linear_layer.bias");
+                    }
+                    MSA_TRY(launch_attn_chain_fwd_mma(ap, h->sm_count, h->smem_limit, st));
+                } else if (mma_attn) {
+                    ProfScope ps(h, PROF_ATTN_FWD, st);
+                    AttnChainParams ap = make(g0);
+                    ap.G = 1; ap.tstride = 0;
+                    MSA_TRY(launch_attn_chain_fwd_mma(ap, h->sm_count, h->smem_limit, st));
+                } else {
+                    ProfScope ps(h, PROF_ATTN_FWD, st);
+                    MSA_TRY(launch_attn_chain_fwd(make(g0), h->sm_count, h->smem_limit, st));
+                }
             }
         }
     }
@@ -1233,17 +1293,34 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* const* par
             bp.G = NG; bp.tstride = tstride;
             for (int g = 0; g < NG; ++g) bp.mask_g[g] = c.p_attn_dropout > 0.f ? h->masks[g] + secs[iAttn].off : nullptr;
             MSA_TRY(launch_attn_chain_bwd_mma(bp, h->sm_count, h->smem_limit, st));
-        } else if (mma_attn) {       // per-task weights: one launch per task (G = 1, that task's pointers)
-            for (int g = 0; g < NG; ++g) {
-                ProfScope ps(h, PROF_ATTN_BWD, st);
-                AttnChainBwdParams bp = make(g);
-                bp.G = 1; bp.tstride = 0;
-                MSA_TRY(launch_attn_chain_bwd_mma(bp, h->sm_count, h->smem_limit, st));
-            }
-        } else {
-            for (int g = 0; g < NG; ++g) {
-                ProfScope ps(h, PROF_ATTN_BWD, st);
-                MSA_TRY(launch_attn_chain_bwd(make(g), h->sm_count, h->smem_limit, st));
+        } else {       // per-task weights: chunks of tasks on the streamed-weight kernel, single tasks on the single-task kernels
+            for (const auto& ch : pt_chunks(h, NG, B, T, L, true)) {
+                const int g0 = ch.first, Gc = ch.second;
+                if (Gc >= 2) {
+                    ProfScope ps(h, PROF_ATTN_BWD + PROF_BASE, st);
+                    MSA_TRY(pt_frag_ensure(h));
+                    AttnChainBwdParams bp = make(g0);
+                    bp.G = Gc; bp.tstride = tstride; bp.pt = 1;
+                    bp.wfrag = static_cast<const uint4*>(h->pt_frag); bp.wfrag_stride = (int64_t)(h->pt_frag_task_bytes / sizeof(uint4));
+                    for (int i = 0; i < Gc; ++i) {
+                        const int g = g0 + i;
+                        bp.mask_g[i] = c.p_attn_dropout > 0.f ? h->masks[g] + secs[iAttn].off : nullptr;
+                        bp.whh_g[i] = PG(g, "decoder.attention_rnn.weight_hh");
+                        bp.wq_g[i] = PG(g, at + "query_layer.linear_layer.weight");
+                        bp.wloc_g[i] = PG(g, at + "location_layer.location_conv1d.weight");
+                        bp.wld_g[i] = PG(g, at + "location_layer.location_dense.linear_layer.weight");
+                        bp.v_g[i] = PG(g, at + "v.linear_layer.weight");
+                    }
+                    MSA_TRY(launch_attn_chain_bwd_mma(bp, h->sm_count, h->smem_limit, st));
+                } else if (mma_attn) {
+                    ProfScope ps(h, PROF_ATTN_BWD, st);
+                    AttnChainBwdParams bp = make(g0);
+                    bp.G = 1; bp.tstride = 0;
+                    MSA_TRY(launch_attn_chain_bwd_mma(bp, h->sm_count, h->smem_limit, st));
+                } else {
+                    ProfScope ps(h, PROF_ATTN_BWD, st);
+                    MSA_TRY(launch_attn_chain_bwd(make(g0), h->sm_count, h->smem_limit, st));
+                }
             }
         }
     }

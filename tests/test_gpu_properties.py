@@ -173,3 +173,55 @@ def test_grouped_pass_equals_the_passes_one_by_one(shape, monkeypatch):
         tol = 1e-3 if tf32 else (5e-5 if mode == 4 else 1e-6)
         assert e_loss < tol and e_bn < tol and e_g < tol, (g, e_loss, e_bn, e_g)
     ref.check_abort()
+
+
+@pytest.mark.parametrize("shape", [("small", 4, 3, 9, 8, 0, 4, 4), ("small", 8, 4, 9, 8, 0, 4, 4), ("small", 5, 3, 11, 9, 0, 4, 4),
+                                   ("small", 3, 8, 9, 8, 0, 4, 3), ("small", 2, 1, 9, 8, 0, 4, 4),
+                                   ("default", 4, 4, 10, 16, 0, 4, 4), ("default", 7, 4, 10, 16, 0, 4, 4), ("default", 6, 2, 12, 20, 0, 4, 3),
+                                   ("default", 8, 4, 10, 16, 1, 1, 4), ("default", 8, 4, 10, 16, 1, 1, 2)])
+def test_per_task_weight_groups_equal_the_passes_one_by_one(shape, monkeypatch):
+    """Groups whose tasks have their OWN weights (the test-split passes / later inner steps of a meta-batch, maml.py:56-76): the
+    attention chains of up to MSA_PT_GROUP tasks share a launch, every task's recurrent weights streamed as fragments
+    (chain_mma.cu, PT variants).  Per-task losses, BatchNorm statistics and gradients equal those of G separate passes with the
+    single-task fp32-FMA kernels: 5e-5 of the gradient norm with fp32 GEMMs (grouped kernels forced, MSA_CHAIN_MMA=4), 1e-3 under
+    the bench policy (TF32 backward GEMMs)."""
+    which, G, B, T, L, tf32, mode, ptg = shape
+    monkeypatch.setenv("MSA_CHAIN_MMA", str(mode))
+    monkeypatch.setenv("MSA_PT_GROUP", str(ptg))
+    monkeypatch.setenv("MSA_PT_BWD", "1")         # the backward chains too (off by default: not faster than single-task launches)
+    cfg = pkg.small_params() if which == "small" else pkg.default_params()
+    eng, flat, bds, masks = _group_case(cfg, G, B, T, L, tf32)
+    gen = torch.Generator(device="cpu").manual_seed(77)
+    plist = []
+    for g in range(G):          # every task its own weights: theta + a task-specific perturbation of every parameter
+        noise = torch.randn(flat.numel(), generator=gen).to(flat.device)
+        plist.append((flat * (1.0 + 0.05 * noise) + 0.002 * noise).contiguous())
+    bn_g = [eng.new_bn_stats() for _ in range(G)]
+    grads_g = [eng.new_flat() for _ in range(G)]
+    eng.profile(True)
+    loss_g = eng.forward_group(plist, bn_g, bds, masks)
+    eng.backward_group(plist, grads_g)
+    torch.cuda.synchronize()
+    eng.check_abort()
+    prof = eng.profile_read()
+    eng.profile(False)
+    n_chunks = -(-G // ptg)
+    sizes = [G // n_chunks + (1 if i < G % n_chunks else 0) for i in range(n_chunks)]
+    want = sum(1 for s_ in sizes if s_ >= 2)          # chunks of two or more tasks are ONE launch each of the per-task-weight kernels
+    assert prof["attn_chain_fwd_grp"][1] == want and prof["attn_chain_bwd_grp"][1] == want, (prof, sizes)
+    monkeypatch.setenv("MSA_CHAIN_MMA", "0")
+    from msa_tts_b200.engine import Engine
+    ref = Engine(cfg, gemm_tf32=tf32)             # single-task fp32-FMA recurrences
+    for g in range(G):
+        bn, gr = ref.new_bn_stats(), ref.new_flat()
+        _, loss = ref.forward(plist[g], bn, bds[g], masks[g], outputs=False)
+        ref.backward(plist[g], gr)
+        torch.cuda.synchronize()
+        gn = float(gr.double().norm())
+        e_loss = abs(float(loss_g[g]) - float(loss)) / abs(float(loss))
+        e_bn = float((bn_g[g] - bn).double().norm() / bn.double().norm())
+        e_g = float((grads_g[g] - gr).double().norm()) / gn
+        print(f"task {g}: loss {e_loss:.2e} bn {e_bn:.2e} grad {e_g:.2e}")
+        tol = 1e-3 if tf32 else 5e-5
+        assert e_loss < tol and e_bn < tol and e_g < tol, (g, e_loss, e_bn, e_g)
+    ref.check_abort()
