@@ -285,6 +285,27 @@ int msa_gemm_nt(int64_t M, int64_t N, int64_t K, float alpha, const float* A, in
 int msa_gemm(int trans_a, int trans_b, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda,
              const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int mode, float* scratch, void* stream);
 
+/* ---- convolution building block (exported for tests / profiles) ---------------------------------------------------
+ * The k-tap "same" convolutions of Encoder / Postnet (ConvNorm -> torch.nn.Conv1d, modules_tacotron2nv/encoder.py:36-37,
+ * decoder.py:63-72, layers.py ConvNorm) and the two contractions of their autograd backward, as IMPLICIT GEMMs on the tcgen05
+ * kernel: activations are channels-last [B][T][C]; the tap shift is a coordinate offset of a 3-D TMA tensor map whose
+ * out-of-bounds zero fill is the convolution's padding, so no im2col matrix exists.  wp = tap-major copy [K][Cout][Cin] of the
+ * native weight [Cout][Cin][K] (msa_conv1d_repack).  mode 0 = 3xTF32 (fp32-accurate), 1 = single TF32.
+ *   msa_conv1d_fwd: y[B*T][Cout] = conv(x, w) + bias; stats (optional, msa_conv1d_stat_slabs x [3][Cout] floats): per 32-row slab
+ *     of y the (count, mean, M2) of every channel -- BatchNorm's batch statistics without another pass over y;
+ *   msa_conv1d_dx:  dx[B*T][Cin] = the transposed convolution of dy;
+ *   msa_conv1d_dw:  dw[Cout][Cin][K] = (accumulate ? dw : 0) + scale * sum_{b,t} dy[b,t,co] x[b,t+k-pad,ci] (native layout).
+ * Channels multiples of 4, K odd; scratch (msa_conv1d_scratch_floats floats, or NULL) holds K-split partial tiles. */
+size_t msa_conv1d_scratch_floats(int B, int T, int Cin, int Cout, int K);
+int msa_conv1d_stat_slabs(int B, int T, int Cin, int Cout, int K, int have_scratch);
+int msa_conv1d_repack(const float* w, float* wp, int Cout, int Cin, int K, void* stream);
+int msa_conv1d_fwd(const float* x, int B, int T, int Cin, const float* wp, int Cout, int K, const float* bias, float* y, int mode,
+                   float* scratch, float* stats, void* stream);
+int msa_conv1d_dx(const float* dy, int B, int T, int Cout, const float* wp, int Cin, int K, float* dx, int mode, float* scratch,
+                  void* stream);
+int msa_conv1d_dw(const float* dy, const float* x, int B, int T, int Cout, int Cin, int K, float scale, int accumulate, float* dw,
+                  int mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,12 @@ SIGNATURES = {
     "msa_gemm_nt_scratch_floats": (SZ, [I64, I64, I64]),
     "msa_gemm_nt": (I, [I64, I64, I64, F, V, I64, V, I64, F, V, I64, I, V, V]),
     "msa_gemm": (I, [I, I, I64, I64, I64, F, V, I64, V, I64, F, V, I64, I, V, V]),
+    "msa_conv1d_scratch_floats": (SZ, [I, I, I, I, I]),
+    "msa_conv1d_stat_slabs": (I, [I, I, I, I, I, I]),
+    "msa_conv1d_repack": (I, [V, V, I, I, I, V]),
+    "msa_conv1d_fwd": (I, [V, I, I, I, V, I, I, V, V, I, V, V, V]),
+    "msa_conv1d_dx": (I, [V, I, I, I, V, I, I, V, I, V, V]),
+    "msa_conv1d_dw": (I, [V, V, I, I, I, I, I, F, I, V, I, V]),
     "msa_flat_sgd_step": (I, [V, V, V, V, I64, F, F, F, F, I, I, V]),
     "msa_flat_axpy": (I, [V, V, I64, F, I, V]),
     "msa_flat_reptile_delta": (I, [V, V, V, I64, F, I, V]),

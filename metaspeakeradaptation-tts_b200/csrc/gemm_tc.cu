@@ -13,6 +13,17 @@
 //     A.B ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo,   x_hi = the 19 bits the tensor core reads, x_lo = x - x_hi (exact in fp32)
 // (three MMAs per k-step on tiles of the four operand arrays; the lo arrays are produced by a streaming split kernel), which
 // is fp32-accurate to ~2^-21.  Mode 1 is the plain single TF32 product (backward-pass policy).
+//
+// Implicit convolutions (Encoder / Postnet: conv1d "same" + BatchNorm, encoder.py:36-37, decoder.py:63-72).  The same kernel runs the
+// three contractions of a k-tap convolution on channels-last activations x [B][T][Ci] WITHOUT an im2col matrix:
+//   forward          y[b,t,co]  = bias[co] + sum_k sum_ci x[b,t+k-pad,ci] . Wp[k][co][ci]     K blocks = (tap, 32 input channels)
+//   input gradient   dx[b,t,ci] = sum_k sum_co dy[b,t-k+pad,co] . Wp[k][co][ci]               K blocks = (tap, 32 output channels)
+//   weight gradient  dW[co][ci][k] = sum_{b,t} dy[b,t,co] . x[b,t+k-pad,ci]                    K blocks = (batch row, 32 time steps)
+// The activation operand is a 3-D tensor map {channels, T, B}: the tap shift is a coordinate offset and TMA's out-of-bounds
+// zero fill IS the convolution's zero padding (per batch row).  Wp[k][co][ci] is the tap-major repack of the native weight
+// (one small kernel per pass for all layers); the weight gradient is stored straight into the native [Co][Ci][K] layout.
+// The forward epilogue also emits per-channel (count, mean, M2) of every 32-row slab of the output, so BatchNorm's batch statistics
+// need no extra pass over y (merged with Chan's update in a fixed order by the normalisation kernel).
 #include <cuda.h>
 
 #include <algorithm>
@@ -53,6 +64,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 // shared-memory matrix descriptor: K-major operand tile [rows][32 floats] with the 128-byte swizzle TMA wrote
 // (canonical layout ((8,n),2):((8,SBO),1) in 16-byte units: LBO = 1, SBO = 8 rows * 128 B = 64, version 1, layout SWIZZLE_128B)
@@ -100,27 +115,53 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // x_lo = x - (the 19 bits the tensor core reads), exact in fp32
+__device__ __forceinline__ float tc_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 __device__ __forceinline__ float tc_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// Implicit-convolution addressing (mode 0: plain GEMM).  mode 1 (forward / input gradient): M tile = 128 time steps of ONE batch row
+// (grid.x = B * tilesT), K block kb = (tap kb / cb, channel block kb % cb); A = 3-D activation map at time t0 + sign * (tap - pad),
+// B = 2-D map over Wp viewed as [taps * brows][.].  mode 2 (weight gradient): grid.z = tap, K block kb = (batch row kb / cb, time
+// block kb % cb), both operands MN-major 3-D activation maps, B shifted by tap - pad; the output element (row, col) of tap z lives
+// at C[row * ldc + col * out_cs + z].
+struct TcConv {
+    int mode, taps, cb, pad, sign, Tn, tilesT, brows, out_cs;
+};
 
 // grid = (M tiles, N tiles, K splits).  Split z handles the K blocks [z * kb_per_split, ...) and, when `partial` is given, stores
 // its raw accumulator tile to partial[z][M][N] (ker_splitk_reduce applies alpha / beta in a fixed order); otherwise it writes C.
 // kSplit (3xTF32): only the fp32 tiles A and B come in by TMA; the four converter / epilogue warps derive the lo tiles in shared
 // memory (same swizzled position, 32 KB further up) while the next stage is in flight, which halves the bytes every SM ingests.
-template <bool kSplit>
+// kMode 2 (single TF32 product with round-to-nearest operands): tcgen05.mma kind::tf32 TRUNCATES its fp32 operands to 19 bits (a
+// biased rounding, twice the error of cuBLAS's TF32 path); the converter warps rewrite both tiles in place with cvt.rna.tf32.f32
+// before the MMA warp reads them.
+template <int kMode>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float* __restrict__ C, int ldc,
                int M, int N, int K, float alpha, float beta, float* __restrict__ partial, int kb_per_split,
-               const float* __restrict__ bias1, const float* __restrict__ bias2, int amn, int bmn) {
+               const float* __restrict__ bias1, const float* __restrict__ bias2, int amn, int bmn, TcConv cv, float* __restrict__ stats) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte aligned operand tiles (swizzle atom = 8 rows x 128 B), then the barriers
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr bool kSplit = kMode == 0, kRn = kMode == 2;
     constexpr int kOps = kSplit ? 4 : 2;
     TcSmem* sb = reinterpret_cast<TcSmem*>(tiles + (size_t)kTcStages * kOps * kTcTileBytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * kTcBM, n0 = blockIdx.y * kTcBN;
     const int num_kb = (K + kTcBK - 1) / kTcBK;
-    const int kb0 = blockIdx.z * kb_per_split;
+    const int kb0 = cv.mode == 2 ? 0 : blockIdx.z * kb_per_split;
     const int nkb = min(num_kb, kb0 + kb_per_split) - kb0;          // >= 1 (host)
+    // output rows of this tile: [orow0, orow0 + orows)
+    int orow0 = m0, orows = min(kTcBM, M - m0), cbat = 0, ct0 = 0;
+    if (cv.mode == 1) {
+        cbat = blockIdx.x / cv.tilesT;
+        ct0 = (blockIdx.x - cbat * cv.tilesT) * kTcBM;
+        orow0 = cbat * cv.Tn + ct0;
+        orows = min(kTcBM, cv.Tn - ct0);
+    }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kTcStages; ++s) { mbar_init(&sb->full[s], 1); mbar_init(&sb->conv[s], kTcConv); mbar_init(&sb->empty[s], 1); }
@@ -144,12 +185,27 @@ k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 mbar_wait(&sb->empty[s], (it & 1) ^ 1);                       // slot free (first pass: passes immediately)
                 mbar_expect_tx(&sb->full[s], 2 * kTcTileBytes);
                 uint8_t* st = tiles + (size_t)s * kOps * kTcTileBytes;
-                if (!amn) tma_load_2d(st, &mapA, (kb0 + i) * kTcBK, m0, &sb->full[s]);
+                const int kb = kb0 + i;
+                if (cv.mode == 1) {
+                    const int tap = kb / cv.cb, c0 = (kb - tap * cv.cb) * kTcBK;
+                    tma_load_3d(st, &mapA, c0, ct0 + cv.sign * (tap - cv.pad), cbat, &sb->full[s]);
+                    if (!bmn) tma_load_2d(st + kTcTileBytes, &mapB, c0, tap * cv.brows + n0, &sb->full[s]);
+                    else
+                        for (int b = 0; b < 4; ++b) tma_load_2d(st + kTcTileBytes + b * 4096, &mapB, n0 + 32 * b, tap * cv.brows + c0, &sb->full[s]);
+                    continue;
+                }
+                if (cv.mode == 2) {
+                    const int bb = kb / cv.cb, t0 = (kb - bb * cv.cb) * kTcBK, tap = blockIdx.z;
+                    for (int b = 0; b < 4; ++b) tma_load_3d(st + b * 4096, &mapA, m0 + 32 * b, t0, bb, &sb->full[s]);
+                    for (int b = 0; b < 4; ++b) tma_load_3d(st + kTcTileBytes + b * 4096, &mapB, n0 + 32 * b, t0 + tap - cv.pad, bb, &sb->full[s]);
+                    continue;
+                }
+                if (!amn) tma_load_2d(st, &mapA, kb * kTcBK, m0, &sb->full[s]);
                 else
-                    for (int b = 0; b < 4; ++b) tma_load_2d(st + b * 4096, &mapA, m0 + 32 * b, (kb0 + i) * kTcBK, &sb->full[s]);
-                if (!bmn) tma_load_2d(st + kTcTileBytes, &mapB, (kb0 + i) * kTcBK, n0, &sb->full[s]);
+                    for (int b = 0; b < 4; ++b) tma_load_2d(st + b * 4096, &mapA, m0 + 32 * b, kb * kTcBK, &sb->full[s]);
+                if (!bmn) tma_load_2d(st + kTcTileBytes, &mapB, kb * kTcBK, n0, &sb->full[s]);
                 else
-                    for (int b = 0; b < 4; ++b) tma_load_2d(st + kTcTileBytes + b * 4096, &mapB, n0 + 32 * b, (kb0 + i) * kTcBK, &sb->full[s]);
+                    for (int b = 0; b < 4; ++b) tma_load_2d(st + kTcTileBytes + b * 4096, &mapB, n0 + 32 * b, kb * kTcBK, &sb->full[s]);
             }
         }
     } else if (warp == 1) {
@@ -157,7 +213,7 @@ k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (lane == 0) {
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % kTcStages, it = i / kTcStages;
-                mbar_wait(kSplit ? &sb->conv[s] : &sb->full[s], it & 1);
+                mbar_wait((kSplit || kRn) ? &sb->conv[s] : &sb->full[s], it & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = smem_u32(tiles + (size_t)s * kOps * kTcTileBytes);
                 const uint32_t idesc = kTcIdesc | (amn ? 1u << 15 : 0u) | (bmn ? 1u << 16 : 0u);
@@ -200,6 +256,23 @@ k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 mbar_arrive(&sb->conv[s]);
             }
         }
+        if (kRn) {
+            // ===== both tiles in place: fp32 -> nearest TF32 value =====
+            const int ct = threadIdx.x - 64;
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % kTcStages, it = i / kTcStages;
+                mbar_wait(&sb->full[s], it & 1);
+                float4* t4 = reinterpret_cast<float4*>(tiles + (size_t)s * kOps * kTcTileBytes);
+                constexpr int kPer = 2 * kTcTileBytes / 16 / kTcConv;
+                float4 v[kPer];
+#pragma unroll
+                for (int j = 0; j < kPer; ++j) v[j] = t4[ct + j * kTcConv];
+#pragma unroll
+                for (int j = 0; j < kPer; ++j) t4[ct + j * kTcConv] = make_float4(tc_rn(v[j].x), tc_rn(v[j].y), tc_rn(v[j].z), tc_rn(v[j].w));
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&sb->conv[s]);
+            }
+        }
         if (warp >= 6) goto done;                                              // converter-only warps
         // ===== epilogue: TMEM -> registers -> shared (transpose) -> global; warp q handles TMEM lanes [32q, 32q+32) =====
         // (a thread owns an accumulator ROW; going through a 32 x 33 tile in the now idle operand ring turns the stores into
@@ -207,8 +280,9 @@ k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_wait(&sb->tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float* xp = reinterpret_cast<float*>(tiles) + q * (32 * 33);
-        float* obase = partial != nullptr ? partial + (size_t)blockIdx.z * M * N : C;
+        float* obase = partial != nullptr ? partial + (size_t)blockIdx.z * M * N : (cv.mode == 2 ? C + blockIdx.z : C);
         const int ldo = partial != nullptr ? N : ldc;
+        const int ocs = partial != nullptr || cv.out_cs < 1 ? 1 : cv.out_cs;      // column stride of the output
 #pragma unroll 1
         for (int cc = 0; cc < kTcBN / 32; ++cc) {
             uint32_t v[32];
@@ -229,8 +303,8 @@ k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             __syncwarp();
             const int col = n0 + cc * 32 + lane;
             if (col < N) {
-                const int rows = min(32, M - (m0 + q * 32));
-                float* out = obase + (size_t)(m0 + q * 32) * ldo + col;
+                const int rows = min(32, orows - q * 32);
+                float* out = obase + (size_t)(orow0 + q * 32) * ldo + (size_t)col * ocs;
                 if (partial == nullptr && beta != 0.f) {
                     // C is read for all 32 rows before the first store: one memory round trip per tile column block instead of 32
                     // dependent ones (most products of the pass accumulate onto a bias-filled C with beta = 1)
@@ -245,8 +319,30 @@ k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const float sc = partial != nullptr ? 1.f : alpha;
                     float bs = 0.f;
                     if (partial == nullptr && bias1 != nullptr) bs = bias1[col] + (bias2 != nullptr ? bias2[col] : 0.f);
+                    if (stats != nullptr && partial == nullptr) {
+                        // BatchNorm batch statistics of this 32-row slab: (count, mean, M2) per output channel, two passes over the tile
+                        float sum = 0.f;
 #pragma unroll 8
-                    for (int r = 0; r < rows; ++r) out[(size_t)r * ldo] = sc * xp[r * 33 + lane] + bs;
+                        for (int r = 0; r < rows; ++r) {
+                            const float v = sc * xp[r * 33 + lane] + bs;
+                            out[(size_t)r * ldo] = v;
+                            sum += v;
+                        }
+                        const float cnt = rows > 0 ? (float)rows : 0.f, mu = rows > 0 ? sum / cnt : 0.f;
+                        float m2 = 0.f;
+#pragma unroll 8
+                        for (int r = 0; r < rows; ++r) {
+                            const float dv = sc * xp[r * 33 + lane] + bs - mu;
+                            m2 += dv * dv;
+                        }
+                        float* so = stats + (size_t)(blockIdx.x * 4 + q) * 3 * N + col;
+                        so[0] = cnt;
+                        so[N] = mu;
+                        so[2 * (size_t)N] = m2;
+                    } else {
+#pragma unroll 8
+                        for (int r = 0; r < rows; ++r) out[(size_t)r * ldo] = sc * xp[r * 33 + lane] + bs;
+                    }
                 }
             }
             __syncwarp();
@@ -271,6 +367,78 @@ __global__ void ker_splitk_reduce(const float* __restrict__ partial, int splits,
         float* out = C + (size_t)r * ldc + c;
         const float bs = bias1 != nullptr ? bias1[c] + (bias2 != nullptr ? bias2[c] : 0.f) : 0.f;
         *out = beta != 0.f ? alpha * s + beta * *out + bs : alpha * s + bs;
+    }
+}
+
+// The same reduction for a convolution's forward product, one block per (32 rows, 32 columns): also emits the slab's BatchNorm
+// statistics (count, mean, M2) per column like the unsplit epilogue does.  block = (32 columns, 8 row groups of 4 rows)
+__global__ void __launch_bounds__(256) ker_splitk_reduce_stats(const float* __restrict__ partial, int splits, int M, int N, float* __restrict__ C,
+                                                                 int ldc, float alpha, const float* __restrict__ bias, float* __restrict__ stats) {
+    __shared__ float sh[8][33];
+    __shared__ float mu_s[32];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int col = blockIdx.y * 32 + cx, r0 = blockIdx.x * 32 + ry * 4;
+    const size_t n = (size_t)M * N;
+    const float bs = (bias != nullptr && col < N) ? bias[col] : 0.f;
+    const int nrow = min(32, M - blockIdx.x * 32);
+    float v[4];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        v[j] = 0.f;
+        const int r = r0 + j;
+        if (r < M && col < N) {
+            float a = partial[(size_t)r * N + col];
+            for (int z = 1; z < splits; ++z) a += partial[(size_t)z * n + (size_t)r * N + col];
+            v[j] = alpha * a + bs;
+            C[(size_t)r * ldc + col] = v[j];
+            sum += v[j];
+        }
+    }
+    sh[ry][cx] = sum;
+    __syncthreads();
+    if (ry == 0) {
+        float t = 0.f;
+        for (int j = 0; j < 8; ++j) t += sh[j][cx];
+        mu_s[cx] = t / (float)nrow;
+    }
+    __syncthreads();
+    const float mu = mu_s[cx];
+    float m2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (r0 + j < M) m2 += (v[j] - mu) * (v[j] - mu);
+    __syncthreads();
+    sh[ry][cx] = m2;
+    __syncthreads();
+    if (ry == 0 && col < N) {
+        float t = 0.f;
+        for (int j = 0; j < 8; ++j) t += sh[j][cx];
+        float* so = stats + (size_t)blockIdx.x * 3 * N + col;
+        so[0] = (float)nrow;
+        so[N] = mu;
+        so[2 * (size_t)N] = t;
+    }
+}
+
+// Wp[k][co][ci] <- W[co][ci][k] for up to 8 layers in one launch (blockIdx.y = layer)
+struct RepackTab {
+    const float* src[8];
+    float* dst[8];
+    int co[8], ci[8], k[8];
+};
+__global__ void ker_conv_repack(RepackTab tab) {
+    const int l = blockIdx.y;
+    const float* __restrict__ src = tab.src[l];
+    float* __restrict__ dst = tab.dst[l];
+    const int Co = tab.co[l], Ci = tab.ci[l], K = tab.k[l];
+    const int64_t n = (int64_t)Co * Ci * K;
+    // thread = one destination element: reads are K-strided (served from L1 / L2: a warp touches 32 * K consecutive floats), writes coalesced
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % Ci);
+        const int64_t t = i / Ci;
+        const int co = (int)(t % Co), k = (int)(t / Co);
+        dst[i] = src[((int64_t)co * Ci + ci) * K + k];
     }
 }
 
@@ -307,6 +475,130 @@ static int make_map(CUtensorMap* map, const float* base, int rows, int K, int ld
     return 0;
 }
 
+// channels-last activation [B][Tn][C] as a 3-D map {C, Tn, B}; box {32 channels, rows time steps, 1}
+static int make_map_act(CUtensorMap* map, const float* base, int B, int Tn, int C, int rows, bool mn) {
+    EncodeTiledFn enc = get_encode();
+    MSA_CHECK(enc != nullptr, MSA_E_NODEVICE, "conv_tc: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Tn, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)C * sizeof(float), (cuuint64_t)Tn * C * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)kTcBK, (cuuint32_t)rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MSA_CHECK(r == CUDA_SUCCESS, MSA_E_ARG, "conv_tc: cuTensorMapEncodeTiled failed (%d) for a [%d][%d][%d] activation", (int)r, B, Tn, C);
+    return 0;
+}
+
+bool conv_tc_supported(int B, int Tn, int Ci, int Co, int K, const float* x, const float* w) {
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return B >= 1 && Tn >= 1 && Ci >= 4 && Co >= 4 && (Ci % 4) == 0 && (Co % 4) == 0 && K >= 1 && (K & 1) == 1 && K <= 15 && al16(x) && al16(w);
+}
+static int conv_plan_splits(int B, int Tn, int N, int num_kb) {
+    const int64_t tiles = (int64_t)B * ((Tn + kTcBM - 1) / kTcBM) * ((N + kTcBN - 1) / kTcBN);
+    int64_t splits = std::min<int64_t>(148 / std::max<int64_t>(tiles, 1), num_kb / 4);
+    if (splits < 2) return 1;
+    const int64_t per = (num_kb + splits - 1) / splits;
+    return (int)((num_kb + per - 1) / per);
+}
+// K-split scratch of the forward / input-gradient product with N output channels and C contraction channels
+size_t conv_tc_scratch_floats(int B, int Tn, int C, int N, int K) {
+    const int splits = conv_plan_splits(B, Tn, N, K * ((C + kTcBK - 1) / kTcBK));
+    return splits > 1 ? (size_t)splits * B * Tn * N + 64 : 64;
+}
+// slabs of the forward statistics: stats[slabs][3][Co]
+int conv_tc_stat_slabs(int B, int Tn, int Ci, int Co, int K, bool have_scratch) {
+    const int splits = have_scratch ? conv_plan_splits(B, Tn, Co, K * ((Ci + kTcBK - 1) / kTcBK)) : 1;
+    return splits > 1 ? (B * Tn + 31) / 32 : B * ((Tn + kTcBM - 1) / kTcBM) * 4;
+}
+
+template <int kMode>
+static int launch_tc(dim3 grid, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap& mB, float* C, int ldc, int M, int N, int K, float alpha,
+                     float beta, float* partial, int per, const float* bias1, const float* bias2, int amn, int bmn, const TcConv& cv, float* stats) {
+    const size_t smem = (size_t)kTcStages * (kMode == 0 ? 4 : 2) * kTcTileBytes + sizeof(TcSmem) + 1024;
+    static bool attr = false;
+    if (!attr) { MSA_CUDA(cudaFuncSetAttribute(k_gemm_tf32_nt<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    k_gemm_tf32_nt<kMode><<<grid, kTcThreads, smem, st>>>(mA, mB, C, ldc, M, N, K, alpha, beta, partial, per, bias1, bias2, amn, bmn, cv, stats);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+
+// y[B*Tn][Co] = conv1d_same(x[B][Tn][Ci], Wp[K][Co][Ci]) + bias; stats (optional): conv_tc_stat_slabs x [3][Co] slab statistics of y
+int conv_tc_fwd(const float* x, int B, int Tn, int Ci, const float* wp, int Co, int K, const float* bias, float* y, int mode, float* scratch,
+                float* stats, cudaStream_t st) {
+    CUtensorMap mA, mB;
+    MSA_TRY(make_map_act(&mA, x, B, Tn, Ci, kTcBM, false));
+    MSA_TRY(make_map(&mB, wp, K * Co, Ci, Ci, false));
+    const int cb = (Ci + kTcBK - 1) / kTcBK, tilesT = (Tn + kTcBM - 1) / kTcBM, num_kb = K * cb, M = B * Tn;
+    const int splits = scratch != nullptr ? conv_plan_splits(B, Tn, Co, num_kb) : 1;
+    const int per = (num_kb + splits - 1) / splits;
+    float* partial = splits > 1 ? scratch : nullptr;
+    const TcConv cv{1, K, cb, (K - 1) / 2, 1, Tn, tilesT, Co, 1};
+    const dim3 grid((unsigned)(B * tilesT), (unsigned)((Co + kTcBN - 1) / kTcBN), (unsigned)splits);
+    if (mode == 0) MSA_TRY(launch_tc<0>(grid, st, mA, mB, y, Co, M, Co, num_kb * kTcBK, 1.f, 0.f, partial, per, bias, nullptr, 0, 0, cv, stats));
+    else if (mode == 2) MSA_TRY(launch_tc<2>(grid, st, mA, mB, y, Co, M, Co, num_kb * kTcBK, 1.f, 0.f, partial, per, bias, nullptr, 0, 0, cv, stats));
+    else MSA_TRY(launch_tc<1>(grid, st, mA, mB, y, Co, M, Co, num_kb * kTcBK, 1.f, 0.f, partial, per, bias, nullptr, 0, 0, cv, stats));
+    if (splits > 1) {
+        if (stats != nullptr) {
+            ker_splitk_reduce_stats<<<dim3((unsigned)((M + 31) / 32), (unsigned)((Co + 31) / 32)), 256, 0, st>>>(partial, splits, M, Co, y, Co, 1.f, bias, stats);
+        } else {
+            const int64_t n = (int64_t)M * Co;
+            ker_splitk_reduce<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(partial, splits, M, Co, y, Co, 1.f, 0.f, bias, nullptr);
+        }
+        MSA_LAUNCH_CHECK();
+    }
+    return 0;
+}
+// dx[B*Tn][Ci] = sum_k dy[b, t - k + pad, :] . Wp[k]   (the transposed convolution of the forward)
+int conv_tc_dx(const float* dy, int B, int Tn, int Co, const float* wp, int Ci, int K, float* dx, int mode, float* scratch, cudaStream_t st) {
+    CUtensorMap mA, mB;
+    MSA_TRY(make_map_act(&mA, dy, B, Tn, Co, kTcBM, false));
+    MSA_TRY(make_map(&mB, wp, Ci, K * Co, Ci, true));          // [K rows = (tap, co)][N = ci], N contiguous
+    const int cb = (Co + kTcBK - 1) / kTcBK, tilesT = (Tn + kTcBM - 1) / kTcBM, num_kb = K * cb, M = B * Tn;
+    const int splits = scratch != nullptr ? conv_plan_splits(B, Tn, Ci, num_kb) : 1;
+    const int per = (num_kb + splits - 1) / splits;
+    float* partial = splits > 1 ? scratch : nullptr;
+    const TcConv cv{1, K, cb, (K - 1) / 2, -1, Tn, tilesT, Co, 1};
+    const dim3 grid((unsigned)(B * tilesT), (unsigned)((Ci + kTcBN - 1) / kTcBN), (unsigned)splits);
+    if (mode == 0) MSA_TRY(launch_tc<0>(grid, st, mA, mB, dx, Ci, M, Ci, num_kb * kTcBK, 1.f, 0.f, partial, per, nullptr, nullptr, 0, 1, cv, nullptr));
+    else if (mode == 2) MSA_TRY(launch_tc<2>(grid, st, mA, mB, dx, Ci, M, Ci, num_kb * kTcBK, 1.f, 0.f, partial, per, nullptr, nullptr, 0, 1, cv, nullptr));
+    else MSA_TRY(launch_tc<1>(grid, st, mA, mB, dx, Ci, M, Ci, num_kb * kTcBK, 1.f, 0.f, partial, per, nullptr, nullptr, 0, 1, cv, nullptr));
+    if (splits > 1) {
+        const int64_t n = (int64_t)M * Ci;
+        ker_splitk_reduce<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(partial, splits, M, Ci, dx, Ci, 1.f, 0.f, nullptr, nullptr);
+        MSA_LAUNCH_CHECK();
+    }
+    return 0;
+}
+// dW[Co][Ci][K] = (accumulate ? dW : 0) + scale * sum_{b,t} dy[b,t,co] x[b,t+k-pad,ci], native parameter layout
+int conv_tc_dw(const float* dy, const float* x, int B, int Tn, int Co, int Ci, int K, float scale, int accumulate, float* dw, int mode,
+               cudaStream_t st) {
+    CUtensorMap mA, mB;
+    MSA_TRY(make_map_act(&mA, dy, B, Tn, Co, kTcBK, true));
+    MSA_TRY(make_map_act(&mB, x, B, Tn, Ci, kTcBK, true));
+    const int tb = (Tn + kTcBK - 1) / kTcBK, num_kb = B * tb;
+    const TcConv cv{2, K, tb, (K - 1) / 2, 1, Tn, 1, 0, K};
+    const dim3 grid((unsigned)((Co + kTcBM - 1) / kTcBM), (unsigned)((Ci + kTcBN - 1) / kTcBN), (unsigned)K);
+    const float beta = accumulate ? 1.f : 0.f;
+    if (mode == 0) MSA_TRY(launch_tc<0>(grid, st, mA, mB, dw, Ci * K, Co, Ci, num_kb * kTcBK, scale, beta, nullptr, num_kb, nullptr, nullptr, 1, 1, cv, nullptr));
+    else if (mode == 2) MSA_TRY(launch_tc<2>(grid, st, mA, mB, dw, Ci * K, Co, Ci, num_kb * kTcBK, scale, beta, nullptr, num_kb, nullptr, nullptr, 1, 1, cv, nullptr));
+    else MSA_TRY(launch_tc<1>(grid, st, mA, mB, dw, Ci * K, Co, Ci, num_kb * kTcBK, scale, beta, nullptr, num_kb, nullptr, nullptr, 1, 1, cv, nullptr));
+    return 0;
+}
+// Wp[k][co][ci] <- W[co][ci][k], n <= 8 layers in one launch
+int conv_tc_repack(int n, const float* const* src, float* const* dst, const int* co, const int* ci, const int* k, cudaStream_t st) {
+    MSA_CHECK(n >= 1 && n <= 8, MSA_E_ARG, "conv_tc_repack: %d layers", n);
+    RepackTab tab{};
+    int64_t big = 0;
+    for (int i = 0; i < n; ++i) {
+        tab.src[i] = src[i]; tab.dst[i] = dst[i]; tab.co[i] = co[i]; tab.ci[i] = ci[i]; tab.k[i] = k[i];
+        big = std::max<int64_t>(big, (int64_t)co[i] * ci[i] * k[i]);
+    }
+    ker_conv_repack<<<dim3((unsigned)std::min<int64_t>((big + 255) / 256, 148 * 4), (unsigned)n), 256, 0, st>>>(tab);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+
 bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb, const float* C, int64_t ldc) {
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     (void)C; (void)ldc;
@@ -327,7 +619,8 @@ size_t gemm_tc_scratch_floats(int64_t M, int64_t N, int64_t K) {
     return splits > 1 ? (size_t)splits * M * N + 64 : 64;
 }
 
-// mode 0: 3xTF32 (fp32-accurate); mode 1: single TF32 product.  `scratch` (gemm_tc_scratch_floats(M, N, K) floats, 16-byte
+// mode 0: 3xTF32 (fp32-accurate); mode 1: single TF32 product (operands truncated by the tensor core); mode 2: single TF32 product
+// with round-to-nearest operands (cuBLAS's TF32 accuracy).  `scratch` (gemm_tc_scratch_floats(M, N, K) floats, 16-byte
 // aligned) holds the partial tiles of a K split; with scratch == nullptr the K range is not split.
 int gemm_tc_nt(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
                float* C, int64_t ldc, int mode, float* scratch, cudaStream_t st, const float* bias1, const float* bias2) {
@@ -349,18 +642,10 @@ int gemm_tc(bool ta, bool tb, int64_t M, int64_t N, int64_t K, float alpha, cons
     const int per = (num_kb + splits - 1) / splits;
     float* partial = splits > 1 ? scratch : nullptr;
     const dim3 grid((unsigned)((M + kTcBM - 1) / kTcBM), (unsigned)((N + kTcBN - 1) / kTcBN), (unsigned)splits);
-    if (mode == 0) {
-        const size_t smem = (size_t)kTcStages * 4 * kTcTileBytes + sizeof(TcSmem) + 1024;
-        static bool attr0 = false;
-        if (!attr0) { MSA_CUDA(cudaFuncSetAttribute(k_gemm_tf32_nt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr0 = true; }
-        k_gemm_tf32_nt<true><<<grid, kTcThreads, smem, st>>>(mA, mB, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta, partial, per, bias1, bias2, amn, bmn);
-    } else {
-        const size_t smem = (size_t)kTcStages * 2 * kTcTileBytes + sizeof(TcSmem) + 1024;
-        static bool attr1 = false;
-        if (!attr1) { MSA_CUDA(cudaFuncSetAttribute(k_gemm_tf32_nt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr1 = true; }
-        k_gemm_tf32_nt<false><<<grid, kTcThreads, smem, st>>>(mA, mB, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta, partial, per, bias1, bias2, amn, bmn);
-    }
-    MSA_LAUNCH_CHECK();
+    const TcConv cv{0, 0, 0, 0, 0, 0, 0, 0, 1};
+    if (mode == 0) MSA_TRY(launch_tc<0>(grid, st, mA, mB, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta, partial, per, bias1, bias2, amn, bmn, cv, nullptr));
+    else if (mode == 2) MSA_TRY(launch_tc<2>(grid, st, mA, mB, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta, partial, per, bias1, bias2, amn, bmn, cv, nullptr));
+    else MSA_TRY(launch_tc<1>(grid, st, mA, mB, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta, partial, per, bias1, bias2, amn, bmn, cv, nullptr));
     if (splits > 1) {
         const int64_t n = M * N;
         ker_splitk_reduce<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(partial, splits, (int)M, (int)N, C, (int)ldc,
@@ -382,5 +667,35 @@ int msa_gemm(int trans_a, int trans_b, int64_t M, int64_t N, int64_t K, float al
              int64_t ldb, float beta, float* C, int64_t ldc, int mode, float* scratch, void* stream) {
     return msa::gemm_tc(trans_a != 0, trans_b != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, mode, scratch, (cudaStream_t)stream,
                         nullptr, nullptr);
+}
+
+size_t msa_conv1d_scratch_floats(int B, int T, int Cin, int Cout, int K) {
+    return std::max(msa::conv_tc_scratch_floats(B, T, Cin, Cout, K), msa::conv_tc_scratch_floats(B, T, Cout, Cin, K));
+}
+int msa_conv1d_stat_slabs(int B, int T, int Cin, int Cout, int K, int have_scratch) {
+    return msa::conv_tc_stat_slabs(B, T, Cin, Cout, K, have_scratch != 0);
+}
+int msa_conv1d_repack(const float* w, float* wp, int Cout, int Cin, int K, void* stream) {
+    MSA_CHECK(w && wp, MSA_E_ARG, "msa_conv1d_repack: null argument");
+    const float* src[1] = {w};
+    float* dst[1] = {wp};
+    return msa::conv_tc_repack(1, src, dst, &Cout, &Cin, &K, (cudaStream_t)stream);
+}
+int msa_conv1d_fwd(const float* x, int B, int T, int Cin, const float* wp, int Cout, int K, const float* bias, float* y, int mode,
+                   float* scratch, float* stats, void* stream) {
+    MSA_CHECK(x && wp && y, MSA_E_ARG, "msa_conv1d_fwd: null argument");
+    MSA_CHECK(msa::conv_tc_supported(B, T, Cin, Cout, K, x, wp), MSA_E_UNSUPPORTED, "msa_conv1d_fwd: channels must be multiples of 4, K odd, 16-byte aligned operands");
+    return msa::conv_tc_fwd(x, B, T, Cin, wp, Cout, K, bias, y, mode, scratch, stats, (cudaStream_t)stream);
+}
+int msa_conv1d_dx(const float* dy, int B, int T, int Cout, const float* wp, int Cin, int K, float* dx, int mode, float* scratch, void* stream) {
+    MSA_CHECK(dy && wp && dx, MSA_E_ARG, "msa_conv1d_dx: null argument");
+    MSA_CHECK(msa::conv_tc_supported(B, T, Cin, Cout, K, dy, wp), MSA_E_UNSUPPORTED, "msa_conv1d_dx: channels must be multiples of 4, K odd, 16-byte aligned operands");
+    return msa::conv_tc_dx(dy, B, T, Cout, wp, Cin, K, dx, mode, scratch, (cudaStream_t)stream);
+}
+int msa_conv1d_dw(const float* dy, const float* x, int B, int T, int Cout, int Cin, int K, float scale, int accumulate, float* dw, int mode,
+                  void* stream) {
+    MSA_CHECK(dy && x && dw, MSA_E_ARG, "msa_conv1d_dw: null argument");
+    MSA_CHECK(msa::conv_tc_supported(B, T, Cin, Cout, K, dy, x), MSA_E_UNSUPPORTED, "msa_conv1d_dw: channels must be multiples of 4, K odd, 16-byte aligned operands");
+    return msa::conv_tc_dw(dy, x, B, T, Cout, Cin, K, scale, accumulate, dw, mode, (cudaStream_t)stream);
 }
 }

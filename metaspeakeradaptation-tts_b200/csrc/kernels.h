@@ -200,6 +200,10 @@ constexpr int kRedTickets = 256, kRedChunks = 16, kRedCols = 8192;
 constexpr int64_t kRedScrFloats = kRedTickets + (int64_t)kRedChunks * kRedCols;
 int k_colsum(const float* x, int64_t rows, int N, int ld, float* out, float scale, int accumulate, float* out2, float* red_scr, cudaStream_t st);
 int k_bn_stats(const float* y, int64_t rows, int C, float* mean, float* invstd, float* running, int Cpad, float* red_scr, cudaStream_t st);
+// BatchNorm (train) from the slab statistics of the conv epilogue ([nslab][3][C]: count, mean, M2) + activation + dropout in ONE
+// kernel: every block merges the slabs of its 32 channels (Chan's update, slab order), block row 0 also stores mean / invstd / running
+int k_bn_slab_act_drop_fwd(const float* y, const float* slabs, int nslab, int64_t rows, int C, float* mean, float* invstd, float* running,
+                           int Cpad, const float* gamma, const float* beta, const uint8_t* mask, float ds, int act, float* out, cudaStream_t st);
 int k_bn_eval_stats(const float* running, int C, int Cpad, float* mean, float* invstd, cudaStream_t st);
 // act: 0 none, 1 relu, 2 tanh
 int k_bn_act_drop_fwd(const float* y, const float* mean, const float* invstd, const float* gamma, const float* beta,
@@ -327,6 +331,16 @@ int gemm_tc_nt(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int
 int gemm_tc(bool ta, bool tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb,
             float beta, float* C, int64_t ldc, int mode, float* scratch, cudaStream_t st, const float* bias1 = nullptr,
             const float* bias2 = nullptr);
+// Implicit convolutions on the same kernel (channels-last activations [B][Tn][C], wp = tap-major weight copy [K][Co][Ci]); mode as above
+bool conv_tc_supported(int B, int Tn, int Ci, int Co, int K, const float* x, const float* w);
+size_t conv_tc_scratch_floats(int B, int Tn, int C, int N, int K);
+int conv_tc_stat_slabs(int B, int Tn, int Ci, int Co, int K, bool have_scratch);
+int conv_tc_fwd(const float* x, int B, int Tn, int Ci, const float* wp, int Co, int K, const float* bias, float* y, int mode, float* scratch,
+                float* stats, cudaStream_t st);
+int conv_tc_dx(const float* dy, int B, int Tn, int Co, const float* wp, int Ci, int K, float* dx, int mode, float* scratch, cudaStream_t st);
+int conv_tc_dw(const float* dy, const float* x, int B, int Tn, int Co, int Ci, int K, float scale, int accumulate, float* dw, int mode,
+               cudaStream_t st);
+int conv_tc_repack(int n, const float* const* src, float* const* dst, const int* co, const int* ci, const int* k, cudaStream_t st);
 
 int k_abort_guard(unsigned int* abort_word, float* sumsq, int raise, cudaStream_t st);   // raise: set the word; else NaN -> *sumsq if set
 int k_fill_canary(float* p, int64_t n, cudaStream_t st);   // n floats (multiple of 4, 16-byte aligned) <- 0xFFFFFFFF

@@ -242,6 +242,56 @@ __global__ void ker_bn_act_drop_fwd(const float* __restrict__ y, const float* __
         out[i] = v;
     }
 }
+// BatchNorm statistics merged from slab statistics (count, mean, M2) [nslab][3][C] + normalise + activation + dropout.
+// grid (channel groups of 32, row chunks), block (32 channels, 8 row lanes): a warp touches 32 consecutive channels of one row.
+__global__ void __launch_bounds__(256) ker_bn_slab_act_drop_fwd(const float* __restrict__ y, const float* __restrict__ slabs, int nslab, int64_t rows,
+                                                                  int C, float* mean, float* invstd, float* running, int Cpad,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  const uint8_t* __restrict__ mask, float ds, int act, float* out) {
+    __shared__ float m_s[32], is_s[32], g_s[32], b_s[32];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
+    if (ry == 0 && c < C) {
+        float n = 0.f, m = 0.f, M2 = 0.f;
+        for (int sl = 0; sl < nslab; ++sl) {
+            const float* sp = slabs + (size_t)sl * 3 * C + c;
+            const float np = sp[0];
+            if (np <= 0.f) continue;
+            const float mp = sp[C], qp = sp[2 * (size_t)C];
+            const float delta = mp - m, nn = n + np;
+            m += delta * np / nn;
+            M2 += qp + delta * delta * n * np / nn;
+            n = nn;
+        }
+        const float var = M2 / (float)rows;
+        const float is = 1.f / sqrtf(var + 1e-5f);
+        m_s[cx] = m;
+        is_s[cx] = is;
+        g_s[cx] = gamma[c];
+        b_s[cx] = beta[c];
+        if (blockIdx.y == 0) {
+            mean[c] = m;
+            invstd[c] = is;
+            if (running) {
+                const float unb = rows > 1 ? M2 / (float)(rows - 1) : var;
+                running[c] = 0.9f * running[c] + 0.1f * m;
+                running[Cpad + c] = 0.9f * running[Cpad + c] + 0.1f * unb;
+            }
+        }
+    }
+    __syncthreads();
+    if (c >= C) return;
+    const int64_t rc = (rows + gridDim.y - 1) / gridDim.y;
+    const int64_t r0 = (int64_t)blockIdx.y * rc, r1 = r0 + rc < rows ? r0 + rc : rows;
+    const float m = m_s[cx], is = is_s[cx], g = g_s[cx], be = b_s[cx];
+    for (int64_t r = r0 + ry; r < r1; r += 8) {
+        const int64_t i = r * C + c;
+        const float u = g * (y[i] - m) * is + be;
+        float v = act_fwd(u, act);
+        if (mask) v = mask[i] ? v * ds : 0.f;
+        out[i] = v;
+    }
+}
 __device__ __forceinline__ float bn_du(float dout, float u, uint8_t keep, bool has_mask, float ds, int act) {
     float d = has_mask ? (keep ? dout * ds : 0.f) : dout;
     if (act == 1) d = u > 0.f ? d : 0.f;
@@ -686,6 +736,17 @@ int k_bn_eval_stats(const float* running, int C, int Cpad, float* mean, float* i
 int k_bn_act_drop_fwd(const float* y, const float* mean, const float* invstd, const float* gamma, const float* beta,
                       const uint8_t* mask, float ds, int act, float* out, int64_t rows, int C, cudaStream_t st) {
     ker_bn_act_drop_fwd<<<grid_for(rows * C), kTh, 0, ST>>>(y, mean, invstd, gamma, beta, mask, ds, act, out, rows * C, C);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_bn_slab_act_drop_fwd(const float* y, const float* slabs, int nslab, int64_t rows, int C, float* mean, float* invstd, float* running,
+                           int Cpad, const float* gamma, const float* beta, const uint8_t* mask, float ds, int act, float* out, cudaStream_t st) {
+    const int cg = cdiv(C, 32);
+    int64_t P = (2 * 148 + cg - 1) / cg;
+    if (P > rows / 8) P = rows / 8;
+    if (P < 1) P = 1;
+    ker_bn_slab_act_drop_fwd<<<dim3(cg, (unsigned)P), 256, 0, ST>>>(y, slabs, nslab, rows, C, mean, invstd, running, Cpad, gamma, beta, mask, ds,
+                                                                    act, out);
     MSA_LAUNCH_CHECK();
     return 0;
 }

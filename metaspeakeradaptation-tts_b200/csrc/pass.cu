@@ -44,6 +44,7 @@ struct Dims {
     int B, T, L;
     int C, Kc, nEnc, Hh, Ds, Dsin, E, Pd, Ha, Hd, A, F, Kl, M, Cp, Kp, nPost, Cmax;
     int64_t BL, TB, BT, TBL;
+    int conv_tc;      // convolutions as implicit GEMMs (gemm_tc.cu): no im2col buffers, tap-major weight copies instead
 };
 
 }  // namespace msa
@@ -86,6 +87,9 @@ struct msa_handle {
     long long tc_min = 100000000LL;
     long long tc_min_bwd = 30000000LL;     // mode 3: smallest backward contraction (MACs) routed to the tcgen05 kernel
     bool tc_enabled = true;
+    // Encoder / postnet convolutions as implicit GEMMs on the tcgen05 kernel (activation operand = shifted 3-D TMA map, BatchNorm
+    // statistics from the epilogue) under the tensor-core GEMM policies; the strict fp32 policy keeps im2col + cuBLAS.  Env MSA_CONV_TC=0: off.
+    bool conv_tc = false;
     int rec_flags = -1;    // hand-off variant of the persistent kernels; -1 = per-kernel default (env MSA_REC_FLAGS overrides, development only)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
     std::vector<int> prof_id;
@@ -201,14 +205,23 @@ static Dims make_dims(const msa_config& c, int B, int T, int L) {
     d.M = c.n_mel; d.Cp = c.post_dim; d.Kp = c.post_kernel; d.nPost = c.post_n_convs;
     d.Cmax = std::max(d.M, d.Cp);
     d.BL = (int64_t)B * L; d.TB = (int64_t)T * B; d.BT = d.TB; d.TBL = d.TB * L;
+    d.conv_tc = 0;
     return d;
+}
+// slab statistics of the largest convolution output: [slabs][3][channels]
+static int64_t conv_stats_floats(const Dims& d) {
+    const int64_t rows = std::max(d.BL, d.BT), tmax = std::max(d.T, d.L);
+    const int64_t slabs = (rows + 31) / 32 + 4 * (int64_t)d.B * ((tmax + 127) / 128);
+    return slabs * 3 * std::max(d.C, d.Cmax);
 }
 
 // ---- workspace -------------------------------------------------------------------------------------
 #define WS_LIST(X)                                                                                     \
     X(spk_vec, d.B * d.Ds)                                                                             \
     X(enc_x, (d.nEnc + 1) * d.BL * d.C) X(enc_y, d.nEnc * d.BL * d.C) X(enc_bn, d.nEnc * 2 * d.C)      \
-    X(enc_col, d.nEnc * d.BL * d.Kc * d.C) X(x3_tm, d.BL * d.C)            \
+    X(enc_col, d.conv_tc ? 0 : d.nEnc * d.BL * d.Kc * d.C) X(x3_tm, d.BL * d.C)            \
+    X(enc_wp, d.conv_tc ? (int64_t)d.nEnc * d.Kc * d.C * d.C : 0) X(post_wp, d.conv_tc ? (int64_t)d.nPost * d.Kp * d.Cmax * d.Cmax : 0) \
+    X(conv_stats, d.conv_tc ? conv_stats_floats(d) : 0) \
     X(enc_zx, 2 * d.BL * 4 * d.Hh) X(enc_g, 2 * d.BL * 4 * d.Hh) X(enc_c, 2 * d.BL * d.Hh)             \
     X(enc_h, 2 * d.BL * d.Hh) X(memory, d.BL * d.E)                                                    \
     X(frames, (d.TB + d.B) * d.M) X(target, d.BT * d.M) X(p1, (d.TB + d.B) * d.Pd)                     \
@@ -220,11 +233,11 @@ static Dims make_dims(const msa_config& c, int B, int T, int L) {
     X(zd, d.TB * 4 * d.Hd) X(hd, d.TB * d.Hd) X(cd, d.TB * d.Hd) X(gd, d.TB * 4 * d.Hd)                \
     X(mel_tm, d.TB * d.M) X(gate_tm, d.TB)                                                             \
     X(post_x, (d.nPost + 1) * d.BT * d.Cmax) X(post_y, d.nPost * d.BT * d.Cmax)                        \
-    X(post_bn, d.nPost * 2 * d.Cmax) X(post_col, d.nPost * d.BT * d.Kp * d.Cmax)                       \
+    X(post_bn, d.nPost * 2 * d.Cmax) X(post_col, d.conv_tc ? 0 : d.nPost * d.BT * d.Kp * d.Cmax)                       \
     X(post_bt, d.BT * d.M) X(gate_bt, d.BT) X(red_scr, kRedScrFloats) \
     X(loss_part, 1024) X(loss, 32) X(dpre, d.BT * d.M) X(dpost, d.BT * d.M) X(dgate, d.BT)             \
     X(bdx0, d.BT * d.Cmax) X(bdx1, d.BT * d.Cmax) X(bdy, d.BT * d.Cmax)                                \
-    X(bdcol, d.BT * d.Kp * d.Cmax)                            \
+    X(bdcol, d.conv_tc ? 0 : d.BT * d.Kp * d.Cmax)                            \
     X(bn_scr, 2 * std::max(d.Cmax, d.C)) X(dmel_bt, d.BT * d.M) X(dmel_tm, d.TB * d.M)                 \
     X(dgate_tm, d.TB) X(dhd, d.TB * d.Hd) X(dzd, d.TB * 4 * d.Hd) X(dha, d.TB * d.Ha)                  \
     X(dctx, d.TB * d.E) X(da_ext, d.TBL) X(dza, d.TB * 4 * d.Ha) X(dq, d.TB * d.A) X(de, d.TBL)        \
@@ -233,7 +246,7 @@ static Dims make_dims(const msa_config& c, int B, int T, int L) {
     X(dmw, d.BL * 4 * d.Ha) X(dmem, d.BL * d.E) X(dxp, (d.TB + d.B) * d.Pd)                            \
     X(dp1, (d.TB + d.B) * d.Pd) X(denc_h, 2 * d.BL * d.Hh) X(dzx, 2 * d.BL * 4 * d.Hh)                 \
     X(dx3_tm, d.BL * d.C) X(edx0, d.BL * d.C) X(edx1, d.BL * d.C) X(edy, d.BL * d.C)                   \
-    X(edcol, d.BL * d.Kc * d.C) X(dspk, d.B * d.Ds)                             \
+    X(edcol, d.conv_tc ? 0 : d.BL * d.Kc * d.C) X(dspk, d.B * d.Ds)                             \
     X(wloc_part, (int64_t)wloc_grad_partials(d.T, d.B) * d.F * 2 * d.Kl) X(gemm_lo, tc_scratch_floats(d)) X(prof, kProfFloats) X(trace, kTraceFloats)
 
 constexpr int64_t kProfFloats = 2 * 6 * 256 * 8;
@@ -275,6 +288,12 @@ static Ws ws_layout(const Dims& d, void* base) {
     o += kBlasWs;
     w.total_bytes = o;
     return w;
+}
+
+static Dims make_dims_h(const msa_handle* h, int B, int T, int L) {
+    Dims d = make_dims(h->cfg, B, T, L);
+    d.conv_tc = h->conv_tc ? 1 : 0;
+    return d;
 }
 
 // ---- mask sections ---------------------------------------------------------------------------------
@@ -326,7 +345,7 @@ static int gemm(msa_handle* h, bool ta, bool tb, int64_t M, int64_t N, int64_t K
     const bool route = own_ok && ((h->tc_mode == 2 && !tf32 && nt && tc_size) || (h->tc_mode == 1 && nt && tc_size) ||
                                   (h->tc_mode == 3 && (nt ? (tc_size || tf32) : macs >= h->tc_min_bwd)));
     if (route)
-        return gemm_tc(ta, tb, M, N, K, alpha, A, lda, Bm, ldb, beta, Cm, ldc, tf32 ? 1 : 0,
+        return gemm_tc(ta, tb, M, N, K, alpha, A, lda, Bm, ldb, beta, Cm, ldc, tf32 ? 2 : 0,
                        (h->gemm_scratch && gemm_tc_scratch_floats(M, N, K) <= h->gemm_scratch_floats) ? h->gemm_scratch : nullptr,
                        h->cur_stream, bias1, bias2);
     if (bias1 != nullptr) {
@@ -354,11 +373,22 @@ static int gemm_batched(msa_handle* h, bool ta, bool tb, int64_t M, int64_t N, i
 }
 
 // conv1d ("same") + BatchNorm(train) + activation + dropout, channels-last rows = B*Tn
+// wp != nullptr: implicit GEMM on the tcgen05 kernel (wp = tap-major copy of the weight, stats = slab-statistics scratch): two
+// launches per layer (three when the product is split over K) and no im2col matrix
 static int conv_bn_fwd(msa_handle* h, cudaStream_t st, const float* params, const std::string& pfx, const float* x, float* y,
-                       float* xout, float* col, float* bn_mean, float* bn_invstd, float* running, int B, int Tn,
+                       float* xout, float* col, const float* wp, float* stats, float* bn_mean, float* bn_invstd, float* running, int B, int Tn,
                        int Ci, int Co, int K, int act, const uint8_t* mask, float* red_scr) {
     // col (im2col of the layer input) is a per-layer buffer: the backward pass reuses it
     const int64_t rows = (int64_t)B * Tn;
+    if (wp != nullptr) {
+        const bool tf32 = h->cfg.gemm_tf32 >= 2 || (h->cfg.gemm_tf32 == 1 && h->in_bwd);
+        float* scr = (h->gemm_scratch && conv_tc_scratch_floats(B, Tn, Ci, Co, K) <= h->gemm_scratch_floats) ? h->gemm_scratch : nullptr;
+        MSA_TRY(conv_tc_fwd(x, B, Tn, Ci, wp, Co, K, params + h->off(pfx + ".0.conv.bias"), y, tf32 ? 2 : 0, scr, stats, st));
+        MSA_TRY(k_bn_slab_act_drop_fwd(y, stats, conv_tc_stat_slabs(B, Tn, Ci, Co, K, scr != nullptr), rows, Co, bn_mean, bn_invstd, running,
+                                       (int)align_up(Co), params + h->off(pfx + ".1.weight"), params + h->off(pfx + ".1.bias"), mask, 2.0f, act,
+                                       xout, st));
+        return 0;
+    }
     // im2col columns are in (ci, k) order: the native weight [Co][Ci*K] is the GEMM operand
     MSA_TRY(k_im2col(x, col, B, Tn, Ci, K, st));
     MSA_TRY(gemm(h, false, true, rows, Co, (int64_t)K * Ci, 1.f, col, (int64_t)K * Ci, params + h->off(pfx + ".0.conv.weight"),
@@ -371,20 +401,51 @@ static int conv_bn_fwd(msa_handle* h, cudaStream_t st, const float* params, cons
 // backward of the above: dout -> dx (through dropout, act, BN, conv); parameter grads into `grads`
 static int conv_bn_bwd(msa_handle* h, cudaStream_t st, const float* params, float* grads, float gs, int acc,
                        const std::string& pfx, const float* x, const float* y, const float* dout, float* dx, float* dy, float* col,
-                       float* dcol, float* scr, const float* bn_mean, const float* bn_invstd, int B, int Tn,
+                       const float* wp, float* dcol, float* scr, const float* bn_mean, const float* bn_invstd, int B, int Tn,
                        int Ci, int Co, int K, int act, const uint8_t* mask, bool need_dx, float* red_scr) {
-    (void)x;      // the im2col of x is still in `col` (written by conv_bn_fwd of the same pass)
+    // im2col route: the im2col of x is still in `col` (written by conv_bn_fwd of the same pass); implicit route (wp): x itself
     const float* wt = params + h->off(pfx + ".0.conv.weight");
     const int64_t rows = (int64_t)B * Tn, KC = (int64_t)K * Ci;
     MSA_TRY(k_bn_act_drop_bwd(dout, y, bn_mean, bn_invstd, params + h->off(pfx + ".1.weight"), params + h->off(pfx + ".1.bias"),
                               mask, 2.0f, act, dy, grads + h->off(pfx + ".1.weight"), grads + h->off(pfx + ".1.bias"), scr, rows,
                               Co, gs, acc, red_scr, st));
     MSA_TRY(k_colsum(dy, rows, Co, Co, grads + h->off(pfx + ".0.conv.bias"), gs, acc, nullptr, red_scr, st));
+    if (wp != nullptr) {
+        const bool tf32 = h->cfg.gemm_tf32 >= 2 || (h->cfg.gemm_tf32 == 1 && h->in_bwd);
+        MSA_TRY(conv_tc_dw(dy, x, B, Tn, Co, Ci, K, gs, acc, grads + h->off(pfx + ".0.conv.weight"), tf32 ? 2 : 0, st));
+        if (need_dx) {
+            float* sc = (h->gemm_scratch && conv_tc_scratch_floats(B, Tn, Co, Ci, K) <= h->gemm_scratch_floats) ? h->gemm_scratch : nullptr;
+            MSA_TRY(conv_tc_dx(dy, B, Tn, Co, wp, Ci, K, dx, tf32 ? 2 : 0, sc, st));
+        }
+        return 0;
+    }
     // dW = dy^T . col lands in the parameter layout [Co][Ci][K] directly (scaled / accumulated by the GEMM itself)
     MSA_TRY(gemm(h, true, false, Co, KC, rows, gs, dy, Co, col, KC, acc ? 1.f : 0.f, grads + h->off(pfx + ".0.conv.weight"), KC));
     if (need_dx) {
         MSA_TRY(gemm(h, false, false, rows, KC, Co, 1.f, dy, Co, wt, KC, 0.f, dcol, KC));
         MSA_TRY(k_col2im(dcol, dx, B, Tn, Ci, K, st));
+    }
+    return 0;
+}
+
+// Wp[k][co][ci] copies of every encoder / postnet conv weight of one task, eight layers per launch
+static int conv_repack_all(msa_handle* h, const Dims& d, const Ws& w, const float* params, cudaStream_t st) {
+    std::vector<const float*> src;
+    std::vector<float*> dst;
+    std::vector<int> co, ci, k;
+    for (int i = 0; i < d.nEnc; ++i) {
+        src.push_back(params + h->off("encoder.convolutions." + std::to_string(i) + ".0.conv.weight"));
+        dst.push_back(w.enc_wp + (int64_t)i * d.Kc * d.C * d.C);
+        co.push_back(d.C); ci.push_back(d.C); k.push_back(d.Kc);
+    }
+    for (int i = 0; i < d.nPost; ++i) {
+        src.push_back(params + h->off("postnet.convolutions." + std::to_string(i) + ".0.conv.weight"));
+        dst.push_back(w.post_wp + (int64_t)i * d.Kp * d.Cmax * d.Cmax);
+        co.push_back(i == d.nPost - 1 ? d.M : d.Cp); ci.push_back(i == 0 ? d.M : d.Cp); k.push_back(d.Kp);
+    }
+    for (size_t i0 = 0; i0 < src.size(); i0 += 8) {
+        const int n = (int)std::min<size_t>(8, src.size() - i0);
+        MSA_TRY(conv_tc_repack(n, src.data() + i0, dst.data() + i0, co.data() + i0, ci.data() + i0, k.data() + i0, st));
     }
     return 0;
 }
@@ -475,6 +536,12 @@ int msa_create(const msa_config* cfg, int device, msa_handle** out) {
         h->tc_mode = atoi(e);
         h->tc_enabled = h->tc_mode != 0;
         if (h->tc_mode == 1) h->tc_min = 0;
+    }
+    {
+        const msa_config& c = h->cfg;
+        const bool env_on = !(getenv("MSA_CONV_TC") && atoi(getenv("MSA_CONV_TC")) == 0);
+        h->conv_tc = env_on && h->tc_enabled && c.gemm_tf32 >= 1 && c.enc_dim % 4 == 0 && c.post_dim % 4 == 0 && c.n_mel % 4 == 0 &&
+                     (c.enc_kernel & 1) && (c.post_kernel & 1) && c.enc_kernel <= 15 && c.post_kernel <= 15;
     }
     if (const char* e = getenv("MSA_GEMM_TC_MIN")) h->tc_min = atoll(e);
     if (const char* e = getenv("MSA_GEMM_TC_MIN_BWD")) h->tc_min_bwd = atoll(e);
@@ -579,7 +646,7 @@ int msa_masks_generate(msa_handle* h, uint8_t* masks, int B, int T, int L, uint6
 
 size_t msa_workspace_bytes(const msa_handle* h, int B, int T, int L) {
     if (!h || B <= 0 || T <= 0 || L <= 0) return 0;
-    return ws_layout(make_dims(h->cfg, B, T, L), nullptr).total_bytes;
+    return ws_layout(make_dims_h(h, B, T, L), nullptr).total_bytes;
 }
 
 }  // extern "C"
@@ -696,7 +763,7 @@ struct StageFork {
 static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride, const float* const* params_g, const TaskIO* ios, int B, int T,
                               int L, cudaStream_t st) {
     MSA_TRY(train_check(h));
-    const Dims d = make_dims(h->cfg, B, T, L);
+    const Dims d = make_dims_h(h, B, T, L);
     std::vector<Ws> W;
     for (int g = 0; g < G; ++g) W.push_back(ws_layout(d, wsp + (size_t)g * ws_stride));
     MSA_CUDA(cudaSetDevice(h->device));
@@ -742,13 +809,15 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
         } else {
             MSA_TRY(k_embedding_fwd(P("speaker_embedder.weight"), io.spk_ids, w.spk_vec, B, d.Ds, c.num_speakers, st));
         }
+        if (d.conv_tc) MSA_TRY(conv_repack_all(h, d, w, params, st));      // tap-major copies of this task's conv weights (forward + backward)
         // encoder (tacotron2nv.py:88, encoder.py:35-52)
         MSA_TRY(k_embedding_fwd(P("embedding.weight"), io.tokens, w.enc_x, (int)d.BL, d.C, c.n_symbols, st));
         const int64_t ex = d.BL * d.C;
         for (int i = 0; i < d.nEnc; ++i) {
             float* run = io.bn_stats ? io.bn_stats + h->bn_offs[i] : nullptr;
             MSA_TRY(conv_bn_fwd(h, st, params, "encoder.convolutions." + std::to_string(i), w.enc_x + i * ex, w.enc_y + i * ex,
-                                w.enc_x + (i + 1) * ex, w.enc_col + i * d.BL * d.Kc * d.C,
+                                w.enc_x + (i + 1) * ex, d.conv_tc ? nullptr : w.enc_col + i * d.BL * d.Kc * d.C,
+                                d.conv_tc ? w.enc_wp + (int64_t)i * d.Kc * d.C * d.C : nullptr, w.conv_stats,
                                 w.enc_bn + i * 2 * d.C, w.enc_bn + i * 2 * d.C + d.C, run, B, L, d.C, d.C, d.Kc, 1, mk(i), w.red_scr));
         }
         MSA_TRY(k_transpose01(w.enc_x + d.nEnc * ex, w.x3_tm, B, L, d.C, st));
@@ -961,7 +1030,8 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
             const int ci = i == 0 ? d.M : d.Cp, co = i == d.nPost - 1 ? d.M : d.Cp;
             float* run = io.bn_stats ? io.bn_stats + h->bn_offs[d.nEnc + i] : nullptr;
             MSA_TRY(conv_bn_fwd(h, st, params, "postnet.convolutions." + std::to_string(i), w.post_x + i * px, w.post_y + i * px,
-                                w.post_x + (i + 1) * px, w.post_col + i * d.BT * d.Kp * d.Cmax,
+                                w.post_x + (i + 1) * px, d.conv_tc ? nullptr : w.post_col + i * d.BT * d.Kp * d.Cmax,
+                                d.conv_tc ? w.post_wp + (int64_t)i * d.Kp * d.Cmax * d.Cmax : nullptr, w.conv_stats,
                                 w.post_bn + i * 2 * d.Cmax, w.post_bn + i * 2 * d.Cmax + d.Cmax, run, B, T, ci, co, d.Kp,
                                 i < d.nPost - 1 ? 2 : 0, mk(iPost + i), w.red_scr));
         }
@@ -1001,7 +1071,7 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
     MSA_CHECK(h && wsp && params && tokens && token_lengths && mels && mel_lengths && masks, MSA_E_ARG, "msa_train_forward: null argument");
     MSA_CHECK(B >= 1 && T >= 1 && L >= 1, MSA_E_ARG, "msa_train_forward: bad dims B=%d T=%d L=%d", B, T, L);
     MSA_CHECK(h->cfg.spk_mode == 2 ? speaker_ids != nullptr : speaker_vecs != nullptr, MSA_E_ARG, "msa_train_forward: speaker input missing");
-    const size_t need = ws_layout(make_dims(h->cfg, B, T, L), nullptr).total_bytes;
+    const size_t need = ws_layout(make_dims_h(h, B, T, L), nullptr).total_bytes;
     MSA_CHECK(ws_bytes >= need, MSA_E_WORKSPACE, "msa_train_forward: workspace %zu < %zu bytes", ws_bytes, need);
     MSA_CHECK(((uintptr_t)wsp & 255) == 0, MSA_E_ARG, "msa_train_forward: workspace must be 256-byte aligned");
     TaskIO io{bn_stats, tokens, token_lengths, mel_lengths, speaker_ids, mels, speaker_vecs, stop_targets, masks,
@@ -1011,7 +1081,7 @@ int msa_train_forward(msa_handle* h, void* wsp, size_t ws_bytes, const float* pa
 
 size_t msa_group_workspace_bytes(const msa_handle* h, int G, int B, int T, int L) {
     if (!h || G < 1 || G > kGroupMax || B <= 0 || T <= 0 || L <= 0) return 0;
-    return (size_t)G * ((ws_layout(make_dims(h->cfg, B, T, L), nullptr).total_bytes + 255) / 256 * 256);
+    return (size_t)G * ((ws_layout(make_dims_h(h, B, T, L), nullptr).total_bytes + 255) / 256 * 256);
 }
 
 int msa_train_forward_group(msa_handle* h, int G, void* wsp, size_t ws_bytes, const float* const* params, float* const* bn_stats,
@@ -1166,8 +1236,8 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* const* par
             const int ci = i == 0 ? d.M : d.Cp, co = i == d.nPost - 1 ? d.M : d.Cp;
             float* dx = pingpong[i & 1];
             MSA_TRY(conv_bn_bwd(h, st, params, grads, gs, acc, "postnet.convolutions." + std::to_string(i), w.post_x + i * px,
-                                w.post_y + i * px, dcur, dx, w.bdy, w.post_col + i * d.BT * d.Kp * d.Cmax,
-                                w.bdcol, w.bn_scr,
+                                w.post_y + i * px, dcur, dx, w.bdy, d.conv_tc ? nullptr : w.post_col + i * d.BT * d.Kp * d.Cmax,
+                                d.conv_tc ? w.post_wp + (int64_t)i * d.Kp * d.Cmax * d.Cmax : nullptr, w.bdcol, w.bn_scr,
                                 w.post_bn + i * 2 * d.Cmax, w.post_bn + i * 2 * d.Cmax + d.Cmax, B, T, ci, co, d.Kp,
                                 i < d.nPost - 1 ? 2 : 0, mk(iPost + i), true, w.red_scr));
             dcur = dx;
@@ -1470,8 +1540,8 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* const* par
         for (int i = d.nEnc - 1; i >= 0; --i) {
             float* dx = epp[i & 1];
             MSA_TRY(conv_bn_bwd(h, st, params, grads, gs, acc, "encoder.convolutions." + std::to_string(i), w.enc_x + i * ex,
-                                w.enc_y + i * ex, dcur, dx, w.edy, w.enc_col + i * d.BL * d.Kc * d.C,
-                                w.edcol, w.bn_scr, w.enc_bn + i * 2 * d.C, w.enc_bn + i * 2 * d.C + d.C, B, L, d.C, d.C, d.Kc, 1, mk(i),
+                                w.enc_y + i * ex, dcur, dx, w.edy, d.conv_tc ? nullptr : w.enc_col + i * d.BL * d.Kc * d.C,
+                                d.conv_tc ? w.enc_wp + (int64_t)i * d.Kc * d.C * d.C : nullptr, w.edcol, w.bn_scr, w.enc_bn + i * 2 * d.C, w.enc_bn + i * 2 * d.C + d.C, B, L, d.C, d.C, d.Kc, 1, mk(i),
                                 true, w.red_scr));
             dcur = dx;
         }
