@@ -27,6 +27,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -34,7 +35,9 @@
 namespace msa {
 
 constexpr int kTcBM = 128, kTcBN = 128, kTcBK = 32;        // CTA tile; BK floats = one 128-byte swizzle row
-constexpr int kTcStages = 3;
+constexpr int kTcStages = 3;                                // 3xTF32: four 16 KB tiles per stage
+constexpr int kTcStagesPlain = 6;                           // single-product modes: two tiles per stage, twice the depth (the
+                                                            // round-to-nearest pass adds a hop between TMA and MMA)
 constexpr int kTcTileBytes = kTcBM * kTcBK * 4;             // 16 KB per operand tile
 constexpr int kTcThreads = 320;                             // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-9 lo-tile converters, 2-5 epilogue
 constexpr int kTcConv = kTcThreads - 64;                    // converter threads
@@ -108,7 +111,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 struct TcSmem {
-    uint64_t full[kTcStages], conv[kTcStages], empty[kTcStages], tmem_full;
+    uint64_t full[kTcStagesPlain], conv[kTcStagesPlain], empty[kTcStagesPlain], tmem_full;
     uint32_t tmem_base;
 };
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -146,9 +149,10 @@ k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte aligned operand tiles (swizzle atom = 8 rows x 128 B), then the barriers
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    constexpr bool kSplit = kMode == 0, kRn = kMode == 2;
+    constexpr bool kSplit = kMode == 0, kRn = kMode == 2 || kMode == 3, kRnBonly = kMode == 3;
     constexpr int kOps = kSplit ? 4 : 2;
-    TcSmem* sb = reinterpret_cast<TcSmem*>(tiles + (size_t)kTcStages * kOps * kTcTileBytes);
+    constexpr int kSt = kSplit ? kTcStages : kTcStagesPlain;
+    TcSmem* sb = reinterpret_cast<TcSmem*>(tiles + (size_t)kSt * kOps * kTcTileBytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * kTcBM, n0 = blockIdx.y * kTcBN;
     const int num_kb = (K + kTcBK - 1) / kTcBK;
@@ -164,7 +168,7 @@ k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kTcStages; ++s) { mbar_init(&sb->full[s], 1); mbar_init(&sb->conv[s], kTcConv); mbar_init(&sb->empty[s], 1); }
+        for (int s = 0; s < kSt; ++s) { mbar_init(&sb->full[s], 1); mbar_init(&sb->conv[s], kTcConv); mbar_init(&sb->empty[s], 1); }
         mbar_init(&sb->tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -176,12 +180,16 @@ k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_acc = sb->tmem_base;
+    // programmatic dependent launch: everything above (barriers, TMEM) overlapped the tail of the previous kernel of the stream; its
+    // memory is visible after the wait.  Our own successor may start its prologue as soon as every CTA of this grid got here.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % kTcStages, it = i / kTcStages;
+                const int s = i % kSt, it = i / kSt;
                 mbar_wait(&sb->empty[s], (it & 1) ^ 1);                       // slot free (first pass: passes immediately)
                 mbar_expect_tx(&sb->full[s], 2 * kTcTileBytes);
                 uint8_t* st = tiles + (size_t)s * kOps * kTcTileBytes;
@@ -212,7 +220,7 @@ k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % kTcStages, it = i / kTcStages;
+                const int s = i % kSt, it = i / kSt;
                 mbar_wait((kSplit || kRn) ? &sb->conv[s] : &sb->full[s], it & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = smem_u32(tiles + (size_t)s * kOps * kTcTileBytes);
@@ -242,7 +250,7 @@ k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             // ===== lo tiles: [A | B] (32 KB, as TMA swizzled them) -> [A_lo | B_lo] at the same positions 32 KB further up =====
             const int ct = threadIdx.x - 64;                                   // 0 .. kTcConv-1
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % kTcStages, it = i / kTcStages;
+                const int s = i % kSt, it = i / kSt;
                 mbar_wait(&sb->full[s], it & 1);
                 const float4* src = reinterpret_cast<const float4*>(tiles + (size_t)s * kOps * kTcTileBytes);
                 float4* dst = reinterpret_cast<float4*>(tiles + (size_t)s * kOps * kTcTileBytes + 2 * kTcTileBytes);
@@ -257,13 +265,13 @@ k_gemm_tf32_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
         }
         if (kRn) {
-            // ===== both tiles in place: fp32 -> nearest TF32 value =====
+            // ===== both tiles (mode 3: the B tile only -- A holds TF32-exact values already) in place: fp32 -> nearest TF32 value =====
             const int ct = threadIdx.x - 64;
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % kTcStages, it = i / kTcStages;
+                const int s = i % kSt, it = i / kSt;
                 mbar_wait(&sb->full[s], it & 1);
-                float4* t4 = reinterpret_cast<float4*>(tiles + (size_t)s * kOps * kTcTileBytes);
-                constexpr int kPer = 2 * kTcTileBytes / 16 / kTcConv;
+                float4* t4 = reinterpret_cast<float4*>(tiles + (size_t)s * kOps * kTcTileBytes + (kRnBonly ? kTcTileBytes : 0));
+                constexpr int kPer = (kRnBonly ? 1 : 2) * kTcTileBytes / 16 / kTcConv;
                 float4 v[kPer];
 #pragma unroll
                 for (int j = 0; j < kPer; ++j) v[j] = t4[ct + j * kTcConv];
@@ -427,18 +435,26 @@ struct RepackTab {
     float* dst[8];
     int co[8], ci[8], k[8];
 };
-__global__ void ker_conv_repack(RepackTab tab) {
+// block = (output channel co, chunk of 256 input channels): the chunk's [ci][k] run is contiguous in W (coalesced reads into shared
+// memory), every tap's [ci] run is contiguous in Wp (coalesced writes)
+constexpr int kRepackCi = 256, kRepackKmax = 15;
+__global__ void __launch_bounds__(256) ker_conv_repack(RepackTab tab) {
+    __shared__ float sh[kRepackCi * kRepackKmax];
     const int l = blockIdx.y;
     const float* __restrict__ src = tab.src[l];
     float* __restrict__ dst = tab.dst[l];
     const int Co = tab.co[l], Ci = tab.ci[l], K = tab.k[l];
-    const int64_t n = (int64_t)Co * Ci * K;
-    // thread = one destination element: reads are K-strided (served from L1 / L2: a warp touches 32 * K consecutive floats), writes coalesced
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int ci = (int)(i % Ci);
-        const int64_t t = i / Ci;
-        const int co = (int)(t % Co), k = (int)(t / Co);
-        dst[i] = src[((int64_t)co * Ci + ci) * K + k];
+    const int chunks = (Ci + kRepackCi - 1) / kRepackCi;
+    for (int job = blockIdx.x; job < Co * chunks; job += gridDim.x) {
+        const int co = job / chunks, ci0 = (job - co * chunks) * kRepackCi, nci = min(kRepackCi, Ci - ci0);
+        const float* s0 = src + ((int64_t)co * Ci + ci0) * K;
+        for (int i = threadIdx.x; i < nci * K; i += blockDim.x) sh[i] = s0[i];
+        __syncthreads();
+        for (int i = threadIdx.x; i < nci * K; i += blockDim.x) {
+            const int k = i / nci, ci = i - k * nci;
+            dst[((int64_t)k * Co + co) * Ci + ci0 + ci] = sh[ci * K + k];
+        }
+        __syncthreads();
     }
 }
 
@@ -512,13 +528,27 @@ int conv_tc_stat_slabs(int B, int Tn, int Ci, int Co, int K, bool have_scratch) 
     return splits > 1 ? (B * Tn + 31) / 32 : B * ((Tn + kTcBM - 1) / kTcBM) * 4;
 }
 
+static bool tc_pdl() {
+    static const bool on = !(getenv("MSA_GEMM_PDL") && atoi(getenv("MSA_GEMM_PDL")) == 0);
+    return on;
+}
 template <int kMode>
 static int launch_tc(dim3 grid, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap& mB, float* C, int ldc, int M, int N, int K, float alpha,
                      float beta, float* partial, int per, const float* bias1, const float* bias2, int amn, int bmn, const TcConv& cv, float* stats) {
-    const size_t smem = (size_t)kTcStages * (kMode == 0 ? 4 : 2) * kTcTileBytes + sizeof(TcSmem) + 1024;
+    const size_t smem = (size_t)(kMode == 0 ? kTcStages * 4 : kTcStagesPlain * 2) * kTcTileBytes + sizeof(TcSmem) + 1024;
     static bool attr = false;
     if (!attr) { MSA_CUDA(cudaFuncSetAttribute(k_gemm_tf32_nt<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    k_gemm_tf32_nt<kMode><<<grid, kTcThreads, smem, st>>>(mA, mB, C, ldc, M, N, K, alpha, beta, partial, per, bias1, bias2, amn, bmn, cv, stats);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = tc_pdl() ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    MSA_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tf32_nt<kMode>, mA, mB, C, ldc, M, N, K, alpha, beta, partial, per, bias1, bias2, amn, bmn, cv, stats));
     MSA_LAUNCH_CHECK();
     return 0;
 }
@@ -537,6 +567,7 @@ int conv_tc_fwd(const float* x, int B, int Tn, int Ci, const float* wp, int Co, 
     const dim3 grid((unsigned)(B * tilesT), (unsigned)((Co + kTcBN - 1) / kTcBN), (unsigned)splits);
     if (mode == 0) MSA_TRY(launch_tc<0>(grid, st, mA, mB, y, Co, M, Co, num_kb * kTcBK, 1.f, 0.f, partial, per, bias, nullptr, 0, 0, cv, stats));
     else if (mode == 2) MSA_TRY(launch_tc<2>(grid, st, mA, mB, y, Co, M, Co, num_kb * kTcBK, 1.f, 0.f, partial, per, bias, nullptr, 0, 0, cv, stats));
+    else if (mode == 3) MSA_TRY(launch_tc<3>(grid, st, mA, mB, y, Co, M, Co, num_kb * kTcBK, 1.f, 0.f, partial, per, bias, nullptr, 0, 0, cv, stats));
     else MSA_TRY(launch_tc<1>(grid, st, mA, mB, y, Co, M, Co, num_kb * kTcBK, 1.f, 0.f, partial, per, bias, nullptr, 0, 0, cv, stats));
     if (splits > 1) {
         if (stats != nullptr) {
@@ -562,6 +593,7 @@ int conv_tc_dx(const float* dy, int B, int Tn, int Co, const float* wp, int Ci, 
     const dim3 grid((unsigned)(B * tilesT), (unsigned)((Ci + kTcBN - 1) / kTcBN), (unsigned)splits);
     if (mode == 0) MSA_TRY(launch_tc<0>(grid, st, mA, mB, dx, Ci, M, Ci, num_kb * kTcBK, 1.f, 0.f, partial, per, nullptr, nullptr, 0, 1, cv, nullptr));
     else if (mode == 2) MSA_TRY(launch_tc<2>(grid, st, mA, mB, dx, Ci, M, Ci, num_kb * kTcBK, 1.f, 0.f, partial, per, nullptr, nullptr, 0, 1, cv, nullptr));
+    else if (mode == 3) MSA_TRY(launch_tc<3>(grid, st, mA, mB, dx, Ci, M, Ci, num_kb * kTcBK, 1.f, 0.f, partial, per, nullptr, nullptr, 0, 1, cv, nullptr));
     else MSA_TRY(launch_tc<1>(grid, st, mA, mB, dx, Ci, M, Ci, num_kb * kTcBK, 1.f, 0.f, partial, per, nullptr, nullptr, 0, 1, cv, nullptr));
     if (splits > 1) {
         const int64_t n = (int64_t)M * Ci;
@@ -582,6 +614,7 @@ int conv_tc_dw(const float* dy, const float* x, int B, int Tn, int Co, int Ci, i
     const float beta = accumulate ? 1.f : 0.f;
     if (mode == 0) MSA_TRY(launch_tc<0>(grid, st, mA, mB, dw, Ci * K, Co, Ci, num_kb * kTcBK, scale, beta, nullptr, num_kb, nullptr, nullptr, 1, 1, cv, nullptr));
     else if (mode == 2) MSA_TRY(launch_tc<2>(grid, st, mA, mB, dw, Ci * K, Co, Ci, num_kb * kTcBK, scale, beta, nullptr, num_kb, nullptr, nullptr, 1, 1, cv, nullptr));
+    else if (mode == 3) MSA_TRY(launch_tc<3>(grid, st, mA, mB, dw, Ci * K, Co, Ci, num_kb * kTcBK, scale, beta, nullptr, num_kb, nullptr, nullptr, 1, 1, cv, nullptr));
     else MSA_TRY(launch_tc<1>(grid, st, mA, mB, dw, Ci * K, Co, Ci, num_kb * kTcBK, scale, beta, nullptr, num_kb, nullptr, nullptr, 1, 1, cv, nullptr));
     return 0;
 }
@@ -592,9 +625,10 @@ int conv_tc_repack(int n, const float* const* src, float* const* dst, const int*
     int64_t big = 0;
     for (int i = 0; i < n; ++i) {
         tab.src[i] = src[i]; tab.dst[i] = dst[i]; tab.co[i] = co[i]; tab.ci[i] = ci[i]; tab.k[i] = k[i];
-        big = std::max<int64_t>(big, (int64_t)co[i] * ci[i] * k[i]);
+        MSA_CHECK(k[i] <= kRepackKmax, MSA_E_UNSUPPORTED, "conv_tc_repack: %d taps", k[i]);
+        big = std::max<int64_t>(big, (int64_t)co[i] * ((ci[i] + kRepackCi - 1) / kRepackCi));
     }
-    ker_conv_repack<<<dim3((unsigned)std::min<int64_t>((big + 255) / 256, 148 * 4), (unsigned)n), 256, 0, st>>>(tab);
+    ker_conv_repack<<<dim3((unsigned)std::min<int64_t>(big, 148 * 2), (unsigned)n), 256, 0, st>>>(tab);
     MSA_LAUNCH_CHECK();
     return 0;
 }
@@ -620,7 +654,8 @@ size_t gemm_tc_scratch_floats(int64_t M, int64_t N, int64_t K) {
 }
 
 // mode 0: 3xTF32 (fp32-accurate); mode 1: single TF32 product (operands truncated by the tensor core); mode 2: single TF32 product
-// with round-to-nearest operands (cuBLAS's TF32 accuracy).  `scratch` (gemm_tc_scratch_floats(M, N, K) floats, 16-byte
+// with round-to-nearest operands (cuBLAS's TF32 accuracy); mode 3: the same when A already holds TF32-exact values (only B is rounded
+// in shared memory: the kernel is bound by shared-memory traffic, the rounding pass of a tile costs as much as its TMA write + MMA read).  `scratch` (gemm_tc_scratch_floats(M, N, K) floats, 16-byte
 // aligned) holds the partial tiles of a K split; with scratch == nullptr the K range is not split.
 int gemm_tc_nt(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
                float* C, int64_t ldc, int mode, float* scratch, cudaStream_t st, const float* bias1, const float* bias2) {
@@ -645,6 +680,7 @@ int gemm_tc(bool ta, bool tb, int64_t M, int64_t N, int64_t K, float alpha, cons
     const TcConv cv{0, 0, 0, 0, 0, 0, 0, 0, 1};
     if (mode == 0) MSA_TRY(launch_tc<0>(grid, st, mA, mB, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta, partial, per, bias1, bias2, amn, bmn, cv, nullptr));
     else if (mode == 2) MSA_TRY(launch_tc<2>(grid, st, mA, mB, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta, partial, per, bias1, bias2, amn, bmn, cv, nullptr));
+    else if (mode == 3) MSA_TRY(launch_tc<3>(grid, st, mA, mB, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta, partial, per, bias1, bias2, amn, bmn, cv, nullptr));
     else MSA_TRY(launch_tc<1>(grid, st, mA, mB, C, (int)ldc, (int)M, (int)N, (int)K, alpha, beta, partial, per, bias1, bias2, amn, bmn, cv, nullptr));
     if (splits > 1) {
         const int64_t n = M * N;

@@ -198,7 +198,9 @@ int k_fill_rows(float* y, const float* b1, const float* b2, int64_t rows, int N,
 // kRedChunks x kRedCols floats of partials; shared by the column reductions of one stream (they run back to back).
 constexpr int kRedTickets = 256, kRedChunks = 16, kRedCols = 8192;
 constexpr int64_t kRedScrFloats = kRedTickets + (int64_t)kRedChunks * kRedCols;
-int k_colsum(const float* x, int64_t rows, int N, int ld, float* out, float scale, int accumulate, float* out2, float* red_scr, cudaStream_t st);
+// x_round (optional, x itself or another [rows][ld] array): x written back rounded to the nearest TF32 value (the sum uses the unrounded values)
+int k_colsum(const float* x, int64_t rows, int N, int ld, float* out, float scale, int accumulate, float* out2, float* red_scr, cudaStream_t st,
+             float* x_round = nullptr);
 int k_bn_stats(const float* y, int64_t rows, int C, float* mean, float* invstd, float* running, int Cpad, float* red_scr, cudaStream_t st);
 // BatchNorm (train) from the slab statistics of the conv epilogue ([nslab][3][C]: count, mean, M2) + activation + dropout in ONE
 // kernel: every block merges the slabs of its 32 channels (Chan's update, slab order), block row 0 also stores mean / invstd / running

@@ -123,8 +123,10 @@ __device__ __forceinline__ void red_chunk(int64_t rows, int64_t& r0, int64_t& r1
     r1 = r0 + rc < rows ? r0 + rc : rows;
 }
 // out[n] = sum_r x[r*ld + n]
-__global__ void ker_colsum(const float* __restrict__ x, int64_t rows, int N, int ld, float* out, float scale, int accumulate, float* out2,
-                           float* part, unsigned int* ticket) {
+// xr (optional, may alias nothing else): every element read is written back rounded to the nearest TF32 value -- the sum is taken
+// over the unrounded values, the consumers of x after this kernel are single-TF32 tensor-core products (which would truncate)
+__global__ void ker_colsum(const float* x, int64_t rows, int N, int ld, float* out, float scale, int accumulate, float* out2,
+                           float* part, unsigned int* ticket, float* xr) {
     __shared__ float sh[8][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int n = blockIdx.x * 32 + cx;
@@ -132,7 +134,15 @@ __global__ void ker_colsum(const float* __restrict__ x, int64_t rows, int N, int
     red_chunk(rows, r0, r1);
     float s = 0.f;
     if (n < N)
-        for (int64_t r = r0 + ry; r < r1; r += 8) s += x[r * ld + n];
+        for (int64_t r = r0 + ry; r < r1; r += 8) {
+            const float v = x[r * ld + n];
+            s += v;
+            if (xr) {
+                uint32_t q;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q) : "f"(v));
+                xr[r * ld + n] = __uint_as_float(q);
+            }
+        }
     sh[ry][cx] = s;
     __syncthreads();
     float t = 0.f;
@@ -249,18 +259,49 @@ __global__ void __launch_bounds__(256) ker_bn_slab_act_drop_fwd(const float* __r
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   const uint8_t* __restrict__ mask, float ds, int act, float* out) {
     __shared__ float m_s[32], is_s[32], g_s[32], b_s[32];
+    __shared__ float pn[8][33], pm[8][33], pq[8][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cx;
+    // slab merge in two levels, both in a fixed order: row lane ry merges the slabs [ry * per, (ry + 1) * per) (all loads issued before
+    // the first dependent update), then row lane 0 merges the eight partial triples
+    {
+        constexpr int kMaxPer = 8;
+        const int per = (nslab + 7) / 8;
+        float n = 0.f, m = 0.f, M2 = 0.f;
+        if (c < C) {
+            for (int s0 = ry * per; s0 < min(nslab, (ry + 1) * per); s0 += kMaxPer) {
+                float np[kMaxPer], mp[kMaxPer], qp[kMaxPer];
+#pragma unroll
+                for (int j = 0; j < kMaxPer; ++j) {
+                    const int sl = s0 + j;
+                    const bool ok = sl < min(nslab, (ry + 1) * per);
+                    const float* sp = slabs + (size_t)(ok ? sl : 0) * 3 * C + c;
+                    np[j] = ok ? sp[0] : 0.f;
+                    mp[j] = ok ? sp[C] : 0.f;
+                    qp[j] = ok ? sp[2 * (size_t)C] : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < kMaxPer; ++j) {
+                    if (np[j] <= 0.f) continue;
+                    const float delta = mp[j] - m, nn = n + np[j];
+                    m += delta * np[j] / nn;
+                    M2 += qp[j] + delta * delta * n * np[j] / nn;
+                    n = nn;
+                }
+            }
+        }
+        pn[ry][cx] = n; pm[ry][cx] = m; pq[ry][cx] = M2;
+    }
+    __syncthreads();
     if (ry == 0 && c < C) {
         float n = 0.f, m = 0.f, M2 = 0.f;
-        for (int sl = 0; sl < nslab; ++sl) {
-            const float* sp = slabs + (size_t)sl * 3 * C + c;
-            const float np = sp[0];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float np = pn[j][cx];
             if (np <= 0.f) continue;
-            const float mp = sp[C], qp = sp[2 * (size_t)C];
-            const float delta = mp - m, nn = n + np;
+            const float delta = pm[j][cx] - m, nn = n + np;
             m += delta * np / nn;
-            M2 += qp + delta * delta * n * np / nn;
+            M2 += pq[j][cx] + delta * delta * n * np / nn;
             n = nn;
         }
         const float var = M2 / (float)rows;
@@ -356,7 +397,8 @@ __global__ void ker_bn_bwd_apply(const float* __restrict__ dout, const float* __
         const float is = invstd[c], g = gamma[c];
         const float xh = (y[i] - mean[c]) * is;
         const float du = bn_du(dout[i], g * xh + beta[c], mask ? mask[i] : 1, mask != nullptr, ds, act);
-        dy[i] = g * is * (du - scratch[c] * inv_n - xh * scratch[C + c] * inv_n);
+        float v = g * is * (du - scratch[c] * inv_n - xh * scratch[C + c] * inv_n);
+        dy[i] = v;
     }
 }
 __global__ void ker_bn_param_grads(const float* __restrict__ scratch, float* ggamma, float* gbeta, int C, float scale, int accumulate) {
@@ -712,11 +754,12 @@ static int red_chunks(int64_t rows, int ncolgroups, const float* red_scr) {
     if (p > kRedChunks) p = kRedChunks;
     return p < 1 ? 1 : (int)p;
 }
-int k_colsum(const float* x, int64_t rows, int N, int ld, float* out, float scale, int acc, float* out2, float* red_scr, cudaStream_t st) {
+int k_colsum(const float* x, int64_t rows, int N, int ld, float* out, float scale, int acc, float* out2, float* red_scr, cudaStream_t st,
+             float* x_round) {
     MSA_CHECK(!red_scr || (cdiv(N, 32) <= kRedTickets && (int64_t)N <= kRedCols), MSA_E_ARG, "colsum: %d columns exceed the reduction scratch", N);
     const int P = red_chunks(rows, cdiv(N, 32), red_scr);
     ker_colsum<<<dim3(cdiv(N, 32), P), 256, 0, ST>>>(x, rows, N, ld, out, scale, acc, out2, red_scr ? red_scr + kRedTickets : nullptr,
-                                                     reinterpret_cast<unsigned int*>(red_scr));
+                                                     reinterpret_cast<unsigned int*>(red_scr), x_round);
     MSA_LAUNCH_CHECK();
     return 0;
 }

@@ -406,16 +406,19 @@ static int conv_bn_bwd(msa_handle* h, cudaStream_t st, const float* params, floa
     // im2col route: the im2col of x is still in `col` (written by conv_bn_fwd of the same pass); implicit route (wp): x itself
     const float* wt = params + h->off(pfx + ".0.conv.weight");
     const int64_t rows = (int64_t)B * Tn, KC = (int64_t)K * Ci;
+    const bool tf32_tc = wp != nullptr && (h->cfg.gemm_tf32 >= 2 || (h->cfg.gemm_tf32 == 1 && h->in_bwd));
     MSA_TRY(k_bn_act_drop_bwd(dout, y, bn_mean, bn_invstd, params + h->off(pfx + ".1.weight"), params + h->off(pfx + ".1.bias"),
                               mask, 2.0f, act, dy, grads + h->off(pfx + ".1.weight"), grads + h->off(pfx + ".1.bias"), scr, rows,
                               Co, gs, acc, red_scr, st));
-    MSA_TRY(k_colsum(dy, rows, Co, Co, grads + h->off(pfx + ".0.conv.bias"), gs, acc, nullptr, red_scr, st));
+    // implicit route under the TF32 policy: the bias-gradient reduction (over the unrounded dy) also stores dy back rounded to the
+    // nearest TF32 value -- its two consumers below are single-TF32 tensor-core products, which would otherwise TRUNCATE it
+    MSA_TRY(k_colsum(dy, rows, Co, Co, grads + h->off(pfx + ".0.conv.bias"), gs, acc, nullptr, red_scr, st, tf32_tc ? dy : nullptr));
     if (wp != nullptr) {
         const bool tf32 = h->cfg.gemm_tf32 >= 2 || (h->cfg.gemm_tf32 == 1 && h->in_bwd);
-        MSA_TRY(conv_tc_dw(dy, x, B, Tn, Co, Ci, K, gs, acc, grads + h->off(pfx + ".0.conv.weight"), tf32 ? 2 : 0, st));
+        MSA_TRY(conv_tc_dw(dy, x, B, Tn, Co, Ci, K, gs, acc, grads + h->off(pfx + ".0.conv.weight"), tf32 ? 3 : 0, st));
         if (need_dx) {
             float* sc = (h->gemm_scratch && conv_tc_scratch_floats(B, Tn, Co, Ci, K) <= h->gemm_scratch_floats) ? h->gemm_scratch : nullptr;
-            MSA_TRY(conv_tc_dx(dy, B, Tn, Co, wp, Ci, K, dx, tf32 ? 2 : 0, sc, st));
+            MSA_TRY(conv_tc_dx(dy, B, Tn, Co, wp, Ci, K, dx, tf32 ? 3 : 0, sc, st));
         }
         return 0;
     }

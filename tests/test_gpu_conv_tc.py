@@ -51,7 +51,7 @@ def test_conv_forward_input_gradient_weight_gradient(shape, split):
     assert torch.equal(wp, w.permute(2, 0, 1).contiguous())
     scratch = torch.empty(int(lib.msa_conv1d_scratch_floats(B, T, Ci, Co, K)) + 4, device="cuda") if split else None
     nslab = int(lib.msa_conv1d_stat_slabs(B, T, Ci, Co, K, int(split)))
-    for mode, tol in ((0, 4e-6 + 1e-8 * K * max(Ci, Co)), (1, 2e-3), (2, 8e-4)):      # 3xTF32: fp32-accurate; single TF32 truncated / rounded to nearest
+    for mode, tol in ((0, 4e-6 + 1e-8 * K * max(Ci, Co)), (1, 2e-3), (2, 8e-4), (3, 1.2e-3)):      # 3xTF32: fp32-accurate; single TF32 truncated / rounded to nearest / B rounded only (the pass feeds it a TF32-exact A)
         y = torch.full((B, T, Co), float("nan"), device="cuda")
         stats = torch.full((nslab, 3, Co), float("nan"), device="cuda")
         _lib.check(lib.msa_conv1d_fwd(P(x), B, T, Ci, P(wp), Co, K, P(b), P(y), mode, P(scratch), P(stats), _stream()), "fwd")
