@@ -336,7 +336,10 @@ static int gemm(msa_handle* h, bool ta, bool tb, int64_t M, int64_t N, int64_t K
     // tensor-core policies: 3xTF32 split where fp32 accuracy is required (forward of policy 1), single TF32 otherwise
     // (measured on B200, profiles/r01_gemm_tc_v14.txt: the kernel has ~10 us of fixed cost, so short-K / small products stay on cuBLAS)
     const long long macs = (long long)M * N * K;
-    const bool tc_size = macs >= h->tc_min && (macs >= 3 * h->tc_min || K >= 1024);
+    // fp32-accurate products (3xTF32 against cuBLAS's SIMT sgemm): measured per shape on B200 (profiles/r02_gemm_shapes.txt) the
+    // kernel also wins the small products with a long (>= 768) or a very short (<= 128) contraction
+    const bool tc_small = !tf32 && (K >= 768 || K <= 128) && macs >= 10000000LL;
+    const bool tc_size = (macs >= h->tc_min && (macs >= 3 * h->tc_min || K >= 1024)) || tc_small;
     const bool nt = !ta && tb;
     const bool own_ok = h->tc_enabled && h->cfg.gemm_tf32 >= 1 && N >= 8 && M * N >= 4096 && gemm_tc_supported(M, N, K, A, lda, Bm, ldb, Cm, ldc) &&
                         (tf32 || (h->gemm_scratch && gemm_tc_scratch_floats(M, N, K) <= h->gemm_scratch_floats));
@@ -344,6 +347,9 @@ static int gemm(msa_handle* h, bool ta, bool tb, int64_t M, int64_t N, int64_t K
     // contractions with MN-major operands (dX = dY . W, dW = dY^T . X)
     const bool route = own_ok && ((h->tc_mode == 2 && !tf32 && nt && tc_size) || (h->tc_mode == 1 && nt && tc_size) ||
                                   (h->tc_mode == 3 && (nt ? (tc_size || tf32) : macs >= h->tc_min_bwd)));
+    static const bool log_env = getenv("MSA_GEMM_LOG") != nullptr;      // development: one line per product (shape, pass half, route)
+    if (log_env) fprintf(stderr, "gemm ta=%d tb=%d M=%lld N=%lld K=%lld bwd=%d tf32=%d own=%d\n", (int)ta, (int)tb, (long long)M, (long long)N,
+                         (long long)K, (int)h->in_bwd, (int)tf32, (int)route);
     if (route)
         return gemm_tc(ta, tb, M, N, K, alpha, A, lda, Bm, ldb, beta, Cm, ldc, tf32 ? 2 : 0,
                        (h->gemm_scratch && gemm_tc_scratch_floats(M, N, K) <= h->gemm_scratch_floats) ? h->gemm_scratch : nullptr,

@@ -20,6 +20,9 @@ class MAML(MetaTrainer):
     def __init__(self, **params):
         super().__init__(**params)
         if params.get("track_higher_grads", False):
+            # maml.py:70-71.  The target is restated and pinned on the CPU (oracle.meta.maml2_task, tests/test_oracle.py); a
+            # finite-difference Hessian-vector product over the first-order kernels was measured and is NOT offered: in float32 it
+            # misses the exact meta-gradient by 20-100 % at every step size (profiles/r02_second_order_fd.txt)
             raise NotImplementedError("second-order MAML needs double-backward through the fused kernels "
                                       "(SURVEY.md 8f item 2); use track_higher_grads=False (FOMAML)")
 

@@ -79,6 +79,35 @@ def fomaml_task(P0, cfg, task, task_masks, crit, names, n_inner, inner_lr):
     return loss, g, out, P, stats
 
 
+def maml2_task(P0, cfg, task, task_masks, crit, names, n_inner, inner_lr, weight_decay=0.0):
+    """Second-order MAML task gradient d loss_test(theta_n) / d theta_0, differentiated THROUGH the inner SGD steps
+    (maml.py:44-54 with track_higher_grads=True, maml.py:70-71: autograd.grad(loss_test, fmodel.parameters(time=0))).
+    Plain double backward: the inner gradients are taken with create_graph=True and the fast weights stay in the graph."""
+    x_tr, stop_tr = unpack_batch(task["train"])
+    x_te, stop_te = unpack_batch(task["test"])
+    P_init = {k: v.detach().clone().requires_grad_(True) for k, v in P0.items()}
+    P = dict(P_init)
+    stats = M.fresh_bn_stats(P0, cfg)
+    for it in range(n_inner):
+        out = M.forward(P, cfg, x_tr["inputs"], x_tr["input_lengths"], x_tr["melspecs"], x_tr["melspec_lengths"], x_tr["speaker_vecs"],
+                        task_masks[it], stats, True)
+        loss = M.loss_fn(out, (x_tr["melspecs"], stop_tr), x_tr["melspec_lengths"], **crit)
+        g = torch.autograd.grad(loss, [P[n] for n in names], create_graph=True, allow_unused=True)
+        newP = dict(P)
+        for n, gn in zip(names, g):
+            gn = torch.zeros_like(P[n]) if gn is None else gn
+            if weight_decay != 0:
+                gn = gn + weight_decay * P[n]
+            newP[n] = P[n] - inner_lr * gn
+        P = newP
+    out = M.forward(P, cfg, x_te["inputs"], x_te["input_lengths"], x_te["melspecs"], x_te["melspec_lengths"], x_te["speaker_vecs"],
+                    task_masks[n_inner], stats, True)
+    loss = M.loss_fn(out, (x_te["melspecs"], stop_te), x_te["melspec_lengths"], **crit)
+    grads = torch.autograd.grad(loss, [P_init[n] for n in names], allow_unused=True)
+    grads = [torch.zeros_like(P_init[n]) if g is None else g for n, g in zip(names, grads)]
+    return loss.detach(), dict(zip(names, grads))
+
+
 def reptile_task(P0, cfg, task, task_masks, crit, names, n_inner, inner_lr):
     """Reptile task 'gradient' -(theta_T - theta_0) (reptile.py:42,73-77)."""
     P, stats, _ = adapt_task(P0, cfg, task, task_masks, crit, names, n_inner, inner_lr)

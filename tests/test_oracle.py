@@ -95,3 +95,37 @@ def test_infer_small(name):
     assert np.array_equal(lens.numpy(), z["mel_lengths"])          # bit-exact stop bookkeeping
     assert lens.dtype == torch.int32
     assert rel(post, z["mel_post"]) < TOL and rel(align, z["align"]) < TOL
+
+
+def test_second_order_maml_oracle_matches_a_float64_hessian_vector_difference():
+    """oracle.meta.maml2_task (maml.py:70-71, track_higher_grads=True: the test loss differentiated through the inner SGD step) against
+    an independent evaluation of the same quantity in float64: g_test - lr * H_train . g_test with the Hessian-vector product taken as a
+    central difference of first-order gradients at a relative step of 1e-7.  (The same difference in float32 is off by 20-100 % at
+    every step size -- profiles/r02_second_order_fd.txt -- which is why the CUDA path offers no finite-difference second-order mode.)"""
+    import msa_tts_b200 as pkg
+    from msa_tts_b200 import synth
+    from oracle import meta as OMeta
+    from oracle import model as OM
+    cfg = pkg.small_params()
+    crit = dict(reduction="none", pos_weight=10.0)
+    B, T, L, lr = 3, 10, 8, 0.05
+    names = OM.param_names(cfg)
+    to64 = lambda d: {k: (v.double() if v.dtype.is_floating_point else v) for k, v in d.items()}
+    P = to64(synth.init_params(cfg, 5))
+    task = {k: tuple(x.double() if hasattr(x, "dtype") and x.dtype == torch.float32 else x for x in v)
+            for k, v in synth.make_task(cfg, B, T, L, 3).items()}
+    masks = [synth.make_masks(cfg, B, T, L, 900 + i) for i in range(2)]
+    _, g2 = OMeta.maml2_task(P, cfg, task, masks, crit, names, 1, lr)
+    stats = OM.fresh_bn_stats(P, cfg)
+    _, g, _ = OMeta.loss_and_grads(P, cfg, task["train"], masks[0], stats, crit, names)
+    th1 = OMeta.sgd_step(P, g, names, lr)
+    _, v, _ = OMeta.loss_and_grads(th1, cfg, task["test"], masks[1], stats, crit, names)
+    norm = lambda d: float(torch.sqrt(sum((d[n] ** 2).sum() for n in names)))
+    eps = 1e-7 * norm(P) / norm(v)
+    gp = OMeta.loss_and_grads({n: P[n] + eps * v[n] for n in names}, cfg, task["train"], masks[0], OM.fresh_bn_stats(P, cfg), crit, names)[1]
+    gm = OMeta.loss_and_grads({n: P[n] - eps * v[n] for n in names}, cfg, task["train"], masks[0], OM.fresh_bn_stats(P, cfg), crit, names)[1]
+    fd = {n: v[n] - lr * (gp[n] - gm[n]) / (2 * eps) for n in names}
+    err = norm({n: fd[n] - g2[n] for n in names}) / norm(g2)
+    first_order_gap = norm({n: v[n] - g2[n] for n in names}) / norm(g2)
+    assert err < 1e-6, err
+    assert first_order_gap > 0.1          # the second-order term is not a rounding-level correction at this shape
