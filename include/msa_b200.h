@@ -266,6 +266,11 @@ int msa_ewc_penalty(const float* p, const float* mu, const float* fisher, int64_
                     float* out, void* stream);
 int msa_ewc_sgd_step(float* p, const float* g, const float* mu, const float* fisher, int64_t n, float lr,
                      float lam, float* partials, float* penalty_out, void* stream);
+/* The same penalty for any other optimizer (continual_ewc.py:213 builds self.optim with get_optimizer from ANY torch.optim class;
+ * 345-357: loss += importance * penalty before loss.backward()): g += 2*lam*F*(p-mu) and the penalty at p in one pass; the
+ * optimizer step (msa_flat_adam_step, msa_flat_sgd_step with momentum) follows on the completed gradient. */
+int msa_ewc_penalty_grad(const float* p, float* g, const float* mu, const float* fisher, int64_t n, float lam,
+                         float* partials, float* penalty_out, void* stream);
 
 /* ---- tensor-core GEMM building block (exported for tests / profiles) ------------------------------------------
  * C[M,N] = alpha * A[M,K] . B[N,K]^T + beta * C, row-major, both operands K-contiguous (torch.nn.functional.linear's

@@ -87,6 +87,7 @@ SIGNATURES = {
     "msa_ewc_fisher_accum": (I, [V, V, I64, F, I, V]),
     "msa_ewc_penalty": (I, [V, V, V, I64, V, V, V]),
     "msa_ewc_sgd_step": (I, [V, V, V, V, I64, F, F, V, V, V]),
+    "msa_ewc_penalty_grad": (I, [V, V, V, V, I64, F, V, V, V]),
 }
 
 _lib = None

@@ -135,8 +135,9 @@ __global__ void __launch_bounds__(kFlatThreads) k_fisher(float* f, const float* 
     }
 }
 
-// penalty partials; if g != nullptr also the fused SGD step p -= lr*(g + 2*lam*F*(p-mu))
-__global__ void __launch_bounds__(kFlatThreads) k_ewc(float* p, const float* __restrict__ g, const float* __restrict__ mu,
+// penalty partials; do_step 1: also the fused SGD step p -= lr*(g + 2*lam*F*(p-mu)); do_step 2: the penalty gradient added to g
+// (g += 2*lam*F*(p-mu), p untouched) for an optimizer whose update is not plain SGD
+__global__ void __launch_bounds__(kFlatThreads) k_ewc(float* p, float* g, const float* __restrict__ mu,
                                                     const float* __restrict__ f, int64_t n4, float lr, float lam,
                                                     float* partials, int do_step) {
     __shared__ float red[33];
@@ -145,8 +146,10 @@ __global__ void __launch_bounds__(kFlatThreads) k_ewc(float* p, const float* __r
         float4 pv = ld4(p, i), mv = ld4(mu, i), fv = ld4(f, i);
         float4 gv = do_step ? ld4(g, i) : make_float4(0, 0, 0, 0);
         FOR4(float d = C4(pv) - C4(mv); s += C4(fv) * d * d;
-             if (do_step) C4(pv) = C4(pv) - lr * (C4(gv) + 2.f * lam * C4(fv) * d);)
-        if (do_step) st4(p, i, pv);
+             if (do_step == 1) C4(pv) = C4(pv) - lr * (C4(gv) + 2.f * lam * C4(fv) * d);
+             if (do_step == 2) C4(gv) = C4(gv) + 2.f * lam * C4(fv) * d;)
+        if (do_step == 1) st4(p, i, pv);
+        if (do_step == 2) st4(g, i, gv);
     }
     s = block_sum(s, red);
     if (threadIdx.x == 0) partials[blockIdx.x] = s;
@@ -259,7 +262,19 @@ int msa_ewc_sgd_step(float* p, const float* g, const float* mu, const float* fis
     MSA_TRY(check_flat(p, n)); MSA_TRY(check_flat(g, n)); MSA_TRY(check_flat(mu, n)); MSA_TRY(check_flat(fisher, n));
     MSA_CHECK(partials && penalty_out, MSA_E_ARG, "msa_ewc_sgd_step: null scratch/out");
     int grid = flat_grid(n / 4);
-    k_ewc<<<grid, kFlatThreads, 0, (cudaStream_t)stream>>>(p, g, mu, fisher, n / 4, lr, lam, partials, 1);
+    k_ewc<<<grid, kFlatThreads, 0, (cudaStream_t)stream>>>(p, const_cast<float*>(g), mu, fisher, n / 4, lr, lam, partials, 1);
+    MSA_LAUNCH_CHECK();
+    k_final_sum<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, grid, penalty_out);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+
+int msa_ewc_penalty_grad(const float* p, float* g, const float* mu, const float* fisher, int64_t n, float lam, float* partials,
+                         float* penalty_out, void* stream) {
+    MSA_TRY(check_flat(p, n)); MSA_TRY(check_flat(g, n)); MSA_TRY(check_flat(mu, n)); MSA_TRY(check_flat(fisher, n));
+    MSA_CHECK(partials && penalty_out, MSA_E_ARG, "msa_ewc_penalty_grad: null scratch/out");
+    int grid = flat_grid(n / 4);
+    k_ewc<<<grid, kFlatThreads, 0, (cudaStream_t)stream>>>(const_cast<float*>(p), g, mu, fisher, n / 4, 0.f, lam, partials, 2);
     MSA_LAUNCH_CHECK();
     k_final_sum<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, grid, penalty_out);
     MSA_LAUNCH_CHECK();

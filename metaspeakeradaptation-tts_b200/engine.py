@@ -545,6 +545,14 @@ class Engine:
         self.launches += 2
         return out
 
+    def ewc_penalty_grad(self, p, g, mu, fisher, lam: float) -> torch.Tensor:
+        """g += 2*lam*F*(p - mu) in place; returns the penalty sum F (p - mu)^2 at p (one pass over the four buffers)."""
+        out = torch.empty(1, device=self.device)
+        _lib.check(self.lib.msa_ewc_penalty_grad(_ptr(p), _ptr(g), _ptr(mu), _ptr(fisher), p.numel(), lam, _ptr(self._partials),
+                                                 _ptr(out), _stream()), "msa_ewc_penalty_grad")
+        self.launches += 2
+        return out
+
     def ewc_sgd_step(self, p, g, mu, fisher, lr: float, lam: float) -> torch.Tensor:
         out = torch.empty(1, device=self.device)
         _lib.check(self.lib.msa_ewc_sgd_step(_ptr(p), _ptr(g), _ptr(mu), _ptr(fisher), p.numel(), lr, lam, _ptr(self._partials),

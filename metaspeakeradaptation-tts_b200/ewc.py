@@ -37,6 +37,12 @@ class EWC:
         m = model or self.model
         return m.engine.ewc_penalty(m.flat, self.means, self.fisher).reshape(())
 
+    def add_penalty_grad(self, grads_flat: torch.Tensor, importance: float) -> torch.Tensor:
+        """grads += d(importance * penalty)/d theta = 2*importance*F*(theta - mu) (what ``loss += ewc_importance * penalty`` adds to
+        ``loss.backward()``, continual_ewc.py:345-355) for optimizers other than plain SGD; returns the penalty (fused, one pass)."""
+        m = self.model
+        return m.engine.ewc_penalty_grad(m.flat, grads_flat, self.means, self.fisher, importance).reshape(())
+
     def sgd_step(self, grads_flat: torch.Tensor, lr: float, importance: float) -> torch.Tensor:
         """theta -= lr * (g + 2*importance*F*(theta - mu)); returns the penalty at the OLD theta (fused, one pass)."""
         m = self.model

@@ -294,3 +294,56 @@ def test_few_shot_adaptation_then_infer_like_infer_py():
     assert not unexpected and not missing
     post2, lens2, _ = spk_model.infer(q_inp, q_len, q_spk, prenet_masks=pm)
     assert torch.equal(post2, post) and torch.equal(lens2, lens)
+
+
+@pytest.mark.parametrize("optim", [{"optimizer_name": "Adam", "optim_params": {"lr": "1e-3", "betas": "(0.9, 0.98)", "weight_decay": "1e-6"}},
+                                   {"optimizer_name": "SGD", "optim_params": {"lr": "0.01", "momentum": "0.9", "nesterov": "True"}}])
+def test_ewc_training_steps_with_any_torch_optimizer_like_continual_ewc_py(optim):
+    """continual_ewc.py:213 builds ``self.optim = get_optimizer(self.model, **params["optim"])`` from ANY torch.optim class and
+    345-357 adds ``ewc_importance * penalty`` to the loss before ``backward()``: two training steps through ``train_step`` (penalty
+    gradient fused into one pass over the flat buffers, then the Adam / momentum-SGD kernels) against the oracle's gradients +
+    the penalty gradient stepped by the real torch.optim class."""
+    from msa_tts_b200.continual import train_step
+    from msa_tts_b200.helpers import optimizer_hparams
+    cfg = pkg.small_params()
+    B, T, L = 3, 9, 8
+    P = synth.init_params(cfg, 7)
+    names = OM.param_names(cfg)
+    buf = [synth.make_batch(cfg, B, T, L, 400 + i) for i in range(2)]
+    bmasks = [synth.make_masks(cfg, B, T, L, 500 + i) for i in range(2)]
+    F_ = OMeta.ewc_fisher(P, cfg, buf, bmasks, CRIT, names)
+    model = _model(cfg, P)
+    ewc = pkg.EWC(model, buf, masks=bmasks)
+    g = torch.Generator().manual_seed(1)
+    P2 = {n: v + 0.01 * torch.randn(v.shape, generator=g) for n, v in P.items()}
+    model.load_state_dict(P2, strict=False)
+    lam = 50.0
+    h = optimizer_hparams(optim)
+    kw = {k: v for k, v in h.items() if k != "name"}
+    ref_p = {n: P2[n].clone().requires_grad_(True) for n in names}
+    ref_opt = getattr(torch.optim, h["name"])([ref_p[n] for n in names], **kw)
+    stats = OM.fresh_bn_stats(P2, cfg)
+    for step in range(2):
+        batch = synth.make_batch(cfg, B, T, L, 600 + step)
+        masks = synth.make_masks(cfg, B, T, L, 700 + step)
+        cur = {n: ref_p[n].detach().clone() for n in names}
+        o_loss, o_g, _ = OMeta.loss_and_grads({**P2, **cur}, cfg, batch, masks, stats, CRIT, names)
+        o_pen = OMeta.ewc_penalty(cur, F_, P, names)
+        out = train_step(model, batch, optim, ewc=ewc, importance=lam, masks=masks)
+        assert abs(float(out["loss"]) - float(o_loss)) < 1e-3 * abs(float(o_loss))
+        assert abs(float(out["penalty"]) - float(o_pen)) < 1e-3 * abs(float(o_pen)) + 1e-9
+        # (1) the completed gradient = task gradient + penalty gradient, against the oracle
+        gd = {n: v.cpu().clone() for n, v in model.engine.dict_from_flat(model.grad_flat).items()}
+        want = {n: o_g[n] + 2.0 * lam * F_[n] * (cur[n] - P[n]) for n in names}
+        gn = float(torch.sqrt(sum((want[n].double() ** 2).sum() for n in names)))
+        assert max(float((gd[n].double() - want[n].double()).norm()) / gn for n in names) < TOL
+        # (2) the update rule: the real torch.optim class stepped with the SAME gradient values (Adam turns rounding-level
+        # differences of near-zero gradient elements into full-size steps, so the rule is checked apart from the gradient)
+        for n in names:
+            ref_p[n].grad = gd[n]
+        ref_opt.step()
+        new = model.engine.dict_from_flat(model.flat)
+        moved = float(torch.sqrt(sum(((ref_p[n].detach() - P2[n]).double() ** 2).sum() for n in names)))
+        err = float(torch.sqrt(sum(((new[n].cpu() - ref_p[n].detach()).double() ** 2).sum() for n in names)))
+        print(f"{h['name']} step {step}: |theta - theta_ref| / |theta_ref - theta_0| = {err / moved:.2e}")
+        assert err < 1e-5 * moved
