@@ -82,6 +82,11 @@ typedef struct msa_config {
     float p_dec_dropout;
     float gate_threshold;
     float loss_pos_weight;
+    /* tacotron2nv.py:88-121 */
+    int32_t freeze_charemb;       /* embedded characters detached: no gradient to embedding.weight */
+    int32_t freeze_encoder;       /* encoder output detached: no gradient to encoder.* / embedding.weight */
+    int32_t freeze_decoder;       /* decoder outputs detached: only the postnet receives gradients */
+    int32_t residual_encoder;     /* use_residual_encoder: encoder output + embedded characters */
 } msa_config;
 
 typedef struct msa_handle msa_handle;

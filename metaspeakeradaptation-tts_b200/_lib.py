@@ -19,7 +19,8 @@ class MsaConfig(C.Structure):
         "n_mel", "prenet_dim", "attn_rnn_dim", "dec_rnn_dim", "attn_dim", "loc_filters", "loc_kernel", "post_dim",
         "post_kernel", "post_n_convs", "attn_norm", "forward_attn", "trans_agent", "windowing", "forward_attn_mask",
         "max_decoder_steps", "early_stopping", "loss_reduction", "gemm_tf32")] + [(n, C.c_float) for n in (
-        "p_attn_dropout", "p_dec_dropout", "gate_threshold", "loss_pos_weight")]
+        "p_attn_dropout", "p_dec_dropout", "gate_threshold", "loss_pos_weight")] + [(n, C.c_int32) for n in (
+        "freeze_charemb", "freeze_encoder", "freeze_decoder", "residual_encoder")]
 
 
 # name -> (restype, argtypes); every symbol declared in include/msa_b200.h

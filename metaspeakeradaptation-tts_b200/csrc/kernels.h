@@ -190,6 +190,8 @@ size_t attn_chain_pt_frag_bytes(const msa_config& cfg, int sm_count);      // pe
 
 // ---------------- element-wise / layout / reduction kernels (model_kernels.cu) ----------------
 int k_embedding_fwd(const float* w, const int64_t* tok, float* x, int rows, int C, int n_symbols, cudaStream_t st);
+int k_embedding_add(const float* w, const int64_t* tok, float* x, int rows, int C, int ld, int n_symbols, cudaStream_t st);   // x[:, :C] += w[tok]
+int k_add_cols(float* dst, const float* src, int64_t rows, int C, int ld, cudaStream_t st);                                  // dst += src[:, :C]
 int k_embedding_bwd(const float* dx, const int64_t* tok, float* gw, int rows, int C, int n_symbols, float scale, int accumulate, cudaStream_t st);
 int k_im2col(const float* x, float* col, int B, int T, int C, int K, cudaStream_t st);
 int k_col2im(const float* dcol, float* dx, int B, int T, int C, int K, cudaStream_t st);

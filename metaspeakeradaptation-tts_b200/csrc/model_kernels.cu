@@ -26,6 +26,24 @@ __global__ void ker_embedding_fwd(const float* __restrict__ w, const int64_t* __
         x[i] = w[id * C + c];
     }
 }
+// use_residual_encoder (tacotron2nv.py:94-96): x[row][c] += w[tok[row]][c] for the first C columns of rows of width ld
+__global__ void ker_embedding_add(const float* __restrict__ w, const int64_t* __restrict__ tok, float* x, int64_t n, int C, int ld, int nsym) {
+    GSL(i, n) {
+        const int64_t row = i / C;
+        const int c = (int)(i % C);
+        int64_t id = tok[row];
+        id = id < 0 ? 0 : (id >= nsym ? nsym - 1 : id);
+        x[row * ld + c] += w[id * C + c];
+    }
+}
+// ... and its backward: dst[row][c] += src[row][c] (src rows of width ld)
+__global__ void ker_add_cols(float* dst, const float* __restrict__ src, int64_t n, int C, int ld) {
+    GSL(i, n) {
+        const int64_t row = i / C;
+        const int c = (int)(i % C);
+        dst[i] += src[row * ld + c];
+    }
+}
 // deterministic scatter-add: one thread per (symbol, channel) scans the token list in order
 __global__ void ker_embedding_bwd(const float* __restrict__ dx, const int64_t* __restrict__ tok, float* gw, int rows, int C,
                                   int nsym, float scale, int accumulate) {
@@ -719,6 +737,17 @@ __global__ void ker_masks(uint8_t* masks, MaskSecTable tb, long long lo, long lo
 int k_embedding_fwd(const float* w, const int64_t* tok, float* x, int rows, int C, int nsym, cudaStream_t st) {
     const int64_t n = (int64_t)rows * C;
     ker_embedding_fwd<<<grid_for(n), kTh, 0, ST>>>(w, tok, x, n, C, nsym);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_embedding_add(const float* w, const int64_t* tok, float* x, int rows, int C, int ld, int nsym, cudaStream_t st) {
+    const int64_t n = (int64_t)rows * C;
+    ker_embedding_add<<<grid_for(n), kTh, 0, ST>>>(w, tok, x, n, C, ld, nsym);
+    MSA_LAUNCH_CHECK();
+    return 0;
+}
+int k_add_cols(float* dst, const float* src, int64_t rows, int C, int ld, cudaStream_t st) {
+    ker_add_cols<<<grid_for(rows * C), kTh, 0, ST>>>(dst, src, rows * C, C, ld);
     MSA_LAUNCH_CHECK();
     return 0;
 }

@@ -884,6 +884,8 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
         auto mk = [&](int i) { return io.masks + secs[i].off; };
         h->gemm_scratch = w.gemm_lo; h->gemm_scratch_floats = (size_t)w.n_gemm_lo;
         MSA_TRY(k_build_memory(w.enc_h, w.spk_vec, w.memory, B, L, d.Hh, d.Ds, st));
+        if (c.residual_encoder)      // tacotron2nv.py:94-96: + the embedded characters
+            MSA_TRY(k_embedding_add(P("embedding.weight"), io.tokens, w.memory, (int)d.BL, d.C, d.E, c.n_symbols, st));
         MSA_TRY(gemm(h, false, true, d.BL, d.A, d.E, 1.f, w.memory, d.E, P(at + "inputs_layer.linear_layer.weight"), d.E, 0.f, w.pm, d.A));
         const float* Wia = P("decoder.attention_rnn.weight_ih");
         MSA_TRY(gemm(h, false, true, H4a, d.BL, d.E, 1.f, Wia + d.Pd, ldA, w.memory, d.E, 0.f, w.mw_rm, d.BL));
@@ -1185,6 +1187,18 @@ int msa_loss_grads(msa_handle* h, void* wsp, float* d_mel, float* d_mel_post, fl
 
 namespace msa {
 
+// grads of every parameter whose name starts with one of `prefixes` (or with none of them: invert) <- 0 unless accumulating:
+// a detached sub-graph leaves p.grad = None in the reference (tacotron2nv.py:90-121), which mix_grad / the optimizers read as zero
+static int zero_grads(const msa_handle* h, float* grads, const std::vector<std::string>& prefixes, bool invert, int acc, cudaStream_t st) {
+    if (acc) return 0;
+    for (size_t i = 0; i < h->names.size(); ++i) {
+        bool hit = false;
+        for (const auto& p : prefixes) hit = hit || h->names[i].compare(0, p.size(), p) == 0;
+        if (hit != invert) MSA_CUDA(cudaMemsetAsync(grads + h->offs[i], 0, sizeof(float) * (size_t)h->numels[i], st));
+    }
+    return 0;
+}
+
 // Backward of train_forward_impl: the gradient of task g's loss w.r.t. the shared parameters goes to grads_g[g]
 // (= autograd.grad(loss_g, fast_weights), maml.py:54 / 71-74); the three reverse-time recurrences run once for the whole group.
 static int train_backward_impl(msa_handle* h, char* wsp, const float* const* params_g, const float* const* d_mel, const float* const* d_mel_post,
@@ -1251,6 +1265,10 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* const* par
                                 i < d.nPost - 1 ? 2 : 0, mk(iPost + i), true, w.red_scr));
             dcur = dx;
         }
+        if (c.freeze_decoder) {      // tacotron2nv.py:118-121: mel / gate / alignments detached, nothing flows further back
+            MSA_TRY(zero_grads(h, grads, {"postnet."}, true, acc, st));
+            continue;
+        }
         // d(pre-postnet mel) = loss term + residual + postnet input (tacotron2nv.py:123-124)
         MSA_TRY(k_add3(w.dpre, w.dpost, dcur, w.dmel_bt, d.BT * d.M, st));
         MSA_TRY(k_transpose01(w.dmel_bt, w.dmel_tm, B, T, d.M, st));
@@ -1272,6 +1290,7 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* const* par
         MSA_TRY(k_colsum(w.dgate_tm, d.TB, 1, 1, G("decoder.gate_layer.linear_layer.bias"), gs, acc, nullptr, w.red_scr, st));
     }
     MSA_TRY(fk.end(W));
+    if (c.freeze_decoder) return 0;
     // ---- decoder RNN chain backward (persistent) ----
     {
         auto make = [&](int g) {
@@ -1475,6 +1494,10 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* const* par
         }
     }
     MSA_TRY(fk.end(W));
+    if (c.freeze_encoder) {      // tacotron2nv.py:99-101: the encoder output (incl. the residual term) is detached
+        for (int g = 0; g < NG; ++g) MSA_TRY(zero_grads(h, grads_g[g], {"encoder.", "embedding."}, false, acc, st));
+        return 0;
+    }
     // ---- encoder BiLSTM backward (persistent) ----
     {
         auto make = [&](int g) {
@@ -1554,6 +1577,12 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* const* par
                                 true, w.red_scr));
             dcur = dx;
         }
+        if (c.freeze_charemb) {      // tacotron2nv.py:90-92: the embedded characters are detached (encoder input and residual term)
+            MSA_TRY(zero_grads(h, grads, {"embedding."}, false, acc, st));
+            continue;
+        }
+        if (c.residual_encoder)      // d(embedded) += d(encoder output) = the encoder columns of d(memory)
+            MSA_TRY(k_add_cols(const_cast<float*>(dcur), w.dmem, d.BL, d.C, d.E, st));
         MSA_TRY(k_embedding_bwd(dcur, h->tokens[g], G("embedding.weight"), (int)d.BL, d.C, c.n_symbols, gs, acc, st));
     }
     MSA_TRY(fk.end(W));
@@ -1789,6 +1818,7 @@ int msa_infer(msa_handle* h, void* wsp, size_t ws_bytes, const float* params, co
         MSA_TRY(launch_lstm_rec_fwd(lp, h->sm_count, h->smem_limit, st));
     }
     MSA_TRY(k_build_memory(w.enc_h, w.spk_vec, w.memory, B, L, d.Hh, d.Ds, st));
+    if (c.residual_encoder) MSA_TRY(k_embedding_add(P("embedding.weight"), tokens, w.memory, (int)d.BL, d.C, d.E, c.n_symbols, st));
     const std::string at = "decoder.attention_layer.";
     MSA_TRY(gemm(h, false, true, d.BL, d.A, d.E, 1.f, w.memory, d.E, P(at + "inputs_layer.linear_layer.weight"), d.E, 0.f, w.pm, d.A));
 

@@ -27,9 +27,6 @@ def make_c_config(cfg: dict, reduction: str = "none", pos_weight: float = 10.0, 
         raise NotImplementedError("n_frames_per_step > 1 cannot train in the reference (SURVEY.md Q14)")
     if cfg.get("mask_padding", False):
         raise NotImplementedError("mask_padding=True breaks backward in the reference (SURVEY.md Q3)")
-    for k in ("freeze_charemb", "freeze_encoder", "freeze_decoder", "use_residual_encoder"):
-        if cfg.get(k, False):
-            raise NotImplementedError(f"{k}=True is outside the implemented hot path")
     if cfg["symbols_embedding_dim"] != cfg["encoder_embedding_dim"]:
         raise ValueError("symbols_embedding_dim must equal encoder_embedding_dim (tacotron2nv.py:88)")
     ha, hd = rnn_dims(cfg)
@@ -65,6 +62,10 @@ def make_c_config(cfg: dict, reduction: str = "none", pos_weight: float = 10.0, 
     c.p_dec_dropout = cfg["p_decoder_dropout"]
     c.gate_threshold = cfg["gate_threshold"]
     c.loss_pos_weight = pos_weight
+    c.freeze_charemb = int(bool(cfg.get("freeze_charemb", False)))          # tacotron2nv.py:88-121
+    c.freeze_encoder = int(bool(cfg.get("freeze_encoder", False)))
+    c.freeze_decoder = int(bool(cfg.get("freeze_decoder", False)))
+    c.residual_encoder = int(bool(cfg.get("use_residual_encoder", False)))
     return c
 
 

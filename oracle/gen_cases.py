@@ -30,6 +30,13 @@ def _lookup():
     return c
 
 
+def _opt(**kw):
+    """tacotron2nv.py:88-121: freeze_charemb / freeze_encoder / freeze_decoder / use_residual_encoder."""
+    c = pkg.small_params()
+    c.update(kw)
+    return c
+
+
 def speaker_input(cfg, batch):
     """What the trainers pass as ``speaker_vecs`` (metatrainer.py:95-117): ids for "learnable_lookup", vectors otherwise."""
     return batch[5] if cfg["speaker_emb_type"] == "learnable_lookup" else batch[6]
@@ -43,13 +50,18 @@ CASES = {
     # speaker_emb_type="learnable_lookup" (tacotron2nv.py:31-34,104-105): nn.Embedding over speaker ids, rows of several speakers
     "small_train_lookup": lambda: (_lookup(), 16, (4, 11, 10), CRIT),
     "small_train_sigmoid": lambda: (_small(norm="sigmoid"), 15, (4, 13, 10), CRIT),
+    "small_train_residual": lambda: (_opt(use_residual_encoder=True), 17, (3, 12, 9), CRIT),
+    "small_train_freeze_charemb": lambda: (_opt(freeze_charemb=True, use_residual_encoder=True), 18, (3, 11, 9), CRIT),
+    "small_train_freeze_encoder": lambda: (_opt(freeze_encoder=True), 19, (3, 12, 10), CRIT),
+    "small_train_freeze_decoder": lambda: (_opt(freeze_decoder=True), 20, (4, 12, 9), CRIT),
     # BASELINE.json configs[0]: default dims, batch 4, 200 mel frames, 80 mels
     "default_train_b4_t200": lambda: (pkg.default_params(), 0, (4, 200, 64), CRIT),
 }
 
 
-def _infer(early=False, thr=0.5, **attn):
+def _infer(early=False, thr=0.5, residual=False, **attn):
     c = _small(**attn)
+    c["use_residual_encoder"] = residual
     c["max_decoder_steps"] = 24
     c["decoder_no_early_stopping"] = not early
     c["gate_threshold"] = thr
@@ -60,6 +72,7 @@ INFER_CASES = {
     "small_infer": lambda: (_infer(), 21, (3, 9), 24),
     # threshold picked by gen_golden.pick_threshold so that the rows stop at different steps
     "small_infer_earlystop": lambda: (_infer(early=True, thr=0.62), 22, (3, 9), 24),
+    "small_infer_residual": lambda: (_infer(residual=True), 24, (3, 10), 24),
     "small_infer_window_fwdmask": lambda: (_infer(windowing=True, forward_attn=True, forward_attn_mask=True,
                                                   trans_agent=True), 23, (3, 14), 24),
 }

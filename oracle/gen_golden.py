@@ -196,10 +196,13 @@ def save_infer_case(name):
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
+    only = sys.argv[1:]          # optional: names of the cases to (re)generate
     for name in CASES:
-        save_train_case(name, full=(name != "default_train_b4_t200"))
+        if not only or name in only:
+            save_train_case(name, full=(name != "default_train_b4_t200"))
     for name in INFER_CASES:
-        save_infer_case(name)
+        if not only or name in only:
+            save_infer_case(name)
     print("golden fixtures written to", GOLD)
 
 

@@ -277,13 +277,22 @@ def forward(P: Dict[str, torch.Tensor], cfg: dict, inputs, input_lengths, melspe
             inter: Optional[dict] = None) -> List[torch.Tensor]:
     """Tacotron2NV.forward, tacotron2nv.py:81-127 -> [mel, mel_post, gate, align]."""
     assert not cfg.get("mask_padding", False), "mask_padding=True breaks backward in the reference (Q3)"
-    enc = encoder(P, cfg, inputs, input_lengths, masks, stats, train, inter)
+    # tacotron2nv.py:88-101: freeze_charemb detaches the embedded characters (both their use by the encoder and by the residual
+    # connection), freeze_encoder the encoder output (incl. the residual term), use_residual_encoder adds the embedded characters
+    Pe = dict(P)
+    if cfg.get("freeze_charemb", False):
+        Pe["embedding.weight"] = P["embedding.weight"].detach()
+    enc = encoder(Pe, cfg, inputs, input_lengths, masks, stats, train, inter)
     if cfg.get("use_residual_encoder", False):
-        enc = enc + P["embedding.weight"][inputs]
+        enc = enc + Pe["embedding.weight"][inputs]
+    if cfg.get("freeze_encoder", False):
+        enc = enc.detach()
     memory = speaker_concat(P, cfg, enc, speaker_vecs)
     if inter is not None:
         inter["memory"] = memory
     mel, gate, align = decoder_forward(P, cfg, memory, melspecs, masks, train, inter)
+    if cfg.get("freeze_decoder", False):          # tacotron2nv.py:118-121: only the postnet learns
+        mel, gate, align = mel.detach(), gate.detach(), align.detach()
     post = postnet(P, cfg, mel, masks, stats, train, inter)
     return [mel, mel + post, gate, align]
 

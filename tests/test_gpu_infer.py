@@ -37,7 +37,7 @@ def _run(name):
     return out, ref, np.load(os.path.join(GOLD, name + ".npz"))
 
 
-@pytest.mark.parametrize("name", ["small_infer", "small_infer_earlystop"])
+@pytest.mark.parametrize("name", ["small_infer", "small_infer_earlystop", "small_infer_residual"])
 def test_infer_small(name):
     (post, lens, align), (o_post, o_lens, o_align), z = _run(name)
     T = int(z["steps"])
