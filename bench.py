@@ -108,12 +108,17 @@ def algo_bytes(cfg, kernel: str, rows: int = B) -> float:
     """Compulsory HBM bytes of one launch (every operand read once, every result written once).
     ``rows``: batch rows the launch carries (B for a single pass, G*B for a grouped launch, kernel names ending in "_grp")."""
     from msa_tts_b200.config import memory_dim, rnn_dims
-    kernel = kernel[:-4] if kernel.endswith("_grp") else kernel
+    pt = kernel.endswith("_pt")
+    kernel = kernel[:-4] if kernel.endswith("_grp") else (kernel[:-3] if pt else kernel)
     Ha, Hd = rnn_dims(cfg)
     E, A = memory_dim(cfg), cfg["attention_params"]["attention_dim"]
     F_, Hh = cfg["attention_params"]["attention_location_n_filters"], cfg["encoder_embedding_dim"] // 2
     TB, BL, TBL = T * rows, rows * L, T * rows * L
     f = 4.0
+    if pt:      # per-task weights: every task's recurrent weight matrix (+ W_q) once
+        G = max(1, rows // B)
+        extra = f * (G - 1) * (4 * Ha * Ha + A * Ha)
+        return algo_bytes(cfg, kernel, rows) + extra
     if kernel == "attn_chain_fwd":
         rd = TB * 4 * Ha + 4 * Ha * Ha + 4 * Ha * BL + A * Ha + BL * A
         wr = TB * (2 * Ha + 4 * Ha + A + 1) + 2 * TBL + TBL * A + TBL * F_
@@ -142,7 +147,7 @@ HAND_OFF_US = 2268 / 1965.0
 
 
 def latency_bound(kernel: str, ms_per_launch: float):
-    kernel = kernel[:-4] if kernel.endswith("_grp") else kernel
+    kernel = kernel[:-4] if kernel.endswith("_grp") else (kernel[:-3] if kernel.endswith("_pt") else kernel)
     steps = L if kernel.startswith("enc_") else T
     bound_ms = steps * HAND_OFFS[kernel] * HAND_OFF_US * 1e-3
     return {"steps": steps, "hand_offs_per_step": HAND_OFFS[kernel], "hand_off_us": HAND_OFF_US, "bound_ms": bound_ms,
@@ -609,12 +614,21 @@ def main():
         for name, (ms, cnt) in prof.items():
             if cnt:
                 rows = B * (eng.group_size(len(mine), B) if name.endswith("_grp") else 1)
+                if name.endswith("_pt"):      # several tasks with their own weights per launch (3 + 3 + 2 for 8 local tasks)
+                    rows = int(round(B * len(mine) * args.steps / cnt))
                 ab = algo_bytes(cfg, name, rows)
                 per = ms / cnt
                 kern.append({"kernel": name, "rows_per_launch": rows, "us_per_step_per_row": per * 1e3 / (L if name.startswith("enc_") else T) / rows,
                              "launches_per_step": cnt / args.steps, "ms_per_launch": per,
                              "share_of_step": ms / ms_dev, "algo_bytes": ab, "achieved_gbs": ab / per / 1e6,
                              "frac": ab / per / 1e6 / peak, "latency_bound": latency_bound(name, per)})
+                if name.endswith("_pt"):
+                    # the launch streams every task's recurrent weights as bf16 hi/lo fragments from L2 on EVERY step
+                    # (148 CTAs x 16 warps x ceil(Ha/256) k16 steps x 2 KB per task, chain_mma.cu): the stream that bounds it
+                    from msa_tts_b200.config import rnn_dims
+                    frag = 148 * 16 * -(-rnn_dims(cfg)[0] // 256) * 2048.0
+                    kern[-1]["l2_stream"] = {"bytes_per_step": frag * rows / B, "achieved_gbs": frag * rows / B * T / per / 1e6,
+                                             "note": "weight fragments of every task re-read from L2 each step (per-task weights cannot stay in shared memory)"}
         for name, (ms, ab) in flat_ms.items():
             kern.append({"kernel": name, "ms_per_launch": ms, "algo_bytes": ab, "achieved_gbs": ab / ms / 1e6,
                          "frac": ab / ms / 1e6 / peak, "timed": "alone, 20 reps"})

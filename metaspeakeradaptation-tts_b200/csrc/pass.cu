@@ -90,6 +90,11 @@ struct msa_handle {
     // Encoder / postnet convolutions as implicit GEMMs on the tcgen05 kernel (activation operand = shifted 3-D TMA map, BatchNorm
     // statistics from the epilogue) under the tensor-core GEMM policies; the strict fp32 policy keeps im2col + cuBLAS.  Env MSA_CONV_TC=0: off.
     bool conv_tc = false;
+    // K split of under-filled product grids (convolutions and plain GEMMs): set per pass -- on for a single pass (its GEMMs run one
+    // after the other and a 32-tile grid leaves most SMs idle), off while the stages of several tasks run side by side on their own
+    // streams (the other tasks' kernels fill the SMs; the partial tiles and reduce launches only cost: 80.8 -> 79.2 ms per meta-step)
+    bool conv_split = true;
+    int conv_split_mode = -1;    // env MSA_CONV_SPLIT: -1 per pass as above, 0 never, 1 always
     int rec_flags = -1;    // hand-off variant of the persistent kernels; -1 = per-kernel default (env MSA_REC_FLAGS overrides, development only)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
     std::vector<int> prof_id;
@@ -352,7 +357,7 @@ static int gemm(msa_handle* h, bool ta, bool tb, int64_t M, int64_t N, int64_t K
                          (long long)K, (int)h->in_bwd, (int)tf32, (int)route);
     if (route)
         return gemm_tc(ta, tb, M, N, K, alpha, A, lda, Bm, ldb, beta, Cm, ldc, tf32 ? 2 : 0,
-                       (h->gemm_scratch && gemm_tc_scratch_floats(M, N, K) <= h->gemm_scratch_floats) ? h->gemm_scratch : nullptr,
+                       (h->gemm_scratch && gemm_tc_scratch_floats(M, N, K) <= h->gemm_scratch_floats && h->conv_split) ? h->gemm_scratch : nullptr,
                        h->cur_stream, bias1, bias2);
     if (bias1 != nullptr) {
         MSA_CHECK(beta == 0.f && ldc == N, MSA_E_ARG, "gemm: a column bias needs beta == 0 and a dense C");
@@ -389,6 +394,7 @@ static int conv_bn_fwd(msa_handle* h, cudaStream_t st, const float* params, cons
     if (wp != nullptr) {
         const bool tf32 = h->cfg.gemm_tf32 >= 2 || (h->cfg.gemm_tf32 == 1 && h->in_bwd);
         float* scr = (h->gemm_scratch && conv_tc_scratch_floats(B, Tn, Ci, Co, K) <= h->gemm_scratch_floats) ? h->gemm_scratch : nullptr;
+        if (!h->conv_split) scr = nullptr;
         MSA_TRY(conv_tc_fwd(x, B, Tn, Ci, wp, Co, K, params + h->off(pfx + ".0.conv.bias"), y, tf32 ? 2 : 0, scr, stats, st));
         MSA_TRY(k_bn_slab_act_drop_fwd(y, stats, conv_tc_stat_slabs(B, Tn, Ci, Co, K, scr != nullptr), rows, Co, bn_mean, bn_invstd, running,
                                        (int)align_up(Co), params + h->off(pfx + ".1.weight"), params + h->off(pfx + ".1.bias"), mask, 2.0f, act,
@@ -424,6 +430,7 @@ static int conv_bn_bwd(msa_handle* h, cudaStream_t st, const float* params, floa
         MSA_TRY(conv_tc_dw(dy, x, B, Tn, Co, Ci, K, gs, acc, grads + h->off(pfx + ".0.conv.weight"), tf32 ? 3 : 0, st));
         if (need_dx) {
             float* sc = (h->gemm_scratch && conv_tc_scratch_floats(B, Tn, Co, Ci, K) <= h->gemm_scratch_floats) ? h->gemm_scratch : nullptr;
+            if (!h->conv_split) sc = nullptr;
             MSA_TRY(conv_tc_dx(dy, B, Tn, Co, wp, Ci, K, dx, tf32 ? 3 : 0, sc, st));
         }
         return 0;
@@ -461,9 +468,13 @@ static int conv_repack_all(msa_handle* h, const Dims& d, const Ws& w, const floa
 
 // event-timing slots: the six single-task recurrences, then the same six as grouped launches (chain_mma.cu with G > 1); the
 // in-kernel phase counters / traces exist once per recurrence (PROF_BASE slots)
-enum ProfId { PROF_ENC_LSTM_FWD = 0, PROF_ATTN_FWD, PROF_DEC_LSTM_FWD, PROF_DEC_LSTM_BWD, PROF_ATTN_BWD, PROF_ENC_LSTM_BWD, PROF_BASE, PROF_N = 2 * PROF_BASE };
+// "_pt": attention-chain launches over several tasks with per-task weights (streamed weight fragments, chain_mma.cu)
+enum ProfId { PROF_ENC_LSTM_FWD = 0, PROF_ATTN_FWD, PROF_DEC_LSTM_FWD, PROF_DEC_LSTM_BWD, PROF_ATTN_BWD, PROF_ENC_LSTM_BWD, PROF_BASE,
+              PROF_ATTN_FWD_PT = 2 * PROF_BASE, PROF_ATTN_BWD_PT, PROF_N };
 static const char* kProfNames[PROF_N] = {"enc_lstm_fwd", "attn_chain_fwd", "dec_lstm_fwd", "dec_lstm_bwd", "attn_chain_bwd", "enc_lstm_bwd",
-                                         "enc_lstm_fwd_grp", "attn_chain_fwd_grp", "dec_lstm_fwd_grp", "dec_lstm_bwd_grp", "attn_chain_bwd_grp", "enc_lstm_bwd_grp"};
+                                         "enc_lstm_fwd_grp", "attn_chain_fwd_grp", "dec_lstm_fwd_grp", "dec_lstm_bwd_grp", "attn_chain_bwd_grp", "enc_lstm_bwd_grp",
+                                         "attn_chain_fwd_pt", "attn_chain_bwd_pt"};
+static int prof_base_id(int id) { return id == PROF_ATTN_FWD_PT ? PROF_ATTN_FWD : (id == PROF_ATTN_BWD_PT ? PROF_ATTN_BWD : id % PROF_BASE); }
 struct ProfScope {
     msa_handle* h; cudaStream_t st; int slot = -1;
     ProfScope(msa_handle* h_, int id, cudaStream_t st_) : h(h_), st(st_) {
@@ -552,6 +563,7 @@ int msa_create(const msa_config* cfg, int device, msa_handle** out) {
         h->conv_tc = env_on && h->tc_enabled && c.gemm_tf32 >= 1 && c.enc_dim % 4 == 0 && c.post_dim % 4 == 0 && c.n_mel % 4 == 0 &&
                      (c.enc_kernel & 1) && (c.post_kernel & 1) && c.enc_kernel <= 15 && c.post_kernel <= 15;
     }
+    if (const char* e = getenv("MSA_CONV_SPLIT")) h->conv_split_mode = atoi(e);
     if (const char* e = getenv("MSA_GEMM_TC_MIN")) h->tc_min = atoll(e);
     if (const char* e = getenv("MSA_GEMM_TC_MIN_BWD")) h->tc_min_bwd = atoll(e);
     build_layout(h);
@@ -791,6 +803,7 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
     const bool mma = use_mma_chains(h, Gk, B, T, L, false, false), mma_attn = use_mma_chains(h, Gk, B, T, L, true, false);
     const int64_t tstride = (int64_t)(ws_stride / sizeof(float));
     StageFork fk(h, st, G);
+    h->conv_split = h->conv_split_mode < 0 ? !fk.on : h->conv_split_mode != 0;
     const int H4e = 4 * d.Hh;
     const std::string at = "decoder.attention_layer.";
     const int H4a = 4 * d.Ha, H4d = 4 * d.Hd, ldA = d.Pd + d.E, ldD = d.Ha + d.E, ldP = d.Hd + d.E;
@@ -931,7 +944,7 @@ static int train_forward_impl(msa_handle* h, int G, char* wsp, size_t ws_stride,
             for (const auto& ch : pt_chunks(h, G, B, T, L, false)) {
                 const int g0 = ch.first, Gc = ch.second;
                 if (Gc >= 2) {
-                    ProfScope ps(h, PROF_ATTN_FWD + PROF_BASE, st);
+                    ProfScope ps(h, PROF_ATTN_FWD_PT, st);
                     MSA_TRY(pt_frag_ensure(h));
                     AttnChainParams ap = make(g0);
                     ap.G = Gc; ap.tstride = tstride; ap.pt = 1;
@@ -1229,6 +1242,7 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* const* par
     const bool mma = use_mma_chains(h, Gk, B, T, L, false, true), mma_attn = use_mma_chains(h, Gk, B, T, L, true, true);
     const int64_t tstride = (int64_t)(ws_stride / sizeof(float));
     StageFork fk(h, st, NG);
+    h->conv_split = h->conv_split_mode < 0 ? !fk.on : h->conv_split_mode != 0;
 
     // ---- stage 1: postnet and projections ----
     MSA_TRY(fk.begin());
@@ -1395,7 +1409,7 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* const* par
             for (const auto& ch : pt_chunks(h, NG, B, T, L, true)) {
                 const int g0 = ch.first, Gc = ch.second;
                 if (Gc >= 2) {
-                    ProfScope ps(h, PROF_ATTN_BWD + PROF_BASE, st);
+                    ProfScope ps(h, PROF_ATTN_BWD_PT, st);
                     MSA_TRY(pt_frag_ensure(h));
                     AttnChainBwdParams bp = make(g0);
                     bp.G = Gc; bp.tstride = tstride; bp.pt = 1;
@@ -1645,7 +1659,7 @@ int msa_debug_raise_abort(msa_handle* h, void* stream) {
 int msa_profile_trace(msa_handle* h, void* wsp, int id, int64_t* out, int ncta) {
     MSA_CHECK(h && wsp && out && h->fwd_valid, MSA_E_STATE, "msa_profile_trace: no forward pass in this workspace");
     MSA_CHECK(id >= 0 && id < PROF_N && ncta >= 1 && ncta <= 256, MSA_E_ARG, "msa_profile_trace: bad kernel id / cta count");
-    id %= PROF_BASE;
+    id = prof_base_id(id);
     const Ws w = ws_layout(h->d, wsp);
     MSA_CUDA(cudaDeviceSynchronize());
     MSA_CUDA(cudaMemcpy(out, reinterpret_cast<const long long*>(w.trace) + (size_t)id * kTraceWordsPerKernel,
@@ -1661,7 +1675,7 @@ int msa_profile_trace_step(msa_handle* h, int t0) {
 int msa_profile_phases(msa_handle* h, void* wsp, int id, int64_t* out, int ncta) {
     MSA_CHECK(h && wsp && out && h->fwd_valid, MSA_E_STATE, "msa_profile_phases: no forward pass in this workspace");
     MSA_CHECK(id >= 0 && id < PROF_N && ncta >= 1 && ncta <= kProfCtas, MSA_E_ARG, "msa_profile_phases: bad kernel id / cta count");
-    id %= PROF_BASE;
+    id = prof_base_id(id);
     const Ws w = ws_layout(h->d, wsp);
     MSA_CUDA(cudaDeviceSynchronize());
     MSA_CUDA(cudaMemcpy(out, reinterpret_cast<const long long*>(w.prof) + (size_t)id * kProfCtas * kProfSlots,

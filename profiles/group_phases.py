@@ -44,7 +44,7 @@ for G in [int(a) for a in sys.argv[1:] if a not in ("pt", "events")] or [8]:
         if not act:
             print(f"G={G} {name}: {ms * 1e3:.0f} us (no phase counters)")
             continue
-        n = steps[name[:-4] if name.endswith('_grp') else name]
+        n = steps[name[:-4] if name.endswith('_grp') else (name[:-3] if name.endswith('_pt') else name)]
         tot = [sum(r) for r in act]
         print(f"G={G} {name}: {ms * 1e3:.0f} us (events), {len(act)} CTAs reporting, {sum(tot) / len(tot) / n:.0f} cycles/step")
         for j in range(8):

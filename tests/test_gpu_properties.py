@@ -208,7 +208,7 @@ def test_per_task_weight_groups_equal_the_passes_one_by_one(shape, monkeypatch):
     n_chunks = -(-G // ptg)
     sizes = [G // n_chunks + (1 if i < G % n_chunks else 0) for i in range(n_chunks)]
     want = sum(1 for s_ in sizes if s_ >= 2)          # chunks of two or more tasks are ONE launch each of the per-task-weight kernels
-    assert prof["attn_chain_fwd_grp"][1] == want and prof["attn_chain_bwd_grp"][1] == want, (prof, sizes)
+    assert prof["attn_chain_fwd_pt"][1] == want and prof["attn_chain_bwd_pt"][1] == want, (prof, sizes)
     monkeypatch.setenv("MSA_CHAIN_MMA", "0")
     from msa_tts_b200.engine import Engine
     ref = Engine(cfg, gemm_tf32=tf32)             # single-task fp32-FMA recurrences
