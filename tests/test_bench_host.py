@@ -21,6 +21,12 @@ def test_algorithmic_bytes_and_latency_bound_of_the_recurrent_kernels():
         assert lb["steps"] == (bench.L if k.startswith("enc_") else bench.T)
         assert abs(lb["bound_ms"] - lb["steps"] * lb["hand_offs_per_step"] * lb["hand_off_us"] * 1e-3) < 1e-12
         assert 0 < lb["frac"] == lb["bound_ms"] / 1.0
+    # per-task-weight launches ("_pt", three tasks = 12 rows): the single-launch bytes at 12 rows + two more recurrent weight matrices
+    from msa_tts_b200.config import rnn_dims
+    Ha, A = rnn_dims(cfg)[0], cfg["attention_params"]["attention_dim"]
+    for k in ("attn_chain_fwd", "attn_chain_bwd"):
+        assert bench.algo_bytes(cfg, k + "_pt", 12) == bench.algo_bytes(cfg, k, 12) + 4.0 * 2 * (4 * Ha * Ha + A * Ha)
+        assert bench.latency_bound(k + "_pt", 2.0)["bound_ms"] == bench.latency_bound(k, 2.0)["bound_ms"] == bench.latency_bound(k + "_grp", 2.0)["bound_ms"]
     # 88.8 MB forward / 114.6 MB backward at the bench shape
     assert abs(bench.algo_bytes(cfg, "attn_chain_fwd") - 88.8e6) < 0.1e6
     assert abs(bench.algo_bytes(cfg, "attn_chain_bwd") - 114.6e6) < 0.1e6
