@@ -91,8 +91,10 @@ struct msa_handle {
     // statistics from the epilogue) under the tensor-core GEMM policies; the strict fp32 policy keeps im2col + cuBLAS.  Env MSA_CONV_TC=0: off.
     bool conv_tc = false;
     // K split of under-filled product grids (convolutions and plain GEMMs): set per pass -- on for a single pass (its GEMMs run one
-    // after the other and a 32-tile grid leaves most SMs idle), off while the stages of several tasks run side by side on their own
-    // streams (the other tasks' kernels fill the SMs; the partial tiles and reduce launches only cost: 80.8 -> 79.2 ms per meta-step)
+    // after the other and a 32-tile grid leaves most SMs idle), off for the single-TF32 products while the stages of several tasks run
+    // side by side on their own streams (the other tasks' kernels fill the SMs; the partial tiles and reduce launches only cost).
+    // The fp32-accurate 3xTF32 products keep their split: the tensor core's fp32 accumulation truncates, an unsplit K = 2560 sum is
+    // accurate to 1.3e-5 instead of 3.6e-6 (tests/test_gpu_conv_tc.py), and the TF32 backward amplifies that difference
     bool conv_split = true;
     int conv_split_mode = -1;    // env MSA_CONV_SPLIT: -1 per pass as above, 0 never, 1 always
     int rec_flags = -1;    // hand-off variant of the persistent kernels; -1 = per-kernel default (env MSA_REC_FLAGS overrides, development only)
@@ -342,8 +344,8 @@ static int gemm(msa_handle* h, bool ta, bool tb, int64_t M, int64_t N, int64_t K
     // (measured on B200, profiles/r01_gemm_tc_v14.txt: the kernel has ~10 us of fixed cost, so short-K / small products stay on cuBLAS)
     const long long macs = (long long)M * N * K;
     // fp32-accurate products (3xTF32 against cuBLAS's SIMT sgemm): measured per shape on B200 (profiles/r02_gemm_shapes.txt) the
-    // kernel also wins the small products with a long (>= 768) or a very short (<= 128) contraction
-    const bool tc_small = !tf32 && (K >= 768 || K <= 128) && macs >= 10000000LL;
+    // kernel also wins or ties the small products (>= 1e7 MACs; one 256-deep prenet product is 2.7 us slower and rides along)
+    const bool tc_small = !tf32 && macs >= 10000000LL;
     const bool tc_size = (macs >= h->tc_min && (macs >= 3 * h->tc_min || K >= 1024)) || tc_small;
     const bool nt = !ta && tb;
     const bool own_ok = h->tc_enabled && h->cfg.gemm_tf32 >= 1 && N >= 8 && M * N >= 4096 && gemm_tc_supported(M, N, K, A, lda, Bm, ldb, Cm, ldc) &&
@@ -357,7 +359,7 @@ static int gemm(msa_handle* h, bool ta, bool tb, int64_t M, int64_t N, int64_t K
                          (long long)K, (int)h->in_bwd, (int)tf32, (int)route);
     if (route)
         return gemm_tc(ta, tb, M, N, K, alpha, A, lda, Bm, ldb, beta, Cm, ldc, tf32 ? 2 : 0,
-                       (h->gemm_scratch && gemm_tc_scratch_floats(M, N, K) <= h->gemm_scratch_floats && h->conv_split) ? h->gemm_scratch : nullptr,
+                       (h->gemm_scratch && gemm_tc_scratch_floats(M, N, K) <= h->gemm_scratch_floats && (h->conv_split || !tf32)) ? h->gemm_scratch : nullptr,
                        h->cur_stream, bias1, bias2);
     if (bias1 != nullptr) {
         MSA_CHECK(beta == 0.f && ldc == N, MSA_E_ARG, "gemm: a column bias needs beta == 0 and a dense C");
@@ -394,7 +396,7 @@ static int conv_bn_fwd(msa_handle* h, cudaStream_t st, const float* params, cons
     if (wp != nullptr) {
         const bool tf32 = h->cfg.gemm_tf32 >= 2 || (h->cfg.gemm_tf32 == 1 && h->in_bwd);
         float* scr = (h->gemm_scratch && conv_tc_scratch_floats(B, Tn, Ci, Co, K) <= h->gemm_scratch_floats) ? h->gemm_scratch : nullptr;
-        if (!h->conv_split) scr = nullptr;
+        if (!h->conv_split && tf32) scr = nullptr;      // the fp32-accurate product keeps its K split (accumulation accuracy, see msa_handle)
         MSA_TRY(conv_tc_fwd(x, B, Tn, Ci, wp, Co, K, params + h->off(pfx + ".0.conv.bias"), y, tf32 ? 2 : 0, scr, stats, st));
         MSA_TRY(k_bn_slab_act_drop_fwd(y, stats, conv_tc_stat_slabs(B, Tn, Ci, Co, K, scr != nullptr), rows, Co, bn_mean, bn_invstd, running,
                                        (int)align_up(Co), params + h->off(pfx + ".1.weight"), params + h->off(pfx + ".1.bias"), mask, 2.0f, act,
