@@ -120,7 +120,10 @@ __device__ __forceinline__ void gate_waitq(int n, AddrFn addr, unsigned int* abo
 #define MSA_RING_FWD 4
 #endif
 constexpr int kRingF = MSA_RING_FWD;  // forward: ring stages of 2 KB per warp (4 stages: 128 KB per SM in flight between product phases)
-constexpr int kRing = 3;              // backward: ring stages of G x 512 bytes per warp
+// backward: a ring stage of a warp holds one k16 step of all G tasks -- G x 512 bytes of weight fragments and G x Bt x 64 bytes of
+// dz(t+1) -- and both travel by cp.async: the depth of the stream no longer depends on registers (two polled k16 steps in registers
+// were what bound the dz gather); five stages at two tasks, three at three or four (shared memory)
+__host__ __device__ constexpr int ring_depth_bwd(int G) { return G <= 2 ? 5 : 3; }
 __device__ __forceinline__ void cp_async16(void* smem, const void* g) {
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(g) : "memory");
@@ -1138,8 +1141,8 @@ __host__ __device__ inline AttnBwdMmaLay attn_bwd_mma_layout(int R, int L, int H
     s.WIN = s.NPmax + Kl - 1 < L ? s.NPmax + Kl - 1 : L;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return r; };
-    // resident B fragments, or (per-task weights) the ring: kRing stages of one k16 step x MTL tasks per warp; W_q^T per task
-    s.bfrag = take(pt ? (size_t)kMW * kRing * MTL * 32 * sizeof(uint4) : (size_t)kMW * s.KS * 2 * 32 * sizeof(uint2));
+    // resident B fragments, or (per-task weights) the ring: stages of one k16 step x MTL tasks per warp (fragments + dz); W_q^T per task
+    s.bfrag = take(pt ? (size_t)kMW * ring_depth_bwd(MTL) * MTL * (32 + (R / MTL) * 4) * sizeof(uint4) : (size_t)kMW * s.KS * 2 * 32 * sizeof(uint2));
     s.bq = take((size_t)(pt ? MTL : 1) * s.KQ * 2 * 32 * sizeof(uint2));
     const int NW = pt ? 2 : 1;
     // partial tiles [kMW][MTL][4][32]; earlier in the step the region holds tq [R*L] and the dconvf partials [4][NPmax][F]
@@ -1202,7 +1205,10 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
     const int KS = lay.KS, KQ = lay.KQ, CKP = lay.CKP, WIN = lay.WIN, FP = lay.FP;
     constexpr int HR = PT ? 1 : 2;                                     // row halves of an m tile that can hold real rows
     uint2* Bfrag = reinterpret_cast<uint2*>(smem_raw + lay.bfrag);    // [kMW][KS][hi|lo][32]  W_hh^T slice
-    uint4* ring = reinterpret_cast<uint4*>(smem_raw + lay.bfrag) + (size_t)w * kRing * MTL * 32;      // PT: [kRing][MTL][32]
+    constexpr int RD = ring_depth_bwd(MTL);                            // PT: ring stages per warp
+    const int ZS = Bt * 4;                                              // PT: dz slots (float4) per task and stage: lanes with lg < Bt
+    const int STG = MTL * (32 + ZS);                                    // PT: uint4 words per stage: [MTL][32] fragments, [MTL][ZS] dz
+    uint4* ring = reinterpret_cast<uint4*>(smem_raw + lay.bfrag) + (size_t)w * RD * STG;
     uint2* Bq = reinterpret_cast<uint2*>(smem_raw + lay.bq);          // [KQ][hi|lo][32]       W_q^T slice
     float* part = reinterpret_cast<float*>(smem_raw + lay.part);
     float* tq_s = part;                                                // [R*L]      d e * (1 - s^2) for the owned attention dim
@@ -1327,20 +1333,25 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
             const int rr = rowok[mt][hr] ? r : 0;
             zrow[mt][hr] = p.dza + gr.task(rr) * gr.tstride + (size_t)gr.brow(rr) * H4;
         }
-    // PT: the ring of streamed B fragments; stage = k16 step s of all MTL tasks, period KS
+    // PT: the ring of streamed B fragments and dz; stage = k16 step s of all MTL tasks.  One commit group per stage fill.
     const uint4* fsrc = PT ? p.wfrag + ((size_t)cta * kMW + wsl) * KS * 32 + lane : nullptr;
-    int rs = 0, rslot = 0;
-    auto ring_issue = [&]() {
-        uint4* dst = ring + (size_t)rslot * MTL * 32 + lane;
+    int rslot = 0;                      // slot of the next stage to consume (= the oldest; refilled right after it was read)
+    auto ring_fill = [&](int slot, int s, bool with_dz, size_t toff) {      // weights of k16 step s (+ dz(t+1) of that step)
+        uint4* dst = ring + (size_t)slot * STG;
 #pragma unroll
-        for (int mt = 0; mt < MTL; ++mt) cp_async16(dst + mt * 32, fsrc + (size_t)mt * p.wfrag_stride + (size_t)rs * 32);
+        for (int mt = 0; mt < MTL; ++mt) cp_async16(dst + mt * 32 + lane, fsrc + (size_t)mt * p.wfrag_stride + (size_t)s * 32);
+        if (with_dz) {
+            const int col = (wsl * KS + s) * 16 + 4 * lj;
+#pragma unroll
+            for (int mt = 0; mt < MTL; ++mt)
+                if (rowok[mt][0] && col < H4) cp_async16(dst + MTL * 32 + mt * ZS + lg * 4 + lj, zrow[mt][0] + toff + col);
+        }
         cp_async_commit();
-        if (++rs == KS) rs = 0;
-        if (++rslot == kRing) rslot = 0;
     };
-    if (PT) {
+    const bool ring_deep = KS >= RD;
+    if (PT && ring_deep) {
 #pragma unroll
-        for (int i = 0; i < kRing; ++i) ring_issue();
+        for (int i = 0; i < RD; ++i) ring_fill(i, i, false, 0);
     }
     ChainProf<true> prof;
     prof.start(p.prof, nullptr, 0);
@@ -1394,7 +1405,54 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
         }
         prof.mark(1, T - 1 - t);
         // ---- C (shadow of the d a hand-off): recurrent tile dz_a(t+1) . W_hh for the owned units ----
-        if (t < T - 1) {
+        if (PT && t < T - 1) {
+            const size_t toff = (size_t)(t + 1) * Bt * H4;
+            auto consume = [&](int slot, int s) {
+                const uint4* stg = ring + (size_t)slot * STG;
+                const int col = (wsl * KS + s) * 16 + 4 * lj;
+#pragma unroll
+                for (int mt = 0; mt < MTL; ++mt) {
+                    float4 cur = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rowok[mt][0] && col < H4) {
+                        cur = *reinterpret_cast<const float4*>(stg + MTL * 32 + mt * ZS + lg * 4 + lj);
+                        if (!ready4(cur)) cur = poll4_slow(zrow[mt][0] + toff + col, p.abort_word);      // copied before it was published
+                    }
+                    const uint4 b = stg[mt * 32 + lane];
+                    const uint32_t bhi[2] = {b.x, b.y}, blo[2] = {b.z, b.w};
+                    uint4 ahi = make_uint4(0u, 0u, 0u, 0u), alo = make_uint4(0u, 0u, 0u, 0u);
+                    split2(cur.x, cur.y, ahi.x, alo.x);
+                    split2(cur.z, cur.w, ahi.z, alo.z);
+                    mma3(acc[mt], ahi, alo, bhi, blo);
+                }
+            };
+            if (ring_deep) {
+                // both operands arrive through the per-warp cp.async ring: the slots hold the fragments of the first RD k16 steps
+                // already (prefetched during the rest of the previous step); their dz parts are requested now, after the dz(t+1) gate
+                for (int i = 0; i < RD; ++i) {
+                    uint4* dst = ring + (size_t)((rslot + i) % RD) * STG;
+                    const int col = (wsl * KS + i) * 16 + 4 * lj;
+#pragma unroll
+                    for (int mt = 0; mt < MTL; ++mt)
+                        if (rowok[mt][0] && col < H4) cp_async16(dst + MTL * 32 + mt * ZS + lg * 4 + lj, zrow[mt][0] + toff + col);
+                    cp_async_commit();
+                }
+                for (int s = 0; s < KS; ++s) {
+                    cp_async_wait<RD - 1>();
+                    consume(rslot, s);
+                    // refill the slot just read: k16 step s + RD of this time step (fragments + dz), or the fragments of the first k16
+                    // steps of the NEXT time step (their dz does not exist yet)
+                    if (s + RD < KS) ring_fill(rslot, s + RD, true, toff);
+                    else ring_fill(rslot, s + RD - KS, false, 0);
+                    if (++rslot == RD) rslot = 0;
+                }
+            } else {      // fewer k16 steps per warp than ring stages (small models): one stage at a time
+                for (int s = 0; s < KS; ++s) {
+                    ring_fill(0, s, true, toff);
+                    cp_async_wait<0>();
+                    consume(0, s);
+                }
+            }
+        } else if (t < T - 1) {
             const size_t toff = (size_t)(t + 1) * Bt * H4;
             constexpr int PF = MSA_PF_BWD;
             float4 zv[PF][MTL][HR];
@@ -1408,15 +1466,9 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
             };
             auto process = [&](int s, float4 (&cur)[MTL][HR]) {
                 const int col = (wsl * KS + s) * 16 + 4 * lj;
-                uint2 bh = make_uint2(0u, 0u), bl = make_uint2(0u, 0u);
-                const uint4* rf = nullptr;
-                if (PT) {
-                    cp_async_wait<kRing - 1>();
-                    rf = ring + (size_t)rslot * MTL * 32 + lane;
-                } else {
-                    const uint2* bf = Bfrag + ((size_t)wsl * KS + s) * 2 * 32;
-                    bh = bf[lane]; bl = bf[32 + lane];
-                }
+                const uint2* bf = Bfrag + ((size_t)wsl * KS + s) * 2 * 32;
+                const uint2 bh = bf[lane], bl = bf[32 + lane];
+                const uint32_t bhi[2] = {bh.x, bh.y}, blo[2] = {bl.x, bl.y};
 #pragma unroll
                 for (int mt = 0; mt < MTL; ++mt) {
 #pragma unroll
@@ -1425,21 +1477,13 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
                             if (!ready4(cur[mt][hr])) cur[mt][hr] = poll4_slow(zrow[mt][hr] + toff + col, p.abort_word);
                         }
                     }
-                    if (PT) {
-                        const uint4 b = rf[mt * 32];
-                        bh = make_uint2(b.x, b.y); bl = make_uint2(b.z, b.w);
-                    }
-                    const uint32_t bhi[2] = {bh.x, bh.y}, blo[2] = {bl.x, bl.y};
-                    uint4 ahi = make_uint4(0u, 0u, 0u, 0u), alo = make_uint4(0u, 0u, 0u, 0u);
+                    uint4 ahi, alo;
                     split2(cur[mt][0].x, cur[mt][0].y, ahi.x, alo.x);
+                    split2(cur[mt][HR - 1].x, cur[mt][HR - 1].y, ahi.y, alo.y);
                     split2(cur[mt][0].z, cur[mt][0].w, ahi.z, alo.z);
-                    if (!PT) {
-                        split2(cur[mt][HR - 1].x, cur[mt][HR - 1].y, ahi.y, alo.y);
-                        split2(cur[mt][HR - 1].z, cur[mt][HR - 1].w, ahi.w, alo.w);
-                    }
+                    split2(cur[mt][HR - 1].z, cur[mt][HR - 1].w, ahi.w, alo.w);
                     mma3(acc[mt], ahi, alo, bhi, blo);
                 }
-                if (PT) ring_issue();      // refills the stage just read with the one kRing ahead
             };
 #pragma unroll
             for (int i = 0; i < PF; ++i)
@@ -1663,7 +1707,7 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
         }
         __syncthreads();
     }
-    if (PT) cp_async_wait<0>();      // the ring runs kRing stages ahead of the last step
+    if (PT) cp_async_wait<0>();      // the ring runs RD stages ahead of the last step
 }
 
 static bool attn_bwd_mma_ok(const msa_config& cfg, int R, int L, int sm_count, size_t smem_limit) {

@@ -716,21 +716,23 @@ static bool use_mma_chains(const msa_handle* h, int G, int B, int T, int L, bool
 // chunk of two or more tasks is one launch of the per-task-weight attention chain, a chunk of one task a single-task launch.
 static std::vector<std::pair<int, int>> pt_chunks(const msa_handle* h, int G, int B, int T, int L, bool bwd) {
     std::vector<std::pair<int, int>> out;      // (first task, tasks)
-    const int cap = h->pt_group;
-    bool ok = G >= 2 && cap >= 2 && (!bwd || h->pt_bwd) && use_mma_chains(h, 2, B, T, L, true, bwd);
-    const int n = ok ? (G + cap - 1) / cap : G;
-    int g0 = 0;
-    for (int i = 0; i < n; ++i) {
-        const int sz = G / n + (i < G % n ? 1 : 0);
-        out.push_back({g0, sz});
-        g0 += sz;
-    }
-    for (auto& ch : out)
-        if (ch.second >= 2 && !attn_chain_pt_supported(h->cfg, ch.second, B, T, L, h->sm_count, h->smem_limit)) ok = false;
-    if (!ok) {
+    const bool want = G >= 2 && h->pt_group >= 2 && (!bwd || h->pt_bwd) && use_mma_chains(h, 2, B, T, L, true, bwd);
+    // the largest chunk size <= pt_group whose launches fit (shared memory: the weight / dz rings grow with the tasks per launch)
+    for (int cap = want ? h->pt_group : 1; cap >= 2; --cap) {
+        const int n = (G + cap - 1) / cap;
+        bool ok = true;
+        int g0 = 0;
         out.clear();
-        for (int g = 0; g < G; ++g) out.push_back({g, 1});
+        for (int i = 0; i < n; ++i) {
+            const int sz = G / n + (i < G % n ? 1 : 0);
+            out.push_back({g0, sz});
+            g0 += sz;
+            if (sz >= 2 && !attn_chain_pt_supported(h->cfg, sz, B, T, L, h->sm_count, h->smem_limit)) ok = false;
+        }
+        if (ok) return out;
     }
+    out.clear();
+    for (int g = 0; g < G; ++g) out.push_back({g, 1});
     return out;
 }
 static int pt_frag_ensure(msa_handle* h) {

@@ -205,10 +205,15 @@ def test_per_task_weight_groups_equal_the_passes_one_by_one(shape, monkeypatch):
     eng.check_abort()
     prof = eng.profile_read()
     eng.profile(False)
-    n_chunks = -(-G // ptg)
-    sizes = [G // n_chunks + (1 if i < G % n_chunks else 0) for i in range(n_chunks)]
-    want = sum(1 for s_ in sizes if s_ >= 2)          # chunks of two or more tasks are ONE launch each of the per-task-weight kernels
-    assert prof["attn_chain_fwd_pt"][1] == want and prof["attn_chain_bwd_pt"][1] == want, (prof, sizes)
+    # chunks of two or more tasks are ONE launch each of the per-task-weight kernels; the chunk size is MSA_PT_GROUP or the largest
+    # smaller size whose rings fit into shared memory (default dims: four tasks do not)
+    def launches(cap):
+        n_chunks = -(-G // cap)
+        sizes = [G // n_chunks + (1 if i < G % n_chunks else 0) for i in range(n_chunks)]
+        return sum(1 for s_ in sizes if s_ >= 2)
+    allowed = {launches(cap) for cap in range(2, ptg + 1)} if which == "default" else {launches(ptg)}
+    assert prof["attn_chain_fwd_pt"][1] in allowed and prof["attn_chain_fwd_pt"][1] >= 1, (prof, allowed)
+    assert prof["attn_chain_bwd_pt"][1] == prof["attn_chain_fwd_pt"][1], prof
     monkeypatch.setenv("MSA_CHAIN_MMA", "0")
     from msa_tts_b200.engine import Engine
     ref = Engine(cfg, gemm_tf32=tf32)             # single-task fp32-FMA recurrences
