@@ -262,11 +262,16 @@ __global__ void __launch_bounds__(kMT, 1) k_lstm_fwd_mma(LstmRecParams p) {
             auto process = [&](int s, float4 (&cur)[NT]) {
                 const int col = (wsl * KS + s) * 16 + 4 * lj;
                 uint32_t bhi[NT][2], blo[NT][2];
+                unsigned int cmax = 0u;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) cmax = umax_acc(cmax, cur[nt]);
+                if (cmax == kCanary) {
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+                        if (rowok[nt] && col < H && !ready4(cur[nt])) cur[nt] = poll4_slow(hrow[nt] + toff + col, p.abort_word);
+                }
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
-                    if (rowok[nt] && col < H) {
-                        if (!ready4(cur[nt])) cur[nt] = poll4_slow(hrow[nt] + toff + col, p.abort_word);
-                    }
                     split2(cur[nt].x, cur[nt].y, bhi[nt][0], blo[nt][0]);
                     split2(cur[nt].z, cur[nt].w, bhi[nt][1], blo[nt][1]);
                 }
@@ -457,14 +462,20 @@ __global__ void __launch_bounds__(kMT, 1) k_lstm_bwd_mma(LstmRecBwdParams p) {
                 const uint2* bf = Bfrag + ((size_t)wsl * KS + s) * 2 * 32;
                 const uint2 bh = bf[lane], bl = bf[32 + lane];
                 const uint32_t bhi[2] = {bh.x, bh.y}, blo[2] = {bl.x, bl.y};
+                unsigned int cmax = 0u;
+#pragma unroll
+                for (int mt = 0; mt < MTL; ++mt)
+#pragma unroll
+                    for (int hr = 0; hr < 2; ++hr) cmax = umax_acc(cmax, cur[mt][hr]);
+                if (cmax == kCanary) {
+#pragma unroll
+                    for (int mt = 0; mt < MTL; ++mt)
+#pragma unroll
+                        for (int hr = 0; hr < 2; ++hr)
+                            if (rowok[mt][hr] && col < H4 && !ready4(cur[mt][hr])) cur[mt][hr] = poll4_slow(zrow[mt][hr] + toff + col, p.abort_word);
+                }
 #pragma unroll
                 for (int mt = 0; mt < MTL; ++mt) {
-#pragma unroll
-                    for (int hr = 0; hr < 2; ++hr) {
-                        if (rowok[mt][hr] && col < H4) {
-                            if (!ready4(cur[mt][hr])) cur[mt][hr] = poll4_slow(zrow[mt][hr] + toff + col, p.abort_word);
-                        }
-                    }
                     uint4 ahi, alo;
                     split2(cur[mt][0].x, cur[mt][0].y, ahi.x, alo.x);     // a0: row g,   logical k 2j, 2j+1
                     split2(cur[mt][1].x, cur[mt][1].y, ahi.y, alo.y);     // a1: row g+8
@@ -949,11 +960,16 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
             auto process = [&](int s, float4 (&cur)[NT]) {
                 const int col = (wsl * KS + s) * 16 + 4 * lj;
                 uint32_t bhi[NT][2], blo[NT][2];
+                unsigned int cmax = 0u;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) cmax = umax_acc(cmax, cur[nt]);
+                if (cmax == kCanary) {
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+                        if (rowok[nt] && col < Ha && !ready4(cur[nt])) cur[nt] = poll4_slow(hrow[nt] + toff + col, p.abort_word);
+                }
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
-                    if (rowok[nt] && col < Ha) {
-                        if (!ready4(cur[nt])) cur[nt] = poll4_slow(hrow[nt] + toff + col, p.abort_word);
-                    }
                     split2(cur[nt].x, cur[nt].y, bhi[nt][0], blo[nt][0]);
                     split2(cur[nt].z, cur[nt].w, bhi[nt][1], blo[nt][1]);
                 }
@@ -1386,14 +1402,18 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
                         const int c = c0 + k * 32;
                         if (c < (H4 >> 2)) { mv[k] = __ldcg(m4 + c); zv[k] = ld_poll4(zr + (size_t)c * 4); }
                     }
+                    unsigned int cmax = 0u;
 #pragma unroll
-                    for (int k = 0; k < NB; ++k) {
-                        const int c = c0 + k * 32;
-                        if (c < (H4 >> 2)) {
-                            if (!ready4(zv[k])) zv[k] = poll4_slow(zr + (size_t)c * 4, p.abort_word);
-                            a += dot4(mv[k], zv[k]);
-                        }
+                    for (int k = 0; k < NB; ++k)
+                        if (c0 + k * 32 < (H4 >> 2)) cmax = umax_acc(cmax, zv[k]);
+                    if (cmax == kCanary) {
+#pragma unroll
+                        for (int k = 0; k < NB; ++k)
+                            if (c0 + k * 32 < (H4 >> 2) && !ready4(zv[k])) zv[k] = poll4_slow(zr + (size_t)(c0 + k * 32) * 4, p.abort_word);
                     }
+#pragma unroll
+                    for (int k = 0; k < NB; ++k)
+                        if (c0 + k * 32 < (H4 >> 2)) a += dot4(mv[k], zv[k]);
                 }
                 a = warp_sum(a);
             }
@@ -1469,14 +1489,20 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
                 const uint2* bf = Bfrag + ((size_t)wsl * KS + s) * 2 * 32;
                 const uint2 bh = bf[lane], bl = bf[32 + lane];
                 const uint32_t bhi[2] = {bh.x, bh.y}, blo[2] = {bl.x, bl.y};
+                unsigned int cmax = 0u;
+#pragma unroll
+                for (int mt = 0; mt < MTL; ++mt)
+#pragma unroll
+                    for (int hr = 0; hr < HR; ++hr) cmax = umax_acc(cmax, cur[mt][hr]);
+                if (cmax == kCanary) {
+#pragma unroll
+                    for (int mt = 0; mt < MTL; ++mt)
+#pragma unroll
+                        for (int hr = 0; hr < HR; ++hr)
+                            if (rowok[mt][hr] && col < H4 && !ready4(cur[mt][hr])) cur[mt][hr] = poll4_slow(zrow[mt][hr] + toff + col, p.abort_word);
+                }
 #pragma unroll
                 for (int mt = 0; mt < MTL; ++mt) {
-#pragma unroll
-                    for (int hr = 0; hr < HR; ++hr) {
-                        if (rowok[mt][hr] && col < H4) {
-                            if (!ready4(cur[mt][hr])) cur[mt][hr] = poll4_slow(zrow[mt][hr] + toff + col, p.abort_word);
-                        }
-                    }
                     uint4 ahi, alo;
                     split2(cur[mt][0].x, cur[mt][0].y, ahi.x, alo.x);
                     split2(cur[mt][HR - 1].x, cur[mt][HR - 1].y, ahi.y, alo.y);

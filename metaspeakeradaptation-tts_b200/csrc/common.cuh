@@ -121,6 +121,13 @@ __device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinter
 constexpr unsigned int kCanary = 0xFFFFFFFFu;
 __device__ __forceinline__ bool is_canary(float x) { return __float_as_uint(x) == kCanary; }
 __device__ __forceinline__ bool ready4(const float4& v) { return !(is_canary(v.x) | is_canary(v.y) | is_canary(v.z) | is_canary(v.w)); }
+// Fast-path test of several polled 128-bit loads at once: the canary is the all-ones word, the largest unsigned value, so "some word
+// is still the canary" == "the unsigned maximum over the words is the canary" (two 3-input max instructions per load, ONE compare and
+// branch per batch; the exact per-load test and the re-poll loop sit behind that branch)
+__device__ __forceinline__ unsigned int umax_acc(unsigned int m, const float4& v) {
+    m = __vimax3_u32(m, __float_as_uint(v.x), __float_as_uint(v.y));
+    return __vimax3_u32(m, __float_as_uint(v.z), __float_as_uint(v.w));
+}
 __device__ __forceinline__ float ld_poll(const float* p) {
     float v;
     asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");

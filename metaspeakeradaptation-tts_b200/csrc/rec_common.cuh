@@ -123,13 +123,18 @@ __device__ __forceinline__ void cta_matvec_fwd(const float* __restrict__ Wsm, in
                 for (int b = 0; b < 4; ++b)
                     h4[b] = (in && tile * 4 + b < B) ? ld_poll4(hs + (size_t)(tile * 4 + b) * Hg + (size_t)c4 * 4)
                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                unsigned int cmax = 0u;
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    if (in && tile * 4 + b < B) {
-                        sg->reset();
-                        while (!ready4(h4[b])) {
-                            if (sg->bail()) break;
-                            h4[b] = ld_poll4(hs + (size_t)(tile * 4 + b) * Hg + (size_t)c4 * 4);
+                for (int b = 0; b < 4; ++b) cmax = umax_acc(cmax, h4[b]);
+                if (cmax == kCanary) {      // some word arrived before it was published: exact test + re-poll per load
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        if (in && tile * 4 + b < B) {
+                            sg->reset();
+                            while (!ready4(h4[b])) {
+                                if (sg->bail()) break;
+                                h4[b] = ld_poll4(hs + (size_t)(tile * 4 + b) * Hg + (size_t)c4 * 4);
+                            }
                         }
                     }
                 }
@@ -219,15 +224,27 @@ __device__ __forceinline__ void poll_copy_rows(float* dst_smem, int dst_stride4,
             const int idx = base + j * NT;
             if (idx < total) v[j] = ld_poll4(src + (size_t)idx * 4);
         }
+        unsigned int cmax = 0u;
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j)
+            if (base + j * NT < total) cmax = umax_acc(cmax, v[j]);
+        if (cmax == kCanary) {      // some word arrived before it was published: exact test + re-poll per load
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j) {
+                const int idx = base + j * NT;
+                if (idx < total) {
+                    sg.reset();
+                    while (!ready4(v[j])) {
+                        if (sg.bail()) break;
+                        v[j] = ld_poll4(src + (size_t)idx * 4);
+                    }
+                }
+            }
+        }
 #pragma unroll
         for (int j = 0; j < kBatch; ++j) {
             const int idx = base + j * NT;
             if (idx < total) {
-                sg.reset();
-                while (!ready4(v[j])) {
-                    if (sg.bail()) break;
-                    v[j] = ld_poll4(src + (size_t)idx * 4);
-                }
                 const int r = idx / n4, c = idx - r * n4;
                 reinterpret_cast<float4*>(dst_smem)[(size_t)r * dst_stride4 + c] = v[j];
             }
@@ -336,13 +353,18 @@ __device__ __forceinline__ void cta_matvec_bwd(const float* __restrict__ WT, int
 #pragma unroll
             for (int b = 0; b < 4; ++b)
                 d4[b] = (bt + b < B) ? ld_poll4(dz + (size_t)(bt + b) * R4 + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+            unsigned int cmax = 0u;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                if (bt + b < B) {
-                    sg.reset();
-                    while (!ready4(d4[b])) {
-                        if (sg.bail()) break;
-                        d4[b] = ld_poll4(dz + (size_t)(bt + b) * R4 + r);
+            for (int b = 0; b < 4; ++b) cmax = umax_acc(cmax, d4[b]);
+            if (cmax == kCanary) {      // some word arrived before it was published: exact test + re-poll per load
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    if (bt + b < B) {
+                        sg.reset();
+                        while (!ready4(d4[b])) {
+                            if (sg.bail()) break;
+                            d4[b] = ld_poll4(dz + (size_t)(bt + b) * R4 + r);
+                        }
                     }
                 }
             }
@@ -385,14 +407,25 @@ __device__ __forceinline__ void cta_pair_dots(const float* __restrict__ MWp, siz
 #pragma unroll
             for (int i = 0; i < kPairMax; ++i)
                 if (pbase + i < npairs) d4[i] = ld_poll4(dz + (size_t)((pair0 + pbase + i) / L) * R4 + r);
+            unsigned int cmax = 0u;
+#pragma unroll
+            for (int i = 0; i < kPairMax; ++i)
+                if (pbase + i < npairs) cmax = umax_acc(cmax, d4[i]);
+            if (cmax == kCanary) {      // some word arrived before it was published: exact test + re-poll per load
+#pragma unroll
+                for (int i = 0; i < kPairMax; ++i) {
+                    if (pbase + i < npairs) {
+                        sg.reset();
+                        while (!ready4(d4[i])) {
+                            if (sg.bail()) break;
+                            d4[i] = ld_poll4(dz + (size_t)((pair0 + pbase + i) / L) * R4 + r);
+                        }
+                    }
+                }
+            }
 #pragma unroll
             for (int i = 0; i < kPairMax; ++i) {
                 if (pbase + i < npairs) {
-                    sg.reset();
-                    while (!ready4(d4[i])) {
-                        if (sg.bail()) break;
-                        d4[i] = ld_poll4(dz + (size_t)((pair0 + pbase + i) / L) * R4 + r);
-                    }
                     accp[i] += dot4(*reinterpret_cast<const float4*>(MWp + (size_t)(pbase + i) * mwp_stride + r), d4[i]);
                 }
             }
