@@ -173,6 +173,13 @@ int msa_train_forward_group(msa_handle* h, int G, void* ws, size_t ws_bytes, con
                             const uint8_t* const* masks, int B, int T, int L, float* loss_out, void* stream);
 int msa_train_backward_group(msa_handle* h, void* ws, size_t ws_bytes, const float* const* params, float* const* grads,
                              int accumulate, float grad_scale, void* stream);
+/* Overlap of the meta-gradient allreduce with the tail of the last backward pass (parallel.py; the reference has no distributed code).
+ * One-shot: the NEXT msa_train_backward / msa_train_backward_group records `cuda_event` (a cudaEvent_t, caller-owned) on its stream
+ * as soon as every gradient outside the encoder is final -- before the encoder BiLSTM recurrence and the encoder convolutions run
+ * (the backward pass produces the postnet, decoder and attention gradients first).  *prefix_floats (optional) receives the length of
+ * the encoder part, which is the PREFIX of the flat layout (embedding.weight, encoder.*): the caller reduces grads[prefix:] when the
+ * event fires and grads[:prefix] after the pass.  cuda_event == NULL only queries the prefix. */
+int msa_backward_mark_event(msa_handle* h, void* cuda_event, int64_t* prefix_floats);
 /* replaces utils/metrics.py:15-22 mcd_batch as called by the trainers' per-task logs (maml.py:78-82,
  * baseline.py, continual_*.py): K * mean_b mean_{t < len_b} ||mel_target - out||_2 with
  * K = 10 / ln(10) * sqrt(2), on the device, from the outputs of the last msa_train_forward in `ws`

@@ -52,6 +52,7 @@ SIGNATURES = {
     "msa_group_workspace_bytes": (SZ, [V, I, I, I, I]),
     "msa_train_forward_group": (I, [V, I, V, SZ, V, V, V, V, V, V, V, V, V, V, I, I, I, V, V]),
     "msa_train_backward_group": (I, [V, V, SZ, V, V, I, F, V]),
+    "msa_backward_mark_event": (I, [V, V, C.POINTER(I64)]),
     "msa_train_loss": (I, [V, V, V, V, I, F, V, V]),
     "msa_train_mcd": (I, [V, V, V, I, V, V]),
     "msa_loss_scratch_floats": (SZ, [I, I, I]),

@@ -125,6 +125,8 @@ struct msa_handle {
     // the forward chains are grouped by three and the backward chains stay single-task launches unless MSA_PT_BWD=1.
     int pt_group = 3;
     bool pt_bwd = false;
+    // one-shot event of the next backward pass (msa_backward_mark_event): recorded when every gradient outside the encoder is final
+    cudaEvent_t bwd_ev = nullptr;
     void* pt_frag = nullptr;
     size_t pt_frag_task_bytes = 0;
     int64_t off(const std::string& n) const { return off_by_name.at(n); }
@@ -1247,6 +1249,14 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* const* par
     const int64_t tstride = (int64_t)(ws_stride / sizeof(float));
     StageFork fk(h, st, NG);
     h->conv_split = h->conv_split_mode < 0 ? !fk.on : h->conv_split_mode != 0;
+    // msa_backward_mark_event: recorded on the pass stream once the gradients of everything but the encoder are final (one-shot;
+    // also on every early return, a waiter must never see an unrecorded event)
+    auto mark_decoder_done = [&]() {
+        if (h->bwd_ev) {
+            cudaEventRecord(h->bwd_ev, st);
+            h->bwd_ev = nullptr;
+        }
+    };
 
     // ---- stage 1: postnet and projections ----
     MSA_TRY(fk.begin());
@@ -1308,7 +1318,7 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* const* par
         MSA_TRY(k_colsum(w.dgate_tm, d.TB, 1, 1, G("decoder.gate_layer.linear_layer.bias"), gs, acc, nullptr, w.red_scr, st));
     }
     MSA_TRY(fk.end(W));
-    if (c.freeze_decoder) return 0;
+    if (c.freeze_decoder) { mark_decoder_done(); return 0; }
     // ---- decoder RNN chain backward (persistent) ----
     {
         auto make = [&](int g) {
@@ -1512,6 +1522,7 @@ static int train_backward_impl(msa_handle* h, char* wsp, const float* const* par
         }
     }
     MSA_TRY(fk.end(W));
+    mark_decoder_done();
     if (c.freeze_encoder) {      // tacotron2nv.py:99-101: the encoder output (incl. the residual term) is detached
         for (int g = 0; g < NG; ++g) MSA_TRY(zero_grads(h, grads_g[g], {"encoder.", "embedding."}, false, acc, st));
         return 0;
@@ -1630,6 +1641,21 @@ int msa_train_backward_group(msa_handle* h, void* wsp, size_t ws_bytes, const fl
     MSA_CHECK(ws_bytes >= (size_t)h->G * std::max<size_t>(h->ws_stride, 1), MSA_E_WORKSPACE, "msa_train_backward_group: workspace too small");
     for (int g = 0; g < h->G; ++g) MSA_CHECK(grads[g] != nullptr && params[g] != nullptr, MSA_E_ARG, "msa_train_backward_group: null buffer of task %d", g);
     return train_backward_impl(h, static_cast<char*>(wsp), params, nullptr, nullptr, nullptr, grads, acc, gs, (cudaStream_t)stream);
+}
+
+int msa_backward_mark_event(msa_handle* h, void* cuda_event, int64_t* prefix_floats) {
+    MSA_CHECK(h, MSA_E_ARG, "msa_backward_mark_event: null handle");
+    if (prefix_floats) {      // the encoder part is the prefix of the flat layout: embedding.weight, encoder.*
+        int64_t end = 0;
+        for (size_t i = 0; i < h->names.size(); ++i) {
+            const std::string& n = h->names[i];
+            if (n.compare(0, 10, "embedding.") != 0 && n.compare(0, 8, "encoder.") != 0) break;
+            end = i + 1 < h->names.size() ? h->offs[i + 1] : h->total;
+        }
+        *prefix_floats = end;
+    }
+    h->bwd_ev = static_cast<cudaEvent_t>(cuda_event);
+    return 0;
 }
 
 int msa_check_abort(msa_handle* h, void* wsp, void* stream) {

@@ -95,6 +95,7 @@ class Engine:
         self._check_layout()
         self._gap_idx = self._make_gap_index()
         self._ws: Optional[torch.Tensor] = None
+        self._enc_prefix: Optional[int] = None
         self._partials = torch.empty(self.lib.msa_flat_partials(), dtype=torch.float32, device=self.device)
         self._keep: tuple = ()
         self.launches = 0   # kernels of this library enqueued by the calls below (bench.py's gpu_launches)
@@ -250,8 +251,20 @@ class Engine:
         self.launches += 1
         return out, loss
 
+    def encoder_prefix(self) -> int:
+        """Floats of the encoder part of a flat buffer (embedding.weight, encoder.*: the prefix of the layout), whose gradients are the
+        LAST ones a backward pass produces."""
+        if self._enc_prefix is None:
+            n = C.c_int64()
+            _lib.check(self.lib.msa_backward_mark_event(self.h, None, C.byref(n)), "msa_backward_mark_event")
+            self._enc_prefix = int(n.value)
+        return self._enc_prefix
+
     def backward(self, params: torch.Tensor, grads: torch.Tensor, accumulate: bool = False, scale: float = 1.0,
-                 d_outputs: Optional[Sequence[torch.Tensor]] = None) -> None:
+                 d_outputs: Optional[Sequence[torch.Tensor]] = None, decoder_done: Optional["torch.cuda.Event"] = None) -> None:
+        """``decoder_done``: a CUDA event the pass records as soon as ``grads[encoder_prefix():]`` is final (msa_backward_mark_event)."""
+        if decoder_done is not None:
+            _lib.check(self.lib.msa_backward_mark_event(self.h, C.c_void_p(decoder_done.cuda_event), None), "msa_backward_mark_event")
         d = [None, None, None] if d_outputs is None else [x.contiguous() for x in d_outputs]
         rc = self.lib.msa_train_backward(self.h, self._ws_ptr(), C.c_size_t(self._ws.numel() - 256), _ptr(params), _ptr(d[0]),
                                          _ptr(d[1]), _ptr(d[2]), _ptr(grads), int(accumulate), C.c_float(scale), _stream())

@@ -19,6 +19,7 @@ from .metatrainer import MetaTrainer
 class MAML(MetaTrainer):
     def __init__(self, **params):
         super().__init__(**params)
+        self._bwd_event = None
         if params.get("track_higher_grads", False):
             # maml.py:70-71.  The target is restated and pinned on the CPU (oracle.meta.maml2_task, tests/test_oracle.py); a
             # finite-difference Hessian-vector product over the first-order kernels was measured and is NOT offered: in float32 it
@@ -74,7 +75,15 @@ class MAML(MetaTrainer):
                 _, loss = eng.forward(fast, bn, inputs, self._masks(i, n_inner, B, T, L), outputs=False)
                 mcds.append(eng.mcd(inputs["melspec_lengths"]))      # maml.py:78-82, on the device: no copy of the mels, no host sync
                 # task_grads = autograd.grad(loss_test, fmodel.parameters(time=-1)); mix_grad weight 1/N (maml.py:73-74, 94-98)
-                eng.backward(fast, self.meta_grad, accumulate=(j > 0), scale=1.0 / N)
+                last = self.shard.world > 1 and j == len(mine) - 1
+                if last:      # the allreduce of everything but the encoder gradients starts while this pass finishes (parallel.py)
+                    if self._bwd_event is None:
+                        self._bwd_event = torch.cuda.Event()
+                        self._bwd_event.record()      # creates the underlying cudaEvent_t (torch creates it lazily)
+                    eng.backward(fast, self.meta_grad, accumulate=(j > 0), scale=1.0 / N, decoder_done=self._bwd_event)
+                    self.shard.allreduce_tail_async(self.meta_grad, eng.encoder_prefix(), self._bwd_event)
+                else:
+                    eng.backward(fast, self.meta_grad, accumulate=(j > 0), scale=1.0 / N)
                 losses.append(loss)
                 j += 1
         sumsq = self._outer_update()

@@ -237,7 +237,7 @@ class MetaTrainer:
     def _outer_update(self) -> torch.Tensor:
         """allreduce(sum) of the locally weighted meta-gradient, grad-norm, clip, optimizer step -- all on flat buffers."""
         eng = self.engine
-        self.shard.allreduce_sum(self.meta_grad)
+        self.shard.allreduce_sum(self.meta_grad, eng.encoder_prefix())       # two parts; the first may already be in flight (parallel.py)
         eng.sumsq(self.meta_grad, self.sumsq)                     # apply_grad's norm / clip_grad_norm_'s total norm
         # a persistent kernel that gave up polling leaves garbage gradients: poison the norm on the device (the update kernels below
         # skip on a non-finite norm, theta and the optimizer state stay intact) and let the host find out without a stall

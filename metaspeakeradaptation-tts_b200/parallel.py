@@ -5,6 +5,11 @@ rank accumulates sum_local w_i g_i into its flat fp32 meta-gradient buffer, and 
 that buffer (121 MB at default dims) over NVLink / NVSwitch yields the averaged meta-gradient on every rank; the
 clip + outer-optimizer update is then replicated (identical on every rank, no broadcast).  The reference has no
 distributed code at all -- this is the B200 design, not a port.
+
+The allreduce is issued in TWO parts, always in the same order on every rank: the tail of the flat buffer (everything but the
+encoder: ~90 % of the bytes) and then the encoder prefix.  A backward pass produces the encoder gradients last, so the rank whose
+last task runs as a plain pass starts the tail part on a side stream as soon as the pass reports those gradients final
+(``msa_backward_mark_event``) and it overlaps the encoder BiLSTM recurrence + encoder convolutions of that pass.
 """
 from __future__ import annotations
 
@@ -22,6 +27,8 @@ class ShardInfo:
     world: int = 1
     local_rank: int = 0
     group: Optional[object] = None
+    _side: Optional[object] = None          # side stream of the early (tail) part of the allreduce
+    _tail_done: bool = False                # the tail part of this meta-step's allreduce is already in flight
 
     @staticmethod
     def from_env(spec=None) -> "ShardInfo":
@@ -35,9 +42,33 @@ class ShardInfo:
         """Indices of the tasks of a meta-batch this rank adapts (task i -> rank i % W)."""
         return [i for i in range(n_tasks) if i % self.world == self.rank]
 
-    def allreduce_sum(self, flat: torch.Tensor) -> None:
-        if self.world > 1:
+    def allreduce_tail_async(self, flat: torch.Tensor, prefix: int, ready: "torch.cuda.Event") -> None:
+        """Start the allreduce of ``flat[prefix:]`` on a side stream once ``ready`` fires (the backward pass that is still running on
+        the current stream has finished writing that part); ``allreduce_sum`` completes the job."""
+        if self.world == 1:
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=flat.device)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ready)
+            dist.all_reduce(flat[prefix:], op=dist.ReduceOp.SUM, group=self.group)
+        self._tail_done = True
+
+    def allreduce_sum(self, flat: torch.Tensor, prefix: int = 0) -> None:
+        """allreduce(SUM) of a flat buffer.  With ``prefix`` > 0 as two collectives -- ``flat[prefix:]`` (skipped if
+        ``allreduce_tail_async`` already issued it), then ``flat[:prefix]`` -- so that every rank issues the same sequence whether or
+        not it could start the first part early."""
+        if self.world == 1:
+            return
+        if prefix <= 0 or prefix >= flat.numel():
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            return
+        if not self._tail_done:
+            dist.all_reduce(flat[prefix:], op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(flat[:prefix], op=dist.ReduceOp.SUM, group=self.group)
+        if self._tail_done:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._tail_done = False
 
     def allreduce_max(self, t: torch.Tensor) -> None:
         if self.world > 1:

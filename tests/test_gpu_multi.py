@@ -60,7 +60,10 @@ def _worker(rank, world, port, kind, n_tasks, n_inner, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-@pytest.mark.parametrize("kind,n_tasks,n_inner", [("maml", 5, 1), ("reptile", 4, 2)])
+# ("maml", 2, 1): one task per rank -- the plain path, whose last backward pass starts the allreduce of everything but the encoder
+# gradients early (msa_backward_mark_event, parallel.py); ("maml", 3, 1): two tasks on rank 0 (grouped), one on rank 1 (plain, early
+# start): both ranks must still issue the same two collectives in the same order
+@pytest.mark.parametrize("kind,n_tasks,n_inner", [("maml", 5, 1), ("maml", 2, 1), ("maml", 3, 1), ("reptile", 4, 2)])
 def test_sharded_meta_steps_equal_unsharded_nccl_world2(kind, n_tasks, n_inner):
     world = 2
     s = socket.socket()
