@@ -648,7 +648,7 @@ __host__ __device__ inline AttnFwdMmaLay attn_fwd_mma_layout(int R, int L, int H
     s.as_ = take((size_t)R * s.LP * sizeof(float));
     s.ah = take((size_t)2 * s.NRown * s.LH * sizeof(float));
     s.wldT = take((size_t)NW * F * A * sizeof(float));
-    s.wloc = take((size_t)NW * F * s.CKP * sizeof(float));
+    s.wloc = take((size_t)NW * 2 * Kl * F * sizeof(float));      // tap-major [2 * Kl][F]: lanes = filters, conflict-free
     s.vs = take((size_t)NW * (A + 4) * sizeof(float));           // v, then b_v at [A]
     s.pm = take((size_t)s.NPmax * A * sizeof(float));
     s.pre = take((size_t)s.NPmax * A * sizeof(float));
@@ -676,7 +676,7 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
     // ask the same L2 slices for the same lines at the same moment
     const int wsl = MSA_SLICE_ROT ? (w + blockIdx.x) % kMW : w;
     const AttnFwdMmaLay lay = attn_fwd_mma_layout(R, L, Ha, A, F, Kl, ncta, NT, PT ? 1 : 0);
-    const int KS = lay.KS, LP = lay.LP, LH = lay.LH, CKP = lay.CKP, RP = lay.RP;
+    const int KS = lay.KS, LP = lay.LP, LH = lay.LH, RP = lay.RP;
     constexpr int NTP = NT < 2 ? NT : 2;
     uint4* Afrag = reinterpret_cast<uint4*>(smem_raw + lay.afrag);
     uint4* ring = Afrag + (size_t)w * kRingF * 128;      // PT: this warp's kRingF stages of [m tile][hi|lo][32] uint4
@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
     float* as_ = reinterpret_cast<float*>(smem_raw + lay.as_);     // [R][LP]   a(t-1)
     float* ah = reinterpret_cast<float*>(smem_raw + lay.ah);       // [2][NRown][LH] a(t-1), cum(t-1) of the owned rows, zero halo
     float* wldT = reinterpret_cast<float*>(smem_raw + lay.wldT);   // [F][A]
-    float* wloc_s = reinterpret_cast<float*>(smem_raw + lay.wloc); // [F][CKP]
+    float* wloc_s = reinterpret_cast<float*>(smem_raw + lay.wloc); // [weight set][2 * Kl][F] (channel-major taps, filter innermost)
     float* vs = reinterpret_cast<float*>(smem_raw + lay.vs);       // [weight set][A + 4]: v, b_v
     float* pm_s = reinterpret_cast<float*>(smem_raw + lay.pm);     // [np][A]
     float* pre_s = reinterpret_cast<float*>(smem_raw + lay.pre);   // [np][A]  loc + pm, then v * tanh(.)
@@ -716,7 +716,7 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
     }
     // small attention weights: one set, or (PT) one per task of the owned positions (at most two: the launcher checks NPmax <= L)
     const int g_lo = r_lo / Bt, nset = PT ? (np > 0 ? r_hi / Bt - g_lo + 1 : 0) : 1;
-    const int WLS = F * CKP, WDS = F * A, VSS = A + 4;      // strides of a weight set
+    const int WLS = 2 * Kl * F, WDS = F * A, VSS = A + 4;      // strides of a weight set
     for (int ws = 0; ws < nset; ++ws) {
         const float* wloc_g = PT ? p.wloc_g[g_lo + ws] : p.wloc;
         const float* wld_g = PT ? p.wld_g[g_lo + ws] : p.wld;
@@ -724,7 +724,7 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
         const float* bv_g = PT ? p.bv_g[g_lo + ws] : p.bv;
         for (int idx = threadIdx.x; idx < F * 2 * Kl; idx += kMT) {
             const int f = idx / (2 * Kl), ck = idx % (2 * Kl);
-            wloc_s[ws * WLS + f * CKP + ck] = __ldg(wloc_g + idx);
+            wloc_s[ws * WLS + ck * F + f] = __ldg(wloc_g + idx);
         }
         for (int idx = threadIdx.x; idx < A * F; idx += kMT) {
             const int d = idx / F, f = idx % F;
@@ -884,30 +884,23 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_fwd_mma(AttnChainParams p) {
         }
         prof.mark(1, t);
         // ---- P3 (shadow of the h hand-off): location features of the owned positions (forward_attn.py:121-127) ----
-        // item (position, filter, tap residue): 8 consecutive lanes share (position, filter); kMT / (8 F) positions per sweep
-        {
-            const int ipp = F * 8, ppi = kMT / ipp;                 // items per position, positions per sweep (threads beyond ppi * ipp idle)
-            const int sub = threadIdx.x / ipp, rem = threadIdx.x - sub * ipp, f = rem >> 3, ks = rem & 7;
-            for (int pb = 0; pb < np; pb += ppi) {
-                const int pi = pb + sub;
-                const bool valid = sub < ppi && pi < np;
-                float cf = 0.f;
-                if (valid) {
-                    const int ro = posrl[4 * pi] - r_lo, l = posrl[4 * pi + 1];
-                    const float* a0 = ah + (size_t)ro * LH + l;
-                    const float* a1 = ah + (size_t)(lay.NRown + ro) * LH + l;
-                    const float* wl = wloc_s + posrl[4 * pi + 3] * WLS + f * CKP;
-                    for (int k = ks; k < Kl; k += 8) cf += wl[k] * a0[k];
-                    for (int k = ks; k < Kl; k += 8) cf += wl[Kl + k] * a1[k];
-                }
-                cf += __shfl_xor_sync(0xffffffffu, cf, 1);
-                cf += __shfl_xor_sync(0xffffffffu, cf, 2);
-                cf += __shfl_xor_sync(0xffffffffu, cf, 4);
-                if (valid && ks == 0) {
-                    cf_s[pi * F + f] = cf;
-                    p.convf[posoff[pi] + ((size_t)t * BtL + posrl[4 * pi + 2]) * F + f] = cf;
-                }
+        // one thread per (position, filter): a warp = the F filters of one position (F = 32), so the alignment / cumulative windows are
+        // broadcast reads and the tap-major weights conflict-free; two independent accumulators (previous alignment, cumulative weights)
+        for (int it = threadIdx.x; it < np * F; it += kMT) {
+            const int pi = it / F, f = it - pi * F;
+            const int ro = posrl[4 * pi] - r_lo, l = posrl[4 * pi + 1];
+            const float* a0 = ah + (size_t)ro * LH + l;
+            const float* a1 = ah + (size_t)(lay.NRown + ro) * LH + l;
+            const float* wl = wloc_s + posrl[4 * pi + 3] * WLS + f;
+            float c0 = 0.f, c1 = 0.f;
+#pragma unroll 4
+            for (int k = 0; k < Kl; ++k) {
+                c0 += wl[k * F] * a0[k];
+                c1 += wl[(Kl + k) * F] * a1[k];
             }
+            const float cf = c0 + c1;
+            cf_s[it] = cf;
+            p.convf[posoff[pi] + ((size_t)t * BtL + posrl[4 * pi + 2]) * F + f] = cf;
         }
         __syncthreads();
         if ((A & 3) == 0) {       // four attention dims per thread: one 128-bit weight load per filter
