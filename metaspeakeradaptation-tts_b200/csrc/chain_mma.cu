@@ -1221,7 +1221,6 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
     uint2* Bq = reinterpret_cast<uint2*>(smem_raw + lay.bq);          // [KQ][hi|lo][32]       W_q^T slice
     float* part = reinterpret_cast<float*>(smem_raw + lay.part);
     float* tq_s = part;                                                // [R*L]      d e * (1 - s^2) for the owned attention dim
-    float* dcp_s = part + ((RL + 3) & ~3);                             // [4][np][F] partial d(conv features)
     float* das = reinterpret_cast<float*>(smem_raw + lay.das);        // [R*L]      d a(t), then d e(t)
     float* als = reinterpret_cast<float*>(smem_raw + lay.als);        // [R*L]      a(t)
     float* wld_s = reinterpret_cast<float*>(smem_raw + lay.wld);      // [A][F]
@@ -1591,56 +1590,25 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
                 a = warp_sum(a);
                 if (lane == 0) st_pub(p.dq + gr.task(r) * gr.tstride + ((size_t)t * Bt + gr.brow(r)) * A + d0, vq_s[PT ? gr.task(r) : 0] * a);
             }
-        // d(conv features)[pi][f] = sum_d dS[pi][d] wld[d][f]: warp (block of 4 positions, quarter of the d range), lane = filter
-        {
-            const int nblk = (np + 3) >> 2;
-            for (int job = w; job < nblk * 4; job += kMW) {
-                const int blk = job >> 2, dq4 = job & 3;
-                const int dlo = part_lo(dq4, A, 4), dhi = part_lo(dq4 + 1, A, 4);
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                const float* ds0 = ds_s + (size_t)(blk * 4) * A;
-                const bool v1 = blk * 4 + 1 < np, v2 = blk * 4 + 2 < np, v3 = blk * 4 + 3 < np;
-                // weight set of the block's first and last position (a block can straddle two tasks)
-                const int st0 = pos_set(p0 + blk * 4), st3 = pos_set(p0 + (blk * 4 + 3 < np ? blk * 4 + 3 : np - 1));
-                if (lane < F && st0 == st3) {
-                    const float* wd = wld_s + st0 * WDS;
-                    for (int d = dlo; d < dhi; ++d) {
-                        const float wv = wd[d * F + lane];
-                        a0 += ds0[d] * wv;
-                        if (v1) a1 += ds0[A + d] * wv;
-                        if (v2) a2 += ds0[2 * A + d] * wv;
-                        if (v3) a3 += ds0[3 * A + d] * wv;
-                    }
-                } else if (lane < F) {
-                    const float* w0 = wld_s + st0 * WDS;
-                    const float* w1 = wld_s + (v1 ? pos_set(p0 + blk * 4 + 1) : 0) * WDS;
-                    const float* w2 = wld_s + (v2 ? pos_set(p0 + blk * 4 + 2) : 0) * WDS;
-                    const float* w3 = wld_s + (v3 ? pos_set(p0 + blk * 4 + 3) : 0) * WDS;
-                    for (int d = dlo; d < dhi; ++d) {
-                        a0 += ds0[d] * w0[d * F + lane];
-                        if (v1) a1 += ds0[A + d] * w1[d * F + lane];
-                        if (v2) a2 += ds0[2 * A + d] * w2[d * F + lane];
-                        if (v3) a3 += ds0[3 * A + d] * w3[d * F + lane];
-                    }
-                }
-                if (lane < F) {
-                    float* o = dcp_s + ((size_t)dq4 * lay.NPmax + blk * 4) * F + lane;
-                    o[0] = a0;
-                    if (v1) o[F] = a1;
-                    if (v2) o[2 * F] = a2;
-                    if (v3) o[3 * F] = a3;
-                }
-            }
-        }
-        __syncthreads();
+        // d(conv features)[pi][f] = sum_d dS[pi][d] wld[d][f]: one thread per (position, filter) -- a warp is the F filters of one
+        // position (F = 32): dS is a broadcast read, the weights are conflict-free; four independent accumulators, fixed order
         for (int it = threadIdx.x; it < np * F; it += kMT) {
             const int pi = it / F, f = it - pi * F, pp = p0 + pi, g = pos_task(pp);
-            const float a = (dcp_s[(size_t)(0 * lay.NPmax + pi) * F + f] + dcp_s[(size_t)(1 * lay.NPmax + pi) * F + f]) +
-                            (dcp_s[(size_t)(2 * lay.NPmax + pi) * F + f] + dcp_s[(size_t)(3 * lay.NPmax + pi) * F + f]);
-            st_pub(p.dconvf + g * gr.tstride + ((size_t)t * BtL + (pp - g * BtL)) * F + f, a);
+            const float* dsr = ds_s + (size_t)pi * A;
+            const float* wd = wld_s + pos_set(pp) * WDS + f;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            int d = 0;
+            for (; d + 3 < A; d += 4) {
+                a0 += dsr[d] * wd[(size_t)d * F];
+                a1 += dsr[d + 1] * wd[(size_t)(d + 1) * F];
+                a2 += dsr[d + 2] * wd[(size_t)(d + 2) * F];
+                a3 += dsr[d + 3] * wd[(size_t)(d + 3) * F];
+            }
+            for (; d < A; ++d) a0 += dsr[d] * wd[(size_t)d * F];
+            st_pub(p.dconvf + g * gr.tstride + ((size_t)t * BtL + (pp - g * BtL)) * F + f, (a0 + a1) + (a2 + a3));
         }
         prof.mark(5, T - 1 - t);
-        __syncthreads();      // tq / dconvf partials are done: the region becomes the partial-tile buffer
+        __syncthreads();      // tq is done: the region becomes the partial-tile buffer
         // ---- F: dq(t) arrives: dq(t) . W_q for the owned units into the same accumulators, then one reduction ----
         for (int s = w; s < KQ; s += kMW) {
             const int col = s * 16 + 4 * lj;
