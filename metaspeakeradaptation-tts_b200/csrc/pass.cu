@@ -120,11 +120,11 @@ struct msa_handle {
     // up to pt_group tasks per attention-chain launch, their recurrent weight slices streamed from L2 as ready-made fragments
     // (chain_mma.cu, PT variants).  pt_frag: the fragment buffer (pt_group x attn_chain_pt_frag_bytes, allocated on first use).
     // Env MSA_PT_GROUP (0 / 1: one launch per task).  Measured on B200 (default dims, B = 4, T = 200; ms per task): forward 2.13 single,
-    // 1.69 / 1.48 / 1.70 in groups of 2 / 3 / 4 (four tasks' fragments, 78 MB, no longer stay in L2 next to MW); backward 2.52 single,
-    // 2.95 / 2.67 / 2.76 grouped (its dz gather and the fragment stream are both bound by the loads a warp keeps in flight) -- so
-    // the forward chains are grouped by three and the backward chains stay single-task launches unless MSA_PT_BWD=1.
+    // 1.49 / 1.43 in groups of 2 / 3 (four tasks' fragments, 78 MB, no longer stay in L2 next to MW); backward 2.42 single, 2.43 / 2.12
+    // in groups of 2 / 3 (both operands of its recurrent tile on a cp.async ring) -- so both chains are grouped by three
+    // (MSA_PT_BWD=0: backward chains as single-task launches).
     int pt_group = 3;
-    bool pt_bwd = false;
+    bool pt_bwd = true;
     // one-shot event of the next backward pass (msa_backward_mark_event): recorded when every gradient outside the encoder is final
     cudaEvent_t bwd_ev = nullptr;
     void* pt_frag = nullptr;
