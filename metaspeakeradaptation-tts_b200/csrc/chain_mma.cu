@@ -128,6 +128,9 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* g) {
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(g) : "memory");
 }
+__device__ __forceinline__ void cp_async16_sa(uint32_t smem_addr, const void* g) {      // shared-window address computed by the caller
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -1344,16 +1347,31 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
     // PT: the ring of streamed B fragments and dz; stage = k16 step s of all MTL tasks.  One commit group per stage fill.
     const uint4* fsrc = PT ? p.wfrag + ((size_t)cta * kMW + wsl) * KS * 32 + lane : nullptr;
     int rslot = 0;                      // slot of the next stage to consume (= the oldest; refilled right after it was read)
-    auto ring_fill = [&](int slot, int s, bool with_dz, size_t toff) {      // weights of k16 step s (+ dz(t+1) of that step)
-        uint4* dst = ring + (size_t)slot * STG;
+    // per-lane constants of the ring traffic, hoisted out of the step loop (the product loop is bound by instruction issue: shared
+    // addresses as 32-bit window offsets, one base pointer per task and operand)
+    const uint32_t ring_sa = PT ? (uint32_t)__cvta_generic_to_shared(ring) : 0u;
+    const uint32_t stg_bytes = (uint32_t)STG * 16u, w_off = (uint32_t)lane * 16u, z_off = (uint32_t)(MTL * 32 + lg * 4 + lj) * 16u;
+    const int colbase = wsl * KS * 16 + 4 * lj;
+    const bool lane_z = PT && lg < Bt;                 // rowok[mt][0] of every task (MTL == G)
+    const uint4* fs[MTL];
+    const float* zb[MTL];
 #pragma unroll
-        for (int mt = 0; mt < MTL; ++mt) cp_async16(dst + mt * 32 + lane, fsrc + (size_t)mt * p.wfrag_stride + (size_t)s * 32);
-        if (with_dz) {
-            const int col = (wsl * KS + s) * 16 + 4 * lj;
+    for (int mt = 0; mt < MTL; ++mt) {
+        fs[mt] = PT ? fsrc + (size_t)mt * p.wfrag_stride : nullptr;
+        zb[mt] = zrow[mt][0] + colbase;
+    }
+    auto ring_fill_dz = [&](int slot, int s, size_t toff) {      // dz(t+1) of k16 step s into its slots of the stage
+        if (lane_z && colbase + s * 16 < H4) {
+            const uint32_t sa = ring_sa + (uint32_t)slot * stg_bytes + z_off;
 #pragma unroll
-            for (int mt = 0; mt < MTL; ++mt)
-                if (rowok[mt][0] && col < H4) cp_async16(dst + MTL * 32 + mt * ZS + lg * 4 + lj, zrow[mt][0] + toff + col);
+            for (int mt = 0; mt < MTL; ++mt) cp_async16_sa(sa + (uint32_t)(mt * ZS) * 16u, zb[mt] + toff + s * 16);
         }
+    };
+    auto ring_fill = [&](int slot, int s, bool with_dz, size_t toff) {      // weights of k16 step s (+ dz(t+1) of that step)
+        const uint32_t sa = ring_sa + (uint32_t)slot * stg_bytes + w_off;
+#pragma unroll
+        for (int mt = 0; mt < MTL; ++mt) cp_async16_sa(sa + (uint32_t)mt * 512u, fs[mt] + (size_t)s * 32);
+        if (with_dz) ring_fill_dz(slot, s, toff);
         cp_async_commit();
     };
     const bool ring_deep = KS >= RD;
@@ -1421,13 +1439,14 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
             const size_t toff = (size_t)(t + 1) * Bt * H4;
             auto consume = [&](int slot, int s) {
                 const uint4* stg = ring + (size_t)slot * STG;
-                const int col = (wsl * KS + s) * 16 + 4 * lj;
+                const bool zok = lane_z && colbase + s * 16 < H4;
+                const float4* zs = reinterpret_cast<const float4*>(stg + MTL * 32 + lg * 4 + lj);
 #pragma unroll
                 for (int mt = 0; mt < MTL; ++mt) {
                     float4 cur = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (rowok[mt][0] && col < H4) {
-                        cur = *reinterpret_cast<const float4*>(stg + MTL * 32 + mt * ZS + lg * 4 + lj);
-                        if (!ready4(cur)) cur = poll4_slow(zrow[mt][0] + toff + col, p.abort_word);      // copied before it was published
+                    if (zok) {
+                        cur = zs[mt * ZS];
+                        if (umax_acc(0u, cur) == kCanary) cur = poll4_slow(zb[mt] + toff + s * 16, p.abort_word);      // copied before it was published
                     }
                     const uint4 b = stg[mt * 32 + lane];
                     const uint32_t bhi[2] = {b.x, b.y}, blo[2] = {b.z, b.w};
@@ -1440,13 +1459,14 @@ __global__ void __launch_bounds__(kMT, 1) k_attn_bwd_mma(AttnChainBwdParams p) {
             if (ring_deep) {
                 // both operands arrive through the per-warp cp.async ring: the slots hold the fragments of the first RD k16 steps
                 // already (prefetched during the rest of the previous step); their dz parts are requested now, after the dz(t+1) gate
-                for (int i = 0; i < RD; ++i) {
-                    uint4* dst = ring + (size_t)((rslot + i) % RD) * STG;
-                    const int col = (wsl * KS + i) * 16 + 4 * lj;
+                {
+                    int sl = rslot;
 #pragma unroll
-                    for (int mt = 0; mt < MTL; ++mt)
-                        if (rowok[mt][0] && col < H4) cp_async16(dst + MTL * 32 + mt * ZS + lg * 4 + lj, zrow[mt][0] + toff + col);
-                    cp_async_commit();
+                    for (int i = 0; i < RD; ++i) {
+                        ring_fill_dz(sl, i, toff);
+                        cp_async_commit();
+                        if (++sl == RD) sl = 0;
+                    }
                 }
                 for (int s = 0; s < KS; ++s) {
                     cp_async_wait<RD - 1>();
