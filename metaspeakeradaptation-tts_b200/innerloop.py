@@ -145,7 +145,10 @@ class DifferentiableAdam:
 
 @contextmanager
 def innerloop_ctx(model: Tacotron2NV, opt: torch.optim.Optimizer, copy_initial_weights: bool = True,
-                  track_higher_grads: bool = False):
+                  track_higher_grads: bool = True):
+    """Same keyword defaults as ``higher.innerloop_ctx`` (``track_higher_grads=True``): a call that omits the keyword asks for the
+    second-order graph like it does with ``higher`` and gets the loud error, never a silent first-order run.  Every reference
+    call site passes ``track_higher_grads=self.params["track_higher_grads"]`` (maml.py:40-41, reptile.py:40-41, infer.py:266-267)."""
     if track_higher_grads:
         raise NotImplementedError("second-order MAML (track_higher_grads=True) needs a double backward through the fused kernels")
     fmodel = FunctionalTacotron2NV(model)

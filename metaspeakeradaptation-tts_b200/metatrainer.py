@@ -277,5 +277,14 @@ class MetaTrainer:
         return path
 
     def _load_checkpoint(self) -> None:
+        """metatrainer.py:138-146: parameters only (the reference copies ``named_parameters()``, so the BatchNorm running statistics of
+        the checkpoint are NOT loaded); a tensor that is missing or has another shape is reported and keeps its initial value."""
+        print(f"Loading checkpoint from  {self.params['finetune_checkpoint_path']}")
         sd = torch.load(self.params["finetune_checkpoint_path"], map_location="cpu")
-        self.load_state_dict(sd)
+        P = {n: v.detach().cpu() for n, v in self.engine.dict_from_flat(self.theta).items()}
+        for n in self.layout.names():
+            if n in sd and tuple(sd[n].shape) == tuple(P[n].shape):
+                P[n] = sd[n].detach().float().cpu()
+            else:
+                print(f"Could not load weights for {n}")
+        self.theta.copy_(self.engine.flat_from_dict(P))
