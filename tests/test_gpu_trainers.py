@@ -222,6 +222,13 @@ def test_checkpoint_round_trip_keeps_the_reference_state_dict_keys(tmp_path):
     assert extra and all(k.endswith(("running_mean", "running_var", "num_batches_tracked")) for k in extra)
     tr2 = MAML(**_params(cfg, _sgd(0.05), _sgd(0.02), n_inner, None, finetune=True, finetune_checkpoint_path=path, init_seed=99))
     assert torch.equal(tr2.theta, tr.theta)                                  # bit-exact through the file
+    # metatrainer.py:141-146: a tensor the checkpoint lacks is reported and keeps its initial value, the others still load
+    sd.pop(names[0])
+    torch.save(sd, path)
+    tr3 = MAML(**_params(cfg, _sgd(0.05), _sgd(0.02), n_inner, None, finetune=True, finetune_checkpoint_path=path, init_seed=99))
+    ref99 = MAML(**_params(cfg, _sgd(0.05), _sgd(0.02), n_inner, None, init_seed=99))
+    d3, d99, d1 = (t.engine.dict_from_flat(t.theta) for t in (tr3, ref99, tr))
+    assert torch.equal(d3[names[0]], d99[names[0]]) and all(torch.equal(d3[n], d1[n]) for n in names[1:])
 
 
 def test_meta_step_on_collated_ragged_batches_from_pinned_memory():
