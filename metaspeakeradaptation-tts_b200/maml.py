@@ -9,7 +9,7 @@ The weighted accumulation is fused into the backward pass of the test split (its
 """
 from __future__ import annotations
 
-from typing import Dict, List
+from typing import Dict
 
 import torch
 
@@ -90,24 +90,3 @@ class MAML(MetaTrainer):
         local = torch.cat(losses) if losses else torch.zeros(0, device=self.device)
         mcd = torch.cat(mcds) if mcds else torch.zeros(0, device=self.device)
         return {"loss_test": local, "mcd": mcd, "task_index": mine, "grad_sumsq": sumsq}
-
-    def _metatrain(self, epoch: int, dataloader_metatrain=None) -> List[dict]:
-        """maml.py:33-108: ``_metatrain(epoch)`` iterates ``self.dataloader_metatrain`` like the reference; an iterable of
-        meta-batches may be passed instead (the reference's DataLoader construction is out of scope)."""
-        dl = dataloader_metatrain if dataloader_metatrain is not None else getattr(self, "dataloader_metatrain", None)
-        if dl is None:
-            raise RuntimeError("MAML._metatrain: set self.dataloader_metatrain (an iterable of {speaker: {train, test}} dicts)")
-        logs = []
-        for items_b in dl:
-            logs.append(self._metatrain_step(items_b))
-        self.engine.abort_flush()
-        return logs
-
-    def run(self, dataloader_metatrain=None, n_epochs: int = 1):
-        if dataloader_metatrain is not None:
-            self.dataloader_metatrain = dataloader_metatrain
-        self.step_global = 0
-        out = []
-        for epoch in range(1, n_epochs + 1):
-            out += self._metatrain(epoch)
-        return out

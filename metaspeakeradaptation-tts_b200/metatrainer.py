@@ -143,10 +143,10 @@ class MetaTrainer:
         return self.engine.generate_masks(B, T, L, seed, self._mask_bufs[key])
 
     # ---- inner loop (higher.innerloop_ctx + diffopt.step, maml.py:40-54) ------------------------------
-    def _adapt(self, task_index: int, batch, n_inner: int):
+    def _adapt(self, task_index: int, batch, n_inner: int, pass0: int = 0):
         """n_inner x (forward, backward, functional SGD / Adam step) on the train split, starting from theta.  The first step reads
         theta itself and writes the updated weights to ``fast`` (the functional update is out of place), so the 121 MB
-        ``fast <- theta`` copy of a literal ``innerloop_ctx`` never happens."""
+        ``fast <- theta`` copy of a literal ``innerloop_ctx`` never happens.  ``pass0``: first pass index of the dropout-mask stream."""
         eng = self.engine
         self.task_bn.copy_(self.base_bn)
         inputs, _ = self._unpack_batch(batch)
@@ -161,7 +161,7 @@ class MetaTrainer:
             self.fast.copy_(self.theta)
         for it in range(n_inner):
             src = self.theta if it == 0 else self.fast
-            _, loss = eng.forward(src, self.task_bn, inputs, self._masks(task_index, it, B, T, L), outputs=False)
+            _, loss = eng.forward(src, self.task_bn, inputs, self._masks(task_index, pass0 + it, B, T, L), outputs=False)
             eng.backward(src, self.task_grad)
             if h["name"] == "Adam":
                 eng.adam_step(src, self.task_grad, self.fast, self.inner_m, self.inner_v, lr=h["lr"], step=it + 1,
@@ -174,13 +174,13 @@ class MetaTrainer:
         return losses
 
     # ---- grouped first inner step ------------------------------------------------------------------------------
-    def _group_plan(self, mine: List[int], batches: Dict[int, tuple]) -> List[List[int]]:
+    def _group_plan(self, mine: List[int], batches: Dict[int, tuple], n_inner: Optional[int] = None) -> List[List[int]]:
         """Tasks whose inner steps can share grouped passes (``plan_task_groups``)."""
         h = self.inner
         stateful = (h["name"] == "Adam") or bool(h.get("momentum", 0.0))
         shapes = {i: (tuple(batches[i][1].shape), batches[i][3].shape[2]) for i in mine}
-        return plan_task_groups(mine, shapes, self.params["n_inner_train"], stateful, self.params.get("group_tasks", True),
-                                self.engine.group_size)
+        n_inner = self.params["n_inner_train"] if n_inner is None else n_inner
+        return plan_task_groups(mine, shapes, n_inner, stateful, self.params.get("group_tasks", True), self.engine.group_size)
 
     def _slot(self, k: int):
         """Per-slot fast weights / gradient / BatchNorm buffers of a group (slot 0 = the buffers of the plain path)."""
@@ -201,7 +201,7 @@ class MetaTrainer:
                          dampening=h.get("dampening", 0.0), weight_decay=h.get("weight_decay", 0.0),
                          nesterov=h.get("nesterov", False), buf=self.inner_buf, first_step=(it == 0))
 
-    def _adapt_group(self, group: List[int], batches: Dict[int, tuple], n_inner: int):
+    def _adapt_group(self, group: List[int], batches: Dict[int, tuple], n_inner: int, pass0: int = 0):
         """First inner step of all tasks of ``group`` as ONE grouped pass from theta, then the remaining inner steps task by task.
         Afterwards slot k holds the adapted weights and the private BatchNorm statistics of task group[k]."""
         eng = self.engine
@@ -212,7 +212,7 @@ class MetaTrainer:
             bds.append(self._unpack_batch(batches[i])[0])
         B, L = bds[0]["inputs"].shape
         T = bds[0]["melspecs"].shape[2]
-        masks = [self._masks(i, 0, B, T, L, slot=k) for k, i in enumerate(group)]
+        masks = [self._masks(i, pass0, B, T, L, slot=k) for k, i in enumerate(group)]
         losses = eng.forward_group(self.theta, [s[2] for s in slots], bds, masks)
         eng.backward_group(self.theta, [s[1] for s in slots])
         for k in range(len(group)):
@@ -224,7 +224,7 @@ class MetaTrainer:
         # the later inner steps have per-task weights: still ONE grouped pass per step (recurrences task by task, everything between
         # them overlapped across the tasks), then the per-task functional update
         for it in range(1, n_inner):
-            masks = [self._masks(i, it, B, T, L, slot=k) for k, i in enumerate(group)]
+            masks = [self._masks(i, pass0 + it, B, T, L, slot=k) for k, i in enumerate(group)]
             lg = eng.forward_group([s_[0] for s_ in slots], [s_[2] for s_ in slots], bds, masks)
             eng.backward_group([s_[0] for s_ in slots], [s_[1] for s_ in slots])
             for k in range(len(group)):
@@ -232,6 +232,104 @@ class MetaTrainer:
                 self._inner_step(fast, grad, fast, it)
                 out[k].append(lg[k:k + 1])
         return out
+
+    # ---- epoch loops (maml.py:19-36, reptile.py:19-36) -------------------------------------------------------------------
+    def _metatrain(self, epoch: int, dataloader_metatrain=None) -> List[dict]:
+        """maml.py:33-108 / reptile.py:33-105: ``_metatrain(epoch)`` iterates ``self.dataloader_metatrain`` like the reference; an
+        iterable of meta-batches may be passed instead (the reference's DataLoader construction is out of scope)."""
+        dl = dataloader_metatrain if dataloader_metatrain is not None else getattr(self, "dataloader_metatrain", None)
+        if dl is None:
+            raise RuntimeError("_metatrain: set self.dataloader_metatrain (an iterable of {speaker: {train, test}} dicts)")
+        logs = [self._metatrain_step(items_b) for items_b in dl]
+        self.engine.abort_flush()
+        return logs
+
+    def run(self, dataloader_metatrain=None, n_epochs: Optional[int] = None, dataloader_metatest=None) -> List[dict]:
+        """maml.py:19-31 / reptile.py:19-31: per epoch one pass over the meta-train loader, a checkpoint every
+        ``ckpt_save_epoch_interval`` epochs and a meta-test every ``metatest_epoch_interval`` epochs (both optional here: a params
+        dict without the key, or without a meta-test loader, skips that part).  Returns the meta-train logs; the meta-test logs of
+        the last meta-test are kept in ``self.last_metatest``."""
+        if dataloader_metatrain is not None:
+            self.dataloader_metatrain = dataloader_metatrain
+        if dataloader_metatest is not None:
+            self.dataloader_metatest = dataloader_metatest
+        n_epochs = int(self.params.get("n_epochs", 1)) if n_epochs is None else n_epochs
+        self.step_global = 0
+        out = []
+        for epoch in range(1, n_epochs + 1):
+            out += self._metatrain(epoch)
+            k = self.params.get("ckpt_save_epoch_interval", 0)
+            if k and epoch % k == 0:
+                self._save_checkpoint()
+            k = self.params.get("metatest_epoch_interval", 0)
+            if k and epoch % k == 0 and getattr(self, "dataloader_metatest", None) is not None:
+                self.last_metatest = self._metatest(epoch)
+        return out
+
+    # ---- meta-test (maml.py:115-179, reptile.py:108-172, baseline.py:299-361) --------------------------------------
+    METATEST_PASS0 = 32      # dropout-mask stream of the meta-test passes (pass indices 32 ..; meta-training uses 0 .. n_inner_train)
+
+    def _metatest_step(self, items_b: Dict[str, Dict[str, tuple]], return_outputs: bool = False) -> dict:
+        """Meta-test on one meta-batch {speaker: {"train": batch, "test": batch}}: per speaker ``n_inner_test`` inner steps on the
+        "train" split starting from theta (the model stays in train mode, maml.py:116), then the loss and the MCD of the ADAPTED
+        weights on the "test" split, no gradient (maml.py:139-149, 167-169).  Nothing persistent moves: theta, the base BatchNorm
+        statistics (higher's functional copy owns its buffers), the outer optimizer state and ``step_global`` stay as they were.
+        Speakers are sharded over the ranks like in meta-training; there is no collective (every rank logs its own speakers).
+        ``return_outputs``: also return every speaker's test-pass outputs ``[out_post, out_inner, out_stop, out_attn]`` (what the
+        reference plots, maml.py:151-165); those passes then run speaker by speaker."""
+        eng = self.engine
+        speakers = list(items_b.keys())
+        mine = self.shard.my_tasks(len(speakers))
+        n_inner = int(self.params.get("n_inner_test", self.params["n_inner_train"]))
+        p0 = self.METATEST_PASS0
+        losses, mcds, outs = [], [], []
+        train = {i: items_b[speakers[i]]["train"] for i in mine}
+        plan = [[i] for i in mine] if return_outputs else self._group_plan(mine, train, n_inner)
+        for group in plan:
+            if len(group) == 1:
+                self._adapt(group[0], train[group[0]], n_inner, pass0=p0)
+                slots = [(self.fast, self.task_grad, self.task_bn)]
+            else:
+                self._adapt_group(group, train, n_inner, pass0=p0)
+                slots = [self._slot(k) for k in range(len(group))]
+            tests = [items_b[speakers[i]]["test"] for i in group]
+            if len(group) > 1 and len({(tuple(b[1].shape), b[3].shape[2]) for b in tests}) == 1:
+                bds = [self._unpack_batch(b)[0] for b in tests]
+                B, L = bds[0]["inputs"].shape
+                T = bds[0]["melspecs"].shape[2]
+                masks = [self._masks(i, p0 + n_inner, B, T, L, slot=k) for k, i in enumerate(group)]
+                lg = eng.forward_group([s_[0] for s_ in slots], [s_[2] for s_ in slots], bds, masks)
+                for k in range(len(group)):
+                    losses.append(lg[k:k + 1])
+                    mcds.append(eng.mcd_group(k, bds[k]["melspec_lengths"]))
+                continue
+            for k, i in enumerate(group):
+                fast, _, bn = slots[k]
+                inputs, _ = self._unpack_batch(tests[k])
+                B, L = inputs["inputs"].shape
+                T = inputs["melspecs"].shape[2]
+                out, loss = eng.forward(fast, bn, inputs, self._masks(i, p0 + n_inner, B, T, L), outputs=return_outputs)
+                losses.append(loss)
+                mcds.append(eng.mcd(inputs["melspec_lengths"]))
+                if return_outputs:
+                    outs.append(out)
+        eng.abort_poll()
+        log = {"loss_test": torch.cat(losses) if losses else torch.zeros(0, device=self.device),
+               "mcd": torch.cat(mcds) if mcds else torch.zeros(0, device=self.device),
+               "task_index": mine, "speakers": [speakers[i] for i in mine]}
+        if return_outputs:
+            log["outputs"] = outs
+        return log
+
+    def _metatest(self, epoch: int, dataloader_metatest=None) -> List[dict]:
+        """maml.py:115-179: ``_metatest(epoch)`` over ``self.dataloader_metatest`` (or the iterable passed in); one log dict per
+        meta-batch with the per-speaker test losses and MCDs as device tensors (plots and TensorBoard are out of scope)."""
+        dl = dataloader_metatest if dataloader_metatest is not None else getattr(self, "dataloader_metatest", None)
+        if dl is None:
+            raise RuntimeError("_metatest: set self.dataloader_metatest (an iterable of {speaker: {train, test}} dicts)")
+        logs = [self._metatest_step(items_b) for items_b in dl]
+        self.engine.abort_flush()
+        return logs
 
     # ---- outer update (maml.py:94-105 / reptile.py:82-89) ----------------------------------------------
     def _outer_update(self) -> torch.Tensor:

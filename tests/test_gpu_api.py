@@ -51,7 +51,7 @@ def test_module_forward_loss_backward_like_baseline_py():
     loss.backward()
     for a, b in zip(out, o_out):
         assert rel(a.detach(), b) < TOL
-    assert abs(float(loss) - float(o_loss)) < TOL * abs(float(o_loss))
+    assert abs(float(loss.detach()) - float(o_loss)) < TOL * abs(float(o_loss))
     names = list(P.keys())
     assert _gerr([p.grad for p in model.parameters()], o_g, names) < TOL
     # stock torch calls of the trainers keep working on the views (maml.py:101-105)

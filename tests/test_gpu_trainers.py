@@ -269,3 +269,56 @@ def test_meta_step_on_collated_ragged_batches_from_pinned_memory():
     for a, b in zip(log["loss_test"].tolist(), losses):
         assert abs(a - b) < TOL * abs(b)
     _check_tensors(tr.engine.dict_from_flat(tr.meta_grad), mixed, names, OMeta.grad_norm(mixed, names), "meta-gradient")
+
+
+@pytest.mark.parametrize("mode", ["grouped", "plain", "outputs"])
+def test_metatest_matches_oracle_and_moves_nothing(mode):
+    """maml.py:115-179 / reptile.py:108-172: ``n_inner_test`` inner steps on the train split, then the test loss and MCD of the adapted
+    weights without a gradient; theta, the base BatchNorm statistics, the outer optimizer state and step_global stay untouched.
+    grouped: the three speakers share grouped passes; plain: speaker by speaker; outputs: the test-pass outputs come back too."""
+    from msa_tts_b200.maml import MAML
+    from msa_tts_b200.reptile import Reptile
+    from oracle import meta as OMeta
+    n_tasks, n_inner_test, lr_in = 3, 2, 0.05
+    cfg, tasks, _, P0, names = _setup(n_tasks, 1)
+    p0 = MAML.METATEST_PASS0
+    import msa_tts_b200.synth as synth
+    masks = {(i, p0 + p): synth.make_masks(cfg, B, T, L, 9000 + 16 * i + p) for i in range(n_tasks) for p in range(n_inner_test + 1)}
+    cls = Reptile if mode == "plain" else MAML
+    tr = cls(**_params(cfg, _sgd(lr_in), _adam(0.01), 1, 1.0, n_inner_test=n_inner_test, group_tasks=(mode != "plain")))
+    tr.injected_masks = masks
+    theta0, bn0 = tr.theta.clone(), tr.base_bn.clone()
+    if mode == "outputs":
+        log = tr._metatest_step(tasks, return_outputs=True)
+    else:
+        log = tr._metatest(1, [tasks])[0]
+    torch.cuda.synchronize()
+    tr.engine.check_abort()
+    assert log["task_index"] == list(range(n_tasks)) and log["speakers"] == list(tasks)
+    for i, spk in enumerate(tasks):
+        loss, _, out, _, _ = OMeta.fomaml_task(P0, cfg, tasks[spk], [masks[(i, p0 + p)] for p in range(n_inner_test + 1)], CRIT, names,
+                                               n_inner_test, lr_in)
+        test = tasks[spk]["test"]
+        mcd = OMeta.mcd_batch(out[0].transpose(1, 2), test[3].transpose(1, 2), test[4].tolist())
+        assert abs(float(log["loss_test"][i]) - float(loss)) < TOL * abs(float(loss))
+        assert abs(float(log["mcd"][i]) - mcd) < TOL * abs(mcd)
+        if mode == "outputs":
+            for a, b in zip(log["outputs"][i], out):
+                assert float((a.cpu().double() - b.detach().double()).norm()) < TOL * float(b.detach().double().norm())
+    assert torch.equal(tr.theta, theta0) and torch.equal(tr.base_bn, bn0) and tr.step_global == 0
+    assert float(tr.outer_m.abs().max()) == 0.0 and float(tr.outer_v.abs().max()) == 0.0
+
+
+def test_run_epoch_loop_like_the_reference(tmp_path):
+    """maml.py:19-31: per epoch the meta-train loader, a checkpoint every ckpt_save_epoch_interval and a meta-test every
+    metatest_epoch_interval epochs."""
+    from msa_tts_b200.maml import MAML
+    cfg, tasks, _, _, _ = _setup(2, 1)
+    tr = MAML(**_params(cfg, _sgd(0.05), _sgd(0.02), 1, None, n_epochs=2, ckpt_save_epoch_interval=2, metatest_epoch_interval=2,
+                        n_inner_test=1, output_path=str(tmp_path)))
+    tr.dataloader_metatrain = [tasks, tasks]
+    tr.dataloader_metatest = [tasks]
+    logs = tr.run()
+    assert len(logs) == 4 and tr.step_global == 4
+    assert os.path.exists(os.path.join(str(tmp_path), "checkpoint_0.pt"))          # step_global // 100 (metatrainer.py:120)
+    assert len(tr.last_metatest) == 1 and tr.last_metatest[0]["loss_test"].numel() == 2

@@ -43,7 +43,7 @@ def test_train_small(name):
     g = torch.autograd.grad(loss, [Pl[n] for n in names], allow_unused=True)
     for key, o in zip(("mel", "mel_post", "gate", "align"), out):
         assert rel(o.detach(), z[key]) < TOL, key
-    assert abs(float(loss) - float(z["loss"])) < TOL * abs(float(z["loss"]))
+    assert abs(float(loss.detach()) - float(z["loss"])) < TOL * abs(float(z["loss"]))
     gn = np.sqrt(sum(float((z["grad/" + n].astype(np.float64) ** 2).sum()) for n in names))
     for n, gi in zip(names, g):
         gi = torch.zeros_like(Pl[n]) if gi is None else gi
@@ -73,7 +73,7 @@ def test_train_default_compact():
     for key, o in zip(("mel", "mel_post", "gate"), out):
         assert rel(o.detach(), z[key]) < TOL, key
     assert rel(out[3].detach()[:, ::8], z["align_sample"]) < TOL
-    assert abs(float(loss) - float(z["loss"])) < TOL * abs(float(z["loss"]))
+    assert abs(float(loss.detach()) - float(z["loss"])) < TOL * abs(float(z["loss"]))
     gn = float(np.sqrt((z["grad_norms"] ** 2).sum()))
     for i, (n, gi) in enumerate(zip(names, g)):
         assert abs(float(gi.double().norm()) - z["grad_norms"][i]) / gn < TOL, n
