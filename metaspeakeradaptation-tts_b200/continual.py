@@ -47,7 +47,8 @@ def adaptive_weight_decay(weightdecay_value: float, spk_similarity: float) -> fl
 
 def sgd_train_step(model, batch: tuple, lr: float, ewc=None, importance: float = 0.0, masks: Optional[dict] = None,
                    weight_decay: float = 0.0) -> dict:
-    """One continual training step with plain SGD: loss (+ importance * EWC penalty), backward, update.
+    """One continual training step with plain SGD: loss (+ importance * EWC penalty), backward, update; returns the loss and the
+    step's MCD log metric as device tensors (no host sync).
     ``weight_decay`` is torch.optim.SGD's (g += wd * p), folded into the same streaming update kernel."""
     eng = model.engine
     bd = batch_to_device(batch, eng.device, model.params["speaker_emb_type"])
@@ -55,14 +56,15 @@ def sgd_train_step(model, batch: tuple, lr: float, ewc=None, importance: float =
     T = bd["melspecs"].shape[2]
     mk = eng.pack_masks(masks, B, T, L) if masks is not None else model._masks(B, T, L)
     _, loss = eng.forward(model.flat, model.bn_flat, bd, mk, outputs=False)
+    mcd = eng.mcd(bd["melspec_lengths"])       # the per-step log metric (baseline.py:217-219, continual_erkd.py:338-342) on the device
     eng.backward(model.flat, model.grad_flat)
     if ewc is not None:
         if weight_decay:
             raise NotImplementedError("EWC step with weight decay: the reference never combines them (continual_ewc.py:338-357)")
         penalty = ewc.sgd_step(model.grad_flat, lr, importance)                     # fused penalty gradient + update
-        return {"loss": loss, "penalty": penalty}
+        return {"loss": loss, "mcd": mcd, "penalty": penalty}
     eng.sgd_step(model.flat, model.grad_flat, lr=lr, weight_decay=weight_decay)
-    return {"loss": loss}
+    return {"loss": loss, "mcd": mcd}
 
 
 def train_step(model, batch: tuple, optim: dict, ewc=None, importance: float = 0.0, masks: Optional[dict] = None) -> dict:
@@ -88,8 +90,8 @@ def train_step(model, batch: tuple, optim: dict, ewc=None, importance: float = 0
     T = bd["melspecs"].shape[2]
     mk = eng.pack_masks(masks, B, T, L) if masks is not None else model._masks(B, T, L)
     _, loss = eng.forward(model.flat, model.bn_flat, bd, mk, outputs=False)
+    out = {"loss": loss, "mcd": eng.mcd(bd["melspec_lengths"])}
     eng.backward(model.flat, model.grad_flat)
-    out = {"loss": loss}
     if ewc is not None:
         out["penalty"] = ewc.add_penalty_grad(model.grad_flat, importance)
     st = model.__dict__.setdefault("_optim_state", {"step": 0})

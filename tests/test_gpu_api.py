@@ -84,7 +84,7 @@ def test_innerloop_fomaml_task_like_maml_py():
         loss_test = criterion(fmodel(**kw), targets, mel_len)
         task_grads = torch.autograd.grad(loss_test, fmodel.parameters(time=-1))                  # maml.py:73-74
     assert torch.equal(theta0, model.flat), "the base model is never touched inside the inner loop"
-    assert abs(float(loss_test) - float(o_loss)) < TOL * abs(float(o_loss))
+    assert abs(float(loss_test.detach()) - float(o_loss)) < TOL * abs(float(o_loss))
     assert _gerr(task_grads, o_g, names) < TOL
     # mix_grad / apply_grad (maml.py:94-99, utils/grad_utils.py:8-31)
     from msa_tts_b200.grad_utils import apply_grad, mix_grad
@@ -156,7 +156,7 @@ def test_innerloop_with_adam_inner_optimizer():
     # the quantities that matter -- test loss and meta-gradient -- at tolerances relative to their own size
     upd = float(torch.sqrt(sum(((Pc[n].detach() - P[n]).double() ** 2).sum() for n in names)))
     dif = float(torch.sqrt(sum(((fast[n].cpu() - Pc[n].detach()).double() ** 2).sum() for n in names)))
-    lerr, gerr = abs(float(loss_test) - float(o_loss)) / abs(float(o_loss)), _gerr(task_grads, o_g, names)
+    lerr, gerr = abs(float(loss_test.detach()) - float(o_loss)) / abs(float(o_loss)), _gerr(task_grads, o_g, names)
     print(f"inner Adam: fast-weight diff / update {dif / upd:.3e}, loss rel {lerr:.3e}, meta-grad err/|G| {gerr:.3e}")
     assert dif < 0.15 * upd, (dif, upd)
     assert lerr < TOL and gerr < TOL, (lerr, gerr)
@@ -220,6 +220,9 @@ def test_erkd_soft_targets_like_continual_erkd_py():
     before = {k: v.clone() for k, v in model.engine.dict_from_flat(model.flat).items()}
     log = sgd_train_step(model, batch, 0.01, masks=masks)
     assert abs(float(log["loss"]) - float(o_loss)) < TOL * abs(float(o_loss))
+    from oracle import meta as OMeta          # the step's log metric (continual_erkd.py:338-342): mcd_batch of the FIRST output
+    o_mcd = OMeta.mcd_batch(o_out[0].detach().transpose(1, 2), batch[3].transpose(1, 2), batch[4].tolist())
+    assert abs(float(log["mcd"]) - o_mcd) < TOL * abs(o_mcd)
     after = model.engine.dict_from_flat(model.flat)
     names = list(P.keys())
     num = sum(float(((after[n] - (before[n] - 0.01 * o_g[n].to(after[n].device))).double() ** 2).sum()) for n in names)
