@@ -88,6 +88,16 @@ class Tacotron2NV(nn.Module):
             _descend(self, name.split(".")).register_buffer("num_batches_tracked", torch.zeros((), dtype=torch.long))
 
     # ---- plumbing ---------------------------------------------------------------------------------
+    def _apply(self, fn, recurse: bool = True):
+        """``model.to(self.device)`` of the reference trainers (metatrainer.py:56, baseline.py:64) is a no-op here: the model is born
+        on its GPU.  A conversion that would move the parameters to another device or dtype (``.cpu()``, ``.half()``, another GPU)
+        would silently detach them from the flat buffer the kernels read, so it is a loud error instead."""
+        probe = fn(self.flat[:1])
+        if probe.device != self.flat.device or probe.dtype != self.flat.dtype:
+            raise RuntimeError(f"Tacotron2NV lives in one flat fp32 buffer on {self.flat.device}: it cannot be converted to "
+                               f"{probe.device} / {probe.dtype} (build it with device=... instead)")
+        return super()._apply(fn, recurse)
+
     def _new_ticket(self) -> int:
         self._ticket += 1
         return self._ticket

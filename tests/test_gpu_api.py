@@ -350,3 +350,19 @@ def test_ewc_training_steps_with_any_torch_optimizer_like_continual_ewc_py(optim
         err = float(torch.sqrt(sum(((new[n].cpu() - ref_p[n].detach()).double() ** 2).sum() for n in names)))
         print(f"{h['name']} step {step}: |theta - theta_ref| / |theta_ref - theta_0| = {err / moved:.2e}")
         assert err < 1e-5 * moved
+
+
+def test_model_to_its_own_device_is_a_noop_and_other_conversions_are_loud():
+    """metatrainer.py:56 / baseline.py:64 call ``self.model.to(self.device)``: the parameters must stay views of the flat buffer the
+    kernels read; a conversion that would detach them (.cpu(), .half()) raises instead of silently training a stale copy."""
+    cfg = pkg.small_params()
+    model = _model(cfg, synth.init_params(cfg, 3))
+    ptrs = [p.data_ptr() for p in model.parameters()]
+    assert model.to(model.engine.device) is model and model.cuda() is model and model.float() is model
+    assert [p.data_ptr() for p in model.parameters()] == ptrs
+    first = next(iter(model.parameters()))
+    assert first.data_ptr() == model.flat.data_ptr() + 4 * model.layout.offsets[model.layout.names()[0]]
+    for bad in (model.cpu, model.half, model.double):
+        with pytest.raises(RuntimeError):
+            bad()
+    assert [p.data_ptr() for p in model.parameters()] == ptrs
