@@ -92,6 +92,8 @@ class MetaTrainer:
         self.outer_v = self.engine.new_flat() if self.outer["name"] == "Adam" else None
         self.sumsq = torch.zeros(1, device=self.device)
         self.step_global = 0
+        self._outer_steps = 0            # outer optimizer steps taken so far: survives run()'s reset of step_global (maml.py:20), like
+        #                                  the state of the reference's torch optimizer does
         self.mask_seed = int(params.get("dataset_random_seed", 1234))
         self._mask_bufs: Dict[tuple, torch.Tensor] = {}
         self._slots: list = []
@@ -345,12 +347,13 @@ class MetaTrainer:
         if o["name"] == "SGD":
             eng.clip_sgd(self.theta, self.meta_grad, self.sumsq, lr=o["lr"], max_norm=thr, momentum=o.get("momentum", 0.0),
                          dampening=o.get("dampening", 0.0), weight_decay=o.get("weight_decay", 0.0), nesterov=o.get("nesterov", False),
-                         buf=self.outer_m, first_step=(self.step_global == 0))
+                         buf=self.outer_m, first_step=(self._outer_steps == 0))
         else:
-            eng.clip_adam(self.theta, self.meta_grad, self.outer_m, self.outer_v, self.sumsq, lr=o["lr"], step=self.step_global + 1,
+            eng.clip_adam(self.theta, self.meta_grad, self.outer_m, self.outer_v, self.sumsq, lr=o["lr"], step=self._outer_steps + 1,
                           betas=o.get("betas", (0.9, 0.999)), eps=o.get("eps", 1e-8), weight_decay=o.get("weight_decay", 0.0),
                           max_norm=thr)
         self.step_global += 1
+        self._outer_steps += 1
         eng.abort_poll()
         return self.sumsq
 

@@ -322,3 +322,6 @@ def test_run_epoch_loop_like_the_reference(tmp_path):
     assert len(logs) == 4 and tr.step_global == 4
     assert os.path.exists(os.path.join(str(tmp_path), "checkpoint_0.pt"))          # step_global // 100 (metatrainer.py:120)
     assert len(tr.last_metatest) == 1 and tr.last_metatest[0]["loss_test"].numel() == 2
+    # a second run() restarts the step counter of the logs (maml.py:20) but not the outer optimizer's own state / step count
+    tr.run(n_epochs=1)
+    assert tr.step_global == 2 and tr._outer_steps == 6
