@@ -142,3 +142,29 @@ def test_task_group_plan():
     assert plan_task_groups(list(range(5)), mixed, 1, False, True, gs) == [[0, 2], [1, 4], [3]]    # ragged speakers: by shape
     many = {i: ((4, 64), 200) for i in range(16)}
     assert plan_task_groups(list(range(16)), many, 5, False, True, gs) == [list(range(8)), list(range(8, 16))]
+
+
+def test_reference_call_surface_names_and_keyword_defaults():
+    """The drop-in surface keeps the names and keyword defaults of what it replaces: ``higher.innerloop_ctx(model, opt,
+    copy_initial_weights=True, track_higher_grads=True)`` (maml.py:40-41 passes the flag explicitly; an omitted flag must not turn
+    into a silent first-order run), ``mix_grad(grad_list, weight_list)`` / ``apply_grad(model, grad)`` (utils/grad_utils.py:8,23),
+    ``run()`` / ``_metatrain(epoch)`` / ``_metatest(epoch)`` on both trainers (maml.py:19,33,115; reptile.py:19,33,108)."""
+    import inspect
+    import msa_tts_b200 as pkg
+    from msa_tts_b200 import grad_utils
+    from msa_tts_b200.maml import MAML
+    from msa_tts_b200.reptile import Reptile
+    sig = inspect.signature(pkg.innerloop_ctx)
+    assert list(sig.parameters)[:2] == ["model", "opt"]
+    assert sig.parameters["track_higher_grads"].default is True and sig.parameters["copy_initial_weights"].default is True
+    mg = inspect.signature(grad_utils.mix_grad).parameters
+    assert list(mg)[:2] == ["grad_list", "weight_list"] and all(p.default is not inspect.Parameter.empty for p in list(mg.values())[2:])
+    assert list(inspect.signature(grad_utils.apply_grad).parameters) == ["model", "grad"]
+    for cls in (MAML, Reptile):
+        for name in ("run", "_metatrain", "_metatest", "_metatrain_step", "_metatest_step", "_unpack_batch", "_save_checkpoint",
+                     "_load_checkpoint"):
+            assert callable(getattr(cls, name)), (cls.__name__, name)
+        for name in ("_metatrain", "_metatest"):       # callable as the reference calls them: (epoch) only
+            ps = list(inspect.signature(getattr(cls, name)).parameters.values())
+            assert ps[1].name == "epoch" and all(p.default is not inspect.Parameter.empty for p in ps[2:])
+        assert all(p.default is not inspect.Parameter.empty for p in list(inspect.signature(cls.run).parameters.values())[1:])
