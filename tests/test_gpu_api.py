@@ -1,6 +1,8 @@
 """The reference-shaped Python surface (Tacotron2NV / Tacotron2Loss / innerloop_ctx / mix_grad / apply_grad / EWC) on the CUDA
 path, written the way the reference trainers call it (maml.py:40-76,94-105; continual_ewc.py:28-89,345-357) and checked
 against the oracle.  Tolerance: fp32, 2e-4 (outputs per tensor, gradients relative to the global gradient norm)."""
+import os
+
 import pytest
 import torch
 
@@ -366,3 +368,50 @@ def test_model_to_its_own_device_is_a_noop_and_other_conversions_are_loud():
         with pytest.raises(RuntimeError):
             bad()
     assert [p.data_ptr() for p in model.parameters()] == ptrs
+
+
+def test_joint_trainer_train_test_run_like_baseline_py(tmp_path):
+    """baseline.py:181-296 (BASELINE configs[0]'s caller): ``_train`` = forward, loss, backward, SGD step per batch; ``_test`` = the
+    test loader in train mode without gradients, mean loss / MCD, ``checkpoint_best.pt`` on improvement; ``run`` = the epoch loop.
+    Against the oracle on the same batches and injected dropout masks."""
+    from msa_tts_b200.baseline import JointTrainer
+    cfg = pkg.small_params()
+    B, T, L, lr = 3, 10, 8, 0.02
+    P0 = synth.init_params(cfg, 5)
+    names = list(P0.keys())
+    batches = [synth.make_batch(cfg, B, T, L, 910 + i) for i in range(2)]
+    test_batches = [synth.make_batch(cfg, B, T, L, 920 + i) for i in range(2)]
+    masks = synth.make_masks(cfg, B, T, L, 930)
+    tr = JointTrainer(model=cfg, criterion={"criterion_type": "Tacotron2Loss", **CRIT}, init_seed=5, n_epochs=1,
+                      optim={"optimizer_name": "SGD", "optim_params": {"lr": str(lr)}}, freeze_charemb=False, freeze_encoder=False,
+                      freeze_decoder=False, ckpt_save_epoch_interval=1, output_path=str(tmp_path))
+    tr.model.injected_masks = masks
+    logs = tr._train(1, batches)
+    P, stats = P0, OM.fresh_bn_stats(P0, cfg)
+    for i, batch in enumerate(batches):
+        o_loss, o_g, o_out = OMeta.loss_and_grads(P, cfg, batch, masks, stats, CRIT, names)
+        o_mcd = OMeta.mcd_batch(o_out[0].transpose(1, 2), batch[3].transpose(1, 2), batch[4].tolist())
+        assert abs(float(logs[i]["loss"]) - float(o_loss)) < TOL * abs(float(o_loss))
+        assert abs(float(logs[i]["mcd"]) - o_mcd) < TOL * abs(o_mcd)
+        P = OMeta.sgd_step(P, o_g, names, lr)
+    got = tr.model.engine.dict_from_flat(tr.model.flat)
+    upd = float(torch.sqrt(sum(((P[n] - P0[n]).double() ** 2).sum() for n in names)))
+    assert max(float((got[n].double().cpu() - P[n].double()).norm()) for n in names) < TOL * upd
+    assert tr.step_global == 2
+    # _test: no gradient step, mean over the batches, best checkpoint with the reference's key set
+    before = tr.model.flat.clone()
+    t = tr._test(1, test_batches)
+    want = [OMeta.loss_and_grads(P, cfg, b, masks, stats, CRIT, names) for b in test_batches]
+    o_loss = sum(float(w[0]) for w in want) / 2
+    o_mcd = sum(OMeta.mcd_batch(w[2][0].transpose(1, 2), b[3].transpose(1, 2), b[4].tolist()) for w, b in zip(want, test_batches)) / 2
+    assert abs(t["loss"] - o_loss) < TOL * abs(o_loss) and abs(t["mcd"] - o_mcd) < TOL * abs(o_mcd)
+    assert t["best"] and tr.best_test_loss == t["loss"] and torch.equal(tr.model.flat, before)
+    sd = torch.load(os.path.join(str(tmp_path), "checkpoint_best.pt"), map_location="cpu")
+    assert [k for k in sd if k in set(names)] == names and torch.equal(sd[names[-1]], got[names[-1]].cpu())
+    # run(): the epoch loop; a second trainer finetunes from the checkpoint it wrote
+    out = tr.run(batches, test_batches, n_epochs=2)
+    assert len(out) == 2 and tr.step_global == 4 and len(tr.train_logs) == 2
+    path = os.path.join(str(tmp_path), "checkpoint_0.pt")
+    assert os.path.exists(path)
+    tr2 = JointTrainer(model=cfg, optim=tr.optim, init_seed=99, finetune=True, finetune_checkpoint_path=path)
+    assert torch.equal(tr2.model.flat, tr.model.flat)
