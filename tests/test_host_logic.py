@@ -168,3 +168,111 @@ def test_reference_call_surface_names_and_keyword_defaults():
             ps = list(inspect.signature(getattr(cls, name)).parameters.values())
             assert ps[1].name == "epoch" and all(p.default is not inspect.Parameter.empty for p in ps[2:])
         assert all(p.default is not inspect.Parameter.empty for p in list(inspect.signature(cls.run).parameters.values())[1:])
+
+
+class _RecordingEngine:
+    """Test double of engine.Engine for the ORCHESTRATION of the trainers only (which call follows which, what is never called);
+    it computes nothing.  The product path has no such thing: MetaTrainer.__init__ builds the real engine or fails."""
+
+    def __init__(self):
+        self.calls = []
+        self.device = torch.device("cpu")
+
+    def _rec(self, name, *a):
+        self.calls.append((name,) + a)
+
+    def forward(self, params, bn, bd, masks, outputs=True):
+        self._rec("forward", params.data_ptr(), int(masks), bool(outputs))
+        out = [torch.zeros(1)] * 4 if outputs else None
+        return out, torch.full((1,), float(len(self.calls)))
+
+    def backward(self, params, grads, accumulate=False, scale=1.0, **kw):
+        self._rec("backward", params.data_ptr())
+
+    def sgd_step(self, p, g, p_out=None, **kw):
+        self._rec("sgd_step", p.data_ptr(), (p if p_out is None else p_out).data_ptr())
+
+    def mcd(self, lens, which=0):
+        self._rec("mcd")
+        return torch.zeros(1)
+
+    def abort_poll(self):
+        self._rec("abort_poll")
+
+    def abort_flush(self):
+        self._rec("abort_flush")
+
+    def group_size(self, n, B):
+        return 1
+
+
+def _bare_trainer(cls, **params):
+    """A trainer object with the attributes its epoch-level methods use, without the CUDA engine of __init__."""
+    from msa_tts_b200.parallel import ShardInfo
+    tr = object.__new__(cls)
+    tr.params = dict(n_inner_train=1, group_tasks=False, **params)
+    tr.engine, tr.shard, tr.device = _RecordingEngine(), ShardInfo(), torch.device("cpu")
+    tr.speaker_emb_type = "static"
+    tr.inner = {"name": "SGD", "lr": 0.1}
+    tr.theta, tr.fast, tr.task_grad = torch.zeros(8), torch.zeros(8), torch.zeros(8)
+    tr.base_bn, tr.task_bn = torch.ones(4), torch.zeros(4)
+    tr.inner_buf = None
+    tr.step_global, tr._outer_steps = 0, 0
+    tr.injected_masks = None
+    tr._masks = lambda i, p, B, T, L, slot=0: 1000 * i + p          # the mask KEY (task, pass) instead of a mask buffer
+    return tr
+
+
+def _toy_task(B=2, T=5, L=3):
+    z = torch.zeros
+    batch = (["a"] * B, z(B, L, dtype=torch.long), z(B, dtype=torch.long), z(B, 4, T), z(B, dtype=torch.long), z(B, dtype=torch.long),
+             z(B, 2), z(B, T))
+    return {"train": batch, "test": batch}
+
+
+def test_metatest_orchestration_adapts_then_evaluates_without_a_gradient_or_an_outer_step():
+    """maml.py:115-179 on a recording engine: per speaker n_inner_test x (forward, backward, inner step) on the train split -- the
+    first step reading theta and writing the fast weights -- then ONE forward + MCD on the test split with the adapted weights, no
+    backward after it, no outer update, theta / base BatchNorm statistics / step counters untouched; the dropout-mask stream of the
+    meta-test passes starts at METATEST_PASS0."""
+    from msa_tts_b200.maml import MAML
+    tr = _bare_trainer(MAML, n_inner_test=2)
+    items = {"s0": _toy_task(), "s1": _toy_task()}
+    log = tr._metatest_step(items)
+    th, fa, p0 = tr.theta.data_ptr(), tr.fast.data_ptr(), MAML.METATEST_PASS0
+    per_task = lambda i: [("forward", th, 1000 * i + p0, False), ("backward", th), ("sgd_step", th, fa),
+                          ("forward", fa, 1000 * i + p0 + 1, False), ("backward", fa), ("sgd_step", fa, fa),
+                          ("forward", fa, 1000 * i + p0 + 2, False), ("mcd",)]
+    assert tr.engine.calls == per_task(0) + per_task(1) + [("abort_poll",)]
+    assert log["task_index"] == [0, 1] and log["speakers"] == ["s0", "s1"] and log["loss_test"].numel() == 2 and log["mcd"].numel() == 2
+    assert tr.step_global == 0 and tr._outer_steps == 0 and float(tr.theta.abs().sum()) == 0.0
+    assert torch.equal(tr.base_bn, torch.ones(4)) and torch.equal(tr.task_bn, tr.base_bn)      # the private copy was re-seeded
+    # with the outputs asked for, the test pass returns them and still takes no gradient
+    tr.engine.calls.clear()
+    log = tr._metatest_step({"s0": _toy_task()}, return_outputs=True)
+    assert [c[0] for c in tr.engine.calls].count("backward") == 2 and tr.engine.calls[-3][:1] == ("forward",) and tr.engine.calls[-3][3]
+    assert len(log["outputs"]) == 1 and len(log["outputs"][0]) == 4
+
+
+def test_run_schedules_checkpoints_and_metatests_like_the_reference_epoch_loop():
+    """maml.py:19-31: ``run`` = per epoch ``_metatrain``; ``_save_checkpoint`` every ckpt_save_epoch_interval, ``_metatest`` every
+    metatest_epoch_interval epochs; step_global restarts at 0."""
+    from msa_tts_b200.reptile import Reptile
+    tr = _bare_trainer(Reptile, n_epochs=4, ckpt_save_epoch_interval=2, metatest_epoch_interval=3)
+    seen = []
+    tr._metatrain_step = lambda items_b: seen.append(("train", items_b)) or {"i": items_b}
+    tr._metatest_step = lambda items_b: seen.append(("test", items_b)) or {"t": items_b}
+    tr._save_checkpoint = lambda path=None: seen.append(("ckpt",))
+    tr.step_global = 17
+    logs = tr.run(dataloader_metatrain=["b0", "b1"], dataloader_metatest=["m0"])
+    want = []
+    for epoch in range(1, 5):
+        want += [("train", "b0"), ("train", "b1")]
+        if epoch % 2 == 0:
+            want.append(("ckpt",))
+        if epoch % 3 == 0:
+            want.append(("test", "m0"))
+    assert seen == want and len(logs) == 8 and tr.last_metatest == [{"t": "m0"}]
+    assert tr.step_global == 0          # the lambdas above do not step; run() reset the counter (maml.py:20)
+    with __import__("pytest").raises(RuntimeError):
+        _bare_trainer(Reptile)._metatest(1)                     # no loader: a loud error, not an empty epoch
