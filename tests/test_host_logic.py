@@ -205,6 +205,25 @@ class _RecordingEngine:
     def group_size(self, n, B):
         return 1
 
+    def encoder_prefix(self):
+        return 0
+
+    def reptile_delta(self, acc, p_T, p_0, w, init):
+        self._rec("reptile_delta", p_T.data_ptr(), p_0.data_ptr(), round(float(w), 6), bool(init))
+
+    def sumsq(self, g, out=None):
+        self._rec("sumsq")
+        return out
+
+    def abort_guard(self, sumsq):
+        self._rec("abort_guard")
+
+    def clip_sgd(self, p, g, sumsq, lr, **kw):
+        self._rec("clip_sgd", p.data_ptr(), bool(kw.get("first_step")))
+
+    def clip_adam(self, p, g, m, v, sumsq, lr, step, **kw):
+        self._rec("clip_adam", p.data_ptr(), int(step))
+
 
 def _bare_trainer(cls, **params):
     """A trainer object with the attributes its epoch-level methods use, without the CUDA engine of __init__."""
@@ -218,6 +237,8 @@ def _bare_trainer(cls, **params):
     tr.base_bn, tr.task_bn = torch.ones(4), torch.zeros(4)
     tr.inner_buf = None
     tr.step_global, tr._outer_steps = 0, 0
+    tr.outer = {"name": "Adam", "lr": 1e-3}
+    tr.meta_grad, tr.sumsq, tr.outer_m, tr.outer_v = torch.zeros(8), torch.zeros(1), torch.zeros(8), torch.zeros(8)
     tr.injected_masks = None
     tr._masks = lambda i, p, B, T, L, slot=0: 1000 * i + p          # the mask KEY (task, pass) instead of a mask buffer
     return tr
@@ -276,3 +297,37 @@ def test_run_schedules_checkpoints_and_metatests_like_the_reference_epoch_loop()
     assert tr.step_global == 0          # the lambdas above do not step; run() reset the counter (maml.py:20)
     with __import__("pytest").raises(RuntimeError):
         _bare_trainer(Reptile)._metatest(1)                     # no loader: a loud error, not an empty epoch
+
+
+def test_reptile_outer_loop_semantics_sequential_by_default_batched_on_request():
+    """reptile.py:37-89 on a recording engine.  Default on one GPU = the reference's literal loop: an outer step after EACH speaker
+    (the next speaker adapts from the updated weights), step_global and the optimizer's step count advancing once per speaker.
+    ``reptile_sequential=False``: every speaker adapts from the same theta, the deltas are mixed with weights 1/N, ONE outer step."""
+    from msa_tts_b200.reptile import Reptile
+    items = {"s0": _toy_task(), "s1": _toy_task()}
+
+    def names(tr):
+        return [c[0] for c in tr.engine.calls]
+    tr = _bare_trainer(Reptile)
+    tr.params["n_inner_train"] = 2
+    tr.sequential = True                                  # what Reptile.__init__ picks when world == 1 and the key is absent
+    tr._metatrain_step(items)
+    th, fa = tr.theta.data_ptr(), tr.fast.data_ptr()
+    spk = ["forward", "backward", "sgd_step", "forward", "backward", "sgd_step", "forward", "mcd", "reptile_delta",
+           "sumsq", "abort_guard", "clip_adam", "abort_poll"]
+    assert names(tr) == spk + spk
+    deltas = [c for c in tr.engine.calls if c[0] == "reptile_delta"]
+    assert deltas == [("reptile_delta", fa, th, 1.0, True)] * 2                                  # reptile.py:75-77, weight 1
+    assert [c[2] for c in tr.engine.calls if c[0] == "clip_adam"] == [1, 2] and tr.step_global == 2 and tr._outer_steps == 2
+    tr = _bare_trainer(Reptile)
+    tr.params["n_inner_train"] = 2
+    tr.sequential = False
+    tr._metatrain_step(items)
+    task = spk[:9]
+    assert names(tr) == task + task + spk[9:]
+    assert [c[3:] for c in tr.engine.calls if c[0] == "reptile_delta"] == [(0.5, True), (0.5, False)]
+    assert tr.step_global == 1 and tr._outer_steps == 1
+    # Reptile.__init__'s choice of the default, without building an engine: sequential unless sharded
+    import inspect
+    src = inspect.getsource(Reptile.__init__)
+    assert "seq = self.shard.world == 1" in src and "cannot be sharded" in src
