@@ -187,7 +187,7 @@ class _RecordingEngine:
         return out, torch.full((1,), float(len(self.calls)))
 
     def backward(self, params, grads, accumulate=False, scale=1.0, **kw):
-        self._rec("backward", params.data_ptr())
+        self._rec("backward", params.data_ptr(), bool(accumulate), round(float(scale), 6))
 
     def sgd_step(self, p, g, p_out=None, **kw):
         self._rec("sgd_step", p.data_ptr(), (p if p_out is None else p_out).data_ptr())
@@ -261,8 +261,8 @@ def test_metatest_orchestration_adapts_then_evaluates_without_a_gradient_or_an_o
     items = {"s0": _toy_task(), "s1": _toy_task()}
     log = tr._metatest_step(items)
     th, fa, p0 = tr.theta.data_ptr(), tr.fast.data_ptr(), MAML.METATEST_PASS0
-    per_task = lambda i: [("forward", th, 1000 * i + p0, False), ("backward", th), ("sgd_step", th, fa),
-                          ("forward", fa, 1000 * i + p0 + 1, False), ("backward", fa), ("sgd_step", fa, fa),
+    per_task = lambda i: [("forward", th, 1000 * i + p0, False), ("backward", th, False, 1.0), ("sgd_step", th, fa),
+                          ("forward", fa, 1000 * i + p0 + 1, False), ("backward", fa, False, 1.0), ("sgd_step", fa, fa),
                           ("forward", fa, 1000 * i + p0 + 2, False), ("mcd",)]
     assert tr.engine.calls == per_task(0) + per_task(1) + [("abort_poll",)]
     assert log["task_index"] == [0, 1] and log["speakers"] == ["s0", "s1"] and log["loss_test"].numel() == 2 and log["mcd"].numel() == 2
@@ -331,3 +331,24 @@ def test_reptile_outer_loop_semantics_sequential_by_default_batched_on_request()
     import inspect
     src = inspect.getsource(Reptile.__init__)
     assert "seq = self.shard.world == 1" in src and "cannot be sharded" in src
+
+
+def test_fomaml_meta_step_orchestration_accumulates_the_weighted_test_gradients():
+    """maml.py:36-105 on a recording engine (plain path, copies not staged): per speaker the inner step(s) from theta, the test-split
+    forward with the adapted weights, its MCD, and a backward that writes ``meta_grad (+)= g / N`` -- first task overwrites, the
+    others accumulate (mix_grad with weights 1/N, maml.py:94-98) -- then ONE outer update."""
+    from msa_tts_b200.maml import MAML
+    tr = _bare_trainer(MAML)
+    tr._stage = lambda batches: batches            # the side-stream H2D staging needs CUDA; _unpack_batch takes plain tuples too
+    tr._bwd_event = None
+    items = {f"s{i}": _toy_task() for i in range(3)}
+    log = tr._metatrain_step(items)
+    th, fa = tr.theta.data_ptr(), tr.fast.data_ptr()
+    want = []
+    for i in range(3):
+        want += [("forward", th, 1000 * i, False), ("backward", th, False, 1.0), ("sgd_step", th, fa),
+                 ("forward", fa, 1000 * i + 1, False), ("mcd",), ("backward", fa, i > 0, round(1.0 / 3, 6))]
+    want += [("sumsq",), ("abort_guard",), ("clip_adam", th, 1), ("abort_poll",)]
+    assert tr.engine.calls == want
+    assert log["task_index"] == [0, 1, 2] and log["loss_test"].numel() == 3 and log["mcd"].numel() == 3
+    assert tr.step_global == 1 and tr._outer_steps == 1
