@@ -208,6 +208,28 @@ class _RecordingEngine:
     def encoder_prefix(self):
         return 0
 
+    def new_flat(self, fill=0.0):
+        return torch.zeros(8)
+
+    def new_bn_stats(self):
+        return torch.zeros(4)
+
+    def forward_group(self, params, bn_stats, batches_dev, masks):
+        ps = [p.data_ptr() for p in params] if isinstance(params, (list, tuple)) else params.data_ptr()
+        self._rec("forward_group", ps, [int(m) for m in masks])
+        return torch.zeros(len(batches_dev))
+
+    def backward_group(self, params, grads, accumulate=False, scale=1.0):
+        ps = [p.data_ptr() for p in params] if isinstance(params, (list, tuple)) else params.data_ptr()
+        self._rec("backward_group", ps, [g.data_ptr() for g in grads])
+
+    def mcd_group(self, g, lens, which=0):
+        self._rec("mcd_group", int(g))
+        return torch.zeros(1)
+
+    def axpy(self, acc, g, w, init):
+        self._rec("axpy", g.data_ptr(), round(float(w), 6), bool(init))
+
     def reptile_delta(self, acc, p_T, p_0, w, init):
         self._rec("reptile_delta", p_T.data_ptr(), p_0.data_ptr(), round(float(w), 6), bool(init))
 
@@ -352,3 +374,31 @@ def test_fomaml_meta_step_orchestration_accumulates_the_weighted_test_gradients(
     assert tr.engine.calls == want
     assert log["task_index"] == [0, 1, 2] and log["loss_test"].numel() == 3 and log["mcd"].numel() == 3
     assert tr.step_global == 1 and tr._outer_steps == 1
+
+
+def test_grouped_fomaml_meta_step_orchestration():
+    """The task-group path (metatrainer.plan_task_groups, include/msa_b200.h "task groups") on a recording engine: ONE grouped pass
+    from theta for the first inner step of all tasks (maml.py:38-41: every task starts from the same weights), per-task functional
+    updates into the slots' fast weights, ONE grouped test pass with per-task weights, and the slots' gradients mixed into the
+    meta-gradient with weights 1/N (first overwrites)."""
+    from msa_tts_b200.maml import MAML
+    tr = _bare_trainer(MAML)
+    tr.params["group_tasks"] = True
+    tr.engine.group_size = lambda n, B: n
+    tr._stage = lambda batches: batches
+    tr._bwd_event, tr._slots = None, []
+    tr._masks = lambda i, p, B, T, L, slot=0: 1000 * i + 10 * slot + p
+    items = {f"s{i}": _toy_task() for i in range(3)}
+    log = tr._metatrain_step(items)
+    th = tr.theta.data_ptr()
+    fast = [tr._slot(k)[0].data_ptr() for k in range(3)]
+    grad = [tr._slot(k)[1].data_ptr() for k in range(3)]
+    assert fast[0] == tr.fast.data_ptr() and len(set(fast)) == 3 and len(set(grad)) == 3       # slot 0 = the plain path's buffers
+    want = [("forward_group", th, [0, 1010, 2020]), ("backward_group", th, grad)]
+    want += [("sgd_step", th, fast[k]) for k in range(3)]
+    want += [("forward_group", fast, [1, 1011, 2021]), ("mcd_group", 0), ("mcd_group", 1), ("mcd_group", 2),
+             ("backward_group", fast, grad)]
+    want += [("axpy", grad[k], round(1.0 / 3, 6), k == 0) for k in range(3)]
+    want += [("sumsq",), ("abort_guard",), ("clip_adam", th, 1), ("abort_poll",)]
+    assert tr.engine.calls == want
+    assert log["task_index"] == [0, 1, 2] and log["loss_test"].numel() == 3 and log["mcd"].numel() == 3
